@@ -1,0 +1,125 @@
+"""Shared parity-case definitions: constructor kwargs, seeds and seeded synthetic inputs.
+
+Used by tests/golden/make_golden.py (reference + oracle, build container only) and by the
+tests (oracle vs golden on CPU, CUDA path vs golden/oracle on the GPU).  Weights are never
+stored: every module is built under ``torch.manual_seed(seed)`` with torch's default inits, which
+consumes the CPU generator identically in the reference and in the product's parameter holders
+(checked through the per-tensor digests in the golden files).
+"""
+import hashlib
+
+import torch
+
+CVIVIT_CASES = {
+    # BASELINE.json configs[0]
+    "cfg1": dict(
+        seed=0,
+        ctor=dict(dim=256, codebook_size=65536, image_size=64, patch_size=16, temporal_patch_size=2,
+                  spatial_depth=2, temporal_depth=2, use_vgg_and_gan=False),
+        video=(1, 3, 5, 64, 64), video_seed=1),
+    # rectangular image / patch, odd temporal patch, small heads, 10-bit codebook, batch 2
+    "rect": dict(
+        seed=3,
+        ctor=dict(dim=128, codebook_size=1024, image_size=(32, 48), patch_size=(8, 16),
+                  temporal_patch_size=3, spatial_depth=1, temporal_depth=2, dim_head=32, heads=4,
+                  use_vgg_and_gan=False),
+        video=(2, 3, 7, 32, 48), video_seed=4),
+    # single image (4-D input, first-frame path only)
+    "image": dict(
+        seed=5,
+        ctor=dict(dim=64, codebook_size=256, image_size=32, patch_size=8, temporal_patch_size=2,
+                  spatial_depth=1, temporal_depth=1, dim_head=32, heads=2, channels=1,
+                  use_vgg_and_gan=False),
+        video=(3, 1, 32, 32), video_seed=6),
+}
+
+MASKGIT_CASES = {
+    "small": dict(
+        seed=10,
+        ctor=dict(dim=128, num_tokens=512, max_seq_len=128, heads=4, dim_head=32, depth=2,
+                  dim_context=96),
+        batch=2, patch_shape=(3, 4, 4), ctx_len=7, ctx_valid=(7, 4), input_seed=11),
+    "wide": dict(  # default head geometry (8 x 64), ragged text lengths
+        seed=12,
+        ctor=dict(dim=256, num_tokens=1024, max_seq_len=256, depth=1, dim_context=768),
+        batch=3, patch_shape=(2, 4, 4), ctx_len=9, ctx_valid=(9, 1, 5), input_seed=13),
+}
+
+CRITIC_CASES = {
+    "small": dict(
+        seed=20,
+        ctor=dict(dim=128, num_tokens=512, max_seq_len=128, has_cross_attn=True, heads=4, dim_head=32,
+                  depth=2, dim_context=96),
+        batch=2, patch_shape=(3, 4, 4), ctx_len=7, ctx_valid=(7, 4), input_seed=21),
+}
+
+# Full Phenaki.sample runs (C-ViViT 'rect'-like tokenizer + MaskGit [+ TokenCritic]).
+SAMPLE_CASES = {
+    "confidence": dict(  # no critic -> 1 - p scores
+        seed=30, steps=6, cond_scale=3.0, num_frames=7, batch=2, ctx_len=6, ctx_valid=(6, 3),
+        critic=False, prime=False, noise_seed=31),
+    "critic_primed": dict(  # token critic + priming with 4 frames, cond_scale 5 (configs[4]-like)
+        seed=32, steps=5, cond_scale=5.0, num_frames=6, batch=2, ctx_len=6, ctx_valid=(2, 6),
+        critic=True, prime=True, prime_frames=4, noise_seed=33),
+}
+
+SAMPLE_CVIVIT = dict(dim=64, codebook_size=256, image_size=(16, 24), patch_size=(8, 8),
+                     temporal_patch_size=3, spatial_depth=1, temporal_depth=1, dim_head=32, heads=2,
+                     use_vgg_and_gan=False)
+SAMPLE_MASKGIT = dict(dim=64, num_tokens=256, max_seq_len=64, heads=2, dim_head=32, depth=2,
+                      dim_context=48)
+SAMPLE_CRITIC = dict(dim=64, num_tokens=256, max_seq_len=64, has_cross_attn=True, heads=2, dim_head=32,
+                     depth=1, dim_context=48)
+
+
+def seeded_randn(shape, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g)
+
+
+def synthetic_text_embeds(batch, ctx_len, dim_context, valid, seed):
+    """(b, L, dim_context) N(0,1) rows with rows >= valid[b] zeroed (= T5 padding, t5.py:95-103)."""
+    e = seeded_randn((batch, ctx_len, dim_context), seed)
+    for b, v in enumerate(valid):
+        e[b, v:] = 0.0
+    return e
+
+
+def token_inputs(case, num_tokens):
+    g = torch.Generator().manual_seed(case["input_seed"])
+    n = 1
+    for d in case["patch_shape"]:
+        n *= d
+    ids = torch.randint(0, num_tokens + 1, (case["batch"], n), generator=g)  # includes mask id
+    ctx = synthetic_text_embeds(case["batch"], case["ctx_len"], case["ctor"]["dim_context"],
+                                case["ctx_valid"], case["input_seed"] + 1000)
+    return ids, ctx
+
+
+def state_digest(sd):
+    """Order-independent digest of a state dict (names, shapes, raw bytes)."""
+    h = hashlib.sha256()
+    for k in sorted(sd):
+        t = sd[k].detach().cpu().contiguous()
+        h.update(k.encode())
+        h.update(str(tuple(t.shape)).encode())
+        h.update(str(t.dtype).encode())
+        h.update(t.numpy().tobytes())
+    return h.hexdigest()
+
+
+class NoiseTape:
+    """Records / replays the uniform draws of the sampling loop in reference order.
+
+    ``tape(shape, tag)`` draws from a private CPU generator seeded with ``seed`` -- the same
+    stream the reference consumed when it ran under ``torch.manual_seed(seed)`` and drew with
+    ``tensor.uniform_()`` (phenaki_pytorch.py:70-71, 88-90)."""
+
+    def __init__(self, seed):
+        self.gen = torch.Generator().manual_seed(seed)
+        self.draws = {}
+
+    def __call__(self, shape, tag):
+        u = torch.zeros(shape).float().uniform_(0, 1, generator=self.gen)
+        self.draws[tag] = u
+        return u
