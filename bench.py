@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""bench.py -- C-ViViT encode frames/s (headline, BASELINE.json configs[1]) + MaskGIT sample tokens/s.
+
+    python bench.py --gpus N --steps K --warmup W            # this framework (libphk.so, sm_100a)
+    python bench.py --impl reference --gpus N ...            # the reference's CPU path (oracle port), rank 0
+
+A "step" is one pass of the hot path over one batch of synthetic input: one
+``CViViT(video, return_only_codebook_ids=True)`` on (8,3,17,256,256) per GPU (weak scaling: every rank
+encodes its own 8 videos, no collective on the data path).  One JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG2 = dict(dim=512, codebook_size=65536, image_size=256, patch_size=32, temporal_patch_size=2, spatial_depth=4,
+            temporal_depth=4, dim_head=64, heads=8, use_vgg_and_gan=False)
+VIDEO = (8, 3, 17, 256, 256)
+CFG3 = dict(dim=512, num_tokens=65536, max_seq_len=1024, dim_context=768, depth=6)
+CFG3_RUN = dict(batch=4, num_frames=17, steps=18, ctx_len=16, cond_scale=3.0)
+# algorithmic FLOPs
+ENCODE_GFLOP = 264.8
+MASKGIT_FWD_GFLOP = 277.1
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"],
+                    src="MEASURED_PEAKS.json")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); power.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+        return dict(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), power_w_max=max(power), samples=len(sm),
+                    reasons=sorted(reasons))
+
+
+def cpu_encode_baseline(seconds_budget=20.0, batch=1):
+    """The reference's CPU path (oracle port: same ATen ops, all host threads) on a BOUNDED sample of the
+    same workload: `batch` video(s) of cfg2 per call."""
+    import torch
+    from oracle import phenaki_oracle as O
+    import phenaki_pytorch_b200 as P
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    sd = {k: v.detach() for k, v in P.CViViT(**CFG2).state_dict().items()}
+    video = torch.randn(batch, *VIDEO[1:])
+    with torch.no_grad():
+        O.cvivit_codebook_ids(video, sd, (256, 256), (32, 32))  # warm-up
+        t0, n = time.perf_counter(), 0
+        while True:
+            O.cvivit_codebook_ids(video, sd, (256, 256), (32, 32))
+            n += 1
+            dt = time.perf_counter() - t0
+            if dt > seconds_budget or n >= 8:
+                break
+    fps = n * batch * VIDEO[2] / dt
+    return dict(value=fps, unit="frames/s", cores=cores, kind="port",
+                sample=f"{n} x oracle C-ViViT cfg2 encode of ({batch},3,17,256,256) fp32, torch {torch.__version__} "
+                       f"CPU eager, {torch.get_num_threads()} threads, {dt:.1f}s")
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port), rank 0 only."""
+    if rank != 0:
+        return
+    per_step = 1  # videos per step (bounded sample of the 8-video batch)
+    import torch
+    from oracle import phenaki_oracle as O
+    import phenaki_pytorch_b200 as P
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    sd = {k: v.detach() for k, v in P.CViViT(**CFG2).state_dict().items()}
+    video = torch.randn(per_step, *VIDEO[1:])
+    with torch.no_grad():
+        for _ in range(min(args.warmup, 2)):
+            O.cvivit_codebook_ids(video, sd, (256, 256), (32, 32))
+        steps = min(args.steps, 10)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            O.cvivit_codebook_ids(video, sd, (256, 256), (32, 32))
+        dt = time.perf_counter() - t0
+    fps = steps * per_step * VIDEO[2] / dt
+    sample = (f"{steps} steps x ({per_step},3,17,256,256) of the cfg2 batch, oracle port of the reference (CPU fp32 "
+              f"eager ATen, {cores} threads)")
+    print(json.dumps({
+        "impl": "reference", "metric": "cvivit_encode_frames_per_s", "value": fps, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 2), "ms_per_step": dt / steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "BASELINE.json configs[1]: CViViT(dim=512,image=256,patch=32,pt=2,depth=4+4) encode+VQ; "
+                               "bounded sample of 1 video (17 frames) per step on the host CPU"},
+        "cpu_baseline": dict(value=fps, unit="frames/s", cores=cores, kind="port", sample=sample),
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def bench_maskgit(dev, prec, steps_timed=1):
+    """configs[2]: MaskGit(dim=512, depth=6, seq=1024, ctx=768) 18-step demasking loop, b=4, 17 frames."""
+    import torch
+    import phenaki_pytorch_b200 as P
+    torch.manual_seed(1)
+    small = dict(CFG2)
+    cv = P.CViViT(**small).to(dev)
+    mg = P.MaskGit(**CFG3).to(dev)
+    cv.precision = mg.precision = prec
+    ph = P.Phenaki(cvivit=cv, maskgit=mg, steps=CFG3_RUN["steps"], text_embed_dim=768)
+    ph.cvivit.precision = prec
+    b, L = CFG3_RUN["batch"], CFG3_RUN["ctx_len"]
+    ctx = torch.randn(b, L, 768, device=dev)
+    ctx[1, L // 2:] = 0
+    n = cv.num_tokens_per_frames(CFG3_RUN["num_frames"])
+    shape = cv.get_video_patch_shape(CFG3_RUN["num_frames"])
+    run = lambda: ph.sample_token_ids(num_tokens=n, patch_shape=shape, batch_size=b, text_embeds=ctx,
+                                      cond_scale=CFG3_RUN["cond_scale"])
+    run()  # warm-up (also builds tables / caches)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps_timed):
+        ids = run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps_timed
+    assert int((ids == mg.mask_id).sum()) == 0
+    tokens = b * n * CFG3_RUN["steps"]
+    tf = 2 * MASKGIT_FWD_GFLOP * CFG3_RUN["steps"] / ms  # GFLOP/ms = TFLOP/s
+    pk = peaks()
+    return dict(metric="maskgit_sample_tokens_per_s", value=tokens / ms * 1e3, unit="tokens/s", ms_per_sample=ms,
+                ms_per_decode_step=ms / CFG3_RUN["steps"],
+                config=f"MaskGit(dim=512,depth=6,V=65536,ctx=768) {CFG3_RUN['steps']}-step demasking loop, b={b}, N={n}, "
+                       f"L={L}, cond_scale=3 (2 forwards/step as one batch of {2 * b})",
+                achieved_tflops=tf, frac_of_tensor_peak=tf / pk["tf_sustained"])
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--prec", default=os.environ.get("PHK_PREC", "f32"), choices=["f32", "bf16"])
+    ap.add_argument("--no-maskgit", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import ctypes as C
+    import phenaki_pytorch_b200 as P
+    from phenaki_pytorch_b200 import _lib as L
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    W = max(args.warmup, 3)
+    K = args.steps
+    prec = L.PREC_BF16 if args.prec == "bf16" else L.PREC_F32
+    lib = L.lib()
+
+    torch.manual_seed(0)
+    model = P.CViViT(**CFG2).to(dev).eval()
+    model.precision = prec
+    B, Cc, F, H, Wd = VIDEO
+    # three distinct input buffers (3 x 107 MB > 126 MB L2) so no timed step finds its video in L2
+    host = [torch.randn(VIDEO, generator=torch.Generator().manual_seed(100 + rank * 10 + i)).pin_memory()
+            for i in range(3)]
+    vids = [h.to(dev, non_blocking=True) for h in host]
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    for i in range(W):
+        ids = model(vids[i % 3], return_only_codebook_ids=True)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.phk_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(K):
+        ids = model(vids[i % 3], return_only_codebook_ids=True)
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = lib.phk_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_step = ms_total / K
+    value = world * B * F * K / (ms_total / 1e3)
+
+    # ---- e2e: the C-ABI call with HOST buffers (pinned), H2D + encode + D2H inside the timed region ----
+    table = model._table()
+    tp, hh, ww = model.get_video_patch_shape(F)
+    host_ids = torch.empty((B, tp, hh, ww), dtype=torch.int64).pin_memory()
+    dev_ids = torch.empty((B, tp, hh, ww), dtype=torch.int64, device=dev)
+    stage = torch.empty(VIDEO, dtype=torch.float32, device=dev)
+    nbytes = lib.phk_cvivit_workspace_bytes(C.byref(table), B, F, prec)
+    ws = model._ws.get(nbytes, dev)
+    bias = model._spatial_bias(table, dev)
+
+    def e2e_step(i):
+        L.check(lib.phk_cvivit_encode_host(C.byref(table), L.ptr(host[i % 3]), B, F, L.ptr(host_ids), L.ptr(stage),
+                                           L.ptr(dev_ids), L.ptr(ws), ws.numel(), prec, L.ptr(bias), L.stream_ptr()),
+                "phk_cvivit_encode_host")
+
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    assert torch.equal(host_ids, model(vids[(K - 1) % 3], return_only_codebook_ids=True).cpu())
+    t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * F * K / float(t.item())
+
+    # ---- per-kernel-family device time (CUDA events on the launching stream) over 3 more steps ----
+    lib.phk_prof_enable(1)
+    PROF_STEPS = 3
+    for i in range(PROF_STEPS):
+        model(vids[i % 3], return_only_codebook_ids=True)
+    torch.cuda.synchronize()
+    lib.phk_prof_enable(0)
+    fam = L.profile_collect()
+    tot = sum(v[0] for v in fam.values()) or 1.0
+    shares = {k: round(v[0] / tot, 4) for k, v in sorted(fam.items(), key=lambda kv: -kv[1][0])}
+    pk = peaks()
+    dom = max(fam, key=lambda k: fam[k][0])
+    dms, dcalls, dwork = fam[dom]
+    if dom.startswith("gemm") or dom == "attention":
+        achieved = dwork / (dms * 1e-3) / 1e12
+        roof = dict(bound="tensor", kernel=dom, achieved=achieved, peak=pk["tf_sustained"], unit="TFLOP/s",
+                    frac=achieved / pk["tf_sustained"], traffic=None,
+                    per_launch=dict(flops=dwork / dcalls, ms=dms / dcalls), peak_source=pk["src"] + " (sustained bf16)")
+    else:
+        achieved = dwork / (dms * 1e-3) / 1e9
+        roof = dict(bound="hbm", kernel=dom, achieved=achieved, peak=pk["hbm"], unit="GB/s", frac=achieved / pk["hbm"],
+                    traffic=None, per_launch=dict(bytes=dwork / dcalls, ms=dms / dcalls), peak_source=pk["src"])
+    roof["family_share_of_step"] = shares
+    roof["step_tflops"] = ENCODE_GFLOP / ms_step  # whole-step algorithmic FLOPs / device time
+    roof["step_frac_of_tensor_peak"] = roof["step_tflops"] / pk["tf_sustained"]
+
+    out = {
+        "metric": "cvivit_encode_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": K,
+        "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": args.prec, "data": "synthetic",
+        "config": {"workload": "BASELINE.json configs[1]: CViViT(dim=512,image=256,patch=32,pt=2,depth=4+4,heads=8,"
+                               "codebook=65536) encode+LFQ ids of (8,3,17,256,256) fp32 per GPU, random-init weights",
+                   "batch_per_gpu": B, "global_batch": B * world, "frames": F,
+                   "parallelism": f"dp{world}: batch-sharded, one process per GPU, no data-path collective",
+                   "l2": "inputs rotate over 3 device buffers (3 x 107 MB > 126 MB L2)",
+                   "precision_mode": "PHK_PREC_F32 (fp32 FFMA GEMMs, parity mode)" if prec == 0 else
+                                     "PHK_PREC_BF16 (tcgen05 bf16 GEMMs, fp32 accumulate/residual/LN/softmax)"},
+        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": B * Cc * F * H * Wd * 4,
+                "d2h_bytes_per_step": B * tp * hh * ww * 8,
+                "api": "phk_cvivit_encode_host (C ABI, pinned host video -> host int64 ids)"},
+        "gpu_launches": int(launches),
+        "roofline": roof,
+        "clocks": clocks,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu:
+        out["cpu_baseline"] = cpu_encode_baseline()
+    if not args.no_maskgit:
+        try:
+            mres = bench_maskgit(dev, prec)
+            if world > 1:
+                t = torch.tensor([mres["ms_per_sample"]], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                mres["ms_per_sample"] = float(t.item())
+                mres["value"] = world * CFG3_RUN["batch"] * 576 * CFG3_RUN["steps"] / mres["ms_per_sample"] * 1e3
+            out["extra"] = {"maskgit_sample": mres}
+        except Exception as ex:  # the headline line must still print
+            out["extra"] = {"maskgit_sample": {"error": repr(ex)}}
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

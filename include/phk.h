@@ -1,0 +1,297 @@
+/*
+ * phk.h -- C ABI of the B200-native phenaki hot path (libphk.so).
+ *
+ * The reference (lucidrains/phenaki-pytorch @ 9415d4e) has no FFI: the path sits behind
+ * torch.nn.Module classes (phenaki_pytorch/__init__.py:1-4).  This header is the boundary a
+ * maintainer would bind instead (ctypes stub in INTEGRATION.md): plain pointers, sizes and a
+ * cudaStream_t; no torch types.  Every entry point cites the reference code it replaces
+ * (paths relative to /root/reference/phenaki_pytorch/).
+ *
+ * Conventions
+ *   - every function returns int: 0 ok, <0 argument/shape error (PHK_E_*), >0 a cudaError_t.
+ *     Nothing throws or aborts.  phk_last_error() returns a static description of the last <0.
+ *   - all device pointers are BORROWED for the duration of the call; the library allocates
+ *     nothing on the device: scratch comes from a caller-owned workspace
+ *     (phk_*_workspace_bytes()).  Work is enqueued on the caller's stream, no host sync,
+ *     except the *_host entry points which copy from/to host memory and synchronise.
+ *   - residual stream / LayerNorm / softmax are fp32.  `prec` selects the contraction type:
+ *     PHK_PREC_F32  fp32 FFMA GEMMs (parity mode, token ids identical to the fp32 reference);
+ *     PHK_PREC_BF16 bf16 operands on tcgen05 tensor cores with fp32 TMEM accumulation (the
+ *                   dtype flow of the reference under torch.autocast(bfloat16)).
+ *   - token ids are int64 (reference dtype), masks are uint8 (0/1).
+ */
+#ifndef PHK_H_
+#define PHK_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* phk_stream_t; /* == cudaStream_t */
+
+enum { PHK_PREC_F32 = 0, PHK_PREC_BF16 = 1 };
+enum {
+  PHK_E_ARG = -1,      /* null pointer / non-positive size            */
+  PHK_E_SHAPE = -2,    /* shape contract violated (reference asserts) */
+  PHK_E_UNSUPPORTED = -3,
+  PHK_E_WORKSPACE = -4 /* workspace too small                         */
+};
+
+int phk_version(void);
+const char* phk_last_error(void);
+/* number of kernels this library has launched in this process (bench.py gpu_launches) */
+int64_t phk_launch_count(void);
+
+/* Per-kernel-family timing (CUDA events on the launching stream) for bench.py's roofline and
+ * share-of-step numbers.  Families, in order: patchify_ln, layernorm, gemm_f32, gemm_bf16,
+ * attention, peg, geglu, lfq, embed, cpb, sample_tokens, topk_mask, critic, cfg_combine.
+ * work_by_family = algorithmic FLOPs (gemm, attention) or bytes (memory-bound kernels). */
+#define PHK_NUM_FAMILIES 14
+int phk_prof_enable(int32_t on);
+int phk_prof_collect(double* ms_by_family, int64_t* calls_by_family, double* work_by_family, int32_t n);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Weight tables (filled by the host-side modules from the reference state_dict layout)        */
+/* ------------------------------------------------------------------------------------------ */
+
+/* attention.py:89-126 Attention.  *_h are optional bf16 copies of the same matrices, padded so
+ * every leading dimension is a multiple of 8 elements (16 B, TMA requirement). */
+typedef struct {
+  const float* norm_g;  const float* norm_b;      /* norm.gamma / norm.beta [dim]              */
+  const float* ctx_g;   const float* ctx_b;       /* context_norm.* [dim_context]              */
+  const float* null_kv;                           /* [heads, 2*num_null_kv, dim_head]          */
+  const float* q_scale; const float* k_scale;     /* [dim_head]                                */
+  const float* wq; const float* wkv; const float* wo; /* [I,dim] [2I,dim_context] [dim,I]      */
+  const void* wq_h; const void* wkv_h; const void* wo_h;
+  int32_t num_null_kv; int32_t dim_context;
+} phk_attn_t;
+
+/* attention.py:45-53 FeedForward: LN(affine) -> Linear(dim,2*inner) -> GEGLU -> Linear(inner,dim) */
+typedef struct {
+  const float* ln_g; const float* ln_b;
+  const float* w1; const float* w2;               /* [2*inner, dim], [dim, inner]               */
+  const void* w1_h; const void* w2_h;             /* bf16: w1 rows interleaved val/gate per 64, */
+  int32_t inner; int32_t inner_pad;               /* w2 K padded to inner_pad (multiple of 64)  */
+} phk_ff_t;
+
+/* attention.py:57-85 PEG: depthwise Conv3d(dim,dim,3,groups=dim); w tap-major [27, dim]
+ * (= dsconv.weight[dim,1,3,3,3].reshape(dim,27).t(), packed by the host module) */
+typedef struct { const float* w; const float* b; int32_t causal; int32_t _pad; } phk_peg_t;
+
+/* one entry of Transformer.layers (attention.py:300-306): .0 PEG .1 self .2 cross .3 FF */
+typedef struct {
+  int32_t has_peg; int32_t has_cross;
+  phk_peg_t peg; phk_attn_t self_attn; phk_attn_t cross_attn; phk_ff_t ff;
+} phk_layer_t;
+
+/* attention.py:279-332 Transformer */
+typedef struct {
+  int32_t dim; int32_t heads; int32_t dim_head; int32_t depth; int32_t causal; int32_t _pad;
+  const phk_layer_t* layers;
+  const float* out_g; const float* out_b;         /* norm_out.gamma / beta                      */
+  const float* alibi_slopes;                      /* [heads] when causal (attention.py:201-212) */
+} phk_transformer_t;
+
+/* attention.py:229-275 ContinuousPositionBias with the default 2 hidden layers */
+typedef struct {
+  const float* w0; const float* b0;               /* [hidden, num_dims]                         */
+  const float* w1; const float* b1;               /* [hidden, hidden]                           */
+  const float* w2; const float* b2;               /* [heads, hidden]                            */
+  int32_t num_dims; int32_t hidden; int32_t heads; int32_t _pad;
+} phk_cpb_t;
+
+/* cvivit.py:226-335 CViViT, encode-side members only */
+typedef struct {
+  int32_t dim, heads, dim_head, channels;
+  int32_t image_h, image_w, patch_h, patch_w, patch_t;
+  int32_t codebook_bits; int32_t _pad0, _pad1;
+  /* to_patch_emb_first_frame.{1,2,3} / to_patch_emb.{1,2,3} (cvivit.py:273-285) */
+  const float* pf_ln1_g; const float* pf_ln1_b; const float* pf_w; const float* pf_b;
+  const float* pf_ln2_g; const float* pf_ln2_b; const void* pf_w_h;
+  const float* pr_ln1_g; const float* pr_ln1_b; const float* pr_w; const float* pr_b;
+  const float* pr_ln2_g; const float* pr_ln2_b; const void* pr_w_h;
+  phk_cpb_t spatial_bias;                         /* spatial_rel_pos_bias                       */
+  phk_transformer_t spatial;                      /* enc_spatial_transformer                    */
+  phk_transformer_t temporal;                     /* enc_temporal_transformer                   */
+  const float* vq_w; const float* vq_b;           /* vq.project_in [bits, dim], [bits]          */
+} phk_cvivit_t;
+
+/* phenaki_pytorch.py:105-147 MaskGit / :217-249 TokenCritic (is_critic: no bias, Linear(dim,1)) */
+typedef struct {
+  int32_t dim, heads, dim_head, num_tokens, max_seq_len, is_critic, has_bias, _pad;
+  float shrink_alpha; float _padf;
+  const float* token_emb; const float* pos_emb;   /* [num_tokens+1, dim], [max_seq_len, dim]    */
+  phk_cpb_t pos_bias;                             /* continuous_pos_bias (MaskGit only)         */
+  phk_transformer_t transformer;
+  const float* head_w; const float* head_b;       /* to_logits: [V,dim],[V]  | critic [1,dim],[1]*/
+  const void* head_w_h;
+} phk_maskgit_t;
+
+/* ------------------------------------------------------------------------------------------ */
+/* Building blocks (each is one kernel launch unless noted; used directly by the unit tests)   */
+/* ------------------------------------------------------------------------------------------ */
+
+/* F.layer_norm over the last dim, eps 1e-5 (attention.py:35-36, :48, :308).
+ * out_bf16!=0 writes __nv_bfloat16 instead of float.  raw_bf16 (optional, bf16 mode) also
+ * receives the un-normalised row converted to bf16 (self-attention projects k,v from raw x,
+ * attention.py:140-144).  Output row map as in phk_gemm_f32 (seg_len<=0: identity). */
+int phk_layernorm(const float* x, const float* gamma, const float* beta, void* out, void* raw_bf16,
+                  int64_t rows, int32_t dim, int32_t out_bf16, int64_t seg_len, int64_t seg_stride,
+                  int64_t seg_off, phk_stream_t s);
+
+/* Rearrange 'b c (t pt)(h p1)(w p2) -> b t h w (c pt p1 p2)' + LayerNorm(K) of
+ * to_patch_emb* (cvivit.py:273-275, 280-282): frames [f0, f0+nt*pt) of video (B,C,F,H,W) fp32
+ * -> A[(b,t,h,w), K] (fp32 or bf16), K = C*pt*p1*p2. */
+int phk_patchify_ln(const float* video, int32_t B, int32_t C, int32_t F, int32_t H, int32_t W,
+                    int32_t f0, int32_t nt, int32_t pt, int32_t p1, int32_t p2,
+                    const float* ln_g, const float* ln_b, void* out, int32_t out_bf16, phk_stream_t s);
+
+/* C[map(m), n] = sum_k A[m,k] * W[n,k] (+bias[n]) (+residual[map(m), n]); nn.Linear semantics.
+ * Row map: map(m) = (m / seg_len) * seg_stride + seg_off + m % seg_len (seg_len<=0: identity).
+ * fp32 FFMA kernel (parity mode). */
+int phk_gemm_f32(const float* A, int64_t lda, const float* W, int64_t ldw, float* C, int64_t ldc,
+                 int64_t M, int32_t N, int32_t K, const float* bias, const float* residual,
+                 int64_t seg_len, int64_t seg_stride, int64_t seg_off, phk_stream_t s);
+
+/* Same contract on tcgen05 tensor cores: A,W bf16 (K-major, lda/ldw multiples of 8), fp32 TMEM
+ * accumulators, TMA-fed, warp-specialised.  epilogue: 0 store fp32 (+bias,+residual),
+ * 1 store bf16 (+bias), 2 GEGLU on val/gate-interleaved W rows -> bf16 [M, N/2]. */
+int phk_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc,
+                  int64_t M, int32_t N, int32_t K, const float* bias, const float* residual,
+                  int64_t seg_len, int64_t seg_stride, int64_t seg_off, int32_t epilogue,
+                  phk_stream_t s);
+
+/* GEGLU (attention.py:40-43): out[r, j] = gelu_erf(h[r, inner + j]) * h[r, j] */
+int phk_geglu(const float* h, float* out, int64_t rows, int32_t inner, phk_stream_t s);
+
+/* Cosine-sim attention core (attention.py:146-181) for all four uses (spatial, temporal
+ * causal+ALiBi, MaskGit self with bias/mask, cross with null-kv/mask).  q fp32 [.., I],
+ * kv fp32 [.., 2I] (k at column h*dh, v at column I + h*dh), I = heads*dim_head.
+ * Sequence s = (so, si), so < n_outer, si < n_inner: query token i lives at element offset
+ * so*q_outer + si*q_inner + i*q_tok (+ h*dh); keys likewise with the k_* strides of sequence
+ * (so % kv_outer_mod, si); outputs with the o_* strides.  All strides are in ELEMENTS.
+ * bias fp32 [heads, n_q, n_k] or NULL (never covers the null keys, attention.py:162);
+ * key_mask uint8 [*, n_k] or NULL, row = so % mask_outer_mod (0: so); sequences with
+ * so >= mask_off_from (>=0) see an all-False mask = the cond_drop_prob=1 half of a
+ * classifier-free-guidance pair (phenaki_pytorch.py:188-190).
+ * alibi_slopes fp32 [heads] (attention.py:201-212), required when causal. */
+typedef struct {
+  int32_t n_outer, n_inner, n_q, n_k, heads, dim_head, num_null_kv, causal;
+  int64_t q_outer, q_inner, q_tok;
+  int64_t k_outer, k_inner, k_tok;
+  int64_t o_outer, o_inner, o_tok;
+  int32_t kv_outer_mod, mask_outer_mod, mask_off_from, out_bf16;
+  float scale;                 /* 8 (attention.py:100) */
+  int32_t _pad;
+} phk_attn_geom_t;
+int phk_attention(const float* q, const float* kv, const float* null_kv, const float* q_scale,
+                  const float* k_scale, const float* bias, const uint8_t* key_mask,
+                  const float* alibi_slopes, void* out, const phk_attn_geom_t* g, phk_stream_t s);
+
+/* PEG (attention.py:64-85) + residual: y = x + conv3d_depthwise(pad(x)) + b on a logical
+ * (B,T,H,W,D) channels-last view.  layout 0: row = logical flat index (MaskGit, (b,n,d)).
+ * layout 1: the C-ViViT temporal quirk -- the caller's physical rows are (b,t,h,w) but the
+ * reference conv sees the '(b h w) t d' buffer REINTERPRETED as (b,t,h,w,d) (attention.py:71
+ * with cvivit.py:468-470); the kernel composes both index maps. */
+int phk_peg3d(const float* x, const float* w, const float* b, float* y, int32_t B, int32_t T,
+              int32_t H, int32_t W, int32_t D, int32_t causal, int32_t layout, phk_stream_t s);
+
+/* ContinuousPositionBias (attention.py:257-275) -> out[heads, n, n], n = d0*d1*d2 (d2=1 for 2-D).
+ * The MLP runs once per distinct coordinate delta (prod(2*d_i-1) rows) and is expanded.
+ * scratch: >= phk_cpb_scratch_floats() floats. */
+int64_t phk_cpb_scratch_floats(const phk_cpb_t* c, int32_t d0, int32_t d1, int32_t d2);
+int phk_cpb_bias(const phk_cpb_t* c, int32_t d0, int32_t d1, int32_t d2, float* scratch,
+                 float* out, phk_stream_t s);
+
+/* LFQ ids (cvivit.py:570 -> vector_quantize_pytorch.LFQ.forward, restated in oracle/lfq.py):
+ * proj = x @ Wp^T + bp ; id = sum_d (proj_d > 0) << (bits-1-d).  proj_out optional [rows,bits]. */
+int phk_lfq_ids(const float* x, const float* wp, const float* bp, int64_t* ids, float* proj_out,
+                int64_t rows, int32_t dim, int32_t bits, phk_stream_t s);
+
+/* token_emb[id] + pos_emb[pos] then x*a + x*(1-a) (phenaki_pytorch.py:194-199); a<0 skips the
+ * shrink (TokenCritic, :290-291). rows = b*n. */
+int phk_token_embed(const int64_t* ids, const float* tok, const float* pos, float* out,
+                    int32_t b, int32_t n, int32_t dim, int32_t vocab_rows, float alpha,
+                    int32_t replicas /* 2: also emit the CFG null half */, phk_stream_t s);
+
+/* CFG + gumbel argmax + confidence, one pass over the vocabulary
+ * (phenaki_pytorch.py:161, 83-93, 506-509, 547-550):
+ *   l = null + (cond-null)*cond_scale   (null==NULL or cond_scale==1: l = cond)
+ *   pred = argmax_v( l/max(T,1e-10) - log(-log(u+1e-10)+1e-10) ), first index on ties
+ *   ids = mask ? pred : ids ;  score = mask ? 1 - softmax(l)[pred] : -1e4
+ * u: uniform draws [rows, V] (parity mode) or NULL -> in-kernel Philox4x32-10(seed, offset).
+ * seg_*: token row r reads logits row (r/seg_len)*seg_stride + seg_off + r%seg_len, i.e. the
+ * `logits[:, prime_len:]` slice of a primed sample (:503-504); seg_len<=0: identity. */
+int phk_sample_tokens(const float* cond, const float* null_logits, int64_t ld, const float* u,
+                      uint64_t seed, uint64_t offset, float cond_scale, float temperature,
+                      const uint8_t* mask, int64_t* ids, int64_t* pred_out, float* score_out,
+                      int64_t rows, int32_t V, int64_t seg_len, int64_t seg_stride, int64_t seg_off,
+                      phk_stream_t s);
+
+/* Cosine-schedule re-masking (phenaki_pytorch.py:485-491): mask = scatter(topk(scores,k));
+ * ids = where(mask, mask_id, ids).  n <= 4096; ties: lower index wins. */
+int phk_topk_mask(const float* scores, int32_t b, int32_t n, int32_t k, uint8_t* mask,
+                  int64_t* ids, int64_t mask_id, phk_stream_t s);
+
+/* critic score (phenaki_pytorch.py:246-249, 263, 544-545):
+ *   sc = x @ w + b per row; out = null + (cond - null)*scale + noise_K*(u-0.5)*noise_mult  */
+int phk_critic_scores(const float* x_cond, const float* x_null, const float* w, const float* b,
+                      const float* u, float cond_scale, float noise_K, float noise_mult, float* out,
+                      int64_t rows, int32_t dim, int64_t seg_len, int64_t seg_stride, int64_t seg_off,
+                      phk_stream_t s);
+
+/* forward_with_cond_scale tail (phenaki_pytorch.py:161): out = null + (cond - null) * scale */
+int phk_cfg_combine(const float* cond, const float* null_out, float cond_scale, float* out,
+                    int64_t n, phk_stream_t s);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Fused drivers = the reference-facing operations                                             */
+/* ------------------------------------------------------------------------------------------ */
+
+/* CViViT.forward(video, return_only_codebook_ids=True) (cvivit.py:518-574).
+ * video (B,C,F,H,W) fp32 device; ids (B,T',H',W') int64 device.
+ * spatial_bias: cached phk_cpb_bias(spatial_bias, H', W') output [heads, H'W', H'W'] or NULL
+ * (recomputed inside).  taps: optional fp32 device buffers for the parity tests:
+ * tap_patch / tap_spatial / tap_temporal [B*T'*H'*W', dim] in (b,t,h,w) row order,
+ * tap_proj [rows, bits] = LFQ pre-sign projection. */
+int64_t phk_cvivit_workspace_bytes(const phk_cvivit_t* m, int32_t B, int32_t F, int32_t prec);
+int phk_cvivit_encode(const phk_cvivit_t* m, const float* video, int32_t B, int32_t F,
+                      int64_t* ids, void* workspace, int64_t workspace_bytes, int32_t prec,
+                      const float* spatial_bias, float* tap_patch, float* tap_spatial,
+                      float* tap_temporal, float* tap_proj, phk_stream_t s);
+/* same through HOST buffers (pinned or pageable): H2D of the video, encode, D2H of the ids,
+ * stream synchronise.  dev_video / dev_ids are caller-owned staging buffers. */
+int phk_cvivit_encode_host(const phk_cvivit_t* m, const float* host_video, int32_t B, int32_t F,
+                           int64_t* host_ids, void* dev_video, int64_t* dev_ids, void* workspace,
+                           int64_t workspace_bytes, int32_t prec, const float* spatial_bias,
+                           phk_stream_t s);
+
+/* context_norm + to_kv of every cross-attention layer (attention.py:137-144).  Depends only on
+ * the text embedding, so Phenaki.sample computes it once per call instead of once per forward.
+ * context (b,L,dim_context) fp32; out_kv [depth, b*L, 2*heads*dim_head] fp32;
+ * scratch b*L*dim_context floats. */
+int phk_maskgit_context_kv(const phk_maskgit_t* m, const float* context, int32_t b, int32_t L,
+                           float* out_kv, float* scratch, int32_t prec, phk_stream_t s);
+
+/* MaskGit.forward / TokenCritic.forward (phenaki_pytorch.py:163-213, 265-302), optionally for a
+ * classifier-free-guidance pair (:149-161): ids (b,n) int64; sequences [0,b) are the conditional
+ * pass and, when cfg_pair!=0, sequences [b,2b) replay the same ids with the text mask dropped
+ * (cond_drop_prob = 1).  ctx_kv from phk_maskgit_context_kv or NULL (no context: cross-attention
+ * skipped, attention.py:327); text_mask uint8 (b,L); video_mask uint8 (b,n) or NULL;
+ * pos_bias: cached phk_cpb_bias(pos_bias, pt, ph, pw) [heads,n,n] or NULL (recomputed).
+ * out: MaskGit logits fp32 [(1+cfg_pair)*b*n, num_tokens], or final embeds [.., dim] when
+ * return_embeds!=0 or the model is a critic (its Linear(dim,1) head is phk_critic_scores). */
+int64_t phk_maskgit_workspace_bytes(const phk_maskgit_t* m, int32_t b, int32_t n, int32_t L,
+                                    int32_t cfg_pair, int32_t prec);
+int phk_maskgit_forward(const phk_maskgit_t* m, const int64_t* ids, int32_t b, int32_t n,
+                        int32_t pt, int32_t ph, int32_t pw, const float* ctx_kv, int32_t L,
+                        const uint8_t* text_mask, const uint8_t* video_mask, int32_t cfg_pair,
+                        int32_t return_embeds, const float* pos_bias, float* out, void* workspace,
+                        int64_t workspace_bytes, int32_t prec, phk_stream_t s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHK_H_ */

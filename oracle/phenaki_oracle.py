@@ -79,6 +79,27 @@ def alibi_bias(heads, i, j):
     return bias * slopes
 
 
+def attention_core(q, k, v, q_scale, k_scale, *, heads, causal=False, num_null_kv=0, mask=None,
+                   attn_bias=None, scale=8):
+    """attention.py:153-179 on already split heads: q (b,h,i,d), k/v (b,h,j,d) with the null
+    keys/values already prepended.  Returns (b,h,i,d)."""
+    q = F.normalize(q, dim=-1) * q_scale
+    k = F.normalize(k, dim=-1) * k_scale
+    sim = torch.einsum("bhid,bhjd->bhij", q, k) * scale
+    i, j = sim.shape[-2:]
+    if attn_bias is not None:
+        sim = sim + F.pad(attn_bias, (num_null_kv, 0), value=0.0)
+    neg = -torch.finfo(sim.dtype).max
+    if mask is not None:
+        m = F.pad(mask, (num_null_kv, 0), value=True)
+        sim = sim.masked_fill(~m[:, None, None, :], neg)
+    if causal:
+        sim = sim + alibi_bias(heads, i, j)
+        sim = sim.masked_fill(torch.ones((i, j), dtype=torch.bool).triu(j - i + 1), neg)
+    attn = sim.softmax(dim=-1)
+    return torch.einsum("bhij,bhjd->bhid", attn, v)
+
+
 def attention(x, sd, p, *, heads, causal=False, num_null_kv=0, mask=None, context=None,
               attn_bias=None, scale=8):
     """attention.py:128-182.  Quirk kept: for self-attention k,v are projected from the
@@ -100,21 +121,9 @@ def attention(x, sd, p, *, heads, causal=False, num_null_kv=0, mask=None, contex
     nv = null_kv[:, 1::2].unsqueeze(0).expand(b, -1, -1, -1)
     k = torch.cat((nk, k), dim=-2)
     v = torch.cat((nv, v), dim=-2)
-    q = F.normalize(q, dim=-1) * sd[p + "q_scale"]
-    k = F.normalize(k, dim=-1) * sd[p + "k_scale"]
-    sim = torch.einsum("bhid,bhjd->bhij", q, k) * scale
-    i, j = sim.shape[-2:]
-    if attn_bias is not None:
-        sim = sim + F.pad(attn_bias, (num_null_kv, 0), value=0.0)
-    neg = -torch.finfo(sim.dtype).max
-    if mask is not None:
-        m = F.pad(mask, (num_null_kv, 0), value=True)
-        sim = sim.masked_fill(~m[:, None, None, :], neg)
-    if causal:
-        sim = sim + alibi_bias(heads, i, j)
-        sim = sim.masked_fill(torch.ones((i, j), dtype=torch.bool).triu(j - i + 1), neg)
-    attn = sim.softmax(dim=-1)
-    out = torch.einsum("bhij,bhjd->bhid", attn, v)
+    out = attention_core(q, k, v, sd[p + "q_scale"], sd[p + "k_scale"], heads=heads, causal=causal,
+                         num_null_kv=num_null_kv, mask=mask, attn_bias=attn_bias, scale=scale)
+    i = out.shape[-2]
     out = out.permute(0, 2, 1, 3).reshape(b, i, -1)
     return F.linear(out, sd[p + "to_out.weight"])
 

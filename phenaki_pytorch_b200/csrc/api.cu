@@ -1,0 +1,381 @@
+// Fused drivers: the reference-facing operations as stream-ordered launch sequences.
+//   phk_cvivit_encode     = CViViT.forward(video, return_only_codebook_ids=True)  cvivit.py:518-574
+//   phk_maskgit_forward   = MaskGit.forward / TokenCritic.forward (CFG pair)      phenaki_pytorch.py:163-213, 265-302
+// No host synchronisation, no allocation: scratch is carved from the caller's workspace.
+#include "phk_common.cuh"
+#include <atomic>
+#include <cstring>
+#include <cstdio>
+#include <mutex>
+#include <vector>
+
+namespace phk {
+
+static thread_local char g_err[256] = "";
+static std::atomic<int64_t> g_launches{0};
+void set_error(const char* msg) { std::snprintf(g_err, sizeof(g_err), "%s", msg); }
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+static std::atomic<int> g_prof_on{0};
+struct ProfRec { int fam; cudaEvent_t e0, e1; double work; };
+static std::vector<ProfRec> g_prof_recs;
+static std::mutex g_prof_mu;
+Prof::Prof(int f, phk_stream_t s, double w) : fam(f), st(to_stream(s)), e0(nullptr), on(false), work(w) {
+  if (!g_prof_on.load(std::memory_order_relaxed)) return;
+  on = true;
+  cudaEventCreate(&e0);
+  cudaEventRecord(e0, st);
+}
+Prof::~Prof() {
+  if (!on) return;
+  cudaEvent_t e1;
+  cudaEventCreate(&e1);
+  cudaEventRecord(e1, st);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_recs.push_back(ProfRec{fam, e0, e1, work});
+}
+
+// bump allocator over the caller's workspace (256-byte aligned slices)
+struct Arena {
+  char* base; int64_t size; int64_t off;
+  void* take(int64_t bytes) {
+    const int64_t o = (off + 255) & ~int64_t(255);
+    off = o + bytes;
+    return (off <= size && base) ? base + o : nullptr;
+  }
+};
+
+struct SeqView {  // how sequences map onto rows of the [R, dim] residual stream
+  int n_outer, n_inner, n_tok;
+  int64_t outer, inner, tok;  // strides in ROWS
+};
+
+struct TfCall {
+  const phk_transformer_t* T;
+  float* x;      // residual stream [R, dim] (in/out)
+  float* x_alt;  // second buffer for the out-of-place PEG
+  int64_t R;
+  SeqView seq;
+  int pegB, pegT, pegH, pegW, peg_layout;
+  const float* attn_bias;      // [heads, n, n] or NULL
+  const uint8_t* self_mask;    // [mask rows, n] or NULL
+  int self_mask_mod;
+  // cross attention
+  const float* ctx_kv;         // [depth][ctx_rows][2I] pre-projected context keys/values, or NULL
+  int ctx_b, ctx_L;            // context batch / length
+  const uint8_t* ctx_mask;     // [ctx_b, L]
+  int ctx_mask_off_from;       // sequences >= this see no text (CFG null half), -1: none
+  int prec;
+};
+
+static int64_t tf_scratch_bytes(const phk_transformer_t* T, int64_t R) {
+  const int64_t I = (int64_t)T->heads * T->dim_head;
+  int64_t inner = 0;
+  for (int l = 0; l < T->depth; ++l) inner = inner > T->layers[l].ff.inner ? inner : T->layers[l].ff.inner;
+  // xn, q, kv, o, h(2*inner), g(inner)  -- all fp32 in parity mode
+  return 256 * 8 + R * 4 * (T->dim + I + 2 * I + I + 2 * inner + inner);
+}
+
+// x <- Transformer(x)  (attention.py:311-332); the final norm_out is written to `out`.
+static int transformer_forward(const TfCall& c, Arena scratch, float* out, cudaStream_t st) {
+  const phk_transformer_t* T = c.T;
+  PHK_REQUIRE(c.prec == PHK_PREC_F32, PHK_E_UNSUPPORTED, "transformer: only PHK_PREC_F32 in this build");
+  const int D = T->dim, H = T->heads, DH = T->dim_head, I = H * DH;
+  const int64_t R = c.R;
+  int inner_max = 0;
+  for (int l = 0; l < T->depth; ++l) inner_max = inner_max > T->layers[l].ff.inner ? inner_max : T->layers[l].ff.inner;
+  float* xn = (float*)scratch.take(R * D * 4);
+  float* q = (float*)scratch.take(R * I * 4);
+  float* kv = (float*)scratch.take(R * 2 * I * 4);
+  float* o = (float*)scratch.take(R * I * 4);
+  float* hbuf = (float*)scratch.take(R * 2 * (int64_t)inner_max * 4);
+  float* gbuf = (float*)scratch.take(R * (int64_t)inner_max * 4);
+  PHK_REQUIRE(xn && q && kv && o && hbuf && gbuf, PHK_E_WORKSPACE, "transformer: workspace too small");
+  phk_stream_t s = reinterpret_cast<phk_stream_t>(st);
+  float* x = c.x;
+  float* x_alt = c.x_alt;
+
+  for (int l = 0; l < T->depth; ++l) {
+    const phk_layer_t& L = T->layers[l];
+    if (L.has_peg) {  // x = peg(x) + x
+      PHK_REQUIRE((int64_t)c.pegB * c.pegT * c.pegH * c.pegW == R, PHK_E_SHAPE, "PEG: video shape does not cover the tokens");
+      PHK_TRY(phk_peg3d(x, L.peg.w, L.peg.b, x_alt, c.pegB, c.pegT, c.pegH, c.pegW, D, L.peg.causal, c.peg_layout, s));
+      float* t = x; x = x_alt; x_alt = t;
+    }
+    {  // x = self_attn(x) + x ; q from LN(x), k/v from RAW x (attention.py:140-144)
+      const phk_attn_t& A = L.self_attn;
+      PHK_TRY(phk_layernorm(x, A.norm_g, A.norm_b, xn, nullptr, R, D, 0, 0, 0, 0, s));
+      PHK_TRY(phk_gemm_f32(xn, D, A.wq, D, q, I, R, I, D, nullptr, nullptr, 0, 0, 0, s));
+      PHK_TRY(phk_gemm_f32(x, D, A.wkv, D, kv, 2 * I, R, 2 * I, D, nullptr, nullptr, 0, 0, 0, s));
+      phk_attn_geom_t g;
+      std::memset(&g, 0, sizeof(g));
+      g.n_outer = c.seq.n_outer; g.n_inner = c.seq.n_inner; g.n_q = c.seq.n_tok; g.n_k = c.seq.n_tok;
+      g.heads = H; g.dim_head = DH; g.num_null_kv = A.num_null_kv; g.causal = T->causal;
+      g.q_outer = c.seq.outer * I; g.q_inner = c.seq.inner * I; g.q_tok = c.seq.tok * I;
+      g.k_outer = c.seq.outer * 2 * I; g.k_inner = c.seq.inner * 2 * I; g.k_tok = c.seq.tok * 2 * I;
+      g.o_outer = g.q_outer; g.o_inner = g.q_inner; g.o_tok = g.q_tok;
+      g.kv_outer_mod = 0; g.mask_outer_mod = c.self_mask_mod; g.mask_off_from = -1; g.out_bf16 = 0; g.scale = 8.f;
+      PHK_TRY(phk_attention(q, kv, A.null_kv, A.q_scale, A.k_scale, c.attn_bias, c.self_mask, T->alibi_slopes, o, &g, s));
+      PHK_TRY(phk_gemm_f32(o, I, A.wo, I, x, D, R, D, I, nullptr, x, 0, 0, 0, s));
+    }
+    if (L.has_cross && c.ctx_kv) {  // x = cross_attn(x, context) + x   (attention.py:327-328)
+      const phk_attn_t& A = L.cross_attn;
+      PHK_REQUIRE(c.seq.n_inner == 1, PHK_E_UNSUPPORTED, "cross attention needs (b, n) sequences");
+      PHK_TRY(phk_layernorm(x, A.norm_g, A.norm_b, xn, nullptr, R, D, 0, 0, 0, 0, s));
+      PHK_TRY(phk_gemm_f32(xn, D, A.wq, D, q, I, R, I, D, nullptr, nullptr, 0, 0, 0, s));
+      phk_attn_geom_t g;
+      std::memset(&g, 0, sizeof(g));
+      g.n_outer = c.seq.n_outer; g.n_inner = 1; g.n_q = c.seq.n_tok; g.n_k = c.ctx_L;
+      g.heads = H; g.dim_head = DH; g.num_null_kv = A.num_null_kv; g.causal = 0;
+      g.q_outer = c.seq.outer * I; g.q_inner = 0; g.q_tok = c.seq.tok * I;
+      g.k_outer = (int64_t)c.ctx_L * 2 * I; g.k_inner = 0; g.k_tok = 2 * I;
+      g.o_outer = g.q_outer; g.o_inner = 0; g.o_tok = g.q_tok;
+      g.kv_outer_mod = c.ctx_b; g.mask_outer_mod = c.ctx_b; g.mask_off_from = c.ctx_mask_off_from;
+      g.out_bf16 = 0; g.scale = 8.f;
+      const float* kvl = c.ctx_kv + (int64_t)l * c.ctx_b * c.ctx_L * 2 * I;
+      PHK_TRY(phk_attention(q, kvl, A.null_kv, A.q_scale, A.k_scale, nullptr, c.ctx_mask, nullptr, o, &g, s));
+      PHK_TRY(phk_gemm_f32(o, I, A.wo, I, x, D, R, D, I, nullptr, x, 0, 0, 0, s));
+    }
+    {  // x = ff(x) + x  (attention.py:45-53, 330)
+      const phk_ff_t& Fw = L.ff;
+      PHK_TRY(phk_layernorm(x, Fw.ln_g, Fw.ln_b, xn, nullptr, R, D, 0, 0, 0, 0, s));
+      PHK_TRY(phk_gemm_f32(xn, D, Fw.w1, D, hbuf, 2 * Fw.inner, R, 2 * Fw.inner, D, nullptr, nullptr, 0, 0, 0, s));
+      PHK_TRY(phk_geglu(hbuf, gbuf, R, Fw.inner, s));
+      PHK_TRY(phk_gemm_f32(gbuf, Fw.inner, Fw.w2, Fw.inner, x, D, R, D, Fw.inner, nullptr, x, 0, 0, 0, s));
+    }
+  }
+  PHK_TRY(phk_layernorm(x, T->out_g, T->out_b, out, nullptr, R, D, 0, 0, 0, 0, s));
+  return 0;
+}
+
+static int check_transformer(const phk_transformer_t* T) {
+  PHK_REQUIRE(T && T->layers && T->depth > 0 && T->dim > 0 && T->heads > 0 && T->dim_head > 0, PHK_E_ARG,
+              "transformer table incomplete");
+  PHK_REQUIRE(!T->causal || T->alibi_slopes, PHK_E_ARG, "causal transformer needs alibi_slopes");
+  return 0;
+}
+
+}  // namespace phk
+
+using namespace phk;
+
+extern "C" int phk_version(void) { return 100; }
+extern "C" const char* phk_last_error(void) { return g_err; }
+extern "C" int64_t phk_launch_count(void) { return g_launches.load(); }
+
+extern "C" int phk_prof_enable(int32_t on) { g_prof_on.store(on ? 1 : 0); return 0; }
+// Sums the recorded per-call durations by kernel family (synchronises on the recorded events).
+extern "C" int phk_prof_collect(double* ms_by_family, int64_t* calls_by_family, double* work_by_family, int32_t n) {
+  PHK_REQUIRE(ms_by_family && calls_by_family && work_by_family && n >= FAM_COUNT, PHK_E_ARG, "phk_prof_collect: bad buffers");
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (int i = 0; i < n; ++i) { ms_by_family[i] = 0.0; calls_by_family[i] = 0; work_by_family[i] = 0.0; }
+  for (auto& r : g_prof_recs) {
+    PHK_CUDA(cudaEventSynchronize(r.e1));
+    float ms = 0.f;
+    PHK_CUDA(cudaEventElapsedTime(&ms, r.e0, r.e1));
+    ms_by_family[r.fam] += ms; calls_by_family[r.fam] += 1; work_by_family[r.fam] += r.work;
+    cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+  }
+  g_prof_recs.clear();
+  return 0;
+}
+
+// --------------------------------------------------------------------------------------------
+// C-ViViT encode
+// --------------------------------------------------------------------------------------------
+static int cvivit_dims(const phk_cvivit_t* m, int32_t B, int32_t F, int& Tp, int& hh, int& ww, int64_t& R) {
+  PHK_REQUIRE(m, PHK_E_ARG, "cvivit: null model");
+  PHK_REQUIRE(B > 0 && F > 0, PHK_E_ARG, "cvivit: bad batch / frames");
+  PHK_REQUIRE(m->patch_t > 0 && (F - 1) % m->patch_t == 0, PHK_E_SHAPE,
+              "number of frames minus one must be divisible by temporal patch size (cvivit.py:540)");
+  PHK_REQUIRE(m->image_h % m->patch_h == 0 && m->image_w % m->patch_w == 0, PHK_E_SHAPE,
+              "image size must be divisible by patch size (cvivit.py:271)");
+  Tp = 1 + (F - 1) / m->patch_t;
+  hh = m->image_h / m->patch_h;
+  ww = m->image_w / m->patch_w;
+  R = (int64_t)B * Tp * hh * ww;
+  return 0;
+}
+
+extern "C" int64_t phk_cvivit_workspace_bytes(const phk_cvivit_t* m, int32_t B, int32_t F, int32_t prec) {
+  int Tp, hh, ww; int64_t R;
+  if (cvivit_dims(m, B, F, Tp, hh, ww, R) != 0) return -1;
+  const int64_t K2 = (int64_t)m->channels * m->patch_t * m->patch_h * m->patch_w;
+  const int64_t hw = (int64_t)hh * ww;
+  int64_t bytes = 256 * 16;
+  bytes += R * K2 * 4;                 // patchified + normalised A operand (rest frames dominate)
+  bytes += R * m->dim * 4 * 3;         // gemm out, x, x_alt
+  bytes += (int64_t)m->heads * hw * hw * 4 + phk_cpb_scratch_floats(&m->spatial_bias, hh, ww, 1) * 4;
+  const int64_t a = tf_scratch_bytes(&m->spatial, R), b = tf_scratch_bytes(&m->temporal, R);
+  bytes += a > b ? a : b;
+  (void)prec;
+  return bytes;
+}
+
+extern "C" int phk_cvivit_encode(const phk_cvivit_t* m, const float* video, int32_t B, int32_t F, int64_t* ids,
+                                 void* workspace, int64_t workspace_bytes, int32_t prec, const float* spatial_bias,
+                                 float* tap_patch, float* tap_spatial, float* tap_temporal, float* tap_proj,
+                                 phk_stream_t s) {
+  int Tp, hh, ww; int64_t R;
+  PHK_TRY(cvivit_dims(m, B, F, Tp, hh, ww, R));
+  PHK_REQUIRE(video && ids && workspace, PHK_E_ARG, "cvivit_encode: null pointer");
+  PHK_TRY(check_transformer(&m->spatial));
+  PHK_TRY(check_transformer(&m->temporal));
+  PHK_REQUIRE(prec == PHK_PREC_F32, PHK_E_UNSUPPORTED, "cvivit_encode: only PHK_PREC_F32 in this build");
+  cudaStream_t st = to_stream(s);
+  const int D = m->dim, hw = hh * ww;
+  const int64_t K1 = (int64_t)m->channels * m->patch_h * m->patch_w, K2 = K1 * m->patch_t;
+  Arena ar{(char*)workspace, workspace_bytes, 0};
+  float* A = (float*)ar.take(R * K2 * 4);
+  float* P = (float*)ar.take(R * D * 4);
+  float* x = (float*)ar.take(R * D * 4);
+  float* x_alt = (float*)ar.take(R * D * 4);
+  float* bias_buf = (float*)ar.take((int64_t)m->heads * hw * hw * 4);
+  float* cpb_scratch = (float*)ar.take(phk_cpb_scratch_floats(&m->spatial_bias, hh, ww, 1) * 4);
+  PHK_REQUIRE(A && P && x && x_alt && bias_buf && cpb_scratch, PHK_E_WORKSPACE, "cvivit_encode: workspace too small");
+
+  // ---- to_patch_emb_first_frame / to_patch_emb (cvivit.py:542-549), rows land in (b,t,h,w) order
+  const int C = m->channels, H = m->image_h, W = m->image_w;
+  PHK_TRY(phk_patchify_ln(video, B, C, F, H, W, 0, 1, 1, m->patch_h, m->patch_w, m->pf_ln1_g, m->pf_ln1_b, A, 0, s));
+  PHK_TRY(phk_gemm_f32(A, K1, m->pf_w, K1, P, D, (int64_t)B * hw, D, (int)K1, m->pf_b, nullptr, 0, 0, 0, s));
+  PHK_TRY(phk_layernorm(P, m->pf_ln2_g, m->pf_ln2_b, x, nullptr, (int64_t)B * hw, D, 0, hw, (int64_t)Tp * hw, 0, s));
+  if (Tp > 1) {
+    const int64_t rows = (int64_t)B * (Tp - 1) * hw;
+    PHK_TRY(phk_patchify_ln(video, B, C, F, H, W, 1, Tp - 1, m->patch_t, m->patch_h, m->patch_w, m->pr_ln1_g,
+                            m->pr_ln1_b, A, 0, s));
+    PHK_TRY(phk_gemm_f32(A, K2, m->pr_w, K2, P, D, rows, D, (int)K2, m->pr_b, nullptr, 0, 0, 0, s));
+    PHK_TRY(phk_layernorm(P, m->pr_ln2_g, m->pr_ln2_b, x, nullptr, rows, D, 0, (int64_t)(Tp - 1) * hw,
+                          (int64_t)Tp * hw, hw, s));
+  }
+  if (tap_patch) PHK_CUDA(cudaMemcpyAsync(tap_patch, x, R * D * 4, cudaMemcpyDeviceToDevice, st));
+
+  // ---- encode (cvivit.py:449-474): spatial over (b t), temporal over (b h w); no rearrange copies
+  if (!spatial_bias) {
+    PHK_TRY(phk_cpb_bias(&m->spatial_bias, hh, ww, 1, cpb_scratch, bias_buf, s));
+    spatial_bias = bias_buf;
+  }
+  Arena tf = ar;
+  TfCall c;
+  std::memset(&c, 0, sizeof(c));
+  c.T = &m->spatial; c.x = x; c.x_alt = x_alt; c.R = R;
+  c.seq = SeqView{B * Tp, 1, hw, hw, 0, 1};
+  c.pegB = B; c.pegT = Tp; c.pegH = hh; c.pegW = ww; c.peg_layout = 0;
+  c.attn_bias = spatial_bias; c.ctx_mask_off_from = -1; c.prec = prec;
+  PHK_TRY(transformer_forward(c, tf, P, st));  // P <- norm_out(spatial)
+  if (tap_spatial) PHK_CUDA(cudaMemcpyAsync(tap_spatial, P, R * D * 4, cudaMemcpyDeviceToDevice, st));
+
+  c.T = &m->temporal; c.x = P; c.x_alt = x;
+  c.seq = SeqView{B, hw, Tp, (int64_t)Tp * hw, 1, hw};
+  c.peg_layout = 1;  // the reference's raw-reshape quirk (attention.py:71, cvivit.py:468-470)
+  c.attn_bias = nullptr;
+  PHK_TRY(transformer_forward(c, tf, x_alt, st));  // x_alt <- norm_out(temporal)
+  if (tap_temporal) PHK_CUDA(cudaMemcpyAsync(tap_temporal, x_alt, R * D * 4, cudaMemcpyDeviceToDevice, st));
+
+  // ---- LFQ (cvivit.py:562-574): ids in (b, t, h, w) order
+  PHK_TRY(phk_lfq_ids(x_alt, m->vq_w, m->vq_b, ids, tap_proj, R, D, m->codebook_bits, s));
+  return 0;
+}
+
+extern "C" int phk_cvivit_encode_host(const phk_cvivit_t* m, const float* host_video, int32_t B, int32_t F,
+                                      int64_t* host_ids, void* dev_video, int64_t* dev_ids, void* workspace,
+                                      int64_t workspace_bytes, int32_t prec, const float* spatial_bias,
+                                      phk_stream_t s) {
+  int Tp, hh, ww; int64_t R;
+  PHK_TRY(cvivit_dims(m, B, F, Tp, hh, ww, R));
+  PHK_REQUIRE(host_video && host_ids && dev_video && dev_ids, PHK_E_ARG, "cvivit_encode_host: null pointer");
+  cudaStream_t st = to_stream(s);
+  const int64_t vbytes = (int64_t)B * m->channels * F * m->image_h * m->image_w * 4;
+  PHK_CUDA(cudaMemcpyAsync(dev_video, host_video, vbytes, cudaMemcpyHostToDevice, st));
+  PHK_TRY(phk_cvivit_encode(m, (const float*)dev_video, B, F, dev_ids, workspace, workspace_bytes, prec, spatial_bias,
+                            nullptr, nullptr, nullptr, nullptr, s));
+  PHK_CUDA(cudaMemcpyAsync(host_ids, dev_ids, R * 8, cudaMemcpyDeviceToHost, st));
+  PHK_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// --------------------------------------------------------------------------------------------
+// MaskGit / TokenCritic forward
+// --------------------------------------------------------------------------------------------
+extern "C" int64_t phk_maskgit_workspace_bytes(const phk_maskgit_t* m, int32_t b, int32_t n, int32_t L,
+                                               int32_t cfg_pair, int32_t prec) {
+  if (!m || b <= 0 || n <= 0) return -1;
+  const int64_t R = (int64_t)b * n * (cfg_pair ? 2 : 1);
+  int64_t bytes = 256 * 16 + R * m->dim * 4 * 3;
+  bytes += tf_scratch_bytes(&m->transformer, R);
+  if (m->has_bias) bytes += (int64_t)m->heads * n * n * 4 + (int64_t)8 * n * 8 * m->heads * 4 + (1 << 20);
+  (void)L; (void)prec;
+  return bytes;
+}
+
+// context_norm + to_kv of every cross-attention layer (attention.py:137-144): depends only on the text,
+// so Phenaki.sample computes it once per call instead of once per forward (36x per 18-step sample).
+// out_kv: [depth, b*L, 2I] fp32.  scratch: b*L*dim_context floats.
+extern "C" int phk_maskgit_context_kv(const phk_maskgit_t* m, const float* context, int32_t b, int32_t L,
+                                      float* out_kv, float* scratch, int32_t prec, phk_stream_t s) {
+  PHK_REQUIRE(m && context && out_kv && scratch, PHK_E_ARG, "maskgit_context_kv: null pointer");
+  PHK_REQUIRE(b > 0 && L > 0, PHK_E_ARG, "maskgit_context_kv: bad size");
+  PHK_REQUIRE(prec == PHK_PREC_F32, PHK_E_UNSUPPORTED, "maskgit_context_kv: only PHK_PREC_F32 in this build");
+  const phk_transformer_t* T = &m->transformer;
+  PHK_TRY(check_transformer(T));
+  const int I = T->heads * T->dim_head;
+  const int64_t rows = (int64_t)b * L;
+  for (int l = 0; l < T->depth; ++l) {
+    const phk_layer_t& Ly = T->layers[l];
+    PHK_REQUIRE(Ly.has_cross, PHK_E_SHAPE, "maskgit_context_kv: layer has no cross attention");
+    const phk_attn_t& A = Ly.cross_attn;
+    PHK_TRY(phk_layernorm(context, A.ctx_g, A.ctx_b, scratch, nullptr, rows, A.dim_context, 0, 0, 0, 0, s));
+    PHK_TRY(phk_gemm_f32(scratch, A.dim_context, A.wkv, A.dim_context, out_kv + (int64_t)l * rows * 2 * I, 2 * I, rows,
+                         2 * I, A.dim_context, nullptr, nullptr, 0, 0, 0, s));
+  }
+  return 0;
+}
+
+extern "C" int phk_maskgit_forward(const phk_maskgit_t* m, const int64_t* ids, int32_t b, int32_t n, int32_t pt,
+                                   int32_t ph, int32_t pw, const float* ctx_kv, int32_t L, const uint8_t* text_mask,
+                                   const uint8_t* video_mask, int32_t cfg_pair, int32_t return_embeds,
+                                   const float* pos_bias, float* out, void* workspace, int64_t workspace_bytes,
+                                   int32_t prec, phk_stream_t s) {
+  PHK_REQUIRE(m && ids && out && workspace, PHK_E_ARG, "maskgit_forward: null pointer");
+  PHK_REQUIRE(b > 0 && n > 0, PHK_E_ARG, "maskgit_forward: bad size");
+  PHK_REQUIRE((int64_t)pt * ph * pw == n, PHK_E_SHAPE, "video patch shape must cover the token sequence");
+  PHK_REQUIRE(n <= m->max_seq_len, PHK_E_SHAPE,
+              "the video token sequence length is greater than max_seq_len (phenaki_pytorch.py:196)");
+  PHK_REQUIRE(prec == PHK_PREC_F32, PHK_E_UNSUPPORTED, "maskgit_forward: only PHK_PREC_F32 in this build");
+  PHK_REQUIRE(!ctx_kv || text_mask, PHK_E_ARG, "maskgit_forward: context without text mask");
+  const phk_transformer_t* T = &m->transformer;
+  PHK_TRY(check_transformer(T));
+  cudaStream_t st = to_stream(s);
+  const int reps = cfg_pair ? 2 : 1;
+  const int D = m->dim;
+  const int64_t R = (int64_t)b * n * reps;
+  Arena ar{(char*)workspace, workspace_bytes, 0};
+  float* x = (float*)ar.take(R * D * 4);
+  float* x_alt = (float*)ar.take(R * D * 4);
+  float* emb = (float*)ar.take(R * D * 4);
+  PHK_REQUIRE(x && x_alt && emb, PHK_E_WORKSPACE, "maskgit_forward: workspace too small");
+  if (m->has_bias && !pos_bias) {
+    float* bias_buf = (float*)ar.take((int64_t)m->heads * n * n * 4);
+    float* sc = (float*)ar.take(phk_cpb_scratch_floats(&m->pos_bias, pt, ph, pw) * 4);
+    PHK_REQUIRE(bias_buf && sc, PHK_E_WORKSPACE, "maskgit_forward: workspace too small (bias)");
+    PHK_TRY(phk_cpb_bias(&m->pos_bias, pt, ph, pw, sc, bias_buf, s));
+    pos_bias = bias_buf;
+  }
+  PHK_TRY(phk_token_embed(ids, m->token_emb, m->pos_emb, x, b, n, D, m->num_tokens + 1,
+                          m->is_critic ? -1.f : m->shrink_alpha, reps, s));
+  TfCall c;
+  std::memset(&c, 0, sizeof(c));
+  c.T = T; c.x = x; c.x_alt = x_alt; c.R = R;
+  c.seq = SeqView{b * reps, 1, n, n, 0, 1};
+  c.pegB = b * reps; c.pegT = pt; c.pegH = ph; c.pegW = pw; c.peg_layout = 0;
+  c.attn_bias = m->has_bias ? pos_bias : nullptr;
+  c.self_mask = video_mask; c.self_mask_mod = b;
+  c.ctx_kv = ctx_kv; c.ctx_b = b; c.ctx_L = L; c.ctx_mask = text_mask;
+  c.ctx_mask_off_from = cfg_pair ? b : -1;
+  c.prec = prec;
+  float* embeds = (return_embeds || m->is_critic) ? out : emb;
+  PHK_TRY(transformer_forward(c, ar, embeds, st));
+  if (return_embeds || m->is_critic) return 0;
+  // to_logits (phenaki_pytorch.py:213)
+  PHK_TRY(phk_gemm_f32(embeds, D, m->head_w, D, out, m->num_tokens, R, m->num_tokens, D, m->head_b, nullptr, 0, 0, 0, s));
+  return 0;
+}

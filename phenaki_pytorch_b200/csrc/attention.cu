@@ -1,0 +1,253 @@
+// Cosine-sim multi-head attention core, fp32 (attention.py:146-181), all four uses of the
+// reference with one kernel: C-ViViT spatial (bias), C-ViViT temporal (causal + ALiBi),
+// MaskGit self (3-D bias, optional key mask), cross (null-kv, text mask, CFG half dropped).
+//
+// Flash-style: one CTA per (query tile of 64, head, sequence); keys/values streamed in
+// chunks of 64 through shared memory with an online softmax, S and P never touch HBM.
+//   q,k  : l2-normalised over dim_head (F.normalize, eps 1e-12) then * q_scale / k_scale
+//   sim  : q.k * scale (+ bias) ; key mask / causal -> -FLT_MAX ; softmax ; . v
+// Sequences are addressed with (outer, inner, token) strides so neither the spatial
+// '(b t)(h w)' nor the temporal '(b h w) t' view is ever materialised (cvivit.py:458,468).
+#include "phk_common.cuh"
+
+namespace phk {
+
+constexpr int TQ = 64, TK = 64, ATT_THREADS = 256;
+
+template <int DH>
+struct AttSmem {
+  float q[DH][TQ + 4];   // d-major (transposed) normalised queries
+  float k[DH][TK + 4];   // d-major normalised keys of the current chunk
+  float v[TK][DH + 4];   // values of the current chunk
+  float p[TQ][TK + 4];   // probabilities of the current chunk
+};
+
+template <int DH>
+__global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const float* __restrict__ q,
+                                                                const float* __restrict__ kv,
+                                                                const float* __restrict__ null_kv,
+                                                                const float* __restrict__ q_scale,
+                                                                const float* __restrict__ k_scale,
+                                                                const float* __restrict__ bias,
+                                                                const uint8_t* __restrict__ key_mask,
+                                                                const float* __restrict__ alibi_slopes,
+                                                                void* __restrict__ out, phk_attn_geom_t g) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  AttSmem<DH>& sm = *reinterpret_cast<AttSmem<DH>*>(smem_raw);
+  const int qt = blockIdx.x, h = blockIdx.y, seq = blockIdx.z;
+  const int so = seq / g.n_inner, si = seq - so * g.n_inner;
+  const int kv_so = g.kv_outer_mod > 0 ? so % g.kv_outer_mod : so;
+  const int mask_row = g.mask_outer_mod > 0 ? so % g.mask_outer_mod : so;
+  const bool mask_dropped = g.mask_off_from >= 0 && so >= g.mask_off_from;
+  const int I = g.heads * DH;
+  const int nnull = g.num_null_kv;
+  const int nk_total = g.n_k + nnull;
+  const int q0 = qt * TQ;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+
+  const float* qbase = q + (int64_t)so * g.q_outer + (int64_t)si * g.q_inner + (int64_t)h * DH;
+  const float* kbase = kv + (int64_t)kv_so * g.k_outer + (int64_t)si * g.k_inner + (int64_t)h * DH;
+
+  // ---- load + normalise the query tile (warp per row, lanes over d) ----
+  constexpr int DPL = (DH + 31) / 32;  // d's per lane
+  for (int r = wid; r < TQ; r += ATT_THREADS / 32) {
+    const int qi = q0 + r;
+    float x[DPL];
+    float ss = 0.f;
+#pragma unroll
+    for (int c = 0; c < DPL; ++c) {
+      const int d = lane + 32 * c;
+      x[c] = (qi < g.n_q && d < DH) ? qbase[(int64_t)qi * g.q_tok + d] : 0.f;
+      ss += x[c] * x[c];
+    }
+    const float nrm = fmaxf(sqrtf(warp_sum(ss)), 1e-12f);
+#pragma unroll
+    for (int c = 0; c < DPL; ++c) {
+      const int d = lane + 32 * c;
+      if (d < DH) sm.q[d][r] = (x[c] / nrm) * q_scale[d];
+    }
+  }
+
+  float m_run[4], l_run[4];
+  constexpr int CW = DH / 16;  // output columns per thread
+  float o_acc[4][CW];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    m_run[i] = -INFINITY;
+    l_run[i] = 0.f;
+#pragma unroll
+    for (int c = 0; c < CW; ++c) o_acc[i][c] = 0.f;
+  }
+  const float slope = (g.causal && alibi_slopes) ? alibi_slopes[h] : 0.f;
+  const int row_shift = g.n_k - g.n_q;  // query i sits at key position i + (j - i) (attention.py:196)
+
+  for (int j0 = 0; j0 < nk_total; j0 += TK) {
+    __syncthreads();  // previous chunk fully consumed (also orders the q tile on the first pass)
+    // ---- load key / value chunk ----
+    for (int r = wid; r < TK; r += ATT_THREADS / 32) {
+      const int jj = j0 + r;
+      const float* kp = nullptr;
+      const float* vp = nullptr;
+      if (jj < nnull) {
+        kp = null_kv + ((int64_t)h * 2 * nnull + 2 * jj) * DH;  // 'h (n r) d', r=0 key, r=1 value (:148)
+        vp = kp + DH;
+      } else if (jj < nk_total) {
+        kp = kbase + (int64_t)(jj - nnull) * g.k_tok;
+        vp = kp + I;
+      }
+      float x[DPL];
+      float ss = 0.f;
+#pragma unroll
+      for (int c = 0; c < DPL; ++c) {
+        const int d = lane + 32 * c;
+        x[c] = (kp && d < DH) ? kp[d] : 0.f;
+        ss += x[c] * x[c];
+        if (d < DH) sm.v[r][d] = vp ? vp[d] : 0.f;
+      }
+      const float nrm = fmaxf(sqrtf(warp_sum(ss)), 1e-12f);
+#pragma unroll
+      for (int c = 0; c < DPL; ++c) {
+        const int d = lane + 32 * c;
+        if (d < DH) sm.k[d][r] = (x[c] / nrm) * k_scale[d];
+      }
+    }
+    __syncthreads();
+    // ---- S = q k^T ----
+    float s[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
+#pragma unroll 8
+    for (int d = 0; d < DH; ++d) {
+      const float4 a = *reinterpret_cast<const float4*>(&sm.q[d][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&sm.k[d][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s[i][j] = fmaf(av[i], bv[j], s[i][j]);
+    }
+    // ---- scale, bias, masks, online softmax ----
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int qi = q0 + ty * 4 + i;
+      float rmax = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int jj = j0 + tx * 4 + j;
+        float val = s[i][j] * g.scale;
+        if (jj >= nk_total || qi >= g.n_q) {
+          val = -INFINITY;  // padding, contributes nothing
+        } else {
+          const int kj = jj - nnull;  // index among the real keys
+          if (bias && kj >= 0) val += bias[((int64_t)h * g.n_q + qi) * g.n_k + kj];
+          if (key_mask && kj >= 0 && (mask_dropped || !key_mask[(int64_t)mask_row * g.n_k + kj])) val = -FLT_MAX;
+          if (g.causal) {
+            const int pos = qi + row_shift;
+            val += -fabsf((float)(jj - pos)) * slope;
+            if (jj > pos) val = -FLT_MAX;
+          }
+        }
+        s[i][j] = val;
+        rmax = fmaxf(rmax, val);
+      }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) rmax = fmaxf(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
+      const float m_new = fmaxf(m_run[i], rmax);
+      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;  // fully padded query row
+      const float corr = expf(m_run[i] - m_use);
+      float rsum = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float pv = expf(s[i][j] - m_use);
+        rsum += pv;
+        sm.p[ty * 4 + i][tx * 4 + j] = pv;
+      }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) rsum += __shfl_xor_sync(0xffffffffu, rsum, o);
+      l_run[i] = l_run[i] * corr + rsum;
+      m_run[i] = m_new;
+#pragma unroll
+      for (int c = 0; c < CW; ++c) o_acc[i][c] *= corr;
+    }
+    __syncthreads();
+    // ---- O += P V ----
+#pragma unroll 4
+    for (int j = 0; j < TK; ++j) {
+      float vv[CW];
+#pragma unroll
+      for (int c = 0; c < CW; ++c) vv[c] = sm.v[j][tx * CW + c];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float pv = sm.p[ty * 4 + i][j];
+#pragma unroll
+        for (int c = 0; c < CW; ++c) o_acc[i][c] = fmaf(pv, vv[c], o_acc[i][c]);
+      }
+    }
+  }
+  // ---- normalise and store 'b h n d -> b n (h d)' (:181) ----
+  const int64_t obase = (int64_t)so * g.o_outer + (int64_t)si * g.o_inner + (int64_t)h * DH;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int qi = q0 + ty * 4 + i;
+    if (qi >= g.n_q) continue;
+    const float inv = 1.f / l_run[i];
+#pragma unroll
+    for (int c = 0; c < CW; ++c) {
+      const float ov = o_acc[i][c] * inv;
+      const int64_t off = obase + (int64_t)qi * g.o_tok + tx * CW + c;
+      if (g.out_bf16) reinterpret_cast<__nv_bfloat16*>(out)[off] = __float2bfloat16_rn(ov);
+      else reinterpret_cast<float*>(out)[off] = ov;
+    }
+  }
+}
+
+template <int DH>
+static int launch_attention(const float* q, const float* kv, const float* null_kv, const float* q_scale,
+                            const float* k_scale, const float* bias, const uint8_t* key_mask,
+                            const float* alibi_slopes, void* out, const phk_attn_geom_t& g, cudaStream_t st) {
+  const size_t smem = sizeof(AttSmem<DH>);
+  static bool configured = false;
+  if (!configured) {
+    PHK_CUDA(cudaFuncSetAttribute(attention_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  dim3 grid((unsigned)((g.n_q + TQ - 1) / TQ), (unsigned)g.heads, (unsigned)(g.n_outer * g.n_inner));
+  attention_kernel<DH><<<grid, ATT_THREADS, smem, st>>>(q, kv, null_kv, q_scale, k_scale, bias, key_mask,
+                                                        alibi_slopes, out, g);
+  PHK_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace phk
+
+using namespace phk;
+
+extern "C" int phk_attention(const float* q, const float* kv, const float* null_kv, const float* q_scale,
+                             const float* k_scale, const float* bias, const uint8_t* key_mask,
+                             const float* alibi_slopes, void* out, const phk_attn_geom_t* g, phk_stream_t s) {
+  Prof prof_(FAM_ATTENTION, s, g ? 4.0 * (double)g->n_outer * g->n_inner * g->heads * g->n_q * (g->n_k + g->num_null_kv) * g->dim_head : 0.0);
+  PHK_REQUIRE(q && kv && q_scale && k_scale && out && g, PHK_E_ARG, "phk_attention: null pointer");
+  PHK_REQUIRE(g->n_outer > 0 && g->n_inner > 0 && g->n_q > 0 && g->n_k >= 0 && g->heads > 0, PHK_E_ARG,
+              "phk_attention: bad geometry");
+  PHK_REQUIRE(g->num_null_kv == 0 || null_kv, PHK_E_ARG, "phk_attention: null_kv missing");
+  PHK_REQUIRE(g->n_k + g->num_null_kv > 0, PHK_E_SHAPE, "phk_attention: no keys");
+  PHK_REQUIRE(!g->causal || (g->num_null_kv == 0 && alibi_slopes), PHK_E_UNSUPPORTED,
+              "phk_attention: causal attention takes ALiBi slopes and no null-kv (attention.py:109-110,303)");
+  PHK_REQUIRE((int64_t)g->n_outer * g->n_inner <= 65535 * 1 || true, PHK_E_UNSUPPORTED, "");
+  PHK_REQUIRE((int64_t)g->n_outer * g->n_inner <= 2147483647LL && g->heads <= 65535, PHK_E_UNSUPPORTED,
+              "phk_attention: grid too large");
+  cudaStream_t st = to_stream(s);
+  // gridDim.z is limited to 65535: fold sequences if needed
+  PHK_REQUIRE((int64_t)g->n_outer * g->n_inner <= 65535, PHK_E_UNSUPPORTED, "phk_attention: more than 65535 sequences");
+  switch (g->dim_head) {
+    case 16: return launch_attention<16>(q, kv, null_kv, q_scale, k_scale, bias, key_mask, alibi_slopes, out, *g, st);
+    case 32: return launch_attention<32>(q, kv, null_kv, q_scale, k_scale, bias, key_mask, alibi_slopes, out, *g, st);
+    case 64: return launch_attention<64>(q, kv, null_kv, q_scale, k_scale, bias, key_mask, alibi_slopes, out, *g, st);
+    case 128: return launch_attention<128>(q, kv, null_kv, q_scale, k_scale, bias, key_mask, alibi_slopes, out, *g, st);
+    default: PHK_REQUIRE(false, PHK_E_UNSUPPORTED, "phk_attention: dim_head must be 16, 32, 64 or 128");
+  }
+  return 0;
+}

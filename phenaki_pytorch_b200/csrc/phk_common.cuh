@@ -1,0 +1,78 @@
+// Shared device/host helpers for libphk (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <float.h>
+#include "../../include/phk.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libphk is written for sm_100a (B200) only"
+#endif
+
+namespace phk {
+
+void set_error(const char* msg);
+void count_launch(int n = 1);
+
+#define PHK_REQUIRE(cond, code, msg) \
+  do { if (!(cond)) { ::phk::set_error(msg); return (code); } } while (0)
+
+// returns cudaError after a launch (sticky errors surface here without a sync)
+#define PHK_LAUNCH_CHECK() \
+  do { ::phk::count_launch(); cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return (int)e__; } while (0)
+
+#define PHK_CUDA(call) \
+  do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return (int)e__; } while (0)
+
+#define PHK_TRY(call) \
+  do { int r__ = (call); if (r__ != 0) return r__; } while (0)
+
+static inline cudaStream_t to_stream(phk_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+constexpr int kNumSMs = 148;
+
+// Optional per-kernel-family timing with CUDA events on the launching stream (bench.py roofline /
+// share-of-step numbers).  Off by default: zero overhead beyond one relaxed load per entry point.
+enum Family { FAM_PATCHIFY = 0, FAM_LAYERNORM, FAM_GEMM_F32, FAM_GEMM_BF16, FAM_ATTENTION, FAM_PEG, FAM_GEGLU,
+              FAM_LFQ, FAM_EMBED, FAM_CPB, FAM_SAMPLE, FAM_TOPK, FAM_CRITIC, FAM_CFG, FAM_COUNT };
+struct Prof {
+  Prof(int fam, phk_stream_t s, double work = 0.0);
+  ~Prof();
+  int fam; cudaStream_t st; cudaEvent_t e0; bool on; double work;
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Block-wide sum for blockDim.x <= 1024 (multiple of 32). `red` is >= 32 floats of smem.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();  // protect `red` from a previous use
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  float t = (lane < nw) ? red[lane] : 0.f;
+  t = warp_sum(t);
+  return t;
+}
+
+__device__ __forceinline__ float gelu_erf(float x) {
+  // F.gelu default (approximate='none'): 0.5 * x * (1 + erf(x / sqrt(2)))
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+}  // namespace phk

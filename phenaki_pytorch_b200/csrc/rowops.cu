@@ -1,0 +1,688 @@
+// Row-wise / memory-bound kernels of the phenaki hot path (sm_100a).
+// Every kernel cites the reference code it replaces (paths relative to
+// /root/reference/phenaki_pytorch/).  All are HBM/L2-bound: coalesced 16-byte accesses,
+// no tensor cores on purpose.
+#include "phk_common.cuh"
+
+namespace phk {
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm (attention.py:29-36, :48, :308): two-pass mean / variance, eps 1e-5, fp32.
+// Warp-per-row fast path for dim % 128 == 0 && dim <= 1024; block-per-row otherwise.
+// ------------------------------------------------------------------------------------------
+template <int VEC /* float4 per lane */>
+__global__ void __launch_bounds__(256) ln_warp_kernel(const float* __restrict__ x, const float* __restrict__ g,
+                                                      const float* __restrict__ b, void* __restrict__ out,
+                                                      __nv_bfloat16* __restrict__ raw, int64_t rows, int dim,
+                                                      int out_bf16, int64_t seg_len, int64_t seg_stride,
+                                                      int64_t seg_off) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int64_t orow = seg_len > 0 ? (row / seg_len) * seg_stride + seg_off + row % seg_len : row;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * dim);
+  float4 v[VEC];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    v[j] = xr[lane + 32 * j];
+    s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+  }
+  const float mean = warp_sum(s) / (float)dim;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    float a = v[j].x - mean, bb = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+    q += (a * a + bb * bb) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)dim + 1e-5f);
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  const float4* b4 = reinterpret_cast<const float4*>(b);
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    const int c4 = lane + 32 * j;
+    const float4 gg = g4[c4], bb = b4[c4];
+    float4 o;
+    o.x = (v[j].x - mean) * rstd * gg.x + bb.x;
+    o.y = (v[j].y - mean) * rstd * gg.y + bb.y;
+    o.z = (v[j].z - mean) * rstd * gg.z + bb.z;
+    o.w = (v[j].w - mean) * rstd * gg.w + bb.w;
+    if (out_bf16) {
+      uint2 p = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+      reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + orow * dim)[c4] = p;
+    } else {
+      reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + orow * dim)[c4] = o;
+    }
+    if (raw) {
+      uint2 p = make_uint2(pack_bf16x2(v[j].x, v[j].y), pack_bf16x2(v[j].z, v[j].w));
+      reinterpret_cast<uint2*>(raw + orow * dim)[c4] = p;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) ln_block_kernel(const float* __restrict__ x, const float* __restrict__ g,
+                                                       const float* __restrict__ b, void* __restrict__ out,
+                                                       __nv_bfloat16* __restrict__ raw, int dim, int out_bf16,
+                                                       int64_t seg_len, int64_t seg_stride, int64_t seg_off) {
+  extern __shared__ float srow[];
+  __shared__ float red[32];
+  const int64_t row = blockIdx.x;
+  const int64_t orow = seg_len > 0 ? (row / seg_len) * seg_stride + seg_off + row % seg_len : row;
+  const float* xr = x + row * dim;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < dim; i += blockDim.x) { float t = xr[i]; srow[i] = t; s += t; }
+  const float mean = block_sum(s, red) / (float)dim;
+  float q = 0.f;
+  for (int i = threadIdx.x; i < dim; i += blockDim.x) { float d = srow[i] - mean; q += d * d; }
+  const float rstd = rsqrtf(block_sum(q, red) / (float)dim + 1e-5f);
+  for (int i = threadIdx.x; i < dim; i += blockDim.x) {
+    const float o = (srow[i] - mean) * rstd * g[i] + b[i];
+    if (out_bf16) reinterpret_cast<__nv_bfloat16*>(out)[orow * dim + i] = __float2bfloat16_rn(o);
+    else reinterpret_cast<float*>(out)[orow * dim + i] = o;
+    if (raw) raw[orow * dim + i] = __float2bfloat16_rn(srow[i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Patchify + LayerNorm(K) (cvivit.py:273-275 / 280-282).  One CTA per token; the token's K
+// pixels are gathered as p2-float contiguous runs (128 B for p2=32) straight from the
+// (B,C,F,H,W) video -- the single HBM-visible read of the encoder -- into shared memory,
+// normalised in place and written as one dense row of the GEMM A operand.
+// ------------------------------------------------------------------------------------------
+template <bool VEC4>
+__global__ void __launch_bounds__(256) patchify_ln_kernel(const float* __restrict__ video, int C, int F, int H,
+                                                          int W, int f0, int nt, int pt, int p1, int p2,
+                                                          const float* __restrict__ g, const float* __restrict__ b,
+                                                          void* __restrict__ out, int out_bf16) {
+  extern __shared__ float srow[];
+  __shared__ float red[32];
+  const int hh = H / p1, ww = W / p2;
+  int tok = blockIdx.x;
+  const int wi = tok % ww; tok /= ww;
+  const int hi = tok % hh; tok /= hh;
+  const int ti = tok % nt;
+  const int bi = tok / nt;
+  const int K = C * pt * p1 * p2;
+  const int64_t plane = (int64_t)H * W;
+  const float* base = video + ((int64_t)bi * C * F + f0 + (int64_t)ti * pt) * plane + (int64_t)hi * p1 * W + wi * p2;
+  float s = 0.f;
+  if (VEC4) {
+    const int runs = p2 >> 2;  // float4 per patch row
+    for (int i = threadIdx.x; i < (K >> 2); i += blockDim.x) {
+      const int dx4 = i % runs;
+      int r = i / runs;  // (c, dt, dy)
+      const int dy = r % p1; r /= p1;
+      const int dt = r % pt;
+      const int c = r / pt;
+      const float4 v = __ldg(reinterpret_cast<const float4*>(base + ((int64_t)c * F + dt) * plane + (int64_t)dy * W) + dx4);
+      reinterpret_cast<float4*>(srow)[i] = v;
+      s += (v.x + v.y) + (v.z + v.w);
+    }
+  } else {
+    for (int i = threadIdx.x; i < K; i += blockDim.x) {
+      const int dx = i % p2;
+      int r = i / p2;
+      const int dy = r % p1; r /= p1;
+      const int dt = r % pt;
+      const int c = r / pt;
+      const float v = __ldg(base + ((int64_t)c * F + dt) * plane + (int64_t)dy * W + dx);
+      srow[i] = v;
+      s += v;
+    }
+  }
+  const float mean = block_sum(s, red) / (float)K;
+  float q = 0.f;
+  for (int i = threadIdx.x; i < K; i += blockDim.x) { const float d = srow[i] - mean; q += d * d; }
+  const float rstd = rsqrtf(block_sum(q, red) / (float)K + 1e-5f);
+  const int64_t orow = (int64_t)blockIdx.x * K;
+  if (VEC4) {
+    for (int i = threadIdx.x; i < (K >> 2); i += blockDim.x) {
+      const float4 v = reinterpret_cast<float4*>(srow)[i];
+      const float4 gg = __ldg(reinterpret_cast<const float4*>(g) + i);
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(b) + i);
+      float4 o;
+      o.x = (v.x - mean) * rstd * gg.x + bb.x;
+      o.y = (v.y - mean) * rstd * gg.y + bb.y;
+      o.z = (v.z - mean) * rstd * gg.z + bb.z;
+      o.w = (v.w - mean) * rstd * gg.w + bb.w;
+      if (out_bf16)
+        reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + orow)[i] =
+            make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+      else
+        reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + orow)[i] = o;
+    }
+  } else {
+    for (int i = threadIdx.x; i < K; i += blockDim.x) {
+      const float o = (srow[i] - mean) * rstd * g[i] + b[i];
+      if (out_bf16) reinterpret_cast<__nv_bfloat16*>(out)[orow + i] = __float2bfloat16_rn(o);
+      else reinterpret_cast<float*>(out)[orow + i] = o;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// GEGLU (attention.py:40-43): x, gate = chunk(2); gelu(gate) * x
+// ------------------------------------------------------------------------------------------
+__global__ void geglu_kernel(const float* __restrict__ h, float* __restrict__ out, int64_t rows, int inner) {
+  const int64_t total = rows * inner;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / inner;
+    const int j = (int)(i - r * inner);
+    const float val = h[r * 2 * inner + j];
+    const float gate = h[r * 2 * inner + inner + j];
+    out[i] = gelu_erf(gate) * val;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// token + position embedding and gradient-shrink forward value (phenaki_pytorch.py:194-199)
+// ------------------------------------------------------------------------------------------
+__global__ void token_embed_kernel(const int64_t* __restrict__ ids, const float* __restrict__ tok,
+                                   const float* __restrict__ pos, float* __restrict__ out, int n, int dim,
+                                   float alpha, float one_minus_alpha, int shrink, int64_t id_rows) {
+  const int64_t row = blockIdx.x;
+  const int p = (int)(row % n);
+  const int64_t id = ids[row % id_rows];  // the CFG null half replays the same ids
+  const float* t = tok + id * dim;
+  const float* pe = pos + (int64_t)p * dim;
+  for (int i = threadIdx.x; i < dim; i += blockDim.x) {
+    float x = __fadd_rn(pe[i], t[i]);  // pos_emb(arange) + token_emb(x)
+    if (shrink) x = __fadd_rn(__fmul_rn(x, alpha), __fmul_rn(x, one_minus_alpha));
+    out[row * dim + i] = x;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// LFQ ids (oracle/lfq.py; call site cvivit.py:570).  Warp per row.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) lfq_kernel(const float* __restrict__ x, const float* __restrict__ wp,
+                                                  const float* __restrict__ bp, int64_t* __restrict__ ids,
+                                                  float* __restrict__ proj, int64_t rows, int dim, int bits) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* xr = x + row * dim;
+  int64_t id = 0;
+  for (int d = 0; d < bits; ++d) {
+    const float* w = wp + (int64_t)d * dim;
+    float acc = 0.f;
+    for (int i = lane; i < dim; i += 32) acc = fmaf(xr[i], __ldg(w + i), acc);
+    acc = warp_sum(acc) + bp[d];
+    if (proj && lane == 0) proj[row * bits + d] = acc;
+    if (acc > 0.f) id |= (int64_t)1 << (bits - 1 - d);
+  }
+  if (lane == 0) ids[row] = id;
+}
+
+// ------------------------------------------------------------------------------------------
+// PEG depthwise 3x3x3 conv + bias + residual (attention.py:64-85, caller :323).
+// w is tap-major [27][D] (packed by the host module from dsconv.weight[D,1,3,3,3]).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int64_t peg_phys_row(int64_t r_log, int T, int HW, int layout) {
+  if (layout == 0) return r_log;
+  // reference buffer is '(b h w) t d' reinterpreted as (b,t,h,w,d); ours is stored (b,t,h,w)
+  const int64_t s = r_log / T;
+  const int tau = (int)(r_log - s * T);
+  const int64_t b2 = s / HW;
+  const int hw = (int)(s - b2 * HW);
+  return (b2 * T + tau) * HW + hw;
+}
+
+__global__ void __launch_bounds__(128) peg_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                  const float* __restrict__ bias, float* __restrict__ y, int T, int H,
+                                                  int W, int D, int pad_t0, int layout) {
+  // grid.x = logical positions, threads cover D in float4 steps
+  const int64_t r_log = blockIdx.x;
+  const int HW = H * W;
+  int rem = (int)(r_log % ((int64_t)T * HW));
+  const int64_t bi = r_log / ((int64_t)T * HW);
+  const int t = rem / HW; rem -= t * HW;
+  const int h = rem / W;
+  const int wq = rem - h * W;
+  const int64_t out_row = peg_phys_row(r_log, T, HW, layout);
+  for (int d4 = threadIdx.x; d4 < (D >> 2); d4 += blockDim.x) {
+    float4 acc = __ldg(reinterpret_cast<const float4*>(bias) + d4);
+#pragma unroll
+    for (int kt = 0; kt < 3; ++kt) {
+      const int ts = t + kt - pad_t0;
+      if (ts < 0 || ts >= T) continue;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        const int hs = h + kh - 1;
+        if (hs < 0 || hs >= H) continue;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const int ws = wq + kw - 1;
+          if (ws < 0 || ws >= W) continue;
+          const int64_t src_log = ((bi * T + ts) * H + hs) * W + ws;
+          const int64_t src = peg_phys_row(src_log, T, HW, layout);
+          const float4 xv = __ldg(reinterpret_cast<const float4*>(x + src * D) + d4);
+          const float4 wv = __ldg(reinterpret_cast<const float4*>(w + (int64_t)((kt * 3 + kh) * 3 + kw) * D) + d4);
+          acc.x = fmaf(xv.x, wv.x, acc.x);
+          acc.y = fmaf(xv.y, wv.y, acc.y);
+          acc.z = fmaf(xv.z, wv.z, acc.z);
+          acc.w = fmaf(xv.w, wv.w, acc.w);
+        }
+      }
+    }
+    const float4 xs = __ldg(reinterpret_cast<const float4*>(x + out_row * D) + d4);
+    float4 o = make_float4(acc.x + xs.x, acc.y + xs.y, acc.z + xs.z, acc.w + xs.w);
+    reinterpret_cast<float4*>(y + out_row * D)[d4] = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// ContinuousPositionBias (attention.py:257-275).  Weight-only: MLP over distinct deltas
+// (table kernel), then expansion to (heads, n, n).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cpb_table_kernel(phk_cpb_t c, int d0, int d1, int d2,
+                                                        float* __restrict__ table) {
+  extern __shared__ float sm[];
+  float* h1 = sm;
+  float* h2 = sm + c.hidden;
+  const int u = blockIdx.x;
+  const int s1 = 2 * d1 - 1, s2 = 2 * d2 - 1;
+  int delta[3];
+  delta[0] = u / (s1 * s2) - (d0 - 1);
+  delta[1] = (u / s2) % s1 - (d1 - 1);
+  delta[2] = u % s2 - (d2 - 1);
+  float in[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int a = delta[i] < 0 ? -delta[i] : delta[i];
+    const float sg = delta[i] > 0 ? 1.f : (delta[i] < 0 ? -1.f : 0.f);
+    in[i] = sg * logf((float)(a + 1));  // sign(rel) * log(|rel| + 1)   (attention.py:266)
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int j = threadIdx.x; j < c.hidden; j += blockDim.x) {
+    float a = c.b0[j];
+    for (int i = 0; i < c.num_dims; ++i) a = fmaf(in[i], c.w0[j * c.num_dims + i], a);
+    h1[j] = a > 0.f ? a : 0.1f * a;
+  }
+  __syncthreads();
+  for (int j = wid; j < c.hidden; j += nw) {
+    float a = 0.f;
+    for (int k = lane; k < c.hidden; k += 32) a = fmaf(h1[k], c.w1[(int64_t)j * c.hidden + k], a);
+    a = warp_sum(a) + c.b1[j];
+    if (lane == 0) h2[j] = a > 0.f ? a : 0.1f * a;
+  }
+  __syncthreads();
+  for (int j = wid; j < c.heads; j += nw) {
+    float a = 0.f;
+    for (int k = lane; k < c.hidden; k += 32) a = fmaf(h2[k], c.w2[(int64_t)j * c.hidden + k], a);
+    a = warp_sum(a) + c.b2[j];
+    if (lane == 0) table[(int64_t)u * c.heads + j] = a;
+  }
+}
+
+__global__ void cpb_expand_kernel(const float* __restrict__ table, float* __restrict__ out, int heads, int d0,
+                                  int d1, int d2) {
+  const int n = d0 * d1 * d2;
+  const int64_t total = (int64_t)n * n;
+  const int s1 = 2 * d1 - 1, s2 = 2 * d2 - 1;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(idx / n), j = (int)(idx % n);
+    const int i0 = i / (d1 * d2), i1 = (i / d2) % d1, i2 = i % d2;
+    const int j0 = j / (d1 * d2), j1 = (j / d2) % d1, j2 = j % d2;
+    const int u = ((i0 - j0 + d0 - 1) * s1 + (i1 - j1 + d1 - 1)) * s2 + (i2 - j2 + d2 - 1);
+    for (int h = 0; h < heads; ++h) out[(int64_t)h * total + idx] = table[(int64_t)u * heads + h];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// CFG + gumbel argmax + confidence (phenaki_pytorch.py:161, 83-93, 506-509, 547-550).
+// One CTA per token row, single pass over the V logits: running (argmax of perturbed logit,
+// max / sum-exp of the guided logit).  fp32 op sequence mirrors the eager reference
+// (sub, mul, add, div, add -- no FMA contraction) so argmax decisions agree bit for bit
+// whenever logf agrees.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t* out) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+struct ArgBest { float y; int idx; };
+__device__ __forceinline__ ArgBest better(ArgBest a, ArgBest b) {
+  // larger y wins; ties -> lower index (torch.argmax returns the first maximal index)
+  if (b.y > a.y || (b.y == a.y && b.idx < a.idx)) return b;
+  return a;
+}
+
+__global__ void __launch_bounds__(512) sample_tokens_kernel(const float* __restrict__ cond,
+                                                            const float* __restrict__ nul, int64_t ld,
+                                                            const float* __restrict__ u, uint64_t seed,
+                                                            uint64_t offset, float cond_scale, float temperature,
+                                                            const uint8_t* __restrict__ mask,
+                                                            int64_t* __restrict__ ids, int64_t* __restrict__ pred_out,
+                                                            float* __restrict__ score_out, int V, int64_t seg_len,
+                                                            int64_t seg_stride, int64_t seg_off) {
+  __shared__ float s_y[16], s_m[16], s_s[16];
+  __shared__ int s_i[16];
+  const int64_t row = blockIdx.x;
+  // logits[:, prime_len:] (phenaki_pytorch.py:503-504): token row -> row of the (b, prime+n) logits
+  const int64_t lrow = seg_len > 0 ? (row / seg_len) * seg_stride + seg_off + row % seg_len : row;
+  const float* cr = cond + lrow * ld;
+  const float* nr = nul ? nul + lrow * ld : nullptr;
+  const float* ur = u ? u + row * (int64_t)V : nullptr;
+  const float T = fmaxf(temperature, 1e-10f);
+  ArgBest best{-FLT_MAX, 0x7fffffff};
+  float m = -FLT_MAX, ssum = 0.f;
+  for (int v0 = threadIdx.x * 4; v0 < V; v0 += blockDim.x * 4) {
+    float uu[4];
+    if (ur) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) uu[j] = (v0 + j < V) ? ur[v0 + j] : 0.5f;
+    } else {
+      const uint64_t ctr = offset + (uint64_t)row * (uint64_t)((V + 3) / 4) + (uint64_t)(v0 >> 2);
+      uint32_t r[4];
+      philox4x32_10((uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) uu[j] = (float)(r[j] >> 8) * (1.0f / 16777216.0f);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int v = v0 + j;
+      if (v >= V) break;
+      float l = cr[v];
+      if (nr) { const float nn = nr[v]; l = __fadd_rn(nn, __fmul_rn(__fsub_rn(l, nn), cond_scale)); }
+      const float g = -logf(__fadd_rn(-logf(__fadd_rn(uu[j], 1e-10f)), 1e-10f));
+      const float y = __fadd_rn(__fdiv_rn(l, T), g);
+      if (y > best.y) { best.y = y; best.idx = v; }
+      if (l > m) { ssum = ssum * expf(m - l) + 1.f; m = l; } else { ssum += expf(l - m); }
+    }
+  }
+  // block combine
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ArgBest ob{__shfl_xor_sync(0xffffffffu, best.y, o), __shfl_xor_sync(0xffffffffu, best.idx, o)};
+    best = better(best, ob);
+    const float om = __shfl_xor_sync(0xffffffffu, m, o), os = __shfl_xor_sync(0xffffffffu, ssum, o);
+    const float nm = fmaxf(m, om);
+    ssum = ssum * expf(m - nm) + os * expf(om - nm);
+    m = nm;
+  }
+  if (lane == 0) { s_y[wid] = best.y; s_i[wid] = best.idx; s_m[wid] = m; s_s[wid] = ssum; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < nw; ++w) {
+      best = better(best, ArgBest{s_y[w], s_i[w]});
+      const float nm = fmaxf(m, s_m[w]);
+      ssum = ssum * expf(m - nm) + s_s[w] * expf(s_m[w] - nm);
+      m = nm;
+    }
+    const int pred = best.idx;
+    float l = cr[pred];
+    if (nr) { const float nn = nr[pred]; l = __fadd_rn(nn, __fmul_rn(__fsub_rn(l, nn), cond_scale)); }
+    const float p = expf(l - m) / ssum;
+    const bool mk = mask ? mask[row] != 0 : true;
+    if (pred_out) pred_out[row] = pred;
+    if (ids && mk) ids[row] = pred;                                   // where(mask, pred, ids)   (:509)
+    if (score_out) score_out[row] = mk ? (1.0f - p) : -1e4f;          // (:547-550)
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Cosine-schedule re-masking (phenaki_pytorch.py:485-491).  Rank by counting: element i is in
+// the top-k iff fewer than k elements beat it (greater score, or equal score and lower index).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) topk_mask_kernel(const float* __restrict__ scores, int n, int k,
+                                                         uint8_t* __restrict__ mask, int64_t* __restrict__ ids,
+                                                         int64_t mask_id) {
+  extern __shared__ float sc[];
+  const int64_t row = blockIdx.x;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) sc[i] = scores[row * n + i];
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float si = sc[i];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) {
+      const float sj = sc[j];
+      rank += (sj > si) || (sj == si && j < i);
+    }
+    const uint8_t mk = rank < k;
+    mask[row * n + i] = mk;
+    if (mk) ids[row * n + i] = mask_id;                               // where(mask, mask_id, ids)  (:491)
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Critic head + CFG + annealed noise (phenaki_pytorch.py:246-249, 263, 544-545).  Warp per row.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) critic_scores_kernel(const float* __restrict__ xc, const float* __restrict__ xn,
+                                                            const float* __restrict__ w, const float* __restrict__ b,
+                                                            const float* __restrict__ u, float cond_scale,
+                                                            float noise_K, float noise_mult, float* __restrict__ out,
+                                                            int64_t rows, int dim, int64_t seg_len, int64_t seg_stride,
+                                                            int64_t seg_off) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int64_t xrow = seg_len > 0 ? (row / seg_len) * seg_stride + seg_off + row % seg_len : row;  // scores[:, prime:] (:528-529)
+  float a = 0.f, c = 0.f;
+  for (int i = lane; i < dim; i += 32) {
+    const float wi = __ldg(w + i);
+    a = fmaf(xc[xrow * dim + i], wi, a);
+    if (xn) c = fmaf(xn[xrow * dim + i], wi, c);
+  }
+  a = warp_sum(a) + b[0];
+  float sc = a;
+  if (xn) { c = warp_sum(c) + b[0]; sc = __fadd_rn(c, __fmul_rn(__fsub_rn(a, c), cond_scale)); }
+  if (u) sc = __fadd_rn(sc, __fmul_rn(__fmul_rn(noise_K, __fsub_rn(u[row], 0.5f)), noise_mult));
+  if (lane == 0) out[row] = sc;
+}
+
+// null + (cond - null) * scale  (phenaki_pytorch.py:161), eager op order (sub, mul, add)
+__global__ void cfg_combine_kernel(const float* __restrict__ cond, const float* __restrict__ nul, float scale,
+                                   float* __restrict__ out, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float nn = nul[i];
+    out[i] = __fadd_rn(nn, __fmul_rn(__fsub_rn(cond[i], nn), scale));
+  }
+}
+
+}  // namespace phk
+
+// ==========================================================================================
+// C ABI
+// ==========================================================================================
+using namespace phk;
+
+extern "C" int phk_layernorm(const float* x, const float* gamma, const float* beta, void* out, void* raw_bf16,
+                             int64_t rows, int32_t dim, int32_t out_bf16, int64_t seg_len, int64_t seg_stride,
+                             int64_t seg_off, phk_stream_t s) {
+  Prof prof_(FAM_LAYERNORM, s, (double)rows * dim * 8.0);
+  PHK_REQUIRE(x && gamma && beta && out, PHK_E_ARG, "phk_layernorm: null pointer");
+  PHK_REQUIRE(rows >= 0 && dim > 0, PHK_E_ARG, "phk_layernorm: bad size");
+  if (rows == 0) return 0;
+  cudaStream_t st = to_stream(s);
+  __nv_bfloat16* raw = reinterpret_cast<__nv_bfloat16*>(raw_bf16);
+  if (dim % 128 == 0 && dim <= 1024) {
+    const int wpb = 8;
+    const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
+    switch (dim / 128) {
+      case 1: ln_warp_kernel<1><<<grid, 256, 0, st>>>(x, gamma, beta, out, raw, rows, dim, out_bf16, seg_len, seg_stride, seg_off); break;
+      case 2: ln_warp_kernel<2><<<grid, 256, 0, st>>>(x, gamma, beta, out, raw, rows, dim, out_bf16, seg_len, seg_stride, seg_off); break;
+      case 3: ln_warp_kernel<3><<<grid, 256, 0, st>>>(x, gamma, beta, out, raw, rows, dim, out_bf16, seg_len, seg_stride, seg_off); break;
+      case 4: ln_warp_kernel<4><<<grid, 256, 0, st>>>(x, gamma, beta, out, raw, rows, dim, out_bf16, seg_len, seg_stride, seg_off); break;
+      case 5: ln_warp_kernel<5><<<grid, 256, 0, st>>>(x, gamma, beta, out, raw, rows, dim, out_bf16, seg_len, seg_stride, seg_off); break;
+      case 6: ln_warp_kernel<6><<<grid, 256, 0, st>>>(x, gamma, beta, out, raw, rows, dim, out_bf16, seg_len, seg_stride, seg_off); break;
+      case 7: ln_warp_kernel<7><<<grid, 256, 0, st>>>(x, gamma, beta, out, raw, rows, dim, out_bf16, seg_len, seg_stride, seg_off); break;
+      default: ln_warp_kernel<8><<<grid, 256, 0, st>>>(x, gamma, beta, out, raw, rows, dim, out_bf16, seg_len, seg_stride, seg_off); break;
+    }
+  } else {
+    PHK_REQUIRE(dim <= 12288, PHK_E_UNSUPPORTED, "phk_layernorm: dim > 12288");
+    ln_block_kernel<<<(unsigned)rows, 256, dim * sizeof(float), st>>>(x, gamma, beta, out, raw, dim, out_bf16, seg_len, seg_stride, seg_off);
+  }
+  PHK_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int phk_patchify_ln(const float* video, int32_t B, int32_t C, int32_t F, int32_t H, int32_t W, int32_t f0,
+                               int32_t nt, int32_t pt, int32_t p1, int32_t p2, const float* ln_g, const float* ln_b,
+                               void* out, int32_t out_bf16, phk_stream_t s) {
+  Prof prof_(FAM_PATCHIFY, s, (double)B * C * nt * pt * H * W * 8.0);
+  PHK_REQUIRE(video && ln_g && ln_b && out, PHK_E_ARG, "phk_patchify_ln: null pointer");
+  PHK_REQUIRE(B > 0 && C > 0 && F > 0 && H > 0 && W > 0 && pt > 0 && p1 > 0 && p2 > 0 && nt >= 0, PHK_E_ARG,
+              "phk_patchify_ln: bad size");
+  PHK_REQUIRE(H % p1 == 0 && W % p2 == 0, PHK_E_SHAPE, "image size must be divisible by patch size (cvivit.py:271)");
+  PHK_REQUIRE(f0 >= 0 && f0 + nt * pt <= F, PHK_E_SHAPE, "frame range outside the video");
+  if (nt == 0) return 0;
+  const int K = C * pt * p1 * p2;
+  PHK_REQUIRE(K <= 14336, PHK_E_UNSUPPORTED, "patch feature size > 14336 floats (56 KB smem row)");
+  const unsigned grid = (unsigned)((int64_t)B * nt * (H / p1) * (W / p2));
+  const size_t smem = (size_t)K * sizeof(float);
+  const bool vec = (p2 % 4 == 0) && (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(video) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  if (smem > 48 * 1024) {
+    PHK_CUDA(cudaFuncSetAttribute(patchify_ln_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 57344));
+    PHK_CUDA(cudaFuncSetAttribute(patchify_ln_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 57344));
+  }
+  if (vec) patchify_ln_kernel<true><<<grid, 256, smem, to_stream(s)>>>(video, C, F, H, W, f0, nt, pt, p1, p2, ln_g, ln_b, out, out_bf16);
+  else patchify_ln_kernel<false><<<grid, 256, smem, to_stream(s)>>>(video, C, F, H, W, f0, nt, pt, p1, p2, ln_g, ln_b, out, out_bf16);
+  PHK_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int phk_geglu(const float* h, float* out, int64_t rows, int32_t inner, phk_stream_t s) {
+  Prof prof_(FAM_GEGLU, s, (double)rows * inner * 12.0);
+  PHK_REQUIRE(h && out, PHK_E_ARG, "phk_geglu: null pointer");
+  PHK_REQUIRE(rows >= 0 && inner > 0, PHK_E_ARG, "phk_geglu: bad size");
+  if (rows == 0) return 0;
+  const int64_t total = rows * inner;
+  const unsigned grid = (unsigned)((total + 255) / 256 < (int64_t)kNumSMs * 16 ? (total + 255) / 256 : kNumSMs * 16);
+  geglu_kernel<<<grid, 256, 0, to_stream(s)>>>(h, out, rows, inner);
+  PHK_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int phk_token_embed(const int64_t* ids, const float* tok, const float* pos, float* out, int32_t b, int32_t n,
+                               int32_t dim, int32_t vocab_rows, float alpha, int32_t replicas, phk_stream_t s) {
+  Prof prof_(FAM_EMBED, s);
+  PHK_REQUIRE(ids && tok && pos && out, PHK_E_ARG, "phk_token_embed: null pointer");
+  PHK_REQUIRE(b > 0 && n > 0 && dim > 0 && vocab_rows > 0, PHK_E_ARG, "phk_token_embed: bad size");
+  const int shrink = alpha >= 0.f;
+  // (1 - alpha) is evaluated in double by the reference's Python and rounded to fp32 at the mul
+  const float oma = (float)(1.0 - (double)alpha);
+  if (replicas < 1) replicas = 1;
+  token_embed_kernel<<<(unsigned)(b * n * replicas), 128, 0, to_stream(s)>>>(ids, tok, pos, out, n, dim, alpha, oma, shrink,
+                                                                              (int64_t)b * n);
+  PHK_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int phk_lfq_ids(const float* x, const float* wp, const float* bp, int64_t* ids, float* proj_out,
+                           int64_t rows, int32_t dim, int32_t bits, phk_stream_t s) {
+  Prof prof_(FAM_LFQ, s);
+  PHK_REQUIRE(x && wp && bp && ids, PHK_E_ARG, "phk_lfq_ids: null pointer");
+  PHK_REQUIRE(rows >= 0 && dim > 0 && bits > 0 && bits <= 62, PHK_E_ARG, "phk_lfq_ids: bad size");
+  if (rows == 0) return 0;
+  lfq_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, to_stream(s)>>>(x, wp, bp, ids, proj_out, rows, dim, bits);
+  PHK_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int phk_peg3d(const float* x, const float* w, const float* b, float* y, int32_t B, int32_t T, int32_t H,
+                         int32_t W, int32_t D, int32_t causal, int32_t layout, phk_stream_t s) {
+  Prof prof_(FAM_PEG, s, (double)B * T * H * W * D * 8.0);
+  PHK_REQUIRE(x && w && b && y && x != y, PHK_E_ARG, "phk_peg3d: null or aliased pointer");
+  PHK_REQUIRE(B > 0 && T > 0 && H > 0 && W > 0 && D > 0, PHK_E_ARG, "phk_peg3d: bad size");
+  PHK_REQUIRE(D % 4 == 0, PHK_E_UNSUPPORTED, "phk_peg3d: dim must be a multiple of 4");
+  const int64_t rows = (int64_t)B * T * H * W;
+  peg_kernel<<<(unsigned)rows, 128, 0, to_stream(s)>>>(x, w, b, y, T, H, W, D, causal ? 2 : 1, layout);
+  PHK_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int64_t phk_cpb_scratch_floats(const phk_cpb_t* c, int32_t d0, int32_t d1, int32_t d2) {
+  if (!c || d0 <= 0 || d1 <= 0 || d2 <= 0) return 0;
+  return (int64_t)(2 * d0 - 1) * (2 * d1 - 1) * (2 * d2 - 1) * c->heads;
+}
+
+extern "C" int phk_cpb_bias(const phk_cpb_t* c, int32_t d0, int32_t d1, int32_t d2, float* scratch, float* out,
+                            phk_stream_t s) {
+  Prof prof_(FAM_CPB, s);
+  PHK_REQUIRE(c && scratch && out, PHK_E_ARG, "phk_cpb_bias: null pointer");
+  PHK_REQUIRE(d0 > 0 && d1 > 0 && d2 > 0, PHK_E_ARG, "phk_cpb_bias: bad dims");
+  PHK_REQUIRE(c->num_dims == 2 || c->num_dims == 3, PHK_E_UNSUPPORTED, "phk_cpb_bias: num_dims must be 2 or 3");
+  PHK_REQUIRE(c->num_dims == 3 || d2 == 1, PHK_E_SHAPE, "phk_cpb_bias: 2-D bias needs d2 == 1");
+  PHK_REQUIRE(c->hidden > 0 && c->hidden <= 4096 && c->heads > 0, PHK_E_UNSUPPORTED, "phk_cpb_bias: hidden > 4096");
+  const int U = (2 * d0 - 1) * (2 * d1 - 1) * (2 * d2 - 1);
+  cpb_table_kernel<<<U, 256, 2 * c->hidden * sizeof(float), to_stream(s)>>>(*c, d0, d1, d2, scratch);
+  PHK_LAUNCH_CHECK();
+  const int64_t total = (int64_t)d0 * d1 * d2 * d0 * d1 * d2;
+  const unsigned grid = (unsigned)((total + 255) / 256 < (int64_t)kNumSMs * 8 ? (total + 255) / 256 : kNumSMs * 8);
+  cpb_expand_kernel<<<grid, 256, 0, to_stream(s)>>>(scratch, out, c->heads, d0, d1, d2);
+  PHK_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int phk_sample_tokens(const float* cond, const float* null_logits, int64_t ld, const float* u,
+                                 uint64_t seed, uint64_t offset, float cond_scale, float temperature,
+                                 const uint8_t* mask, int64_t* ids, int64_t* pred_out, float* score_out, int64_t rows,
+                                 int32_t V, int64_t seg_len, int64_t seg_stride, int64_t seg_off, phk_stream_t s) {
+  Prof prof_(FAM_SAMPLE, s, (double)rows * V * 8.0);
+  PHK_REQUIRE(cond, PHK_E_ARG, "phk_sample_tokens: null logits");
+  PHK_REQUIRE(rows >= 0 && V > 0 && ld >= V, PHK_E_ARG, "phk_sample_tokens: bad size");
+  if (rows == 0) return 0;
+  const float* nul = (cond_scale == 1.0f) ? nullptr : null_logits;  // cond_scale == 1 returns logits (:157-158)
+  PHK_REQUIRE(cond_scale == 1.0f || null_logits, PHK_E_ARG, "phk_sample_tokens: cond_scale != 1 needs null logits");
+  const int threads = V >= 8192 ? 512 : (V >= 1024 ? 256 : 64);
+  sample_tokens_kernel<<<(unsigned)rows, threads, 0, to_stream(s)>>>(cond, nul, ld, u, seed, offset, cond_scale,
+                                                                     temperature, mask, ids, pred_out, score_out, V, seg_len,
+                                                                     seg_stride, seg_off);
+  PHK_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int phk_topk_mask(const float* scores, int32_t b, int32_t n, int32_t k, uint8_t* mask, int64_t* ids,
+                             int64_t mask_id, phk_stream_t s) {
+  Prof prof_(FAM_TOPK, s);
+  PHK_REQUIRE(scores && mask && ids, PHK_E_ARG, "phk_topk_mask: null pointer");
+  PHK_REQUIRE(b > 0 && n > 0 && n <= 8192, PHK_E_UNSUPPORTED, "phk_topk_mask: n must be in (0, 8192]");
+  PHK_REQUIRE(k >= 0 && k <= n, PHK_E_SHAPE, "phk_topk_mask: k out of range (torch.topk would raise)");
+  int threads = ((n + 31) / 32) * 32;
+  if (threads > 1024) threads = 1024;
+  topk_mask_kernel<<<b, threads, n * sizeof(float), to_stream(s)>>>(scores, n, k, mask, ids, mask_id);
+  PHK_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int phk_critic_scores(const float* x_cond, const float* x_null, const float* w, const float* b,
+                                 const float* u, float cond_scale, float noise_K, float noise_mult, float* out,
+                                 int64_t rows, int32_t dim, int64_t seg_len, int64_t seg_stride, int64_t seg_off,
+                                 phk_stream_t s) {
+  Prof prof_(FAM_CRITIC, s);
+  PHK_REQUIRE(x_cond && w && b && out, PHK_E_ARG, "phk_critic_scores: null pointer");
+  PHK_REQUIRE(rows >= 0 && dim > 0, PHK_E_ARG, "phk_critic_scores: bad size");
+  if (rows == 0) return 0;
+  const float* xn = (cond_scale == 1.0f) ? nullptr : x_null;
+  PHK_REQUIRE(cond_scale == 1.0f || x_null, PHK_E_ARG, "phk_critic_scores: cond_scale != 1 needs the null pass");
+  critic_scores_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, to_stream(s)>>>(x_cond, xn, w, b, u, cond_scale,
+                                                                             noise_K, noise_mult, out, rows, dim, seg_len,
+                                                                             seg_stride, seg_off);
+  PHK_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int phk_cfg_combine(const float* cond, const float* null_out, float cond_scale, float* out, int64_t n,
+                               phk_stream_t s) {
+  Prof prof_(FAM_CFG, s);
+  PHK_REQUIRE(cond && null_out && out, PHK_E_ARG, "phk_cfg_combine: null pointer");
+  PHK_REQUIRE(n >= 0, PHK_E_ARG, "phk_cfg_combine: bad size");
+  if (n == 0) return 0;
+  const int64_t blocks = (n + 255) / 256;
+  cfg_combine_kernel<<<(unsigned)(blocks < (int64_t)kNumSMs * 16 ? blocks : kNumSMs * 16), 256, 0, to_stream(s)>>>(
+      cond, null_out, cond_scale, out, n);
+  PHK_LAUNCH_CHECK();
+  return 0;
+}

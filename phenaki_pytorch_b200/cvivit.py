@@ -1,0 +1,229 @@
+"""C-ViViT video tokenizer -- drop-in for ``phenaki_pytorch.CViViT`` on the encode hot path.
+
+Same constructor keywords, attribute names and state-dict layout as the reference
+(/root/reference/phenaki_pytorch/cvivit.py:226-335); ``forward(video,
+return_only_codebook_ids=True)`` (cvivit.py:518-574) runs entirely in libphk.so
+(phk_cvivit_encode).  Training losses, discriminator and VGG (cvivit.py:59-213, 576-671) are out
+of scope and raise.
+"""
+import copy
+import ctypes as C
+import math
+from pathlib import Path
+
+import torch
+from torch import nn
+
+from . import _lib as L
+from .modules import (ContinuousPositionBias, Keep, Transformer, Workspace, _NoParams, cpb_table,
+                      transformer_table, weights_signature)
+
+
+def _pair(v):
+    r = (v, v) if not isinstance(v, tuple) else v
+    assert len(r) == 2
+    return r
+
+
+class LFQ(nn.Module):
+    """Parameter holder with upstream ``vector_quantize_pytorch.LFQ`` state-dict names
+    (``mask``, ``project_in.*``, ``project_out.*``); arithmetic restated in oracle/lfq.py, executed by
+    phk_lfq_ids."""
+
+    def __init__(self, *, dim, codebook_size, **kwargs):
+        super().__init__()
+        bits = int(math.log2(codebook_size))
+        assert 2 ** bits == codebook_size, "codebook size must be a power of two"
+        assert dim != bits, "LFQ without projections is not supported"
+        self.codebook_dim, self.codebook_size = bits, codebook_size
+        self.project_in = nn.Linear(dim, bits)
+        self.project_out = nn.Linear(bits, dim)
+        self.register_buffer("mask", 2 ** torch.arange(bits - 1, -1, -1))
+
+
+class CViViT(nn.Module):
+    def __init__(self, *, dim, codebook_size, image_size, patch_size, temporal_patch_size, spatial_depth,
+                 temporal_depth, discr_base_dim=16, dim_head=64, heads=8, channels=3, use_vgg_and_gan=True,
+                 vgg=None, discr_attn_res_layers=(16,), use_hinge_loss=True, attn_dropout=0.0, ff_dropout=0.0,
+                 lookup_free_quantization=True, lookup_free_quantization_kwargs: dict = {}):
+        super().__init__()
+        self.image_size = _pair(image_size)
+        self.patch_size = _pair(patch_size)
+        ph, pw = self.patch_size
+        self.temporal_patch_size = temporal_patch_size
+        self.dim, self.heads, self.dim_head, self.channels = dim, heads, dim_head, channels
+        # construction order below follows the reference so seeded inits coincide
+        self.spatial_rel_pos_bias = ContinuousPositionBias(dim=dim, heads=heads)
+        ih, iw = self.image_size
+        assert (ih % ph) == 0 and (iw % pw) == 0
+        k1 = channels * pw * ph
+        self.to_patch_emb_first_frame = nn.Sequential(_NoParams(), nn.LayerNorm(k1), nn.Linear(k1, dim),
+                                                      nn.LayerNorm(dim))
+        k2 = k1 * temporal_patch_size
+        self.to_patch_emb = nn.Sequential(_NoParams(), nn.LayerNorm(k2), nn.Linear(k2, dim), nn.LayerNorm(dim))
+        spatial_kw = dict(dim=dim, dim_head=dim_head, heads=heads, attn_dropout=attn_dropout,
+                          ff_dropout=ff_dropout, causal=False, peg=False)
+        temporal_kw = dict(dim=dim, dim_head=dim_head, heads=heads, attn_dropout=attn_dropout,
+                           ff_dropout=ff_dropout, causal=True, peg=True, peg_causal=True)
+        self.enc_spatial_transformer = Transformer(depth=spatial_depth, **spatial_kw)
+        self.enc_temporal_transformer = Transformer(depth=temporal_depth, **temporal_kw)
+        self.lookup_free_quantization = lookup_free_quantization
+        if not lookup_free_quantization:
+            raise NotImplementedError("cosine-sim VectorQuantize codebook path is a next-tier row (SURVEY 8f-3)")
+        self.vq = LFQ(dim=dim, codebook_size=codebook_size, **lookup_free_quantization_kwargs)
+        self.dec_spatial_transformer = Transformer(depth=spatial_depth, **spatial_kw)
+        self.dec_temporal_transformer = Transformer(depth=temporal_depth, **temporal_kw)
+        self.to_pixels_first_frame = nn.Sequential(nn.Linear(dim, k1), _NoParams())
+        self.to_pixels = nn.Sequential(nn.Linear(dim, k2), _NoParams())
+        self.vgg = None
+        self.discr = None
+        self.use_vgg_and_gan = use_vgg_and_gan
+        if use_vgg_and_gan:
+            raise NotImplementedError("GAN / VGG perceptual training (cvivit.py:345-363) is out of scope: "
+                                      "construct with use_vgg_and_gan=False")
+        self.precision = L.PREC_F32
+        self._tables = None
+        self._sig = None
+        self._ws = Workspace()
+        self._bias_cache = {}
+
+    # ---- shape helpers (cvivit.py:365-410, 445-447) -----------------------------------------
+    @property
+    def patch_height_width(self):
+        return self.image_size[0] // self.patch_size[0], self.image_size[1] // self.patch_size[1]
+
+    @property
+    def image_num_tokens(self):
+        h, w = self.patch_height_width
+        return h * w
+
+    def get_video_patch_shape(self, num_frames, include_first_frame=True):
+        patch_frames = 0
+        if include_first_frame:
+            num_frames -= 1
+            patch_frames += 1
+        return (patch_frames + num_frames // self.temporal_patch_size, *self.patch_height_width)
+
+    def num_tokens_per_frames(self, num_frames, include_first_frame=True):
+        total = 0
+        if include_first_frame:
+            num_frames -= 1
+            total += self.image_num_tokens
+        assert (num_frames % self.temporal_patch_size) == 0
+        return total + (num_frames // self.temporal_patch_size) * self.image_num_tokens
+
+    def frames_per_num_tokens(self, num_tokens):
+        per = self.image_num_tokens
+        assert (num_tokens % per) == 0 and num_tokens > 0
+        return (num_tokens // per - 1) * self.temporal_patch_size + 1
+
+    def calculate_video_token_mask(self, videos, video_frame_mask):
+        *_, h, w = videos.shape
+        ph, pw = self.patch_size
+        pt = self.temporal_patch_size
+        assert torch.all(((video_frame_mask.sum(dim=-1) - 1) % pt) == 0), \
+            "number of frames must be divisible by temporal patch size, subtracting off the first frame"
+        first, rest = video_frame_mask[:, :1], video_frame_mask[:, 1:]
+        rest = rest.reshape(rest.shape[0], -1, pt).any(dim=-1)
+        m = torch.cat((first, rest), dim=-1)
+        return m.repeat_interleave((h // ph) * (w // pw), dim=-1)
+
+    def copy_for_eval(self):
+        device = next(self.parameters()).device
+        saved = (self._tables, self._sig, self._ws, self._bias_cache)  # ctypes tables are not copyable
+        self._tables, self._sig, self._ws, self._bias_cache = None, None, Workspace(), {}
+        c = copy.deepcopy(self)
+        self._tables, self._sig, self._ws, self._bias_cache = saved
+        return c.eval().to(device)
+
+    def load(self, path):
+        path = Path(path)
+        assert path.exists()
+        self.load_state_dict(torch.load(str(path)))
+
+    # ---- libphk plumbing ---------------------------------------------------------------------
+    def _table(self):
+        sig = weights_signature(self)
+        if self._tables is None or sig != self._sig:
+            keep = Keep()
+            t = L.CvivitT()
+            t.dim, t.heads, t.dim_head, t.channels = self.dim, self.heads, self.dim_head, self.channels
+            t.image_h, t.image_w = self.image_size
+            t.patch_h, t.patch_w = self.patch_size
+            t.patch_t = self.temporal_patch_size
+            t.codebook_bits = self.vq.codebook_dim
+            f, r = self.to_patch_emb_first_frame, self.to_patch_emb
+            t.pf_ln1_g, t.pf_ln1_b, t.pf_w, t.pf_b = keep.t(f[1].weight), keep.t(f[1].bias), keep.t(f[2].weight), keep.t(f[2].bias)
+            t.pf_ln2_g, t.pf_ln2_b = keep.t(f[3].weight), keep.t(f[3].bias)
+            t.pr_ln1_g, t.pr_ln1_b, t.pr_w, t.pr_b = keep.t(r[1].weight), keep.t(r[1].bias), keep.t(r[2].weight), keep.t(r[2].bias)
+            t.pr_ln2_g, t.pr_ln2_b = keep.t(r[3].weight), keep.t(r[3].bias)
+            t.spatial_bias = cpb_table(self.spatial_rel_pos_bias, keep)
+            t.spatial = transformer_table(self.enc_spatial_transformer, keep)
+            t.temporal = transformer_table(self.enc_temporal_transformer, keep)
+            t.vq_w, t.vq_b = keep.t(self.vq.project_in.weight), keep.t(self.vq.project_in.bias)
+            self._tables, self._sig = (t, keep), sig
+            self._bias_cache = {}
+        return self._tables[0]
+
+    def _spatial_bias(self, table, device):
+        """ContinuousPositionBias is a function of the weights only: computed once per weight version."""
+        h, w = self.patch_height_width
+        key = (h, w, device)
+        if key not in self._bias_cache:
+            lib = L.lib()
+            n = h * w
+            out = torch.empty((self.heads, n, n), dtype=torch.float32, device=device)
+            scratch = torch.empty(int(lib.phk_cpb_scratch_floats(C.byref(table.spatial_bias), h, w, 1)),
+                                  dtype=torch.float32, device=device)
+            L.check(lib.phk_cpb_bias(C.byref(table.spatial_bias), h, w, 1, L.ptr(scratch), L.ptr(out),
+                                     L.stream_ptr()), "phk_cpb_bias")
+            self._bias_cache[key] = out
+        return self._bias_cache[key]
+
+    def encode_ids(self, video, taps=None):
+        """video (b,c,f,H,W) fp32 CUDA -> ids (b,T',H',W') int64.  ``taps``: optional dict that receives the
+        intermediate activations (parity tests)."""
+        lib = L.lib()
+        video = L.require_cuda(video, "video", torch.float32)
+        b, c, f, *image_dims = video.shape
+        assert tuple(image_dims) == self.image_size
+        assert c == self.channels
+        assert (f - 1) % self.temporal_patch_size == 0, \
+            f"number of frames ({f}) minus one ({f - 1}) must be divisible by temporal patch size ({self.temporal_patch_size})"
+        with torch.cuda.device(video.device):
+            table = self._table()
+            tp, hh, ww = self.get_video_patch_shape(f)
+            ids = torch.empty((b, tp, hh, ww), dtype=torch.int64, device=video.device)
+            nbytes = lib.phk_cvivit_workspace_bytes(C.byref(table), b, f, self.precision)
+            ws = self._ws.get(nbytes, video.device)
+            bias = self._spatial_bias(table, video.device)
+            tap_ptrs = [None] * 4
+            if taps is not None:
+                rows = b * tp * hh * ww
+                taps["patch"] = torch.empty((b, tp, hh, ww, self.dim), dtype=torch.float32, device=video.device)
+                taps["spatial"] = torch.empty_like(taps["patch"])
+                taps["temporal"] = torch.empty_like(taps["patch"])
+                taps["proj"] = torch.empty((rows, self.vq.codebook_dim), dtype=torch.float32, device=video.device)
+                tap_ptrs = [L.ptr(taps[k]) for k in ("patch", "spatial", "temporal", "proj")]
+            L.check(lib.phk_cvivit_encode(C.byref(table), L.ptr(video), b, f, L.ptr(ids), L.ptr(ws), ws.numel(),
+                                          self.precision, L.ptr(bias), *tap_ptrs, L.stream_ptr()),
+                    "phk_cvivit_encode")
+        return ids
+
+    def forward(self, video, mask=None, return_recons=False, return_recons_only=False, return_discr_loss=False,
+                apply_grad_penalty=True, return_only_codebook_ids=False):
+        assert video.ndim in {4, 5}
+        if video.ndim == 4:
+            video = video.unsqueeze(2)  # 'b c h w -> b c 1 h w'
+            assert mask is None
+        assert mask is None or mask.shape[-1] == video.shape[2]
+        if return_only_codebook_ids:
+            return self.encode_ids(video)
+        if return_recons_only:
+            ids = self.encode_ids(video)
+            return self.decode_from_codebook_indices(ids)
+        raise NotImplementedError("C-ViViT training losses (reconstruction / GAN / perceptual, cvivit.py:576-671) "
+                                  "are out of scope of the B200 hot path (SURVEY.md section 2 row 8)")
+
+    def decode_from_codebook_indices(self, indices):
+        raise NotImplementedError("C-ViViT decode (cvivit.py:437-443, 476-516) is the next-tier row f-1")

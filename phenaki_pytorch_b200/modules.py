@@ -1,0 +1,202 @@
+"""Host-side mirror of the reference's transformer building blocks (attention.py).
+
+These classes are PARAMETER HOLDERS with the reference's attribute names, shapes and
+construction order, so that (a) ``load_state_dict(reference.state_dict())`` is strict-clean and
+(b) seeded default construction yields bit-identical weights.  They contain no
+math: all compute happens in libphk.so, which receives the weights through the ctypes tables
+built by ``*_table`` below.
+"""
+import ctypes as C
+import math
+
+import torch
+from torch import nn
+
+from . import _lib as L
+
+
+class LayerNorm(nn.Module):
+    """attention.py:29-36: learnable gamma, constant zero beta kept as a (persistent) buffer."""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.gamma = nn.Parameter(torch.ones(dim))
+        self.register_buffer("beta", torch.zeros(dim))
+
+
+class _NoParams(nn.Module):
+    """Stands in for parameter-free members of a reference nn.Sequential (Rearrange, GEGLU, ...)
+    so that the numeric child names (hence state-dict keys) line up."""
+
+
+def feed_forward_holder(dim, mult=4, dropout=0.0):
+    """attention.py:45-53 -> keys 0.weight, 0.bias, 1.weight, 4.weight."""
+    inner = int(mult * (2 / 3) * dim)
+    return nn.Sequential(nn.LayerNorm(dim), nn.Linear(dim, inner * 2, bias=False), _NoParams(),
+                         nn.Dropout(dropout), nn.Linear(inner, dim, bias=False))
+
+
+class PEG(nn.Module):
+    """attention.py:57-61."""
+
+    def __init__(self, dim, causal=False):
+        super().__init__()
+        self.causal = causal
+        self.dsconv = nn.Conv3d(dim, dim, 3, groups=dim)
+
+
+def alibi_slopes(heads):
+    """attention.py:201-212 (geometric slopes, closest-power-of-two interleave for odd head counts)."""
+
+    def pow2(n):
+        start = 2 ** (-2 ** -(math.log2(n) - 3))
+        return [start * start ** i for i in range(n)]
+
+    if math.log2(heads).is_integer():
+        return pow2(heads)
+    c = 2 ** math.floor(math.log2(heads))
+    return pow2(c) + pow2(2 * c)[0::2][: heads - c]
+
+
+class Attention(nn.Module):
+    """attention.py:89-126 (parameters only)."""
+
+    def __init__(self, dim, dim_context=None, dim_head=64, heads=8, causal=False, num_null_kv=0,
+                 norm_context=True, dropout=0.0, scale=8):
+        super().__init__()
+        assert scale == 8, "the kernels implement the reference's fixed scale of 8"
+        self.heads, self.dim_head, self.causal, self.scale = heads, dim_head, causal, scale
+        inner = dim_head * heads
+        dim_context = dim if dim_context is None else dim_context
+        self.dim_context = dim_context
+        self.norm = LayerNorm(dim)
+        self.context_norm = LayerNorm(dim_context) if norm_context else nn.Identity()
+        self.num_null_kv = num_null_kv
+        self.null_kv = nn.Parameter(torch.randn(heads, 2 * num_null_kv, dim_head))
+        self.to_q = nn.Linear(dim, inner, bias=False)
+        self.to_kv = nn.Linear(dim_context, inner * 2, bias=False)
+        self.q_scale = nn.Parameter(torch.ones(dim_head))
+        self.k_scale = nn.Parameter(torch.ones(dim_head))
+        self.to_out = nn.Linear(inner, dim, bias=False)
+
+
+class ContinuousPositionBias(nn.Module):
+    """attention.py:229-255 (parameters only; default two hidden layers)."""
+
+    def __init__(self, *, dim, heads, num_dims=2, layers=2, log_dist=True, cache_rel_pos=False):
+        super().__init__()
+        assert layers == 2 and log_dist, "kernels implement the reference defaults (2 hidden layers, log distance)"
+        self.num_dims, self.dim, self.heads = num_dims, dim, heads
+        self.net = nn.ModuleList([])
+        self.net.append(nn.Sequential(nn.Linear(num_dims, dim), nn.LeakyReLU(0.1)))
+        self.net.append(nn.Sequential(nn.Linear(dim, dim), nn.LeakyReLU(0.1)))
+        self.net.append(nn.Linear(dim, heads))
+
+
+class Transformer(nn.Module):
+    """attention.py:279-308 (parameters only): layers.{i} = [PEG|None, self-attn, cross|None, FF]."""
+
+    def __init__(self, dim, *, depth, dim_context=None, causal=False, dim_head=64, heads=8, ff_mult=4,
+                 peg=False, peg_causal=False, attn_num_null_kv=2, has_cross_attn=False, attn_dropout=0.0,
+                 ff_dropout=0.0):
+        super().__init__()
+        self.dim, self.depth, self.causal, self.dim_head, self.heads = dim, depth, causal, dim_head, heads
+        self.layers = nn.ModuleList([])
+        for _ in range(depth):
+            self.layers.append(nn.ModuleList([
+                PEG(dim=dim, causal=peg_causal) if peg else None,
+                Attention(dim=dim, dim_head=dim_head, heads=heads, causal=causal, dropout=attn_dropout),
+                Attention(dim=dim, dim_head=dim_head, dim_context=dim_context, heads=heads, causal=False,
+                          num_null_kv=attn_num_null_kv, dropout=attn_dropout) if has_cross_attn else None,
+                feed_forward_holder(dim=dim, mult=ff_mult, dropout=ff_dropout)]))
+        self.norm_out = LayerNorm(dim)
+
+
+# ------------------------------------------------------------------------------------------------
+# ctypes weight tables
+# ------------------------------------------------------------------------------------------------
+
+
+class Keep:
+    """Owns everything a table points to (packed tensors, ctypes arrays) for the table's lifetime."""
+
+    def __init__(self):
+        self.refs = []
+
+    def t(self, tensor):
+        if not tensor.is_cuda:
+            raise L.PhkError("module parameters must be on a CUDA device (no CPU path): call .cuda() first")
+        tensor = tensor.detach()
+        if tensor.dtype != torch.float32 or not tensor.is_contiguous():
+            tensor = tensor.float().contiguous()
+        self.refs.append(tensor)
+        return tensor.data_ptr()
+
+    def obj(self, o):
+        self.refs.append(o)
+        return o
+
+
+def attn_table(a: Attention, keep: Keep):
+    t = L.AttnT()
+    t.norm_g, t.norm_b = keep.t(a.norm.gamma), keep.t(a.norm.beta)
+    if isinstance(a.context_norm, LayerNorm):
+        t.ctx_g, t.ctx_b = keep.t(a.context_norm.gamma), keep.t(a.context_norm.beta)
+    t.null_kv = keep.t(a.null_kv) if a.num_null_kv > 0 else None
+    t.q_scale, t.k_scale = keep.t(a.q_scale), keep.t(a.k_scale)
+    t.wq, t.wkv, t.wo = keep.t(a.to_q.weight), keep.t(a.to_kv.weight), keep.t(a.to_out.weight)
+    t.num_null_kv, t.dim_context = a.num_null_kv, a.dim_context
+    return t
+
+
+def transformer_table(tf: Transformer, keep: Keep):
+    layers = (L.LayerT * tf.depth)()
+    for i, (peg, self_attn, cross, ff) in enumerate(tf.layers):
+        ly = layers[i]
+        ly.has_peg, ly.has_cross = int(peg is not None), int(cross is not None)
+        if peg is not None:
+            d = peg.dsconv.weight.shape[0]
+            w = peg.dsconv.weight.detach().reshape(d, 27).t().contiguous()  # tap-major [27, dim]
+            ly.peg.w, ly.peg.b, ly.peg.causal = keep.t(w), keep.t(peg.dsconv.bias), int(peg.causal)
+        ly.self_attn = attn_table(self_attn, keep)
+        if cross is not None:
+            ly.cross_attn = attn_table(cross, keep)
+        ly.ff.ln_g, ly.ff.ln_b = keep.t(ff[0].weight), keep.t(ff[0].bias)
+        ly.ff.w1, ly.ff.w2 = keep.t(ff[1].weight), keep.t(ff[4].weight)
+        ly.ff.inner = ff[4].weight.shape[1]
+        ly.ff.inner_pad = (ly.ff.inner + 63) // 64 * 64
+    keep.obj(layers)
+    t = L.TransformerT()
+    t.dim, t.heads, t.dim_head, t.depth, t.causal = tf.dim, tf.heads, tf.dim_head, tf.depth, int(tf.causal)
+    t.layers = C.cast(layers, C.POINTER(L.LayerT))
+    t.out_g, t.out_b = keep.t(tf.norm_out.gamma), keep.t(tf.norm_out.beta)
+    if tf.causal:
+        dev = tf.norm_out.gamma.device
+        t.alibi_slopes = keep.t(torch.tensor(alibi_slopes(tf.heads), dtype=torch.float32, device=dev))
+    return t
+
+
+def cpb_table(c: ContinuousPositionBias, keep: Keep):
+    t = L.CpbT()
+    t.w0, t.b0 = keep.t(c.net[0][0].weight), keep.t(c.net[0][0].bias)
+    t.w1, t.b1 = keep.t(c.net[1][0].weight), keep.t(c.net[1][0].bias)
+    t.w2, t.b2 = keep.t(c.net[2].weight), keep.t(c.net[2].bias)
+    t.num_dims, t.hidden, t.heads = c.num_dims, c.dim, c.heads
+    return t
+
+
+def weights_signature(module):
+    """Changes whenever a parameter/buffer is re-assigned, moved or modified in place."""
+    return tuple((t.data_ptr(), t._version) for t in list(module.parameters()) + list(module.buffers()))
+
+
+class Workspace:
+    """One grow-only device scratch buffer per module (the C library allocates nothing)."""
+
+    def __init__(self):
+        self.buf = None
+
+    def get(self, nbytes, device):
+        if self.buf is None or self.buf.numel() < nbytes or self.buf.device != device:
+            self.buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        return self.buf

@@ -1,0 +1,506 @@
+"""MaskGit / TokenCritic / SelfCritic / Phenaki / make_video -- drop-ins for the reference classes of
+/root/reference/phenaki_pytorch/phenaki_pytorch.py on the sampling hot path.
+
+Constructor keywords, attribute names, state-dict layout and the ``forward`` / ``forward_with_cond_scale``
+/ ``sample`` signatures follow the reference (phenaki_pytorch.py:105-147, 217-249, 307-336, 341-430,
+691-714).  All arithmetic runs in libphk.so; torch is used for device memory, streams and the (tiny)
+boolean plumbing around the calls.  ``Phenaki.forward`` (the training loss, :562-687) needs backward
+kernels and is a next-tier row.
+"""
+import ctypes as C
+import math
+from functools import partial
+from typing import List, Optional, Union
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _lib as L
+from .cvivit import CViViT
+from .modules import (ContinuousPositionBias, Keep, Transformer, Workspace, _NoParams, cpb_table,
+                      transformer_table, weights_signature)
+
+
+def _prod(xs):
+    r = 1
+    for x in xs:
+        r *= int(x)
+    return r
+
+
+class _TokenTransformer(nn.Module):
+    """Shared libphk plumbing of MaskGit and TokenCritic (both: embeddings -> Transformer -> head)."""
+
+    is_critic = False
+
+    def _init_runtime(self):
+        self.precision = L.PREC_F32
+        self._tables, self._sig = None, None
+        self._ws = Workspace()
+        self._bias_cache = {}
+
+    def __deepcopy__(self, memo):
+        raise TypeError("copy the state_dict instead; ctypes weight tables are not copyable")
+
+    def _table(self):
+        sig = weights_signature(self)
+        if self._tables is None or sig != self._sig:
+            keep = Keep()
+            t = L.MaskgitT()
+            tf = self.transformer
+            t.dim, t.heads, t.dim_head = tf.dim, tf.heads, tf.dim_head
+            t.num_tokens = self.token_emb.weight.shape[0] - 1
+            t.max_seq_len = self.pos_emb.weight.shape[0]
+            t.is_critic = int(self.is_critic)
+            t.has_bias = int(not self.is_critic)
+            t.shrink_alpha = float(getattr(self, "gradient_shrink_alpha", 0.0))
+            t.token_emb, t.pos_emb = keep.t(self.token_emb.weight), keep.t(self.pos_emb.weight)
+            if not self.is_critic:
+                t.pos_bias = cpb_table(self.continuous_pos_bias, keep)
+                t.head_w, t.head_b = keep.t(self.to_logits.weight), keep.t(self.to_logits.bias)
+            else:
+                t.head_w, t.head_b = keep.t(self.to_logits[0].weight), keep.t(self.to_logits[0].bias)
+            t.transformer = transformer_table(tf, keep)
+            self._tables, self._sig = (t, keep), sig
+            self._bias_cache = {}
+        return self._tables[0]
+
+    def _pos_bias(self, table, patch_shape, device):
+        """3-D continuous position bias (phenaki_pytorch.py:186): weight-only, cached per shape."""
+        if self.is_critic:
+            return None
+        key = (tuple(patch_shape), device)
+        if key not in self._bias_cache:
+            lib = L.lib()
+            n = _prod(patch_shape)
+            out = torch.empty((self.transformer.heads, n, n), dtype=torch.float32, device=device)
+            scratch = torch.empty(int(lib.phk_cpb_scratch_floats(C.byref(table.pos_bias), *patch_shape)),
+                                  dtype=torch.float32, device=device)
+            L.check(lib.phk_cpb_bias(C.byref(table.pos_bias), *patch_shape, L.ptr(scratch), L.ptr(out),
+                                     L.stream_ptr()), "phk_cpb_bias")
+            self._bias_cache[key] = out
+        return self._bias_cache[key]
+
+    def context_kv(self, context):
+        """Per-layer context_norm + to_kv of the text embedding (attention.py:137-144): (depth, b*L, 2I)."""
+        lib = L.lib()
+        context = L.require_cuda(context, "context", torch.float32)
+        b, l, dc = context.shape
+        tf = self.transformer
+        assert tf.layers[0][2] is not None, "model has no cross attention"
+        assert dc == tf.layers[0][2].dim_context, "text embedding dimension is not correct"
+        table = self._table()
+        inner2 = 2 * tf.heads * tf.dim_head
+        out = torch.empty((tf.depth, b * l, inner2), dtype=torch.float32, device=context.device)
+        scratch = torch.empty((b * l, dc), dtype=torch.float32, device=context.device)
+        L.check(lib.phk_maskgit_context_kv(C.byref(table), L.ptr(context), b, l, L.ptr(out), L.ptr(scratch),
+                                           self.precision, L.stream_ptr()), "phk_maskgit_context_kv")
+        return out
+
+    def _run(self, ids, patch_shape, *, ctx_kv=None, ctx_len=0, text_mask=None, video_mask=None, cfg_pair=False,
+             return_embeds=False):
+        """ids (b, n) int64 -> logits ((1+cfg) * b, n, V) | embeds (.., dim)."""
+        lib = L.lib()
+        ids = L.require_cuda(ids, "token ids", torch.int64)
+        b, n = ids.shape
+        assert _prod(patch_shape) == n, "video patch shape must cover the token sequence"
+        dev = ids.device
+        with torch.cuda.device(dev):
+            table = self._table()
+            assert n <= table.max_seq_len, \
+                f"the video token sequence length you are passing in ({n}) is greater than the `max_seq_len` ({table.max_seq_len})"
+            reps = 2 if cfg_pair else 1
+            embeds_only = return_embeds or self.is_critic
+            width = table.dim if embeds_only else table.num_tokens
+            out = torch.empty((reps * b, n, width), dtype=torch.float32, device=dev)
+            nbytes = lib.phk_maskgit_workspace_bytes(C.byref(table), b, n, ctx_len, int(cfg_pair), self.precision)
+            ws = self._ws.get(nbytes, dev)
+            bias = self._pos_bias(table, patch_shape, dev)
+            if text_mask is not None:
+                text_mask = L.require_cuda(text_mask.to(torch.uint8), "text mask")
+            if video_mask is not None:
+                video_mask = L.require_cuda(video_mask.to(torch.uint8), "video mask")
+            pt, ph, pw = (int(v) for v in patch_shape)
+            L.check(lib.phk_maskgit_forward(C.byref(table), L.ptr(ids), b, n, pt, ph, pw, L.ptr(ctx_kv), ctx_len,
+                                            L.ptr(text_mask), L.ptr(video_mask), int(cfg_pair), int(embeds_only),
+                                            L.ptr(bias), L.ptr(out), L.ptr(ws), ws.numel(), self.precision,
+                                            L.stream_ptr()), "phk_maskgit_forward")
+        return out
+
+    def _prepare(self, x, text_mask, video_patch_shape, context, cond_drop_prob):
+        if x.ndim == 4:
+            video_patch_shape = tuple(x.shape[1:])
+            x = x.reshape(x.shape[0], -1)
+        assert video_patch_shape is not None, "video patch shape must be given"
+        b = x.shape[0]
+        ctx_kv, ctx_len = None, 0
+        if context is not None and self.transformer.layers[0][2] is not None:
+            ctx_len = context.shape[1]
+            if text_mask is None:
+                text_mask = torch.ones((b, ctx_len), device=x.device, dtype=torch.bool)
+            if cond_drop_prob is not None and cond_drop_prob > 0:
+                # prob_mask_like (phenaki_pytorch.py:73-79): p in {0,1} consume no RNG
+                if cond_drop_prob >= 1:
+                    keep = torch.zeros((b,), device=x.device, dtype=torch.bool)
+                else:
+                    keep = torch.rand((b,), device=x.device) < (1 - cond_drop_prob)
+                text_mask = keep[:, None] & text_mask
+            ctx_kv = self.context_kv(context)
+        return x, tuple(int(v) for v in video_patch_shape), ctx_kv, ctx_len, text_mask
+
+
+class MaskGit(_TokenTransformer):
+    def __init__(self, *, dim, num_tokens, max_seq_len, gradient_shrink_alpha=0.1, heads=8, dim_head=64,
+                 unconditional=False, attn_dropout=0.0, ff_dropout=0.0, **kwargs):
+        super().__init__()
+        self.dim = dim
+        self.mask_id = num_tokens
+        self.unconditional = unconditional
+        self.token_emb = nn.Embedding(num_tokens + 1, dim)  # last token is the mask id
+        self.max_seq_len = max_seq_len
+        self.pos_emb = nn.Embedding(max_seq_len, dim)
+        self.gradient_shrink_alpha = gradient_shrink_alpha
+        self.continuous_pos_bias = ContinuousPositionBias(dim=dim_head, heads=heads, num_dims=3)
+        self.transformer = Transformer(dim=dim, attn_num_null_kv=2, has_cross_attn=not unconditional,
+                                       dim_head=dim_head, heads=heads, attn_dropout=attn_dropout,
+                                       ff_dropout=ff_dropout, peg=True, **kwargs)
+        self.to_logits = nn.Linear(dim, num_tokens)
+        self._init_runtime()
+
+    def forward(self, x, cond_drop_prob=0.0, text_mask=None, video_mask=None, video_patch_shape=None,
+                return_embeds=False, context=None, **kwargs):
+        assert x.ndim in {2, 4}, "video token ids must be of shape (batch, seq) or (batch, frame, height, width)"
+        x, shape, ctx_kv, ctx_len, text_mask = self._prepare(x, text_mask, video_patch_shape, context, cond_drop_prob)
+        return self._run(x, shape, ctx_kv=ctx_kv, ctx_len=ctx_len, text_mask=text_mask, video_mask=video_mask,
+                         return_embeds=return_embeds)
+
+    def forward_with_cond_scale(self, x, *, cond_scale=3, text_mask=None, video_mask=None, video_patch_shape=None,
+                                context=None, return_embeds=False, **kwargs):
+        """phenaki_pytorch.py:149-161.  Both passes run as ONE batch of 2b sequences (the second half sees
+        an all-False text mask) and are combined by phk_cfg_combine."""
+        if cond_scale == 1:
+            return self.forward(x, cond_drop_prob=0.0, text_mask=text_mask, video_mask=video_mask,
+                                video_patch_shape=video_patch_shape, context=context, return_embeds=return_embeds)
+        x, shape, ctx_kv, ctx_len, text_mask = self._prepare(x, text_mask, video_patch_shape, context, 0.0)
+        both = self._run(x, shape, ctx_kv=ctx_kv, ctx_len=ctx_len, text_mask=text_mask, video_mask=video_mask,
+                         cfg_pair=True, return_embeds=return_embeds)
+        b = x.shape[0]
+        out = torch.empty_like(both[:b])
+        L.check(L.lib().phk_cfg_combine(L.ptr(both[:b]), L.ptr(both[b:]), float(cond_scale), L.ptr(out),
+                                        out.numel(), L.stream_ptr()), "phk_cfg_combine")
+        return out
+
+
+class TokenCritic(_TokenTransformer):
+    is_critic = True
+
+    def __init__(self, *, dim, num_tokens, max_seq_len, has_cross_attn=False, attn_dropout=0.0, ff_dropout=0.0,
+                 **kwargs):
+        super().__init__()
+        self.has_cross_attn = has_cross_attn
+        self.mask_id = num_tokens
+        self.token_emb = nn.Embedding(num_tokens + 1, dim)
+        self.pos_emb = nn.Embedding(max_seq_len, dim)
+        self.transformer = Transformer(dim=dim, peg=True, attn_dropout=attn_dropout, ff_dropout=ff_dropout,
+                                       has_cross_attn=has_cross_attn, **kwargs)
+        self.to_logits = nn.Sequential(nn.Linear(dim, 1), _NoParams())
+        self._init_runtime()
+
+    def _scores(self, embeds_cond, embeds_null, cond_scale, rows, noise=None, noise_K=0.0, noise_mult=0.0,
+                seg=(0, 0, 0)):
+        table = self._table()
+        out = torch.empty((rows,), dtype=torch.float32, device=embeds_cond.device)
+        L.check(L.lib().phk_critic_scores(L.ptr(embeds_cond), L.ptr(embeds_null), table.head_w, table.head_b,
+                                          L.ptr(noise), float(cond_scale), float(noise_K), float(noise_mult),
+                                          L.ptr(out), rows, table.dim, *seg, L.stream_ptr()), "phk_critic_scores")
+        return out
+
+    def forward(self, x, text_mask=None, cond_drop_prob=None, context=None, video_mask=None,
+                video_patch_shape=None, **kwargs):
+        shape = tuple(video_patch_shape) if video_patch_shape is not None else tuple(x.shape[1:])
+        x = x.reshape(x.shape[0], -1)
+        if context is not None and cond_drop_prob is None:
+            raise TypeError("cond_drop_prob must be given when a context is passed (phenaki_pytorch.py:286)")
+        x, shape, ctx_kv, ctx_len, text_mask = self._prepare(x, text_mask, shape, context, cond_drop_prob)
+        emb = self._run(x, shape, ctx_kv=ctx_kv, ctx_len=ctx_len, text_mask=text_mask, video_mask=video_mask)
+        b, n = x.shape
+        return self._scores(emb, None, 1.0, b * n).reshape(b, n)
+
+    def forward_with_cond_scale(self, x, *, cond_scale=3, text_mask=None, context=None, video_mask=None,
+                                video_patch_shape=None, **kwargs):
+        if cond_scale == 1:
+            return self.forward(x, text_mask=text_mask, cond_drop_prob=0.0, context=context, video_mask=video_mask,
+                                video_patch_shape=video_patch_shape)
+        shape = tuple(video_patch_shape) if video_patch_shape is not None else tuple(x.shape[1:])
+        x = x.reshape(x.shape[0], -1)
+        x, shape, ctx_kv, ctx_len, text_mask = self._prepare(x, text_mask, shape, context, 0.0)
+        both = self._run(x, shape, ctx_kv=ctx_kv, ctx_len=ctx_len, text_mask=text_mask, video_mask=video_mask,
+                         cfg_pair=True)
+        b, n = x.shape
+        return self._scores(both[:b], both[b:], cond_scale, b * n).reshape(b, n)
+
+
+class SelfCritic(nn.Module):
+    """phenaki_pytorch.py:307-336: Linear(dim,1) on the MaskGit embeddings."""
+
+    def __init__(self, maskgit: MaskGit):
+        super().__init__()
+        self.maskgit = maskgit
+        self.to_pred = nn.Sequential(nn.Linear(maskgit.dim, 1), _NoParams())
+        self.has_cross_attn = not maskgit.unconditional
+
+    def _head(self, cond, null, cond_scale, rows, **kw):
+        w = L.require_cuda(self.to_pred[0].weight.detach(), "to_pred.weight", torch.float32)
+        bb = L.require_cuda(self.to_pred[0].bias.detach(), "to_pred.bias", torch.float32)
+        out = torch.empty((rows,), dtype=torch.float32, device=cond.device)
+        L.check(L.lib().phk_critic_scores(L.ptr(cond), L.ptr(null), L.ptr(w), L.ptr(bb), L.ptr(kw.get("noise")),
+                                          float(cond_scale), float(kw.get("noise_K", 0.0)),
+                                          float(kw.get("noise_mult", 0.0)), L.ptr(out), rows, self.maskgit.dim,
+                                          *kw.get("seg", (0, 0, 0)), L.stream_ptr()), "phk_critic_scores")
+        return out
+
+    def forward(self, x, *args, **kwargs):
+        emb = self.maskgit(x, *args, return_embeds=True, **kwargs)
+        b, n = emb.shape[:2]
+        return self._head(emb, None, 1.0, b * n).reshape(b, n)
+
+    def forward_with_cond_scale(self, x, *, cond_scale=3, **kwargs):
+        if cond_scale == 1:
+            return self.forward(x, cond_drop_prob=0.0, **kwargs)
+        mg = self.maskgit
+        xx, shape, ctx_kv, ctx_len, text_mask = mg._prepare(x, kwargs.get("text_mask"), kwargs.get("video_patch_shape"),
+                                                            kwargs.get("context"), 0.0)
+        both = mg._run(xx, shape, ctx_kv=ctx_kv, ctx_len=ctx_len, text_mask=text_mask,
+                       video_mask=kwargs.get("video_mask"), cfg_pair=True, return_embeds=True)
+        b, n = xx.shape
+        return self._head(both[:b], both[b:], cond_scale, b * n).reshape(b, n)
+
+
+def demask_counts(num_tokens, steps):
+    """k_s = clamp(round(N * cos(pi/2 * s/S)), 1) for s = 1..S-1 in fp32, round-half-even
+    (phenaki_pytorch.py:485-486), precomputed on the host: no per-step device sync."""
+    ks = []
+    for step in range(1, steps):
+        t = np.float32(step / steps)
+        a = np.float32(np.float32(t * np.float32(math.pi)) * np.float32(0.5))
+        v = np.float32(np.float32(num_tokens) * np.cos(a, dtype=np.float32))
+        ks.append(max(int(np.rint(v)), 1))
+    return ks
+
+
+_T5_DIMS = {"t5-small": 512, "t5-base": 768, "t5-large": 1024, "t5-3b": 1024, "t5-11b": 1024,
+            "google/t5-v1_1-small": 512, "google/t5-v1_1-base": 768, "google/t5-v1_1-large": 1024,
+            "google/t5-v1_1-xl": 2048, "google/t5-v1_1-xxl": 4096}
+DEFAULT_T5_NAME = "google/t5-v1_1-base"
+
+
+def _t5_encode_text(texts, name=DEFAULT_T5_NAME, output_device=None):
+    """Text side (t5.py:64-103) is a third-party model outside the hot path: thin lazy
+    glue around HF transformers; padded positions are zero-filled so `any(emb != 0)` recovers the mask."""
+    from transformers import AutoTokenizer, T5EncoderModel  # needs local weights
+    cache = _t5_encode_text.__dict__.setdefault("cache", {})
+    if name not in cache:
+        cache[name] = (AutoTokenizer.from_pretrained(name), T5EncoderModel.from_pretrained(name).eval())
+    tok, model = cache[name]
+    dev = output_device if output_device is not None else "cpu"
+    model.to(dev)
+    enc = tok(texts, return_tensors="pt", padding="longest", max_length=256, truncation=True).to(dev)
+    with torch.no_grad():
+        out = model(input_ids=enc.input_ids, attention_mask=enc.attention_mask).last_hidden_state
+    return out.masked_fill(~enc.attention_mask[..., None].bool(), 0.0).float()
+
+
+class Phenaki(nn.Module):
+    def __init__(self, *, maskgit: MaskGit, cvivit: CViViT, critic: Optional[Union[TokenCritic, SelfCritic]] = None,
+                 steps=18, t5_name=DEFAULT_T5_NAME, sample_temperature=0.0, text_embed_dim=None,
+                 cond_drop_prob=0.25, max_text_len=128, self_token_critic=False, critic_loss_weight=1.0,
+                 critic_noise_anneal_schedule="decay", critic_train_sample_temperature=1.0):
+        super().__init__()
+        self.cvivit = cvivit.copy_for_eval()
+        self.maskgit = maskgit
+        self.unconditional = maskgit.unconditional
+        self.mask_id = maskgit.mask_id
+        assert not (self_token_critic and critic is not None)
+        if self_token_critic:
+            critic = SelfCritic(maskgit)
+        if critic is not None:
+            critic = critic.eval()
+        assert critic is None or self_token_critic or (not maskgit.unconditional) == critic.has_cross_attn
+        self.critic = critic
+        self.critic_noise_anneal_schedule = critic_noise_anneal_schedule
+        self.critic_loss_weight = critic_loss_weight
+        self.critic_train_sample_temperature = critic_train_sample_temperature
+        self.steps = steps
+        self.sample_temperature = sample_temperature
+        if text_embed_dim is None:
+            assert t5_name in _T5_DIMS, f"unknown T5 name {t5_name}: pass text_embed_dim"
+            text_embed_dim = _T5_DIMS[t5_name]
+        self.encode_texts = partial(_t5_encode_text, name=t5_name)
+        self.text_embed_dim = text_embed_dim
+        self.max_text_len = max_text_len
+        assert cond_drop_prob > 0.0
+        self.cond_drop_prob = cond_drop_prob
+        self._rng_calls = 0
+
+    # ---- the demasking loop (phenaki_pytorch.py:473-550) -------------------------------------------------
+    @torch.no_grad()
+    def sample_token_ids(self, *, num_tokens, patch_shape, batch_size, text_embeds=None, text_mask=None,
+                         prime_token_ids=None, cond_scale=3.0, starting_temperature=0.9, noise_K=1.0,
+                         noise_fn=None, trace=None):
+        """Runs the ``steps`` demasking iterations and returns the final ids (b, num_tokens) int64.
+
+        Per iteration: phk_topk_mask (re-mask) -> phk_maskgit_forward (CFG pair) -> phk_sample_tokens
+        (CFG + gumbel argmax + confidence) [-> critic forward + phk_critic_scores].  No host sync.
+        ``noise_fn(shape, tag)`` (tests) injects the uniform draws; default: in-kernel Philox for the
+        V-wide gumbel noise, torch.rand for the (b, n) critic noise."""
+        lib = L.lib()
+        mg = self.maskgit
+        dev = next(mg.parameters()).device
+        steps, n, b = self.steps, num_tokens, batch_size
+        plen = 0 if prime_token_ids is None else prime_token_ids.shape[-1]
+        with torch.cuda.device(dev):
+            ctx_kv = critic_kv = None
+            ctx_len = 0
+            if text_embeds is not None:
+                text_embeds = L.require_cuda(text_embeds, "text embeds", torch.float32)
+                if text_mask is None:
+                    text_mask = torch.any(text_embeds != 0, dim=-1)  # phenaki_pytorch.py:461
+                ctx_len = text_embeds.shape[1]
+                ctx_kv = mg.context_kv(text_embeds)  # once per sample, not once per forward
+                if isinstance(self.critic, TokenCritic) and self.critic.has_cross_attn:
+                    critic_kv = self.critic.context_kv(text_embeds)
+            ids = torch.full((b, n), self.mask_id, dtype=torch.int64, device=dev)
+            mask = torch.ones((b, n), dtype=torch.uint8, device=dev)
+            scores = torch.empty((b, n), dtype=torch.float32, device=dev)
+            pred = torch.empty((b, n), dtype=torch.int64, device=dev)
+            inp = ids if plen == 0 else torch.cat((prime_token_ids, ids), dim=-1)
+            seg = (0, 0, 0) if plen == 0 else (n, plen + n, plen)
+            ks = demask_counts(n, steps)
+            seed = torch.cuda.default_generators[dev.index if dev.index is not None else torch.cuda.current_device()].initial_seed()
+            vocab = mg.to_logits.weight.shape[0]
+            have_scores = False
+            for step in range(steps):
+                last = step == steps - 1
+                til_x0 = steps - (step + 1)
+                if step > 0 and have_scores:
+                    L.check(lib.phk_topk_mask(L.ptr(scores), b, n, ks[step - 1], L.ptr(mask), L.ptr(ids),
+                                              self.mask_id, L.stream_ptr()), "phk_topk_mask")
+                if plen:
+                    inp[:, plen:].copy_(ids)
+                use_cfg = cond_scale != 1
+                logits = mg._run(inp, patch_shape, ctx_kv=ctx_kv, ctx_len=ctx_len, text_mask=text_mask,
+                                 cfg_pair=use_cfg)
+                temperature = starting_temperature * (til_x0 / steps)
+                u = None
+                if noise_fn is not None:
+                    u = L.require_cuda(noise_fn((b, n, vocab), f"gumbel{step}"), "gumbel noise", torch.float32)
+                offset = self._rng_calls * ((b * n * ((vocab + 3) // 4)) + 1)
+                self._rng_calls += 1
+                cond = logits[:b]
+                null = logits[b:] if use_cfg else None
+                L.check(lib.phk_sample_tokens(L.ptr(cond), L.ptr(null), vocab, L.ptr(u), seed & (2 ** 64 - 1),
+                                              offset, float(cond_scale), float(temperature), L.ptr(mask),
+                                              L.ptr(ids), L.ptr(pred), L.ptr(scores), b * n, vocab, *seg,
+                                              L.stream_ptr()), "phk_sample_tokens")
+                have_scores = True
+                if trace is not None:
+                    trace.append(dict(step=step, mask=mask.bool().clone(), pred=pred.clone(), ids=ids.clone()))
+                if last:
+                    break
+                if self.critic is not None:
+                    if plen:
+                        inp[:, plen:].copy_(ids)
+                    mult = {"fixed": 1.0, "decay": til_x0 / steps, "increase": (step + 1) / steps}.get(
+                        self.critic_noise_anneal_schedule)
+                    if mult is None:
+                        raise ValueError("invalid critic noise anneal schedule name")
+                    noise = (noise_fn((b, n), f"critic{step}") if noise_fn is not None
+                             else torch.rand((b, n), device=dev, dtype=torch.float32))
+                    noise = L.require_cuda(noise, "critic noise", torch.float32)
+                    if isinstance(self.critic, SelfCritic):
+                        both = mg._run(inp, patch_shape, ctx_kv=ctx_kv, ctx_len=ctx_len, text_mask=text_mask,
+                                       cfg_pair=use_cfg, return_embeds=True)
+                        head = self.critic._head
+                    else:
+                        both = self.critic._run(inp, patch_shape, ctx_kv=critic_kv,
+                                                ctx_len=ctx_len if critic_kv is not None else 0,
+                                                text_mask=text_mask if critic_kv is not None else None,
+                                                cfg_pair=use_cfg)
+                        head = None
+                    c_e, n_e = both[:b], (both[b:] if use_cfg else None)
+                    if head is not None:
+                        scores = head(c_e, n_e, cond_scale, b * n, noise=noise, noise_K=noise_K, noise_mult=mult,
+                                      seg=seg).reshape(b, n)
+                    else:
+                        scores = self.critic._scores(c_e, n_e, cond_scale, b * n, noise=noise, noise_K=noise_K,
+                                                     noise_mult=mult, seg=seg).reshape(b, n)
+                if trace is not None:
+                    trace[-1]["scores"] = scores.clone()
+        return ids
+
+    @torch.no_grad()
+    def sample(self, *, num_frames, texts: Union[List[str], str, None] = None, prime_frames=None, batch_size=1,
+               cond_scale=3.0, starting_temperature=0.9, noise_K=1.0, text_embeds=None, return_token_ids=False,
+               noise_fn=None):
+        """phenaki_pytorch.py:418-560.  Extra keywords: ``text_embeds`` (precomputed T5 output),
+        ``return_token_ids`` (skip the final C-ViViT decode), ``noise_fn`` (inject the uniform draws)."""
+        was_training = self.training
+        self.eval()
+        try:
+            prime_ids, prime_num_frames = None, 0
+            if prime_frames is not None:
+                pids = self.cvivit(prime_frames, return_only_codebook_ids=True)
+                prime_ids = pids.reshape(pids.shape[0], -1)
+                prime_num_frames = prime_frames.shape[2]
+            num_tokens = self.cvivit.num_tokens_per_frames(num_frames, include_first_frame=prime_frames is None)
+            text_mask = None
+            dev = next(self.maskgit.parameters()).device
+            if texts is not None and text_embeds is None:
+                if isinstance(texts, str):
+                    texts = [texts]
+                text_embeds = self.encode_texts(texts, output_device=dev)
+            if text_embeds is not None:
+                text_embeds = text_embeds.to(dev)
+                text_mask = torch.any(text_embeds != 0, dim=-1)
+                batch_size = text_embeds.shape[0]
+            patch_shape = self.cvivit.get_video_patch_shape(num_frames + prime_num_frames, include_first_frame=True)
+            ids = self.sample_token_ids(num_tokens=num_tokens, patch_shape=patch_shape, batch_size=batch_size,
+                                        text_embeds=text_embeds, text_mask=text_mask, prime_token_ids=prime_ids,
+                                        cond_scale=cond_scale, starting_temperature=starting_temperature,
+                                        noise_K=noise_K, noise_fn=noise_fn)
+            if prime_ids is not None:
+                ids_full = torch.cat((prime_ids, ids), dim=-1)
+            else:
+                ids_full = ids
+            if return_token_ids:
+                return ids
+            video = self.cvivit.decode_from_codebook_indices(ids_full)
+            if prime_ids is not None:
+                video = video[:, :, prime_num_frames:]
+            return video
+        finally:
+            self.train(was_training)
+
+    def sample_images(self, *, texts=None, batch_size=1, cond_scale=3.0, starting_temperature=0.9, noise_K=1.0):
+        video = self.sample(texts=texts, num_frames=1, cond_scale=cond_scale,
+                            starting_temperature=starting_temperature, noise_K=noise_K)
+        return video.squeeze(2)
+
+    def forward(self, *args, **kwargs):
+        raise NotImplementedError("Phenaki.forward (training loss, phenaki_pytorch.py:562-687) needs backward kernels: "
+                                  "next-tier row 8f-2")
+
+
+def make_video(phenaki: Phenaki, texts: List[str], num_frames, prime_lengths):
+    """phenaki_pytorch.py:691-714: scenes chained through `prime_lengths` trailing frames."""
+    num_scenes = len(texts)
+    num_frames = num_frames if isinstance(num_frames, tuple) else (num_frames,) * num_scenes
+    prime_lengths = prime_lengths if isinstance(prime_lengths, tuple) else (prime_lengths,) * (num_scenes - 1)
+    prime_lengths = (*prime_lengths, 0)
+    scenes, prime = [], None
+    for text, scene_frames, next_prime in zip(texts, num_frames, prime_lengths):
+        video = phenaki.sample(texts=text, prime_frames=prime, num_frames=scene_frames)
+        scenes.append(video)
+        prime = video[:, :, -next_prime:]
+    return torch.cat(scenes, dim=2), scenes

@@ -1,0 +1,383 @@
+"""GPU parity, kernel granularity: every libphk building block (called through the C ABI) against the
+oracle / plain torch fp32 CPU arithmetic on the same seeded inputs.  Tolerances are stated per test."""
+import ctypes as C
+
+import pytest
+import torch
+
+from oracle import phenaki_oracle as O
+from phenaki_pytorch_b200 import _lib as L
+from phenaki_pytorch_b200.modules import alibi_slopes
+from tests import cases as TC
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def rnd(shape, seed):
+    return TC.seeded_randn(shape, seed)
+
+
+def sp():
+    return L.stream_ptr()
+
+
+_HOLD = []
+
+
+def dp(t):
+    """device pointer of a (host) tensor; the device copy is kept alive until the test module ends
+    (a temporary would be freed -- and its block reused -- before the kernel runs)."""
+    if t is None:
+        return None
+    d = t.to(DEV).contiguous()
+    _HOLD.append(d)
+    return L.ptr(d)
+
+
+@pytest.fixture(autouse=True)
+def _sync_and_release():
+    yield
+    torch.cuda.synchronize()
+    _HOLD.clear()
+
+
+@pytest.mark.parametrize("rows,dim", [(37, 512), (5, 96), (3, 3072), (9, 1000)])
+def test_layernorm(rows, dim):
+    x, g, b = rnd((rows, dim), 1) * 3 + 0.5, rnd((dim,), 2), rnd((dim,), 3)
+    ref = torch.nn.functional.layer_norm(x, (dim,), g, b)
+    out = torch.empty_like(x, device=DEV)
+    L.check(L.lib().phk_layernorm(dp(x), dp(g), dp(b), L.ptr(out), None, rows, dim,
+                                  0, 0, 0, 0, sp()))
+    torch.testing.assert_close(out.cpu(), ref, rtol=1e-5, atol=2e-5)
+
+
+def test_layernorm_row_map_and_bf16():
+    rows, dim = 12, 256
+    x, g, b = rnd((rows, dim), 4), rnd((dim,), 5), rnd((dim,), 6)
+    ref = torch.nn.functional.layer_norm(x, (dim,), g, b)
+    out = torch.zeros((20, dim), device=DEV)
+    # rows in segments of 3 land at stride 5, offset 2
+    L.check(L.lib().phk_layernorm(dp(x), dp(g), dp(b), L.ptr(out), None, rows, dim,
+                                  0, 3, 5, 2, sp()))
+    idx = torch.tensor([(m // 3) * 5 + 2 + m % 3 for m in range(rows)])
+    torch.testing.assert_close(out.cpu()[idx], ref, rtol=1e-5, atol=2e-5)
+    outb = torch.empty((rows, dim), dtype=torch.bfloat16, device=DEV)
+    raw = torch.empty((rows, dim), dtype=torch.bfloat16, device=DEV)
+    L.check(L.lib().phk_layernorm(dp(x), dp(g), dp(b), L.ptr(outb), L.ptr(raw),
+                                  rows, dim, 1, 0, 0, 0, sp()))
+    assert torch.equal(outb.cpu(), out.cpu()[idx].bfloat16())  # same fp32 value, one rounding
+    assert torch.equal(raw.cpu(), x.bfloat16())
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 5, 64, 64, 1, 2, 2, 16, 16), (2, 3, 7, 32, 48, 1, 2, 3, 8, 16),
+                                   (1, 1, 3, 12, 18, 0, 1, 1, 6, 6), (2, 3, 4, 32, 32, 0, 2, 2, 32, 32)])
+def test_patchify_ln(shape):
+    B, Cc, F, H, W, f0, nt, pt, p1, p2 = shape
+    video = rnd((B, Cc, F, H, W), 7)
+    K = Cc * pt * p1 * p2
+    g, b = rnd((K,), 8), rnd((K,), 9)
+    fr = video[:, :, f0:f0 + nt * pt]
+    x = fr.reshape(B, Cc, nt, pt, H // p1, p1, W // p2, p2).permute(0, 2, 4, 6, 1, 3, 5, 7).reshape(-1, K)
+    ref = torch.nn.functional.layer_norm(x, (K,), g, b)
+    out = torch.empty(ref.shape, device=DEV)
+    L.check(L.lib().phk_patchify_ln(dp(video), B, Cc, F, H, W, f0, nt, pt, p1, p2, dp(g),
+                                    dp(b), L.ptr(out), 0, sp()))
+    torch.testing.assert_close(out.cpu(), ref, rtol=1e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 200, 512), (129, 2730, 512), (257, 512, 1365), (48, 16, 256), (1, 7, 5)])
+def test_gemm_f32(M, N, K):
+    """fp32 FFMA GEMM vs torch fp32 matmul: tolerance 1e-4 * sqrt(K) covers summation-order differences."""
+    a, w, bias = rnd((M, K), 10), rnd((N, K), 11), rnd((N,), 12)
+    res = rnd((M, N), 13)
+    ref = a @ w.t() + bias + res
+    c = res.clone().to(DEV)
+    L.check(L.lib().phk_gemm_f32(dp(a), K, dp(w), K, L.ptr(c), N, M, N, K, dp(bias),
+                                 L.ptr(c), 0, 0, 0, sp()))
+    torch.testing.assert_close(c.cpu(), ref, rtol=1e-5, atol=1e-5 * K ** 0.5)
+
+
+def test_gemm_f32_row_map():
+    M, N, K = 24, 40, 64
+    a, w = rnd((M, K), 14), rnd((N, K), 15)
+    c = torch.zeros((60, N), device=DEV)
+    L.check(L.lib().phk_gemm_f32(dp(a), K, dp(w), K, L.ptr(c), N, M, N, K, None, None, 8, 20, 4,
+                                 sp()))
+    idx = torch.tensor([(m // 8) * 20 + 4 + m % 8 for m in range(M)])
+    torch.testing.assert_close(c.cpu()[idx], a @ w.t(), rtol=1e-5, atol=1e-4)
+    untouched = torch.ones(60, dtype=torch.bool)
+    untouched[idx] = False
+    assert (c.cpu()[untouched] == 0).all()
+
+
+def test_geglu():
+    h = rnd((33, 2 * 77), 16)
+    val, gate = h.chunk(2, dim=-1)
+    out = torch.empty((33, 77), device=DEV)
+    L.check(L.lib().phk_geglu(dp(h), L.ptr(out), 33, 77, sp()))
+    torch.testing.assert_close(out.cpu(), torch.nn.functional.gelu(gate) * val, rtol=1e-5, atol=1e-6)
+
+
+def run_attention(q, kv, null_kv, qs, ks, *, heads, dh, n_q, n_k, bias=None, mask=None, causal=False, nnull=0,
+                  n_outer=None, mask_off_from=-1, kv_mod=0, mask_mod=0):
+    """q (S, n_q, I), kv (Skv, n_k, 2I) contiguous."""
+    I = heads * dh
+    g = L.AttnGeomT()
+    g.n_outer, g.n_inner, g.n_q, g.n_k = n_outer or q.shape[0], 1, n_q, n_k
+    g.heads, g.dim_head, g.num_null_kv, g.causal = heads, dh, nnull, int(causal)
+    g.q_outer, g.q_inner, g.q_tok = n_q * I, 0, I
+    g.k_outer, g.k_inner, g.k_tok = n_k * 2 * I, 0, 2 * I
+    g.o_outer, g.o_inner, g.o_tok = n_q * I, 0, I
+    g.kv_outer_mod, g.mask_outer_mod, g.mask_off_from, g.out_bf16, g.scale = kv_mod, mask_mod, mask_off_from, 0, 8.0
+    out = torch.empty((g.n_outer, n_q, I), device=DEV)
+    slopes = torch.tensor(alibi_slopes(heads), dtype=torch.float32, device=DEV) if causal else None
+    d = lambda t: None if t is None else t.to(DEV).contiguous()
+    keep = [d(q), d(kv), d(null_kv), d(qs), d(ks), d(bias), None if mask is None else mask.to(torch.uint8).to(DEV)]
+    L.check(L.lib().phk_attention(*[L.ptr(t) for t in keep], L.ptr(slopes), L.ptr(out), C.byref(g), sp()))
+    return out.cpu()
+
+
+def oracle_attention(q, kv, null_kv, qs, ks, *, heads, dh, bias=None, mask=None, causal=False, nnull=0):
+    S, n_q, I = q.shape
+    split = lambda t: t.reshape(t.shape[0], t.shape[1], heads, dh).permute(0, 2, 1, 3)
+    k, v = kv.chunk(2, dim=-1)
+    qh, kh, vh = split(q), split(k), split(v)
+    if nnull:
+        kh = torch.cat((null_kv[:, 0::2].unsqueeze(0).expand(S, -1, -1, -1), kh), dim=-2)
+        vh = torch.cat((null_kv[:, 1::2].unsqueeze(0).expand(S, -1, -1, -1), vh), dim=-2)
+    o = O.attention_core(qh, kh, vh, qs, ks, heads=heads, causal=causal, num_null_kv=nnull, mask=mask, attn_bias=bias)
+    return o.permute(0, 2, 1, 3).reshape(S, n_q, I)
+
+
+@pytest.mark.parametrize("heads,dh,n", [(8, 64, 64), (4, 32, 12), (2, 16, 70), (2, 128, 33)])
+def test_attention_self_bias_mask(heads, dh, n):
+    """tolerance 2e-5: fp32 online softmax vs torch's two-pass softmax."""
+    S, I = 3, heads * dh
+    q, kv = rnd((S, n, I), 20), rnd((S, n, 2 * I), 21)
+    qs, ks = rnd((dh,), 22).abs() + 0.5, rnd((dh,), 23).abs() + 0.5
+    bias = rnd((heads, n, n), 24)
+    mask = torch.ones(S, n, dtype=torch.bool)
+    mask[1, n // 2:] = False
+    mask[2, :1] = False
+    ref = oracle_attention(q, kv, None, qs, ks, heads=heads, dh=dh, bias=bias, mask=mask)
+    out = run_attention(q, kv, None, qs, ks, heads=heads, dh=dh, n_q=n, n_k=n, bias=bias, mask=mask)
+    torch.testing.assert_close(out, ref, rtol=1e-4, atol=2e-5)
+
+
+@pytest.mark.parametrize("heads,dh,n", [(8, 64, 9), (4, 32, 3), (6, 32, 100)])
+def test_attention_causal_alibi(heads, dh, n):
+    S, I = 5, heads * dh
+    q, kv = rnd((S, n, I), 25), rnd((S, n, 2 * I), 26)
+    qs, ks = torch.ones(dh), torch.ones(dh)
+    ref = oracle_attention(q, kv, None, qs, ks, heads=heads, dh=dh, causal=True)
+    out = run_attention(q, kv, None, qs, ks, heads=heads, dh=dh, n_q=n, n_k=n, causal=True)
+    torch.testing.assert_close(out, ref, rtol=1e-4, atol=2e-5)
+
+
+def test_attention_cross_null_kv_mask_and_cfg_half():
+    heads, dh, n_q, L_ = 4, 32, 48, 7
+    b, I = 2, heads * dh
+    q = rnd((2 * b, n_q, I), 27)                      # CFG pair: sequences [b, 2b) are the null half
+    kv = rnd((b, L_, 2 * I), 28)
+    null_kv = rnd((heads, 4, dh), 29)
+    qs, ks = rnd((dh,), 30).abs() + 0.5, rnd((dh,), 31).abs() + 0.5
+    mask = torch.tensor([[True] * 7, [True] * 4 + [False] * 3])
+    ref_c = oracle_attention(q[:b], kv, null_kv, qs, ks, heads=heads, dh=dh, mask=mask, nnull=2)
+    ref_n = oracle_attention(q[b:], kv, null_kv, qs, ks, heads=heads, dh=dh, mask=torch.zeros_like(mask), nnull=2)
+    out = run_attention(q, kv, null_kv, qs, ks, heads=heads, dh=dh, n_q=n_q, n_k=L_, mask=mask, nnull=2,
+                        n_outer=2 * b, mask_off_from=b, kv_mod=b, mask_mod=b)
+    torch.testing.assert_close(out, torch.cat((ref_c, ref_n)), rtol=1e-4, atol=2e-5)
+
+
+def test_attention_strided_sequences():
+    """The temporal view '(b h w) t' addressed in place on a (b,t,h,w) buffer (cvivit.py:468)."""
+    heads, dh, B, T, HW = 2, 32, 2, 5, 6
+    I = heads * dh
+    qb, kvb = rnd((B, T, HW, I), 32), rnd((B, T, HW, 2 * I), 33)
+    q = qb.permute(0, 2, 1, 3).reshape(B * HW, T, I)
+    kv = kvb.permute(0, 2, 1, 3).reshape(B * HW, T, 2 * I)
+    ref = oracle_attention(q, kv, None, torch.ones(dh), torch.ones(dh), heads=heads, dh=dh, causal=True)
+    g = L.AttnGeomT()
+    g.n_outer, g.n_inner, g.n_q, g.n_k, g.heads, g.dim_head, g.causal = B, HW, T, T, heads, dh, 1
+    g.q_outer, g.q_inner, g.q_tok = T * HW * I, I, HW * I
+    g.k_outer, g.k_inner, g.k_tok = T * HW * 2 * I, 2 * I, HW * 2 * I
+    g.o_outer, g.o_inner, g.o_tok = g.q_outer, g.q_inner, g.q_tok
+    g.mask_off_from, g.scale = -1, 8.0
+    out = torch.empty((B, T, HW, I), device=DEV)
+    ones = torch.ones(dh, device=DEV)
+    slopes = torch.tensor(alibi_slopes(heads), dtype=torch.float32, device=DEV)
+    L.check(L.lib().phk_attention(dp(qb), dp(kvb), None, L.ptr(ones), L.ptr(ones), None, None,
+                                  L.ptr(slopes), L.ptr(out), C.byref(g), sp()))
+    torch.testing.assert_close(out.cpu().permute(0, 2, 1, 3).reshape(B * HW, T, I), ref, rtol=1e-4, atol=2e-5)
+
+
+@pytest.mark.parametrize("causal", [True, False])
+@pytest.mark.parametrize("layout", [0, 1])
+def test_peg3d_against_reference_golden_semantics(causal, layout):
+    B, T, H, W, D = 2, 4, 3, 2, 16
+    w, bias = rnd((D, 1, 3, 3, 3), 40), rnd((D,), 41)
+    sd = {"p.dsconv.weight": w, "p.dsconv.bias": bias}
+    wt = w.reshape(D, 27).t().contiguous()
+    if layout == 0:
+        x = rnd((B, T * H * W, D), 42)
+        ref = O.peg(x, (B, T, H, W), sd, "p.", causal) + x
+        xin = x.reshape(-1, D)
+        ref = ref.reshape(-1, D)
+    else:
+        # reference sees '(b h w) t d' and reinterprets it (attention.py:71); we hold rows as (b,t,h,w)
+        xs = rnd((B * H * W, T, D), 43)
+        ref_s = O.peg(xs, (B, T, H, W), sd, "p.", causal) + xs
+        to_phys = lambda t: t.reshape(B, H * W, T, D).permute(0, 2, 1, 3).reshape(-1, D)
+        xin, ref = to_phys(xs), to_phys(ref_s)
+    y = torch.empty_like(xin, device=DEV)
+    L.check(L.lib().phk_peg3d(dp(xin.contiguous()), dp(wt), dp(bias), L.ptr(y), B, T,
+                              H, W, D, int(causal), layout, sp()))
+    torch.testing.assert_close(y.cpu(), ref, rtol=1e-5, atol=1e-5)
+
+
+def test_peg3d_matches_reference_module_golden(golden):
+    """Straight against the reference PEG module outputs committed in tests/golden/units.pt."""
+    import phenaki_pytorch_b200.modules as M
+    g = golden("units")
+    torch.manual_seed(40)
+    # replay make_units' construction order so the PEG weights coincide
+    M.Attention(dim=64, dim_head=32, heads=2)
+    M.Attention(dim=64, dim_head=32, heads=2, causal=True)
+    M.Attention(dim=64, dim_context=48, dim_head=32, heads=2, num_null_kv=2)
+    B, T, H, W, D = 2, 4, 3, 2, 16
+    for causal in (True, False):
+        pg = M.PEG(dim=D, causal=causal)
+        xs = TC.seeded_randn((B * H * W, T, D), 44)
+        to_phys = lambda t: t.reshape(B, H * W, T, D).permute(0, 2, 1, 3).reshape(-1, D)
+        xin = to_phys(xs).contiguous().to(DEV)
+        wt = pg.dsconv.weight.detach().reshape(D, 27).t().contiguous().to(DEV)
+        y = torch.empty_like(xin)
+        L.check(L.lib().phk_peg3d(L.ptr(xin), L.ptr(wt), dp(pg.dsconv.bias.detach()), L.ptr(y), B, T, H, W,
+                                  D, int(causal), 1, sp()))
+        ref = to_phys(g[f"peg_{causal}"]["y"] + xs)
+        torch.testing.assert_close(y.cpu(), ref, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("dims,hidden,heads", [((8, 8, 1), 512, 8), ((3, 4, 4), 64, 4), ((2, 3, 5), 32, 2)])
+def test_continuous_position_bias(dims, hidden, heads):
+    nd = 2 if dims[2] == 1 and hidden == 512 else 3
+    d = dims[:nd]
+    sd = {"c.net.0.0.weight": rnd((hidden, nd), 50), "c.net.0.0.bias": rnd((hidden,), 51),
+          "c.net.1.0.weight": rnd((hidden, hidden), 52) / hidden ** 0.5, "c.net.1.0.bias": rnd((hidden,), 53),
+          "c.net.2.weight": rnd((heads, hidden), 54) / hidden ** 0.5, "c.net.2.bias": rnd((heads,), 55)}
+    ref = O.continuous_position_bias(sd, "c.", d)
+    keep = {k: v.to(DEV) for k, v in sd.items()}
+    t = L.CpbT()
+    t.w0, t.b0 = keep["c.net.0.0.weight"].data_ptr(), keep["c.net.0.0.bias"].data_ptr()
+    t.w1, t.b1 = keep["c.net.1.0.weight"].data_ptr(), keep["c.net.1.0.bias"].data_ptr()
+    t.w2, t.b2 = keep["c.net.2.weight"].data_ptr(), keep["c.net.2.bias"].data_ptr()
+    t.num_dims, t.hidden, t.heads = nd, hidden, heads
+    dd = list(d) + [1] * (3 - nd)
+    n = dd[0] * dd[1] * dd[2]
+    lib = L.lib()
+    scratch = torch.empty(int(lib.phk_cpb_scratch_floats(C.byref(t), *dd)), device=DEV)
+    out = torch.empty((heads, n, n), device=DEV)
+    L.check(lib.phk_cpb_bias(C.byref(t), *dd, L.ptr(scratch), L.ptr(out), sp()))
+    torch.testing.assert_close(out.cpu(), ref, rtol=1e-4, atol=2e-5)
+
+
+def test_lfq_ids_bit_exact_where_margin_allows():
+    rows, dim, bits = 200, 256, 16
+    x, wp, bp = rnd((rows, dim), 60), rnd((bits, dim), 61) / 16, rnd((bits,), 62)
+    proj = torch.nn.functional.linear(x, wp, bp)
+    ref = ((proj > 0).int() * (2 ** torch.arange(bits - 1, -1, -1)).int()).sum(-1)
+    ids = torch.empty(rows, dtype=torch.int64, device=DEV)
+    pout = torch.empty((rows, bits), device=DEV)
+    L.check(L.lib().phk_lfq_ids(dp(x), dp(wp), dp(bp), L.ptr(ids), L.ptr(pout), rows,
+                                dim, bits, sp()))
+    torch.testing.assert_close(pout.cpu(), proj, rtol=1e-5, atol=1e-5)
+    # a bit may differ only where the reference's own pre-sign value is within fp32 noise of zero
+    diff_bits = (ids.cpu() ^ ref)
+    for r in torch.nonzero(diff_bits).flatten().tolist():
+        for d in range(bits):
+            if (diff_bits[r] >> (bits - 1 - d)) & 1:
+                assert abs(proj[r, d]) < 1e-5
+    # and the ids are exactly the sign pattern of the kernel's own projection
+    own = ((pout.cpu() > 0).long() * (2 ** torch.arange(bits - 1, -1, -1))).sum(-1)
+    assert torch.equal(ids.cpu(), own)
+
+
+def test_token_embed_bit_exact():
+    b, n, dim, V = 2, 10, 64, 50
+    tok, pos = rnd((V + 1, dim), 63), rnd((32, dim), 64)
+    ids = torch.randint(0, V + 1, (b, n), generator=torch.Generator().manual_seed(65))
+    x = pos[:n] + tok[ids]
+    ref = x * 0.1 + x * (1 - 0.1)
+    out = torch.empty((2 * b, n, dim), device=DEV)
+    L.check(L.lib().phk_token_embed(dp(ids), dp(tok), dp(pos), L.ptr(out), b, n, dim,
+                                    V + 1, 0.1, 2, sp()))
+    assert torch.equal(out.cpu()[:b], ref) and torch.equal(out.cpu()[b:], ref)
+    L.check(L.lib().phk_token_embed(dp(ids), dp(tok), dp(pos), L.ptr(out), b, n, dim,
+                                    V + 1, -1.0, 1, sp()))
+    assert torch.equal(out.cpu()[:b], x)
+
+
+@pytest.mark.parametrize("V,scale,T", [(512, 3.0, 0.45), (65536, 3.0, 0.9), (1000, 1.0, 0.0), (4099, 5.0, 0.05)])
+def test_sample_tokens_matches_reference_ops(V, scale, T):
+    """CFG + gumbel argmax + confidence vs the reference op sequence (phenaki_pytorch.py:83-93,161,547-550).
+    ids must be identical; scores within 1e-6 (fp32 softmax)."""
+    rows = 12
+    cond, null = rnd((rows, V), 70), rnd((rows, V), 71)
+    u = torch.zeros(rows, V).uniform_(0, 1, generator=torch.Generator().manual_seed(72))
+    mask = torch.tensor([1, 0] * (rows // 2), dtype=torch.bool)
+    old = torch.arange(rows)
+    logits = cond if scale == 1.0 else null + (cond - null) * scale
+    pred = O.gumbel_sample(logits, T, u)
+    ref_ids = torch.where(mask, pred, old)
+    p = logits.softmax(-1).gather(1, pred[:, None]).squeeze(1)
+    ref_sc = torch.where(mask, 1 - p, torch.tensor(-1e4))
+    ids, pr, sc = old.clone().to(DEV), torch.empty(rows, dtype=torch.int64, device=DEV), torch.empty(rows, device=DEV)
+    L.check(L.lib().phk_sample_tokens(dp(cond), dp(null), V, dp(u), 0, 0, scale, T,
+                                      dp(mask.to(torch.uint8)), L.ptr(ids), L.ptr(pr), L.ptr(sc), rows, V,
+                                      0, 0, 0, sp()))
+    assert torch.equal(pr.cpu(), pred)
+    assert torch.equal(ids.cpu(), ref_ids)
+    torch.testing.assert_close(sc.cpu(), ref_sc, rtol=1e-5, atol=1e-6)
+
+
+def test_sample_tokens_philox_is_uniform_and_deterministic():
+    rows, V = 64, 1024
+    z = torch.zeros((rows, V), device=DEV)
+    out = []
+    for seed in (1, 1, 2):
+        pr = torch.empty(rows, dtype=torch.int64, device=DEV)
+        L.check(L.lib().phk_sample_tokens(L.ptr(z), None, V, None, seed, 0, 1.0, 1.0, None, None, L.ptr(pr), None,
+                                          rows, V, 0, 0, 0, sp()))
+        out.append(pr.cpu())
+    assert torch.equal(out[0], out[1]) and not torch.equal(out[0], out[2])
+    assert out[0].min() >= 0 and out[0].max() < V and out[0].unique().numel() > rows // 2  # flat logits -> spread
+
+
+@pytest.mark.parametrize("b,n,k", [(2, 576, 441), (3, 48, 1), (1, 1000, 999), (2, 36, 36)])
+def test_topk_mask_matches_torch_topk_scatter(b, n, k):
+    scores = rnd((b, n), 80)
+    ids = torch.arange(b * n).reshape(b, n)
+    _, idx = scores.topk(k, dim=-1)
+    ref_mask = torch.zeros(b, n).scatter(1, idx, 1).bool()
+    ref_ids = torch.where(ref_mask, -7, ids)
+    m, i = torch.empty((b, n), dtype=torch.uint8, device=DEV), ids.clone().to(DEV)
+    L.check(L.lib().phk_topk_mask(dp(scores), b, n, k, L.ptr(m), L.ptr(i), -7, sp()))
+    assert torch.equal(m.cpu().bool(), ref_mask) and torch.equal(i.cpu(), ref_ids)
+
+
+def test_critic_scores_and_cfg_combine():
+    rows, dim = 50, 128
+    xc, xn, w, bb = rnd((rows, dim), 90), rnd((rows, dim), 91), rnd((dim,), 92), rnd((1,), 93)
+    u = torch.rand(rows, generator=torch.Generator().manual_seed(94))
+    c, nn_ = xc @ w + bb, xn @ w + bb
+    ref = nn_ + (c - nn_) * 5.0 + 1.5 * (u - 0.5) * 0.75
+    out = torch.empty(rows, device=DEV)
+    L.check(L.lib().phk_critic_scores(dp(xc), dp(xn), dp(w), dp(bb),
+                                      dp(u), 5.0, 1.5, 0.75, L.ptr(out), rows, dim, 0, 0, 0, sp()))
+    torch.testing.assert_close(out.cpu(), ref, rtol=1e-5, atol=2e-5)
+    a, bnull = rnd((1000,), 95), rnd((1000,), 96)
+    o = torch.empty(1000, device=DEV)
+    L.check(L.lib().phk_cfg_combine(dp(a), dp(bnull), 3.0, L.ptr(o), 1000, sp()))
+    assert torch.equal(o.cpu(), bnull + (a - bnull) * 3.0)  # same op order -> bit exact

@@ -1,0 +1,153 @@
+"""CPU suite (``-m "not gpu"``): the oracle restatement against the committed golden vectors that the
+UNMODIFIED reference produced (tests/golden/make_golden.py), plus host logic of the product."""
+import math
+
+import pytest
+import torch
+
+from oracle import phenaki_oracle as O
+from tests import cases as C
+import phenaki_pytorch_b200 as P
+from phenaki_pytorch_b200.phenaki import demask_counts
+
+torch.set_num_threads(max(1, min(8, torch.get_num_threads())))
+
+# float outputs: the oracle re-runs the same ATen ops; MKL may pick another kernel -> summation order only
+FTOL = dict(rtol=1e-5, atol=1e-5)
+
+
+def pair(v):
+    return v if isinstance(v, tuple) else (v, v)
+
+
+def build(cls, case_or_kwargs, seed):
+    torch.manual_seed(seed)
+    return cls(**case_or_kwargs)
+
+
+@pytest.mark.parametrize("name", list(C.CVIVIT_CASES))
+def test_oracle_cvivit_ids_match_reference_golden(golden, name):
+    case, g = C.CVIVIT_CASES[name], golden(f"cvivit_{name}")
+    model = build(P.CViViT, case["ctor"], case["seed"])
+    sd = model.state_dict()
+    assert C.state_digest(sd) == g["state_digest"], "seeded construction must reproduce the reference weights"
+    assert len(sd) == g["n_state"]
+    video = C.seeded_randn(case["video"], case["video_seed"])
+    with torch.no_grad():
+        ids, proj = O.cvivit_codebook_ids(video, sd, pair(case["ctor"]["image_size"]), pair(case["ctor"]["patch_size"]),
+                                          return_margin=True)
+    assert ids.dtype == torch.int64
+    assert torch.equal(ids, g["ids"])  # integer output: bit-exact
+    torch.testing.assert_close(proj.reshape(g["proj"].shape), g["proj"], **FTOL)
+
+
+@pytest.mark.parametrize("name", ["rect", "image"])
+def test_oracle_cvivit_decode_matches_reference_golden(golden, name):
+    case, g = C.CVIVIT_CASES[name], golden(f"cvivit_{name}")
+    sd = build(P.CViViT, case["ctor"], case["seed"]).state_dict()
+    with torch.no_grad():
+        rec = O.cvivit_decode_from_ids(g["ids"].reshape(g["ids"].shape[0], -1), sd, pair(case["ctor"]["image_size"]),
+                                       pair(case["ctor"]["patch_size"]))
+    torch.testing.assert_close(rec, g["recon"], **FTOL)
+
+
+@pytest.mark.parametrize("name", list(C.MASKGIT_CASES))
+def test_oracle_maskgit_matches_reference_golden(golden, name):
+    case, g = C.MASKGIT_CASES[name], golden(f"maskgit_{name}")
+    sd = build(P.MaskGit, case["ctor"], case["seed"]).state_dict()
+    assert C.state_digest(sd) == g["state_digest"]
+    ids, ctx = C.token_inputs(case, case["ctor"]["num_tokens"])
+    kw = dict(video_patch_shape=case["patch_shape"], heads=case["ctor"].get("heads", 8), context=ctx,
+              text_mask=torch.any(ctx != 0, dim=-1))
+    with torch.no_grad():
+        torch.testing.assert_close(O.maskgit_forward(ids, sd, **kw), g["cond"], **FTOL)
+        torch.testing.assert_close(O.maskgit_forward(ids, sd, cond_drop=True, **kw), g["null"], **FTOL)
+        torch.testing.assert_close(O.continuous_position_bias(sd, "continuous_pos_bias.", case["patch_shape"]),
+                                   g["bias"], **FTOL)
+
+
+def test_oracle_critic_matches_reference_golden(golden):
+    case, g = C.CRITIC_CASES["small"], golden("critic_small")
+    sd = build(P.TokenCritic, case["ctor"], case["seed"]).state_dict()
+    assert C.state_digest(sd) == g["state_digest"]
+    ids, ctx = C.token_inputs(case, case["ctor"]["num_tokens"])
+    kw = dict(video_patch_shape=case["patch_shape"], heads=case["ctor"]["heads"], context=ctx,
+              text_mask=torch.any(ctx != 0, dim=-1))
+    with torch.no_grad():
+        torch.testing.assert_close(O.critic_forward(ids, sd, **kw), g["cond"], **FTOL)
+        cfg = O.with_cond_scale(lambda cond_drop: O.critic_forward(ids, sd, cond_drop=cond_drop, **kw), 5.0)
+        torch.testing.assert_close(cfg, g["cfg"], **FTOL)
+
+
+def _sample_models(case):
+    torch.manual_seed(case["seed"])
+    cv = P.CViViT(**C.SAMPLE_CVIVIT)
+    mg = P.MaskGit(**C.SAMPLE_MASKGIT)
+    cr = P.TokenCritic(**C.SAMPLE_CRITIC) if case["critic"] else None
+    return cv, mg, cr
+
+
+@pytest.mark.parametrize("name", list(C.SAMPLE_CASES))
+def test_oracle_sampling_loop_matches_reference_golden(golden, name):
+    """The full demasking loop (token ids: integer, must be identical) replayed with the same uniform draws."""
+    case, g = C.SAMPLE_CASES[name], golden(f"sample_{name}")
+    cv, mg, cr = _sample_models(case)
+    assert C.state_digest(cv.state_dict()) == g["cvivit_digest"]
+    assert C.state_digest(mg.state_dict()) == g["maskgit_digest"]
+    ctx = C.synthetic_text_embeds(case["batch"], case["ctx_len"], C.SAMPLE_MASKGIT["dim_context"], case["ctx_valid"],
+                                  case["seed"] + 1000)
+    tape = C.NoiseTape(case["noise_seed"])
+    with torch.no_grad():
+        ids = O.sample_token_ids(mg.state_dict(), num_tokens=g["num_tokens"], patch_shape=g["patch_shape"],
+                                 batch=case["batch"], steps=case["steps"], heads=C.SAMPLE_MASKGIT["heads"],
+                                 text_embeds=ctx, prime_ids=g["prime_ids"], cond_scale=case["cond_scale"],
+                                 critic_sd=cr.state_dict() if cr else None, noise_fn=tape)
+    assert torch.equal(ids, g["final_ids"])
+
+
+def test_units_attention_and_peg_match_reference_golden(golden):
+    """Re-derives the inputs of tests/golden/make_golden.py:make_units and checks shapes/finite-ness of the
+    committed module outputs (the module-level pin itself ran in the build container)."""
+    g = golden("units")
+    for k in ("self", "causal", "cross"):
+        assert g[k]["y"].shape == (2, 12, 64) and torch.isfinite(g[k]["y"]).all()
+    for k in ("peg_True", "peg_False"):
+        assert g[k]["y"].shape == (12, 4, 16)
+
+
+def test_demask_schedule_matches_reference_formula():
+    """phenaki_pytorch.py:485-486 evaluated with torch (as the reference does) vs the host-side table."""
+    for n, steps in [(576, 18), (448, 18), (48, 6), (36, 5), (1024, 24), (1, 3)]:
+        ref = O.demask_schedule(n, steps)
+        assert demask_counts(n, steps) == ref
+    assert O.demask_schedule(576, 18) == [574, 567, 556, 541, 522, 499, 472, 441, 407, 370, 330, 288, 243, 197, 149,
+                                          100, 50]  # SURVEY.md 8a-14 probe of the reference
+
+
+def test_shape_helpers_follow_reference():
+    torch.manual_seed(0)
+    m = P.CViViT(**C.SAMPLE_CVIVIT)
+    assert m.patch_height_width == (2, 3) and m.image_num_tokens == 6
+    assert m.get_video_patch_shape(7) == (3, 2, 3)
+    assert m.num_tokens_per_frames(7) == 18 and m.num_tokens_per_frames(6, include_first_frame=False) == 12
+    assert m.frames_per_num_tokens(18) == 7
+    fm = torch.tensor([[1, 1, 1, 1, 0, 0, 0], [1, 1, 1, 1, 1, 1, 1]], dtype=torch.bool)
+    vm = m.calculate_video_token_mask(torch.zeros(2, 3, 7, 16, 24), fm)
+    assert vm.shape == (2, 18) and vm[0].sum() == 12 and vm[1].all()
+    with pytest.raises(AssertionError):
+        m.num_tokens_per_frames(6)
+
+
+def test_product_has_no_cpu_fallback():
+    """CPU tensors must be refused loudly -- there is no PyTorch / oracle fallback on the product path."""
+    torch.manual_seed(0)
+    m = P.CViViT(**C.SAMPLE_CVIVIT)
+    from phenaki_pytorch_b200._lib import PhkError
+    with pytest.raises(PhkError):
+        m(torch.zeros(1, 3, 4, 16, 24), return_only_codebook_ids=True)
+    import os
+    src = os.path.join(os.path.dirname(P.__file__))
+    for fn in os.listdir(src):
+        if fn.endswith(".py"):
+            text = open(os.path.join(src, fn)).read()
+            assert "import oracle" not in text and "from oracle" not in text, f"{fn} imports the oracle"
