@@ -76,21 +76,40 @@ static int64_t tf_scratch_bytes(const phk_transformer_t* T, int64_t R) {
   return 256 * 8 + R * 4 * (T->dim + I + 2 * I + I + 2 * inner + inner);
 }
 
-// x <- Transformer(x)  (attention.py:311-332); the final norm_out is written to `out`.
-static int transformer_forward(const TfCall& c, Arena scratch, float* out, cudaStream_t st) {
+// y = act @ W^T (+bias)(+residual) in the selected contraction type.  `act` is fp32 (parity mode) or bf16.
+static int linear(int prec, const void* act, int64_t lda, const float* w32, const void* w16, int64_t ldw, float* C,
+                  int64_t ldc, int64_t M, int N, int K, const float* bias, const float* residual, phk_stream_t s) {
+  if (prec == PHK_PREC_BF16) {
+    PHK_REQUIRE(w16, PHK_E_ARG, "bf16 mode needs the packed bf16 weight copies (*_h) in the weight table");
+    return phk_gemm_bf16(act, lda, w16, ldw, C, ldc, M, N, K, bias, residual, 0, 0, 0, 0, s);
+  }
+  return phk_gemm_f32((const float*)act, lda, w32, ldw, C, ldc, M, N, K, bias, residual, 0, 0, 0, s);
+}
+
+// x <- Transformer(x)  (attention.py:311-332); the final norm_out is written to `out` (fp32) and, in bf16
+// mode, optionally also to `out_h` (bf16, the A operand of a following head GEMM).
+//   parity mode : every buffer fp32, FFMA GEMMs.
+//   bf16 mode   : residual stream / LayerNorm / softmax fp32; LayerNorm emits bf16 GEMM operands (plus the
+//                 un-normalised bf16 row for the self-attention k,v projection, attention.py:140-144); GEMMs on
+//                 tcgen05 with fp32 accumulation; FF first linear fused with GEGLU; attention output bf16.
+static int transformer_forward(const TfCall& c, Arena scratch, float* out, void* out_h, cudaStream_t st) {
   const phk_transformer_t* T = c.T;
-  PHK_REQUIRE(c.prec == PHK_PREC_F32, PHK_E_UNSUPPORTED, "transformer: only PHK_PREC_F32 in this build");
+  const bool h16 = c.prec == PHK_PREC_BF16;
+  PHK_REQUIRE(c.prec == PHK_PREC_F32 || h16, PHK_E_ARG, "transformer: unknown precision mode");
   const int D = T->dim, H = T->heads, DH = T->dim_head, I = H * DH;
   const int64_t R = c.R;
   int inner_max = 0;
   for (int l = 0; l < T->depth; ++l) inner_max = inner_max > T->layers[l].ff.inner ? inner_max : T->layers[l].ff.inner;
-  float* xn = (float*)scratch.take(R * D * 4);
+  const int64_t ab = h16 ? 2 : 4;  // activation bytes
+  void* xn = scratch.take(R * D * ab);
+  void* xraw = h16 ? scratch.take(R * D * 2) : nullptr;
   float* q = (float*)scratch.take(R * I * 4);
   float* kv = (float*)scratch.take(R * 2 * I * 4);
-  float* o = (float*)scratch.take(R * I * 4);
-  float* hbuf = (float*)scratch.take(R * 2 * (int64_t)inner_max * 4);
-  float* gbuf = (float*)scratch.take(R * (int64_t)inner_max * 4);
-  PHK_REQUIRE(xn && q && kv && o && hbuf && gbuf, PHK_E_WORKSPACE, "transformer: workspace too small");
+  void* o = scratch.take(R * I * ab);
+  float* hbuf = h16 ? nullptr : (float*)scratch.take(R * 2 * (int64_t)inner_max * 4);
+  void* gbuf = scratch.take(R * (int64_t)(h16 ? (inner_max + 63) / 64 * 64 * 2 : inner_max * 4));
+  PHK_REQUIRE(xn && q && kv && o && gbuf && (h16 ? xraw != nullptr : hbuf != nullptr), PHK_E_WORKSPACE,
+              "transformer: workspace too small");
   phk_stream_t s = reinterpret_cast<phk_stream_t>(st);
   float* x = c.x;
   float* x_alt = c.x_alt;
@@ -104,9 +123,9 @@ static int transformer_forward(const TfCall& c, Arena scratch, float* out, cudaS
     }
     {  // x = self_attn(x) + x ; q from LN(x), k/v from RAW x (attention.py:140-144)
       const phk_attn_t& A = L.self_attn;
-      PHK_TRY(phk_layernorm(x, A.norm_g, A.norm_b, xn, nullptr, R, D, 0, 0, 0, 0, s));
-      PHK_TRY(phk_gemm_f32(xn, D, A.wq, D, q, I, R, I, D, nullptr, nullptr, 0, 0, 0, s));
-      PHK_TRY(phk_gemm_f32(x, D, A.wkv, D, kv, 2 * I, R, 2 * I, D, nullptr, nullptr, 0, 0, 0, s));
+      PHK_TRY(phk_layernorm(x, A.norm_g, A.norm_b, xn, xraw, R, D, h16, 0, 0, 0, s));
+      PHK_TRY(linear(c.prec, xn, D, A.wq, A.wq_h, D, q, I, R, I, D, nullptr, nullptr, s));
+      PHK_TRY(linear(c.prec, h16 ? xraw : (const void*)x, D, A.wkv, A.wkv_h, D, kv, 2 * I, R, 2 * I, D, nullptr, nullptr, s));
       phk_attn_geom_t g;
       std::memset(&g, 0, sizeof(g));
       g.n_outer = c.seq.n_outer; g.n_inner = c.seq.n_inner; g.n_q = c.seq.n_tok; g.n_k = c.seq.n_tok;
@@ -114,15 +133,15 @@ static int transformer_forward(const TfCall& c, Arena scratch, float* out, cudaS
       g.q_outer = c.seq.outer * I; g.q_inner = c.seq.inner * I; g.q_tok = c.seq.tok * I;
       g.k_outer = c.seq.outer * 2 * I; g.k_inner = c.seq.inner * 2 * I; g.k_tok = c.seq.tok * 2 * I;
       g.o_outer = g.q_outer; g.o_inner = g.q_inner; g.o_tok = g.q_tok;
-      g.kv_outer_mod = 0; g.mask_outer_mod = c.self_mask_mod; g.mask_off_from = -1; g.out_bf16 = 0; g.scale = 8.f;
+      g.kv_outer_mod = 0; g.mask_outer_mod = c.self_mask_mod; g.mask_off_from = -1; g.out_bf16 = h16; g.scale = 8.f;
       PHK_TRY(phk_attention(q, kv, A.null_kv, A.q_scale, A.k_scale, c.attn_bias, c.self_mask, T->alibi_slopes, o, &g, s));
-      PHK_TRY(phk_gemm_f32(o, I, A.wo, I, x, D, R, D, I, nullptr, x, 0, 0, 0, s));
+      PHK_TRY(linear(c.prec, o, I, A.wo, A.wo_h, I, x, D, R, D, I, nullptr, x, s));
     }
     if (L.has_cross && c.ctx_kv) {  // x = cross_attn(x, context) + x   (attention.py:327-328)
       const phk_attn_t& A = L.cross_attn;
       PHK_REQUIRE(c.seq.n_inner == 1, PHK_E_UNSUPPORTED, "cross attention needs (b, n) sequences");
-      PHK_TRY(phk_layernorm(x, A.norm_g, A.norm_b, xn, nullptr, R, D, 0, 0, 0, 0, s));
-      PHK_TRY(phk_gemm_f32(xn, D, A.wq, D, q, I, R, I, D, nullptr, nullptr, 0, 0, 0, s));
+      PHK_TRY(phk_layernorm(x, A.norm_g, A.norm_b, xn, nullptr, R, D, h16, 0, 0, 0, s));
+      PHK_TRY(linear(c.prec, xn, D, A.wq, A.wq_h, D, q, I, R, I, D, nullptr, nullptr, s));
       phk_attn_geom_t g;
       std::memset(&g, 0, sizeof(g));
       g.n_outer = c.seq.n_outer; g.n_inner = 1; g.n_q = c.seq.n_tok; g.n_k = c.ctx_L;
@@ -131,20 +150,29 @@ static int transformer_forward(const TfCall& c, Arena scratch, float* out, cudaS
       g.k_outer = (int64_t)c.ctx_L * 2 * I; g.k_inner = 0; g.k_tok = 2 * I;
       g.o_outer = g.q_outer; g.o_inner = 0; g.o_tok = g.q_tok;
       g.kv_outer_mod = c.ctx_b; g.mask_outer_mod = c.ctx_b; g.mask_off_from = c.ctx_mask_off_from;
-      g.out_bf16 = 0; g.scale = 8.f;
+      g.out_bf16 = h16; g.scale = 8.f;
       const float* kvl = c.ctx_kv + (int64_t)l * c.ctx_b * c.ctx_L * 2 * I;
       PHK_TRY(phk_attention(q, kvl, A.null_kv, A.q_scale, A.k_scale, nullptr, c.ctx_mask, nullptr, o, &g, s));
-      PHK_TRY(phk_gemm_f32(o, I, A.wo, I, x, D, R, D, I, nullptr, x, 0, 0, 0, s));
+      PHK_TRY(linear(c.prec, o, I, A.wo, A.wo_h, I, x, D, R, D, I, nullptr, x, s));
     }
     {  // x = ff(x) + x  (attention.py:45-53, 330)
       const phk_ff_t& Fw = L.ff;
-      PHK_TRY(phk_layernorm(x, Fw.ln_g, Fw.ln_b, xn, nullptr, R, D, 0, 0, 0, 0, s));
-      PHK_TRY(phk_gemm_f32(xn, D, Fw.w1, D, hbuf, 2 * Fw.inner, R, 2 * Fw.inner, D, nullptr, nullptr, 0, 0, 0, s));
-      PHK_TRY(phk_geglu(hbuf, gbuf, R, Fw.inner, s));
-      PHK_TRY(phk_gemm_f32(gbuf, Fw.inner, Fw.w2, Fw.inner, x, D, R, D, Fw.inner, nullptr, x, 0, 0, 0, s));
+      PHK_TRY(phk_layernorm(x, Fw.ln_g, Fw.ln_b, xn, nullptr, R, D, h16, 0, 0, 0, s));
+      if (h16) {
+        PHK_REQUIRE(Fw.w1_h && Fw.w2_h && Fw.inner_pad % 64 == 0 && Fw.inner_pad >= Fw.inner, PHK_E_ARG,
+                    "bf16 mode needs the packed feed-forward weights");
+        // first linear + GEGLU in one kernel (value/gate rows interleaved per 64), bf16 [R, inner_pad] out
+        PHK_TRY(phk_gemm_bf16(xn, D, Fw.w1_h, D, gbuf, Fw.inner_pad, R, 2 * Fw.inner_pad, D, nullptr, nullptr, 0, 0, 0, 2, s));
+        PHK_TRY(phk_gemm_bf16(gbuf, Fw.inner_pad, Fw.w2_h, Fw.inner_pad, x, D, R, D, Fw.inner_pad, nullptr, x, 0, 0, 0, 0, s));
+      } else {
+        PHK_TRY(phk_gemm_f32((const float*)xn, D, Fw.w1, D, hbuf, 2 * Fw.inner, R, 2 * Fw.inner, D, nullptr, nullptr, 0, 0, 0, s));
+        PHK_TRY(phk_geglu(hbuf, (float*)gbuf, R, Fw.inner, s));
+        PHK_TRY(phk_gemm_f32((const float*)gbuf, Fw.inner, Fw.w2, Fw.inner, x, D, R, D, Fw.inner, nullptr, x, 0, 0, 0, s));
+      }
     }
   }
-  PHK_TRY(phk_layernorm(x, T->out_g, T->out_b, out, nullptr, R, D, 0, 0, 0, 0, s));
+  if (out) PHK_TRY(phk_layernorm(x, T->out_g, T->out_b, out, nullptr, R, D, 0, 0, 0, 0, s));
+  if (out_h) PHK_TRY(phk_layernorm(x, T->out_g, T->out_b, out_h, nullptr, R, D, 1, 0, 0, 0, s));
   return 0;
 }
 
@@ -221,7 +249,8 @@ extern "C" int phk_cvivit_encode(const phk_cvivit_t* m, const float* video, int3
   PHK_REQUIRE(video && ids && workspace, PHK_E_ARG, "cvivit_encode: null pointer");
   PHK_TRY(check_transformer(&m->spatial));
   PHK_TRY(check_transformer(&m->temporal));
-  PHK_REQUIRE(prec == PHK_PREC_F32, PHK_E_UNSUPPORTED, "cvivit_encode: only PHK_PREC_F32 in this build");
+  PHK_REQUIRE(prec == PHK_PREC_F32 || prec == PHK_PREC_BF16, PHK_E_ARG, "cvivit_encode: unknown precision mode");
+  const int h16 = prec == PHK_PREC_BF16;
   cudaStream_t st = to_stream(s);
   const int D = m->dim, hw = hh * ww;
   const int64_t K1 = (int64_t)m->channels * m->patch_h * m->patch_w, K2 = K1 * m->patch_t;
@@ -236,14 +265,14 @@ extern "C" int phk_cvivit_encode(const phk_cvivit_t* m, const float* video, int3
 
   // ---- to_patch_emb_first_frame / to_patch_emb (cvivit.py:542-549), rows land in (b,t,h,w) order
   const int C = m->channels, H = m->image_h, W = m->image_w;
-  PHK_TRY(phk_patchify_ln(video, B, C, F, H, W, 0, 1, 1, m->patch_h, m->patch_w, m->pf_ln1_g, m->pf_ln1_b, A, 0, s));
-  PHK_TRY(phk_gemm_f32(A, K1, m->pf_w, K1, P, D, (int64_t)B * hw, D, (int)K1, m->pf_b, nullptr, 0, 0, 0, s));
+  PHK_TRY(phk_patchify_ln(video, B, C, F, H, W, 0, 1, 1, m->patch_h, m->patch_w, m->pf_ln1_g, m->pf_ln1_b, A, h16, s));
+  PHK_TRY(linear(prec, A, K1, m->pf_w, m->pf_w_h, K1, P, D, (int64_t)B * hw, D, (int)K1, m->pf_b, nullptr, s));
   PHK_TRY(phk_layernorm(P, m->pf_ln2_g, m->pf_ln2_b, x, nullptr, (int64_t)B * hw, D, 0, hw, (int64_t)Tp * hw, 0, s));
   if (Tp > 1) {
     const int64_t rows = (int64_t)B * (Tp - 1) * hw;
     PHK_TRY(phk_patchify_ln(video, B, C, F, H, W, 1, Tp - 1, m->patch_t, m->patch_h, m->patch_w, m->pr_ln1_g,
-                            m->pr_ln1_b, A, 0, s));
-    PHK_TRY(phk_gemm_f32(A, K2, m->pr_w, K2, P, D, rows, D, (int)K2, m->pr_b, nullptr, 0, 0, 0, s));
+                            m->pr_ln1_b, A, h16, s));
+    PHK_TRY(linear(prec, A, K2, m->pr_w, m->pr_w_h, K2, P, D, rows, D, (int)K2, m->pr_b, nullptr, s));
     PHK_TRY(phk_layernorm(P, m->pr_ln2_g, m->pr_ln2_b, x, nullptr, rows, D, 0, (int64_t)(Tp - 1) * hw,
                           (int64_t)Tp * hw, hw, s));
   }
@@ -261,14 +290,14 @@ extern "C" int phk_cvivit_encode(const phk_cvivit_t* m, const float* video, int3
   c.seq = SeqView{B * Tp, 1, hw, hw, 0, 1};
   c.pegB = B; c.pegT = Tp; c.pegH = hh; c.pegW = ww; c.peg_layout = 0;
   c.attn_bias = spatial_bias; c.ctx_mask_off_from = -1; c.prec = prec;
-  PHK_TRY(transformer_forward(c, tf, P, st));  // P <- norm_out(spatial)
+  PHK_TRY(transformer_forward(c, tf, P, nullptr, st));  // P <- norm_out(spatial)
   if (tap_spatial) PHK_CUDA(cudaMemcpyAsync(tap_spatial, P, R * D * 4, cudaMemcpyDeviceToDevice, st));
 
   c.T = &m->temporal; c.x = P; c.x_alt = x;
   c.seq = SeqView{B, hw, Tp, (int64_t)Tp * hw, 1, hw};
   c.peg_layout = 1;  // the reference's raw-reshape quirk (attention.py:71, cvivit.py:468-470)
   c.attn_bias = nullptr;
-  PHK_TRY(transformer_forward(c, tf, x_alt, st));  // x_alt <- norm_out(temporal)
+  PHK_TRY(transformer_forward(c, tf, x_alt, nullptr, st));  // x_alt <- norm_out(temporal)
   if (tap_temporal) PHK_CUDA(cudaMemcpyAsync(tap_temporal, x_alt, R * D * 4, cudaMemcpyDeviceToDevice, st));
 
   // ---- LFQ (cvivit.py:562-574): ids in (b, t, h, w) order
@@ -314,7 +343,8 @@ extern "C" int phk_maskgit_context_kv(const phk_maskgit_t* m, const float* conte
                                       float* out_kv, float* scratch, int32_t prec, phk_stream_t s) {
   PHK_REQUIRE(m && context && out_kv && scratch, PHK_E_ARG, "maskgit_context_kv: null pointer");
   PHK_REQUIRE(b > 0 && L > 0, PHK_E_ARG, "maskgit_context_kv: bad size");
-  PHK_REQUIRE(prec == PHK_PREC_F32, PHK_E_UNSUPPORTED, "maskgit_context_kv: only PHK_PREC_F32 in this build");
+  PHK_REQUIRE(prec == PHK_PREC_F32 || prec == PHK_PREC_BF16, PHK_E_ARG, "maskgit_context_kv: unknown precision mode");
+  const int h16 = prec == PHK_PREC_BF16;
   const phk_transformer_t* T = &m->transformer;
   PHK_TRY(check_transformer(T));
   const int I = T->heads * T->dim_head;
@@ -323,9 +353,9 @@ extern "C" int phk_maskgit_context_kv(const phk_maskgit_t* m, const float* conte
     const phk_layer_t& Ly = T->layers[l];
     PHK_REQUIRE(Ly.has_cross, PHK_E_SHAPE, "maskgit_context_kv: layer has no cross attention");
     const phk_attn_t& A = Ly.cross_attn;
-    PHK_TRY(phk_layernorm(context, A.ctx_g, A.ctx_b, scratch, nullptr, rows, A.dim_context, 0, 0, 0, 0, s));
-    PHK_TRY(phk_gemm_f32(scratch, A.dim_context, A.wkv, A.dim_context, out_kv + (int64_t)l * rows * 2 * I, 2 * I, rows,
-                         2 * I, A.dim_context, nullptr, nullptr, 0, 0, 0, s));
+    PHK_TRY(phk_layernorm(context, A.ctx_g, A.ctx_b, scratch, nullptr, rows, A.dim_context, h16, 0, 0, 0, s));
+    PHK_TRY(linear(prec, scratch, A.dim_context, A.wkv, A.wkv_h, A.dim_context, out_kv + (int64_t)l * rows * 2 * I, 2 * I,
+                   rows, 2 * I, A.dim_context, nullptr, nullptr, s));
   }
   return 0;
 }
@@ -340,7 +370,8 @@ extern "C" int phk_maskgit_forward(const phk_maskgit_t* m, const int64_t* ids, i
   PHK_REQUIRE((int64_t)pt * ph * pw == n, PHK_E_SHAPE, "video patch shape must cover the token sequence");
   PHK_REQUIRE(n <= m->max_seq_len, PHK_E_SHAPE,
               "the video token sequence length is greater than max_seq_len (phenaki_pytorch.py:196)");
-  PHK_REQUIRE(prec == PHK_PREC_F32, PHK_E_UNSUPPORTED, "maskgit_forward: only PHK_PREC_F32 in this build");
+  PHK_REQUIRE(prec == PHK_PREC_F32 || prec == PHK_PREC_BF16, PHK_E_ARG, "maskgit_forward: unknown precision mode");
+  const int h16 = prec == PHK_PREC_BF16;
   PHK_REQUIRE(!ctx_kv || text_mask, PHK_E_ARG, "maskgit_forward: context without text mask");
   const phk_transformer_t* T = &m->transformer;
   PHK_TRY(check_transformer(T));
@@ -372,10 +403,9 @@ extern "C" int phk_maskgit_forward(const phk_maskgit_t* m, const int64_t* ids, i
   c.ctx_kv = ctx_kv; c.ctx_b = b; c.ctx_L = L; c.ctx_mask = text_mask;
   c.ctx_mask_off_from = cfg_pair ? b : -1;
   c.prec = prec;
-  float* embeds = (return_embeds || m->is_critic) ? out : emb;
-  PHK_TRY(transformer_forward(c, ar, embeds, st));
-  if (return_embeds || m->is_critic) return 0;
-  // to_logits (phenaki_pytorch.py:213)
-  PHK_TRY(phk_gemm_f32(embeds, D, m->head_w, D, out, m->num_tokens, R, m->num_tokens, D, m->head_b, nullptr, 0, 0, 0, s));
+  if (return_embeds || m->is_critic) return transformer_forward(c, ar, out, nullptr, st);
+  // to_logits (phenaki_pytorch.py:213): the final LayerNorm feeds the head GEMM directly (bf16 operand in bf16 mode)
+  PHK_TRY(transformer_forward(c, ar, h16 ? nullptr : emb, h16 ? (void*)emb : nullptr, st));
+  PHK_TRY(linear(prec, emb, D, m->head_w, m->head_w_h, D, out, m->num_tokens, R, m->num_tokens, D, m->head_b, nullptr, s));
   return 0;
 }

@@ -143,9 +143,10 @@ class CViViT(nn.Module):
 
     # ---- libphk plumbing ---------------------------------------------------------------------
     def _table(self):
-        sig = weights_signature(self)
+        sig = (weights_signature(self), self.precision)
         if self._tables is None or sig != self._sig:
             keep = Keep()
+            h16 = self.precision == L.PREC_BF16
             t = L.CvivitT()
             t.dim, t.heads, t.dim_head, t.channels = self.dim, self.heads, self.dim_head, self.channels
             t.image_h, t.image_w = self.image_size
@@ -158,8 +159,10 @@ class CViViT(nn.Module):
             t.pr_ln1_g, t.pr_ln1_b, t.pr_w, t.pr_b = keep.t(r[1].weight), keep.t(r[1].bias), keep.t(r[2].weight), keep.t(r[2].bias)
             t.pr_ln2_g, t.pr_ln2_b = keep.t(r[3].weight), keep.t(r[3].bias)
             t.spatial_bias = cpb_table(self.spatial_rel_pos_bias, keep)
-            t.spatial = transformer_table(self.enc_spatial_transformer, keep)
-            t.temporal = transformer_table(self.enc_temporal_transformer, keep)
+            t.spatial = transformer_table(self.enc_spatial_transformer, keep, h16)
+            t.temporal = transformer_table(self.enc_temporal_transformer, keep, h16)
+            if h16:
+                t.pf_w_h, t.pr_w_h = keep.h(f[2].weight), keep.h(r[2].weight)
             t.vq_w, t.vq_b = keep.t(self.vq.project_in.weight), keep.t(self.vq.project_in.bias)
             self._tables, self._sig = (t, keep), sig
             self._bias_cache = {}

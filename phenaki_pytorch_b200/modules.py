@@ -136,9 +136,40 @@ class Keep:
         self.refs.append(o)
         return o
 
+    def h(self, tensor):
+        """bf16 copy (the tcgen05 GEMM operand); leading dimension must be a multiple of 8 for TMA."""
+        if not tensor.is_cuda:
+            raise L.PhkError("module parameters must be on a CUDA device (no CPU path): call .cuda() first")
+        t = tensor.detach().to(torch.bfloat16).contiguous()
+        assert t.shape[-1] % 8 == 0, "bf16 mode needs every GEMM K dimension to be a multiple of 8"
+        self.refs.append(t)
+        return t.data_ptr()
 
-def attn_table(a: Attention, keep: Keep):
+
+def pack_geglu_w1(w1, inner, inner_pad):
+    """[2*inner, dim] -> [2*inner_pad, dim] bf16 with rows grouped as [64 value rows | 64 gate rows] per
+    128-row tile, so the GEMM epilogue can apply gelu(gate) * value inside one accumulator tile
+    (attention.py:40-43: value = first half, gate = second half).  Padding rows are zero."""
+    dim = w1.shape[1]
+    w = w1.detach().to(torch.bfloat16)
+    val = torch.zeros((inner_pad, dim), dtype=torch.bfloat16, device=w.device)
+    gate = torch.zeros_like(val)
+    val[:inner], gate[:inner] = w[:inner], w[inner:]
+    g = inner_pad // 64
+    return torch.stack((val.reshape(g, 64, dim), gate.reshape(g, 64, dim)), dim=1).reshape(2 * inner_pad, dim).contiguous()
+
+
+def pack_w2(w2, inner, inner_pad):
+    """[dim, inner] -> [dim, inner_pad] bf16, zero-padded K."""
+    out = torch.zeros((w2.shape[0], inner_pad), dtype=torch.bfloat16, device=w2.device)
+    out[:, :inner] = w2.detach().to(torch.bfloat16)
+    return out
+
+
+def attn_table(a: Attention, keep: Keep, bf16=False):
     t = L.AttnT()
+    if bf16:
+        t.wq_h, t.wkv_h, t.wo_h = keep.h(a.to_q.weight), keep.h(a.to_kv.weight), keep.h(a.to_out.weight)
     t.norm_g, t.norm_b = keep.t(a.norm.gamma), keep.t(a.norm.beta)
     if isinstance(a.context_norm, LayerNorm):
         t.ctx_g, t.ctx_b = keep.t(a.context_norm.gamma), keep.t(a.context_norm.beta)
@@ -149,7 +180,7 @@ def attn_table(a: Attention, keep: Keep):
     return t
 
 
-def transformer_table(tf: Transformer, keep: Keep):
+def transformer_table(tf: Transformer, keep: Keep, bf16=False):
     layers = (L.LayerT * tf.depth)()
     for i, (peg, self_attn, cross, ff) in enumerate(tf.layers):
         ly = layers[i]
@@ -158,13 +189,18 @@ def transformer_table(tf: Transformer, keep: Keep):
             d = peg.dsconv.weight.shape[0]
             w = peg.dsconv.weight.detach().reshape(d, 27).t().contiguous()  # tap-major [27, dim]
             ly.peg.w, ly.peg.b, ly.peg.causal = keep.t(w), keep.t(peg.dsconv.bias), int(peg.causal)
-        ly.self_attn = attn_table(self_attn, keep)
+        ly.self_attn = attn_table(self_attn, keep, bf16)
         if cross is not None:
-            ly.cross_attn = attn_table(cross, keep)
+            ly.cross_attn = attn_table(cross, keep, bf16)
         ly.ff.ln_g, ly.ff.ln_b = keep.t(ff[0].weight), keep.t(ff[0].bias)
         ly.ff.w1, ly.ff.w2 = keep.t(ff[1].weight), keep.t(ff[4].weight)
         ly.ff.inner = ff[4].weight.shape[1]
         ly.ff.inner_pad = (ly.ff.inner + 63) // 64 * 64
+        if bf16:
+            w1h = pack_geglu_w1(ff[1].weight, ly.ff.inner, ly.ff.inner_pad)
+            w2h = pack_w2(ff[4].weight, ly.ff.inner, ly.ff.inner_pad)
+            keep.refs += [w1h, w2h]
+            ly.ff.w1_h, ly.ff.w2_h = w1h.data_ptr(), w2h.data_ptr()
     keep.obj(layers)
     t = L.TransformerT()
     t.dim, t.heads, t.dim_head, t.depth, t.causal = tf.dim, tf.heads, tf.dim_head, tf.depth, int(tf.causal)

@@ -44,9 +44,10 @@ class _TokenTransformer(nn.Module):
         raise TypeError("copy the state_dict instead; ctypes weight tables are not copyable")
 
     def _table(self):
-        sig = weights_signature(self)
+        sig = (weights_signature(self), self.precision)
         if self._tables is None or sig != self._sig:
             keep = Keep()
+            h16 = self.precision == L.PREC_BF16
             t = L.MaskgitT()
             tf = self.transformer
             t.dim, t.heads, t.dim_head = tf.dim, tf.heads, tf.dim_head
@@ -59,9 +60,11 @@ class _TokenTransformer(nn.Module):
             if not self.is_critic:
                 t.pos_bias = cpb_table(self.continuous_pos_bias, keep)
                 t.head_w, t.head_b = keep.t(self.to_logits.weight), keep.t(self.to_logits.bias)
+                if h16:
+                    t.head_w_h = keep.h(self.to_logits.weight)
             else:
                 t.head_w, t.head_b = keep.t(self.to_logits[0].weight), keep.t(self.to_logits[0].bias)
-            t.transformer = transformer_table(tf, keep)
+            t.transformer = transformer_table(tf, keep, h16)
             self._tables, self._sig = (t, keep), sig
             self._bias_cache = {}
         return self._tables[0]

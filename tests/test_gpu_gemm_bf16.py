@@ -1,0 +1,83 @@
+"""GPU: the tcgen05/TMEM/TMA bf16 GEMM (phk_gemm_bf16) against torch fp32 matmul of the SAME bf16-rounded
+operands (so the only difference is fp32 summation order: tolerance 2e-3 * sqrt(K/512) absolute on O(sqrt(K)) sums)."""
+import pytest
+import torch
+
+from phenaki_pytorch_b200 import _lib as L
+from tests import cases as TC
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def operands(M, N, K, lda=None, ldw=None, seed=0):
+    lda, ldw = lda or K, ldw or K
+    a = torch.zeros((M, lda))
+    w = torch.zeros((N, ldw))
+    a[:, :K] = TC.seeded_randn((M, K), seed)
+    w[:, :K] = TC.seeded_randn((N, K), seed + 1)
+    return a.bfloat16(), w.bfloat16()
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 128, 512), (4608, 512, 512), (300, 200, 520), (77, 64, 48),
+                                   (129, 1024, 768), (512, 512, 3072), (1000, 40, 136)])
+def test_gemm_bf16_fp32_out_bias_residual(M, N, K):
+    a, w = operands(M, N, K)
+    bias, res = TC.seeded_randn((N,), 5), TC.seeded_randn((M, N), 6)
+    ref = a.float() @ w.float().t() + bias + res
+    ad, wd, bd = a.to(DEV), w.to(DEV), bias.to(DEV)
+    c = res.clone().to(DEV)
+    L.check(L.lib().phk_gemm_bf16(L.ptr(ad), K, L.ptr(wd), K, L.ptr(c), N, M, N, K, L.ptr(bd), L.ptr(c), 0, 0, 0, 0,
+                                  L.stream_ptr()), "phk_gemm_bf16")
+    torch.cuda.synchronize()
+    torch.testing.assert_close(c.cpu(), ref, rtol=1e-4, atol=2e-3 * max(1.0, (K / 512) ** 0.5))
+
+
+def test_gemm_bf16_padded_leading_dims_and_row_map():
+    M, N, K = 130, 96, 1365           # FF second linear of the reference: K = int(4*2/3*512) (attention.py:46)
+    a, w = operands(M, N, K, lda=1408, ldw=1408)
+    ref = a[:, :K].float() @ w[:, :K].float().t()
+    ad, wd = a.to(DEV), w.to(DEV)
+    c = torch.zeros((400, N), device=DEV)
+    L.check(L.lib().phk_gemm_bf16(L.ptr(ad), 1408, L.ptr(wd), 1408, L.ptr(c), N, M, N, K, None, None, 10, 30, 7, 0,
+                                  L.stream_ptr()), "phk_gemm_bf16")
+    idx = torch.tensor([(m // 10) * 30 + 7 + m % 10 for m in range(M)])
+    torch.testing.assert_close(c.cpu()[idx], ref, rtol=1e-4, atol=4e-3)
+    rest = torch.ones(400, dtype=torch.bool)
+    rest[idx] = False
+    assert (c.cpu()[rest] == 0).all()
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 512), (100, 72, 200)])
+def test_gemm_bf16_bf16_out(M, N, K):
+    a, w = operands(M, N, K, seed=3)
+    bias = TC.seeded_randn((N,), 9)
+    ref = (a.float() @ w.float().t() + bias)
+    ad, wd, bd = a.to(DEV), w.to(DEV), bias.to(DEV)
+    c = torch.empty((M, N), dtype=torch.bfloat16, device=DEV)
+    L.check(L.lib().phk_gemm_bf16(L.ptr(ad), K, L.ptr(wd), K, L.ptr(c), N, M, N, K, L.ptr(bd), None, 0, 0, 0, 1,
+                                  L.stream_ptr()), "phk_gemm_bf16")
+    torch.testing.assert_close(c.cpu().float(), ref, rtol=1e-2, atol=5e-2)  # one bf16 rounding of O(sqrt(K)) values
+
+
+@pytest.mark.parametrize("M,inner,K", [(300, 1365, 512), (64, 170, 64)])
+def test_gemm_bf16_geglu_epilogue(M, inner, K):
+    """W rows packed [64 value | 64 gate] per 128-column tile; out = gelu(gate) * value (attention.py:40-43)."""
+    inner_pad = (inner + 63) // 64 * 64
+    a = TC.seeded_randn((M, K), 11).bfloat16()
+    w1 = (TC.seeded_randn((2 * inner, K), 12) / K ** 0.5).bfloat16()
+    packed = torch.zeros((2 * inner_pad, K), dtype=torch.bfloat16)
+    for g in range(inner_pad // 64):
+        lo, hi = g * 64, min(g * 64 + 64, inner)
+        if hi > lo:
+            packed[g * 128: g * 128 + (hi - lo)] = w1[lo:hi]                       # values
+            packed[g * 128 + 64: g * 128 + 64 + (hi - lo)] = w1[inner + lo: inner + hi]   # gates
+    h = a.float() @ w1.float().t()
+    ref = torch.nn.functional.gelu(h[:, inner:]) * h[:, :inner]
+    ad, wd = a.to(DEV), packed.to(DEV)
+    out = torch.full((M, inner_pad), 7.0, dtype=torch.bfloat16, device=DEV)
+    L.check(L.lib().phk_gemm_bf16(L.ptr(ad), K, L.ptr(wd), K, L.ptr(out), inner_pad, M, 2 * inner_pad, K, None, None,
+                                  0, 0, 0, 2, L.stream_ptr()), "phk_gemm_bf16")
+    o = out.cpu().float()
+    torch.testing.assert_close(o[:, :inner], ref, rtol=1e-2, atol=1e-2)
+    assert (o[:, inner:] == 0).all()  # K-padding of the next GEMM must be exact zeros
