@@ -204,6 +204,119 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const float* __r
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Short sequences (n <= 16): the C-ViViT temporal transformer attends over T' = 9 tokens
+// (cvivit.py:468-470), 4096 (sequence, head) pairs per layer at config 2.  A 64-wide tile would be
+// 98 % padding, so here ONE WARP owns one (sequence, head): q/k/v rows live in registers (lane = d),
+// normalised q/k are staged in 2 x n x (DH+1) floats of shared memory for the n*n dot products,
+// softmax runs one row per lane, and P.V accumulates back in registers.  No tensor tile on purpose.
+// ------------------------------------------------------------------------------------------
+constexpr int SMALL_N = 16, SMALL_WARPS = 4;
+
+template <int DH>
+__global__ void __launch_bounds__(SMALL_WARPS * 32) attention_small_kernel(
+    const float* __restrict__ q, const float* __restrict__ kv, const float* __restrict__ q_scale,
+    const float* __restrict__ k_scale, const float* __restrict__ alibi_slopes, void* __restrict__ out,
+    phk_attn_geom_t g) {
+  constexpr int DPL = DH / 32;
+  __shared__ float s_q[SMALL_WARPS][SMALL_N][DH + 1];
+  __shared__ float s_k[SMALL_WARPS][SMALL_N][DH + 1];
+  __shared__ float s_p[SMALL_WARPS][SMALL_N][SMALL_N + 1];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t pair = (int64_t)blockIdx.x * SMALL_WARPS + w;
+  const int64_t npairs = (int64_t)g.n_outer * g.n_inner * g.heads;
+  if (pair >= npairs) return;  // whole warp exits together
+  const int h = (int)(pair % g.heads);
+  const int seq = (int)(pair / g.heads);
+  const int so = seq / g.n_inner, si = seq - so * g.n_inner;
+  const int n = g.n_q, I = g.heads * DH;
+  const float* qb = q + (int64_t)so * g.q_outer + (int64_t)si * g.q_inner + (int64_t)h * DH;
+  const float* kb = kv + (int64_t)so * g.k_outer + (int64_t)si * g.k_inner + (int64_t)h * DH;
+  float qs[DPL], ks[DPL];
+#pragma unroll
+  for (int c = 0; c < DPL; ++c) { qs[c] = q_scale[lane + 32 * c]; ks[c] = k_scale[lane + 32 * c]; }
+  float v[SMALL_N][DPL];
+#pragma unroll
+  for (int i = 0; i < SMALL_N; ++i) {
+    if (i < n) {
+      float xq[DPL], xk[DPL], sq = 0.f, sk = 0.f;
+#pragma unroll
+      for (int c = 0; c < DPL; ++c) {
+        xq[c] = qb[(int64_t)i * g.q_tok + lane + 32 * c];
+        xk[c] = kb[(int64_t)i * g.k_tok + lane + 32 * c];
+        v[i][c] = kb[(int64_t)i * g.k_tok + I + lane + 32 * c];
+        sq += xq[c] * xq[c];
+        sk += xk[c] * xk[c];
+      }
+      const float nq = fmaxf(sqrtf(warp_sum(sq)), 1e-12f), nk = fmaxf(sqrtf(warp_sum(sk)), 1e-12f);
+#pragma unroll
+      for (int c = 0; c < DPL; ++c) {
+        s_q[w][i][lane + 32 * c] = (xq[c] / nq) * qs[c];
+        s_k[w][i][lane + 32 * c] = (xk[c] / nk) * ks[c];
+      }
+    }
+  }
+  __syncwarp();
+  // scores: lanes stride over the n*n (i, j) pairs
+  const float slope = (g.causal && alibi_slopes) ? alibi_slopes[h] : 0.f;
+  for (int p = lane; p < n * n; p += 32) {
+    const int i = p / n, j = p - i * n;
+    float acc = 0.f;
+    if (!g.causal || j <= i) {
+#pragma unroll 16
+      for (int d = 0; d < DH; ++d) acc = fmaf(s_q[w][i][d], s_k[w][j][d], acc);
+      acc *= g.scale;
+      if (g.causal) acc += -fabsf((float)(j - i)) * slope;
+    } else {
+      acc = -FLT_MAX;
+    }
+    s_p[w][i][j] = acc;
+  }
+  __syncwarp();
+  if (lane < n) {  // softmax, one row per lane
+    float m = -FLT_MAX;
+    for (int j = 0; j < n; ++j) m = fmaxf(m, s_p[w][lane][j]);
+    float sum = 0.f;
+    for (int j = 0; j < n; ++j) { const float e = expf(s_p[w][lane][j] - m); s_p[w][lane][j] = e; sum += e; }
+    const float inv = 1.f / sum;
+    for (int j = 0; j < n; ++j) s_p[w][lane][j] *= inv;
+  }
+  __syncwarp();
+  const int64_t ob = (int64_t)so * g.o_outer + (int64_t)si * g.o_inner + (int64_t)h * DH;
+#pragma unroll
+  for (int i = 0; i < SMALL_N; ++i) {
+    if (i < n) {
+      float o[DPL];
+#pragma unroll
+      for (int c = 0; c < DPL; ++c) o[c] = 0.f;
+#pragma unroll
+      for (int j = 0; j < SMALL_N; ++j) {
+        if (j < n) {
+          const float pv = s_p[w][i][j];
+#pragma unroll
+          for (int c = 0; c < DPL; ++c) o[c] = fmaf(pv, v[j][c], o[c]);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < DPL; ++c) {
+        const int64_t off = ob + (int64_t)i * g.o_tok + lane + 32 * c;
+        if (g.out_bf16) reinterpret_cast<__nv_bfloat16*>(out)[off] = __float2bfloat16_rn(o[c]);
+        else reinterpret_cast<float*>(out)[off] = o[c];
+      }
+    }
+  }
+}
+
+template <int DH>
+static int launch_attention_small(const float* q, const float* kv, const float* q_scale, const float* k_scale,
+                                  const float* alibi_slopes, void* out, const phk_attn_geom_t& g, cudaStream_t st) {
+  const int64_t npairs = (int64_t)g.n_outer * g.n_inner * g.heads;
+  attention_small_kernel<DH><<<(unsigned)((npairs + SMALL_WARPS - 1) / SMALL_WARPS), SMALL_WARPS * 32, 0, st>>>(
+      q, kv, q_scale, k_scale, alibi_slopes, out, g);
+  PHK_LAUNCH_CHECK();
+  return 0;
+}
+
 template <int DH>
 static int launch_attention(const float* q, const float* kv, const float* null_kv, const float* q_scale,
                             const float* k_scale, const float* bias, const uint8_t* key_mask,
@@ -242,6 +355,11 @@ extern "C" int phk_attention(const float* q, const float* kv, const float* null_
   cudaStream_t st = to_stream(s);
   // gridDim.z is limited to 65535: fold sequences if needed
   PHK_REQUIRE((int64_t)g->n_outer * g->n_inner <= 65535, PHK_E_UNSUPPORTED, "phk_attention: more than 65535 sequences");
+  if (g->n_q == g->n_k && g->n_k <= SMALL_N && g->num_null_kv == 0 && !bias && !key_mask &&
+      (g->dim_head == 64 || g->dim_head == 32)) {
+    if (g->dim_head == 64) return launch_attention_small<64>(q, kv, q_scale, k_scale, alibi_slopes, out, *g, st);
+    return launch_attention_small<32>(q, kv, q_scale, k_scale, alibi_slopes, out, *g, st);
+  }
   switch (g->dim_head) {
     case 16: return launch_attention<16>(q, kv, null_kv, q_scale, k_scale, bias, key_mask, alibi_slopes, out, *g, st);
     case 32: return launch_attention<32>(q, kv, null_kv, q_scale, k_scale, bias, key_mask, alibi_slopes, out, *g, st);

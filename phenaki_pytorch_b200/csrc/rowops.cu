@@ -231,43 +231,43 @@ __device__ __forceinline__ int64_t peg_phys_row(int64_t r_log, int T, int HW, in
 __global__ void __launch_bounds__(128) peg_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                   const float* __restrict__ bias, float* __restrict__ y, int T, int H,
                                                   int W, int D, int pad_t0, int layout) {
-  // grid.x = logical positions, threads cover D in float4 steps
-  const int64_t r_log = blockIdx.x;
+  // one CTA per logical position; the 27 neighbour rows are resolved once (the index maps need divisions),
+  // then every thread streams float4 channels: x rows and the tap-major weights are read fully coalesced.
+  __shared__ int s_src[27];
+  __shared__ int s_out;
+  const int r_log = blockIdx.x;
   const int HW = H * W;
-  int rem = (int)(r_log % ((int64_t)T * HW));
-  const int64_t bi = r_log / ((int64_t)T * HW);
-  const int t = rem / HW; rem -= t * HW;
-  const int h = rem / W;
-  const int wq = rem - h * W;
-  const int64_t out_row = peg_phys_row(r_log, T, HW, layout);
+  if (threadIdx.x < 27) {
+    int rem = r_log % (T * HW);
+    const int bi = r_log / (T * HW);
+    const int t = rem / HW; rem -= t * HW;
+    const int h = rem / W;
+    const int wq = rem - h * W;
+    const int kt = threadIdx.x / 9, kh = (threadIdx.x / 3) % 3, kw = threadIdx.x % 3;
+    const int ts = t + kt - pad_t0, hs = h + kh - 1, ws = wq + kw - 1;
+    int src = -1;
+    if (ts >= 0 && ts < T && hs >= 0 && hs < H && ws >= 0 && ws < W)
+      src = (int)peg_phys_row(((int64_t)(bi * T + ts) * H + hs) * W + ws, T, HW, layout);
+    s_src[threadIdx.x] = src;
+    if (threadIdx.x == 0) s_out = (int)peg_phys_row(r_log, T, HW, layout);
+  }
+  __syncthreads();
+  const int64_t out_row = s_out;
   for (int d4 = threadIdx.x; d4 < (D >> 2); d4 += blockDim.x) {
     float4 acc = __ldg(reinterpret_cast<const float4*>(bias) + d4);
 #pragma unroll
-    for (int kt = 0; kt < 3; ++kt) {
-      const int ts = t + kt - pad_t0;
-      if (ts < 0 || ts >= T) continue;
-#pragma unroll
-      for (int kh = 0; kh < 3; ++kh) {
-        const int hs = h + kh - 1;
-        if (hs < 0 || hs >= H) continue;
-#pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-          const int ws = wq + kw - 1;
-          if (ws < 0 || ws >= W) continue;
-          const int64_t src_log = ((bi * T + ts) * H + hs) * W + ws;
-          const int64_t src = peg_phys_row(src_log, T, HW, layout);
-          const float4 xv = __ldg(reinterpret_cast<const float4*>(x + src * D) + d4);
-          const float4 wv = __ldg(reinterpret_cast<const float4*>(w + (int64_t)((kt * 3 + kh) * 3 + kw) * D) + d4);
-          acc.x = fmaf(xv.x, wv.x, acc.x);
-          acc.y = fmaf(xv.y, wv.y, acc.y);
-          acc.z = fmaf(xv.z, wv.z, acc.z);
-          acc.w = fmaf(xv.w, wv.w, acc.w);
-        }
-      }
+    for (int tap = 0; tap < 27; ++tap) {
+      const int src = s_src[tap];
+      if (src < 0) continue;
+      const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (int64_t)src * D) + d4);
+      const float4 wv = __ldg(reinterpret_cast<const float4*>(w + (int64_t)tap * D) + d4);
+      acc.x = fmaf(xv.x, wv.x, acc.x);
+      acc.y = fmaf(xv.y, wv.y, acc.y);
+      acc.z = fmaf(xv.z, wv.z, acc.z);
+      acc.w = fmaf(xv.w, wv.w, acc.w);
     }
     const float4 xs = __ldg(reinterpret_cast<const float4*>(x + out_row * D) + d4);
-    float4 o = make_float4(acc.x + xs.x, acc.y + xs.y, acc.z + xs.z, acc.w + xs.w);
-    reinterpret_cast<float4*>(y + out_row * D)[d4] = o;
+    reinterpret_cast<float4*>(y + out_row * D)[d4] = make_float4(acc.x + xs.x, acc.y + xs.y, acc.z + xs.z, acc.w + xs.w);
   }
 }
 
@@ -374,6 +374,7 @@ __global__ void __launch_bounds__(512) sample_tokens_kernel(const float* __restr
   const float* nr = nul ? nul + lrow * ld : nullptr;
   const float* ur = u ? u + row * (int64_t)V : nullptr;
   const float T = fmaxf(temperature, 1e-10f);
+  const float inv_T = 1.0f / T;
   ArgBest best{-FLT_MAX, 0x7fffffff};
   float m = -FLT_MAX, ssum = 0.f;
   for (int v0 = threadIdx.x * 4; v0 < V; v0 += blockDim.x * 4) {
@@ -387,6 +388,26 @@ __global__ void __launch_bounds__(512) sample_tokens_kernel(const float* __restr
       philox4x32_10((uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
 #pragma unroll
       for (int j = 0; j < 4; ++j) uu[j] = (float)(r[j] >> 8) * (1.0f / 16777216.0f);
+    }
+    if (!ur && v0 + 3 < V && ((ld & 3) == 0)) {
+      // statistical mode (in-kernel noise): vectorised loads and fast intrinsics; not bit-comparable anyway
+      const float4 c4 = *reinterpret_cast<const float4*>(cr + v0);
+      float l4[4] = {c4.x, c4.y, c4.z, c4.w};
+      if (nr) {
+        const float4 n4 = *reinterpret_cast<const float4*>(nr + v0);
+        const float nn[4] = {n4.x, n4.y, n4.z, n4.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) l4[j] = fmaf(l4[j] - nn[j], cond_scale, nn[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float l = l4[j];
+        const float g = -__logf(-__logf(uu[j] + 1e-10f) + 1e-10f);
+        const float y = fmaf(l, inv_T, g);
+        if (y > best.y) { best.y = y; best.idx = v0 + j; }
+        if (l > m) { ssum = ssum * __expf(m - l) + 1.f; m = l; } else { ssum += __expf(l - m); }
+      }
+      continue;
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -598,6 +619,7 @@ extern "C" int phk_peg3d(const float* x, const float* w, const float* b, float* 
   PHK_REQUIRE(B > 0 && T > 0 && H > 0 && W > 0 && D > 0, PHK_E_ARG, "phk_peg3d: bad size");
   PHK_REQUIRE(D % 4 == 0, PHK_E_UNSUPPORTED, "phk_peg3d: dim must be a multiple of 4");
   const int64_t rows = (int64_t)B * T * H * W;
+  PHK_REQUIRE(rows < (1LL << 31), PHK_E_UNSUPPORTED, "phk_peg3d: more than 2^31 positions");
   peg_kernel<<<(unsigned)rows, 128, 0, to_stream(s)>>>(x, w, b, y, T, H, W, D, causal ? 2 : 1, layout);
   PHK_LAUNCH_CHECK();
   return 0;

@@ -381,3 +381,14 @@ def test_critic_scores_and_cfg_combine():
     o = torch.empty(1000, device=DEV)
     L.check(L.lib().phk_cfg_combine(dp(a), dp(bnull), 3.0, L.ptr(o), 1000, sp()))
     assert torch.equal(o.cpu(), bnull + (a - bnull) * 3.0)  # same op order -> bit exact
+
+
+@pytest.mark.parametrize("heads,dh,n,causal", [(8, 64, 9, False), (2, 32, 16, True), (3, 64, 1, True)])
+def test_attention_short_sequence_warp_kernel(heads, dh, n, causal):
+    """n <= 16 without bias/mask/null-kv takes the one-warp-per-(sequence, head) kernel."""
+    S, I = 7, heads * dh
+    q, kv = rnd((S, n, I), 120), rnd((S, n, 2 * I), 121)
+    qs, ks = rnd((dh,), 122).abs() + 0.5, rnd((dh,), 123).abs() + 0.5
+    ref = oracle_attention(q, kv, None, qs, ks, heads=heads, dh=dh, causal=causal)
+    out = run_attention(q, kv, None, qs, ks, heads=heads, dh=dh, n_q=n, n_k=n, causal=causal)
+    torch.testing.assert_close(out, ref, rtol=1e-4, atol=2e-5)
