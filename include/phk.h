@@ -163,6 +163,9 @@ int phk_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* 
                   int64_t seg_len, int64_t seg_stride, int64_t seg_off, int32_t epilogue,
                   phk_stream_t s);
 
+/* debug aid: per-CTA clock64 phase stamps of phk_gemm_bf16 (16 x int64 per CTA); NULL disables */
+int phk_debug_gemm_trace(long long* device_buffer);
+
 /* GEGLU (attention.py:40-43): out[r, j] = gelu_erf(h[r, inner + j]) * h[r, j] */
 int phk_geglu(const float* h, float* out, int64_t rows, int32_t inner, phk_stream_t s);
 

@@ -2,14 +2,16 @@
 //   C[map(m), n] = sum_k A[m,k] * W[n,k]  (+bias) (+residual)        nn.Linear semantics
 // A, W bf16, K-major (row-major [rows, K]); fp32 accumulation in TMEM.
 //
-//   * TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) stages 128x64 A and BLOCK_Nx64 W tiles into a
-//     3-deep shared-memory ring; out-of-bounds rows / K tail are zero-filled by the TMA unit.
-//   * one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BLOCK_N, K=16), four per
-//     64-wide k-block; tcgen05.commit releases the smem slot / publishes the accumulator via mbarriers.
-//   * warp specialisation: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 =
-//     epilogue (tcgen05.ld 32x32b -> registers -> fused bias / residual / row-map / GEGLU -> global).
-//   * 96 KB of smem and 128 TMEM columns per CTA -> two CTAs per SM, so one CTA's epilogue overlaps the
-//     other's main loop.
+// Persistent, warp-specialised (one CTA per SM, static round-robin tile scheduler):
+//   warp 0     TMA producer: cp.async.bulk.tensor.2d (SWIZZLE_128B) stages 128x64 A and 128x64 W tiles into a
+//              4-deep shared-memory ring; out-of-bounds rows / the K tail are zero-filled by the TMA unit.
+//   warp 1     TMEM allocator + MMA issuer: one thread issues tcgen05.mma.cta_group::1.kind::f16
+//              (M=128, N=128, K=16), four per k-block; tcgen05.commit frees the smem slot and publishes the
+//              accumulator.  Two 128-column accumulators in TMEM, so tile i+1 is multiplied while tile i drains.
+//   warps 2..5 epilogue: tcgen05.ld (32x32b) -> registers -> bias -> padded smem tile; then fully coalesced
+//              row-wise write-out (512 B per warp instruction) with the residual add / row map / bf16 pack.
+// Tiles are walked m-fastest so the CTAs running concurrently share the same W tile (L2) while the A panel
+// stays L2-resident.
 // Epilogues: 0 fp32 (+bias,+residual)   1 bf16 (+bias)   2 GEGLU (attention.py:40-43) on W rows packed as
 // [64 value rows | 64 gate rows] per 128-column tile -> bf16 [M, N/2].
 #include "phk_common.cuh"
@@ -20,15 +22,22 @@
 namespace phk {
 
 constexpr int GM = 128;       // BLOCK_M = UMMA_M
+constexpr int GN = 128;       // BLOCK_N = UMMA_N
 constexpr int GK = 64;        // BLOCK_K: 64 bf16 = 128 B = one SWIZZLE_128B row
-constexpr int GSTAGES = 3;
+constexpr int GSTAGES = 4;
 constexpr int GTHREADS = 192;
-constexpr int A_STAGE_BYTES = GM * GK * 2;  // 16 KB
+constexpr int STAGE_BYTES = GM * GK * 2;          // 16 KB per operand per stage
+constexpr int CPAD = 132;                          // fp32 staging row stride (floats): conflict-free 128-bit rows
+constexpr int CSTAGE_BYTES = GM * CPAD * 4;        // 67.6 KB
+constexpr int RING_BYTES = GSTAGES * 2 * STAGE_BYTES;
+constexpr int SMEM_TOTAL = RING_BYTES + CSTAGE_BYTES + 256 /*barriers*/ + 1024 /*manual 1024-B alignment*/;
 
 struct EpiParams {
   void* C; int64_t ldc; int64_t M; int N; int K;
   const float* bias; const float* residual;
   int64_t seg_len, seg_stride, seg_off;
+  int m_tiles, n_tiles;
+  long long* trace;  // debug: per-CTA clock64 stamps of the first tile (NULL in production)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -39,10 +48,13 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 // Bounded wait: a protocol bug must surface as a trap (launch failure), never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  const long long t0 = clock64();
-  while (true) {
+  long long t0 = 0;
+  for (uint32_t spin = 0;; ++spin) {
     uint32_t done;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -52,7 +64,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity)
         : "memory");
     if (done) return;
-    if (clock64() - t0 > 4000000000LL) __trap();
+    if ((spin & 1023u) == 1023u) {
+      if (t0 == 0) t0 = clock64();
+      else if (clock64() - t0 > 4000000000LL) __trap();
+    }
   }
 }
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1) {
@@ -95,30 +110,25 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-template <int BLOCK_N>
-struct GemmSmem {
-  static constexpr int B_STAGE_BYTES = BLOCK_N * GK * 2;
-  static constexpr int TILE_BYTES = GSTAGES * (A_STAGE_BYTES + B_STAGE_BYTES);
-  static constexpr int TOTAL = TILE_BYTES + 128 /*barriers*/ + 1024 /*manual 1024-B alignment*/;
-};
-
-template <int BLOCK_N, int EPI>
+template <int EPI>
 __global__ void __launch_bounds__(GTHREADS, 1) gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmB,
                                                                 EpiParams p) {
   extern __shared__ uint8_t smem_raw[];
-  using SM = GemmSmem<BLOCK_N>;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-B alignment
-  const uint32_t sA = base, sB = base + GSTAGES * A_STAGE_BYTES;
-  const uint32_t bars = base + SM::TILE_BYTES;
-  // full[s] @ bars + 8s ; empty[s] @ bars + 8(S+s) ; tmem_full @ bars + 16S ; tmem ptr slot @ bars + 16S + 8
-  const uint32_t bar_tmem_full = bars + 16 * GSTAGES;
-  const uint32_t tmem_slot = bar_tmem_full + 8;
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sA = base, sB = base + GSTAGES * STAGE_BYTES;
+  float* cstage = reinterpret_cast<float*>(base_ptr + RING_BYTES);
+  const uint32_t bars = base + RING_BYTES + CSTAGE_BYTES;
+  // full[s] @ +8s ; empty[s] @ +8(S+s) ; tmem_full[a] @ +16S+8a ; tmem_empty[a] @ +16S+16+8a ; tmem slot @ +16S+32
+  const uint32_t bar_tfull = bars + 16 * GSTAGES, bar_tempty = bar_tfull + 16, tmem_slot = bar_tfull + 32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t m0 = (int64_t)blockIdx.y * GM;
-  const int n0 = blockIdx.x * BLOCK_N;
   const int num_kb = (p.K + GK - 1) / GK;
+  const int num_tiles = p.m_tiles * p.n_tiles;
+  const long long t_start = clock64();
+#define PHK_STAMP(slot) do { if (p.trace) p.trace[blockIdx.x * 16 + (slot)] = clock64() - t_start; } while (0)
 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -127,11 +137,14 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_bf16_kernel(const __grid_con
       mbar_init(bars + 8 * s, 1);
       mbar_init(bars + 8 * (GSTAGES + s), 1);
     }
-    mbar_init(bar_tmem_full, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tfull + 8 * a, 1);
+      mbar_init(bar_tempty + 8 * a, 4);  // one arrival per epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {  // TMEM: BLOCK_N fp32 accumulator columns (power of two >= 32)
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(BLOCK_N)
+  if (warp == 1) {  // TMEM: two 128-column fp32 accumulators
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(2 * GN)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -140,137 +153,247 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_bf16_kernel(const __grid_con
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  if (threadIdx.x == 0) PHK_STAMP(0);  // setup done
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(bars + 8 * (GSTAGES + stage), phase ^ 1);  // slot free (passes immediately on the first lap)
-        const uint32_t full = bars + 8 * stage;
-        mbar_expect_tx(full, A_STAGE_BYTES + SM::B_STAGE_BYTES);
-        tma_load_2d(&tmA, full, sA + stage * A_STAGE_BYTES, kb * GK, (int)m0);
-        tma_load_2d(&tmB, full, sB + stage * SM::B_STAGE_BYTES, kb * GK, n0);
-        if (++stage == GSTAGES) { stage = 0; phase ^= 1; }
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile % p.m_tiles) * GM, n0 = (tile / p.m_tiles) * GN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(bars + 8 * (GSTAGES + stage), phase ^ 1);  // slot free (passes immediately on the first lap)
+          const uint32_t full = bars + 8 * stage;
+          mbar_expect_tx(full, 2 * STAGE_BYTES);
+          tma_load_2d(&tmA, full, sA + stage * STAGE_BYTES, kb * GK, m0);
+          tma_load_2d(&tmB, full, sB + stage * STAGE_BYTES, kb * GK, n0);
+          if (tile == (int)blockIdx.x && kb == 0) PHK_STAMP(1);            // first TMA issued
+          if (tile == (int)blockIdx.x && kb == num_kb - 1) PHK_STAMP(2);   // last TMA of the first tile issued
+          if (++stage == GSTAGES) { stage = 0; phase ^= 1; }
+        }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       // cute::UMMA::InstrDescriptor: c=F32 (bit 4), a=b=BF16 (bits 7,10), K-major both, N>>3 @17, M>>4 @24
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) |
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(GN >> 3) << 17) |
                              ((uint32_t)(GM >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(bars + 8 * stage, phase);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t use = (uint32_t)(it >> 1);
+        mbar_wait(bar_tempty + 8 * acc, (use & 1) ^ 1);  // epilogue has drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint64_t da = umma_desc(sA + stage * A_STAGE_BYTES);
-        const uint64_t db = umma_desc(sB + stage * SM::B_STAGE_BYTES);
+        const uint32_t d_tmem = tmem_base + acc * GN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(bars + 8 * stage, phase);
+          if (it == 0 && kb == 0) PHK_STAMP(3);            // first operands landed
+          if (it == 0 && kb == num_kb - 1) PHK_STAMP(4);   // last operands landed
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint64_t da = umma_desc(sA + stage * STAGE_BYTES);
+          const uint64_t db = umma_desc(sB + stage * STAGE_BYTES);
 #pragma unroll
-        for (int k = 0; k < GK / 16; ++k)  // +32 B per UMMA_K inside the 128-B swizzle row => +2 in the address field
-          umma_f16(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-        umma_commit(bars + 8 * (GSTAGES + stage));  // frees the smem slot once these MMAs have read it
-        if (++stage == GSTAGES) { stage = 0; phase ^= 1; }
+          for (int k = 0; k < GK / 16; ++k)  // +32 B per UMMA_K inside the 128-B swizzle row => +2 in the address field
+            umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          umma_commit(bars + 8 * (GSTAGES + stage));  // frees the smem slot once these MMAs have read it
+          if (++stage == GSTAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(bar_tfull + 8 * acc);  // accumulator complete
+        if (it == 0) PHK_STAMP(5);                         // all MMAs of the first tile issued
       }
-      umma_commit(bar_tmem_full);  // accumulator complete
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
-    const int lg = warp & 3;  // TMEM lane group this warp may access
-    mbar_wait(bar_tmem_full, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int64_t m = m0 + lg * 32 + lane;
-    const bool row_ok = m < p.M;
-    int64_t orow = m;
-    if (row_ok && p.seg_len > 0) {
-      const int64_t q = m / p.seg_len;
-      orow = q * p.seg_stride + p.seg_off + (m - q * p.seg_len);
-    }
-    const uint32_t trow = tmem_base + ((uint32_t)(lg * 32) << 16);
-    if (EPI == 2) {
-      // [64 value | 64 gate] per 128-wide tile -> out[m, n0/2 + c] = gelu(gate_c) * value_c
-      static_assert(EPI != 2 || BLOCK_N == 128, "GEGLU epilogue needs 128-wide tiles");
-      __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.C) + orow * p.ldc + n0 / 2;
+    const int lg = warp & 3;        // TMEM lane group this warp may access (rows lg*32 .. +31 of the tile)
+    const int ew = warp - 2;        // 0..3: rows ew, ew+4, ... in the coalesced write-out
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t use = (uint32_t)(it >> 1);
+      const int64_t m0 = (int64_t)(tile % p.m_tiles) * GM;
+      const int n0 = (tile / p.m_tiles) * GN;
+      // residual prefetch: while the main loop of this tile runs, pull the residual tile into the staging buffer
+      // with coalesced 512-B row loads (the previous tile's write-out finished at the barrier below)
+      const bool res_vec = EPI == 0 && p.residual && (p.ldc % 4 == 0) && (p.N % 4 == 0) &&
+                           ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
+      if (res_vec) {
+        const int col = n0 + lane * 4;
+        const uint32_t seg_len = (uint32_t)p.seg_len;
+#pragma unroll 1
+        for (int rb = 0; rb < 32; rb += 8) {
+          float4 rv[8];
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t val[32], gate[32];
-        tmem_ld32(trow + c * 32, val);
-        tmem_ld32(trow + 64 + c * 32, gate);
-        if (row_ok) {
+          for (int u = 0; u < 8; ++u) {
+            const int r = (rb + u) * 4 + ew;
+            const uint32_t m = (uint32_t)m0 + r;
+            uint32_t orow = m;
+            if (seg_len > 0) { const uint32_t q = m / seg_len; orow = q * (uint32_t)p.seg_stride + (uint32_t)p.seg_off + (m - q * seg_len); }
+            rv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m < (uint32_t)p.M && col < p.N) rv[u] = *reinterpret_cast<const float4*>(p.residual + (int64_t)orow * p.ldc + col);
+          }
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint32_t pk[4];
+          for (int u = 0; u < 8; ++u)
+            *reinterpret_cast<float4*>(cstage + ((rb + u) * 4 + ew) * CPAD + lane * 4) = rv[u];
+        }
+        epi_bar_sync();  // residual tile complete before the row-per-thread accumulate below
+      }
+      mbar_wait(bar_tfull + 8 * acc, use & 1);
+      if (it == 0 && threadIdx.x == 64) PHK_STAMP(6);      // accumulator ready
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t trow = tmem_base + acc * GN + ((uint32_t)(lg * 32) << 16);
+      float* srow = cstage + (lg * 32 + lane) * CPAD;
+      if (EPI == 2) {
+        // [64 value | 64 gate] -> 64 outputs gelu(gate) * value, staged as fp32 in columns 0..63
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float a = gelu_erf(__uint_as_float(gate[j + 2 * e])) * __uint_as_float(val[j + 2 * e]);
-              const float b = gelu_erf(__uint_as_float(gate[j + 2 * e + 1])) * __uint_as_float(val[j + 2 * e + 1]);
-              pk[e] = pack_bf16x2(a, b);
+        for (int c = 0; c < 2; ++c) {
+          uint32_t val[32], gate[32];
+          tmem_ld32(trow + c * 32, val);
+          tmem_ld32(trow + 64 + c * 32, gate);
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 o;
+            o.x = gelu_erf(__uint_as_float(gate[j])) * __uint_as_float(val[j]);
+            o.y = gelu_erf(__uint_as_float(gate[j + 1])) * __uint_as_float(val[j + 1]);
+            o.z = gelu_erf(__uint_as_float(gate[j + 2])) * __uint_as_float(val[j + 2]);
+            o.w = gelu_erf(__uint_as_float(gate[j + 3])) * __uint_as_float(val[j + 3]);
+            *reinterpret_cast<float4*>(srow + c * 32 + j) = o;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < GN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(trow + c * 32, v);
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                   __uint_as_float(v[j + 3]));
+            if (res_vec) {  // accumulate onto the prefetched residual
+              const float4 rr = *reinterpret_cast<const float4*>(srow + c * 32 + j);
+              o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
             }
-            *reinterpret_cast<uint4*>(out + c * 32 + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<float4*>(srow + c * 32 + j) = o;
           }
         }
       }
-    } else {
-      const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
-#pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld32(trow + c * 32, v);
-        if (!row_ok) continue;
-        const int nb = n0 + c * 32;
-        if (nb >= p.N) continue;
-        float f[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        const bool full = nb + 32 <= p.N;
+      // accumulator drained: hand it back to the MMA warp before the (slower) global write-out
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+      epi_bar_sync();  // whole 128 x 128 tile staged
+      if (it == 0 && threadIdx.x == 64) PHK_STAMP(7);      // tile staged in smem
+
+      // ---- coalesced write-out: one row per warp instruction ----
+      const int ncols = EPI == 2 ? GN / 2 : GN;
+      const int ncol0 = EPI == 2 ? n0 / 2 : n0;
+      const int nlim = EPI == 2 ? p.N / 2 : p.N;
+      if (EPI == 0) {
+        const int col = ncol0 + lane * 4;
+        const bool vec = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && (col + 3 < nlim);
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p.bias) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (full || nb + j < p.N) f[j] += __ldg(p.bias + nb + j);
+          if (col < nlim) bv.x = __ldg(p.bias + col);
+          if (col + 1 < nlim) bv.y = __ldg(p.bias + col + 1);
+          if (col + 2 < nlim) bv.z = __ldg(p.bias + col + 2);
+          if (col + 3 < nlim) bv.w = __ldg(p.bias + col + 3);
         }
-        if (EPI == 0) {
-          float* crow = reinterpret_cast<float*>(p.C) + orow * p.ldc + nb;
-          if (full && vec_ok) {
-            if (p.residual) {
-              const float4* rr = reinterpret_cast<const float4*>(p.residual + orow * p.ldc + nb);
+        const uint32_t seg_len = (uint32_t)p.seg_len;
+        // fast path (whole tile uniform): vector rows, residual already folded in (or absent), full M tile
+        const bool fast = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && (p.N % 4 == 0) &&
+                          (res_vec || !p.residual) && (m0 + GM <= p.M) && seg_len == 0;
+        if (fast) {
+          if (col < nlim) {
+            float* cbase = reinterpret_cast<float*>(p.C) + (m0 + ew) * p.ldc + col;
+            const float* sbase = cstage + ew * CPAD + lane * 4;
+#pragma unroll 1
+            for (int rb = 0; rb < 32; rb += 8) {
+              float4 o[8];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 r = rr[j];
-                f[4 * j] += r.x; f[4 * j + 1] += r.y; f[4 * j + 2] += r.z; f[4 * j + 3] += r.w;
+              for (int u = 0; u < 8; ++u) o[u] = *reinterpret_cast<const float4*>(sbase + (rb + u) * 4 * CPAD);
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                o[u].x += bv.x; o[u].y += bv.y; o[u].z += bv.z; o[u].w += bv.w;
+                *reinterpret_cast<float4*>(cbase + (int64_t)(rb + u) * 4 * p.ldc) = o[u];
               }
             }
+          }
+        } else
+        // general path, 8 rows per batch: all residual loads of a batch are issued before the first store (C may
+        // alias the residual -- in-place x = f(x) + x -- so the compiler cannot reorder them itself)
+#pragma unroll 1
+        for (int rb = 0; rb < 32; rb += 8) {
+          int64_t off[8];
+          float4 rv[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              reinterpret_cast<float4*>(crow)[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-          } else {
-            for (int j = 0; j < 32 && nb + j < p.N; ++j) {
-              float o = f[j];
-              if (p.residual) o += p.residual[orow * p.ldc + nb + j];
-              crow[j] = o;
+          for (int u = 0; u < 8; ++u) {
+            const int r = (rb + u) * 4 + ew;
+            const uint32_t m = (uint32_t)m0 + r;
+            uint32_t orow = m;
+            if (seg_len > 0) { const uint32_t q = m / seg_len; orow = q * (uint32_t)p.seg_stride + (uint32_t)p.seg_off + (m - q * seg_len); }
+            off[u] = (m < (uint32_t)p.M && col < nlim) ? (int64_t)orow * p.ldc + col : -1;
+            rv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!res_vec && vec && p.residual && off[u] >= 0) rv[u] = *reinterpret_cast<const float4*>(p.residual + off[u]);
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            if (off[u] < 0) continue;
+            const int r = (rb + u) * 4 + ew;
+            float4 o = *reinterpret_cast<const float4*>(cstage + r * CPAD + lane * 4);
+            o.x += bv.x + rv[u].x; o.y += bv.y + rv[u].y; o.z += bv.z + rv[u].z; o.w += bv.w + rv[u].w;
+            float* crow = reinterpret_cast<float*>(p.C) + off[u];
+            if (vec) {
+              *reinterpret_cast<float4*>(crow) = o;
+            } else {  // ragged N / unaligned C: scalar tail
+              const float ov[4] = {o.x, o.y, o.z, o.w};
+              for (int j = 0; j < 4; ++j)
+                if (col + j < nlim) crow[j] = ov[j] + ((p.residual && !res_vec) ? p.residual[off[u] + j] : 0.f);
             }
           }
-        } else {
-          __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(p.C) + orow * p.ldc + nb;
-          if (full && (p.ldc % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0)) {
+        }
+      } else {
+        // bf16 outputs: EPI 1 -> 128 columns (4 per lane), EPI 2 -> 64 columns (2 per lane)
+        constexpr int CPL = EPI == 2 ? 2 : 4;
+        const int col = ncol0 + lane * CPL;
+        float bv[CPL];
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              reinterpret_cast<uint4*>(crow)[j] =
-                  make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
-                             pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+        for (int j = 0; j < CPL; ++j) bv[j] = (p.bias && col + j < nlim) ? __ldg(p.bias + col + j) : 0.f;
+        const bool vec = (p.ldc % CPL == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && (col + CPL - 1 < nlim);
+        const uint32_t seg_len = (uint32_t)p.seg_len;
+#pragma unroll 4
+        for (int rr = 0; rr < 32; ++rr) {
+          const int r = rr * 4 + ew;
+          const uint32_t m = (uint32_t)m0 + r;
+          if (m >= (uint32_t)p.M) break;
+          int64_t orow = m;
+          if (seg_len > 0) { const uint32_t q = m / seg_len; orow = q * (uint32_t)p.seg_stride + (uint32_t)p.seg_off + (m - q * seg_len); }
+          float o[CPL];
+#pragma unroll
+          for (int j = 0; j < CPL; ++j) o[j] = cstage[r * CPAD + lane * CPL + j] + bv[j];
+          __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(p.C) + orow * p.ldc + col;
+          if (vec) {
+            if (CPL == 4) *reinterpret_cast<uint2*>(crow) = make_uint2(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]));
+            else *reinterpret_cast<uint32_t*>(crow) = pack_bf16x2(o[0], o[1]);
           } else {
-            for (int j = 0; j < 32 && nb + j < p.N; ++j) crow[j] = __float2bfloat16_rn(f[j]);
+#pragma unroll
+            for (int j = 0; j < CPL; ++j)
+              if (col + j < nlim) crow[j] = __float2bfloat16_rn(o[j]);
           }
         }
       }
+      (void)ncols;
+      epi_bar_sync();  // staging tile free for the next accumulator
+      if (it == 0 && threadIdx.x == 64) PHK_STAMP(8);      // tile written out
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
   __syncthreads();
+  if (threadIdx.x == 0) PHK_STAMP(9);  // CTA done
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BLOCK_N) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * GN) : "memory");
   }
 }
 
@@ -336,16 +459,17 @@ static int get_tensor_map(const void* ptr, int64_t rows, int64_t cols, int64_t l
   return 0;
 }
 
-template <int BLOCK_N, int EPI>
+static long long* g_gemm_trace = nullptr;
+
+template <int EPI>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const EpiParams& p, cudaStream_t st) {
-  using SM = GemmSmem<BLOCK_N>;
   static bool configured = false;
   if (!configured) {
-    PHK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BLOCK_N, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+    PHK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
     configured = true;
   }
-  dim3 grid((unsigned)((p.N + BLOCK_N - 1) / BLOCK_N), (unsigned)((p.M + GM - 1) / GM));
-  gemm_bf16_kernel<BLOCK_N, EPI><<<grid, GTHREADS, SM::TOTAL, st>>>(ta, tb, p);
+  const int tiles = p.m_tiles * p.n_tiles;
+  gemm_bf16_kernel<EPI><<<tiles < kNumSMs ? tiles : kNumSMs, GTHREADS, SMEM_TOTAL, st>>>(ta, tb, p);
   PHK_LAUNCH_CHECK();
   return 0;
 }
@@ -364,18 +488,20 @@ extern "C" int phk_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t 
                   (reinterpret_cast<uintptr_t>(W) & 15) == 0,
               PHK_E_ARG, "phk_gemm_bf16: operands must be 16-byte aligned with leading dimensions multiple of 8 (TMA)");
   PHK_REQUIRE(epilogue >= 0 && epilogue <= 2, PHK_E_ARG, "phk_gemm_bf16: unknown epilogue");
-  PHK_REQUIRE(epilogue != 2 || (N % 128 == 0 && !bias && !residual && ldc % 8 == 0 &&
-                                (reinterpret_cast<uintptr_t>(C) & 15) == 0),
-              PHK_E_ARG, "phk_gemm_bf16: GEGLU epilogue needs N % 128 == 0, aligned bf16 output, no bias/residual");
-  PHK_REQUIRE((M + GM - 1) / GM <= 65535, PHK_E_UNSUPPORTED, "phk_gemm_bf16: M too large");
+  PHK_REQUIRE(epilogue != 2 || (N % 128 == 0 && !bias && !residual), PHK_E_ARG,
+              "phk_gemm_bf16: GEGLU epilogue needs N % 128 == 0 and no bias/residual");
+  PHK_REQUIRE(M < (1LL << 31) - GM, PHK_E_UNSUPPORTED, "phk_gemm_bf16: M too large");
   if (M == 0) return 0;
-  const int block_n = (epilogue == 2 || N > 64) ? 128 : 64;
   CUtensorMap ta, tb;
   PHK_TRY(get_tensor_map(A, M, K, lda, GM, &ta));
-  PHK_TRY(get_tensor_map(W, N, K, ldw, block_n, &tb));
-  EpiParams p{C, ldc, M, N, K, bias, residual, seg_len, seg_stride, seg_off};
+  PHK_TRY(get_tensor_map(W, N, K, ldw, GN, &tb));
+  EpiParams p{C, ldc, M, N, K, bias, residual, seg_len, seg_stride, seg_off, (int)((M + GM - 1) / GM), (N + GN - 1) / GN, g_gemm_trace};
+  PHK_REQUIRE((int64_t)p.m_tiles * p.n_tiles < (1LL << 31), PHK_E_UNSUPPORTED, "phk_gemm_bf16: too many tiles");
   cudaStream_t st = to_stream(s);
-  if (epilogue == 2) return launch_gemm<128, 2>(ta, tb, p, st);
-  if (epilogue == 1) return block_n == 128 ? launch_gemm<128, 1>(ta, tb, p, st) : launch_gemm<64, 1>(ta, tb, p, st);
-  return block_n == 128 ? launch_gemm<128, 0>(ta, tb, p, st) : launch_gemm<64, 0>(ta, tb, p, st);
+  if (epilogue == 2) return launch_gemm<2>(ta, tb, p, st);
+  if (epilogue == 1) return launch_gemm<1>(ta, tb, p, st);
+  return launch_gemm<0>(ta, tb, p, st);
 }
+
+// debug: device buffer of 16 x int64 per CTA receiving clock64 stamps (relative to CTA start) of the first tile
+extern "C" int phk_debug_gemm_trace(long long* device_buffer) { g_gemm_trace = device_buffer; return 0; }
