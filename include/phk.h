@@ -193,6 +193,16 @@ int phk_attention(const float* q, const float* kv, const float* null_kv, const f
                   const float* k_scale, const float* bias, const uint8_t* key_mask,
                   const float* alibi_slopes, void* out, const phk_attn_geom_t* g, phk_stream_t s);
 
+/* Tensor-core (tcgen05) variant of the attention core for long self-attention sequences (MaskGit, n = T'H'W'):
+ * q fp32 [n_seq*n, heads*64], kv fp32 [n_seq*n, 2*heads*64] (token-major projection outputs), bias fp32
+ * [heads, n, n] or NULL -> out bf16 [n_seq*n, heads*64].  dim_head 64, no null-kv / key mask / causal (those take
+ * phk_attention).  q,k are l2-normalised and scaled, v transposed into head-major bf16 operands in `scratch`
+ * (>= phk_attention_tc_scratch_bytes), then S = QK^T and O = PV run on tcgen05 with S, P never leaving the SM. */
+int64_t phk_attention_tc_scratch_bytes(int32_t n_seq, int32_t n, int32_t heads);
+int phk_attention_tc(const float* q, const float* kv, const float* q_scale, const float* k_scale,
+                     const float* bias, void* out_bf16, int32_t n_seq, int32_t n, int32_t heads, float scale,
+                     void* scratch, int64_t scratch_bytes, phk_stream_t s);
+
 /* PEG (attention.py:64-85) + residual: y = x + conv3d_depthwise(pad(x)) + b on a logical
  * (B,T,H,W,D) channels-last view.  layout 0: row = logical flat index (MaskGit, (b,n,d)).
  * layout 1: the C-ViViT temporal quirk -- the caller's physical rows are (b,t,h,w) but the

@@ -91,6 +91,8 @@ PROTOTYPES = {
     "phk_debug_gemm_trace": [vp],
     "phk_geglu": [vp, vp, i64, i32, vp],
     "phk_attention": [vp, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(AttnGeomT), vp],
+    "phk_attention_tc_scratch_bytes": [i32, i32, i32],
+    "phk_attention_tc": [vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, vp, i64, vp],
     "phk_peg3d": [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
     "phk_cpb_scratch_floats": [C.POINTER(CpbT), i32, i32, i32],
     "phk_cpb_bias": [C.POINTER(CpbT), i32, i32, i32, vp, vp, vp],
@@ -108,7 +110,7 @@ PROTOTYPES = {
     "phk_maskgit_forward": [C.POINTER(MaskgitT), vp, i32, i32, i32, i32, i32, vp, i32, vp, vp, i32, i32, vp, vp,
                             vp, i64, i32, vp],
 }
-_RESTYPES = {"phk_last_error": C.c_char_p, "phk_launch_count": i64, "phk_cpb_scratch_floats": i64,
+_RESTYPES = {"phk_attention_tc_scratch_bytes": i64, "phk_last_error": C.c_char_p, "phk_launch_count": i64, "phk_cpb_scratch_floats": i64,
              "phk_cvivit_workspace_bytes": i64, "phk_maskgit_workspace_bytes": i64}
 
 FAMILIES = ["patchify_ln", "layernorm", "gemm_f32", "gemm_bf16", "attention", "peg", "geglu", "lfq", "embed",

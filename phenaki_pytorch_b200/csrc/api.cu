@@ -73,7 +73,8 @@ static int64_t tf_scratch_bytes(const phk_transformer_t* T, int64_t R) {
   int64_t inner = 0;
   for (int l = 0; l < T->depth; ++l) inner = inner > T->layers[l].ff.inner ? inner : T->layers[l].ff.inner;
   // xn, q, kv, o, h(2*inner), g(inner)  -- all fp32 in parity mode
-  return 256 * 8 + R * 4 * (T->dim + I + 2 * I + I + 2 * inner + inner);
+  // + head-major bf16 q/k/v^T operands of the tensor-core attention (bf16 mode): 3 * R * I * 2 bytes + padding
+  return 256 * 12 + R * 4 * (T->dim + I + 2 * I + I + 2 * inner + inner) + R * I * 6 + 64 * 64 * 2 * (R / 64 + 64);
 }
 
 // y = act @ W^T (+bias)(+residual) in the selected contraction type.  `act` is fp32 (parity mode) or bf16.
@@ -134,7 +135,17 @@ static int transformer_forward(const TfCall& c, Arena scratch, float* out, void*
       g.k_outer = c.seq.outer * 2 * I; g.k_inner = c.seq.inner * 2 * I; g.k_tok = c.seq.tok * 2 * I;
       g.o_outer = g.q_outer; g.o_inner = g.q_inner; g.o_tok = g.q_tok;
       g.kv_outer_mod = 0; g.mask_outer_mod = c.self_mask_mod; g.mask_off_from = -1; g.out_bf16 = h16; g.scale = 8.f;
-      PHK_TRY(phk_attention(q, kv, A.null_kv, A.q_scale, A.k_scale, c.attn_bias, c.self_mask, T->alibi_slopes, o, &g, s));
+      const bool tc_ok = h16 && DH == 64 && !T->causal && A.num_null_kv == 0 && !c.self_mask && c.seq.n_inner == 1 &&
+                         c.seq.tok == 1 && c.seq.outer == c.seq.n_tok && c.seq.n_tok >= 64;
+      if (tc_ok) {  // tcgen05 path: S/P stay in TMEM / smem
+        const int64_t ab = phk_attention_tc_scratch_bytes(c.seq.n_outer, c.seq.n_tok, H);
+        Arena tmp = scratch;
+        void* asc = tmp.take(ab);
+        PHK_REQUIRE(asc, PHK_E_WORKSPACE, "transformer: workspace too small (attention operands)");
+        PHK_TRY(phk_attention_tc(q, kv, A.q_scale, A.k_scale, c.attn_bias, o, c.seq.n_outer, c.seq.n_tok, H, 8.f, asc, ab, s));
+      } else {
+        PHK_TRY(phk_attention(q, kv, A.null_kv, A.q_scale, A.k_scale, c.attn_bias, c.self_mask, T->alibi_slopes, o, &g, s));
+      }
       PHK_TRY(linear(c.prec, o, I, A.wo, A.wo_h, I, x, D, R, D, I, nullptr, x, s));
     }
     if (L.has_cross && c.ctx_kv) {  // x = cross_attn(x, context) + x   (attention.py:327-328)

@@ -1,0 +1,409 @@
+// Tensor-core cosine-sim attention for long sequences (MaskGit self-attention, attention.py:146-181 with the 3-D
+// continuous position bias, n = T'H'W' = 576..1024 tokens, dim_head 64), sm_100a only.
+//
+//   phk_attention_prep : q/k fp32 (projection outputs) -> l2-normalise, * q_scale*8 / k_scale, bf16, head-major
+//                        [seq, head, n, 64]; v -> bf16 TRANSPOSED [seq, head, 64, n_pad] so that P.V is a K-major GEMM.
+//   phk_attention_tc   : one CTA per (128-query tile, head, sequence); keys streamed in chunks of 64.
+//       warp 0      TMA producer (3-D tensor maps, SWIZZLE_128B; out-of-range rows zero-filled)
+//       warp 1      tcgen05.mma issuer: S[128x64] = Q K^T (4 x K=16) into TMEM cols 0..63,
+//                   O[128x64] += P V (4 x K=16) into TMEM cols 64..127
+//       warps 2..5  softmax, one query row per thread: tcgen05.ld S -> + bias -> online max/sum (fp32) ->
+//                   P = exp(s - m) as bf16 into a SWIZZLE_128B smem tile (the A operand of the PV MMA);
+//                   O is rescaled in TMEM (tcgen05.ld / tcgen05.st) when the running max moves.
+//   S and P never touch HBM; 48 KB smem + 128 TMEM columns per CTA -> several CTAs per SM overlap MMA and softmax.
+#include "phk_common.cuh"
+#include <cuda.h>
+#include <mutex>
+#include <unordered_map>
+
+namespace phk {
+namespace {
+
+constexpr int AQ = 128;   // queries per CTA (UMMA M)
+constexpr int AKC = 64;   // keys per chunk (UMMA N for S, K extent for PV)
+constexpr int ADH = 64;   // dim_head
+constexpr int ATHREADS = 192;
+constexpr int SQ_BYTES = AQ * ADH * 2, SK_BYTES = AKC * ADH * 2, SV_BYTES = ADH * AKC * 2, SP_BYTES = AQ * AKC * 2;
+constexpr int ATT_SMEM = SQ_BYTES + SK_BYTES + SV_BYTES + SP_BYTES + 128 + 1024;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  long long t0 = 0;
+  for (uint32_t spin = 0;; ++spin) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) return;
+    if ((spin & 1023u) == 1023u) {  // bounded: a protocol bug must trap, not hang the GPU
+      if (t0 == 0) t0 = clock64();
+      else if (clock64() - t0 > 4000000000LL) __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {  // K-major, SWIZZLE_128B (see gemm_tcgen05.cu)
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_c), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]),
+        "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
+        "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+struct AttTcParams {
+  const float* bias;        // [heads, n_q, n_k] fp32 or NULL
+  __nv_bfloat16* out;       // [.., heads*64] bf16; token i of sequence s at (s*o_seq + i*o_tok) elements
+  int n_q, n_k, heads;
+  int64_t o_seq, o_tok;
+};
+
+__global__ void __launch_bounds__(ATHREADS, 2) attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                                   const __grid_constant__ CUtensorMap tmK,
+                                                                   const __grid_constant__ CUtensorMap tmV,
+                                                                   AttTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sQ = base, sK = sQ + SQ_BYTES, sV = sK + SK_BYTES, sP = sV + SV_BYTES;
+  uint8_t* sP_ptr = base_ptr + SQ_BYTES + SK_BYTES + SV_BYTES;
+  const uint32_t bars = sP + SP_BYTES;
+  const uint32_t b_qfull = bars, b_kfull = bars + 8, b_kempty = bars + 16, b_vfull = bars + 24, b_vempty = bars + 32,
+                 b_sfull = bars + 40, b_sempty = bars + 48, b_pfull = bars + 56, b_pvdone = bars + 64,
+                 tmem_slot = bars + 72;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * AQ, h = blockIdx.y, seq = blockIdx.z;
+  const int sh = seq * p.heads + h;
+  const int nch = (p.n_k + AKC - 1) / AKC;
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQ) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmK) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmV) : "memory");
+    mbar_init(b_qfull, 1); mbar_init(b_kfull, 1); mbar_init(b_kempty, 1); mbar_init(b_vfull, 1);
+    mbar_init(b_vempty, 1); mbar_init(b_sfull, 1); mbar_init(b_sempty, 4); mbar_init(b_pfull, 4);
+    mbar_init(b_pvdone, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(128) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  const uint32_t tS = tmem_base, tO = tmem_base + AKC;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(b_qfull, SQ_BYTES);
+      tma_load_3d(&tmQ, b_qfull, sQ, 0, q0, sh);
+      for (int j = 0; j < nch; ++j) {
+        mbar_wait(b_kempty, (j & 1) ^ 1);
+        mbar_expect_tx(b_kfull, SK_BYTES);
+        tma_load_3d(&tmK, b_kfull, sK, 0, j * AKC, sh);
+        mbar_wait(b_vempty, (j & 1) ^ 1);
+        mbar_expect_tx(b_vfull, SV_BYTES);
+        tma_load_3d(&tmV, b_vfull, sV, j * AKC, 0, sh);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // M=128, N=64, bf16 x bf16 -> f32, both K-major (cute::UMMA::InstrDescriptor)
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(AKC >> 3) << 17) | ((uint32_t)(AQ >> 4) << 24);
+      mbar_wait(b_qfull, 0);
+      for (int j = 0; j < nch; ++j) {
+        mbar_wait(b_kfull, j & 1);
+        mbar_wait(b_sempty, (j & 1) ^ 1);  // softmax has read S of the previous chunk
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint64_t dq = umma_desc(sQ), dk = umma_desc(sK);
+#pragma unroll
+        for (int k = 0; k < ADH / 16; ++k) umma_f16(tS, dq + 2 * k, dk + 2 * k, idesc, k != 0);
+        umma_commit(b_kempty);
+        umma_commit(b_sfull);
+        mbar_wait(b_pfull, j & 1);          // P written (and O rescaled) by the softmax warps
+        mbar_wait(b_vfull, j & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint64_t dp = umma_desc(sP), dv = umma_desc(sV);
+#pragma unroll
+        for (int k = 0; k < AKC / 16; ++k) umma_f16(tO, dp + 2 * k, dv + 2 * k, idesc, (j | k) != 0);
+        umma_commit(b_vempty);
+        umma_commit(b_pvdone);
+      }
+    }
+  } else {
+    const int lg = warp & 3;
+    const int r = lg * 32 + lane;       // query row inside the tile == TMEM lane
+    const int qi = q0 + r;
+    const bool valid = qi < p.n_q;
+    const uint32_t lane_off = (uint32_t)(lg * 32) << 16;
+    const float* brow = (p.bias && valid) ? p.bias + ((int64_t)h * p.n_q + qi) * p.n_k : nullptr;
+    const bool bias_vec = (p.n_k % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int j = 0; j < nch; ++j) {
+      const int k0 = j * AKC;
+      // bias for this chunk: issued before waiting for S so the L2 latency overlaps the QK^T MMA
+      float bv[AKC];
+      if (brow && bias_vec && k0 + AKC <= p.n_k) {
+#pragma unroll
+        for (int c = 0; c < AKC / 4; ++c) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(brow + k0) + c);
+          bv[4 * c] = t.x; bv[4 * c + 1] = t.y; bv[4 * c + 2] = t.z; bv[4 * c + 3] = t.w;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < AKC; ++c) bv[c] = (brow && k0 + c < p.n_k) ? __ldg(brow + k0 + c) : 0.f;
+      }
+      mbar_wait(b_sfull, j & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      uint32_t sv[2][32];
+      tmem_ld32(tS + lane_off, sv[0]);
+      tmem_ld32(tS + lane_off + 32, sv[1]);
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(b_sempty);  // S may be overwritten by the next QK^T
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < AKC; ++c) {
+        float s = __uint_as_float(sv[c >> 5][c & 31]) + bv[c];
+        if (k0 + c >= p.n_k) s = -INFINITY;  // zero-filled padding keys
+        bv[c] = s;
+        mx = fmaxf(mx, s);
+      }
+      const float m_new = fmaxf(m_run, mx);
+      const float alpha = __expf(m_run - m_new);  // 0 on the first chunk (m_run = -inf)
+      float lsum = 0.f;
+      uint32_t pk[AKC / 2];
+#pragma unroll
+      for (int c = 0; c < AKC; c += 2) {
+        const float p0 = __expf(bv[c] - m_new), p1 = __expf(bv[c + 1] - m_new);
+        lsum += p0 + p1;
+        pk[c >> 1] = pack_bf16x2(p0, p1);
+      }
+      l_run = l_run * alpha + lsum;
+      m_run = m_new;
+      if (j > 0) {
+        mbar_wait(b_pvdone, (j - 1) & 1);  // previous P.V finished: P buffer free, O stable
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (__any_sync(0xffffffffu, alpha != 1.0f)) {  // rescale the running output in TMEM
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t ov[32];
+            tmem_ld32(tO + lane_off + half * 32, ov);
+#pragma unroll
+            for (int c = 0; c < 32; ++c) ov[c] = __float_as_uint(__uint_as_float(ov[c]) * alpha);
+            tmem_st32(tO + lane_off + half * 32, ov);
+          }
+        }
+      }
+      // P row -> SWIZZLE_128B K-major tile: 16-byte chunk c of row r lives at chunk (c ^ (r & 7))
+      uint8_t* prow = sP_ptr + r * 128;
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<uint4*>(prow + ((c ^ (r & 7)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(b_pfull);
+    }
+    mbar_wait(b_pvdone, (nch - 1) & 1);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const float inv = 1.f / l_run;
+    __nv_bfloat16* orow = p.out + (int64_t)seq * p.o_seq + (int64_t)qi * p.o_tok + h * ADH;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      uint32_t ov[32];
+      tmem_ld32(tO + lane_off + half * 32, ov);
+      if (valid) {
+#pragma unroll
+        for (int c = 0; c < 32; c += 8) {
+          uint32_t w[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            w[e] = pack_bf16x2(__uint_as_float(ov[c + 2 * e]) * inv, __uint_as_float(ov[c + 2 * e + 1]) * inv);
+          *reinterpret_cast<uint4*>(orow + half * 32 + c) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(128) : "memory");
+  }
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// prep: projection outputs (fp32, token-major [rows, heads*64] / [rows, 2*heads*64]) -> head-major bf16 operands
+// --------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) attention_prep_kernel(const float* __restrict__ q, const float* __restrict__ kv,
+                                                             const float* __restrict__ q_scale,
+                                                             const float* __restrict__ k_scale,
+                                                             __nv_bfloat16* __restrict__ Qh, __nv_bfloat16* __restrict__ Kh,
+                                                             __nv_bfloat16* __restrict__ Vt, int n, int n_pad, int heads,
+                                                             float scale) {
+  __shared__ float vt[64][65];
+  const int t0 = blockIdx.x * 64, h = blockIdx.y, seq = blockIdx.z;
+  const int I = heads * 64;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t sh = (int64_t)seq * heads + h;
+  for (int tt = w; tt < 64; tt += 8) {
+    const int tok = t0 + tt;
+    float xq[2] = {0.f, 0.f}, xk[2] = {0.f, 0.f}, xv[2] = {0.f, 0.f};
+    if (tok < n) {
+      const int64_t row = (int64_t)seq * n + tok;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        xq[c] = q[row * I + h * 64 + lane + 32 * c];
+        xk[c] = kv[row * 2 * I + h * 64 + lane + 32 * c];
+        xv[c] = kv[row * 2 * I + I + h * 64 + lane + 32 * c];
+      }
+    }
+    const float nq = fmaxf(sqrtf(warp_sum(xq[0] * xq[0] + xq[1] * xq[1])), 1e-12f);
+    const float nk = fmaxf(sqrtf(warp_sum(xk[0] * xk[0] + xk[1] * xk[1])), 1e-12f);
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const int d = lane + 32 * c;
+      vt[tt][d] = xv[c];
+      if (tok < n) {
+        // F.normalize then * q_scale (attention.py:153-155); the fixed scale 8 (:157) is folded into q (exact in bf16)
+        Qh[(sh * n + tok) * 64 + d] = __float2bfloat16_rn((xq[c] / nq) * q_scale[d] * scale);
+        Kh[(sh * n + tok) * 64 + d] = __float2bfloat16_rn((xk[c] / nk) * k_scale[d]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 64 * 64; idx += blockDim.x) {
+    const int d = idx >> 6, tt = idx & 63;
+    if (t0 + tt < n_pad) Vt[(sh * 64 + d) * n_pad + t0 + tt] = __float2bfloat16_rn(t0 + tt < n ? vt[tt][d] : 0.f);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  });
+  return fn;
+}
+
+// bf16 [d2][d1][d0] with d0 contiguous; box [1][b1][64]; SWIZZLE_128B; zero OOB fill
+int make_map_3d(const void* ptr, int64_t d0, int64_t d1, int64_t d2, int64_t stride1_elems, int64_t stride2_elems,
+                int box1, CUtensorMap* out) {
+  EncodeTiledFn fn = encode_fn();
+  PHK_REQUIRE(fn, PHK_E_UNSUPPORTED, "cuTensorMapEncodeTiled not available from the driver");
+  const cuuint64_t gdim[3] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2};
+  const cuuint64_t gstride[2] = {(cuuint64_t)stride1_elems * 2, (cuuint64_t)stride2_elems * 2};
+  const cuuint32_t box[3] = {64, (cuuint32_t)box1, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PHK_REQUIRE(r == CUDA_SUCCESS, PHK_E_ARG, "cuTensorMapEncodeTiled rejected an attention operand");
+  return 0;
+}
+
+}  // namespace
+}  // namespace phk
+
+using namespace phk;
+
+extern "C" int64_t phk_attention_tc_scratch_bytes(int32_t n_seq, int32_t n, int32_t heads) {
+  const int64_t n_pad = (n + 63) / 64 * 64;
+  return (int64_t)n_seq * heads * (2 * (int64_t)n * 64 + 64 * n_pad) * 2 + 3 * 256;
+}
+
+// Self-attention core on tensor cores: q fp32 [n_seq*n, heads*64], kv fp32 [n_seq*n, 2*heads*64] (token-major
+// projection outputs), bias fp32 [heads, n, n] or NULL -> out bf16 [n_seq*n, heads*64].  dim_head 64, no null-kv,
+// no key mask, not causal (everything else takes phk_attention).  scratch >= phk_attention_tc_scratch_bytes.
+extern "C" int phk_attention_tc(const float* q, const float* kv, const float* q_scale, const float* k_scale,
+                                const float* bias, void* out_bf16, int32_t n_seq, int32_t n, int32_t heads,
+                                float scale, void* scratch, int64_t scratch_bytes, phk_stream_t s) {
+  Prof prof_(FAM_ATTENTION, s, 4.0 * (double)n_seq * heads * n * n * 64);
+  PHK_REQUIRE(q && kv && q_scale && k_scale && out_bf16 && scratch, PHK_E_ARG, "phk_attention_tc: null pointer");
+  PHK_REQUIRE(n_seq > 0 && n > 0 && heads > 0 && n_seq <= 65535 && heads <= 65535, PHK_E_ARG, "phk_attention_tc: bad size");
+  PHK_REQUIRE(scratch_bytes >= phk_attention_tc_scratch_bytes(n_seq, n, heads), PHK_E_WORKSPACE,
+              "phk_attention_tc: scratch too small");
+  cudaStream_t st = to_stream(s);
+  const int64_t n_pad = (n + 63) / 64 * 64;
+  const int64_t SH = (int64_t)n_seq * heads;
+  auto align = [](char* p) { return (char*)(((uintptr_t)p + 255) & ~(uintptr_t)255); };
+  char* base = align((char*)scratch);
+  __nv_bfloat16* Qh = (__nv_bfloat16*)base;
+  __nv_bfloat16* Kh = (__nv_bfloat16*)align(base + SH * n * 64 * 2);
+  __nv_bfloat16* Vt = (__nv_bfloat16*)align((char*)Kh + SH * n * 64 * 2);
+  dim3 pg((unsigned)((n_pad + 63) / 64), (unsigned)heads, (unsigned)n_seq);
+  attention_prep_kernel<<<pg, 256, 0, st>>>(q, kv, q_scale, k_scale, Qh, Kh, Vt, n, (int)n_pad, heads, scale);
+  PHK_LAUNCH_CHECK();
+  CUtensorMap tq, tk, tv;
+  PHK_TRY(make_map_3d(Qh, 64, n, SH, 64, (int64_t)n * 64, AQ, &tq));
+  PHK_TRY(make_map_3d(Kh, 64, n, SH, 64, (int64_t)n * 64, AKC, &tk));
+  PHK_TRY(make_map_3d(Vt, n_pad, 64, SH, n_pad, 64 * n_pad, ADH, &tv));
+  static bool configured = false;
+  if (!configured) {
+    PHK_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    configured = true;
+  }
+  AttTcParams p{bias, (__nv_bfloat16*)out_bf16, n, n, heads, (int64_t)n * heads * 64, (int64_t)heads * 64};
+  dim3 grid((unsigned)((n + AQ - 1) / AQ), (unsigned)heads, (unsigned)n_seq);
+  attention_tc_kernel<<<grid, ATHREADS, ATT_SMEM, st>>>(tq, tk, tv, p);
+  PHK_LAUNCH_CHECK();
+  return 0;
+}

@@ -81,3 +81,28 @@ def test_gemm_bf16_geglu_epilogue(M, inner, K):
     o = out.cpu().float()
     torch.testing.assert_close(o[:, :inner], ref, rtol=1e-2, atol=1e-2)
     assert (o[:, inner:] == 0).all()  # K-padding of the next GEMM must be exact zeros
+
+
+@pytest.mark.parametrize("n_seq,n,heads,with_bias", [(2, 576, 8, True), (3, 64, 2, True), (1, 200, 4, False), (2, 640, 8, True)])
+def test_attention_tensor_core_matches_oracle(n_seq, n, heads, with_bias):
+    """tcgen05 attention (bf16 operands, fp32 softmax) vs the fp32 oracle core: |err| <= 0.02 on O(1) outputs."""
+    from oracle import phenaki_oracle as O
+    dh, I = 64, heads * 64
+    q, kv = TC.seeded_randn((n_seq, n, I), 200), TC.seeded_randn((n_seq, n, 2 * I), 201)
+    qs, ks = TC.seeded_randn((dh,), 202).abs() * 0.3 + 0.7, TC.seeded_randn((dh,), 203).abs() * 0.3 + 0.7
+    bias = TC.seeded_randn((heads, n, n), 204) if with_bias else None
+    split = lambda t: t.reshape(n_seq, n, heads, dh).permute(0, 2, 1, 3)
+    k, v = kv.chunk(2, dim=-1)
+    ref = O.attention_core(split(q), split(k), split(v), qs, ks, heads=heads, attn_bias=bias)
+    ref = ref.permute(0, 2, 1, 3).reshape(n_seq, n, I)
+    lib = L.lib()
+    qd, kvd, qsd, ksd = q.to(DEV), kv.to(DEV), qs.to(DEV), ks.to(DEV)
+    bd = bias.to(DEV) if with_bias else None
+    out = torch.empty((n_seq, n, I), dtype=torch.bfloat16, device=DEV)
+    nbytes = lib.phk_attention_tc_scratch_bytes(n_seq, n, heads)
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=DEV)
+    L.check(lib.phk_attention_tc(L.ptr(qd), L.ptr(kvd), L.ptr(qsd), L.ptr(ksd), L.ptr(bd), L.ptr(out), n_seq, n, heads,
+                                 8.0, L.ptr(scratch), nbytes, L.stream_ptr()), "phk_attention_tc")
+    torch.cuda.synchronize()
+    err = (out.cpu().float() - ref).abs().max().item()
+    assert err <= 0.02, f"max |err| {err}"
