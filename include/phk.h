@@ -304,6 +304,27 @@ int phk_maskgit_forward(const phk_maskgit_t* m, const int64_t* ids, int32_t b, i
                         int32_t return_embeds, const float* pos_bias, float* out, void* workspace,
                         int64_t workspace_bytes, int32_t prec, phk_stream_t s);
 
+/* Fused logits head for the sampling loop (phenaki_pytorch.py:213 + 161 + 83-93 + 506-509 + 547-550): a tcgen05
+ * GEMM whose epilogue applies bias, classifier-free guidance, gumbel noise (in-kernel Philox, same counter layout as
+ * phk_sample_tokens with u == NULL) and reduces argmax / online softmax over the vocabulary, so the (b, n, V) logits
+ * never reach HBM.  emb bf16 [ceil(n_tokens/64)*128, dim]: token t's conditional embedding at row (t/64)*128 + t%64,
+ * its null-condition embedding 64 rows below.  Outputs as phk_sample_tokens. */
+int64_t phk_head_sample_scratch_bytes(int32_t n_tokens);
+int phk_head_sample(const void* emb, int64_t ld_emb, const void* W, int64_t ldw, const float* bias,
+                    int32_t n_tokens, int32_t V, int32_t dim, float cond_scale, float temperature,
+                    uint64_t seed, uint64_t offset, const uint8_t* mask, int64_t* ids, int64_t* pred_out,
+                    float* score_out, void* scratch, int64_t scratch_bytes, phk_stream_t s);
+
+/* One demasking iteration's network half for the sampling loop (phenaki_pytorch.py:495-509, 547-550): MaskGit forward
+ * of the CFG pair (as phk_maskgit_forward with cfg_pair=1) + phk_head_sample.  bf16 weights required, cond_scale != 1,
+ * no priming.  ids_in (b,n) = current (partly masked) ids; ids/pred_out/score_out/mask as phk_sample_tokens. */
+int64_t phk_maskgit_sample_workspace_bytes(const phk_maskgit_t* m, int32_t b, int32_t n, int32_t L);
+int phk_maskgit_sample_step(const phk_maskgit_t* m, const int64_t* ids_in, int32_t b, int32_t n, int32_t pt,
+                            int32_t ph, int32_t pw, const float* ctx_kv, int32_t L, const uint8_t* text_mask,
+                            const uint8_t* video_mask, const float* pos_bias, float cond_scale, float temperature,
+                            uint64_t seed, uint64_t offset, const uint8_t* mask, int64_t* ids, int64_t* pred_out,
+                            float* score_out, void* workspace, int64_t workspace_bytes, phk_stream_t s);
+
 #ifdef __cplusplus
 }
 #endif

@@ -66,6 +66,7 @@ struct TfCall {
   const uint8_t* ctx_mask;     // [ctx_b, L]
   int ctx_mask_off_from;       // sequences >= this see no text (CFG null half), -1: none
   int prec;
+  int pair_interleave;         // bf16 final-norm rows land as [64 cond | 64 null] per 128-row tile (fused sampling head)
 };
 
 static int64_t tf_scratch_bytes(const phk_transformer_t* T, int64_t R) {
@@ -183,7 +184,14 @@ static int transformer_forward(const TfCall& c, Arena scratch, float* out, void*
     }
   }
   if (out) PHK_TRY(phk_layernorm(x, T->out_g, T->out_b, out, nullptr, R, D, 0, 0, 0, 0, s));
-  if (out_h) PHK_TRY(phk_layernorm(x, T->out_g, T->out_b, out_h, nullptr, R, D, 1, 0, 0, 0, s));
+  if (out_h && c.pair_interleave) {
+    // token t: conditional row -> (t/64)*128 + t%64, null-condition row -> +64 (operand layout of phk_head_sample)
+    const int64_t half = R / 2;
+    PHK_TRY(phk_layernorm(x, T->out_g, T->out_b, out_h, nullptr, half, D, 1, 64, 128, 0, s));
+    PHK_TRY(phk_layernorm(x + half * D, T->out_g, T->out_b, out_h, nullptr, half, D, 1, 64, 128, 64, s));
+  } else if (out_h) {
+    PHK_TRY(phk_layernorm(x, T->out_g, T->out_b, out_h, nullptr, R, D, 1, 0, 0, 0, s));
+  }
   return 0;
 }
 
@@ -419,4 +427,64 @@ extern "C" int phk_maskgit_forward(const phk_maskgit_t* m, const int64_t* ids, i
   PHK_TRY(transformer_forward(c, ar, h16 ? nullptr : emb, h16 ? (void*)emb : nullptr, st));
   PHK_TRY(linear(prec, emb, D, m->head_w, m->head_w_h, D, out, m->num_tokens, R, m->num_tokens, D, m->head_b, nullptr, s));
   return 0;
+}
+
+// One demasking iteration's network half, fully fused for the sampling loop (phenaki_pytorch.py:495-509, 547-550):
+// MaskGit forward for the CFG pair, then logits head + CFG + gumbel argmax + confidence in ONE GEMM kernel whose
+// epilogue reduces over the vocabulary -- the (2b, n, V) logits are never written.  bf16 mode, cond_scale != 1,
+// no priming (those cases use phk_maskgit_forward + phk_sample_tokens).
+extern "C" int64_t phk_maskgit_sample_workspace_bytes(const phk_maskgit_t* m, int32_t b, int32_t n, int32_t L) {
+  if (!m || b <= 0 || n <= 0) return -1;
+  const int64_t tokens = (int64_t)b * n;
+  return phk_maskgit_workspace_bytes(m, b, n, L, 1, PHK_PREC_BF16) + ((tokens + 63) / 64) * 128 * m->dim * 2 +
+         phk_head_sample_scratch_bytes((int32_t)tokens) + 1024;
+}
+
+extern "C" int phk_maskgit_sample_step(const phk_maskgit_t* m, const int64_t* ids_in, int32_t b, int32_t n, int32_t pt,
+                                       int32_t ph, int32_t pw, const float* ctx_kv, int32_t L,
+                                       const uint8_t* text_mask, const uint8_t* video_mask, const float* pos_bias,
+                                       float cond_scale, float temperature, uint64_t seed, uint64_t offset,
+                                       const uint8_t* mask, int64_t* ids, int64_t* pred_out, float* score_out,
+                                       void* workspace, int64_t workspace_bytes, phk_stream_t s) {
+  PHK_REQUIRE(m && ids_in && workspace, PHK_E_ARG, "maskgit_sample_step: null pointer");
+  PHK_REQUIRE(b > 0 && n > 0 && (int64_t)pt * ph * pw == n, PHK_E_SHAPE, "video patch shape must cover the token sequence");
+  PHK_REQUIRE(n <= m->max_seq_len, PHK_E_SHAPE,
+              "the video token sequence length is greater than max_seq_len (phenaki_pytorch.py:196)");
+  PHK_REQUIRE(!m->is_critic && m->head_w_h && cond_scale != 1.0f, PHK_E_UNSUPPORTED,
+              "maskgit_sample_step: needs a MaskGit table with bf16 weights and classifier-free guidance");
+  PHK_REQUIRE(!ctx_kv || text_mask, PHK_E_ARG, "maskgit_sample_step: context without text mask");
+  PHK_REQUIRE(workspace_bytes >= phk_maskgit_sample_workspace_bytes(m, b, n, L), PHK_E_WORKSPACE,
+              "maskgit_sample_step: workspace too small");
+  const phk_transformer_t* T = &m->transformer;
+  PHK_TRY(check_transformer(T));
+  cudaStream_t st = to_stream(s);
+  const int D = m->dim;
+  const int64_t tokens = (int64_t)b * n, R = 2 * tokens;
+  Arena ar{(char*)workspace, workspace_bytes, 0};
+  float* x = (float*)ar.take(R * D * 4);
+  float* x_alt = (float*)ar.take(R * D * 4);
+  void* emb_h = ar.take(((tokens + 63) / 64) * 128 * D * 2);
+  const int64_t hb = phk_head_sample_scratch_bytes((int32_t)tokens);
+  void* hsc = ar.take(hb);
+  PHK_REQUIRE(x && x_alt && emb_h && hsc, PHK_E_WORKSPACE, "maskgit_sample_step: workspace too small");
+  if (m->has_bias && !pos_bias) {
+    float* bias_buf = (float*)ar.take((int64_t)m->heads * n * n * 4);
+    float* sc = (float*)ar.take(phk_cpb_scratch_floats(&m->pos_bias, pt, ph, pw) * 4);
+    PHK_REQUIRE(bias_buf && sc, PHK_E_WORKSPACE, "maskgit_sample_step: workspace too small (bias)");
+    PHK_TRY(phk_cpb_bias(&m->pos_bias, pt, ph, pw, sc, bias_buf, s));
+    pos_bias = bias_buf;
+  }
+  PHK_TRY(phk_token_embed(ids_in, m->token_emb, m->pos_emb, x, b, n, D, m->num_tokens + 1, m->shrink_alpha, 2, s));
+  TfCall c;
+  std::memset(&c, 0, sizeof(c));
+  c.T = T; c.x = x; c.x_alt = x_alt; c.R = R;
+  c.seq = SeqView{2 * b, 1, n, n, 0, 1};
+  c.pegB = 2 * b; c.pegT = pt; c.pegH = ph; c.pegW = pw; c.peg_layout = 0;
+  c.attn_bias = m->has_bias ? pos_bias : nullptr;
+  c.self_mask = video_mask; c.self_mask_mod = b;
+  c.ctx_kv = ctx_kv; c.ctx_b = b; c.ctx_L = L; c.ctx_mask = text_mask; c.ctx_mask_off_from = b;
+  c.prec = PHK_PREC_BF16; c.pair_interleave = 1;
+  PHK_TRY(transformer_forward(c, ar, nullptr, emb_h, st));
+  return phk_head_sample(emb_h, D, m->head_w_h, D, m->head_b, (int32_t)tokens, m->num_tokens, D, cond_scale, temperature,
+                         seed, offset, mask, ids, pred_out, score_out, hsc, hb, s);
 }

@@ -25,7 +25,8 @@ constexpr int GM = 128;       // BLOCK_M = UMMA_M
 constexpr int GN = 128;       // BLOCK_N = UMMA_N
 constexpr int GK = 64;        // BLOCK_K: 64 bf16 = 128 B = one SWIZZLE_128B row
 constexpr int GSTAGES = 4;
-constexpr int GTHREADS = 192;
+constexpr int GTHREADS = 192;      // warps: 0 TMA, 1 MMA, 2..5 epilogue
+constexpr int GTHREADS_HEAD = 320; // fused sampling head: + warps 6..9 share the vocabulary-wide epilogue math
 constexpr int STAGE_BYTES = GM * GK * 2;          // 16 KB per operand per stage
 constexpr int CPAD = 132;                          // fp32 staging row stride (floats): conflict-free 128-bit rows
 constexpr int CSTAGE_BYTES = GM * CPAD * 4;        // 67.6 KB
@@ -38,6 +39,12 @@ struct EpiParams {
   int64_t seg_len, seg_stride, seg_off;
   int m_tiles, n_tiles;
   long long* trace;  // debug: per-CTA clock64 stamps of the first tile (NULL in production)
+  // EPI 3 (fused logits head + CFG + gumbel argmax + online softmax, phenaki_pytorch.py:161,83-93,547-550)
+  int n_splits, tiles_per_split, n_tokens;
+  float cond_scale, inv_T;
+  unsigned long long seed, offset;
+  float4* part_f;  // [n_tokens, n_splits] {best_y, l_at_best, max_l, sum_exp}
+  int* part_i;     // [n_tokens, n_splits] argmax index
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -110,10 +117,22 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t* out) {  // identical to rowops.cu
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 template <int EPI>
-__global__ void __launch_bounds__(GTHREADS, 1) gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(GTHREADS_HEAD, 1) gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmB,
                                                                 EpiParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -127,6 +146,21 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_bf16_kernel(const __grid_con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb = (p.K + GK - 1) / GK;
   const int num_tiles = p.m_tiles * p.n_tiles;
+  // tile schedule.  EPI 0..2: round-robin over all tiles, m-fastest.  EPI 3: this CTA owns ONE 128-row tile
+  // (64 tokens x {cond, null}) and walks a contiguous range of vocabulary tiles, keeping its reductions in registers.
+  const int my_tiles = EPI == 3
+      ? max(0, min(p.tiles_per_split, p.n_tiles - (int)(blockIdx.x % p.n_splits) * p.tiles_per_split))
+      : ((int)blockIdx.x < num_tiles ? (num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0);
+  auto tile_of = [&](int i, int& m0, int& n0) {
+    if (EPI == 3) {
+      m0 = (int)(blockIdx.x / p.n_splits) * GM;
+      n0 = ((int)(blockIdx.x % p.n_splits) * p.tiles_per_split + i) * GN;
+    } else {
+      const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+      m0 = (tile % p.m_tiles) * GM;
+      n0 = (tile / p.m_tiles) * GN;
+    }
+  };
   const long long t_start = clock64();
 #define PHK_STAMP(slot) do { if (p.trace) p.trace[blockIdx.x * 16 + (slot)] = clock64() - t_start; } while (0)
 
@@ -155,21 +189,92 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_bf16_kernel(const __grid_con
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   if (threadIdx.x == 0) PHK_STAMP(0);  // setup done
 
+  // ---- EPI 3: per-thread running reductions over the vocabulary (token t = te & 63, column quarter = te >> 6) ----
+  float sm_best = -FLT_MAX, sm_lbest = 0.f, sm_max = -FLT_MAX, sm_sum = 0.f;
+  int sm_idx = 0x7fffffff;
+  auto head_bar = [&]() { asm volatile("bar.sync 2, 256;" ::: "memory"); };
+  // rows t (cond) and 64+t (null) of the staged tile belong to the same token; 256 threads x 32 columns
+  auto head_reduce = [&](int m0, int n0) {
+    const int te = (int)threadIdx.x - 64, t = te & 63, quarter = te >> 6;
+    const int tok = (m0 / GM) * 64 + t;
+    if (tok >= p.n_tokens) return;
+    const float* crow = cstage + t * CPAD + quarter * 32;
+    const float* nrow = cstage + (64 + t) * CPAD + quarter * 32;
+    const unsigned long long ctr0 = p.offset + (unsigned long long)tok * (unsigned long long)((p.N + 3) / 4);
+#pragma unroll 2
+    for (int c = 0; c < 32; c += 4) {
+      const int v0 = n0 + quarter * 32 + c;
+      if (v0 >= p.N) break;
+      const float4 cv = *reinterpret_cast<const float4*>(crow + c);
+      const float4 nv = *reinterpret_cast<const float4*>(nrow + c);
+      const float cc[4] = {cv.x, cv.y, cv.z, cv.w}, nn[4] = {nv.x, nv.y, nv.z, nv.w};
+      float bb[4] = {0.f, 0.f, 0.f, 0.f};
+      if (p.bias) {
+        if (v0 + 3 < p.N) { const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + v0)); bb[0] = b4.x; bb[1] = b4.y; bb[2] = b4.z; bb[3] = b4.w; }
+        else { for (int j = 0; j < 4; ++j) if (v0 + j < p.N) bb[j] = __ldg(p.bias + v0 + j); }
+      }
+      uint32_t rnd[4];
+      const unsigned long long ctr = ctr0 + (unsigned long long)(v0 >> 2);
+      philox4x32_10((uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u, (uint32_t)p.seed, (uint32_t)(p.seed >> 32), rnd);
+      float l4[4];
+      float gm = -FLT_MAX;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float cb = cc[j] + bb[j], nb = nn[j] + bb[j];
+        l4[j] = (v0 + j < p.N) ? fmaf(cb - nb, p.cond_scale, nb) : -FLT_MAX;
+        gm = fmaxf(gm, l4[j]);
+        const float u = (float)(rnd[j] >> 8) * (1.0f / 16777216.0f);
+        const float g = -__logf(-__logf(u + 1e-10f) + 1e-10f);
+        const float y = fmaf(l4[j], p.inv_T, g);
+        if (v0 + j < p.N && y > sm_best) { sm_best = y; sm_idx = v0 + j; sm_lbest = l4[j]; }
+      }
+      if (gm > sm_max) { sm_sum *= __expf(sm_max - gm); sm_max = gm; }  // one rescale per 4 logits
+#pragma unroll
+      for (int j = 0; j < 4; ++j) sm_sum += __expf(l4[j] - sm_max);
+    }
+  };
+  // combine the four column quarters of every token through smem, then one partial per (token, vocabulary split)
+  auto head_publish = [&]() {
+    const int te = (int)threadIdx.x - 64, t = te & 63, quarter = te >> 6;
+    float* ex = cstage;  // [64][3][6]
+    if (quarter > 0) {
+      float* e = ex + (t * 3 + quarter - 1) * 6;
+      e[0] = sm_best; e[1] = sm_lbest; e[2] = sm_max; e[3] = sm_sum; e[4] = __int_as_float(sm_idx);
+    }
+    head_bar();
+    const int tok = (int)(blockIdx.x / p.n_splits) * 64 + t;
+    if (quarter == 0 && tok < p.n_tokens) {
+      for (int qq = 0; qq < 3; ++qq) {
+        const float* e = ex + (t * 3 + qq) * 6;
+        const float oy = e[0], ol = e[1], om = e[2], os = e[3];
+        const int oi = __float_as_int(e[4]);
+        if (oy > sm_best || (oy == sm_best && oi < sm_idx)) { sm_best = oy; sm_idx = oi; sm_lbest = ol; }
+        const float nm = fmaxf(sm_max, om);
+        sm_sum = sm_sum * __expf(sm_max - nm) + os * __expf(om - nm);
+        sm_max = nm;
+      }
+      const int64_t slot = (int64_t)tok * p.n_splits + (blockIdx.x % p.n_splits);
+      p.part_f[slot] = make_float4(sm_best, sm_lbest, sm_max, sm_sum);
+      p.part_i[slot] = sm_idx;
+    }
+  };
+
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile % p.m_tiles) * GM, n0 = (tile / p.m_tiles) * GN;
+      for (int it = 0; it < my_tiles; ++it) {
+        int m0, n0;
+        tile_of(it, m0, n0);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(bars + 8 * (GSTAGES + stage), phase ^ 1);  // slot free (passes immediately on the first lap)
           const uint32_t full = bars + 8 * stage;
           mbar_expect_tx(full, 2 * STAGE_BYTES);
           tma_load_2d(&tmA, full, sA + stage * STAGE_BYTES, kb * GK, m0);
           tma_load_2d(&tmB, full, sB + stage * STAGE_BYTES, kb * GK, n0);
-          if (tile == (int)blockIdx.x && kb == 0) PHK_STAMP(1);            // first TMA issued
-          if (tile == (int)blockIdx.x && kb == num_kb - 1) PHK_STAMP(2);   // last TMA of the first tile issued
+          if (it == 0 && kb == 0) PHK_STAMP(1);            // first TMA issued
+          if (it == 0 && kb == num_kb - 1) PHK_STAMP(2);   // last TMA of the first tile issued
           if (++stage == GSTAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -182,8 +287,7 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_bf16_kernel(const __grid_con
                              ((uint32_t)(GM >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int it = 0; it < my_tiles; ++it) {
         const int acc = it & 1;
         const uint32_t use = (uint32_t)(it >> 1);
         mbar_wait(bar_tempty + 8 * acc, (use & 1) ^ 1);  // epilogue has drained this accumulator
@@ -206,16 +310,28 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_bf16_kernel(const __grid_con
         if (it == 0) PHK_STAMP(5);                         // all MMAs of the first tile issued
       }
     }
+  } else if (warp >= 6) {
+    // ===================== extra math warps of the fused sampling head =====================
+    if (EPI == 3) {
+      for (int it = 0; it < my_tiles; ++it) {
+        int m0, n0;
+        tile_of(it, m0, n0);
+        head_bar();            // tile staged by warps 2..5
+        head_reduce(m0, n0);
+        head_bar();            // tile consumed
+      }
+      head_publish();
+    }
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int lg = warp & 3;        // TMEM lane group this warp may access (rows lg*32 .. +31 of the tile)
     const int ew = warp - 2;        // 0..3: rows ew, ew+4, ... in the coalesced write-out
-    int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int it = 0; it < my_tiles; ++it) {
       const int acc = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
-      const int64_t m0 = (int64_t)(tile % p.m_tiles) * GM;
-      const int n0 = (tile / p.m_tiles) * GN;
+      int m0i, n0;
+      tile_of(it, m0i, n0);
+      const int64_t m0 = m0i;
       // residual prefetch: while the main loop of this tile runs, pull the residual tile into the staging buffer
       // with coalesced 512-B row loads (the previous tile's write-out finished at the barrier below)
       const bool res_vec = EPI == 0 && p.residual && (p.ldc % 4 == 0) && (p.N % 4 == 0) &&
@@ -287,6 +403,12 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_bf16_kernel(const __grid_con
       epi_bar_sync();  // whole 128 x 128 tile staged
       if (it == 0 && threadIdx.x == 64) PHK_STAMP(7);      // tile staged in smem
 
+      if (EPI == 3) {
+        head_bar();                      // + warps 6..9: the staged tile is complete
+        head_reduce((int)m0, n0);
+        head_bar();                      // staging tile free for the next accumulator
+        continue;
+      }
       // ---- coalesced write-out: one row per warp instruction ----
       const int ncols = EPI == 2 ? GN / 2 : GN;
       const int ncol0 = EPI == 2 ? n0 / 2 : n0;
@@ -388,6 +510,7 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_bf16_kernel(const __grid_con
       epi_bar_sync();  // staging tile free for the next accumulator
       if (it == 0 && threadIdx.x == 64) PHK_STAMP(8);      // tile written out
     }
+    if (EPI == 3) head_publish();
   }
   __syncthreads();
   if (threadIdx.x == 0) PHK_STAMP(9);  // CTA done
@@ -461,6 +584,30 @@ static int get_tensor_map(const void* ptr, int64_t rows, int64_t cols, int64_t l
 
 static long long* g_gemm_trace = nullptr;
 
+// combines the per-split partials of the fused head: pred = argmax, score = 1 - softmax(l)[pred]
+// (phenaki_pytorch.py:506-509, 547-550); same output semantics as sample_tokens_kernel.
+__global__ void head_finalize_kernel(const float4* __restrict__ part_f, const int* __restrict__ part_i, int n_splits,
+                                     int n_tokens, const uint8_t* __restrict__ mask, int64_t* __restrict__ ids,
+                                     int64_t* __restrict__ pred_out, float* __restrict__ score_out) {
+  const int tok = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tok >= n_tokens) return;
+  float by = -FLT_MAX, bl = 0.f, m = -FLT_MAX, ssum = 0.f;
+  int bi = 0x7fffffff;
+  for (int s = 0; s < n_splits; ++s) {
+    const float4 f = part_f[(int64_t)tok * n_splits + s];
+    const int i = part_i[(int64_t)tok * n_splits + s];
+    if (f.x > by || (f.x == by && i < bi)) { by = f.x; bi = i; bl = f.y; }
+    const float nm = fmaxf(m, f.z);
+    ssum = ssum * __expf(m - nm) + f.w * __expf(f.z - nm);
+    m = nm;
+  }
+  const float prob = __expf(bl - m) / ssum;
+  const bool mk = mask ? mask[tok] != 0 : true;
+  if (pred_out) pred_out[tok] = bi;
+  if (ids && mk) ids[tok] = bi;
+  if (score_out) score_out[tok] = mk ? 1.0f - prob : -1e4f;
+}
+
 template <int EPI>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const EpiParams& p, cudaStream_t st) {
   static bool configured = false;
@@ -469,7 +616,8 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const EpiPa
     configured = true;
   }
   const int tiles = p.m_tiles * p.n_tiles;
-  gemm_bf16_kernel<EPI><<<tiles < kNumSMs ? tiles : kNumSMs, GTHREADS, SMEM_TOTAL, st>>>(ta, tb, p);
+  const int grid = EPI == 3 ? p.m_tiles * p.n_splits : (tiles < kNumSMs ? tiles : kNumSMs);
+  gemm_bf16_kernel<EPI><<<grid, EPI == 3 ? GTHREADS_HEAD : GTHREADS, SMEM_TOTAL, st>>>(ta, tb, p);
   PHK_LAUNCH_CHECK();
   return 0;
 }
@@ -495,7 +643,7 @@ extern "C" int phk_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t 
   CUtensorMap ta, tb;
   PHK_TRY(get_tensor_map(A, M, K, lda, GM, &ta));
   PHK_TRY(get_tensor_map(W, N, K, ldw, GN, &tb));
-  EpiParams p{C, ldc, M, N, K, bias, residual, seg_len, seg_stride, seg_off, (int)((M + GM - 1) / GM), (N + GN - 1) / GN, g_gemm_trace};
+  EpiParams p{C, ldc, M, N, K, bias, residual, seg_len, seg_stride, seg_off, (int)((M + GM - 1) / GM), (N + GN - 1) / GN, g_gemm_trace, 1, 0, 0, 1.f, 1.f, 0ull, 0ull, nullptr, nullptr};
   PHK_REQUIRE((int64_t)p.m_tiles * p.n_tiles < (1LL << 31), PHK_E_UNSUPPORTED, "phk_gemm_bf16: too many tiles");
   cudaStream_t st = to_stream(s);
   if (epilogue == 2) return launch_gemm<2>(ta, tb, p, st);
@@ -505,3 +653,48 @@ extern "C" int phk_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t 
 
 // debug: device buffer of 16 x int64 per CTA receiving clock64 stamps (relative to CTA start) of the first tile
 extern "C" int phk_debug_gemm_trace(long long* device_buffer) { g_gemm_trace = device_buffer; return 0; }
+
+// Fused logits head (phenaki_pytorch.py:213 + 161 + 83-93 + 506-509 + 547-550): the (b, N, V) logits never reach HBM.
+// emb: bf16 [m_tiles*128, dim] with row (t/64)*128 + t%64 = conditional embedding of token t and row +64 = the
+// null-condition (cond_drop_prob=1) embedding of the same token (rows of missing tokens may hold anything).
+// W: to_logits.weight bf16 [V, dim]; bias fp32 [V].  Noise: in-kernel Philox4x32-10 with the counter layout of
+// phk_sample_tokens (statistical mode).  scratch >= phk_head_sample_scratch_bytes(n_tokens).
+extern "C" int64_t phk_head_sample_scratch_bytes(int32_t n_tokens) {
+  const int m_tiles = (n_tokens + 63) / 64;
+  const int n_splits = m_tiles >= kNumSMs ? 1 : kNumSMs / m_tiles;
+  return (int64_t)n_tokens * n_splits * 20 + 512;
+}
+
+extern "C" int phk_head_sample(const void* emb, int64_t ld_emb, const void* W, int64_t ldw, const float* bias,
+                               int32_t n_tokens, int32_t V, int32_t dim, float cond_scale, float temperature,
+                               uint64_t seed, uint64_t offset, const uint8_t* mask, int64_t* ids, int64_t* pred_out,
+                               float* score_out, void* scratch, int64_t scratch_bytes, phk_stream_t s) {
+  Prof prof_(FAM_GEMM_BF16, s, 4.0 * (double)n_tokens * V * dim);
+  PHK_REQUIRE(emb && W && scratch, PHK_E_ARG, "phk_head_sample: null pointer");
+  PHK_REQUIRE(n_tokens > 0 && V > 0 && dim > 0 && ld_emb >= dim && ldw >= dim, PHK_E_ARG, "phk_head_sample: bad size");
+  PHK_REQUIRE(ld_emb % 8 == 0 && ldw % 8 == 0 && (reinterpret_cast<uintptr_t>(emb) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(W) & 15) == 0,
+              PHK_E_ARG, "phk_head_sample: operands must be 16-byte aligned with leading dimensions multiple of 8 (TMA)");
+  PHK_REQUIRE(scratch_bytes >= phk_head_sample_scratch_bytes(n_tokens), PHK_E_WORKSPACE, "phk_head_sample: scratch too small");
+  const int m_tiles = (n_tokens + 63) / 64;
+  const int n_tiles = (V + GN - 1) / GN;
+  int n_splits = m_tiles >= kNumSMs ? 1 : kNumSMs / m_tiles;
+  if (n_splits > n_tiles) n_splits = n_tiles;
+  const int tps = (n_tiles + n_splits - 1) / n_splits;
+  CUtensorMap ta, tb;
+  PHK_TRY(get_tensor_map(emb, (int64_t)m_tiles * GM, dim, ld_emb, GM, &ta));
+  PHK_TRY(get_tensor_map(W, V, dim, ldw, GN, &tb));
+  char* sc = (char*)(((uintptr_t)scratch + 255) & ~(uintptr_t)255);
+  float4* part_f = (float4*)sc;
+  int* part_i = (int*)(sc + (int64_t)n_tokens * n_splits * 16);
+  const float T = temperature > 1e-10f ? temperature : 1e-10f;
+  EpiParams p{nullptr, 0, (int64_t)m_tiles * GM, V, dim, bias, nullptr, 0, 0, 0, m_tiles, n_tiles, nullptr,
+              n_splits, tps, n_tokens, cond_scale, 1.0f / T, (unsigned long long)seed, (unsigned long long)offset,
+              part_f, part_i};
+  cudaStream_t st = to_stream(s);
+  PHK_TRY(launch_gemm<3>(ta, tb, p, st));
+  head_finalize_kernel<<<(n_tokens + 127) / 128, 128, 0, st>>>(part_f, part_i, n_splits, n_tokens, mask, ids, pred_out,
+                                                              score_out);
+  PHK_LAUNCH_CHECK();
+  return 0;
+}

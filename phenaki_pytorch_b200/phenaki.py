@@ -131,6 +131,27 @@ class _TokenTransformer(nn.Module):
                                             L.stream_ptr()), "phk_maskgit_forward")
         return out
 
+    def _sample_step(self, ids_in, patch_shape, *, ctx_kv, ctx_len, text_mask, cond_scale, temperature, seed,
+                     offset, mask, ids, pred, scores):
+        """Fused demasking iteration (bf16 mode): CFG-pair forward + logits head + gumbel argmax + confidence in
+        libphk (phk_maskgit_sample_step); the (2b, n, V) logits are never materialised."""
+        lib = L.lib()
+        b, n = ids_in.shape
+        dev = ids_in.device
+        with torch.cuda.device(dev):
+            table = self._table()
+            nbytes = lib.phk_maskgit_sample_workspace_bytes(C.byref(table), b, n, ctx_len)
+            ws = self._ws.get(nbytes, dev)
+            bias = self._pos_bias(table, patch_shape, dev)
+            if text_mask is not None:
+                text_mask = L.require_cuda(text_mask.to(torch.uint8), "text mask")
+            pt, ph, pw = (int(v) for v in patch_shape)
+            L.check(lib.phk_maskgit_sample_step(C.byref(table), L.ptr(ids_in), b, n, pt, ph, pw, L.ptr(ctx_kv), ctx_len,
+                                                L.ptr(text_mask), None, L.ptr(bias), float(cond_scale),
+                                                float(temperature), seed, offset, L.ptr(mask), L.ptr(ids), L.ptr(pred),
+                                                L.ptr(scores), L.ptr(ws), ws.numel(), L.stream_ptr()),
+                    "phk_maskgit_sample_step")
+
     def _prepare(self, x, text_mask, video_patch_shape, context, cond_drop_prob):
         if x.ndim == 4:
             video_patch_shape = tuple(x.shape[1:])
@@ -345,6 +366,7 @@ class Phenaki(nn.Module):
         assert cond_drop_prob > 0.0
         self.cond_drop_prob = cond_drop_prob
         self._rng_calls = 0
+        self.fused_head = True  # bf16 mode: logits head + CFG + gumbel argmax fused into one GEMM (no (b,n,V) logits)
 
     # ---- the demasking loop (phenaki_pytorch.py:473-550) -------------------------------------------------
     @torch.no_grad()
@@ -392,20 +414,28 @@ class Phenaki(nn.Module):
                 if plen:
                     inp[:, plen:].copy_(ids)
                 use_cfg = cond_scale != 1
-                logits = mg._run(inp, patch_shape, ctx_kv=ctx_kv, ctx_len=ctx_len, text_mask=text_mask,
-                                 cfg_pair=use_cfg)
                 temperature = starting_temperature * (til_x0 / steps)
-                u = None
-                if noise_fn is not None:
-                    u = L.require_cuda(noise_fn((b, n, vocab), f"gumbel{step}"), "gumbel noise", torch.float32)
                 offset = self._rng_calls * ((b * n * ((vocab + 3) // 4)) + 1)
                 self._rng_calls += 1
-                cond = logits[:b]
-                null = logits[b:] if use_cfg else None
-                L.check(lib.phk_sample_tokens(L.ptr(cond), L.ptr(null), vocab, L.ptr(u), seed & (2 ** 64 - 1),
-                                              offset, float(cond_scale), float(temperature), L.ptr(mask),
-                                              L.ptr(ids), L.ptr(pred), L.ptr(scores), b * n, vocab, *seg,
-                                              L.stream_ptr()), "phk_sample_tokens")
+                fused = (self.fused_head and mg.precision == L.PREC_BF16 and noise_fn is None and use_cfg and plen == 0
+                         and trace is None)
+                if fused:
+                    # one launch sequence per iteration, logits never leave the SM (statistical-noise mode)
+                    mg._sample_step(inp, patch_shape, ctx_kv=ctx_kv, ctx_len=ctx_len, text_mask=text_mask,
+                                    cond_scale=cond_scale, temperature=temperature, seed=seed & (2 ** 64 - 1),
+                                    offset=offset, mask=mask, ids=ids, pred=pred, scores=scores)
+                else:
+                    logits = mg._run(inp, patch_shape, ctx_kv=ctx_kv, ctx_len=ctx_len, text_mask=text_mask,
+                                     cfg_pair=use_cfg)
+                    u = None
+                    if noise_fn is not None:
+                        u = L.require_cuda(noise_fn((b, n, vocab), f"gumbel{step}"), "gumbel noise", torch.float32)
+                    cond = logits[:b]
+                    null = logits[b:] if use_cfg else None
+                    L.check(lib.phk_sample_tokens(L.ptr(cond), L.ptr(null), vocab, L.ptr(u), seed & (2 ** 64 - 1),
+                                                  offset, float(cond_scale), float(temperature), L.ptr(mask),
+                                                  L.ptr(ids), L.ptr(pred), L.ptr(scores), b * n, vocab, *seg,
+                                                  L.stream_ptr()), "phk_sample_tokens")
                 have_scores = True
                 if trace is not None:
                     trace.append(dict(step=step, mask=mask.bool().clone(), pred=pred.clone(), ids=ids.clone()))

@@ -84,3 +84,54 @@ def test_sampling_runs_in_bf16_mode_and_is_deterministic():
                               noise_fn=lambda s, t: tape(s, t).to(DEV)).cpu())
     assert torch.equal(outs[0], outs[1])
     assert (outs[0] < C.SAMPLE_MASKGIT["num_tokens"]).all()
+
+
+def test_fused_sampling_head_matches_unfused_path():
+    """phk_maskgit_sample_step (logits never materialised) vs phk_maskgit_forward + phk_sample_tokens with the same
+    Philox counters: identical sampled ids (same GEMM arithmetic), confidence within 1e-4 (softmax summation order)."""
+    import ctypes as Cc
+    torch.manual_seed(7)
+    cfg = dict(dim=128, num_tokens=1000, max_seq_len=256, heads=2, dim_head=64, depth=2, dim_context=96)
+    mg = P.MaskGit(**cfg).to(DEV).eval()
+    mg.precision = L.PREC_BF16
+    b, shape = 3, (3, 6, 8)
+    n = 144
+    g = torch.Generator().manual_seed(1)
+    ids0 = torch.randint(0, cfg["num_tokens"] + 1, (b, n), generator=g).to(DEV)
+    ctx = C.synthetic_text_embeds(b, 5, 96, (5, 2, 4), 2).to(DEV)
+    tmask = torch.any(ctx != 0, dim=-1)
+    mask = (torch.rand(b, n, generator=g) < 0.7).to(torch.uint8).to(DEV)
+    kv = mg.context_kv(ctx)
+    lib = L.lib()
+    seed, offset, scale, temp = 1234, 77, 3.0, 0.6
+    # unfused
+    logits = mg._run(ids0, shape, ctx_kv=kv, ctx_len=5, text_mask=tmask, cfg_pair=True)
+    ids_a, pred_a, sc_a = ids0.clone(), torch.empty_like(ids0), torch.empty((b, n), device=DEV)
+    L.check(lib.phk_sample_tokens(L.ptr(logits[:b]), L.ptr(logits[b:]), 1000, None, seed, offset, scale, temp,
+                                  L.ptr(mask), L.ptr(ids_a), L.ptr(pred_a), L.ptr(sc_a), b * n, 1000, 0, 0, 0,
+                                  L.stream_ptr()))
+    # fused
+    ids_b, pred_b, sc_b = ids0.clone(), torch.empty_like(ids0), torch.empty((b, n), device=DEV)
+    mg._sample_step(ids_b, shape, ctx_kv=kv, ctx_len=5, text_mask=tmask, cond_scale=scale, temperature=temp, seed=seed,
+                    offset=offset, mask=mask, ids=ids_b, pred=pred_b, scores=sc_b)
+    torch.cuda.synchronize()
+    assert torch.equal(pred_a, pred_b)
+    assert torch.equal(ids_a, ids_b)
+    torch.testing.assert_close(sc_a, sc_b, rtol=1e-4, atol=1e-4)
+
+
+def test_bf16_sampling_with_fused_head_is_deterministic():
+    case = C.SAMPLE_CASES["confidence"]
+    torch.manual_seed(case["seed"])
+    cv = P.CViViT(**C.SAMPLE_CVIVIT)
+    mg = P.MaskGit(dim=128, num_tokens=256, max_seq_len=64, heads=2, dim_head=64, depth=2, dim_context=48)
+    mg.precision = L.PREC_BF16
+    ph = P.Phenaki(cvivit=cv.to(DEV), maskgit=mg.to(DEV), steps=6, text_embed_dim=48)
+    ctx = C.synthetic_text_embeds(2, 6, 48, (6, 3), 3).to(DEV)
+    outs = []
+    for seed in (11, 11, 12):
+        torch.manual_seed(seed)
+        ph._rng_calls = 0
+        outs.append(ph.sample(num_frames=7, text_embeds=ctx, return_token_ids=True).cpu())
+    assert torch.equal(outs[0], outs[1]) and not torch.equal(outs[0], outs[2])
+    assert (outs[0] >= 0).all() and (outs[0] < 256).all()
