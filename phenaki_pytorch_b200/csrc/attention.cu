@@ -32,6 +32,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const float* __r
                                                                 const uint8_t* __restrict__ key_mask,
                                                                 const float* __restrict__ alibi_slopes,
                                                                 void* __restrict__ out, phk_attn_geom_t g) {
+  pdl_prologue();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   AttSmem<DH>& sm = *reinterpret_cast<AttSmem<DH>*>(smem_raw);
   const int qt = blockIdx.x, h = blockIdx.y, seq = blockIdx.z;
@@ -218,6 +219,7 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) attention_small_kernel(
     const float* __restrict__ q, const float* __restrict__ kv, const float* __restrict__ q_scale,
     const float* __restrict__ k_scale, const float* __restrict__ alibi_slopes, void* __restrict__ out,
     phk_attn_geom_t g) {
+  pdl_prologue();
   constexpr int DPL = DH / 32;
   __shared__ float s_q[SMALL_WARPS][SMALL_N][DH + 1];
   __shared__ float s_k[SMALL_WARPS][SMALL_N][DH + 1];
@@ -307,12 +309,110 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) attention_small_kernel(
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Few keys (null-kv + text length <= 64): MaskGit / TokenCritic cross-attention over the T5 context
+// (attention.py:137-168 with num_null_kv = 2).  The 64-wide key tile of the generic kernel would be ~70 % padding
+// and every CTA would re-normalise the same keys, so here the (<= 64) normalised keys and values of one
+// (context sequence, head) are staged once per CTA and each WARP streams queries: lane = d, scores by warp
+// reduction, online softmax with warp-uniform scalars, P.V accumulated in registers.
+// ------------------------------------------------------------------------------------------
+constexpr int FEW_KEYS = 64, FEW_WARPS = 8, FEW_QTILE = 64;
+
+template <int DH>
+__global__ void __launch_bounds__(FEW_WARPS * 32) attention_fewkeys_kernel(
+    const float* __restrict__ q, const float* __restrict__ kv, const float* __restrict__ null_kv,
+    const float* __restrict__ q_scale, const float* __restrict__ k_scale, const uint8_t* __restrict__ key_mask,
+    void* __restrict__ out, phk_attn_geom_t g) {
+  pdl_prologue();
+  constexpr int DPL = DH / 32;
+  __shared__ float s_k[FEW_KEYS][DH];
+  __shared__ float s_v[FEW_KEYS][DH];
+  __shared__ uint8_t s_ok[FEW_KEYS];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int h = blockIdx.y, seq = blockIdx.z;
+  const int so = seq / g.n_inner, si = seq - so * g.n_inner;
+  const int kv_so = g.kv_outer_mod > 0 ? so % g.kv_outer_mod : so;
+  const int mask_row = g.mask_outer_mod > 0 ? so % g.mask_outer_mod : so;
+  const bool mask_dropped = g.mask_off_from >= 0 && so >= g.mask_off_from;
+  const int I = g.heads * DH, nnull = g.num_null_kv, nk = g.n_k + nnull;
+  const float* kbase = kv + (int64_t)kv_so * g.k_outer + (int64_t)si * g.k_inner + (int64_t)h * DH;
+  for (int j = w; j < nk; j += FEW_WARPS) {
+    const float* kp;
+    const float* vp;
+    if (j < nnull) { kp = null_kv + ((int64_t)h * 2 * nnull + 2 * j) * DH; vp = kp + DH; }   // 'h (n r) d' (:148)
+    else { kp = kbase + (int64_t)(j - nnull) * g.k_tok; vp = kp + I; }
+    float x[DPL], ss = 0.f;
+#pragma unroll
+    for (int c = 0; c < DPL; ++c) { x[c] = kp[lane + 32 * c]; ss += x[c] * x[c]; s_v[j][lane + 32 * c] = vp[lane + 32 * c]; }
+    const float nrm = fmaxf(sqrtf(warp_sum(ss)), 1e-12f);
+#pragma unroll
+    for (int c = 0; c < DPL; ++c) s_k[j][lane + 32 * c] = (x[c] / nrm) * k_scale[lane + 32 * c];
+    if (lane == 0) {
+      const int kj = j - nnull;
+      s_ok[j] = !(key_mask && kj >= 0 && (mask_dropped || !key_mask[(int64_t)mask_row * g.n_k + kj]));
+    }
+  }
+  __syncthreads();
+  float qs[DPL];
+#pragma unroll
+  for (int c = 0; c < DPL; ++c) qs[c] = q_scale[lane + 32 * c] * g.scale;
+  const float* qb = q + (int64_t)so * g.q_outer + (int64_t)si * g.q_inner + (int64_t)h * DH;
+  const int64_t ob = (int64_t)so * g.o_outer + (int64_t)si * g.o_inner + (int64_t)h * DH;
+  const int q_end = min(g.n_q, (int)(blockIdx.x + 1) * FEW_QTILE);
+  for (int qi = blockIdx.x * FEW_QTILE + w; qi < q_end; qi += FEW_WARPS) {
+    float x[DPL], ss = 0.f;
+#pragma unroll
+    for (int c = 0; c < DPL; ++c) { x[c] = qb[(int64_t)qi * g.q_tok + lane + 32 * c]; ss += x[c] * x[c]; }
+    const float nrm = fmaxf(sqrtf(warp_sum(ss)), 1e-12f);
+#pragma unroll
+    for (int c = 0; c < DPL; ++c) x[c] = (x[c] / nrm) * qs[c];  // scale (8) folded into the query
+    // scores: key j's dot product is reduced across the warp and kept by lane (j & 31), slot (j >> 5); the softmax
+    // then costs one exp per lane instead of two per key
+    float sc[2] = {-INFINITY, -INFINITY};
+    for (int j = 0; j < nk; ++j) {
+      float d = 0.f;
+#pragma unroll
+      for (int c = 0; c < DPL; ++c) d = fmaf(x[c], s_k[j][lane + 32 * c], d);
+      float s = warp_sum(d);
+      if (!s_ok[j]) s = -FLT_MAX;  // masked_fill(~mask, -finfo.max) (:168)
+      if ((j & 31) == lane) sc[j >> 5] = s;
+    }
+    const float m = warp_max(fmaxf(sc[0], sc[1]));
+    const float p0 = __expf(sc[0] - m), p1 = __expf(sc[1] - m);  // exp(-inf) = 0 for unused slots
+    const float l = warp_sum(p0 + p1);
+    float o[DPL];
+#pragma unroll
+    for (int c = 0; c < DPL; ++c) o[c] = 0.f;
+    for (int j = 0; j < nk; ++j) {
+      const float pj = __shfl_sync(0xffffffffu, (j >> 5) ? p1 : p0, j & 31);
+#pragma unroll
+      for (int c = 0; c < DPL; ++c) o[c] = fmaf(pj, s_v[j][lane + 32 * c], o[c]);
+    }
+    const float inv = 1.f / l;
+#pragma unroll
+    for (int c = 0; c < DPL; ++c) {
+      const int64_t off = ob + (int64_t)qi * g.o_tok + lane + 32 * c;
+      if (g.out_bf16) reinterpret_cast<__nv_bfloat16*>(out)[off] = __float2bfloat16_rn(o[c] * inv);
+      else reinterpret_cast<float*>(out)[off] = o[c] * inv;
+    }
+  }
+}
+
+template <int DH>
+static int launch_attention_fewkeys(const float* q, const float* kv, const float* null_kv, const float* q_scale,
+                                    const float* k_scale, const uint8_t* key_mask, void* out, const phk_attn_geom_t& g,
+                                    cudaStream_t st) {
+  dim3 grid((unsigned)((g.n_q + FEW_QTILE - 1) / FEW_QTILE), (unsigned)g.heads, (unsigned)(g.n_outer * g.n_inner));
+  PHK_CUDA(launch_pdl(attention_fewkeys_kernel<DH>, dim3(grid), dim3(FEW_WARPS * 32), (size_t)(0), st, q, kv, null_kv, q_scale, k_scale, key_mask, out, g));
+  PHK_LAUNCH_CHECK();
+  return 0;
+}
+
 template <int DH>
 static int launch_attention_small(const float* q, const float* kv, const float* q_scale, const float* k_scale,
                                   const float* alibi_slopes, void* out, const phk_attn_geom_t& g, cudaStream_t st) {
   const int64_t npairs = (int64_t)g.n_outer * g.n_inner * g.heads;
-  attention_small_kernel<DH><<<(unsigned)((npairs + SMALL_WARPS - 1) / SMALL_WARPS), SMALL_WARPS * 32, 0, st>>>(
-      q, kv, q_scale, k_scale, alibi_slopes, out, g);
+  PHK_CUDA(launch_pdl(attention_small_kernel<DH>, dim3((unsigned)((npairs + SMALL_WARPS - 1) / SMALL_WARPS)), dim3(SMALL_WARPS * 32), (size_t)(0), st, q, kv, q_scale, k_scale, alibi_slopes, out, g));
   PHK_LAUNCH_CHECK();
   return 0;
 }
@@ -328,8 +428,7 @@ static int launch_attention(const float* q, const float* kv, const float* null_k
     configured = true;
   }
   dim3 grid((unsigned)((g.n_q + TQ - 1) / TQ), (unsigned)g.heads, (unsigned)(g.n_outer * g.n_inner));
-  attention_kernel<DH><<<grid, ATT_THREADS, smem, st>>>(q, kv, null_kv, q_scale, k_scale, bias, key_mask,
-                                                        alibi_slopes, out, g);
+  PHK_CUDA(launch_pdl(attention_kernel<DH>, dim3(grid), dim3(ATT_THREADS), (size_t)(smem), st, q, kv, null_kv, q_scale, k_scale, bias, key_mask, alibi_slopes, out, g));
   PHK_LAUNCH_CHECK();
   return 0;
 }
@@ -359,6 +458,10 @@ extern "C" int phk_attention(const float* q, const float* kv, const float* null_
       (g->dim_head == 64 || g->dim_head == 32)) {
     if (g->dim_head == 64) return launch_attention_small<64>(q, kv, q_scale, k_scale, alibi_slopes, out, *g, st);
     return launch_attention_small<32>(q, kv, q_scale, k_scale, alibi_slopes, out, *g, st);
+  }
+  if (!g->causal && !bias && g->n_k + g->num_null_kv <= FEW_KEYS && (g->dim_head == 64 || g->dim_head == 32)) {
+    if (g->dim_head == 64) return launch_attention_fewkeys<64>(q, kv, null_kv, q_scale, k_scale, key_mask, out, *g, st);
+    return launch_attention_fewkeys<32>(q, kv, null_kv, q_scale, k_scale, key_mask, out, *g, st);
   }
   switch (g->dim_head) {
     case 16: return launch_attention<16>(q, kv, null_kv, q_scale, k_scale, bias, key_mask, alibi_slopes, out, *g, st);

@@ -108,6 +108,7 @@ __global__ void __launch_bounds__(ATHREADS, 2) attention_tc_kernel(const __grid_
                                                                    const __grid_constant__ CUtensorMap tmK,
                                                                    const __grid_constant__ CUtensorMap tmV,
                                                                    AttTcParams p) {
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -141,6 +142,7 @@ __global__ void __launch_bounds__(ATHREADS, 2) attention_tc_kernel(const __grid_
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   const uint32_t tS = tmem_base, tO = tmem_base + AKC;
+  pdl_wait();  // prologue above overlapped the previous kernel
 
   if (warp == 0) {
     if (lane == 0) {
@@ -291,6 +293,7 @@ __global__ void __launch_bounds__(256) attention_prep_kernel(const float* __rest
                                                              __nv_bfloat16* __restrict__ Qh, __nv_bfloat16* __restrict__ Kh,
                                                              __nv_bfloat16* __restrict__ Vt, int n, int n_pad, int heads,
                                                              float scale) {
+  pdl_prologue();
   __shared__ float vt[64][65];
   const int t0 = blockIdx.x * 64, h = blockIdx.y, seq = blockIdx.z;
   const int I = heads * 64;
@@ -390,7 +393,7 @@ extern "C" int phk_attention_tc(const float* q, const float* kv, const float* q_
   __nv_bfloat16* Kh = (__nv_bfloat16*)align(base + SH * n * 64 * 2);
   __nv_bfloat16* Vt = (__nv_bfloat16*)align((char*)Kh + SH * n * 64 * 2);
   dim3 pg((unsigned)((n_pad + 63) / 64), (unsigned)heads, (unsigned)n_seq);
-  attention_prep_kernel<<<pg, 256, 0, st>>>(q, kv, q_scale, k_scale, Qh, Kh, Vt, n, (int)n_pad, heads, scale);
+  PHK_CUDA(launch_pdl(attention_prep_kernel, dim3(pg), dim3(256), (size_t)(0), st, q, kv, q_scale, k_scale, Qh, Kh, Vt, n, (int)n_pad, heads, scale));
   PHK_LAUNCH_CHECK();
   CUtensorMap tq, tk, tv;
   PHK_TRY(make_map_3d(Qh, 64, n, SH, 64, (int64_t)n * 64, AQ, &tq));
@@ -403,7 +406,7 @@ extern "C" int phk_attention_tc(const float* q, const float* kv, const float* q_
   }
   AttTcParams p{bias, (__nv_bfloat16*)out_bf16, n, n, heads, (int64_t)n * heads * 64, (int64_t)heads * 64};
   dim3 grid((unsigned)((n + AQ - 1) / AQ), (unsigned)heads, (unsigned)n_seq);
-  attention_tc_kernel<<<grid, ATHREADS, ATT_SMEM, st>>>(tq, tk, tv, p);
+  PHK_CUDA(launch_pdl(attention_tc_kernel, dim3(grid), dim3(ATHREADS), (size_t)(ATT_SMEM), st, tq, tk, tv, p));
   PHK_LAUNCH_CHECK();
   return 0;
 }

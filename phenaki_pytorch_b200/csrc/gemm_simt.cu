@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_f32_kernel(const float* __res
                                                               float* __restrict__ C, int64_t ldc, int64_t M, int N,
                                                               int K, const float* __restrict__ bias,
                                                               const float* __restrict__ residual, RowMap map) {
+  pdl_prologue();
   __shared__ __align__(16) float As[2][BK][BM + 4];
   __shared__ __align__(16) float Bs[2][BK][BN + 4];
   const int64_t m0 = (int64_t)blockIdx.y * BM;
@@ -148,8 +149,8 @@ extern "C" int phk_gemm_f32(const float* A, int64_t lda, const float* W, int64_t
   PHK_REQUIRE(grid.y <= 65535, PHK_E_UNSUPPORTED, "phk_gemm_f32: M too large");
   RowMap map{seg_len, seg_stride, seg_off};
   // residual shares C's leading dimension and row map (in-place `x = f(x) + x`, attention.py:323-330)
-  if (aligned) gemm_f32_kernel<true><<<grid, THREADS, 0, to_stream(s)>>>(A, lda, W, ldw, C, ldc, M, N, K, bias, residual, map);
-  else gemm_f32_kernel<false><<<grid, THREADS, 0, to_stream(s)>>>(A, lda, W, ldw, C, ldc, M, N, K, bias, residual, map);
+  if (aligned) PHK_CUDA(launch_pdl(gemm_f32_kernel<true>, dim3(grid), dim3(THREADS), (size_t)(0), to_stream(s), A, lda, W, ldw, C, ldc, M, N, K, bias, residual, map));
+  else PHK_CUDA(launch_pdl(gemm_f32_kernel<false>, dim3(grid), dim3(THREADS), (size_t)(0), to_stream(s), A, lda, W, ldw, C, ldc, M, N, K, bias, residual, map));
   PHK_LAUNCH_CHECK();
   return 0;
 }

@@ -8,8 +8,10 @@
 //   warp 1     TMEM allocator + MMA issuer: one thread issues tcgen05.mma.cta_group::1.kind::f16
 //              (M=128, N=128, K=16), four per k-block; tcgen05.commit frees the smem slot and publishes the
 //              accumulator.  Two 128-column accumulators in TMEM, so tile i+1 is multiplied while tile i drains.
-//   warps 2..5 epilogue: tcgen05.ld (32x32b) -> registers -> bias -> padded smem tile; then fully coalesced
-//              row-wise write-out (512 B per warp instruction) with the residual add / row map / bf16 pack.
+//   warps 2..9 epilogue (two per TMEM lane group): residual-tile prefetch during the main loop; tcgen05.ld (32x32b)
+//              -> registers -> padded smem tile; then fully coalesced row-wise write-out (512 B per warp
+//              instruction) with bias / row map / bf16 pack / GEGLU.  EPI 3 (fused sampling head) adds warps
+//              10..17 to the vocabulary-wide reduction.
 // Tiles are walked m-fastest so the CTAs running concurrently share the same W tile (L2) while the A panel
 // stays L2-resident.
 // Epilogues: 0 fp32 (+bias,+residual)   1 bf16 (+bias)   2 GEGLU (attention.py:40-43) on W rows packed as
@@ -25,8 +27,11 @@ constexpr int GM = 128;       // BLOCK_M = UMMA_M
 constexpr int GN = 128;       // BLOCK_N = UMMA_N
 constexpr int GK = 64;        // BLOCK_K: 64 bf16 = 128 B = one SWIZZLE_128B row
 constexpr int GSTAGES = 4;
-constexpr int GTHREADS = 192;      // warps: 0 TMA, 1 MMA, 2..5 epilogue
-constexpr int GTHREADS_HEAD = 320; // fused sampling head: + warps 6..9 share the vocabulary-wide epilogue math
+constexpr int EPI_WARPS = 8;        // epilogue warps 2..9: two per TMEM lane group, each drains half the columns
+constexpr int HEAD_WARPS = 16;      // fused sampling head: warps 2..17 share the vocabulary-wide epilogue math
+constexpr int HEAD_COLS = GN / (HEAD_WARPS / 2);  // columns per thread per tile (64 tokens x HEAD_WARPS/2 groups)
+constexpr int GTHREADS = 64 + EPI_WARPS * 32;       // 320
+constexpr int GTHREADS_HEAD = 64 + HEAD_WARPS * 32; // 576
 constexpr int STAGE_BYTES = GM * GK * 2;          // 16 KB per operand per stage
 constexpr int CPAD = 132;                          // fp32 staging row stride (floats): conflict-free 128-bit rows
 constexpr int CSTAGE_BYTES = GM * CPAD * 4;        // 67.6 KB
@@ -129,12 +134,26 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
   }
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory"); }
+
+// erf with |err| <= 1.5e-7 (Abramowitz-Stegun 7.1.26): one ex2 + one rcp instead of erff's long polynomial; used
+// only where the result is rounded to bf16 anyway (GEGLU epilogue of the bf16 mode)
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float e = 1.0f - poly * t * __expf(-z * z);  // erf(|x|/sqrt2)
+  return 0.5f * x * (1.0f + copysignf(e, x));
+}
 
 template <int EPI>
 __global__ void __launch_bounds__(GTHREADS_HEAD, 1) gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                                const __grid_constant__ CUtensorMap tmB,
-                                                                EpiParams p) {
+                                                                     const __grid_constant__ CUtensorMap tmB,
+                                                                     EpiParams p) {
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-B alignment
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -173,7 +192,7 @@ __global__ void __launch_bounds__(GTHREADS_HEAD, 1) gemm_bf16_kernel(const __gri
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
-      mbar_init(bar_tempty + 8 * a, 4);  // one arrival per epilogue warp
+      mbar_init(bar_tempty + 8 * a, EPI_WARPS);  // one arrival per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -187,23 +206,24 @@ __global__ void __launch_bounds__(GTHREADS_HEAD, 1) gemm_bf16_kernel(const __gri
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();  // everything above (barriers, tensor-map prefetch, TMEM allocation) overlapped the previous kernel
   if (threadIdx.x == 0) PHK_STAMP(0);  // setup done
 
-  // ---- EPI 3: per-thread running reductions over the vocabulary (token t = te & 63, column quarter = te >> 6) ----
+  // ---- EPI 3: per-thread running reductions over the vocabulary (token t = te & 63, column group = te >> 6) ----
   float sm_best = -FLT_MAX, sm_lbest = 0.f, sm_max = -FLT_MAX, sm_sum = 0.f;
   int sm_idx = 0x7fffffff;
-  auto head_bar = [&]() { asm volatile("bar.sync 2, 256;" ::: "memory"); };
-  // rows t (cond) and 64+t (null) of the staged tile belong to the same token; 256 threads x 32 columns
+  auto head_bar = [&]() { asm volatile("bar.sync 2, %0;" ::"n"(HEAD_WARPS * 32) : "memory"); };
+  // rows t (cond) and 64+t (null) of the staged tile belong to the same token; HEAD_WARPS*32 threads x HEAD_COLS columns
   auto head_reduce = [&](int m0, int n0) {
-    const int te = (int)threadIdx.x - 64, t = te & 63, quarter = te >> 6;
+    const int te = (int)threadIdx.x - 64, t = te & 63, grp = te >> 6;
     const int tok = (m0 / GM) * 64 + t;
     if (tok >= p.n_tokens) return;
-    const float* crow = cstage + t * CPAD + quarter * 32;
-    const float* nrow = cstage + (64 + t) * CPAD + quarter * 32;
+    const float* crow = cstage + t * CPAD + grp * HEAD_COLS;
+    const float* nrow = cstage + (64 + t) * CPAD + grp * HEAD_COLS;
     const unsigned long long ctr0 = p.offset + (unsigned long long)tok * (unsigned long long)((p.N + 3) / 4);
-#pragma unroll 2
-    for (int c = 0; c < 32; c += 4) {
-      const int v0 = n0 + quarter * 32 + c;
+#pragma unroll
+    for (int c = 0; c < HEAD_COLS; c += 4) {
+      const int v0 = n0 + grp * HEAD_COLS + c;
       if (v0 >= p.N) break;
       const float4 cv = *reinterpret_cast<const float4*>(crow + c);
       const float4 nv = *reinterpret_cast<const float4*>(nrow + c);
@@ -233,19 +253,20 @@ __global__ void __launch_bounds__(GTHREADS_HEAD, 1) gemm_bf16_kernel(const __gri
       for (int j = 0; j < 4; ++j) sm_sum += __expf(l4[j] - sm_max);
     }
   };
-  // combine the four column quarters of every token through smem, then one partial per (token, vocabulary split)
+  // combine the column groups of every token through smem, then one partial per (token, vocabulary split)
   auto head_publish = [&]() {
-    const int te = (int)threadIdx.x - 64, t = te & 63, quarter = te >> 6;
-    float* ex = cstage;  // [64][3][6]
-    if (quarter > 0) {
-      float* e = ex + (t * 3 + quarter - 1) * 6;
+    constexpr int NG = HEAD_WARPS / 2;  // column groups per token
+    const int te = (int)threadIdx.x - 64, t = te & 63, grp = te >> 6;
+    float* ex = cstage;  // [64][NG-1][6]
+    if (grp > 0) {
+      float* e = ex + (t * (NG - 1) + grp - 1) * 6;
       e[0] = sm_best; e[1] = sm_lbest; e[2] = sm_max; e[3] = sm_sum; e[4] = __int_as_float(sm_idx);
     }
     head_bar();
     const int tok = (int)(blockIdx.x / p.n_splits) * 64 + t;
-    if (quarter == 0 && tok < p.n_tokens) {
-      for (int qq = 0; qq < 3; ++qq) {
-        const float* e = ex + (t * 3 + qq) * 6;
+    if (grp == 0 && tok < p.n_tokens) {
+      for (int qq = 0; qq < NG - 1; ++qq) {
+        const float* e = ex + (t * (NG - 1) + qq) * 6;
         const float oy = e[0], ol = e[1], om = e[2], os = e[3];
         const int oi = __float_as_int(e[4]);
         if (oy > sm_best || (oy == sm_best && oi < sm_idx)) { sm_best = oy; sm_idx = oi; sm_lbest = ol; }
@@ -307,25 +328,26 @@ __global__ void __launch_bounds__(GTHREADS_HEAD, 1) gemm_bf16_kernel(const __gri
           if (++stage == GSTAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(bar_tfull + 8 * acc);  // accumulator complete
-        if (it == 0) PHK_STAMP(5);                         // all MMAs of the first tile issued
+        if (it == 0) PHK_STAMP(5);         // all MMAs of the first tile issued
       }
     }
-  } else if (warp >= 6) {
+  } else if (warp >= 2 + EPI_WARPS) {
     // ===================== extra math warps of the fused sampling head =====================
     if (EPI == 3) {
       for (int it = 0; it < my_tiles; ++it) {
         int m0, n0;
         tile_of(it, m0, n0);
-        head_bar();            // tile staged by warps 2..5
+        head_bar();            // tile staged by the epilogue warps
         head_reduce(m0, n0);
         head_bar();            // tile consumed
       }
       head_publish();
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue: warps 2..9, two per TMEM lane group =====================
+    const int ew = warp - 2;        // 0..7: rows ew, ew+8, ... in the coalesced write-out
     const int lg = warp & 3;        // TMEM lane group this warp may access (rows lg*32 .. +31 of the tile)
-    const int ew = warp - 2;        // 0..3: rows ew, ew+4, ... in the coalesced write-out
+    const int chalf = ew >> 2;      // which half of the accumulator columns this warp drains
     for (int it = 0; it < my_tiles; ++it) {
       const int acc = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
@@ -340,11 +362,11 @@ __global__ void __launch_bounds__(GTHREADS_HEAD, 1) gemm_bf16_kernel(const __gri
         const int col = n0 + lane * 4;
         const uint32_t seg_len = (uint32_t)p.seg_len;
 #pragma unroll 1
-        for (int rb = 0; rb < 32; rb += 8) {
+        for (int rb = 0; rb < GM / EPI_WARPS; rb += 8) {
           float4 rv[8];
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
-            const int r = (rb + u) * 4 + ew;
+            const int r = (rb + u) * EPI_WARPS + ew;
             const uint32_t m = (uint32_t)m0 + r;
             uint32_t orow = m;
             if (seg_len > 0) { const uint32_t q = m / seg_len; orow = q * (uint32_t)p.seg_stride + (uint32_t)p.seg_off + (m - q * seg_len); }
@@ -353,7 +375,7 @@ __global__ void __launch_bounds__(GTHREADS_HEAD, 1) gemm_bf16_kernel(const __gri
           }
 #pragma unroll
           for (int u = 0; u < 8; ++u)
-            *reinterpret_cast<float4*>(cstage + ((rb + u) * 4 + ew) * CPAD + lane * 4) = rv[u];
+            *reinterpret_cast<float4*>(cstage + ((rb + u) * EPI_WARPS + ew) * CPAD + lane * 4) = rv[u];
         }
         epi_bar_sync();  // residual tile complete before the row-per-thread accumulate below
       }
@@ -364,24 +386,23 @@ __global__ void __launch_bounds__(GTHREADS_HEAD, 1) gemm_bf16_kernel(const __gri
       float* srow = cstage + (lg * 32 + lane) * CPAD;
       if (EPI == 2) {
         // [64 value | 64 gate] -> 64 outputs gelu(gate) * value, staged as fp32 in columns 0..63
+        const int c = chalf;
+        uint32_t val[32], gate[32];
+        tmem_ld32(trow + c * 32, val);
+        tmem_ld32(trow + 64 + c * 32, gate);
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t val[32], gate[32];
-          tmem_ld32(trow + c * 32, val);
-          tmem_ld32(trow + 64 + c * 32, gate);
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 o;
-            o.x = gelu_erf(__uint_as_float(gate[j])) * __uint_as_float(val[j]);
-            o.y = gelu_erf(__uint_as_float(gate[j + 1])) * __uint_as_float(val[j + 1]);
-            o.z = gelu_erf(__uint_as_float(gate[j + 2])) * __uint_as_float(val[j + 2]);
-            o.w = gelu_erf(__uint_as_float(gate[j + 3])) * __uint_as_float(val[j + 3]);
-            *reinterpret_cast<float4*>(srow + c * 32 + j) = o;
-          }
+        for (int j = 0; j < 32; j += 4) {
+          float4 o;
+          o.x = gelu_erf_fast(__uint_as_float(gate[j])) * __uint_as_float(val[j]);
+          o.y = gelu_erf_fast(__uint_as_float(gate[j + 1])) * __uint_as_float(val[j + 1]);
+          o.z = gelu_erf_fast(__uint_as_float(gate[j + 2])) * __uint_as_float(val[j + 2]);
+          o.w = gelu_erf_fast(__uint_as_float(gate[j + 3])) * __uint_as_float(val[j + 3]);
+          *reinterpret_cast<float4*>(srow + c * 32 + j) = o;
         }
       } else {
 #pragma unroll
-        for (int c = 0; c < GN / 32; ++c) {
+        for (int cc = 0; cc < 2; ++cc) {
+          const int c = chalf * 2 + cc;
           uint32_t v[32];
           tmem_ld32(trow + c * 32, v);
 #pragma unroll
@@ -400,17 +421,17 @@ __global__ void __launch_bounds__(GTHREADS_HEAD, 1) gemm_bf16_kernel(const __gri
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
-      epi_bar_sync();  // whole 128 x 128 tile staged
-      if (it == 0 && threadIdx.x == 64) PHK_STAMP(7);      // tile staged in smem
-
       if (EPI == 3) {
-        head_bar();                      // + warps 6..9: the staged tile is complete
+        head_bar();                      // all epilogue + math warps: the staged tile is complete
         head_reduce((int)m0, n0);
         head_bar();                      // staging tile free for the next accumulator
         continue;
       }
+      epi_bar_sync();  // whole 128 x 128 tile staged
+      if (it == 0 && threadIdx.x == 64) PHK_STAMP(7);      // tile staged in smem
+
       // ---- coalesced write-out: one row per warp instruction ----
-      const int ncols = EPI == 2 ? GN / 2 : GN;
+      constexpr int RPW = GM / EPI_WARPS;  // rows per warp
       const int ncol0 = EPI == 2 ? n0 / 2 : n0;
       const int nlim = EPI == 2 ? p.N / 2 : p.N;
       if (EPI == 0) {
@@ -432,14 +453,14 @@ __global__ void __launch_bounds__(GTHREADS_HEAD, 1) gemm_bf16_kernel(const __gri
             float* cbase = reinterpret_cast<float*>(p.C) + (m0 + ew) * p.ldc + col;
             const float* sbase = cstage + ew * CPAD + lane * 4;
 #pragma unroll 1
-            for (int rb = 0; rb < 32; rb += 8) {
+            for (int rb = 0; rb < RPW; rb += 8) {
               float4 o[8];
 #pragma unroll
-              for (int u = 0; u < 8; ++u) o[u] = *reinterpret_cast<const float4*>(sbase + (rb + u) * 4 * CPAD);
+              for (int u = 0; u < 8; ++u) o[u] = *reinterpret_cast<const float4*>(sbase + (rb + u) * EPI_WARPS * CPAD);
 #pragma unroll
               for (int u = 0; u < 8; ++u) {
                 o[u].x += bv.x; o[u].y += bv.y; o[u].z += bv.z; o[u].w += bv.w;
-                *reinterpret_cast<float4*>(cbase + (int64_t)(rb + u) * 4 * p.ldc) = o[u];
+                *reinterpret_cast<float4*>(cbase + (int64_t)(rb + u) * EPI_WARPS * p.ldc) = o[u];
               }
             }
           }
@@ -447,12 +468,12 @@ __global__ void __launch_bounds__(GTHREADS_HEAD, 1) gemm_bf16_kernel(const __gri
         // general path, 8 rows per batch: all residual loads of a batch are issued before the first store (C may
         // alias the residual -- in-place x = f(x) + x -- so the compiler cannot reorder them itself)
 #pragma unroll 1
-        for (int rb = 0; rb < 32; rb += 8) {
+        for (int rb = 0; rb < RPW; rb += 8) {
           int64_t off[8];
           float4 rv[8];
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
-            const int r = (rb + u) * 4 + ew;
+            const int r = (rb + u) * EPI_WARPS + ew;
             const uint32_t m = (uint32_t)m0 + r;
             uint32_t orow = m;
             if (seg_len > 0) { const uint32_t q = m / seg_len; orow = q * (uint32_t)p.seg_stride + (uint32_t)p.seg_off + (m - q * seg_len); }
@@ -463,7 +484,7 @@ __global__ void __launch_bounds__(GTHREADS_HEAD, 1) gemm_bf16_kernel(const __gri
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
             if (off[u] < 0) continue;
-            const int r = (rb + u) * 4 + ew;
+            const int r = (rb + u) * EPI_WARPS + ew;
             float4 o = *reinterpret_cast<const float4*>(cstage + r * CPAD + lane * 4);
             o.x += bv.x + rv[u].x; o.y += bv.y + rv[u].y; o.z += bv.z + rv[u].z; o.w += bv.w + rv[u].w;
             float* crow = reinterpret_cast<float*>(p.C) + off[u];
@@ -486,8 +507,8 @@ __global__ void __launch_bounds__(GTHREADS_HEAD, 1) gemm_bf16_kernel(const __gri
         const bool vec = (p.ldc % CPL == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && (col + CPL - 1 < nlim);
         const uint32_t seg_len = (uint32_t)p.seg_len;
 #pragma unroll 4
-        for (int rr = 0; rr < 32; ++rr) {
-          const int r = rr * 4 + ew;
+        for (int rr = 0; rr < RPW; ++rr) {
+          const int r = rr * EPI_WARPS + ew;
           const uint32_t m = (uint32_t)m0 + r;
           if (m >= (uint32_t)p.M) break;
           int64_t orow = m;
@@ -506,7 +527,6 @@ __global__ void __launch_bounds__(GTHREADS_HEAD, 1) gemm_bf16_kernel(const __gri
           }
         }
       }
-      (void)ncols;
       epi_bar_sync();  // staging tile free for the next accumulator
       if (it == 0 && threadIdx.x == 64) PHK_STAMP(8);      // tile written out
     }
@@ -589,6 +609,7 @@ static long long* g_gemm_trace = nullptr;
 __global__ void head_finalize_kernel(const float4* __restrict__ part_f, const int* __restrict__ part_i, int n_splits,
                                      int n_tokens, const uint8_t* __restrict__ mask, int64_t* __restrict__ ids,
                                      int64_t* __restrict__ pred_out, float* __restrict__ score_out) {
+  pdl_prologue();
   const int tok = blockIdx.x * blockDim.x + threadIdx.x;
   if (tok >= n_tokens) return;
   float by = -FLT_MAX, bl = 0.f, m = -FLT_MAX, ssum = 0.f;
@@ -617,7 +638,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const EpiPa
   }
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = EPI == 3 ? p.m_tiles * p.n_splits : (tiles < kNumSMs ? tiles : kNumSMs);
-  gemm_bf16_kernel<EPI><<<grid, EPI == 3 ? GTHREADS_HEAD : GTHREADS, SMEM_TOTAL, st>>>(ta, tb, p);
+  PHK_CUDA(launch_pdl(gemm_bf16_kernel<EPI>, dim3(grid), dim3(EPI == 3 ? GTHREADS_HEAD : GTHREADS), (size_t)(SMEM_TOTAL), st, ta, tb, p));
   PHK_LAUNCH_CHECK();
   return 0;
 }
@@ -693,8 +714,7 @@ extern "C" int phk_head_sample(const void* emb, int64_t ld_emb, const void* W, i
               part_f, part_i};
   cudaStream_t st = to_stream(s);
   PHK_TRY(launch_gemm<3>(ta, tb, p, st));
-  head_finalize_kernel<<<(n_tokens + 127) / 128, 128, 0, st>>>(part_f, part_i, n_splits, n_tokens, mask, ids, pred_out,
-                                                              score_out);
+  PHK_CUDA(launch_pdl(head_finalize_kernel, dim3((n_tokens + 127) / 128), dim3(128), (size_t)(0), st, part_f, part_i, n_splits, n_tokens, mask, ids, pred_out, score_out));
   PHK_LAUNCH_CHECK();
   return 0;
 }

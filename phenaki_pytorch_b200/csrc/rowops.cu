@@ -16,6 +16,7 @@ __global__ void __launch_bounds__(256) ln_warp_kernel(const float* __restrict__ 
                                                       __nv_bfloat16* __restrict__ raw, int64_t rows, int dim,
                                                       int out_bf16, int64_t seg_len, int64_t seg_stride,
                                                       int64_t seg_off) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -64,6 +65,7 @@ __global__ void __launch_bounds__(256) ln_block_kernel(const float* __restrict__
                                                        const float* __restrict__ b, void* __restrict__ out,
                                                        __nv_bfloat16* __restrict__ raw, int dim, int out_bf16,
                                                        int64_t seg_len, int64_t seg_stride, int64_t seg_off) {
+  pdl_prologue();
   extern __shared__ float srow[];
   __shared__ float red[32];
   const int64_t row = blockIdx.x;
@@ -94,6 +96,7 @@ __global__ void __launch_bounds__(256) patchify_ln_kernel(const float* __restric
                                                           int W, int f0, int nt, int pt, int p1, int p2,
                                                           const float* __restrict__ g, const float* __restrict__ b,
                                                           void* __restrict__ out, int out_bf16) {
+  pdl_prologue();
   extern __shared__ float srow[];
   __shared__ float red[32];
   const int hh = H / p1, ww = W / p2;
@@ -164,6 +167,7 @@ __global__ void __launch_bounds__(256) patchify_ln_kernel(const float* __restric
 // GEGLU (attention.py:40-43): x, gate = chunk(2); gelu(gate) * x
 // ------------------------------------------------------------------------------------------
 __global__ void geglu_kernel(const float* __restrict__ h, float* __restrict__ out, int64_t rows, int inner) {
+  pdl_prologue();
   const int64_t total = rows * inner;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / inner;
@@ -180,6 +184,7 @@ __global__ void geglu_kernel(const float* __restrict__ h, float* __restrict__ ou
 __global__ void token_embed_kernel(const int64_t* __restrict__ ids, const float* __restrict__ tok,
                                    const float* __restrict__ pos, float* __restrict__ out, int n, int dim,
                                    float alpha, float one_minus_alpha, int shrink, int64_t id_rows) {
+  pdl_prologue();
   const int64_t row = blockIdx.x;
   const int p = (int)(row % n);
   const int64_t id = ids[row % id_rows];  // the CFG null half replays the same ids
@@ -198,6 +203,7 @@ __global__ void token_embed_kernel(const int64_t* __restrict__ ids, const float*
 __global__ void __launch_bounds__(256) lfq_kernel(const float* __restrict__ x, const float* __restrict__ wp,
                                                   const float* __restrict__ bp, int64_t* __restrict__ ids,
                                                   float* __restrict__ proj, int64_t rows, int dim, int bits) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -231,6 +237,7 @@ __device__ __forceinline__ int64_t peg_phys_row(int64_t r_log, int T, int HW, in
 __global__ void __launch_bounds__(128) peg_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                   const float* __restrict__ bias, float* __restrict__ y, int T, int H,
                                                   int W, int D, int pad_t0, int layout) {
+  pdl_prologue();
   // one CTA per logical position; the 27 neighbour rows are resolved once (the index maps need divisions),
   // then every thread streams float4 channels: x rows and the tap-major weights are read fully coalesced.
   __shared__ int s_src[27];
@@ -277,6 +284,7 @@ __global__ void __launch_bounds__(128) peg_kernel(const float* __restrict__ x, c
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) cpb_table_kernel(phk_cpb_t c, int d0, int d1, int d2,
                                                         float* __restrict__ table) {
+  pdl_prologue();
   extern __shared__ float sm[];
   float* h1 = sm;
   float* h2 = sm + c.hidden;
@@ -317,6 +325,7 @@ __global__ void __launch_bounds__(256) cpb_table_kernel(phk_cpb_t c, int d0, int
 
 __global__ void cpb_expand_kernel(const float* __restrict__ table, float* __restrict__ out, int heads, int d0,
                                   int d1, int d2) {
+  pdl_prologue();
   const int n = d0 * d1 * d2;
   const int64_t total = (int64_t)n * n;
   const int s1 = 2 * d1 - 1, s2 = 2 * d2 - 1;
@@ -365,6 +374,7 @@ __global__ void __launch_bounds__(512) sample_tokens_kernel(const float* __restr
                                                             int64_t* __restrict__ ids, int64_t* __restrict__ pred_out,
                                                             float* __restrict__ score_out, int V, int64_t seg_len,
                                                             int64_t seg_stride, int64_t seg_off) {
+  pdl_prologue();
   __shared__ float s_y[16], s_m[16], s_s[16];
   __shared__ int s_i[16];
   const int64_t row = blockIdx.x;
@@ -459,6 +469,7 @@ __global__ void __launch_bounds__(512) sample_tokens_kernel(const float* __restr
 __global__ void __launch_bounds__(1024) topk_mask_kernel(const float* __restrict__ scores, int n, int k,
                                                          uint8_t* __restrict__ mask, int64_t* __restrict__ ids,
                                                          int64_t mask_id) {
+  pdl_prologue();
   extern __shared__ float sc[];
   const int64_t row = blockIdx.x;
   for (int i = threadIdx.x; i < n; i += blockDim.x) sc[i] = scores[row * n + i];
@@ -485,6 +496,7 @@ __global__ void __launch_bounds__(256) critic_scores_kernel(const float* __restr
                                                             float noise_K, float noise_mult, float* __restrict__ out,
                                                             int64_t rows, int dim, int64_t seg_len, int64_t seg_stride,
                                                             int64_t seg_off) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -505,6 +517,7 @@ __global__ void __launch_bounds__(256) critic_scores_kernel(const float* __restr
 // null + (cond - null) * scale  (phenaki_pytorch.py:161), eager op order (sub, mul, add)
 __global__ void cfg_combine_kernel(const float* __restrict__ cond, const float* __restrict__ nul, float scale,
                                    float* __restrict__ out, int64_t n) {
+  pdl_prologue();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float nn = nul[i];
     out[i] = __fadd_rn(nn, __fmul_rn(__fsub_rn(cond[i], nn), scale));
@@ -531,18 +544,18 @@ extern "C" int phk_layernorm(const float* x, const float* gamma, const float* be
     const int wpb = 8;
     const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
     switch (dim / 128) {
-      case 1: ln_warp_kernel<1><<<grid, 256, 0, st>>>(x, gamma, beta, out, raw, rows, dim, out_bf16, seg_len, seg_stride, seg_off); break;
-      case 2: ln_warp_kernel<2><<<grid, 256, 0, st>>>(x, gamma, beta, out, raw, rows, dim, out_bf16, seg_len, seg_stride, seg_off); break;
-      case 3: ln_warp_kernel<3><<<grid, 256, 0, st>>>(x, gamma, beta, out, raw, rows, dim, out_bf16, seg_len, seg_stride, seg_off); break;
-      case 4: ln_warp_kernel<4><<<grid, 256, 0, st>>>(x, gamma, beta, out, raw, rows, dim, out_bf16, seg_len, seg_stride, seg_off); break;
-      case 5: ln_warp_kernel<5><<<grid, 256, 0, st>>>(x, gamma, beta, out, raw, rows, dim, out_bf16, seg_len, seg_stride, seg_off); break;
-      case 6: ln_warp_kernel<6><<<grid, 256, 0, st>>>(x, gamma, beta, out, raw, rows, dim, out_bf16, seg_len, seg_stride, seg_off); break;
-      case 7: ln_warp_kernel<7><<<grid, 256, 0, st>>>(x, gamma, beta, out, raw, rows, dim, out_bf16, seg_len, seg_stride, seg_off); break;
-      default: ln_warp_kernel<8><<<grid, 256, 0, st>>>(x, gamma, beta, out, raw, rows, dim, out_bf16, seg_len, seg_stride, seg_off); break;
+      case 1: PHK_CUDA(launch_pdl(ln_warp_kernel<1>, dim3(grid), dim3(256), (size_t)(0), st, x, gamma, beta, out, raw, rows, dim, out_bf16, seg_len, seg_stride, seg_off)); break;
+      case 2: PHK_CUDA(launch_pdl(ln_warp_kernel<2>, dim3(grid), dim3(256), (size_t)(0), st, x, gamma, beta, out, raw, rows, dim, out_bf16, seg_len, seg_stride, seg_off)); break;
+      case 3: PHK_CUDA(launch_pdl(ln_warp_kernel<3>, dim3(grid), dim3(256), (size_t)(0), st, x, gamma, beta, out, raw, rows, dim, out_bf16, seg_len, seg_stride, seg_off)); break;
+      case 4: PHK_CUDA(launch_pdl(ln_warp_kernel<4>, dim3(grid), dim3(256), (size_t)(0), st, x, gamma, beta, out, raw, rows, dim, out_bf16, seg_len, seg_stride, seg_off)); break;
+      case 5: PHK_CUDA(launch_pdl(ln_warp_kernel<5>, dim3(grid), dim3(256), (size_t)(0), st, x, gamma, beta, out, raw, rows, dim, out_bf16, seg_len, seg_stride, seg_off)); break;
+      case 6: PHK_CUDA(launch_pdl(ln_warp_kernel<6>, dim3(grid), dim3(256), (size_t)(0), st, x, gamma, beta, out, raw, rows, dim, out_bf16, seg_len, seg_stride, seg_off)); break;
+      case 7: PHK_CUDA(launch_pdl(ln_warp_kernel<7>, dim3(grid), dim3(256), (size_t)(0), st, x, gamma, beta, out, raw, rows, dim, out_bf16, seg_len, seg_stride, seg_off)); break;
+      default: PHK_CUDA(launch_pdl(ln_warp_kernel<8>, dim3(grid), dim3(256), (size_t)(0), st, x, gamma, beta, out, raw, rows, dim, out_bf16, seg_len, seg_stride, seg_off)); break;
     }
   } else {
     PHK_REQUIRE(dim <= 12288, PHK_E_UNSUPPORTED, "phk_layernorm: dim > 12288");
-    ln_block_kernel<<<(unsigned)rows, 256, dim * sizeof(float), st>>>(x, gamma, beta, out, raw, dim, out_bf16, seg_len, seg_stride, seg_off);
+    PHK_CUDA(launch_pdl(ln_block_kernel, dim3((unsigned)rows), dim3(256), (size_t)(dim * sizeof(float)), st, x, gamma, beta, out, raw, dim, out_bf16, seg_len, seg_stride, seg_off));
   }
   PHK_LAUNCH_CHECK();
   return 0;
@@ -568,8 +581,8 @@ extern "C" int phk_patchify_ln(const float* video, int32_t B, int32_t C, int32_t
     PHK_CUDA(cudaFuncSetAttribute(patchify_ln_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 57344));
     PHK_CUDA(cudaFuncSetAttribute(patchify_ln_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 57344));
   }
-  if (vec) patchify_ln_kernel<true><<<grid, 256, smem, to_stream(s)>>>(video, C, F, H, W, f0, nt, pt, p1, p2, ln_g, ln_b, out, out_bf16);
-  else patchify_ln_kernel<false><<<grid, 256, smem, to_stream(s)>>>(video, C, F, H, W, f0, nt, pt, p1, p2, ln_g, ln_b, out, out_bf16);
+  if (vec) PHK_CUDA(launch_pdl(patchify_ln_kernel<true>, dim3(grid), dim3(256), (size_t)(smem), to_stream(s), video, C, F, H, W, f0, nt, pt, p1, p2, ln_g, ln_b, out, out_bf16));
+  else PHK_CUDA(launch_pdl(patchify_ln_kernel<false>, dim3(grid), dim3(256), (size_t)(smem), to_stream(s), video, C, F, H, W, f0, nt, pt, p1, p2, ln_g, ln_b, out, out_bf16));
   PHK_LAUNCH_CHECK();
   return 0;
 }
@@ -581,7 +594,7 @@ extern "C" int phk_geglu(const float* h, float* out, int64_t rows, int32_t inner
   if (rows == 0) return 0;
   const int64_t total = rows * inner;
   const unsigned grid = (unsigned)((total + 255) / 256 < (int64_t)kNumSMs * 16 ? (total + 255) / 256 : kNumSMs * 16);
-  geglu_kernel<<<grid, 256, 0, to_stream(s)>>>(h, out, rows, inner);
+  PHK_CUDA(launch_pdl(geglu_kernel, dim3(grid), dim3(256), (size_t)(0), to_stream(s), h, out, rows, inner));
   PHK_LAUNCH_CHECK();
   return 0;
 }
@@ -595,8 +608,7 @@ extern "C" int phk_token_embed(const int64_t* ids, const float* tok, const float
   // (1 - alpha) is evaluated in double by the reference's Python and rounded to fp32 at the mul
   const float oma = (float)(1.0 - (double)alpha);
   if (replicas < 1) replicas = 1;
-  token_embed_kernel<<<(unsigned)(b * n * replicas), 128, 0, to_stream(s)>>>(ids, tok, pos, out, n, dim, alpha, oma, shrink,
-                                                                              (int64_t)b * n);
+  PHK_CUDA(launch_pdl(token_embed_kernel, dim3((unsigned)(b * n * replicas)), dim3(128), (size_t)(0), to_stream(s), ids, tok, pos, out, n, dim, alpha, oma, shrink, (int64_t)b * n));
   PHK_LAUNCH_CHECK();
   return 0;
 }
@@ -607,7 +619,7 @@ extern "C" int phk_lfq_ids(const float* x, const float* wp, const float* bp, int
   PHK_REQUIRE(x && wp && bp && ids, PHK_E_ARG, "phk_lfq_ids: null pointer");
   PHK_REQUIRE(rows >= 0 && dim > 0 && bits > 0 && bits <= 62, PHK_E_ARG, "phk_lfq_ids: bad size");
   if (rows == 0) return 0;
-  lfq_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, to_stream(s)>>>(x, wp, bp, ids, proj_out, rows, dim, bits);
+  PHK_CUDA(launch_pdl(lfq_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), (size_t)(0), to_stream(s), x, wp, bp, ids, proj_out, rows, dim, bits));
   PHK_LAUNCH_CHECK();
   return 0;
 }
@@ -620,7 +632,7 @@ extern "C" int phk_peg3d(const float* x, const float* w, const float* b, float* 
   PHK_REQUIRE(D % 4 == 0, PHK_E_UNSUPPORTED, "phk_peg3d: dim must be a multiple of 4");
   const int64_t rows = (int64_t)B * T * H * W;
   PHK_REQUIRE(rows < (1LL << 31), PHK_E_UNSUPPORTED, "phk_peg3d: more than 2^31 positions");
-  peg_kernel<<<(unsigned)rows, 128, 0, to_stream(s)>>>(x, w, b, y, T, H, W, D, causal ? 2 : 1, layout);
+  PHK_CUDA(launch_pdl(peg_kernel, dim3((unsigned)rows), dim3(128), (size_t)(0), to_stream(s), x, w, b, y, T, H, W, D, causal ? 2 : 1, layout));
   PHK_LAUNCH_CHECK();
   return 0;
 }
@@ -639,11 +651,11 @@ extern "C" int phk_cpb_bias(const phk_cpb_t* c, int32_t d0, int32_t d1, int32_t 
   PHK_REQUIRE(c->num_dims == 3 || d2 == 1, PHK_E_SHAPE, "phk_cpb_bias: 2-D bias needs d2 == 1");
   PHK_REQUIRE(c->hidden > 0 && c->hidden <= 4096 && c->heads > 0, PHK_E_UNSUPPORTED, "phk_cpb_bias: hidden > 4096");
   const int U = (2 * d0 - 1) * (2 * d1 - 1) * (2 * d2 - 1);
-  cpb_table_kernel<<<U, 256, 2 * c->hidden * sizeof(float), to_stream(s)>>>(*c, d0, d1, d2, scratch);
+  PHK_CUDA(launch_pdl(cpb_table_kernel, dim3(U), dim3(256), (size_t)(2 * c->hidden * sizeof(float)), to_stream(s), *c, d0, d1, d2, scratch));
   PHK_LAUNCH_CHECK();
   const int64_t total = (int64_t)d0 * d1 * d2 * d0 * d1 * d2;
   const unsigned grid = (unsigned)((total + 255) / 256 < (int64_t)kNumSMs * 8 ? (total + 255) / 256 : kNumSMs * 8);
-  cpb_expand_kernel<<<grid, 256, 0, to_stream(s)>>>(scratch, out, c->heads, d0, d1, d2);
+  PHK_CUDA(launch_pdl(cpb_expand_kernel, dim3(grid), dim3(256), (size_t)(0), to_stream(s), scratch, out, c->heads, d0, d1, d2));
   PHK_LAUNCH_CHECK();
   return 0;
 }
@@ -659,9 +671,7 @@ extern "C" int phk_sample_tokens(const float* cond, const float* null_logits, in
   const float* nul = (cond_scale == 1.0f) ? nullptr : null_logits;  // cond_scale == 1 returns logits (:157-158)
   PHK_REQUIRE(cond_scale == 1.0f || null_logits, PHK_E_ARG, "phk_sample_tokens: cond_scale != 1 needs null logits");
   const int threads = V >= 8192 ? 512 : (V >= 1024 ? 256 : 64);
-  sample_tokens_kernel<<<(unsigned)rows, threads, 0, to_stream(s)>>>(cond, nul, ld, u, seed, offset, cond_scale,
-                                                                     temperature, mask, ids, pred_out, score_out, V, seg_len,
-                                                                     seg_stride, seg_off);
+  PHK_CUDA(launch_pdl(sample_tokens_kernel, dim3((unsigned)rows), dim3(threads), (size_t)(0), to_stream(s), cond, nul, ld, u, seed, offset, cond_scale, temperature, mask, ids, pred_out, score_out, V, seg_len, seg_stride, seg_off));
   PHK_LAUNCH_CHECK();
   return 0;
 }
@@ -674,7 +684,7 @@ extern "C" int phk_topk_mask(const float* scores, int32_t b, int32_t n, int32_t 
   PHK_REQUIRE(k >= 0 && k <= n, PHK_E_SHAPE, "phk_topk_mask: k out of range (torch.topk would raise)");
   int threads = ((n + 31) / 32) * 32;
   if (threads > 1024) threads = 1024;
-  topk_mask_kernel<<<b, threads, n * sizeof(float), to_stream(s)>>>(scores, n, k, mask, ids, mask_id);
+  PHK_CUDA(launch_pdl(topk_mask_kernel, dim3(b), dim3(threads), (size_t)(n * sizeof(float)), to_stream(s), scores, n, k, mask, ids, mask_id));
   PHK_LAUNCH_CHECK();
   return 0;
 }
@@ -689,9 +699,7 @@ extern "C" int phk_critic_scores(const float* x_cond, const float* x_null, const
   if (rows == 0) return 0;
   const float* xn = (cond_scale == 1.0f) ? nullptr : x_null;
   PHK_REQUIRE(cond_scale == 1.0f || x_null, PHK_E_ARG, "phk_critic_scores: cond_scale != 1 needs the null pass");
-  critic_scores_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, to_stream(s)>>>(x_cond, xn, w, b, u, cond_scale,
-                                                                             noise_K, noise_mult, out, rows, dim, seg_len,
-                                                                             seg_stride, seg_off);
+  PHK_CUDA(launch_pdl(critic_scores_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), (size_t)(0), to_stream(s), x_cond, xn, w, b, u, cond_scale, noise_K, noise_mult, out, rows, dim, seg_len, seg_stride, seg_off));
   PHK_LAUNCH_CHECK();
   return 0;
 }
@@ -703,8 +711,7 @@ extern "C" int phk_cfg_combine(const float* cond, const float* null_out, float c
   PHK_REQUIRE(n >= 0, PHK_E_ARG, "phk_cfg_combine: bad size");
   if (n == 0) return 0;
   const int64_t blocks = (n + 255) / 256;
-  cfg_combine_kernel<<<(unsigned)(blocks < (int64_t)kNumSMs * 16 ? blocks : kNumSMs * 16), 256, 0, to_stream(s)>>>(
-      cond, null_out, cond_scale, out, n);
+  PHK_CUDA(launch_pdl(cfg_combine_kernel, dim3((unsigned)(blocks < (int64_t)kNumSMs * 16 ? blocks : kNumSMs * 16)), dim3(256), (size_t)(0), to_stream(s), cond, null_out, cond_scale, out, n));
   PHK_LAUNCH_CHECK();
   return 0;
 }
