@@ -304,16 +304,23 @@ int phk_maskgit_forward(const phk_maskgit_t* m, const int64_t* ids, int32_t b, i
                         int32_t return_embeds, const float* pos_bias, float* out, void* workspace,
                         int64_t workspace_bytes, int32_t prec, phk_stream_t s);
 
-/* Fused logits head for the sampling loop (phenaki_pytorch.py:213 + 161 + 83-93 + 506-509 + 547-550): a tcgen05
- * GEMM whose epilogue applies bias, classifier-free guidance, gumbel noise (in-kernel Philox, same counter layout as
- * phk_sample_tokens with u == NULL) and reduces argmax / online softmax over the vocabulary, so the (b, n, V) logits
- * never reach HBM.  emb bf16 [ceil(n_tokens/64)*128, dim]: token t's conditional embedding at row (t/64)*128 + t%64,
- * its null-condition embedding 64 rows below.  Outputs as phk_sample_tokens. */
+/* e_cfg = norm_out(x_null) + cond_scale * (norm_out(x_cond) - norm_out(x_null)) as bf16 [rows, dim]
+ * (attention.py:308,332 + phenaki_pytorch.py:161).  to_logits is linear, so applying the classifier-free-guidance
+ * combination to the final embeddings equals applying it to the two logits tensors; dim % 128 == 0, dim <= 1024. */
+int phk_layernorm_cfg(const float* x_cond, const float* x_null, const float* gamma, const float* beta,
+                      float cond_scale, void* out_bf16, int64_t rows, int32_t dim, phk_stream_t s);
+
+/* Fused logits head for the sampling loop (phenaki_pytorch.py:213 + 83-93 + 506-509 + 547-550): a tcgen05 GEMM whose
+ * epilogue applies bias and gumbel noise (in-kernel Philox, same counter layout as phk_sample_tokens with u == NULL)
+ * and reduces argmax / online softmax over the vocabulary straight out of TMEM, so the (b, n, V) logits never exist
+ * in memory.  emb bf16 [emb_rows >= n_tokens, dim <= 512] = guided embeddings (phk_layernorm_cfg, or plain norm_out
+ * rows when there is no guidance); the 128-token A panel stays resident in shared memory, W streams through TMA.
+ * Outputs as phk_sample_tokens. */
 int64_t phk_head_sample_scratch_bytes(int32_t n_tokens);
-int phk_head_sample(const void* emb, int64_t ld_emb, const void* W, int64_t ldw, const float* bias,
-                    int32_t n_tokens, int32_t V, int32_t dim, float cond_scale, float temperature,
-                    uint64_t seed, uint64_t offset, const uint8_t* mask, int64_t* ids, int64_t* pred_out,
-                    float* score_out, void* scratch, int64_t scratch_bytes, phk_stream_t s);
+int phk_head_sample(const void* emb, int64_t ld_emb, int64_t emb_rows, const void* W, int64_t ldw, const float* bias,
+                    int32_t n_tokens, int32_t V, int32_t dim, float temperature, uint64_t seed, uint64_t offset,
+                    const uint8_t* mask, int64_t* ids, int64_t* pred_out, float* score_out, void* scratch,
+                    int64_t scratch_bytes, phk_stream_t s);
 
 /* One demasking iteration's network half for the sampling loop (phenaki_pytorch.py:495-509, 547-550): MaskGit forward
  * of the CFG pair (as phk_maskgit_forward with cfg_pair=1) + phk_head_sample.  bf16 weights required, cond_scale != 1,

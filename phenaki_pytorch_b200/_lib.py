@@ -108,7 +108,8 @@ PROTOTYPES = {
     "phk_maskgit_context_kv": [C.POINTER(MaskgitT), vp, i32, i32, vp, vp, i32, vp],
     "phk_maskgit_workspace_bytes": [C.POINTER(MaskgitT), i32, i32, i32, i32, i32],
     "phk_head_sample_scratch_bytes": [i32],
-    "phk_head_sample": [vp, i64, vp, i64, vp, i32, i32, i32, f32, f32, u64, u64, vp, vp, vp, vp, vp, i64, vp],
+    "phk_layernorm_cfg": [vp, vp, vp, vp, f32, vp, i64, i32, vp],
+    "phk_head_sample": [vp, i64, i64, vp, i64, vp, i32, i32, i32, f32, u64, u64, vp, vp, vp, vp, vp, i64, vp],
     "phk_maskgit_sample_workspace_bytes": [C.POINTER(MaskgitT), i32, i32, i32],
     "phk_maskgit_sample_step": [C.POINTER(MaskgitT), vp, i32, i32, i32, i32, i32, vp, i32, vp, vp, vp, f32, f32, u64,
                                 u64, vp, vp, vp, vp, vp, i64, vp],

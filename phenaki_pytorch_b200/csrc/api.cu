@@ -66,7 +66,7 @@ struct TfCall {
   const uint8_t* ctx_mask;     // [ctx_b, L]
   int ctx_mask_off_from;       // sequences >= this see no text (CFG null half), -1: none
   int prec;
-  int pair_interleave;         // bf16 final-norm rows land as [64 cond | 64 null] per 128-row tile (fused sampling head)
+  void* out_cfg; float cfg_scale;  // bf16 [R/2, dim]: norm_out of the null half + scale * (cond - null) (fused head)
 };
 
 static int64_t tf_scratch_bytes(const phk_transformer_t* T, int64_t R) {
@@ -184,14 +184,12 @@ static int transformer_forward(const TfCall& c, Arena scratch, float* out, void*
     }
   }
   if (out) PHK_TRY(phk_layernorm(x, T->out_g, T->out_b, out, nullptr, R, D, 0, 0, 0, 0, s));
-  if (out_h && c.pair_interleave) {
-    // token t: conditional row -> (t/64)*128 + t%64, null-condition row -> +64 (operand layout of phk_head_sample)
+  if (c.out_cfg) {
+    // classifier-free guidance folded before the (linear) logits head: rows [0,R/2) conditional, [R/2,R) null
     const int64_t half = R / 2;
-    PHK_TRY(phk_layernorm(x, T->out_g, T->out_b, out_h, nullptr, half, D, 1, 64, 128, 0, s));
-    PHK_TRY(phk_layernorm(x + half * D, T->out_g, T->out_b, out_h, nullptr, half, D, 1, 64, 128, 64, s));
-  } else if (out_h) {
-    PHK_TRY(phk_layernorm(x, T->out_g, T->out_b, out_h, nullptr, R, D, 1, 0, 0, 0, s));
+    PHK_TRY(phk_layernorm_cfg(x, x + half * D, T->out_g, T->out_b, c.cfg_scale, c.out_cfg, half, D, s));
   }
+  if (out_h) PHK_TRY(phk_layernorm(x, T->out_g, T->out_b, out_h, nullptr, R, D, 1, 0, 0, 0, s));
   return 0;
 }
 
@@ -436,7 +434,7 @@ extern "C" int phk_maskgit_forward(const phk_maskgit_t* m, const int64_t* ids, i
 extern "C" int64_t phk_maskgit_sample_workspace_bytes(const phk_maskgit_t* m, int32_t b, int32_t n, int32_t L) {
   if (!m || b <= 0 || n <= 0) return -1;
   const int64_t tokens = (int64_t)b * n;
-  return phk_maskgit_workspace_bytes(m, b, n, L, 1, PHK_PREC_BF16) + ((tokens + 63) / 64) * 128 * m->dim * 2 +
+  return phk_maskgit_workspace_bytes(m, b, n, L, 1, PHK_PREC_BF16) + tokens * m->dim * 2 +
          phk_head_sample_scratch_bytes((int32_t)tokens) + 1024;
 }
 
@@ -450,8 +448,8 @@ extern "C" int phk_maskgit_sample_step(const phk_maskgit_t* m, const int64_t* id
   PHK_REQUIRE(b > 0 && n > 0 && (int64_t)pt * ph * pw == n, PHK_E_SHAPE, "video patch shape must cover the token sequence");
   PHK_REQUIRE(n <= m->max_seq_len, PHK_E_SHAPE,
               "the video token sequence length is greater than max_seq_len (phenaki_pytorch.py:196)");
-  PHK_REQUIRE(!m->is_critic && m->head_w_h && cond_scale != 1.0f, PHK_E_UNSUPPORTED,
-              "maskgit_sample_step: needs a MaskGit table with bf16 weights and classifier-free guidance");
+  PHK_REQUIRE(!m->is_critic && m->head_w_h && cond_scale != 1.0f && m->dim <= 512 && m->dim % 128 == 0, PHK_E_UNSUPPORTED,
+              "maskgit_sample_step: needs a MaskGit table with bf16 weights, dim % 128 == 0, dim <= 512 and guidance");
   PHK_REQUIRE(!ctx_kv || text_mask, PHK_E_ARG, "maskgit_sample_step: context without text mask");
   PHK_REQUIRE(workspace_bytes >= phk_maskgit_sample_workspace_bytes(m, b, n, L), PHK_E_WORKSPACE,
               "maskgit_sample_step: workspace too small");
@@ -463,7 +461,7 @@ extern "C" int phk_maskgit_sample_step(const phk_maskgit_t* m, const int64_t* id
   Arena ar{(char*)workspace, workspace_bytes, 0};
   float* x = (float*)ar.take(R * D * 4);
   float* x_alt = (float*)ar.take(R * D * 4);
-  void* emb_h = ar.take(((tokens + 63) / 64) * 128 * D * 2);
+  void* emb_h = ar.take(tokens * D * 2);
   const int64_t hb = phk_head_sample_scratch_bytes((int32_t)tokens);
   void* hsc = ar.take(hb);
   PHK_REQUIRE(x && x_alt && emb_h && hsc, PHK_E_WORKSPACE, "maskgit_sample_step: workspace too small");
@@ -483,8 +481,8 @@ extern "C" int phk_maskgit_sample_step(const phk_maskgit_t* m, const int64_t* id
   c.attn_bias = m->has_bias ? pos_bias : nullptr;
   c.self_mask = video_mask; c.self_mask_mod = b;
   c.ctx_kv = ctx_kv; c.ctx_b = b; c.ctx_L = L; c.ctx_mask = text_mask; c.ctx_mask_off_from = b;
-  c.prec = PHK_PREC_BF16; c.pair_interleave = 1;
-  PHK_TRY(transformer_forward(c, ar, nullptr, emb_h, st));
-  return phk_head_sample(emb_h, D, m->head_w_h, D, m->head_b, (int32_t)tokens, m->num_tokens, D, cond_scale, temperature,
+  c.prec = PHK_PREC_BF16; c.out_cfg = emb_h; c.cfg_scale = cond_scale;
+  PHK_TRY(transformer_forward(c, ar, nullptr, nullptr, st));
+  return phk_head_sample(emb_h, D, tokens, m->head_w_h, D, m->head_b, (int32_t)tokens, m->num_tokens, D, temperature,
                          seed, offset, mask, ids, pred_out, score_out, hsc, hb, s);
 }

@@ -604,31 +604,6 @@ static int get_tensor_map(const void* ptr, int64_t rows, int64_t cols, int64_t l
 
 static long long* g_gemm_trace = nullptr;
 
-// combines the per-split partials of the fused head: pred = argmax, score = 1 - softmax(l)[pred]
-// (phenaki_pytorch.py:506-509, 547-550); same output semantics as sample_tokens_kernel.
-__global__ void head_finalize_kernel(const float4* __restrict__ part_f, const int* __restrict__ part_i, int n_splits,
-                                     int n_tokens, const uint8_t* __restrict__ mask, int64_t* __restrict__ ids,
-                                     int64_t* __restrict__ pred_out, float* __restrict__ score_out) {
-  pdl_prologue();
-  const int tok = blockIdx.x * blockDim.x + threadIdx.x;
-  if (tok >= n_tokens) return;
-  float by = -FLT_MAX, bl = 0.f, m = -FLT_MAX, ssum = 0.f;
-  int bi = 0x7fffffff;
-  for (int s = 0; s < n_splits; ++s) {
-    const float4 f = part_f[(int64_t)tok * n_splits + s];
-    const int i = part_i[(int64_t)tok * n_splits + s];
-    if (f.x > by || (f.x == by && i < bi)) { by = f.x; bi = i; bl = f.y; }
-    const float nm = fmaxf(m, f.z);
-    ssum = ssum * __expf(m - nm) + f.w * __expf(f.z - nm);
-    m = nm;
-  }
-  const float prob = __expf(bl - m) / ssum;
-  const bool mk = mask ? mask[tok] != 0 : true;
-  if (pred_out) pred_out[tok] = bi;
-  if (ids && mk) ids[tok] = bi;
-  if (score_out) score_out[tok] = mk ? 1.0f - prob : -1e4f;
-}
-
 template <int EPI>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const EpiParams& p, cudaStream_t st) {
   static bool configured = false;
@@ -674,47 +649,3 @@ extern "C" int phk_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t 
 
 // debug: device buffer of 16 x int64 per CTA receiving clock64 stamps (relative to CTA start) of the first tile
 extern "C" int phk_debug_gemm_trace(long long* device_buffer) { g_gemm_trace = device_buffer; return 0; }
-
-// Fused logits head (phenaki_pytorch.py:213 + 161 + 83-93 + 506-509 + 547-550): the (b, N, V) logits never reach HBM.
-// emb: bf16 [m_tiles*128, dim] with row (t/64)*128 + t%64 = conditional embedding of token t and row +64 = the
-// null-condition (cond_drop_prob=1) embedding of the same token (rows of missing tokens may hold anything).
-// W: to_logits.weight bf16 [V, dim]; bias fp32 [V].  Noise: in-kernel Philox4x32-10 with the counter layout of
-// phk_sample_tokens (statistical mode).  scratch >= phk_head_sample_scratch_bytes(n_tokens).
-extern "C" int64_t phk_head_sample_scratch_bytes(int32_t n_tokens) {
-  const int m_tiles = (n_tokens + 63) / 64;
-  const int n_splits = m_tiles >= kNumSMs ? 1 : kNumSMs / m_tiles;
-  return (int64_t)n_tokens * n_splits * 20 + 512;
-}
-
-extern "C" int phk_head_sample(const void* emb, int64_t ld_emb, const void* W, int64_t ldw, const float* bias,
-                               int32_t n_tokens, int32_t V, int32_t dim, float cond_scale, float temperature,
-                               uint64_t seed, uint64_t offset, const uint8_t* mask, int64_t* ids, int64_t* pred_out,
-                               float* score_out, void* scratch, int64_t scratch_bytes, phk_stream_t s) {
-  Prof prof_(FAM_GEMM_BF16, s, 4.0 * (double)n_tokens * V * dim);
-  PHK_REQUIRE(emb && W && scratch, PHK_E_ARG, "phk_head_sample: null pointer");
-  PHK_REQUIRE(n_tokens > 0 && V > 0 && dim > 0 && ld_emb >= dim && ldw >= dim, PHK_E_ARG, "phk_head_sample: bad size");
-  PHK_REQUIRE(ld_emb % 8 == 0 && ldw % 8 == 0 && (reinterpret_cast<uintptr_t>(emb) & 15) == 0 &&
-                  (reinterpret_cast<uintptr_t>(W) & 15) == 0,
-              PHK_E_ARG, "phk_head_sample: operands must be 16-byte aligned with leading dimensions multiple of 8 (TMA)");
-  PHK_REQUIRE(scratch_bytes >= phk_head_sample_scratch_bytes(n_tokens), PHK_E_WORKSPACE, "phk_head_sample: scratch too small");
-  const int m_tiles = (n_tokens + 63) / 64;
-  const int n_tiles = (V + GN - 1) / GN;
-  int n_splits = m_tiles >= kNumSMs ? 1 : kNumSMs / m_tiles;
-  if (n_splits > n_tiles) n_splits = n_tiles;
-  const int tps = (n_tiles + n_splits - 1) / n_splits;
-  CUtensorMap ta, tb;
-  PHK_TRY(get_tensor_map(emb, (int64_t)m_tiles * GM, dim, ld_emb, GM, &ta));
-  PHK_TRY(get_tensor_map(W, V, dim, ldw, GN, &tb));
-  char* sc = (char*)(((uintptr_t)scratch + 255) & ~(uintptr_t)255);
-  float4* part_f = (float4*)sc;
-  int* part_i = (int*)(sc + (int64_t)n_tokens * n_splits * 16);
-  const float T = temperature > 1e-10f ? temperature : 1e-10f;
-  EpiParams p{nullptr, 0, (int64_t)m_tiles * GM, V, dim, bias, nullptr, 0, 0, 0, m_tiles, n_tiles, nullptr,
-              n_splits, tps, n_tokens, cond_scale, 1.0f / T, (unsigned long long)seed, (unsigned long long)offset,
-              part_f, part_i};
-  cudaStream_t st = to_stream(s);
-  PHK_TRY(launch_gemm<3>(ta, tb, p, st));
-  PHK_CUDA(launch_pdl(head_finalize_kernel, dim3((n_tokens + 127) / 128), dim3(128), (size_t)(0), st, part_f, part_i, n_splits, n_tokens, mask, ids, pred_out, score_out));
-  PHK_LAUNCH_CHECK();
-  return 0;
-}

@@ -86,16 +86,59 @@ def test_sampling_runs_in_bf16_mode_and_is_deterministic():
     assert (outs[0] < C.SAMPLE_MASKGIT["num_tokens"]).all()
 
 
-def test_fused_sampling_head_matches_unfused_path():
-    """phk_maskgit_sample_step (logits never materialised) vs phk_maskgit_forward + phk_sample_tokens with the same
-    Philox counters: identical sampled ids (same GEMM arithmetic), confidence within 1e-4 (softmax summation order)."""
-    import ctypes as Cc
+def test_layernorm_cfg_combination():
+    """e_cfg = LN(x_null) + s*(LN(x_cond) - LN(x_null)) (guidance folded before the linear logits head)."""
+    rows, dim, scale = 70, 512, 3.0
+    xc, xn = C.seeded_randn((rows, dim), 300) * 2 + 0.3, C.seeded_randn((rows, dim), 301)
+    g, b = C.seeded_randn((dim,), 302), C.seeded_randn((dim,), 303)
+    ln = lambda t: torch.nn.functional.layer_norm(t, (dim,), g, b)
+    ref = ln(xn) + (ln(xc) - ln(xn)) * scale
+    xcd, xnd, gd, bd = xc.to(DEV), xn.to(DEV), g.to(DEV), b.to(DEV)
+    out = torch.empty((rows, dim), dtype=torch.bfloat16, device=DEV)
+    L.check(L.lib().phk_layernorm_cfg(L.ptr(xcd), L.ptr(xnd), L.ptr(gd), L.ptr(bd), scale, L.ptr(out), rows, dim,
+                                      L.stream_ptr()))
+    torch.testing.assert_close(out.cpu().float(), ref, rtol=1e-2, atol=3e-2)  # one bf16 rounding
+
+
+@pytest.mark.parametrize("n_tokens,V,dim", [(300, 1000, 128), (2304, 4096, 512), (64, 130, 256)])
+def test_fused_head_kernel_matches_gemm_plus_sample_tokens(n_tokens, V, dim):
+    """phk_head_sample (logits only ever in TMEM) vs phk_gemm_bf16 -> logits -> phk_sample_tokens with the same
+    Philox counters: identical sampled ids (same MMA arithmetic), confidence within 1e-4 (softmax summation order)."""
+    lib = L.lib()
+    emb = (C.seeded_randn((n_tokens, dim), 310)).bfloat16().to(DEV)
+    W = (C.seeded_randn((V, dim), 311) / dim ** 0.5).bfloat16().to(DEV)
+    bias = C.seeded_randn((V,), 312).to(DEV)
+    g = torch.Generator().manual_seed(5)
+    mask = (torch.rand(n_tokens, generator=g) < 0.6).to(torch.uint8).to(DEV)
+    ids0 = torch.randint(0, V, (n_tokens,), generator=g).to(DEV)
+    seed, offset, temp = 99, 1234567, 0.55
+    logits = torch.empty((n_tokens, V), device=DEV)
+    L.check(lib.phk_gemm_bf16(L.ptr(emb), dim, L.ptr(W), dim, L.ptr(logits), V, n_tokens, V, dim, L.ptr(bias), None,
+                              0, 0, 0, 0, L.stream_ptr()))
+    ids_a, pred_a, sc_a = ids0.clone(), torch.empty_like(ids0), torch.empty(n_tokens, device=DEV)
+    L.check(lib.phk_sample_tokens(L.ptr(logits), None, V, None, seed, offset, 1.0, temp, L.ptr(mask), L.ptr(ids_a),
+                                  L.ptr(pred_a), L.ptr(sc_a), n_tokens, V, 0, 0, 0, L.stream_ptr()))
+    ids_b, pred_b, sc_b = ids0.clone(), torch.empty_like(ids0), torch.empty(n_tokens, device=DEV)
+    nb = lib.phk_head_sample_scratch_bytes(n_tokens)
+    scratch = torch.empty(nb, dtype=torch.uint8, device=DEV)
+    L.check(lib.phk_head_sample(L.ptr(emb), dim, n_tokens, L.ptr(W), dim, L.ptr(bias), n_tokens, V, dim, temp, seed,
+                                offset, L.ptr(mask), L.ptr(ids_b), L.ptr(pred_b), L.ptr(sc_b), L.ptr(scratch), nb,
+                                L.stream_ptr()))
+    torch.cuda.synchronize()
+    assert torch.equal(pred_a, pred_b)
+    assert torch.equal(ids_a, ids_b)
+    torch.testing.assert_close(sc_a, sc_b, rtol=1e-4, atol=1e-4)
+
+
+def test_fused_sample_step_agrees_with_unfused_path():
+    """Model level: guidance folded into the embeddings (fused) vs combined on the logits (reference order).  Same
+    noise counters; the two differ only by bf16 rounding of the guided embedding, so the sampled ids agree on the large
+    majority of tokens and the confidences are close."""
     torch.manual_seed(7)
     cfg = dict(dim=128, num_tokens=1000, max_seq_len=256, heads=2, dim_head=64, depth=2, dim_context=96)
     mg = P.MaskGit(**cfg).to(DEV).eval()
     mg.precision = L.PREC_BF16
-    b, shape = 3, (3, 6, 8)
-    n = 144
+    b, shape, n = 3, (3, 6, 8), 144
     g = torch.Generator().manual_seed(1)
     ids0 = torch.randint(0, cfg["num_tokens"] + 1, (b, n), generator=g).to(DEV)
     ctx = C.synthetic_text_embeds(b, 5, 96, (5, 2, 4), 2).to(DEV)
@@ -104,20 +147,20 @@ def test_fused_sampling_head_matches_unfused_path():
     kv = mg.context_kv(ctx)
     lib = L.lib()
     seed, offset, scale, temp = 1234, 77, 3.0, 0.6
-    # unfused
     logits = mg._run(ids0, shape, ctx_kv=kv, ctx_len=5, text_mask=tmask, cfg_pair=True)
     ids_a, pred_a, sc_a = ids0.clone(), torch.empty_like(ids0), torch.empty((b, n), device=DEV)
     L.check(lib.phk_sample_tokens(L.ptr(logits[:b]), L.ptr(logits[b:]), 1000, None, seed, offset, scale, temp,
                                   L.ptr(mask), L.ptr(ids_a), L.ptr(pred_a), L.ptr(sc_a), b * n, 1000, 0, 0, 0,
                                   L.stream_ptr()))
-    # fused
     ids_b, pred_b, sc_b = ids0.clone(), torch.empty_like(ids0), torch.empty((b, n), device=DEV)
     mg._sample_step(ids_b, shape, ctx_kv=kv, ctx_len=5, text_mask=tmask, cond_scale=scale, temperature=temp, seed=seed,
                     offset=offset, mask=mask, ids=ids_b, pred=pred_b, scores=sc_b)
     torch.cuda.synchronize()
-    assert torch.equal(pred_a, pred_b)
-    assert torch.equal(ids_a, ids_b)
-    torch.testing.assert_close(sc_a, sc_b, rtol=1e-4, atol=1e-4)
+    agree = (pred_a == pred_b).float().mean().item()
+    assert agree >= 0.9, f"only {agree:.3f} of the sampled ids agree"
+    same = pred_a == pred_b
+    torch.testing.assert_close(sc_a[same], sc_b[same], rtol=0.05, atol=2e-3)
+    assert torch.equal(ids_b[mask == 0], ids0[mask == 0]) and torch.equal(ids_b[mask == 1], pred_b[mask == 1])
 
 
 def test_bf16_sampling_with_fused_head_is_deterministic():
