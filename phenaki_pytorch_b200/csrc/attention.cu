@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const float* __r
 // normalised q/k are staged in 2 x n x (DH+1) floats of shared memory for the n*n dot products,
 // softmax runs one row per lane, and P.V accumulates back in registers.  No tensor tile on purpose.
 // ------------------------------------------------------------------------------------------
-constexpr int SMALL_N = 16, SMALL_WARPS = 4;
+constexpr int SMALL_N = 16, SMALL_WARPS = 8;
 
 template <int DH>
 __global__ void __launch_bounds__(SMALL_WARPS * 32) attention_small_kernel(
@@ -221,10 +221,13 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) attention_small_kernel(
     phk_attn_geom_t g) {
   pdl_prologue();
   constexpr int DPL = DH / 32;
-  __shared__ float s_q[SMALL_WARPS][SMALL_N][DH + 1];
-  __shared__ float s_k[SMALL_WARPS][SMALL_N][DH + 1];
-  __shared__ float s_p[SMALL_WARPS][SMALL_N][SMALL_N + 1];
+  constexpr int LDQ = DH + 1;
+  extern __shared__ float small_smem[];  // per warp: q[n][DH+1], k[n][DH+1], p[n][n+1] (sized by the actual n)
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int LDP = g.n_q + 1;
+  float* s_q = small_smem + (size_t)w * (2 * g.n_q * LDQ + g.n_q * LDP);
+  float* s_k = s_q + g.n_q * LDQ;
+  float* s_p = s_k + g.n_q * LDQ;
   const int64_t pair = (int64_t)blockIdx.x * SMALL_WARPS + w;
   const int64_t npairs = (int64_t)g.n_outer * g.n_inner * g.heads;
   if (pair >= npairs) return;  // whole warp exits together
@@ -253,8 +256,8 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) attention_small_kernel(
       const float nq = fmaxf(sqrtf(warp_sum(sq)), 1e-12f), nk = fmaxf(sqrtf(warp_sum(sk)), 1e-12f);
 #pragma unroll
       for (int c = 0; c < DPL; ++c) {
-        s_q[w][i][lane + 32 * c] = (xq[c] / nq) * qs[c];
-        s_k[w][i][lane + 32 * c] = (xk[c] / nk) * ks[c];
+        s_q[i * LDQ + lane + 32 * c] = (xq[c] / nq) * qs[c];
+        s_k[i * LDQ + lane + 32 * c] = (xk[c] / nk) * ks[c];
       }
     }
   }
@@ -266,22 +269,22 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) attention_small_kernel(
     float acc = 0.f;
     if (!g.causal || j <= i) {
 #pragma unroll 16
-      for (int d = 0; d < DH; ++d) acc = fmaf(s_q[w][i][d], s_k[w][j][d], acc);
+      for (int d = 0; d < DH; ++d) acc = fmaf(s_q[i * LDQ + d], s_k[j * LDQ + d], acc);
       acc *= g.scale;
       if (g.causal) acc += -fabsf((float)(j - i)) * slope;
     } else {
       acc = -FLT_MAX;
     }
-    s_p[w][i][j] = acc;
+    s_p[i * LDP + j] = acc;
   }
   __syncwarp();
   if (lane < n) {  // softmax, one row per lane
     float m = -FLT_MAX;
-    for (int j = 0; j < n; ++j) m = fmaxf(m, s_p[w][lane][j]);
+    for (int j = 0; j < n; ++j) m = fmaxf(m, s_p[lane * LDP + j]);
     float sum = 0.f;
-    for (int j = 0; j < n; ++j) { const float e = expf(s_p[w][lane][j] - m); s_p[w][lane][j] = e; sum += e; }
+    for (int j = 0; j < n; ++j) { const float e = expf(s_p[lane * LDP + j] - m); s_p[lane * LDP + j] = e; sum += e; }
     const float inv = 1.f / sum;
-    for (int j = 0; j < n; ++j) s_p[w][lane][j] *= inv;
+    for (int j = 0; j < n; ++j) s_p[lane * LDP + j] *= inv;
   }
   __syncwarp();
   const int64_t ob = (int64_t)so * g.o_outer + (int64_t)si * g.o_inner + (int64_t)h * DH;
@@ -294,7 +297,7 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) attention_small_kernel(
 #pragma unroll
       for (int j = 0; j < SMALL_N; ++j) {
         if (j < n) {
-          const float pv = s_p[w][i][j];
+          const float pv = s_p[i * LDP + j];
 #pragma unroll
           for (int c = 0; c < DPL; ++c) o[c] = fmaf(pv, v[j][c], o[c]);
         }
@@ -325,8 +328,9 @@ __global__ void __launch_bounds__(FEW_WARPS * 32) attention_fewkeys_kernel(
     void* __restrict__ out, phk_attn_geom_t g) {
   pdl_prologue();
   constexpr int DPL = DH / 32;
-  __shared__ float s_k[FEW_KEYS][DH];
+  __shared__ float s_k[FEW_KEYS][DH + 1];   // +1: lane = key reads are bank-conflict free
   __shared__ float s_v[FEW_KEYS][DH];
+  __shared__ float s_qw[FEW_WARPS][DH];     // the warp's current (normalised, scaled) query, read as broadcasts
   __shared__ uint8_t s_ok[FEW_KEYS];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int h = blockIdx.y, seq = blockIdx.z;
@@ -336,20 +340,25 @@ __global__ void __launch_bounds__(FEW_WARPS * 32) attention_fewkeys_kernel(
   const bool mask_dropped = g.mask_off_from >= 0 && so >= g.mask_off_from;
   const int I = g.heads * DH, nnull = g.num_null_kv, nk = g.n_k + nnull;
   const float* kbase = kv + (int64_t)kv_so * g.k_outer + (int64_t)si * g.k_inner + (int64_t)h * DH;
-  for (int j = w; j < nk; j += FEW_WARPS) {
-    const float* kp;
-    const float* vp;
-    if (j < nnull) { kp = null_kv + ((int64_t)h * 2 * nnull + 2 * j) * DH; vp = kp + DH; }   // 'h (n r) d' (:148)
-    else { kp = kbase + (int64_t)(j - nnull) * g.k_tok; vp = kp + I; }
+  for (int j = w; j < FEW_KEYS; j += FEW_WARPS) {
     float x[DPL], ss = 0.f;
+    if (j < nk) {
+      const float* kp;
+      const float* vp;
+      if (j < nnull) { kp = null_kv + ((int64_t)h * 2 * nnull + 2 * j) * DH; vp = kp + DH; }   // 'h (n r) d' (:148)
+      else { kp = kbase + (int64_t)(j - nnull) * g.k_tok; vp = kp + I; }
 #pragma unroll
-    for (int c = 0; c < DPL; ++c) { x[c] = kp[lane + 32 * c]; ss += x[c] * x[c]; s_v[j][lane + 32 * c] = vp[lane + 32 * c]; }
+      for (int c = 0; c < DPL; ++c) { x[c] = kp[lane + 32 * c]; ss += x[c] * x[c]; s_v[j][lane + 32 * c] = vp[lane + 32 * c]; }
+    } else {
+#pragma unroll
+      for (int c = 0; c < DPL; ++c) { x[c] = 0.f; s_v[j][lane + 32 * c] = 0.f; }
+    }
     const float nrm = fmaxf(sqrtf(warp_sum(ss)), 1e-12f);
 #pragma unroll
     for (int c = 0; c < DPL; ++c) s_k[j][lane + 32 * c] = (x[c] / nrm) * k_scale[lane + 32 * c];
     if (lane == 0) {
       const int kj = j - nnull;
-      s_ok[j] = !(key_mask && kj >= 0 && (mask_dropped || !key_mask[(int64_t)mask_row * g.n_k + kj]));
+      s_ok[j] = j < nk && !(key_mask && kj >= 0 && (mask_dropped || !key_mask[(int64_t)mask_row * g.n_k + kj]));
     }
   }
   __syncthreads();
@@ -359,26 +368,32 @@ __global__ void __launch_bounds__(FEW_WARPS * 32) attention_fewkeys_kernel(
   const float* qb = q + (int64_t)so * g.q_outer + (int64_t)si * g.q_inner + (int64_t)h * DH;
   const int64_t ob = (int64_t)so * g.o_outer + (int64_t)si * g.o_inner + (int64_t)h * DH;
   const int q_end = min(g.n_q, (int)(blockIdx.x + 1) * FEW_QTILE);
+  const bool two = nk > 32;
+  // per-lane key state: lane owns key `lane` (and key lane+32 when there are more than 32)
+  const float ok0 = lane < nk ? (s_ok[lane] ? 0.f : -FLT_MAX) : -INFINITY;   // 0: live, -FLT_MAX: masked, -inf: absent
+  const float ok1 = (two && lane + 32 < nk) ? (s_ok[lane + 32] ? 0.f : -FLT_MAX) : -INFINITY;
   for (int qi = blockIdx.x * FEW_QTILE + w; qi < q_end; qi += FEW_WARPS) {
     float x[DPL], ss = 0.f;
 #pragma unroll
     for (int c = 0; c < DPL; ++c) { x[c] = qb[(int64_t)qi * g.q_tok + lane + 32 * c]; ss += x[c] * x[c]; }
     const float nrm = fmaxf(sqrtf(warp_sum(ss)), 1e-12f);
+    __syncwarp();
 #pragma unroll
-    for (int c = 0; c < DPL; ++c) x[c] = (x[c] / nrm) * qs[c];  // scale (8) folded into the query
-    // scores: key j's dot product is reduced across the warp and kept by lane (j & 31), slot (j >> 5); the softmax
-    // then costs one exp per lane instead of two per key
-    float sc[2] = {-INFINITY, -INFINITY};
-    for (int j = 0; j < nk; ++j) {
-      float d = 0.f;
-#pragma unroll
-      for (int c = 0; c < DPL; ++c) d = fmaf(x[c], s_k[j][lane + 32 * c], d);
-      float s = warp_sum(d);
-      if (!s_ok[j]) s = -FLT_MAX;  // masked_fill(~mask, -finfo.max) (:168)
-      if ((j & 31) == lane) sc[j >> 5] = s;
+    for (int c = 0; c < DPL; ++c) s_qw[w][lane + 32 * c] = (x[c] / nrm) * qs[c];  // scale (8) folded into the query
+    __syncwarp();
+    // scores: lane = key; the query is broadcast from shared memory, no shuffles
+    float s0 = 0.f, s1 = 0.f;
+    if (two) {
+#pragma unroll 16
+      for (int d = 0; d < DH; ++d) { const float qd = s_qw[w][d]; s0 = fmaf(qd, s_k[lane][d], s0); s1 = fmaf(qd, s_k[lane + 32][d], s1); }
+    } else {
+#pragma unroll 16
+      for (int d = 0; d < DH; ++d) s0 = fmaf(s_qw[w][d], s_k[lane][d], s0);
     }
-    const float m = warp_max(fmaxf(sc[0], sc[1]));
-    const float p0 = __expf(sc[0] - m), p1 = __expf(sc[1] - m);  // exp(-inf) = 0 for unused slots
+    s0 = ok0 == 0.f ? s0 : ok0;   // masked_fill(~mask, -finfo.max) (:168); absent keys -> -inf
+    s1 = ok1 == 0.f ? s1 : ok1;
+    const float m = warp_max(fmaxf(s0, s1));
+    const float p0 = __expf(s0 - m), p1 = __expf(s1 - m);
     const float l = warp_sum(p0 + p1);
     float o[DPL];
 #pragma unroll
@@ -412,7 +427,14 @@ template <int DH>
 static int launch_attention_small(const float* q, const float* kv, const float* q_scale, const float* k_scale,
                                   const float* alibi_slopes, void* out, const phk_attn_geom_t& g, cudaStream_t st) {
   const int64_t npairs = (int64_t)g.n_outer * g.n_inner * g.heads;
-  PHK_CUDA(launch_pdl(attention_small_kernel<DH>, dim3((unsigned)((npairs + SMALL_WARPS - 1) / SMALL_WARPS)), dim3(SMALL_WARPS * 32), (size_t)(0), st, q, kv, q_scale, k_scale, alibi_slopes, out, g));
+  const size_t smem = (size_t)SMALL_WARPS * (2 * g.n_q * (DH + 1) + g.n_q * (g.n_q + 1)) * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    PHK_CUDA(cudaFuncSetAttribute(attention_small_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(SMALL_WARPS * (2 * SMALL_N * (DH + 1) + SMALL_N * (SMALL_N + 1)) * sizeof(float))));
+    configured = true;
+  }
+  PHK_CUDA(launch_pdl(attention_small_kernel<DH>, dim3((unsigned)((npairs + SMALL_WARPS - 1) / SMALL_WARPS)), dim3(SMALL_WARPS * 32), smem, st, q, kv, q_scale, k_scale, alibi_slopes, out, g));
   PHK_LAUNCH_CHECK();
   return 0;
 }

@@ -200,6 +200,7 @@ __global__ void token_embed_kernel(const int64_t* __restrict__ ids, const float*
 // ------------------------------------------------------------------------------------------
 // LFQ ids (oracle/lfq.py; call site cvivit.py:570).  Warp per row.
 // ------------------------------------------------------------------------------------------
+template <int XPL /* x values per lane = dim / 32 */>
 __global__ void __launch_bounds__(256) lfq_kernel(const float* __restrict__ x, const float* __restrict__ wp,
                                                   const float* __restrict__ bp, int64_t* __restrict__ ids,
                                                   float* __restrict__ proj, int64_t rows, int dim, int bits) {
@@ -209,13 +210,37 @@ __global__ void __launch_bounds__(256) lfq_kernel(const float* __restrict__ x, c
   if (row >= rows) return;
   const float* xr = x + row * dim;
   int64_t id = 0;
-  for (int d = 0; d < bits; ++d) {
-    const float* w = wp + (int64_t)d * dim;
-    float acc = 0.f;
-    for (int i = lane; i < dim; i += 32) acc = fmaf(xr[i], __ldg(w + i), acc);
-    acc = warp_sum(acc) + bp[d];
-    if (proj && lane == 0) proj[row * bits + d] = acc;
-    if (acc > 0.f) id |= (int64_t)1 << (bits - 1 - d);
+  if (XPL > 0) {
+    // the token row stays in registers; all `bits` dot products advance together (independent FMA chains)
+    float xv[XPL > 0 ? XPL : 1];
+#pragma unroll
+    for (int i = 0; i < XPL; ++i) xv[i] = xr[lane + 32 * i];
+    for (int d0 = 0; d0 < bits; d0 += 8) {
+      float acc[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+#pragma unroll
+      for (int i = 0; i < XPL; ++i)
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (d0 + e < bits) acc[e] = fmaf(xv[i], __ldg(wp + (int64_t)(d0 + e) * dim + lane + 32 * i), acc[e]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        if (d0 + e >= bits) break;
+        const float a = warp_sum(acc[e]) + bp[d0 + e];
+        if (proj && lane == 0) proj[row * bits + d0 + e] = a;
+        if (a > 0.f) id |= (int64_t)1 << (bits - 1 - d0 - e);
+      }
+    }
+  } else {
+    for (int d = 0; d < bits; ++d) {
+      const float* w = wp + (int64_t)d * dim;
+      float acc = 0.f;
+      for (int i = lane; i < dim; i += 32) acc = fmaf(xr[i], __ldg(w + i), acc);
+      acc = warp_sum(acc) + bp[d];
+      if (proj && lane == 0) proj[row * bits + d] = acc;
+      if (acc > 0.f) id |= (int64_t)1 << (bits - 1 - d);
+    }
   }
   if (lane == 0) ids[row] = id;
 }
@@ -275,6 +300,69 @@ __global__ void __launch_bounds__(128) peg_kernel(const float* __restrict__ x, c
     }
     const float4 xs = __ldg(reinterpret_cast<const float4*>(x + out_row * D) + d4);
     reinterpret_cast<float4*>(y + out_row * D)[d4] = make_float4(acc.x + xs.x, acc.y + xs.y, acc.z + xs.z, acc.w + xs.w);
+  }
+}
+
+// Frame-tiled variant: one CTA per (logical frame (b,t), 64-channel chunk).  The (up to) three temporal slices the
+// 3x3x3 stencil touches are staged once in shared memory (3 x H*W x 64 floats) together with the 27 x 64 taps, so
+// every x row is fetched 3 times from L2 instead of 27.  Used when the frame fits (H*W <= 128).
+constexpr int PEG_CH = 64;
+__global__ void __launch_bounds__(256) peg_tiled_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, float* __restrict__ y, int T,
+                                                        int H, int W, int D, int pad_t0, int layout) {
+  pdl_prologue();
+  extern __shared__ float peg_smem[];
+  const int P = H * W;
+  float* s_x = peg_smem;                       // [3][P][PEG_CH]
+  float* s_w = s_x + 3 * P * PEG_CH;           // [27][PEG_CH]
+  int* s_row = reinterpret_cast<int*>(s_w + 27 * PEG_CH);  // [3][P] physical rows (-1: slice outside the clip)
+  const int frame = blockIdx.x, ch0 = blockIdx.y * PEG_CH;
+  const int t = frame % T, bi = frame / T;
+  for (int i = threadIdx.x; i < 3 * P; i += blockDim.x) {
+    const int kt = i / P, pp = i - kt * P;
+    const int ts = t + kt - pad_t0;
+    s_row[i] = (ts >= 0 && ts < T) ? (int)peg_phys_row(((int64_t)bi * T + ts) * P + pp, T, P, layout) : -1;
+  }
+  for (int i = threadIdx.x; i < 27 * (PEG_CH / 4); i += blockDim.x) {
+    const int tap = i / (PEG_CH / 4), c4 = i - tap * (PEG_CH / 4);
+    reinterpret_cast<float4*>(s_w)[i] = __ldg(reinterpret_cast<const float4*>(w + (int64_t)tap * D + ch0) + c4);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * P * (PEG_CH / 4); i += blockDim.x) {
+    const int rowi = i / (PEG_CH / 4), c4 = i - rowi * (PEG_CH / 4);
+    const int r = s_row[rowi];
+    reinterpret_cast<float4*>(s_x)[i] = r >= 0 ? __ldg(reinterpret_cast<const float4*>(x + (int64_t)r * D + ch0) + c4)
+                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncthreads();
+  const int c4 = threadIdx.x & 15, pg = threadIdx.x >> 4;  // 16 channel quads x 16 position groups
+  const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + ch0) + c4);
+  for (int pp = pg; pp < P; pp += 16) {
+    const int h = pp / W, wq = pp - h * W;
+    float4 acc = bv;
+#pragma unroll
+    for (int kt = 0; kt < 3; ++kt) {
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        const int hs = h + kh - 1;
+        if (hs < 0 || hs >= H) continue;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const int ws = wq + kw - 1;
+          if (ws < 0 || ws >= W) continue;
+          const float4 xv = reinterpret_cast<const float4*>(s_x)[(kt * P + hs * W + ws) * (PEG_CH / 4) + c4];
+          const float4 wv = reinterpret_cast<const float4*>(s_w)[((kt * 3 + kh) * 3 + kw) * (PEG_CH / 4) + c4];
+          acc.x = fmaf(xv.x, wv.x, acc.x);
+          acc.y = fmaf(xv.y, wv.y, acc.y);
+          acc.z = fmaf(xv.z, wv.z, acc.z);
+          acc.w = fmaf(xv.w, wv.w, acc.w);
+        }
+      }
+    }
+    const float4 xs = reinterpret_cast<const float4*>(s_x)[(pad_t0 * P + pp) * (PEG_CH / 4) + c4];  // residual: slice ts == t
+    const int orow = s_row[pad_t0 * P + pp];
+    reinterpret_cast<float4*>(y + (int64_t)orow * D + ch0)[c4] =
+        make_float4(acc.x + xs.x, acc.y + xs.y, acc.z + xs.z, acc.w + xs.w);
   }
 }
 
@@ -619,7 +707,11 @@ extern "C" int phk_lfq_ids(const float* x, const float* wp, const float* bp, int
   PHK_REQUIRE(x && wp && bp && ids, PHK_E_ARG, "phk_lfq_ids: null pointer");
   PHK_REQUIRE(rows >= 0 && dim > 0 && bits > 0 && bits <= 62, PHK_E_ARG, "phk_lfq_ids: bad size");
   if (rows == 0) return 0;
-  PHK_CUDA(launch_pdl(lfq_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), (size_t)(0), to_stream(s), x, wp, bp, ids, proj_out, rows, dim, bits));
+  const dim3 lg((unsigned)((rows + 7) / 8)), lb(256);
+  if (dim == 512) PHK_CUDA(launch_pdl(lfq_kernel<16>, lg, lb, (size_t)0, to_stream(s), x, wp, bp, ids, proj_out, rows, dim, bits));
+  else if (dim == 256) PHK_CUDA(launch_pdl(lfq_kernel<8>, lg, lb, (size_t)0, to_stream(s), x, wp, bp, ids, proj_out, rows, dim, bits));
+  else if (dim == 1024) PHK_CUDA(launch_pdl(lfq_kernel<32>, lg, lb, (size_t)0, to_stream(s), x, wp, bp, ids, proj_out, rows, dim, bits));
+  else PHK_CUDA(launch_pdl(lfq_kernel<0>, lg, lb, (size_t)0, to_stream(s), x, wp, bp, ids, proj_out, rows, dim, bits));
   PHK_LAUNCH_CHECK();
   return 0;
 }
@@ -632,7 +724,20 @@ extern "C" int phk_peg3d(const float* x, const float* w, const float* b, float* 
   PHK_REQUIRE(D % 4 == 0, PHK_E_UNSUPPORTED, "phk_peg3d: dim must be a multiple of 4");
   const int64_t rows = (int64_t)B * T * H * W;
   PHK_REQUIRE(rows < (1LL << 31), PHK_E_UNSUPPORTED, "phk_peg3d: more than 2^31 positions");
-  PHK_CUDA(launch_pdl(peg_kernel, dim3((unsigned)rows), dim3(128), (size_t)(0), to_stream(s), x, w, b, y, T, H, W, D, causal ? 2 : 1, layout));
+  const int P = H * W;
+  if (P <= 128 && D % PEG_CH == 0) {
+    const size_t smem = (size_t)(3 * P * PEG_CH + 27 * PEG_CH) * sizeof(float) + (size_t)3 * P * sizeof(int);
+    static bool configured = false;
+    if (!configured) {
+      PHK_CUDA(cudaFuncSetAttribute(peg_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)((3 * 128 * PEG_CH + 27 * PEG_CH) * sizeof(float) + 3 * 128 * sizeof(int))));
+      configured = true;
+    }
+    PHK_CUDA(launch_pdl(peg_tiled_kernel, dim3((unsigned)(B * T), (unsigned)(D / PEG_CH)), dim3(256), smem, to_stream(s), x, w,
+                        b, y, T, H, W, D, causal ? 2 : 1, layout));
+  } else {
+    PHK_CUDA(launch_pdl(peg_kernel, dim3((unsigned)rows), dim3(128), (size_t)(0), to_stream(s), x, w, b, y, T, H, W, D, causal ? 2 : 1, layout));
+  }
   PHK_LAUNCH_CHECK();
   return 0;
 }
