@@ -214,7 +214,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const float* __r
 // ------------------------------------------------------------------------------------------
 constexpr int SMALL_N = 16, SMALL_WARPS = 8;
 
-template <int DH>
+// NMAX: compile-time bound of the unrolled row loops (the exact n of the workload when possible: no predicated-off slots)
+template <int DH, int NMAX>
 __global__ void __launch_bounds__(SMALL_WARPS * 32) attention_small_kernel(
     const float* __restrict__ q, const float* __restrict__ kv, const float* __restrict__ q_scale,
     const float* __restrict__ k_scale, const float* __restrict__ alibi_slopes, void* __restrict__ out,
@@ -240,9 +241,9 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) attention_small_kernel(
   float qs[DPL], ks[DPL];
 #pragma unroll
   for (int c = 0; c < DPL; ++c) { qs[c] = q_scale[lane + 32 * c]; ks[c] = k_scale[lane + 32 * c]; }
-  float v[SMALL_N][DPL];
+  float v[NMAX][DPL];
 #pragma unroll
-  for (int i = 0; i < SMALL_N; ++i) {
+  for (int i = 0; i < NMAX; ++i) {
     if (i < n) {
       float xq[DPL], xk[DPL], sq = 0.f, sk = 0.f;
 #pragma unroll
@@ -289,13 +290,13 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) attention_small_kernel(
   __syncwarp();
   const int64_t ob = (int64_t)so * g.o_outer + (int64_t)si * g.o_inner + (int64_t)h * DH;
 #pragma unroll
-  for (int i = 0; i < SMALL_N; ++i) {
+  for (int i = 0; i < NMAX; ++i) {
     if (i < n) {
       float o[DPL];
 #pragma unroll
       for (int c = 0; c < DPL; ++c) o[c] = 0.f;
 #pragma unroll
-      for (int j = 0; j < SMALL_N; ++j) {
+      for (int j = 0; j < NMAX; ++j) {
         if (j < n) {
           const float pv = s_p[i * LDP + j];
 #pragma unroll
@@ -314,102 +315,114 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) attention_small_kernel(
 
 // ------------------------------------------------------------------------------------------
 // Few keys (null-kv + text length <= 64): MaskGit / TokenCritic cross-attention over the T5 context
-// (attention.py:137-168 with num_null_kv = 2).  The 64-wide key tile of the generic kernel would be ~70 % padding
-// and every CTA would re-normalise the same keys, so here the (<= 64) normalised keys and values of one
-// (context sequence, head) are staged once per CTA and each WARP streams queries: lane = d, scores by warp
-// reduction, online softmax with warp-uniform scalars, P.V accumulated in registers.
+// (attention.py:137-168 with num_null_kv = 2).  A 64-wide key tile would be ~70 % padding, so the mapping is turned
+// around: ONE THREAD OWNS ONE QUERY.  Its normalised query (dim_head registers) meets every key / value as a
+// shared-memory BROADCAST (all lanes read the same address), i.e. ~2.5 issue slots per (query, key) dot product
+// instead of ~10 with a lane=d or lane=key mapping.  Two passes over the (few) keys: scores + row max (scores parked
+// in shared memory), then p = exp(s - m), sum and P.V -- no online rescale of the dim_head-wide accumulator.
 // ------------------------------------------------------------------------------------------
-constexpr int FEW_KEYS = 64, FEW_WARPS = 8, FEW_QTILE = 64;
+constexpr int FEW_KEYS = 64, FEW_THREADS = 128;
 
 template <int DH>
-__global__ void __launch_bounds__(FEW_WARPS * 32) attention_fewkeys_kernel(
+__global__ void __launch_bounds__(FEW_THREADS) attention_fewkeys_kernel(
     const float* __restrict__ q, const float* __restrict__ kv, const float* __restrict__ null_kv,
     const float* __restrict__ q_scale, const float* __restrict__ k_scale, const uint8_t* __restrict__ key_mask,
     void* __restrict__ out, phk_attn_geom_t g) {
   pdl_prologue();
   constexpr int DPL = DH / 32;
-  __shared__ float s_k[FEW_KEYS][DH + 1];   // +1: lane = key reads are bank-conflict free
-  __shared__ float s_v[FEW_KEYS][DH];
-  __shared__ float s_qw[FEW_WARPS][DH];     // the warp's current (normalised, scaled) query, read as broadcasts
-  __shared__ uint8_t s_ok[FEW_KEYS];
+  extern __shared__ __align__(16) float few_smem[];
+  const int I = g.heads * DH, nnull = g.num_null_kv, nk = g.n_k + nnull;
+  float* s_k = few_smem;                 // [nk][DH]
+  float* s_v = s_k + nk * DH;            // [nk][DH]
+  float* s_s = s_v + nk * DH;            // [nk][FEW_THREADS] scores, one column per query thread
+  float* s_flag = s_s + nk * FEW_THREADS;  // [nk] 0: live key, -FLT_MAX: masked (masked_fill(~mask, -finfo.max), :168)
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int h = blockIdx.y, seq = blockIdx.z;
   const int so = seq / g.n_inner, si = seq - so * g.n_inner;
   const int kv_so = g.kv_outer_mod > 0 ? so % g.kv_outer_mod : so;
   const int mask_row = g.mask_outer_mod > 0 ? so % g.mask_outer_mod : so;
   const bool mask_dropped = g.mask_off_from >= 0 && so >= g.mask_off_from;
-  const int I = g.heads * DH, nnull = g.num_null_kv, nk = g.n_k + nnull;
   const float* kbase = kv + (int64_t)kv_so * g.k_outer + (int64_t)si * g.k_inner + (int64_t)h * DH;
-  for (int j = w; j < FEW_KEYS; j += FEW_WARPS) {
+  for (int j = w; j < nk; j += FEW_THREADS / 32) {  // warp per key: l2-normalise, * k_scale
+    const float* kp;
+    const float* vp;
+    if (j < nnull) { kp = null_kv + ((int64_t)h * 2 * nnull + 2 * j) * DH; vp = kp + DH; }   // 'h (n r) d' (:148)
+    else { kp = kbase + (int64_t)(j - nnull) * g.k_tok; vp = kp + I; }
     float x[DPL], ss = 0.f;
-    if (j < nk) {
-      const float* kp;
-      const float* vp;
-      if (j < nnull) { kp = null_kv + ((int64_t)h * 2 * nnull + 2 * j) * DH; vp = kp + DH; }   // 'h (n r) d' (:148)
-      else { kp = kbase + (int64_t)(j - nnull) * g.k_tok; vp = kp + I; }
 #pragma unroll
-      for (int c = 0; c < DPL; ++c) { x[c] = kp[lane + 32 * c]; ss += x[c] * x[c]; s_v[j][lane + 32 * c] = vp[lane + 32 * c]; }
-    } else {
-#pragma unroll
-      for (int c = 0; c < DPL; ++c) { x[c] = 0.f; s_v[j][lane + 32 * c] = 0.f; }
-    }
+    for (int c = 0; c < DPL; ++c) { x[c] = kp[lane + 32 * c]; ss += x[c] * x[c]; s_v[j * DH + lane + 32 * c] = vp[lane + 32 * c]; }
     const float nrm = fmaxf(sqrtf(warp_sum(ss)), 1e-12f);
 #pragma unroll
-    for (int c = 0; c < DPL; ++c) s_k[j][lane + 32 * c] = (x[c] / nrm) * k_scale[lane + 32 * c];
+    for (int c = 0; c < DPL; ++c) s_k[j * DH + lane + 32 * c] = (x[c] / nrm) * k_scale[lane + 32 * c];
     if (lane == 0) {
       const int kj = j - nnull;
-      s_ok[j] = j < nk && !(key_mask && kj >= 0 && (mask_dropped || !key_mask[(int64_t)mask_row * g.n_k + kj]));
+      const bool dead = key_mask && kj >= 0 && (mask_dropped || !key_mask[(int64_t)mask_row * g.n_k + kj]);
+      s_flag[j] = dead ? -FLT_MAX : 0.f;
     }
   }
   __syncthreads();
-  float qs[DPL];
+  const int qi = blockIdx.x * FEW_THREADS + threadIdx.x;
+  if (qi >= g.n_q) return;
+  // this thread's query: load (DH floats), l2-normalise, * q_scale * scale(8)
+  float qv[DH];
+  const float4* qp = reinterpret_cast<const float4*>(q + (int64_t)so * g.q_outer + (int64_t)si * g.q_inner +
+                                                     (int64_t)qi * g.q_tok + (int64_t)h * DH);
+  float ss = 0.f;
 #pragma unroll
-  for (int c = 0; c < DPL; ++c) qs[c] = q_scale[lane + 32 * c] * g.scale;
-  const float* qb = q + (int64_t)so * g.q_outer + (int64_t)si * g.q_inner + (int64_t)h * DH;
-  const int64_t ob = (int64_t)so * g.o_outer + (int64_t)si * g.o_inner + (int64_t)h * DH;
-  const int q_end = min(g.n_q, (int)(blockIdx.x + 1) * FEW_QTILE);
-  const bool two = nk > 32;
-  // per-lane key state: lane owns key `lane` (and key lane+32 when there are more than 32)
-  const float ok0 = lane < nk ? (s_ok[lane] ? 0.f : -FLT_MAX) : -INFINITY;   // 0: live, -FLT_MAX: masked, -inf: absent
-  const float ok1 = (two && lane + 32 < nk) ? (s_ok[lane + 32] ? 0.f : -FLT_MAX) : -INFINITY;
-  for (int qi = blockIdx.x * FEW_QTILE + w; qi < q_end; qi += FEW_WARPS) {
-    float x[DPL], ss = 0.f;
+  for (int c = 0; c < DH / 4; ++c) {
+    const float4 t = qp[c];
+    qv[4 * c] = t.x; qv[4 * c + 1] = t.y; qv[4 * c + 2] = t.z; qv[4 * c + 3] = t.w;
+    ss += (t.x * t.x + t.y * t.y) + (t.z * t.z + t.w * t.w);
+  }
+  const float inv_n = g.scale / fmaxf(sqrtf(ss), 1e-12f);
 #pragma unroll
-    for (int c = 0; c < DPL; ++c) { x[c] = qb[(int64_t)qi * g.q_tok + lane + 32 * c]; ss += x[c] * x[c]; }
-    const float nrm = fmaxf(sqrtf(warp_sum(ss)), 1e-12f);
-    __syncwarp();
+  for (int d = 0; d < DH; ++d) qv[d] = qv[d] * inv_n * q_scale[d];
+  // pass 1: scores (keys are shared-memory broadcasts) and the row max
+  float m = -INFINITY;
+  for (int j = 0; j < nk; ++j) {
+    const float4* kr = reinterpret_cast<const float4*>(s_k + j * DH);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
-    for (int c = 0; c < DPL; ++c) s_qw[w][lane + 32 * c] = (x[c] / nrm) * qs[c];  // scale (8) folded into the query
-    __syncwarp();
-    // scores: lane = key; the query is broadcast from shared memory, no shuffles
-    float s0 = 0.f, s1 = 0.f;
-    if (two) {
-#pragma unroll 16
-      for (int d = 0; d < DH; ++d) { const float qd = s_qw[w][d]; s0 = fmaf(qd, s_k[lane][d], s0); s1 = fmaf(qd, s_k[lane + 32][d], s1); }
-    } else {
-#pragma unroll 16
-      for (int d = 0; d < DH; ++d) s0 = fmaf(s_qw[w][d], s_k[lane][d], s0);
+    for (int c = 0; c < DH / 4; ++c) {
+      const float4 kk = kr[c];
+      a0 = fmaf(qv[4 * c], kk.x, a0); a1 = fmaf(qv[4 * c + 1], kk.y, a1);
+      a2 = fmaf(qv[4 * c + 2], kk.z, a2); a3 = fmaf(qv[4 * c + 3], kk.w, a3);
     }
-    s0 = ok0 == 0.f ? s0 : ok0;   // masked_fill(~mask, -finfo.max) (:168); absent keys -> -inf
-    s1 = ok1 == 0.f ? s1 : ok1;
-    const float m = warp_max(fmaxf(s0, s1));
-    const float p0 = __expf(s0 - m), p1 = __expf(s1 - m);
-    const float l = warp_sum(p0 + p1);
-    float o[DPL];
+    float sc = (a0 + a1) + (a2 + a3);
+    if (s_flag[j] != 0.f) sc = -FLT_MAX;
+    s_s[j * FEW_THREADS + threadIdx.x] = sc;
+    m = fmaxf(m, sc);
+  }
+  // pass 2: p = exp(s - m), l = sum p, o = sum p * v  (the query registers are reused as the output accumulator)
 #pragma unroll
-    for (int c = 0; c < DPL; ++c) o[c] = 0.f;
-    for (int j = 0; j < nk; ++j) {
-      const float pj = __shfl_sync(0xffffffffu, (j >> 5) ? p1 : p0, j & 31);
+  for (int d = 0; d < DH; ++d) qv[d] = 0.f;
+  float l = 0.f;
+  for (int j = 0; j < nk; ++j) {
+    const float pj = __expf(s_s[j * FEW_THREADS + threadIdx.x] - m);
+    l += pj;
+    const float4* vr = reinterpret_cast<const float4*>(s_v + j * DH);
 #pragma unroll
-      for (int c = 0; c < DPL; ++c) o[c] = fmaf(pj, s_v[j][lane + 32 * c], o[c]);
+    for (int c = 0; c < DH / 4; ++c) {
+      const float4 vv = vr[c];
+      qv[4 * c] = fmaf(pj, vv.x, qv[4 * c]); qv[4 * c + 1] = fmaf(pj, vv.y, qv[4 * c + 1]);
+      qv[4 * c + 2] = fmaf(pj, vv.z, qv[4 * c + 2]); qv[4 * c + 3] = fmaf(pj, vv.w, qv[4 * c + 3]);
     }
-    const float inv = 1.f / l;
+  }
+  const float inv = 1.f / l;
+  const int64_t off = (int64_t)so * g.o_outer + (int64_t)si * g.o_inner + (int64_t)qi * g.o_tok + (int64_t)h * DH;
+  if (g.out_bf16) {
+    __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(out) + off;
 #pragma unroll
-    for (int c = 0; c < DPL; ++c) {
-      const int64_t off = ob + (int64_t)qi * g.o_tok + lane + 32 * c;
-      if (g.out_bf16) reinterpret_cast<__nv_bfloat16*>(out)[off] = __float2bfloat16_rn(o[c] * inv);
-      else reinterpret_cast<float*>(out)[off] = o[c] * inv;
-    }
+    for (int c = 0; c < DH / 8; ++c)
+      reinterpret_cast<uint4*>(op)[c] = make_uint4(pack_bf16x2(qv[8 * c] * inv, qv[8 * c + 1] * inv),
+                                                    pack_bf16x2(qv[8 * c + 2] * inv, qv[8 * c + 3] * inv),
+                                                    pack_bf16x2(qv[8 * c + 4] * inv, qv[8 * c + 5] * inv),
+                                                    pack_bf16x2(qv[8 * c + 6] * inv, qv[8 * c + 7] * inv));
+  } else {
+    float* op = reinterpret_cast<float*>(out) + off;
+#pragma unroll
+    for (int c = 0; c < DH / 4; ++c)
+      reinterpret_cast<float4*>(op)[c] = make_float4(qv[4 * c] * inv, qv[4 * c + 1] * inv, qv[4 * c + 2] * inv, qv[4 * c + 3] * inv);
   }
 }
 
@@ -417,8 +430,34 @@ template <int DH>
 static int launch_attention_fewkeys(const float* q, const float* kv, const float* null_kv, const float* q_scale,
                                     const float* k_scale, const uint8_t* key_mask, void* out, const phk_attn_geom_t& g,
                                     cudaStream_t st) {
-  dim3 grid((unsigned)((g.n_q + FEW_QTILE - 1) / FEW_QTILE), (unsigned)g.heads, (unsigned)(g.n_outer * g.n_inner));
-  PHK_CUDA(launch_pdl(attention_fewkeys_kernel<DH>, dim3(grid), dim3(FEW_WARPS * 32), (size_t)(0), st, q, kv, null_kv, q_scale, k_scale, key_mask, out, g));
+  const int nk = g.n_k + g.num_null_kv;
+  const size_t smem = (size_t)(2 * nk * DH + nk * FEW_THREADS + nk) * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    PHK_CUDA(cudaFuncSetAttribute(attention_fewkeys_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)((2 * FEW_KEYS * DH + FEW_KEYS * FEW_THREADS + FEW_KEYS) * sizeof(float))));
+    configured = true;
+  }
+  dim3 grid((unsigned)((g.n_q + FEW_THREADS - 1) / FEW_THREADS), (unsigned)g.heads, (unsigned)(g.n_outer * g.n_inner));
+  PHK_CUDA(launch_pdl(attention_fewkeys_kernel<DH>, grid, dim3(FEW_THREADS), smem, st, q, kv, null_kv, q_scale, k_scale,
+                      key_mask, out, g));
+  PHK_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int DH, int NMAX>
+static int launch_attention_small_n(const float* q, const float* kv, const float* q_scale, const float* k_scale,
+                                    const float* alibi_slopes, void* out, const phk_attn_geom_t& g, cudaStream_t st) {
+  const int64_t npairs = (int64_t)g.n_outer * g.n_inner * g.heads;
+  const size_t smem = (size_t)SMALL_WARPS * (2 * g.n_q * (DH + 1) + g.n_q * (g.n_q + 1)) * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    PHK_CUDA(cudaFuncSetAttribute(attention_small_kernel<DH, NMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(SMALL_WARPS * (2 * SMALL_N * (DH + 1) + SMALL_N * (SMALL_N + 1)) * sizeof(float))));
+    configured = true;
+  }
+  PHK_CUDA(launch_pdl(attention_small_kernel<DH, NMAX>, dim3((unsigned)((npairs + SMALL_WARPS - 1) / SMALL_WARPS)),
+                      dim3(SMALL_WARPS * 32), smem, st, q, kv, q_scale, k_scale, alibi_slopes, out, g));
   PHK_LAUNCH_CHECK();
   return 0;
 }
@@ -426,17 +465,12 @@ static int launch_attention_fewkeys(const float* q, const float* kv, const float
 template <int DH>
 static int launch_attention_small(const float* q, const float* kv, const float* q_scale, const float* k_scale,
                                   const float* alibi_slopes, void* out, const phk_attn_geom_t& g, cudaStream_t st) {
-  const int64_t npairs = (int64_t)g.n_outer * g.n_inner * g.heads;
-  const size_t smem = (size_t)SMALL_WARPS * (2 * g.n_q * (DH + 1) + g.n_q * (g.n_q + 1)) * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    PHK_CUDA(cudaFuncSetAttribute(attention_small_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)(SMALL_WARPS * (2 * SMALL_N * (DH + 1) + SMALL_N * (SMALL_N + 1)) * sizeof(float))));
-    configured = true;
-  }
-  PHK_CUDA(launch_pdl(attention_small_kernel<DH>, dim3((unsigned)((npairs + SMALL_WARPS - 1) / SMALL_WARPS)), dim3(SMALL_WARPS * 32), smem, st, q, kv, q_scale, k_scale, alibi_slopes, out, g));
-  PHK_LAUNCH_CHECK();
-  return 0;
+  const int n = g.n_q;
+  if (n <= 3) return launch_attention_small_n<DH, 3>(q, kv, q_scale, k_scale, alibi_slopes, out, g, st);
+  if (n <= 5) return launch_attention_small_n<DH, 5>(q, kv, q_scale, k_scale, alibi_slopes, out, g, st);
+  if (n <= 9) return launch_attention_small_n<DH, 9>(q, kv, q_scale, k_scale, alibi_slopes, out, g, st);
+  if (n <= 12) return launch_attention_small_n<DH, 12>(q, kv, q_scale, k_scale, alibi_slopes, out, g, st);
+  return launch_attention_small_n<DH, 16>(q, kv, q_scale, k_scale, alibi_slopes, out, g, st);
 }
 
 template <int DH>
@@ -481,7 +515,9 @@ extern "C" int phk_attention(const float* q, const float* kv, const float* null_
     if (g->dim_head == 64) return launch_attention_small<64>(q, kv, q_scale, k_scale, alibi_slopes, out, *g, st);
     return launch_attention_small<32>(q, kv, q_scale, k_scale, alibi_slopes, out, *g, st);
   }
-  if (!g->causal && !bias && g->n_k + g->num_null_kv <= FEW_KEYS && (g->dim_head == 64 || g->dim_head == 32)) {
+  if (!g->causal && !bias && g->n_k + g->num_null_kv <= FEW_KEYS && (g->dim_head == 64 || g->dim_head == 32) &&
+      g->q_tok % 4 == 0 && g->q_outer % 4 == 0 && g->q_inner % 4 == 0 && g->o_tok % 8 == 0 && g->o_outer % 8 == 0 &&
+      g->o_inner % 8 == 0 && (reinterpret_cast<uintptr_t>(q) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
     if (g->dim_head == 64) return launch_attention_fewkeys<64>(q, kv, null_kv, q_scale, k_scale, key_mask, out, *g, st);
     return launch_attention_fewkeys<32>(q, kv, null_kv, q_scale, k_scale, key_mask, out, *g, st);
   }

@@ -305,65 +305,102 @@ __global__ void __launch_bounds__(128) peg_kernel(const float* __restrict__ x, c
 
 // Frame-tiled variant: one CTA per (logical frame (b,t), 64-channel chunk).  The (up to) three temporal slices the
 // 3x3x3 stencil touches are staged once in shared memory (3 x H*W x 64 floats) together with the 27 x 64 taps, so
-// every x row is fetched 3 times from L2 instead of 27.  Used when the frame fits (H*W <= 128).
+// every x row is fetched 3 times from L2 instead of 27.  Each thread owns a channel quad and one image ROW: for every
+// (kt, kh) it pulls the W (+2 halo) neighbours of that row into registers once and applies the three kw taps to all W
+// outputs -- ~1/4 of the issue slots of a tap-by-tap loop.  Used when the frame fits (H*W <= 128) and W is 4, 8 or 16.
 constexpr int PEG_CH = 64;
+template <int WW>
 __global__ void __launch_bounds__(256) peg_tiled_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                         const float* __restrict__ bias, float* __restrict__ y, int T,
-                                                        int H, int W, int D, int pad_t0, int layout) {
+                                                        int H, int D, int pad_t0, int layout) {
   pdl_prologue();
   extern __shared__ float peg_smem[];
-  const int P = H * W;
-  float* s_x = peg_smem;                       // [3][P][PEG_CH]
-  float* s_w = s_x + 3 * P * PEG_CH;           // [27][PEG_CH]
-  int* s_row = reinterpret_cast<int*>(s_w + 27 * PEG_CH);  // [3][P] physical rows (-1: slice outside the clip)
+  const int P = H * WW;
+  float4* s_x = reinterpret_cast<float4*>(peg_smem);                  // [3][P][16] channel quads
+  float4* s_w = s_x + 3 * P * (PEG_CH / 4);                           // [27][16]
+  int* s_row = reinterpret_cast<int*>(s_w + 27 * (PEG_CH / 4));       // [3][P] physical rows (-1: outside the clip)
   const int frame = blockIdx.x, ch0 = blockIdx.y * PEG_CH;
   const int t = frame % T, bi = frame / T;
-  for (int i = threadIdx.x; i < 3 * P; i += blockDim.x) {
+  const int nthr = blockDim.x;
+  for (int i = threadIdx.x; i < 3 * P; i += nthr) {
     const int kt = i / P, pp = i - kt * P;
     const int ts = t + kt - pad_t0;
     s_row[i] = (ts >= 0 && ts < T) ? (int)peg_phys_row(((int64_t)bi * T + ts) * P + pp, T, P, layout) : -1;
   }
-  for (int i = threadIdx.x; i < 27 * (PEG_CH / 4); i += blockDim.x) {
-    const int tap = i / (PEG_CH / 4), c4 = i - tap * (PEG_CH / 4);
-    reinterpret_cast<float4*>(s_w)[i] = __ldg(reinterpret_cast<const float4*>(w + (int64_t)tap * D + ch0) + c4);
+  for (int i = threadIdx.x; i < 27 * (PEG_CH / 4); i += nthr)
+    s_w[i] = __ldg(reinterpret_cast<const float4*>(w + (int64_t)(i / (PEG_CH / 4)) * D + ch0) + (i % (PEG_CH / 4)));
+  __syncthreads();
+  const int total = 3 * P * (PEG_CH / 4);
+  for (int i0 = threadIdx.x; i0 < total; i0 += 8 * nthr) {  // 8 independent 16-byte loads in flight per thread
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = i0 + u * nthr;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < total) {
+        const int r = s_row[i / (PEG_CH / 4)];
+        if (r >= 0) v[u] = __ldg(reinterpret_cast<const float4*>(x + (int64_t)r * D + ch0) + (i % (PEG_CH / 4)));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) if (i0 + u * nthr < total) s_x[i0 + u * nthr] = v[u];
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 3 * P * (PEG_CH / 4); i += blockDim.x) {
-    const int rowi = i / (PEG_CH / 4), c4 = i - rowi * (PEG_CH / 4);
-    const int r = s_row[rowi];
-    reinterpret_cast<float4*>(s_x)[i] = r >= 0 ? __ldg(reinterpret_cast<const float4*>(x + (int64_t)r * D + ch0) + c4)
-                                                : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  __syncthreads();
-  const int c4 = threadIdx.x & 15, pg = threadIdx.x >> 4;  // 16 channel quads x 16 position groups
+  const int c4 = threadIdx.x & 15, h = threadIdx.x >> 4;  // 16 channel quads x H rows
+  if (h >= H) return;
   const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + ch0) + c4);
-  for (int pp = pg; pp < P; pp += 16) {
-    const int h = pp / W, wq = pp - h * W;
-    float4 acc = bv;
+  float4 acc[WW];
 #pragma unroll
-    for (int kt = 0; kt < 3; ++kt) {
+  for (int i = 0; i < WW; ++i) acc[i] = bv;
 #pragma unroll
-      for (int kh = 0; kh < 3; ++kh) {
-        const int hs = h + kh - 1;
-        if (hs < 0 || hs >= H) continue;
+  for (int kt = 0; kt < 3; ++kt) {
 #pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-          const int ws = wq + kw - 1;
-          if (ws < 0 || ws >= W) continue;
-          const float4 xv = reinterpret_cast<const float4*>(s_x)[(kt * P + hs * W + ws) * (PEG_CH / 4) + c4];
-          const float4 wv = reinterpret_cast<const float4*>(s_w)[((kt * 3 + kh) * 3 + kw) * (PEG_CH / 4) + c4];
-          acc.x = fmaf(xv.x, wv.x, acc.x);
-          acc.y = fmaf(xv.y, wv.y, acc.y);
-          acc.z = fmaf(xv.z, wv.z, acc.z);
-          acc.w = fmaf(xv.w, wv.w, acc.w);
+    for (int kh = 0; kh < 3; ++kh) {
+      const int hs = h + kh - 1;
+      if (hs < 0 || hs >= H) continue;
+      float4 xr[WW + 2];
+      xr[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+      xr[WW + 1] = xr[0];
+      const float4* src = s_x + (kt * P + hs * WW) * (PEG_CH / 4) + c4;
+#pragma unroll
+      for (int i = 0; i < WW; ++i) xr[i + 1] = src[i * (PEG_CH / 4)];
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const float4 wv = s_w[((kt * 3 + kh) * 3 + kw) * (PEG_CH / 4) + c4];
+#pragma unroll
+        for (int i = 0; i < WW; ++i) {
+          acc[i].x = fmaf(xr[i + kw].x, wv.x, acc[i].x);
+          acc[i].y = fmaf(xr[i + kw].y, wv.y, acc[i].y);
+          acc[i].z = fmaf(xr[i + kw].z, wv.z, acc[i].z);
+          acc[i].w = fmaf(xr[i + kw].w, wv.w, acc[i].w);
         }
       }
     }
-    const float4 xs = reinterpret_cast<const float4*>(s_x)[(pad_t0 * P + pp) * (PEG_CH / 4) + c4];  // residual: slice ts == t
+  }
+#pragma unroll
+  for (int i = 0; i < WW; ++i) {
+    const int pp = h * WW + i;
+    const float4 xs = s_x[(pad_t0 * P + pp) * (PEG_CH / 4) + c4];  // residual: slice ts == t
     const int orow = s_row[pad_t0 * P + pp];
     reinterpret_cast<float4*>(y + (int64_t)orow * D + ch0)[c4] =
-        make_float4(acc.x + xs.x, acc.y + xs.y, acc.z + xs.z, acc.w + xs.w);
+        make_float4(acc[i].x + xs.x, acc[i].y + xs.y, acc[i].z + xs.z, acc[i].w + xs.w);
   }
+}
+
+template <int WW>
+static int launch_peg_tiled(const float* x, const float* w, const float* b, float* y, int B, int T, int H, int D,
+                            int pad_t0, int layout, cudaStream_t st) {
+  const int P = H * WW;
+  const size_t smem = (size_t)(3 * P * PEG_CH + 27 * PEG_CH) * sizeof(float) + (size_t)3 * P * sizeof(int);
+  static bool configured = false;
+  if (!configured) {
+    PHK_CUDA(cudaFuncSetAttribute(peg_tiled_kernel<WW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)((3 * 128 * PEG_CH + 27 * PEG_CH) * sizeof(float) + 3 * 128 * sizeof(int))));
+    configured = true;
+  }
+  PHK_CUDA(launch_pdl(peg_tiled_kernel<WW>, dim3((unsigned)(B * T), (unsigned)(D / PEG_CH)), dim3((unsigned)(16 * H)), smem,
+                      st, x, w, b, y, T, H, D, pad_t0, layout));
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -725,16 +762,11 @@ extern "C" int phk_peg3d(const float* x, const float* w, const float* b, float* 
   const int64_t rows = (int64_t)B * T * H * W;
   PHK_REQUIRE(rows < (1LL << 31), PHK_E_UNSUPPORTED, "phk_peg3d: more than 2^31 positions");
   const int P = H * W;
-  if (P <= 128 && D % PEG_CH == 0) {
-    const size_t smem = (size_t)(3 * P * PEG_CH + 27 * PEG_CH) * sizeof(float) + (size_t)3 * P * sizeof(int);
-    static bool configured = false;
-    if (!configured) {
-      PHK_CUDA(cudaFuncSetAttribute(peg_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)((3 * 128 * PEG_CH + 27 * PEG_CH) * sizeof(float) + 3 * 128 * sizeof(int))));
-      configured = true;
-    }
-    PHK_CUDA(launch_pdl(peg_tiled_kernel, dim3((unsigned)(B * T), (unsigned)(D / PEG_CH)), dim3(256), smem, to_stream(s), x, w,
-                        b, y, T, H, W, D, causal ? 2 : 1, layout));
+  if (P <= 128 && D % PEG_CH == 0 && H <= 16 && (W == 4 || W == 8 || W == 16)) {
+    const int pad = causal ? 2 : 1;
+    if (W == 8) PHK_TRY(launch_peg_tiled<8>(x, w, b, y, B, T, H, D, pad, layout, to_stream(s)));
+    else if (W == 4) PHK_TRY(launch_peg_tiled<4>(x, w, b, y, B, T, H, D, pad, layout, to_stream(s)));
+    else PHK_TRY(launch_peg_tiled<16>(x, w, b, y, B, T, H, D, pad, layout, to_stream(s)));
   } else {
     PHK_CUDA(launch_pdl(peg_kernel, dim3((unsigned)rows), dim3(128), (size_t)(0), to_stream(s), x, w, b, y, T, H, W, D, causal ? 2 : 1, layout));
   }
