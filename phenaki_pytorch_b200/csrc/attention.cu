@@ -241,24 +241,29 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) attention_small_kernel(
   float qs[DPL], ks[DPL];
 #pragma unroll
   for (int c = 0; c < DPL; ++c) { qs[c] = q_scale[lane + 32 * c]; ks[c] = k_scale[lane + 32 * c]; }
-  float v[NMAX][DPL];
+  float v[NMAX][DPL], xq[NMAX][DPL], xk[NMAX][DPL];
+  // all 3n row loads are issued before the first reduction (one exposed memory latency instead of n)
+#pragma unroll
+  for (int i = 0; i < NMAX; ++i) {
+#pragma unroll
+    for (int c = 0; c < DPL; ++c) {
+      const bool in = i < n;
+      xq[i][c] = in ? qb[(int64_t)i * g.q_tok + lane + 32 * c] : 0.f;
+      xk[i][c] = in ? kb[(int64_t)i * g.k_tok + lane + 32 * c] : 0.f;
+      v[i][c] = in ? kb[(int64_t)i * g.k_tok + I + lane + 32 * c] : 0.f;
+    }
+  }
 #pragma unroll
   for (int i = 0; i < NMAX; ++i) {
     if (i < n) {
-      float xq[DPL], xk[DPL], sq = 0.f, sk = 0.f;
+      float sq = 0.f, sk = 0.f;
 #pragma unroll
-      for (int c = 0; c < DPL; ++c) {
-        xq[c] = qb[(int64_t)i * g.q_tok + lane + 32 * c];
-        xk[c] = kb[(int64_t)i * g.k_tok + lane + 32 * c];
-        v[i][c] = kb[(int64_t)i * g.k_tok + I + lane + 32 * c];
-        sq += xq[c] * xq[c];
-        sk += xk[c] * xk[c];
-      }
+      for (int c = 0; c < DPL; ++c) { sq += xq[i][c] * xq[i][c]; sk += xk[i][c] * xk[i][c]; }
       const float nq = fmaxf(sqrtf(warp_sum(sq)), 1e-12f), nk = fmaxf(sqrtf(warp_sum(sk)), 1e-12f);
 #pragma unroll
       for (int c = 0; c < DPL; ++c) {
-        s_q[i * LDQ + lane + 32 * c] = (xq[c] / nq) * qs[c];
-        s_k[i * LDQ + lane + 32 * c] = (xk[c] / nk) * ks[c];
+        s_q[i * LDQ + lane + 32 * c] = (xq[i][c] / nq) * qs[c];
+        s_k[i * LDQ + lane + 32 * c] = (xk[i][c] / nk) * ks[c];
       }
     }
   }
@@ -321,7 +326,10 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) attention_small_kernel(
 // instead of ~10 with a lane=d or lane=key mapping.  Two passes over the (few) keys: scores + row max (scores parked
 // in shared memory), then p = exp(s - m), sum and P.V -- no online rescale of the dim_head-wide accumulator.
 // ------------------------------------------------------------------------------------------
-constexpr int FEW_KEYS = 64, FEW_THREADS = 128;
+// 4 threads split dim_head, and every thread carries QPT queries so that each 16-byte key / value chunk read from
+// shared memory feeds QPT x 4 FMAs (the kernel is shared-memory-bandwidth bound otherwise: LDS.128 = 4 wavefronts)
+constexpr int FEW_KEYS = 64, FEW_THREADS = 128, TPQ = 4, QPT = 4;
+constexpr int FEW_QUERIES = FEW_THREADS / TPQ * QPT;  // 128 queries per CTA
 
 template <int DH>
 __global__ void __launch_bounds__(FEW_THREADS) attention_fewkeys_kernel(
@@ -330,12 +338,13 @@ __global__ void __launch_bounds__(FEW_THREADS) attention_fewkeys_kernel(
     void* __restrict__ out, phk_attn_geom_t g) {
   pdl_prologue();
   constexpr int DPL = DH / 32;
+  constexpr int DP = DH / TPQ;  // d's per thread
   extern __shared__ __align__(16) float few_smem[];
   const int I = g.heads * DH, nnull = g.num_null_kv, nk = g.n_k + nnull;
-  float* s_k = few_smem;                 // [nk][DH]
-  float* s_v = s_k + nk * DH;            // [nk][DH]
-  float* s_s = s_v + nk * DH;            // [nk][FEW_THREADS] scores, one column per query thread
-  float* s_flag = s_s + nk * FEW_THREADS;  // [nk] 0: live key, -FLT_MAX: masked (masked_fill(~mask, -finfo.max), :168)
+  float* s_k = few_smem;                  // [nk][DH]
+  float* s_v = s_k + nk * DH;             // [nk][DH]
+  float* s_s = s_v + nk * DH;             // [nk][FEW_QUERIES] scores, one column per query
+  float* s_flag = s_s + nk * FEW_QUERIES; // [nk] 0: live key, -FLT_MAX: masked (masked_fill(~mask, -finfo.max), :168)
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int h = blockIdx.y, seq = blockIdx.z;
   const int so = seq / g.n_inner, si = seq - so * g.n_inner;
@@ -361,68 +370,104 @@ __global__ void __launch_bounds__(FEW_THREADS) attention_fewkeys_kernel(
     }
   }
   __syncthreads();
-  const int qi = blockIdx.x * FEW_THREADS + threadIdx.x;
-  if (qi >= g.n_q) return;
-  // this thread's query: load (DH floats), l2-normalise, * q_scale * scale(8)
-  float qv[DH];
-  const float4* qp = reinterpret_cast<const float4*>(q + (int64_t)so * g.q_outer + (int64_t)si * g.q_inner +
-                                                     (int64_t)qi * g.q_tok + (int64_t)h * DH);
-  float ss = 0.f;
+  const int tg = threadIdx.x / TPQ, part = threadIdx.x % TPQ;
+  const int ql0 = tg * QPT;                               // first local query of this thread group
+  const int q0 = blockIdx.x * FEW_QUERIES + ql0;
+  float qv[QPT][DP];
+  float ss[QPT];
+  const float* qbase = q + (int64_t)so * g.q_outer + (int64_t)si * g.q_inner + (int64_t)h * DH + part * DP;
 #pragma unroll
-  for (int c = 0; c < DH / 4; ++c) {
-    const float4 t = qp[c];
-    qv[4 * c] = t.x; qv[4 * c + 1] = t.y; qv[4 * c + 2] = t.z; qv[4 * c + 3] = t.w;
-    ss += (t.x * t.x + t.y * t.y) + (t.z * t.z + t.w * t.w);
+  for (int u = 0; u < QPT; ++u) {
+    ss[u] = 0.f;
+    const bool valid = q0 + u < g.n_q;
+#pragma unroll
+    for (int c = 0; c < DP / 4; ++c) {
+      const float4 t = valid ? reinterpret_cast<const float4*>(qbase + (int64_t)(q0 + u) * g.q_tok)[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+      qv[u][4 * c] = t.x; qv[u][4 * c + 1] = t.y; qv[u][4 * c + 2] = t.z; qv[u][4 * c + 3] = t.w;
+      ss[u] += (t.x * t.x + t.y * t.y) + (t.z * t.z + t.w * t.w);
+    }
   }
-  const float inv_n = g.scale / fmaxf(sqrtf(ss), 1e-12f);
 #pragma unroll
-  for (int d = 0; d < DH; ++d) qv[d] = qv[d] * inv_n * q_scale[d];
-  // pass 1: scores (keys are shared-memory broadcasts) and the row max
-  float m = -INFINITY;
+  for (int u = 0; u < QPT; ++u) {
+    ss[u] += __shfl_xor_sync(0xffffffffu, ss[u], 1);
+    ss[u] += __shfl_xor_sync(0xffffffffu, ss[u], 2);
+    const float inv_n = g.scale / fmaxf(sqrtf(ss[u]), 1e-12f);
+#pragma unroll
+    for (int d = 0; d < DP; ++d) qv[u][d] = qv[u][d] * inv_n * q_scale[part * DP + d];
+  }
+  // pass 1: scores and row maxima; every key chunk read from shared memory is used by QPT queries
+  float m[QPT];
+#pragma unroll
+  for (int u = 0; u < QPT; ++u) m[u] = -INFINITY;
   for (int j = 0; j < nk; ++j) {
-    const float4* kr = reinterpret_cast<const float4*>(s_k + j * DH);
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    const float4* kr = reinterpret_cast<const float4*>(s_k + j * DH + part * DP);
+    float a[QPT];
 #pragma unroll
-    for (int c = 0; c < DH / 4; ++c) {
+    for (int u = 0; u < QPT; ++u) a[u] = 0.f;
+#pragma unroll
+    for (int c = 0; c < DP / 4; ++c) {
       const float4 kk = kr[c];
-      a0 = fmaf(qv[4 * c], kk.x, a0); a1 = fmaf(qv[4 * c + 1], kk.y, a1);
-      a2 = fmaf(qv[4 * c + 2], kk.z, a2); a3 = fmaf(qv[4 * c + 3], kk.w, a3);
-    }
-    float sc = (a0 + a1) + (a2 + a3);
-    if (s_flag[j] != 0.f) sc = -FLT_MAX;
-    s_s[j * FEW_THREADS + threadIdx.x] = sc;
-    m = fmaxf(m, sc);
-  }
-  // pass 2: p = exp(s - m), l = sum p, o = sum p * v  (the query registers are reused as the output accumulator)
 #pragma unroll
-  for (int d = 0; d < DH; ++d) qv[d] = 0.f;
-  float l = 0.f;
+      for (int u = 0; u < QPT; ++u) {
+        a[u] = fmaf(qv[u][4 * c], kk.x, a[u]); a[u] = fmaf(qv[u][4 * c + 1], kk.y, a[u]);
+        a[u] = fmaf(qv[u][4 * c + 2], kk.z, a[u]); a[u] = fmaf(qv[u][4 * c + 3], kk.w, a[u]);
+      }
+    }
+    const bool dead = s_flag[j] != 0.f;
+#pragma unroll
+    for (int u = 0; u < QPT; ++u) {
+      float sc = a[u];
+      sc += __shfl_xor_sync(0xffffffffu, sc, 1);
+      sc += __shfl_xor_sync(0xffffffffu, sc, 2);
+      if (dead) sc = -FLT_MAX;
+      if (part == u) s_s[j * FEW_QUERIES + ql0 + u] = sc;  // spread the QPT stores over the 4 threads of the group
+      m[u] = fmaxf(m[u], sc);
+    }
+  }
+  __syncwarp();
+  // pass 2: p = exp(s - m), l = sum p, o = sum p * v  (the query registers are reused as the output accumulators)
+  float l[QPT];
+#pragma unroll
+  for (int u = 0; u < QPT; ++u) {
+    l[u] = 0.f;
+#pragma unroll
+    for (int d = 0; d < DP; ++d) qv[u][d] = 0.f;
+  }
   for (int j = 0; j < nk; ++j) {
-    const float pj = __expf(s_s[j * FEW_THREADS + threadIdx.x] - m);
-    l += pj;
-    const float4* vr = reinterpret_cast<const float4*>(s_v + j * DH);
+    const float4 s4 = *reinterpret_cast<const float4*>(s_s + j * FEW_QUERIES + ql0);
+    const float pj[QPT] = {__expf(s4.x - m[0]), __expf(s4.y - m[1]), __expf(s4.z - m[2]), __expf(s4.w - m[3])};
+    const float4* vr = reinterpret_cast<const float4*>(s_v + j * DH + part * DP);
 #pragma unroll
-    for (int c = 0; c < DH / 4; ++c) {
+    for (int u = 0; u < QPT; ++u) l[u] += pj[u];
+#pragma unroll
+    for (int c = 0; c < DP / 4; ++c) {
       const float4 vv = vr[c];
-      qv[4 * c] = fmaf(pj, vv.x, qv[4 * c]); qv[4 * c + 1] = fmaf(pj, vv.y, qv[4 * c + 1]);
-      qv[4 * c + 2] = fmaf(pj, vv.z, qv[4 * c + 2]); qv[4 * c + 3] = fmaf(pj, vv.w, qv[4 * c + 3]);
+#pragma unroll
+      for (int u = 0; u < QPT; ++u) {
+        qv[u][4 * c] = fmaf(pj[u], vv.x, qv[u][4 * c]); qv[u][4 * c + 1] = fmaf(pj[u], vv.y, qv[u][4 * c + 1]);
+        qv[u][4 * c + 2] = fmaf(pj[u], vv.z, qv[u][4 * c + 2]); qv[u][4 * c + 3] = fmaf(pj[u], vv.w, qv[u][4 * c + 3]);
+      }
     }
   }
-  const float inv = 1.f / l;
-  const int64_t off = (int64_t)so * g.o_outer + (int64_t)si * g.o_inner + (int64_t)qi * g.o_tok + (int64_t)h * DH;
-  if (g.out_bf16) {
-    __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(out) + off;
 #pragma unroll
-    for (int c = 0; c < DH / 8; ++c)
-      reinterpret_cast<uint4*>(op)[c] = make_uint4(pack_bf16x2(qv[8 * c] * inv, qv[8 * c + 1] * inv),
-                                                    pack_bf16x2(qv[8 * c + 2] * inv, qv[8 * c + 3] * inv),
-                                                    pack_bf16x2(qv[8 * c + 4] * inv, qv[8 * c + 5] * inv),
-                                                    pack_bf16x2(qv[8 * c + 6] * inv, qv[8 * c + 7] * inv));
-  } else {
-    float* op = reinterpret_cast<float*>(out) + off;
+  for (int u = 0; u < QPT; ++u) {
+    if (q0 + u >= g.n_q) continue;
+    const float inv = 1.f / l[u];
+    const int64_t off = (int64_t)so * g.o_outer + (int64_t)si * g.o_inner + (int64_t)(q0 + u) * g.o_tok + (int64_t)h * DH + part * DP;
+    if (g.out_bf16) {
+      __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(out) + off;
 #pragma unroll
-    for (int c = 0; c < DH / 4; ++c)
-      reinterpret_cast<float4*>(op)[c] = make_float4(qv[4 * c] * inv, qv[4 * c + 1] * inv, qv[4 * c + 2] * inv, qv[4 * c + 3] * inv);
+      for (int c = 0; c < DP / 8; ++c)
+        reinterpret_cast<uint4*>(op)[c] = make_uint4(pack_bf16x2(qv[u][8 * c] * inv, qv[u][8 * c + 1] * inv),
+                                                      pack_bf16x2(qv[u][8 * c + 2] * inv, qv[u][8 * c + 3] * inv),
+                                                      pack_bf16x2(qv[u][8 * c + 4] * inv, qv[u][8 * c + 5] * inv),
+                                                      pack_bf16x2(qv[u][8 * c + 6] * inv, qv[u][8 * c + 7] * inv));
+    } else {
+      float* op = reinterpret_cast<float*>(out) + off;
+#pragma unroll
+      for (int c = 0; c < DP / 4; ++c)
+        reinterpret_cast<float4*>(op)[c] = make_float4(qv[u][4 * c] * inv, qv[u][4 * c + 1] * inv, qv[u][4 * c + 2] * inv, qv[u][4 * c + 3] * inv);
+    }
   }
 }
 
@@ -431,16 +476,162 @@ static int launch_attention_fewkeys(const float* q, const float* kv, const float
                                     const float* k_scale, const uint8_t* key_mask, void* out, const phk_attn_geom_t& g,
                                     cudaStream_t st) {
   const int nk = g.n_k + g.num_null_kv;
-  const size_t smem = (size_t)(2 * nk * DH + nk * FEW_THREADS + nk) * sizeof(float);
+  const size_t smem = (size_t)(2 * nk * DH + nk * FEW_QUERIES + nk) * sizeof(float);
   static bool configured = false;
   if (!configured) {
     PHK_CUDA(cudaFuncSetAttribute(attention_fewkeys_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)((2 * FEW_KEYS * DH + FEW_KEYS * FEW_THREADS + FEW_KEYS) * sizeof(float))));
+                                  (int)((2 * FEW_KEYS * DH + FEW_KEYS * FEW_QUERIES + FEW_KEYS) * sizeof(float))));
     configured = true;
   }
-  dim3 grid((unsigned)((g.n_q + FEW_THREADS - 1) / FEW_THREADS), (unsigned)g.heads, (unsigned)(g.n_outer * g.n_inner));
+  dim3 grid((unsigned)((g.n_q + FEW_QUERIES - 1) / FEW_QUERIES), (unsigned)g.heads, (unsigned)(g.n_outer * g.n_inner));
   PHK_CUDA(launch_pdl(attention_fewkeys_kernel<DH>, grid, dim3(FEW_THREADS), smem, st, q, kv, null_kv, q_scale, k_scale,
                       key_mask, out, g));
+  PHK_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Short sequences, thread-per-query variant (the one used): a CTA holds G = 128 / n (sequence, head) groups; thread
+// (group, i) owns query i AND stages key / value row i of its group (each thread normalises its own rows: no
+// shuffles).  Scores, softmax and P.V then run entirely in registers against the group's keys / values in shared
+// memory -- ~1500 issue slots per 32 queries instead of per 9.
+// ------------------------------------------------------------------------------------------
+constexpr int ROWS_THREADS = 256, ROWS_QUERIES = ROWS_THREADS / 4;
+template <int DH, int NMAX>
+__global__ void __launch_bounds__(ROWS_THREADS) attention_rows_kernel(const float* __restrict__ q, const float* __restrict__ kv,
+                                                                      const float* __restrict__ q_scale,
+                                                                      const float* __restrict__ k_scale,
+                                                                      const float* __restrict__ alibi_slopes,
+                                                                      void* __restrict__ out, phk_attn_geom_t g) {
+  pdl_prologue();
+  constexpr int DP = DH / 4;  // 4 threads share one query / one staged key+value row
+  extern __shared__ __align__(16) float rows_smem[];  // [G][n*DH + 16] keys, then the same for values
+  const int n = g.n_q, G = ROWS_QUERIES / n;
+  const int GS = n * DH + 16;  // group stride: the +16 floats stagger the banks of neighbouring groups
+  const int ql = threadIdx.x >> 2, part = threadIdx.x & 3;
+  const int grp = ql / n, i = ql - grp * n;
+  const int64_t pair = (int64_t)blockIdx.x * G + grp;
+  const int64_t npairs = (int64_t)g.n_outer * g.n_inner * g.heads;
+  const bool active = grp < G && pair < npairs;
+  float* s_k = rows_smem + (size_t)(grp < G ? grp : 0) * GS;
+  float* s_v = rows_smem + (size_t)G * GS + (size_t)(grp < G ? grp : 0) * GS;
+  const int I = g.heads * DH;
+  float qv[DP];
+  float4 kr[DP / 4];
+  int h = 0;
+  int64_t obase = 0;
+  float sq = 0.f, sk = 0.f;
+  if (active) {
+    h = (int)(pair % g.heads);
+    const int seq = (int)(pair / g.heads);
+    const int so = seq / g.n_inner, si = seq - so * g.n_inner;
+    const float4* qp = reinterpret_cast<const float4*>(q + (int64_t)so * g.q_outer + (int64_t)si * g.q_inner +
+                                                       (int64_t)i * g.q_tok + (int64_t)h * DH + part * DP);
+    const float4* kp = reinterpret_cast<const float4*>(kv + (int64_t)so * g.k_outer + (int64_t)si * g.k_inner +
+                                                       (int64_t)i * g.k_tok + (int64_t)h * DH + part * DP);
+    const float4* vp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(kp) + I);
+    obase = (int64_t)so * g.o_outer + (int64_t)si * g.o_inner + (int64_t)i * g.o_tok + (int64_t)h * DH + part * DP;
+#pragma unroll
+    for (int c = 0; c < DP / 4; ++c) {
+      const float4 t = qp[c];
+      qv[4 * c] = t.x; qv[4 * c + 1] = t.y; qv[4 * c + 2] = t.z; qv[4 * c + 3] = t.w;
+      sq += (t.x * t.x + t.y * t.y) + (t.z * t.z + t.w * t.w);
+      kr[c] = kp[c];
+      sk += (kr[c].x * kr[c].x + kr[c].y * kr[c].y) + (kr[c].z * kr[c].z + kr[c].w * kr[c].w);
+      reinterpret_cast<float4*>(s_v + i * DH + part * DP)[c] = vp[c];
+    }
+  } else {
+#pragma unroll
+    for (int d = 0; d < DP; ++d) qv[d] = 0.f;
+#pragma unroll
+    for (int c = 0; c < DP / 4; ++c) kr[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  sq += __shfl_xor_sync(0xffffffffu, sq, 1); sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+  sk += __shfl_xor_sync(0xffffffffu, sk, 1); sk += __shfl_xor_sync(0xffffffffu, sk, 2);
+  if (active) {
+    const float iq = g.scale / fmaxf(sqrtf(sq), 1e-12f), ik = 1.f / fmaxf(sqrtf(sk), 1e-12f);
+#pragma unroll
+    for (int c = 0; c < DP / 4; ++c) {
+      const float4 ks = *reinterpret_cast<const float4*>(k_scale + part * DP + 4 * c);
+      reinterpret_cast<float4*>(s_k + i * DH + part * DP)[c] =
+          make_float4(kr[c].x * ik * ks.x, kr[c].y * ik * ks.y, kr[c].z * ik * ks.z, kr[c].w * ik * ks.w);
+      const float4 qs = *reinterpret_cast<const float4*>(q_scale + part * DP + 4 * c);
+      qv[4 * c] *= iq * qs.x; qv[4 * c + 1] *= iq * qs.y; qv[4 * c + 2] *= iq * qs.z; qv[4 * c + 3] *= iq * qs.w;
+    }
+  }
+  __syncthreads();
+  const float slope = (g.causal && alibi_slopes && active) ? alibi_slopes[h] : 0.f;
+  float sc[NMAX];
+  float m = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < NMAX; ++j) {
+    float a0 = 0.f, a1 = 0.f;
+    if (j < n) {
+      const float4* krow = reinterpret_cast<const float4*>(s_k + j * DH + part * DP);
+#pragma unroll
+      for (int c = 0; c < DP / 4; ++c) {
+        const float4 kk = krow[c];
+        a0 = fmaf(qv[4 * c], kk.x, a0); a1 = fmaf(qv[4 * c + 1], kk.y, a1);
+        a0 = fmaf(qv[4 * c + 2], kk.z, a0); a1 = fmaf(qv[4 * c + 3], kk.w, a1);
+      }
+    }
+    float sj = a0 + a1;
+    sj += __shfl_xor_sync(0xffffffffu, sj, 1);
+    sj += __shfl_xor_sync(0xffffffffu, sj, 2);
+    const bool live = j < n && (!g.causal || j <= i);
+    if (g.causal) sj += -fabsf((float)(j - i)) * slope;  // ALiBi (attention.py:170-174)
+    sc[j] = live ? sj : -INFINITY;
+    m = fmaxf(m, sc[j]);
+  }
+  if (!active) return;
+  float l = 0.f;
+#pragma unroll
+  for (int d = 0; d < DP; ++d) qv[d] = 0.f;  // reuse as the output accumulator
+#pragma unroll
+  for (int j = 0; j < NMAX; ++j) {
+    if (j < n && (!g.causal || j <= i)) {
+      const float pj = __expf(sc[j] - m);
+      l += pj;
+      const float4* vr = reinterpret_cast<const float4*>(s_v + j * DH + part * DP);
+#pragma unroll
+      for (int c = 0; c < DP / 4; ++c) {
+        const float4 vv = vr[c];
+        qv[4 * c] = fmaf(pj, vv.x, qv[4 * c]); qv[4 * c + 1] = fmaf(pj, vv.y, qv[4 * c + 1]);
+        qv[4 * c + 2] = fmaf(pj, vv.z, qv[4 * c + 2]); qv[4 * c + 3] = fmaf(pj, vv.w, qv[4 * c + 3]);
+      }
+    }
+  }
+  const float inv = 1.f / l;
+  if (g.out_bf16) {
+    __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(out) + obase;
+#pragma unroll
+    for (int c = 0; c < DP / 8; ++c)
+      reinterpret_cast<uint4*>(op)[c] = make_uint4(pack_bf16x2(qv[8 * c] * inv, qv[8 * c + 1] * inv),
+                                                    pack_bf16x2(qv[8 * c + 2] * inv, qv[8 * c + 3] * inv),
+                                                    pack_bf16x2(qv[8 * c + 4] * inv, qv[8 * c + 5] * inv),
+                                                    pack_bf16x2(qv[8 * c + 6] * inv, qv[8 * c + 7] * inv));
+  } else {
+    float* op = reinterpret_cast<float*>(out) + obase;
+#pragma unroll
+    for (int c = 0; c < DP / 4; ++c)
+      reinterpret_cast<float4*>(op)[c] = make_float4(qv[4 * c] * inv, qv[4 * c + 1] * inv, qv[4 * c + 2] * inv, qv[4 * c + 3] * inv);
+  }
+}
+
+template <int DH, int NMAX>
+static int launch_attention_rows(const float* q, const float* kv, const float* q_scale, const float* k_scale,
+                                 const float* alibi_slopes, void* out, const phk_attn_geom_t& g, cudaStream_t st) {
+  const int n = g.n_q, G = ROWS_QUERIES / n;
+  const int64_t npairs = (int64_t)g.n_outer * g.n_inner * g.heads;
+  const size_t smem = (size_t)2 * G * (n * DH + 16) * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    PHK_CUDA(cudaFuncSetAttribute(attention_rows_kernel<DH, NMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(2 * ROWS_QUERIES * (DH + 16) * sizeof(float))));
+    configured = true;
+  }
+  PHK_CUDA(launch_pdl(attention_rows_kernel<DH, NMAX>, dim3((unsigned)((npairs + G - 1) / G)), dim3(ROWS_THREADS), smem, st, q,
+                      kv, q_scale, k_scale, alibi_slopes, out, g));
   PHK_LAUNCH_CHECK();
   return 0;
 }
@@ -466,6 +657,18 @@ template <int DH>
 static int launch_attention_small(const float* q, const float* kv, const float* q_scale, const float* k_scale,
                                   const float* alibi_slopes, void* out, const phk_attn_geom_t& g, cudaStream_t st) {
   const int n = g.n_q;
+  const bool aligned = g.q_tok % 4 == 0 && g.q_outer % 4 == 0 && g.q_inner % 4 == 0 && g.k_tok % 4 == 0 &&
+                       g.k_outer % 4 == 0 && g.k_inner % 4 == 0 && g.o_tok % 8 == 0 && g.o_outer % 8 == 0 &&
+                       g.o_inner % 8 == 0 && (reinterpret_cast<uintptr_t>(q) & 15) == 0 &&
+                       (reinterpret_cast<uintptr_t>(kv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+                       (reinterpret_cast<uintptr_t>(q_scale) & 15) == 0 && (reinterpret_cast<uintptr_t>(k_scale) & 15) == 0;
+  if (aligned) {  // thread-per-query kernel
+    if (n <= 3) return launch_attention_rows<DH, 3>(q, kv, q_scale, k_scale, alibi_slopes, out, g, st);
+    if (n <= 5) return launch_attention_rows<DH, 5>(q, kv, q_scale, k_scale, alibi_slopes, out, g, st);
+    if (n <= 9) return launch_attention_rows<DH, 9>(q, kv, q_scale, k_scale, alibi_slopes, out, g, st);
+    if (n <= 12) return launch_attention_rows<DH, 12>(q, kv, q_scale, k_scale, alibi_slopes, out, g, st);
+    return launch_attention_rows<DH, 16>(q, kv, q_scale, k_scale, alibi_slopes, out, g, st);
+  }
   if (n <= 3) return launch_attention_small_n<DH, 3>(q, kv, q_scale, k_scale, alibi_slopes, out, g, st);
   if (n <= 5) return launch_attention_small_n<DH, 5>(q, kv, q_scale, k_scale, alibi_slopes, out, g, st);
   if (n <= 9) return launch_attention_small_n<DH, 9>(q, kv, q_scale, k_scale, alibi_slopes, out, g, st);

@@ -24,7 +24,8 @@ constexpr int AKC = 64;   // keys per chunk (UMMA N for S, K extent for PV)
 constexpr int ADH = 64;   // dim_head
 constexpr int ATHREADS = 192;
 constexpr int SQ_BYTES = AQ * ADH * 2, SK_BYTES = AKC * ADH * 2, SV_BYTES = ADH * AKC * 2, SP_BYTES = AQ * AKC * 2;
-constexpr int ATT_SMEM = SQ_BYTES + SK_BYTES + SV_BYTES + SP_BYTES + 128 + 1024;
+constexpr int SB_BYTES = 2 * AQ * 128;  // bias tile: two [128 rows x 32 fp32] SWIZZLE_128B boxes
+constexpr int ATT_SMEM = SQ_BYTES + SK_BYTES + SV_BYTES + SP_BYTES + SB_BYTES + 128 + 1024;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -54,6 +55,11 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint32_t bar
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {  // K-major, SWIZZLE_128B (see gemm_tcgen05.cu)
   uint64_t d = 0;
@@ -102,11 +108,13 @@ struct AttTcParams {
   __nv_bfloat16* out;       // [.., heads*64] bf16; token i of sequence s at (s*o_seq + i*o_tok) elements
   int n_q, n_k, heads;
   int64_t o_seq, o_tok;
+  int bias_tma;  // 1: the bias tile arrives through TMA (tmB) into shared memory, 0: direct loads
 };
 
 __global__ void __launch_bounds__(ATHREADS, 2) attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
                                                                    const __grid_constant__ CUtensorMap tmK,
                                                                    const __grid_constant__ CUtensorMap tmV,
+                                                                   const __grid_constant__ CUtensorMap tmB,
                                                                    AttTcParams p) {
   pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
@@ -114,10 +122,12 @@ __global__ void __launch_bounds__(ATHREADS, 2) attention_tc_kernel(const __grid_
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t sQ = base, sK = sQ + SQ_BYTES, sV = sK + SK_BYTES, sP = sV + SV_BYTES;
   uint8_t* sP_ptr = base_ptr + SQ_BYTES + SK_BYTES + SV_BYTES;
-  const uint32_t bars = sP + SP_BYTES;
+  const uint32_t sBias = sP + SP_BYTES;
+  const uint8_t* sBias_ptr = sP_ptr + SP_BYTES;
+  const uint32_t bars = sBias + SB_BYTES;
   const uint32_t b_qfull = bars, b_kfull = bars + 8, b_kempty = bars + 16, b_vfull = bars + 24, b_vempty = bars + 32,
                  b_sfull = bars + 40, b_sempty = bars + 48, b_pfull = bars + 56, b_pvdone = bars + 64,
-                 tmem_slot = bars + 72;
+                 b_bfull = bars + 72, b_bempty = bars + 80, tmem_slot = bars + 88;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * AQ, h = blockIdx.y, seq = blockIdx.z;
   const int sh = seq * p.heads + h;
@@ -129,7 +139,7 @@ __global__ void __launch_bounds__(ATHREADS, 2) attention_tc_kernel(const __grid_
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmV) : "memory");
     mbar_init(b_qfull, 1); mbar_init(b_kfull, 1); mbar_init(b_kempty, 1); mbar_init(b_vfull, 1);
     mbar_init(b_vempty, 1); mbar_init(b_sfull, 1); mbar_init(b_sempty, 4); mbar_init(b_pfull, 4);
-    mbar_init(b_pvdone, 1);
+    mbar_init(b_pvdone, 1); mbar_init(b_bfull, 1); mbar_init(b_bempty, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -149,6 +159,12 @@ __global__ void __launch_bounds__(ATHREADS, 2) attention_tc_kernel(const __grid_
       mbar_expect_tx(b_qfull, SQ_BYTES);
       tma_load_3d(&tmQ, b_qfull, sQ, 0, q0, sh);
       for (int j = 0; j < nch; ++j) {
+        if (p.bias_tma) {  // bias tile of this (head, query tile, key chunk): rows h*n_q + q0.., two 32-column boxes
+          mbar_wait(b_bempty, (j & 1) ^ 1);
+          mbar_expect_tx(b_bfull, SB_BYTES);
+          tma_load_2d(&tmB, b_bfull, sBias, j * AKC, h * p.n_q + q0);
+          tma_load_2d(&tmB, b_bfull, sBias + AQ * 128, j * AKC + 32, h * p.n_q + q0);
+        }
         mbar_wait(b_kempty, (j & 1) ^ 1);
         mbar_expect_tx(b_kfull, SK_BYTES);
         tma_load_3d(&tmK, b_kfull, sK, 0, j * AKC, sh);
@@ -192,17 +208,19 @@ __global__ void __launch_bounds__(ATHREADS, 2) attention_tc_kernel(const __grid_
     float m_run = -INFINITY, l_run = 0.f;
     for (int j = 0; j < nch; ++j) {
       const int k0 = j * AKC;
-      // bias for this chunk: issued before waiting for S so the L2 latency overlaps the QK^T MMA
       float bv[AKC];
-      if (brow && bias_vec && k0 + AKC <= p.n_k) {
+      if (!p.bias_tma) {
+        // direct path (no bias, or a bias whose row pitch TMA cannot address): issued before waiting for S
+        if (brow && bias_vec && k0 + AKC <= p.n_k) {
 #pragma unroll
-        for (int c = 0; c < AKC / 4; ++c) {
-          const float4 t = __ldg(reinterpret_cast<const float4*>(brow + k0) + c);
-          bv[4 * c] = t.x; bv[4 * c + 1] = t.y; bv[4 * c + 2] = t.z; bv[4 * c + 3] = t.w;
+          for (int c = 0; c < AKC / 4; ++c) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(brow + k0) + c);
+            bv[4 * c] = t.x; bv[4 * c + 1] = t.y; bv[4 * c + 2] = t.z; bv[4 * c + 3] = t.w;
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < AKC; ++c) bv[c] = (brow && k0 + c < p.n_k) ? __ldg(brow + k0 + c) : 0.f;
         }
-      } else {
-#pragma unroll
-        for (int c = 0; c < AKC; ++c) bv[c] = (brow && k0 + c < p.n_k) ? __ldg(brow + k0 + c) : 0.f;
       }
       mbar_wait(b_sfull, j & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -212,6 +230,21 @@ __global__ void __launch_bounds__(ATHREADS, 2) attention_tc_kernel(const __grid_
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(b_sempty);  // S may be overwritten by the next QK^T
+      if (p.bias_tma) {
+        // this row of the TMA-staged tile: 16-byte chunk c of row r sits at chunk (c ^ (r & 7)) (SWIZZLE_128B)
+        mbar_wait(b_bfull, j & 1);
+#pragma unroll
+        for (int sb = 0; sb < 2; ++sb) {
+          const uint8_t* rowp = sBias_ptr + sb * (AQ * 128) + r * 128;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 t = *reinterpret_cast<const float4*>(rowp + ((c ^ (r & 7)) << 4));
+            bv[sb * 32 + 4 * c] = t.x; bv[sb * 32 + 4 * c + 1] = t.y; bv[sb * 32 + 4 * c + 2] = t.z; bv[sb * 32 + 4 * c + 3] = t.w;
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(b_bempty);  // tile consumed (values are in registers)
+      }
       float mx = -INFINITY;
 #pragma unroll
       for (int c = 0; c < AKC; ++c) {
@@ -348,6 +381,21 @@ EncodeTiledFn encode_fn() {
 }
 
 // bf16 [d2][d1][d0] with d0 contiguous; box [1][b1][64]; SWIZZLE_128B; zero OOB fill
+// fp32 [rows][cols] bias, box [128 rows][32 cols = 128 B], SWIZZLE_128B, zero OOB fill
+int make_map_bias(const float* ptr, int64_t rows, int64_t cols, CUtensorMap* out) {
+  EncodeTiledFn fn = encode_fn();
+  PHK_REQUIRE(fn, PHK_E_UNSUPPORTED, "cuTensorMapEncodeTiled not available from the driver");
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)cols * 4};
+  const cuuint32_t box[2] = {32, (cuuint32_t)AQ};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PHK_REQUIRE(r == CUDA_SUCCESS, PHK_E_ARG, "cuTensorMapEncodeTiled rejected the attention bias");
+  return 0;
+}
+
 int make_map_3d(const void* ptr, int64_t d0, int64_t d1, int64_t d2, int64_t stride1_elems, int64_t stride2_elems,
                 int box1, CUtensorMap* out) {
   EncodeTiledFn fn = encode_fn();
@@ -404,9 +452,12 @@ extern "C" int phk_attention_tc(const float* q, const float* kv, const float* q_
     PHK_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
     configured = true;
   }
-  AttTcParams p{bias, (__nv_bfloat16*)out_bf16, n, n, heads, (int64_t)n * heads * 64, (int64_t)heads * 64};
+  const int bias_tma = bias && (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(bias) & 15) == 0);
+  CUtensorMap tb = tq;  // placeholder when unused
+  if (bias_tma) PHK_TRY(make_map_bias(bias, (int64_t)heads * n, n, &tb));
+  AttTcParams p{bias, (__nv_bfloat16*)out_bf16, n, n, heads, (int64_t)n * heads * 64, (int64_t)heads * 64, bias_tma};
   dim3 grid((unsigned)((n + AQ - 1) / AQ), (unsigned)heads, (unsigned)n_seq);
-  PHK_CUDA(launch_pdl(attention_tc_kernel, dim3(grid), dim3(ATHREADS), (size_t)(ATT_SMEM), st, tq, tk, tv, p));
+  PHK_CUDA(launch_pdl(attention_tc_kernel, dim3(grid), dim3(ATHREADS), (size_t)(ATT_SMEM), st, tq, tk, tv, tb, p));
   PHK_LAUNCH_CHECK();
   return 0;
 }
