@@ -300,7 +300,21 @@ def main():
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     assert torch.equal(host_ids, model(vids[(K - 1) % 3], return_only_codebook_ids=True).cpu())
-    e2e_value = world * B * F * K / S.max_over_ranks(e2e_s, dev)
+    e2e_sync_value = world * B * F * K / S.max_over_ranks(e2e_s, dev)
+
+    # the same through the public streaming API (CViViT.encode_host_iter -> phk_encode_pipe_*): every step still does
+    # its own H2D from pinned memory and D2H of the ids, but batch i+1's copy overlaps batch i's encode
+    for _ in model.encode_host_iter((host[i % 3] for i in range(3)), device=dev):
+        pass
+    barrier()
+    t0 = time.perf_counter()
+    last = None
+    for last in model.encode_host_iter((host[i % 3] for i in range(K)), device=dev):
+        pass
+    torch.cuda.synchronize()
+    e2e_pipe_s = time.perf_counter() - t0
+    assert torch.equal(last, host_ids)
+    e2e_value = world * B * F * K / S.max_over_ranks(e2e_pipe_s, dev)
 
     # ---- per-kernel-family device time (CUDA events on the launching stream) over 3 more steps ----
     lib.phk_prof_enable(1)
@@ -341,7 +355,10 @@ def main():
                                      "PHK_PREC_BF16 (tcgen05 bf16 GEMMs, fp32 accumulate/residual/LN/softmax)"},
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": B * Cc * F * H * Wd * 4,
                 "d2h_bytes_per_step": B * tp * hh * ww * 8,
-                "api": "phk_cvivit_encode_host (C ABI, pinned host video -> host int64 ids)"},
+                "api": "CViViT.encode_host_iter -> phk_encode_pipe_submit/wait (C ABI; pinned host video -> host int64 "
+                       "ids every step, the H2D of step i+1 overlaps the encode of step i)",
+                "sync_call_value": e2e_sync_value,
+                "sync_call_api": "phk_cvivit_encode_host (one blocking call per step: H2D, encode, D2H, sync)"},
         "gpu_launches": int(launches),
         "roofline": roof,
         "clocks": clocks,

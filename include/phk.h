@@ -118,6 +118,19 @@ typedef struct {
   const float* vq_w; const float* vq_b;           /* vq.project_in [bits, dim], [bits]          */
 } phk_cvivit_t;
 
+/* cvivit.py:323-335 the decoder half of CViViT (vq.project_out, dec_* transformers, to_pixels*) */
+typedef struct {
+  int32_t dim, heads, dim_head, channels;
+  int32_t image_h, image_w, patch_h, patch_w;
+  int32_t patch_t, codebook_bits;
+  const float* vq_out_w; const float* vq_out_b;   /* vq.project_out [dim, bits], [dim]          */
+  phk_cpb_t spatial_bias;                         /* spatial_rel_pos_bias (shared with encode)  */
+  phk_transformer_t temporal;                     /* dec_temporal_transformer                   */
+  phk_transformer_t spatial;                      /* dec_spatial_transformer                    */
+  const float* px_first_w; const float* px_first_b; const void* px_first_w_h; /* to_pixels_first_frame.0 [C*p1*p2, dim] */
+  const float* px_w; const float* px_b; const void* px_w_h;                   /* to_pixels.0 [C*pt*p1*p2, dim]          */
+} phk_cvivit_dec_t;
+
 /* phenaki_pytorch.py:105-147 MaskGit / :217-249 TokenCritic (is_critic: no bias, Linear(dim,1)) */
 typedef struct {
   int32_t dim, heads, dim_head, num_tokens, max_seq_len, is_critic, has_bias, _pad;
@@ -136,7 +149,8 @@ typedef struct {
 /* F.layer_norm over the last dim, eps 1e-5 (attention.py:35-36, :48, :308).
  * out_bf16!=0 writes __nv_bfloat16 instead of float.  raw_bf16 (optional, bf16 mode) also
  * receives the un-normalised row converted to bf16 (self-attention projects k,v from raw x,
- * attention.py:140-144).  Output row map as in phk_gemm_f32 (seg_len<=0: identity). */
+ * attention.py:140-144).  Row map as in phk_gemm_f32: seg_len>0 places the OUTPUT row (scatter), seg_len<0 picks
+ * the INPUT row with |seg_len| (gather; `rows` then counts output rows), seg_len==0: identity. */
 int phk_layernorm(const float* x, const float* gamma, const float* beta, void* out, void* raw_bf16,
                   int64_t rows, int32_t dim, int32_t out_bf16, int64_t seg_len, int64_t seg_stride,
                   int64_t seg_off, phk_stream_t s);
@@ -223,6 +237,17 @@ int phk_cpb_bias(const phk_cpb_t* c, int32_t d0, int32_t d1, int32_t d2, float* 
 int phk_lfq_ids(const float* x, const float* wp, const float* bp, int64_t* ids, float* proj_out,
                 int64_t rows, int32_t dim, int32_t bits, phk_stream_t s);
 
+/* LFQ indices_to_codes + project_out (cvivit.py:437-439 -> LFQ.indices_to_codes, oracle/lfq.py):
+ * out[r, :] = w_out @ (bit_j(id_r) ? +1 : -1)_j + b_out, bits MSB first; w_out [dim, bits]; out fp32 [rows, dim]. */
+int phk_lfq_codes(const int64_t* ids, const float* w_out, const float* b_out, float* out,
+                  int64_t rows, int32_t dim, int32_t bits, phk_stream_t s);
+
+/* Rearrange 'b t h w (c pt p1 p2) -> b c (t pt) (h p1) (w p2)' (cvivit.py:286-295), the mirror of phk_patchify_ln:
+ * P fp32 [B*nt*(H/p1)*(W/p2), ldp >= C*pt*p1*p2] -> frames [f0, f0 + nt*pt) of video (B,C,F,H,W) fp32. */
+int phk_unpatchify(const float* P, int64_t ldp, float* video, int32_t B, int32_t C, int32_t F,
+                   int32_t H, int32_t W, int32_t f0, int32_t nt, int32_t pt, int32_t p1, int32_t p2,
+                   phk_stream_t s);
+
 /* token_emb[id] + pos_emb[pos] then x*a + x*(1-a) (phenaki_pytorch.py:194-199); a<0 skips the
  * shrink (TokenCritic, :290-291). rows = b*n. */
 int phk_token_embed(const int64_t* ids, const float* tok, const float* pos, float* out,
@@ -280,6 +305,33 @@ int phk_cvivit_encode_host(const phk_cvivit_t* m, const float* host_video, int32
                            int64_t* host_ids, void* dev_video, int64_t* dev_ids, void* workspace,
                            int64_t workspace_bytes, int32_t prec, const float* spatial_bias,
                            phk_stream_t s);
+
+/* Pipelined variant of phk_cvivit_encode_host for a stream of batches (what a tokenisation job over a dataset does):
+ * submit() enqueues H2D on the pipe's own copy stream, encode + D2H of the ids on the caller's stream `s`, and
+ * returns at once; the copy of batch i+1 overlaps the encode of batch i.  The caller owns `depth` staging slots:
+ * dev_video_slots = depth x (B,C,F,H,W) floats, dev_ids_slots = depth x B*T'*H'*W' int64 (slot = ticket % depth), and
+ * must keep B, F fixed while tickets are in flight.  host_video should be pinned and must stay untouched until
+ * wait(ticket) returns.  wait(ticket) blocks until that
+ * batch's host_ids are valid; at most `depth` tickets may be in flight.  Host-side objects only (one stream, 3*depth
+ * events); no device memory is allocated. */
+typedef struct phk_encode_pipe phk_encode_pipe_t;
+int phk_encode_pipe_create(phk_encode_pipe_t** pipe, int32_t depth);
+int phk_encode_pipe_destroy(phk_encode_pipe_t* pipe);
+int phk_encode_pipe_submit(phk_encode_pipe_t* pipe, const phk_cvivit_t* m, const float* host_video, int32_t B,
+                           int32_t F, int64_t* host_ids, void* dev_video_slots, int64_t* dev_ids_slots,
+                           void* workspace, int64_t workspace_bytes, int32_t prec, const float* spatial_bias,
+                           phk_stream_t s, int64_t* ticket);
+int phk_encode_pipe_wait(phk_encode_pipe_t* pipe, int64_t ticket);
+
+/* CViViT.decode_from_codebook_indices(ids) / CViViT.decode(tokens) (cvivit.py:437-443, 476-516):
+ * LFQ indices_to_codes -> dec_temporal_transformer -> dec_spatial_transformer -> to_pixels un-patchify.
+ * ids (B, T'*H'*W') int64 device, or ids == NULL and tokens [B*T'*H'*W', dim] fp32 (decode of float tokens);
+ * video (B, C, 1 + (T'-1)*pt, H, W) fp32 device.  taps: optional fp32 [B*T'*H'*W', dim] in (b,t,h,w) order. */
+int64_t phk_cvivit_decode_workspace_bytes(const phk_cvivit_dec_t* m, int32_t B, int32_t Tp, int32_t prec);
+int phk_cvivit_decode(const phk_cvivit_dec_t* m, const int64_t* ids, const float* tokens, int32_t B,
+                      int32_t Tp, float* video, void* workspace, int64_t workspace_bytes, int32_t prec,
+                      const float* spatial_bias, float* tap_codes, float* tap_temporal,
+                      float* tap_spatial, phk_stream_t s);
 
 /* context_norm + to_kv of every cross-attention layer (attention.py:137-144).  Depends only on
  * the text embedding, so Phenaki.sample computes it once per call instead of once per forward.

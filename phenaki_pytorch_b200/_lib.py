@@ -57,6 +57,16 @@ class CvivitT(C.Structure):
                 ("vq_w", c_f), ("vq_b", c_f)]
 
 
+class CvivitDecT(C.Structure):
+    _fields_ = [("dim", C.c_int32), ("heads", C.c_int32), ("dim_head", C.c_int32), ("channels", C.c_int32),
+                ("image_h", C.c_int32), ("image_w", C.c_int32), ("patch_h", C.c_int32), ("patch_w", C.c_int32),
+                ("patch_t", C.c_int32), ("codebook_bits", C.c_int32),
+                ("vq_out_w", c_f), ("vq_out_b", c_f),
+                ("spatial_bias", CpbT), ("temporal", TransformerT), ("spatial", TransformerT),
+                ("px_first_w", c_f), ("px_first_b", c_f), ("px_first_w_h", c_f),
+                ("px_w", c_f), ("px_b", c_f), ("px_w_h", c_f)]
+
+
 class MaskgitT(C.Structure):
     _fields_ = [("dim", C.c_int32), ("heads", C.c_int32), ("dim_head", C.c_int32), ("num_tokens", C.c_int32),
                 ("max_seq_len", C.c_int32), ("is_critic", C.c_int32), ("has_bias", C.c_int32), ("_pad", C.c_int32),
@@ -97,6 +107,8 @@ PROTOTYPES = {
     "phk_cpb_scratch_floats": [C.POINTER(CpbT), i32, i32, i32],
     "phk_cpb_bias": [C.POINTER(CpbT), i32, i32, i32, vp, vp, vp],
     "phk_lfq_ids": [vp, vp, vp, vp, vp, i64, i32, i32, vp],
+    "phk_lfq_codes": [vp, vp, vp, vp, i64, i32, i32, vp],
+    "phk_unpatchify": [vp, i64, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp],
     "phk_token_embed": [vp, vp, vp, vp, i32, i32, i32, i32, f32, i32, vp],
     "phk_sample_tokens": [vp, vp, i64, vp, u64, u64, f32, f32, vp, vp, vp, vp, i64, i32, i64, i64, i64, vp],
     "phk_topk_mask": [vp, i32, i32, i32, vp, vp, i64, vp],
@@ -105,6 +117,12 @@ PROTOTYPES = {
     "phk_cvivit_workspace_bytes": [C.POINTER(CvivitT), i32, i32, i32],
     "phk_cvivit_encode": [C.POINTER(CvivitT), vp, i32, i32, vp, vp, i64, i32, vp, vp, vp, vp, vp, vp],
     "phk_cvivit_encode_host": [C.POINTER(CvivitT), vp, i32, i32, vp, vp, vp, vp, i64, i32, vp, vp],
+    "phk_encode_pipe_create": [C.POINTER(vp), i32],
+    "phk_encode_pipe_destroy": [vp],
+    "phk_encode_pipe_submit": [vp, C.POINTER(CvivitT), vp, i32, i32, vp, vp, vp, vp, i64, i32, vp, vp, C.POINTER(i64)],
+    "phk_encode_pipe_wait": [vp, i64],
+    "phk_cvivit_decode_workspace_bytes": [C.POINTER(CvivitDecT), i32, i32, i32],
+    "phk_cvivit_decode": [C.POINTER(CvivitDecT), vp, vp, i32, i32, vp, vp, i64, i32, vp, vp, vp, vp, vp],
     "phk_maskgit_context_kv": [C.POINTER(MaskgitT), vp, i32, i32, vp, vp, i32, vp],
     "phk_maskgit_workspace_bytes": [C.POINTER(MaskgitT), i32, i32, i32, i32, i32],
     "phk_head_sample_scratch_bytes": [i32],
@@ -118,7 +136,7 @@ PROTOTYPES = {
 }
 _RESTYPES = {"phk_attention_tc_scratch_bytes": i64, "phk_head_sample_scratch_bytes": i64,
              "phk_maskgit_sample_workspace_bytes": i64, "phk_last_error": C.c_char_p, "phk_launch_count": i64, "phk_cpb_scratch_floats": i64,
-             "phk_cvivit_workspace_bytes": i64, "phk_maskgit_workspace_bytes": i64}
+             "phk_cvivit_workspace_bytes": i64, "phk_cvivit_decode_workspace_bytes": i64, "phk_maskgit_workspace_bytes": i64}
 
 FAMILIES = ["patchify_ln", "layernorm", "gemm_f32", "gemm_bf16", "attention", "peg", "geglu", "lfq", "embed",
             "cpb", "sample_tokens", "topk_mask", "critic", "cfg_combine"]

@@ -67,6 +67,9 @@ struct TfCall {
   int ctx_mask_off_from;       // sequences >= this see no text (CFG null half), -1: none
   int prec;
   void* out_cfg; float cfg_scale;  // bf16 [R/2, dim]: norm_out of the null half + scale * (cond - null) (fused head)
+  // decoder tail: norm_out gathered into two dense operands (activation type of the mode) -- rows of the first
+  // frame (t == 0) and of the remaining frames, each in (b,t,h,w) order (cvivit.py:506)
+  void* out_first; void* out_rest; int split_B, split_T, split_hw;
 };
 
 static int64_t tf_scratch_bytes(const phk_transformer_t* T, int64_t R) {
@@ -190,6 +193,15 @@ static int transformer_forward(const TfCall& c, Arena scratch, float* out, void*
     PHK_TRY(phk_layernorm_cfg(x, x + half * D, T->out_g, T->out_b, c.cfg_scale, c.out_cfg, half, D, s));
   }
   if (out_h) PHK_TRY(phk_layernorm(x, T->out_g, T->out_b, out_h, nullptr, R, D, 1, 0, 0, 0, s));
+  if (c.out_first) {
+    const int64_t hw = c.split_hw, per = (int64_t)c.split_T * hw;
+    PHK_REQUIRE((int64_t)c.split_B * per == R, PHK_E_SHAPE, "transformer: frame split does not cover the tokens");
+    PHK_TRY(phk_layernorm(x, T->out_g, T->out_b, c.out_first, nullptr, c.split_B * hw, D, h16, -hw, per, 0, s));
+    if (c.split_T > 1) {
+      PHK_REQUIRE(c.out_rest, PHK_E_ARG, "transformer: out_rest missing");
+      PHK_TRY(phk_layernorm(x, T->out_g, T->out_b, c.out_rest, nullptr, c.split_B * (per - hw), D, h16, -(per - hw), per, hw, s));
+    }
+  }
   return 0;
 }
 
@@ -336,6 +348,179 @@ extern "C" int phk_cvivit_encode_host(const phk_cvivit_t* m, const float* host_v
                             nullptr, nullptr, nullptr, nullptr, s));
   PHK_CUDA(cudaMemcpyAsync(host_ids, dev_ids, R * 8, cudaMemcpyDeviceToHost, st));
   PHK_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// --------------------------------------------------------------------------------------------
+// Host-buffer encode pipeline: the H2D copy of call i+1 (107 MB at cfg2, ~2 ms of PCIe) runs on the pipe's own copy
+// stream while call i is still encoding on the caller's stream; the caller provides `depth` staging slots.
+// --------------------------------------------------------------------------------------------
+struct phk_encode_pipe {
+  int depth;
+  int64_t next;                          // next ticket
+  cudaStream_t copy;
+  std::vector<cudaEvent_t> h2d_done;     // [depth] copy stream: the slot's video has landed
+  std::vector<cudaEvent_t> slot_free;    // [depth] compute stream: the encode that read the slot has finished
+  std::vector<cudaEvent_t> done;         // [depth] compute stream: the slot's ids are in host memory
+};
+
+extern "C" int phk_encode_pipe_create(phk_encode_pipe_t** out, int32_t depth) {
+  PHK_REQUIRE(out && depth >= 1 && depth <= 8, PHK_E_ARG, "phk_encode_pipe_create: depth must be 1..8");
+  phk_encode_pipe* p = new phk_encode_pipe();
+  p->depth = depth; p->next = 0; p->copy = nullptr;
+  cudaError_t e = cudaStreamCreateWithFlags(&p->copy, cudaStreamNonBlocking);
+  for (int i = 0; i < depth && e == cudaSuccess; ++i) {
+    cudaEvent_t a = nullptr, b = nullptr, c = nullptr;
+    e = cudaEventCreateWithFlags(&a, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c, cudaEventDisableTiming);
+    p->h2d_done.push_back(a); p->slot_free.push_back(b); p->done.push_back(c);
+  }
+  if (e != cudaSuccess) { phk_encode_pipe_destroy(p); PHK_CUDA(e); }
+  *out = p;
+  return 0;
+}
+
+extern "C" int phk_encode_pipe_destroy(phk_encode_pipe_t* p) {
+  if (!p) return 0;
+  for (auto ev : p->h2d_done) if (ev) cudaEventDestroy(ev);
+  for (auto ev : p->slot_free) if (ev) cudaEventDestroy(ev);
+  for (auto ev : p->done) if (ev) cudaEventDestroy(ev);
+  if (p->copy) cudaStreamDestroy(p->copy);
+  delete p;
+  return 0;
+}
+
+extern "C" int phk_encode_pipe_submit(phk_encode_pipe_t* p, const phk_cvivit_t* m, const float* host_video, int32_t B,
+                                      int32_t F, int64_t* host_ids, void* dev_video_slots, int64_t* dev_ids_slots,
+                                      void* workspace, int64_t workspace_bytes, int32_t prec,
+                                      const float* spatial_bias, phk_stream_t s, int64_t* ticket) {
+  int Tp, hh, ww; int64_t R;
+  PHK_REQUIRE(p, PHK_E_ARG, "phk_encode_pipe_submit: null pipe");
+  PHK_TRY(cvivit_dims(m, B, F, Tp, hh, ww, R));
+  PHK_REQUIRE(host_video && host_ids && dev_video_slots && dev_ids_slots, PHK_E_ARG, "phk_encode_pipe_submit: null pointer");
+  cudaStream_t st = to_stream(s);
+  const int slot = (int)(p->next % p->depth);
+  const int64_t vbytes = (int64_t)B * m->channels * F * m->image_h * m->image_w * 4;
+  char* dv = (char*)dev_video_slots + (int64_t)slot * vbytes;
+  int64_t* di = dev_ids_slots + (int64_t)slot * R;
+  // the slot's previous occupant must have been consumed before it is overwritten (no-op for a fresh event)
+  PHK_CUDA(cudaStreamWaitEvent(p->copy, p->slot_free[slot], 0));
+  PHK_CUDA(cudaMemcpyAsync(dv, host_video, vbytes, cudaMemcpyHostToDevice, p->copy));
+  PHK_CUDA(cudaEventRecord(p->h2d_done[slot], p->copy));
+  PHK_CUDA(cudaStreamWaitEvent(st, p->h2d_done[slot], 0));
+  PHK_TRY(phk_cvivit_encode(m, (const float*)dv, B, F, di, workspace, workspace_bytes, prec, spatial_bias, nullptr,
+                            nullptr, nullptr, nullptr, s));
+  PHK_CUDA(cudaEventRecord(p->slot_free[slot], st));
+  PHK_CUDA(cudaMemcpyAsync(host_ids, di, R * 8, cudaMemcpyDeviceToHost, st));
+  PHK_CUDA(cudaEventRecord(p->done[slot], st));
+  if (ticket) *ticket = p->next;
+  p->next += 1;
+  return 0;
+}
+
+extern "C" int phk_encode_pipe_wait(phk_encode_pipe_t* p, int64_t ticket) {
+  PHK_REQUIRE(p, PHK_E_ARG, "phk_encode_pipe_wait: null pipe");
+  PHK_REQUIRE(ticket >= 0 && ticket < p->next && ticket >= p->next - p->depth, PHK_E_ARG,
+              "phk_encode_pipe_wait: ticket is not in flight (already overwritten or never submitted)");
+  PHK_CUDA(cudaEventSynchronize(p->done[(int)(ticket % p->depth)]));
+  return 0;
+}
+
+// --------------------------------------------------------------------------------------------
+// C-ViViT decode (cvivit.py:437-443, 476-516)
+// --------------------------------------------------------------------------------------------
+static int cvivit_dec_dims(const phk_cvivit_dec_t* m, int32_t B, int32_t Tp, int& hh, int& ww, int64_t& R) {
+  PHK_REQUIRE(m, PHK_E_ARG, "cvivit_decode: null model");
+  PHK_REQUIRE(B > 0 && Tp > 0, PHK_E_ARG, "cvivit_decode: bad batch / token-frame count");
+  PHK_REQUIRE(m->patch_h > 0 && m->patch_w > 0 && m->patch_t > 0 && m->image_h % m->patch_h == 0 &&
+              m->image_w % m->patch_w == 0, PHK_E_SHAPE, "image size must be divisible by patch size (cvivit.py:271)");
+  hh = m->image_h / m->patch_h;
+  ww = m->image_w / m->patch_w;
+  R = (int64_t)B * Tp * hh * ww;
+  return 0;
+}
+
+extern "C" int64_t phk_cvivit_decode_workspace_bytes(const phk_cvivit_dec_t* m, int32_t B, int32_t Tp, int32_t prec) {
+  int hh, ww; int64_t R;
+  if (cvivit_dec_dims(m, B, Tp, hh, ww, R) != 0) return -1;
+  const int64_t hw = (int64_t)hh * ww, K1 = (int64_t)m->channels * m->patch_h * m->patch_w, K2 = K1 * m->patch_t;
+  const int64_t g1 = (int64_t)B * hw * K1, g2 = (int64_t)B * (Tp - 1) * hw * K2;
+  int64_t bytes = 256 * 16;
+  bytes += R * m->dim * 4 * 4;                       // x, x_alt, norm_out(temporal), gathered GEMM operands
+  bytes += (g1 > g2 ? g1 : g2) * 4;                  // to_pixels output before the un-patchify scatter
+  bytes += (int64_t)m->heads * hw * hw * 4 + phk_cpb_scratch_floats(&m->spatial_bias, hh, ww, 1) * 4;
+  const int64_t a = tf_scratch_bytes(&m->spatial, R), b = tf_scratch_bytes(&m->temporal, R);
+  bytes += a > b ? a : b;
+  (void)prec;
+  return bytes;
+}
+
+extern "C" int phk_cvivit_decode(const phk_cvivit_dec_t* m, const int64_t* ids, const float* tokens, int32_t B,
+                                 int32_t Tp, float* video, void* workspace, int64_t workspace_bytes, int32_t prec,
+                                 const float* spatial_bias, float* tap_codes, float* tap_temporal,
+                                 float* tap_spatial, phk_stream_t s) {
+  int hh, ww; int64_t R;
+  PHK_TRY(cvivit_dec_dims(m, B, Tp, hh, ww, R));
+  PHK_REQUIRE((ids || tokens) && video && workspace, PHK_E_ARG, "cvivit_decode: null pointer");
+  PHK_TRY(check_transformer(&m->spatial));
+  PHK_TRY(check_transformer(&m->temporal));
+  PHK_REQUIRE(prec == PHK_PREC_F32 || prec == PHK_PREC_BF16, PHK_E_ARG, "cvivit_decode: unknown precision mode");
+  const int h16 = prec == PHK_PREC_BF16;
+  cudaStream_t st = to_stream(s);
+  const int D = m->dim, hw = hh * ww, C = m->channels;
+  const int64_t K1 = (int64_t)C * m->patch_h * m->patch_w, K2 = K1 * m->patch_t;
+  const int64_t rows1 = (int64_t)B * hw, rows2 = (int64_t)B * (Tp - 1) * hw;
+  const int F = 1 + (Tp - 1) * m->patch_t;
+  const int64_t ab = h16 ? 2 : 4;
+  Arena ar{(char*)workspace, workspace_bytes, 0};
+  float* x = (float*)ar.take(R * D * 4);
+  float* x_alt = (float*)ar.take(R * D * 4);
+  float* P = (float*)ar.take(R * D * 4);
+  char* Afirst = (char*)ar.take(rows1 * D * ab);
+  char* Arest = (char*)ar.take((rows2 > 0 ? rows2 : 1) * D * ab);
+  float* G = (float*)ar.take((rows1 * K1 > rows2 * K2 ? rows1 * K1 : rows2 * K2) * 4);
+  float* bias_buf = (float*)ar.take((int64_t)m->heads * hw * hw * 4);
+  float* cpb_scratch = (float*)ar.take(phk_cpb_scratch_floats(&m->spatial_bias, hh, ww, 1) * 4);
+  PHK_REQUIRE(x && x_alt && P && Afirst && Arest && G && bias_buf && cpb_scratch, PHK_E_WORKSPACE,
+              "cvivit_decode: workspace too small");
+
+  // ---- codes = vq.indices_to_codes(ids) (cvivit.py:437-439), rows in (b,t,h,w) order
+  if (ids) PHK_TRY(phk_lfq_codes(ids, m->vq_out_w, m->vq_out_b, x, R, D, m->codebook_bits, s));
+  else PHK_CUDA(cudaMemcpyAsync(x, tokens, R * D * 4, cudaMemcpyDeviceToDevice, st));
+  if (tap_codes) PHK_CUDA(cudaMemcpyAsync(tap_codes, x, R * D * 4, cudaMemcpyDeviceToDevice, st));
+
+  // ---- decode (cvivit.py:476-502): temporal over (b h w), then spatial over (b t)
+  Arena tf = ar;
+  TfCall c;
+  std::memset(&c, 0, sizeof(c));
+  c.T = &m->temporal; c.x = x; c.x_alt = x_alt; c.R = R;
+  c.seq = SeqView{B, hw, Tp, (int64_t)Tp * hw, 1, hw};
+  c.pegB = B; c.pegT = Tp; c.pegH = hh; c.pegW = ww;
+  c.peg_layout = 1;  // same raw-reshape quirk as the encoder (attention.py:71, cvivit.py:489-491)
+  c.ctx_mask_off_from = -1; c.prec = prec;
+  PHK_TRY(transformer_forward(c, tf, P, nullptr, st));  // P <- norm_out(temporal)
+  if (tap_temporal) PHK_CUDA(cudaMemcpyAsync(tap_temporal, P, R * D * 4, cudaMemcpyDeviceToDevice, st));
+
+  if (!spatial_bias) {
+    PHK_TRY(phk_cpb_bias(&m->spatial_bias, hh, ww, 1, cpb_scratch, bias_buf, s));
+    spatial_bias = bias_buf;
+  }
+  c.T = &m->spatial; c.x = P; c.x_alt = x;
+  c.seq = SeqView{B * Tp, 1, hw, hw, 0, 1};
+  c.peg_layout = 0;
+  c.attn_bias = spatial_bias;
+  c.out_first = Afirst; c.out_rest = Arest; c.split_B = B; c.split_T = Tp; c.split_hw = hw;
+  PHK_TRY(transformer_forward(c, tf, tap_spatial, nullptr, st));
+
+  // ---- to_pixels_first_frame / to_pixels (cvivit.py:506-514): Linear + un-patchify scatter
+  PHK_TRY(linear(prec, Afirst, D, m->px_first_w, m->px_first_w_h, D, G, K1, rows1, (int)K1, D, m->px_first_b, nullptr, s));
+  PHK_TRY(phk_unpatchify(G, K1, video, B, C, F, m->image_h, m->image_w, 0, 1, 1, m->patch_h, m->patch_w, s));
+  if (Tp > 1) {
+    PHK_TRY(linear(prec, Arest, D, m->px_w, m->px_w_h, D, G, K2, rows2, (int)K2, D, m->px_b, nullptr, s));
+    PHK_TRY(phk_unpatchify(G, K2, video, B, C, F, m->image_h, m->image_w, 1, Tp - 1, m->patch_t, m->patch_h,
+                           m->patch_w, s));
+  }
   return 0;
 }
 

@@ -20,8 +20,11 @@ __global__ void __launch_bounds__(256) ln_warp_kernel(const float* __restrict__ 
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
-  const int64_t orow = seg_len > 0 ? (row / seg_len) * seg_stride + seg_off + row % seg_len : row;
-  const float4* xr = reinterpret_cast<const float4*>(x + row * dim);
+  // seg_len > 0: scatter (the map places the OUTPUT row); seg_len < 0: gather (the map picks the INPUT row)
+  const int64_t sl = seg_len < 0 ? -seg_len : seg_len;
+  const int64_t mrow = sl > 0 ? (row / sl) * seg_stride + seg_off + row % sl : row;
+  const int64_t orow = seg_len < 0 ? row : mrow;
+  const float4* xr = reinterpret_cast<const float4*>(x + (seg_len < 0 ? mrow : row) * dim);
   float4 v[VEC];
   float s = 0.f;
 #pragma unroll
@@ -69,8 +72,10 @@ __global__ void __launch_bounds__(256) ln_block_kernel(const float* __restrict__
   extern __shared__ float srow[];
   __shared__ float red[32];
   const int64_t row = blockIdx.x;
-  const int64_t orow = seg_len > 0 ? (row / seg_len) * seg_stride + seg_off + row % seg_len : row;
-  const float* xr = x + row * dim;
+  const int64_t sl = seg_len < 0 ? -seg_len : seg_len;
+  const int64_t mrow = sl > 0 ? (row / sl) * seg_stride + seg_off + row % sl : row;
+  const int64_t orow = seg_len < 0 ? row : mrow;
+  const float* xr = x + (seg_len < 0 ? mrow : row) * dim;
   float s = 0.f;
   for (int i = threadIdx.x; i < dim; i += blockDim.x) { float t = xr[i]; srow[i] = t; s += t; }
   const float mean = block_sum(s, red) / (float)dim;
@@ -649,6 +654,59 @@ __global__ void cfg_combine_kernel(const float* __restrict__ cond, const float* 
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// LFQ indices_to_codes + project_out (cvivit.py:437-439; vector-quantize-pytorch LFQ.indices_to_codes):
+// bit j (MSB first) of the id selects +1 / -1, then Linear(bits, dim).  One thread per output element; the
+// [dim, bits] weight (32 KB at dim 512) stays in L1.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) lfq_codes_kernel(const int64_t* __restrict__ ids, const float* __restrict__ w,
+                                                        const float* __restrict__ b, float* __restrict__ out,
+                                                        int64_t rows, int dim, int bits) {
+  pdl_prologue();
+  const int64_t total = rows * dim;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / dim;
+    const int d = (int)(i - r * dim);
+    const int64_t id = ids[r];
+    const float* wr = w + (int64_t)d * bits;
+    float acc = 0.f;
+    for (int j = 0; j < bits; ++j) {
+      const float wv = __ldg(wr + j);
+      acc += ((id >> (bits - 1 - j)) & 1) ? wv : -wv;
+    }
+    out[i] = acc + __ldg(b + d);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Un-patchify (cvivit.py:286-295: Rearrange 'b t h w (c pt p1 p2) -> b c (t pt) (h p1) (w p2)'), the mirror of
+// patchify_ln: P [B*nt*hh*ww, C*pt*p1*p2] -> frames [f0, f0 + nt*pt) of video (B,C,F,H,W).  Threads walk the
+// OUTPUT in memory order (coalesced stores); the matching reads are p2-float contiguous runs of one P row.
+// ------------------------------------------------------------------------------------------
+template <int V /* floats per thread: 4 or 1 */>
+__global__ void __launch_bounds__(256) unpatchify_kernel(const float* __restrict__ P, int64_t ldp,
+                                                         float* __restrict__ video, int B, int C, int F, int H,
+                                                         int W, int f0, int nt, int pt, int p1, int p2) {
+  pdl_prologue();
+  const int hh = H / p1, ww = W / p2, Wv = W / V;
+  const int64_t total = (int64_t)B * C * nt * pt * H * Wv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i;
+    const int xv = (int)(r % Wv); r /= Wv;
+    const int y = (int)(r % H); r /= H;
+    const int f = (int)(r % (nt * pt)); r /= (nt * pt);
+    const int c = (int)(r % C);
+    const int b = (int)(r / C);
+    const int x = xv * V;
+    const int ti = f / pt, dt = f - ti * pt, hi = y / p1, dy = y - hi * p1, wi = x / p2, dx = x - wi * p2;
+    const int64_t row = (((int64_t)b * nt + ti) * hh + hi) * ww + wi;
+    const int64_t col = (((int64_t)c * pt + dt) * p1 + dy) * p2 + dx;
+    float* dst = video + ((((int64_t)b * C + c) * F + f0 + f) * H + y) * W + x;
+    if (V == 4) *reinterpret_cast<float4*>(dst) = *reinterpret_cast<const float4*>(P + row * ldp + col);
+    else *dst = P[row * ldp + col];
+  }
+}
 }  // namespace phk
 
 // ==========================================================================================
@@ -749,6 +807,40 @@ extern "C" int phk_lfq_ids(const float* x, const float* wp, const float* bp, int
   else if (dim == 256) PHK_CUDA(launch_pdl(lfq_kernel<8>, lg, lb, (size_t)0, to_stream(s), x, wp, bp, ids, proj_out, rows, dim, bits));
   else if (dim == 1024) PHK_CUDA(launch_pdl(lfq_kernel<32>, lg, lb, (size_t)0, to_stream(s), x, wp, bp, ids, proj_out, rows, dim, bits));
   else PHK_CUDA(launch_pdl(lfq_kernel<0>, lg, lb, (size_t)0, to_stream(s), x, wp, bp, ids, proj_out, rows, dim, bits));
+  PHK_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int phk_lfq_codes(const int64_t* ids, const float* w_out, const float* b_out, float* out, int64_t rows,
+                             int32_t dim, int32_t bits, phk_stream_t s) {
+  Prof prof_(FAM_LFQ, s, (double)rows * dim * 4.0);
+  PHK_REQUIRE(ids && w_out && b_out && out, PHK_E_ARG, "phk_lfq_codes: null pointer");
+  PHK_REQUIRE(rows >= 0 && dim > 0 && bits > 0 && bits <= 62, PHK_E_ARG, "phk_lfq_codes: bad size");
+  if (rows == 0) return 0;
+  const int64_t blocks = (rows * dim + 255) / 256;
+  const unsigned grid = (unsigned)(blocks < (int64_t)kNumSMs * 16 ? blocks : kNumSMs * 16);
+  PHK_CUDA(launch_pdl(lfq_codes_kernel, dim3(grid), dim3(256), (size_t)0, to_stream(s), ids, w_out, b_out, out, rows, dim, bits));
+  PHK_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int phk_unpatchify(const float* P, int64_t ldp, float* video, int32_t B, int32_t C, int32_t F, int32_t H,
+                              int32_t W, int32_t f0, int32_t nt, int32_t pt, int32_t p1, int32_t p2, phk_stream_t s) {
+  Prof prof_(FAM_PATCHIFY, s, (double)B * C * nt * pt * H * W * 8.0);
+  PHK_REQUIRE(P && video, PHK_E_ARG, "phk_unpatchify: null pointer");
+  PHK_REQUIRE(B > 0 && C > 0 && F > 0 && H > 0 && W > 0 && pt > 0 && p1 > 0 && p2 > 0 && nt >= 0, PHK_E_ARG,
+              "phk_unpatchify: bad size");
+  PHK_REQUIRE(H % p1 == 0 && W % p2 == 0, PHK_E_SHAPE, "image size must be divisible by patch size (cvivit.py:271)");
+  PHK_REQUIRE(f0 >= 0 && f0 + nt * pt <= F, PHK_E_SHAPE, "frame range outside the video");
+  PHK_REQUIRE(ldp >= (int64_t)C * pt * p1 * p2, PHK_E_ARG, "phk_unpatchify: ldp smaller than the patch feature size");
+  if (nt == 0) return 0;
+  const bool vec = (p2 % 4 == 0) && (ldp % 4 == 0) && ((reinterpret_cast<uintptr_t>(video) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(P) & 15) == 0);
+  const int64_t total = (int64_t)B * C * nt * pt * H * (W / (vec ? 4 : 1));
+  const int64_t blocks = (total + 255) / 256;
+  const unsigned grid = (unsigned)(blocks < (int64_t)kNumSMs * 16 ? blocks : kNumSMs * 16);
+  if (vec) PHK_CUDA(launch_pdl(unpatchify_kernel<4>, dim3(grid), dim3(256), (size_t)0, to_stream(s), P, ldp, video, B, C, F, H, W, f0, nt, pt, p1, p2));
+  else PHK_CUDA(launch_pdl(unpatchify_kernel<1>, dim3(grid), dim3(256), (size_t)0, to_stream(s), P, ldp, video, B, C, F, H, W, f0, nt, pt, p1, p2));
   PHK_LAUNCH_CHECK();
   return 0;
 }

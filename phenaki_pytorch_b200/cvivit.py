@@ -84,6 +84,8 @@ class CViViT(nn.Module):
         self.precision = L.PREC_F32
         self._tables = None
         self._sig = None
+        self._dec_tables = None
+        self._dec_sig = None
         self._ws = Workspace()
         self._bias_cache = {}
 
@@ -130,10 +132,11 @@ class CViViT(nn.Module):
 
     def copy_for_eval(self):
         device = next(self.parameters()).device
-        saved = (self._tables, self._sig, self._ws, self._bias_cache)  # ctypes tables are not copyable
-        self._tables, self._sig, self._ws, self._bias_cache = None, None, Workspace(), {}
+        saved = (self._tables, self._sig, self._dec_tables, self._dec_sig, self._ws, self._bias_cache)
+        self._tables, self._sig, self._dec_tables, self._dec_sig = None, None, None, None  # ctypes tables are not copyable
+        self._ws, self._bias_cache = Workspace(), {}
         c = copy.deepcopy(self)
-        self._tables, self._sig, self._ws, self._bias_cache = saved
+        self._tables, self._sig, self._dec_tables, self._dec_sig, self._ws, self._bias_cache = saved
         return c.eval().to(device)
 
     def load(self, path):
@@ -167,6 +170,29 @@ class CViViT(nn.Module):
             self._tables, self._sig = (t, keep), sig
             self._bias_cache = {}
         return self._tables[0]
+
+    def _dec_table(self):
+        sig = (weights_signature(self), self.precision)
+        if self._dec_tables is None or sig != self._dec_sig:
+            keep = Keep()
+            h16 = self.precision == L.PREC_BF16
+            t = L.CvivitDecT()
+            t.dim, t.heads, t.dim_head, t.channels = self.dim, self.heads, self.dim_head, self.channels
+            t.image_h, t.image_w = self.image_size
+            t.patch_h, t.patch_w = self.patch_size
+            t.patch_t = self.temporal_patch_size
+            t.codebook_bits = self.vq.codebook_dim
+            t.vq_out_w, t.vq_out_b = keep.t(self.vq.project_out.weight), keep.t(self.vq.project_out.bias)
+            t.spatial_bias = cpb_table(self.spatial_rel_pos_bias, keep)
+            t.temporal = transformer_table(self.dec_temporal_transformer, keep, h16)
+            t.spatial = transformer_table(self.dec_spatial_transformer, keep, h16)
+            f, r = self.to_pixels_first_frame[0], self.to_pixels[0]
+            t.px_first_w, t.px_first_b = keep.t(f.weight), keep.t(f.bias)
+            t.px_w, t.px_b = keep.t(r.weight), keep.t(r.bias)
+            if h16:
+                t.px_first_w_h, t.px_w_h = keep.h(f.weight), keep.h(r.weight)
+            self._dec_tables, self._dec_sig = (t, keep), sig
+        return self._dec_tables[0]
 
     def _spatial_bias(self, table, device):
         """ContinuousPositionBias is a function of the weights only: computed once per weight version."""
@@ -213,20 +239,117 @@ class CViViT(nn.Module):
                     "phk_cvivit_encode")
         return ids
 
+    def encode_host_iter(self, videos, device=None, depth=2):
+        """Tokenises a stream of HOST batches: `videos` yields (b,c,f,H,W) fp32 CPU tensors of one shape (pinned memory
+        gives the full PCIe rate); yields the (b,T',H',W') int64 ids of each batch as CPU tensors, in order.  The H2D
+        copy of batch i+1 overlaps the encode of batch i (phk_encode_pipe_*); nothing is staged by torch."""
+        lib = L.lib()
+        device = torch.device(device) if device is not None else next(self.parameters()).device
+        assert device.type == "cuda", "this framework has no CPU path"
+        pipe = C.c_void_p()
+        L.check(lib.phk_encode_pipe_create(C.byref(pipe), depth), "phk_encode_pipe_create")
+        shape, inflight, submitted = None, [], 0
+        try:
+            with torch.cuda.device(device):
+                table = self._table()
+                bias = self._spatial_bias(table, device)
+
+                def retire():
+                    ticket, host_ids, _keep = inflight.pop(0)
+                    L.check(lib.phk_encode_pipe_wait(pipe, ticket), "phk_encode_pipe_wait")
+                    return host_ids
+
+                for video in videos:
+                    if video.is_cuda or video.dtype != torch.float32:
+                        raise L.PhkError("encode_host_iter takes fp32 CPU batches (use forward() for device tensors)")
+                    video = video.contiguous()
+                    if shape is None:
+                        shape = tuple(video.shape)
+                        b, c, f, *image_dims = shape
+                        assert tuple(image_dims) == self.image_size and c == self.channels
+                        assert (f - 1) % self.temporal_patch_size == 0
+                        tp, hh, ww = self.get_video_patch_shape(f)
+                        stage = torch.empty((depth, *shape), dtype=torch.float32, device=device)
+                        dev_ids = torch.empty((depth, b, tp, hh, ww), dtype=torch.int64, device=device)
+                        host = [torch.empty((b, tp, hh, ww), dtype=torch.int64).pin_memory() for _ in range(depth)]
+                        nbytes = lib.phk_cvivit_workspace_bytes(C.byref(table), b, f, self.precision)
+                        ws = self._ws.get(nbytes, device)
+                    assert tuple(video.shape) == shape, "all batches of one stream must have the same shape"
+                    if len(inflight) == depth:
+                        yield retire().clone()
+                    ticket = C.c_int64()
+                    slot_host = host[submitted % depth]
+                    L.check(lib.phk_encode_pipe_submit(pipe, C.byref(table), L.ptr(video), b, f, L.ptr(slot_host),
+                                                       L.ptr(stage), L.ptr(dev_ids), L.ptr(ws), ws.numel(),
+                                                       self.precision, L.ptr(bias), L.stream_ptr(), C.byref(ticket)),
+                            "phk_encode_pipe_submit")
+                    assert ticket.value == submitted
+                    submitted += 1
+                    inflight.append((ticket.value, slot_host, video))
+                while inflight:
+                    yield retire().clone()
+        finally:
+            torch.cuda.synchronize(device)
+            lib.phk_encode_pipe_destroy(pipe)
+
+    def encode_host(self, video, device=None):
+        """One host batch -> host ids (H2D, encode, D2H, synchronise)."""
+        return next(self.encode_host_iter([video], device=device, depth=1))
+
     def forward(self, video, mask=None, return_recons=False, return_recons_only=False, return_discr_loss=False,
                 apply_grad_penalty=True, return_only_codebook_ids=False):
         assert video.ndim in {4, 5}
-        if video.ndim == 4:
+        is_image = video.ndim == 4
+        if is_image:
             video = video.unsqueeze(2)  # 'b c h w -> b c 1 h w'
             assert mask is None
         assert mask is None or mask.shape[-1] == video.shape[2]
         if return_only_codebook_ids:
             return self.encode_ids(video)
         if return_recons_only:
-            ids = self.encode_ids(video)
-            return self.decode_from_codebook_indices(ids)
+            # decode(project_out(sign(project_in(tokens)))) = decode(indices_to_codes(ids))  (cvivit.py:570-581)
+            recon = self.decode_from_codebook_indices(self.encode_ids(video))
+            return recon.squeeze(2) if is_image else recon
         raise NotImplementedError("C-ViViT training losses (reconstruction / GAN / perceptual, cvivit.py:576-671) "
                                   "are out of scope of the B200 hot path (SURVEY.md section 2 row 8)")
 
-    def decode_from_codebook_indices(self, indices):
-        raise NotImplementedError("C-ViViT decode (cvivit.py:437-443, 476-516) is the next-tier row f-1")
+    def _decode(self, ids, tokens, b, tp, device, taps=None):
+        lib = L.lib()
+        with torch.cuda.device(device):
+            enc = self._table()  # the position-bias cache is keyed on the encoder table's weight version
+            table = self._dec_table()
+            f = 1 + (tp - 1) * self.temporal_patch_size
+            video = torch.empty((b, self.channels, f, *self.image_size), dtype=torch.float32, device=device)
+            nbytes = lib.phk_cvivit_decode_workspace_bytes(C.byref(table), b, tp, self.precision)
+            ws = self._ws.get(nbytes, device)
+            bias = self._spatial_bias(enc, device)
+            tap_ptrs = [None] * 3
+            if taps is not None:
+                h, w = self.patch_height_width
+                for k in ("codes", "temporal", "spatial"):
+                    taps[k] = torch.empty((b, tp, h, w, self.dim), dtype=torch.float32, device=device)
+                tap_ptrs = [L.ptr(taps[k]) for k in ("codes", "temporal", "spatial")]
+            L.check(lib.phk_cvivit_decode(C.byref(table), L.ptr(ids), L.ptr(tokens), b, tp, L.ptr(video), L.ptr(ws),
+                                          ws.numel(), self.precision, L.ptr(bias), *tap_ptrs, L.stream_ptr()),
+                    "phk_cvivit_decode")
+        return video
+
+    def decode_from_codebook_indices(self, indices, taps=None):
+        """ids (b, n) or (b, t, h, w) int64 CUDA -> video (b, c, f, H, W) fp32 (cvivit.py:437-443): LFQ
+        indices_to_codes, decoder transformers and to_pixels, all inside phk_cvivit_decode."""
+        indices = L.require_cuda(indices, "indices", torch.int64)
+        b = indices.shape[0]
+        n = indices[0].numel()
+        per = self.image_num_tokens
+        assert n > 0 and n % per == 0, f"number of tokens ({n}) must be a multiple of tokens per frame ({per})"
+        return self._decode(indices.reshape(b, n), None, b, n // per, indices.device, taps)
+
+    def decode(self, tokens):
+        """tokens (b, t, h, w, d) or (b, (t h w), d) fp32 CUDA -> video (cvivit.py:476-516)."""
+        tokens = L.require_cuda(tokens, "tokens", torch.float32)
+        b, d = tokens.shape[0], tokens.shape[-1]
+        assert d == self.dim
+        n = tokens[0].numel() // d
+        per = self.image_num_tokens
+        assert n > 0 and n % per == 0
+        return self._decode(None, tokens.reshape(b, n, d), b, n // per, tokens.device)

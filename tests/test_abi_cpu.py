@@ -55,9 +55,9 @@ def test_struct_sizes_match_the_c_side():
     src = r'''
 #include <stdio.h>
 #include "phk.h"
-int main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(phk_attn_t), sizeof(phk_ff_t), sizeof(phk_peg_t),
+int main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(phk_attn_t), sizeof(phk_ff_t), sizeof(phk_peg_t),
  sizeof(phk_layer_t), sizeof(phk_transformer_t), sizeof(phk_cpb_t), sizeof(phk_cvivit_t), sizeof(phk_maskgit_t),
- sizeof(phk_attn_geom_t));return 0;}'''
+ sizeof(phk_attn_geom_t), sizeof(phk_cvivit_dec_t));return 0;}'''
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, "s.c")
         open(c, "w").write(src)
@@ -65,5 +65,5 @@ int main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(phk_attn_t), s
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
         sizes = [int(v) for v in subprocess.check_output([exe]).split()]
     mine = [ctypes.sizeof(t) for t in (L.AttnT, L.FFT, L.PegT, L.LayerT, L.TransformerT, L.CpbT, L.CvivitT,
-                                       L.MaskgitT, L.AttnGeomT)]
+                                       L.MaskgitT, L.AttnGeomT, L.CvivitDecT)]
     assert mine == sizes

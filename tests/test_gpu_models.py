@@ -184,3 +184,23 @@ def test_sampling_is_seed_deterministic_and_fills_every_token():
         outs.append(ph.sample(num_frames=7, text_embeds=ctx, return_token_ids=True).cpu())
     assert torch.equal(outs[0], outs[1]) and not torch.equal(outs[0], outs[2])
     assert (outs[0] >= 0).all() and (outs[0] < C.SAMPLE_MASKGIT["num_tokens"]).all()  # no mask id left
+
+
+@pytest.mark.parametrize("depth", [1, 2, 3])
+def test_encode_host_stream_matches_device_encode(depth):
+    """CViViT.encode_host_iter (phk_encode_pipe_*): pinned host batches in, host ids out, copies overlapped with the
+    previous batch's encode -- every batch must carry exactly the ids of the plain device call, in order."""
+    case = C.CVIVIT_CASES["rect"]
+    torch.manual_seed(case["seed"])
+    model = P.CViViT(**case["ctor"]).to(DEV).eval()
+    batches = [C.seeded_randn(case["video"], 100 + i).pin_memory() for i in range(7)]
+    want = [model(v.to(DEV), return_only_codebook_ids=True).cpu() for v in batches]
+    got = list(model.encode_host_iter(iter(batches), depth=depth))
+    assert len(got) == len(want)
+    for i, (a, b) in enumerate(zip(got, want)):
+        assert not a.is_cuda and a.dtype == torch.int64 and torch.equal(a, b), f"batch {i}"
+    assert torch.equal(model.encode_host(batches[3]), want[3])
+    with pytest.raises(P._lib.PhkError):
+        next(model.encode_host_iter([batches[0].to(DEV)]))            # device tensors go through forward()
+    with pytest.raises(AssertionError):
+        list(model.encode_host_iter([batches[0], batches[1][:1]]))    # one shape per stream
