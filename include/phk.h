@@ -179,6 +179,10 @@ int phk_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* 
 
 /* debug aid: per-CTA clock64 phase stamps of phk_gemm_bf16 (16 x int64 per CTA); NULL disables */
 int phk_debug_gemm_trace(long long* device_buffer);
+/* tests / A-B measurements: force the tcgen05 GEMM variant: 0 automatic, 1 one CTA per 128x128 tile, 2 CTA pairs
+ * (cta_group::2) with 256x128 tiles, 3 CTA pairs with 256x256 tiles (2 and 3 apply when M > 128); < 0 restores the
+ * PHK_GEMM_MODE environment default. */
+int phk_debug_gemm_mode(int32_t mode);
 
 /* GEGLU (attention.py:40-43): out[r, j] = gelu_erf(h[r, inner + j]) * h[r, j] */
 int phk_geglu(const float* h, float* out, int64_t rows, int32_t inner, phk_stream_t s);

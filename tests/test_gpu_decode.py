@@ -3,8 +3,6 @@
 
 Bars: fp32 parity mode |err| <= 2e-4 + 2e-4*|ref| (same as the encoder activations); bf16 mode
 |err| <= 0.06 + 0.03*|ref| on the decoder activations and pixels (pixels are a Linear of a LayerNorm output, O(1))."""
-import ctypes as CT
-
 import pytest
 import torch
 
@@ -37,7 +35,8 @@ def test_lfq_codes_kernel_matches_oracle():
         ref = O.lfq_indices_to_codes(ids[None], sd)[0]
         out = torch.empty(rows, dim, device=DEV)
         d = {k: v.to(DEV) for k, v in sd.items()}
-        L.check(L.lib().phk_lfq_codes(L.ptr(ids.to(DEV)), L.ptr(d["vq.project_out.weight"]), L.ptr(d["vq.project_out.bias"]),
+        idd = ids.to(DEV)   # named: device copies must outlive the launch
+        L.check(L.lib().phk_lfq_codes(L.ptr(idd), L.ptr(d["vq.project_out.weight"]), L.ptr(d["vq.project_out.bias"]),
                                       L.ptr(out), rows, dim, bits, L.stream_ptr()))
         torch.testing.assert_close(out.cpu(), ref, rtol=1e-5, atol=1e-5)
 
@@ -50,7 +49,8 @@ def test_unpatchify_is_the_inverse_rearrange(B, C_, F, H, W, f0, nt, pt, p1, p2)
     g = torch.Generator().manual_seed(1)
     Pm = torch.randn(B * nt * hh * ww, K, generator=g)
     video = torch.full((B, C_, F, H, W), -7.0, device=DEV)
-    L.check(L.lib().phk_unpatchify(L.ptr(Pm.to(DEV)), K, L.ptr(video), B, C_, F, H, W, f0, nt, pt, p1, p2, L.stream_ptr()))
+    Pd = Pm.to(DEV)
+    L.check(L.lib().phk_unpatchify(L.ptr(Pd), K, L.ptr(video), B, C_, F, H, W, f0, nt, pt, p1, p2, L.stream_ptr()))
     # 'b t h w (c pt p1 p2) -> b c (t pt) (h p1) (w p2)'  (cvivit.py:286-295)
     ref = Pm.reshape(B, nt, hh, ww, C_, pt, p1, p2).permute(0, 4, 1, 5, 2, 6, 3, 7).reshape(B, C_, nt * pt, H, W)
     assert torch.equal(video[:, :, f0:f0 + nt * pt].cpu(), ref)          # pure data movement: bit-exact

@@ -106,3 +106,93 @@ def test_attention_tensor_core_matches_oracle(n_seq, n, heads, with_bias):
     torch.cuda.synchronize()
     err = (out.cpu().float() - ref).abs().max().item()
     assert err <= 0.02, f"max |err| {err}"
+
+
+@pytest.fixture
+def gemm_mode():
+    """Forces one tcgen05 GEMM variant (1 one-CTA 128x128, 2 CTA pairs 256x128, 3 CTA pairs 256x256) for a test."""
+    lib = L.lib()
+    yield lambda m: L.check(lib.phk_debug_gemm_mode(m))
+    lib.phk_debug_gemm_mode(-1)
+
+
+@pytest.mark.parametrize("mode", [1, 2, 3])
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (600, 700, 200), (4608, 512, 512), (1300, 1000, 1408), (129, 96, 72)])
+def test_gemm_variants_fp32_out_bias_residual_rowmap(gemm_mode, mode, M, N, K):
+    """Every kernel variant (cta_group::1 and the cta_group::2 pair kernels) on ragged M / N / K, with bias, in-place
+    residual and the output row map."""
+    gemm_mode(mode)
+    Kp = (K + 7) // 8 * 8
+    a, w = operands(M, N, K, lda=Kp, ldw=Kp, seed=20)
+    bias, res = TC.seeded_randn((N,), 25), TC.seeded_randn((M, N), 26)
+    ref = a[:, :K].float() @ w[:, :K].float().t() + bias + res
+    ad, wd, bd = a.to(DEV), w.to(DEV), bias.to(DEV)
+    c = res.clone().to(DEV)
+    L.check(L.lib().phk_gemm_bf16(L.ptr(ad), Kp, L.ptr(wd), Kp, L.ptr(c), N, M, N, K, L.ptr(bd), L.ptr(c), 0, 0, 0, 0,
+                                  L.stream_ptr()), "phk_gemm_bf16")
+    torch.testing.assert_close(c.cpu(), ref, rtol=1e-4, atol=2e-3 * max(1.0, (K / 512) ** 0.5))
+    # row map: output row = (m // 50) * 64 + 3 + m % 50
+    rows = (M + 49) // 50 * 64 + 8
+    c2 = torch.zeros((rows, N), device=DEV)
+    L.check(L.lib().phk_gemm_bf16(L.ptr(ad), Kp, L.ptr(wd), Kp, L.ptr(c2), N, M, N, K, None, None, 50, 64, 3, 0,
+                                  L.stream_ptr()), "phk_gemm_bf16")
+    idx = torch.tensor([(m // 50) * 64 + 3 + m % 50 for m in range(M)])
+    torch.testing.assert_close(c2.cpu()[idx], ref - bias - res, rtol=1e-4, atol=2e-3 * max(1.0, (K / 512) ** 0.5))
+
+
+@pytest.mark.parametrize("mode", [1, 2, 3])
+def test_gemm_variants_bf16_out_and_geglu(gemm_mode, mode):
+    gemm_mode(mode)
+    M, N, K = 700, 520, 256
+    a, w = operands(M, N, K, seed=30)
+    bias = TC.seeded_randn((N,), 31)
+    ref = a.float() @ w.float().t() + bias
+    c = torch.empty((M, N), dtype=torch.bfloat16, device=DEV)
+    ad, wd, bd = a.to(DEV), w.to(DEV), bias.to(DEV)   # named: the device copies must outlive the launch
+    L.check(L.lib().phk_gemm_bf16(L.ptr(ad), K, L.ptr(wd), K, L.ptr(c), N, M, N, K, L.ptr(bd), None, 0, 0, 0, 1,
+                                  L.stream_ptr()), "phk_gemm_bf16")
+    torch.testing.assert_close(c.cpu().float(), ref, rtol=1e-2, atol=5e-2)
+    # GEGLU: W rows packed [64 value | 64 gate]; 5 groups -> a 256-wide pair tile with a ragged second half
+    inner, K2 = 300, 512
+    inner_pad = (inner + 63) // 64 * 64
+    a2 = TC.seeded_randn((M, K2), 32).bfloat16()
+    w1 = (TC.seeded_randn((2 * inner, K2), 33) / K2 ** 0.5).bfloat16()
+    packed = torch.zeros((2 * inner_pad, K2), dtype=torch.bfloat16)
+    for g in range(inner_pad // 64):
+        lo, hi = g * 64, min(g * 64 + 64, inner)
+        packed[g * 128: g * 128 + (hi - lo)] = w1[lo:hi]
+        packed[g * 128 + 64: g * 128 + 64 + (hi - lo)] = w1[inner + lo: inner + hi]
+    h = a2.float() @ w1.float().t()
+    ref2 = torch.nn.functional.gelu(h[:, inner:]) * h[:, :inner]     # exact erf GELU (attention.py:40-43)
+    out = torch.full((M, inner_pad), 7.0, dtype=torch.bfloat16, device=DEV)
+    a2d, pd = a2.to(DEV), packed.to(DEV)
+    L.check(L.lib().phk_gemm_bf16(L.ptr(a2d), K2, L.ptr(pd), K2, L.ptr(out), inner_pad, M, 2 * inner_pad, K2, None, None,
+                                  0, 0, 0, 2, L.stream_ptr()), "phk_gemm_bf16")
+    o = out.cpu().float()
+    torch.testing.assert_close(o[:, :inner], ref2, rtol=1e-2, atol=1e-2)
+    assert (o[:, inner:] == 0).all()
+
+
+def test_geglu_epilogue_activation_error_is_below_bf16_rounding():
+    """The epilogue's sigmoid-form fit of erf-GELU: |gelu_fit(g) * v - gelu_erf(g) * v| stays within one bf16 ulp of the
+    result (+1e-4 * |v| absolute near zero) over the whole gate range, including |g| > 8 where the fit is clamped."""
+    M, K = 256, 64
+    gates = torch.linspace(-12.0, 12.0, M)
+    a = torch.zeros((M, K))
+    a[:, 0] = gates            # gate pre-activation = a[:,0] * 1
+    a[:, 1] = 1.0              # value pre-activation = 1 * v_j
+    w = torch.zeros((128, K))
+    vals = torch.linspace(0.25, 2.0, 64)
+    w[:64, 1] = vals           # value rows
+    w[64:, 0] = 1.0            # gate rows
+    ab, wb = a.bfloat16(), w.bfloat16()
+    g = ab[:, 0].float()[:, None]
+    v = wb[:64, 1].float()[None, :]
+    ref = torch.nn.functional.gelu(g.double()).float() * v
+    out = torch.empty((M, 64), dtype=torch.bfloat16, device=DEV)
+    abd, wbd = ab.to(DEV), wb.to(DEV)
+    L.check(L.lib().phk_gemm_bf16(L.ptr(abd), K, L.ptr(wbd), K, L.ptr(out), 64, M, 128, K, None, None, 0, 0, 0, 2,
+                                  L.stream_ptr()), "phk_gemm_bf16")
+    err = (out.cpu().float() - ref).abs()
+    bound = ref.abs() * 2.0 ** -8 + 1e-4 * v
+    assert (err <= bound).all(), f"max excess {(err - bound).max():.2e}"

@@ -21,9 +21,9 @@ e0.record(); run(); e1.record(); torch.cuda.synchronize()
 lib.phk_debug_gemm_trace(None)
 t = trace.cpu().reshape(148, 16)
 tiles = ((M + 127) // 128) * ((N + 127) // 128)
-used = t[: min(tiles, 148)]
+used = t[t[:, 9] > 0]  # CTAs that ran (one-CTA kernel: min(tiles, 148); CTA-pair kernel: 2 x pairs)
 names = ["setup", "tma0_issued", "tmaLast_issued", "ops0_landed", "opsLast_landed", "mma_issued", "acc_ready", "staged", "written", "cta_done"]
-print(f"M={M} N={N} K={K} epi={epi}: tiles={tiles} event time {e0.elapsed_time(e1)*1e3:.1f} us")
+print(f"M={M} N={N} K={K} epi={epi} PHK_GEMM_MODE={os.environ.get('PHK_GEMM_MODE', '0')}: 128x128 tiles={tiles} CTAs={used.shape[0]} event time {e0.elapsed_time(e1)*1e3:.1f} us")
 for i, n in enumerate(names):
     col = used[:, i].float()
     print(f"  {n:16s} mean {col.mean():9.0f}  min {col.min():9.0f}  max {col.max():9.0f} cycles")
