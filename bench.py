@@ -178,6 +178,8 @@ def bench_maskgit(dev, prec, steps_timed=1):
     cv.precision = mg.precision = prec
     ph = P.Phenaki(cvivit=cv, maskgit=mg, steps=CFG3_RUN["steps"], text_embed_dim=768)
     ph.cvivit.precision = prec
+    if os.environ.get("PHK_FUSED_HEAD") is not None:   # A/B: fused logits-head kernel vs head GEMM + sampling kernel
+        ph.fused_head = os.environ["PHK_FUSED_HEAD"] != "0"
     b, L = CFG3_RUN["batch"], CFG3_RUN["ctx_len"]
     ctx = torch.randn(b, L, 768, device=dev)
     ctx[1, L // 2:] = 0
@@ -202,7 +204,7 @@ def bench_maskgit(dev, prec, steps_timed=1):
                 ms_per_decode_step=ms / CFG3_RUN["steps"],
                 config=f"MaskGit(dim=512,depth=6,V=65536,ctx=768) {CFG3_RUN['steps']}-step demasking loop, b={b}, N={n}, "
                        f"L={L}, cond_scale=3 (2 forwards/step as one batch of {2 * b})",
-                achieved_tflops=tf, frac_of_tensor_peak=tf / pk["tf_sustained"])
+                achieved_tflops=tf, frac_of_tensor_peak=tf / pk["tf_sustained"], fused_head=bool(ph.fused_head))
 
 
 def main():

@@ -241,6 +241,14 @@ int phk_cpb_bias(const phk_cpb_t* c, int32_t d0, int32_t d1, int32_t d2, float* 
 int phk_lfq_ids(const float* x, const float* wp, const float* bp, int64_t* ids, float* proj_out,
                 int64_t rows, int32_t dim, int32_t bits, phk_stream_t s);
 
+/* LayerNorm (attention.py:308,332: the temporal transformer's norm_out) fused with phk_lfq_ids: the normalised row
+ * stays in registers.  out_norm (optional fp32 [rows, dim]) and proj_out (optional [rows, bits]) receive the
+ * intermediate values for the parity tests; shapes outside dim % 128 == 0, dim <= 1024, bits <= 16 fall back to
+ * phk_layernorm + phk_lfq_ids and then need out_norm as the row buffer. */
+int phk_layernorm_lfq(const float* x, const float* gamma, const float* beta, const float* wp, const float* bp,
+                      int64_t* ids, float* out_norm, float* proj_out, int64_t rows, int32_t dim, int32_t bits,
+                      phk_stream_t s);
+
 /* LFQ indices_to_codes + project_out (cvivit.py:437-439 -> LFQ.indices_to_codes, oracle/lfq.py):
  * out[r, :] = w_out @ (bit_j(id_r) ? +1 : -1)_j + b_out, bits MSB first; w_out [dim, bits]; out fp32 [rows, dim]. */
 int phk_lfq_codes(const int64_t* ids, const float* w_out, const float* b_out, float* out,

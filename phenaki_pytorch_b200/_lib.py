@@ -108,6 +108,7 @@ PROTOTYPES = {
     "phk_cpb_scratch_floats": [C.POINTER(CpbT), i32, i32, i32],
     "phk_cpb_bias": [C.POINTER(CpbT), i32, i32, i32, vp, vp, vp],
     "phk_lfq_ids": [vp, vp, vp, vp, vp, i64, i32, i32, vp],
+    "phk_layernorm_lfq": [vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, vp],
     "phk_lfq_codes": [vp, vp, vp, vp, i64, i32, i32, vp],
     "phk_unpatchify": [vp, i64, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp],
     "phk_token_embed": [vp, vp, vp, vp, i32, i32, i32, i32, f32, i32, vp],

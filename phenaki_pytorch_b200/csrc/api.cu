@@ -70,6 +70,7 @@ struct TfCall {
   // decoder tail: norm_out gathered into two dense operands (activation type of the mode) -- rows of the first
   // frame (t == 0) and of the remaining frames, each in (b,t,h,w) order (cvivit.py:506)
   void* out_first; void* out_rest; int split_B, split_T, split_hw;
+  float** x_final;  // optional: receives the buffer holding the residual stream BEFORE norm_out (c.x or c.x_alt)
 };
 
 static int64_t tf_scratch_bytes(const phk_transformer_t* T, int64_t R) {
@@ -186,6 +187,7 @@ static int transformer_forward(const TfCall& c, Arena scratch, float* out, void*
       }
     }
   }
+  if (c.x_final) *c.x_final = x;
   if (out) PHK_TRY(phk_layernorm(x, T->out_g, T->out_b, out, nullptr, R, D, 0, 0, 0, 0, s));
   if (c.out_cfg) {
     // classifier-free guidance folded before the (linear) logits head: rows [0,R/2) conditional, [R/2,R) null
@@ -326,11 +328,16 @@ extern "C" int phk_cvivit_encode(const phk_cvivit_t* m, const float* video, int3
   c.seq = SeqView{B, hw, Tp, (int64_t)Tp * hw, 1, hw};
   c.peg_layout = 1;  // the reference's raw-reshape quirk (attention.py:71, cvivit.py:468-470)
   c.attn_bias = nullptr;
-  PHK_TRY(transformer_forward(c, tf, x_alt, nullptr, st));  // x_alt <- norm_out(temporal)
-  if (tap_temporal) PHK_CUDA(cudaMemcpyAsync(tap_temporal, x_alt, R * D * 4, cudaMemcpyDeviceToDevice, st));
-
-  // ---- LFQ (cvivit.py:562-574): ids in (b, t, h, w) order
-  PHK_TRY(phk_lfq_ids(x_alt, m->vq_w, m->vq_b, ids, tap_proj, R, D, m->codebook_bits, s));
+  // norm_out of the temporal transformer is fused with the LFQ projection + sign quantisation (cvivit.py:562-574):
+  // the normalised tokens are only written when a parity test taps them; ids come out in (b, t, h, w) order
+  float* xf = nullptr;
+  c.x_final = &xf;
+  PHK_TRY(transformer_forward(c, tf, nullptr, nullptr, st));
+  float* norm_buf = x_alt;  // not used by the temporal transformer (its stream alternates between P and x)
+  PHK_TRY(phk_layernorm_lfq(xf, m->temporal.out_g, m->temporal.out_b, m->vq_w, m->vq_b, ids,
+                            (tap_temporal || D % 128 != 0 || D > 1024 || m->codebook_bits > 16) ? norm_buf : nullptr,
+                            tap_proj, R, D, m->codebook_bits, s));
+  if (tap_temporal) PHK_CUDA(cudaMemcpyAsync(tap_temporal, norm_buf, R * D * 4, cudaMemcpyDeviceToDevice, st));
   return 0;
 }
 

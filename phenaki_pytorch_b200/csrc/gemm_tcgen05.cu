@@ -180,6 +180,79 @@ __device__ __forceinline__ bool epi_residual_prefetch(const EpiParams& p, float*
   return res_vec;
 }
 
+// GEGLU epilogue of a whole tile of NCH 128-column chunks, each packed [64 value | 64 gate] (attention.py:40-43).
+// All accumulator columns this thread needs (16 value + 16 gate per chunk of ONE row) are pulled out of TMEM first and
+// the accumulator is released at once, so the MMA warp never waits for epilogue math.  The bf16 results (NCH x 128 B
+// per row) go through a swizzled shared-memory tile and leave as fully coalesced 16-B-per-lane rows: one row per
+// thread straight from registers made every warp store touch 32 different lines (~8 clk per line in the LSU).
+template <int NCH, typename Release, typename Stamp>
+__device__ __forceinline__ void epi_geglu_tile(const EpiParams& p, void* stage, uint32_t tmem_tile, int64_t m0, int n0,
+                                               int ew, int lg, int part, int lane, Release&& release, Stamp&& stamp) {
+  constexpr int W = 64 / EPI_PARTS;
+  static_assert(W == 16, "two 16-B units per thread and chunk");
+  constexpr int U = NCH * 8;  // 16-B units per staged row
+  const uint32_t trow = tmem_tile + ((uint32_t)(lg * 32) << 16);
+  uint32_t val[NCH][W], gate[NCH][W];
+#pragma unroll
+  for (int h = 0; h < NCH; ++h) {
+    tmem_ld16(trow + h * 128 + part * W, val[h]);
+    tmem_ld16(trow + h * 128 + 64 + part * W, gate[h]);
+  }
+  tmem_ld_wait();
+  stamp(10);  // accumulator columns in registers
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncwarp();
+  release();
+  const uint32_t seg_len = (uint32_t)p.seg_len;
+  const bool coalesced = (p.ldc % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+  const int r = lg * 32 + lane;  // this thread's row of the tile
+  uint4* srow = reinterpret_cast<uint4*>(stage) + r * U;
+#pragma unroll
+  for (int h = 0; h < NCH; ++h) {
+    uint32_t pk[W / 2];
+#pragma unroll
+    for (int j = 0; j < W; j += 2)
+      pk[j / 2] = pack_bf16x2(geglu_fast(__uint_as_float(gate[h][j]), __uint_as_float(val[h][j])),
+                              geglu_fast(__uint_as_float(gate[h][j + 1]), __uint_as_float(val[h][j + 1])));
+    if (coalesced) {
+      // logical unit u of row r lives at (u & ~7) | ((u ^ r) & 7): conflict-free for the row-per-lane stores here
+      // and for the unit-per-lane loads below
+      const int u0 = h * 8 + part * 2;
+      srow[(u0 & ~7) | ((u0 ^ r) & 7)] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      srow[((u0 + 1) & ~7) | (((u0 + 1) ^ r) & 7)] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+    } else {  // odd leading dimension / unaligned C: 4-byte stores from registers
+      const uint32_t m = (uint32_t)m0 + r;
+      const int col = (n0 + h * 128) / 2 + part * W;
+      if (m < (uint32_t)p.M && col < p.N / 2) {
+        int64_t orow = m;
+        if (seg_len > 0) { const uint32_t q = m / seg_len; orow = q * (uint32_t)p.seg_stride + (uint32_t)p.seg_off + (m - q * seg_len); }
+        __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(p.C) + orow * p.ldc + col;
+#pragma unroll
+        for (int j = 0; j < W / 2; ++j) *reinterpret_cast<uint32_t*>(crow + 2 * j) = pk[j];
+      }
+    }
+  }
+  if (!coalesced) return;  // uniform over the CTA
+  stamp(11);               // this thread's outputs computed and staged
+  epi_bar_sync();          // tile staged
+  stamp(7);
+  constexpr int RPI = 32 / U;                 // rows per warp instruction (4 or 2)
+  const int rl = lane / U, u = lane % U;      // this lane's row within the instruction and its 16-B unit
+  const bool chunk_ok = (n0 + (u >> 3) * 128) < p.N;
+#pragma unroll
+  for (int i = 0; i < GM / (EPI_WARPS * RPI); ++i) {
+    const int rr = (i * EPI_WARPS + ew) * RPI + rl;
+    const uint32_t m = (uint32_t)m0 + rr;
+    const uint4 v = reinterpret_cast<const uint4*>(stage)[rr * U + ((u & ~7) | ((u ^ rr) & 7))];
+    if (m < (uint32_t)p.M && chunk_ok) {
+      int64_t orow = m;
+      if (seg_len > 0) { const uint32_t q = m / seg_len; orow = q * (uint32_t)p.seg_stride + (uint32_t)p.seg_off + (m - q * seg_len); }
+      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) + orow * p.ldc + n0 / 2 + u * 8) = v;
+    }
+  }
+  epi_bar_sync();          // staging tile free for the next accumulator
+}
+
 // Drains one chunk and writes it out.  `release()` is called as soon as the TMEM columns have been read (the MMA
 // warp may then overwrite them), before the slower global write-out.
 template <int EPI, typename Release>
@@ -188,40 +261,6 @@ __device__ __forceinline__ void epi_chunk(const EpiParams& p, float* cstage, uin
   const uint32_t trow = tmem_chunk + ((uint32_t)(lg * 32) << 16);
   float* srow = cstage + (lg * 32 + lane) * CPAD;
   const uint32_t seg_len = (uint32_t)p.seg_len;
-  if (EPI == 2) {
-    // [64 value | 64 gate] -> 64 outputs gelu(gate) * value; this thread owns 16 consecutive outputs of ONE row and
-    // stores them straight from registers: 32 B = one full sector per store pair, no staging round trip
-    constexpr int W = 64 / EPI_PARTS;
-    uint32_t val[W], gate[W];
-    tmem_ld16(trow + part * W, val);
-    tmem_ld16(trow + 64 + part * W, gate);
-    tmem_ld_wait();
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncwarp();
-    release();
-    uint32_t pk[W / 2];
-#pragma unroll
-    for (int j = 0; j < W; j += 2)
-      pk[j / 2] = pack_bf16x2(geglu_fast(__uint_as_float(gate[j]), __uint_as_float(val[j])),
-                              geglu_fast(__uint_as_float(gate[j + 1]), __uint_as_float(val[j + 1])));
-    const uint32_t m = (uint32_t)m0 + lg * 32 + lane;
-    const int col = n0 / 2 + part * W;
-    if (m < (uint32_t)p.M) {
-      int64_t orow = m;
-      if (seg_len > 0) { const uint32_t q = m / seg_len; orow = q * (uint32_t)p.seg_stride + (uint32_t)p.seg_off + (m - q * seg_len); }
-      __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(p.C) + orow * p.ldc + col;
-      if ((p.ldc % 16 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 31) == 0)) {
-        static_assert(W == 16, "one 256-bit store per thread");
-        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
-                     ::"l"(crow), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
-                     : "memory");
-      } else {
-#pragma unroll
-        for (int j = 0; j < W / 2; ++j) *reinterpret_cast<uint32_t*>(crow + 2 * j) = pk[j];
-      }
-    }
-    return;
-  }
   {
     const int c = part;  // 32 of the 128 columns
     uint32_t v[32];
@@ -459,8 +498,13 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_bf16_kernel(const __grid_con
       mbar_wait(bar_tfull + 8 * acc, use & 1);
       if (it == 0 && threadIdx.x == 64) PHK_STAMP(6);      // accumulator ready
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      epi_chunk<EPI>(p, cstage, tmem_base + acc * GN, m0, n0, res_vec, ew, lg, part, lane,
-                     [&]() { if (lane == 0) mbar_arrive(bar_tempty + 8 * acc); });
+      if (EPI == 2)
+        epi_geglu_tile<1>(p, cstage, tmem_base + acc * GN, m0, n0, ew, lg, part, lane,
+                          [&]() { if (lane == 0) mbar_arrive(bar_tempty + 8 * acc); },
+                          [&](int slot) { if (it == 0 && threadIdx.x == 64) PHK_STAMP(slot); });
+      else
+        epi_chunk<EPI>(p, cstage, tmem_base + acc * GN, m0, n0, res_vec, ew, lg, part, lane,
+                       [&]() { if (lane == 0) mbar_arrive(bar_tempty + 8 * acc); });
       if (it == 0 && threadIdx.x == 64) PHK_STAMP(8);      // tile written out
     }
   }
@@ -540,7 +584,7 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {  // arrives on 
 }
 
 __host__ __device__ constexpr int pair_stages(int epi) { return epi == 2 ? 6 : 4; }
-__host__ __device__ constexpr int pair_cstage_bytes(int epi) { return epi == 2 ? 0 : CSTAGE_BYTES; }
+__host__ __device__ constexpr int pair_cstage_bytes(int epi) { return epi == 2 ? GM * 256 /* bf16 tile */ : CSTAGE_BYTES; }
 __host__ __device__ constexpr int pair_smem_bytes(int epi) {
   return pair_stages(epi) * 2 * STAGE_BYTES + pair_cstage_bytes(epi) + 256 + 1024;
 }
@@ -675,12 +719,18 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_bf16_pair_kernel(const __gri
       mbar_wait(bar_tfull + 8 * acc, use & 1);
       if (it == 0 && threadIdx.x == 64) PHK_STAMP(6);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (EPI == 2) {
+        epi_geglu_tile<BN / 128>(p, cstage, tmem_base + acc * BN, m0, n0, ew, lg, part, lane,
+                                 [&]() { if (lane == 0) mbar_arrive_remote(tempty_leader + 8 * acc); },
+                                 [&](int slot) { if (it == 0 && threadIdx.x == 64) PHK_STAMP(slot); });
+      } else {
 #pragma unroll
-      for (int h = 0; h < BN / 128; ++h) {
-        if (h > 0) res_vec = epi_residual_prefetch<EPI>(p, cstage, m0, n0 + h * 128, ew, lane);
-        const bool last = h == BN / 128 - 1;
-        epi_chunk<EPI>(p, cstage, tmem_base + acc * BN + h * 128, m0, n0 + h * 128, res_vec, ew, lg, part, lane,
-                       [&]() { if (last && lane == 0) mbar_arrive_remote(tempty_leader + 8 * acc); });
+        for (int h = 0; h < BN / 128; ++h) {
+          if (h > 0) res_vec = epi_residual_prefetch<EPI>(p, cstage, m0, n0 + h * 128, ew, lane);
+          const bool last = h == BN / 128 - 1;
+          epi_chunk<EPI>(p, cstage, tmem_base + acc * BN + h * 128, m0, n0 + h * 128, res_vec, ew, lg, part, lane,
+                         [&]() { if (last && lane == 0) mbar_arrive_remote(tempty_leader + 8 * acc); });
+        }
       }
       if (it == 0 && threadIdx.x == 64) PHK_STAMP(8);
     }

@@ -251,6 +251,91 @@ __global__ void __launch_bounds__(256) lfq_kernel(const float* __restrict__ x, c
 }
 
 // ------------------------------------------------------------------------------------------
+// norm_out LayerNorm of the temporal transformer (attention.py:308,332) fused with the LFQ projection and sign
+// quantisation (cvivit.py:570): the normalised row never leaves registers.  project_in's [bits, dim] weight is
+// staged once per CTA in shared memory (32 KB at dim 512); each warp normalises R rows and advances all
+// bits x R dot products together, so every 16-B weight read from shared memory feeds R FMAs x 4.
+// ------------------------------------------------------------------------------------------
+template <int VEC /* float4 per lane = dim / 128 */, int R /* rows per warp */>
+__global__ void __launch_bounds__(256) ln_lfq_kernel(const float* __restrict__ x, const float* __restrict__ g,
+                                                     const float* __restrict__ b, const float* __restrict__ wp,
+                                                     const float* __restrict__ bp, int64_t* __restrict__ ids,
+                                                     float* __restrict__ out_norm, float* __restrict__ proj,
+                                                     int64_t rows, int dim, int bits) {
+  constexpr int MAXB = 16;
+  extern __shared__ float4 swp[];  // [bits][dim / 4]
+  pdl_trigger();
+  const int d4 = dim >> 2;
+  for (int i = threadIdx.x; i < bits * d4; i += blockDim.x) swp[i] = __ldg(reinterpret_cast<const float4*>(wp) + i);
+  pdl_wait();  // the weights above are not produced by the previous kernel; x is
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t row0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * R;
+  if (row0 >= rows) return;
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  const float4* b4 = reinterpret_cast<const float4*>(b);
+  float4 y[R][VEC];
+#pragma unroll
+  for (int rr = 0; rr < R; ++rr) {
+    const int64_t row = row0 + rr < rows ? row0 + rr : rows - 1;  // tail rows recompute the last row (not stored)
+    const float4* xr = reinterpret_cast<const float4*>(x + row * dim);
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      y[rr][j] = xr[lane + 32 * j];
+      s += (y[rr][j].x + y[rr][j].y) + (y[rr][j].z + y[rr][j].w);
+    }
+    const float mean = warp_sum(s) / (float)dim;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const float a = y[rr][j].x - mean, bb = y[rr][j].y - mean, c = y[rr][j].z - mean, d = y[rr][j].w - mean;
+      q += (a * a + bb * bb) + (c * c + d * d);
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)dim + 1e-5f);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const float4 gg = g4[lane + 32 * j], bb = b4[lane + 32 * j];
+      y[rr][j].x = (y[rr][j].x - mean) * rstd * gg.x + bb.x;
+      y[rr][j].y = (y[rr][j].y - mean) * rstd * gg.y + bb.y;
+      y[rr][j].z = (y[rr][j].z - mean) * rstd * gg.z + bb.z;
+      y[rr][j].w = (y[rr][j].w - mean) * rstd * gg.w + bb.w;
+      if (out_norm && row0 + rr < rows) reinterpret_cast<float4*>(out_norm + row * dim)[lane + 32 * j] = y[rr][j];
+    }
+  }
+  float acc[R][MAXB];
+#pragma unroll
+  for (int rr = 0; rr < R; ++rr)
+#pragma unroll
+    for (int e = 0; e < MAXB; ++e) acc[rr][e] = 0.f;
+#pragma unroll
+  for (int e = 0; e < MAXB; ++e) {
+    if (e < bits) {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        const float4 w = swp[e * d4 + lane + 32 * j];
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr)
+          acc[rr][e] = fmaf(y[rr][j].x, w.x, fmaf(y[rr][j].y, w.y, fmaf(y[rr][j].z, w.z, fmaf(y[rr][j].w, w.w, acc[rr][e]))));
+      }
+    }
+  }
+#pragma unroll
+  for (int rr = 0; rr < R; ++rr) {
+    int64_t id = 0;
+#pragma unroll
+    for (int e = 0; e < MAXB; ++e) {
+      if (e < bits) {
+        const float a = warp_sum(acc[rr][e]) + __ldg(bp + e);
+        if (proj && lane == 0 && row0 + rr < rows) proj[(row0 + rr) * bits + e] = a;
+        if (a > 0.f) id |= (int64_t)1 << (bits - 1 - e);
+      }
+    }
+    if (lane == 0 && row0 + rr < rows) ids[row0 + rr] = id;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // PEG depthwise 3x3x3 conv + bias + residual (attention.py:64-85, caller :323).
 // w is tap-major [27][D] (packed by the host module from dsconv.weight[D,1,3,3,3]).
 // ------------------------------------------------------------------------------------------
@@ -807,6 +892,50 @@ extern "C" int phk_lfq_ids(const float* x, const float* wp, const float* bp, int
   else if (dim == 256) PHK_CUDA(launch_pdl(lfq_kernel<8>, lg, lb, (size_t)0, to_stream(s), x, wp, bp, ids, proj_out, rows, dim, bits));
   else if (dim == 1024) PHK_CUDA(launch_pdl(lfq_kernel<32>, lg, lb, (size_t)0, to_stream(s), x, wp, bp, ids, proj_out, rows, dim, bits));
   else PHK_CUDA(launch_pdl(lfq_kernel<0>, lg, lb, (size_t)0, to_stream(s), x, wp, bp, ids, proj_out, rows, dim, bits));
+  PHK_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int VEC>
+static int launch_ln_lfq(const float* x, const float* g, const float* b, const float* wp, const float* bp, int64_t* ids,
+                         float* out_norm, float* proj, int64_t rows, int dim, int bits, cudaStream_t st) {
+  constexpr int R = 2;
+  const size_t smem = (size_t)bits * dim * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    PHK_CUDA(cudaFuncSetAttribute(ln_lfq_kernel<VEC, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 1024 * 4));
+    configured = true;
+  }
+  const unsigned grid = (unsigned)((rows + 8 * R - 1) / (8 * R));
+  PHK_CUDA(launch_pdl(ln_lfq_kernel<VEC, R>, dim3(grid), dim3(256), smem, st, x, g, b, wp, bp, ids, out_norm, proj, rows, dim, bits));
+  return 0;
+}
+
+extern "C" int phk_layernorm_lfq(const float* x, const float* gamma, const float* beta, const float* wp,
+                                 const float* bp, int64_t* ids, float* out_norm, float* proj_out, int64_t rows,
+                                 int32_t dim, int32_t bits, phk_stream_t s) {
+  PHK_REQUIRE(x && gamma && beta && wp && bp && ids, PHK_E_ARG, "phk_layernorm_lfq: null pointer");
+  PHK_REQUIRE(rows >= 0 && dim > 0 && bits > 0 && bits <= 62, PHK_E_ARG, "phk_layernorm_lfq: bad size");
+  if (rows == 0) return 0;
+  const bool fused = dim % 128 == 0 && dim <= 1024 && bits <= 16 && (reinterpret_cast<uintptr_t>(wp) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+  if (!fused) {  // general shapes: LayerNorm then the stand-alone LFQ kernel (out_norm doubles as the scratch row buffer)
+    PHK_REQUIRE(out_norm, PHK_E_UNSUPPORTED, "phk_layernorm_lfq: this shape needs out_norm as scratch");
+    PHK_TRY(phk_layernorm(x, gamma, beta, out_norm, nullptr, rows, dim, 0, 0, 0, 0, s));
+    return phk_lfq_ids(out_norm, wp, bp, ids, proj_out, rows, dim, bits, s);
+  }
+  Prof prof_(FAM_LFQ, s, (double)rows * dim * 4.0);
+  cudaStream_t st = to_stream(s);
+  switch (dim / 128) {
+    case 1: PHK_TRY(launch_ln_lfq<1>(x, gamma, beta, wp, bp, ids, out_norm, proj_out, rows, dim, bits, st)); break;
+    case 2: PHK_TRY(launch_ln_lfq<2>(x, gamma, beta, wp, bp, ids, out_norm, proj_out, rows, dim, bits, st)); break;
+    case 3: PHK_TRY(launch_ln_lfq<3>(x, gamma, beta, wp, bp, ids, out_norm, proj_out, rows, dim, bits, st)); break;
+    case 4: PHK_TRY(launch_ln_lfq<4>(x, gamma, beta, wp, bp, ids, out_norm, proj_out, rows, dim, bits, st)); break;
+    case 5: PHK_TRY(launch_ln_lfq<5>(x, gamma, beta, wp, bp, ids, out_norm, proj_out, rows, dim, bits, st)); break;
+    case 6: PHK_TRY(launch_ln_lfq<6>(x, gamma, beta, wp, bp, ids, out_norm, proj_out, rows, dim, bits, st)); break;
+    case 7: PHK_TRY(launch_ln_lfq<7>(x, gamma, beta, wp, bp, ids, out_norm, proj_out, rows, dim, bits, st)); break;
+    default: PHK_TRY(launch_ln_lfq<8>(x, gamma, beta, wp, bp, ids, out_norm, proj_out, rows, dim, bits, st)); break;
+  }
   PHK_LAUNCH_CHECK();
   return 0;
 }

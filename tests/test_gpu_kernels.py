@@ -392,3 +392,29 @@ def test_attention_short_sequence_warp_kernel(heads, dh, n, causal):
     ref = oracle_attention(q, kv, None, qs, ks, heads=heads, dh=dh, causal=causal)
     out = run_attention(q, kv, None, qs, ks, heads=heads, dh=dh, n_q=n, n_k=n, causal=causal)
     torch.testing.assert_close(out, ref, rtol=1e-4, atol=2e-5)
+
+
+@pytest.mark.parametrize("rows,dim,bits", [(4608, 512, 16), (37, 256, 16), (50, 128, 10), (9, 1024, 8), (21, 96, 6)])
+def test_layernorm_lfq_fused_matches_separate_kernels(rows, dim, bits):
+    """norm_out + LFQ in one kernel (phk_layernorm_lfq) against LayerNorm followed by phk_lfq_ids and the oracle;
+    (21, 96, 6) takes the documented fallback (dim % 128 != 0)."""
+    x = rnd((rows, dim), 41) * 1.7 + 0.3
+    g, b = rnd((dim,), 42) * 0.2 + 1.0, rnd((dim,), 43) * 0.1
+    wp, bp = rnd((bits, dim), 44) / dim ** 0.5, rnd((bits,), 45) * 0.05
+    y = torch.nn.functional.layer_norm(x, (dim,), g, b)
+    proj_ref = y @ wp.t() + bp
+    ids_ref = ((proj_ref > 0).long() * (2 ** torch.arange(bits - 1, -1, -1))).sum(-1)
+    ids = torch.zeros(rows, dtype=torch.int64, device=DEV)
+    out = torch.zeros(rows, dim, device=DEV)
+    proj = torch.zeros(rows, bits, device=DEV)
+    L.check(L.lib().phk_layernorm_lfq(dp(x), dp(g), dp(b), dp(wp), dp(bp), L.ptr(ids), L.ptr(out), L.ptr(proj), rows, dim,
+                                      bits, L.stream_ptr()))
+    torch.testing.assert_close(out.cpu(), y, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(proj.cpu(), proj_ref, rtol=1e-4, atol=1e-5)
+    safe = proj_ref.abs().min(dim=-1).values > 1e-5           # ids must agree wherever no bit sits on the sign boundary
+    assert torch.equal(ids.cpu()[safe], ids_ref[safe]) and safe.float().mean() > 0.99
+    if dim % 128 == 0:                                        # taps are optional on the fused path
+        ids2 = torch.zeros_like(ids)
+        L.check(L.lib().phk_layernorm_lfq(dp(x), dp(g), dp(b), dp(wp), dp(bp), L.ptr(ids2), None, None, rows, dim, bits,
+                                          L.stream_ptr()))
+        assert torch.equal(ids2, ids)

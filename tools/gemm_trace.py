@@ -22,7 +22,7 @@ lib.phk_debug_gemm_trace(None)
 t = trace.cpu().reshape(148, 16)
 tiles = ((M + 127) // 128) * ((N + 127) // 128)
 used = t[t[:, 9] > 0]  # CTAs that ran (one-CTA kernel: min(tiles, 148); CTA-pair kernel: 2 x pairs)
-names = ["setup", "tma0_issued", "tmaLast_issued", "ops0_landed", "opsLast_landed", "mma_issued", "acc_ready", "staged", "written", "cta_done"]
+names = ["setup", "tma0_issued", "tmaLast_issued", "ops0_landed", "opsLast_landed", "mma_issued", "acc_ready", "staged", "written", "cta_done", "geglu_tmem_read", "geglu_math_done"]
 print(f"M={M} N={N} K={K} epi={epi} PHK_GEMM_MODE={os.environ.get('PHK_GEMM_MODE', '0')}: 128x128 tiles={tiles} CTAs={used.shape[0]} event time {e0.elapsed_time(e1)*1e3:.1f} us")
 for i, n in enumerate(names):
     col = used[:, i].float()
