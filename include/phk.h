@@ -177,6 +177,13 @@ int phk_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* 
                   int64_t seg_len, int64_t seg_stride, int64_t seg_off, int32_t epilogue,
                   phk_stream_t s);
 
+/* Two independent products C1 = A1 W1^T [M,N1] and C2 = A2 W2^T [M,N2] (bf16 operands, fp32 outputs, no bias) in ONE
+ * launch: the q and k,v projections of a self-attention block read different inputs (LayerNorm(x) vs raw x,
+ * attention.py:140-146) and are each a single wave of tiles; launched together their tiles pipeline. */
+int phk_gemm_bf16_x2(const void* A1, int64_t lda1, const void* W1, int64_t ldw1, float* C1, int64_t ldc1,
+                     int32_t N1, int32_t K1, const void* A2, int64_t lda2, const void* W2, int64_t ldw2,
+                     float* C2, int64_t ldc2, int32_t N2, int32_t K2, int64_t M, phk_stream_t s);
+
 /* debug aid: per-CTA clock64 phase stamps of phk_gemm_bf16 (16 x int64 per CTA); NULL disables */
 int phk_debug_gemm_trace(long long* device_buffer);
 /* tests / A-B measurements: force the tcgen05 GEMM variant: 0 automatic, 1 one CTA per 128x128 tile, 2 CTA pairs

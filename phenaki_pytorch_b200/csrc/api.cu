@@ -130,8 +130,12 @@ static int transformer_forward(const TfCall& c, Arena scratch, float* out, void*
     {  // x = self_attn(x) + x ; q from LN(x), k/v from RAW x (attention.py:140-144)
       const phk_attn_t& A = L.self_attn;
       PHK_TRY(phk_layernorm(x, A.norm_g, A.norm_b, xn, xraw, R, D, h16, 0, 0, 0, s));
-      PHK_TRY(linear(c.prec, xn, D, A.wq, A.wq_h, D, q, I, R, I, D, nullptr, nullptr, s));
-      PHK_TRY(linear(c.prec, h16 ? xraw : (const void*)x, D, A.wkv, A.wkv_h, D, kv, 2 * I, R, 2 * I, D, nullptr, nullptr, s));
+      if (h16 && R > 128 && A.wq_h && A.wkv_h) {  // both projections in one launch (their tiles pipeline)
+        PHK_TRY(phk_gemm_bf16_x2(xn, D, A.wq_h, D, q, I, I, D, xraw, D, A.wkv_h, D, kv, 2 * I, 2 * I, D, R, s));
+      } else {
+        PHK_TRY(linear(c.prec, xn, D, A.wq, A.wq_h, D, q, I, R, I, D, nullptr, nullptr, s));
+        PHK_TRY(linear(c.prec, h16 ? xraw : (const void*)x, D, A.wkv, A.wkv_h, D, kv, 2 * I, R, 2 * I, D, nullptr, nullptr, s));
+      }
       phk_attn_geom_t g;
       std::memset(&g, 0, sizeof(g));
       g.n_outer = c.seq.n_outer; g.n_inner = c.seq.n_inner; g.n_q = c.seq.n_tok; g.n_k = c.seq.n_tok;

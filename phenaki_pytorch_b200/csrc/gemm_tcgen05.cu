@@ -381,10 +381,17 @@ __device__ __forceinline__ void epi_chunk(const EpiParams& p, float* cstage, uin
 // ---------------------------------------------------------------------------------------------------
 // One-CTA kernel: 128 x 128 tiles, tcgen05.mma.cta_group::1 (small problems: fewer than 256 rows)
 // ---------------------------------------------------------------------------------------------------
-template <int EPI>
+// DUAL: two independent problems (own operands, output, N and K) in ONE launch -- the q and k,v projections of a
+// self-attention block, which read different inputs (LayerNorm(x) vs raw x, attention.py:140-144) and are each a
+// single wave of tiles: together they make ~3 tiles per CTA, so prologue, epilogue and main loop overlap across tiles
+// instead of being paid twice.
+template <int EPI, bool DUAL>
 __global__ void __launch_bounds__(GTHREADS, 1) gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmB,
-                                                                EpiParams p) {
+                                                                const __grid_constant__ EpiParams p,
+                                                                const __grid_constant__ CUtensorMap tmA2,
+                                                                const __grid_constant__ CUtensorMap tmB2,
+                                                                const __grid_constant__ EpiParams p2) {
   pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-B alignment
@@ -395,21 +402,30 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_bf16_kernel(const __grid_con
   // full[s] @ +8s ; empty[s] @ +8(S+s) ; tmem_full[a] @ +16S+8a ; tmem_empty[a] @ +16S+16+8a ; tmem slot @ +16S+32
   const uint32_t bar_tfull = bars + 16 * GSTAGES, bar_tempty = bar_tfull + 16, tmem_slot = bar_tfull + 32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_kb = (p.K + GK - 1) / GK;
-  const int num_tiles = p.m_tiles * p.n_tiles;
-  // tile schedule: round-robin over all tiles, m-fastest
+  const int tiles1 = p.m_tiles * p.n_tiles;
+  const int num_tiles = tiles1 + (DUAL ? p2.m_tiles * p2.n_tiles : 0);
+  // tile schedule: round-robin over all tiles (problem 1 first), m-fastest; returns true for a tile of problem 2
   const int my_tiles = (int)blockIdx.x < num_tiles ? (num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-  auto tile_of = [&](int i, int& m0, int& n0) {
-    const int tile = (int)blockIdx.x + i * (int)gridDim.x;
-    m0 = (tile % p.m_tiles) * GM;
-    n0 = (tile / p.m_tiles) * GN;
+  auto tile_of = [&](int i, int& m0, int& n0) -> bool {
+    int tile = (int)blockIdx.x + i * (int)gridDim.x;
+    const bool second = DUAL && tile >= tiles1;
+    if (second) tile -= tiles1;
+    const int mt = second ? p2.m_tiles : p.m_tiles;
+    m0 = (tile % mt) * GM;
+    n0 = (tile / mt) * GN;
+    return second;
   };
+  auto kblocks = [&](bool second) { return ((second ? p2.K : p.K) + GK - 1) / GK; };
   const long long t_start = clock64();
 #define PHK_STAMP(slot) do { if (p.trace) p.trace[blockIdx.x * 16 + (slot)] = clock64() - t_start; } while (0)
 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    if (DUAL) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA2) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB2) : "memory");
+    }
     for (int s = 0; s < GSTAGES; ++s) {
       mbar_init(bars + 8 * s, 1);
       mbar_init(bars + 8 * (GSTAGES + s), 1);
@@ -440,13 +456,16 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_bf16_kernel(const __grid_con
       uint32_t phase = 0;
       for (int it = 0; it < my_tiles; ++it) {
         int m0, n0;
-        tile_of(it, m0, n0);
+        const bool second = tile_of(it, m0, n0);
+        const int num_kb = kblocks(second);
+        const CUtensorMap* ma = second ? &tmA2 : &tmA;
+        const CUtensorMap* mb = second ? &tmB2 : &tmB;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(bars + 8 * (GSTAGES + stage), phase ^ 1);  // slot free (passes immediately on the first lap)
           const uint32_t full = bars + 8 * stage;
           mbar_expect_tx(full, 2 * STAGE_BYTES);
-          tma_load_2d(&tmA, full, sA + stage * STAGE_BYTES, kb * GK, m0);
-          tma_load_2d(&tmB, full, sB + stage * STAGE_BYTES, kb * GK, n0);
+          tma_load_2d(ma, full, sA + stage * STAGE_BYTES, kb * GK, m0);
+          tma_load_2d(mb, full, sB + stage * STAGE_BYTES, kb * GK, n0);
           if (it == 0 && kb == 0) PHK_STAMP(1);            // first TMA issued
           if (it == 0 && kb == num_kb - 1) PHK_STAMP(2);   // last TMA of the first tile issued
           if (++stage == GSTAGES) { stage = 0; phase ^= 1; }
@@ -467,6 +486,8 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_bf16_kernel(const __grid_con
         mbar_wait(bar_tempty + 8 * acc, (use & 1) ^ 1);  // epilogue has drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d_tmem = tmem_base + acc * GN;
+        int m0u, n0u;
+        const int num_kb = kblocks(tile_of(it, m0u, n0u));
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(bars + 8 * stage, phase);
           if (it == 0 && kb == 0) PHK_STAMP(3);            // first operands landed
@@ -493,17 +514,17 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_bf16_kernel(const __grid_con
       const int acc = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
       int m0, n0;
-      tile_of(it, m0, n0);
-      const bool res_vec = epi_residual_prefetch<EPI>(p, cstage, m0, n0, ew, lane);
+      const EpiParams& pp = tile_of(it, m0, n0) ? p2 : p;
+      const bool res_vec = epi_residual_prefetch<EPI>(pp, cstage, m0, n0, ew, lane);
       mbar_wait(bar_tfull + 8 * acc, use & 1);
       if (it == 0 && threadIdx.x == 64) PHK_STAMP(6);      // accumulator ready
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (EPI == 2)
-        epi_geglu_tile<1>(p, cstage, tmem_base + acc * GN, m0, n0, ew, lg, part, lane,
+        epi_geglu_tile<1>(pp, cstage, tmem_base + acc * GN, m0, n0, ew, lg, part, lane,
                           [&]() { if (lane == 0) mbar_arrive(bar_tempty + 8 * acc); },
                           [&](int slot) { if (it == 0 && threadIdx.x == 64) PHK_STAMP(slot); });
       else
-        epi_chunk<EPI>(p, cstage, tmem_base + acc * GN, m0, n0, res_vec, ew, lg, part, lane,
+        epi_chunk<EPI>(pp, cstage, tmem_base + acc * GN, m0, n0, res_vec, ew, lg, part, lane,
                        [&]() { if (lane == 0) mbar_arrive(bar_tempty + 8 * acc); });
       if (it == 0 && threadIdx.x == 64) PHK_STAMP(8);      // tile written out
     }
@@ -589,10 +610,13 @@ __host__ __device__ constexpr int pair_smem_bytes(int epi) {
   return pair_stages(epi) * 2 * STAGE_BYTES + pair_cstage_bytes(epi) + 256 + 1024;
 }
 
-template <int EPI, int BN>
+template <int EPI, int BN, bool DUAL>
 __global__ void __launch_bounds__(GTHREADS, 1) gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                      const __grid_constant__ CUtensorMap tmB,
-                                                                     EpiParams p) {
+                                                                     const __grid_constant__ EpiParams p,
+                                                                     const __grid_constant__ CUtensorMap tmA2,
+                                                                     const __grid_constant__ CUtensorMap tmB2,
+                                                                     const __grid_constant__ EpiParams p2) {
   static_assert(BN == 128 || BN == 256, "pair tile is 256 x 128 or 256 x 256");
   constexpr int B_BYTES = (BN / 2) * GK * 2;       // this CTA's half of the W tile per stage
   constexpr int TMEM_COLS = 2 * BN;                // two accumulators of BN fp32 columns
@@ -612,20 +636,30 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_bf16_pair_kernel(const __gri
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_rank();
   const bool leader = rank == 0;
-  const int num_kb = (p.K + GK - 1) / GK;
-  const int num_tiles = p.m_tiles * p.n_tiles;      // pair tiles: m_tiles = ceil(M / 256), n_tiles = ceil(N / BN)
+  const int tiles1 = p.m_tiles * p.n_tiles;         // pair tiles: m_tiles = ceil(M / 256), n_tiles = ceil(N / BN)
+  const int num_tiles = tiles1 + (DUAL ? p2.m_tiles * p2.n_tiles : 0);
   const int pair = (int)blockIdx.x >> 1, num_pairs = (int)gridDim.x >> 1;
   const int my_tiles = pair < num_tiles ? (num_tiles - 1 - pair) / num_pairs + 1 : 0;
-  auto tile_of = [&](int i, int& m0, int& n0) {     // m0: this CTA's 128 rows; n0: start of the BN-wide tile
-    const int tile = pair + i * num_pairs;
-    m0 = (tile % p.m_tiles) * (2 * GM) + (int)rank * GM;
-    n0 = (tile / p.m_tiles) * BN;
+  // m0: this CTA's 128 rows; n0: start of the BN-wide tile; returns true for a tile of the second problem (DUAL)
+  auto tile_of = [&](int i, int& m0, int& n0) -> bool {
+    int tile = pair + i * num_pairs;
+    const bool second = DUAL && tile >= tiles1;
+    if (second) tile -= tiles1;
+    const int mt = second ? p2.m_tiles : p.m_tiles;
+    m0 = (tile % mt) * (2 * GM) + (int)rank * GM;
+    n0 = (tile / mt) * BN;
+    return second;
   };
+  auto kblocks = [&](bool second) { return ((second ? p2.K : p.K) + GK - 1) / GK; };
   const long long t_start = clock64();
 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    if (DUAL) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA2) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB2) : "memory");
+    }
     for (int s = 0; s < NS; ++s) {
       mbar_init(bars + 8 * s, 1);                   // full: the leader's expect_tx arrival (used in the leader only)
       mbar_init(bars + 8 * (NS + s), 1);       // empty: one multicast commit
@@ -658,13 +692,16 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_bf16_pair_kernel(const __gri
       uint32_t phase = 0;
       for (int it = 0; it < my_tiles; ++it) {
         int m0, n0;
-        tile_of(it, m0, n0);
+        const bool second = tile_of(it, m0, n0);
+        const int num_kb = kblocks(second);
+        const CUtensorMap* ma = second ? &tmA2 : &tmA;
+        const CUtensorMap* mb = second ? &tmB2 : &tmB;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(bars + 8 * (NS + stage), phase ^ 1);  // slot free in THIS CTA (multicast commit)
           if (leader) mbar_expect_tx(bars + 8 * stage, 2 * (STAGE_BYTES + B_BYTES));  // bytes of both CTAs
           const uint32_t full = map_to_cta(bars + 8 * stage, 0);                     // the leader's full barrier
-          tma_load_2d_pair(&tmA, full, sA + stage * STAGE_BYTES, kb * GK, m0);
-          tma_load_2d_pair(&tmB, full, sB + stage * STAGE_BYTES, kb * GK, n0 + (int)rank * (BN / 2));
+          tma_load_2d_pair(ma, full, sA + stage * STAGE_BYTES, kb * GK, m0);
+          tma_load_2d_pair(mb, full, sB + stage * STAGE_BYTES, kb * GK, n0 + (int)rank * (BN / 2));
           if (it == 0 && kb == 0) PHK_STAMP(1);
           if (it == 0 && kb == num_kb - 1) PHK_STAMP(2);
           if (++stage == NS) { stage = 0; phase ^= 1; }
@@ -689,6 +726,8 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_bf16_pair_kernel(const __gri
         mbar_wait_cluster(bar_tempty + 8 * acc, (use & 1) ^ 1);  // both CTAs have drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d_tmem = tmem_base + acc * BN;
+        int m0u, n0u;
+        const int num_kb = kblocks(tile_of(it, m0u, n0u));
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait_cluster(bars + 8 * stage, phase);            // both CTAs' operands have landed
           if (it == 0 && kb == 0) PHK_STAMP(3);
@@ -714,21 +753,21 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_bf16_pair_kernel(const __gri
       const int acc = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
       int m0, n0;
-      tile_of(it, m0, n0);
-      bool res_vec = epi_residual_prefetch<EPI>(p, cstage, m0, n0, ew, lane);
+      const EpiParams& pp = tile_of(it, m0, n0) ? p2 : p;
+      bool res_vec = epi_residual_prefetch<EPI>(pp, cstage, m0, n0, ew, lane);
       mbar_wait(bar_tfull + 8 * acc, use & 1);
       if (it == 0 && threadIdx.x == 64) PHK_STAMP(6);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (EPI == 2) {
-        epi_geglu_tile<BN / 128>(p, cstage, tmem_base + acc * BN, m0, n0, ew, lg, part, lane,
+        epi_geglu_tile<BN / 128>(pp, cstage, tmem_base + acc * BN, m0, n0, ew, lg, part, lane,
                                  [&]() { if (lane == 0) mbar_arrive_remote(tempty_leader + 8 * acc); },
                                  [&](int slot) { if (it == 0 && threadIdx.x == 64) PHK_STAMP(slot); });
       } else {
 #pragma unroll
         for (int h = 0; h < BN / 128; ++h) {
-          if (h > 0) res_vec = epi_residual_prefetch<EPI>(p, cstage, m0, n0 + h * 128, ew, lane);
+          if (h > 0) res_vec = epi_residual_prefetch<EPI>(pp, cstage, m0, n0 + h * 128, ew, lane);
           const bool last = h == BN / 128 - 1;
-          epi_chunk<EPI>(p, cstage, tmem_base + acc * BN + h * 128, m0, n0 + h * 128, res_vec, ew, lg, part, lane,
+          epi_chunk<EPI>(pp, cstage, tmem_base + acc * BN + h * 128, m0, n0 + h * 128, res_vec, ew, lg, part, lane,
                          [&]() { if (last && lane == 0) mbar_arrive_remote(tempty_leader + 8 * acc); });
         }
       }
@@ -813,25 +852,40 @@ template <int EPI>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const EpiParams& p, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    PHK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    PHK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<EPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
     configured = true;
   }
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
-  PHK_CUDA(launch_pdl(gemm_bf16_kernel<EPI>, dim3(grid), dim3(GTHREADS), (size_t)(SMEM_TOTAL), st, ta, tb, p));
+  PHK_CUDA(launch_pdl(gemm_bf16_kernel<EPI, false>, dim3(grid), dim3(GTHREADS), (size_t)(SMEM_TOTAL), st, ta, tb, p, ta, tb, p));
+  PHK_LAUNCH_CHECK();
+  return 0;
+}
+
+static int launch_gemm_dual(const CUtensorMap& ta, const CUtensorMap& tb, const EpiParams& p, const CUtensorMap& ta2,
+                            const CUtensorMap& tb2, const EpiParams& p2, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    PHK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    configured = true;
+  }
+  const int tiles = p.m_tiles * p.n_tiles + p2.m_tiles * p2.n_tiles;
+  const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+  PHK_CUDA(launch_pdl(gemm_bf16_kernel<0, true>, dim3(grid), dim3(GTHREADS), (size_t)(SMEM_TOTAL), st, ta, tb, p, ta2, tb2, p2));
   PHK_LAUNCH_CHECK();
   return 0;
 }
 
 // clusters of two CTAs (+ programmatic dependent launch); one pair per TPC, persistent over the pair tiles
-template <int EPI, int BN>
-static int launch_gemm_pair(const CUtensorMap& ta, const CUtensorMap& tb, const EpiParams& p, cudaStream_t st) {
+template <int EPI, int BN, bool DUAL>
+static int launch_gemm_pair(const CUtensorMap& ta, const CUtensorMap& tb, const EpiParams& p, const CUtensorMap& ta2,
+                            const CUtensorMap& tb2, const EpiParams& p2, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    PHK_CUDA(cudaFuncSetAttribute(gemm_bf16_pair_kernel<EPI, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair_smem_bytes(EPI)));
+    PHK_CUDA(cudaFuncSetAttribute(gemm_bf16_pair_kernel<EPI, BN, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair_smem_bytes(EPI)));
     configured = true;
   }
-  const int tiles = p.m_tiles * p.n_tiles, max_pairs = kNumSMs / 2;
+  const int tiles = p.m_tiles * p.n_tiles + (DUAL ? p2.m_tiles * p2.n_tiles : 0), max_pairs = kNumSMs / 2;
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(GTHREADS); cfg.dynamicSmemBytes = pair_smem_bytes(EPI); cfg.stream = st;
@@ -841,7 +895,7 @@ static int launch_gemm_pair(const CUtensorMap& ta, const CUtensorMap& tb, const 
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = 2;
-  PHK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_pair_kernel<EPI, BN>, ta, tb, p));
+  PHK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_pair_kernel<EPI, BN, DUAL>, ta, tb, p, ta2, tb2, p2));
   PHK_LAUNCH_CHECK();
   return 0;
 }
@@ -849,9 +903,9 @@ static int launch_gemm_pair(const CUtensorMap& ta, const CUtensorMap& tb, const 
 template <int BN>
 static int launch_gemm_pair_epi(int epilogue, const CUtensorMap& ta, const CUtensorMap& tb, const EpiParams& p,
                                 cudaStream_t st) {
-  if (epilogue == 2) return launch_gemm_pair<2, BN>(ta, tb, p, st);
-  if (epilogue == 1) return launch_gemm_pair<1, BN>(ta, tb, p, st);
-  return launch_gemm_pair<0, BN>(ta, tb, p, st);
+  if (epilogue == 2) return launch_gemm_pair<2, BN, false>(ta, tb, p, ta, tb, p, st);
+  if (epilogue == 1) return launch_gemm_pair<1, BN, false>(ta, tb, p, ta, tb, p, st);
+  return launch_gemm_pair<0, BN, false>(ta, tb, p, ta, tb, p, st);
 }
 
 // 0: automatic; 1: always the one-CTA kernel; 2 / 3: CTA pairs with BN = 128 / 256 whenever M > 128 (A/B measurements)
@@ -911,6 +965,45 @@ extern "C" int phk_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t 
   if (epilogue == 2) return launch_gemm<2>(ta, tb, p, st);
   if (epilogue == 1) return launch_gemm<1>(ta, tb, p, st);
   return launch_gemm<0>(ta, tb, p, st);
+}
+
+// Two independent products C1 = A1 W1^T and C2 = A2 W2^T (fp32 outputs, same M) in one launch: the q and k,v
+// projections of a self-attention block (attention.py:140-146).
+extern "C" int phk_gemm_bf16_x2(const void* A1, int64_t lda1, const void* W1, int64_t ldw1, float* C1, int64_t ldc1,
+                                int32_t N1, int32_t K1, const void* A2, int64_t lda2, const void* W2, int64_t ldw2,
+                                float* C2, int64_t ldc2, int32_t N2, int32_t K2, int64_t M, phk_stream_t s) {
+  Prof prof_(FAM_GEMM_BF16, s, 2.0 * (double)M * ((double)N1 * K1 + (double)N2 * K2));
+  PHK_REQUIRE(A1 && W1 && C1 && A2 && W2 && C2, PHK_E_ARG, "phk_gemm_bf16_x2: null pointer");
+  PHK_REQUIRE(M >= 0 && N1 > 0 && K1 > 0 && N2 > 0 && K2 > 0 && lda1 >= K1 && ldw1 >= K1 && lda2 >= K2 && ldw2 >= K2,
+              PHK_E_ARG, "phk_gemm_bf16_x2: bad size");
+  PHK_REQUIRE(lda1 % 8 == 0 && ldw1 % 8 == 0 && lda2 % 8 == 0 && ldw2 % 8 == 0 &&
+                  ((reinterpret_cast<uintptr_t>(A1) | reinterpret_cast<uintptr_t>(W1) | reinterpret_cast<uintptr_t>(A2) |
+                    reinterpret_cast<uintptr_t>(W2)) & 15) == 0,
+              PHK_E_ARG, "phk_gemm_bf16_x2: operands must be 16-byte aligned with leading dimensions multiple of 8 (TMA)");
+  PHK_REQUIRE(M < (1LL << 31) - GM, PHK_E_UNSUPPORTED, "phk_gemm_bf16_x2: M too large");
+  if (M == 0) return 0;
+  CUtensorMap ta, tb, ta2, tb2;
+  PHK_TRY(get_tensor_map(A1, M, K1, lda1, GM, &ta));
+  PHK_TRY(get_tensor_map(A2, M, K2, lda2, GM, &ta2));
+  const int m_pairs = (int)((M + 2 * GM - 1) / (2 * GM));
+  const int mode = gemm_mode();
+  // measured (profiles/r01_gemm_modes.txt): with fp32 outputs the 256 x 256 pair tile's two-chunk epilogue costs more
+  // than the halved operand traffic saves at K = 512, so the pair variant is only taken when forced (tests, A/B runs)
+  const bool pair = M > GM && mode >= 2;
+  if (pair) {
+    PHK_TRY(get_tensor_map(W1, N1, K1, ldw1, 128, &tb));
+    PHK_TRY(get_tensor_map(W2, N2, K2, ldw2, 128, &tb2));
+    EpiParams p{C1, ldc1, M, N1, K1, nullptr, nullptr, 0, 0, 0, m_pairs, (N1 + 255) / 256, nullptr};
+    EpiParams p2{C2, ldc2, M, N2, K2, nullptr, nullptr, 0, 0, 0, m_pairs, (N2 + 255) / 256, nullptr};
+    return launch_gemm_pair<0, 256, true>(ta, tb, p, ta2, tb2, p2, to_stream(s));
+  }
+  PHK_TRY(get_tensor_map(W1, N1, K1, ldw1, GN, &tb));
+  PHK_TRY(get_tensor_map(W2, N2, K2, ldw2, GN, &tb2));
+  const int mt = (int)((M + GM - 1) / GM);
+  EpiParams p{C1, ldc1, M, N1, K1, nullptr, nullptr, 0, 0, 0, mt, (N1 + GN - 1) / GN, nullptr};
+  EpiParams p2{C2, ldc2, M, N2, K2, nullptr, nullptr, 0, 0, 0, mt, (N2 + GN - 1) / GN, nullptr};
+  PHK_REQUIRE((int64_t)mt * (p.n_tiles + p2.n_tiles) < (1LL << 31), PHK_E_UNSUPPORTED, "phk_gemm_bf16_x2: too many tiles");
+  return launch_gemm_dual(ta, tb, p, ta2, tb2, p2, to_stream(s));
 }
 
 // debug / tests: force the kernel choice (0 automatic, 1 one-CTA, 2 CTA pairs 256x128, 3 CTA pairs 256x256; < 0 returns

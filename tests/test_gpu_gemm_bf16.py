@@ -196,3 +196,35 @@ def test_geglu_epilogue_activation_error_is_below_bf16_rounding():
     err = (out.cpu().float() - ref).abs()
     bound = ref.abs() * 2.0 ** -8 + 1e-4 * v
     assert (err <= bound).all(), f"max excess {(err - bound).max():.2e}"
+
+
+@pytest.mark.parametrize("M,N1,N2,K1,K2", [(4608, 512, 1024, 512, 512), (300, 200, 130, 72, 136), (129, 64, 64, 64, 64)])
+def test_gemm_x2_two_problems_in_one_launch(M, N1, N2, K1, K2):
+    """phk_gemm_bf16_x2 (q and k,v projections of one attention block in a single persistent launch) equals two
+    separate phk_gemm_bf16 calls bit for bit when both use the one-CTA kernel (same tiles, same K order), and the fp32
+    product of the bf16 operands in every variant."""
+    a1, w1 = operands(M, N1, K1, seed=50)
+    a2, w2 = operands(M, N2, K2, seed=52)
+    d = [t.to(DEV) for t in (a1, w1, a2, w2)]
+    c1 = torch.full((M, N1), 3.0, device=DEV)
+    c2 = torch.full((M, N2), 3.0, device=DEV)
+    lib = L.lib()
+    L.check(lib.phk_gemm_bf16_x2(L.ptr(d[0]), K1, L.ptr(d[1]), K1, L.ptr(c1), N1, N1, K1, L.ptr(d[2]), K2, L.ptr(d[3]), K2,
+                                 L.ptr(c2), N2, N2, K2, M, L.stream_ptr()), "phk_gemm_bf16_x2")
+    torch.testing.assert_close(c1.cpu(), a1.float() @ w1.float().t(), rtol=1e-4, atol=2e-3)
+    torch.testing.assert_close(c2.cpu(), a2.float() @ w2.float().t(), rtol=1e-4, atol=2e-3)
+    L.check(lib.phk_debug_gemm_mode(1))   # one-CTA kernels on both sides: same tiles, same K order -> identical bits
+    try:
+        s1, s2, t1, t2 = torch.empty_like(c1), torch.empty_like(c2), torch.empty_like(c1), torch.empty_like(c2)
+        L.check(lib.phk_gemm_bf16(L.ptr(d[0]), K1, L.ptr(d[1]), K1, L.ptr(s1), N1, M, N1, K1, None, None, 0, 0, 0, 0, L.stream_ptr()))
+        L.check(lib.phk_gemm_bf16(L.ptr(d[2]), K2, L.ptr(d[3]), K2, L.ptr(s2), N2, M, N2, K2, None, None, 0, 0, 0, 0, L.stream_ptr()))
+        L.check(lib.phk_gemm_bf16_x2(L.ptr(d[0]), K1, L.ptr(d[1]), K1, L.ptr(t1), N1, N1, K1, L.ptr(d[2]), K2, L.ptr(d[3]),
+                                     K2, L.ptr(t2), N2, N2, K2, M, L.stream_ptr()), "phk_gemm_bf16_x2")
+        assert torch.equal(s1, t1) and torch.equal(s2, t2)
+        L.check(lib.phk_debug_gemm_mode(3))   # the CTA-pair variant of the two-problem launch
+        L.check(lib.phk_gemm_bf16_x2(L.ptr(d[0]), K1, L.ptr(d[1]), K1, L.ptr(t1), N1, N1, K1, L.ptr(d[2]), K2, L.ptr(d[3]),
+                                     K2, L.ptr(t2), N2, N2, K2, M, L.stream_ptr()), "phk_gemm_bf16_x2")
+        torch.testing.assert_close(t1.cpu(), a1.float() @ w1.float().t(), rtol=1e-4, atol=2e-3)
+        torch.testing.assert_close(t2.cpu(), a2.float() @ w2.float().t(), rtol=1e-4, atol=2e-3)
+    finally:
+        lib.phk_debug_gemm_mode(-1)

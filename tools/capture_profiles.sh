@@ -1,0 +1,18 @@
+#!/bin/bash
+# Runs on the GPU box (under gpurun): everything profiles/ is built from.  Output: gpurun_out/r01/
+# usage: bash tools/capture_profiles.sh
+set -u
+O=gpurun_out/r01
+mkdir -p $O
+NCU="ncu --clock-control none --cache-control none"
+python bench.py > $O/bench_bf16.json 2> $O/bench_bf16.err
+python bench.py --prec f32 --no-cpu > $O/bench_f32.json 2> $O/bench_f32.err
+python bench.py --impl reference --steps 5 --warmup 1 > $O/bench_reference.json 2> $O/bench_reference.err
+python tools/op_bench.py 50 > $O/op_bench.txt 2>&1
+for w in encode decode maskgit; do
+  $NCU --metrics gpu__time_duration.sum --csv --log-file $O/launches_${w}_bf16.csv python tools/profile_step.py $w bf16 3 > $O/p_$w.log 2>&1
+done
+# one --set full capture of the dominant kernel family (GEMM): 16 launches from the middle of the second encode step
+$NCU --set full --import-source on -k regex:gemm_bf16 -s 45 -c 16 -o $O/gemm_full -f python tools/profile_step.py encode bf16 2 > $O/p_gemm_full.log 2>&1
+$NCU --set full --import-source on -k regex:"attention_tc_kernel|attention_prep|attention_rows|patchify_ln|peg_tiled|ln_lfq|ln_warp" -s 40 -c 14 -o $O/rest_full -f python tools/profile_step.py encode bf16 2 > $O/p_rest_full.log 2>&1
+ls -la $O

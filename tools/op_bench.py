@@ -61,6 +61,12 @@ for (M, N, K, epi, name) in [(4608, 512, 512, 0, "gemm q/out-proj (+res)"), (460
     timeit(name + f" {M}x{N}x{K}", lambda: L.check(lib.phk_gemm_bf16(L.ptr(a), K, L.ptr(w), K, L.ptr(c), c.shape[1], M, N, K, None, res, 0, 0, 0, epi, sp())),
            2.0 * M * N * K, "TFLOP/s")
 
+a1 = torch.randn(R, D, device=dev).to(bf); a2 = torch.randn(R, D, device=dev).to(bf)
+w1 = torch.randn(I, D, device=dev).to(bf); w2 = torch.randn(2 * I, D, device=dev).to(bf)
+c1 = torch.zeros(R, I, device=dev); c2 = torch.zeros(R, 2 * I, device=dev)
+timeit("gemm q + kv in one launch (x2)", lambda: L.check(lib.phk_gemm_bf16_x2(L.ptr(a1), D, L.ptr(w1), D, L.ptr(c1), I, I, D, L.ptr(a2), D, L.ptr(w2), D, L.ptr(c2), 2 * I, 2 * I, D, R, sp())),
+       2.0 * R * 3 * I * D, "TFLOP/s")
+
 # temporal attention (n=9, causal) on the (b,t,h,w) layout
 q, kv = torch.randn(R, I, device=dev), torch.randn(R, 2 * I, device=dev)
 ones = torch.ones(64, device=dev)

@@ -1,5 +1,5 @@
 """Runs a few steps of one workload for ncu (launch list / --set full captures).
-usage: python tools/profile_step.py {encode|maskgit} {f32|bf16} [steps]"""
+usage: python tools/profile_step.py {encode|decode|maskgit} {f32|bf16} [steps]"""
 import os
 import sys
 
@@ -21,6 +21,12 @@ if what == "encode":
     video = torch.randn(bench.VIDEO, device=dev)
     for _ in range(steps):
         model(video, return_only_codebook_ids=True)
+elif what == "decode":
+    model = P.CViViT(**bench.CFG2).to(dev).eval()
+    model.precision = prec
+    ids = torch.randint(0, 65536, (8, 9, 8, 8), device=dev)
+    for _ in range(steps):
+        model.decode_from_codebook_indices(ids)
 else:
     cv = P.CViViT(**bench.CFG2).to(dev)
     mg = P.MaskGit(**bench.CFG3).to(dev)
