@@ -332,35 +332,50 @@ __global__ void __launch_bounds__(256) attention_prep_kernel(const float* __rest
   const int I = heads * 64;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t sh = (int64_t)seq * heads + h;
-  for (int tt = w; tt < 64; tt += 8) {
-    const int tok = t0 + tt;
-    float xq[2] = {0.f, 0.f}, xk[2] = {0.f, 0.f}, xv[2] = {0.f, 0.f};
-    if (tok < n) {
-      const int64_t row = (int64_t)seq * n + tok;
+  // lane owns dims (2 lane, 2 lane + 1): one 8-byte load per operand and token, one 4-byte bf16x2 store per output
+  const float2 qs = reinterpret_cast<const float2*>(q_scale)[lane], ks = reinterpret_cast<const float2*>(k_scale)[lane];
+  // 8 tokens per warp, all loads of 4 tokens in flight before the first reduction
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        xq[c] = q[row * I + h * 64 + lane + 32 * c];
-        xk[c] = kv[row * 2 * I + h * 64 + lane + 32 * c];
-        xv[c] = kv[row * 2 * I + I + h * 64 + lane + 32 * c];
+  for (int g = 0; g < 2; ++g) {
+    float2 xq[4], xk[4], xv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int tt = w * 8 + g * 4 + u, tok = t0 + tt;
+      xq[u] = xk[u] = xv[u] = make_float2(0.f, 0.f);
+      if (tok < n) {
+        const int64_t row = (int64_t)seq * n + tok;
+        xq[u] = reinterpret_cast<const float2*>(q + row * I + h * 64)[lane];
+        xk[u] = reinterpret_cast<const float2*>(kv + row * 2 * I + h * 64)[lane];
+        xv[u] = reinterpret_cast<const float2*>(kv + row * 2 * I + I + h * 64)[lane];
       }
     }
-    const float nq = fmaxf(sqrtf(warp_sum(xq[0] * xq[0] + xq[1] * xq[1])), 1e-12f);
-    const float nk = fmaxf(sqrtf(warp_sum(xk[0] * xk[0] + xk[1] * xk[1])), 1e-12f);
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      const int d = lane + 32 * c;
-      vt[tt][d] = xv[c];
+    for (int u = 0; u < 4; ++u) {
+      const int tt = w * 8 + g * 4 + u, tok = t0 + tt;
+      const float nq = fmaxf(sqrtf(warp_sum(xq[u].x * xq[u].x + xq[u].y * xq[u].y)), 1e-12f);
+      const float nk = fmaxf(sqrtf(warp_sum(xk[u].x * xk[u].x + xk[u].y * xk[u].y)), 1e-12f);
+      vt[tt][2 * lane] = xv[u].x;
+      vt[tt][2 * lane + 1] = xv[u].y;
       if (tok < n) {
         // F.normalize then * q_scale (attention.py:153-155); the fixed scale 8 (:157) is folded into q (exact in bf16)
-        Qh[(sh * n + tok) * 64 + d] = __float2bfloat16_rn((xq[c] / nq) * q_scale[d] * scale);
-        Kh[(sh * n + tok) * 64 + d] = __float2bfloat16_rn((xk[c] / nk) * k_scale[d]);
+        reinterpret_cast<uint32_t*>(Qh + (sh * n + tok) * 64)[lane] =
+            pack_bf16x2((xq[u].x / nq) * qs.x * scale, (xq[u].y / nq) * qs.y * scale);
+        reinterpret_cast<uint32_t*>(Kh + (sh * n + tok) * 64)[lane] = pack_bf16x2((xk[u].x / nk) * ks.x, (xk[u].y / nk) * ks.y);
       }
     }
   }
   __syncthreads();
-  for (int idx = threadIdx.x; idx < 64 * 64; idx += blockDim.x) {
-    const int d = idx >> 6, tt = idx & 63;
-    if (t0 + tt < n_pad) Vt[(sh * 64 + d) * n_pad + t0 + tt] = __float2bfloat16_rn(t0 + tt < n ? vt[tt][d] : 0.f);
+  // V^T: thread -> (d, token pair): 64 d x 32 pairs = 2048 bf16x2 stores; a warp writes 128 contiguous bytes of one d row
+  const bool pair_ok = (n_pad % 2 == 0);
+  for (int idx = threadIdx.x; idx < 64 * 32; idx += blockDim.x) {
+    const int d = idx >> 5, tt = (idx & 31) * 2;
+    const float v0 = t0 + tt < n ? vt[tt][d] : 0.f, v1 = t0 + tt + 1 < n ? vt[tt + 1][d] : 0.f;
+    __nv_bfloat16* dst = Vt + (sh * 64 + d) * n_pad + t0 + tt;
+    if (pair_ok && t0 + tt + 1 < n_pad) *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(v0, v1);
+    else {
+      if (t0 + tt < n_pad) dst[0] = __float2bfloat16_rn(v0);
+      if (t0 + tt + 1 < n_pad) dst[1] = __float2bfloat16_rn(v1);
+    }
   }
 }
 
