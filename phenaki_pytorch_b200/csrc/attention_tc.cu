@@ -352,15 +352,16 @@ __global__ void __launch_bounds__(256) attention_prep_kernel(const float* __rest
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int tt = w * 8 + g * 4 + u, tok = t0 + tt;
-      const float nq = fmaxf(sqrtf(warp_sum(xq[u].x * xq[u].x + xq[u].y * xq[u].y)), 1e-12f);
-      const float nk = fmaxf(sqrtf(warp_sum(xk[u].x * xk[u].x + xk[u].y * xk[u].y)), 1e-12f);
+      // 1 / max(||x||, 1e-12) (F.normalize, attention.py:153-154) once per token instead of a division per element
+      const float iq = 1.0f / fmaxf(sqrtf(warp_sum(xq[u].x * xq[u].x + xq[u].y * xq[u].y)), 1e-12f);
+      const float ik = 1.0f / fmaxf(sqrtf(warp_sum(xk[u].x * xk[u].x + xk[u].y * xk[u].y)), 1e-12f);
       vt[tt][2 * lane] = xv[u].x;
       vt[tt][2 * lane + 1] = xv[u].y;
       if (tok < n) {
         // F.normalize then * q_scale (attention.py:153-155); the fixed scale 8 (:157) is folded into q (exact in bf16)
         reinterpret_cast<uint32_t*>(Qh + (sh * n + tok) * 64)[lane] =
-            pack_bf16x2((xq[u].x / nq) * qs.x * scale, (xq[u].y / nq) * qs.y * scale);
-        reinterpret_cast<uint32_t*>(Kh + (sh * n + tok) * 64)[lane] = pack_bf16x2((xk[u].x / nk) * ks.x, (xk[u].y / nk) * ks.y);
+            pack_bf16x2((xq[u].x * iq) * qs.x * scale, (xq[u].y * iq) * qs.y * scale);
+        reinterpret_cast<uint32_t*>(Kh + (sh * n + tok) * 64)[lane] = pack_bf16x2((xk[u].x * ik) * ks.x, (xk[u].y * ik) * ks.y);
       }
     }
   }

@@ -202,6 +202,84 @@ __global__ void token_embed_kernel(const int64_t* __restrict__ ids, const float*
   }
 }
 
+// Persistent variant for p2 % 4 == 0 and K <= NJ * 1024: each thread owns the same NJ float4 positions of every token, so
+// its gather offsets are computed once, gamma / beta (2 x 24 KB per token at K = 6144 -- twice the video bytes when
+// every CTA re-reads them from L2) are staged once per CTA in shared memory, and the token itself stays in registers
+// between the two LayerNorm passes.  ~60 registers -> 4 CTAs per SM keep ~96 KB of video loads in flight per SM.
+template <int NJ>
+__global__ void __launch_bounds__(256, 4) patchify_ln_reg_kernel(const float* __restrict__ video, int C, int F, int H,
+                                                                 int W, int f0, int nt, int pt, int p1, int p2,
+                                                                 const float* __restrict__ g, const float* __restrict__ b,
+                                                                 void* __restrict__ out, int out_bf16, int tokens) {
+  pdl_trigger();
+  extern __shared__ float4 sgb[];  // [K4] gamma, [K4] beta
+  __shared__ float red[32];
+  const int hh = H / p1, ww = W / p2;
+  const int K = C * pt * p1 * p2, K4 = K >> 2;
+  const int plane = H * W;
+  const int runs = p2 >> 2;
+  int off[NJ];  // float offset of this thread's j-th float4 inside the token's (c, dt, dy, dx) gather; -1: none
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    const int i = threadIdx.x + 256 * j;
+    off[j] = -1;
+    if (i < K4) {
+      const int dx4 = i % runs;
+      int r = i / runs;  // (c, dt, dy)
+      const int dy = r % p1; r /= p1;
+      const int dt = r % pt;
+      const int c = r / pt;
+      off[j] = (c * F + dt) * plane + dy * W + dx4 * 4;
+      sgb[i] = __ldg(reinterpret_cast<const float4*>(g) + i);
+      sgb[K4 + i] = __ldg(reinterpret_cast<const float4*>(b) + i);
+    }
+  }
+  pdl_wait();  // gamma / beta are weights; the video may come from the previous kernel (decode -> encode chains)
+  for (int token = blockIdx.x; token < tokens; token += gridDim.x) {
+    int tok = token;
+    const int wi = tok % ww; tok /= ww;
+    const int hi = tok % hh; tok /= hh;
+    const int ti = tok % nt;
+    const int bi = tok / nt;
+    const float* base = video + ((int64_t)bi * C * F + f0 + (int64_t)ti * pt) * plane + (int64_t)hi * p1 * W + wi * p2;
+    float4 v[NJ];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (off[j] >= 0) v[j] = __ldg(reinterpret_cast<const float4*>(base + off[j]));
+    }
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+    const float mean = block_sum(s, red) / (float)K;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j)
+      if (off[j] >= 0) {
+        const float a = v[j].x - mean, bq = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+        q += (a * a + bq * bq) + (c * c + d * d);
+      }
+    const float rstd = rsqrtf(block_sum(q, red) / (float)K + 1e-5f);
+    const int64_t orow = (int64_t)token * K;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      if (off[j] < 0) continue;
+      const int i = threadIdx.x + 256 * j;
+      const float4 gg = sgb[i], bb = sgb[K4 + i];
+      float4 o;
+      o.x = (v[j].x - mean) * rstd * gg.x + bb.x;
+      o.y = (v[j].y - mean) * rstd * gg.y + bb.y;
+      o.z = (v[j].z - mean) * rstd * gg.z + bb.z;
+      o.w = (v[j].w - mean) * rstd * gg.w + bb.w;
+      if (out_bf16)
+        reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + orow)[i] =
+            make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+      else
+        reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + orow)[i] = o;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // LFQ ids (oracle/lfq.py; call site cvivit.py:570).  Warp per row.
 // ------------------------------------------------------------------------------------------
@@ -750,15 +828,26 @@ __global__ void __launch_bounds__(256) lfq_codes_kernel(const int64_t* __restric
                                                         int64_t rows, int dim, int bits) {
   pdl_prologue();
   const int64_t total = rows * dim;
+  const bool vec = (bits % 4 == 0) && ((reinterpret_cast<uintptr_t>(w) & 15) == 0);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / dim;
     const int d = (int)(i - r * dim);
     const int64_t id = ids[r];
     const float* wr = w + (int64_t)d * bits;
     float acc = 0.f;
-    for (int j = 0; j < bits; ++j) {
-      const float wv = __ldg(wr + j);
-      acc += ((id >> (bits - 1 - j)) & 1) ? wv : -wv;
+    if (vec) {  // the weight row of this output (bits floats, 64 B at 16 bits) as 16-byte loads, all issued up front
+      for (int j = 0; j < bits; j += 4) {
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(wr + j));
+        acc += ((id >> (bits - 1 - j)) & 1) ? wv.x : -wv.x;
+        acc += ((id >> (bits - 2 - j)) & 1) ? wv.y : -wv.y;
+        acc += ((id >> (bits - 3 - j)) & 1) ? wv.z : -wv.z;
+        acc += ((id >> (bits - 4 - j)) & 1) ? wv.w : -wv.w;
+      }
+    } else {
+      for (int j = 0; j < bits; ++j) {
+        const float wv = __ldg(wr + j);
+        acc += ((id >> (bits - 1 - j)) & 1) ? wv : -wv;
+      }
     }
     out[i] = acc + __ldg(b + d);
   }
@@ -845,6 +934,22 @@ extern "C" int phk_patchify_ln(const float* video, int32_t B, int32_t C, int32_t
   const size_t smem = (size_t)K * sizeof(float);
   const bool vec = (p2 % 4 == 0) && (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(video) & 15) == 0) &&
                    ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  if (vec && K <= 6 * 1024 && ((reinterpret_cast<uintptr_t>(ln_g) | reinterpret_cast<uintptr_t>(ln_b)) & 15) == 0) {
+    // persistent, register-resident variant (4 CTAs per SM; gamma / beta staged once per CTA: 2 * K * 4 bytes of smem)
+    PHK_REQUIRE((int64_t)C * F * H * W < (1LL << 31), PHK_E_UNSUPPORTED, "phk_patchify_ln: one video exceeds 2^31 elements");
+    const unsigned pgrid = grid < 4u * kNumSMs ? grid : 4u * kNumSMs;
+    const size_t gsmem = (size_t)2 * K * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+      PHK_CUDA(cudaFuncSetAttribute(patchify_ln_reg_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 49152));
+      PHK_CUDA(cudaFuncSetAttribute(patchify_ln_reg_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 49152));
+      configured = true;
+    }
+    if (K <= 3 * 1024) PHK_CUDA(launch_pdl(patchify_ln_reg_kernel<3>, dim3(pgrid), dim3(256), gsmem, to_stream(s), video, C, F, H, W, f0, nt, pt, p1, p2, ln_g, ln_b, out, out_bf16, (int)grid));
+    else PHK_CUDA(launch_pdl(patchify_ln_reg_kernel<6>, dim3(pgrid), dim3(256), gsmem, to_stream(s), video, C, F, H, W, f0, nt, pt, p1, p2, ln_g, ln_b, out, out_bf16, (int)grid));
+    PHK_LAUNCH_CHECK();
+    return 0;
+  }
   if (smem > 48 * 1024) {
     PHK_CUDA(cudaFuncSetAttribute(patchify_ln_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 57344));
     PHK_CUDA(cudaFuncSetAttribute(patchify_ln_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 57344));
