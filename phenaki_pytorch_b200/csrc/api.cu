@@ -4,9 +4,11 @@
 // No host synchronisation, no allocation: scratch is carved from the caller's workspace.
 #include "phk_common.cuh"
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <cstdio>
 #include <mutex>
+#include <unordered_map>
 #include <vector>
 
 namespace phk {
@@ -275,10 +277,10 @@ extern "C" int64_t phk_cvivit_workspace_bytes(const phk_cvivit_t* m, int32_t B, 
   return bytes;
 }
 
-extern "C" int phk_cvivit_encode(const phk_cvivit_t* m, const float* video, int32_t B, int32_t F, int64_t* ids,
-                                 void* workspace, int64_t workspace_bytes, int32_t prec, const float* spatial_bias,
-                                 float* tap_patch, float* tap_spatial, float* tap_temporal, float* tap_proj,
-                                 phk_stream_t s) {
+static int cvivit_encode_impl(const phk_cvivit_t* m, const float* video, int32_t B, int32_t F, int64_t* ids,
+                              void* workspace, int64_t workspace_bytes, int32_t prec, const float* spatial_bias,
+                              float* tap_patch, float* tap_spatial, float* tap_temporal, float* tap_proj,
+                              phk_stream_t s) {
   int Tp, hh, ww; int64_t R;
   PHK_TRY(cvivit_dims(m, B, F, Tp, hh, ww, R));
   PHK_REQUIRE(video && ids && workspace, PHK_E_ARG, "cvivit_encode: null pointer");
@@ -342,6 +344,117 @@ extern "C" int phk_cvivit_encode(const phk_cvivit_t* m, const float* video, int3
                             (tap_temporal || D % 128 != 0 || D > 1024 || m->codebook_bits > 16) ? norm_buf : nullptr,
                             tap_proj, R, D, m->codebook_bits, s));
   if (tap_temporal) PHK_CUDA(cudaMemcpyAsync(tap_temporal, norm_buf, R * D * 4, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+// ---- CUDA-graph replay of the encode --------------------------------------------------------------------------
+// One encode is ~75 dependent launches of 3-40 us each; on a slow host the ~0.4-0.7 ms of launch calls per step is
+// as long as the GPU work (0.85 ms in bf16 mode).  The launch sequence is a pure function of (weight table contents,
+// buffers, shape, precision), so the second call with the same key captures it on a library-owned stream and later
+// calls replay the instantiated graph on the caller's stream (one cudaGraphLaunch).  The first call always runs
+// eagerly (one-time cudaFuncSetAttribute / tensor-map creation happen outside capture).  Disabled by PHK_GRAPH=0,
+// while the per-family profiler is on, and when a parity test taps intermediates.
+struct EncodeGraphKey {
+  uint64_t table_hash;
+  const void *video, *ids, *ws, *bias;
+  int64_t ws_bytes;
+  int B, F, prec, device;
+  bool operator==(const EncodeGraphKey& o) const {
+    return table_hash == o.table_hash && video == o.video && ids == o.ids && ws == o.ws && bias == o.bias &&
+           ws_bytes == o.ws_bytes && B == o.B && F == o.F && prec == o.prec && device == o.device;
+  }
+};
+struct EncodeGraphKeyHash {
+  size_t operator()(const EncodeGraphKey& k) const {
+    uint64_t h = k.table_hash;
+    const uint64_t v[] = {(uint64_t)(uintptr_t)k.video, (uint64_t)(uintptr_t)k.ids, (uint64_t)(uintptr_t)k.ws,
+                          (uint64_t)(uintptr_t)k.bias, (uint64_t)k.ws_bytes,
+                          ((uint64_t)k.B << 40) ^ ((uint64_t)k.F << 20) ^ ((uint64_t)k.prec << 8) ^ (uint64_t)k.device};
+    for (uint64_t x : v) h = (h ^ x) * 0x100000001b3ull;
+    return (size_t)h;
+  }
+};
+struct EncodeGraphEntry { cudaGraphExec_t exec; int launches; int seen; };
+
+static uint64_t fnv(const void* p, size_t n, uint64_t h) {
+  const unsigned char* c = (const unsigned char*)p;
+  for (size_t i = 0; i < n; ++i) h = (h ^ c[i]) * 0x100000001b3ull;
+  return h;
+}
+static uint64_t hash_transformer(const phk_transformer_t& T, uint64_t h) {
+  h = fnv(&T, sizeof(T), h);
+  if (T.layers && T.depth > 0) h = fnv(T.layers, sizeof(phk_layer_t) * (size_t)T.depth, h);
+  return h;
+}
+
+static int graphs_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = std::getenv("PHK_GRAPH"); on = (e && e[0] == '0') ? 0 : 1; }
+  return on;
+}
+
+extern "C" int phk_cvivit_encode(const phk_cvivit_t* m, const float* video, int32_t B, int32_t F, int64_t* ids,
+                                 void* workspace, int64_t workspace_bytes, int32_t prec, const float* spatial_bias,
+                                 float* tap_patch, float* tap_spatial, float* tap_temporal, float* tap_proj,
+                                 phk_stream_t s) {
+  const bool taps = tap_patch || tap_spatial || tap_temporal || tap_proj;
+  if (!m || taps || !spatial_bias || !graphs_enabled() || g_prof_on.load(std::memory_order_relaxed))
+    return cvivit_encode_impl(m, video, B, F, ids, workspace, workspace_bytes, prec, spatial_bias, tap_patch, tap_spatial,
+                              tap_temporal, tap_proj, s);
+  static std::unordered_map<EncodeGraphKey, EncodeGraphEntry, EncodeGraphKeyHash> cache;
+  static std::mutex mu;
+  static cudaStream_t cap = nullptr;
+  static bool broken = false;  // a capture failed once: stay on the eager path
+  int dev = 0;
+  PHK_CUDA(cudaGetDevice(&dev));
+  uint64_t th = fnv(m, sizeof(*m), 0xcbf29ce484222325ull);
+  th = hash_transformer(m->spatial, th);
+  th = hash_transformer(m->temporal, th);
+  const EncodeGraphKey key{th, video, ids, workspace, spatial_bias, workspace_bytes, B, F, prec, dev};
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = cache.find(key);
+  if (it != cache.end() && it->second.exec) {
+    PHK_CUDA(cudaGraphLaunch(it->second.exec, to_stream(s)));
+    count_launch(it->second.launches);
+    return 0;
+  }
+  if (broken || it == cache.end()) {  // first sighting of this key (or graphs unusable): run eagerly
+    if (!broken) {
+      if (cache.size() > 64) {  // bounded: drop everything (graphs are cheap to rebuild)
+        for (auto& kv : cache) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+        cache.clear();
+      }
+      cache.emplace(key, EncodeGraphEntry{nullptr, 0, 1});
+    }
+    return cvivit_encode_impl(m, video, B, F, ids, workspace, workspace_bytes, prec, spatial_bias, nullptr, nullptr,
+                              nullptr, nullptr, s);
+  }
+  // second sighting: capture on the library's stream, instantiate, replay on the caller's stream
+  if (!cap) PHK_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+  const int64_t l0 = g_launches.load();
+  cudaGraph_t graph = nullptr;
+  cudaError_t e = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
+  int rc = 0;
+  if (e == cudaSuccess) {
+    rc = cvivit_encode_impl(m, video, B, F, ids, workspace, workspace_bytes, prec, spatial_bias, nullptr, nullptr, nullptr,
+                            nullptr, reinterpret_cast<phk_stream_t>(cap));
+    e = cudaStreamEndCapture(cap, &graph);
+  }
+  const int launches = (int)(g_launches.load() - l0);
+  g_launches.store(l0);  // the captured launches did not execute
+  cudaGraphExec_t exec = nullptr;
+  if (e == cudaSuccess && rc == 0 && graph) e = cudaGraphInstantiate(&exec, graph, 0);
+  if (graph) cudaGraphDestroy(graph);
+  if (e != cudaSuccess || rc != 0 || !exec) {
+    cudaGetLastError();  // clear the sticky capture error; fall back for good
+    broken = true;
+    return cvivit_encode_impl(m, video, B, F, ids, workspace, workspace_bytes, prec, spatial_bias, nullptr, nullptr,
+                              nullptr, nullptr, s);
+  }
+  it->second.exec = exec;
+  it->second.launches = launches;
+  PHK_CUDA(cudaGraphLaunch(exec, to_stream(s)));
+  count_launch(launches);
   return 0;
 }
 

@@ -618,6 +618,99 @@ __global__ void __launch_bounds__(ROWS_THREADS) attention_rows_kernel(const floa
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Short self-attention sequences with dim_head 64 (temporal axis of C-ViViT: n = T' = 9, causal + ALiBi,
+// attention.py:128-182, 186-227): one WARP per (sequence, head), nothing staged in shared memory.  Lane l holds dims
+// (2l, 2l+1) of every token's q, k and v (3n coalesced 256-B row loads, all in flight together); cosine-sim
+// normalisation, the n(n+1)/2 causal dot products and the softmax run on warp shuffles, the P.V product is two FMAs
+// per (i, j) and lane.  33 MB of q / kv / out traffic at cfg2 bound the kernel, not shuffles (~0.3 k per warp).
+// ------------------------------------------------------------------------------------------
+template <int NMAX>
+__global__ void __launch_bounds__(256) attention_warp64_kernel(const float* __restrict__ q, const float* __restrict__ kv,
+                                                               const float* __restrict__ q_scale,
+                                                               const float* __restrict__ k_scale,
+                                                               const float* __restrict__ alibi_slopes,
+                                                               void* __restrict__ out, phk_attn_geom_t g) {
+  pdl_prologue();
+  const int lane = threadIdx.x & 31;
+  const int64_t pair = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t npairs = (int64_t)g.n_outer * g.n_inner * g.heads;
+  if (pair >= npairs) return;  // whole warp exits together
+  const int h = (int)(pair % g.heads);
+  const int seq = (int)(pair / g.heads);
+  const int so = seq / g.n_inner, si = seq - so * g.n_inner;
+  const int n = g.n_q, I = g.heads * 64;
+  const float* qb = q + (int64_t)so * g.q_outer + (int64_t)si * g.q_inner + (int64_t)h * 64;
+  const float* kb = kv + (int64_t)so * g.k_outer + (int64_t)si * g.k_inner + (int64_t)h * 64;
+  const float2 qs = reinterpret_cast<const float2*>(q_scale)[lane], ks = reinterpret_cast<const float2*>(k_scale)[lane];
+  float2 xq[NMAX], xk[NMAX], xv[NMAX];
+#pragma unroll
+  for (int i = 0; i < NMAX; ++i) {
+    xq[i] = xk[i] = xv[i] = make_float2(0.f, 0.f);
+    if (i < n) {
+      xq[i] = reinterpret_cast<const float2*>(qb + (int64_t)i * g.q_tok)[lane];
+      xk[i] = reinterpret_cast<const float2*>(kb + (int64_t)i * g.k_tok)[lane];
+      xv[i] = reinterpret_cast<const float2*>(kb + (int64_t)i * g.k_tok + I)[lane];
+    }
+  }
+  // F.normalize(q), F.normalize(k) then * q_scale / k_scale (attention.py:153-155)
+#pragma unroll
+  for (int i = 0; i < NMAX; ++i) {
+    if (i < n) {
+      // 1 / max(||x||, 1e-12) as one rsqrt per token (the kernel is instruction-bound: ~2.8 k instructions per warp
+      // with IEEE sqrt / divide / expf, profiles/r01_small_kernels_ncu.txt); the fixed scale 8 is folded into q
+      const float iq = rsqrtf(fmaxf(warp_sum(xq[i].x * xq[i].x + xq[i].y * xq[i].y), 1e-24f)) * g.scale;
+      const float ik = rsqrtf(fmaxf(warp_sum(xk[i].x * xk[i].x + xk[i].y * xk[i].y), 1e-24f));
+      xq[i].x = (xq[i].x * iq) * qs.x; xq[i].y = (xq[i].y * iq) * qs.y;
+      xk[i].x = (xk[i].x * ik) * ks.x; xk[i].y = (xk[i].y * ik) * ks.y;
+    }
+  }
+  const float slope = (g.causal && alibi_slopes) ? alibi_slopes[h] : 0.f;
+  const int64_t ob = (int64_t)so * g.o_outer + (int64_t)si * g.o_inner + (int64_t)h * 64;
+#pragma unroll
+  for (int i = 0; i < NMAX; ++i) {
+    if (i < n) {
+      float sc[NMAX];
+      float m = -FLT_MAX;
+#pragma unroll
+      for (int j = 0; j < NMAX; ++j) {
+        sc[j] = -FLT_MAX;
+        if (j < n && (!g.causal || j <= i)) {
+          float a = warp_sum(fmaf(xq[i].x, xk[j].x, xq[i].y * xk[j].y));             // identical in every lane
+          if (g.causal) a += -fabsf((float)(j - i)) * slope;                           // ALiBi (attention.py:214-227)
+          sc[j] = a;
+          m = fmaxf(m, a);
+        }
+      }
+      float sum = 0.f;
+      float2 o = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < NMAX; ++j) {
+        if (j < n && (!g.causal || j <= i)) {
+          const float e = __expf(sc[j] - m);
+          sum += e;
+          o.x = fmaf(e, xv[j].x, o.x);
+          o.y = fmaf(e, xv[j].y, o.y);
+        }
+      }
+      const float inv = __fdividef(1.f, sum);
+      const int64_t off = ob + (int64_t)i * g.o_tok;
+      if (g.out_bf16) reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(out) + off)[lane] = pack_bf16x2(o.x * inv, o.y * inv);
+      else reinterpret_cast<float2*>(reinterpret_cast<float*>(out) + off)[lane] = make_float2(o.x * inv, o.y * inv);
+    }
+  }
+}
+
+template <int NMAX>
+static int launch_attention_warp64(const float* q, const float* kv, const float* q_scale, const float* k_scale,
+                                   const float* alibi_slopes, void* out, const phk_attn_geom_t& g, cudaStream_t st) {
+  const int64_t npairs = (int64_t)g.n_outer * g.n_inner * g.heads;
+  PHK_CUDA(launch_pdl(attention_warp64_kernel<NMAX>, dim3((unsigned)((npairs + 7) / 8)), dim3(256), (size_t)0, st, q, kv,
+                      q_scale, k_scale, alibi_slopes, out, g));
+  PHK_LAUNCH_CHECK();
+  return 0;
+}
+
 template <int DH, int NMAX>
 static int launch_attention_rows(const float* q, const float* kv, const float* q_scale, const float* k_scale,
                                  const float* alibi_slopes, void* out, const phk_attn_geom_t& g, cudaStream_t st) {
@@ -662,6 +755,13 @@ static int launch_attention_small(const float* q, const float* kv, const float* 
                        g.o_inner % 8 == 0 && (reinterpret_cast<uintptr_t>(q) & 15) == 0 &&
                        (reinterpret_cast<uintptr_t>(kv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
                        (reinterpret_cast<uintptr_t>(q_scale) & 15) == 0 && (reinterpret_cast<uintptr_t>(k_scale) & 15) == 0;
+  if (aligned && DH == 64) {  // warp per (sequence, head), registers + shuffles only
+    if (n <= 3) return launch_attention_warp64<3>(q, kv, q_scale, k_scale, alibi_slopes, out, g, st);
+    if (n <= 5) return launch_attention_warp64<5>(q, kv, q_scale, k_scale, alibi_slopes, out, g, st);
+    if (n <= 9) return launch_attention_warp64<9>(q, kv, q_scale, k_scale, alibi_slopes, out, g, st);
+    if (n <= 12) return launch_attention_warp64<12>(q, kv, q_scale, k_scale, alibi_slopes, out, g, st);
+    return launch_attention_warp64<16>(q, kv, q_scale, k_scale, alibi_slopes, out, g, st);
+  }
   if (aligned) {  // thread-per-query kernel
     if (n <= 3) return launch_attention_rows<DH, 3>(q, kv, q_scale, k_scale, alibi_slopes, out, g, st);
     if (n <= 5) return launch_attention_rows<DH, 5>(q, kv, q_scale, k_scale, alibi_slopes, out, g, st);

@@ -88,6 +88,7 @@ class CViViT(nn.Module):
         self._dec_sig = None
         self._ws = Workspace()
         self._bias_cache = {}
+        self._ids_buf = {}
 
     # ---- shape helpers (cvivit.py:365-410, 445-447) -----------------------------------------
     @property
@@ -132,11 +133,11 @@ class CViViT(nn.Module):
 
     def copy_for_eval(self):
         device = next(self.parameters()).device
-        saved = (self._tables, self._sig, self._dec_tables, self._dec_sig, self._ws, self._bias_cache)
+        saved = (self._tables, self._sig, self._dec_tables, self._dec_sig, self._ws, self._bias_cache, self._ids_buf)
         self._tables, self._sig, self._dec_tables, self._dec_sig = None, None, None, None  # ctypes tables are not copyable
-        self._ws, self._bias_cache = Workspace(), {}
+        self._ws, self._bias_cache, self._ids_buf = Workspace(), {}, {}
         c = copy.deepcopy(self)
-        self._tables, self._sig, self._dec_tables, self._dec_sig, self._ws, self._bias_cache = saved
+        self._tables, self._sig, self._dec_tables, self._dec_sig, self._ws, self._bias_cache, self._ids_buf = saved
         return c.eval().to(device)
 
     def load(self, path):
@@ -222,7 +223,12 @@ class CViViT(nn.Module):
         with torch.cuda.device(video.device):
             table = self._table()
             tp, hh, ww = self.get_video_patch_shape(f)
-            ids = torch.empty((b, tp, hh, ww), dtype=torch.int64, device=video.device)
+            # the kernels write into a module-owned buffer with a STABLE address (the library replays a captured CUDA
+            # graph when every pointer of the call repeats); the caller gets its own copy, as in the reference
+            key = (b, tp, hh, ww, video.device)
+            ids = self._ids_buf.get(key)
+            if ids is None:
+                ids = self._ids_buf[key] = torch.empty((b, tp, hh, ww), dtype=torch.int64, device=video.device)
             nbytes = lib.phk_cvivit_workspace_bytes(C.byref(table), b, f, self.precision)
             ws = self._ws.get(nbytes, video.device)
             bias = self._spatial_bias(table, video.device)
@@ -237,7 +243,7 @@ class CViViT(nn.Module):
             L.check(lib.phk_cvivit_encode(C.byref(table), L.ptr(video), b, f, L.ptr(ids), L.ptr(ws), ws.numel(),
                                           self.precision, L.ptr(bias), *tap_ptrs, L.stream_ptr()),
                     "phk_cvivit_encode")
-        return ids
+            return ids.clone()
 
     def encode_host_iter(self, videos, device=None, depth=2):
         """Tokenises a stream of HOST batches: `videos` yields (b,c,f,H,W) fp32 CPU tensors of one shape (pinned memory

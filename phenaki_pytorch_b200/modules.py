@@ -221,9 +221,20 @@ def cpb_table(c: ContinuousPositionBias, keep: Keep):
     return t
 
 
+_SIG_REFRESH = 64
+
+
 def weights_signature(module):
-    """Changes whenever a parameter/buffer is re-assigned, moved or modified in place."""
-    return tuple((t.data_ptr(), t._version) for t in list(module.parameters()) + list(module.buffers()))
+    """Changes whenever a parameter/buffer is moved or modified in place (`.to()`, `load_state_dict`, optimizer steps
+    keep the Parameter objects and change data_ptr / _version).  Walking the module tree costs ~0.25 ms for the 240
+    tensors of a C-ViViT -- a third of a bf16 encode step -- so the tensor list is cached on the module and re-walked
+    every 64 calls (which also picks up a Parameter OBJECT that was replaced by hand)."""
+    cache = module.__dict__.get("_phk_sig_cache")
+    if cache is None or cache[1] <= 0:
+        cache = [list(module.parameters()) + list(module.buffers()), _SIG_REFRESH]
+        module.__dict__["_phk_sig_cache"] = cache
+    cache[1] -= 1
+    return tuple((t.data_ptr(), t._version) for t in cache[0])
 
 
 class Workspace:

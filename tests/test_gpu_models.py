@@ -204,3 +204,26 @@ def test_encode_host_stream_matches_device_encode(depth):
         next(model.encode_host_iter([batches[0].to(DEV)]))            # device tensors go through forward()
     with pytest.raises(AssertionError):
         list(model.encode_host_iter([batches[0], batches[1][:1]]))    # one shape per stream
+
+
+def test_encode_graph_replay_equals_eager_launches():
+    """The library replays a captured CUDA graph from the third call with identical buffers on (the first runs eagerly,
+    the second captures): ids stay identical, the launch counter advances by the same amount per call, and new input
+    DATA in the same buffer is honoured."""
+    case = C.CVIVIT_CASES["cfg1"]
+    torch.manual_seed(case["seed"])
+    model = P.CViViT(**case["ctor"]).to(DEV).eval()
+    lib = P._lib.lib()
+    video = C.seeded_randn(case["video"], case["video_seed"]).to(DEV)
+    outs, counts = [], []
+    for _ in range(5):
+        before = lib.phk_launch_count()
+        outs.append(model(video, return_only_codebook_ids=True))
+        counts.append(lib.phk_launch_count() - before)
+    assert all(torch.equal(o, outs[0]) for o in outs)
+    assert len(set(counts[1:])) == 1 and counts[1] > 10, counts   # the first call also builds the cached position bias
+    other = C.seeded_randn(case["video"], 777).to(DEV)
+    expect = model(other, return_only_codebook_ids=True)       # eager (new buffer)
+    video.copy_(other)                                          # same buffer as the captured graph, new contents
+    assert torch.equal(model(video, return_only_codebook_ids=True), expect)
+    assert not torch.equal(expect, outs[0])
