@@ -44,6 +44,11 @@ struct EpiParams {
   int64_t seg_len, seg_stride, seg_off;
   int m_tiles, n_tiles;
   long long* trace;  // debug: per-CTA clock64 stamps of the first tile (NULL in production)
+  // fp32 epilogue through the TMA unit (identity row map, C 16-B aligned, residual == C or none): C as a tensor map
+  // with [128 rows x 32 floats] SWIZZLE_128B boxes; the residual tile is bulk-LOADED into the staging boxes while the
+  // main loop runs and the finished tile is bulk-STORED from them, so the epilogue warps issue no global accesses
+  int tma_epi;
+  alignas(64) CUtensorMap tmC;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -253,6 +258,78 @@ __device__ __forceinline__ void epi_geglu_tile(const EpiParams& p, void* stage, 
   epi_bar_sync();          // staging tile free for the next accumulator
 }
 
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// fp32 chunk (128 rows x 128 columns) through the TMA unit.  Staging = four [128 rows x 128 B] SWIZZLE_128B boxes (one
+// per 32-column part): thread (row r, part c) owns exactly one 128-byte swizzled row of box c, so its eight 16-byte
+// accesses are conflict-free and need no other thread's data.  Order per chunk:
+//   store thread: wait until the previous chunk's bulk stores have READ the boxes; barrier;
+//   store thread: bulk-load the residual tile (C itself: x = f(x) + x) into the boxes (mbarrier `bar_res`);
+//   all: accumulator columns TMEM -> registers, + residual (own swizzled row) + bias, back into the boxes; release the
+//        accumulator; fence.proxy.async; barrier;  store thread: four bulk stores + commit.
+// part 1, BEFORE the accumulator-ready wait (overlaps the main loop)
+__device__ __forceinline__ void epi_tma_begin(const EpiParams& p, uint32_t stage_s, uint32_t bar_res, int m0, int n0,
+                                              int ew, int lane) {
+  const bool store_thread = ew == 0 && lane == 0;
+  if (store_thread) tma_store_wait_read();
+  epi_bar_sync();  // the boxes are free (the previous chunk's bulk stores have read them)
+  if (p.residual && store_thread) {
+    mbar_expect_tx(bar_res, 4 * GM * 128);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) tma_load_2d(&p.tmC, bar_res, stage_s + c * (GM * 128), n0 + 32 * c, m0);
+  }
+}
+// part 2, after the accumulator-ready wait
+template <typename Release>
+__device__ __forceinline__ void epi_tma_finish(const EpiParams& p, uint8_t* stage, uint32_t stage_s, uint32_t bar_res,
+                                               uint32_t& res_phase, uint32_t tmem_chunk, int m0, int n0, int ew, int lg,
+                                               int part, int lane, Release&& release) {
+  const uint32_t trow = tmem_chunk + ((uint32_t)(lg * 32) << 16);
+  uint32_t v[32];
+  tmem_ld32(trow + part * 32, v);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncwarp();
+  release();
+  const int r = lg * 32 + lane;
+  float4* box_row = reinterpret_cast<float4*>(stage + part * (GM * 128) + r * 128);
+  if (p.residual) { mbar_wait(bar_res, res_phase); res_phase ^= 1; }
+  const int col0 = n0 + part * 32;
+  const bool bias_vec = p.bias && (col0 + 31 < p.N) && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                           __uint_as_float(v[4 * j + 3]));
+    const int pos = j ^ (r & 7);
+    if (p.residual) { const float4 rr = box_row[pos]; o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w; }
+    if (bias_vec) {
+      const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
+      o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+    } else if (p.bias) {
+      const int c = col0 + 4 * j;
+      if (c < p.N) o.x += __ldg(p.bias + c);
+      if (c + 1 < p.N) o.y += __ldg(p.bias + c + 1);
+      if (c + 2 < p.N) o.z += __ldg(p.bias + c + 2);
+      if (c + 3 < p.N) o.w += __ldg(p.bias + c + 3);
+    }
+    box_row[pos] = o;
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the TMA unit
+  epi_bar_sync();  // whole chunk staged
+  if (ew == 0 && lane == 0) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (n0 + 32 * c < p.N) tma_store_2d(&p.tmC, stage_s + c * (GM * 128), n0 + 32 * c, m0);  // OOB rows / columns are clipped
+    tma_store_commit();
+  }
+}
+
 // Drains one chunk and writes it out.  `release()` is called as soon as the TMEM columns have been read (the MMA
 // warp may then overwrite them), before the slower global write-out.
 template <int EPI, typename Release>
@@ -434,6 +511,7 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_bf16_kernel(const __grid_con
       mbar_init(bar_tfull + 8 * a, 1);
       mbar_init(bar_tempty + 8 * a, EPI_WARPS);  // one arrival per epilogue warp
     }
+    mbar_init(tmem_slot + 8, 1);  // residual tile landed (TMA epilogue)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {  // TMEM: two 128-column fp32 accumulators
@@ -510,16 +588,25 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_bf16_kernel(const __grid_con
     const int ew = warp - 2;        // 0..15: rows ew, ew+16, ... in the coalesced write-out
     const int lg = warp & 3;        // TMEM lane group this warp may access (rows lg*32 .. +31 of the tile)
     const int part = ew >> 2;       // which quarter of the accumulator columns this warp drains
+    const uint32_t bar_res = tmem_slot + 8;
+    uint32_t res_phase = 0;
     for (int it = 0; it < my_tiles; ++it) {
       const int acc = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
       int m0, n0;
       const EpiParams& pp = tile_of(it, m0, n0) ? p2 : p;
-      const bool res_vec = epi_residual_prefetch<EPI>(pp, cstage, m0, n0, ew, lane);
+      const bool tma = EPI == 0 && pp.tma_epi;
+      bool res_vec = false;
+      if (tma) epi_tma_begin(pp, base + RING_BYTES, bar_res, m0, n0, ew, lane);
+      else res_vec = epi_residual_prefetch<EPI>(pp, cstage, m0, n0, ew, lane);
       mbar_wait(bar_tfull + 8 * acc, use & 1);
       if (it == 0 && threadIdx.x == 64) PHK_STAMP(6);      // accumulator ready
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (EPI == 2)
+      if (tma)
+        epi_tma_finish(pp, reinterpret_cast<uint8_t*>(cstage), base + RING_BYTES, bar_res, res_phase,
+                       tmem_base + acc * GN, m0, n0, ew, lg, part, lane,
+                       [&]() { if (lane == 0) mbar_arrive(bar_tempty + 8 * acc); });
+      else if (EPI == 2)
         epi_geglu_tile<1>(pp, cstage, tmem_base + acc * GN, m0, n0, ew, lg, part, lane,
                           [&]() { if (lane == 0) mbar_arrive(bar_tempty + 8 * acc); },
                           [&](int slot) { if (it == 0 && threadIdx.x == 64) PHK_STAMP(slot); });
@@ -528,6 +615,7 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_bf16_kernel(const __grid_con
                        [&]() { if (lane == 0) mbar_arrive(bar_tempty + 8 * acc); });
       if (it == 0 && threadIdx.x == 64) PHK_STAMP(8);      // tile written out
     }
+    if (EPI == 0 && ew == 0 && lane == 0) tma_store_wait_all();  // bulk stores complete before the CTA exits
   }
   __syncthreads();
   if (threadIdx.x == 0) PHK_STAMP(9);  // CTA done
@@ -668,6 +756,7 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_bf16_pair_kernel(const __gri
       mbar_init(bar_tfull + 8 * a, 1);              // one multicast commit
       mbar_init(bar_tempty + 8 * a, 2 * EPI_WARPS); // every epilogue warp of BOTH CTAs (used in the leader only)
     }
+    mbar_init(tmem_slot + 8, 1);                    // residual tile landed (TMA epilogue)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {  // the same warp of both CTAs allocates the pair's TMEM columns
@@ -749,16 +838,30 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_bf16_pair_kernel(const __gri
     // ===================== epilogue (both CTAs): own 128 rows x BN columns =====================
     const int ew = warp - 2, lg = warp & 3, part = ew >> 2;
     const uint32_t tempty_leader = map_to_cta(bar_tempty, 0);
+    const uint32_t bar_res = tmem_slot + 8, stage_s = base + RING;
+    uint32_t res_phase = 0;
     for (int it = 0; it < my_tiles; ++it) {
       const int acc = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
       int m0, n0;
       const EpiParams& pp = tile_of(it, m0, n0) ? p2 : p;
-      bool res_vec = epi_residual_prefetch<EPI>(pp, cstage, m0, n0, ew, lane);
+      const bool tma = EPI == 0 && pp.tma_epi;
+      bool res_vec = false;
+      if (tma) epi_tma_begin(pp, stage_s, bar_res, m0, n0, ew, lane);
+      else res_vec = epi_residual_prefetch<EPI>(pp, cstage, m0, n0, ew, lane);
       mbar_wait(bar_tfull + 8 * acc, use & 1);
       if (it == 0 && threadIdx.x == 64) PHK_STAMP(6);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (EPI == 2) {
+      if (tma) {
+#pragma unroll
+        for (int h = 0; h < BN / 128; ++h) {
+          if (h > 0) epi_tma_begin(pp, stage_s, bar_res, m0, n0 + h * 128, ew, lane);
+          const bool last = h == BN / 128 - 1;
+          epi_tma_finish(pp, reinterpret_cast<uint8_t*>(cstage), stage_s, bar_res, res_phase,
+                         tmem_base + acc * BN + h * 128, m0, n0 + h * 128, ew, lg, part, lane,
+                         [&]() { if (last && lane == 0) mbar_arrive_remote(tempty_leader + 8 * acc); });
+        }
+      } else if (EPI == 2) {
         epi_geglu_tile<BN / 128>(pp, cstage, tmem_base + acc * BN, m0, n0, ew, lg, part, lane,
                                  [&]() { if (lane == 0) mbar_arrive_remote(tempty_leader + 8 * acc); },
                                  [&](int slot) { if (it == 0 && threadIdx.x == 64) PHK_STAMP(slot); });
@@ -773,6 +876,7 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_bf16_pair_kernel(const __gri
       }
       if (it == 0 && threadIdx.x == 64) PHK_STAMP(8);
     }
+    if (EPI == 0 && ew == 0 && lane == 0) tma_store_wait_all();  // bulk stores complete before the CTA exits
   }
   __syncthreads();
   if (threadIdx.x == 0) PHK_STAMP(9);
@@ -843,6 +947,44 @@ static int get_tensor_map(const void* ptr, int64_t rows, int64_t cols, int64_t l
   if (cache.size() > 8192) cache.clear();
   cache.emplace(key, m);
   *out = m;
+  return 0;
+}
+
+// fp32 [rows, cols] output, row pitch ld floats; box = [128 rows, 32 floats = 128 B], SWIZZLE_128B (TMA epilogue)
+static int get_c_map(const void* ptr, int64_t rows, int64_t cols, int64_t ld, CUtensorMap* out) {
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  static std::mutex mu;
+  const MapKey key{ptr, rows, cols, ld, -32};
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) { *out = it->second; return 0; }
+  EncodeTiledFn fn = encode_fn();
+  PHK_REQUIRE(fn, PHK_E_UNSUPPORTED, "cuTensorMapEncodeTiled not available from the driver");
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
+  const cuuint32_t box[2] = {32, (cuuint32_t)GM};
+  const cuuint32_t estr[2] = {1, 1};
+  CUtensorMap m;
+  const CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PHK_REQUIRE(r == CUDA_SUCCESS, PHK_E_ARG, "cuTensorMapEncodeTiled rejected the output (alignment / pitch)");
+  if (cache.size() > 8192) cache.clear();
+  cache.emplace(key, m);
+  *out = m;
+  return 0;
+}
+
+// the TMA epilogue applies to plain fp32 outputs: identity row map, 16-byte aligned rows, residual == C (or none)
+static int maybe_tma_epilogue(EpiParams& p, int epilogue) {
+  static int on = -1;
+  if (on < 0) { const char* e = std::getenv("PHK_GEMM_TMA_EPI"); on = (e && e[0] == '0') ? 0 : 1; }
+  p.tma_epi = 0;
+  if (!on || epilogue != 0 || p.seg_len != 0 || p.ldc % 4 != 0 || (reinterpret_cast<uintptr_t>(p.C) & 15) != 0 ||
+      (p.residual && p.residual != p.C))
+    return 0;
+  PHK_TRY(get_c_map(p.C, p.M, p.N, p.ldc, &p.tmC));
+  p.tma_epi = 1;
   return 0;
 }
 
@@ -957,11 +1099,13 @@ extern "C" int phk_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t 
     PHK_TRY(get_tensor_map(W, N, K, ldw, bn / 2, &tb));
     EpiParams p{C, ldc, M, N, K, bias, residual, seg_len, seg_stride, seg_off, m_pairs, (N + bn - 1) / bn, g_gemm_trace};
     PHK_REQUIRE((int64_t)p.m_tiles * p.n_tiles < (1LL << 31), PHK_E_UNSUPPORTED, "phk_gemm_bf16: too many tiles");
+    PHK_TRY(maybe_tma_epilogue(p, epilogue));
     return wide ? launch_gemm_pair_epi<256>(epilogue, ta, tb, p, st) : launch_gemm_pair_epi<128>(epilogue, ta, tb, p, st);
   }
   PHK_TRY(get_tensor_map(W, N, K, ldw, GN, &tb));
   EpiParams p{C, ldc, M, N, K, bias, residual, seg_len, seg_stride, seg_off, (int)((M + GM - 1) / GM), (N + GN - 1) / GN, g_gemm_trace};
   PHK_REQUIRE((int64_t)p.m_tiles * p.n_tiles < (1LL << 31), PHK_E_UNSUPPORTED, "phk_gemm_bf16: too many tiles");
+  PHK_TRY(maybe_tma_epilogue(p, epilogue));
   if (epilogue == 2) return launch_gemm<2>(ta, tb, p, st);
   if (epilogue == 1) return launch_gemm<1>(ta, tb, p, st);
   return launch_gemm<0>(ta, tb, p, st);
@@ -995,6 +1139,8 @@ extern "C" int phk_gemm_bf16_x2(const void* A1, int64_t lda1, const void* W1, in
     PHK_TRY(get_tensor_map(W2, N2, K2, ldw2, 128, &tb2));
     EpiParams p{C1, ldc1, M, N1, K1, nullptr, nullptr, 0, 0, 0, m_pairs, (N1 + 255) / 256, nullptr};
     EpiParams p2{C2, ldc2, M, N2, K2, nullptr, nullptr, 0, 0, 0, m_pairs, (N2 + 255) / 256, nullptr};
+    PHK_TRY(maybe_tma_epilogue(p, 0));
+    PHK_TRY(maybe_tma_epilogue(p2, 0));
     return launch_gemm_pair<0, 256, true>(ta, tb, p, ta2, tb2, p2, to_stream(s));
   }
   PHK_TRY(get_tensor_map(W1, N1, K1, ldw1, GN, &tb));
@@ -1003,6 +1149,7 @@ extern "C" int phk_gemm_bf16_x2(const void* A1, int64_t lda1, const void* W1, in
   EpiParams p{C1, ldc1, M, N1, K1, nullptr, nullptr, 0, 0, 0, mt, (N1 + GN - 1) / GN, nullptr};
   EpiParams p2{C2, ldc2, M, N2, K2, nullptr, nullptr, 0, 0, 0, mt, (N2 + GN - 1) / GN, nullptr};
   PHK_REQUIRE((int64_t)mt * (p.n_tiles + p2.n_tiles) < (1LL << 31), PHK_E_UNSUPPORTED, "phk_gemm_bf16_x2: too many tiles");
+  // (measured: the bulk-store epilogue does not pay for the two-problem launch -- 16.2 vs 15.5 us -- so it stays off)
   return launch_gemm_dual(ta, tb, p, ta2, tb2, p2, to_stream(s));
 }
 
