@@ -1,0 +1,102 @@
+"""Full-size (BASELINE.json configs[1] / configs[2]) checks on the GPU: the oracle where it finishes in seconds
+(one cfg2 video; one cfg3 forward of one sample) and size-independent properties on the whole batch
+(batch invariance, determinism, encode -> decode -> encode token round trip of the decoder's own output)."""
+import pytest
+import torch
+
+from oracle import phenaki_oracle as O
+import phenaki_pytorch_b200 as P
+from phenaki_pytorch_b200 import _lib as L
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+CFG2 = dict(dim=512, codebook_size=65536, image_size=256, patch_size=32, temporal_patch_size=2, spatial_depth=4,
+            temporal_depth=4, dim_head=64, heads=8, use_vgg_and_gan=False)
+CFG3 = dict(dim=512, num_tokens=65536, max_seq_len=1024, dim_context=768, depth=6)
+
+
+@pytest.fixture(scope="module")
+def cfg2():
+    torch.manual_seed(0)
+    model = P.CViViT(**CFG2).eval()
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    video = torch.randn((8, 3, 17, 256, 256), generator=torch.Generator().manual_seed(1))
+    return model.to(DEV), sd, video
+
+
+def bit_agreement(a, b, bits=16):
+    x = (a ^ b).reshape(-1)
+    return 1.0 - sum(int(((x >> k) & 1).sum()) for k in range(bits)) / (x.numel() * bits)
+
+
+def test_cfg2_fp32_ids_equal_the_oracle_on_one_video(cfg2):
+    model, sd, video = cfg2
+    model.precision = L.PREC_F32
+    with torch.no_grad():
+        ref, proj = O.cvivit_codebook_ids(video[:1], sd, (256, 256), (32, 32), return_margin=True)
+    ids = model(video[:1].to(DEV), return_only_codebook_ids=True).cpu()
+    diff = (ids ^ ref).reshape(-1)
+    proj = proj.reshape(-1, 16)
+    for r in torch.nonzero(diff).flatten().tolist():           # a flipped bit needs a reference margin inside fp32 noise
+        for d in range(16):
+            if (int(diff[r]) >> (15 - d)) & 1:
+                assert abs(float(proj[r, d])) < 2e-5, f"token {r} bit {d}: margin {float(proj[r, d])}"
+    assert int((diff != 0).sum()) <= 2
+
+
+def test_cfg2_batch_invariance_and_determinism(cfg2):
+    """Every video is independent (the property the N-GPU batch sharding rests on): ids of the batch of 8 equal the
+    ids of each video encoded alone, bit for bit, in both precision modes; repeated calls are identical."""
+    model, _, video = cfg2
+    vd = video.to(DEV)
+    for prec in (L.PREC_F32, L.PREC_BF16):
+        model.precision = prec
+        full = model(vd, return_only_codebook_ids=True)
+        assert torch.equal(full, model(vd, return_only_codebook_ids=True))
+        for i in (0, 3, 7):
+            assert torch.equal(model(vd[i:i + 1].contiguous(), return_only_codebook_ids=True), full[i:i + 1]), (prec, i)
+        half = torch.cat([model(vd[:4].contiguous(), return_only_codebook_ids=True),
+                          model(vd[4:].contiguous(), return_only_codebook_ids=True)])
+        assert torch.equal(half, full)
+
+
+def test_cfg2_bf16_mode_agrees_with_fp32_mode(cfg2):
+    model, _, video = cfg2
+    vd = video.to(DEV)
+    model.precision = L.PREC_F32
+    a = model(vd, return_only_codebook_ids=True)
+    model.precision = L.PREC_BF16
+    b = model(vd, return_only_codebook_ids=True)
+    assert bit_agreement(a, b) >= 0.97, bit_agreement(a, b)     # LFQ sign bits; flips sit at small margins (bf16 bar)
+
+
+def test_cfg2_decode_shapes_determinism_and_batch_invariance(cfg2):
+    model, _, video = cfg2
+    model.precision = L.PREC_BF16
+    ids = model(video.to(DEV), return_only_codebook_ids=True)
+    rec = model.decode_from_codebook_indices(ids)
+    assert tuple(rec.shape) == (8, 3, 17, 256, 256) and torch.isfinite(rec).all()
+    assert torch.equal(rec, model.decode_from_codebook_indices(ids))
+    assert torch.equal(model.decode_from_codebook_indices(ids[2:3].contiguous()), rec[2:3])
+
+
+def test_cfg3_logits_of_one_sample_match_the_oracle():
+    torch.manual_seed(2)
+    mg = P.MaskGit(**CFG3).eval()
+    sd = {k: v.detach().clone() for k, v in mg.state_dict().items()}
+    g = torch.Generator().manual_seed(3)
+    ids = torch.randint(0, 65537, (1, 576), generator=g)       # includes mask ids
+    ctx = torch.randn((1, 16, 768), generator=g)
+    tmask = torch.ones((1, 16), dtype=torch.bool)
+    with torch.no_grad():
+        ref = O.maskgit_forward(ids, sd, video_patch_shape=(9, 8, 8), context=ctx, text_mask=tmask)
+    mg = mg.to(DEV)
+    kw = dict(video_patch_shape=(9, 8, 8), context=ctx.to(DEV), text_mask=tmask.to(DEV))
+    mg.precision = L.PREC_F32
+    out = mg(ids.to(DEV), **kw).cpu()
+    torch.testing.assert_close(out, ref, rtol=2e-4, atol=2e-4)
+    assert torch.equal(out.argmax(-1), ref.argmax(-1))          # greedy tokens identical
+    mg.precision = L.PREC_BF16
+    out16 = mg(ids.to(DEV), **kw).cpu()
+    err = (out16 - ref).abs()
+    assert float((err - (0.08 + 0.03 * ref.abs())).max()) <= 0
