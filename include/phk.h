@@ -177,12 +177,14 @@ int phk_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* 
                   int64_t seg_len, int64_t seg_stride, int64_t seg_off, int32_t epilogue,
                   phk_stream_t s);
 
-/* Two independent products C1 = A1 W1^T [M,N1] and C2 = A2 W2^T [M,N2] (bf16 operands, fp32 outputs, no bias) in ONE
- * launch: the q and k,v projections of a self-attention block read different inputs (LayerNorm(x) vs raw x,
- * attention.py:140-146) and are each a single wave of tiles; launched together their tiles pipeline. */
+/* Two independent products C1 = A1 W1^T (+bias1) [M1,N1] and C2 = A2 W2^T (+bias2) [M2,N2] (bf16 operands, fp32
+ * outputs) in ONE launch: the q and k,v projections of a self-attention block read different inputs (LayerNorm(x) vs
+ * raw x, attention.py:140-146) and are each a single wave of tiles; the first-frame and rest-frames patch embeddings
+ * (cvivit.py:542-549) are 16 + 128 tiles.  Launched together their tiles pipeline / fill the machine. */
 int phk_gemm_bf16_x2(const void* A1, int64_t lda1, const void* W1, int64_t ldw1, float* C1, int64_t ldc1,
-                     int32_t N1, int32_t K1, const void* A2, int64_t lda2, const void* W2, int64_t ldw2,
-                     float* C2, int64_t ldc2, int32_t N2, int32_t K2, int64_t M, phk_stream_t s);
+                     int64_t M1, int32_t N1, int32_t K1, const float* bias1, const void* A2, int64_t lda2,
+                     const void* W2, int64_t ldw2, float* C2, int64_t ldc2, int64_t M2, int32_t N2, int32_t K2,
+                     const float* bias2, phk_stream_t s);
 
 /* debug aid: per-CTA clock64 phase stamps of phk_gemm_bf16 (16 x int64 per CTA); NULL disables */
 int phk_debug_gemm_trace(long long* device_buffer);

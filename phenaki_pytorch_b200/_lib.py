@@ -98,7 +98,7 @@ PROTOTYPES = {
     "phk_patchify_ln": [vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, i32, vp],
     "phk_gemm_f32": [vp, i64, vp, i64, vp, i64, i64, i32, i32, vp, vp, i64, i64, i64, vp],
     "phk_gemm_bf16": [vp, i64, vp, i64, vp, i64, i64, i32, i32, vp, vp, i64, i64, i64, i32, vp],
-    "phk_gemm_bf16_x2": [vp, i64, vp, i64, vp, i64, i32, i32, vp, i64, vp, i64, vp, i64, i32, i32, i64, vp],
+    "phk_gemm_bf16_x2": [vp, i64, vp, i64, vp, i64, i64, i32, i32, vp, vp, i64, vp, i64, vp, i64, i64, i32, i32, vp, vp],
     "phk_debug_gemm_trace": [vp],
     "phk_debug_gemm_mode": [i32],
     "phk_geglu": [vp, vp, i64, i32, vp],

@@ -133,7 +133,7 @@ static int transformer_forward(const TfCall& c, Arena scratch, float* out, void*
       const phk_attn_t& A = L.self_attn;
       PHK_TRY(phk_layernorm(x, A.norm_g, A.norm_b, xn, xraw, R, D, h16, 0, 0, 0, s));
       if (h16 && R > 128 && A.wq_h && A.wkv_h) {  // both projections in one launch (their tiles pipeline)
-        PHK_TRY(phk_gemm_bf16_x2(xn, D, A.wq_h, D, q, I, I, D, xraw, D, A.wkv_h, D, kv, 2 * I, 2 * I, D, R, s));
+        PHK_TRY(phk_gemm_bf16_x2(xn, D, A.wq_h, D, q, I, R, I, D, nullptr, xraw, D, A.wkv_h, D, kv, 2 * I, R, 2 * I, D, nullptr, s));
       } else {
         PHK_TRY(linear(c.prec, xn, D, A.wq, A.wq_h, D, q, I, R, I, D, nullptr, nullptr, s));
         PHK_TRY(linear(c.prec, h16 ? xraw : (const void*)x, D, A.wkv, A.wkv_h, D, kv, 2 * I, R, 2 * I, D, nullptr, nullptr, s));
@@ -302,6 +302,21 @@ static int cvivit_encode_impl(const phk_cvivit_t* m, const float* video, int32_t
 
   // ---- to_patch_emb_first_frame / to_patch_emb (cvivit.py:542-549), rows land in (b,t,h,w) order
   const int C = m->channels, H = m->image_h, W = m->image_w;
+  if (h16 && Tp > 1 && m->pf_w_h && m->pr_w_h) {
+    // bf16 mode: both patch embeddings in ONE two-problem GEMM launch (16 + 128 tiles at cfg2: the first-frame
+    // product alone occupied 16 SMs for 24 us).  A_rest at A, A_first behind it; outputs share P.
+    const int64_t rows1 = (int64_t)B * hw, rows2 = (int64_t)B * (Tp - 1) * hw;
+    char* A_first = (char*)A + ((rows2 * K2 * 2 + 255) / 256) * 256;
+    PHK_REQUIRE((A_first - (char*)A) + rows1 * K1 * 2 <= R * K2 * 4, PHK_E_WORKSPACE, "cvivit_encode: workspace too small");
+    PHK_TRY(phk_patchify_ln(video, B, C, F, H, W, 0, 1, 1, m->patch_h, m->patch_w, m->pf_ln1_g, m->pf_ln1_b, A_first, 1, s));
+    PHK_TRY(phk_patchify_ln(video, B, C, F, H, W, 1, Tp - 1, m->patch_t, m->patch_h, m->patch_w, m->pr_ln1_g,
+                            m->pr_ln1_b, A, 1, s));
+    PHK_TRY(phk_gemm_bf16_x2(A_first, K1, m->pf_w_h, K1, P, D, rows1, D, (int)K1, m->pf_b, A, K2, m->pr_w_h, K2,
+                             P + rows1 * D, D, rows2, D, (int)K2, m->pr_b, s));
+    PHK_TRY(phk_layernorm(P, m->pf_ln2_g, m->pf_ln2_b, x, nullptr, rows1, D, 0, hw, (int64_t)Tp * hw, 0, s));
+    PHK_TRY(phk_layernorm(P + rows1 * D, m->pr_ln2_g, m->pr_ln2_b, x, nullptr, rows2, D, 0, (int64_t)(Tp - 1) * hw,
+                          (int64_t)Tp * hw, hw, s));
+  } else {
   PHK_TRY(phk_patchify_ln(video, B, C, F, H, W, 0, 1, 1, m->patch_h, m->patch_w, m->pf_ln1_g, m->pf_ln1_b, A, h16, s));
   PHK_TRY(linear(prec, A, K1, m->pf_w, m->pf_w_h, K1, P, D, (int64_t)B * hw, D, (int)K1, m->pf_b, nullptr, s));
   PHK_TRY(phk_layernorm(P, m->pf_ln2_g, m->pf_ln2_b, x, nullptr, (int64_t)B * hw, D, 0, hw, (int64_t)Tp * hw, 0, s));
@@ -312,6 +327,7 @@ static int cvivit_encode_impl(const phk_cvivit_t* m, const float* video, int32_t
     PHK_TRY(linear(prec, A, K2, m->pr_w, m->pr_w_h, K2, P, D, rows, D, (int)K2, m->pr_b, nullptr, s));
     PHK_TRY(phk_layernorm(P, m->pr_ln2_g, m->pr_ln2_b, x, nullptr, rows, D, 0, (int64_t)(Tp - 1) * hw,
                           (int64_t)Tp * hw, hw, s));
+  }
   }
   if (tap_patch) PHK_CUDA(cudaMemcpyAsync(tap_patch, x, R * D * 4, cudaMemcpyDeviceToDevice, st));
 

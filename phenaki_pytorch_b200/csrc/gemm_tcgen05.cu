@@ -1111,44 +1111,44 @@ extern "C" int phk_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t 
   return launch_gemm<0>(ta, tb, p, st);
 }
 
-// Two independent products C1 = A1 W1^T and C2 = A2 W2^T (fp32 outputs, same M) in one launch: the q and k,v
-// projections of a self-attention block (attention.py:140-146).
+// Two independent products C1 = A1 W1^T (+bias1) [M1,N1] and C2 = A2 W2^T (+bias2) [M2,N2] (fp32 outputs) in one
+// launch: the q and k,v projections of a self-attention block (attention.py:140-146), or the first-frame and
+// rest-frames patch embeddings (cvivit.py:542-549: 16 + 128 tiles, neither of which fills the machine alone).
 extern "C" int phk_gemm_bf16_x2(const void* A1, int64_t lda1, const void* W1, int64_t ldw1, float* C1, int64_t ldc1,
-                                int32_t N1, int32_t K1, const void* A2, int64_t lda2, const void* W2, int64_t ldw2,
-                                float* C2, int64_t ldc2, int32_t N2, int32_t K2, int64_t M, phk_stream_t s) {
-  Prof prof_(FAM_GEMM_BF16, s, 2.0 * (double)M * ((double)N1 * K1 + (double)N2 * K2));
+                                int64_t M1, int32_t N1, int32_t K1, const float* bias1, const void* A2, int64_t lda2,
+                                const void* W2, int64_t ldw2, float* C2, int64_t ldc2, int64_t M2, int32_t N2,
+                                int32_t K2, const float* bias2, phk_stream_t s) {
+  Prof prof_(FAM_GEMM_BF16, s, 2.0 * ((double)M1 * N1 * K1 + (double)M2 * N2 * K2));
   PHK_REQUIRE(A1 && W1 && C1 && A2 && W2 && C2, PHK_E_ARG, "phk_gemm_bf16_x2: null pointer");
-  PHK_REQUIRE(M >= 0 && N1 > 0 && K1 > 0 && N2 > 0 && K2 > 0 && lda1 >= K1 && ldw1 >= K1 && lda2 >= K2 && ldw2 >= K2,
-              PHK_E_ARG, "phk_gemm_bf16_x2: bad size");
+  PHK_REQUIRE(M1 > 0 && M2 > 0 && N1 > 0 && K1 > 0 && N2 > 0 && K2 > 0 && lda1 >= K1 && ldw1 >= K1 && lda2 >= K2 &&
+                  ldw2 >= K2, PHK_E_ARG, "phk_gemm_bf16_x2: bad size");
   PHK_REQUIRE(lda1 % 8 == 0 && ldw1 % 8 == 0 && lda2 % 8 == 0 && ldw2 % 8 == 0 &&
                   ((reinterpret_cast<uintptr_t>(A1) | reinterpret_cast<uintptr_t>(W1) | reinterpret_cast<uintptr_t>(A2) |
                     reinterpret_cast<uintptr_t>(W2)) & 15) == 0,
               PHK_E_ARG, "phk_gemm_bf16_x2: operands must be 16-byte aligned with leading dimensions multiple of 8 (TMA)");
-  PHK_REQUIRE(M < (1LL << 31) - GM, PHK_E_UNSUPPORTED, "phk_gemm_bf16_x2: M too large");
-  if (M == 0) return 0;
+  PHK_REQUIRE(M1 < (1LL << 31) - 2 * GM && M2 < (1LL << 31) - 2 * GM, PHK_E_UNSUPPORTED, "phk_gemm_bf16_x2: M too large");
   CUtensorMap ta, tb, ta2, tb2;
-  PHK_TRY(get_tensor_map(A1, M, K1, lda1, GM, &ta));
-  PHK_TRY(get_tensor_map(A2, M, K2, lda2, GM, &ta2));
-  const int m_pairs = (int)((M + 2 * GM - 1) / (2 * GM));
+  PHK_TRY(get_tensor_map(A1, M1, K1, lda1, GM, &ta));
+  PHK_TRY(get_tensor_map(A2, M2, K2, lda2, GM, &ta2));
   const int mode = gemm_mode();
   // measured (profiles/r01_gemm_modes.txt): with fp32 outputs the 256 x 256 pair tile's two-chunk epilogue costs more
   // than the halved operand traffic saves at K = 512, so the pair variant is only taken when forced (tests, A/B runs)
-  const bool pair = M > GM && mode >= 2;
+  const bool pair = M1 > GM && M2 > GM && mode >= 2;
   if (pair) {
     PHK_TRY(get_tensor_map(W1, N1, K1, ldw1, 128, &tb));
     PHK_TRY(get_tensor_map(W2, N2, K2, ldw2, 128, &tb2));
-    EpiParams p{C1, ldc1, M, N1, K1, nullptr, nullptr, 0, 0, 0, m_pairs, (N1 + 255) / 256, nullptr};
-    EpiParams p2{C2, ldc2, M, N2, K2, nullptr, nullptr, 0, 0, 0, m_pairs, (N2 + 255) / 256, nullptr};
+    EpiParams p{C1, ldc1, M1, N1, K1, bias1, nullptr, 0, 0, 0, (int)((M1 + 2 * GM - 1) / (2 * GM)), (N1 + 255) / 256, nullptr};
+    EpiParams p2{C2, ldc2, M2, N2, K2, bias2, nullptr, 0, 0, 0, (int)((M2 + 2 * GM - 1) / (2 * GM)), (N2 + 255) / 256, nullptr};
     PHK_TRY(maybe_tma_epilogue(p, 0));
     PHK_TRY(maybe_tma_epilogue(p2, 0));
     return launch_gemm_pair<0, 256, true>(ta, tb, p, ta2, tb2, p2, to_stream(s));
   }
   PHK_TRY(get_tensor_map(W1, N1, K1, ldw1, GN, &tb));
   PHK_TRY(get_tensor_map(W2, N2, K2, ldw2, GN, &tb2));
-  const int mt = (int)((M + GM - 1) / GM);
-  EpiParams p{C1, ldc1, M, N1, K1, nullptr, nullptr, 0, 0, 0, mt, (N1 + GN - 1) / GN, nullptr};
-  EpiParams p2{C2, ldc2, M, N2, K2, nullptr, nullptr, 0, 0, 0, mt, (N2 + GN - 1) / GN, nullptr};
-  PHK_REQUIRE((int64_t)mt * (p.n_tiles + p2.n_tiles) < (1LL << 31), PHK_E_UNSUPPORTED, "phk_gemm_bf16_x2: too many tiles");
+  EpiParams p{C1, ldc1, M1, N1, K1, bias1, nullptr, 0, 0, 0, (int)((M1 + GM - 1) / GM), (N1 + GN - 1) / GN, nullptr};
+  EpiParams p2{C2, ldc2, M2, N2, K2, bias2, nullptr, 0, 0, 0, (int)((M2 + GM - 1) / GM), (N2 + GN - 1) / GN, nullptr};
+  PHK_REQUIRE((int64_t)p.m_tiles * p.n_tiles + (int64_t)p2.m_tiles * p2.n_tiles < (1LL << 31), PHK_E_UNSUPPORTED,
+              "phk_gemm_bf16_x2: too many tiles");
   // (measured: the bulk-store epilogue does not pay for the two-problem launch -- 16.2 vs 15.5 us -- so it stays off)
   return launch_gemm_dual(ta, tb, p, ta2, tb2, p2, to_stream(s));
 }

@@ -209,8 +209,8 @@ def test_gemm_x2_two_problems_in_one_launch(M, N1, N2, K1, K2):
     c1 = torch.full((M, N1), 3.0, device=DEV)
     c2 = torch.full((M, N2), 3.0, device=DEV)
     lib = L.lib()
-    L.check(lib.phk_gemm_bf16_x2(L.ptr(d[0]), K1, L.ptr(d[1]), K1, L.ptr(c1), N1, N1, K1, L.ptr(d[2]), K2, L.ptr(d[3]), K2,
-                                 L.ptr(c2), N2, N2, K2, M, L.stream_ptr()), "phk_gemm_bf16_x2")
+    L.check(lib.phk_gemm_bf16_x2(L.ptr(d[0]), K1, L.ptr(d[1]), K1, L.ptr(c1), N1, M, N1, K1, None, L.ptr(d[2]), K2, L.ptr(d[3]),
+                                 K2, L.ptr(c2), N2, M, N2, K2, None, L.stream_ptr()), "phk_gemm_bf16_x2")
     torch.testing.assert_close(c1.cpu(), a1.float() @ w1.float().t(), rtol=1e-4, atol=2e-3)
     torch.testing.assert_close(c2.cpu(), a2.float() @ w2.float().t(), rtol=1e-4, atol=2e-3)
     L.check(lib.phk_debug_gemm_mode(1))   # one-CTA kernels on both sides: same tiles, same K order -> identical bits
@@ -218,13 +218,28 @@ def test_gemm_x2_two_problems_in_one_launch(M, N1, N2, K1, K2):
         s1, s2, t1, t2 = torch.empty_like(c1), torch.empty_like(c2), torch.empty_like(c1), torch.empty_like(c2)
         L.check(lib.phk_gemm_bf16(L.ptr(d[0]), K1, L.ptr(d[1]), K1, L.ptr(s1), N1, M, N1, K1, None, None, 0, 0, 0, 0, L.stream_ptr()))
         L.check(lib.phk_gemm_bf16(L.ptr(d[2]), K2, L.ptr(d[3]), K2, L.ptr(s2), N2, M, N2, K2, None, None, 0, 0, 0, 0, L.stream_ptr()))
-        L.check(lib.phk_gemm_bf16_x2(L.ptr(d[0]), K1, L.ptr(d[1]), K1, L.ptr(t1), N1, N1, K1, L.ptr(d[2]), K2, L.ptr(d[3]),
-                                     K2, L.ptr(t2), N2, N2, K2, M, L.stream_ptr()), "phk_gemm_bf16_x2")
+        L.check(lib.phk_gemm_bf16_x2(L.ptr(d[0]), K1, L.ptr(d[1]), K1, L.ptr(t1), N1, M, N1, K1, None, L.ptr(d[2]), K2,
+                                     L.ptr(d[3]), K2, L.ptr(t2), N2, M, N2, K2, None, L.stream_ptr()), "phk_gemm_bf16_x2")
         assert torch.equal(s1, t1) and torch.equal(s2, t2)
         L.check(lib.phk_debug_gemm_mode(3))   # the CTA-pair variant of the two-problem launch
-        L.check(lib.phk_gemm_bf16_x2(L.ptr(d[0]), K1, L.ptr(d[1]), K1, L.ptr(t1), N1, N1, K1, L.ptr(d[2]), K2, L.ptr(d[3]),
-                                     K2, L.ptr(t2), N2, N2, K2, M, L.stream_ptr()), "phk_gemm_bf16_x2")
+        L.check(lib.phk_gemm_bf16_x2(L.ptr(d[0]), K1, L.ptr(d[1]), K1, L.ptr(t1), N1, M, N1, K1, None, L.ptr(d[2]), K2,
+                                     L.ptr(d[3]), K2, L.ptr(t2), N2, M, N2, K2, None, L.stream_ptr()), "phk_gemm_bf16_x2")
         torch.testing.assert_close(t1.cpu(), a1.float() @ w1.float().t(), rtol=1e-4, atol=2e-3)
         torch.testing.assert_close(t2.cpu(), a2.float() @ w2.float().t(), rtol=1e-4, atol=2e-3)
     finally:
         lib.phk_debug_gemm_mode(-1)
+
+
+def test_gemm_x2_different_row_counts_and_biases():
+    """The two problems of one launch may differ in M, N, K and bias: first-frame (512 x 3072) and rest-frames
+    (4096 x 6144) patch embeddings of cfg2 (cvivit.py:542-549), scaled down."""
+    M1, N1, K1, M2, N2, K2 = 128, 256, 384, 1000, 256, 768
+    a1, w1 = operands(M1, N1, K1, seed=60)
+    a2, w2 = operands(M2, N2, K2, seed=62)
+    b1, b2 = TC.seeded_randn((N1,), 64), TC.seeded_randn((N2,), 65)
+    d = [t.to(DEV) for t in (a1, w1, a2, w2, b1, b2)]
+    c1, c2 = torch.zeros((M1, N1), device=DEV), torch.zeros((M2, N2), device=DEV)
+    L.check(L.lib().phk_gemm_bf16_x2(L.ptr(d[0]), K1, L.ptr(d[1]), K1, L.ptr(c1), N1, M1, N1, K1, L.ptr(d[4]), L.ptr(d[2]), K2,
+                                     L.ptr(d[3]), K2, L.ptr(c2), N2, M2, N2, K2, L.ptr(d[5]), L.stream_ptr()), "phk_gemm_bf16_x2")
+    torch.testing.assert_close(c1.cpu(), a1.float() @ w1.float().t() + b1, rtol=1e-4, atol=3e-3)
+    torch.testing.assert_close(c2.cpu(), a2.float() @ w2.float().t() + b2, rtol=1e-4, atol=3e-3)

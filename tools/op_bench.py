@@ -64,7 +64,7 @@ for (M, N, K, epi, name) in [(4608, 512, 512, 0, "gemm q/out-proj (+res)"), (460
 a1 = torch.randn(R, D, device=dev).to(bf); a2 = torch.randn(R, D, device=dev).to(bf)
 w1 = torch.randn(I, D, device=dev).to(bf); w2 = torch.randn(2 * I, D, device=dev).to(bf)
 c1 = torch.zeros(R, I, device=dev); c2 = torch.zeros(R, 2 * I, device=dev)
-timeit("gemm q + kv in one launch (x2)", lambda: L.check(lib.phk_gemm_bf16_x2(L.ptr(a1), D, L.ptr(w1), D, L.ptr(c1), I, I, D, L.ptr(a2), D, L.ptr(w2), D, L.ptr(c2), 2 * I, 2 * I, D, R, sp())),
+timeit("gemm q + kv in one launch (x2)", lambda: L.check(lib.phk_gemm_bf16_x2(L.ptr(a1), D, L.ptr(w1), D, L.ptr(c1), I, R, I, D, None, L.ptr(a2), D, L.ptr(w2), D, L.ptr(c2), 2 * I, R, 2 * I, D, None, sp())),
        2.0 * R * 3 * I * D, "TFLOP/s")
 
 # temporal attention (n=9, causal) on the (b,t,h,w) layout
