@@ -123,3 +123,14 @@ class NoiseTape:
         u = torch.zeros(shape).float().uniform_(0, 1, generator=self.gen)
         self.draws[tag] = u
         return u
+
+# make_video (phenaki_pytorch.py:691-714): three scenes chained through the trailing `prime` frames of the previous
+# scene, TokenCritic scoring, default cond_scale 3 -- BASELINE.json configs[4] in miniature (one prompt per scene).
+MAKE_VIDEO_CASE = dict(seed=50, steps=4, texts=("a cat", "a dog", "a fish"), num_frames=(7, 6, 6), prime_lengths=4,
+                       ctx_len=5, ctx_valid=(5, 3, 4), noise_seed=51)
+
+
+def make_video_text_table(case):
+    """text -> (1, L, dim_context) synthetic T5 embedding (zero rows = padding)."""
+    return {t: synthetic_text_embeds(1, case["ctx_len"], SAMPLE_MASKGIT["dim_context"], (v,), case["seed"] + 100 + i)
+            for i, (t, v) in enumerate(zip(case["texts"], case["ctx_valid"]))}

@@ -194,6 +194,35 @@ def make_sample(ref):
                    os.path.join(OUT, f"sample_{name}.pt"))
 
 
+def make_makevideo(ref):
+    """make_video (phenaki_pytorch.py:691-714): scenes chained by priming; reference vs oracle replay of the whole chain."""
+    case = C.MAKE_VIDEO_CASE
+    print("[make_video]")
+    torch.manual_seed(case["seed"])
+    cvivit = ref.CViViT(**C.SAMPLE_CVIVIT)
+    maskgit = ref.MaskGit(**C.SAMPLE_MASKGIT)
+    critic = ref.TokenCritic(**C.SAMPLE_CRITIC)
+    phenaki = ref.Phenaki(cvivit=cvivit, maskgit=maskgit, critic=critic, steps=case["steps"],
+                          text_embed_dim=C.SAMPLE_MASKGIT["dim_context"]).eval()
+    table = C.make_video_text_table(case)
+    phenaki.encode_texts = lambda texts, output_device=None: table[texts[0]]
+    torch.manual_seed(case["noise_seed"])
+    video, scenes = ref.make_video(phenaki, texts=list(case["texts"]), num_frames=case["num_frames"],
+                                   prime_lengths=case["prime_lengths"])
+    # oracle replay of the chain with the same uniform stream
+    cv_sd = {k: v.detach().clone() for k, v in phenaki.cvivit.state_dict().items()}
+    mg_sd = {k: v.detach().clone() for k, v in maskgit.state_dict().items()}
+    cr_sd = {k: v.detach().clone() for k, v in critic.state_dict().items()}
+    from tests.chain import oracle_make_video
+    o_video, o_scenes = oracle_make_video(case, cv_sd, mg_sd, cr_sd, table, C.NoiseTape(case["noise_seed"]))
+    for i, (a, b) in enumerate(zip(o_scenes, scenes)):
+        same(a, b, f"make_video scene {i}")
+    same(o_video, video, "make_video whole video")
+    torch.save(dict(cvivit_digest=C.state_digest(cv_sd), maskgit_digest=C.state_digest(mg_sd),
+                    critic_digest=C.state_digest(cr_sd), video=video, scenes=scenes),
+               os.path.join(OUT, "make_video.pt"))
+
+
 def make_units(ref):
     """Kernel-granularity goldens straight from reference attention.py modules."""
     from phenaki_pytorch import attention as A
@@ -241,7 +270,7 @@ def make_units(ref):
 
 if __name__ == "__main__":
     ref = load_reference()
-    which = sys.argv[1:] or ["units", "cvivit", "maskgit", "critic", "sample"]
+    which = sys.argv[1:] or ["units", "cvivit", "maskgit", "critic", "sample", "makevideo"]
     for w in which:
         globals()["make_" + w](ref)
     print("golden fixtures written to", OUT)

@@ -153,3 +153,25 @@ def test_sampled_video_matches_reference_golden(golden, name):
                       noise_fn=lambda shape, tag: tape(shape, tag).to(DEV))
     assert tuple(video.shape) == tuple(g["video"].shape)
     torch.testing.assert_close(video.cpu(), g["video"], rtol=RTOL, atol=ATOL)
+
+
+def test_make_video_scene_chain_matches_reference_golden(golden):
+    """make_video end to end (BASELINE configs[4] in miniature): 3 scenes, TokenCritic, each scene primed with the
+    last 4 decoded frames of the previous one (re-encoded by C-ViViT), uniform draws replayed, pixels vs the reference."""
+    case, g = C.MAKE_VIDEO_CASE, golden("make_video")
+    torch.manual_seed(case["seed"])
+    cv, mg, cr = P.CViViT(**C.SAMPLE_CVIVIT), P.MaskGit(**C.SAMPLE_MASKGIT), P.TokenCritic(**C.SAMPLE_CRITIC)
+    assert C.state_digest(cv.state_dict()) == g["cvivit_digest"] and C.state_digest(cr.state_dict()) == g["critic_digest"]
+    ph = P.Phenaki(cvivit=cv.to(DEV), maskgit=mg.to(DEV), critic=cr.to(DEV), steps=case["steps"],
+                   text_embed_dim=C.SAMPLE_MASKGIT["dim_context"])
+    table = C.make_video_text_table(case)
+    ph.encode_texts = lambda texts, output_device=None: table[texts[0]].to(DEV)    # stands in for T5 (no weights here)
+    tape = C.NoiseTape(case["noise_seed"])
+    sample = ph.sample
+    ph.sample = lambda **kw: sample(noise_fn=lambda shape, tag: tape(shape, tag).to(DEV), **kw)
+    video, scenes = P.make_video(ph, texts=list(case["texts"]), num_frames=case["num_frames"],
+                                 prime_lengths=case["prime_lengths"])
+    assert tuple(video.shape) == tuple(g["video"].shape) and len(scenes) == 3
+    torch.testing.assert_close(video.cpu(), g["video"], rtol=RTOL, atol=ATOL)
+    for a, b in zip(scenes, g["scenes"]):
+        torch.testing.assert_close(a.cpu(), b, rtol=RTOL, atol=ATOL)

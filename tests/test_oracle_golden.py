@@ -151,3 +151,18 @@ def test_product_has_no_cpu_fallback():
         if fn.endswith(".py"):
             text = open(os.path.join(src, fn)).read()
             assert "import oracle" not in text and "from oracle" not in text, f"{fn} imports the oracle"
+
+
+def test_oracle_make_video_chain_matches_reference_golden(golden):
+    """make_video (phenaki_pytorch.py:691-714): three scenes, TokenCritic, priming with the previous scene's last frames."""
+    from tests.chain import oracle_make_video
+    case, g = C.MAKE_VIDEO_CASE, golden("make_video")
+    torch.manual_seed(case["seed"])
+    cv, mg, cr = P.CViViT(**C.SAMPLE_CVIVIT), P.MaskGit(**C.SAMPLE_MASKGIT), P.TokenCritic(**C.SAMPLE_CRITIC)
+    sds = [m.state_dict() for m in (cv, mg, cr)]
+    assert [C.state_digest(sd) for sd in sds] == [g["cvivit_digest"], g["maskgit_digest"], g["critic_digest"]]
+    video, scenes = oracle_make_video(case, *sds, C.make_video_text_table(case), C.NoiseTape(case["noise_seed"]))
+    assert tuple(video.shape) == (1, 3, sum(case["num_frames"]), *C.SAMPLE_CVIVIT["image_size"])
+    torch.testing.assert_close(video, g["video"], **FTOL)
+    for a, b in zip(scenes, g["scenes"]):
+        torch.testing.assert_close(a, b, **FTOL)
