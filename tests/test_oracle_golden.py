@@ -166,3 +166,27 @@ def test_oracle_make_video_chain_matches_reference_golden(golden):
     torch.testing.assert_close(video, g["video"], **FTOL)
     for a, b in zip(scenes, g["scenes"]):
         torch.testing.assert_close(a, b, **FTOL)
+
+
+def test_weight_signature_cache_tracks_in_place_updates_moves_and_replaced_parameters():
+    """The product rebuilds its weight tables when the (cached) signature changes: in-place updates (optimizer steps,
+    load_state_dict) and dtype/device moves are seen at once; a Parameter OBJECT replaced by hand within 64 calls."""
+    from phenaki_pytorch_b200.modules import weights_signature, _SIG_REFRESH
+    torch.manual_seed(0)
+    m = P.CViViT(**C.CVIVIT_CASES["image"]["ctor"])
+    s0 = weights_signature(m)
+    assert weights_signature(m) == s0
+    with torch.no_grad():
+        m.vq.project_in.weight.add_(1.0)
+    s1 = weights_signature(m)
+    assert s1 != s0
+    m.load_state_dict({k: v.clone() for k, v in m.state_dict().items()})
+    s2 = weights_signature(m)
+    assert s2 != s1
+    m.double()                                       # nn.Module._apply keeps the Parameter objects, moves the data
+    assert weights_signature(m) != s2
+    m.float()
+    s3 = weights_signature(m)
+    m.vq.project_in.weight = torch.nn.Parameter(m.vq.project_in.weight.detach().clone())
+    seen = [weights_signature(m) for _ in range(_SIG_REFRESH + 1)]
+    assert seen[-1] != s3

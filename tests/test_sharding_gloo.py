@@ -70,3 +70,23 @@ def test_two_rank_gloo_encode_matches_single_process(tmp_path, n_videos):
     assert torch.equal(r["full"], r["ref"])          # integer ids: bit-exact, whatever the shard boundaries
     assert r["slowest"] == 11.0
     assert r["seeds"] == [7, 8]
+
+
+def test_bench_reference_arm_under_torchrun_prints_one_line():
+    """`bench.py --impl reference` launched the way the driver launches N>1 (torchrun, 2 ranks, CPU only here): rank 0
+    alone runs and prints ONE JSON line with the contract's keys; the other rank exits 0 without work."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2",
+           "--steps", "1", "--warmup", "1"]
+    env = dict(os.environ, OMP_NUM_THREADS="8")
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "cvivit_encode_frames_per_s" and d["n_gpus"] == 2
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
