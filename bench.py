@@ -322,12 +322,12 @@ def main():
             dist.barrier()
 
     # setup, untimed: the library captures one CUDA graph per (input buffer, shape) on the second call with that key
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()   # polls from here on (the first NVML calls take ~10 ms); only samples inside the timed window are reported
     for v in vids:
         for _ in range(3):
             model(v, return_only_codebook_ids=True)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()   # polls from the warm-up on; only samples inside the timed window are reported
     for i in range(W):
         ids = model(vids[i % 3], return_only_codebook_ids=True)
     barrier()

@@ -2,21 +2,27 @@
 //   C[map(m), n] = sum_k A[m,k] * W[n,k]  (+bias) (+residual)        nn.Linear semantics
 // A, W bf16, K-major (row-major [rows, K]); fp32 accumulation in TMEM.
 //
-// Persistent, warp-specialised (one CTA per SM, static round-robin tile scheduler):
-//   warp 0     TMA producer: cp.async.bulk.tensor.2d (SWIZZLE_128B) stages 128x64 A and 128x64 W tiles into a
-//              4-deep shared-memory ring; out-of-bounds rows / the K tail are zero-filled by the TMA unit.
-//   warp 1     TMEM allocator + MMA issuer: one thread issues tcgen05.mma.cta_group::1.kind::f16
-//              (M=128, N=128, K=16), four per k-block; tcgen05.commit frees the smem slot and publishes the
-//              accumulator.  Two 128-column accumulators in TMEM, so tile i+1 is multiplied while tile i drains.
-//   warps 2..17 epilogue (four per TMEM lane group, each drains a quarter of the columns): residual-tile prefetch
-//              during the main loop; tcgen05.ld (32x32b) -> registers -> padded smem tile; then fully coalesced
-//              row-wise write-out (512 B per warp instruction) with bias / row map / bf16 pack / GEGLU.  Sixteen
-//              warps because the epilogue math is a per-warp dependency chain (GEGLU: ~30 instructions per
-//              output): with eight warps the MMA warp spent most of its time waiting for a drained accumulator.
-// Tiles are walked m-fastest so the CTAs running concurrently share the same W tile (L2) while the A panel
-// stays L2-resident.
-// Epilogues: 0 fp32 (+bias,+residual)   1 bf16 (+bias)   2 GEGLU (attention.py:40-43) on W rows packed as
-// [64 value rows | 64 gate rows] per 128-column tile -> bf16 [M, N/2].
+// Three kernels behind phk_gemm_bf16 / phk_gemm_bf16_x2 (dispatch rule and measurements at the host entry points):
+//   gemm_bf16_kernel<EPI, DUAL>            one CTA per 128 x 128 tile, tcgen05.mma.cta_group::1
+//   gemm_bf16_pair_kernel<EPI, BN, DUAL>   clusters of two CTAs per 256 x BN tile (BN = 128 / 256), cta_group::2
+//   DUAL                                    two independent problems in one persistent launch
+// All are persistent and warp-specialised (one CTA per SM, static round-robin tile scheduler, m-fastest so concurrent
+// CTAs share the W tile in L2 while the A panel stays L2-resident):
+//   warp 0      TMA producer: cp.async.bulk.tensor.2d (SWIZZLE_128B) stages 128x64 A and W tiles into a 4..6-deep
+//               shared-memory ring; out-of-bounds rows / the K tail are zero-filled by the TMA unit.
+//   warp 1      TMEM allocator + MMA issuer: one thread issues tcgen05.mma.kind::f16 (K = 16), four per k-block;
+//               tcgen05.commit frees the smem slot and publishes the accumulator.  Two accumulators in TMEM, so tile
+//               i+1 is multiplied while tile i drains.
+//   warps 2..17 epilogue (four per TMEM lane group, each drains a quarter of the columns).  Sixteen warps because the
+//               epilogue math is a per-warp dependency chain: with eight the MMA warp mostly waited for a drained
+//               accumulator.
+// Epilogues: 0 fp32 (+bias, +residual, row map) -- through the TMA unit when the row map is the identity: the
+//              residual tile is bulk-loaded into SWIZZLE_128B staging boxes during the main loop and the result tile
+//              bulk-stored from them; otherwise staged in a padded smem tile and written with coalesced rows
+//            1 bf16 (+bias)
+//            2 GEGLU (attention.py:40-43) on W rows packed [64 value rows | 64 gate rows] per 128-column tile ->
+//              bf16 [M, N/2]: accumulator read out of TMEM and released at once, fitted sigmoid-form GELU, swizzled
+//              bf16 staging tile, coalesced 16-byte stores.
 #include "phk_common.cuh"
 #include <cuda.h>
 #include <cstdlib>
