@@ -314,7 +314,12 @@ int phk_cfg_combine(const float* cond, const float* null_out, float cond_scale, 
  * spatial_bias: cached phk_cpb_bias(spatial_bias, H', W') output [heads, H'W', H'W'] or NULL
  * (recomputed inside).  taps: optional fp32 device buffers for the parity tests:
  * tap_patch / tap_spatial / tap_temporal [B*T'*H'*W', dim] in (b,t,h,w) row order,
- * tap_proj [rows, bits] = LFQ pre-sign projection. */
+ * tap_proj [rows, bits] = LFQ pre-sign projection.
+ * Launch cost: the ~75 launches of one call are a pure function of (table contents, buffers, shape, prec).  With
+ * spatial_bias given and no taps, the second call with an identical key is captured into a CUDA graph on a
+ * library-owned stream and later calls replay it on `s` (one cudaGraphLaunch; env PHK_GRAPH=0 keeps every call
+ * eager).  The graph only bakes in addresses: new data in the same buffers (video, weights updated in place) is
+ * honoured; a table with different pointers or dims is a different key. */
 int64_t phk_cvivit_workspace_bytes(const phk_cvivit_t* m, int32_t B, int32_t F, int32_t prec);
 int phk_cvivit_encode(const phk_cvivit_t* m, const float* video, int32_t B, int32_t F,
                       int64_t* ids, void* workspace, int64_t workspace_bytes, int32_t prec,
