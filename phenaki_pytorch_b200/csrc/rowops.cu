@@ -934,6 +934,11 @@ extern "C" int phk_patchify_ln(const float* video, int32_t B, int32_t C, int32_t
   const size_t smem = (size_t)K * sizeof(float);
   const bool vec = (p2 % 4 == 0) && (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(video) & 15) == 0) &&
                    ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  {  // token gathered by the TMA unit, double-buffered per CTA (patchify_tma.cu); 1 = shape not eligible
+    const int rc = patchify_ln_tma_launch(video, B, C, F, H, W, f0, nt, pt, p1, p2, ln_g, ln_b, out, out_bf16, to_stream(s));
+    if (rc == 0) { PHK_LAUNCH_CHECK(); return 0; }
+    if (rc != 1) return rc;
+  }
   if (vec && K <= 6 * 1024 && ((reinterpret_cast<uintptr_t>(ln_g) | reinterpret_cast<uintptr_t>(ln_b)) & 15) == 0) {
     // persistent, register-resident variant (4 CTAs per SM; gamma / beta staged once per CTA: 2 * K * 4 bytes of smem)
     PHK_REQUIRE((int64_t)C * F * H * W < (1LL << 31), PHK_E_UNSUPPORTED, "phk_patchify_ln: one video exceeds 2^31 elements");
