@@ -302,7 +302,7 @@ def maskgit_forward(ids, sd, *, video_patch_shape, heads=8, context=None, text_m
         text_mask = torch.zeros_like(text_mask)
     x = _token_embed(ids, sd, p)
     a = gradient_shrink_alpha
-    x = x * a + x * (1 - a)  # forward value of the gradient-shrink trick (:199)
+    x = x * a + x.detach() * (1 - a)  # the gradient-shrink trick (:199): same forward value, gradient scaled by a
     x = transformer(x, sd, p + "transformer.", heads=heads, video_shape=(b, *video_patch_shape),
                     attn_bias=bias, context=context, self_attn_mask=video_mask,
                     cross_attn_context_mask=text_mask, attn_num_null_kv=2)
@@ -424,3 +424,70 @@ def sample_token_ids(maskgit_sd, *, num_tokens, patch_shape, batch, steps=18, he
             if trace is not None:
                 trace[-1]["scores"] = scores.clone()
     return ids
+
+
+# --------------------------------------------------------------------------------------
+# training loss (phenaki_pytorch.py:562-687); differentiable through torch autograd when the
+# state-dict tensors require grad -- the gradient oracle of the training-step kernels
+# --------------------------------------------------------------------------------------
+
+
+def mask_subset_with_prob(mask, prob, u):
+    """phenaki_pytorch.py:43-55 (get_mask_subset_with_prob) with the uniform draw ``u`` (b, n) made explicit.
+    Kept as is: the subset is chosen by RANK of the draw, the padding only shifts the ranks."""
+    b, n = mask.shape
+    num_tokens = mask.sum(dim=-1)
+    num_pads = n - num_tokens
+    num_masked = (prob * num_tokens).round().clamp(min=1)
+    ranks = u.argsort(dim=-1)
+    ranks = ranks - num_pads[:, None]
+    ranks = ranks.masked_fill(ranks < 0, n)
+    return ranks < num_masked[:, None]
+
+
+def train_draws(batch, seq, steps):
+    """The draws of one Phenaki.forward in reference order, from the global CPU generator:
+    ``rand_step`` (:614) then the uniform behind the random permutation (:48)."""
+    rand_step = torch.randint(0, steps, (batch,))
+    u = torch.rand((batch, seq))
+    return rand_step, u
+
+
+def train_token_mask(rand_step, u, steps, video_mask=None):
+    """phenaki_pytorch.py:614-620: cosine schedule -> which tokens are replaced by the mask id."""
+    b, n = u.shape
+    prob = torch.cos(rand_step * math.pi * 0.5 / steps)
+    if video_mask is None:
+        video_mask = torch.ones((b, n), dtype=torch.bool)
+    return mask_subset_with_prob(video_mask, prob, u)
+
+
+def maskgit_train_loss(ids, sd, token_mask, *, video_patch_shape, heads=8, context=None, text_mask=None,
+                       video_mask=None, mask_id=None, return_logits=False, p=""):
+    """phenaki_pytorch.py:620-640: masked input -> MaskGit logits -> cross entropy at the masked positions.
+    ``cond_drop_prob`` is 0 in the reference's training forward (it overwrites the argument at :594, SURVEY defects),
+    so no text dropout and no RNG.  ids (b, n) int64, token_mask (b, n) bool."""
+    if mask_id is None:
+        mask_id = sd[p + "to_logits.weight"].shape[0]
+    b, n = ids.shape
+    if video_mask is None:
+        video_mask = torch.ones((b, n), dtype=torch.bool)  # :617-618
+    masked = torch.where(token_mask, mask_id, ids)
+    logits = maskgit_forward(masked, sd, video_patch_shape=video_patch_shape, heads=heads, context=context,
+                             text_mask=text_mask, video_mask=video_mask, p=p)
+    loss = F.cross_entropy(logits[token_mask], ids[token_mask])
+    return (loss, logits) if return_logits else loss
+
+
+def critic_train_loss(ids, pred_ids, token_mask, critic_sd, *, video_patch_shape, heads=8, context=None,
+                      text_mask=None, video_mask=None, p=""):
+    """phenaki_pytorch.py:652-680: critic input = predictions at the masked positions, labels = "was changed";
+    binary cross entropy with logits over ALL positions."""
+    b, n = ids.shape
+    if video_mask is None:
+        video_mask = torch.ones((b, n), dtype=torch.bool)
+    critic_input = torch.where(token_mask, pred_ids, ids)
+    scores = critic_forward(critic_input, critic_sd, video_patch_shape=video_patch_shape, heads=heads,
+                            context=context, text_mask=text_mask, video_mask=video_mask, p=p)
+    labels = (ids != pred_ids).float()
+    return F.binary_cross_entropy_with_logits(scores, labels)

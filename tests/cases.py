@@ -134,3 +134,24 @@ def make_video_text_table(case):
     """text -> (1, L, dim_context) synthetic T5 embedding (zero rows = padding)."""
     return {t: synthetic_text_embeds(1, case["ctx_len"], SAMPLE_MASKGIT["dim_context"], (v,), case["seed"] + 100 + i)
             for i, (t, v) in enumerate(zip(case["texts"], case["ctx_valid"]))}
+
+
+# Phenaki.forward training loss + gradients (phenaki_pytorch.py:562-687): the reference under ``torch.manual_seed(noise_seed)``
+# draws rand_step, the permutation uniform and (with a critic) the V-wide gumbel uniform, in that order.
+TRAIN_CASES = {
+    "generator": dict(  # MaskGit only (critic=None): cross entropy at the masked positions
+        seed=60, steps=18, maskgit=MASKGIT_CASES["small"]["ctor"], critic=None, batch=2, patch_shape=(3, 4, 4),
+        ctx_len=7, ctx_valid=(7, 4), input_seed=61, noise_seed=62),
+    "with_critic": dict(  # + TokenCritic: gumbel-sampled predictions -> BCE, loss = ce + critic_loss_weight * bce
+        seed=63, steps=6, maskgit=SAMPLE_MASKGIT, critic=SAMPLE_CRITIC, batch=3, patch_shape=(3, 2, 3),
+        ctx_len=6, ctx_valid=(6, 1, 4), input_seed=64, noise_seed=65),
+}
+
+
+def train_inputs(case):
+    """ids (b, t, h, w) int64 in [0, V) and synthetic text embeddings."""
+    g = torch.Generator().manual_seed(case["input_seed"])
+    ids = torch.randint(0, case["maskgit"]["num_tokens"], (case["batch"], *case["patch_shape"]), generator=g)
+    ctx = synthetic_text_embeds(case["batch"], case["ctx_len"], case["maskgit"]["dim_context"], case["ctx_valid"],
+                                case["input_seed"] + 1000)
+    return ids, ctx

@@ -268,9 +268,65 @@ def make_units(ref):
     torch.save(gold, os.path.join(OUT, "units.pt"))
 
 
+def make_train(ref):
+    """Phenaki.forward (training loss, phenaki_pytorch.py:562-687) and its gradients: the reference's autograd vs
+    autograd through the functional oracle, on the same weights, inputs and random draws."""
+    for name, case in C.TRAIN_CASES.items():
+        print(f"[train/{name}]")
+        torch.manual_seed(case["seed"])
+        cvivit = ref.CViViT(**C.SAMPLE_CVIVIT)
+        maskgit = ref.MaskGit(**case["maskgit"])
+        critic = ref.TokenCritic(**case["critic"]) if case["critic"] else None
+        phenaki = ref.Phenaki(cvivit=cvivit, maskgit=maskgit, critic=critic, steps=case["steps"],
+                              text_embed_dim=case["maskgit"]["dim_context"]).train()
+        ids, ctx = C.train_inputs(case)
+        heads = case["maskgit"].get("heads", 8)
+        b, n = ids.shape[0], ids[0].numel()
+        torch.manual_seed(case["noise_seed"])
+        loss = phenaki(video_codebook_ids=ids, text_embeds=ctx)
+        loss.backward()
+        mg_sd = {k: v.detach().clone() for k, v in maskgit.state_dict().items()}
+        cr_sd = {k: v.detach().clone() for k, v in critic.state_dict().items()} if critic else None
+        mg_grads = {k: p.grad.detach().clone() for k, p in maskgit.named_parameters() if p.grad is not None}
+        cr_grads = ({k: p.grad.detach().clone() for k, p in critic.named_parameters() if p.grad is not None}
+                    if critic else None)
+        no_grad = sorted(k for k, p in maskgit.named_parameters() if p.grad is None)
+        print("  maskgit parameters without gradient:", no_grad)
+
+        # ---- oracle replay: same draws (global generator, reference order), autograd over the functional restatement
+        def leaf(sd):
+            return {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+
+        o_mg, o_cr = leaf(mg_sd), (leaf(cr_sd) if cr_sd else None)
+        tmask = torch.any(ctx != 0, dim=-1)
+        torch.manual_seed(case["noise_seed"])
+        rand_step, u = O.train_draws(b, n, case["steps"])
+        token_mask = O.train_token_mask(rand_step, u, case["steps"])
+        flat = ids.reshape(b, n)
+        kw = dict(video_patch_shape=case["patch_shape"], heads=heads, context=ctx, text_mask=tmask)
+        o_loss, logits = O.maskgit_train_loss(flat, o_mg, token_mask, return_logits=True, **kw)
+        gold = dict(maskgit_digest=C.state_digest(mg_sd), token_mask=token_mask, rand_step=rand_step)
+        if critic is not None:
+            gu = torch.zeros_like(logits).uniform_(0, 1)  # gumbel_noise (:83-86) draws from the global generator
+            pred = O.gumbel_sample(logits.detach(), phenaki.critic_train_sample_temperature, gu)
+            bce = O.critic_train_loss(flat, pred, token_mask, o_cr, **kw)
+            gold.update(critic_digest=C.state_digest(cr_sd), pred_ids=pred, ce=o_loss.detach().clone(),
+                        bce=bce.detach().clone())
+            o_loss = o_loss + bce * phenaki.critic_loss_weight
+        o_loss.backward()
+        same(o_loss.detach(), loss.detach(), "training loss")
+        for k, g in mg_grads.items():
+            same(o_mg[k].grad, g, f"d loss / d maskgit.{k}")
+        if critic is not None:
+            for k, g in cr_grads.items():
+                same(o_cr[k].grad, g, f"d loss / d critic.{k}")
+        gold.update(loss=loss.detach().clone(), maskgit_grads=mg_grads, critic_grads=cr_grads)
+        torch.save(gold, os.path.join(OUT, f"train_{name}.pt"))
+
+
 if __name__ == "__main__":
     ref = load_reference()
-    which = sys.argv[1:] or ["units", "cvivit", "maskgit", "critic", "sample", "makevideo"]
+    which = sys.argv[1:] or ["units", "cvivit", "maskgit", "critic", "sample", "makevideo", "train"]
     for w in which:
         globals()["make_" + w](ref)
     print("golden fixtures written to", OUT)

@@ -190,3 +190,51 @@ def test_weight_signature_cache_tracks_in_place_updates_moves_and_replaced_param
     m.vq.project_in.weight = torch.nn.Parameter(m.vq.project_in.weight.detach().clone())
     seen = [weights_signature(m) for _ in range(_SIG_REFRESH + 1)]
     assert seen[-1] != s3
+
+
+def _train_modules(case):
+    """Same construction order as tests/golden/make_golden.py::make_train (seeded default inits)."""
+    torch.manual_seed(case["seed"])
+    P.CViViT(**C.SAMPLE_CVIVIT)
+    maskgit = P.MaskGit(**case["maskgit"])
+    critic = P.TokenCritic(**case["critic"]) if case["critic"] else None
+    return maskgit, critic
+
+
+@pytest.mark.parametrize("name", list(C.TRAIN_CASES))
+def test_oracle_training_loss_and_gradients_match_reference_golden(golden, name):
+    """Phenaki.forward (phenaki_pytorch.py:562-687): loss and every parameter gradient of the reference's autograd
+    equal autograd through the functional oracle, with the reference's random draws replayed."""
+    case, g = C.TRAIN_CASES[name], golden(f"train_{name}")
+    maskgit, critic = _train_modules(case)
+    mg_sd = maskgit.state_dict()
+    assert C.state_digest(mg_sd) == g["maskgit_digest"]
+
+    def leaf(sd):
+        return {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+
+    o_mg = leaf(mg_sd)
+    ids, ctx = C.train_inputs(case)
+    b, n = ids.shape[0], ids[0].numel()
+    torch.manual_seed(case["noise_seed"])
+    rand_step, u = O.train_draws(b, n, case["steps"])
+    token_mask = O.train_token_mask(rand_step, u, case["steps"])
+    assert torch.equal(rand_step, g["rand_step"]) and torch.equal(token_mask, g["token_mask"])
+    kw = dict(video_patch_shape=case["patch_shape"], heads=case["maskgit"].get("heads", 8), context=ctx,
+              text_mask=torch.any(ctx != 0, dim=-1))
+    loss, logits = O.maskgit_train_loss(ids.reshape(b, n), o_mg, token_mask, return_logits=True, **kw)
+    o_cr = None
+    if critic is not None:
+        cr_sd = critic.state_dict()
+        assert C.state_digest(cr_sd) == g["critic_digest"]
+        o_cr = leaf(cr_sd)
+        pred = O.gumbel_sample(logits.detach(), 1.0, torch.zeros_like(logits).uniform_(0, 1))
+        assert torch.equal(pred, g["pred_ids"])
+        loss = loss + O.critic_train_loss(ids.reshape(b, n), pred, token_mask, o_cr, **kw) * 1.0
+    loss.backward()
+    torch.testing.assert_close(loss.detach(), g["loss"], **FTOL)
+    for k, ref in g["maskgit_grads"].items():
+        torch.testing.assert_close(o_mg[k].grad, ref, rtol=1e-4, atol=1e-6, msg=lambda m, k=k: f"maskgit.{k}: {m}")
+    if critic is not None:
+        for k, ref in g["critic_grads"].items():
+            torch.testing.assert_close(o_cr[k].grad, ref, rtol=1e-4, atol=1e-6, msg=lambda m, k=k: f"critic.{k}: {m}")
