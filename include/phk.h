@@ -410,6 +410,33 @@ int phk_maskgit_sample_step(const phk_maskgit_t* m, const int64_t* ids_in, int32
                             uint64_t seed, uint64_t offset, const uint8_t* mask, int64_t* ids, int64_t* pred_out,
                             float* score_out, void* workspace, int64_t workspace_bytes, phk_stream_t s);
 
+/* ------------------------------------------------------------------------------------------ */
+/* Training step: Phenaki.forward (phenaki_pytorch.py:562-687)                   */
+/* ------------------------------------------------------------------------------------------ */
+
+/* One forward + loss + backward of MaskGit (masked cross entropy, :620-640) or TokenCritic (BCE with logits,
+ * :652-675) in fp32: what `loss = phenaki(...); loss.backward()` computes for that network under torch autograd.
+ *   ids_in  (b,n) int64   network input: ids with the mask id at the masked positions (MaskGit) or with the sampled
+ *                         predictions at the masked positions (critic)
+ *   targets (b,n) int64 + token_mask (b,n) uint8   MaskGit: loss = mean over masked rows of CE(logits, target)
+ *   labels  (b,n) float 0/1                        critic : loss = mean over all rows of BCE_with_logits(score, label)
+ *   context (b,L,dim_context) fp32 raw text embeddings or NULL; text_mask (b,L) uint8; video_mask (b,n) uint8 or NULL
+ *   grads   a table of the SAME layout as `m` whose float pointers address ZERO-FILLED gradient buffers of the
+ *           parameters' shapes (peg.w tap-major [27, dim] like the weight table; bf16 members and scalars unused);
+ *           d(loss_scale * loss)/d(parameter) is ACCUMULATED into it.  Parameters without a gradient in the reference
+ *           (beta buffers, the self-attention context_norm) are not touched.
+ *   loss_out device float: the UNSCALED loss.  logits_out: optional fp32 [b*n, num_tokens] that receives the MaskGit
+ *           logits (the critic branch samples its input from them, :646).
+ * The gradient-shrink trick (:199) scales the embedding gradients by shrink_alpha, as autograd does.  cond_drop_prob is
+ * 0 in the reference's training forward (:594 overwrites the argument), so there is no text dropout.
+ * STATUS: parity (fp32 FFMA) path; bf16 tcgen05 backward GEMMs are not built yet. */
+int64_t phk_maskgit_train_workspace_bytes(const phk_maskgit_t* m, int32_t b, int32_t n, int32_t L, int32_t keep_logits);
+int phk_maskgit_train_step(const phk_maskgit_t* m, const phk_maskgit_t* grads, const int64_t* ids_in,
+                           const int64_t* targets, const uint8_t* token_mask, const float* labels, int32_t b, int32_t n,
+                           int32_t pt, int32_t ph, int32_t pw, const float* context, int32_t L,
+                           const uint8_t* text_mask, const uint8_t* video_mask, float loss_scale, float* loss_out,
+                           float* logits_out, void* workspace, int64_t workspace_bytes, phk_stream_t s);
+
 #ifdef __cplusplus
 }
 #endif

@@ -221,6 +221,93 @@ def cpb_table(c: ContinuousPositionBias, keep: Keep):
     return t
 
 
+class GradKeep:
+    """Gradient twin of ``Keep`` for phk_maskgit_train_step: hands out pointers into zero-filled gradient buffers of
+    the parameters' shapes and remembers which parameters were given one (the reference leaves ``p.grad = None`` for
+    the rest, e.g. the self-attention ``context_norm``)."""
+
+    def __init__(self, params):
+        """params: iterable of nn.Parameter, all on one CUDA device.  One flat fp32 buffer, one view per parameter
+        in iteration order (a single contiguous bucket for a data-parallel gradient all-reduce)."""
+        self.params = list(params)
+        dev = self.params[0].device
+        self.flat = torch.zeros(sum(p.numel() for p in self.params), dtype=torch.float32, device=dev)
+        self.views, off = {}, 0
+        for p in self.params:
+            self.views[p] = self.flat[off:off + p.numel()].view(p.shape)
+            off += p.numel()
+        self.used, self.packed, self.refs = set(), [], []
+
+    def g(self, param):
+        self.used.add(param)
+        return self.views[param].data_ptr()
+
+    def peg(self, conv_weight):
+        """dsconv.weight [D,1,3,3,3] is handed to the kernels tap-major [27, D]: its gradient comes back in that
+        layout in a side buffer and is folded into the parameter's view by ``finish``."""
+        d = conv_weight.shape[0]
+        buf = torch.zeros((27, d), dtype=torch.float32, device=conv_weight.device)
+        self.packed.append((conv_weight, buf))
+        self.used.add(conv_weight)
+        return buf.data_ptr()
+
+    def obj(self, o):
+        self.refs.append(o)
+        return o
+
+    def finish(self):
+        for param, buf in self.packed:
+            self.views[param].copy_(buf.t().reshape(param.shape))
+
+    def grad_of(self, param):
+        return self.views[param] if param in self.used else None
+
+
+def attn_grad_table(a: Attention, gk: GradKeep, cross: bool):
+    t = L.AttnT()
+    t.norm_g = gk.g(a.norm.gamma)
+    if cross and isinstance(a.context_norm, LayerNorm):
+        t.ctx_g = gk.g(a.context_norm.gamma)
+    t.null_kv = gk.g(a.null_kv) if a.num_null_kv > 0 else None
+    gk.used.add(a.null_kv)  # autograd hands an (empty) gradient to a (heads, 0, dim_head) parameter too
+    t.q_scale, t.k_scale = gk.g(a.q_scale), gk.g(a.k_scale)
+    t.wq, t.wkv, t.wo = gk.g(a.to_q.weight), gk.g(a.to_kv.weight), gk.g(a.to_out.weight)
+    t.num_null_kv, t.dim_context = a.num_null_kv, a.dim_context
+    return t
+
+
+def transformer_grad_table(tf: Transformer, gk: GradKeep, with_cross: bool):
+    """Same layout as ``transformer_table`` with every float pointer addressing the parameter's gradient buffer."""
+    layers = (L.LayerT * tf.depth)()
+    for i, (peg, self_attn, cross, ff) in enumerate(tf.layers):
+        ly = layers[i]
+        ly.has_peg, ly.has_cross = int(peg is not None), int(cross is not None)
+        if peg is not None:
+            ly.peg.w, ly.peg.b, ly.peg.causal = gk.peg(peg.dsconv.weight), gk.g(peg.dsconv.bias), int(peg.causal)
+        ly.self_attn = attn_grad_table(self_attn, gk, cross=False)
+        if cross is not None and with_cross:
+            ly.cross_attn = attn_grad_table(cross, gk, cross=True)
+        ly.ff.ln_g, ly.ff.ln_b = gk.g(ff[0].weight), gk.g(ff[0].bias)
+        ly.ff.w1, ly.ff.w2 = gk.g(ff[1].weight), gk.g(ff[4].weight)
+        ly.ff.inner = ff[4].weight.shape[1]
+        ly.ff.inner_pad = (ly.ff.inner + 63) // 64 * 64
+    gk.obj(layers)
+    t = L.TransformerT()
+    t.dim, t.heads, t.dim_head, t.depth, t.causal = tf.dim, tf.heads, tf.dim_head, tf.depth, int(tf.causal)
+    t.layers = C.cast(layers, C.POINTER(L.LayerT))
+    t.out_g = gk.g(tf.norm_out.gamma)
+    return t
+
+
+def cpb_grad_table(c: ContinuousPositionBias, gk: GradKeep):
+    t = L.CpbT()
+    t.w0, t.b0 = gk.g(c.net[0][0].weight), gk.g(c.net[0][0].bias)
+    t.w1, t.b1 = gk.g(c.net[1][0].weight), gk.g(c.net[1][0].bias)
+    t.w2, t.b2 = gk.g(c.net[2].weight), gk.g(c.net[2].bias)
+    t.num_dims, t.hidden, t.heads = c.num_dims, c.dim, c.heads
+    return t
+
+
 _SIG_REFRESH = 64
 
 

@@ -18,8 +18,10 @@ from torch import nn
 
 from . import _lib as L
 from .cvivit import CViViT
-from .modules import (ContinuousPositionBias, Keep, Transformer, Workspace, _NoParams, cpb_table,
-                      transformer_table, weights_signature)
+import os
+
+from .modules import (ContinuousPositionBias, GradKeep, Keep, Transformer, Workspace, _NoParams, cpb_grad_table,
+                      cpb_table, transformer_grad_table, transformer_table, weights_signature)
 
 
 def _prod(xs):
@@ -151,6 +153,76 @@ class _TokenTransformer(nn.Module):
                                                 float(temperature), seed, offset, L.ptr(mask), L.ptr(ids), L.ptr(pred),
                                                 L.ptr(scores), L.ptr(ws), ws.numel(), L.stream_ptr()),
                     "phk_maskgit_sample_step")
+
+    def _grad_table(self, with_cross):
+        """Zero-filled gradient buffers (one flat fp32 bucket, parameters() order) and the phk_maskgit_t-shaped table
+        that addresses them; same member-by-member layout as ``_table``."""
+        gk = GradKeep(self.parameters())
+        t = L.MaskgitT()
+        tf = self.transformer
+        t.dim, t.heads, t.dim_head = tf.dim, tf.heads, tf.dim_head
+        t.num_tokens = self.token_emb.weight.shape[0] - 1
+        t.max_seq_len = self.pos_emb.weight.shape[0]
+        t.is_critic, t.has_bias = int(self.is_critic), int(not self.is_critic)
+        t.token_emb, t.pos_emb = gk.g(self.token_emb.weight), gk.g(self.pos_emb.weight)
+        if not self.is_critic:
+            t.pos_bias = cpb_grad_table(self.continuous_pos_bias, gk)
+            t.head_w, t.head_b = gk.g(self.to_logits.weight), gk.g(self.to_logits.bias)
+        else:
+            t.head_w, t.head_b = gk.g(self.to_logits[0].weight), gk.g(self.to_logits[0].bias)
+        t.transformer = transformer_grad_table(tf, gk, with_cross)
+        return t, gk
+
+    def train_step(self, ids_in, patch_shape, *, targets=None, token_mask=None, labels=None, context=None,
+                   text_mask=None, video_mask=None, loss_scale=1.0, keep_logits=False):
+        """One forward + loss + backward in libphk (phk_maskgit_train_step, fp32): returns (loss 0-d tensor,
+        GradKeep with d(loss_scale * loss)/d(parameter), logits or None).  MaskGit: masked cross entropy against
+        ``targets`` at ``token_mask``; TokenCritic: BCE with logits against ``labels``."""
+        lib = L.lib()
+        if self.precision != L.PREC_F32:
+            raise L.PhkError("the training step is built for the fp32 parity mode only (bf16 backward GEMMs: next step)")
+        ids_in = L.require_cuda(ids_in, "token ids", torch.int64)
+        b, n = ids_in.shape
+        assert _prod(patch_shape) == n, "video patch shape must cover the token sequence"
+        dev = ids_in.device
+        with torch.cuda.device(dev):
+            table = self._table()
+            assert n <= table.max_seq_len, \
+                f"the video token sequence length you are passing in ({n}) is greater than the `max_seq_len` ({table.max_seq_len})"
+            has_cross = context is not None and self.transformer.layers[0][2] is not None
+            ctx_len = 0
+            if has_cross:
+                context = L.require_cuda(context, "text embeds", torch.float32)
+                assert context.shape[0] == b and context.shape[-1] == self.transformer.layers[0][2].dim_context, \
+                    "text embedding dimension is not correct"
+                ctx_len = context.shape[1]
+                if text_mask is None:
+                    text_mask = torch.ones((b, ctx_len), device=dev, dtype=torch.bool)
+                text_mask = L.require_cuda(text_mask.to(torch.uint8), "text mask")
+            else:
+                context = text_mask = None
+            if video_mask is not None:
+                video_mask = L.require_cuda(video_mask.to(torch.uint8), "video mask")
+            if self.is_critic:
+                labels = L.require_cuda(labels.reshape(b, n).float(), "critic labels", torch.float32)
+            else:
+                targets = L.require_cuda(targets.reshape(b, n), "target ids", torch.int64)
+                token_mask = L.require_cuda(token_mask.reshape(b, n).to(torch.uint8), "token mask")
+            gtable, gk = self._grad_table(has_cross)
+            logits = None
+            if keep_logits and not self.is_critic:
+                logits = torch.empty((b, n, table.num_tokens), dtype=torch.float32, device=dev)
+            loss = torch.zeros((), dtype=torch.float32, device=dev)
+            nbytes = lib.phk_maskgit_train_workspace_bytes(C.byref(table), b, n, ctx_len, int(logits is not None))
+            ws = self._ws.get(nbytes, dev)
+            pt, ph, pw = (int(v) for v in patch_shape)
+            L.check(lib.phk_maskgit_train_step(C.byref(table), C.byref(gtable), L.ptr(ids_in), L.ptr(targets),
+                                               L.ptr(token_mask), L.ptr(labels), b, n, pt, ph, pw, L.ptr(context),
+                                               ctx_len, L.ptr(text_mask), L.ptr(video_mask), float(loss_scale),
+                                               L.ptr(loss), L.ptr(logits), L.ptr(ws), ws.numel(), L.stream_ptr()),
+                    "phk_maskgit_train_step")
+            gk.finish()
+        return loss, gk, logits
 
     def _prepare(self, x, text_mask, video_patch_shape, context, cond_drop_prob):
         if x.ndim == 4:
@@ -299,6 +371,35 @@ class SelfCritic(nn.Module):
                        video_mask=kwargs.get("video_mask"), cfg_pair=True, return_embeds=True)
         b, n = xx.shape
         return self._head(both[:b], both[b:], cond_scale, b * n).reshape(b, n)
+
+
+class _TrainStepFn(torch.autograd.Function):
+    """Connects phk_maskgit_train_step to torch autograd: forward returns the loss that libphk computed, backward hands
+    the gradients libphk computed in the same call to the parameters (scaled by the upstream gradient), so
+    ``loss.backward()`` followed by any torch optimizer works as with the reference."""
+
+    @staticmethod
+    def forward(ctx, loss, grad_keep, *params):
+        ctx.grads = [grad_keep.grad_of(p) for p in params]
+        return loss.clone()
+
+    @staticmethod
+    def backward(ctx, gout):
+        return (None, None, *[None if g is None else g * gout for g in ctx.grads])
+
+
+def get_mask_subset_with_prob(mask, prob, u=None):
+    """phenaki_pytorch.py:43-55: chooses round(prob * n_valid) (>= 1) positions per row by the RANK of a uniform draw.
+    ``u`` (b, n) injects the draw (tests); boolean plumbing on the device, no arithmetic of the network."""
+    batch, seq_len = mask.shape
+    num_tokens = mask.sum(dim=-1)
+    num_pads = seq_len - num_tokens
+    num_masked = (prob * num_tokens).round().clamp(min=1)
+    if u is None:
+        u = torch.rand((batch, seq_len), device=mask.device)
+    ranks = u.argsort(dim=-1) - num_pads[:, None]
+    ranks = ranks.masked_fill(ranks < 0, seq_len)
+    return ranks < num_masked[:, None]
 
 
 def demask_counts(num_tokens, steps):
@@ -520,9 +621,94 @@ class Phenaki(nn.Module):
                             starting_temperature=starting_temperature, noise_K=noise_K)
         return video.squeeze(2)
 
-    def forward(self, *args, **kwargs):
-        raise NotImplementedError("Phenaki.forward (training loss, phenaki_pytorch.py:562-687) needs backward kernels: "
-                                  "next-tier row 8f-2")
+    def forward(self, videos=None, *, texts: Optional[List[str]] = None, video_codebook_ids=None,
+                video_frame_mask=None, text_embeds=None, cond_drop_prob=None, only_train_generator=False,
+                only_train_critic=False, draw_fn=None):
+        """Training loss (phenaki_pytorch.py:562-687): masked-token cross entropy of MaskGit (+ TokenCritic BCE).
+        The returned scalar is connected to the parameters through ``_TrainStepFn``: ``loss.backward()`` fills
+        ``p.grad`` with the gradients the hand-written backward kernels computed (phk_maskgit_train_step).
+        ``draw_fn(shape, tag)`` (tests) injects the draws 'rand_step' (b,), 'perm' (b, n) and 'gumbel' (b, n, V).
+        fp32 parity mode only; SelfCritic training and the bf16 backward are not built.  The kernels' math is pinned
+        on the CPU (tests/test_train_mirror_cpu.py) but the CUDA path has not been validated on a GPU yet, so the entry
+        is opt-in: set PHK_EXPERIMENTAL=1."""
+        if os.environ.get("PHK_EXPERIMENTAL", "0") != "1":
+            raise NotImplementedError("Phenaki.forward (training step, SURVEY 8f-2) is built but not yet validated on "
+                                      "a GPU: set PHK_EXPERIMENTAL=1 to use it")
+        assert not (only_train_generator and only_train_critic)
+        assert (videos is not None) ^ (video_codebook_ids is not None), "either raw video or codebook ids"
+        assert ((text_embeds is not None) ^ (texts is not None)) ^ self.unconditional, \
+            "either raw text of text embeds must be given, and if unconditional, none should be given"
+        assert not (text_embeds is not None and text_embeds.shape[-1] != self.text_embed_dim), \
+            "text embedding dimension is not correct"
+        if isinstance(self.critic, SelfCritic) and not only_train_generator:
+            raise NotImplementedError("SelfCritic training needs a second backward through MaskGit: not built")
+        mg = self.maskgit
+        dev = next(mg.parameters()).device
+        if video_codebook_ids is None:
+            assert videos.ndim in {4, 5}
+            if videos.ndim == 4:
+                videos = videos.unsqueeze(2)
+            with torch.no_grad():
+                self.cvivit.eval()
+                video_codebook_ids = self.cvivit(videos, return_only_codebook_ids=True)
+        text_mask = None
+        if not self.unconditional:
+            if text_embeds is None:
+                with torch.no_grad():
+                    text_embeds = self.encode_texts(texts, output_device=dev)
+            text_embeds = text_embeds.to(dev)
+            text_mask = torch.any(text_embeds != 0, dim=-1)
+        # the reference overwrites cond_drop_prob with 0 here (:594, SURVEY defects): no text dropout while training
+        video_mask = None
+        if video_frame_mask is not None:
+            video_mask = self.cvivit.calculate_video_token_mask(videos, video_frame_mask=video_frame_mask)
+        patch_shape = tuple(int(v) for v in video_codebook_ids.shape[1:])
+        ids = video_codebook_ids.reshape(video_codebook_ids.shape[0], -1).to(dev)
+        batch, seq = ids.shape
+        draw = draw_fn if draw_fn is not None else (lambda shape, tag: None)
+        rand_step = draw((batch,), "rand_step")
+        if rand_step is None:
+            rand_step = torch.randint(0, self.steps, (batch,), device=dev)
+        mask_token_prob = torch.cos(rand_step.to(dev) * math.pi * 0.5 / self.steps)  # cosine schedule (:615)
+        if video_mask is None:
+            video_mask = torch.ones((batch, seq), device=dev, dtype=torch.bool)
+        u = draw((batch, seq), "perm")
+        mask_token_mask = get_mask_subset_with_prob(video_mask, mask_token_prob, None if u is None else u.to(dev))
+        masked_input = torch.where(mask_token_mask, self.mask_id, ids)
+        need_critic = self.critic is not None and not only_train_generator
+        kw = dict(context=text_embeds, text_mask=text_mask, video_mask=video_mask)
+        loss = None
+        if only_train_critic:
+            with torch.no_grad():
+                logits = mg._run(masked_input, patch_shape, ctx_kv=None if text_embeds is None else mg.context_kv(text_embeds),
+                                 ctx_len=0 if text_embeds is None else text_embeds.shape[1], text_mask=text_mask,
+                                 video_mask=video_mask)
+        else:
+            ce, gk, logits = mg.train_step(masked_input, patch_shape, targets=ids, token_mask=mask_token_mask,
+                                           keep_logits=need_critic, **kw)
+            loss = _TrainStepFn.apply(ce, gk, *mg.parameters())
+        if not need_critic:
+            return loss
+        # sample the predicted masked tokens (:646) and train the critic to tell which ones were changed (:650-675)
+        vocab = logits.shape[-1]
+        gu = draw((batch, seq, vocab), "gumbel")
+        pred = torch.empty((batch, seq), dtype=torch.int64, device=dev)
+        ones = torch.ones((batch, seq), dtype=torch.uint8, device=dev)
+        scratch_ids = torch.empty_like(pred)
+        seed = torch.cuda.default_generators[dev.index if dev.index is not None else torch.cuda.current_device()].initial_seed()
+        offset = self._rng_calls * ((batch * seq * ((vocab + 3) // 4)) + 1)
+        self._rng_calls += 1
+        L.check(L.lib().phk_sample_tokens(L.ptr(logits), None, vocab, L.ptr(None if gu is None else L.require_cuda(
+            gu.to(dev), "gumbel noise", torch.float32)), seed & (2 ** 64 - 1), offset, 1.0,
+            float(self.critic_train_sample_temperature), L.ptr(ones), L.ptr(scratch_ids), L.ptr(pred), None,
+            batch * seq, vocab, 0, 0, 0, L.stream_ptr()), "phk_sample_tokens")
+        critic_input = torch.where(mask_token_mask, pred, ids)
+        labels = (ids != pred).float()
+        weight = 1.0 if only_train_critic else self.critic_loss_weight
+        ckw = kw if self.critic.has_cross_attn else dict(video_mask=video_mask)
+        bce, cgk, _ = self.critic.train_step(critic_input, patch_shape, labels=labels, **ckw)
+        critic_loss = _TrainStepFn.apply(bce, cgk, *self.critic.parameters())
+        return critic_loss * weight if loss is None else loss + critic_loss * weight
 
 
 def make_video(phenaki: Phenaki, texts: List[str], num_frames, prime_lengths):

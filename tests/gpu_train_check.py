@@ -1,0 +1,73 @@
+"""Runs the CUDA training step (Phenaki.forward -> phk_maskgit_train_step) on cuda:0 against the reference's
+autograd loss and gradients stored in tests/golden/train_*.pt and prints one line per case.
+
+Stand-alone on purpose (python tests/gpu_train_check.py [case ...]): tests/test_gpu_train.py runs it in a child
+process, so a fault in the not-yet-validated kernels cannot take the rest of the GPU suite down with it.
+"""
+import os
+import sys
+
+os.environ["PHK_EXPERIMENTAL"] = "1"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+import phenaki_pytorch_b200 as P  # noqa: E402
+from oracle import phenaki_oracle as O  # noqa: E402  (the checker)
+from tests import cases as C  # noqa: E402
+
+
+def check_case(name, verbose=True):
+    case = C.TRAIN_CASES[name]
+    g = torch.load(os.path.join(ROOT, "tests", "golden", f"train_{name}.pt"), weights_only=False)
+    torch.manual_seed(case["seed"])
+    cvivit = P.CViViT(**C.SAMPLE_CVIVIT)
+    maskgit = P.MaskGit(**case["maskgit"])
+    critic = P.TokenCritic(**case["critic"]) if case["critic"] else None
+    assert C.state_digest(maskgit.state_dict()) == g["maskgit_digest"]
+    dev = torch.device("cuda:0")
+    phenaki = P.Phenaki(cvivit=cvivit.to(dev), maskgit=maskgit.to(dev), critic=None if critic is None else critic.to(dev),
+                        steps=case["steps"], text_embed_dim=case["maskgit"]["dim_context"]).train()
+    ids, ctx = C.train_inputs(case)
+    b, n = ids.shape[0], ids[0].numel()
+    vocab = case["maskgit"]["num_tokens"]
+    # the reference's draws, in its order, from the CPU generator it used (tests/golden/make_golden.py::make_train)
+    torch.manual_seed(case["noise_seed"])
+    rand_step, u = O.train_draws(b, n, case["steps"])
+    draws = {"rand_step": rand_step, "perm": u}
+    if critic is not None:
+        draws["gumbel"] = torch.zeros((b, n, vocab)).uniform_(0, 1)
+    loss = phenaki(video_codebook_ids=ids.to(dev), text_embeds=ctx.to(dev), draw_fn=lambda shape, tag: draws[tag])
+    loss.backward()
+    torch.cuda.synchronize()
+    worst = 0.0
+    torch.testing.assert_close(loss.detach().cpu(), g["loss"], rtol=1e-4, atol=1e-5)
+
+    def compare(module, ref_grads, who):
+        nonlocal worst
+        named = dict(module.named_parameters())
+        for k, p in named.items():
+            if k not in ref_grads:
+                assert p.grad is None, f"{who}.{k}: the reference leaves this gradient unset"
+                continue
+            assert p.grad is not None, f"{who}.{k}: no gradient"
+            ref = ref_grads[k]
+            got = p.grad.detach().cpu()
+            scale = max(ref.abs().max().item(), 1e-12)
+            err = (got - ref).abs().max().item() / scale
+            worst = max(worst, err)
+            if verbose:
+                print(f"  {who}.{k:60s} max|ref| {scale:.3e}  max err / max|ref| {err:.2e}")
+            torch.testing.assert_close(got, ref, rtol=2e-3, atol=2e-4 * scale, msg=lambda m, k=k: f"{who}.{k}: {m}")
+
+    compare(phenaki.maskgit, g["maskgit_grads"], "maskgit")
+    if critic is not None:
+        compare(phenaki.critic, g["critic_grads"], "critic")
+    print(f"TRAIN_OK {name} loss {loss.item():.6f} worst relative gradient error {worst:.2e}")
+
+
+if __name__ == "__main__":
+    names = sys.argv[1:] or list(C.TRAIN_CASES)
+    for nm in names:
+        check_case(nm)
