@@ -14,7 +14,15 @@
 // against the reference there.  The tcgen05 (bf16) backward GEMMs are the next step on top of it.
 // STATUS: written after the round's GPU budget was spent -- compiled for sm_100a, math pinned on the CPU, not yet run
 // on a GPU (tests/test_gpu_train.py runs it once PHK_EXPERIMENTAL=1).
+#ifdef PHK_CUDA_EMU  // tests/cuda_emu: the same source compiled by g++ and executed thread by thread on the CPU
+#include "../../tests/cuda_emu/cuda_emu.h"
+#define PHK_KERNEL_LAUNCH(kernel, grid, block, smem, st, ...) ::emu::launch(grid, block, smem, [&]() { kernel(__VA_ARGS__); })
+#define PHK_DYNAMIC_SMEM(type, name) type* name = reinterpret_cast<type*>(::emu::S.dyn_smem)
+#else
 #include "phk_common.cuh"
+#define PHK_KERNEL_LAUNCH(kernel, grid, block, smem, st, ...) kernel<<<grid, block, smem, st>>>(__VA_ARGS__)
+#define PHK_DYNAMIC_SMEM(type, name) extern __shared__ type name[]
+#endif
 #include <cstring>
 #include <new>
 
@@ -94,7 +102,7 @@ int sgemm(const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbk,
   PHK_REQUIRE(M < (1LL << 31) && N < (1LL << 31) && K < (1LL << 31), PHK_E_UNSUPPORTED, "train: GEMM too large");
   dim3 grid((unsigned)((N + GB - 1) / GB), (unsigned)((M + GB - 1) / GB));
   PHK_REQUIRE(grid.y <= 65535, PHK_E_UNSUPPORTED, "train: GEMM M too large");
-  sgemm_strided_kernel<<<grid, 256, 0, st>>>(A, sam, sak, B, sbk, sbn, C, ldc, (int)M, (int)N, (int)K, accumulate);
+  PHK_KERNEL_LAUNCH(sgemm_strided_kernel, dim3(grid), dim3(256), (size_t)(0), st, A, sam, sak, B, sbk, sbn, C, ldc, (int)M, (int)N, (int)K, accumulate);
   PHK_LAUNCH_CHECK();
   return 0;
 }
@@ -122,7 +130,7 @@ int colsum(const float* x, int64_t rows, int cols, int64_t ld, float* out, cudaS
   int chunks = (int)((rows + 63) / 64);
   if (chunks > 64) chunks = 64;
   if (chunks < 1) chunks = 1;
-  colsum_kernel<<<dim3((unsigned)((cols + 255) / 256), (unsigned)chunks), 256, 0, st>>>(x, rows, cols, ld, out);
+  PHK_KERNEL_LAUNCH(colsum_kernel, dim3((unsigned)((cols + 255) / 256), (unsigned)chunks), dim3(256), (size_t)(0), st, x, rows, cols, ld, out);
   PHK_LAUNCH_CHECK();
   return 0;
 }
@@ -188,11 +196,11 @@ __global__ void __launch_bounds__(256) ln_bwd_dgb_kernel(const float* __restrict
 // dx (+)= LN_bwd(x; g)(dy); dgamma += ..; dbeta += .. (dbeta NULL: the custom LayerNorm's beta is a buffer)
 int ln_backward(const float* x, const float* g, const float* dy, float* dx, int accumulate, float* dgamma, float* dbeta,
                 float2* stats, int64_t rows, int dim, cudaStream_t st) {
-  ln_bwd_dx_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, g, dy, dx, stats, rows, dim, accumulate);
+  PHK_KERNEL_LAUNCH(ln_bwd_dx_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), (size_t)(0), st, x, g, dy, dx, stats, rows, dim, accumulate);
   PHK_LAUNCH_CHECK();
   int chunks = (int)((rows + 63) / 64);
   if (chunks > 64) chunks = 64;
-  ln_bwd_dgb_kernel<<<dim3((unsigned)((dim + 255) / 256), (unsigned)chunks), 256, 0, st>>>(x, dy, stats, rows, dim, dgamma,
+  PHK_KERNEL_LAUNCH(ln_bwd_dgb_kernel, dim3((unsigned)((dim + 255) / 256), (unsigned)chunks), dim3(256), (size_t)(0), st, x, dy, stats, rows, dim, dgamma,
                                                                                            dbeta);
   PHK_LAUNCH_CHECK();
   return 0;
@@ -271,7 +279,7 @@ __global__ void __launch_bounds__(128) attn_bwd_probs_kernel(const float* __rest
                                                              const float* __restrict__ bias,
                                                              const uint8_t* __restrict__ key_mask, float* __restrict__ P,
                                                              float* __restrict__ dS, AttnBwdGeom g) {
-  extern __shared__ float srow[];
+  PHK_DYNAMIC_SMEM(float, srow);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int nkt = g.nnull + g.m;
   float* sp = srow + (size_t)wid * 2 * nkt;  // scores -> probabilities
@@ -475,21 +483,21 @@ int attention_backward(const float* q, const float* kv, const phk_attn_t& A, con
   B.P = B.vv + bh * nkt * g.dh;
   B.dS = B.P + bh * g.n * nkt;
   const int64_t prep_warps = bh * (g.n + nkt);
-  attn_bwd_prep_kernel<<<(unsigned)((prep_warps + 7) / 8), 256, 0, st>>>(q, kv, A.null_kv, A.q_scale, A.k_scale, B.qh, B.kh,
+  PHK_KERNEL_LAUNCH(attn_bwd_prep_kernel, dim3((unsigned)((prep_warps + 7) / 8)), dim3(256), (size_t)(0), st, q, kv, A.null_kv, A.q_scale, A.k_scale, B.qh, B.kh,
                                                                         B.vv, g);
   PHK_LAUNCH_CHECK();
   const size_t smem = (size_t)4 * 2 * nkt * sizeof(float);
   PHK_REQUIRE(smem <= 48 * 1024, PHK_E_UNSUPPORTED, "train: more than 1536 keys per sequence");
-  attn_bwd_probs_kernel<<<(unsigned)((bh * g.n + 3) / 4), 128, smem, st>>>(B.qh, B.kh, B.vv, dO, bias, key_mask, B.P, B.dS, g);
+  PHK_KERNEL_LAUNCH(attn_bwd_probs_kernel, dim3((unsigned)((bh * g.n + 3) / 4)), dim3(128), (size_t)(smem), st, B.qh, B.kh, B.vv, dO, bias, key_mask, B.P, B.dS, g);
   PHK_LAUNCH_CHECK();
-  attn_bwd_dq_kernel<<<(unsigned)((bh * g.n + 7) / 8), 256, 0, st>>>(q, B.kh, B.dS, A.q_scale, dq, (float*)G.q_scale, g);
+  PHK_KERNEL_LAUNCH(attn_bwd_dq_kernel, dim3((unsigned)((bh * g.n + 7) / 8)), dim3(256), (size_t)(0), st, q, B.kh, B.dS, A.q_scale, dq, (float*)G.q_scale, g);
   PHK_LAUNCH_CHECK();
-  attn_bwd_dkv_kernel<<<(unsigned)((bh * nkt + 7) / 8), 256, 0, st>>>(kv, A.null_kv, B.qh, dO, B.P, B.dS, A.k_scale, dkv,
+  PHK_KERNEL_LAUNCH(attn_bwd_dkv_kernel, dim3((unsigned)((bh * nkt + 7) / 8)), dim3(256), (size_t)(0), st, kv, A.null_kv, B.qh, dO, B.P, B.dS, A.k_scale, dkv,
                                                                      (float*)G.null_kv, (float*)G.k_scale, g);
   PHK_LAUNCH_CHECK();
   if (dbias) {
     const int64_t total = (int64_t)g.H * g.n * g.m;
-    attn_bwd_dbias_kernel<<<(unsigned)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096), 256, 0, st>>>(B.dS, dbias, g);
+    PHK_KERNEL_LAUNCH(attn_bwd_dbias_kernel, dim3((unsigned)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096)), dim3(256), (size_t)(0), st, B.dS, dbias, g);
     PHK_LAUNCH_CHECK();
   }
   return 0;
@@ -615,30 +623,30 @@ int cpb_backward(const phk_cpb_t& c, const phk_cpb_t& G, const float* dbias, int
   float* da1 = a2 + U * hid;
   float* da2 = da1 + U * hid;
   float* dtable = da2 + U * hid;
-  cpb_inputs_kernel<<<(unsigned)((U + 127) / 128), 128, 0, st>>>(in, nd, d0, d1, d2);
+  PHK_KERNEL_LAUNCH(cpb_inputs_kernel, dim3((unsigned)((U + 127) / 128)), dim3(128), (size_t)(0), st, in, nd, d0, d1, d2);
   PHK_LAUNCH_CHECK();
   // forward activations: a1 = lrelu(in W0^T + b0), a2 = lrelu(a1 W1^T + b1)     (B(k,n) = W[n*K + k])
   PHK_TRY(sgemm(in, nd, 1, c.w0, 1, nd, a1, hid, U, hid, nd, 0, st));
-  bias_lrelu_kernel<<<ew_grid(U * hid), 256, 0, st>>>(a1, c.b0, U, hid);
+  PHK_KERNEL_LAUNCH(bias_lrelu_kernel, dim3(ew_grid(U * hid)), dim3(256), (size_t)(0), st, a1, c.b0, U, hid);
   PHK_LAUNCH_CHECK();
   PHK_TRY(sgemm(a1, hid, 1, c.w1, 1, hid, a2, hid, U, hid, hid, 0, st));
-  bias_lrelu_kernel<<<ew_grid(U * hid), 256, 0, st>>>(a2, c.b1, U, hid);
+  PHK_KERNEL_LAUNCH(bias_lrelu_kernel, dim3(ew_grid(U * hid)), dim3(256), (size_t)(0), st, a2, c.b1, U, hid);
   PHK_LAUNCH_CHECK();
   // dtable[u, h] = sum over the (i, j) pairs with delta u
   PHK_CUDA(cudaMemsetAsync(dtable, 0, U * H * sizeof(float), st));
   const int64_t nn = (int64_t)d0 * d1 * d2 * d0 * d1 * d2;
-  cpb_dtable_kernel<<<ew_grid(nn), 256, 0, st>>>(dbias, dtable, H, d0, d1, d2);
+  PHK_KERNEL_LAUNCH(cpb_dtable_kernel, dim3(ew_grid(nn)), dim3(256), (size_t)(0), st, dbias, dtable, H, d0, d1, d2);
   PHK_LAUNCH_CHECK();
   // last layer: table = a2 W2^T + b2
   PHK_TRY(wgrad(dtable, a2, (float*)G.w2, U, H, hid, st));
   PHK_TRY(colsum(dtable, U, H, H, (float*)G.b2, st));
   PHK_TRY(dgrad(dtable, c.w2, da2, U, H, hid, 0, st));
-  lrelu_bwd_kernel<<<ew_grid(U * hid), 256, 0, st>>>(da2, a2, U * hid);
+  PHK_KERNEL_LAUNCH(lrelu_bwd_kernel, dim3(ew_grid(U * hid)), dim3(256), (size_t)(0), st, da2, a2, U * hid);
   PHK_LAUNCH_CHECK();
   PHK_TRY(wgrad(da2, a1, (float*)G.w1, U, hid, hid, st));
   PHK_TRY(colsum(da2, U, hid, hid, (float*)G.b1, st));
   PHK_TRY(dgrad(da2, c.w1, da1, U, hid, hid, 0, st));
-  lrelu_bwd_kernel<<<ew_grid(U * hid), 256, 0, st>>>(da1, a1, U * hid);
+  PHK_KERNEL_LAUNCH(lrelu_bwd_kernel, dim3(ew_grid(U * hid)), dim3(256), (size_t)(0), st, da1, a1, U * hid);
   PHK_LAUNCH_CHECK();
   PHK_TRY(wgrad(da1, in, (float*)G.w0, U, hid, nd, st));
   PHK_TRY(colsum(da1, U, hid, hid, (float*)G.b0, st));
@@ -902,11 +910,11 @@ extern "C" int phk_maskgit_train_step(const phk_maskgit_t* m, const phk_maskgit_
   if (m->is_critic) {
     float* dscore = ar.f(R);
     PHK_REQUIRE(dscore, PHK_E_WORKSPACE, "maskgit_train_step: workspace too small");
-    bce_rows_kernel<<<(unsigned)((R + 7) / 8), 256, 0, st>>>(emb, m->head_w, m->head_b, labels, loss_scale, row_loss, dscore, R, D);
+    PHK_KERNEL_LAUNCH(bce_rows_kernel, dim3((unsigned)((R + 7) / 8)), dim3(256), (size_t)(0), st, emb, m->head_w, m->head_b, labels, loss_scale, row_loss, dscore, R, D);
     PHK_LAUNCH_CHECK();
     PHK_TRY(wgrad(dscore, emb, (float*)grads->head_w, R, 1, D, st));
     PHK_TRY(colsum(dscore, R, 1, 1, (float*)grads->head_b, st));
-    outer_kernel<<<ew_grid(R * D), 256, 0, st>>>(dscore, m->head_w, dtmp, R, D);
+    PHK_KERNEL_LAUNCH(outer_kernel, dim3(ew_grid(R * D)), dim3(256), (size_t)(0), st, dscore, m->head_w, dtmp, R, D);
     PHK_LAUNCH_CHECK();
   } else {
     float* logits = logits_out ? logits_out : ar.f(R * (int64_t)V);
@@ -918,15 +926,15 @@ extern "C" int phk_maskgit_train_step(const phk_maskgit_t* m, const phk_maskgit_
       PHK_REQUIRE(dl, PHK_E_WORKSPACE, "maskgit_train_step: workspace too small (dlogits)");
       PHK_CUDA(cudaMemcpyAsync(dl, logits, R * (int64_t)V * 4, cudaMemcpyDeviceToDevice, st));
     }
-    mask_count_kernel<<<1, 256, 0, st>>>(token_mask, R, cnt);
+    PHK_KERNEL_LAUNCH(mask_count_kernel, dim3(1), dim3(256), (size_t)(0), st, token_mask, R, cnt);
     PHK_LAUNCH_CHECK();
-    ce_rows_kernel<<<(unsigned)R, 256, 0, st>>>(dl, targets, token_mask, cnt, loss_scale, row_loss, V);
+    PHK_KERNEL_LAUNCH(ce_rows_kernel, dim3((unsigned)R), dim3(256), (size_t)(0), st, dl, targets, token_mask, cnt, loss_scale, row_loss, V);
     PHK_LAUNCH_CHECK();
     PHK_TRY(wgrad(dl, emb, (float*)grads->head_w, R, V, D, st));
     PHK_TRY(colsum(dl, R, V, V, (float*)grads->head_b, st));
     PHK_TRY(dgrad(dl, m->head_w, dtmp, R, V, D, 0, st));
   }
-  loss_reduce_kernel<<<1, 1024, 0, st>>>(row_loss, R, loss_out);
+  PHK_KERNEL_LAUNCH(loss_reduce_kernel, dim3(1), dim3(1024), (size_t)(0), st, row_loss, R, loss_out);
   PHK_LAUNCH_CHECK();
 
   // ---------------------------------------------------------------- backward through the transformer
@@ -958,7 +966,7 @@ extern "C" int phk_maskgit_train_step(const phk_maskgit_t* m, const phk_maskgit_
     // feed forward: x4 = x3 + geglu(LN(x3) W1^T) W2^T
     PHK_TRY(dgrad(dx, Ly.ff.w2, dg, R, D, inner, 0, st));
     PHK_TRY(wgrad(dx, S.g, (float*)Gy.ff.w2, R, D, inner, st));
-    geglu_bwd_kernel<<<ew_grid(R * inner), 256, 0, st>>>(S.h, dg, dh, R, inner);
+    PHK_KERNEL_LAUNCH(geglu_bwd_kernel, dim3(ew_grid(R * inner)), dim3(256), (size_t)(0), st, S.h, dg, dh, R, inner);
     PHK_LAUNCH_CHECK();
     PHK_TRY(wgrad(dh, S.xn3, (float*)Gy.ff.w1, R, 2 * inner, D, st));
     PHK_TRY(dgrad(dh, Ly.ff.w1, dtmp, R, 2 * inner, D, 0, st));
@@ -996,12 +1004,12 @@ extern "C" int phk_maskgit_train_step(const phk_maskgit_t* m, const phk_maskgit_
     }
     // PEG: x1 = x0 + conv(x0) + b
     PHK_TRY(colsum(dx, R, D, D, (float*)Gy.peg.b, st));
-    peg_bwd_kernel<<<(unsigned)R, 128, 0, st>>>(S.x0, Ly.peg.w, dx, dx_alt, (float*)Gy.peg.w, pt, ph, pw, D, Ly.peg.causal ? 2 : 1);
+    PHK_KERNEL_LAUNCH(peg_bwd_kernel, dim3((unsigned)R), dim3(128), (size_t)(0), st, S.x0, Ly.peg.w, dx, dx_alt, (float*)Gy.peg.w, pt, ph, pw, D, Ly.peg.causal ? 2 : 1);
     PHK_LAUNCH_CHECK();
     float* t = dx; dx = dx_alt; dx_alt = t;
   }
   // ---------------------------------------------------------------- embeddings, position-bias MLP
-  embed_bwd_kernel<<<(unsigned)R, 128, 0, st>>>(ids_in, dx, (float*)grads->token_emb, (float*)grads->pos_emb, n, D,
+  PHK_KERNEL_LAUNCH(embed_bwd_kernel, dim3((unsigned)R), dim3(128), (size_t)(0), st, ids_in, dx, (float*)grads->token_emb, (float*)grads->pos_emb, n, D,
                                                m->is_critic ? 1.0f : m->shrink_alpha);
   PHK_LAUNCH_CHECK();
   if (m->has_bias) {

@@ -1,0 +1,108 @@
+// TEST INFRASTRUCTURE: a single-threaded CPU executor for plain (non tensor-core) CUDA kernels, so that the build
+// container -- which has nvcc but no GPU -- can RUN the kernels of csrc/train.cu and check them against the reference
+// gradients before any GPU time is spent (tests/test_train_emulated_cpu.py).
+//
+// Every CUDA thread of a block is a ucontext fiber; blocks run one after another.  __syncthreads() and the warp
+// shuffles are barriers between fibers (round-robin scheduler), so the lock-step semantics the kernels rely on
+// (warp_sum, block_sum, shared-memory staging) are reproduced exactly; atomics are plain read-modify-writes.
+// `__shared__` variables become function-local statics (one block is resident at a time).
+// Only what csrc/train.cu uses is provided.
+#pragma once
+#include <ucontext.h>
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <vector>
+#include "../../include/phk.h"
+
+struct dim3 {
+  unsigned x, y, z;
+  dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
+};
+struct float2 { float x, y; };
+static inline float2 make_float2(float a, float b) { return float2{a, b}; }
+typedef void* cudaStream_t;
+typedef int cudaError_t;
+enum { cudaSuccess = 0, cudaMemcpyDeviceToDevice = 3 };
+
+namespace emu {
+struct Group { int alive = 0, count = 0; unsigned gen = 0; };
+struct State {
+  dim3 t_idx, b_idx, b_dim, g_dim;
+  void* dyn_smem = nullptr;
+};
+extern State S;
+void yield();
+void barrier(Group& g);
+Group& block_group();
+Group& warp_group();
+float* warp_xchg();
+void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body);
+}  // namespace emu
+
+#define threadIdx (::emu::S.t_idx)
+#define blockIdx (::emu::S.b_idx)
+#define blockDim (::emu::S.b_dim)
+#define gridDim (::emu::S.g_dim)
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __restrict__
+#define __launch_bounds__(...)
+#define __shared__ static
+#define PHK_CUDA_EMU_ACTIVE 1
+
+static inline void __syncthreads() { ::emu::barrier(::emu::block_group()); }
+static inline float __shfl_xor_sync(unsigned, float v, int lane_mask) {
+  float* x = ::emu::warp_xchg();
+  const int lane = (int)(threadIdx.x & 31);
+  x[lane] = v;
+  ::emu::barrier(::emu::warp_group());
+  const float r = x[lane ^ lane_mask];
+  ::emu::barrier(::emu::warp_group());
+  return r;
+}
+static inline float atomicAdd(float* p, float v) { const float o = *p; *p = o + v; return o; }
+static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
+template <typename T> static inline T __ldg(const T* p) { return *p; }
+static inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { memset(p, v, n); return 0; }
+static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, int, cudaStream_t) { memmove(d, s, n); return 0; }
+static inline cudaError_t cudaGetLastError() { return 0; }
+
+namespace phk {
+void set_error(const char* msg);
+static inline void count_launch(int = 1) {}
+#define PHK_REQUIRE(cond, code, msg) \
+  do { if (!(cond)) { ::phk::set_error(msg); return (code); } } while (0)
+#define PHK_LAUNCH_CHECK() do { } while (0)
+#define PHK_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return (int)e__; } while (0)
+#define PHK_TRY(call) do { int r__ = (call); if (r__ != 0) return r__; } while (0)
+static inline cudaStream_t to_stream(phk_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+constexpr int kNumSMs = 148;
+
+// same definitions as csrc/phk_common.cuh
+__device__ __forceinline__ float warp_sum(float v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  float t = (lane < nw) ? red[lane] : 0.f;
+  t = warp_sum(t);
+  return t;
+}
+}  // namespace phk

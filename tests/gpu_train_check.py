@@ -54,12 +54,15 @@ def check_case(name, verbose=True):
             assert p.grad is not None, f"{who}.{k}: no gradient"
             ref = ref_grads[k]
             got = p.grad.detach().cpu()
+            if ref.numel() == 0:
+                assert got.shape == ref.shape
+                continue
             scale = max(ref.abs().max().item(), 1e-12)
             err = (got - ref).abs().max().item() / scale
             worst = max(worst, err)
             if verbose:
                 print(f"  {who}.{k:60s} max|ref| {scale:.3e}  max err / max|ref| {err:.2e}")
-            torch.testing.assert_close(got, ref, rtol=2e-3, atol=2e-4 * scale, msg=lambda m, k=k: f"{who}.{k}: {m}")
+            torch.testing.assert_close(got, ref, rtol=2e-3, atol=2e-4 * scale + 1e-7, msg=lambda m, k=k: f"{who}.{k}: {m}")
 
     compare(phenaki.maskgit, g["maskgit_grads"], "maskgit")
     if critic is not None:
