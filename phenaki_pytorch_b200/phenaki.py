@@ -17,6 +17,7 @@ import torch
 from torch import nn
 
 from . import _lib as L
+from . import sharding
 from .cvivit import CViViT
 import os
 
@@ -379,13 +380,17 @@ class _TrainStepFn(torch.autograd.Function):
     ``loss.backward()`` followed by any torch optimizer works as with the reference."""
 
     @staticmethod
-    def forward(ctx, loss, grad_keep, *params):
+    def forward(ctx, loss, grad_keep, sync, *params):
+        ctx.keep, ctx.sync = grad_keep, sync
         ctx.grads = [grad_keep.grad_of(p) for p in params]
         return loss.clone()
 
     @staticmethod
     def backward(ctx, gout):
-        return (None, None, *[None if g is None else g * gout for g in ctx.grads])
+        if ctx.sync:  # data parallel: average the one flat gradient bucket over the ranks (DDP's all-reduce)
+            sharding.all_reduce_mean_(ctx.keep.flat)
+            ctx.sync = False
+        return (None, None, None, *[None if g is None else g * gout for g in ctx.grads])
 
 
 def get_mask_subset_with_prob(mask, prob, u=None):
@@ -467,6 +472,9 @@ class Phenaki(nn.Module):
         assert cond_drop_prob > 0.0
         self.cond_drop_prob = cond_drop_prob
         self._rng_calls = 0
+        # training under torch.distributed: average the gradient bucket over the ranks in backward() (what the
+        # reference gets from Accelerate's DDP wrapper, phenaki_trainer.py); no-op without a process group
+        self.sync_gradients = True
         self.fused_head = True  # bf16 mode: logits head + CFG + gumbel argmax fused into one GEMM (no (b,n,V) logits)
 
     # ---- the demasking loop (phenaki_pytorch.py:473-550) -------------------------------------------------
@@ -686,7 +694,7 @@ class Phenaki(nn.Module):
         else:
             ce, gk, logits = mg.train_step(masked_input, patch_shape, targets=ids, token_mask=mask_token_mask,
                                            keep_logits=need_critic, **kw)
-            loss = _TrainStepFn.apply(ce, gk, *mg.parameters())
+            loss = _TrainStepFn.apply(ce, gk, self.sync_gradients, *mg.parameters())
         if not need_critic:
             return loss
         # sample the predicted masked tokens (:646) and train the critic to tell which ones were changed (:650-675)
@@ -707,7 +715,7 @@ class Phenaki(nn.Module):
         weight = 1.0 if only_train_critic else self.critic_loss_weight
         ckw = kw if self.critic.has_cross_attn else dict(video_mask=video_mask)
         bce, cgk, _ = self.critic.train_step(critic_input, patch_shape, labels=labels, **ckw)
-        critic_loss = _TrainStepFn.apply(bce, cgk, *self.critic.parameters())
+        critic_loss = _TrainStepFn.apply(bce, cgk, self.sync_gradients, *self.critic.parameters())
         return critic_loss * weight if loss is None else loss + critic_loss * weight
 
 

@@ -2,7 +2,12 @@
 sample (demasking loop), so ranks take contiguous batch shards, weights are replicated and the data path has no
 collective.  The only exchanges are off the timed path: an optional gather of the ids to rank 0 and the max-over-ranks
 reduction of the measured time.  Works over any ``torch.distributed`` backend (nccl on the GPU box, gloo in the CPU
-tests)."""
+tests).
+
+Training adds the one collective the reference implies (DDP's gradient all-reduce in
+PhenakiTrainer): the training step writes every gradient of a network into ONE flat fp32 bucket
+(modules.GradKeep.flat), so the exchange is a single all-reduce over that buffer -- no bucket packing copy.
+"""
 import torch
 import torch.distributed as dist
 
@@ -65,3 +70,14 @@ def rank_seed(seed, rank=None):
     single-process run, whose one global generator would interleave all samples)."""
     r, _ = world()
     return int(seed) + (r if rank is None else rank)
+
+
+def all_reduce_mean_(flat, group=None):
+    """In-place mean over ranks of a flat gradient bucket (what DistributedDataParallel does to every bucket); a
+    no-op without a process group.  NCCL over NVLink on the GPU box, gloo in the CPU tests."""
+    _, w = world()
+    if w == 1:
+        return flat
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat.div_(w)
+    return flat

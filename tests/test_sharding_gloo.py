@@ -90,3 +90,61 @@ def test_bench_reference_arm_under_torchrun_prints_one_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "cvivit_encode_frames_per_s" and d["n_gpus"] == 2
     assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def _train_worker(rank, world_size, port, out):
+    """Data-parallel training step on two gloo ranks: each rank runs the (emulated, CPU-executed) CUDA training step on
+    its contiguous batch shard; backward() all-reduces the flat gradient bucket."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), PHK_EXPERIMENTAL="1")
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
+    try:
+        torch.set_num_threads(2)
+        import phenaki_pytorch_b200 as P
+        from oracle import phenaki_oracle as O
+        from tests import emu_runtime
+        emu_runtime.route_product_to_emulator(emu_runtime.build_emu())
+        case = C.TRAIN_CASES["with_critic"]
+        torch.manual_seed(case["seed"])
+        cvivit, maskgit = P.CViViT(**C.SAMPLE_CVIVIT), P.MaskGit(**case["maskgit"])       # replicated weights
+        phenaki = P.Phenaki(cvivit=cvivit, maskgit=maskgit, steps=case["steps"],
+                            text_embed_dim=case["maskgit"]["dim_context"]).train()
+        ids, ctx = C.train_inputs(case)
+        b, n = ids.shape[0], ids[0].numel()
+        torch.manual_seed(case["noise_seed"])
+        rand_step, u = O.train_draws(b, n, case["steps"])
+        lo, hi = S.shard_range(b, rank, world_size)
+        draws = {"rand_step": rand_step[lo:hi], "perm": u[lo:hi]}
+        loss = phenaki(video_codebook_ids=S.shard_batch(ids), text_embeds=S.shard_batch(ctx),
+                       draw_fn=lambda shape, tag: draws[tag])
+        loss.backward()
+        if rank == 0:
+            # reference: DDP semantics = mean over ranks of each rank's own gradient (autograd through the oracle)
+            ref = None
+            for r in range(world_size):
+                a, z = S.shard_range(b, r, world_size)
+                sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v)
+                      for k, v in maskgit.state_dict().items()}
+                tm = O.train_token_mask(rand_step[a:z], u[a:z], case["steps"])
+                O.maskgit_train_loss(ids[a:z].reshape(z - a, n), sd, tm, video_patch_shape=case["patch_shape"],
+                                     heads=case["maskgit"]["heads"], context=ctx[a:z],
+                                     text_mask=torch.any(ctx[a:z] != 0, dim=-1)).backward()
+                g = {k: v.grad for k, v in sd.items() if v.is_floating_point() and v.grad is not None}
+                ref = g if ref is None else {k: ref[k] + g[k] for k in g}
+            ref = {k: v / world_size for k, v in ref.items()}
+            got = {k: p.grad for k, p in maskgit.named_parameters() if p.grad is not None}
+            torch.save(dict(ref=ref, got=got), out)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_training_step_averages_the_gradient_bucket(tmp_path):
+    out = str(tmp_path / "train.pt")
+    mp.spawn(_train_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    r = torch.load(out)
+    assert set(r["got"]) <= set(r["ref"]) and len(r["got"]) > 40  # the oracle also differentiates the beta buffers
+    for k in r["got"]:
+        ref = r["ref"][k]
+        if ref.numel() == 0:
+            continue
+        scale = max(ref.abs().max().item(), 1e-12)
+        torch.testing.assert_close(r["got"][k], ref, rtol=1e-3, atol=1e-4 * scale + 1e-7, msg=lambda m, k=k: f"{k}: {m}")

@@ -4,55 +4,24 @@ Python path (MaskGit.train_step -> ctypes tables -> phk_maskgit_train_step), aga
 gradients (tests/golden/train_*.pt).  The forward building blocks the driver calls are CPU statements of the
 include/phk.h contracts here (their CUDA versions are covered by the -m gpu suite); everything else -- the driver's
 buffer wiring, the gradient table, every backward kernel's indexing and synchronisation -- is the shipped code."""
-import contextlib
-import ctypes
-import os
-import subprocess
-
 import pytest
 import torch
 
 import phenaki_pytorch_b200 as P
-from phenaki_pytorch_b200 import _lib as L
-from phenaki_pytorch_b200 import modules as M
 from tests import cases as C
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-EMU_DIR = os.path.join(ROOT, "tests", "cuda_emu")
-EMU_LIB = os.path.join(EMU_DIR, "_build", "libphk_train_emu.so")
-SOURCES = [os.path.join(ROOT, "phenaki_pytorch_b200", "csrc", "train.cu"), os.path.join(EMU_DIR, "cuda_emu.cpp")]
+from tests import emu_runtime
 
 
 @pytest.fixture(scope="module")
 def emu():
-    deps = SOURCES + [os.path.join(EMU_DIR, "cuda_emu.h"), os.path.join(ROOT, "include", "phk.h")]
-    if not os.path.exists(EMU_LIB) or any(os.path.getmtime(d) > os.path.getmtime(EMU_LIB) for d in deps):
-        os.makedirs(os.path.dirname(EMU_LIB), exist_ok=True)
-        subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-DPHK_CUDA_EMU", "-x", "c++", *SOURCES,
-                               "-o", EMU_LIB])
-    lib = ctypes.CDLL(EMU_LIB)
-    for name in ("phk_maskgit_train_workspace_bytes", "phk_maskgit_train_step"):
-        fn = getattr(lib, name)
-        fn.argtypes = L.PROTOTYPES[name]
-        fn.restype = L._RESTYPES.get(name, ctypes.c_int)
-    lib.phk_last_error.restype = ctypes.c_char_p
-    return lib
+    return emu_runtime.build_emu()
 
 
 @pytest.fixture
 def on_cpu(emu, monkeypatch):
     """Routes the product's host path to the emulated library with CPU tensors (test only)."""
-    monkeypatch.setattr(L, "lib", lambda: emu)
-    monkeypatch.setattr(L, "require_cuda", lambda t, name, dtype=None: t.contiguous())
-    monkeypatch.setattr(L, "stream_ptr", lambda: None)
-    monkeypatch.setattr(torch.cuda, "device", lambda dev: contextlib.nullcontext())
-
-    def keep_t(self, tensor):
-        tensor = tensor.detach().float().contiguous()
-        self.refs.append(tensor)
-        return tensor.data_ptr()
-
-    monkeypatch.setattr(M.Keep, "t", keep_t)
+    emu_runtime.route_product_to_emulator(emu, monkeypatch)
 
 
 def _modules(case):
