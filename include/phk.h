@@ -414,8 +414,10 @@ int phk_maskgit_sample_step(const phk_maskgit_t* m, const int64_t* ids_in, int32
 /* Training step: Phenaki.forward (phenaki_pytorch.py:562-687)                   */
 /* ------------------------------------------------------------------------------------------ */
 
-/* One forward + loss + backward of MaskGit (masked cross entropy, :620-640) or TokenCritic (BCE with logits,
+/* One forward + loss + backward of MaskGit (masked cross entropy, :620-640) or of a critic (BCE with logits,
  * :652-675) in fp32: what `loss = phenaki(...); loss.backward()` computes for that network under torch autograd.
+ * The head follows the arguments: `labels` given -> head_w [1, dim], head_b [1] + BCE (a TokenCritic table, or a
+ * MaskGit table whose head members point at SelfCritic.to_pred, :307-336); otherwise to_logits + cross entropy.
  *   ids_in  (b,n) int64   network input: ids with the mask id at the masked positions (MaskGit) or with the sampled
  *                         predictions at the masked positions (critic)
  *   targets (b,n) int64 + token_mask (b,n) uint8   MaskGit: loss = mean over masked rows of CE(logits, target)
@@ -430,7 +432,7 @@ int phk_maskgit_sample_step(const phk_maskgit_t* m, const int64_t* ids_in, int32
  * The gradient-shrink trick (:199) scales the embedding gradients by shrink_alpha, as autograd does.  cond_drop_prob is
  * 0 in the reference's training forward (:594 overwrites the argument), so there is no text dropout.
  * STATUS: parity (fp32 FFMA) path; bf16 tcgen05 backward GEMMs are not built yet. */
-int64_t phk_maskgit_train_workspace_bytes(const phk_maskgit_t* m, int32_t b, int32_t n, int32_t L, int32_t keep_logits);
+int64_t phk_maskgit_train_workspace_bytes(const phk_maskgit_t* m, int32_t b, int32_t n, int32_t L, int32_t bce_head);
 int phk_maskgit_train_step(const phk_maskgit_t* m, const phk_maskgit_t* grads, const int64_t* ids_in,
                            const int64_t* targets, const uint8_t* token_mask, const float* labels, int32_t b, int32_t n,
                            int32_t pt, int32_t ph, int32_t pw, const float* context, int32_t L,

@@ -491,3 +491,17 @@ def critic_train_loss(ids, pred_ids, token_mask, critic_sd, *, video_patch_shape
                             context=context, text_mask=text_mask, video_mask=video_mask, p=p)
     labels = (ids != pred_ids).float()
     return F.binary_cross_entropy_with_logits(scores, labels)
+
+
+def self_critic_train_loss(ids, pred_ids, token_mask, maskgit_sd, to_pred_w, to_pred_b, *, video_patch_shape, heads=8,
+                           context=None, text_mask=None, video_mask=None):
+    """Same with a SelfCritic (phenaki_pytorch.py:307-336): Linear(dim, 1) on the MaskGit embeddings
+    (``return_embeds=True``), so this loss also differentiates MaskGit."""
+    b, n = ids.shape
+    if video_mask is None:
+        video_mask = torch.ones((b, n), dtype=torch.bool)
+    critic_input = torch.where(token_mask, pred_ids, ids)
+    emb = maskgit_forward(critic_input, maskgit_sd, video_patch_shape=video_patch_shape, heads=heads, context=context,
+                          text_mask=text_mask, video_mask=video_mask, return_embeds=True)
+    scores = F.linear(emb, to_pred_w, to_pred_b).squeeze(-1)
+    return F.binary_cross_entropy_with_logits(scores, (ids != pred_ids).float())

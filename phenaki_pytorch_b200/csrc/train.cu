@@ -769,7 +769,7 @@ int64_t layer_save_floats(const phk_transformer_t* T, const phk_layer_t& L, int6
 using namespace phk;
 
 extern "C" int64_t phk_maskgit_train_workspace_bytes(const phk_maskgit_t* m, int32_t b, int32_t n, int32_t L,
-                                                     int32_t keep_logits) {
+                                                     int32_t bce_head) {
   if (!m || b <= 0 || n <= 0 || L < 0 || !m->transformer.layers) return -1;
   const phk_transformer_t* T = &m->transformer;
   const int64_t R = (int64_t)b * n, CR = (int64_t)b * L, D = m->dim, I = (int64_t)T->heads * T->dim_head;
@@ -780,8 +780,7 @@ extern "C" int64_t phk_maskgit_train_workspace_bytes(const phk_maskgit_t* m, int
     if (T->layers[l].has_cross && T->layers[l].cross_attn.dim_context > dc) dc = T->layers[l].cross_attn.dim_context;
   }
   f += R * D * 2;                                            // x (embedding output), final embeddings
-  f += m->is_critic ? 3 * R : R * (int64_t)m->num_tokens + 2 * R;  // (d)logits in place or the differentiated copy; row losses
-  (void)keep_logits;
+  f += bce_head ? 3 * R : R * (int64_t)m->num_tokens + 2 * R;  // (d)logits in place or the differentiated copy; row losses
   f += R * (D * 3 + I * 4 + 3 * inner) + CR * (2 * I + dc);  // dxa dxb dtmp | dq dkv(2) do | dh(2) dg | dckv dctxn
   f += 2 * (R > CR ? R : CR);                                // LayerNorm statistics
   const int64_t a1 = attn_bwd_scratch_floats(b, T->heads, n, n, T->dim_head);
@@ -808,10 +807,15 @@ extern "C" int phk_maskgit_train_step(const phk_maskgit_t* m, const phk_maskgit_
   PHK_REQUIRE(b > 0 && n > 0 && (int64_t)pt * ph * pw == n, PHK_E_SHAPE, "video patch shape must cover the token sequence");
   PHK_REQUIRE(n <= m->max_seq_len, PHK_E_SHAPE,
               "the video token sequence length is greater than max_seq_len (phenaki_pytorch.py:196)");
-  PHK_REQUIRE(m->is_critic ? labels != nullptr : (targets && token_mask), PHK_E_ARG,
-              "maskgit_train_step: a MaskGit needs targets + token_mask, a critic needs labels");
+  // head: labels given -> Linear(dim, 1) + BCE with logits (TokenCritic, or SelfCritic.to_pred on a MaskGit body,
+  // phenaki_pytorch.py:307-336); otherwise to_logits + masked cross entropy
+  const bool bce = labels != nullptr;
+  PHK_REQUIRE(bce || (targets && token_mask), PHK_E_ARG,
+              "maskgit_train_step: pass labels (critic head) or targets + token_mask (MaskGit head)");
+  PHK_REQUIRE(bce || !m->is_critic, PHK_E_ARG, "maskgit_train_step: a TokenCritic table needs labels");
+  PHK_REQUIRE(!(bce && logits_out), PHK_E_ARG, "maskgit_train_step: the critic head has no logits to hand back");
   PHK_REQUIRE(!context || (text_mask && L > 0), PHK_E_ARG, "maskgit_train_step: context without text mask / length");
-  PHK_REQUIRE(workspace_bytes >= phk_maskgit_train_workspace_bytes(m, b, n, L, logits_out ? 1 : 0), PHK_E_WORKSPACE,
+  PHK_REQUIRE(workspace_bytes >= phk_maskgit_train_workspace_bytes(m, b, n, L, bce ? 1 : 0), PHK_E_WORKSPACE,
               "maskgit_train_step: workspace too small");
   const phk_transformer_t* T = &m->transformer;
   const phk_transformer_t* GT = &grads->transformer;
@@ -907,7 +911,7 @@ extern "C" int phk_maskgit_train_step(const phk_maskgit_t* m, const phk_maskgit_
   float* cnt = ar.f(64);
   float2* stats = reinterpret_cast<float2*>(ar.f(2 * (R > CR ? R : CR)));
   PHK_REQUIRE(dxa && dxb && dtmp && row_loss && cnt && stats, PHK_E_WORKSPACE, "maskgit_train_step: workspace too small (bwd)");
-  if (m->is_critic) {
+  if (bce) {
     float* dscore = ar.f(R);
     PHK_REQUIRE(dscore, PHK_E_WORKSPACE, "maskgit_train_step: workspace too small");
     PHK_KERNEL_LAUNCH(bce_rows_kernel, dim3((unsigned)((R + 7) / 8)), dim3(256), (size_t)(0), st, emb, m->head_w, m->head_b, labels, loss_scale, row_loss, dscore, R, D);

@@ -155,10 +155,11 @@ class _TokenTransformer(nn.Module):
                                                 L.ptr(scores), L.ptr(ws), ws.numel(), L.stream_ptr()),
                     "phk_maskgit_sample_step")
 
-    def _grad_table(self, with_cross):
-        """Zero-filled gradient buffers (one flat fp32 bucket, parameters() order) and the phk_maskgit_t-shaped table
-        that addresses them; same member-by-member layout as ``_table``."""
-        gk = GradKeep(self.parameters())
+    def _grad_table(self, with_cross, owner=None, head=None):
+        """Zero-filled gradient buffers (one flat fp32 bucket in ``owner.parameters()`` order) and the
+        phk_maskgit_t-shaped table that addresses them; same member-by-member layout as ``_table``.
+        ``head``: an nn.Linear(dim, 1) that replaces the network's own head (SelfCritic.to_pred)."""
+        gk = GradKeep((owner if owner is not None else self).parameters())
         t = L.MaskgitT()
         tf = self.transformer
         t.dim, t.heads, t.dim_head = tf.dim, tf.heads, tf.dim_head
@@ -168,6 +169,9 @@ class _TokenTransformer(nn.Module):
         t.token_emb, t.pos_emb = gk.g(self.token_emb.weight), gk.g(self.pos_emb.weight)
         if not self.is_critic:
             t.pos_bias = cpb_grad_table(self.continuous_pos_bias, gk)
+        if head is not None:
+            t.head_w, t.head_b = gk.g(head.weight), gk.g(head.bias)
+        elif not self.is_critic:
             t.head_w, t.head_b = gk.g(self.to_logits.weight), gk.g(self.to_logits.bias)
         else:
             t.head_w, t.head_b = gk.g(self.to_logits[0].weight), gk.g(self.to_logits[0].bias)
@@ -175,13 +179,16 @@ class _TokenTransformer(nn.Module):
         return t, gk
 
     def train_step(self, ids_in, patch_shape, *, targets=None, token_mask=None, labels=None, context=None,
-                   text_mask=None, video_mask=None, loss_scale=1.0, keep_logits=False):
+                   text_mask=None, video_mask=None, loss_scale=1.0, keep_logits=False, head=None, owner=None):
         """One forward + loss + backward in libphk (phk_maskgit_train_step, fp32): returns (loss 0-d tensor,
-        GradKeep with d(loss_scale * loss)/d(parameter), logits or None).  MaskGit: masked cross entropy against
-        ``targets`` at ``token_mask``; TokenCritic: BCE with logits against ``labels``."""
+        GradKeep with d(loss_scale * loss)/d(parameter), logits or None).  ``labels`` given: Linear(dim, 1) head + BCE
+        with logits (TokenCritic; or ``head`` = SelfCritic.to_pred on this MaskGit, gradients laid out for
+        ``owner.parameters()``); otherwise masked cross entropy against ``targets`` at ``token_mask``."""
         lib = L.lib()
         if self.precision != L.PREC_F32:
             raise L.PhkError("the training step is built for the fp32 parity mode only (bf16 backward GEMMs: next step)")
+        bce = labels is not None
+        assert bce or not self.is_critic, "a TokenCritic trains against labels"
         ids_in = L.require_cuda(ids_in, "token ids", torch.int64)
         b, n = ids_in.shape
         assert _prod(patch_shape) == n, "video patch shape must cover the token sequence"
@@ -190,6 +197,10 @@ class _TokenTransformer(nn.Module):
             table = self._table()
             assert n <= table.max_seq_len, \
                 f"the video token sequence length you are passing in ({n}) is greater than the `max_seq_len` ({table.max_seq_len})"
+            keep = Keep()
+            if head is not None:  # same body, another head: a shallow copy of the table with the head members swapped
+                table = L.MaskgitT.from_buffer_copy(table)
+                table.head_w, table.head_b, table.head_w_h = keep.t(head.weight), keep.t(head.bias), None
             has_cross = context is not None and self.transformer.layers[0][2] is not None
             ctx_len = 0
             if has_cross:
@@ -204,17 +215,18 @@ class _TokenTransformer(nn.Module):
                 context = text_mask = None
             if video_mask is not None:
                 video_mask = L.require_cuda(video_mask.to(torch.uint8), "video mask")
-            if self.is_critic:
+            if bce:
                 labels = L.require_cuda(labels.reshape(b, n).float(), "critic labels", torch.float32)
+                targets = token_mask = None
             else:
                 targets = L.require_cuda(targets.reshape(b, n), "target ids", torch.int64)
                 token_mask = L.require_cuda(token_mask.reshape(b, n).to(torch.uint8), "token mask")
-            gtable, gk = self._grad_table(has_cross)
+            gtable, gk = self._grad_table(has_cross, owner=owner, head=head)
             logits = None
-            if keep_logits and not self.is_critic:
+            if keep_logits and not bce:
                 logits = torch.empty((b, n, table.num_tokens), dtype=torch.float32, device=dev)
             loss = torch.zeros((), dtype=torch.float32, device=dev)
-            nbytes = lib.phk_maskgit_train_workspace_bytes(C.byref(table), b, n, ctx_len, int(logits is not None))
+            nbytes = lib.phk_maskgit_train_workspace_bytes(C.byref(table), b, n, ctx_len, int(bce))
             ws = self._ws.get(nbytes, dev)
             pt, ph, pw = (int(v) for v in patch_shape)
             L.check(lib.phk_maskgit_train_step(C.byref(table), C.byref(gtable), L.ptr(ids_in), L.ptr(targets),
@@ -361,6 +373,11 @@ class SelfCritic(nn.Module):
         emb = self.maskgit(x, *args, return_embeds=True, **kwargs)
         b, n = emb.shape[:2]
         return self._head(emb, None, 1.0, b * n).reshape(b, n)
+
+    def train_step(self, ids_in, patch_shape, *, labels, **kw):
+        """BCE training step of the self critic: the MaskGit body with ``to_pred`` as its head; the gradient bucket
+        follows ``self.parameters()`` (MaskGit's parameters, then to_pred)."""
+        return self.maskgit.train_step(ids_in, patch_shape, labels=labels, head=self.to_pred[0], owner=self, **kw)
 
     def forward_with_cond_scale(self, x, *, cond_scale=3, **kwargs):
         if cond_scale == 1:
@@ -636,7 +653,7 @@ class Phenaki(nn.Module):
         The returned scalar is connected to the parameters through ``_TrainStepFn``: ``loss.backward()`` fills
         ``p.grad`` with the gradients the hand-written backward kernels computed (phk_maskgit_train_step).
         ``draw_fn(shape, tag)`` (tests) injects the draws 'rand_step' (b,), 'perm' (b, n) and 'gumbel' (b, n, V).
-        fp32 parity mode only; SelfCritic training and the bf16 backward are not built.  The kernels' math is pinned
+        fp32 parity mode only (the bf16 backward is not built).  The kernels' math is pinned
         on the CPU (tests/test_train_mirror_cpu.py) but the CUDA path has not been validated on a GPU yet, so the entry
         is opt-in: set PHK_EXPERIMENTAL=1."""
         if os.environ.get("PHK_EXPERIMENTAL", "0") != "1":
@@ -648,8 +665,6 @@ class Phenaki(nn.Module):
             "either raw text of text embeds must be given, and if unconditional, none should be given"
         assert not (text_embeds is not None and text_embeds.shape[-1] != self.text_embed_dim), \
             "text embedding dimension is not correct"
-        if isinstance(self.critic, SelfCritic) and not only_train_generator:
-            raise NotImplementedError("SelfCritic training needs a second backward through MaskGit: not built")
         mg = self.maskgit
         dev = next(mg.parameters()).device
         if video_codebook_ids is None:
@@ -714,6 +729,7 @@ class Phenaki(nn.Module):
         labels = (ids != pred).float()
         weight = 1.0 if only_train_critic else self.critic_loss_weight
         ckw = kw if self.critic.has_cross_attn else dict(video_mask=video_mask)
+        # (a SelfCritic differentiates MaskGit a second time: autograd adds the two contributions to p.grad)
         bce, cgk, _ = self.critic.train_step(critic_input, patch_shape, labels=labels, **ckw)
         critic_loss = _TrainStepFn.apply(bce, cgk, self.sync_gradients, *self.critic.parameters())
         return critic_loss * weight if loss is None else loss + critic_loss * weight

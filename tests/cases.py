@@ -145,6 +145,9 @@ TRAIN_CASES = {
     "with_critic": dict(  # + TokenCritic: gumbel-sampled predictions -> BCE, loss = ce + critic_loss_weight * bce
         seed=63, steps=6, maskgit=SAMPLE_MASKGIT, critic=SAMPLE_CRITIC, batch=3, patch_shape=(3, 2, 3),
         ctx_len=6, ctx_valid=(6, 1, 4), input_seed=64, noise_seed=65),
+    "self_critic": dict(  # self_token_critic=True: Linear(dim,1) on the MaskGit embeddings, both losses reach MaskGit
+        seed=66, steps=8, maskgit=SAMPLE_MASKGIT, critic=None, self_critic=True, batch=2, patch_shape=(3, 2, 3),
+        ctx_len=5, ctx_valid=(3, 5), input_seed=67, noise_seed=68),
 }
 
 

@@ -277,7 +277,9 @@ def make_train(ref):
         cvivit = ref.CViViT(**C.SAMPLE_CVIVIT)
         maskgit = ref.MaskGit(**case["maskgit"])
         critic = ref.TokenCritic(**case["critic"]) if case["critic"] else None
+        self_critic = case.get("self_critic", False)
         phenaki = ref.Phenaki(cvivit=cvivit, maskgit=maskgit, critic=critic, steps=case["steps"],
+                              self_token_critic=self_critic,
                               text_embed_dim=case["maskgit"]["dim_context"]).train()
         ids, ctx = C.train_inputs(case)
         heads = case["maskgit"].get("heads", 8)
@@ -313,7 +315,20 @@ def make_train(ref):
             gold.update(critic_digest=C.state_digest(cr_sd), pred_ids=pred, ce=o_loss.detach().clone(),
                         bce=bce.detach().clone())
             o_loss = o_loss + bce * phenaki.critic_loss_weight
+        if self_critic:
+            lin = phenaki.critic.to_pred[0]
+            o_w, o_b = lin.weight.detach().clone().requires_grad_(True), lin.bias.detach().clone().requires_grad_(True)
+            gu = torch.zeros_like(logits).uniform_(0, 1)
+            pred = O.gumbel_sample(logits.detach(), phenaki.critic_train_sample_temperature, gu)
+            bce = O.self_critic_train_loss(flat, pred, token_mask, o_mg, o_w, o_b, **kw)
+            gold.update(pred_ids=pred, ce=o_loss.detach().clone(), bce=bce.detach().clone(),
+                        to_pred_weight=lin.weight.detach().clone(), to_pred_bias=lin.bias.detach().clone(),
+                        to_pred_grads=dict(weight=lin.weight.grad.detach().clone(), bias=lin.bias.grad.detach().clone()))
+            o_loss = o_loss + bce * phenaki.critic_loss_weight
         o_loss.backward()
+        if self_critic:
+            same(o_w.grad, lin.weight.grad, "d loss / d to_pred.weight")
+            same(o_b.grad, lin.bias.grad, "d loss / d to_pred.bias")
         same(o_loss.detach(), loss.detach(), "training loss")
         for k, g in mg_grads.items():
             same(o_mg[k].grad, g, f"d loss / d maskgit.{k}")

@@ -27,8 +27,9 @@ def check_case(name, verbose=True):
     critic = P.TokenCritic(**case["critic"]) if case["critic"] else None
     assert C.state_digest(maskgit.state_dict()) == g["maskgit_digest"]
     dev = torch.device("cuda:0")
-    phenaki = P.Phenaki(cvivit=cvivit.to(dev), maskgit=maskgit.to(dev), critic=None if critic is None else critic.to(dev),
-                        steps=case["steps"], text_embed_dim=case["maskgit"]["dim_context"]).train()
+    phenaki = P.Phenaki(cvivit=cvivit, maskgit=maskgit, critic=critic, steps=case["steps"],
+                        self_token_critic=case.get("self_critic", False),
+                        text_embed_dim=case["maskgit"]["dim_context"]).to(dev).train()
     ids, ctx = C.train_inputs(case)
     b, n = ids.shape[0], ids[0].numel()
     vocab = case["maskgit"]["num_tokens"]
@@ -36,7 +37,7 @@ def check_case(name, verbose=True):
     torch.manual_seed(case["noise_seed"])
     rand_step, u = O.train_draws(b, n, case["steps"])
     draws = {"rand_step": rand_step, "perm": u}
-    if critic is not None:
+    if phenaki.critic is not None:
         draws["gumbel"] = torch.zeros((b, n, vocab)).uniform_(0, 1)
     loss = phenaki(video_codebook_ids=ids.to(dev), text_embeds=ctx.to(dev), draw_fn=lambda shape, tag: draws[tag])
     loss.backward()
@@ -67,6 +68,8 @@ def check_case(name, verbose=True):
     compare(phenaki.maskgit, g["maskgit_grads"], "maskgit")
     if critic is not None:
         compare(phenaki.critic, g["critic_grads"], "critic")
+    if case.get("self_critic"):
+        compare(phenaki.critic.to_pred[0], g["to_pred_grads"], "to_pred")
     print(f"TRAIN_OK {name} loss {loss.item():.6f} worst relative gradient error {worst:.2e}")
 
 

@@ -231,8 +231,16 @@ def test_oracle_training_loss_and_gradients_match_reference_golden(golden, name)
         pred = O.gumbel_sample(logits.detach(), 1.0, torch.zeros_like(logits).uniform_(0, 1))
         assert torch.equal(pred, g["pred_ids"])
         loss = loss + O.critic_train_loss(ids.reshape(b, n), pred, token_mask, o_cr, **kw) * 1.0
+    if case.get("self_critic"):
+        w, bb = g["to_pred_weight"].clone().requires_grad_(True), g["to_pred_bias"].clone().requires_grad_(True)
+        pred = O.gumbel_sample(logits.detach(), 1.0, torch.zeros_like(logits).uniform_(0, 1))
+        assert torch.equal(pred, g["pred_ids"])
+        loss = loss + O.self_critic_train_loss(ids.reshape(b, n), pred, token_mask, o_mg, w, bb, **kw)
     loss.backward()
     torch.testing.assert_close(loss.detach(), g["loss"], **FTOL)
+    if case.get("self_critic"):
+        torch.testing.assert_close(w.grad, g["to_pred_grads"]["weight"], rtol=1e-4, atol=1e-6)
+        torch.testing.assert_close(bb.grad, g["to_pred_grads"]["bias"], rtol=1e-4, atol=1e-6)
     for k, ref in g["maskgit_grads"].items():
         torch.testing.assert_close(o_mg[k].grad, ref, rtol=1e-4, atol=1e-6, msg=lambda m, k=k: f"maskgit.{k}: {m}")
     if critic is not None:

@@ -26,9 +26,12 @@ def on_cpu(emu, monkeypatch):
 
 def _modules(case):
     torch.manual_seed(case["seed"])
-    P.CViViT(**C.SAMPLE_CVIVIT)
+    cvivit = P.CViViT(**C.SAMPLE_CVIVIT)
     maskgit = P.MaskGit(**case["maskgit"])
     critic = P.TokenCritic(**case["critic"]) if case["critic"] else None
+    if case.get("self_critic"):  # built inside Phenaki's constructor, after the networks (same order as the reference)
+        critic = P.Phenaki(cvivit=cvivit, maskgit=maskgit, self_token_critic=True,
+                           text_embed_dim=case["maskgit"]["dim_context"]).critic
     return maskgit, critic
 
 
@@ -61,6 +64,21 @@ def test_cuda_training_step_executed_on_the_cpu_matches_reference_autograd(golde
                                           keep_logits=critic is not None)
     ref_loss = g["ce"] if critic is not None else g["loss"]
     torch.testing.assert_close(loss, ref_loss, rtol=1e-5, atol=1e-6)
+    if case.get("self_critic"):
+        # SelfCritic (phenaki_pytorch.py:307-336): the MaskGit body with to_pred as head; MaskGit's gradient is the sum
+        # of both passes, the bucket follows SelfCritic.parameters() (MaskGit's parameters, then to_pred)
+        assert torch.equal(critic.to_pred[0].weight.detach(), g["to_pred_weight"])
+        pred = g["pred_ids"]
+        closs, cgk, _ = critic.train_step(torch.where(token_mask, pred, flat), case["patch_shape"],
+                                          labels=(flat != pred).float(), context=ctx, text_mask=tmask, video_mask=vmask)
+        torch.testing.assert_close(closs, g["bce"], rtol=1e-5, atol=1e-6)
+        lin = critic.to_pred[0]
+        torch.testing.assert_close(cgk.grad_of(lin.weight), g["to_pred_grads"]["weight"], rtol=1e-3, atol=1e-7)
+        torch.testing.assert_close(cgk.grad_of(lin.bias), g["to_pred_grads"]["bias"], rtol=1e-3, atol=1e-7)
+        assert cgk.flat.numel() == gk.flat.numel() + lin.weight.numel() + lin.bias.numel()
+        gk.flat += cgk.flat[:gk.flat.numel()]
+        _compare(maskgit, gk, g["maskgit_grads"], "maskgit")
+        return
     _compare(maskgit, gk, g["maskgit_grads"], "maskgit")
     if critic is not None:
         # the logits handed back for the critic's sampling are the forward logits, not their gradient

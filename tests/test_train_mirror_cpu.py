@@ -39,6 +39,17 @@ def test_backward_formulas_match_reference_autograd(golden, name):
             total = loss + closs
             for k, ref in g["critic_grads"].items():
                 torch.testing.assert_close(cgrads[k], ref, rtol=2e-4, atol=2e-6, msg=lambda m, k=k: f"critic.{k}: {m}")
+        if case.get("self_critic"):
+            pred = g["pred_ids"]
+            closs, sgrads, _ = M.train_step(mg_sd, torch.where(token_mask, pred, flat), None, None, (flat != pred).float(),
+                                            patch_shape=case["patch_shape"], heads=heads, context=ctx, text_mask=tmask,
+                                            is_critic=False, video_mask=vmask,
+                                            head=(g["to_pred_weight"], g["to_pred_bias"]))
+            torch.testing.assert_close(closs, g["bce"], rtol=1e-5, atol=1e-6)
+            total = loss + closs
+            torch.testing.assert_close(sgrads["to_pred.weight"], g["to_pred_grads"]["weight"], rtol=2e-4, atol=2e-6)
+            torch.testing.assert_close(sgrads["to_pred.bias"], g["to_pred_grads"]["bias"], rtol=2e-4, atol=2e-6)
+            grads = {k: v + sgrads[k] for k, v in grads.items()}  # both losses differentiate MaskGit
     torch.testing.assert_close(total, g["loss"], rtol=1e-5, atol=1e-6)
     for k, ref in g["maskgit_grads"].items():
         torch.testing.assert_close(grads[k], ref, rtol=2e-4, atol=2e-6, msg=lambda m, k=k: f"maskgit.{k}: {m}")

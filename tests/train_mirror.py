@@ -184,8 +184,10 @@ def bce_fwd_bwd(scores, labels):
 
 # ---------------------------------------------------------------- the driver (phk_maskgit_train_step), mirrored
 def train_step(sd, ids_in, targets, token_mask, labels, *, patch_shape, heads, context, text_mask, is_critic,
-               shrink_alpha=0.1, loss_scale=1.0, video_mask=None):
-    """Returns (loss, grads dict keyed like the state dict, logits or None).  sd: plain state dict (no autograd)."""
+               shrink_alpha=0.1, loss_scale=1.0, video_mask=None, head=None):
+    """Returns (loss, grads dict keyed like the state dict, logits or None).  sd: plain state dict (no autograd).
+    ``labels`` given -> Linear(dim,1) + BCE head (``head`` = (weight, bias) of SelfCritic.to_pred on a MaskGit body,
+    its gradients come back as 'to_pred.weight' / 'to_pred.bias')."""
     b, n = ids_in.shape
     p = "transformer."
     D = sd["token_emb.weight"].shape[1]
@@ -244,13 +246,14 @@ def train_step(sd, ids_in, targets, token_mask, labels, *, patch_shape, heads, c
     emb = ln_fwd(xf, sd[p + "norm_out.gamma"], sd[p + "norm_out.beta"])
     R = b * n
     logits = None
-    if is_critic:
-        w, bb = sd["to_logits.0.weight"], sd["to_logits.0.bias"]
+    if labels is not None:
+        w, bb = head if head is not None else (sd["to_logits.0.weight"], sd["to_logits.0.bias"])
+        hk = "to_pred." if head is not None else "to_logits.0."
         scores = (emb.reshape(R, D) @ w.t()).squeeze(-1) + bb
         loss, dsc = bce_fwd_bwd(scores, labels.reshape(R))
         dsc = dsc * loss_scale
-        grads["to_logits.0.weight"] = (dsc[:, None] * emb.reshape(R, D)).sum(0, keepdim=True)
-        grads["to_logits.0.bias"] = dsc.sum().reshape(1)
+        grads[hk + "weight"] = (dsc[:, None] * emb.reshape(R, D)).sum(0, keepdim=True)
+        grads[hk + "bias"] = dsc.sum().reshape(1)
         demb = (dsc[:, None] * w).reshape(b, n, D)
     else:
         w, bb = sd["to_logits.weight"], sd["to_logits.bias"]
