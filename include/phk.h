@@ -431,13 +431,17 @@ int phk_maskgit_sample_step(const phk_maskgit_t* m, const int64_t* ids_in, int32
  *           logits (the critic branch samples its input from them, :646).
  * The gradient-shrink trick (:199) scales the embedding gradients by shrink_alpha, as autograd does.  cond_drop_prob is
  * 0 in the reference's training forward (:594 overwrites the argument), so there is no text dropout.
- * STATUS: parity (fp32 FFMA) path; bf16 tcgen05 backward GEMMs are not built yet. */
-int64_t phk_maskgit_train_workspace_bytes(const phk_maskgit_t* m, int32_t b, int32_t n, int32_t L, int32_t bce_head);
+ * prec: PHK_PREC_F32 = fp32 FFMA products (parity with the fp32 reference); PHK_PREC_BF16 = the forward, dgrad and
+ * wgrad product of every nn.Linear on the tcgen05 GEMM (phk_gemm_bf16) with operands converted on the fly from the
+ * fp32 activations / master weights (the dtype flow of torch.autocast(bfloat16)); LayerNorm, softmax, GEGLU, the
+ * attention core and all gradients of non-matrix parameters stay fp32 in both modes. */
+int64_t phk_maskgit_train_workspace_bytes(const phk_maskgit_t* m, int32_t b, int32_t n, int32_t L, int32_t bce_head,
+                                          int32_t prec);
 int phk_maskgit_train_step(const phk_maskgit_t* m, const phk_maskgit_t* grads, const int64_t* ids_in,
                            const int64_t* targets, const uint8_t* token_mask, const float* labels, int32_t b, int32_t n,
                            int32_t pt, int32_t ph, int32_t pw, const float* context, int32_t L,
                            const uint8_t* text_mask, const uint8_t* video_mask, float loss_scale, float* loss_out,
-                           float* logits_out, void* workspace, int64_t workspace_bytes, phk_stream_t s);
+                           float* logits_out, void* workspace, int64_t workspace_bytes, int32_t prec, phk_stream_t s);
 
 #ifdef __cplusplus
 }

@@ -114,6 +114,10 @@ int dgrad(const float* dY, const float* W, float* dX, int64_t M, int64_t N, int6
 int wgrad(const float* dY, const float* X, float* dW, int64_t M, int64_t N, int64_t K, cudaStream_t st) {
   return sgemm(dY, 1, N, X, K, 1, dW, K, N, K, M, 1, st);
 }
+inline unsigned ew_grid_fwd(int64_t total) {
+  const int64_t b = (total + 255) / 256;
+  return (unsigned)(b < 1 ? 1 : (b > kNumSMs * 16 ? kNumSMs * 16 : b));
+}
 
 // out[c] += sum_r x[r, c]   (bias gradients); grid (ceil(C/256), row chunks), atomics across chunks
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, int64_t rows, int cols, int64_t ld,
@@ -133,6 +137,94 @@ int colsum(const float* x, int64_t rows, int cols, int64_t ld, float* out, cudaS
   PHK_KERNEL_LAUNCH(colsum_kernel, dim3((unsigned)((cols + 255) / 256), (unsigned)chunks), dim3(256), (size_t)(0), st, x, rows, cols, ld, out);
   PHK_LAUNCH_CHECK();
   return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// bf16 mode (PHK_PREC_BF16): the three products of every nn.Linear run on the tcgen05 GEMM of gemm_tcgen05.cu
+// (C = A.W^T, bf16 operands K-major, fp32 accumulate -- the dtype flow of torch.autocast(bfloat16)); the operands are
+// converted on the fly from the fp32 activations / master weights:
+//   forward  Y[M,N]  = X.W^T          A = bf16(X) [M,K]        W = bf16(W) [N,K]
+//   dgrad    dX[M,K] (+)= dY.W        A = bf16(dY) [M,N]       W = bf16(W)^T [K,N]
+//   wgrad    dW[N,K] += dY^T.X        A = bf16(dY)^T [N,M]     W = bf16(X)^T [K,M]
+// Leading dimensions are padded to a multiple of 8 elements (TMA); the tensor maps stop at the true extent, so the
+// padding is never read.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ src, int64_t rows, int cols,
+                                                        __nv_bfloat16* __restrict__ dst, int64_t ldd) {
+  const int64_t total = rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols;
+    dst[r * ldd + (i - r * cols)] = __float2bfloat16_rn(src[i]);
+  }
+}
+// dst[c, r] = bf16(src[r, c]); 32 x 32 tiles through shared memory so that both sides are coalesced
+__global__ void __launch_bounds__(256) cast_transpose_bf16_kernel(const float* __restrict__ src, int64_t rows, int cols,
+                                                                  __nv_bfloat16* __restrict__ dst, int64_t ldd) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t r0 = (int64_t)blockIdx.y * 32;
+  const int c0 = blockIdx.x * 32;
+  for (int i = ty; i < 32; i += 8) {
+    const int64_t r = r0 + i;
+    const int c = c0 + tx;
+    tile[i][tx] = (r < rows && c < cols) ? src[r * cols + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i;
+    const int64_t r = r0 + tx;
+    if (c < cols && r < rows) dst[(int64_t)c * ldd + r] = __float2bfloat16_rn(tile[tx][i]);
+  }
+}
+
+struct TcScratch { __nv_bfloat16* a; __nv_bfloat16* b; int64_t elems; };  // two operand buffers of `elems` bf16 each
+inline int64_t pad8(int64_t v) { return (v + 7) / 8 * 8; }
+
+int cast_to(const float* src, int64_t rows, int64_t cols, bool transpose, __nv_bfloat16* dst, int64_t cap, int64_t* ld,
+            cudaStream_t st) {
+  PHK_REQUIRE(rows > 0 && cols > 0 && cols < (1LL << 31), PHK_E_ARG, "train: bad operand shape");
+  if (!transpose) {
+    *ld = pad8(cols);
+    PHK_REQUIRE(rows * *ld <= cap, PHK_E_WORKSPACE, "train: tensor-core operand scratch too small");
+    PHK_KERNEL_LAUNCH(cast_bf16_kernel, dim3(ew_grid_fwd(rows * cols)), dim3(256), (size_t)(0), st, src, rows, (int)cols, dst, *ld);
+  } else {
+    *ld = pad8(rows);
+    PHK_REQUIRE(cols * *ld <= cap, PHK_E_WORKSPACE, "train: tensor-core operand scratch too small");
+    PHK_REQUIRE((rows + 31) / 32 <= 65535, PHK_E_UNSUPPORTED, "train: operand too tall for the transposing cast");
+    PHK_KERNEL_LAUNCH(cast_transpose_bf16_kernel, dim3((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32)), dim3(256), (size_t)(0), st, src, rows, (int)cols, dst, *ld);
+  }
+  PHK_LAUNCH_CHECK();
+  return 0;
+}
+
+// Y[M,N] = X[M,K].W[N,K]^T (+bias) (+residual: `residual` must be Y itself, i.e. Y already holds the residual)
+int linear_fwd(int prec, const TcScratch& tc, const float* X, const float* W, float* Y, int64_t M, int64_t N, int64_t K,
+               const float* bias, const float* residual, phk_stream_t s) {
+  if (prec != PHK_PREC_BF16)
+    return phk_gemm_f32(X, K, W, K, Y, N, M, (int32_t)N, (int32_t)K, bias, residual, 0, 0, 0, s);
+  int64_t lda = 0, ldw = 0;
+  PHK_TRY(cast_to(X, M, K, false, tc.a, tc.elems, &lda, to_stream(s)));
+  PHK_TRY(cast_to(W, N, K, false, tc.b, tc.elems, &ldw, to_stream(s)));
+  if (residual && residual != Y) PHK_CUDA(cudaMemcpyAsync(Y, residual, M * N * 4, cudaMemcpyDeviceToDevice, to_stream(s)));
+  return phk_gemm_bf16(tc.a, lda, tc.b, ldw, Y, N, M, (int32_t)N, (int32_t)K, bias, residual ? Y : nullptr, 0, 0, 0, 0, s);
+}
+// dX[M,K] (+)= dY[M,N] . W[N,K]
+int dgrad_p(int prec, const TcScratch& tc, const float* dY, const float* W, float* dX, int64_t M, int64_t N, int64_t K,
+            int accumulate, phk_stream_t s) {
+  if (prec != PHK_PREC_BF16) return dgrad(dY, W, dX, M, N, K, accumulate, to_stream(s));
+  int64_t lda = 0, ldw = 0;
+  PHK_TRY(cast_to(dY, M, N, false, tc.a, tc.elems, &lda, to_stream(s)));
+  PHK_TRY(cast_to(W, N, K, true, tc.b, tc.elems, &ldw, to_stream(s)));  // W^T [K, N]
+  return phk_gemm_bf16(tc.a, lda, tc.b, ldw, dX, K, M, (int32_t)K, (int32_t)N, nullptr, accumulate ? dX : nullptr, 0, 0, 0, 0, s);
+}
+// dW[N,K] += dY[M,N]^T . X[M,K]
+int wgrad_p(int prec, const TcScratch& tc, const float* dY, const float* X, float* dW, int64_t M, int64_t N, int64_t K,
+            phk_stream_t s) {
+  if (prec != PHK_PREC_BF16) return wgrad(dY, X, dW, M, N, K, to_stream(s));
+  int64_t lda = 0, ldw = 0;
+  PHK_TRY(cast_to(dY, M, N, true, tc.a, tc.elems, &lda, to_stream(s)));  // dY^T [N, M]
+  PHK_TRY(cast_to(X, M, K, true, tc.b, tc.elems, &ldw, to_stream(s)));   // X^T  [K, M]
+  return phk_gemm_bf16(tc.a, lda, tc.b, ldw, dW, K, N, (int32_t)K, (int32_t)M, nullptr, dW, 0, 0, 0, 0, s);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -763,13 +855,37 @@ int64_t layer_save_floats(const phk_transformer_t* T, const phk_layer_t& L, int6
   return f + 64 * 20;
 }
 
+// elements of ONE bf16 operand buffer of the tensor-core products (bf16 mode): every operand of every product of the
+// step -- activations / gradients [tokens, width] and weights [width, feature], straight or transposed, leading
+// dimension padded to 8 -- fits
+int64_t tc_scratch_elems(const phk_maskgit_t* m, int64_t R, int64_t CR, bool bce) {
+  const phk_transformer_t* T = &m->transformer;
+  int64_t inner = 0, dc = 0;
+  for (int l = 0; l < T->depth; ++l) {
+    if (T->layers[l].ff.inner > inner) inner = T->layers[l].ff.inner;
+    if (T->layers[l].has_cross && T->layers[l].cross_attn.dim_context > dc) dc = T->layers[l].cross_attn.dim_context;
+  }
+  const int64_t I = (int64_t)T->heads * T->dim_head, D = m->dim;
+  int64_t width = 2 * inner;
+  if (2 * I > width) width = 2 * I;
+  if (D > width) width = D;
+  if (dc > width) width = dc;
+  if (!bce && m->num_tokens > width) width = m->num_tokens;
+  int64_t feat = D;
+  if (I > feat) feat = I;
+  if (inner > feat) feat = inner;
+  if (dc > feat) feat = dc;
+  const int64_t tokens = pad8(R > CR ? R : CR) + 8;
+  return (tokens > feat + 8 ? tokens : feat + 8) * (width + 8);
+}
+
 }  // namespace
 }  // namespace phk
 
 using namespace phk;
 
 extern "C" int64_t phk_maskgit_train_workspace_bytes(const phk_maskgit_t* m, int32_t b, int32_t n, int32_t L,
-                                                     int32_t bce_head) {
+                                                     int32_t bce_head, int32_t prec) {
   if (!m || b <= 0 || n <= 0 || L < 0 || !m->transformer.layers) return -1;
   const phk_transformer_t* T = &m->transformer;
   const int64_t R = (int64_t)b * n, CR = (int64_t)b * L, D = m->dim, I = (int64_t)T->heads * T->dim_head;
@@ -791,7 +907,8 @@ extern "C" int64_t phk_maskgit_train_workspace_bytes(const phk_maskgit_t* m, int
     const int64_t U = 8 * (int64_t)n;
     f += 2 * (int64_t)T->heads * n * n + U * m->pos_bias.heads + U * (3 + 4 * (int64_t)m->pos_bias.hidden + m->pos_bias.heads) + 128;
   }
-  const int64_t bytes = f * 4 + 256 * 64;
+  int64_t bytes = f * 4 + 256 * 64;
+  if (prec == PHK_PREC_BF16) bytes += 2 * (tc_scratch_elems(m, R, CR, bce_head != 0) * 2 + 256);
   return bytes;
 }
 
@@ -802,7 +919,7 @@ extern "C" int phk_maskgit_train_step(const phk_maskgit_t* m, const phk_maskgit_
                                       int32_t n, int32_t pt, int32_t ph, int32_t pw, const float* context, int32_t L,
                                       const uint8_t* text_mask, const uint8_t* video_mask, float loss_scale,
                                       float* loss_out, float* logits_out, void* workspace, int64_t workspace_bytes,
-                                      phk_stream_t s) {
+                                      int32_t prec, phk_stream_t s) {
   PHK_REQUIRE(m && grads && ids_in && loss_out && workspace, PHK_E_ARG, "maskgit_train_step: null pointer");
   PHK_REQUIRE(b > 0 && n > 0 && (int64_t)pt * ph * pw == n, PHK_E_SHAPE, "video patch shape must cover the token sequence");
   PHK_REQUIRE(n <= m->max_seq_len, PHK_E_SHAPE,
@@ -815,7 +932,8 @@ extern "C" int phk_maskgit_train_step(const phk_maskgit_t* m, const phk_maskgit_
   PHK_REQUIRE(bce || !m->is_critic, PHK_E_ARG, "maskgit_train_step: a TokenCritic table needs labels");
   PHK_REQUIRE(!(bce && logits_out), PHK_E_ARG, "maskgit_train_step: the critic head has no logits to hand back");
   PHK_REQUIRE(!context || (text_mask && L > 0), PHK_E_ARG, "maskgit_train_step: context without text mask / length");
-  PHK_REQUIRE(workspace_bytes >= phk_maskgit_train_workspace_bytes(m, b, n, L, bce ? 1 : 0), PHK_E_WORKSPACE,
+  PHK_REQUIRE(prec == PHK_PREC_F32 || prec == PHK_PREC_BF16, PHK_E_ARG, "maskgit_train_step: unknown precision mode");
+  PHK_REQUIRE(workspace_bytes >= phk_maskgit_train_workspace_bytes(m, b, n, L, bce ? 1 : 0, prec), PHK_E_WORKSPACE,
               "maskgit_train_step: workspace too small");
   const phk_transformer_t* T = &m->transformer;
   const phk_transformer_t* GT = &grads->transformer;
@@ -826,6 +944,13 @@ extern "C" int phk_maskgit_train_step(const phk_maskgit_t* m, const phk_maskgit_
   const int D = m->dim, H = T->heads, DH = T->dim_head, I = H * DH, V = m->num_tokens;
   const int64_t R = (int64_t)b * n, CR = (int64_t)b * L;
   Arena ar{(char*)workspace, workspace_bytes, 0};
+  TcScratch tc{nullptr, nullptr, 0};
+  if (prec == PHK_PREC_BF16) {  // operand buffers of the tcgen05 products (activations stay fp32 everywhere else)
+    tc.elems = tc_scratch_elems(m, R, CR, bce);
+    tc.a = reinterpret_cast<__nv_bfloat16*>(ar.f((tc.elems + 1) / 2));
+    tc.b = reinterpret_cast<__nv_bfloat16*>(ar.f((tc.elems + 1) / 2));
+    PHK_REQUIRE(tc.a && tc.b, PHK_E_WORKSPACE, "maskgit_train_step: workspace too small (tensor-core operands)");
+  }
 
   // ---------------------------------------------------------------- forward (saving activations)
   float* x = ar.f(R * D);
@@ -865,15 +990,15 @@ extern "C" int phk_maskgit_train_step(const phk_maskgit_t* m, const phk_maskgit_
     // self attention: q from LN(x1), k/v from RAW x1 (attention.py:140-144)
     const phk_attn_t& A = Ly.self_attn;
     PHK_TRY(phk_layernorm(S.x1, A.norm_g, A.norm_b, S.xn1, nullptr, R, D, 0, 0, 0, 0, s));
-    PHK_TRY(phk_gemm_f32(S.xn1, D, A.wq, D, S.q1, I, R, I, D, nullptr, nullptr, 0, 0, 0, s));
-    PHK_TRY(phk_gemm_f32(S.x1, D, A.wkv, D, S.kv1, 2 * I, R, 2 * I, D, nullptr, nullptr, 0, 0, 0, s));
+    PHK_TRY(linear_fwd(prec, tc, S.xn1, A.wq, S.q1, R, I, D, nullptr, nullptr, s));
+    PHK_TRY(linear_fwd(prec, tc, S.x1, A.wkv, S.kv1, R, 2 * I, D, nullptr, nullptr, s));
     std::memset(&ag, 0, sizeof(ag));
     ag.n_outer = b; ag.n_inner = 1; ag.n_q = n; ag.n_k = n; ag.heads = H; ag.dim_head = DH; ag.num_null_kv = A.num_null_kv;
     ag.q_outer = (int64_t)n * I; ag.q_tok = I; ag.k_outer = (int64_t)n * 2 * I; ag.k_tok = 2 * I;
     ag.o_outer = ag.q_outer; ag.o_tok = I; ag.mask_off_from = -1; ag.scale = 8.f;
     PHK_REQUIRE(A.num_null_kv == 0, PHK_E_UNSUPPORTED, "maskgit_train_step: self-attention null-kv is not supported");
     PHK_TRY(phk_attention(S.q1, S.kv1, A.null_kv, A.q_scale, A.k_scale, bias, video_mask, nullptr, S.o1, &ag, s));
-    PHK_TRY(phk_gemm_f32(S.o1, I, A.wo, I, S.x2, D, R, D, I, nullptr, S.x1, 0, 0, 0, s));  // x2 = x1 + o Wo^T
+    PHK_TRY(linear_fwd(prec, tc, S.o1, A.wo, S.x2, R, D, I, nullptr, S.x1, s));  // x2 = x1 + o Wo^T
     const bool cross = Ly.has_cross && context;
     if (cross) {
       const phk_attn_t& Cx = Ly.cross_attn;
@@ -881,23 +1006,23 @@ extern "C" int phk_maskgit_train_step(const phk_maskgit_t* m, const phk_maskgit_
       S.ctxn = ar.f(CR * dc); S.ckv = ar.f(CR * 2 * I); S.xn2 = ar.f(R * D); S.q2 = ar.f(R * I); S.o2 = ar.f(R * I);
       PHK_REQUIRE(S.ctxn && S.ckv && S.xn2 && S.q2 && S.o2, PHK_E_WORKSPACE, "maskgit_train_step: workspace too small (cross)");
       PHK_TRY(phk_layernorm(context, Cx.ctx_g, Cx.ctx_b, S.ctxn, nullptr, CR, dc, 0, 0, 0, 0, s));
-      PHK_TRY(phk_gemm_f32(S.ctxn, dc, Cx.wkv, dc, S.ckv, 2 * I, CR, 2 * I, dc, nullptr, nullptr, 0, 0, 0, s));
+      PHK_TRY(linear_fwd(prec, tc, S.ctxn, Cx.wkv, S.ckv, CR, 2 * I, dc, nullptr, nullptr, s));
       PHK_TRY(phk_layernorm(S.x2, Cx.norm_g, Cx.norm_b, S.xn2, nullptr, R, D, 0, 0, 0, 0, s));
-      PHK_TRY(phk_gemm_f32(S.xn2, D, Cx.wq, D, S.q2, I, R, I, D, nullptr, nullptr, 0, 0, 0, s));
+      PHK_TRY(linear_fwd(prec, tc, S.xn2, Cx.wq, S.q2, R, I, D, nullptr, nullptr, s));
       std::memset(&ag, 0, sizeof(ag));
       ag.n_outer = b; ag.n_inner = 1; ag.n_q = n; ag.n_k = L; ag.heads = H; ag.dim_head = DH; ag.num_null_kv = Cx.num_null_kv;
       ag.q_outer = (int64_t)n * I; ag.q_tok = I; ag.k_outer = (int64_t)L * 2 * I; ag.k_tok = 2 * I;
       ag.o_outer = ag.q_outer; ag.o_tok = I; ag.kv_outer_mod = b; ag.mask_outer_mod = b; ag.mask_off_from = -1; ag.scale = 8.f;
       PHK_TRY(phk_attention(S.q2, S.ckv, Cx.null_kv, Cx.q_scale, Cx.k_scale, nullptr, text_mask, nullptr, S.o2, &ag, s));
-      PHK_TRY(phk_gemm_f32(S.o2, I, Cx.wo, I, S.x3, D, R, D, I, nullptr, S.x2, 0, 0, 0, s));  // x3 = x2 + o2 Wo^T
+      PHK_TRY(linear_fwd(prec, tc, S.o2, Cx.wo, S.x3, R, D, I, nullptr, S.x2, s));  // x3 = x2 + o2 Wo^T
     } else {
       PHK_CUDA(cudaMemcpyAsync(S.x3, S.x2, R * D * 4, cudaMemcpyDeviceToDevice, st));
     }
     // feed forward (attention.py:45-53)
     PHK_TRY(phk_layernorm(S.x3, Ly.ff.ln_g, Ly.ff.ln_b, S.xn3, nullptr, R, D, 0, 0, 0, 0, s));
-    PHK_TRY(phk_gemm_f32(S.xn3, D, Ly.ff.w1, D, S.h, 2 * inner, R, 2 * inner, D, nullptr, nullptr, 0, 0, 0, s));
+    PHK_TRY(linear_fwd(prec, tc, S.xn3, Ly.ff.w1, S.h, R, 2 * inner, D, nullptr, nullptr, s));
     PHK_TRY(phk_geglu(S.h, S.g, R, inner, s));
-    PHK_TRY(phk_gemm_f32(S.g, inner, Ly.ff.w2, inner, xout, D, R, D, inner, nullptr, S.x3, 0, 0, 0, s));  // x4 = x3 + g W2^T
+    PHK_TRY(linear_fwd(prec, tc, S.g, Ly.ff.w2, xout, R, D, inner, nullptr, S.x3, s));  // x4 = x3 + g W2^T
     xin = xout;
   }
   const float* xf = xin;
@@ -916,14 +1041,14 @@ extern "C" int phk_maskgit_train_step(const phk_maskgit_t* m, const phk_maskgit_
     PHK_REQUIRE(dscore, PHK_E_WORKSPACE, "maskgit_train_step: workspace too small");
     PHK_KERNEL_LAUNCH(bce_rows_kernel, dim3((unsigned)((R + 7) / 8)), dim3(256), (size_t)(0), st, emb, m->head_w, m->head_b, labels, loss_scale, row_loss, dscore, R, D);
     PHK_LAUNCH_CHECK();
-    PHK_TRY(wgrad(dscore, emb, (float*)grads->head_w, R, 1, D, st));
+    PHK_TRY(wgrad(dscore, emb, (float*)grads->head_w, R, 1, D, st));  // [1, dim]: not worth a tensor-core launch
     PHK_TRY(colsum(dscore, R, 1, 1, (float*)grads->head_b, st));
     PHK_KERNEL_LAUNCH(outer_kernel, dim3(ew_grid(R * D)), dim3(256), (size_t)(0), st, dscore, m->head_w, dtmp, R, D);
     PHK_LAUNCH_CHECK();
   } else {
     float* logits = logits_out ? logits_out : ar.f(R * (int64_t)V);
     PHK_REQUIRE(logits, PHK_E_WORKSPACE, "maskgit_train_step: workspace too small (logits)");
-    PHK_TRY(phk_gemm_f32(emb, D, m->head_w, D, logits, V, R, V, D, m->head_b, nullptr, 0, 0, 0, s));
+    PHK_TRY(linear_fwd(prec, tc, emb, m->head_w, logits, R, V, D, m->head_b, nullptr, s));
     float* dl = logits;
     if (logits_out) {  // the caller keeps the logits (critic sampling, :646): differentiate a copy
       dl = ar.f(R * (int64_t)V);
@@ -934,9 +1059,9 @@ extern "C" int phk_maskgit_train_step(const phk_maskgit_t* m, const phk_maskgit_
     PHK_LAUNCH_CHECK();
     PHK_KERNEL_LAUNCH(ce_rows_kernel, dim3((unsigned)R), dim3(256), (size_t)(0), st, dl, targets, token_mask, cnt, loss_scale, row_loss, V);
     PHK_LAUNCH_CHECK();
-    PHK_TRY(wgrad(dl, emb, (float*)grads->head_w, R, V, D, st));
+    PHK_TRY(wgrad_p(prec, tc, dl, emb, (float*)grads->head_w, R, V, D, s));
     PHK_TRY(colsum(dl, R, V, V, (float*)grads->head_b, st));
-    PHK_TRY(dgrad(dl, m->head_w, dtmp, R, V, D, 0, st));
+    PHK_TRY(dgrad_p(prec, tc, dl, m->head_w, dtmp, R, V, D, 0, s));
   }
   PHK_KERNEL_LAUNCH(loss_reduce_kernel, dim3(1), dim3(1024), (size_t)(0), st, row_loss, R, loss_out);
   PHK_LAUNCH_CHECK();
@@ -968,12 +1093,12 @@ extern "C" int phk_maskgit_train_step(const phk_maskgit_t* m, const phk_maskgit_
     const LayerSave& S = sv[l];
     const int inner = Ly.ff.inner;
     // feed forward: x4 = x3 + geglu(LN(x3) W1^T) W2^T
-    PHK_TRY(dgrad(dx, Ly.ff.w2, dg, R, D, inner, 0, st));
-    PHK_TRY(wgrad(dx, S.g, (float*)Gy.ff.w2, R, D, inner, st));
+    PHK_TRY(dgrad_p(prec, tc, dx, Ly.ff.w2, dg, R, D, inner, 0, s));
+    PHK_TRY(wgrad_p(prec, tc, dx, S.g, (float*)Gy.ff.w2, R, D, inner, s));
     PHK_KERNEL_LAUNCH(geglu_bwd_kernel, dim3(ew_grid(R * inner)), dim3(256), (size_t)(0), st, S.h, dg, dh, R, inner);
     PHK_LAUNCH_CHECK();
-    PHK_TRY(wgrad(dh, S.xn3, (float*)Gy.ff.w1, R, 2 * inner, D, st));
-    PHK_TRY(dgrad(dh, Ly.ff.w1, dtmp, R, 2 * inner, D, 0, st));
+    PHK_TRY(wgrad_p(prec, tc, dh, S.xn3, (float*)Gy.ff.w1, R, 2 * inner, D, s));
+    PHK_TRY(dgrad_p(prec, tc, dh, Ly.ff.w1, dtmp, R, 2 * inner, D, 0, s));
     PHK_TRY(ln_backward(S.x3, Ly.ff.ln_g, dtmp, dx, 1, (float*)Gy.ff.ln_g, (float*)Gy.ff.ln_b, stats, R, D, st));
     // cross attention: x3 = x2 + attn(LN(x2) Wq^T, LN_ctx(context) Wkv^T) Wo^T
     if (S.o2) {
@@ -981,30 +1106,30 @@ extern "C" int phk_maskgit_train_step(const phk_maskgit_t* m, const phk_maskgit_
       const phk_attn_t& Gx = Gy.cross_attn;
       const int dc = Cx.dim_context;
       PHK_REQUIRE(Cx.num_null_kv <= 8, PHK_E_UNSUPPORTED, "maskgit_train_step: more than 8 null key/values");
-      PHK_TRY(dgrad(dx, Cx.wo, dob, R, D, I, 0, st));
-      PHK_TRY(wgrad(dx, S.o2, (float*)Gx.wo, R, D, I, st));
+      PHK_TRY(dgrad_p(prec, tc, dx, Cx.wo, dob, R, D, I, 0, s));
+      PHK_TRY(wgrad_p(prec, tc, dx, S.o2, (float*)Gx.wo, R, D, I, s));
       const AttnBwdGeom g2{b, H, n, L, Cx.num_null_kv, DH};
       PHK_TRY(attention_backward(S.q2, S.ckv, Cx, Gx, nullptr, text_mask, dob, dq, dckv, nullptr, g2, asc, st));
-      PHK_TRY(wgrad(dq, S.xn2, (float*)Gx.wq, R, I, D, st));
-      PHK_TRY(dgrad(dq, Cx.wq, dtmp, R, I, D, 0, st));
+      PHK_TRY(wgrad_p(prec, tc, dq, S.xn2, (float*)Gx.wq, R, I, D, s));
+      PHK_TRY(dgrad_p(prec, tc, dq, Cx.wq, dtmp, R, I, D, 0, s));
       PHK_TRY(ln_backward(S.x2, Cx.norm_g, dtmp, dx, 1, (float*)Gx.norm_g, nullptr, stats, R, D, st));
-      PHK_TRY(wgrad(dckv, S.ctxn, (float*)Gx.wkv, CR, 2 * I, dc, st));
-      PHK_TRY(dgrad(dckv, Cx.wkv, dctxn, CR, 2 * I, dc, 0, st));
+      PHK_TRY(wgrad_p(prec, tc, dckv, S.ctxn, (float*)Gx.wkv, CR, 2 * I, dc, s));
+      PHK_TRY(dgrad_p(prec, tc, dckv, Cx.wkv, dctxn, CR, 2 * I, dc, 0, s));
       PHK_TRY(ln_backward(context, Cx.ctx_g, dctxn, nullptr, 0, (float*)Gx.ctx_g, nullptr, stats, CR, dc, st));
     }
     // self attention: x2 = x1 + attn(LN(x1) Wq^T, x1 Wkv^T) Wo^T
     {
       const phk_attn_t& A = Ly.self_attn;
       const phk_attn_t& GA = Gy.self_attn;
-      PHK_TRY(dgrad(dx, A.wo, dob, R, D, I, 0, st));
-      PHK_TRY(wgrad(dx, S.o1, (float*)GA.wo, R, D, I, st));
+      PHK_TRY(dgrad_p(prec, tc, dx, A.wo, dob, R, D, I, 0, s));
+      PHK_TRY(wgrad_p(prec, tc, dx, S.o1, (float*)GA.wo, R, D, I, s));
       const AttnBwdGeom g1{b, H, n, n, 0, DH};
       PHK_TRY(attention_backward(S.q1, S.kv1, A, GA, bias, video_mask, dob, dq, dkv, dbias, g1, asc, st));
-      PHK_TRY(wgrad(dq, S.xn1, (float*)GA.wq, R, I, D, st));
-      PHK_TRY(wgrad(dkv, S.x1, (float*)GA.wkv, R, 2 * I, D, st));
-      PHK_TRY(dgrad(dq, A.wq, dtmp, R, I, D, 0, st));
+      PHK_TRY(wgrad_p(prec, tc, dq, S.xn1, (float*)GA.wq, R, I, D, s));
+      PHK_TRY(wgrad_p(prec, tc, dkv, S.x1, (float*)GA.wkv, R, 2 * I, D, s));
+      PHK_TRY(dgrad_p(prec, tc, dq, A.wq, dtmp, R, I, D, 0, s));
       PHK_TRY(ln_backward(S.x1, A.norm_g, dtmp, dx, 1, (float*)GA.norm_g, nullptr, stats, R, D, st));
-      PHK_TRY(dgrad(dkv, A.wkv, dx, R, 2 * I, D, 1, st));  // the raw-x path of k, v
+      PHK_TRY(dgrad_p(prec, tc, dkv, A.wkv, dx, R, 2 * I, D, 1, s));  // the raw-x path of k, v
     }
     // PEG: x1 = x0 + conv(x0) + b
     PHK_TRY(colsum(dx, R, D, D, (float*)Gy.peg.b, st));

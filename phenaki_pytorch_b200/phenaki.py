@@ -180,13 +180,12 @@ class _TokenTransformer(nn.Module):
 
     def train_step(self, ids_in, patch_shape, *, targets=None, token_mask=None, labels=None, context=None,
                    text_mask=None, video_mask=None, loss_scale=1.0, keep_logits=False, head=None, owner=None):
-        """One forward + loss + backward in libphk (phk_maskgit_train_step, fp32): returns (loss 0-d tensor,
+        """One forward + loss + backward in libphk (phk_maskgit_train_step; ``self.precision`` selects fp32 FFMA or
+        tcgen05 bf16 products, everything else is fp32 in both modes): returns (loss 0-d tensor,
         GradKeep with d(loss_scale * loss)/d(parameter), logits or None).  ``labels`` given: Linear(dim, 1) head + BCE
         with logits (TokenCritic; or ``head`` = SelfCritic.to_pred on this MaskGit, gradients laid out for
         ``owner.parameters()``); otherwise masked cross entropy against ``targets`` at ``token_mask``."""
         lib = L.lib()
-        if self.precision != L.PREC_F32:
-            raise L.PhkError("the training step is built for the fp32 parity mode only (bf16 backward GEMMs: next step)")
         bce = labels is not None
         assert bce or not self.is_critic, "a TokenCritic trains against labels"
         ids_in = L.require_cuda(ids_in, "token ids", torch.int64)
@@ -226,13 +225,14 @@ class _TokenTransformer(nn.Module):
             if keep_logits and not bce:
                 logits = torch.empty((b, n, table.num_tokens), dtype=torch.float32, device=dev)
             loss = torch.zeros((), dtype=torch.float32, device=dev)
-            nbytes = lib.phk_maskgit_train_workspace_bytes(C.byref(table), b, n, ctx_len, int(bce))
+            nbytes = lib.phk_maskgit_train_workspace_bytes(C.byref(table), b, n, ctx_len, int(bce), self.precision)
             ws = self._ws.get(nbytes, dev)
             pt, ph, pw = (int(v) for v in patch_shape)
             L.check(lib.phk_maskgit_train_step(C.byref(table), C.byref(gtable), L.ptr(ids_in), L.ptr(targets),
                                                L.ptr(token_mask), L.ptr(labels), b, n, pt, ph, pw, L.ptr(context),
                                                ctx_len, L.ptr(text_mask), L.ptr(video_mask), float(loss_scale),
-                                               L.ptr(loss), L.ptr(logits), L.ptr(ws), ws.numel(), L.stream_ptr()),
+                                               L.ptr(loss), L.ptr(logits), L.ptr(ws), ws.numel(), self.precision,
+                                               L.stream_ptr()),
                     "phk_maskgit_train_step")
             gk.finish()
         return loss, gk, logits
@@ -653,7 +653,7 @@ class Phenaki(nn.Module):
         The returned scalar is connected to the parameters through ``_TrainStepFn``: ``loss.backward()`` fills
         ``p.grad`` with the gradients the hand-written backward kernels computed (phk_maskgit_train_step).
         ``draw_fn(shape, tag)`` (tests) injects the draws 'rand_step' (b,), 'perm' (b, n) and 'gumbel' (b, n, V).
-        fp32 parity mode only (the bf16 backward is not built).  The kernels' math is pinned
+        ``maskgit.precision`` selects fp32 (parity) or bf16 tensor-core products.  The kernels' math is pinned
         on the CPU (tests/test_train_mirror_cpu.py) but the CUDA path has not been validated on a GPU yet, so the entry
         is opt-in: set PHK_EXPERIMENTAL=1."""
         if os.environ.get("PHK_EXPERIMENTAL", "0") != "1":

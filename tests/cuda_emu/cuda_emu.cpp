@@ -129,6 +129,25 @@ extern "C" int phk_gemm_f32(const float* A, int64_t lda, const float* W, int64_t
   return 0;
 }
 
+// tcgen05 GEMM contract (include/phk.h): bf16 operands, fp32 accumulate, epilogue 0 (fp32 out + bias + residual)
+extern "C" int phk_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int64_t M,
+                             int32_t N, int32_t K, const float* bias, const float* residual, int64_t seg_len, int64_t,
+                             int64_t, int32_t epilogue, phk_stream_t) {
+  if (seg_len > 0 || epilogue != 0 || lda % 8 || ldw % 8 || lda < K || ldw < K) return PHK_E_ARG;
+  const __nv_bfloat16* a = (const __nv_bfloat16*)A;
+  const __nv_bfloat16* w = (const __nv_bfloat16*)W;
+  float* c = (float*)C;
+  for (int64_t m = 0; m < M; ++m)
+    for (int n = 0; n < N; ++n) {
+      float acc = 0.f;
+      for (int k = 0; k < K; ++k) acc += __bfloat162float(a[m * lda + k]) * __bfloat162float(w[(int64_t)n * ldw + k]);
+      if (bias) acc += bias[n];
+      if (residual) acc += residual[m * ldc + n];
+      c[m * ldc + n] = acc;
+    }
+  return 0;
+}
+
 extern "C" int phk_geglu(const float* h, float* out, int64_t rows, int32_t inner, phk_stream_t) {
   for (int64_t r = 0; r < rows; ++r)
     for (int j = 0; j < inner; ++j) {

@@ -25,6 +25,20 @@ struct dim3 {
 };
 struct float2 { float x, y; };
 static inline float2 make_float2(float a, float b) { return float2{a, b}; }
+struct __nv_bfloat16 { uint16_t bits; };
+static inline __nv_bfloat16 __float2bfloat16_rn(float f) {  // round to nearest even, like the device intrinsic
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return __nv_bfloat16{(uint16_t)((u >> 16) | 0x40)};
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return __nv_bfloat16{(uint16_t)(u >> 16)};
+}
+static inline float __bfloat162float(__nv_bfloat16 h) {
+  const uint32_t u = (uint32_t)h.bits << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
 typedef void* cudaStream_t;
 typedef int cudaError_t;
 enum { cudaSuccess = 0, cudaMemcpyDeviceToDevice = 3 };

@@ -55,3 +55,10 @@ def route_product_to_emulator(lib, patch=_Setter):
         return tensor.data_ptr()
 
     patch.setattr(M.Keep, "t", keep_t)
+
+    def keep_h(self, tensor):
+        t = tensor.detach().to(torch.bfloat16).contiguous()
+        self.refs.append(t)
+        return t.data_ptr()
+
+    patch.setattr(M.Keep, "h", keep_h)

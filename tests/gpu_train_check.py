@@ -18,7 +18,9 @@ from oracle import phenaki_oracle as O  # noqa: E402  (the checker)
 from tests import cases as C  # noqa: E402
 
 
-def check_case(name, verbose=True):
+def check_case(name, verbose=True, bf16=False):
+    """bf16=True: tcgen05 products (PHK_PREC_BF16); the bar is then closeness to the fp32 reference (5 % of each
+    gradient tensor's largest entry), not parity."""
     case = C.TRAIN_CASES[name]
     g = torch.load(os.path.join(ROOT, "tests", "golden", f"train_{name}.pt"), weights_only=False)
     torch.manual_seed(case["seed"])
@@ -30,6 +32,11 @@ def check_case(name, verbose=True):
     phenaki = P.Phenaki(cvivit=cvivit, maskgit=maskgit, critic=critic, steps=case["steps"],
                         self_token_critic=case.get("self_critic", False),
                         text_embed_dim=case["maskgit"]["dim_context"]).to(dev).train()
+    if bf16:
+        from phenaki_pytorch_b200 import _lib as L
+        phenaki.maskgit.precision = L.PREC_BF16
+        if critic is not None:
+            critic.precision = L.PREC_BF16
     ids, ctx = C.train_inputs(case)
     b, n = ids.shape[0], ids[0].numel()
     vocab = case["maskgit"]["num_tokens"]
@@ -43,7 +50,11 @@ def check_case(name, verbose=True):
     loss.backward()
     torch.cuda.synchronize()
     worst = 0.0
-    torch.testing.assert_close(loss.detach().cpu(), g["loss"], rtol=1e-4, atol=1e-5)
+    if bf16 and phenaki.critic is not None:
+        # the sampled predictions (an argmax over noisy bf16-product logits) may differ from the fp32 run, and with them
+        # the critic's inputs: only the generator half is comparable
+        print("  (bf16: critic half not compared -- its inputs are sampled from the logits)")
+    torch.testing.assert_close(loss.detach().cpu(), g["loss"], rtol=5e-2 if bf16 else 1e-4, atol=1e-5)
 
     def compare(module, ref_grads, who):
         nonlocal worst
@@ -63,17 +74,21 @@ def check_case(name, verbose=True):
             worst = max(worst, err)
             if verbose:
                 print(f"  {who}.{k:60s} max|ref| {scale:.3e}  max err / max|ref| {err:.2e}")
-            torch.testing.assert_close(got, ref, rtol=2e-3, atol=2e-4 * scale + 1e-7, msg=lambda m, k=k: f"{who}.{k}: {m}")
+            if bf16:
+                assert scale < 1e-7 or err < 5e-2, f"{who}.{k}: max err / max|ref| = {err:.3e}"
+            else:
+                torch.testing.assert_close(got, ref, rtol=2e-3, atol=2e-4 * scale + 1e-7, msg=lambda m, k=k: f"{who}.{k}: {m}")
 
-    compare(phenaki.maskgit, g["maskgit_grads"], "maskgit")
-    if critic is not None:
+    if not (bf16 and case.get("self_critic")):
+        compare(phenaki.maskgit, g["maskgit_grads"], "maskgit")
+    if critic is not None and not bf16:
         compare(phenaki.critic, g["critic_grads"], "critic")
-    if case.get("self_critic"):
+    if case.get("self_critic") and not bf16:
         compare(phenaki.critic.to_pred[0], g["to_pred_grads"], "to_pred")
-    print(f"TRAIN_OK {name} loss {loss.item():.6f} worst relative gradient error {worst:.2e}")
+    print(f"TRAIN_OK {name}{' bf16' if bf16 else ''} loss {loss.item():.6f} worst relative gradient error {worst:.2e}")
 
 
 if __name__ == "__main__":
-    names = sys.argv[1:] or list(C.TRAIN_CASES)
-    for nm in names:
-        check_case(nm)
+    args = [a for a in sys.argv[1:] if a != "--bf16"]
+    for nm in args or list(C.TRAIN_CASES):
+        check_case(nm, bf16="--bf16" in sys.argv)

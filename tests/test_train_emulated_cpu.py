@@ -121,3 +121,37 @@ def test_emulated_step_with_a_gradient_scale_and_without_text(golden, on_cpu):
     torch.testing.assert_close(l3, ref.detach(), rtol=1e-5, atol=1e-6)
     torch.testing.assert_close(g3.grad_of(maskgit.to_logits.weight), sd["to_logits.weight"].grad, rtol=1e-3, atol=1e-7)
     torch.testing.assert_close(g3.grad_of(maskgit.token_emb.weight), sd["token_emb.weight"].grad, rtol=1e-3, atol=1e-7)
+
+
+@pytest.mark.parametrize("name", ["generator", "with_critic"])
+def test_emulated_bf16_mode_step_tracks_the_fp32_reference(golden, on_cpu, name):
+    """PHK_PREC_BF16: forward / dgrad / wgrad products through the tcgen05 GEMM contract (here its CPU stand-in: bf16
+    operands, fp32 accumulation) with operands cast / transposed on the fly by the shipped kernels.  The dtype flow is
+    torch.autocast's, so the bar is closeness to the fp32 reference: loss within 2 %, every gradient tensor within 5 % of
+    its largest entry and at a cosine similarity above 0.995."""
+    from phenaki_pytorch_b200 import _lib as L
+    case, g = C.TRAIN_CASES[name], golden(f"train_{name}")
+    maskgit, critic = _modules(case)
+    maskgit.precision = L.PREC_BF16
+    ids, ctx = C.train_inputs(case)
+    b, n = ids.shape[0], ids[0].numel()
+    flat, token_mask = ids.reshape(b, n), g["token_mask"]
+    inp = torch.where(token_mask, case["maskgit"]["num_tokens"], flat)
+    loss, gk, _ = maskgit.train_step(inp, case["patch_shape"], targets=flat, token_mask=token_mask, context=ctx,
+                                     text_mask=torch.any(ctx != 0, dim=-1))
+    ref_loss = g["ce"] if critic is not None else g["loss"]
+    torch.testing.assert_close(loss, ref_loss, rtol=2e-2, atol=0)
+    worst = 0.0
+    for k, p in maskgit.named_parameters():
+        ref = g["maskgit_grads"].get(k)
+        if ref is None or ref.numel() == 0:
+            continue
+        got = gk.grad_of(p)
+        scale = ref.abs().max().item()
+        if scale < 1e-7:
+            continue  # analytically zero gradients (e.g. the bias of the last position-bias layer): rounding noise
+        err = (got - ref).abs().max().item() / scale
+        cos = torch.nn.functional.cosine_similarity(got.flatten(), ref.flatten(), dim=0).item()
+        worst = max(worst, err)
+        assert err < 5e-2 and cos > 0.995, f"{k}: max err / max|ref| {err:.3e}, cosine {cos:.5f}"
+    assert worst > 1e-5, "bf16 mode produced fp32-exact gradients: the tensor-core path was not taken"

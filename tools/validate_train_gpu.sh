@@ -10,6 +10,11 @@ for c in with_critic self_critic generator; do
   timeout 300 python tests/gpu_train_check.py $c > $O/check_$c.log 2>&1; echo "exit=$?" >> $O/check_$c.log
   tail -3 $O/check_$c.log
 done
+for c in generator with_critic; do
+  timeout 300 python tests/gpu_train_check.py --bf16 $c > $O/check_bf16_$c.log 2>&1; echo "exit=$?" >> $O/check_bf16_$c.log
+  tail -3 $O/check_bf16_$c.log
+done
 timeout 600 compute-sanitizer --tool memcheck --error-exitcode 3 python tests/gpu_train_check.py with_critic > $O/memcheck.log 2>&1; echo "exit=$?" >> $O/memcheck.log
 tail -5 $O/memcheck.log
-timeout 600 python tools/train_bench.py 4 3 > $O/train_bench.json 2> $O/train_bench.err; cat $O/train_bench.json
+timeout 600 python tools/train_bench.py 4 3 f32 > $O/train_bench_f32.json 2> $O/train_bench_f32.err; cat $O/train_bench_f32.json
+timeout 600 python tools/train_bench.py 4 5 bf16 > $O/train_bench_bf16.json 2> $O/train_bench_bf16.err; cat $O/train_bench_bf16.json
