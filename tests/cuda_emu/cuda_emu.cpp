@@ -49,15 +49,46 @@ Group& block_group() { return g_block; }
 Group& warp_group() { return g_warps[fibers[cur].tid >> 5]; }
 float* warp_xchg() { return xchg.data() + (size_t)(fibers[cur].tid >> 5) * 32; }
 
+// PHK_EMU_SHUFFLE=<seed>: blocks run in a random order and, inside a block, the runnable threads are resumed in a fresh
+// random order every scheduler round.  The default (in-order) schedule would hide a missing __syncthreads() or an
+// assumption about block order; the tests run both.
+static uint64_t g_rng = 0;
+static bool g_shuffle = false;
+static uint64_t next_rand() {
+  g_rng ^= g_rng << 13; g_rng ^= g_rng >> 7; g_rng ^= g_rng << 17;
+  return g_rng;
+}
+static void set_shuffle(uint64_t seed) {
+  g_shuffle = seed != 0;
+  g_rng = 0x9E3779B97F4A7C15ull ^ (seed * 0x100000001b3ull);
+  if (!g_rng) g_rng = 1;
+}
+static void init_schedule() {
+  static bool done = false;
+  if (done) return;
+  done = true;
+  const char* e = getenv("PHK_EMU_SHUFFLE");
+  if (e && *e) set_shuffle((uint64_t)strtoull(e, nullptr, 10));
+}
+template <typename T> static void shuffle(std::vector<T>& v) {
+  for (size_t i = v.size(); i > 1; --i) std::swap(v[i - 1], v[next_rand() % i]);
+}
+
+void set_schedule_seed(uint64_t seed) { init_schedule(); set_shuffle(seed); }
+
 void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body) {
+  init_schedule();
   const unsigned nt = block.x * block.y * block.z;
   if (block.y != 1 || block.z != 1) { fprintf(stderr, "cuda_emu: only 1-D blocks\n"); abort(); }
   if (fibers.size() < nt) { fibers.resize(nt); stacks.resize((size_t)nt * kStack); }
   dyn.assign(smem + 16, 0);
   const unsigned nw = (nt + 31) / 32;
-  for (unsigned bz = 0; bz < grid.z; ++bz)
-    for (unsigned by = 0; by < grid.y; ++by)
-      for (unsigned bx = 0; bx < grid.x; ++bx) {
+  std::vector<uint64_t> order((size_t)grid.x * grid.y * grid.z);
+  for (size_t i = 0; i < order.size(); ++i) order[i] = i;
+  if (g_shuffle) shuffle(order);
+  std::vector<unsigned> tids(nt);
+  for (uint64_t lin : order) {
+        const unsigned bx = (unsigned)(lin % grid.x), by = (unsigned)((lin / grid.x) % grid.y), bz = (unsigned)(lin / ((uint64_t)grid.x * grid.y));
         g_body = &body;
         g_block = Group{(int)nt, 0, 0};
         g_warps.assign(nw, Group{});
@@ -75,7 +106,10 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
         unsigned remaining = nt;
         while (remaining) {
           const unsigned long before = events;
-          for (unsigned t = 0; t < nt; ++t) {
+          for (unsigned t = 0; t < nt; ++t) tids[t] = t;
+          if (g_shuffle) shuffle(tids);
+          for (unsigned ti = 0; ti < nt; ++ti) {
+            const unsigned t = tids[ti];
             Fiber& f = fibers[t];
             if (f.done) continue;
             cur = (int)t;
@@ -98,6 +132,8 @@ static char g_err[256];
 void set_error(const char* msg) { snprintf(g_err, sizeof(g_err), "%s", msg); }
 }  // namespace phk
 extern "C" const char* phk_last_error(void) { return phk::g_err; }
+// test hook: 0 = in-order schedule, otherwise the seed of the random block / thread order
+extern "C" void phk_emu_set_shuffle(uint64_t seed) { emu::set_schedule_seed(seed); }
 
 extern "C" int phk_layernorm(const float* x, const float* gamma, const float* beta, void* out, void* raw_bf16, int64_t rows,
                              int32_t dim, int32_t out_bf16, int64_t seg_len, int64_t, int64_t, phk_stream_t) {

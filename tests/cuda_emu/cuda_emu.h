@@ -56,6 +56,7 @@ Group& block_group();
 Group& warp_group();
 float* warp_xchg();
 void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body);
+void set_schedule_seed(uint64_t seed);
 }  // namespace emu
 
 #define threadIdx (::emu::S.t_idx)

@@ -30,6 +30,8 @@ def build_emu():
         fn.argtypes = L.PROTOTYPES[name]
         fn.restype = L._RESTYPES.get(name, ctypes.c_int)
     lib.phk_last_error.restype = ctypes.c_char_p
+    lib.phk_emu_set_shuffle.argtypes = [ctypes.c_uint64]
+    lib.phk_emu_set_shuffle.restype = None
     return lib
 
 

@@ -48,8 +48,17 @@ def _compare(module, gk, ref, who):
         torch.testing.assert_close(got, ref[k], rtol=1e-3, atol=1e-4 * scale + 1e-7, msg=lambda m, k=k: f"{who}.{k}: {m}")
 
 
+@pytest.fixture(params=[0, 1, 2], ids=["in-order", "shuffle1", "shuffle2"])
+def schedule(emu, request):
+    """In-order schedule, then two random block / thread orders: a missing __syncthreads() or a dependence on block
+    order passes the first and fails the others."""
+    emu.phk_emu_set_shuffle(request.param)
+    yield request.param
+    emu.phk_emu_set_shuffle(0)
+
+
 @pytest.mark.parametrize("name", list(C.TRAIN_CASES))
-def test_cuda_training_step_executed_on_the_cpu_matches_reference_autograd(golden, on_cpu, name):
+def test_cuda_training_step_executed_on_the_cpu_matches_reference_autograd(golden, on_cpu, schedule, name):
     case, g = C.TRAIN_CASES[name], golden(f"train_{name}")
     maskgit, critic = _modules(case)
     ids, ctx = C.train_inputs(case)
