@@ -77,10 +77,11 @@ class CViViT(nn.Module):
         self.to_pixels = nn.Sequential(nn.Linear(dim, k2), _NoParams())
         self.vgg = None
         self.discr = None
+        # the reference's default (use_vgg_and_gan=True, cvivit.py:345-363) builds a VGG16 and a Discriminator that only
+        # the GAN / perceptual TRAINING losses use.  Those losses are out of scope, so neither is
+        # built here: the tokenizer constructs with the reference's defaults, encodes and decodes, and loads the
+        # reference's checkpoints (load_state_dict drops their `discr.*` entries); forward() raises for the loss paths.
         self.use_vgg_and_gan = use_vgg_and_gan
-        if use_vgg_and_gan:
-            raise NotImplementedError("GAN / VGG perceptual training (cvivit.py:345-363) is out of scope: "
-                                      "construct with use_vgg_and_gan=False")
         self.precision = L.PREC_F32
         self._tables = None
         self._sig = None
@@ -139,6 +140,13 @@ class CViViT(nn.Module):
         c = copy.deepcopy(self)
         self._tables, self._sig, self._dec_tables, self._dec_sig, self._ws, self._bias_cache, self._ids_buf = saved
         return c.eval().to(device)
+
+    def load_state_dict(self, state_dict, *args, **kwargs):
+        """Reference checkpoints of a tokenizer trained with use_vgg_and_gan=True carry the discriminator
+        (`discr.*`; the VGG is already hidden by the reference's remove_vgg, cvivit.py:35-49): those entries belong
+        to the training losses this module does not build and are dropped; everything else loads as given."""
+        kept = {k: v for k, v in state_dict.items() if not (k.startswith("discr.") or k.startswith("vgg."))}
+        return super().load_state_dict(kept, *args, **kwargs)
 
     def load(self, path):
         path = Path(path)

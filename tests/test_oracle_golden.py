@@ -246,3 +246,23 @@ def test_oracle_training_loss_and_gradients_match_reference_golden(golden, name)
     if critic is not None:
         for k, ref in g["critic_grads"].items():
             torch.testing.assert_close(o_cr[k].grad, ref, rtol=1e-4, atol=1e-6, msg=lambda m, k=k: f"critic.{k}: {m}")
+
+
+def test_cvivit_constructs_with_the_reference_defaults_and_loads_gan_checkpoints():
+    """The reference's default is use_vgg_and_gan=True (cvivit.py:227-249): the tokenizer must still construct (the
+    GAN / VGG members belong to training losses that are out of scope) and accept a checkpoint that carries the
+    discriminator, without disturbing the seeded weights or the state-dict layout."""
+    case = C.CVIVIT_CASES["image"]
+    kw = {k: v for k, v in case["ctor"].items() if k != "use_vgg_and_gan"}
+    torch.manual_seed(case["seed"])
+    a = P.CViViT(**kw)                                    # reference defaults
+    torch.manual_seed(case["seed"])
+    b = P.CViViT(**case["ctor"])                          # use_vgg_and_gan=False
+    assert a.use_vgg_and_gan and a.discr is None and a.vgg is None
+    assert C.state_digest(a.state_dict()) == C.state_digest(b.state_dict())
+    sd = dict(b.state_dict())
+    sd["discr.layers.0.0.weight"] = torch.zeros(3)        # what a reference GAN checkpoint adds
+    missing = a.load_state_dict(sd)                       # strict
+    assert not missing.missing_keys and not missing.unexpected_keys
+    with pytest.raises(NotImplementedError):
+        a(torch.zeros(1, 1, 32, 32), return_recons=True)  # the loss paths stay unavailable
