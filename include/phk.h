@@ -424,7 +424,7 @@ int phk_maskgit_sample_step(const phk_maskgit_t* m, const int64_t* ids_in, int32
  *   labels  (b,n) float 0/1                        critic : loss = mean over all rows of BCE_with_logits(score, label)
  *   context (b,L,dim_context) fp32 raw text embeddings or NULL; text_mask (b,L) uint8; video_mask (b,n) uint8 or NULL
  *   grads   a table of the SAME layout as `m` whose float pointers address ZERO-FILLED gradient buffers of the
- *           parameters' shapes (peg.w tap-major [27, dim] like the weight table; bf16 members and scalars unused);
+ *           parameters' shapes (peg.w in the parameter's own [dim, 1, 3, 3, 3] layout; bf16 members and scalars unused);
  *           d(loss_scale * loss)/d(parameter) is ACCUMULATED into it.  Parameters without a gradient in the reference
  *           (beta buffers, the self-attention context_norm) are not touched.
  *   loss_out device float: the UNSCALED loss.  logits_out: optional fp32 [b*n, num_tokens] that receives the MaskGit

@@ -599,7 +599,8 @@ int attention_backward(const float* q, const float* kv, const phk_attn_t& A, con
 // PEG backward (attention.py:64-85 + residual; mirror peg_bwd), layout 0 (rows are the logical (b,t,h,w) order):
 //   y[o] = x[o] + b + sum_tap w[tap] * x[o + off(tap)],  off = (kt - pad_t0, kh - 1, kw - 1)
 //   dx[p] = dy[p] + sum_tap w[tap] * dy[p - off(tap)] ;  dw[tap] += sum_o dy[o] * x[o + off(tap)] ;  db += sum_o dy[o]
-// One CTA per position (neighbour rows resolved once), threads over channels.
+// One CTA per position (neighbour rows resolved once), threads over channels.  The weights arrive tap-major [27, D]
+// (the forward's layout); the gradient is accumulated in the parameter's own layout dsconv.weight[D, 1, 3, 3, 3].
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) peg_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                       const float* __restrict__ dy, float* __restrict__ dx,
@@ -629,7 +630,7 @@ __global__ void __launch_bounds__(128) peg_bwd_kernel(const float* __restrict__ 
       const int o = s_out[tap];
       if (o >= 0) acc = fmaf(w[(int64_t)tap * D + d], dy[(int64_t)o * D + d], acc);
       const int sidx = s_src[tap];
-      if (sidx >= 0) atomicAdd(dw + (int64_t)tap * D + d, dyp * x[(int64_t)sidx * D + d]);
+      if (sidx >= 0) atomicAdd(dw + (int64_t)d * 27 + tap, dyp * x[(int64_t)sidx * D + d]);  // dsconv.weight[d, 0, kt, kh, kw]
     }
     dx[(int64_t)p * D + d] = acc;
   }

@@ -101,6 +101,7 @@ class Transformer(nn.Module):
                  ff_dropout=0.0):
         super().__init__()
         self.dim, self.depth, self.causal, self.dim_head, self.heads = dim, depth, causal, dim_head, heads
+        self.attn_dropout, self.ff_dropout = attn_dropout, ff_dropout  # inference ignores them; the training step refuses > 0
         self.layers = nn.ModuleList([])
         for _ in range(depth):
             self.layers.append(nn.ModuleList([
@@ -236,28 +237,15 @@ class GradKeep:
         for p in self.params:
             self.views[p] = self.flat[off:off + p.numel()].view(p.shape)
             off += p.numel()
-        self.used, self.packed, self.refs = set(), [], []
+        self.used, self.refs = set(), []
 
     def g(self, param):
         self.used.add(param)
         return self.views[param].data_ptr()
 
-    def peg(self, conv_weight):
-        """dsconv.weight [D,1,3,3,3] is handed to the kernels tap-major [27, D]: its gradient comes back in that
-        layout in a side buffer and is folded into the parameter's view by ``finish``."""
-        d = conv_weight.shape[0]
-        buf = torch.zeros((27, d), dtype=torch.float32, device=conv_weight.device)
-        self.packed.append((conv_weight, buf))
-        self.used.add(conv_weight)
-        return buf.data_ptr()
-
     def obj(self, o):
         self.refs.append(o)
         return o
-
-    def finish(self):
-        for param, buf in self.packed:
-            self.views[param].copy_(buf.t().reshape(param.shape))
 
     def grad_of(self, param):
         return self.views[param] if param in self.used else None
@@ -283,7 +271,8 @@ def transformer_grad_table(tf: Transformer, gk: GradKeep, with_cross: bool):
         ly = layers[i]
         ly.has_peg, ly.has_cross = int(peg is not None), int(cross is not None)
         if peg is not None:
-            ly.peg.w, ly.peg.b, ly.peg.causal = gk.peg(peg.dsconv.weight), gk.g(peg.dsconv.bias), int(peg.causal)
+            # gradient in the parameter's own [D, 1, 3, 3, 3] = [D, 27] layout (the WEIGHT table is tap-major [27, D])
+            ly.peg.w, ly.peg.b, ly.peg.causal = gk.g(peg.dsconv.weight), gk.g(peg.dsconv.bias), int(peg.causal)
         ly.self_attn = attn_grad_table(self_attn, gk, cross=False)
         if cross is not None and with_cross:
             ly.cross_attn = attn_grad_table(cross, gk, cross=True)

@@ -188,6 +188,9 @@ class _TokenTransformer(nn.Module):
         lib = L.lib()
         bce = labels is not None
         assert bce or not self.is_critic, "a TokenCritic trains against labels"
+        if self.transformer.attn_dropout > 0 or self.transformer.ff_dropout > 0:
+            raise NotImplementedError("the training step has no dropout kernels: construct with attn_dropout = "
+                                      "ff_dropout = 0 (the reference's defaults)")
         ids_in = L.require_cuda(ids_in, "token ids", torch.int64)
         b, n = ids_in.shape
         assert _prod(patch_shape) == n, "video patch shape must cover the token sequence"
@@ -234,7 +237,6 @@ class _TokenTransformer(nn.Module):
                                                L.ptr(loss), L.ptr(logits), L.ptr(ws), ws.numel(), self.precision,
                                                L.stream_ptr()),
                     "phk_maskgit_train_step")
-            gk.finish()
         return loss, gk, logits
 
     def _prepare(self, x, text_mask, video_patch_shape, context, cond_drop_prob):

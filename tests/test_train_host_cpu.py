@@ -36,13 +36,10 @@ def test_gradient_table_covers_exactly_the_parameters_the_reference_differentiat
         assert used == set(ref), (used ^ set(ref))
         assert gk.flat.numel() == sum(p.numel() for p in named.values())
         assert table.transformer.depth == module.transformer.depth
-        # the tap-major PEG gradient is folded back into the Conv3d layout
+        # every gradient view aliases the one flat bucket (the unit of the data-parallel all-reduce)
         w = module.transformer.layers[0][0].dsconv.weight
-        param, buf = gk.packed[0]
-        assert param is w
-        buf.copy_(torch.arange(buf.numel(), dtype=torch.float32).reshape(buf.shape))
-        gk.finish()
-        assert torch.equal(gk.grad_of(w).reshape(w.shape[0], 27), buf.t())
+        gk.flat.fill_(3.0)
+        assert gk.grad_of(w).shape == w.shape and bool((gk.grad_of(w) == 3.0).all())
 
 
 def _fake_train_step(module, heads):
