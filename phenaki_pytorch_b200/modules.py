@@ -229,14 +229,16 @@ class GradKeep:
 
     def __init__(self, params):
         """params: iterable of nn.Parameter, all on one CUDA device.  One flat fp32 buffer, one view per parameter
-        in iteration order (a single contiguous bucket for a data-parallel gradient all-reduce)."""
+        in iteration order (a single contiguous bucket for a data-parallel gradient all-reduce); every view starts on
+        a 256-byte boundary so that the tensor-core wgrad can write it through the TMA epilogue."""
         self.params = list(params)
         dev = self.params[0].device
-        self.flat = torch.zeros(sum(p.numel() for p in self.params), dtype=torch.float32, device=dev)
-        self.views, off = {}, 0
+        offsets, off = [], 0
         for p in self.params:
-            self.views[p] = self.flat[off:off + p.numel()].view(p.shape)
-            off += p.numel()
+            offsets.append(off)
+            off += (p.numel() + 63) // 64 * 64
+        self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.views = {p: self.flat[o:o + p.numel()].view(p.shape) for p, o in zip(self.params, offsets)}
         self.used, self.refs = set(), []
 
     def g(self, param):

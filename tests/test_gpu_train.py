@@ -24,7 +24,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_training_step_matches_reference_autograd(name):
     env = dict(os.environ, PHK_EXPERIMENTAL="1")
     out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "gpu_train_check.py"), name], cwd=ROOT, env=env,
-                         capture_output=True, text=True, timeout=240)
+                         capture_output=True, text=True, timeout=180)
     sys.stdout.write(out.stdout[-4000:])
     sys.stderr.write(out.stderr[-4000:])
     assert out.returncode == 0 and f"TRAIN_OK {name}" in out.stdout

@@ -34,7 +34,7 @@ def test_gradient_table_covers_exactly_the_parameters_the_reference_differentiat
         named = dict(module.named_parameters())
         used = {k for k, p in named.items() if gk.grad_of(p) is not None}
         assert used == set(ref), (used ^ set(ref))
-        assert gk.flat.numel() == sum(p.numel() for p in named.values())
+        assert gk.flat.numel() >= sum(p.numel() for p in named.values()) and gk.grad_of(w_any := next(iter(named.values()))).data_ptr() % 256 == gk.flat.data_ptr() % 256
         assert table.transformer.depth == module.transformer.depth
         # every gradient view aliases the one flat bucket (the unit of the data-parallel all-reduce)
         w = module.transformer.layers[0][0].dsconv.weight
