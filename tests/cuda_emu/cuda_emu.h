@@ -16,6 +16,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <algorithm>
+#include <utility>
 #include <vector>
 #include "../../include/phk.h"
 
@@ -25,6 +27,12 @@ struct dim3 {
 };
 struct float2 { float x, y; };
 static inline float2 make_float2(float a, float b) { return float2{a, b}; }
+struct alignas(16) float4 { float x, y, z, w; };
+static inline float4 make_float4(float a, float b, float c, float d) { return float4{a, b, c, d}; }
+struct alignas(8) uint2 { unsigned x, y; };
+static inline uint2 make_uint2(unsigned a, unsigned b) { return uint2{a, b}; }
+struct alignas(16) uint4 { unsigned x, y, z, w; };
+static inline uint4 make_uint4(unsigned a, unsigned b, unsigned c, unsigned d) { return uint4{a, b, c, d}; }
 struct __nv_bfloat16 { uint16_t bits; };
 static inline __nv_bfloat16 __float2bfloat16_rn(float f) {  // round to nearest even, like the device intrinsic
   uint32_t u;
@@ -39,9 +47,14 @@ static inline float __bfloat162float(__nv_bfloat16 h) {
   memcpy(&f, &u, 4);
   return f;
 }
+struct __nv_bfloat162 { __nv_bfloat16 x, y; };
+static inline __nv_bfloat162 __floats2bfloat162_rn(float a, float b) {
+  return __nv_bfloat162{__float2bfloat16_rn(a), __float2bfloat16_rn(b)};
+}
 typedef void* cudaStream_t;
 typedef int cudaError_t;
-enum { cudaSuccess = 0, cudaMemcpyDeviceToDevice = 3 };
+enum { cudaSuccess = 0, cudaMemcpyDeviceToDevice = 3, cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+template <typename K> static inline cudaError_t cudaFuncSetAttribute(K, int, int) { return 0; }
 
 namespace emu {
 struct Group { int alive = 0, count = 0; unsigned gen = 0; };
@@ -70,6 +83,7 @@ void set_schedule_seed(uint64_t seed);
 #define __forceinline__ inline
 #define __restrict__
 #define __launch_bounds__(...)
+#define __align__(n) __attribute__((aligned(n)))
 #define __shared__ static
 #define PHK_CUDA_EMU_ACTIVE 1
 
@@ -83,9 +97,21 @@ static inline float __shfl_xor_sync(unsigned, float v, int lane_mask) {
   ::emu::barrier(::emu::warp_group());
   return r;
 }
+static inline void __syncwarp(unsigned = 0xffffffffu) { ::emu::barrier(::emu::warp_group()); }
 static inline float atomicAdd(float* p, float v) { const float o = *p; *p = o + v; return o; }
 static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 template <typename T> static inline T __ldg(const T* p) { return *p; }
+// round-to-nearest single operations (the kernels use them to forbid FMA contraction; build with -ffp-contract=off)
+static inline float __fadd_rn(float a, float b) { return a + b; }
+static inline float __fsub_rn(float a, float b) { return a - b; }
+static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline float __fdiv_rn(float a, float b) { return a / b; }
+static inline float __fdividef(float a, float b) { return a / b; }
+#define __expf(x) expf(x)
+#define __logf(x) logf(x)
+static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((uint64_t)a * b) >> 32); }
+using std::max;
+using std::min;
 static inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { memset(p, v, n); return 0; }
 static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, int, cudaStream_t) { memmove(d, s, n); return 0; }
 static inline cudaError_t cudaGetLastError() { return 0; }
@@ -100,6 +126,24 @@ static inline void count_launch(int = 1) {}
 #define PHK_TRY(call) do { int r__ = (call); if (r__ != 0) return r__; } while (0)
 static inline cudaStream_t to_stream(phk_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 constexpr int kNumSMs = 148;
+enum Family { FAM_PATCHIFY = 0, FAM_LAYERNORM, FAM_GEMM_F32, FAM_GEMM_BF16, FAM_ATTENTION, FAM_PEG, FAM_GEGLU,
+              FAM_LFQ, FAM_EMBED, FAM_CPB, FAM_SAMPLE, FAM_TOPK, FAM_CRITIC, FAM_CFG, FAM_COUNT };
+struct Prof { Prof(int, phk_stream_t, double = 0.0) {} };
+static inline void pdl_trigger() {}
+static inline void pdl_wait() {}
+static inline void pdl_prologue() {}
+int patchify_ln_tma_launch(const float*, int, int, int, int, int, int, int, int, int, int, const float*, const float*, void*,
+                           int, cudaStream_t);
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t,
+                                     Args&&... args) {
+  ::emu::launch(grid, block, smem, [&]() { kernel(static_cast<KArgs>(args)...); });
+  return 0;
+}
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  return (uint32_t)__float2bfloat16_rn(lo).bits | ((uint32_t)__float2bfloat16_rn(hi).bits << 16);
+}
 
 // same definitions as csrc/phk_common.cuh
 __device__ __forceinline__ float warp_sum(float v) {

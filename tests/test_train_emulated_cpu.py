@@ -1,9 +1,10 @@
-"""CPU: csrc/train.cu itself -- the CUDA source of the training step -- compiled by g++ against tests/cuda_emu (every
-CUDA thread a fiber, __syncthreads / warp shuffles as barriers) and EXECUTED on the CPU through the product's own
-Python path (MaskGit.train_step -> ctypes tables -> phk_maskgit_train_step), against the reference's autograd loss and
-gradients (tests/golden/train_*.pt).  The forward building blocks the driver calls are CPU statements of the
-include/phk.h contracts here (their CUDA versions are covered by the -m gpu suite); everything else -- the driver's
-buffer wiring, the gradient table, every backward kernel's indexing and synchronisation -- is the shipped code."""
+"""CPU: the CUDA sources of the training step -- csrc/train.cu and the validated fp32 kernels it launches (rowops.cu,
+gemm_simt.cu, attention.cu) -- compiled by g++ against tests/cuda_emu (every CUDA thread a fiber, __syncthreads / warp
+shuffles as barriers) and EXECUTED on the CPU through the product's own Python path (MaskGit.train_step -> ctypes
+tables -> phk_maskgit_train_step), against the reference's autograd loss and gradients (tests/golden/train_*.pt).
+Every kernel of the fp32 step is the shipped source; the one stand-in is the tcgen05 GEMM of the bf16 mode (its
+include/phk.h contract stated on the CPU).  That the GPU-validated forward kernels give the reference's numbers here
+too is the evidence that the executor is faithful."""
 import pytest
 import torch
 
