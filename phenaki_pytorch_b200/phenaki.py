@@ -25,6 +25,12 @@ from .modules import (ContinuousPositionBias, GradKeep, Keep, Transformer, Works
                       cpb_table, transformer_grad_table, transformer_table, weights_signature)
 
 
+def _noise_seed(dev):
+    """Key of the in-kernel Philox noise: the seed of torch's CUDA generator of that device (``torch.manual_seed``
+    sets it), so seeded runs repeat."""
+    return torch.cuda.default_generators[dev.index if dev.index is not None else torch.cuda.current_device()].initial_seed()
+
+
 def _prod(xs):
     r = 1
     for x in xs:
@@ -530,7 +536,7 @@ class Phenaki(nn.Module):
             inp = ids if plen == 0 else torch.cat((prime_token_ids, ids), dim=-1)
             seg = (0, 0, 0) if plen == 0 else (n, plen + n, plen)
             ks = demask_counts(n, steps)
-            seed = torch.cuda.default_generators[dev.index if dev.index is not None else torch.cuda.current_device()].initial_seed()
+            seed = _noise_seed(dev)
             vocab = mg.to_logits.weight.shape[0]
             have_scores = False
             for step in range(steps):
@@ -720,7 +726,7 @@ class Phenaki(nn.Module):
         pred = torch.empty((batch, seq), dtype=torch.int64, device=dev)
         ones = torch.ones((batch, seq), dtype=torch.uint8, device=dev)
         scratch_ids = torch.empty_like(pred)
-        seed = torch.cuda.default_generators[dev.index if dev.index is not None else torch.cuda.current_device()].initial_seed()
+        seed = _noise_seed(dev)
         offset = self._rng_calls * ((batch * seq * ((vocab + 3) // 4)) + 1)
         self._rng_calls += 1
         L.check(L.lib().phk_sample_tokens(L.ptr(logits), None, vocab, L.ptr(None if gu is None else L.require_cuda(

@@ -137,13 +137,23 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
 }  // namespace emu
 
 namespace phk {
-static char g_err[256];
-void set_error(const char* msg) { snprintf(g_err, sizeof(g_err), "%s", msg); }
 // patchify_tma.cu (TMA) is not part of the emulated build: "shape not eligible" sends phk_patchify_ln to its plain kernels
 int patchify_ln_tma_launch(const float*, int, int, int, int, int, int, int, int, int, int, const float*, const float*, void*,
                            int, cudaStream_t) { return 1; }
 }  // namespace phk
-extern "C" const char* phk_last_error(void) { return phk::g_err; }
+// tensor-core / TMA entry points the drivers reference in bf16 mode: not part of the emulated build
+extern "C" int phk_gemm_bf16_x2(const void*, int64_t, const void*, int64_t, float*, int64_t, int64_t, int32_t, int32_t,
+                                const float*, const void*, int64_t, const void*, int64_t, float*, int64_t, int64_t, int32_t,
+                                int32_t, const float*, phk_stream_t) { return PHK_E_UNSUPPORTED; }
+extern "C" int64_t phk_attention_tc_scratch_bytes(int32_t, int32_t, int32_t) { return 0; }
+extern "C" int phk_attention_tc(const float*, const float*, const float*, const float*, const float*, void*, int32_t, int32_t,
+                                int32_t, float, void*, int64_t, phk_stream_t) { return PHK_E_UNSUPPORTED; }
+extern "C" int phk_layernorm_cfg(const float*, const float*, const float*, const float*, float, void*, int64_t, int32_t,
+                                 phk_stream_t) { return PHK_E_UNSUPPORTED; }
+extern "C" int64_t phk_head_sample_scratch_bytes(int32_t) { return 0; }
+extern "C" int phk_head_sample(const void*, int64_t, int64_t, const void*, int64_t, const float*, int32_t, int32_t, int32_t,
+                               float, uint64_t, uint64_t, const uint8_t*, int64_t*, int64_t*, float*, void*, int64_t,
+                               phk_stream_t) { return PHK_E_UNSUPPORTED; }
 // test hook: 0 = in-order schedule, otherwise the seed of the random block / thread order
 extern "C" void phk_emu_set_shuffle(uint64_t seed) { emu::set_schedule_seed(seed); }
 

@@ -55,6 +55,30 @@ typedef void* cudaStream_t;
 typedef int cudaError_t;
 enum { cudaSuccess = 0, cudaMemcpyDeviceToDevice = 3, cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 template <typename K> static inline cudaError_t cudaFuncSetAttribute(K, int, int) { return 0; }
+// ---- host-side runtime calls of the drivers (api.cu): one in-order "stream", so events and waits are no-ops, copies are
+// memcpy, and stream capture reports failure (the drivers then keep launching eagerly, as with PHK_GRAPH=0)
+typedef void* cudaEvent_t;
+typedef void* cudaGraph_t;
+typedef void* cudaGraphExec_t;
+enum { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2,
+       cudaStreamCaptureModeThreadLocal = 1, cudaErrorStreamCaptureUnsupported = 900 };
+static inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = nullptr; return 0; }
+static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = nullptr; return 0; }
+static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return 0; }
+static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
+static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return 0; }
+static inline cudaError_t cudaEventDestroy(cudaEvent_t) { return 0; }
+static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = nullptr; return 0; }
+static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
+static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return 0; }
+static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
+static inline cudaError_t cudaStreamBeginCapture(cudaStream_t, int) { return cudaErrorStreamCaptureUnsupported; }
+static inline cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t* g) { *g = nullptr; return cudaErrorStreamCaptureUnsupported; }
+static inline cudaError_t cudaGraphInstantiate(cudaGraphExec_t* e, cudaGraph_t, unsigned long long) { *e = nullptr; return cudaErrorStreamCaptureUnsupported; }
+static inline cudaError_t cudaGraphLaunch(cudaGraphExec_t, cudaStream_t) { return cudaErrorStreamCaptureUnsupported; }
+static inline cudaError_t cudaGraphDestroy(cudaGraph_t) { return 0; }
+static inline cudaError_t cudaGraphExecDestroy(cudaGraphExec_t) { return 0; }
+static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return 0; }
 
 namespace emu {
 struct Group { int alive = 0, count = 0; unsigned gen = 0; };
@@ -118,7 +142,7 @@ static inline cudaError_t cudaGetLastError() { return 0; }
 
 namespace phk {
 void set_error(const char* msg);
-static inline void count_launch(int = 1) {}
+void count_launch(int n = 1);
 #define PHK_REQUIRE(cond, code, msg) \
   do { if (!(cond)) { ::phk::set_error(msg); return (code); } } while (0)
 #define PHK_LAUNCH_CHECK() do { } while (0)
@@ -128,7 +152,11 @@ static inline cudaStream_t to_stream(phk_stream_t s) { return reinterpret_cast<c
 constexpr int kNumSMs = 148;
 enum Family { FAM_PATCHIFY = 0, FAM_LAYERNORM, FAM_GEMM_F32, FAM_GEMM_BF16, FAM_ATTENTION, FAM_PEG, FAM_GEGLU,
               FAM_LFQ, FAM_EMBED, FAM_CPB, FAM_SAMPLE, FAM_TOPK, FAM_CRITIC, FAM_CFG, FAM_COUNT };
-struct Prof { Prof(int, phk_stream_t, double = 0.0) {} };
+struct Prof {  // defined in api.cu (per-family event timing; the events are no-ops here)
+  Prof(int fam, phk_stream_t s, double work = 0.0);
+  ~Prof();
+  int fam; cudaStream_t st; cudaEvent_t e0; bool on; double work;
+};
 static inline void pdl_trigger() {}
 static inline void pdl_wait() {}
 static inline void pdl_prologue() {}

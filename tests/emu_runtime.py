@@ -16,7 +16,7 @@ EMU_DIR = os.path.join(ROOT, "tests", "cuda_emu")
 EMU_LIB = os.path.join(EMU_DIR, "_build", "libphk_train_emu.so")
 CSRC = os.path.join(ROOT, "phenaki_pytorch_b200", "csrc")
 # the product's plain-CUDA sources (no tensor cores / TMA): compiled unchanged apart from the two textual rewrites below
-KERNEL_SOURCES = ["rowops.cu", "gemm_simt.cu", "attention.cu"]
+KERNEL_SOURCES = ["rowops.cu", "gemm_simt.cu", "attention.cu", "api.cu"]  # api.cu: the drivers (host code)
 SOURCES = [os.path.join(CSRC, "train.cu"), os.path.join(EMU_DIR, "cuda_emu.cpp")]
 
 
@@ -91,3 +91,5 @@ def route_product_to_emulator(lib, patch=_Setter):
         return t.data_ptr()
 
     patch.setattr(M.Keep, "h", keep_h)
+    from phenaki_pytorch_b200 import phenaki as PH
+    patch.setattr(PH, "_noise_seed", lambda dev: torch.initial_seed())  # no CUDA generator without a GPU
