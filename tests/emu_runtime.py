@@ -91,5 +91,25 @@ def route_product_to_emulator(lib, patch=_Setter):
         return t.data_ptr()
 
     patch.setattr(M.Keep, "h", keep_h)
+    def poisoned_workspace(self, nbytes, device):
+        # fresh host pages are zero and would hide a kernel that reads scratch it never wrote: hand out 0xFF bytes
+        # (fp32 NaN, int64 -1) on every call instead
+        if self.buf is None or self.buf.numel() < nbytes or self.buf.device != device:
+            self.buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        self.buf.fill_(0xFF)
+        return self.buf
+
+    patch.setattr(M.Workspace, "get", poisoned_workspace)
+    real_empty = torch.empty
+
+    def poisoned_empty(*size, **kw):
+        t = real_empty(*size, **kw)
+        if t.dtype in (torch.float32, torch.bfloat16):
+            t.fill_(float("nan"))
+        elif t.dtype in (torch.int64, torch.uint8):
+            t.fill_(-1 if t.dtype == torch.int64 else 255)
+        return t
+
+    patch.setattr(torch, "empty", poisoned_empty)  # outputs the kernels are expected to overwrite completely
     from phenaki_pytorch_b200 import phenaki as PH
     patch.setattr(PH, "_noise_seed", lambda dev: torch.initial_seed())  # no CUDA generator without a GPU

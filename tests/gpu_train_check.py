@@ -18,7 +18,7 @@ from oracle import phenaki_oracle as O  # noqa: E402  (the checker)
 from tests import cases as C  # noqa: E402
 
 
-def check_case(name, verbose=True, bf16=False):
+def check_case(name, verbose=True, bf16=False, device="cuda:0"):
     """bf16=True: tcgen05 products (PHK_PREC_BF16); the bar is then closeness to the fp32 reference (5 % of each
     gradient tensor's largest entry), not parity."""
     case = C.TRAIN_CASES[name]
@@ -28,7 +28,7 @@ def check_case(name, verbose=True, bf16=False):
     maskgit = P.MaskGit(**case["maskgit"])
     critic = P.TokenCritic(**case["critic"]) if case["critic"] else None
     assert C.state_digest(maskgit.state_dict()) == g["maskgit_digest"]
-    dev = torch.device("cuda:0")
+    dev = torch.device(device)
     phenaki = P.Phenaki(cvivit=cvivit, maskgit=maskgit, critic=critic, steps=case["steps"],
                         self_token_critic=case.get("self_critic", False),
                         text_embed_dim=case["maskgit"]["dim_context"]).to(dev).train()
@@ -48,7 +48,8 @@ def check_case(name, verbose=True, bf16=False):
         draws["gumbel"] = torch.zeros((b, n, vocab)).uniform_(0, 1)
     loss = phenaki(video_codebook_ids=ids.to(dev), text_embeds=ctx.to(dev), draw_fn=lambda shape, tag: draws[tag])
     loss.backward()
-    torch.cuda.synchronize()
+    if dev.type == "cuda":
+        torch.cuda.synchronize()
     worst = 0.0
     if bf16 and phenaki.critic is not None:
         # the sampled predictions (an argmax over noisy bf16-product logits) may differ from the fp32 run, and with them

@@ -199,3 +199,13 @@ def test_emulated_step_default_head_width_and_ragged_sizes(on_cpu, schedule):
             continue
         scale = max(want.abs().max().item(), 1e-12)
         torch.testing.assert_close(got, want, rtol=1e-3, atol=1e-4 * scale + 1e-7, msg=lambda m, k=k: f"{k}: {m}")
+
+
+@pytest.mark.parametrize("name", list(C.TRAIN_CASES))
+def test_phenaki_forward_end_to_end_on_the_emulator(on_cpu, monkeypatch, name):
+    """The exact check the first GPU run will perform (tests/gpu_train_check.py): Phenaki.forward with the reference's
+    draws injected -> MaskGit step -> gumbel sampling of the critic's input (phk_sample_tokens) -> TokenCritic /
+    SelfCritic step -> loss.backward() through the autograd bridge -> loss and every p.grad against the reference."""
+    monkeypatch.setenv("PHK_EXPERIMENTAL", "1")
+    from tests import gpu_train_check
+    gpu_train_check.check_case(name, verbose=False, device="cpu")
