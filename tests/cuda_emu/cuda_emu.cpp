@@ -3,6 +3,14 @@
 // emulated thread by thread), stated below from its include/phk.h contract.
 #include "cuda_emu.h"
 #include <setjmp.h>
+#if defined(__SANITIZE_ADDRESS__)  // PHK_EMU_ASAN=1 build: tell AddressSanitizer about the fiber stacks
+#include <sanitizer/common_interface_defs.h>
+#define EMU_ASAN_START(save, bottom, size) __sanitizer_start_switch_fiber(save, bottom, size)
+#define EMU_ASAN_FINISH(save, bottom, size) __sanitizer_finish_switch_fiber(save, bottom, size)
+#else
+#define EMU_ASAN_START(save, bottom, size) do { } while (0)
+#define EMU_ASAN_FINISH(save, bottom, size) do { } while (0)
+#endif
 
 namespace emu {
 State S;
@@ -15,8 +23,12 @@ struct Fiber {
   bool started = false;
   bool done = false;
   unsigned tid = 0;
+  void* asan_fake = nullptr;
 };
 jmp_buf sched_jb;
+void* sched_fake = nullptr;
+const void* sched_bottom = nullptr;
+size_t sched_size = 0;
 constexpr size_t kStack = 128 * 1024;
 std::vector<Fiber> fibers;
 std::vector<char> stacks;
@@ -33,19 +45,23 @@ void on_exit_group(Group& g) {
   if (g.alive > 0 && g.count == g.alive) { g.count = 0; g.gen += 1; }
 }
 void trampoline() {
+  EMU_ASAN_FINISH(nullptr, &sched_bottom, &sched_size);
   (*g_body)();
   Fiber& f = fibers[cur];
   f.done = true;
   events += 1;
   on_exit_group(g_block);
   on_exit_group(g_warps[f.tid >> 5]);
+  EMU_ASAN_START(nullptr, sched_bottom, sched_size);
   _longjmp(sched_jb, 1);
 }
 }  // namespace
 
 void yield() {
   Fiber& f = fibers[cur];
+  EMU_ASAN_START(&f.asan_fake, sched_bottom, sched_size);
   if (!_setjmp(f.jb)) _longjmp(sched_jb, 1);
+  EMU_ASAN_FINISH(f.asan_fake, &sched_bottom, &sched_size);
 }
 void barrier(Group& g) {
   const unsigned gen = g.gen;
@@ -123,11 +139,13 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
             cur = (int)t;
             S.t_idx = dim3(t, 0, 0); S.b_idx = dim3(bx, by, bz); S.b_dim = block; S.g_dim = grid;
             S.dyn_smem = dyn.data();
+            EMU_ASAN_START(&sched_fake, stacks.data() + (size_t)t * kStack, kStack);
             if (!_setjmp(sched_jb)) {
               if (f.started) _longjmp(f.jb, 1);
               f.started = true;
               setcontext(&f.ctx);
             }
+            EMU_ASAN_FINISH(sched_fake, nullptr, nullptr);
             if (f.done) { remaining -= 1; }
           }
           if (events == before) { fprintf(stderr, "cuda_emu: deadlock (a barrier some threads never reach)\n"); abort(); }

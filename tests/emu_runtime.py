@@ -13,7 +13,10 @@ from phenaki_pytorch_b200 import modules as M
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EMU_DIR = os.path.join(ROOT, "tests", "cuda_emu")
-EMU_LIB = os.path.join(EMU_DIR, "_build", "libphk_train_emu.so")
+# PHK_EMU_ASAN=1 (with libasan preloaded into the python process, see tests/test_emulated_asan_cpu.py): the kernels run under
+# AddressSanitizer, i.e. every out-of-bounds access of a kernel to a torch buffer or the workspace is reported
+ASAN = os.environ.get("PHK_EMU_ASAN", "0") == "1"
+EMU_LIB = os.path.join(EMU_DIR, "_build", "libphk_train_emu_asan.so" if ASAN else "libphk_train_emu.so")
 CSRC = os.path.join(ROOT, "phenaki_pytorch_b200", "csrc")
 # the product's plain-CUDA sources (no tensor cores / TMA): compiled unchanged apart from the two textual rewrites below
 KERNEL_SOURCES = ["rowops.cu", "gemm_simt.cu", "attention.cu", "api.cu"]  # api.cu: the drivers (host code)
@@ -43,8 +46,9 @@ def build_emu():
             rewritten.append(out)
         tmp = EMU_LIB + f".{os.getpid()}.tmp"
         try:
-            subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-U_FORTIFY_SOURCE", "-D_FORTIFY_SOURCE=0", "-DPHK_CUDA_EMU",
-                                   "-x", "c++", *SOURCES, *rewritten, "-o", tmp])
+            san = ["-fsanitize=address", "-fno-omit-frame-pointer", "-g"] if ASAN else []
+            subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-U_FORTIFY_SOURCE",
+                                   "-D_FORTIFY_SOURCE=0", "-DPHK_CUDA_EMU", *san, "-x", "c++", *SOURCES, *rewritten, "-o", tmp])
         finally:
             for r in rewritten:
                 os.remove(r)
