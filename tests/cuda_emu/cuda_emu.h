@@ -112,12 +112,15 @@ void set_schedule_seed(uint64_t seed);
 #define PHK_CUDA_EMU_ACTIVE 1
 
 static inline void __syncthreads() { ::emu::barrier(::emu::block_group()); }
-static inline float __shfl_xor_sync(unsigned, float v, int lane_mask) {
+template <typename T>
+static inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {  // any 32-bit type travels as raw bits
+  static_assert(sizeof(T) == 4, "cuda_emu: 32-bit shuffles only");
   float* x = ::emu::warp_xchg();
   const int lane = (int)(threadIdx.x & 31);
-  x[lane] = v;
+  memcpy(&x[lane], &v, 4);
   ::emu::barrier(::emu::warp_group());
-  const float r = x[lane ^ lane_mask];
+  T r;
+  memcpy(&r, &x[lane ^ lane_mask], 4);
   ::emu::barrier(::emu::warp_group());
   return r;
 }
