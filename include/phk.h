@@ -400,15 +400,33 @@ int phk_head_sample(const void* emb, int64_t ld_emb, int64_t emb_rows, const voi
                     const uint8_t* mask, int64_t* ids, int64_t* pred_out, float* score_out, void* scratch,
                     int64_t scratch_bytes, phk_stream_t s);
 
+/* The tail of one demasking iteration restricted to the tokens that are still masked.  Rows do not interact after the
+ * last attention, and the reference keeps the prediction and the confidence only where the mask is set
+ * (`ids = where(mask, pred, ids)`, phenaki_pytorch.py:509; `where(mask, 1 - p, -1e4)`, :547-550), so the final LayerNorm,
+ * the guidance combination and the logits head are computed for the masked rows only: positions are compacted (exactly
+ * k per sequence -- the count phk_topk_mask was given, known on the host), norm_out + CFG are gathered into a bf16
+ * [b*k, dim] operand, phk_head_sample runs on those rows and the results are scattered back.
+ * x_cond / x_null fp32 [b*n, dim]: the residual stream BEFORE norm_out of the two halves; head_w bf16 [V, ldw];
+ * mask / ids / pred_out / score_out as phk_sample_tokens, with score = -1e4 and pred = id at unmasked positions. */
+int64_t phk_sample_tail_scratch_bytes(int32_t b, int32_t k, int32_t dim);
+int phk_sample_tail(const float* x_cond, const float* x_null, const float* gamma, const float* beta, float cond_scale,
+                    const void* head_w, int64_t ldw, const float* head_b, int32_t b, int32_t n, int32_t k, int32_t V,
+                    int32_t dim, float temperature, uint64_t seed, uint64_t offset, const uint8_t* mask, int64_t* ids,
+                    int64_t* pred_out, float* score_out, void* scratch, int64_t scratch_bytes, phk_stream_t s);
+
 /* One demasking iteration's network half for the sampling loop (phenaki_pytorch.py:495-509, 547-550): MaskGit forward
  * of the CFG pair (as phk_maskgit_forward with cfg_pair=1) + phk_head_sample.  bf16 weights required, cond_scale != 1,
- * no priming.  ids_in (b,n) = current (partly masked) ids; ids/pred_out/score_out/mask as phk_sample_tokens. */
+ * no priming.  ids_in (b,n) = current (partly masked) ids; ids/pred_out/score_out/mask as phk_sample_tokens.
+ * masked_per_seq: the number of set mask entries of EVERY sequence when the caller knows it (the k it gave
+ * phk_topk_mask), else 0.  With 0 < masked_per_seq < n the final LayerNorm, the guidance and the logits head run on the
+ * masked rows only (phk_sample_tail); pred_out is then the current id at unmasked positions. */
 int64_t phk_maskgit_sample_workspace_bytes(const phk_maskgit_t* m, int32_t b, int32_t n, int32_t L);
 int phk_maskgit_sample_step(const phk_maskgit_t* m, const int64_t* ids_in, int32_t b, int32_t n, int32_t pt,
                             int32_t ph, int32_t pw, const float* ctx_kv, int32_t L, const uint8_t* text_mask,
                             const uint8_t* video_mask, const float* pos_bias, float cond_scale, float temperature,
                             uint64_t seed, uint64_t offset, const uint8_t* mask, int64_t* ids, int64_t* pred_out,
-                            float* score_out, void* workspace, int64_t workspace_bytes, phk_stream_t s);
+                            float* score_out, int32_t masked_per_seq, void* workspace, int64_t workspace_bytes,
+                            phk_stream_t s);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Training step: Phenaki.forward (phenaki_pytorch.py:562-687)                   */

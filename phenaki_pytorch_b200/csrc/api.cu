@@ -759,8 +759,10 @@ extern "C" int phk_maskgit_forward(const phk_maskgit_t* m, const int64_t* ids, i
 extern "C" int64_t phk_maskgit_sample_workspace_bytes(const phk_maskgit_t* m, int32_t b, int32_t n, int32_t L) {
   if (!m || b <= 0 || n <= 0) return -1;
   const int64_t tokens = (int64_t)b * n;
-  return phk_maskgit_workspace_bytes(m, b, n, L, 1, PHK_PREC_BF16) + tokens * m->dim * 2 +
-         phk_head_sample_scratch_bytes((int32_t)tokens) + 1024;
+  // the masked-rows-only tail (phk_sample_tail) never needs more than the all-rows one: its largest case is k = n
+  const int64_t tail = phk_sample_tail_scratch_bytes(b, n, m->dim);
+  const int64_t full = tokens * m->dim * 2 + phk_head_sample_scratch_bytes((int32_t)tokens);
+  return phk_maskgit_workspace_bytes(m, b, n, L, 1, PHK_PREC_BF16) + (tail > full ? tail : full) + 1024;
 }
 
 extern "C" int phk_maskgit_sample_step(const phk_maskgit_t* m, const int64_t* ids_in, int32_t b, int32_t n, int32_t pt,
@@ -768,8 +770,10 @@ extern "C" int phk_maskgit_sample_step(const phk_maskgit_t* m, const int64_t* id
                                        const uint8_t* text_mask, const uint8_t* video_mask, const float* pos_bias,
                                        float cond_scale, float temperature, uint64_t seed, uint64_t offset,
                                        const uint8_t* mask, int64_t* ids, int64_t* pred_out, float* score_out,
-                                       void* workspace, int64_t workspace_bytes, phk_stream_t s) {
+                                       int32_t masked_per_seq, void* workspace, int64_t workspace_bytes,
+                                       phk_stream_t s) {
   PHK_REQUIRE(m && ids_in && workspace, PHK_E_ARG, "maskgit_sample_step: null pointer");
+  PHK_REQUIRE(masked_per_seq >= 0 && masked_per_seq <= n, PHK_E_ARG, "maskgit_sample_step: masked_per_seq out of range");
   PHK_REQUIRE(b > 0 && n > 0 && (int64_t)pt * ph * pw == n, PHK_E_SHAPE, "video patch shape must cover the token sequence");
   PHK_REQUIRE(n <= m->max_seq_len, PHK_E_SHAPE,
               "the video token sequence length is greater than max_seq_len (phenaki_pytorch.py:196)");
@@ -786,10 +790,13 @@ extern "C" int phk_maskgit_sample_step(const phk_maskgit_t* m, const int64_t* id
   Arena ar{(char*)workspace, workspace_bytes, 0};
   float* x = (float*)ar.take(R * D * 4);
   float* x_alt = (float*)ar.take(R * D * 4);
-  void* emb_h = ar.take(tokens * D * 2);
-  const int64_t hb = phk_head_sample_scratch_bytes((int32_t)tokens);
+  // masked rows only (phk_sample_tail) when the caller vouches for the per-sequence count and it saves work
+  static const bool compact_ok = [] { const char* e = std::getenv("PHK_HEAD_COMPACT"); return !(e && e[0] == '0'); }();
+  const bool compact = compact_ok && mask && ids && masked_per_seq > 0 && masked_per_seq < n;
+  const int64_t hb = compact ? phk_sample_tail_scratch_bytes(b, masked_per_seq, D) : phk_head_sample_scratch_bytes((int32_t)tokens);
+  void* emb_h = compact ? nullptr : ar.take(tokens * D * 2);
   void* hsc = ar.take(hb);
-  PHK_REQUIRE(x && x_alt && emb_h && hsc, PHK_E_WORKSPACE, "maskgit_sample_step: workspace too small");
+  PHK_REQUIRE(x && x_alt && (compact || emb_h) && hsc, PHK_E_WORKSPACE, "maskgit_sample_step: workspace too small");
   if (m->has_bias && !pos_bias) {
     float* bias_buf = (float*)ar.take((int64_t)m->heads * n * n * 4);
     float* sc = (float*)ar.take(phk_cpb_scratch_floats(&m->pos_bias, pt, ph, pw) * 4);
@@ -807,7 +814,13 @@ extern "C" int phk_maskgit_sample_step(const phk_maskgit_t* m, const int64_t* id
   c.self_mask = video_mask; c.self_mask_mod = b;
   c.ctx_kv = ctx_kv; c.ctx_b = b; c.ctx_L = L; c.ctx_mask = text_mask; c.ctx_mask_off_from = b;
   c.prec = PHK_PREC_BF16; c.out_cfg = emb_h; c.cfg_scale = cond_scale;
+  float* xf = nullptr;
+  c.x_final = &xf;  // the residual stream before norm_out: rows [0, tokens) conditional, [tokens, 2 tokens) null
   PHK_TRY(transformer_forward(c, ar, nullptr, nullptr, st));
+  if (compact)
+    return phk_sample_tail(xf, xf + tokens * D, T->out_g, T->out_b, cond_scale, m->head_w_h, D, m->head_b, b, n,
+                           masked_per_seq, m->num_tokens, D, temperature, seed, offset, mask, ids, pred_out, score_out,
+                           hsc, hb, s);
   return phk_head_sample(emb_h, D, tokens, m->head_w_h, D, m->head_b, (int32_t)tokens, m->num_tokens, D, temperature,
                          seed, offset, mask, ids, pred_out, score_out, hsc, hb, s);
 }

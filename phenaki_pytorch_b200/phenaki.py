@@ -141,9 +141,11 @@ class _TokenTransformer(nn.Module):
         return out
 
     def _sample_step(self, ids_in, patch_shape, *, ctx_kv, ctx_len, text_mask, cond_scale, temperature, seed,
-                     offset, mask, ids, pred, scores):
+                     offset, mask, ids, pred, scores, masked_per_seq=0):
         """Fused demasking iteration (bf16 mode): CFG-pair forward + logits head + gumbel argmax + confidence in
-        libphk (phk_maskgit_sample_step); the (2b, n, V) logits are never materialised."""
+        libphk (phk_maskgit_sample_step); the (2b, n, V) logits are never materialised.  ``masked_per_seq``: how many
+        tokens of EVERY sequence are masked, when known (the demasking schedule knows it): the final LayerNorm, the
+        guidance and the logits head then run on those rows only."""
         lib = L.lib()
         b, n = ids_in.shape
         dev = ids_in.device
@@ -158,7 +160,8 @@ class _TokenTransformer(nn.Module):
             L.check(lib.phk_maskgit_sample_step(C.byref(table), L.ptr(ids_in), b, n, pt, ph, pw, L.ptr(ctx_kv), ctx_len,
                                                 L.ptr(text_mask), None, L.ptr(bias), float(cond_scale),
                                                 float(temperature), seed, offset, L.ptr(mask), L.ptr(ids), L.ptr(pred),
-                                                L.ptr(scores), L.ptr(ws), ws.numel(), L.stream_ptr()),
+                                                L.ptr(scores), int(masked_per_seq), L.ptr(ws), ws.numel(),
+                                                L.stream_ptr()),
                     "phk_maskgit_sample_step")
 
     def _grad_table(self, with_cross, owner=None, head=None):
@@ -555,9 +558,12 @@ class Phenaki(nn.Module):
                          and trace is None)
                 if fused:
                     # one launch sequence per iteration, logits never leave the SM (statistical-noise mode)
+                    # exactly ks[step - 1] tokens per sequence were re-masked above (all n at the first step): the head
+                    # only has to look at those rows
                     mg._sample_step(inp, patch_shape, ctx_kv=ctx_kv, ctx_len=ctx_len, text_mask=text_mask,
                                     cond_scale=cond_scale, temperature=temperature, seed=seed & (2 ** 64 - 1),
-                                    offset=offset, mask=mask, ids=ids, pred=pred, scores=scores)
+                                    offset=offset, mask=mask, ids=ids, pred=pred, scores=scores,
+                                    masked_per_seq=n if step == 0 else ks[step - 1])
                 else:
                     logits = mg._run(inp, patch_shape, ctx_kv=ctx_kv, ctx_len=ctx_len, text_mask=text_mask,
                                      cfg_pair=use_cfg)

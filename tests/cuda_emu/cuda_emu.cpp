@@ -166,12 +166,49 @@ extern "C" int phk_gemm_bf16_x2(const void*, int64_t, const void*, int64_t, floa
 extern "C" int64_t phk_attention_tc_scratch_bytes(int32_t, int32_t, int32_t) { return 0; }
 extern "C" int phk_attention_tc(const float*, const float*, const float*, const float*, const float*, void*, int32_t, int32_t,
                                 int32_t, float, void*, int64_t, phk_stream_t) { return PHK_E_UNSUPPORTED; }
-extern "C" int phk_layernorm_cfg(const float*, const float*, const float*, const float*, float, void*, int64_t, int32_t,
-                                 phk_stream_t) { return PHK_E_UNSUPPORTED; }
-extern "C" int64_t phk_head_sample_scratch_bytes(int32_t) { return 0; }
-extern "C" int phk_head_sample(const void*, int64_t, int64_t, const void*, int64_t, const float*, int32_t, int32_t, int32_t,
-                               float, uint64_t, uint64_t, const uint8_t*, int64_t*, int64_t*, float*, void*, int64_t,
-                               phk_stream_t) { return PHK_E_UNSUPPORTED; }
+// phk_layernorm_cfg / phk_head_sample (head_sample.cu, tcgen05) from their include/phk.h contracts, for the drivers'
+// wiring tests: e = s * norm(x_cond) + (1 - s) * norm(x_null) in bf16; logits = e W^T + bias in fp32, then the REAL
+// phk_sample_tokens kernel (the documented equivalence: same Philox counter layout as phk_sample_tokens with u == NULL)
+extern "C" int phk_layernorm_cfg(const float* xc, const float* xn, const float* g, const float* b, float scale, void* out,
+                                 int64_t rows, int32_t dim, phk_stream_t) {
+  __nv_bfloat16* o = (__nv_bfloat16*)out;
+  std::vector<float> acc(dim);
+  for (int64_t r = 0; r < rows; ++r) {
+    for (int c = 0; c < dim; ++c) acc[c] = 0.f;
+    for (int pass = 0; pass < 2; ++pass) {
+      const float* x = (pass ? xn : xc) + r * dim;
+      float mean = 0.f, var = 0.f;
+      for (int c = 0; c < dim; ++c) mean += x[c];
+      mean /= dim;
+      for (int c = 0; c < dim; ++c) var += (x[c] - mean) * (x[c] - mean);
+      const float rstd = 1.0f / sqrtf(var / dim + 1e-5f), w = pass ? 1.0f - scale : scale;
+      for (int c = 0; c < dim; ++c) acc[c] += w * ((x[c] - mean) * rstd * g[c] + b[c]);
+    }
+    for (int c = 0; c < dim; ++c) o[r * dim + c] = __float2bfloat16_rn(acc[c]);
+  }
+  return 0;
+}
+extern "C" int64_t phk_head_sample_scratch_bytes(int32_t n_tokens) { return (int64_t)n_tokens * 64 + 512; }
+extern "C" int phk_sample_tokens(const float*, const float*, int64_t, const float*, uint64_t, uint64_t, float, float,
+                                 const uint8_t*, int64_t*, int64_t*, float*, int64_t, int32_t, int64_t, int64_t, int64_t,
+                                 phk_stream_t);
+extern "C" int phk_head_sample(const void* emb, int64_t ld_emb, int64_t emb_rows, const void* W, int64_t ldw,
+                               const float* bias, int32_t n_tokens, int32_t V, int32_t dim, float temperature, uint64_t seed,
+                               uint64_t offset, const uint8_t* mask, int64_t* ids, int64_t* pred_out, float* score_out, void*,
+                               int64_t, phk_stream_t s) {
+  if (emb_rows < n_tokens || ld_emb % 8 || ldw % 8) return PHK_E_ARG;
+  const __nv_bfloat16* e = (const __nv_bfloat16*)emb;
+  const __nv_bfloat16* w = (const __nv_bfloat16*)W;
+  std::vector<float> logits((size_t)n_tokens * V);
+  for (int64_t r = 0; r < n_tokens; ++r)
+    for (int v = 0; v < V; ++v) {
+      float a = 0.f;
+      for (int k = 0; k < dim; ++k) a += __bfloat162float(e[r * ld_emb + k]) * __bfloat162float(w[(int64_t)v * ldw + k]);
+      logits[(size_t)r * V + v] = a + (bias ? bias[v] : 0.f);
+    }
+  return phk_sample_tokens(logits.data(), nullptr, V, nullptr, seed, offset, 1.0f, temperature, mask, ids, pred_out, score_out,
+                           n_tokens, V, 0, 0, 0, s);
+}
 // test hook: 0 = in-order schedule, otherwise the seed of the random block / thread order
 extern "C" void phk_emu_set_shuffle(uint64_t seed) { emu::set_schedule_seed(seed); }
 

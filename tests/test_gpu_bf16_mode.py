@@ -178,3 +178,45 @@ def test_bf16_sampling_with_fused_head_is_deterministic():
         outs.append(ph.sample(num_frames=7, text_embeds=ctx, return_token_ids=True).cpu())
     assert torch.equal(outs[0], outs[1]) and not torch.equal(outs[0], outs[2])
     assert (outs[0] >= 0).all() and (outs[0] < 256).all()
+
+
+@pytest.mark.parametrize("b,n,k,dim,V", [(4, 576, 100, 512, 4096), (2, 48, 17, 128, 300), (3, 30, 1, 256, 130),
+                                         (4, 576, 441, 512, 1024)])
+def test_sample_tail_on_the_masked_rows_only(b, n, k, dim, V):
+    """phk_sample_tail (csrc/sample_tail.cu + the tcgen05 head on the compact rows) against plain torch arithmetic; the
+    same body runs on the CPU executor in tests/test_sample_tail_emulated_cpu.py."""
+    from tests import tail_cases
+    tail_cases.check_exact_k(L.lib(), torch.device(DEV), b, n, k, dim, V, sync=torch.cuda.synchronize)
+
+
+def test_fused_sample_step_on_masked_rows_equals_the_all_rows_step():
+    """Model level, temperature 0 (pure argmax): telling phk_maskgit_sample_step how many tokens per sequence are masked
+    (head on those rows only) must give the ids of the all-rows step at every masked position, the same confidences,
+    and leave the other positions alone."""
+    torch.manual_seed(8)
+    cfg = dict(dim=128, num_tokens=1000, max_seq_len=256, heads=2, dim_head=64, depth=2, dim_context=96)
+    mg = P.MaskGit(**cfg).to(DEV).eval()
+    mg.precision = L.PREC_BF16
+    b, shape, n, k = 3, (3, 6, 8), 144, 37
+    g = torch.Generator().manual_seed(2)
+    ids0 = torch.randint(0, cfg["num_tokens"] + 1, (b, n), generator=g).to(DEV)
+    ctx = C.synthetic_text_embeds(b, 5, 96, (5, 2, 4), 2).to(DEV)
+    tmask = torch.any(ctx != 0, dim=-1)
+    mask = torch.zeros((b, n), dtype=torch.uint8)
+    for i in range(b):
+        mask[i, torch.randperm(n, generator=g)[:k]] = 1
+    mask = mask.to(DEV)
+    kv = mg.context_kv(ctx)
+    outs = []
+    for count in (0, k):
+        ids, pred, sc = ids0.clone(), torch.empty_like(ids0), torch.empty((b, n), device=DEV)
+        mg._sample_step(ids0, shape, ctx_kv=kv, ctx_len=5, text_mask=tmask, cond_scale=3.0, temperature=0.0, seed=1, offset=0,
+                        mask=mask, ids=ids, pred=pred, scores=sc, masked_per_seq=count)
+        torch.cuda.synchronize()
+        outs.append((ids.cpu(), sc.cpu()))
+    m = mask.cpu().bool()
+    (ids_a, sc_a), (ids_b, sc_b) = outs
+    same = ids_a == ids_b  # (a near-tie of two logits may resolve differently if the two LayerNorm kernels round apart)
+    assert int((~same).sum()) <= max(1, int(0.01 * m.sum())), f"{int((~same).sum())} ids differ"
+    torch.testing.assert_close(sc_a[m & same], sc_b[m & same], rtol=1e-3, atol=1e-4)
+    assert bool((sc_b[~m] == -1e4).all()) and torch.equal(ids_b[~m], ids0.cpu()[~m])
