@@ -419,6 +419,7 @@ extern "C" int phk_head_sample(const void* emb, int64_t ld_emb, int64_t emb_rows
   int n_splits = m_tiles >= kNumSMs ? 1 : kNumSMs / m_tiles;
   if (n_splits > n_tiles) n_splits = n_tiles;
   const int tps = (n_tiles + n_splits - 1) / n_splits;
+  n_splits = (n_tiles + tps - 1) / tps;  // no empty vocabulary splits (e.g. 512 tiles over 49 splits of 11: 47 are enough)
   CUtensorMap ta, tb;
   PHK_TRY(make_map_2d(emb, emb_rows, dim, ld_emb, &ta));  // rows beyond emb_rows are zero-filled by the TMA unit
   PHK_TRY(make_map_2d(W, V, dim, ldw, &tb));
