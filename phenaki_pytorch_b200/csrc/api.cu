@@ -73,6 +73,10 @@ struct TfCall {
   // frame (t == 0) and of the remaining frames, each in (b,t,h,w) order (cvivit.py:506)
   void* out_first; void* out_rest; int split_B, split_T, split_hw;
   float** x_final;  // optional: receives the buffer holding the residual stream BEFORE norm_out (c.x or c.x_alt)
+  // CFG pair (rows [0, R/2) conditional, [R/2, R) null) whose two halves enter with IDENTICAL rows: PEG and
+  // self-attention of the first layer do not see the text, so they are computed for the first half only and copied
+  // (the halves diverge at the first cross-attention).  Requires the n_inner == 1 sequence view.
+  int dup_halves;
 };
 
 static int64_t tf_scratch_bytes(const phk_transformer_t* T, int64_t R) {
@@ -124,23 +128,28 @@ static int transformer_forward(const TfCall& c, Arena scratch, float* out, void*
 
   for (int l = 0; l < T->depth; ++l) {
     const phk_layer_t& L = T->layers[l];
+    // first layer of a CFG pair with identical halves: PEG + self-attention on the first half only
+    const bool dup = l == 0 && c.dup_halves && c.seq.n_inner == 1 && c.seq.n_outer % 2 == 0 && c.pegB % 2 == 0 && R % 2 == 0;
+    const int64_t Rl = dup ? R / 2 : R;
+    const int n_outer = dup ? c.seq.n_outer / 2 : c.seq.n_outer;
+    const int pegB = dup ? c.pegB / 2 : c.pegB;
     if (L.has_peg) {  // x = peg(x) + x
-      PHK_REQUIRE((int64_t)c.pegB * c.pegT * c.pegH * c.pegW == R, PHK_E_SHAPE, "PEG: video shape does not cover the tokens");
-      PHK_TRY(phk_peg3d(x, L.peg.w, L.peg.b, x_alt, c.pegB, c.pegT, c.pegH, c.pegW, D, L.peg.causal, c.peg_layout, s));
+      PHK_REQUIRE((int64_t)pegB * c.pegT * c.pegH * c.pegW == Rl, PHK_E_SHAPE, "PEG: video shape does not cover the tokens");
+      PHK_TRY(phk_peg3d(x, L.peg.w, L.peg.b, x_alt, pegB, c.pegT, c.pegH, c.pegW, D, L.peg.causal, c.peg_layout, s));
       float* t = x; x = x_alt; x_alt = t;
     }
     {  // x = self_attn(x) + x ; q from LN(x), k/v from RAW x (attention.py:140-144)
       const phk_attn_t& A = L.self_attn;
-      PHK_TRY(phk_layernorm(x, A.norm_g, A.norm_b, xn, xraw, R, D, h16, 0, 0, 0, s));
-      if (h16 && R > 128 && A.wq_h && A.wkv_h) {  // both projections in one launch (their tiles pipeline)
-        PHK_TRY(phk_gemm_bf16_x2(xn, D, A.wq_h, D, q, I, R, I, D, nullptr, xraw, D, A.wkv_h, D, kv, 2 * I, R, 2 * I, D, nullptr, s));
+      PHK_TRY(phk_layernorm(x, A.norm_g, A.norm_b, xn, xraw, Rl, D, h16, 0, 0, 0, s));
+      if (h16 && Rl > 128 && A.wq_h && A.wkv_h) {  // both projections in one launch (their tiles pipeline)
+        PHK_TRY(phk_gemm_bf16_x2(xn, D, A.wq_h, D, q, I, Rl, I, D, nullptr, xraw, D, A.wkv_h, D, kv, 2 * I, Rl, 2 * I, D, nullptr, s));
       } else {
-        PHK_TRY(linear(c.prec, xn, D, A.wq, A.wq_h, D, q, I, R, I, D, nullptr, nullptr, s));
-        PHK_TRY(linear(c.prec, h16 ? xraw : (const void*)x, D, A.wkv, A.wkv_h, D, kv, 2 * I, R, 2 * I, D, nullptr, nullptr, s));
+        PHK_TRY(linear(c.prec, xn, D, A.wq, A.wq_h, D, q, I, Rl, I, D, nullptr, nullptr, s));
+        PHK_TRY(linear(c.prec, h16 ? xraw : (const void*)x, D, A.wkv, A.wkv_h, D, kv, 2 * I, Rl, 2 * I, D, nullptr, nullptr, s));
       }
       phk_attn_geom_t g;
       std::memset(&g, 0, sizeof(g));
-      g.n_outer = c.seq.n_outer; g.n_inner = c.seq.n_inner; g.n_q = c.seq.n_tok; g.n_k = c.seq.n_tok;
+      g.n_outer = n_outer; g.n_inner = c.seq.n_inner; g.n_q = c.seq.n_tok; g.n_k = c.seq.n_tok;
       g.heads = H; g.dim_head = DH; g.num_null_kv = A.num_null_kv; g.causal = T->causal;
       g.q_outer = c.seq.outer * I; g.q_inner = c.seq.inner * I; g.q_tok = c.seq.tok * I;
       g.k_outer = c.seq.outer * 2 * I; g.k_inner = c.seq.inner * 2 * I; g.k_tok = c.seq.tok * 2 * I;
@@ -149,16 +158,18 @@ static int transformer_forward(const TfCall& c, Arena scratch, float* out, void*
       const bool tc_ok = h16 && DH == 64 && !T->causal && A.num_null_kv == 0 && !c.self_mask && c.seq.n_inner == 1 &&
                          c.seq.tok == 1 && c.seq.outer == c.seq.n_tok && c.seq.n_tok >= 64;
       if (tc_ok) {  // tcgen05 path: S/P stay in TMEM / smem
-        const int64_t ab = phk_attention_tc_scratch_bytes(c.seq.n_outer, c.seq.n_tok, H);
+        const int64_t ab = phk_attention_tc_scratch_bytes(n_outer, c.seq.n_tok, H);
         Arena tmp = scratch;
         void* asc = tmp.take(ab);
         PHK_REQUIRE(asc, PHK_E_WORKSPACE, "transformer: workspace too small (attention operands)");
-        PHK_TRY(phk_attention_tc(q, kv, A.q_scale, A.k_scale, c.attn_bias, o, c.seq.n_outer, c.seq.n_tok, H, 8.f, asc, ab, s));
+        PHK_TRY(phk_attention_tc(q, kv, A.q_scale, A.k_scale, c.attn_bias, o, n_outer, c.seq.n_tok, H, 8.f, asc, ab, s));
       } else {
         PHK_TRY(phk_attention(q, kv, A.null_kv, A.q_scale, A.k_scale, c.attn_bias, c.self_mask, T->alibi_slopes, o, &g, s));
       }
-      PHK_TRY(linear(c.prec, o, I, A.wo, A.wo_h, I, x, D, R, D, I, nullptr, x, s));
+      PHK_TRY(linear(c.prec, o, I, A.wo, A.wo_h, I, x, D, Rl, D, I, nullptr, x, s));
     }
+    if (dup)  // the null half continues from the same rows
+      PHK_CUDA(cudaMemcpyAsync(x + Rl * D, x, Rl * D * 4, cudaMemcpyDeviceToDevice, st));
     if (L.has_cross && c.ctx_kv) {  // x = cross_attn(x, context) + x   (attention.py:327-328)
       const phk_attn_t& A = L.cross_attn;
       PHK_REQUIRE(c.seq.n_inner == 1, PHK_E_UNSUPPORTED, "cross attention needs (b, n) sequences");
@@ -744,6 +755,7 @@ extern "C" int phk_maskgit_forward(const phk_maskgit_t* m, const int64_t* ids, i
   c.self_mask = video_mask; c.self_mask_mod = b;
   c.ctx_kv = ctx_kv; c.ctx_b = b; c.ctx_L = L; c.ctx_mask = text_mask;
   c.ctx_mask_off_from = cfg_pair ? b : -1;
+  c.dup_halves = cfg_pair ? 1 : 0;  // phk_token_embed wrote the same embeddings for both halves
   c.prec = prec;
   if (return_embeds || m->is_critic) return transformer_forward(c, ar, out, nullptr, st);
   // to_logits (phenaki_pytorch.py:213): the final LayerNorm feeds the head GEMM directly (bf16 operand in bf16 mode)
@@ -814,6 +826,7 @@ extern "C" int phk_maskgit_sample_step(const phk_maskgit_t* m, const int64_t* id
   c.self_mask = video_mask; c.self_mask_mod = b;
   c.ctx_kv = ctx_kv; c.ctx_b = b; c.ctx_L = L; c.ctx_mask = text_mask; c.ctx_mask_off_from = b;
   c.prec = PHK_PREC_BF16; c.out_cfg = emb_h; c.cfg_scale = cond_scale;
+  c.dup_halves = 1;  // phk_token_embed wrote the same embeddings for both halves
   float* xf = nullptr;
   c.x_final = &xf;  // the residual stream before norm_out: rows [0, tokens) conditional, [tokens, 2 tokens) null
   PHK_TRY(transformer_forward(c, ar, nullptr, nullptr, st));
