@@ -268,7 +268,10 @@ def bench_maskgit(dev, prec, steps_timed=1):
                 ms_per_decode_step=ms / CFG3_RUN["steps"],
                 config=f"MaskGit(dim=512,depth=6,V=65536,ctx=768) {CFG3_RUN['steps']}-step demasking loop, b={b}, N={n}, "
                        f"L={L}, cond_scale=3 (2 forwards/step as one batch of {2 * b})",
-                achieved_tflops=tf, frac_of_tensor_peak=tf / pk["tf_sustained"], fused_head=bool(ph.fused_head))
+                achieved_tflops=tf, frac_of_tensor_peak=tf / pk["tf_sustained"], fused_head=bool(ph.fused_head),
+                flops_note="achieved_tflops divides the reference's algorithmic FLOPs (SURVEY 8d: all rows, both CFG halves, "
+                           "every layer) by the time; the step itself runs the logits head on the still-masked rows only "
+                           "and the first layer's PEG + self-attention once for the CFG pair (DESIGN 4.3)")
 
 
 def main():
