@@ -41,12 +41,22 @@ constexpr float kL2Eps = 1e-12f;
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int GB = 64, GK = 16;
 
+// blockIdx.z = z selects one product of a batch: operand X starts at X + (z / div) * x_outer + (z % div) * x_inner
+// (two levels, e.g. (sequence, head) over a token-major [b, n, heads * dim_head] tensor); {1, 1, 0...} = one product
+struct GemmBatch { int count, div; int64_t a_outer, a_inner, b_outer, b_inner, c_outer, c_inner; };
+
 __global__ void __launch_bounds__(256) sgemm_strided_kernel(const float* __restrict__ A, int64_t sam, int64_t sak,
                                                             const float* __restrict__ B, int64_t sbk, int64_t sbn,
                                                             float* __restrict__ C, int64_t ldc, int M, int N, int K,
-                                                            int accumulate) {
+                                                            int accumulate, GemmBatch gb) {
   __shared__ float As[GK][GB + 1];
   __shared__ float Bs[GK][GB + 1];
+  {
+    const int z = blockIdx.z, zo = z / gb.div, zi = z - zo * gb.div;
+    A += zo * gb.a_outer + zi * gb.a_inner;
+    B += zo * gb.b_outer + zi * gb.b_inner;
+    C += zo * gb.c_outer + zi * gb.c_inner;
+  }
   const int m0 = blockIdx.y * GB, n0 = blockIdx.x * GB;
   const int t = threadIdx.x;
   const int tx = t & 15, ty = t >> 4;
@@ -96,15 +106,20 @@ __global__ void __launch_bounds__(256) sgemm_strided_kernel(const float* __restr
   }
 }
 
-int sgemm(const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbk, int64_t sbn, float* C, int64_t ldc,
-          int64_t M, int64_t N, int64_t K, int accumulate, cudaStream_t st) {
+int sgemm_batched(const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbk, int64_t sbn, float* C, int64_t ldc,
+                  int64_t M, int64_t N, int64_t K, int accumulate, const GemmBatch& gb, cudaStream_t st) {
   PHK_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0, PHK_E_ARG, "train: bad GEMM arguments");
   PHK_REQUIRE(M < (1LL << 31) && N < (1LL << 31) && K < (1LL << 31), PHK_E_UNSUPPORTED, "train: GEMM too large");
-  dim3 grid((unsigned)((N + GB - 1) / GB), (unsigned)((M + GB - 1) / GB));
+  PHK_REQUIRE(gb.count >= 1 && gb.count <= 65535 && gb.div >= 1, PHK_E_UNSUPPORTED, "train: GEMM batch too large");
+  dim3 grid((unsigned)((N + GB - 1) / GB), (unsigned)((M + GB - 1) / GB), (unsigned)gb.count);
   PHK_REQUIRE(grid.y <= 65535, PHK_E_UNSUPPORTED, "train: GEMM M too large");
-  PHK_KERNEL_LAUNCH(sgemm_strided_kernel, dim3(grid), dim3(256), (size_t)(0), st, A, sam, sak, B, sbk, sbn, C, ldc, (int)M, (int)N, (int)K, accumulate);
+  PHK_KERNEL_LAUNCH(sgemm_strided_kernel, dim3(grid), dim3(256), (size_t)(0), st, A, sam, sak, B, sbk, sbn, C, ldc, (int)M, (int)N, (int)K, accumulate, gb);
   PHK_LAUNCH_CHECK();
   return 0;
+}
+int sgemm(const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbk, int64_t sbn, float* C, int64_t ldc,
+          int64_t M, int64_t N, int64_t K, int accumulate, cudaStream_t st) {
+  return sgemm_batched(A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, accumulate, GemmBatch{1, 1, 0, 0, 0, 0, 0, 0}, st);
 }
 // dX[M,K] (+)= dY[M,N] . W[N,K]        (nn.Linear dgrad)
 int dgrad(const float* dY, const float* W, float* dX, int64_t M, int64_t N, int64_t K, int accumulate, cudaStream_t st) {
@@ -320,7 +335,8 @@ __global__ void geglu_bwd_kernel(const float* __restrict__ h, const float* __res
 // Attention backward (attention.py:146-181; mirror attn_bwd).  Sequences are (b, n) rows of q [b*n, I] and
 // (b, m) rows of kv [b*m, 2I]; nkt = nnull + m keys per (sequence, head).
 //   prep : qh = l2norm(q) * q_scale, kh = l2norm(k) * k_scale, vv   -> head-major [b, H, n|nkt, dh]
-//   probs: P = softmax(8 qh.kh + bias, masks) ; dP = dO.vv ; dS = P * (dP - sum_j P dP)   -> P, dS [b, H, n, nkt]
+//   S, dP: qh.kh^T and dO.vv^T as two batched register-tiled products                       -> [b, H, n, nkt]
+//   probs: P = softmax(8 S + bias, masks) ; dS = P * (dP - sum_j P dP), in place, rows coalesced
 //   dq   : dqh = 8 dS.kh -> back through scale and l2norm -> dq [b*n, I], dq_scale
 //   dkv  : dkh = 8 dS^T.qh, dvv = P^T.dO -> back through scale and l2norm -> dkv [b*m, 2I], dnull_kv, dk_scale
 // ------------------------------------------------------------------------------------------------------------------
@@ -365,52 +381,37 @@ __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const float* __restr
   }
 }
 
-// one warp per (sequence, head, query); dynamic smem: 2 * nkt floats per warp
-__global__ void __launch_bounds__(128) attn_bwd_probs_kernel(const float* __restrict__ qh, const float* __restrict__ kh,
-                                                             const float* __restrict__ vv, const float* __restrict__ dO,
-                                                             const float* __restrict__ bias,
-                                                             const uint8_t* __restrict__ key_mask, float* __restrict__ P,
-                                                             float* __restrict__ dS, AttnBwdGeom g) {
-  PHK_DYNAMIC_SMEM(float, srow);
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+// one warp per (sequence, head, query).  In: P holds the raw products qh.kh (batched GEMM), dS holds dP = dO.vv.
+// Out (in place): P = softmax(8 qh.kh + bias, masks), dS = P * (dP - sum_j P dP).  Rows are contiguous: coalesced.
+__global__ void __launch_bounds__(256) attn_bwd_softmax_kernel(const float* __restrict__ bias,
+                                                               const uint8_t* __restrict__ key_mask, float* __restrict__ P,
+                                                               float* __restrict__ dS, AttnBwdGeom g) {
+  const int lane = threadIdx.x & 31;
   const int nkt = g.nnull + g.m;
-  float* sp = srow + (size_t)wid * 2 * nkt;  // scores -> probabilities
-  float* sd = sp + nkt;                      // dP
-  const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + wid;
+  const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (w >= (int64_t)g.b * g.H * g.n) return;
   const int i = (int)(w % g.n);
   const int h = (int)((w / g.n) % g.H);
   const int bi = (int)(w / ((int64_t)g.n * g.H));
-  const int I = g.H * g.dh;
-  const float* qr = qh + (((int64_t)bi * g.H + h) * g.n + i) * g.dh;
-  const float* dor = dO + ((int64_t)bi * g.n + i) * I + (int64_t)h * g.dh;
-  const float* kb = kh + ((int64_t)bi * g.H + h) * nkt * g.dh;
-  const float* vb = vv + ((int64_t)bi * g.H + h) * nkt * g.dh;
+  float* Pr = P + w * nkt;    // w = (bi * H + h) * n + i
+  float* dSr = dS + w * nkt;
   float mx = -FLT_MAX;
   for (int j = lane; j < nkt; j += 32) {
-    float s = 0.f, dp = 0.f;
-    for (int d = 0; d < g.dh; ++d) {
-      s = fmaf(qr[d], kb[(int64_t)j * g.dh + d], s);
-      dp = fmaf(dor[d], vb[(int64_t)j * g.dh + d], dp);
-    }
-    s *= 8.0f;                                                                           // scale (attention.py:100)
-    if (bias && j >= g.nnull) s += bias[((int64_t)h * g.n + i) * g.m + (j - g.nnull)];   // never covers null keys (:162)
+    float s = Pr[j] * 8.0f;                                                                // scale (attention.py:100)
+    if (bias && j >= g.nnull) s += bias[((int64_t)h * g.n + i) * g.m + (j - g.nnull)];    // never covers null keys (:162)
     if (key_mask && j >= g.nnull && !key_mask[(int64_t)bi * g.m + (j - g.nnull)]) s = -FLT_MAX;  // (:166-167)
-    sp[j] = s;
-    sd[j] = dp;
+    Pr[j] = s;
     mx = fmaxf(mx, s);
   }
   mx = warp_max(mx);
   float sum = 0.f;
-  for (int j = lane; j < nkt; j += 32) { const float e = expf(sp[j] - mx); sp[j] = e; sum += e; }
+  for (int j = lane; j < nkt; j += 32) { const float e = expf(Pr[j] - mx); Pr[j] = e; sum += e; }
   sum = warp_sum(sum);
   const float inv = 1.0f / sum;
   float dot = 0.f;
-  for (int j = lane; j < nkt; j += 32) { const float p = sp[j] * inv; sp[j] = p; dot += p * sd[j]; }
+  for (int j = lane; j < nkt; j += 32) { const float p = Pr[j] * inv; Pr[j] = p; dot += p * dSr[j]; }
   dot = warp_sum(dot);
-  float* Pr = P + (((int64_t)bi * g.H + h) * g.n + i) * nkt;
-  float* dSr = dS + (((int64_t)bi * g.H + h) * g.n + i) * nkt;
-  for (int j = lane; j < nkt; j += 32) { Pr[j] = sp[j]; dSr[j] = sp[j] * (sd[j] - dot); }
+  for (int j = lane; j < nkt; j += 32) dSr[j] = Pr[j] * (dSr[j] - dot);
 }
 
 // back through `hat = (raw / max(|raw|, eps)) * scale` for one dh-vector held as DPL values per lane:
@@ -578,9 +579,15 @@ int attention_backward(const float* q, const float* kv, const phk_attn_t& A, con
   PHK_KERNEL_LAUNCH(attn_bwd_prep_kernel, dim3((unsigned)((prep_warps + 7) / 8)), dim3(256), (size_t)(0), st, q, kv, A.null_kv, A.q_scale, A.k_scale, B.qh, B.kh,
                                                                         B.vv, g);
   PHK_LAUNCH_CHECK();
-  const size_t smem = (size_t)4 * 2 * nkt * sizeof(float);
-  PHK_REQUIRE(smem <= 48 * 1024, PHK_E_UNSUPPORTED, "train: more than 1536 keys per sequence");
-  PHK_KERNEL_LAUNCH(attn_bwd_probs_kernel, dim3((unsigned)((bh * g.n + 3) / 4)), dim3(128), (size_t)(smem), st, B.qh, B.kh, B.vv, dO, bias, key_mask, B.P, B.dS, g);
+  // S = qh.kh^T and dP = dO.vv^T for every (sequence, head): two batched register-tiled products (a warp-per-row dot
+  // product would read the key rows with a stride of dim_head floats between lanes)
+  const int I = g.H * g.dh;
+  const GemmBatch bs{(int)bh, 1, (int64_t)g.n * g.dh, 0, (int64_t)nkt * g.dh, 0, (int64_t)g.n * nkt, 0};
+  PHK_TRY(sgemm_batched(B.qh, g.dh, 1, B.kh, 1, g.dh, B.P, nkt, g.n, nkt, g.dh, 0, bs, st));
+  const GemmBatch bd{(int)bh, g.H, (int64_t)g.n * I, (int64_t)g.dh, (int64_t)g.H * nkt * g.dh, (int64_t)nkt * g.dh,
+                     (int64_t)g.H * g.n * nkt, (int64_t)g.n * nkt};
+  PHK_TRY(sgemm_batched(dO, I, 1, B.vv, 1, g.dh, B.dS, nkt, g.n, nkt, g.dh, 0, bd, st));
+  PHK_KERNEL_LAUNCH(attn_bwd_softmax_kernel, dim3((unsigned)((bh * g.n + 7) / 8)), dim3(256), (size_t)(0), st, bias, key_mask, B.P, B.dS, g);
   PHK_LAUNCH_CHECK();
   PHK_KERNEL_LAUNCH(attn_bwd_dq_kernel, dim3((unsigned)((bh * g.n + 7) / 8)), dim3(256), (size_t)(0), st, q, B.kh, B.dS, A.q_scale, dq, (float*)G.q_scale, g);
   PHK_LAUNCH_CHECK();
