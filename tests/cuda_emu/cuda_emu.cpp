@@ -159,13 +159,36 @@ namespace phk {
 int patchify_ln_tma_launch(const float*, int, int, int, int, int, int, int, int, int, int, const float*, const float*, void*,
                            int, cudaStream_t) { return 1; }
 }  // namespace phk
-// tensor-core / TMA entry points the drivers reference in bf16 mode: not part of the emulated build
-extern "C" int phk_gemm_bf16_x2(const void*, int64_t, const void*, int64_t, float*, int64_t, int64_t, int32_t, int32_t,
-                                const float*, const void*, int64_t, const void*, int64_t, float*, int64_t, int64_t, int32_t,
-                                int32_t, const float*, phk_stream_t) { return PHK_E_UNSUPPORTED; }
-extern "C" int64_t phk_attention_tc_scratch_bytes(int32_t, int32_t, int32_t) { return 0; }
-extern "C" int phk_attention_tc(const float*, const float*, const float*, const float*, const float*, void*, int32_t, int32_t,
-                                int32_t, float, void*, int64_t, phk_stream_t) { return PHK_E_UNSUPPORTED; }
+// ---------------------------------------------------------------------------------------------------------------------
+// The tcgen05 / TMA entry points (gemm_tcgen05.cu, attention_tc.cu, head_sample.cu) cannot be executed thread by thread;
+// they are represented by their include/phk.h CONTRACTS so that the bf16-mode drivers (weight packing, buffer wiring,
+// the CFG-pair sharing, the masked-rows tail) can run end to end on the CPU.  Numerics: bf16 operands, fp32 accumulation.
+// ---------------------------------------------------------------------------------------------------------------------
+extern "C" int phk_attention(const float*, const float*, const float*, const float*, const float*, const float*,
+                             const uint8_t*, const float*, void*, const phk_attn_geom_t*, phk_stream_t);
+extern "C" int phk_gemm_bf16(const void*, int64_t, const void*, int64_t, void*, int64_t, int64_t, int32_t, int32_t,
+                             const float*, const float*, int64_t, int64_t, int64_t, int32_t, phk_stream_t);
+extern "C" int phk_gemm_bf16_x2(const void* A1, int64_t lda1, const void* W1, int64_t ldw1, float* C1, int64_t ldc1,
+                                int64_t M1, int32_t N1, int32_t K1, const float* bias1, const void* A2, int64_t lda2,
+                                const void* W2, int64_t ldw2, float* C2, int64_t ldc2, int64_t M2, int32_t N2, int32_t K2,
+                                const float* bias2, phk_stream_t s) {
+  const int rc = phk_gemm_bf16(A1, lda1, W1, ldw1, C1, ldc1, M1, N1, K1, bias1, nullptr, 0, 0, 0, 0, s);
+  return rc ? rc : phk_gemm_bf16(A2, lda2, W2, ldw2, C2, ldc2, M2, N2, K2, bias2, nullptr, 0, 0, 0, 0, s);
+}
+extern "C" int64_t phk_attention_tc_scratch_bytes(int32_t, int32_t, int32_t) { return 256; }
+// q fp32 [n_seq*n, heads*64], kv fp32 [n_seq*n, 2*heads*64], bias [heads, n, n] -> out bf16: the fp32 kernel of the same
+// contract (attention.cu) with bf16 output stands in (the real kernel also rounds q, k, v to bf16 first)
+extern "C" int phk_attention_tc(const float* q, const float* kv, const float* q_scale, const float* k_scale,
+                                const float* bias, void* out_bf16, int32_t n_seq, int32_t n, int32_t heads, float scale,
+                                void*, int64_t, phk_stream_t s) {
+  const int I = heads * 64;
+  phk_attn_geom_t g;
+  memset(&g, 0, sizeof(g));
+  g.n_outer = n_seq; g.n_inner = 1; g.n_q = n; g.n_k = n; g.heads = heads; g.dim_head = 64;
+  g.q_outer = (int64_t)n * I; g.q_tok = I; g.k_outer = (int64_t)n * 2 * I; g.k_tok = 2 * I; g.o_outer = g.q_outer; g.o_tok = I;
+  g.mask_off_from = -1; g.out_bf16 = 1; g.scale = scale;
+  return phk_attention(q, kv, nullptr, q_scale, k_scale, bias, nullptr, nullptr, out_bf16, &g, s);
+}
 // phk_layernorm_cfg / phk_head_sample (head_sample.cu, tcgen05) from their include/phk.h contracts, for the drivers'
 // wiring tests: e = s * norm(x_cond) + (1 - s) * norm(x_null) in bf16; logits = e W^T + bias in fp32, then the REAL
 // phk_sample_tokens kernel (the documented equivalence: same Philox counter layout as phk_sample_tokens with u == NULL)
@@ -212,22 +235,46 @@ extern "C" int phk_head_sample(const void* emb, int64_t ld_emb, int64_t emb_rows
 // test hook: 0 = in-order schedule, otherwise the seed of the random block / thread order
 extern "C" void phk_emu_set_shuffle(uint64_t seed) { emu::set_schedule_seed(seed); }
 
-// tcgen05 GEMM contract (include/phk.h): bf16 operands, fp32 accumulate, epilogue 0 (fp32 out + bias + residual)
+// tcgen05 GEMM contract (include/phk.h): bf16 operands K-major, fp32 accumulate; epilogue 0 fp32 (+bias, +residual, row
+// map), 1 bf16 (+bias), 2 GEGLU over [64 value | 64 gate] row groups of W -> bf16 [M, N/2]
 extern "C" int phk_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int64_t M,
-                             int32_t N, int32_t K, const float* bias, const float* residual, int64_t seg_len, int64_t,
-                             int64_t, int32_t epilogue, phk_stream_t) {
-  if (seg_len > 0 || epilogue != 0 || lda % 8 || ldw % 8 || lda < K || ldw < K) return PHK_E_ARG;
+                             int32_t N, int32_t K, const float* bias, const float* residual, int64_t seg_len,
+                             int64_t seg_stride, int64_t seg_off, int32_t epilogue, phk_stream_t) {
+  if (epilogue < 0 || epilogue > 2 || lda % 8 || ldw % 8 || lda < K || ldw < K) return PHK_E_ARG;
+  if (epilogue == 2 && (N % 128 || bias || residual)) return PHK_E_ARG;
   const __nv_bfloat16* a = (const __nv_bfloat16*)A;
   const __nv_bfloat16* w = (const __nv_bfloat16*)W;
-  float* c = (float*)C;
-  for (int64_t m = 0; m < M; ++m)
-    for (int n = 0; n < N; ++n) {
-      float acc = 0.f;
-      for (int k = 0; k < K; ++k) acc += __bfloat162float(a[m * lda + k]) * __bfloat162float(w[(int64_t)n * ldw + k]);
-      if (bias) acc += bias[n];
-      if (residual) acc += residual[m * ldc + n];
-      c[m * ldc + n] = acc;
+  std::vector<float> ar(K);
+  auto dot = [&](int n) {
+    float acc = 0.f;
+    const __nv_bfloat16* wr = w + (int64_t)n * ldw;
+    for (int k = 0; k < K; ++k) acc += ar[k] * __bfloat162float(wr[k]);
+    return acc;
+  };
+  for (int64_t m = 0; m < M; ++m) {
+    const int64_t orow = seg_len > 0 ? (m / seg_len) * seg_stride + seg_off + m % seg_len : m;
+    for (int k = 0; k < K; ++k) ar[k] = __bfloat162float(a[m * lda + k]);
+    if (epilogue == 2) {
+      __nv_bfloat16* o = (__nv_bfloat16*)C;
+      for (int t = 0; t < N / 128; ++t)
+        for (int j = 0; j < 64; ++j) {
+          const float val = dot(t * 128 + j), gate = dot(t * 128 + 64 + j);
+          o[orow * ldc + t * 64 + j] = __float2bfloat16_rn(0.5f * gate * (1.0f + erff(gate * 0.70710678118654752440f)) * val);
+        }
+      continue;
     }
+    for (int n = 0; n < N; ++n) {
+      float acc = dot(n);
+      if (bias) acc += bias[n];
+      if (epilogue == 0) {
+        float* c = (float*)C;
+        if (residual) acc += residual[orow * ldc + n];
+        c[orow * ldc + n] = acc;
+      } else {
+        ((__nv_bfloat16*)C)[orow * ldc + n] = __float2bfloat16_rn(acc);
+      }
+    }
+  }
   return 0;
 }
 
