@@ -66,6 +66,14 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// Plain stream-ordered launch (no programmatic dependent launch: for kernels that do not call pdl_prologue()).
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_plain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                       Args&&... args) {
+  kernel<<<grid, block, smem, st>>>(static_cast<KArgs>(args)...);
+  return cudaGetLastError();
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -12,17 +12,11 @@
 // deliberately plain (one warp per row, coalesced, no tensor cores): this is the parity path that pins the gradient
 // math against the reference's autograd; every formula is restated on the CPU in tests/train_mirror.py and checked
 // against the reference there.  The tcgen05 (bf16) backward GEMMs are the next step on top of it.
-// STATUS: written after the round's GPU budget was spent -- compiled for sm_100a, math pinned on the CPU, not yet run
-// on a GPU (tests/test_gpu_train.py runs it once PHK_EXPERIMENTAL=1).
-#ifdef PHK_CUDA_EMU  // tests/cuda_emu: the same source compiled by g++ and executed thread by thread on the CPU
-#include "../../tests/cuda_emu/cuda_emu.h"
-#define PHK_KERNEL_LAUNCH(kernel, grid, block, smem, st, ...) ::emu::launch(grid, block, smem, [&]() { kernel(__VA_ARGS__); })
-#define PHK_DYNAMIC_SMEM(type, name) type* name = reinterpret_cast<type*>(::emu::S.dyn_smem)
-#else
+// STATUS: written after the round's GPU budget was spent -- compiled for sm_100a and executed on the CPU by tests/cuda_emu
+// (this very source, g++-compiled) against the reference's gradients; not yet run on a GPU.
 #include "phk_common.cuh"
-#define PHK_KERNEL_LAUNCH(kernel, grid, block, smem, st, ...) kernel<<<grid, block, smem, st>>>(__VA_ARGS__)
-#define PHK_DYNAMIC_SMEM(type, name) extern __shared__ type name[]
-#endif
+// the kernels of this file are ordinary stream-ordered launches (they do not use programmatic dependent launch)
+#define PHK_KERNEL_LAUNCH(kernel, grid, block, smem, st, ...) PHK_CUDA(launch_plain(kernel, grid, block, smem, st, __VA_ARGS__))
 #include <cstring>
 #include <new>
 

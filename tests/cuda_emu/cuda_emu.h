@@ -171,6 +171,12 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
   ::emu::launch(grid, block, smem, [&]() { kernel(static_cast<KArgs>(args)...); });
   return 0;
 }
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_plain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t,
+                                       Args&&... args) {
+  ::emu::launch(grid, block, smem, [&]() { kernel(static_cast<KArgs>(args)...); });
+  return 0;
+}
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return (uint32_t)__float2bfloat16_rn(lo).bits | ((uint32_t)__float2bfloat16_rn(hi).bits << 16);
