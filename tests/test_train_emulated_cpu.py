@@ -49,10 +49,10 @@ def _compare(module, gk, ref, who):
         torch.testing.assert_close(got, ref[k], rtol=1e-3, atol=1e-4 * scale + 1e-7, msg=lambda m, k=k: f"{who}.{k}: {m}")
 
 
-@pytest.fixture(params=[0, 1, 2], ids=["in-order", "shuffle1", "shuffle2"])
+@pytest.fixture(params=[0, 1], ids=["in-order", "shuffled"])
 def schedule(emu, request):
-    """In-order schedule, then two random block / thread orders: a missing __syncthreads() or a dependence on block
-    order passes the first and fails the others."""
+    """In-order schedule, then a random block / thread order: a missing __syncthreads() or a dependence on block
+    order passes the first and fails the second."""
     emu.phk_emu_set_shuffle(request.param)
     yield request.param
     emu.phk_emu_set_shuffle(0)
