@@ -400,6 +400,13 @@ int phk_head_sample(const void* emb, int64_t ld_emb, int64_t emb_rows, const voi
                     const uint8_t* mask, int64_t* ids, int64_t* pred_out, float* score_out, void* scratch,
                     int64_t scratch_bytes, phk_stream_t s);
 
+/* phk_head_sample with the noise key in DEVICE memory: rng_state = uint64[2] {seed, offset} (NULL: the by-value pair).
+ * A CUDA graph that captured the call bakes the pointer, not the values, so every replay can draw fresh noise. */
+int phk_head_sample_rng(const void* emb, int64_t ld_emb, int64_t emb_rows, const void* W, int64_t ldw, const float* bias,
+                        int32_t n_tokens, int32_t V, int32_t dim, float temperature, uint64_t seed, uint64_t offset,
+                        const uint64_t* rng_state, const uint8_t* mask, int64_t* ids, int64_t* pred_out, float* score_out,
+                        void* scratch, int64_t scratch_bytes, phk_stream_t s);
+
 /* The tail of one demasking iteration restricted to the tokens that are still masked.  Rows do not interact after the
  * last attention, and the reference keeps the prediction and the confidence only where the mask is set
  * (`ids = where(mask, pred, ids)`, phenaki_pytorch.py:509; `where(mask, 1 - p, -1e4)`, :547-550), so the final LayerNorm,
@@ -407,12 +414,14 @@ int phk_head_sample(const void* emb, int64_t ld_emb, int64_t emb_rows, const voi
  * k per sequence -- the count phk_topk_mask was given, known on the host), norm_out + CFG are gathered into a bf16
  * [b*k, dim] operand, phk_head_sample runs on those rows and the results are scattered back.
  * x_cond / x_null fp32 [b*n, dim]: the residual stream BEFORE norm_out of the two halves; head_w bf16 [V, ldw];
- * mask / ids / pred_out / score_out as phk_sample_tokens, with score = -1e4 and pred = id at unmasked positions. */
+ * mask / ids / pred_out / score_out as phk_sample_tokens, with score = -1e4 and pred = id at unmasked positions;
+ * rng_state as phk_head_sample_rng. */
 int64_t phk_sample_tail_scratch_bytes(int32_t b, int32_t k, int32_t dim);
 int phk_sample_tail(const float* x_cond, const float* x_null, const float* gamma, const float* beta, float cond_scale,
                     const void* head_w, int64_t ldw, const float* head_b, int32_t b, int32_t n, int32_t k, int32_t V,
-                    int32_t dim, float temperature, uint64_t seed, uint64_t offset, const uint8_t* mask, int64_t* ids,
-                    int64_t* pred_out, float* score_out, void* scratch, int64_t scratch_bytes, phk_stream_t s);
+                    int32_t dim, float temperature, uint64_t seed, uint64_t offset, const uint64_t* rng_state,
+                    const uint8_t* mask, int64_t* ids, int64_t* pred_out, float* score_out, void* scratch,
+                    int64_t scratch_bytes, phk_stream_t s);
 
 /* One demasking iteration's network half for the sampling loop (phenaki_pytorch.py:495-509, 547-550): MaskGit forward
  * of the CFG pair (as phk_maskgit_forward with cfg_pair=1) + phk_head_sample.  bf16 weights required, cond_scale != 1,
@@ -427,6 +436,27 @@ int phk_maskgit_sample_step(const phk_maskgit_t* m, const int64_t* ids_in, int32
                             uint64_t seed, uint64_t offset, const uint8_t* mask, int64_t* ids, int64_t* pred_out,
                             float* score_out, int32_t masked_per_seq, void* workspace, int64_t workspace_bytes,
                             phk_stream_t s);
+
+/* rng_state[1] += stride on the stream (device-resident noise key, see phk_head_sample_rng) */
+int phk_rng_advance(uint64_t* rng_state, uint64_t stride, phk_stream_t s);
+
+/* One WHOLE demasking iteration (phenaki_pytorch.py:485-509, 547-550) as one call:
+ *   [k_remask > 0:  mask = scatter(topk(scores, k_remask)); ids = where(mask, mask_id, ids)]      (phk_topk_mask)
+ *   -> MaskGit forward of the CFG pair on ids -> tail on the masked rows -> ids, pred, scores updated IN PLACE
+ *   -> rng_state[1] += b*n*ceil(V/4) + 1 (the noise counters the iteration consumed).
+ * k_remask == 0 is the first iteration (every token masked: mask must be all ones).  rng_state: device uint64[2]
+ * {seed, offset}.  With PHK_STEP_GRAPH=1 the launch sequence is captured into a CUDA graph the second time the same
+ * arguments are seen (same table contents, pointers, shape, scalars) and later calls are ONE cudaGraphLaunch -- the
+ * noise key and the token state live in device memory, so nothing that changes between calls is baked in.  Buffers
+ * must therefore be stable across calls.  bf16 weights, cond_scale != 1, no priming (as phk_maskgit_sample_step). */
+int phk_maskgit_demask_iteration(const phk_maskgit_t* m, int64_t* ids, uint8_t* mask, float* scores, int64_t* pred,
+                                 int32_t b, int32_t n, int32_t pt, int32_t ph, int32_t pw, const float* ctx_kv, int32_t L,
+                                 const uint8_t* text_mask, const float* pos_bias, float cond_scale, float temperature,
+                                 uint64_t* rng_state, int32_t k_remask, void* workspace, int64_t workspace_bytes,
+                                 phk_stream_t s);
+
+/* tests / A-B runs: 1 = phk_maskgit_demask_iteration replays a CUDA graph, 0 = eager, < 0 = the PHK_STEP_GRAPH default */
+int phk_debug_step_graph(int32_t on);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Training step: Phenaki.forward (phenaki_pytorch.py:562-687)                   */

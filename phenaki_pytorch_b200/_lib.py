@@ -135,8 +135,13 @@ PROTOTYPES = {
     "phk_maskgit_sample_step": [C.POINTER(MaskgitT), vp, i32, i32, i32, i32, i32, vp, i32, vp, vp, vp, f32, f32, u64,
                                 u64, vp, vp, vp, vp, i32, vp, i64, vp],
     "phk_sample_tail_scratch_bytes": [i32, i32, i32],
-    "phk_sample_tail": [vp, vp, vp, vp, f32, vp, i64, vp, i32, i32, i32, i32, i32, f32, u64, u64, vp, vp, vp, vp, vp, i64,
-                        vp],
+    "phk_sample_tail": [vp, vp, vp, vp, f32, vp, i64, vp, i32, i32, i32, i32, i32, f32, u64, u64, vp, vp, vp, vp, vp, vp,
+                        i64, vp],
+    "phk_head_sample_rng": [vp, i64, i64, vp, i64, vp, i32, i32, i32, f32, u64, u64, vp, vp, vp, vp, vp, vp, i64, vp],
+    "phk_rng_advance": [vp, u64, vp],
+    "phk_debug_step_graph": [i32],
+    "phk_maskgit_demask_iteration": [C.POINTER(MaskgitT), vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, i32, vp, vp, f32, f32,
+                                     vp, i32, vp, i64, vp],
     "phk_maskgit_forward": [C.POINTER(MaskgitT), vp, i32, i32, i32, i32, i32, vp, i32, vp, vp, i32, i32, vp, vp,
                             vp, i64, i32, vp],
     "phk_maskgit_train_workspace_bytes": [C.POINTER(MaskgitT), i32, i32, i32, i32, i32],

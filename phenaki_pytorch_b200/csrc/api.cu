@@ -777,13 +777,13 @@ extern "C" int64_t phk_maskgit_sample_workspace_bytes(const phk_maskgit_t* m, in
   return phk_maskgit_workspace_bytes(m, b, n, L, 1, PHK_PREC_BF16) + (tail > full ? tail : full) + 1024;
 }
 
-extern "C" int phk_maskgit_sample_step(const phk_maskgit_t* m, const int64_t* ids_in, int32_t b, int32_t n, int32_t pt,
-                                       int32_t ph, int32_t pw, const float* ctx_kv, int32_t L,
-                                       const uint8_t* text_mask, const uint8_t* video_mask, const float* pos_bias,
-                                       float cond_scale, float temperature, uint64_t seed, uint64_t offset,
-                                       const uint8_t* mask, int64_t* ids, int64_t* pred_out, float* score_out,
-                                       int32_t masked_per_seq, void* workspace, int64_t workspace_bytes,
-                                       phk_stream_t s) {
+static int sample_step_impl(const phk_maskgit_t* m, const int64_t* ids_in, int32_t b, int32_t n, int32_t pt,
+                            int32_t ph, int32_t pw, const float* ctx_kv, int32_t L,
+                            const uint8_t* text_mask, const uint8_t* video_mask, const float* pos_bias,
+                            float cond_scale, float temperature, uint64_t seed, uint64_t offset, const uint64_t* rng_state,
+                            const uint8_t* mask, int64_t* ids, int64_t* pred_out, float* score_out,
+                            int32_t masked_per_seq, void* workspace, int64_t workspace_bytes,
+                            phk_stream_t s) {
   PHK_REQUIRE(m && ids_in && workspace, PHK_E_ARG, "maskgit_sample_step: null pointer");
   PHK_REQUIRE(masked_per_seq >= 0 && masked_per_seq <= n, PHK_E_ARG, "maskgit_sample_step: masked_per_seq out of range");
   PHK_REQUIRE(b > 0 && n > 0 && (int64_t)pt * ph * pw == n, PHK_E_SHAPE, "video patch shape must cover the token sequence");
@@ -832,8 +832,119 @@ extern "C" int phk_maskgit_sample_step(const phk_maskgit_t* m, const int64_t* id
   PHK_TRY(transformer_forward(c, ar, nullptr, nullptr, st));
   if (compact)
     return phk_sample_tail(xf, xf + tokens * D, T->out_g, T->out_b, cond_scale, m->head_w_h, D, m->head_b, b, n,
-                           masked_per_seq, m->num_tokens, D, temperature, seed, offset, mask, ids, pred_out, score_out,
-                           hsc, hb, s);
-  return phk_head_sample(emb_h, D, tokens, m->head_w_h, D, m->head_b, (int32_t)tokens, m->num_tokens, D, temperature,
-                         seed, offset, mask, ids, pred_out, score_out, hsc, hb, s);
+                           masked_per_seq, m->num_tokens, D, temperature, seed, offset, rng_state, mask, ids, pred_out,
+                           score_out, hsc, hb, s);
+  return phk_head_sample_rng(emb_h, D, tokens, m->head_w_h, D, m->head_b, (int32_t)tokens, m->num_tokens, D, temperature,
+                             seed, offset, rng_state, mask, ids, pred_out, score_out, hsc, hb, s);
+}
+
+extern "C" int phk_maskgit_sample_step(const phk_maskgit_t* m, const int64_t* ids_in, int32_t b, int32_t n, int32_t pt,
+                                       int32_t ph, int32_t pw, const float* ctx_kv, int32_t L,
+                                       const uint8_t* text_mask, const uint8_t* video_mask, const float* pos_bias,
+                                       float cond_scale, float temperature, uint64_t seed, uint64_t offset,
+                                       const uint8_t* mask, int64_t* ids, int64_t* pred_out, float* score_out,
+                                       int32_t masked_per_seq, void* workspace, int64_t workspace_bytes,
+                                       phk_stream_t s) {
+  return sample_step_impl(m, ids_in, b, n, pt, ph, pw, ctx_kv, L, text_mask, video_mask, pos_bias, cond_scale, temperature,
+                          seed, offset, nullptr, mask, ids, pred_out, score_out, masked_per_seq, workspace, workspace_bytes, s);
+}
+
+// ---- one whole demasking iteration, optionally replayed as a CUDA graph ---------------------------------------------
+// Everything that changes between calls lives in device memory (ids / mask / scores / pred are updated in place, the
+// noise key is rng_state), so the launch sequence is a pure function of the arguments and a captured graph stays valid:
+// same scheme as phk_cvivit_encode (first sighting of a key eager, second captured, then one cudaGraphLaunch).
+static int demask_iteration_impl(const phk_maskgit_t* m, int64_t* ids, uint8_t* mask, float* scores, int64_t* pred,
+                                 int32_t b, int32_t n, int32_t pt, int32_t ph, int32_t pw, const float* ctx_kv, int32_t L,
+                                 const uint8_t* text_mask, const float* pos_bias, float cond_scale, float temperature,
+                                 uint64_t* rng_state, int32_t k_remask, void* workspace, int64_t workspace_bytes,
+                                 phk_stream_t s) {
+  if (k_remask > 0) PHK_TRY(phk_topk_mask(scores, b, n, k_remask, mask, ids, (int64_t)m->num_tokens, s));
+  PHK_TRY(sample_step_impl(m, ids, b, n, pt, ph, pw, ctx_kv, L, text_mask, nullptr, pos_bias, cond_scale, temperature, 0, 0,
+                           rng_state, mask, ids, pred, scores, k_remask > 0 ? k_remask : n, workspace, workspace_bytes, s));
+  const uint64_t stride = (uint64_t)b * (uint64_t)n * (uint64_t)((m->num_tokens + 3) / 4) + 1;
+  return phk_rng_advance(rng_state, stride, s);
+}
+
+static std::atomic<int> g_step_graph{-1};  // -1: PHK_STEP_GRAPH from the environment; 0 / 1: phk_debug_step_graph
+static int step_graphs_enabled() {
+  const int v = g_step_graph.load(std::memory_order_relaxed);
+  if (v >= 0) return v;
+  static int env = -1;
+  if (env < 0) { const char* e = std::getenv("PHK_STEP_GRAPH"); env = (e && e[0] == '1') ? 1 : 0; }
+  return env;
+}
+// tests / A-B runs: 1 replays phk_maskgit_demask_iteration as a CUDA graph, 0 keeps it eager, < 0 back to PHK_STEP_GRAPH
+extern "C" int phk_debug_step_graph(int32_t on) { g_step_graph.store(on < 0 ? -1 : (on ? 1 : 0)); return 0; }
+
+extern "C" int phk_maskgit_demask_iteration(const phk_maskgit_t* m, int64_t* ids, uint8_t* mask, float* scores,
+                                            int64_t* pred, int32_t b, int32_t n, int32_t pt, int32_t ph, int32_t pw,
+                                            const float* ctx_kv, int32_t L, const uint8_t* text_mask, const float* pos_bias,
+                                            float cond_scale, float temperature, uint64_t* rng_state, int32_t k_remask,
+                                            void* workspace, int64_t workspace_bytes, phk_stream_t s) {
+  PHK_REQUIRE(m && ids && mask && scores && pred && rng_state && workspace, PHK_E_ARG, "maskgit_demask_iteration: null pointer");
+  PHK_REQUIRE(k_remask >= 0 && k_remask <= n, PHK_E_ARG, "maskgit_demask_iteration: k_remask out of range");
+  if (!step_graphs_enabled() || !pos_bias || g_prof_on.load(std::memory_order_relaxed))
+    return demask_iteration_impl(m, ids, mask, scores, pred, b, n, pt, ph, pw, ctx_kv, L, text_mask, pos_bias, cond_scale,
+                                 temperature, rng_state, k_remask, workspace, workspace_bytes, s);
+  struct Entry { cudaGraphExec_t exec; int launches; };
+  static std::unordered_map<uint64_t, Entry> cache;
+  static std::mutex mu;
+  static cudaStream_t cap = nullptr;
+  static bool broken = false;
+  int dev = 0;
+  PHK_CUDA(cudaGetDevice(&dev));
+  // key: table contents + every pointer and scalar of the call (a 64-bit FNV of them; the values behind the pointers
+  // -- token state, noise key, weights -- are read at replay time)
+  uint64_t key = fnv(m, sizeof(*m), 0xcbf29ce484222325ull);
+  key = hash_transformer(m->transformer, key);
+  const void* ptrs[] = {ids, mask, scores, pred, ctx_kv, text_mask, pos_bias, rng_state, workspace};
+  key = fnv(ptrs, sizeof(ptrs), key);
+  const int64_t ints[] = {b, n, pt, ph, pw, L, k_remask, dev, workspace_bytes};
+  key = fnv(ints, sizeof(ints), key);
+  const float fl[] = {cond_scale, temperature};
+  key = fnv(fl, sizeof(fl), key);
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = cache.find(key);
+  if (it != cache.end() && it->second.exec) {
+    PHK_CUDA(cudaGraphLaunch(it->second.exec, to_stream(s)));
+    count_launch(it->second.launches);
+    return 0;
+  }
+  if (broken || it == cache.end()) {  // first sighting (or graphs unusable): eager
+    if (!broken) {
+      if (cache.size() > 512) {
+        for (auto& kv : cache) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+        cache.clear();
+      }
+      cache.emplace(key, Entry{nullptr, 0});
+    }
+    return demask_iteration_impl(m, ids, mask, scores, pred, b, n, pt, ph, pw, ctx_kv, L, text_mask, pos_bias, cond_scale,
+                                 temperature, rng_state, k_remask, workspace, workspace_bytes, s);
+  }
+  if (!cap) PHK_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+  const int64_t l0 = g_launches.load();
+  cudaGraph_t graph = nullptr;
+  cudaError_t e = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
+  int rc = 0;
+  if (e == cudaSuccess) {
+    rc = demask_iteration_impl(m, ids, mask, scores, pred, b, n, pt, ph, pw, ctx_kv, L, text_mask, pos_bias, cond_scale,
+                               temperature, rng_state, k_remask, workspace, workspace_bytes, reinterpret_cast<phk_stream_t>(cap));
+    e = cudaStreamEndCapture(cap, &graph);
+  }
+  const int launches = (int)(g_launches.load() - l0);
+  g_launches.store(l0);  // the captured launches did not execute
+  cudaGraphExec_t exec = nullptr;
+  if (e == cudaSuccess && rc == 0 && graph) e = cudaGraphInstantiate(&exec, graph, 0);
+  if (graph) cudaGraphDestroy(graph);
+  if (e != cudaSuccess || rc != 0 || !exec) {
+    cudaGetLastError();
+    broken = true;
+    return demask_iteration_impl(m, ids, mask, scores, pred, b, n, pt, ph, pw, ctx_kv, L, text_mask, pos_bias, cond_scale,
+                                 temperature, rng_state, k_remask, workspace, workspace_bytes, s);
+  }
+  it->second.exec = exec;
+  it->second.launches = launches;
+  PHK_CUDA(cudaGraphLaunch(exec, to_stream(s)));
+  count_launch(launches);
+  return 0;
 }

@@ -105,6 +105,7 @@ struct HeadParams {
   int n_tokens, V, K, n_tiles, n_splits, tiles_per_split;
   float inv_T;
   unsigned long long seed, offset;
+  const unsigned long long* rng;  // optional device {seed, offset} overriding the two above (see phk_head_sample_rng)
   float4* part_f;  // [n_tokens, n_splits] {best_y, l_at_best, max_l, sum_exp}
   int* part_i;     // [n_tokens, n_splits] argmax index
 };
@@ -198,7 +199,9 @@ __global__ void __launch_bounds__(HTHREADS, 1) head_sample_kernel(const __grid_c
     const bool valid = tok < p.n_tokens;
     float best = -FLT_MAX, lbest = 0.f, mx = -FLT_MAX, ssum = 0.f;
     int bidx = 0x7fffffff;
-    const unsigned long long ctr0 = p.offset + (unsigned long long)tok * (unsigned long long)((p.V + 3) / 4);
+    // noise key: by value, or read from device memory so that a captured CUDA graph draws fresh noise on every replay
+    const unsigned long long seed = p.rng ? p.rng[0] : p.seed;
+    const unsigned long long ctr0 = (p.rng ? p.rng[1] : p.offset) + (unsigned long long)tok * (unsigned long long)((p.V + 3) / 4);
     for (int it = 0; it < my_tiles; ++it) {
       const int acc = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
@@ -222,7 +225,7 @@ __global__ void __launch_bounds__(HTHREADS, 1) head_sample_kernel(const __grid_c
         }
         uint32_t rnd[4];
         const unsigned long long ctr = ctr0 + (unsigned long long)(v0 >> 2);
-        philox4x32_10((uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u, (uint32_t)p.seed, (uint32_t)(p.seed >> 32), rnd);
+        philox4x32_10((uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), rnd);
         float l4[4];
         float gm = -FLT_MAX;
 #pragma unroll
@@ -405,6 +408,15 @@ extern "C" int phk_head_sample(const void* emb, int64_t ld_emb, int64_t emb_rows
                                const float* bias, int32_t n_tokens, int32_t V, int32_t dim, float temperature,
                                uint64_t seed, uint64_t offset, const uint8_t* mask, int64_t* ids, int64_t* pred_out,
                                float* score_out, void* scratch, int64_t scratch_bytes, phk_stream_t s) {
+  return phk_head_sample_rng(emb, ld_emb, emb_rows, W, ldw, bias, n_tokens, V, dim, temperature, seed, offset, nullptr, mask,
+                             ids, pred_out, score_out, scratch, scratch_bytes, s);
+}
+
+extern "C" int phk_head_sample_rng(const void* emb, int64_t ld_emb, int64_t emb_rows, const void* W, int64_t ldw,
+                                   const float* bias, int32_t n_tokens, int32_t V, int32_t dim, float temperature,
+                                   uint64_t seed, uint64_t offset, const uint64_t* rng_state, const uint8_t* mask,
+                                   int64_t* ids, int64_t* pred_out, float* score_out, void* scratch, int64_t scratch_bytes,
+                                   phk_stream_t s) {
   Prof prof_(FAM_GEMM_BF16, s, 2.0 * (double)n_tokens * V * dim);
   PHK_REQUIRE(emb && W && scratch, PHK_E_ARG, "phk_head_sample: null pointer");
   PHK_REQUIRE(n_tokens > 0 && V > 0 && dim > 0 && ld_emb >= dim && ldw >= dim && emb_rows >= n_tokens, PHK_E_ARG,
@@ -428,7 +440,7 @@ extern "C" int phk_head_sample(const void* emb, int64_t ld_emb, int64_t emb_rows
   int* part_i = (int*)(sc + (int64_t)n_tokens * n_splits * 16);
   const float T = temperature > 1e-10f ? temperature : 1e-10f;
   HeadParams p{bias, n_tokens, V, dim, n_tiles, n_splits, tps, 1.0f / T, (unsigned long long)seed,
-               (unsigned long long)offset, part_f, part_i};
+               (unsigned long long)offset, reinterpret_cast<const unsigned long long*>(rng_state), part_f, part_i};
   cudaStream_t st = to_stream(s);
   static bool configured = false;
   if (!configured) {

@@ -118,6 +118,12 @@ __global__ void tail_scatter_kernel(const int* __restrict__ index, const int64_t
   }
 }
 
+// rng_state[1] += stride: the noise counters one iteration consumed (device-resident key of a replayed graph)
+__global__ void rng_advance_kernel(unsigned long long* rng_state, unsigned long long stride) {
+  pdl_prologue();
+  if (blockIdx.x == 0 && threadIdx.x == 0) rng_state[1] += stride;
+}
+
 struct TailBufs { int* index; __nv_bfloat16* emb; uint8_t* ones; int64_t* ids_c; int64_t* pred_c; float* score_c; char* head; int64_t head_bytes; };
 
 int64_t align256(int64_t v) { return (v + 255) & ~int64_t(255); }
@@ -150,8 +156,9 @@ extern "C" int64_t phk_sample_tail_scratch_bytes(int32_t b, int32_t k, int32_t d
 extern "C" int phk_sample_tail(const float* x_cond, const float* x_null, const float* gamma, const float* beta,
                                float cond_scale, const void* head_w, int64_t ldw, const float* head_b, int32_t b,
                                int32_t n, int32_t k, int32_t V, int32_t dim, float temperature, uint64_t seed,
-                               uint64_t offset, const uint8_t* mask, int64_t* ids, int64_t* pred_out, float* score_out,
-                               void* scratch, int64_t scratch_bytes, phk_stream_t s) {
+                               uint64_t offset, const uint64_t* rng_state, const uint8_t* mask, int64_t* ids,
+                               int64_t* pred_out, float* score_out, void* scratch, int64_t scratch_bytes,
+                               phk_stream_t s) {
   PHK_REQUIRE(x_cond && x_null && gamma && beta && head_w && mask && ids && scratch, PHK_E_ARG, "phk_sample_tail: null pointer");
   PHK_REQUIRE(b > 0 && n > 0 && k > 0 && k <= n && V > 0, PHK_E_ARG, "phk_sample_tail: bad size");
   PHK_REQUIRE(dim % 128 == 0 && dim <= 1024, PHK_E_UNSUPPORTED, "phk_sample_tail: dim must be a multiple of 128, <= 1024");
@@ -177,14 +184,22 @@ extern "C" int phk_sample_tail(const float* x_cond, const float* x_null, const f
   }
   PHK_LAUNCH_CHECK();
   PHK_CUDA(cudaMemsetAsync(t.ones, 1, rows, st));
-  PHK_TRY(phk_head_sample(t.emb, dim, rows, head_w, ldw, head_b, (int32_t)rows, V, dim, temperature, seed, offset, t.ones,
-                          t.ids_c, t.pred_c, t.score_c, t.head, t.head_bytes, s));
+  PHK_TRY(phk_head_sample_rng(t.emb, dim, rows, head_w, ldw, head_b, (int32_t)rows, V, dim, temperature, seed, offset,
+                              rng_state, t.ones, t.ids_c, t.pred_c, t.score_c, t.head, t.head_bytes, s));
   const unsigned g1 = (unsigned)((tokens + 255) / 256 < 1184 ? (tokens + 255) / 256 : 1184);
   PHK_CUDA(launch_pdl(tail_init_kernel, dim3(g1), dim3(256), (size_t)0, st, (const int64_t*)ids, pred_out, score_out, tokens));
   PHK_LAUNCH_CHECK();
   const unsigned g2 = (unsigned)((rows + 255) / 256 < 1184 ? (rows + 255) / 256 : 1184);
   PHK_CUDA(launch_pdl(tail_scatter_kernel, dim3(g2), dim3(256), (size_t)0, st, (const int*)t.index, (const int64_t*)t.pred_c,
                       (const float*)t.score_c, ids, pred_out, score_out, rows));
+  PHK_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int phk_rng_advance(uint64_t* rng_state, uint64_t stride, phk_stream_t s) {
+  PHK_REQUIRE(rng_state, PHK_E_ARG, "phk_rng_advance: null pointer");
+  PHK_CUDA(launch_pdl(rng_advance_kernel, dim3(1), dim3(32), (size_t)0, to_stream(s),
+                      reinterpret_cast<unsigned long long*>(rng_state), (unsigned long long)stride));
   PHK_LAUNCH_CHECK();
   return 0;
 }

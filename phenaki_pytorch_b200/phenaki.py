@@ -503,6 +503,11 @@ class Phenaki(nn.Module):
         # training under torch.distributed: average the gradient bucket over the ranks in backward() (what the
         # reference gets from Accelerate's DDP wrapper, phenaki_trainer.py); no-op without a process group
         self.sync_gradients = True
+        # bf16 mode, no critic: one C call per demasking iteration with all state in device memory
+        # (phk_maskgit_demask_iteration), replayed as ONE CUDA-graph launch per iteration when PHK_STEP_GRAPH=1.
+        # Opt-in until its first GPU run; same noise counters as the default path.
+        self.iteration_call = os.environ.get("PHK_STEP_GRAPH", "0") == "1"
+        self._iter_bufs = {}
         self.fused_head = True  # bf16 mode: logits head + CFG + gumbel argmax fused into one GEMM (no (b,n,V) logits)
 
     # ---- the demasking loop (phenaki_pytorch.py:473-550) -------------------------------------------------
@@ -542,6 +547,10 @@ class Phenaki(nn.Module):
             seed = _noise_seed(dev)
             vocab = mg.to_logits.weight.shape[0]
             have_scores = False
+            if (self.iteration_call and self.fused_head and mg.precision == L.PREC_BF16 and noise_fn is None
+                    and cond_scale != 1 and plen == 0 and trace is None and self.critic is None):
+                return self._sample_by_iterations(b, n, patch_shape, ctx_kv, ctx_len, text_mask, cond_scale,
+                                                  starting_temperature, ks, seed, vocab, dev)
             for step in range(steps):
                 last = step == steps - 1
                 til_x0 = steps - (step + 1)
@@ -611,6 +620,46 @@ class Phenaki(nn.Module):
                 if trace is not None:
                     trace[-1]["scores"] = scores.clone()
         return ids
+
+    def _sample_by_iterations(self, b, n, patch_shape, ctx_kv, ctx_len, text_mask, cond_scale, starting_temperature,
+                              ks, seed, vocab, dev):
+        """The demasking loop as ``steps`` calls of phk_maskgit_demask_iteration.  Token state, mask, scores, the text
+        keys / values and the noise key live in buffers that persist across ``sample`` calls, so the library sees the
+        same arguments at iteration s of every sample and can replay one captured CUDA graph per iteration."""
+        lib, mg, steps = L.lib(), self.maskgit, self.steps
+        key = (b, n, ctx_len, dev)
+        bufs = self._iter_bufs.get(key)
+        if bufs is None:
+            bufs = self._iter_bufs[key] = dict(
+                ids=torch.empty((b, n), dtype=torch.int64, device=dev), mask=torch.empty((b, n), dtype=torch.uint8, device=dev),
+                scores=torch.empty((b, n), dtype=torch.float32, device=dev), pred=torch.empty((b, n), dtype=torch.int64, device=dev),
+                rng=torch.empty((2,), dtype=torch.int64, device=dev),
+                ctx_kv=None if ctx_kv is None else torch.empty_like(ctx_kv),
+                text_mask=None if text_mask is None else torch.empty(text_mask.shape, dtype=torch.uint8, device=dev))
+        bufs["ids"].fill_(self.mask_id)
+        bufs["mask"].fill_(1)
+        bufs["scores"].zero_()
+        if ctx_kv is not None:
+            bufs["ctx_kv"].copy_(ctx_kv)
+            bufs["text_mask"].copy_(text_mask.to(torch.uint8))
+        stride = b * n * ((vocab + 3) // 4) + 1
+        as_i64 = lambda v: v - (1 << 64) if v >= (1 << 63) else v  # uint64 bit pattern in an int64 tensor
+        bufs["rng"].copy_(torch.tensor([as_i64(seed & (2 ** 64 - 1)), as_i64((self._rng_calls * stride) & (2 ** 64 - 1))],
+                                       dtype=torch.int64))
+        with torch.cuda.device(dev):
+            table = mg._table()
+            ws = mg._ws.get(lib.phk_maskgit_sample_workspace_bytes(C.byref(table), b, n, ctx_len), dev)
+            bias = mg._pos_bias(table, patch_shape, dev)
+            pt, ph, pw = (int(v) for v in patch_shape)
+            for step in range(steps):
+                temperature = starting_temperature * ((steps - (step + 1)) / steps)
+                L.check(lib.phk_maskgit_demask_iteration(
+                    C.byref(table), L.ptr(bufs["ids"]), L.ptr(bufs["mask"]), L.ptr(bufs["scores"]), L.ptr(bufs["pred"]),
+                    b, n, pt, ph, pw, L.ptr(bufs["ctx_kv"]), ctx_len, L.ptr(bufs["text_mask"]), L.ptr(bias),
+                    float(cond_scale), float(temperature), L.ptr(bufs["rng"]), 0 if step == 0 else ks[step - 1],
+                    L.ptr(ws), ws.numel(), L.stream_ptr()), "phk_maskgit_demask_iteration")
+        self._rng_calls += steps
+        return bufs["ids"].clone()
 
     @torch.no_grad()
     def sample(self, *, num_frames, texts: Union[List[str], str, None] = None, prime_frames=None, batch_size=1,

@@ -100,6 +100,14 @@ template <typename T> static void shuffle(std::vector<T>& v) {
 
 void set_schedule_seed(uint64_t seed) { init_schedule(); set_shuffle(seed); }
 
+// ---- stream capture: a graph is the list of operations submitted between Begin and End, replayed in order ----------
+struct Graph { std::vector<std::function<void()>> nodes; };
+static Graph* g_capturing = nullptr;
+void submit(std::function<void()> op) {
+  if (g_capturing) g_capturing->nodes.push_back(std::move(op));
+  else op();
+}
+
 void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body) {
   init_schedule();
   const unsigned nt = block.x * block.y * block.z;
@@ -154,6 +162,30 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
 }
 }  // namespace emu
 
+cudaError_t cudaStreamBeginCapture(cudaStream_t, int) {
+  if (emu::g_capturing) return cudaErrorInvalidValue;
+  emu::g_capturing = new emu::Graph();
+  return 0;
+}
+cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t* g) {
+  *g = emu::g_capturing;
+  emu::g_capturing = nullptr;
+  return *g ? 0 : cudaErrorInvalidValue;
+}
+cudaError_t cudaGraphInstantiate(cudaGraphExec_t* e, cudaGraph_t g, unsigned long long) {
+  *e = new emu::Graph(*static_cast<emu::Graph*>(g));
+  return 0;
+}
+static long g_graph_launches = 0;
+cudaError_t cudaGraphLaunch(cudaGraphExec_t e, cudaStream_t) {
+  g_graph_launches += 1;
+  for (auto& op : static_cast<emu::Graph*>(e)->nodes) emu::submit(op);
+  return 0;
+}
+extern "C" long phk_emu_graph_launches(void) { return g_graph_launches; }  // test hook
+cudaError_t cudaGraphDestroy(cudaGraph_t g) { delete static_cast<emu::Graph*>(g); return 0; }
+cudaError_t cudaGraphExecDestroy(cudaGraphExec_t e) { delete static_cast<emu::Graph*>(e); return 0; }
+
 namespace phk {
 // patchify_tma.cu (TMA) is not part of the emulated build: "shape not eligible" sends phk_patchify_ln to its plain kernels
 int patchify_ln_tma_launch(const float*, int, int, int, int, int, int, int, int, int, int, const float*, const float*, void*,
@@ -194,43 +226,56 @@ extern "C" int phk_attention_tc(const float* q, const float* kv, const float* q_
 // phk_sample_tokens kernel (the documented equivalence: same Philox counter layout as phk_sample_tokens with u == NULL)
 extern "C" int phk_layernorm_cfg(const float* xc, const float* xn, const float* g, const float* b, float scale, void* out,
                                  int64_t rows, int32_t dim, phk_stream_t) {
-  __nv_bfloat16* o = (__nv_bfloat16*)out;
-  std::vector<float> acc(dim);
-  for (int64_t r = 0; r < rows; ++r) {
-    for (int c = 0; c < dim; ++c) acc[c] = 0.f;
-    for (int pass = 0; pass < 2; ++pass) {
-      const float* x = (pass ? xn : xc) + r * dim;
-      float mean = 0.f, var = 0.f;
-      for (int c = 0; c < dim; ++c) mean += x[c];
-      mean /= dim;
-      for (int c = 0; c < dim; ++c) var += (x[c] - mean) * (x[c] - mean);
-      const float rstd = 1.0f / sqrtf(var / dim + 1e-5f), w = pass ? 1.0f - scale : scale;
-      for (int c = 0; c < dim; ++c) acc[c] += w * ((x[c] - mean) * rstd * g[c] + b[c]);
+  emu::submit([=]() {
+    __nv_bfloat16* o = (__nv_bfloat16*)out;
+    std::vector<float> acc(dim);
+    for (int64_t r = 0; r < rows; ++r) {
+      for (int c = 0; c < dim; ++c) acc[c] = 0.f;
+      for (int pass = 0; pass < 2; ++pass) {
+        const float* x = (pass ? xn : xc) + r * dim;
+        float mean = 0.f, var = 0.f;
+        for (int c = 0; c < dim; ++c) mean += x[c];
+        mean /= dim;
+        for (int c = 0; c < dim; ++c) var += (x[c] - mean) * (x[c] - mean);
+        const float rstd = 1.0f / sqrtf(var / dim + 1e-5f), w = pass ? 1.0f - scale : scale;
+        for (int c = 0; c < dim; ++c) acc[c] += w * ((x[c] - mean) * rstd * g[c] + b[c]);
+      }
+      for (int c = 0; c < dim; ++c) o[r * dim + c] = __float2bfloat16_rn(acc[c]);
     }
-    for (int c = 0; c < dim; ++c) o[r * dim + c] = __float2bfloat16_rn(acc[c]);
-  }
+  });
   return 0;
 }
 extern "C" int64_t phk_head_sample_scratch_bytes(int32_t n_tokens) { return (int64_t)n_tokens * 64 + 512; }
 extern "C" int phk_sample_tokens(const float*, const float*, int64_t, const float*, uint64_t, uint64_t, float, float,
                                  const uint8_t*, int64_t*, int64_t*, float*, int64_t, int32_t, int64_t, int64_t, int64_t,
                                  phk_stream_t);
+extern "C" int phk_head_sample_rng(const void* emb, int64_t ld_emb, int64_t emb_rows, const void* W, int64_t ldw,
+                                   const float* bias, int32_t n_tokens, int32_t V, int32_t dim, float temperature,
+                                   uint64_t seed, uint64_t offset, const uint64_t* rng_state, const uint8_t* mask,
+                                   int64_t* ids, int64_t* pred_out, float* score_out, void*, int64_t, phk_stream_t s) {
+  if (emb_rows < n_tokens || ld_emb % 8 || ldw % 8) return PHK_E_ARG;
+  emu::submit([=]() {  // one stream-ordered operation; the device-resident noise key is read when it RUNS
+    const __nv_bfloat16* e = (const __nv_bfloat16*)emb;
+    const __nv_bfloat16* w = (const __nv_bfloat16*)W;
+    std::vector<float> logits((size_t)n_tokens * V);
+    for (int64_t r = 0; r < n_tokens; ++r)
+      for (int v = 0; v < V; ++v) {
+        float a = 0.f;
+        for (int k = 0; k < dim; ++k) a += __bfloat162float(e[r * ld_emb + k]) * __bfloat162float(w[(int64_t)v * ldw + k]);
+        logits[(size_t)r * V + v] = a + (bias ? bias[v] : 0.f);
+      }
+    const uint64_t sd = rng_state ? rng_state[0] : seed, of = rng_state ? rng_state[1] : offset;
+    phk_sample_tokens(logits.data(), nullptr, V, nullptr, sd, of, 1.0f, temperature, mask, ids, pred_out, score_out, n_tokens,
+                      V, 0, 0, 0, s);
+  });
+  return 0;
+}
 extern "C" int phk_head_sample(const void* emb, int64_t ld_emb, int64_t emb_rows, const void* W, int64_t ldw,
                                const float* bias, int32_t n_tokens, int32_t V, int32_t dim, float temperature, uint64_t seed,
-                               uint64_t offset, const uint8_t* mask, int64_t* ids, int64_t* pred_out, float* score_out, void*,
-                               int64_t, phk_stream_t s) {
-  if (emb_rows < n_tokens || ld_emb % 8 || ldw % 8) return PHK_E_ARG;
-  const __nv_bfloat16* e = (const __nv_bfloat16*)emb;
-  const __nv_bfloat16* w = (const __nv_bfloat16*)W;
-  std::vector<float> logits((size_t)n_tokens * V);
-  for (int64_t r = 0; r < n_tokens; ++r)
-    for (int v = 0; v < V; ++v) {
-      float a = 0.f;
-      for (int k = 0; k < dim; ++k) a += __bfloat162float(e[r * ld_emb + k]) * __bfloat162float(w[(int64_t)v * ldw + k]);
-      logits[(size_t)r * V + v] = a + (bias ? bias[v] : 0.f);
-    }
-  return phk_sample_tokens(logits.data(), nullptr, V, nullptr, seed, offset, 1.0f, temperature, mask, ids, pred_out, score_out,
-                           n_tokens, V, 0, 0, 0, s);
+                               uint64_t offset, const uint8_t* mask, int64_t* ids, int64_t* pred_out, float* score_out,
+                               void* sc, int64_t sb, phk_stream_t s) {
+  return phk_head_sample_rng(emb, ld_emb, emb_rows, W, ldw, bias, n_tokens, V, dim, temperature, seed, offset, nullptr, mask,
+                             ids, pred_out, score_out, sc, sb, s);
 }
 // test hook: 0 = in-order schedule, otherwise the seed of the random block / thread order
 extern "C" void phk_emu_set_shuffle(uint64_t seed) { emu::set_schedule_seed(seed); }
@@ -242,6 +287,7 @@ extern "C" int phk_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t 
                              int64_t seg_stride, int64_t seg_off, int32_t epilogue, phk_stream_t) {
   if (epilogue < 0 || epilogue > 2 || lda % 8 || ldw % 8 || lda < K || ldw < K) return PHK_E_ARG;
   if (epilogue == 2 && (N % 128 || bias || residual)) return PHK_E_ARG;
+  emu::submit([=]() {
   const __nv_bfloat16* a = (const __nv_bfloat16*)A;
   const __nv_bfloat16* w = (const __nv_bfloat16*)W;
   std::vector<float> ar(K);
@@ -275,6 +321,6 @@ extern "C" int phk_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t 
       }
     }
   }
+  });
   return 0;
 }
-

@@ -17,6 +17,7 @@
 #include <cstring>
 #include <functional>
 #include <algorithm>
+#include <tuple>
 #include <utility>
 #include <vector>
 #include "../../include/phk.h"
@@ -61,7 +62,7 @@ typedef void* cudaEvent_t;
 typedef void* cudaGraph_t;
 typedef void* cudaGraphExec_t;
 enum { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2,
-       cudaStreamCaptureModeThreadLocal = 1, cudaErrorStreamCaptureUnsupported = 900 };
+       cudaStreamCaptureModeThreadLocal = 1, cudaErrorStreamCaptureUnsupported = 900, cudaErrorInvalidValue = 1 };
 static inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = nullptr; return 0; }
 static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = nullptr; return 0; }
 static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return 0; }
@@ -72,12 +73,12 @@ static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) {
 static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
 static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return 0; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
-static inline cudaError_t cudaStreamBeginCapture(cudaStream_t, int) { return cudaErrorStreamCaptureUnsupported; }
-static inline cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t* g) { *g = nullptr; return cudaErrorStreamCaptureUnsupported; }
-static inline cudaError_t cudaGraphInstantiate(cudaGraphExec_t* e, cudaGraph_t, unsigned long long) { *e = nullptr; return cudaErrorStreamCaptureUnsupported; }
-static inline cudaError_t cudaGraphLaunch(cudaGraphExec_t, cudaStream_t) { return cudaErrorStreamCaptureUnsupported; }
-static inline cudaError_t cudaGraphDestroy(cudaGraph_t) { return 0; }
-static inline cudaError_t cudaGraphExecDestroy(cudaGraphExec_t) { return 0; }
+cudaError_t cudaStreamBeginCapture(cudaStream_t, int);
+cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t* g);
+cudaError_t cudaGraphInstantiate(cudaGraphExec_t* e, cudaGraph_t g, unsigned long long);
+cudaError_t cudaGraphLaunch(cudaGraphExec_t e, cudaStream_t);
+cudaError_t cudaGraphDestroy(cudaGraph_t g);
+cudaError_t cudaGraphExecDestroy(cudaGraphExec_t e);
 static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return 0; }
 
 namespace emu {
@@ -93,6 +94,9 @@ Group& block_group();
 Group& warp_group();
 float* warp_xchg();
 void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body);
+// one stream-ordered operation: executed now, or -- between cudaStreamBeginCapture / EndCapture -- recorded as a node of
+// the graph under construction (arguments by value: exactly what a captured CUDA graph bakes in)
+void submit(std::function<void()> op);
 void set_schedule_seed(uint64_t seed);
 }  // namespace emu
 
@@ -139,8 +143,14 @@ static inline float __fdividef(float a, float b) { return a / b; }
 static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((uint64_t)a * b) >> 32); }
 using std::max;
 using std::min;
-static inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { memset(p, v, n); return 0; }
-static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, int, cudaStream_t) { memmove(d, s, n); return 0; }
+static inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) {
+  ::emu::submit([=]() { memset(p, v, n); });
+  return 0;
+}
+static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, int, cudaStream_t) {
+  ::emu::submit([=]() { memmove(d, s, n); });
+  return 0;
+}
 static inline cudaError_t cudaGetLastError() { return 0; }
 
 namespace phk {
@@ -148,7 +158,7 @@ void set_error(const char* msg);
 void count_launch(int n = 1);
 #define PHK_REQUIRE(cond, code, msg) \
   do { if (!(cond)) { ::phk::set_error(msg); return (code); } } while (0)
-#define PHK_LAUNCH_CHECK() do { } while (0)
+#define PHK_LAUNCH_CHECK() do { ::phk::count_launch(); } while (0)
 #define PHK_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return (int)e__; } while (0)
 #define PHK_TRY(call) do { int r__ = (call); if (r__ != 0) return r__; } while (0)
 static inline cudaStream_t to_stream(phk_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
@@ -168,13 +178,15 @@ int patchify_ln_tma_launch(const float*, int, int, int, int, int, int, int, int,
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t,
                                      Args&&... args) {
-  ::emu::launch(grid, block, smem, [&]() { kernel(static_cast<KArgs>(args)...); });
+  auto params = std::make_tuple(static_cast<KArgs>(args)...);  // kernel parameters are copied at launch (or capture) time
+  ::emu::submit([=]() { ::emu::launch(grid, block, smem, [&]() { std::apply(kernel, params); }); });
   return 0;
 }
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_plain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t,
                                        Args&&... args) {
-  ::emu::launch(grid, block, smem, [&]() { kernel(static_cast<KArgs>(args)...); });
+  auto params = std::make_tuple(static_cast<KArgs>(args)...);
+  ::emu::submit([=]() { ::emu::launch(grid, block, smem, [&]() { std::apply(kernel, params); }); });
   return 0;
 }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }

@@ -36,7 +36,7 @@ def run_tail(lib, xc, xn, gamma, beta, W, bias, mask, ids, *, b, n, k, V, dim, s
     nb = lib.phk_sample_tail_scratch_bytes(b, k, dim)
     scratch = torch.empty(int(nb), dtype=torch.uint8, device=dev)
     L.check(lib.phk_sample_tail(L.ptr(xc), L.ptr(xn), L.ptr(gamma), L.ptr(beta), scale, L.ptr(W), dim, L.ptr(bias), b, n, k,
-                                V, dim, temperature, seed, offset, L.ptr(mask), L.ptr(ids), L.ptr(pred), L.ptr(score),
+                                V, dim, temperature, seed, offset, None, L.ptr(mask), L.ptr(ids), L.ptr(pred), L.ptr(score),
                                 L.ptr(scratch), nb, L.stream_ptr()), "phk_sample_tail")
     return pred, score
 

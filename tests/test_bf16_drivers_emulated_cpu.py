@@ -4,6 +4,8 @@ include/phk.h contracts (tests/cuda_emu/cuda_emu.cpp: bf16 operands, fp32 accumu
 logic of bf16 mode -- bf16 weight packing (GEGLU row interleave, padding), buffer wiring, the CFG-pair sharing of the
 first layer, the masked-rows tail of the demasking step -- not the tensor-core kernels themselves, which only the B200
 run exercises."""
+import ctypes
+
 import pytest
 import torch
 
@@ -29,3 +31,40 @@ def _product_on_the_cpu(_emu_lib, monkeypatch):
     monkeypatch.setattr(G, "DEV", "cpu")
     monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
     monkeypatch.setattr(torch.cuda, "manual_seed_all", lambda *a, **k: None, raising=False)
+
+
+def test_demasking_iterations_as_replayed_graphs_equal_the_default_loop(_emu_lib):
+    """phk_maskgit_demask_iteration (one call per iteration, all state in device memory) -- eager, and captured /
+    replayed as a graph (the executor records the operations submitted between BeginCapture and EndCapture with their
+    arguments BY VALUE, i.e. it bakes in exactly what a CUDA graph bakes in) -- must produce the ids of the default loop
+    for three consecutive sample() calls: the second call captures, the third replays, and each call draws fresh noise,
+    so a value wrongly baked into the graph (noise key, k, temperature, a stale pointer) shows up as a difference."""
+    from phenaki_pytorch_b200 import _lib as L
+    from tests import cases as C
+    import phenaki_pytorch_b200 as P
+    case = C.SAMPLE_CASES["confidence"]
+
+    def run(iteration_call, graph):
+        torch.manual_seed(case["seed"])
+        cv = P.CViViT(**C.SAMPLE_CVIVIT)
+        mg = P.MaskGit(dim=128, num_tokens=256, max_seq_len=64, heads=2, dim_head=64, depth=2, dim_context=48)
+        mg.precision = L.PREC_BF16
+        ph = P.Phenaki(cvivit=cv, maskgit=mg, steps=5, text_embed_dim=48)
+        ph.iteration_call = iteration_call
+        _emu_lib.phk_debug_step_graph(graph)
+        ctx = C.synthetic_text_embeds(2, 6, 48, (6, 3), 3)
+        torch.manual_seed(11)
+        outs = [ph.sample(num_frames=7, text_embeds=ctx, return_token_ids=True).clone() for _ in range(3)]
+        _emu_lib.phk_debug_step_graph(-1)
+        return outs
+
+    base = run(False, 0)
+    assert not torch.equal(base[0], base[1]) and not torch.equal(base[1], base[2])  # fresh noise per call
+    _emu_lib.phk_emu_graph_launches.restype = ctypes.c_long
+    for graph in (0, 1):
+        before = _emu_lib.phk_emu_graph_launches()
+        got = run(True, graph)
+        replays = _emu_lib.phk_emu_graph_launches() - before
+        assert replays == (10 if graph else 0)  # 5 iterations each: captured + launched in call 2, replayed in call 3
+        for i in range(3):
+            assert torch.equal(got[i], base[i]), f"graph={graph}, call {i}"

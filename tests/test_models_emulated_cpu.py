@@ -15,7 +15,7 @@ from tests import test_gpu_models as G
 _MODELS = ["test_cvivit_token_ids_match_reference_golden", "test_cvivit_state_dict_roundtrip_changes_nothing",
            "test_cvivit_shape_contract_errors", "test_maskgit_logits_match_reference_golden",
            "test_maskgit_sequence_length_contract", "test_token_critic_scores_match_reference_golden",
-           "test_sampling_loop_token_ids_match_reference_golden"]
+           "test_sampling_loop_token_ids_match_reference_golden", "test_encode_graph_replay_equals_eager_launches"]
 for _n in _MODELS:
     globals()[_n] = getattr(G, _n)
 _DECODE = [n for n in dir(D) if n.startswith("test_") and "bf16" not in n and n != "test_decode_token_count_contract"]  # (that one checks the refusal of CPU tensors)
