@@ -116,6 +116,10 @@ typedef struct {
   phk_transformer_t spatial;                      /* enc_spatial_transformer                    */
   phk_transformer_t temporal;                     /* enc_temporal_transformer                   */
   const float* vq_w; const float* vq_b;           /* vq.project_in [bits, dim], [bits]          */
+  /* lookup_free_quantization=False (cvivit.py:321): the cosine-sim codebook vq._codebook.embed[0] [codebook_size, dim]
+   * (unit rows); vq_w / vq_b are then NULL and codebook_bits 0 */
+  const float* codebook; const void* codebook_h;
+  int32_t codebook_size; int32_t _pad2;
 } phk_cvivit_t;
 
 /* cvivit.py:323-335 the decoder half of CViViT (vq.project_out, dec_* transformers, to_pixels*) */
@@ -257,6 +261,14 @@ int phk_lfq_ids(const float* x, const float* wp, const float* bp, int64_t* ids, 
 int phk_layernorm_lfq(const float* x, const float* gamma, const float* beta, const float* wp, const float* bp,
                       int64_t* ids, float* out_norm, float* proj_out, int64_t rows, int32_t dim, int32_t bits,
                       phk_stream_t s);
+
+/* Cosine-sim VectorQuantize ids (cvivit.py:321, :568-570 with lookup_free_quantization=False; oracle/lfq.py):
+ * ids[r] = argmax_c l2norm(x[r]) . codebook[c] = argmax_c x[r] . codebook[c] (unit codebook rows), first maximum on ties.
+ * PHK_PREC_F32: x fp32 [rows, dim], fp32 FFMA similarities strip by strip; PHK_PREC_BF16: x bf16 [rows, dim], the fused
+ * tcgen05 head at temperature 0 (dim <= 512): the [rows, K] similarities are never stored. */
+int64_t phk_vq_cosine_scratch_bytes(int64_t rows, int32_t K, int32_t prec);
+int phk_vq_cosine_ids(const void* x, const float* codebook, const void* codebook_h, int64_t* ids, int64_t rows,
+                      int32_t dim, int32_t K, void* scratch, int64_t scratch_bytes, int32_t prec, phk_stream_t s);
 
 /* LFQ indices_to_codes + project_out (cvivit.py:437-439 -> LFQ.indices_to_codes, oracle/lfq.py):
  * out[r, :] = w_out @ (bit_j(id_r) ? +1 : -1)_j + b_out, bits MSB first; w_out [dim, bits]; out fp32 [rows, dim]. */

@@ -62,10 +62,44 @@ class LFQ(nn.Module):
         return out, indices, torch.zeros((), device=x.device)
 
 
-class VectorQuantize(nn.Module):
-    """Placeholder so ``from vector_quantize_pytorch import VectorQuantize`` resolves.
-    The cosine-sim codebook path (cvivit.py:321) is a next-tier row."""
+class _CosineSimCodebook(nn.Module):
+    """Buffers of upstream ``CosineSimCodebook`` for one codebook without k-means init (restated from memory of
+    vector-quantize-pytorch 1.11-1.14, unverifiable here): ``embed`` = l2-normalised kaiming-uniform rows."""
 
-    def __init__(self, *a, **k):
+    def __init__(self, dim, codebook_size):
         super().__init__()
-        raise NotImplementedError("cosine-sim VectorQuantize is out of scope (SURVEY 8f-3)")
+        embed = torch.empty(1, codebook_size, dim)
+        nn.init.kaiming_uniform_(embed)
+        embed = torch.nn.functional.normalize(embed, dim=-1)
+        self.register_buffer("initted", torch.Tensor([True]))
+        self.register_buffer("cluster_size", torch.zeros(1, codebook_size))
+        self.register_buffer("embed_avg", embed.clone())
+        self.register_buffer("embed", embed)
+
+
+class VectorQuantize(nn.Module):
+    """Eval-mode arithmetic of ``vector_quantize_pytorch.VectorQuantize(dim, codebook_size, use_cosine_sim=True)``
+    (the reference's non-LFQ tokenizer, cvivit.py:321; call sites :441 ``vq.codebook[indices]`` and :570
+    ``vq(tokens, mask=...)``).  PARITY UNPINNED like LFQ above: the dependency is absent, so this restatement -- from
+    memory of upstream 1.11-1.14 -- DEFINES the step:
+        x_n   = l2norm(x)
+        idx   = argmax_c  x_n . embed_c            (embed rows are unit vectors)
+        out   = embed[idx]                          (project_in / project_out are Identity when codebook_dim == dim)
+        loss  = 0 (the commitment loss, EMA update and straight-through estimator are training-only)
+    State-dict names follow upstream: ``_codebook.{initted, cluster_size, embed_avg, embed}``."""
+
+    def __init__(self, *, dim, codebook_size, use_cosine_sim=True, **unused_training_kwargs):
+        super().__init__()
+        assert use_cosine_sim, "the reference only builds the cosine-sim codebook (cvivit.py:321)"
+        self.dim, self.codebook_size = dim, codebook_size
+        self._codebook = _CosineSimCodebook(dim, codebook_size)
+
+    @property
+    def codebook(self):
+        return self._codebook.embed[0]
+
+    def forward(self, x, mask=None, **unused):
+        flat = torch.nn.functional.normalize(x.float(), dim=-1)
+        dist = flat @ self.codebook.t()
+        indices = dist.argmax(dim=-1)
+        return self.codebook[indices], indices, torch.zeros((1,), device=x.device)

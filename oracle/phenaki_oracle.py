@@ -229,6 +229,10 @@ def cvivit_codebook_ids(video, sd, image_size, patch_size, return_margin=False):
     tokens = cvivit_patch_embed(video, sd, patch_size, pt)
     tokens = cvivit_encode_tokens(tokens, sd, heads)
     b, t, h, w, d = tokens.shape
+    if "vq._codebook.embed" in sd:  # lookup_free_quantization=False: cosine-sim codebook (cvivit.py:321, oracle/lfq.py)
+        dist = F.normalize(tokens.reshape(b, t * h * w, d), dim=-1) @ sd["vq._codebook.embed"][0].t()
+        ids = dist.argmax(dim=-1).reshape(b, t, h, w)
+        return (ids, dist.reshape(b, t, h, w, -1)) if return_margin else ids
     proj = lfq_project(tokens.reshape(b, t * h * w, d), sd)
     ids = lfq_indices_from_projection(proj, sd).reshape(b, t, h, w)
     if return_margin:
@@ -272,7 +276,10 @@ def cvivit_decode_from_ids(ids, sd, image_size, patch_size):
     dim, heads, pt, channels = cvivit_geometry(sd, image_size, patch_size)
     h, w = image_size[0] // patch_size[0], image_size[1] // patch_size[1]
     b = ids.shape[0]
-    codes = lfq_indices_to_codes(ids.reshape(b, -1), sd).reshape(b, -1, h, w, dim)
+    if "vq._codebook.embed" in sd:  # codes = vq.codebook[indices] (cvivit.py:441)
+        codes = sd["vq._codebook.embed"][0][ids.reshape(b, -1)].reshape(b, -1, h, w, dim)
+    else:
+        codes = lfq_indices_to_codes(ids.reshape(b, -1), sd).reshape(b, -1, h, w, dim)
     return cvivit_decode(codes, sd, patch_size, pt, heads, channels)
 
 

@@ -54,7 +54,8 @@ class CvivitT(C.Structure):
                 ("pr_ln1_g", c_f), ("pr_ln1_b", c_f), ("pr_w", c_f), ("pr_b", c_f), ("pr_ln2_g", c_f),
                 ("pr_ln2_b", c_f), ("pr_w_h", c_f),
                 ("spatial_bias", CpbT), ("spatial", TransformerT), ("temporal", TransformerT),
-                ("vq_w", c_f), ("vq_b", c_f)]
+                ("vq_w", c_f), ("vq_b", c_f),
+                ("codebook", c_f), ("codebook_h", c_f), ("codebook_size", C.c_int32), ("_pad2", C.c_int32)]
 
 
 class CvivitDecT(C.Structure):
@@ -140,6 +141,8 @@ PROTOTYPES = {
     "phk_head_sample_rng": [vp, i64, i64, vp, i64, vp, i32, i32, i32, f32, u64, u64, vp, vp, vp, vp, vp, vp, i64, vp],
     "phk_rng_advance": [vp, u64, vp],
     "phk_debug_step_graph": [i32],
+    "phk_vq_cosine_scratch_bytes": [i64, i32, i32],
+    "phk_vq_cosine_ids": [vp, vp, vp, vp, i64, i32, i32, vp, i64, i32, vp],
     "phk_maskgit_demask_iteration": [C.POINTER(MaskgitT), vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, i32, vp, vp, f32, f32,
                                      vp, i32, vp, i64, vp],
     "phk_maskgit_forward": [C.POINTER(MaskgitT), vp, i32, i32, i32, i32, i32, vp, i32, vp, vp, i32, i32, vp, vp,
@@ -149,7 +152,7 @@ PROTOTYPES = {
                                vp, vp, f32, vp, vp, vp, i64, i32, vp],
 }
 _RESTYPES = {"phk_attention_tc_scratch_bytes": i64, "phk_head_sample_scratch_bytes": i64,
-             "phk_maskgit_sample_workspace_bytes": i64, "phk_sample_tail_scratch_bytes": i64, "phk_maskgit_train_workspace_bytes": i64, "phk_last_error": C.c_char_p, "phk_launch_count": i64, "phk_cpb_scratch_floats": i64,
+             "phk_maskgit_sample_workspace_bytes": i64, "phk_sample_tail_scratch_bytes": i64, "phk_vq_cosine_scratch_bytes": i64, "phk_maskgit_train_workspace_bytes": i64, "phk_last_error": C.c_char_p, "phk_launch_count": i64, "phk_cpb_scratch_floats": i64,
              "phk_cvivit_workspace_bytes": i64, "phk_cvivit_decode_workspace_bytes": i64, "phk_maskgit_workspace_bytes": i64}
 
 FAMILIES = ["patchify_ln", "layernorm", "gemm_f32", "gemm_bf16", "attention", "peg", "geglu", "lfq", "embed",

@@ -284,7 +284,7 @@ extern "C" int64_t phk_cvivit_workspace_bytes(const phk_cvivit_t* m, int32_t B, 
   bytes += (int64_t)m->heads * hw * hw * 4 + phk_cpb_scratch_floats(&m->spatial_bias, hh, ww, 1) * 4;
   const int64_t a = tf_scratch_bytes(&m->spatial, R), b = tf_scratch_bytes(&m->temporal, R);
   bytes += a > b ? a : b;
-  (void)prec;
+  if (m->codebook) bytes += phk_vq_cosine_scratch_bytes(R, m->codebook_size, prec) + 256;
   return bytes;
 }
 
@@ -367,6 +367,17 @@ static int cvivit_encode_impl(const phk_cvivit_t* m, const float* video, int32_t
   c.x_final = &xf;
   PHK_TRY(transformer_forward(c, tf, nullptr, nullptr, st));
   float* norm_buf = x_alt;  // not used by the temporal transformer (its stream alternates between P and x)
+  if (m->codebook) {
+    // lookup_free_quantization=False (cvivit.py:321, 568-570): norm_out, then the nearest unit codebook row by cosine
+    PHK_REQUIRE(m->codebook_size > 0, PHK_E_ARG, "cvivit_encode: codebook without a size");
+    const int64_t vb = phk_vq_cosine_scratch_bytes(R, m->codebook_size, prec);
+    void* vsc = tf.take(vb);
+    PHK_REQUIRE(vsc, PHK_E_WORKSPACE, "cvivit_encode: workspace too small (codebook lookup)");
+    if (tap_temporal || !h16) PHK_TRY(phk_layernorm(xf, m->temporal.out_g, m->temporal.out_b, norm_buf, nullptr, R, D, 0, 0, 0, 0, s));
+    if (tap_temporal) PHK_CUDA(cudaMemcpyAsync(tap_temporal, norm_buf, R * D * 4, cudaMemcpyDeviceToDevice, st));
+    if (h16) PHK_TRY(phk_layernorm(xf, m->temporal.out_g, m->temporal.out_b, norm_buf, nullptr, R, D, 1, 0, 0, 0, s));
+    return phk_vq_cosine_ids(norm_buf, m->codebook, m->codebook_h, ids, R, D, m->codebook_size, vsc, vb, prec, s);
+  }
   PHK_TRY(phk_layernorm_lfq(xf, m->temporal.out_g, m->temporal.out_b, m->vq_w, m->vq_b, ids,
                             (tap_temporal || D % 128 != 0 || D > 1024 || m->codebook_bits > 16) ? norm_buf : nullptr,
                             tap_proj, R, D, m->codebook_bits, s));

@@ -41,6 +41,36 @@ class LFQ(nn.Module):
         self.register_buffer("mask", 2 ** torch.arange(bits - 1, -1, -1))
 
 
+class _CosineSimCodebook(nn.Module):
+    """Buffers of upstream ``CosineSimCodebook`` (one codebook, no k-means init): unit-norm kaiming-uniform rows."""
+
+    def __init__(self, dim, codebook_size):
+        super().__init__()
+        embed = torch.empty(1, codebook_size, dim)
+        nn.init.kaiming_uniform_(embed)
+        embed = torch.nn.functional.normalize(embed, dim=-1)
+        self.register_buffer("initted", torch.Tensor([True]))
+        self.register_buffer("cluster_size", torch.zeros(1, codebook_size))
+        self.register_buffer("embed_avg", embed.clone())
+        self.register_buffer("embed", embed)
+
+
+class VectorQuantize(nn.Module):
+    """Buffer holder with upstream ``vector_quantize_pytorch.VectorQuantize(use_cosine_sim=True)`` state-dict names
+    (``_codebook.{initted, cluster_size, embed_avg, embed}``) for ``lookup_free_quantization=False`` (cvivit.py:321);
+    arithmetic restated in oracle/lfq.py, executed by phk_vq_cosine_ids."""
+
+    def __init__(self, *, dim, codebook_size, use_cosine_sim=True, **kwargs):
+        super().__init__()
+        assert use_cosine_sim
+        self.dim, self.codebook_size = dim, codebook_size
+        self._codebook = _CosineSimCodebook(dim, codebook_size)
+
+    @property
+    def codebook(self):
+        return self._codebook.embed[0]
+
+
 class CViViT(nn.Module):
     def __init__(self, *, dim, codebook_size, image_size, patch_size, temporal_patch_size, spatial_depth,
                  temporal_depth, discr_base_dim=16, dim_head=64, heads=8, channels=3, use_vgg_and_gan=True,
@@ -68,9 +98,10 @@ class CViViT(nn.Module):
         self.enc_spatial_transformer = Transformer(depth=spatial_depth, **spatial_kw)
         self.enc_temporal_transformer = Transformer(depth=temporal_depth, **temporal_kw)
         self.lookup_free_quantization = lookup_free_quantization
-        if not lookup_free_quantization:
-            raise NotImplementedError("cosine-sim VectorQuantize codebook path is a next-tier row (SURVEY 8f-3)")
-        self.vq = LFQ(dim=dim, codebook_size=codebook_size, **lookup_free_quantization_kwargs)
+        if lookup_free_quantization:
+            self.vq = LFQ(dim=dim, codebook_size=codebook_size, **lookup_free_quantization_kwargs)
+        else:
+            self.vq = VectorQuantize(dim=dim, codebook_size=codebook_size, use_cosine_sim=True)
         self.dec_spatial_transformer = Transformer(depth=spatial_depth, **spatial_kw)
         self.dec_temporal_transformer = Transformer(depth=temporal_depth, **temporal_kw)
         self.to_pixels_first_frame = nn.Sequential(nn.Linear(dim, k1), _NoParams())
@@ -164,7 +195,7 @@ class CViViT(nn.Module):
             t.image_h, t.image_w = self.image_size
             t.patch_h, t.patch_w = self.patch_size
             t.patch_t = self.temporal_patch_size
-            t.codebook_bits = self.vq.codebook_dim
+            t.codebook_bits = self.vq.codebook_dim if self.lookup_free_quantization else 0
             f, r = self.to_patch_emb_first_frame, self.to_patch_emb
             t.pf_ln1_g, t.pf_ln1_b, t.pf_w, t.pf_b = keep.t(f[1].weight), keep.t(f[1].bias), keep.t(f[2].weight), keep.t(f[2].bias)
             t.pf_ln2_g, t.pf_ln2_b = keep.t(f[3].weight), keep.t(f[3].bias)
@@ -175,7 +206,12 @@ class CViViT(nn.Module):
             t.temporal = transformer_table(self.enc_temporal_transformer, keep, h16)
             if h16:
                 t.pf_w_h, t.pr_w_h = keep.h(f[2].weight), keep.h(r[2].weight)
-            t.vq_w, t.vq_b = keep.t(self.vq.project_in.weight), keep.t(self.vq.project_in.bias)
+            if self.lookup_free_quantization:
+                t.vq_w, t.vq_b = keep.t(self.vq.project_in.weight), keep.t(self.vq.project_in.bias)
+            else:  # cosine-sim codebook (unit rows)
+                t.codebook, t.codebook_size = keep.t(self.vq.codebook), self.vq.codebook_size
+                if h16:
+                    t.codebook_h = keep.h(self.vq.codebook)
             self._tables, self._sig = (t, keep), sig
             self._bias_cache = {}
         return self._tables[0]
@@ -190,8 +226,10 @@ class CViViT(nn.Module):
             t.image_h, t.image_w = self.image_size
             t.patch_h, t.patch_w = self.patch_size
             t.patch_t = self.temporal_patch_size
-            t.codebook_bits = self.vq.codebook_dim
-            t.vq_out_w, t.vq_out_b = keep.t(self.vq.project_out.weight), keep.t(self.vq.project_out.bias)
+            if self.lookup_free_quantization:
+                t.codebook_bits = self.vq.codebook_dim
+                t.vq_out_w, t.vq_out_b = keep.t(self.vq.project_out.weight), keep.t(self.vq.project_out.bias)
+            # (cosine-sim codebook: decode_from_codebook_indices gathers the codes and decodes float tokens)
             t.spatial_bias = cpb_table(self.spatial_rel_pos_bias, keep)
             t.temporal = transformer_table(self.dec_temporal_transformer, keep, h16)
             t.spatial = transformer_table(self.dec_spatial_transformer, keep, h16)
@@ -246,8 +284,9 @@ class CViViT(nn.Module):
                 taps["patch"] = torch.empty((b, tp, hh, ww, self.dim), dtype=torch.float32, device=video.device)
                 taps["spatial"] = torch.empty_like(taps["patch"])
                 taps["temporal"] = torch.empty_like(taps["patch"])
-                taps["proj"] = torch.empty((rows, self.vq.codebook_dim), dtype=torch.float32, device=video.device)
-                tap_ptrs = [L.ptr(taps[k]) for k in ("patch", "spatial", "temporal", "proj")]
+                if self.lookup_free_quantization:
+                    taps["proj"] = torch.empty((rows, self.vq.codebook_dim), dtype=torch.float32, device=video.device)
+                tap_ptrs = [L.ptr(taps.get(k)) for k in ("patch", "spatial", "temporal", "proj")]
             L.check(lib.phk_cvivit_encode(C.byref(table), L.ptr(video), b, f, L.ptr(ids), L.ptr(ws), ws.numel(),
                                           self.precision, L.ptr(bias), *tap_ptrs, L.stream_ptr()),
                     "phk_cvivit_encode")
@@ -356,6 +395,10 @@ class CViViT(nn.Module):
         n = indices[0].numel()
         per = self.image_num_tokens
         assert n > 0 and n % per == 0, f"number of tokens ({n}) must be a multiple of tokens per frame ({per})"
+        if not self.lookup_free_quantization:
+            # codes = vq.codebook[indices] (cvivit.py:441): a row gather (data movement), then decode of float tokens
+            codes = self.vq.codebook.index_select(0, indices.reshape(-1)).reshape(b, n, self.dim).contiguous()
+            return self._decode(None, codes, b, n // per, indices.device, taps)
         return self._decode(indices.reshape(b, n), None, b, n // per, indices.device, taps)
 
     def decode(self, tokens):

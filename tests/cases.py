@@ -31,6 +31,12 @@ CVIVIT_CASES = {
                   spatial_depth=1, temporal_depth=1, dim_head=32, heads=2, channels=1,
                   use_vgg_and_gan=False),
         video=(3, 1, 32, 32), video_seed=6),
+    # lookup_free_quantization=False: the cosine-sim VectorQuantize codebook (cvivit.py:321)
+    "cosine_vq": dict(
+        seed=7,
+        ctor=dict(dim=64, codebook_size=300, image_size=32, patch_size=8, temporal_patch_size=2, spatial_depth=1,
+                  temporal_depth=1, dim_head=32, heads=2, use_vgg_and_gan=False, lookup_free_quantization=False),
+        video=(2, 3, 5, 32, 32), video_seed=8),
 }
 
 MASKGIT_CASES = {

@@ -19,7 +19,7 @@ ASAN = os.environ.get("PHK_EMU_ASAN", "0") == "1"
 EMU_LIB = os.path.join(EMU_DIR, "_build", "libphk_train_emu_asan.so" if ASAN else "libphk_train_emu.so")
 CSRC = os.path.join(ROOT, "phenaki_pytorch_b200", "csrc")
 # the product's plain-CUDA sources (no tensor cores / TMA): compiled unchanged apart from the two textual rewrites below
-KERNEL_SOURCES = ["rowops.cu", "gemm_simt.cu", "attention.cu", "sample_tail.cu", "train.cu", "api.cu"]  # api.cu: the drivers (host code)
+KERNEL_SOURCES = ["rowops.cu", "gemm_simt.cu", "attention.cu", "sample_tail.cu", "vq.cu", "train.cu", "api.cu"]  # api.cu: the drivers (host code)
 SOURCES = [os.path.join(EMU_DIR, "cuda_emu.cpp")]
 
 

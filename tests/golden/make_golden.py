@@ -58,10 +58,12 @@ def make_cvivit(ref):
         model = ref.CViViT(**case["ctor"]).eval()
         sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
         video = C.seeded_randn(case["video"], case["video_seed"])
-        taps, handles = hook_outputs({
-            "patch_first": model.to_patch_emb_first_frame, "patch_rest": model.to_patch_emb,
-            "spatial": model.enc_spatial_transformer, "temporal": model.enc_temporal_transformer,
-            "proj": model.vq.project_in})
+        lfq = case["ctor"].get("lookup_free_quantization", True)
+        mods = {"patch_first": model.to_patch_emb_first_frame, "patch_rest": model.to_patch_emb,
+                "spatial": model.enc_spatial_transformer, "temporal": model.enc_temporal_transformer}
+        if lfq:
+            mods["proj"] = model.vq.project_in
+        taps, handles = hook_outputs(mods)
         with torch.no_grad():
             ids = model(video, return_only_codebook_ids=True)
             recon = model.decode_from_codebook_indices(ids.reshape(ids.shape[0], -1))
@@ -75,7 +77,10 @@ def make_cvivit(ref):
             o_patch = O.cvivit_patch_embed(v5, sd, patch_size, pt)
             o_recon = O.cvivit_decode_from_ids(ids.reshape(ids.shape[0], -1), sd, image_size, patch_size)
         same(o_ids, ids, "codebook ids")
-        same(o_proj.reshape(taps["proj"].shape), taps["proj"], "LFQ pre-sign projection")
+        if lfq:
+            same(o_proj.reshape(taps["proj"].shape), taps["proj"], "LFQ pre-sign projection")
+        else:  # cosine-sim codebook: the similarities (their top-2 gap is the margin of an id) come from the oracle
+            taps["proj"] = o_proj.reshape(o_proj.shape[0], -1, o_proj.shape[-1])
         same(o_patch[:, :1], taps["patch_first"], "first-frame patch embed")
         if "patch_rest" in taps:
             same(o_patch[:, 1:], taps["patch_rest"], "rest-frames patch embed")

@@ -220,3 +220,21 @@ def test_fused_sample_step_on_masked_rows_equals_the_all_rows_step():
     assert int((~same).sum()) <= max(1, int(0.01 * m.sum())), f"{int((~same).sum())} ids differ"
     torch.testing.assert_close(sc_a[m & same], sc_b[m & same], rtol=1e-3, atol=1e-4)
     assert bool((sc_b[~m] == -1e4).all()) and torch.equal(ids_b[~m], ids0.cpu()[~m])
+
+
+def test_cosine_vq_ids_in_bf16_mode_against_fp32_reference_golden(golden):
+    """lookup_free_quantization=False in bf16 mode: the nearest-code search runs on the fused tcgen05 head at temperature 0
+    (phk_vq_cosine_ids).  An id may differ from the fp32 reference's only where the reference's similarities of the two
+    candidates are within bf16 noise (0.03 in cosine units), and at least 85 % of the ids agree."""
+    case, g = C.CVIVIT_CASES["cosine_vq"], golden("cvivit_cosine_vq")
+    torch.manual_seed(case["seed"])
+    model = P.CViViT(**case["ctor"]).to(DEV).eval()
+    model.precision = L.PREC_BF16
+    video = C.seeded_randn(case["video"], case["video_seed"]).to(DEV)
+    got = model(video, return_only_codebook_ids=True).cpu().reshape(-1)
+    want, sims = g["ids"].reshape(-1), g["proj"].reshape(-1, g["proj"].shape[-1])
+    assert bool(((got >= 0) & (got < case["ctor"]["codebook_size"])).all())
+    differ = torch.nonzero(got != want).flatten().tolist()
+    for r in differ:
+        assert abs(float(sims[r, got[r]] - sims[r, want[r]])) < 0.03, f"token {r}: a clearly worse code was chosen"
+    assert len(differ) <= 0.15 * want.numel(), f"{len(differ)} of {want.numel()} ids differ"

@@ -96,7 +96,10 @@ def test_decode_from_codebook_indices_matches_reference_golden(golden, name):
     sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
     b, t, h, w = g["ids"].shape
     with torch.no_grad():
-        codes = O.lfq_indices_to_codes(g["ids"].reshape(b, -1), sd).reshape(b, t, h, w, -1)
+        if "vq._codebook.embed" in sd:  # cosine-sim codebook: codes = vq.codebook[indices] (cvivit.py:441)
+            codes = sd["vq._codebook.embed"][0][g["ids"].reshape(b, -1)].reshape(b, t, h, w, -1)
+        else:
+            codes = O.lfq_indices_to_codes(g["ids"].reshape(b, -1), sd).reshape(b, t, h, w, -1)
     torch.testing.assert_close(taps["codes"].cpu(), codes, rtol=1e-5, atol=1e-5)
     torch.testing.assert_close(rec.cpu(), g["recon"], rtol=RTOL, atol=ATOL)
     # 4-D ids and the float-token entry point give the same video
