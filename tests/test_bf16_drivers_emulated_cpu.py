@@ -11,6 +11,7 @@ import torch
 
 from tests import emu_runtime
 from tests import test_gpu_bf16_mode as G
+from tests import test_gpu_zz_after_last_gpu_call as Z
 
 _NAMES = ["test_cvivit_bf16_mode_against_fp32_reference_golden", "test_maskgit_bf16_mode_against_fp32_reference_golden",
           "test_layernorm_cfg_combination",
@@ -18,7 +19,7 @@ _NAMES = ["test_cvivit_bf16_mode_against_fp32_reference_golden", "test_maskgit_b
           "test_fused_sample_step_on_masked_rows_equals_the_all_rows_step",
           "test_cosine_vq_ids_in_bf16_mode_against_fp32_reference_golden"]
 for _n in _NAMES:
-    globals()[_n] = getattr(G, _n)
+    globals()[_n] = getattr(G, _n) if hasattr(G, _n) else getattr(Z, _n)
 
 
 @pytest.fixture(scope="module")
@@ -30,6 +31,7 @@ def _emu_lib():
 def _product_on_the_cpu(_emu_lib, monkeypatch):
     emu_runtime.route_product_to_emulator(_emu_lib, monkeypatch)
     monkeypatch.setattr(G, "DEV", "cpu")
+    monkeypatch.setattr(Z, "DEV", "cpu")
     monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
     monkeypatch.setattr(torch.cuda, "manual_seed_all", lambda *a, **k: None, raising=False)
 

@@ -84,7 +84,7 @@ def _model(name, prec):
     return case, model
 
 
-@pytest.mark.parametrize("name", list(C.CVIVIT_CASES))
+@pytest.mark.parametrize("name", [n for n in C.CVIVIT_CASES if n != "cosine_vq"])  # cosine_vq: test_gpu_zz_*
 def test_decode_from_codebook_indices_matches_reference_golden(golden, name):
     case, model = _model(name, L.PREC_F32)
     g = golden(f"cvivit_{name}")

@@ -36,7 +36,7 @@ def assert_ids_match(ids, ref_ids, ref_proj, bits):
     return len(bad)
 
 
-@pytest.mark.parametrize("name", list(C.CVIVIT_CASES))
+@pytest.mark.parametrize("name", [n for n in C.CVIVIT_CASES if n != "cosine_vq"])  # cosine_vq: test_gpu_zz_*
 def test_cvivit_token_ids_match_reference_golden(golden, name):
     case, g = C.CVIVIT_CASES[name], golden(f"cvivit_{name}")
     torch.manual_seed(case["seed"])

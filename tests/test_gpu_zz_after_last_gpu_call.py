@@ -1,0 +1,84 @@
+"""GPU: tests of the code written AFTER round 1's last GPU call (DESIGN sections 4.3, 8, 9): the masked-rows tail of the
+demasking step, the shared first layer of a CFG pair, the cosine-sim VectorQuantize tokenizer.  All of it passes on the
+CPU executor (tests/test_*_emulated_cpu.py run these same bodies); this file sorts after the validated suites so that,
+under `pytest -x`, a surprise here cannot hide their results."""
+import pytest
+import torch
+
+import phenaki_pytorch_b200 as P
+from phenaki_pytorch_b200 import _lib as L
+from tests import cases as C
+from tests import test_gpu_decode as D
+from tests import test_gpu_models as G
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.mark.parametrize("b,n,k,dim,V", [(4, 576, 100, 512, 4096), (2, 48, 17, 128, 300), (3, 30, 1, 256, 130),
+                                         (4, 576, 441, 512, 1024)])
+def test_sample_tail_on_the_masked_rows_only(b, n, k, dim, V):
+    """phk_sample_tail (csrc/sample_tail.cu + the tcgen05 head on the compact rows) against plain torch arithmetic; the
+    same body runs on the CPU executor in tests/test_sample_tail_emulated_cpu.py."""
+    from tests import tail_cases
+    tail_cases.check_exact_k(L.lib(), torch.device(DEV), b, n, k, dim, V, sync=torch.cuda.synchronize)
+
+
+def test_fused_sample_step_on_masked_rows_equals_the_all_rows_step():
+    """Model level, temperature 0 (pure argmax): telling phk_maskgit_sample_step how many tokens per sequence are masked
+    (head on those rows only) must give the ids of the all-rows step at every masked position, the same confidences,
+    and leave the other positions alone."""
+    torch.manual_seed(8)
+    cfg = dict(dim=128, num_tokens=1000, max_seq_len=256, heads=2, dim_head=64, depth=2, dim_context=96)
+    mg = P.MaskGit(**cfg).to(DEV).eval()
+    mg.precision = L.PREC_BF16
+    b, shape, n, k = 3, (3, 6, 8), 144, 37
+    g = torch.Generator().manual_seed(2)
+    ids0 = torch.randint(0, cfg["num_tokens"] + 1, (b, n), generator=g).to(DEV)
+    ctx = C.synthetic_text_embeds(b, 5, 96, (5, 2, 4), 2).to(DEV)
+    tmask = torch.any(ctx != 0, dim=-1)
+    mask = torch.zeros((b, n), dtype=torch.uint8)
+    for i in range(b):
+        mask[i, torch.randperm(n, generator=g)[:k]] = 1
+    mask = mask.to(DEV)
+    kv = mg.context_kv(ctx)
+    outs = []
+    for count in (0, k):
+        ids, pred, sc = ids0.clone(), torch.empty_like(ids0), torch.empty((b, n), device=DEV)
+        mg._sample_step(ids0, shape, ctx_kv=kv, ctx_len=5, text_mask=tmask, cond_scale=3.0, temperature=0.0, seed=1, offset=0,
+                        mask=mask, ids=ids, pred=pred, scores=sc, masked_per_seq=count)
+        torch.cuda.synchronize()
+        outs.append((ids.cpu(), sc.cpu()))
+    m = mask.cpu().bool()
+    (ids_a, sc_a), (ids_b, sc_b) = outs
+    same = ids_a == ids_b  # (a near-tie of two logits may resolve differently if the two LayerNorm kernels round apart)
+    assert int((~same).sum()) <= max(1, int(0.01 * m.sum())), f"{int((~same).sum())} ids differ"
+    torch.testing.assert_close(sc_a[m & same], sc_b[m & same], rtol=1e-3, atol=1e-4)
+    assert bool((sc_b[~m] == -1e4).all()) and torch.equal(ids_b[~m], ids0.cpu()[~m])
+
+
+def test_cosine_vq_ids_in_bf16_mode_against_fp32_reference_golden(golden):
+    """lookup_free_quantization=False in bf16 mode: the nearest-code search runs on the fused tcgen05 head at temperature 0
+    (phk_vq_cosine_ids).  An id may differ from the fp32 reference's only where the reference's similarities of the two
+    candidates are within bf16 noise (0.03 in cosine units), and at least 85 % of the ids agree."""
+    case, g = C.CVIVIT_CASES["cosine_vq"], golden("cvivit_cosine_vq")
+    torch.manual_seed(case["seed"])
+    model = P.CViViT(**case["ctor"]).to(DEV).eval()
+    model.precision = L.PREC_BF16
+    video = C.seeded_randn(case["video"], case["video_seed"]).to(DEV)
+    got = model(video, return_only_codebook_ids=True).cpu().reshape(-1)
+    want, sims = g["ids"].reshape(-1), g["proj"].reshape(-1, g["proj"].shape[-1])
+    assert bool(((got >= 0) & (got < case["ctor"]["codebook_size"])).all())
+    differ = torch.nonzero(got != want).flatten().tolist()
+    for r in differ:
+        assert abs(float(sims[r, got[r]] - sims[r, want[r]])) < 0.03, f"token {r}: a clearly worse code was chosen"
+    assert len(differ) <= 0.15 * want.numel(), f"{len(differ)} of {want.numel()} ids differ"
+
+
+def test_cosine_vq_token_ids_match_reference_golden(golden):
+    """lookup_free_quantization=False, fp32 parity mode: ids identical to the reference's (stage taps as for LFQ)."""
+    G.test_cvivit_token_ids_match_reference_golden(golden, "cosine_vq")
+
+
+def test_cosine_vq_decode_matches_reference_golden(golden):
+    D.test_decode_from_codebook_indices_matches_reference_golden(golden, "cosine_vq")

@@ -18,6 +18,9 @@ _MODELS = ["test_cvivit_token_ids_match_reference_golden", "test_cvivit_state_di
            "test_sampling_loop_token_ids_match_reference_golden"]
 for _n in _MODELS:
     globals()[_n] = getattr(G, _n)
+from tests import test_gpu_zz_after_last_gpu_call as Z  # noqa: E402
+test_cosine_vq_token_ids_match_reference_golden = Z.test_cosine_vq_token_ids_match_reference_golden
+test_cosine_vq_decode_matches_reference_golden = Z.test_cosine_vq_decode_matches_reference_golden
 # not repeated here: the refusal of CPU tensors (meaningless under the executor) and, to keep the CPU suite short, the
 # sampled-video / make_video chains (their pieces -- sampling loops with priming, decode -- are covered above and below)
 _SKIP = {"test_decode_token_count_contract", "test_sampled_video_matches_reference_golden",

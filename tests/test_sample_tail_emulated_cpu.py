@@ -2,7 +2,7 @@
 norm_out + guidance, head on the compact rows, scatter) executed from the shipped source, against plain torch
 arithmetic.  The tcgen05 head itself (phk_head_sample) is represented by its contract here -- a bf16-operand product
 followed by the REAL phk_sample_tokens kernel; on the B200 the same checks run through the real head
-(tests/test_gpu_bf16_mode.py)."""
+(tests/test_gpu_zz_after_last_gpu_call.py)."""
 import pytest
 import torch
 
