@@ -784,10 +784,11 @@ class Phenaki(nn.Module):
         seed = _noise_seed(dev)
         offset = self._rng_calls * ((batch * seq * ((vocab + 3) // 4)) + 1)
         self._rng_calls += 1
-        L.check(L.lib().phk_sample_tokens(L.ptr(logits), None, vocab, L.ptr(None if gu is None else L.require_cuda(
-            gu.to(dev), "gumbel noise", torch.float32)), seed & (2 ** 64 - 1), offset, 1.0,
-            float(self.critic_train_sample_temperature), L.ptr(ones), L.ptr(scratch_ids), L.ptr(pred), None,
-            batch * seq, vocab, 0, 0, 0, L.stream_ptr()), "phk_sample_tokens")
+        gu_dev = None if gu is None else L.require_cuda(gu.to(dev), "gumbel noise", torch.float32)  # kept alive past the launch
+        L.check(L.lib().phk_sample_tokens(L.ptr(logits), None, vocab, L.ptr(gu_dev), seed & (2 ** 64 - 1), offset, 1.0,
+                                          float(self.critic_train_sample_temperature), L.ptr(ones), L.ptr(scratch_ids),
+                                          L.ptr(pred), None, batch * seq, vocab, 0, 0, 0, L.stream_ptr()),
+                "phk_sample_tokens")
         critic_input = torch.where(mask_token_mask, pred, ids)
         labels = (ids != pred).float()
         weight = 1.0 if only_train_critic else self.critic_loss_weight
