@@ -129,3 +129,19 @@ nb = lib.phk_head_sample_scratch_bytes(2304)
 sc = torch.empty(nb, dtype=torch.uint8, device=dev)
 timeit("fused head 2304 x 65536 x 512", lambda: L.check(lib.phk_head_sample(L.ptr(emb), 512, 2304, L.ptr(W), 512, L.ptr(hb), 2304, 65536, 512, 0.5, 1, 0, L.ptr(mask), L.ptr(hid), L.ptr(pred), L.ptr(score), L.ptr(sc), nb, sp())),
        2.0 * 2304 * 65536 * 512, "TFLOP/s")
+
+# masked-rows tail of the demasking step (csrc/sample_tail.cu) at the row counts of the 18-step schedule, against the
+# all-rows head above: compaction + gathered norm_out/CFG + head on b*k rows + scatter
+xc, xn_ = torch.randn(2304, 512, device=dev), torch.randn(2304, 512, device=dev)
+gm, bt = torch.randn(512, device=dev), torch.randn(512, device=dev)
+ids2 = torch.zeros((4, 576), dtype=torch.int64, device=dev)
+pred2, score2 = torch.zeros_like(ids2), torch.zeros((4, 576), device=dev)
+for k in (574, 441, 288, 100):
+    m2 = torch.zeros((4, 576), dtype=torch.uint8, device=dev)
+    m2[:, :k] = 1
+    nb2 = lib.phk_sample_tail_scratch_bytes(4, k, 512)
+    sc2 = torch.empty(nb2, dtype=torch.uint8, device=dev)
+    timeit(f"sample tail, {k} of 576 tokens masked (b=4)", lambda: L.check(lib.phk_sample_tail(
+        L.ptr(xc), L.ptr(xn_), L.ptr(gm), L.ptr(bt), 3.0, L.ptr(W), 512, L.ptr(hb), 4, 576, k, 65536, 512, 0.5, 1, 0, None,
+        L.ptr(m2), L.ptr(ids2), L.ptr(pred2), L.ptr(score2), L.ptr(sc2), nb2, sp())),
+        2.0 * 4 * k * 65536 * 512, "TFLOP/s")
