@@ -26,6 +26,6 @@ bash tools/validate_train_gpu.sh > $O/train.log 2>&1; tail -12 $O/train.log
 NCU="ncu --clock-control none --cache-control none"
 for w in encode maskgit; do
   PHK_GRAPH=0 timeout 300 $NCU --metrics gpu__time_duration.sum --csv --log-file $O/launches_${w}_bf16.csv python tools/profile_step.py $w bf16 3 > $O/p_$w.log 2>&1
-  python tools/last_step.py $O/launches_${w}_bf16.csv > $O/launches_${w}_bf16.txt 2>&1 || true
+  python tools/last_step.py $O/launches_${w}_bf16.csv $w > $O/launches_${w}_bf16.txt 2>&1 || true
 done
 ls -la $O
