@@ -533,6 +533,7 @@ class Phenaki(nn.Module):
                 text_embeds = L.require_cuda(text_embeds, "text embeds", torch.float32)
                 if text_mask is None:
                     text_mask = torch.any(text_embeds != 0, dim=-1)  # phenaki_pytorch.py:461
+                text_mask = text_mask.to(torch.uint8)  # once per sample: the per-step calls take it as it is
                 ctx_len = text_embeds.shape[1]
                 ctx_kv = mg.context_kv(text_embeds)  # once per sample, not once per forward
                 if isinstance(self.critic, TokenCritic) and self.critic.has_cross_attn:
