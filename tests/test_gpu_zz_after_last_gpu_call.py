@@ -82,3 +82,37 @@ def test_cosine_vq_token_ids_match_reference_golden(golden):
 
 def test_cosine_vq_decode_matches_reference_golden(golden):
     D.test_decode_from_codebook_indices_matches_reference_golden(golden, "cosine_vq")
+
+
+@pytest.mark.parametrize("k", [574, 288, 50])
+def test_cfg3_masked_rows_step_equals_all_rows_step_at_full_size(k):
+    """BASELINE configs[2] sizes (b=4, N=576, V=65536, depth 6, 16 text tokens): the demasking step with the head on the
+    b*k masked rows (18, 9 and 2 token tiles -> 8, 16 and 74 vocabulary splits of the fused head) against the all-rows
+    step, temperature 0: same ids at the masked positions, same confidences, nothing else touched."""
+    torch.manual_seed(3)
+    mg = P.MaskGit(dim=512, num_tokens=65536, max_seq_len=1024, dim_context=768, depth=6).to(DEV).eval()
+    mg.precision = L.PREC_BF16
+    b, shape, n = 4, (9, 8, 8), 576
+    g = torch.Generator().manual_seed(k)
+    ids0 = torch.randint(0, 65537, (b, n), generator=g).to(DEV)
+    ctx = torch.randn((b, 16, 768), generator=g).to(DEV)
+    tmask = torch.ones((b, 16), dtype=torch.bool, device=DEV)
+    mask = torch.zeros((b, n), dtype=torch.uint8)
+    for i in range(b):
+        mask[i, torch.randperm(n, generator=g)[:k]] = 1
+    mask = mask.to(DEV)
+    kv = mg.context_kv(ctx)
+    outs = []
+    for count in (0, k):
+        ids, pred, sc = ids0.clone(), torch.empty_like(ids0), torch.empty((b, n), device=DEV)
+        mg._sample_step(ids0, shape, ctx_kv=kv, ctx_len=16, text_mask=tmask, cond_scale=3.0, temperature=0.0, seed=1, offset=0,
+                        mask=mask, ids=ids, pred=pred, scores=sc, masked_per_seq=count)
+        torch.cuda.synchronize()
+        outs.append((ids.cpu(), sc.cpu()))
+    m = mask.cpu().bool()
+    (ids_a, sc_a), (ids_b, sc_b) = outs
+    same = ids_a == ids_b
+    assert int((~same).sum()) <= max(1, int(0.01 * m.sum())), f"{int((~same).sum())} ids differ"
+    torch.testing.assert_close(sc_a[m & same], sc_b[m & same], rtol=1e-3, atol=1e-4)
+    assert bool((sc_b[~m] == -1e4).all()) and torch.equal(ids_b[~m], ids0.cpu()[~m])
+    assert bool(((ids_b[m] >= 0) & (ids_b[m] < 65536)).all())
