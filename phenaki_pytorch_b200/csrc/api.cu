@@ -785,7 +785,8 @@ extern "C" int64_t phk_maskgit_sample_workspace_bytes(const phk_maskgit_t* m, in
   // the masked-rows-only tail (phk_sample_tail) never needs more than the all-rows one: its largest case is k = n
   const int64_t tail = phk_sample_tail_scratch_bytes(b, n, m->dim);
   const int64_t full = tokens * m->dim * 2 + phk_head_sample_scratch_bytes((int32_t)tokens);
-  return phk_maskgit_workspace_bytes(m, b, n, L, 1, PHK_PREC_BF16) + (tail > full ? tail : full) + 1024;
+  // (+1 MB: the head's per-split partials of a few-row tail, at most 128 * 148 * 20 B, are not monotonic in k)
+  return phk_maskgit_workspace_bytes(m, b, n, L, 1, PHK_PREC_BF16) + (tail > full ? tail : full) + (1 << 20);
 }
 
 static int sample_step_impl(const phk_maskgit_t* m, const int64_t* ids_in, int32_t b, int32_t n, int32_t pt,
