@@ -25,9 +25,11 @@ CFG2 = dict(dim=512, codebook_size=65536, image_size=256, patch_size=32, tempora
 VIDEO = (8, 3, 17, 256, 256)
 CFG3 = dict(dim=512, num_tokens=65536, max_seq_len=1024, dim_context=768, depth=6)
 CFG3_RUN = dict(batch=4, num_frames=17, steps=18, ctx_len=16, cond_scale=3.0)
-# algorithmic FLOPs
-ENCODE_GFLOP = 264.8
-MASKGIT_FWD_GFLOP = 277.1
+# algorithmic FLOPs (2*M*N*K per product, UNPADDED dims)
+ENCODE_GFLOP = 264.8        # whole encode call
+ENCODE_GEMM_GFLOP = 259.28  # its nn.Linear products: patch embed 27.38 + 2 x (projections 38.66 + feed-forward 77.29)
+MASKGIT_FWD_GFLOP = 277.1   # one MaskGit forward at b=4, N=576, L=16 (head 154.6, FF 58.0, self 45.3, cross 15.6, ...)
+MASKGIT_HEAD_GFLOP = 154.6  # to_logits over all b*N rows, one forward
 
 
 def peaks():
@@ -100,32 +102,41 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def report(self, window):
+        """Clock record of one timed window (a perf_counter pair) while the poller keeps running (NVML path only)."""
+        if self.nvml is None:
+            return None
+        return self._nvml_summary(list(self.samples), window)
+
+    def _nvml_summary(self, samples, window):
+        n = self.nvml
+        # keep the samples taken inside the timed window (the poller starts during warm-up so that its first, slow NVML
+        # calls are over); if the window was shorter than one polling period keep the nearest ones
+        inside = [x for x in samples if window[0] <= x[3] <= window[1]] if window else []
+        if len(inside) < 3 and samples and window:
+            mid = 0.5 * (window[0] + window[1])
+            inside = sorted(samples, key=lambda x: abs(x[3] - mid))[:3]
+        samples = [x[:3] for x in (inside or samples)]
+        if not samples:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+        bits = {"hw_slowdown": getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        reasons = sorted(k for k, b in bits.items() if any(r & b for _, r, _ in samples))
+        try:
+            mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+        except Exception:
+            mx = None
+        return dict(sm_mhz=statistics.median(s for s, _, _ in samples), sm_max_mhz=mx,
+                    power_w_max=max(p for _, _, p in samples), samples=len(samples), reasons=reasons,
+                    source="nvml, 2 ms period")
+
     def stop(self):
         if self.nvml is not None:
             self.stop_flag = True
             self.thread.join(timeout=1)
-            n = self.nvml
-            # keep the samples taken inside the timed window (the poller starts during warm-up so that its first,
-            # slow NVML calls are over); if the window was shorter than one polling period keep the nearest ones
-            inside = [x for x in self.samples if self.window[0] <= x[3] <= self.window[1]] if self.window else []
-            if len(inside) < 3 and self.samples and self.window:
-                mid = 0.5 * (self.window[0] + self.window[1])
-                inside = sorted(self.samples, key=lambda x: abs(x[3] - mid))[:3]
-            self.samples = [x[:3] for x in (inside or self.samples)]
-            if not self.samples:
-                return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
-            bits = {"hw_slowdown": getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
-                    "hw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
-                    "sw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
-                    "sw_power_cap": getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
-            reasons = sorted(k for k, b in bits.items() if any(r & b for _, r, _ in self.samples))
-            try:
-                mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
-            except Exception:
-                mx = None
-            return dict(sm_mhz=statistics.median(s for s, _, _ in self.samples), sm_max_mhz=mx,
-                        power_w_max=max(p for _, _, p in self.samples), samples=len(self.samples), reasons=reasons,
-                        source="nvml, 2 ms period")
+            return self._nvml_summary(self.samples, self.window)
         if self.proc is None:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
         time.sleep(0.15)
@@ -173,14 +184,19 @@ def tune_cpu_threads(fn, candidates=None):
     return best
 
 
-def cpu_encode_baseline(seconds_budget=12.0, batch=1):
+def _cfg2_state():
+    import torch
+    import phenaki_pytorch_b200 as P
+    torch.manual_seed(0)
+    return {k: v.detach() for k, v in P.CViViT(**CFG2).state_dict().items()}
+
+
+def cpu_encode_baseline(seconds_budget=12.0, batch=2):
     """The reference's CPU path (oracle port: same ATen ops, all host threads) on a BOUNDED sample of the
     same workload: `batch` video(s) of cfg2 per call."""
     import torch
     from oracle import phenaki_oracle as O
-    import phenaki_pytorch_b200 as P
-    torch.manual_seed(0)
-    sd = {k: v.detach() for k, v in P.CViViT(**CFG2).state_dict().items()}
+    sd = _cfg2_state()
     video = torch.randn(batch, *VIDEO[1:])
     with torch.no_grad():
         cores = tune_cpu_threads(lambda: O.cvivit_codebook_ids(video, sd, (256, 256), (32, 32)))
@@ -197,81 +213,196 @@ def cpu_encode_baseline(seconds_budget=12.0, batch=1):
                        f"CPU eager, {torch.get_num_threads()} threads (best of 8/16/32/64/{os.cpu_count()}), {dt:.1f}s")
 
 
-def run_reference(args, rank, world):
-    """--impl reference: the reference's own CPU implementation of the path (oracle port), rank 0 only."""
-    if rank != 0:
-        return
-    per_step = 2  # videos per step (bounded sample of the 8-video batch)
+def cpu_maskgit_baseline(loop_steps=2):
+    """The reference's demasking loop on the host cores (oracle port), bounded: the first `loop_steps` of the 18
+    iterations at the full b=4 (each iteration = 2 MaskGit forwards + the V-wide gumbel / softmax / top-k tail)."""
     import torch
     from oracle import phenaki_oracle as O
     import phenaki_pytorch_b200 as P
-    torch.manual_seed(0)
-    sd = {k: v.detach() for k, v in P.CViViT(**CFG2).state_dict().items()}
-    video = torch.randn(per_step, *VIDEO[1:])
+    torch.manual_seed(1)
+    sd = {k: v.detach() for k, v in P.MaskGit(**CFG3).state_dict().items()}
+    b, L = CFG3_RUN["batch"], CFG3_RUN["ctx_len"]
+    ctx = torch.randn(b, L, 768)
+
+    class Stop(Exception):
+        pass
+
+    class StopAfter(list):  # the oracle appends one trace record per finished iteration
+        def __init__(self, n):
+            super().__init__()
+            self.n = n
+
+        def append(self, rec):
+            super().append(rec)
+            if len(self) >= self.n:
+                raise Stop()
+
+    def run(steps_run):
+        # the schedule depends on the total step count: run the FIRST iterations of the 18-step loop (the last one
+        # stops before its confidence scores, a few percent of an iteration in the CPU's favour)
+        try:
+            O.sample_token_ids(sd, num_tokens=576, patch_shape=(9, 8, 8), batch=b, steps=CFG3_RUN["steps"],
+                               text_embeds=ctx, cond_scale=CFG3_RUN["cond_scale"],
+                               noise_fn=lambda shape, tag: torch.zeros(shape).uniform_(0, 1), trace=StopAfter(steps_run))
+        except Stop:
+            pass
+
     with torch.no_grad():
-        cores = tune_cpu_threads(lambda: O.cvivit_codebook_ids(video, sd, (256, 256), (32, 32)))
-        for _ in range(min(args.warmup, 2)):
+        torch.set_num_threads(min(32, os.cpu_count() or 1))
+        run(1)  # warm-up (allocator, thread pool)
+        t0 = time.perf_counter()
+        run(loop_steps)
+        dt = time.perf_counter() - t0
+    return dict(value=b * 576 * loop_steps / dt, unit="tokens/s", cores=torch.get_num_threads(), kind="port",
+                s_per_decode_step=dt / loop_steps,
+                sample=f"first {loop_steps} of 18 demasking iterations at b={b}, N=576, V=65536, cond_scale 3 (oracle port of "
+                       f"Phenaki.sample, CPU fp32 eager ATen, {torch.get_num_threads()} threads), {dt:.1f}s")
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port), rank 0 only, on the FULL
+    configs[1] batch (8 videos per step)."""
+    if rank != 0:
+        return
+    per_step = VIDEO[0]
+    import torch
+    from oracle import phenaki_oracle as O
+    sd = _cfg2_state()
+    video = torch.randn(per_step, *VIDEO[1:])
+    small = video[:2].contiguous()
+    with torch.no_grad():
+        cores = tune_cpu_threads(lambda: O.cvivit_codebook_ids(small, sd, (256, 256), (32, 32)))
+        for _ in range(args.warmup):
             O.cvivit_codebook_ids(video, sd, (256, 256), (32, 32))
-        steps = min(args.steps, 200)
+        steps = min(args.steps, 100)
         t0 = time.perf_counter()
         for _ in range(steps):
             O.cvivit_codebook_ids(video, sd, (256, 256), (32, 32))
         dt = time.perf_counter() - t0
     fps = steps * per_step * VIDEO[2] / dt
-    sample = (f"{steps} steps x ({per_step},3,17,256,256) of the cfg2 batch, oracle port of the reference (CPU fp32 "
+    sample = (f"{steps} steps x the full ({per_step},3,17,256,256) cfg2 batch, oracle port of the reference (CPU fp32 "
               f"eager ATen, {cores} threads = best of 8/16/32/64/{os.cpu_count()})")
-    print(json.dumps({
+    out = {
         "impl": "reference", "metric": "cvivit_encode_frames_per_s", "value": fps, "unit": "frames/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 2), "ms_per_step": dt / steps * 1e3,
+        "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": dt / steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "BASELINE.json configs[1]: CViViT(dim=512,image=256,patch=32,pt=2,depth=4+4) encode+VQ; "
-                               "bounded sample of 2 videos (34 frames) per step on the host CPU, thread count auto-tuned"},
+        "config": {"workload": "BASELINE.json configs[1]: CViViT(dim=512,image=256,patch=32,pt=2,depth=4+4,heads=8,"
+                               "codebook=65536) encode+LFQ ids of (8,3,17,256,256) fp32 per GPU, random-init weights",
+                   "batch_per_gpu": per_step, "frames": VIDEO[2],
+                   "note": "host CPU, oracle port of the reference modules (kind: port -- /root/reference is not on the "
+                           "GPU box), thread count auto-tuned"},
         "cpu_baseline": dict(value=fps, unit="frames/s", cores=cores, kind="port", sample=sample),
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    }
+    if not args.no_maskgit:
+        try:
+            out["maskgit"] = cpu_maskgit_baseline()
+        except Exception as ex:
+            out["maskgit"] = {"error": repr(ex)}
+    print(json.dumps(out))
 
 
-def bench_maskgit(dev, prec, steps_timed=1):
-    """configs[2]: MaskGit(dim=512, depth=6, seq=1024, ctx=768) 18-step demasking loop, b=4, 17 frames."""
+def _timed(fn, iters, barrier):
+    """CUDA-event time of `iters` calls on the current stream, bracketed by barrier + synchronize."""
+    import torch
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    out = None
+    for _ in range(iters):
+        out = fn()
+    e1.record()
+    barrier()
+    return e0.elapsed_time(e1), (t0, time.perf_counter()), out
+
+
+def bench_maskgit(dev, prec, world, barrier, sampler, samples_timed=6):
+    """configs[2]: MaskGit(dim=512, depth=6, seq=1024, ctx=768) 18-step demasking loop, b=4 per GPU, 17 frames.
+    Device-resident `value`, `e2e` through Phenaki.sample (pinned host text embeddings in, host ids out), roofline on
+    algorithmic and on executed FLOPs, launches per iteration."""
     import torch
     import phenaki_pytorch_b200 as P
+    from phenaki_pytorch_b200 import _lib as L
+    from phenaki_pytorch_b200 import sharding as S
+    lib = L.lib()
     torch.manual_seed(1)
-    small = dict(CFG2)
-    cv = P.CViViT(**small).to(dev)
+    cv = P.CViViT(**CFG2).to(dev)
     mg = P.MaskGit(**CFG3).to(dev)
     cv.precision = mg.precision = prec
     ph = P.Phenaki(cvivit=cv, maskgit=mg, steps=CFG3_RUN["steps"], text_embed_dim=768)
     ph.cvivit.precision = prec
     if os.environ.get("PHK_FUSED_HEAD") is not None:   # A/B: fused logits-head kernel vs head GEMM + sampling kernel
         ph.fused_head = os.environ["PHK_FUSED_HEAD"] != "0"
-    b, L = CFG3_RUN["batch"], CFG3_RUN["ctx_len"]
-    ctx = torch.randn(b, L, 768, device=dev)
-    ctx[1, L // 2:] = 0
+    b, Lc, steps = CFG3_RUN["batch"], CFG3_RUN["ctx_len"], CFG3_RUN["steps"]
+    host_ctx = torch.randn(b, Lc, 768)
+    host_ctx[1, Lc // 2:] = 0
+    host_ctx = host_ctx.pin_memory()
+    ctx = host_ctx.to(dev)
     n = cv.num_tokens_per_frames(CFG3_RUN["num_frames"])
     shape = cv.get_video_patch_shape(CFG3_RUN["num_frames"])
     run = lambda: ph.sample_token_ids(num_tokens=n, patch_shape=shape, batch_size=b, text_embeds=ctx,
                                       cond_scale=CFG3_RUN["cond_scale"])
-    run()  # warm-up (also builds tables / caches)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps_timed):
-        ids = run()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / steps_timed
+    for _ in range(3):  # warm-up: tables, caches, (one-launch mode) eager call + capture + first replay
+        run()
+    l0 = lib.phk_launch_count()
+    ms_total, window, ids = _timed(run, samples_timed, barrier)
+    launches = lib.phk_launch_count() - l0
+    ms = S.max_over_ranks(ms_total, dev) / samples_timed
     assert int((ids == mg.mask_id).sum()) == 0
-    tokens = b * n * CFG3_RUN["steps"]
-    tf = 2 * MASKGIT_FWD_GFLOP * CFG3_RUN["steps"] / ms  # GFLOP/ms = TFLOP/s
+    # e2e: the public call, host buffers in and out every sample
+    e2e_fn = lambda: ph.sample(num_frames=CFG3_RUN["num_frames"], text_embeds=host_ctx, cond_scale=CFG3_RUN["cond_scale"],
+                               return_token_ids=True).cpu()
+    e2e_fn()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(samples_timed):
+        e2e_fn()
+    torch.cuda.synchronize()
+    e2e_ms = S.max_over_ranks((time.perf_counter() - t0) * 1e3, dev) / samples_timed
+    tokens = b * n * steps
     pk = peaks()
-    return dict(metric="maskgit_sample_tokens_per_s", value=tokens / ms * 1e3, unit="tokens/s", ms_per_sample=ms,
-                ms_per_decode_step=ms / CFG3_RUN["steps"],
-                config=f"MaskGit(dim=512,depth=6,V=65536,ctx=768) {CFG3_RUN['steps']}-step demasking loop, b={b}, N={n}, "
-                       f"L={L}, cond_scale=3 (2 forwards/step as one batch of {2 * b})",
-                achieved_tflops=tf, frac_of_tensor_peak=tf / pk["tf_sustained"], fused_head=bool(ph.fused_head),
-                flops_note="achieved_tflops divides the reference's algorithmic FLOPs (SURVEY 8d: all rows, both CFG halves, "
-                           "every layer) by the time; the step itself runs the logits head on the still-masked rows only "
-                           "and the first layer's PEG + self-attention once for the CFG pair (DESIGN 4.3)")
+    alg_gflop = 2 * MASKGIT_FWD_GFLOP * steps
+    # executed: the logits head only on the still-masked rows (576, k_1, ..., k_17 of 576 per sequence) and the first
+    # layer's PEG + self-attention once for the CFG pair -- DESIGN 4.3
+    ks = [n] + P.phenaki.demask_counts(n, steps)
+    head_rows = sum(ks) / (n * steps)
+    exec_gflop = alg_gflop - 2 * MASKGIT_HEAD_GFLOP * steps * (1 - head_rows) - steps * (45.3 / 6 / 2 + 0.4 / 6 / 2)
+    graphs = int(launches) <= samples_timed * steps  # one cudaGraphLaunch per iteration counted as its kernels by the library
+    out = dict(metric="maskgit_sample_tokens_per_s", value=world * tokens / ms * 1e3, unit="tokens/s", ms_per_sample=ms,
+               ms_per_decode_step=ms / steps, samples_timed=samples_timed, n_gpus=world,
+               config=dict(workload=f"BASELINE.json configs[2]: MaskGit(dim=512,depth=6,V=65536,ctx=768) {steps}-step "
+                                    f"Phenaki.sample demasking loop, b={b} per GPU, N={n}, L={Lc}, cond_scale=3 (2 forwards "
+                                    f"per step as one batch of {2 * b}), in-kernel Philox gumbel noise",
+                           one_launch_per_iteration=bool(getattr(ph, "iteration_call", False)),
+                           fused_head=bool(ph.fused_head)),
+               e2e=dict(value=world * tokens / e2e_ms * 1e3, unit="tokens/s", ms_per_sample=e2e_ms,
+                        h2d_bytes_per_step=int(host_ctx.numel() * 4), d2h_bytes_per_step=int(b * n * 8),
+                        api="Phenaki.sample(text_embeds=<pinned host tensor>, return_token_ids=True).cpu(): text embeddings "
+                            "H2D, text keys/values, 18 iterations, ids D2H inside the timed region"),
+               roofline=dict(bound="tensor", kernel="whole demasking iteration", unit="TFLOP/s",
+                             achieved=alg_gflop / ms, peak=pk["tf_sustained"], frac=alg_gflop / ms / pk["tf_sustained"],
+                             achieved_on_executed_flops=exec_gflop / ms,
+                             frac_on_executed_flops=exec_gflop / ms / pk["tf_sustained"],
+                             algorithmic_gflop_per_sample=alg_gflop, executed_gflop_per_sample=exec_gflop,
+                             peak_source=pk["src"] + " (sustained bf16)", traffic=None,
+                             note="algorithmic = SURVEY 8d (all rows, both CFG halves, every layer: 554.1 GFLOP per "
+                                  "iteration); executed = head on the still-masked rows only, first layer's PEG + "
+                                  "self-attention once per CFG pair"),
+               gpu_launches=int(launches), kernels_per_iteration=launches / (samples_timed * steps),
+               clocks=sampler.report(window) if sampler is not None else None)
+    return out
+
+
+def reference_gpu_leg(dev, maskgit=True):
+    """the reference's own PyTorch path on this B200 (oracle port on CUDA, eager fp32 and autocast
+    bf16) -- the same-box bar the build must beat."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import ref_gpu_bench as R
+    out = dict(encode=R.encode_leg(dev))
+    if maskgit:
+        out["maskgit"] = R.maskgit_leg(dev, iters=1)
+    return out
 
 
 def main():
@@ -280,9 +411,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--prec", default=os.environ.get("PHK_PREC", "bf16"), choices=["f32", "bf16"])
+    ap.add_argument("--prec", default=os.environ.get("PHK_PREC", "bf16"), choices=["f32", "bf16", "bf16x3"])
     ap.add_argument("--no-maskgit", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-refgpu", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -306,7 +438,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     W = max(args.warmup, 3)
     K = args.steps
-    prec = L.PREC_BF16 if args.prec == "bf16" else L.PREC_F32
+    prec = {"bf16": L.PREC_BF16, "f32": L.PREC_F32, "bf16x3": getattr(L, "PREC_BF16X3", L.PREC_F32)}[args.prec]
     lib = L.lib()
 
     torch.manual_seed(0)
@@ -345,15 +477,31 @@ def main():
     t_submit = time.perf_counter() - t_submit   # host time to enqueue the K steps (launch-bound if close to the GPU time)
     e1.record()
     barrier()
-    sampler.window = (t_window, time.perf_counter())
+    enc_window = (t_window, time.perf_counter())
+    sampler.window = enc_window
     ms_total = e0.elapsed_time(e1)
     launches = lib.phk_launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = (sampler.report(enc_window) or None) if rank == 0 else None
     ms_total = S.max_over_ranks(ms_total, dev)   # the job is as slow as its slowest rank
     ms_step = ms_total / K
     value = world * B * F * K / (ms_total / 1e3)
 
+    # the K-step window is tens of milliseconds (power and clocks have not settled): also a long run of the same loop
+    KS = 1500
+    e0.record()
+    t_sus = time.perf_counter()
+    for i in range(KS):
+        model(vids[i % 3], return_only_codebook_ids=True)
+    e1.record()
+    barrier()
+    sus_window = (t_sus, time.perf_counter())
+    sus_ms = S.max_over_ranks(e0.elapsed_time(e1), dev) / KS
+    sustained = dict(steps=KS, ms_per_step=sus_ms, value=world * B * F / sus_ms * 1e3, unit="frames/s",
+                     step_frac_of_tensor_peak=ENCODE_GFLOP / sus_ms / peaks()["tf_sustained"],
+                     clocks=(sampler.report(sus_window) or None) if rank == 0 else None)
+
     # ---- e2e: the C-ABI call with HOST buffers (pinned), H2D + encode + D2H inside the timed region ----
+    KE = min(K, 40)
     table = model._table()
     tp, hh, ww = model.get_video_patch_shape(F)
     host_ids = torch.empty((B, tp, hh, ww), dtype=torch.int64).pin_memory()
@@ -372,12 +520,12 @@ def main():
         e2e_step(i)
     barrier()
     t0 = time.perf_counter()
-    for i in range(K):
+    for i in range(KE):
         e2e_step(i)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    assert torch.equal(host_ids, model(vids[(K - 1) % 3], return_only_codebook_ids=True).cpu())
-    e2e_sync_value = world * B * F * K / S.max_over_ranks(e2e_s, dev)
+    assert torch.equal(host_ids, model(vids[(KE - 1) % 3], return_only_codebook_ids=True).cpu())
+    e2e_sync_value = world * B * F * KE / S.max_over_ranks(e2e_s, dev)
 
     # the same through the public streaming API (CViViT.encode_host_iter -> phk_encode_pipe_*): every step still does
     # its own H2D from pinned memory and D2H of the ids, but batch i+1's copy overlaps batch i's encode
@@ -386,12 +534,12 @@ def main():
     barrier()
     t0 = time.perf_counter()
     last = None
-    for last in model.encode_host_iter((host[i % 3] for i in range(K)), device=dev):
+    for last in model.encode_host_iter((host[i % 3] for i in range(KE)), device=dev):
         pass
     torch.cuda.synchronize()
     e2e_pipe_s = time.perf_counter() - t0
     assert torch.equal(last, host_ids)
-    e2e_value = world * B * F * K / S.max_over_ranks(e2e_pipe_s, dev)
+    e2e_value = world * B * F * KE / S.max_over_ranks(e2e_pipe_s, dev)
 
     # ---- per-kernel-family device time (CUDA events on the launching stream) over 3 more steps ----
     lib.phk_prof_enable(1)
@@ -407,23 +555,31 @@ def main():
     dom = max(fam, key=lambda k: fam[k][0])
     dms, dcalls, dwork = fam[dom]
     if dom.startswith("gemm") or dom == "attention":
-        achieved = dwork / (dms * 1e-3) / 1e12
+        # the family's ALGORITHMIC FLOPs: unpadded 2*M*N*K of the reference's nn.Linear products (the kernels multiply
+        # the zero-padded 1365 -> 1408 feed-forward width as well; that padding is not counted as work)
+        alg = ENCODE_GEMM_GFLOP * 1e9 * PROF_STEPS if dom.startswith("gemm") and prec != L.PREC_F32 else dwork
+        achieved = alg / (dms * 1e-3) / 1e12
         roof = dict(bound="tensor", kernel=dom, achieved=achieved, peak=pk["tf_sustained"], unit="TFLOP/s",
                     frac=achieved / pk["tf_sustained"], traffic=None,
-                    per_launch=dict(flops=dwork / dcalls, ms=dms / dcalls), peak_source=pk["src"] + " (sustained bf16)")
+                    per_launch=dict(flops=alg / dcalls, executed_flops_incl_padding=dwork / dcalls, ms=dms / dcalls),
+                    peak_source=pk["src"] + " (sustained bf16)")
     else:
         achieved = dwork / (dms * 1e-3) / 1e9
         roof = dict(bound="hbm", kernel=dom, achieved=achieved, peak=pk["hbm"], unit="GB/s", frac=achieved / pk["hbm"],
                     traffic=None, per_launch=dict(bytes=dwork / dcalls, ms=dms / dcalls), peak_source=pk["src"])
     # DRAM bytes per launch of the dominant family, from the committed `ncu --set full` capture (not measured live)
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(tpath):
-        tj = json.load(open(tpath)).get(dom)
-        if tj:
-            roof["traffic"], roof["traffic_source"] = tj["dram_bytes_per_launch"], tj["source"]
+    for tname in ("r02_traffic.json", "r01_traffic.json"):
+        tpath = os.path.join(ROOT, "profiles", tname)
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath)).get(dom)
+            if tj:
+                roof["traffic"], roof["traffic_source"] = tj["dram_bytes_per_launch"], tj["source"]
+                break
     roof["family_share_of_step"] = shares
+    roof["family_launches_per_step"] = {k: v[1] // PROF_STEPS for k, v in fam.items()}
     roof["step_tflops"] = ENCODE_GFLOP / ms_step  # whole-step algorithmic FLOPs / device time
     roof["step_frac_of_tensor_peak"] = roof["step_tflops"] / pk["tf_sustained"]
+    roof["step_frac_of_burst_peak"] = roof["step_tflops"] / pk["tf_burst"]
 
     out = {
         "metric": "cvivit_encode_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": K,
@@ -434,10 +590,11 @@ def main():
                    "batch_per_gpu": B, "global_batch": B * world, "frames": F,
                    "parallelism": f"dp{world}: batch-sharded, one process per GPU, no data-path collective",
                    "l2": "inputs rotate over 3 device buffers (3 x 107 MB > 126 MB L2)",
-                   "precision_mode": "PHK_PREC_F32 (fp32 FFMA GEMMs, parity mode)" if prec == 0 else
-                                     "PHK_PREC_BF16 (tcgen05 bf16 GEMMs, fp32 accumulate/residual/LN/softmax)"},
+                   "precision_mode": {"f32": "PHK_PREC_F32 (fp32 FFMA GEMMs, parity mode)",
+                                      "bf16": "PHK_PREC_BF16 (tcgen05 bf16 GEMMs, fp32 accumulate/residual/LN/softmax)",
+                                      "bf16x3": "PHK_PREC_BF16X3 (tcgen05, split-bf16 operands: fp32-grade products)"}[args.prec]},
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": B * Cc * F * H * Wd * 4,
-                "d2h_bytes_per_step": B * tp * hh * ww * 8,
+                "d2h_bytes_per_step": B * tp * hh * ww * 8, "steps": KE,
                 "api": "CViViT.encode_host_iter -> phk_encode_pipe_submit/wait (C ABI; pinned host video -> host int64 "
                        "ids every step, the H2D of step i+1 overlaps the encode of step i)",
                 "sync_call_value": e2e_sync_value,
@@ -445,19 +602,31 @@ def main():
         "gpu_launches": int(launches), "host_submit_ms_per_step": t_submit / K * 1e3,
         "roofline": roof,
         "clocks": clocks,
+        "sustained": sustained,
     }
     if rank == 0 and world == 1 and not args.no_cpu:
         out["cpu_baseline"] = cpu_encode_baseline(batch=2)
     if not args.no_maskgit:
         try:
-            mres = bench_maskgit(dev, prec)
-            if world > 1:
-                mres["ms_per_sample"] = S.max_over_ranks(mres["ms_per_sample"], dev)
-                mres["value"] = world * CFG3_RUN["batch"] * 576 * CFG3_RUN["steps"] / mres["ms_per_sample"] * 1e3
-            out["extra"] = {"maskgit_sample": mres}
+            mres = bench_maskgit(dev, prec, world, barrier, sampler if rank == 0 else None)
+            if rank == 0 and world == 1 and not args.no_cpu:
+                mres["cpu_baseline"] = cpu_maskgit_baseline()
+            out["maskgit"] = mres
+            out["extra"] = {"maskgit_sample": {k: mres[k] for k in ("metric", "value", "unit", "ms_per_sample",
+                                                                   "ms_per_decode_step")}}
         except Exception as ex:  # the headline line must still print
-            out["extra"] = {"maskgit_sample": {"error": repr(ex)}}
+            out["maskgit"] = {"error": repr(ex)}
+    if rank == 0 and world == 1 and not args.no_refgpu:
+        try:
+            out["reference_gpu"] = reference_gpu_leg(dev, maskgit=not args.no_maskgit)
+            out["reference_gpu"]["encode_speedup_vs_autocast_bf16"] = value / out["reference_gpu"]["encode"]["autocast_bf16"]["value"]
+            if "maskgit" in out["reference_gpu"] and "value" in out.get("maskgit", {}):
+                out["reference_gpu"]["maskgit_speedup_vs_autocast_bf16"] = (
+                    out["maskgit"]["value"] / out["reference_gpu"]["maskgit"]["autocast_bf16"]["value"])
+        except Exception as ex:
+            out["reference_gpu"] = {"error": repr(ex)}
     if rank == 0:
+        sampler.stop()
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

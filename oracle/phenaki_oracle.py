@@ -70,12 +70,12 @@ def alibi_slopes(heads):
     return pow2(c) + pow2(2 * c)[0::2][: heads - c]
 
 
-def alibi_bias(heads, i, j):
+def alibi_bias(heads, i, j, device=None):
     """attention.py:195-227 -> (h, i, j) fp32, ``-|col - row| * slope``."""
-    rows = torch.arange(j - i, j)
-    cols = torch.arange(j)
+    rows = torch.arange(j - i, j, device=device)
+    cols = torch.arange(j, device=device)
     bias = -(cols[None, None, :] - rows[None, :, None]).abs()
-    slopes = torch.tensor(alibi_slopes(heads), dtype=torch.float32)[:, None, None]
+    slopes = torch.tensor(alibi_slopes(heads), dtype=torch.float32, device=device)[:, None, None]
     return bias * slopes
 
 
@@ -94,8 +94,8 @@ def attention_core(q, k, v, q_scale, k_scale, *, heads, causal=False, num_null_k
         m = F.pad(mask, (num_null_kv, 0), value=True)
         sim = sim.masked_fill(~m[:, None, None, :], neg)
     if causal:
-        sim = sim + alibi_bias(heads, i, j)
-        sim = sim.masked_fill(torch.ones((i, j), dtype=torch.bool).triu(j - i + 1), neg)
+        sim = sim + alibi_bias(heads, i, j, sim.device)
+        sim = sim.masked_fill(torch.ones((i, j), dtype=torch.bool, device=sim.device).triu(j - i + 1), neg)
     attn = sim.softmax(dim=-1)
     return torch.einsum("bhij,bhjd->bhid", attn, v)
 
@@ -130,7 +130,8 @@ def attention(x, sd, p, *, heads, causal=False, num_null_kv=0, mask=None, contex
 
 def continuous_position_bias(sd, p, dims):
     """attention.py:229-275 -> (heads, n, n), n = prod(dims).  Weight-only function."""
-    pos = [torch.arange(d) for d in dims]
+    dev = sd[p + "net.0.0.weight"].device
+    pos = [torch.arange(d, device=dev) for d in dims]
     grid = torch.stack(torch.meshgrid(*pos, indexing="ij")).reshape(len(dims), -1).t()
     rel = grid[:, None, :] - grid[None, :, :]
     rel = torch.sign(rel) * torch.log(rel.abs() + 1)
@@ -303,7 +304,7 @@ def maskgit_forward(ids, sd, *, video_patch_shape, heads=8, context=None, text_m
         ids = ids.reshape(ids.shape[0], -1)
     b, n = ids.shape
     if text_mask is None:
-        text_mask = torch.ones((b, n), dtype=torch.bool)
+        text_mask = torch.ones((b, n), dtype=torch.bool, device=ids.device)
     bias = continuous_position_bias(sd, p + "continuous_pos_bias.", video_patch_shape)
     if cond_drop:
         text_mask = torch.zeros_like(text_mask)
@@ -325,7 +326,7 @@ def critic_forward(ids, sd, *, video_patch_shape, heads=8, context=None, text_ma
     ids = ids.reshape(b, -1)
     n = ids.shape[1]
     if text_mask is None:
-        text_mask = torch.ones((b, n), dtype=torch.bool)
+        text_mask = torch.ones((b, n), dtype=torch.bool, device=ids.device)
     if context is not None and cond_drop:
         text_mask = torch.zeros_like(text_mask)
     x = _token_embed(ids, sd, p)
@@ -375,18 +376,21 @@ def sample_token_ids(maskgit_sd, *, num_tokens, patch_shape, batch, steps=18, he
                      text_embeds=None, text_mask=None, prime_ids=None, cond_scale=3.0,
                      starting_temperature=0.9, noise_K=1.0, critic_sd=None,
                      critic_has_cross_attn=True, critic_noise_anneal="decay",
-                     noise_fn=torch_noise, mask_id=None, trace=None):
+                     noise_fn=torch_noise, mask_id=None, trace=None, self_critic=None):
     """The demasking loop, phenaki_pytorch.py:473-550 (everything between text encoding and the
     final C-ViViT decode).  ``noise_fn(shape, tag)`` supplies every uniform draw in reference
     order: tag 'gumbel{step}' (b, n, V) then 'critic{step}' (b, n).
+    ``self_critic`` = (to_pred.weight, to_pred.bias): SelfCritic (phenaki_pytorch.py:307-336), Linear(dim, 1) on the
+    MaskGit embeddings of the sampled ids, scored like a TokenCritic.
     Returns final ids (b, num_tokens) int64 (without the prime prefix)."""
     if mask_id is None:
         mask_id = maskgit_sd["to_logits.weight"].shape[0]
     if text_embeds is not None and text_mask is None:
         text_mask = torch.any(text_embeds != 0, dim=-1)
+    dev = maskgit_sd["to_logits.weight"].device
     shape = (batch, num_tokens)
-    ids = torch.full(shape, mask_id, dtype=torch.long)
-    mask = torch.ones(shape, dtype=torch.bool)
+    ids = torch.full(shape, mask_id, dtype=torch.long, device=dev)
+    mask = torch.ones(shape, dtype=torch.bool, device=dev)
     scores = None
     has_prime = prime_ids is not None
     plen = prime_ids.shape[-1] if has_prime else 0
@@ -397,7 +401,7 @@ def sample_token_ids(maskgit_sd, *, num_tokens, patch_shape, batch, steps=18, he
             t = torch.full((1,), step / steps)
             k = (num_tokens * torch.cos(t * math.pi * 0.5)).round().long().clamp(min=1)
             _, idx = scores.topk(k.item(), dim=-1)
-            mask = torch.zeros(shape).scatter(1, idx, 1).bool()
+            mask = torch.zeros(shape, device=dev).scatter(1, idx, 1).bool()
         ids = torch.where(mask, mask_id, ids)
         inp = ids if not has_prime else torch.cat((prime_ids, ids), dim=-1)
         logits = with_cond_scale(
@@ -413,13 +417,21 @@ def sample_token_ids(maskgit_sd, *, num_tokens, patch_shape, batch, steps=18, he
         if trace is not None:
             trace.append(dict(step=step, mask=mask.clone(), pred=pred.clone(), ids=ids.clone()))
         if not last:
-            if critic_sd is not None:
+            if critic_sd is not None or self_critic is not None:
                 cin = ids if not has_prime else torch.cat((prime_ids, ids), dim=-1)
                 ctx = text_embeds if critic_has_cross_attn else None
-                scores = with_cond_scale(
-                    lambda cond_drop: critic_forward(cin, critic_sd, video_patch_shape=patch_shape,
-                                                     heads=heads, context=ctx, text_mask=text_mask,
-                                                     cond_drop=cond_drop), cond_scale)
+                if self_critic is not None:  # SelfCritic.forward (:334-336) under forward_with_cond_scale (:320-332)
+                    scores = with_cond_scale(
+                        lambda cond_drop: F.linear(
+                            maskgit_forward(cin, maskgit_sd, video_patch_shape=patch_shape, heads=heads,
+                                            context=text_embeds, text_mask=text_mask, cond_drop=cond_drop,
+                                            return_embeds=True), self_critic[0], self_critic[1]).squeeze(-1),
+                        cond_scale)
+                else:
+                    scores = with_cond_scale(
+                        lambda cond_drop: critic_forward(cin, critic_sd, video_patch_shape=patch_shape,
+                                                         heads=heads, context=ctx, text_mask=text_mask,
+                                                         cond_drop=cond_drop), cond_scale)
                 if has_prime:
                     scores = scores[:, plen:]
                 mult = {"fixed": 1.0, "decay": til_x0 / steps, "increase": (step + 1) / steps}[critic_noise_anneal]

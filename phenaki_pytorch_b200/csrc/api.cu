@@ -873,7 +873,8 @@ static int demask_iteration_impl(const phk_maskgit_t* m, int64_t* ids, uint8_t* 
   if (k_remask > 0) PHK_TRY(phk_topk_mask(scores, b, n, k_remask, mask, ids, (int64_t)m->num_tokens, s));
   PHK_TRY(sample_step_impl(m, ids, b, n, pt, ph, pw, ctx_kv, L, text_mask, nullptr, pos_bias, cond_scale, temperature, 0, 0,
                            rng_state, mask, ids, pred, scores, k_remask > 0 ? k_remask : n, workspace, workspace_bytes, s));
-  const uint64_t stride = (uint64_t)b * (uint64_t)n * (uint64_t)((m->num_tokens + 3) / 4) + 1;
+  // counters of one V-wide draw, rounded up to a multiple of 4 (phenaki.py: _noise_stride)
+  const uint64_t stride = ((uint64_t)b * (uint64_t)n * (uint64_t)((m->num_tokens + 3) / 4) + 1 + 3) / 4 * 4;
   return phk_rng_advance(rng_state, stride, s);
 }
 
@@ -882,7 +883,7 @@ static int step_graphs_enabled() {
   const int v = g_step_graph.load(std::memory_order_relaxed);
   if (v >= 0) return v;
   static int env = -1;
-  if (env < 0) { const char* e = std::getenv("PHK_STEP_GRAPH"); env = (e && e[0] == '1') ? 1 : 0; }
+  if (env < 0) { const char* e = std::getenv("PHK_STEP_GRAPH"); env = (e && e[0] == '0') ? 0 : 1; }  // default: on
   return env;
 }
 // tests / A-B runs: 1 replays phk_maskgit_demask_iteration as a CUDA graph, 0 keeps it eager, < 0 back to PHK_STEP_GRAPH

@@ -481,11 +481,12 @@ static int launch_attention_fewkeys(const float* q, const float* kv, const float
                                     cudaStream_t st) {
   const int nk = g.n_k + g.num_null_kv;
   const size_t smem = (size_t)(2 * nk * DH + nk * FEW_QUERIES + nk) * sizeof(float);
-  static bool configured = false;
+  static unsigned long long configured_mask = 0;
+  const bool configured = device_configured(&configured_mask);
   if (!configured) {
     PHK_CUDA(cudaFuncSetAttribute(attention_fewkeys_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)((2 * FEW_KEYS * DH + FEW_KEYS * FEW_QUERIES + FEW_KEYS) * sizeof(float))));
-    configured = true;
+    mark_configured(&configured_mask);
   }
   dim3 grid((unsigned)((g.n_q + FEW_QUERIES - 1) / FEW_QUERIES), (unsigned)g.heads, (unsigned)(g.n_outer * g.n_inner));
   PHK_CUDA(launch_pdl(attention_fewkeys_kernel<DH>, grid, dim3(FEW_THREADS), smem, st, q, kv, null_kv, q_scale, k_scale,
@@ -721,11 +722,12 @@ static int launch_attention_rows(const float* q, const float* kv, const float* q
   const int n = g.n_q, G = ROWS_QUERIES / n;
   const int64_t npairs = (int64_t)g.n_outer * g.n_inner * g.heads;
   const size_t smem = (size_t)2 * G * (n * DH + 16) * sizeof(float);
-  static bool configured = false;
+  static unsigned long long configured_mask = 0;
+  const bool configured = device_configured(&configured_mask);
   if (!configured) {
     PHK_CUDA(cudaFuncSetAttribute(attention_rows_kernel<DH, NMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(2 * ROWS_QUERIES * (DH + 16) * sizeof(float))));
-    configured = true;
+    mark_configured(&configured_mask);
   }
   PHK_CUDA(launch_pdl(attention_rows_kernel<DH, NMAX>, dim3((unsigned)((npairs + G - 1) / G)), dim3(ROWS_THREADS), smem, st, q,
                       kv, q_scale, k_scale, alibi_slopes, out, g));
@@ -738,11 +740,12 @@ static int launch_attention_small_n(const float* q, const float* kv, const float
                                     const float* alibi_slopes, void* out, const phk_attn_geom_t& g, cudaStream_t st) {
   const int64_t npairs = (int64_t)g.n_outer * g.n_inner * g.heads;
   const size_t smem = (size_t)SMALL_WARPS * (2 * g.n_q * (DH + 1) + g.n_q * (g.n_q + 1)) * sizeof(float);
-  static bool configured = false;
+  static unsigned long long configured_mask = 0;
+  const bool configured = device_configured(&configured_mask);
   if (!configured) {
     PHK_CUDA(cudaFuncSetAttribute(attention_small_kernel<DH, NMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(SMALL_WARPS * (2 * SMALL_N * (DH + 1) + SMALL_N * (SMALL_N + 1)) * sizeof(float))));
-    configured = true;
+    mark_configured(&configured_mask);
   }
   PHK_CUDA(launch_pdl(attention_small_kernel<DH, NMAX>, dim3((unsigned)((npairs + SMALL_WARPS - 1) / SMALL_WARPS)),
                       dim3(SMALL_WARPS * 32), smem, st, q, kv, q_scale, k_scale, alibi_slopes, out, g));
@@ -785,10 +788,11 @@ static int launch_attention(const float* q, const float* kv, const float* null_k
                             const float* k_scale, const float* bias, const uint8_t* key_mask,
                             const float* alibi_slopes, void* out, const phk_attn_geom_t& g, cudaStream_t st) {
   const size_t smem = sizeof(AttSmem<DH>);
-  static bool configured = false;
+  static unsigned long long configured_mask = 0;
+  const bool configured = device_configured(&configured_mask);
   if (!configured) {
     PHK_CUDA(cudaFuncSetAttribute(attention_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
+    mark_configured(&configured_mask);
   }
   dim3 grid((unsigned)((g.n_q + TQ - 1) / TQ), (unsigned)g.heads, (unsigned)(g.n_outer * g.n_inner));
   PHK_CUDA(launch_pdl(attention_kernel<DH>, dim3(grid), dim3(ATT_THREADS), (size_t)(smem), st, q, kv, null_kv, q_scale, k_scale, bias, key_mask, alibi_slopes, out, g));

@@ -463,10 +463,11 @@ extern "C" int phk_attention_tc(const float* q, const float* kv, const float* q_
   PHK_TRY(make_map_3d(Qh, 64, n, SH, 64, (int64_t)n * 64, AQ, &tq));
   PHK_TRY(make_map_3d(Kh, 64, n, SH, 64, (int64_t)n * 64, AKC, &tk));
   PHK_TRY(make_map_3d(Vt, n_pad, 64, SH, n_pad, 64 * n_pad, ADH, &tv));
-  static bool configured = false;
+  static unsigned long long configured_mask = 0;
+  const bool configured = device_configured(&configured_mask);
   if (!configured) {
     PHK_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-    configured = true;
+    mark_configured(&configured_mask);
   }
   const int bias_tma = bias && (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(bias) & 15) == 0);
   CUtensorMap tb = tq;  // placeholder when unused

@@ -998,10 +998,11 @@ static long long* g_gemm_trace = nullptr;
 
 template <int EPI>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const EpiParams& p, cudaStream_t st) {
-  static bool configured = false;
+  static unsigned long long configured_mask = 0;
+  const bool configured = device_configured(&configured_mask);
   if (!configured) {
     PHK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<EPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-    configured = true;
+    mark_configured(&configured_mask);
   }
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
@@ -1012,10 +1013,11 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const EpiPa
 
 static int launch_gemm_dual(const CUtensorMap& ta, const CUtensorMap& tb, const EpiParams& p, const CUtensorMap& ta2,
                             const CUtensorMap& tb2, const EpiParams& p2, cudaStream_t st) {
-  static bool configured = false;
+  static unsigned long long configured_mask = 0;
+  const bool configured = device_configured(&configured_mask);
   if (!configured) {
     PHK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-    configured = true;
+    mark_configured(&configured_mask);
   }
   const int tiles = p.m_tiles * p.n_tiles + p2.m_tiles * p2.n_tiles;
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
@@ -1028,10 +1030,11 @@ static int launch_gemm_dual(const CUtensorMap& ta, const CUtensorMap& tb, const 
 template <int EPI, int BN, bool DUAL>
 static int launch_gemm_pair(const CUtensorMap& ta, const CUtensorMap& tb, const EpiParams& p, const CUtensorMap& ta2,
                             const CUtensorMap& tb2, const EpiParams& p2, cudaStream_t st) {
-  static bool configured = false;
+  static unsigned long long configured_mask = 0;
+  const bool configured = device_configured(&configured_mask);
   if (!configured) {
     PHK_CUDA(cudaFuncSetAttribute(gemm_bf16_pair_kernel<EPI, BN, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair_smem_bytes(EPI)));
-    configured = true;
+    mark_configured(&configured_mask);
   }
   const int tiles = p.m_tiles * p.n_tiles + (DUAL ? p2.m_tiles * p2.n_tiles : 0), max_pairs = kNumSMs / 2;
   const int pairs = tiles < max_pairs ? tiles : max_pairs;

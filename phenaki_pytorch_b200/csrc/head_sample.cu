@@ -442,10 +442,11 @@ extern "C" int phk_head_sample_rng(const void* emb, int64_t ld_emb, int64_t emb_
   HeadParams p{bias, n_tokens, V, dim, n_tiles, n_splits, tps, 1.0f / T, (unsigned long long)seed,
                (unsigned long long)offset, reinterpret_cast<const unsigned long long*>(rng_state), part_f, part_i};
   cudaStream_t st = to_stream(s);
-  static bool configured = false;
+  static unsigned long long configured_mask = 0;
+  const bool configured = device_configured(&configured_mask);
   if (!configured) {
     PHK_CUDA(cudaFuncSetAttribute(head_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM));
-    configured = true;
+    mark_configured(&configured_mask);
   }
   PHK_CUDA(launch_pdl(head_sample_kernel, dim3(m_tiles * n_splits), dim3(HTHREADS), (size_t)H_SMEM, st, ta, tb, p));
   PHK_LAUNCH_CHECK();

@@ -189,10 +189,11 @@ int patchify_ln_tma_launch(const float* video, int B, int C, int F, int H, int W
       cache.emplace(key, map);
     }
   }
-  static bool configured = false;
+  static unsigned long long configured_mask = 0;
+  const bool configured = device_configured(&configured_mask);
   if (!configured) {
     PHK_CUDA(cudaFuncSetAttribute(patchify_ln_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    configured = true;
+    mark_configured(&configured_mask);
   }
   const int tokens = B * nt * (H / p1) * (W / p2);
   const unsigned grid = (unsigned)(tokens < 2 * kNumSMs ? tokens : 2 * kNumSMs);

@@ -36,6 +36,18 @@ static inline cudaStream_t to_stream(phk_stream_t s) { return reinterpret_cast<c
 
 constexpr int kNumSMs = 148;
 
+// One-time per-DEVICE kernel configuration (cudaFuncSetAttribute is a per-device setting; a process may drive several
+// devices): `mask` is a call-site static, bit d = "done on device d".
+static inline bool device_configured(const unsigned long long* mask) {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return false;
+  return (__atomic_load_n(mask, __ATOMIC_RELAXED) >> d) & 1ull;
+}
+static inline void mark_configured(unsigned long long* mask) {
+  int d = 0;
+  if (cudaGetDevice(&d) == cudaSuccess && d >= 0 && d < 64) __atomic_fetch_or(mask, 1ull << d, __ATOMIC_RELAXED);
+}
+
 // Optional per-kernel-family timing with CUDA events on the launching stream (bench.py roofline /
 // share-of-step numbers).  Off by default: zero overhead beyond one relaxed load per entry point.
 enum Family { FAM_PATCHIFY = 0, FAM_LAYERNORM, FAM_GEMM_F32, FAM_GEMM_BF16, FAM_ATTENTION, FAM_PEG, FAM_GEGLU,

@@ -188,11 +188,14 @@ __global__ void geglu_kernel(const float* __restrict__ h, float* __restrict__ ou
 // ------------------------------------------------------------------------------------------
 __global__ void token_embed_kernel(const int64_t* __restrict__ ids, const float* __restrict__ tok,
                                    const float* __restrict__ pos, float* __restrict__ out, int n, int dim,
-                                   float alpha, float one_minus_alpha, int shrink, int64_t id_rows) {
+                                   float alpha, float one_minus_alpha, int shrink, int64_t id_rows, int vocab_rows) {
   pdl_prologue();
   const int64_t row = blockIdx.x;
   const int p = (int)(row % n);
-  const int64_t id = ids[row % id_rows];  // the CFG null half replays the same ids
+  int64_t id = ids[row % id_rows];  // the CFG null half replays the same ids
+  // an id outside the table is a caller error (nn.Embedding raises; the Python entry points check); here it must at
+  // least never read outside the table
+  id = id < 0 ? 0 : (id >= vocab_rows ? vocab_rows - 1 : id);
   const float* t = tok + id * dim;
   const float* pe = pos + (int64_t)p * dim;
   for (int i = threadIdx.x; i < dim; i += blockDim.x) {
@@ -560,11 +563,12 @@ static int launch_peg_tiled(const float* x, const float* w, const float* b, floa
                             int pad_t0, int layout, cudaStream_t st) {
   const int P = H * WW;
   const size_t smem = (size_t)(3 * P * PEG_CH + 27 * PEG_CH) * sizeof(float) + (size_t)3 * P * sizeof(int);
-  static bool configured = false;
+  static unsigned long long configured_mask = 0;
+  const bool configured = device_configured(&configured_mask);
   if (!configured) {
     PHK_CUDA(cudaFuncSetAttribute(peg_tiled_kernel<WW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)((3 * 128 * PEG_CH + 27 * PEG_CH) * sizeof(float) + 3 * 128 * sizeof(int))));
-    configured = true;
+    mark_configured(&configured_mask);
   }
   PHK_CUDA(launch_pdl(peg_tiled_kernel<WW>, dim3((unsigned)(B * T), (unsigned)(D / PEG_CH)), dim3((unsigned)(16 * H)), smem,
                       st, x, w, b, y, T, H, D, pad_t0, layout));
@@ -944,11 +948,12 @@ extern "C" int phk_patchify_ln(const float* video, int32_t B, int32_t C, int32_t
     PHK_REQUIRE((int64_t)C * F * H * W < (1LL << 31), PHK_E_UNSUPPORTED, "phk_patchify_ln: one video exceeds 2^31 elements");
     const unsigned pgrid = grid < 4u * kNumSMs ? grid : 4u * kNumSMs;
     const size_t gsmem = (size_t)2 * K * sizeof(float);
-    static bool configured = false;
+    static unsigned long long configured_mask = 0;
+  const bool configured = device_configured(&configured_mask);
     if (!configured) {
       PHK_CUDA(cudaFuncSetAttribute(patchify_ln_reg_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 49152));
       PHK_CUDA(cudaFuncSetAttribute(patchify_ln_reg_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 49152));
-      configured = true;
+      mark_configured(&configured_mask);
     }
     if (K <= 3 * 1024) PHK_CUDA(launch_pdl(patchify_ln_reg_kernel<3>, dim3(pgrid), dim3(256), gsmem, to_stream(s), video, C, F, H, W, f0, nt, pt, p1, p2, ln_g, ln_b, out, out_bf16, (int)grid));
     else PHK_CUDA(launch_pdl(patchify_ln_reg_kernel<6>, dim3(pgrid), dim3(256), gsmem, to_stream(s), video, C, F, H, W, f0, nt, pt, p1, p2, ln_g, ln_b, out, out_bf16, (int)grid));
@@ -986,7 +991,7 @@ extern "C" int phk_token_embed(const int64_t* ids, const float* tok, const float
   // (1 - alpha) is evaluated in double by the reference's Python and rounded to fp32 at the mul
   const float oma = (float)(1.0 - (double)alpha);
   if (replicas < 1) replicas = 1;
-  PHK_CUDA(launch_pdl(token_embed_kernel, dim3((unsigned)(b * n * replicas)), dim3(128), (size_t)(0), to_stream(s), ids, tok, pos, out, n, dim, alpha, oma, shrink, (int64_t)b * n));
+  PHK_CUDA(launch_pdl(token_embed_kernel, dim3((unsigned)(b * n * replicas)), dim3(128), (size_t)(0), to_stream(s), ids, tok, pos, out, n, dim, alpha, oma, shrink, (int64_t)b * n, vocab_rows));
   PHK_LAUNCH_CHECK();
   return 0;
 }
@@ -1011,10 +1016,11 @@ static int launch_ln_lfq(const float* x, const float* g, const float* b, const f
                          float* out_norm, float* proj, int64_t rows, int dim, int bits, cudaStream_t st) {
   constexpr int R = 2;
   const size_t smem = (size_t)bits * dim * sizeof(float);
-  static bool configured = false;
+  static unsigned long long configured_mask = 0;
+  const bool configured = device_configured(&configured_mask);
   if (!configured) {
     PHK_CUDA(cudaFuncSetAttribute(ln_lfq_kernel<VEC, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 1024 * 4));
-    configured = true;
+    mark_configured(&configured_mask);
   }
   const unsigned grid = (unsigned)((rows + 8 * R - 1) / (8 * R));
   PHK_CUDA(launch_pdl(ln_lfq_kernel<VEC, R>, dim3(grid), dim3(256), smem, st, x, g, b, wp, bp, ids, out_norm, proj, rows, dim, bits));

@@ -642,9 +642,10 @@ __global__ void __launch_bounds__(128) peg_bwd_kernel(const float* __restrict__ 
 // alpha branch carry gradient.  dtok[id] += a * dx ; dpos[p] += a * dx
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void embed_bwd_kernel(const int64_t* __restrict__ ids, const float* __restrict__ dx, float* __restrict__ dtok,
-                                 float* __restrict__ dpos, int n, int dim, float alpha) {
+                                 float* __restrict__ dpos, int n, int dim, float alpha, int vocab_rows) {
   const int64_t row = blockIdx.x;
-  const int64_t id = ids[row];
+  int64_t id = ids[row];
+  id = id < 0 ? 0 : (id >= vocab_rows ? vocab_rows - 1 : id);  // never scatter outside the table (see token_embed_kernel)
   const int p = (int)(row % n);
   for (int c = threadIdx.x; c < dim; c += blockDim.x) {
     const float v = alpha * dx[row * dim + c];
@@ -1141,7 +1142,7 @@ extern "C" int phk_maskgit_train_step(const phk_maskgit_t* m, const phk_maskgit_
   }
   // ---------------------------------------------------------------- embeddings, position-bias MLP
   PHK_KERNEL_LAUNCH(embed_bwd_kernel, dim3((unsigned)R), dim3(128), (size_t)(0), st, ids_in, dx, (float*)grads->token_emb, (float*)grads->pos_emb, n, D,
-                                               m->is_critic ? 1.0f : m->shrink_alpha);
+                                               m->is_critic ? 1.0f : m->shrink_alpha, m->num_tokens + 1);
   PHK_LAUNCH_CHECK();
   if (m->has_bias) {
     float* csc = ar.f(cpb_bwd_scratch_floats(m->pos_bias, pt, ph, pw));

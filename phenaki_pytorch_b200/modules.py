@@ -303,16 +303,37 @@ _SIG_REFRESH = 64
 
 
 def weights_signature(module):
-    """Changes whenever a parameter/buffer is moved or modified in place (`.to()`, `load_state_dict`, optimizer steps
-    keep the Parameter objects and change data_ptr / _version).  Walking the module tree costs ~0.25 ms for the 240
-    tensors of a C-ViViT -- a third of a bf16 encode step -- so the tensor list is cached on the module and re-walked
-    every 64 calls (which also picks up a Parameter OBJECT that was replaced by hand)."""
+    """Changes whenever a parameter / buffer is moved, modified in place or REPLACED (`.to()`, `load_state_dict`,
+    optimizer steps, `mod.weight = nn.Parameter(...)`): the tuple of (data_ptr, _version) of every tensor, read live
+    from the `_parameters` / `_buffers` dicts of the submodules on every call.  Only the LIST OF SUBMODULES is cached
+    (walking the module tree is the expensive part, ~0.25 ms for a C-ViViT) and re-walked every 64 calls, which picks up
+    a replaced submodule.  Not visible from here: writes through `.data` (`p.data.copy_()`, `p.data.lerp_()` do not
+    bump `_version`) into tensors with derived copies (bf16 weights, packed GEGLU / PEG weights, cached position-bias
+    tables) -- call `invalidate_weights(module)` after such an update."""
     cache = module.__dict__.get("_phk_sig_cache")
     if cache is None or cache[1] <= 0:
-        cache = [list(module.parameters()) + list(module.buffers()), _SIG_REFRESH]
+        cache = [[(m._parameters, m._buffers) for m in module.modules()], _SIG_REFRESH]
         module.__dict__["_phk_sig_cache"] = cache
     cache[1] -= 1
-    return tuple((t.data_ptr(), t._version) for t in cache[0])
+    sig = []
+    for params, bufs in cache[0]:
+        for t in params.values():
+            if t is not None:
+                sig.append((t.data_ptr(), t._version))
+        for t in bufs.values():
+            if t is not None:
+                sig.append((t.data_ptr(), t._version))
+    return tuple(sig)
+
+
+def invalidate_weights(module):
+    """Forces the weight tables (and every derived copy) of `module` and its submodules to be rebuilt at the next call:
+    for updates the signature cannot see (`p.data.copy_()` style writes, e.g. hand-written EMA)."""
+    for m in module.modules():
+        m.__dict__.pop("_phk_sig_cache", None)
+        for name in ("_sig", "_dec_sig"):
+            if name in m.__dict__:
+                m.__dict__[name] = None
 
 
 class Workspace:

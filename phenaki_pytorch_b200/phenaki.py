@@ -31,6 +31,24 @@ def _noise_seed(dev):
     return torch.cuda.default_generators[dev.index if dev.index is not None else torch.cuda.current_device()].initial_seed()
 
 
+def _rng_take(dev, seed, count):
+    """Reserves `count` consecutive Philox counters of the in-kernel noise on `dev` and returns the first one.
+    The running counter IS the offset of torch's CUDA generator of that device: process-wide, per device, restarted by
+    ``torch.manual_seed`` -- so calls of any shape (scene chains with primed, shorter scenes; several Phenaki objects;
+    interleaved training steps) draw from disjoint counter ranges and seeded runs repeat."""
+    gen = torch.cuda.default_generators[dev.index if dev.index is not None else torch.cuda.current_device()]
+    first = int(gen.get_offset())
+    gen.set_offset(first + (int(count) + 3) // 4 * 4)  # torch requires multiples of 4
+    return first & (2 ** 64 - 1)
+
+
+def _noise_stride(rows, vocab):
+    """Philox counters one V-wide gumbel draw over `rows` tokens consumes (4 uniforms per counter), rounded up to a
+    multiple of 4 (the granularity of torch's generator offset); phk_maskgit_demask_iteration advances the device-side
+    counter by the same amount."""
+    return (rows * ((vocab + 3) // 4) + 1 + 3) // 4 * 4
+
+
 def _prod(xs):
     r = 1
     for x in xs:
@@ -50,7 +68,21 @@ class _TokenTransformer(nn.Module):
         self._bias_cache = {}
 
     def __deepcopy__(self, memo):
-        raise TypeError("copy the state_dict instead; ctypes weight tables are not copyable")
+        """copy.deepcopy (EMA wrappers, `copy_for_eval`-style users of the reference): parameters and buffers are
+        copied by torch; the ctypes weight tables, workspace and cached position-bias tables are per-object runtime
+        state and are rebuilt lazily by the copy."""
+        import copy
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        runtime = ("_tables", "_sig", "_ws", "_bias_cache", "_phk_sig_cache")
+        for k, v in self.__dict__.items():
+            if k not in runtime:
+                new.__dict__[k] = copy.deepcopy(v, memo)
+        precision = self.precision
+        new._init_runtime()
+        new.precision = precision
+        return new
 
     def _table(self):
         sig = (weights_signature(self), self.precision)
@@ -248,7 +280,16 @@ class _TokenTransformer(nn.Module):
                     "phk_maskgit_train_step")
         return loss, gk, logits
 
+    def _check_ids(self, x):
+        """nn.Embedding raises on an id outside the table (phenaki_pytorch.py:194); the kernels only clamp.  One device
+        sync, paid at the public forward entries only (the sampling loop produces its ids itself)."""
+        rows = self.token_emb.weight.shape[0]
+        lo, hi = int(x.min()), int(x.max())
+        if lo < 0 or hi >= rows:
+            raise IndexError(f"index out of range in self: token ids span [{lo}, {hi}], the embedding has {rows} rows")
+
     def _prepare(self, x, text_mask, video_patch_shape, context, cond_drop_prob):
+        self._check_ids(x)
         if x.ndim == 4:
             video_patch_shape = tuple(x.shape[1:])
             x = x.reshape(x.shape[0], -1)
@@ -499,16 +540,22 @@ class Phenaki(nn.Module):
         self.max_text_len = max_text_len
         assert cond_drop_prob > 0.0
         self.cond_drop_prob = cond_drop_prob
-        self._rng_calls = 0
         # training under torch.distributed: average the gradient bucket over the ranks in backward() (what the
         # reference gets from Accelerate's DDP wrapper, phenaki_trainer.py); no-op without a process group
         self.sync_gradients = True
-        # bf16 mode, no critic: one C call per demasking iteration with all state in device memory
-        # (phk_maskgit_demask_iteration), replayed as ONE CUDA-graph launch per iteration when PHK_STEP_GRAPH=1.
-        # Opt-in until its first GPU run; same noise counters as the default path.
-        self.iteration_call = os.environ.get("PHK_STEP_GRAPH", "0") == "1"
+        # bf16 mode, no critic: ONE C call per demasking iteration with all state in device memory
+        # (phk_maskgit_demask_iteration), replayed as ONE CUDA-graph launch per iteration from the third sample() with the
+        # same shapes on (BASELINE north_star: one launch per decode iteration).  Validated on the B200 against the
+        # per-step loop (identical ids: same noise counters).  PHK_STEP_GRAPH=0 restores the per-step loop.
+        self.iteration_call = os.environ.get("PHK_STEP_GRAPH", "1") != "0"
         self._iter_bufs = {}
         self.fused_head = True  # bf16 mode: logits head + CFG + gumbel argmax fused into one GEMM (no (b,n,V) logits)
+
+    def _fused_step_supported(self):
+        """Shape limits of the fused demasking step (phk_maskgit_sample_step / phk_head_sample keep the whole
+        embedding row of a token tile in shared memory): other widths take phk_maskgit_forward + phk_sample_tokens."""
+        dim = self.maskgit.dim
+        return dim <= 512 and dim % 128 == 0
 
     # ---- the demasking loop (phenaki_pytorch.py:473-550) -------------------------------------------------
     @torch.no_grad()
@@ -549,7 +596,8 @@ class Phenaki(nn.Module):
             vocab = mg.to_logits.weight.shape[0]
             have_scores = False
             if (self.iteration_call and self.fused_head and mg.precision == L.PREC_BF16 and noise_fn is None
-                    and cond_scale != 1 and plen == 0 and trace is None and self.critic is None):
+                    and cond_scale != 1 and plen == 0 and trace is None and self.critic is None
+                    and self._fused_step_supported()):
                 return self._sample_by_iterations(b, n, patch_shape, ctx_kv, ctx_len, text_mask, cond_scale,
                                                   starting_temperature, ks, seed, vocab, dev)
             for step in range(steps):
@@ -562,10 +610,9 @@ class Phenaki(nn.Module):
                     inp[:, plen:].copy_(ids)
                 use_cfg = cond_scale != 1
                 temperature = starting_temperature * (til_x0 / steps)
-                offset = self._rng_calls * ((b * n * ((vocab + 3) // 4)) + 1)
-                self._rng_calls += 1
+                offset = _rng_take(dev, seed, _noise_stride(b * n, vocab))
                 fused = (self.fused_head and mg.precision == L.PREC_BF16 and noise_fn is None and use_cfg and plen == 0
-                         and trace is None)
+                         and trace is None and self._fused_step_supported())
                 if fused:
                     # one launch sequence per iteration, logits never leave the SM (statistical-noise mode)
                     # exactly ks[step - 1] tokens per sequence were re-masked above (all n at the first step): the head
@@ -643,10 +690,10 @@ class Phenaki(nn.Module):
         if ctx_kv is not None:
             bufs["ctx_kv"].copy_(ctx_kv)
             bufs["text_mask"].copy_(text_mask.to(torch.uint8))
-        stride = b * n * ((vocab + 3) // 4) + 1
+        stride = _noise_stride(b * n, vocab)
         as_i64 = lambda v: v - (1 << 64) if v >= (1 << 63) else v  # uint64 bit pattern in an int64 tensor
-        bufs["rng"].copy_(torch.tensor([as_i64(seed & (2 ** 64 - 1)), as_i64((self._rng_calls * stride) & (2 ** 64 - 1))],
-                                       dtype=torch.int64))
+        first = _rng_take(dev, seed, stride * steps)  # the library advances the device-side counter by `stride` per iteration
+        bufs["rng"].copy_(torch.tensor([as_i64(seed & (2 ** 64 - 1)), as_i64(first)], dtype=torch.int64))
         with torch.cuda.device(dev):
             table = mg._table()
             ws = mg._ws.get(lib.phk_maskgit_sample_workspace_bytes(C.byref(table), b, n, ctx_len), dev)
@@ -659,7 +706,6 @@ class Phenaki(nn.Module):
                     b, n, pt, ph, pw, L.ptr(bufs["ctx_kv"]), ctx_len, L.ptr(bufs["text_mask"]), L.ptr(bias),
                     float(cond_scale), float(temperature), L.ptr(bufs["rng"]), 0 if step == 0 else ks[step - 1],
                     L.ptr(ws), ws.numel(), L.stream_ptr()), "phk_maskgit_demask_iteration")
-        self._rng_calls += steps
         return bufs["ids"].clone()
 
     @torch.no_grad()
@@ -751,6 +797,7 @@ class Phenaki(nn.Module):
             video_mask = self.cvivit.calculate_video_token_mask(videos, video_frame_mask=video_frame_mask)
         patch_shape = tuple(int(v) for v in video_codebook_ids.shape[1:])
         ids = video_codebook_ids.reshape(video_codebook_ids.shape[0], -1).to(dev)
+        mg._check_ids(ids)
         batch, seq = ids.shape
         draw = draw_fn if draw_fn is not None else (lambda shape, tag: None)
         rand_step = draw((batch,), "rand_step")
@@ -783,8 +830,7 @@ class Phenaki(nn.Module):
         ones = torch.ones((batch, seq), dtype=torch.uint8, device=dev)
         scratch_ids = torch.empty_like(pred)
         seed = _noise_seed(dev)
-        offset = self._rng_calls * ((batch * seq * ((vocab + 3) // 4)) + 1)
-        self._rng_calls += 1
+        offset = _rng_take(dev, seed, _noise_stride(batch * seq, vocab))
         gu_dev = None if gu is None else L.require_cuda(gu.to(dev), "gumbel noise", torch.float32)  # kept alive past the launch
         L.check(L.lib().phk_sample_tokens(L.ptr(logits), None, vocab, L.ptr(gu_dev), seed & (2 ** 64 - 1), offset, 1.0,
                                           float(self.critic_train_sample_temperature), L.ptr(ones), L.ptr(scratch_ids),

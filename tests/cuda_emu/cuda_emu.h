@@ -195,6 +195,18 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 
 // same definitions as csrc/phk_common.cuh
+
+// One-time per-DEVICE kernel configuration (cudaFuncSetAttribute is a per-device setting; a process may drive several
+// devices): `mask` is a call-site static, bit d = "done on device d".
+static inline bool device_configured(const unsigned long long* mask) {
+  int d = 0;
+  if (cudaGetDevice(&d) != 0 || d < 0 || d >= 64) return false;
+  return (__atomic_load_n(mask, __ATOMIC_RELAXED) >> d) & 1ull;
+}
+static inline void mark_configured(unsigned long long* mask) {
+  int d = 0;
+  if (cudaGetDevice(&d) == 0 && d >= 0 && d < 64) __atomic_fetch_or(mask, 1ull << d, __ATOMIC_RELAXED);
+}
 __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;

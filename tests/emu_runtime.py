@@ -117,3 +117,18 @@ def route_product_to_emulator(lib, patch=_Setter):
     patch.setattr(torch, "empty", poisoned_empty)  # outputs the kernels are expected to overwrite completely
     from phenaki_pytorch_b200 import phenaki as PH
     patch.setattr(PH, "_noise_seed", lambda dev: torch.initial_seed())  # no CUDA generator without a GPU
+    # ... whose offset is the running noise counter on the GPU (PH._rng_take): restarted by torch.manual_seed
+    counter = [0]
+    real_manual_seed = torch.manual_seed
+
+    def manual_seed(seed):
+        counter[0] = 0
+        return real_manual_seed(seed)
+
+    def rng_take(dev, seed, count):
+        first = counter[0]
+        counter[0] = first + (int(count) + 3) // 4 * 4
+        return first
+
+    patch.setattr(torch, "manual_seed", manual_seed)
+    patch.setattr(PH, "_rng_take", rng_take)

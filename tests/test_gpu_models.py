@@ -190,7 +190,6 @@ def test_sampling_is_seed_deterministic_and_fills_every_token():
     outs = []
     for seed in (5, 5, 6):
         torch.manual_seed(seed)
-        ph._rng_calls = 0
         outs.append(ph.sample(num_frames=7, text_embeds=ctx, return_token_ids=True).cpu())
     assert torch.equal(outs[0], outs[1]) and not torch.equal(outs[0], outs[2])
     assert (outs[0] >= 0).all() and (outs[0] < C.SAMPLE_MASKGIT["num_tokens"]).all()  # no mask id left

@@ -5,7 +5,7 @@ lines = [l for l in open(fn) if not l.startswith('==')]
 rows = [r for r in csv.DictReader(lines) if r.get('Metric Name') == 'gpu__time_duration.sum']
 names = [re.sub(r'\(.*', '', r['Kernel Name']).replace('void phk::', '').replace('phk::', '') for r in rows]
 key = {'maskgit': 'token_embed_kernel', 'decode': 'lfq_codes_kernel'}.get(kind, 'patchify_ln')
-idxs = [i for i, nm in enumerate(names) if nm.startswith(key)]
+idxs = [i for i, nm in enumerate(names) if key in nm]
 start = idxs[-2] if kind == 'encode' else idxs[-1]
 agg, tot = {}, 0.0
 for r, nm in list(zip(rows, names))[start:]:
