@@ -763,12 +763,8 @@ class Phenaki(nn.Module):
         The returned scalar is connected to the parameters through ``_TrainStepFn``: ``loss.backward()`` fills
         ``p.grad`` with the gradients the hand-written backward kernels computed (phk_maskgit_train_step).
         ``draw_fn(shape, tag)`` (tests) injects the draws 'rand_step' (b,), 'perm' (b, n) and 'gumbel' (b, n, V).
-        ``maskgit.precision`` selects fp32 (parity) or bf16 tensor-core products.  The kernels' math is pinned
-        on the CPU (tests/test_train_mirror_cpu.py) but the CUDA path has not been validated on a GPU yet, so the entry
-        is opt-in: set PHK_EXPERIMENTAL=1."""
-        if os.environ.get("PHK_EXPERIMENTAL", "0") != "1":
-            raise NotImplementedError("Phenaki.forward (training step, SURVEY 8f-2) is built but not yet validated on "
-                                      "a GPU: set PHK_EXPERIMENTAL=1 to use it")
+        ``maskgit.precision`` selects fp32 (parity) or bf16 tensor-core products.  Validated on the B200 against the
+        reference's autograd loss and every parameter gradient (tests/test_gpu_train.py, both precision modes)."""
         assert not (only_train_generator and only_train_critic)
         assert (videos is not None) ^ (video_codebook_ids is not None), "either raw video or codebook ids"
         assert ((text_embeds is not None) ^ (texts is not None)) ^ self.unconditional, \

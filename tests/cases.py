@@ -164,3 +164,28 @@ def train_inputs(case):
     ctx = synthetic_text_embeds(case["batch"], case["ctx_len"], case["maskgit"]["dim_context"], case["ctx_valid"],
                                 case["input_seed"] + 1000)
     return ids, ctx
+
+
+# ---- round 2: the paths VERDICT r01 found untested -------------------------------------------------------------------
+# Phenaki(self_token_critic=True).sample (phenaki_pytorch.py:307-336, 512-545): SelfCritic scores drive the re-masking.
+SELF_CRITIC_SAMPLE_CASE = dict(seed=34, steps=5, cond_scale=3.0, num_frames=7, batch=2, ctx_len=6, ctx_valid=(4, 6),
+                               noise_seed=35)
+
+# video_mask (attention.py:164-167 key mask of the self-attention; phenaki_pytorch.py:181-190, 265-302): the first
+# `valid[b]` tokens of sequence b are real, the rest padding.  MaskGit 'small' / TokenCritic 'small' (48 tokens).
+VIDEO_MASK_VALID = dict(maskgit_small=(48, 29), critic_small=(31, 48))
+
+
+def video_mask_of(valid, n):
+    return torch.arange(n)[None, :] < torch.tensor(valid)[:, None]
+
+
+# Phenaki.forward(videos, video_frame_mask=...) (phenaki_pytorch.py:587-612, cvivit.py:365-373): raw videos are
+# tokenised live, frames -> token mask, masked-subset sampling among the valid tokens, key-masked attention, CE + BCE.
+FRAME_MASK_TRAIN_CASE = dict(seed=70, steps=6, maskgit=SAMPLE_MASKGIT, critic=SAMPLE_CRITIC, batch=2,
+                             video=(2, 3, 7, 16, 24), frames_valid=(7, 4), patch_shape=(3, 2, 3), ctx_len=6,
+                             ctx_valid=(6, 2), input_seed=71, noise_seed=72)
+
+
+def frame_mask_of(valid, frames):
+    return torch.arange(frames)[None, :] < torch.tensor(valid)[:, None]

@@ -344,9 +344,148 @@ def make_train(ref):
         torch.save(gold, os.path.join(OUT, f"train_{name}.pt"))
 
 
+def make_selfcritic(ref):
+    """Phenaki(self_token_critic=True).sample: reference vs oracle replay (SelfCritic = Linear(dim,1) on MaskGit embeds)."""
+    case = C.SELF_CRITIC_SAMPLE_CASE
+    print("[sample/self_critic]")
+    torch.manual_seed(case["seed"])
+    cvivit = ref.CViViT(**C.SAMPLE_CVIVIT)
+    maskgit = ref.MaskGit(**C.SAMPLE_MASKGIT)
+    phenaki = ref.Phenaki(cvivit=cvivit, maskgit=maskgit, self_token_critic=True, steps=case["steps"],
+                          text_embed_dim=C.SAMPLE_MASKGIT["dim_context"]).eval()
+    ctx = C.synthetic_text_embeds(case["batch"], case["ctx_len"], C.SAMPLE_MASKGIT["dim_context"], case["ctx_valid"],
+                                  case["seed"] + 1000)
+    phenaki.encode_texts = lambda texts, output_device=None: ctx
+    captured = {}
+    orig_decode = phenaki.cvivit.decode_from_codebook_indices
+    phenaki.cvivit.decode_from_codebook_indices = lambda ids: (captured.__setitem__("ids", ids.clone()), orig_decode(ids))[1]
+    torch.manual_seed(case["noise_seed"])
+    video = phenaki.sample(texts=[f"prompt {i}" for i in range(case["batch"])], num_frames=case["num_frames"],
+                           cond_scale=case["cond_scale"])
+    mg_sd = {k: v.detach().clone() for k, v in maskgit.state_dict().items()}
+    cv_sd = {k: v.detach().clone() for k, v in phenaki.cvivit.state_dict().items()}
+    lin = phenaki.critic.to_pred[0]
+    w, b = lin.weight.detach().clone(), lin.bias.detach().clone()
+    image_size, patch_size, pt = C.SAMPLE_CVIVIT["image_size"], C.SAMPLE_CVIVIT["patch_size"], C.SAMPLE_CVIVIT["temporal_patch_size"]
+    hh, ww = image_size[0] // patch_size[0], image_size[1] // patch_size[1]
+    nf = case["num_frames"]
+    num_tokens, patch_shape = hh * ww * ((nf - 1) // pt + 1), (1 + (nf - 1) // pt, hh, ww)
+    trace = []
+    with torch.no_grad():
+        ids = O.sample_token_ids(mg_sd, num_tokens=num_tokens, patch_shape=patch_shape, batch=case["batch"],
+                                 steps=case["steps"], heads=C.SAMPLE_MASKGIT["heads"], text_embeds=ctx,
+                                 cond_scale=case["cond_scale"], self_critic=(w, b),
+                                 noise_fn=C.NoiseTape(case["noise_seed"]), trace=trace)
+        o_video = O.cvivit_decode_from_ids(ids, cv_sd, image_size, patch_size)
+    same(ids, captured["ids"], "final token ids of Phenaki.sample (self critic)")
+    same(o_video, video, "sampled video (self critic)")
+    torch.save(dict(cvivit_digest=C.state_digest(cv_sd), maskgit_digest=C.state_digest(mg_sd), to_pred_weight=w,
+                    to_pred_bias=b, final_ids=ids, video=video, patch_shape=patch_shape, num_tokens=num_tokens,
+                    trace=[{k: v for k, v in t.items()} for t in trace]), os.path.join(OUT, "sample_self_critic.pt"))
+
+
+def make_vmask(ref):
+    """MaskGit / TokenCritic forward with a video_mask (key mask of the self-attention, attention.py:164-167)."""
+    case = C.MASKGIT_CASES["small"]
+    print("[maskgit/small + video_mask]")
+    torch.manual_seed(case["seed"])
+    model = ref.MaskGit(**case["ctor"]).eval()
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    ids, ctx = C.token_inputs(case, case["ctor"]["num_tokens"])
+    tmask = torch.any(ctx != 0, dim=-1)
+    vmask = C.video_mask_of(C.VIDEO_MASK_VALID["maskgit_small"], ids.shape[1])
+    heads = case["ctor"].get("heads", 8)
+    with torch.no_grad():
+        cond = model(ids, cond_drop_prob=0.0, text_mask=tmask, video_mask=vmask, video_patch_shape=case["patch_shape"], context=ctx)
+        cfg = model.forward_with_cond_scale(ids, cond_scale=3.0, text_mask=tmask, video_mask=vmask,
+                                            video_patch_shape=case["patch_shape"], context=ctx)
+        kw = dict(video_patch_shape=case["patch_shape"], heads=heads, context=ctx, text_mask=tmask, video_mask=vmask)
+        o_cond = O.maskgit_forward(ids, sd, **kw)
+        o_cfg = O.with_cond_scale(lambda cond_drop: O.maskgit_forward(ids, sd, cond_drop=cond_drop, **kw), 3.0)
+    same(o_cond, cond, "logits (cond, video_mask)")
+    same(o_cfg, cfg, "CFG logits (video_mask)")
+    torch.save(dict(state_digest=C.state_digest(sd), cond=cond, cfg=cfg), os.path.join(OUT, "maskgit_small_vmask.pt"))
+
+    case = C.CRITIC_CASES["small"]
+    print("[critic/small + video_mask]")
+    torch.manual_seed(case["seed"])
+    model = ref.TokenCritic(**case["ctor"]).eval()
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    ids, ctx = C.token_inputs(case, case["ctor"]["num_tokens"])
+    tmask = torch.any(ctx != 0, dim=-1)
+    vmask = C.video_mask_of(C.VIDEO_MASK_VALID["critic_small"], ids.shape[1])
+    heads = case["ctor"].get("heads", 8)
+    with torch.no_grad():
+        cond = model(ids, cond_drop_prob=0.0, text_mask=tmask, video_mask=vmask, video_patch_shape=case["patch_shape"], context=ctx)
+        cfg = model.forward_with_cond_scale(ids, cond_scale=5.0, text_mask=tmask, video_mask=vmask,
+                                            video_patch_shape=case["patch_shape"], context=ctx)
+        kw = dict(video_patch_shape=case["patch_shape"], heads=heads, context=ctx, text_mask=tmask, video_mask=vmask)
+        o_cond = O.critic_forward(ids, sd, **kw)
+        o_cfg = O.with_cond_scale(lambda cond_drop: O.critic_forward(ids, sd, cond_drop=cond_drop, **kw), 5.0)
+    same(o_cond, cond, "critic scores (cond, video_mask)")
+    same(o_cfg, cfg, "critic scores (CFG 5, video_mask)")
+    torch.save(dict(state_digest=C.state_digest(sd), cond=cond, cfg=cfg), os.path.join(OUT, "critic_small_vmask.pt"))
+
+
+def make_framemask(ref):
+    """Phenaki.forward(videos, video_frame_mask=...): live tokenisation, frame mask -> token mask
+    (cvivit.py:365-373), masked-subset sampling among the valid tokens, key-masked attention; loss + every gradient."""
+    case = C.FRAME_MASK_TRAIN_CASE
+    print("[train/frame_mask]")
+    torch.manual_seed(case["seed"])
+    cvivit = ref.CViViT(**C.SAMPLE_CVIVIT)
+    maskgit = ref.MaskGit(**case["maskgit"])
+    critic = ref.TokenCritic(**case["critic"])
+    phenaki = ref.Phenaki(cvivit=cvivit, maskgit=maskgit, critic=critic, steps=case["steps"],
+                          text_embed_dim=case["maskgit"]["dim_context"]).train()
+    videos = C.seeded_randn(case["video"], case["input_seed"])
+    ctx = C.synthetic_text_embeds(case["batch"], case["ctx_len"], case["maskgit"]["dim_context"], case["ctx_valid"],
+                                  case["input_seed"] + 1000)
+    fmask = C.frame_mask_of(case["frames_valid"], case["video"][2])
+    torch.manual_seed(case["noise_seed"])
+    loss = phenaki(videos, text_embeds=ctx, video_frame_mask=fmask)
+    loss.backward()
+    heads = case["maskgit"].get("heads", 8)
+    mg_sd = {k: v.detach().clone() for k, v in maskgit.state_dict().items()}
+    cr_sd = {k: v.detach().clone() for k, v in critic.state_dict().items()}
+    cv_sd = {k: v.detach().clone() for k, v in phenaki.cvivit.state_dict().items()}
+    mg_grads = {k: p.grad.detach().clone() for k, p in maskgit.named_parameters() if p.grad is not None}
+    cr_grads = {k: p.grad.detach().clone() for k, p in critic.named_parameters() if p.grad is not None}
+
+    def leaf(sd):
+        return {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+
+    o_mg, o_cr = leaf(mg_sd), leaf(cr_sd)
+    with torch.no_grad():
+        ids = O.cvivit_codebook_ids(videos, cv_sd, C.SAMPLE_CVIVIT["image_size"], C.SAMPLE_CVIVIT["patch_size"])
+        token_valid = phenaki.cvivit.calculate_video_token_mask(videos, video_frame_mask=fmask)
+    b, n = ids.shape[0], ids[0].numel()
+    flat = ids.reshape(b, n)
+    tmask = torch.any(ctx != 0, dim=-1)
+    torch.manual_seed(case["noise_seed"])
+    rand_step, u = O.train_draws(b, n, case["steps"])
+    token_mask = O.train_token_mask(rand_step, u, case["steps"], video_mask=token_valid)
+    kw = dict(video_patch_shape=case["patch_shape"], heads=heads, context=ctx, text_mask=tmask, video_mask=token_valid)
+    o_loss, logits = O.maskgit_train_loss(flat, o_mg, token_mask, return_logits=True, **kw)
+    gu = torch.zeros_like(logits).uniform_(0, 1)
+    pred = O.gumbel_sample(logits.detach(), phenaki.critic_train_sample_temperature, gu)
+    bce = O.critic_train_loss(flat, pred, token_mask, o_cr, **kw)
+    total = o_loss + bce * phenaki.critic_loss_weight
+    total.backward()
+    same(total.detach(), loss.detach(), "training loss (frame mask)")
+    for k, g in mg_grads.items():
+        same(o_mg[k].grad, g, f"d loss / d maskgit.{k}")
+    for k, g in cr_grads.items():
+        same(o_cr[k].grad, g, f"d loss / d critic.{k}")
+    torch.save(dict(maskgit_digest=C.state_digest(mg_sd), critic_digest=C.state_digest(cr_sd), ids=ids,
+                    token_valid=token_valid, token_mask=token_mask, rand_step=rand_step, pred_ids=pred,
+                    ce=o_loss.detach().clone(), bce=bce.detach().clone(), loss=loss.detach().clone(),
+                    maskgit_grads=mg_grads, critic_grads=cr_grads), os.path.join(OUT, "train_frame_mask.pt"))
+
+
 if __name__ == "__main__":
     ref = load_reference()
-    which = sys.argv[1:] or ["units", "cvivit", "maskgit", "critic", "sample", "makevideo", "train"]
+    which = sys.argv[1:] or ["units", "cvivit", "maskgit", "critic", "sample", "makevideo", "train", "selfcritic", "vmask", "framemask"]
     for w in which:
         globals()["make_" + w](ref)
     print("golden fixtures written to", OUT)

@@ -29,7 +29,8 @@ def bit_agreement(a, b, bits=16):
     return 1.0 - sum(int(((x >> k) & 1).sum()) for k in range(bits)) / (x.numel() * bits)
 
 
-def test_cfg2_fp32_ids_equal_the_oracle_on_one_video(cfg2):
+def test_cfg2_fp32_ids_equal_the_cpu_oracle_on_one_video(cfg2):
+    """(all 8 videos against the oracle on CUDA: tests/test_gpu_parity_at_size.py; this one is the CPU-run oracle)"""
     model, sd, video = cfg2
     model.precision = L.PREC_F32
     with torch.no_grad():
@@ -67,7 +68,9 @@ def test_cfg2_bf16_mode_agrees_with_fp32_mode(cfg2):
     a = model(vd, return_only_codebook_ids=True)
     model.precision = L.PREC_BF16
     b = model(vd, return_only_codebook_ids=True)
-    assert bit_agreement(a, b) >= 0.97, bit_agreement(a, b)     # LFQ sign bits; flips sit at small margins (bf16 bar)
+    agree = bit_agreement(a, b)
+    print(f"cfg2: bf16 mode vs fp32 mode LFQ bit agreement {agree:.5f}, id agreement {float((a == b).float().mean()):.4f}")
+    assert agree >= 0.998, agree     # measured 0.9989 (round 2); the reference's own autocast-bf16 path scores 0.9982
 
 
 def test_cfg2_decode_shapes_determinism_and_batch_invariance(cfg2):

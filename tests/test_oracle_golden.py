@@ -266,3 +266,64 @@ def test_cvivit_constructs_with_the_reference_defaults_and_loads_gan_checkpoints
     assert not missing.missing_keys and not missing.unexpected_keys
     with pytest.raises(NotImplementedError):
         a(torch.zeros(1, 1, 32, 32), return_recons=True)  # the loss paths stay unavailable
+
+
+# ---- round 2 goldens: SelfCritic sampling, video_mask, video_frame_mask training (oracle vs committed reference outputs)
+def test_oracle_self_critic_sampling_loop_matches_reference_golden(golden):
+    case, g = C.SELF_CRITIC_SAMPLE_CASE, golden("sample_self_critic")
+    torch.manual_seed(case["seed"])
+    P.CViViT(**C.SAMPLE_CVIVIT)  # consumes the generator like the reference construction order
+    mg = P.MaskGit(**C.SAMPLE_MASKGIT)
+    assert C.state_digest(mg.state_dict()) == g["maskgit_digest"]
+    ctx = C.synthetic_text_embeds(case["batch"], case["ctx_len"], C.SAMPLE_MASKGIT["dim_context"], case["ctx_valid"],
+                                  case["seed"] + 1000)
+    with torch.no_grad():
+        ids = O.sample_token_ids(mg.state_dict(), num_tokens=g["num_tokens"], patch_shape=g["patch_shape"],
+                                 batch=case["batch"], steps=case["steps"], heads=C.SAMPLE_MASKGIT["heads"],
+                                 text_embeds=ctx, cond_scale=case["cond_scale"],
+                                 self_critic=(g["to_pred_weight"], g["to_pred_bias"]),
+                                 noise_fn=C.NoiseTape(case["noise_seed"]))
+    assert torch.equal(ids, g["final_ids"])
+
+
+def test_oracle_video_mask_outputs_match_reference_golden(golden):
+    case, g = C.MASKGIT_CASES["small"], golden("maskgit_small_vmask")
+    torch.manual_seed(case["seed"])
+    sd = P.MaskGit(**case["ctor"]).state_dict()
+    assert C.state_digest(sd) == g["state_digest"]
+    ids, ctx = C.token_inputs(case, case["ctor"]["num_tokens"])
+    vmask = C.video_mask_of(C.VIDEO_MASK_VALID["maskgit_small"], ids.shape[1])
+    with torch.no_grad():
+        out = O.maskgit_forward(ids, sd, video_patch_shape=case["patch_shape"], heads=case["ctor"]["heads"], context=ctx,
+                                text_mask=torch.any(ctx != 0, dim=-1), video_mask=vmask)
+    torch.testing.assert_close(out, g["cond"], rtol=1e-5, atol=1e-5)
+    case, g = C.CRITIC_CASES["small"], golden("critic_small_vmask")
+    torch.manual_seed(case["seed"])
+    sd = P.TokenCritic(**case["ctor"]).state_dict()
+    assert C.state_digest(sd) == g["state_digest"]
+    ids, ctx = C.token_inputs(case, case["ctor"]["num_tokens"])
+    vmask = C.video_mask_of(C.VIDEO_MASK_VALID["critic_small"], ids.shape[1])
+    with torch.no_grad():
+        out = O.critic_forward(ids, sd, video_patch_shape=case["patch_shape"], heads=case["ctor"]["heads"], context=ctx,
+                               text_mask=torch.any(ctx != 0, dim=-1), video_mask=vmask)
+    torch.testing.assert_close(out, g["cond"], rtol=1e-5, atol=1e-5)
+
+
+def test_oracle_frame_mask_training_loss_matches_reference_golden(golden):
+    case, g = C.FRAME_MASK_TRAIN_CASE, golden("train_frame_mask")
+    torch.manual_seed(case["seed"])
+    P.CViViT(**C.SAMPLE_CVIVIT)
+    mg = P.MaskGit(**case["maskgit"])
+    assert C.state_digest(mg.state_dict()) == g["maskgit_digest"]
+    ctx = C.synthetic_text_embeds(case["batch"], case["ctx_len"], case["maskgit"]["dim_context"], case["ctx_valid"],
+                                  case["input_seed"] + 1000)
+    b, n = g["ids"].shape[0], g["ids"][0].numel()
+    torch.manual_seed(case["noise_seed"])
+    rand_step, u = O.train_draws(b, n, case["steps"])
+    token_mask = O.train_token_mask(rand_step, u, case["steps"], video_mask=g["token_valid"])
+    assert torch.equal(token_mask, g["token_mask"]) and not token_mask[~g["token_valid"]].any()
+    with torch.no_grad():
+        ce = O.maskgit_train_loss(g["ids"].reshape(b, n), mg.state_dict(), token_mask, video_patch_shape=case["patch_shape"],
+                                  heads=case["maskgit"]["heads"], context=ctx, text_mask=torch.any(ctx != 0, dim=-1),
+                                  video_mask=g["token_valid"])
+    torch.testing.assert_close(ce, g["ce"], rtol=1e-5, atol=1e-6)

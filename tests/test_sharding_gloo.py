@@ -95,7 +95,7 @@ def test_bench_reference_arm_under_torchrun_prints_one_line():
 def _train_worker(rank, world_size, port, out):
     """Data-parallel training step on two gloo ranks: each rank runs the (emulated, CPU-executed) CUDA training step on
     its contiguous batch shard; backward() all-reduces the flat gradient bucket."""
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), PHK_EXPERIMENTAL="1")
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world_size)
     try:
         torch.set_num_threads(2)

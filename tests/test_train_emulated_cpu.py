@@ -206,6 +206,5 @@ def test_phenaki_forward_end_to_end_on_the_emulator(on_cpu, monkeypatch, name):
     """The exact check the first GPU run will perform (tests/gpu_train_check.py): Phenaki.forward with the reference's
     draws injected -> MaskGit step -> gumbel sampling of the critic's input (phk_sample_tokens) -> TokenCritic /
     SelfCritic step -> loss.backward() through the autograd bridge -> loss and every p.grad against the reference."""
-    monkeypatch.setenv("PHK_EXPERIMENTAL", "1")
     from tests import gpu_train_check
     gpu_train_check.check_case(name, verbose=False, device="cpu")

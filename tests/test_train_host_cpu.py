@@ -64,7 +64,6 @@ def _fake_train_step(module, heads):
 
 @pytest.mark.parametrize("name", ["generator", "with_critic"])
 def test_phenaki_forward_autograd_bridge_with_the_kernels_restated_on_cpu(golden, name, monkeypatch):
-    monkeypatch.setenv("PHK_EXPERIMENTAL", "1")
     case, g = C.TRAIN_CASES[name], golden(f"train_{name}")
     torch.manual_seed(case["seed"])
     cvivit = P.CViViT(**C.SAMPLE_CVIVIT)
@@ -91,9 +90,10 @@ def test_phenaki_forward_autograd_bridge_with_the_kernels_restated_on_cpu(golden
             assert p.grad is None
 
 
-def test_training_entry_is_opt_in_until_validated_on_a_gpu(monkeypatch):
-    monkeypatch.delenv("PHK_EXPERIMENTAL", raising=False)
+def test_training_entry_refuses_cpu_tensors():
+    """No CPU fallback: the training entry raises on CPU inputs like every other entry point."""
+    from phenaki_pytorch_b200 import _lib as L
     torch.manual_seed(0)
     phenaki = P.Phenaki(cvivit=P.CViViT(**C.SAMPLE_CVIVIT), maskgit=P.MaskGit(**C.SAMPLE_MASKGIT), text_embed_dim=48)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises((L.PhkError, RuntimeError, AssertionError)):
         phenaki(video_codebook_ids=torch.zeros((1, 3, 2, 3), dtype=torch.int64), text_embeds=torch.zeros((1, 4, 48)))
