@@ -321,7 +321,9 @@ def test_oracle_frame_mask_training_loss_matches_reference_golden(golden):
     torch.manual_seed(case["noise_seed"])
     rand_step, u = O.train_draws(b, n, case["steps"])
     token_mask = O.train_token_mask(rand_step, u, case["steps"], video_mask=g["token_valid"])
-    assert torch.equal(token_mask, g["token_mask"]) and not token_mask[~g["token_valid"]].any()
+    # (the reference's subset rule ranks ALL positions and only shifts the ranks by the pad count, phenaki_pytorch.py:43-55:
+    # padded positions can be chosen -- replicated, not "fixed")
+    assert torch.equal(token_mask, g["token_mask"])
     with torch.no_grad():
         ce = O.maskgit_train_loss(g["ids"].reshape(b, n), mg.state_dict(), token_mask, video_patch_shape=case["patch_shape"],
                                   heads=case["maskgit"]["heads"], context=ctx, text_mask=torch.any(ctx != 0, dim=-1),
