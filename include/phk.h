@@ -190,6 +190,15 @@ int phk_gemm_bf16_x2(const void* A1, int64_t lda1, const void* W1, int64_t ldw1,
                      const void* W2, int64_t ldw2, float* C2, int64_t ldc2, int64_t M2, int32_t N2, int32_t K2,
                      const float* bias2, phk_stream_t s);
 
+/* The q and k,v projections of one self-attention block (attention.py:140-146: q from LayerNorm(x), k,v from the raw x)
+ * in ONE launch whose epilogue writes the bf16 OPERANDS of the attention core (attention.py:153-157) instead of fp32
+ * projections: Qn[M, I] = F.normalize(q, per 64-wide head) * q_scale * sim_scale, KVn[M, 2I] = [F.normalize(k) * k_scale |
+ * v].  xn / xraw bf16 [M, lda], Wq bf16 [I, ldw], Wkv bf16 [2I, ldw]; dim_head 64, I % 128 == 0.  Consumed by
+ * phk_attention_tc_bf16 / phk_attention_small_bf16. */
+int phk_gemm_bf16_qkv(const void* xn, const void* xraw, int64_t lda, const void* Wq, const void* Wkv, int64_t ldw,
+                      void* Qn, void* KVn, int64_t M, int32_t I, int32_t K, const float* q_scale, const float* k_scale,
+                      float sim_scale, phk_stream_t s);
+
 /* debug aid: per-CTA clock64 phase stamps of phk_gemm_bf16 (16 x int64 per CTA); NULL disables */
 int phk_debug_gemm_trace(long long* device_buffer);
 /* tests / A-B measurements: force the tcgen05 GEMM variant: 0 automatic, 1 one CTA per 128x128 tile, 2 CTA pairs
@@ -224,11 +233,19 @@ int phk_attention(const float* q, const float* kv, const float* null_kv, const f
                   const float* k_scale, const float* bias, const uint8_t* key_mask,
                   const float* alibi_slopes, void* out, const phk_attn_geom_t* g, phk_stream_t s);
 
-/* Tensor-core (tcgen05) variant of the attention core for long self-attention sequences (MaskGit, n = T'H'W'):
- * q fp32 [n_seq*n, heads*64], kv fp32 [n_seq*n, 2*heads*64] (token-major projection outputs), bias fp32
- * [heads, n, n] or NULL -> out bf16 [n_seq*n, heads*64].  dim_head 64, no null-kv / key mask / causal (those take
- * phk_attention).  q,k are l2-normalised and scaled, v transposed into head-major bf16 operands in `scratch`
- * (>= phk_attention_tc_scratch_bytes), then S = QK^T and O = PV run on tcgen05 with S, P never leaving the SM. */
+/* Tensor-core (tcgen05) attention core for self-attention sequences of n >= 64 tokens, dim_head 64, no null-kv / key
+ * mask / causal (those take phk_attention): S = QK^T and O = PV on tcgen05, S and P never leave the SM.
+ * phk_attention_tc_bf16: operands as phk_gemm_bf16_qkv writes them -- Qn bf16 [n_seq*n, ld_q], KVn bf16 [n_seq*n, ld_kv]
+ *   (token-major; 4-D tensor maps pick one head's tile, V is an MN-major operand: no head-major or transposed copy);
+ *   bias fp32 [heads, n, n] or NULL -> out bf16 [n_seq*n, heads*64].
+ * phk_attention_tc: the same from fp32 projections q [n_seq*n, heads*64], kv [n_seq*n, 2*heads*64]: a small kernel first
+ *   writes the normalised bf16 operands into `scratch` (>= phk_attention_tc_scratch_bytes). */
+int phk_attention_tc_bf16(const void* Qn, int64_t ld_q, const void* KVn, int64_t ld_kv, const float* bias,
+                          void* out_bf16, int32_t n_seq, int32_t n, int32_t heads, phk_stream_t s);
+/* Small sequences (n <= 16: the temporal transformer, causal + ALiBi) on the same bf16 operands, one warp per (sequence,
+ * head); geometry strides in elements as for phk_attention. */
+int phk_attention_small_bf16(const void* Qn, const void* KVn, const float* alibi_slopes, void* out,
+                             const phk_attn_geom_t* g, phk_stream_t s);
 int64_t phk_attention_tc_scratch_bytes(int32_t n_seq, int32_t n, int32_t heads);
 int phk_attention_tc(const float* q, const float* kv, const float* q_scale, const float* k_scale,
                      const float* bias, void* out_bf16, int32_t n_seq, int32_t n, int32_t heads, float scale,

@@ -106,6 +106,9 @@ PROTOTYPES = {
     "phk_attention": [vp, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(AttnGeomT), vp],
     "phk_attention_tc_scratch_bytes": [i32, i32, i32],
     "phk_attention_tc": [vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, vp, i64, vp],
+    "phk_attention_tc_bf16": [vp, i64, vp, i64, vp, vp, i32, i32, i32, vp],
+    "phk_attention_small_bf16": [vp, vp, vp, vp, C.POINTER(AttnGeomT), vp],
+    "phk_gemm_bf16_qkv": [vp, vp, i64, vp, vp, i64, vp, vp, i64, i32, i32, vp, vp, f32, vp],
     "phk_peg3d": [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
     "phk_cpb_scratch_floats": [C.POINTER(CpbT), i32, i32, i32],
     "phk_cpb_bias": [C.POINTER(CpbT), i32, i32, i32, vp, vp, vp],

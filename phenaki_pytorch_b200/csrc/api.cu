@@ -141,12 +141,6 @@ static int transformer_forward(const TfCall& c, Arena scratch, float* out, void*
     {  // x = self_attn(x) + x ; q from LN(x), k/v from RAW x (attention.py:140-144)
       const phk_attn_t& A = L.self_attn;
       PHK_TRY(phk_layernorm(x, A.norm_g, A.norm_b, xn, xraw, Rl, D, h16, 0, 0, 0, s));
-      if (h16 && Rl > 128 && A.wq_h && A.wkv_h) {  // both projections in one launch (their tiles pipeline)
-        PHK_TRY(phk_gemm_bf16_x2(xn, D, A.wq_h, D, q, I, Rl, I, D, nullptr, xraw, D, A.wkv_h, D, kv, 2 * I, Rl, 2 * I, D, nullptr, s));
-      } else {
-        PHK_TRY(linear(c.prec, xn, D, A.wq, A.wq_h, D, q, I, Rl, I, D, nullptr, nullptr, s));
-        PHK_TRY(linear(c.prec, h16 ? xraw : (const void*)x, D, A.wkv, A.wkv_h, D, kv, 2 * I, Rl, 2 * I, D, nullptr, nullptr, s));
-      }
       phk_attn_geom_t g;
       std::memset(&g, 0, sizeof(g));
       g.n_outer = n_outer; g.n_inner = c.seq.n_inner; g.n_q = c.seq.n_tok; g.n_k = c.seq.n_tok;
@@ -155,16 +149,36 @@ static int transformer_forward(const TfCall& c, Arena scratch, float* out, void*
       g.k_outer = c.seq.outer * 2 * I; g.k_inner = c.seq.inner * 2 * I; g.k_tok = c.seq.tok * 2 * I;
       g.o_outer = g.q_outer; g.o_inner = g.q_inner; g.o_tok = g.q_tok;
       g.kv_outer_mod = 0; g.mask_outer_mod = c.self_mask_mod; g.mask_off_from = -1; g.out_bf16 = h16; g.scale = 8.f;
-      const bool tc_ok = h16 && DH == 64 && !T->causal && A.num_null_kv == 0 && !c.self_mask && c.seq.n_inner == 1 &&
-                         c.seq.tok == 1 && c.seq.outer == c.seq.n_tok && c.seq.n_tok >= 64;
-      if (tc_ok) {  // tcgen05 path: S/P stay in TMEM / smem
-        const int64_t ab = phk_attention_tc_scratch_bytes(n_outer, c.seq.n_tok, H);
-        Arena tmp = scratch;
-        void* asc = tmp.take(ab);
-        PHK_REQUIRE(asc, PHK_E_WORKSPACE, "transformer: workspace too small (attention operands)");
-        PHK_TRY(phk_attention_tc(q, kv, A.q_scale, A.k_scale, c.attn_bias, o, n_outer, c.seq.n_tok, H, 8.f, asc, ab, s));
+      const bool plain = h16 && DH == 64 && A.num_null_kv == 0 && !c.self_mask;
+      const bool tc_ok = plain && !T->causal && c.seq.n_inner == 1 && c.seq.tok == 1 && c.seq.outer == c.seq.n_tok &&
+                         c.seq.n_tok >= 64;
+      const bool small_ok = plain && !c.attn_bias && c.seq.n_tok <= 16;
+      static const bool fuse_qkv = [] { const char* e = std::getenv("PHK_FUSE_QKV"); return !(e && e[0] == '0'); }();
+      if ((tc_ok || small_ok) && fuse_qkv && I % 128 == 0 && A.wq_h && A.wkv_h) {
+        // q / k,v projections in ONE launch whose epilogue writes the attention core's bf16 operands directly
+        // (l2-normalised q, k times their learned scales, the similarity scale 8 folded into q, v converted): no fp32
+        // q / kv round trip and no separate normalisation pass (attention.py:146-157)
+        void* qn = q;    // [Rl, I] bf16 in the fp32-sized q buffer
+        void* kvn = kv;  // [Rl, 2I] bf16
+        PHK_TRY(phk_gemm_bf16_qkv(xn, xraw, D, A.wq_h, A.wkv_h, D, qn, kvn, Rl, I, D, A.q_scale, A.k_scale, 8.f, s));
+        if (tc_ok) PHK_TRY(phk_attention_tc_bf16(qn, I, kvn, 2 * I, c.attn_bias, o, n_outer, c.seq.n_tok, H, s));
+        else PHK_TRY(phk_attention_small_bf16(qn, kvn, T->alibi_slopes, o, &g, s));
       } else {
-        PHK_TRY(phk_attention(q, kv, A.null_kv, A.q_scale, A.k_scale, c.attn_bias, c.self_mask, T->alibi_slopes, o, &g, s));
+        if (h16 && Rl > 128 && A.wq_h && A.wkv_h) {  // both projections in one launch (their tiles pipeline)
+          PHK_TRY(phk_gemm_bf16_x2(xn, D, A.wq_h, D, q, I, Rl, I, D, nullptr, xraw, D, A.wkv_h, D, kv, 2 * I, Rl, 2 * I, D, nullptr, s));
+        } else {
+          PHK_TRY(linear(c.prec, xn, D, A.wq, A.wq_h, D, q, I, Rl, I, D, nullptr, nullptr, s));
+          PHK_TRY(linear(c.prec, h16 ? xraw : (const void*)x, D, A.wkv, A.wkv_h, D, kv, 2 * I, Rl, 2 * I, D, nullptr, nullptr, s));
+        }
+        if (tc_ok) {  // tcgen05 path from fp32 projections (PHK_FUSE_QKV=0): operands prepared by attention_prep_kernel
+          const int64_t ab = phk_attention_tc_scratch_bytes(n_outer, c.seq.n_tok, H);
+          Arena tmp = scratch;
+          void* asc = tmp.take(ab);
+          PHK_REQUIRE(asc, PHK_E_WORKSPACE, "transformer: workspace too small (attention operands)");
+          PHK_TRY(phk_attention_tc(q, kv, A.q_scale, A.k_scale, c.attn_bias, o, n_outer, c.seq.n_tok, H, 8.f, asc, ab, s));
+        } else {
+          PHK_TRY(phk_attention(q, kv, A.null_kv, A.q_scale, A.k_scale, c.attn_bias, c.self_mask, T->alibi_slopes, o, &g, s));
+        }
       }
       PHK_TRY(linear(c.prec, o, I, A.wo, A.wo_h, I, x, D, Rl, D, I, nullptr, x, s));
     }

@@ -630,8 +630,10 @@ __global__ void __launch_bounds__(ROWS_THREADS) attention_rows_kernel(const floa
 // normalisation, the n(n+1)/2 causal dot products and the softmax run on warp shuffles, the P.V product is two FMAs
 // per (i, j) and lane.  33 MB of q / kv / out traffic at cfg2 bound the kernel, not shuffles (~0.3 k per warp).
 // ------------------------------------------------------------------------------------------
-template <int NMAX>
-__global__ void __launch_bounds__(256) attention_warp64_kernel(const float* __restrict__ q, const float* __restrict__ kv,
+// PRE: q / kv are the bf16 operands phk_gemm_bf16_qkv writes (already l2-normalised, scaled, similarity scale folded
+// into q): half the bytes to read and no normalisation shuffles.
+template <int NMAX, bool PRE = false>
+__global__ void __launch_bounds__(256) attention_warp64_kernel(const void* __restrict__ q_, const void* __restrict__ kv_,
                                                                const float* __restrict__ q_scale,
                                                                const float* __restrict__ k_scale,
                                                                const float* __restrict__ alibi_slopes,
@@ -645,29 +647,45 @@ __global__ void __launch_bounds__(256) attention_warp64_kernel(const float* __re
   const int seq = (int)(pair / g.heads);
   const int so = seq / g.n_inner, si = seq - so * g.n_inner;
   const int n = g.n_q, I = g.heads * 64;
-  const float* qb = q + (int64_t)so * g.q_outer + (int64_t)si * g.q_inner + (int64_t)h * 64;
-  const float* kb = kv + (int64_t)so * g.k_outer + (int64_t)si * g.k_inner + (int64_t)h * 64;
-  const float2 qs = reinterpret_cast<const float2*>(q_scale)[lane], ks = reinterpret_cast<const float2*>(k_scale)[lane];
   float2 xq[NMAX], xk[NMAX], xv[NMAX];
+  const int64_t qoff = (int64_t)so * g.q_outer + (int64_t)si * g.q_inner + (int64_t)h * 64;
+  const int64_t koff = (int64_t)so * g.k_outer + (int64_t)si * g.k_inner + (int64_t)h * 64;
+  if (PRE) {
+    const __nv_bfloat16* qb = reinterpret_cast<const __nv_bfloat16*>(q_) + qoff;
+    const __nv_bfloat16* kb = reinterpret_cast<const __nv_bfloat16*>(kv_) + koff;
 #pragma unroll
-  for (int i = 0; i < NMAX; ++i) {
-    xq[i] = xk[i] = xv[i] = make_float2(0.f, 0.f);
-    if (i < n) {
-      xq[i] = reinterpret_cast<const float2*>(qb + (int64_t)i * g.q_tok)[lane];
-      xk[i] = reinterpret_cast<const float2*>(kb + (int64_t)i * g.k_tok)[lane];
-      xv[i] = reinterpret_cast<const float2*>(kb + (int64_t)i * g.k_tok + I)[lane];
+    for (int i = 0; i < NMAX; ++i) {
+      xq[i] = xk[i] = xv[i] = make_float2(0.f, 0.f);
+      if (i < n) {
+        xq[i] = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(qb + (int64_t)i * g.q_tok)[lane]);
+        xk[i] = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(kb + (int64_t)i * g.k_tok)[lane]);
+        xv[i] = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(kb + (int64_t)i * g.k_tok + I)[lane]);
+      }
     }
-  }
-  // F.normalize(q), F.normalize(k) then * q_scale / k_scale (attention.py:153-155)
+  } else {
+    const float* qb = reinterpret_cast<const float*>(q_) + qoff;
+    const float* kb = reinterpret_cast<const float*>(kv_) + koff;
+    const float2 qs = reinterpret_cast<const float2*>(q_scale)[lane], ks = reinterpret_cast<const float2*>(k_scale)[lane];
 #pragma unroll
-  for (int i = 0; i < NMAX; ++i) {
-    if (i < n) {
-      // 1 / max(||x||, 1e-12) as one rsqrt per token (the kernel is instruction-bound: ~2.8 k instructions per warp
-      // with IEEE sqrt / divide / expf, profiles/r01_small_kernels_ncu.txt); the fixed scale 8 is folded into q
-      const float iq = rsqrtf(fmaxf(warp_sum(xq[i].x * xq[i].x + xq[i].y * xq[i].y), 1e-24f)) * g.scale;
-      const float ik = rsqrtf(fmaxf(warp_sum(xk[i].x * xk[i].x + xk[i].y * xk[i].y), 1e-24f));
-      xq[i].x = (xq[i].x * iq) * qs.x; xq[i].y = (xq[i].y * iq) * qs.y;
-      xk[i].x = (xk[i].x * ik) * ks.x; xk[i].y = (xk[i].y * ik) * ks.y;
+    for (int i = 0; i < NMAX; ++i) {
+      xq[i] = xk[i] = xv[i] = make_float2(0.f, 0.f);
+      if (i < n) {
+        xq[i] = reinterpret_cast<const float2*>(qb + (int64_t)i * g.q_tok)[lane];
+        xk[i] = reinterpret_cast<const float2*>(kb + (int64_t)i * g.k_tok)[lane];
+        xv[i] = reinterpret_cast<const float2*>(kb + (int64_t)i * g.k_tok + I)[lane];
+      }
+    }
+    // F.normalize(q), F.normalize(k) then * q_scale / k_scale (attention.py:153-155)
+#pragma unroll
+    for (int i = 0; i < NMAX; ++i) {
+      if (i < n) {
+        // 1 / max(||x||, 1e-12) as one rsqrt per token (the kernel is instruction-bound: ~2.8 k instructions per warp
+        // with IEEE sqrt / divide / expf, profiles/r01_small_kernels_ncu.txt); the fixed scale 8 is folded into q
+        const float iq = rsqrtf(fmaxf(warp_sum(xq[i].x * xq[i].x + xq[i].y * xq[i].y), 1e-24f)) * g.scale;
+        const float ik = rsqrtf(fmaxf(warp_sum(xk[i].x * xk[i].x + xk[i].y * xk[i].y), 1e-24f));
+        xq[i].x = (xq[i].x * iq) * qs.x; xq[i].y = (xq[i].y * iq) * qs.y;
+        xk[i].x = (xk[i].x * ik) * ks.x; xk[i].y = (xk[i].y * ik) * ks.y;
+      }
     }
   }
   const float slope = (g.causal && alibi_slopes) ? alibi_slopes[h] : 0.f;
@@ -706,11 +724,11 @@ __global__ void __launch_bounds__(256) attention_warp64_kernel(const float* __re
   }
 }
 
-template <int NMAX>
-static int launch_attention_warp64(const float* q, const float* kv, const float* q_scale, const float* k_scale,
+template <int NMAX, bool PRE = false>
+static int launch_attention_warp64(const void* q, const void* kv, const float* q_scale, const float* k_scale,
                                    const float* alibi_slopes, void* out, const phk_attn_geom_t& g, cudaStream_t st) {
   const int64_t npairs = (int64_t)g.n_outer * g.n_inner * g.heads;
-  PHK_CUDA(launch_pdl(attention_warp64_kernel<NMAX>, dim3((unsigned)((npairs + 7) / 8)), dim3(256), (size_t)0, st, q, kv,
+  PHK_CUDA(launch_pdl(attention_warp64_kernel<NMAX, PRE>, dim3((unsigned)((npairs + 7) / 8)), dim3(256), (size_t)0, st, q, kv,
                       q_scale, k_scale, alibi_slopes, out, g));
   PHK_LAUNCH_CHECK();
   return 0;
@@ -840,4 +858,28 @@ extern "C" int phk_attention(const float* q, const float* kv, const float* null_
     default: PHK_REQUIRE(false, PHK_E_UNSUPPORTED, "phk_attention: dim_head must be 16, 32, 64 or 128");
   }
   return 0;
+}
+
+// Small-sequence self-attention (n <= 16, dim_head 64: the temporal transformer, n = T') on the bf16 operands that
+// phk_gemm_bf16_qkv writes: Qn / KVn already l2-normalised and scaled (similarity scale folded into q), addressed
+// through the same geometry (strides in ELEMENTS).  No null-kv, bias or key mask; causal takes ALiBi slopes.
+extern "C" int phk_attention_small_bf16(const void* Qn, const void* KVn, const float* alibi_slopes, void* out,
+                                        const phk_attn_geom_t* g, phk_stream_t s) {
+  Prof prof_(FAM_ATTENTION, s, g ? 4.0 * (double)g->n_outer * g->n_inner * g->heads * g->n_q * g->n_k * g->dim_head : 0.0);
+  PHK_REQUIRE(Qn && KVn && out && g, PHK_E_ARG, "phk_attention_small_bf16: null pointer");
+  PHK_REQUIRE(g->n_outer > 0 && g->n_inner > 0 && g->heads > 0 && g->dim_head == 64 && g->n_q == g->n_k && g->n_q > 0 &&
+                  g->n_q <= 16 && g->num_null_kv == 0, PHK_E_UNSUPPORTED,
+              "phk_attention_small_bf16: needs dim_head 64, n_q == n_k <= 16 and no null-kv");
+  PHK_REQUIRE(!g->causal || alibi_slopes, PHK_E_ARG, "phk_attention_small_bf16: causal attention takes ALiBi slopes");
+  PHK_REQUIRE(g->q_tok % 2 == 0 && g->q_outer % 2 == 0 && g->q_inner % 2 == 0 && g->k_tok % 2 == 0 && g->k_outer % 2 == 0 &&
+                  g->k_inner % 2 == 0 && g->o_tok % 2 == 0 && g->o_outer % 2 == 0 && g->o_inner % 2 == 0 &&
+                  ((reinterpret_cast<uintptr_t>(Qn) | reinterpret_cast<uintptr_t>(KVn) | reinterpret_cast<uintptr_t>(out)) & 7) == 0,
+              PHK_E_ARG, "phk_attention_small_bf16: operands must be 8-byte aligned with even strides");
+  cudaStream_t st = to_stream(s);
+  const int n = g->n_q;
+  if (n <= 3) return launch_attention_warp64<3, true>(Qn, KVn, nullptr, nullptr, alibi_slopes, out, *g, st);
+  if (n <= 5) return launch_attention_warp64<5, true>(Qn, KVn, nullptr, nullptr, alibi_slopes, out, *g, st);
+  if (n <= 9) return launch_attention_warp64<9, true>(Qn, KVn, nullptr, nullptr, alibi_slopes, out, *g, st);
+  if (n <= 12) return launch_attention_warp64<12, true>(Qn, KVn, nullptr, nullptr, alibi_slopes, out, *g, st);
+  return launch_attention_warp64<16, true>(Qn, KVn, nullptr, nullptr, alibi_slopes, out, *g, st);
 }

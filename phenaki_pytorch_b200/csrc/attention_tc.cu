@@ -1,8 +1,12 @@
 // Tensor-core cosine-sim attention for long sequences (MaskGit self-attention, attention.py:146-181 with the 3-D
 // continuous position bias, n = T'H'W' = 576..1024 tokens, dim_head 64), sm_100a only.
 //
-//   phk_attention_prep : q/k fp32 (projection outputs) -> l2-normalise, * q_scale*8 / k_scale, bf16, head-major
-//                        [seq, head, n, 64]; v -> bf16 TRANSPOSED [seq, head, 64, n_pad] so that P.V is a K-major GEMM.
+//   operands           : bf16, TOKEN-major as the projections write them: Qn [rows, heads*64] (l2-normalised, * q_scale * 8),
+//                        KVn [rows, 2*heads*64] (keys normalised * k_scale | values) -- produced directly by the q / k,v
+//                        projection GEMM's epilogue (phk_gemm_bf16_qkv) or, for fp32 projections, by attention_prep_kernel.
+//                        4-D tensor maps (d, head, token, sequence) pick one head's tile out of the token-major rows, so no
+//                        head-major copy exists; V is consumed as an MN-major B operand (rows = keys), so no transposed
+//                        copy either.
 //   phk_attention_tc   : one CTA per (128-query tile, head, sequence); keys streamed in chunks of 64.
 //       warp 0      TMA producer (3-D tensor maps, SWIZZLE_128B; out-of-range rows zero-filled)
 //       warp 1      tcgen05.mma issuer: S[128x64] = Q K^T (4 x K=16) into TMEM cols 0..63,
@@ -51,10 +55,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
   }
 }
-__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2) {
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2,
+                                            int c3) {
   asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1) {
   asm volatile(
@@ -65,6 +70,18 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {  // K-major, SWI
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
   d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// MN-major, SWIZZLE_128B operand (cute::UMMA make_umma_desc<Major::MN>): the tile is [K rows][64 MN elements = 128 B];
+// canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units -- 8 K rows of 128 B form one 1024-byte swizzle atom,
+// the next 8 K rows follow at SBO = 1024 B; LBO (stride between 64-element MN groups) is unused for N = 64.
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(8192 >> 4) << 16;
   d |= (uint64_t)(1024 >> 4) << 32;
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)2 << 61;
@@ -130,7 +147,6 @@ __global__ void __launch_bounds__(ATHREADS, 2) attention_tc_kernel(const __grid_
                  b_bfull = bars + 72, b_bempty = bars + 80, tmem_slot = bars + 88;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * AQ, h = blockIdx.y, seq = blockIdx.z;
-  const int sh = seq * p.heads + h;
   const int nch = (p.n_k + AKC - 1) / AKC;
 
   if (threadIdx.x == 0) {
@@ -157,7 +173,7 @@ __global__ void __launch_bounds__(ATHREADS, 2) attention_tc_kernel(const __grid_
   if (warp == 0) {
     if (lane == 0) {
       mbar_expect_tx(b_qfull, SQ_BYTES);
-      tma_load_3d(&tmQ, b_qfull, sQ, 0, q0, sh);
+      tma_load_4d(&tmQ, b_qfull, sQ, 0, h, q0, seq);
       for (int j = 0; j < nch; ++j) {
         if (p.bias_tma) {  // bias tile of this (head, query tile, key chunk): rows h*n_q + q0.., two 32-column boxes
           mbar_wait(b_bempty, (j & 1) ^ 1);
@@ -167,16 +183,17 @@ __global__ void __launch_bounds__(ATHREADS, 2) attention_tc_kernel(const __grid_
         }
         mbar_wait(b_kempty, (j & 1) ^ 1);
         mbar_expect_tx(b_kfull, SK_BYTES);
-        tma_load_3d(&tmK, b_kfull, sK, 0, j * AKC, sh);
+        tma_load_4d(&tmK, b_kfull, sK, 0, h, j * AKC, seq);
         mbar_wait(b_vempty, (j & 1) ^ 1);
         mbar_expect_tx(b_vfull, SV_BYTES);
-        tma_load_3d(&tmV, b_vfull, sV, j * AKC, 0, sh);
+        tma_load_4d(&tmV, b_vfull, sV, 0, h, j * AKC, seq);   // [64 keys][64 d]: rows = keys (MN-major B operand of P.V)
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // M=128, N=64, bf16 x bf16 -> f32, both K-major (cute::UMMA::InstrDescriptor)
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(AKC >> 3) << 17) | ((uint32_t)(AQ >> 4) << 24);
+      const uint32_t idesc_pv = idesc | (1u << 16);  // B (= V) MN-major: N = 64 dims contiguous, K = keys along rows
       mbar_wait(b_qfull, 0);
       for (int j = 0; j < nch; ++j) {
         mbar_wait(b_kfull, j & 1);
@@ -190,9 +207,10 @@ __global__ void __launch_bounds__(ATHREADS, 2) attention_tc_kernel(const __grid_
         mbar_wait(b_pfull, j & 1);          // P written (and O rescaled) by the softmax warps
         mbar_wait(b_vfull, j & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint64_t dp = umma_desc(sP), dv = umma_desc(sV);
+        const uint64_t dp = umma_desc(sP), dv = umma_desc_mn(sV);
 #pragma unroll
-        for (int k = 0; k < AKC / 16; ++k) umma_f16(tO, dp + 2 * k, dv + 2 * k, idesc, (j | k) != 0);
+        for (int k = 0; k < AKC / 16; ++k)  // 16 keys = two 8-row atoms of V = 2048 B (128 descriptor units) per step
+          umma_f16(tO, dp + 2 * k, dv + 128 * k, idesc_pv, (j | k) != 0);
         umma_commit(b_vempty);
         umma_commit(b_pvdone);
       }
@@ -318,65 +336,33 @@ __global__ void __launch_bounds__(ATHREADS, 2) attention_tc_kernel(const __grid_
 }
 
 // --------------------------------------------------------------------------------------------------------------
-// prep: projection outputs (fp32, token-major [rows, heads*64] / [rows, 2*heads*64]) -> head-major bf16 operands
+// prep (fp32 projection outputs only; the bf16 pipeline gets these operands from the GEMM epilogue): token-major fp32
+// q [rows, I], kv [rows, 2I] -> token-major bf16 Qn [rows, I], KVn [rows, 2I]
 // --------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) attention_prep_kernel(const float* __restrict__ q, const float* __restrict__ kv,
                                                              const float* __restrict__ q_scale,
                                                              const float* __restrict__ k_scale,
-                                                             __nv_bfloat16* __restrict__ Qh, __nv_bfloat16* __restrict__ Kh,
-                                                             __nv_bfloat16* __restrict__ Vt, int n, int n_pad, int heads,
-                                                             float scale) {
+                                                             __nv_bfloat16* __restrict__ Qn, __nv_bfloat16* __restrict__ KVn,
+                                                             int64_t rows, int heads, float scale) {
   pdl_prologue();
-  __shared__ float vt[64][65];
-  const int t0 = blockIdx.x * 64, h = blockIdx.y, seq = blockIdx.z;
   const int I = heads * 64;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int64_t sh = (int64_t)seq * heads + h;
-  // lane owns dims (2 lane, 2 lane + 1): one 8-byte load per operand and token, one 4-byte bf16x2 store per output
+  const int lane = threadIdx.x & 31;
+  // lane owns dims (2 lane, 2 lane + 1) of one head: one 8-byte load per operand, one bf16x2 store per output
   const float2 qs = reinterpret_cast<const float2*>(q_scale)[lane], ks = reinterpret_cast<const float2*>(k_scale)[lane];
-  // 8 tokens per warp, all loads of 4 tokens in flight before the first reduction
-#pragma unroll
-  for (int g = 0; g < 2; ++g) {
-    float2 xq[4], xk[4], xv[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int tt = w * 8 + g * 4 + u, tok = t0 + tt;
-      xq[u] = xk[u] = xv[u] = make_float2(0.f, 0.f);
-      if (tok < n) {
-        const int64_t row = (int64_t)seq * n + tok;
-        xq[u] = reinterpret_cast<const float2*>(q + row * I + h * 64)[lane];
-        xk[u] = reinterpret_cast<const float2*>(kv + row * 2 * I + h * 64)[lane];
-        xv[u] = reinterpret_cast<const float2*>(kv + row * 2 * I + I + h * 64)[lane];
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int tt = w * 8 + g * 4 + u, tok = t0 + tt;
-      // 1 / max(||x||, 1e-12) (F.normalize, attention.py:153-154) once per token instead of a division per element
-      const float iq = 1.0f / fmaxf(sqrtf(warp_sum(xq[u].x * xq[u].x + xq[u].y * xq[u].y)), 1e-12f);
-      const float ik = 1.0f / fmaxf(sqrtf(warp_sum(xk[u].x * xk[u].x + xk[u].y * xk[u].y)), 1e-12f);
-      vt[tt][2 * lane] = xv[u].x;
-      vt[tt][2 * lane + 1] = xv[u].y;
-      if (tok < n) {
-        // F.normalize then * q_scale (attention.py:153-155); the fixed scale 8 (:157) is folded into q (exact in bf16)
-        reinterpret_cast<uint32_t*>(Qh + (sh * n + tok) * 64)[lane] =
-            pack_bf16x2((xq[u].x * iq) * qs.x * scale, (xq[u].y * iq) * qs.y * scale);
-        reinterpret_cast<uint32_t*>(Kh + (sh * n + tok) * 64)[lane] = pack_bf16x2((xk[u].x * ik) * ks.x, (xk[u].y * ik) * ks.y);
-      }
-    }
-  }
-  __syncthreads();
-  // V^T: thread -> (d, token pair): 64 d x 32 pairs = 2048 bf16x2 stores; a warp writes 128 contiguous bytes of one d row
-  const bool pair_ok = (n_pad % 2 == 0);
-  for (int idx = threadIdx.x; idx < 64 * 32; idx += blockDim.x) {
-    const int d = idx >> 5, tt = (idx & 31) * 2;
-    const float v0 = t0 + tt < n ? vt[tt][d] : 0.f, v1 = t0 + tt + 1 < n ? vt[tt + 1][d] : 0.f;
-    __nv_bfloat16* dst = Vt + (sh * 64 + d) * n_pad + t0 + tt;
-    if (pair_ok && t0 + tt + 1 < n_pad) *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(v0, v1);
-    else {
-      if (t0 + tt < n_pad) dst[0] = __float2bfloat16_rn(v0);
-      if (t0 + tt + 1 < n_pad) dst[1] = __float2bfloat16_rn(v1);
-    }
+  const int64_t pairs = rows * heads;
+  for (int64_t pr = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); pr < pairs;
+       pr += (int64_t)gridDim.x * (blockDim.x >> 5)) {
+    const int64_t row = pr / heads;
+    const int h = (int)(pr - row * heads);
+    const float2 xq = reinterpret_cast<const float2*>(q + row * I + h * 64)[lane];
+    const float2 xk = reinterpret_cast<const float2*>(kv + row * 2 * I + h * 64)[lane];
+    const float2 xv = reinterpret_cast<const float2*>(kv + row * 2 * I + I + h * 64)[lane];
+    // 1 / max(||x||, 1e-12) (F.normalize, attention.py:153-154); the fixed scale 8 (:157) is folded into q
+    const float iq = 1.0f / fmaxf(sqrtf(warp_sum(xq.x * xq.x + xq.y * xq.y)), 1e-12f);
+    const float ik = 1.0f / fmaxf(sqrtf(warp_sum(xk.x * xk.x + xk.y * xk.y)), 1e-12f);
+    reinterpret_cast<uint32_t*>(Qn + row * I + h * 64)[lane] = pack_bf16x2((xq.x * iq) * qs.x * scale, (xq.y * iq) * qs.y * scale);
+    reinterpret_cast<uint32_t*>(KVn + row * 2 * I + h * 64)[lane] = pack_bf16x2((xk.x * ik) * ks.x, (xk.y * ik) * ks.y);
+    reinterpret_cast<uint32_t*>(KVn + row * 2 * I + I + h * 64)[lane] = pack_bf16x2(xv.x, xv.y);
   }
 }
 
@@ -412,15 +398,17 @@ int make_map_bias(const float* ptr, int64_t rows, int64_t cols, CUtensorMap* out
   return 0;
 }
 
-int make_map_3d(const void* ptr, int64_t d0, int64_t d1, int64_t d2, int64_t stride1_elems, int64_t stride2_elems,
-                int box1, CUtensorMap* out) {
+// one head's [tokens, 64] tile out of a token-major bf16 matrix [n_seq * n rows, ld elements]: dims (d, head, token,
+// sequence), box [64 d][1][box_tok tokens][1], SWIZZLE_128B; tokens >= n are zero-filled (never the next sequence's)
+int make_map_4d(const void* ptr, int64_t n, int64_t heads, int64_t n_seq, int64_t ld, int box_tok, CUtensorMap* out) {
   EncodeTiledFn fn = encode_fn();
   PHK_REQUIRE(fn, PHK_E_UNSUPPORTED, "cuTensorMapEncodeTiled not available from the driver");
-  const cuuint64_t gdim[3] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2};
-  const cuuint64_t gstride[2] = {(cuuint64_t)stride1_elems * 2, (cuuint64_t)stride2_elems * 2};
-  const cuuint32_t box[3] = {64, (cuuint32_t)box1, 1};
-  const cuuint32_t estr[3] = {1, 1, 1};
-  const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstride, box, estr,
+  // dimension order (d, head, token, sequence): byte strides 128 < 2 ld < 2 n ld grow with the dimension index
+  const cuuint64_t gdim[4] = {64, (cuuint64_t)heads, (cuuint64_t)n, (cuuint64_t)n_seq};
+  const cuuint64_t gstride[3] = {128, (cuuint64_t)ld * 2, (cuuint64_t)n * (cuuint64_t)ld * 2};
+  const cuuint32_t box[4] = {64, 1, (cuuint32_t)box_tok, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstride, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   PHK_REQUIRE(r == CUDA_SUCCESS, PHK_E_ARG, "cuTensorMapEncodeTiled rejected an attention operand");
@@ -433,36 +421,26 @@ int make_map_3d(const void* ptr, int64_t d0, int64_t d1, int64_t d2, int64_t str
 using namespace phk;
 
 extern "C" int64_t phk_attention_tc_scratch_bytes(int32_t n_seq, int32_t n, int32_t heads) {
-  const int64_t n_pad = (n + 63) / 64 * 64;
-  return (int64_t)n_seq * heads * (2 * (int64_t)n * 64 + 64 * n_pad) * 2 + 3 * 256;
+  return (int64_t)n_seq * n * heads * 64 * 3 * 2 + 2 * 256;   // Qn [rows, I] + KVn [rows, 2I], bf16
 }
 
-// Self-attention core on tensor cores: q fp32 [n_seq*n, heads*64], kv fp32 [n_seq*n, 2*heads*64] (token-major
-// projection outputs), bias fp32 [heads, n, n] or NULL -> out bf16 [n_seq*n, heads*64].  dim_head 64, no null-kv,
-// no key mask, not causal (everything else takes phk_attention).  scratch >= phk_attention_tc_scratch_bytes.
-extern "C" int phk_attention_tc(const float* q, const float* kv, const float* q_scale, const float* k_scale,
-                                const float* bias, void* out_bf16, int32_t n_seq, int32_t n, int32_t heads,
-                                float scale, void* scratch, int64_t scratch_bytes, phk_stream_t s) {
+// Core on bf16 operands as phk_gemm_bf16_qkv writes them: Qn [n_seq*n, ld_q] (normalised, scaled), KVn [n_seq*n, ld_kv]
+// (normalised keys in columns [0, heads*64), values in [heads*64, 2*heads*64)); bias fp32 [heads, n, n] or NULL
+// -> out bf16 [n_seq*n, heads*64].
+extern "C" int phk_attention_tc_bf16(const void* Qn, int64_t ld_q, const void* KVn, int64_t ld_kv, const float* bias,
+                                     void* out_bf16, int32_t n_seq, int32_t n, int32_t heads, phk_stream_t s) {
   Prof prof_(FAM_ATTENTION, s, 4.0 * (double)n_seq * heads * n * n * 64);
-  PHK_REQUIRE(q && kv && q_scale && k_scale && out_bf16 && scratch, PHK_E_ARG, "phk_attention_tc: null pointer");
-  PHK_REQUIRE(n_seq > 0 && n > 0 && heads > 0 && n_seq <= 65535 && heads <= 65535, PHK_E_ARG, "phk_attention_tc: bad size");
-  PHK_REQUIRE(scratch_bytes >= phk_attention_tc_scratch_bytes(n_seq, n, heads), PHK_E_WORKSPACE,
-              "phk_attention_tc: scratch too small");
+  PHK_REQUIRE(Qn && KVn && out_bf16, PHK_E_ARG, "phk_attention_tc_bf16: null pointer");
+  PHK_REQUIRE(n_seq > 0 && n > 0 && heads > 0 && n_seq <= 65535 && heads <= 65535, PHK_E_ARG, "phk_attention_tc_bf16: bad size");
+  const int64_t I = (int64_t)heads * 64;
+  PHK_REQUIRE(ld_q >= I && ld_kv >= 2 * I && ld_q % 8 == 0 && ld_kv % 8 == 0 &&
+                  ((reinterpret_cast<uintptr_t>(Qn) | reinterpret_cast<uintptr_t>(KVn) | reinterpret_cast<uintptr_t>(out_bf16)) & 15) == 0,
+              PHK_E_ARG, "phk_attention_tc_bf16: operands must be 16-byte aligned with leading dimensions multiple of 8 (TMA)");
   cudaStream_t st = to_stream(s);
-  const int64_t n_pad = (n + 63) / 64 * 64;
-  const int64_t SH = (int64_t)n_seq * heads;
-  auto align = [](char* p) { return (char*)(((uintptr_t)p + 255) & ~(uintptr_t)255); };
-  char* base = align((char*)scratch);
-  __nv_bfloat16* Qh = (__nv_bfloat16*)base;
-  __nv_bfloat16* Kh = (__nv_bfloat16*)align(base + SH * n * 64 * 2);
-  __nv_bfloat16* Vt = (__nv_bfloat16*)align((char*)Kh + SH * n * 64 * 2);
-  dim3 pg((unsigned)((n_pad + 63) / 64), (unsigned)heads, (unsigned)n_seq);
-  PHK_CUDA(launch_pdl(attention_prep_kernel, dim3(pg), dim3(256), (size_t)(0), st, q, kv, q_scale, k_scale, Qh, Kh, Vt, n, (int)n_pad, heads, scale));
-  PHK_LAUNCH_CHECK();
   CUtensorMap tq, tk, tv;
-  PHK_TRY(make_map_3d(Qh, 64, n, SH, 64, (int64_t)n * 64, AQ, &tq));
-  PHK_TRY(make_map_3d(Kh, 64, n, SH, 64, (int64_t)n * 64, AKC, &tk));
-  PHK_TRY(make_map_3d(Vt, n_pad, 64, SH, n_pad, 64 * n_pad, ADH, &tv));
+  PHK_TRY(make_map_4d(Qn, n, heads, n_seq, ld_q, AQ, &tq));
+  PHK_TRY(make_map_4d(KVn, n, heads, n_seq, ld_kv, AKC, &tk));
+  PHK_TRY(make_map_4d(reinterpret_cast<const __nv_bfloat16*>(KVn) + I, n, heads, n_seq, ld_kv, AKC, &tv));
   static unsigned long long configured_mask = 0;
   const bool configured = device_configured(&configured_mask);
   if (!configured) {
@@ -477,4 +455,30 @@ extern "C" int phk_attention_tc(const float* q, const float* kv, const float* q_
   PHK_CUDA(launch_pdl(attention_tc_kernel, dim3(grid), dim3(ATHREADS), (size_t)(ATT_SMEM), st, tq, tk, tv, tb, p));
   PHK_LAUNCH_CHECK();
   return 0;
+}
+
+// Self-attention core on tensor cores from fp32 projections: q fp32 [n_seq*n, heads*64], kv fp32 [n_seq*n, 2*heads*64]
+// (token-major), bias fp32 [heads, n, n] or NULL -> out bf16 [n_seq*n, heads*64].  dim_head 64, no null-kv, no key
+// mask, not causal (everything else takes phk_attention).  scratch >= phk_attention_tc_scratch_bytes.
+extern "C" int phk_attention_tc(const float* q, const float* kv, const float* q_scale, const float* k_scale,
+                                const float* bias, void* out_bf16, int32_t n_seq, int32_t n, int32_t heads,
+                                float scale, void* scratch, int64_t scratch_bytes, phk_stream_t s) {
+  PHK_REQUIRE(q && kv && q_scale && k_scale && out_bf16 && scratch, PHK_E_ARG, "phk_attention_tc: null pointer");
+  PHK_REQUIRE(n_seq > 0 && n > 0 && heads > 0 && n_seq <= 65535 && heads <= 65535, PHK_E_ARG, "phk_attention_tc: bad size");
+  PHK_REQUIRE(scratch_bytes >= phk_attention_tc_scratch_bytes(n_seq, n, heads), PHK_E_WORKSPACE,
+              "phk_attention_tc: scratch too small");
+  cudaStream_t st = to_stream(s);
+  const int64_t rows = (int64_t)n_seq * n, I = (int64_t)heads * 64;
+  auto align = [](char* p) { return (char*)(((uintptr_t)p + 255) & ~(uintptr_t)255); };
+  __nv_bfloat16* Qn = (__nv_bfloat16*)align((char*)scratch);
+  __nv_bfloat16* KVn = (__nv_bfloat16*)align((char*)Qn + rows * I * 2);
+  {
+    Prof prof_(FAM_ATTENTION, s, 0.0);
+    const int64_t pairs = rows * heads;
+    const unsigned blocks = (unsigned)((pairs + 7) / 8 < 148 * 16 ? (pairs + 7) / 8 : 148 * 16);
+    PHK_CUDA(launch_pdl(attention_prep_kernel, dim3(blocks), dim3(256), (size_t)(0), st, q, kv, q_scale, k_scale, Qn, KVn, rows,
+                        (int)heads, scale));
+    PHK_LAUNCH_CHECK();
+  }
+  return phk_attention_tc_bf16(Qn, I, KVn, 2 * I, bias, out_bf16, n_seq, n, heads, s);
 }

@@ -54,6 +54,10 @@ struct EpiParams {
   // with [128 rows x 32 floats] SWIZZLE_128B boxes; the residual tile is bulk-LOADED into the staging boxes while the
   // main loop runs and the finished tile is bulk-STORED from them, so the epilogue warps issue no global accesses
   int tma_epi;
+  // epilogue 3 (self-attention operands, attention.py:146-157): bf16 output; columns [0, norm_cols) are l2-normalised
+  // per 64-column head (F.normalize, eps 1e-12), multiplied by nscale[col % 64] (q_scale / k_scale) and by nmul (the
+  // fixed similarity scale 8 folded into q); columns >= norm_cols (the value half of to_kv) are only converted
+  const float* nscale; int norm_cols; float nmul;
   alignas(64) CUtensorMap tmC;
 };
 
@@ -429,6 +433,32 @@ __device__ __forceinline__ void epi_chunk(const EpiParams& p, float* cstage, uin
             if (col + j < nlim) crow[j] = ov[j] + ((p.residual && !res_vec) ? p.residual[off[u] + j] : 0.f);
         }
       }
+    }
+  } else if (EPI == 3) {
+    // bf16 attention operands: lane owns columns [4 lane, 4 lane + 4) of the chunk; a head is 64 columns = 16 lanes, so
+    // the squared norm of a (row, head) is a 4-step xor-shuffle over the half warp
+    const int col = ncol0 + lane * 4;
+    const bool norm = ncol0 < p.norm_cols;   // chunks are 128-aligned and norm_cols % 128 == 0 (checked on the host)
+    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (norm) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(p.nscale + ((lane * 4) & 63)));
+      sc = make_float4(t.x * p.nmul, t.y * p.nmul, t.z * p.nmul, t.w * p.nmul);
+    }
+#pragma unroll 4
+    for (int rr = 0; rr < RPW; ++rr) {
+      const int r = rr * EPI_WARPS + ew;
+      const uint32_t m = (uint32_t)m0 + r;
+      float4 o = *reinterpret_cast<const float4*>(cstage + r * CPAD + lane * 4);
+      if (norm) {
+        float ss = o.x * o.x + o.y * o.y + o.z * o.z + o.w * o.w;
+#pragma unroll
+        for (int d = 8; d > 0; d >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, d);
+        const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+        o.x = (o.x * inv) * sc.x; o.y = (o.y * inv) * sc.y; o.z = (o.z * inv) * sc.z; o.w = (o.w * inv) * sc.w;
+      }
+      if (m < (uint32_t)p.M && col < nlim)
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.C) + (int64_t)m * p.ldc + col) =
+            make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
     }
   } else {
     // EPI 1: bf16 outputs, 128 columns (4 per lane)
@@ -1011,17 +1041,18 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const EpiPa
   return 0;
 }
 
+template <int EPI>
 static int launch_gemm_dual(const CUtensorMap& ta, const CUtensorMap& tb, const EpiParams& p, const CUtensorMap& ta2,
                             const CUtensorMap& tb2, const EpiParams& p2, cudaStream_t st) {
   static unsigned long long configured_mask = 0;
   const bool configured = device_configured(&configured_mask);
   if (!configured) {
-    PHK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    PHK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<EPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
     mark_configured(&configured_mask);
   }
   const int tiles = p.m_tiles * p.n_tiles + p2.m_tiles * p2.n_tiles;
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
-  PHK_CUDA(launch_pdl(gemm_bf16_kernel<0, true>, dim3(grid), dim3(GTHREADS), (size_t)(SMEM_TOTAL), st, ta, tb, p, ta2, tb2, p2));
+  PHK_CUDA(launch_pdl(gemm_bf16_kernel<EPI, true>, dim3(grid), dim3(GTHREADS), (size_t)(SMEM_TOTAL), st, ta, tb, p, ta2, tb2, p2));
   PHK_LAUNCH_CHECK();
   return 0;
 }
@@ -1159,7 +1190,39 @@ extern "C" int phk_gemm_bf16_x2(const void* A1, int64_t lda1, const void* W1, in
   PHK_REQUIRE((int64_t)p.m_tiles * p.n_tiles + (int64_t)p2.m_tiles * p2.n_tiles < (1LL << 31), PHK_E_UNSUPPORTED,
               "phk_gemm_bf16_x2: too many tiles");
   // (measured: the bulk-store epilogue does not pay for the two-problem launch -- 16.2 vs 15.5 us -- so it stays off)
-  return launch_gemm_dual(ta, tb, p, ta2, tb2, p2, to_stream(s));
+  return launch_gemm_dual<0>(ta, tb, p, ta2, tb2, p2, to_stream(s));
+}
+
+// The q and k,v projections of a self-attention block (attention.py:140-157) in one launch, written as the bf16 operands
+// of the attention core: Qn[M, I] = normalize_per_head(xn Wq^T) * q_scale * sim_scale, KVn[M, 2I] = [normalize_per_head(
+// xraw Wk^T) * k_scale | xraw Wv^T].  dim_head 64, I % 128 == 0.  Replaces fp32 q / kv round trips + a separate
+// normalisation pass.
+extern "C" int phk_gemm_bf16_qkv(const void* xn, const void* xraw, int64_t lda, const void* Wq, const void* Wkv, int64_t ldw,
+                                 void* Qn, void* KVn, int64_t M, int32_t I, int32_t K, const float* q_scale,
+                                 const float* k_scale, float sim_scale, phk_stream_t s) {
+  Prof prof_(FAM_GEMM_BF16, s, 2.0 * (double)M * 3.0 * I * K);
+  PHK_REQUIRE(xn && xraw && Wq && Wkv && Qn && KVn && q_scale && k_scale, PHK_E_ARG, "phk_gemm_bf16_qkv: null pointer");
+  PHK_REQUIRE(M > 0 && I > 0 && I % 128 == 0 && K > 0 && lda >= K && ldw >= K, PHK_E_ARG,
+              "phk_gemm_bf16_qkv: heads * 64 must be a multiple of 128");
+  PHK_REQUIRE(lda % 8 == 0 && ldw % 8 == 0 &&
+                  ((reinterpret_cast<uintptr_t>(xn) | reinterpret_cast<uintptr_t>(xraw) | reinterpret_cast<uintptr_t>(Wq) |
+                    reinterpret_cast<uintptr_t>(Wkv) | reinterpret_cast<uintptr_t>(q_scale) |
+                    reinterpret_cast<uintptr_t>(k_scale)) & 15) == 0 &&
+                  ((reinterpret_cast<uintptr_t>(Qn) | reinterpret_cast<uintptr_t>(KVn)) & 7) == 0,
+              PHK_E_ARG, "phk_gemm_bf16_qkv: operands must be 16-byte aligned with leading dimensions multiple of 8 (TMA)");
+  PHK_REQUIRE(M < (1LL << 31) - 2 * GM, PHK_E_UNSUPPORTED, "phk_gemm_bf16_qkv: M too large");
+  CUtensorMap ta, tb, ta2, tb2;
+  PHK_TRY(get_tensor_map(xn, M, K, lda, GM, &ta));
+  PHK_TRY(get_tensor_map(xraw, M, K, lda, GM, &ta2));
+  PHK_TRY(get_tensor_map(Wq, I, K, ldw, GN, &tb));
+  PHK_TRY(get_tensor_map(Wkv, 2 * I, K, ldw, GN, &tb2));
+  EpiParams p{Qn, I, M, I, K, nullptr, nullptr, 0, 0, 0, (int)((M + GM - 1) / GM), I / GN, nullptr};
+  EpiParams p2{KVn, 2 * (int64_t)I, M, 2 * I, K, nullptr, nullptr, 0, 0, 0, (int)((M + GM - 1) / GM), 2 * I / GN, nullptr};
+  p.tma_epi = 0; p.nscale = q_scale; p.norm_cols = I; p.nmul = sim_scale;
+  p2.tma_epi = 0; p2.nscale = k_scale; p2.norm_cols = I; p2.nmul = 1.0f;
+  PHK_REQUIRE((int64_t)p.m_tiles * p.n_tiles + (int64_t)p2.m_tiles * p2.n_tiles < (1LL << 31), PHK_E_UNSUPPORTED,
+              "phk_gemm_bf16_qkv: too many tiles");
+  return launch_gemm_dual<3>(ta, tb, p, ta2, tb2, p2, to_stream(s));
 }
 
 // debug / tests: force the kernel choice (0 automatic, 1 one-CTA, 2 CTA pairs 256x128, 3 CTA pairs 256x256; < 0 returns

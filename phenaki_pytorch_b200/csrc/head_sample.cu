@@ -11,8 +11,8 @@
 //   warp 0      TMA: the 128 x dim A panel is loaded ONCE and stays resident in shared memory (dim <= 512: 128 KB);
 //               W tiles (128 vocabulary rows x 64) stream through a 4-stage ring -> L2 traffic is W only.
 //   warp 1      tcgen05.mma issuer, two 128-column TMEM accumulators (MMA of tile i+1 overlaps the math of tile i).
-//   warps 2..17 math: thread = (token, 32-column group); tcgen05.ld straight from TMEM (no smem staging), Philox4x32-10
-//               noise (counter layout of phk_sample_tokens), running (argmax of l/T + g, l at argmax, max l, sum exp).
+//   warps 2..17 math: thread = (token, 32-column group); tcgen05.ld straight from TMEM (no smem staging), Philox4x32-7
+//               noise (phk_common.cuh; counter layout and gumbel transform of phk_sample_tokens), running (argmax of l/T + g, l at argmax, max l, sum exp).
 // Partials per (token, vocabulary slice) are merged by head_finalize_kernel (pred, 1 - softmax(l)[pred], mask).
 #include "phk_common.cuh"
 #include <cuda.h>
@@ -87,19 +87,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr) : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
-                                              uint32_t k1, uint32_t* out) {  // identical to rowops.cu
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
-    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
-    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-  }
-  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
-}
-
 struct HeadParams {
   const float* bias;
   int n_tokens, V, K, n_tiles, n_splits, tiles_per_split;
@@ -214,6 +201,36 @@ __global__ void __launch_bounds__(HTHREADS, 1) head_sample_kernel(const __grid_c
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);  // accumulator slice consumed
       if (!valid || v_base >= p.V) continue;
+      constexpr float LOG2E = 1.4426950408889634f;
+      if (v_base + 32 <= p.V) {
+        // whole 32-column group inside the vocabulary (always, for V % 32 == 0): no per-element bounds tests.
+        // Issue-slot budget per logit (the kernel is bound by them, not by the MMA): Philox-7 ~9, gumbel 5 + 2 MUFU,
+        // perturbed arg-max 4, softmax 2 + 1 MUFU + the running maximum.
+        float mxs = mx * LOG2E;
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) {
+          const int v0 = v_base + c;
+          float l4[4] = {__uint_as_float(raw[c]), __uint_as_float(raw[c + 1]), __uint_as_float(raw[c + 2]),
+                         __uint_as_float(raw[c + 3])};
+          if (p.bias) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + v0));
+            l4[0] += b4.x; l4[1] += b4.y; l4[2] += b4.z; l4[3] += b4.w;
+          }
+          uint32_t rnd[4];
+          const unsigned long long ctr = ctr0 + (unsigned long long)(v0 >> 2);
+          philox4x32<kNoiseRounds>((uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), rnd);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float y = fmaf(l4[j], p.inv_T, gumbel_from_bits(rnd[j]));
+            if (y > best) { best = y; bidx = v0 + j; lbest = l4[j]; }
+          }
+          const float gm = fmaxf(fmaxf(l4[0], l4[1]), fmaxf(l4[2], l4[3]));
+          if (gm > mx) { ssum *= fast_ex2((mx - gm) * LOG2E); mx = gm; mxs = gm * LOG2E; }  // one rescale per 4 logits
+#pragma unroll
+          for (int j = 0; j < 4; ++j) ssum += fast_ex2(fmaf(l4[j], LOG2E, -mxs));
+        }
+        continue;
+      }
 #pragma unroll
       for (int c = 0; c < 32; c += 4) {
         const int v0 = v_base + c;
@@ -225,7 +242,7 @@ __global__ void __launch_bounds__(HTHREADS, 1) head_sample_kernel(const __grid_c
         }
         uint32_t rnd[4];
         const unsigned long long ctr = ctr0 + (unsigned long long)(v0 >> 2);
-        philox4x32_10((uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), rnd);
+        philox4x32<kNoiseRounds>((uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), rnd);
         float l4[4];
         float gm = -FLT_MAX;
 #pragma unroll
@@ -233,14 +250,13 @@ __global__ void __launch_bounds__(HTHREADS, 1) head_sample_kernel(const __grid_c
           const bool in = v0 + j < p.V;
           l4[j] = in ? __uint_as_float(raw[c + j]) + bb[j] : -FLT_MAX;
           gm = fmaxf(gm, l4[j]);
-          const float u = (float)(rnd[j] >> 8) * (1.0f / 16777216.0f);
-          const float g = -__logf(-__logf(u + 1e-10f) + 1e-10f);
-          const float y = fmaf(l4[j], p.inv_T, g);
+          const float y = fmaf(l4[j], p.inv_T, gumbel_from_bits(rnd[j]));
           if (in && y > best) { best = y; bidx = v0 + j; lbest = l4[j]; }
         }
-        if (gm > mx) { ssum *= __expf(mx - gm); mx = gm; }  // one rescale per 4 logits
+        if (gm > mx) { ssum *= fast_ex2((mx - gm) * LOG2E); mx = gm; }  // one rescale per 4 logits
+        const float mxs = mx * LOG2E;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) ssum += __expf(l4[j] - mx);
+        for (int j = 0; j < 4; ++j) ssum += fast_ex2(fmaf(l4[j], LOG2E, -mxs));
       }
     }
     // merge the four column groups of every token, then one partial per (token, vocabulary slice)

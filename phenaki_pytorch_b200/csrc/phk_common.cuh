@@ -114,6 +114,43 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
 
+// ---- in-kernel sampling noise (statistical mode of the demasking loop: phk_sample_tokens without injected draws, the
+// fused logits head).  Counter-based: Philox4x32 keyed by the torch CUDA seed, counter = noise offset + (token, v / 4).
+// 7 rounds: the smallest count the Random123 authors report as passing BigCrush (10 is their safety-margin default); the
+// generator sits in the logits head's epilogue, which is instruction-bound (ncu, profiles/), at 4 IMAD + 2 LOP3 per round.
+constexpr int kNoiseRounds = 7;
+template <int ROUNDS>
+__device__ __forceinline__ void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                           uint32_t* out) {
+#pragma unroll
+  for (int r = 0; r < ROUNDS; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+__device__ __forceinline__ float fast_lg2(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float fast_ex2(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// Gumbel(0, 1) draw -log(-log(u)) (phenaki_pytorch.py:83-86) from 32 random bits: u = (2 k + 1) / 2^24 for the top 23 bits k
+// -- strictly inside (0, 1), so the reference's 1e-10 guards are not needed -- built from the bits directly (no int->float
+// conversion), both logarithms in base 2 on the MUFU unit: g = -ln2 * log2(-log2(u)) - ln(ln 2).
+__device__ __forceinline__ float gumbel_from_bits(uint32_t r) {
+  const float u = __uint_as_float(0x3f800000u | (r >> 9)) - 0.99999994f;  // [1, 2) - (1 - 2^-24): exact
+  const float e = -fast_lg2(u);                                           // > 0
+  return fmaf(-0.69314718f, fast_lg2(e), 0.36651292f);
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

@@ -643,19 +643,6 @@ __global__ void cpb_expand_kernel(const float* __restrict__ table, float* __rest
 // (sub, mul, add, div, add -- no FMA contraction) so argmax decisions agree bit for bit
 // whenever logf agrees.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
-                                              uint32_t k1, uint32_t* out) {
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
-    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
-    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-  }
-  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
-}
-
 struct ArgBest { float y; int idx; };
 __device__ __forceinline__ ArgBest better(ArgBest a, ArgBest b) {
   // larger y wins; ties -> lower index (torch.argmax returns the first maximal index)
@@ -685,16 +672,17 @@ __global__ void __launch_bounds__(512) sample_tokens_kernel(const float* __restr
   ArgBest best{-FLT_MAX, 0x7fffffff};
   float m = -FLT_MAX, ssum = 0.f;
   for (int v0 = threadIdx.x * 4; v0 < V; v0 += blockDim.x * 4) {
-    float uu[4];
+    float uu[4], gg[4];
     if (ur) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) uu[j] = (v0 + j < V) ? ur[v0 + j] : 0.5f;
     } else {
+      // statistical mode: in-kernel Philox noise, the same counters and gumbel transform as the fused logits head
       const uint64_t ctr = offset + (uint64_t)row * (uint64_t)((V + 3) / 4) + (uint64_t)(v0 >> 2);
       uint32_t r[4];
-      philox4x32_10((uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+      philox4x32<kNoiseRounds>((uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) uu[j] = (float)(r[j] >> 8) * (1.0f / 16777216.0f);
+      for (int j = 0; j < 4; ++j) gg[j] = gumbel_from_bits(r[j]);
     }
     if (!ur && v0 + 3 < V && ((ld & 3) == 0)) {
       // statistical mode (in-kernel noise): vectorised loads and fast intrinsics; not bit-comparable anyway
@@ -709,8 +697,7 @@ __global__ void __launch_bounds__(512) sample_tokens_kernel(const float* __restr
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float l = l4[j];
-        const float g = -__logf(-__logf(uu[j] + 1e-10f) + 1e-10f);
-        const float y = fmaf(l, inv_T, g);
+        const float y = fmaf(l, inv_T, gg[j]);
         if (y > best.y) { best.y = y; best.idx = v0 + j; }
         if (l > m) { ssum = ssum * __expf(m - l) + 1.f; m = l; } else { ssum += __expf(l - m); }
       }
@@ -722,8 +709,9 @@ __global__ void __launch_bounds__(512) sample_tokens_kernel(const float* __restr
       if (v >= V) break;
       float l = cr[v];
       if (nr) { const float nn = nr[v]; l = __fadd_rn(nn, __fmul_rn(__fsub_rn(l, nn), cond_scale)); }
-      const float g = -logf(__fadd_rn(-logf(__fadd_rn(uu[j], 1e-10f)), 1e-10f));
-      const float y = __fadd_rn(__fdiv_rn(l, T), g);
+      // injected draws: the reference's op sequence (phenaki_pytorch.py:83-93); in-kernel noise: gumbel_from_bits
+      const float g = ur ? -logf(__fadd_rn(-logf(__fadd_rn(uu[j], 1e-10f)), 1e-10f)) : gg[j];
+      const float y = ur ? __fadd_rn(__fdiv_rn(l, T), g) : fmaf(l, inv_T, g);
       if (y > best.y) { best.y = y; best.idx = v; }
       if (l > m) { ssum = ssum * expf(m - l) + 1.f; m = l; } else { ssum += expf(l - m); }
     }

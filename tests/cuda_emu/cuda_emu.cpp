@@ -221,6 +221,80 @@ extern "C" int phk_attention_tc(const float* q, const float* kv, const float* q_
   g.mask_off_from = -1; g.out_bf16 = 1; g.scale = scale;
   return phk_attention(q, kv, nullptr, q_scale, k_scale, bias, nullptr, nullptr, out_bf16, &g, s);
 }
+// phk_attention_tc_bf16 contract: Qn [n_seq*n, ld_q] / KVn [n_seq*n, ld_kv] bf16, already normalised and scaled (the
+// similarity scale folded into q); softmax(q k^T + bias) v per (sequence, head) -> out bf16 [n_seq*n, heads*64].  Like
+// the kernel: fp32 scores / softmax statistics, probabilities rounded to bf16 before the P.V product.
+extern "C" int phk_attention_tc_bf16(const void* Qn, int64_t ld_q, const void* KVn, int64_t ld_kv, const float* bias,
+                                     void* out_bf16, int32_t n_seq, int32_t n, int32_t heads, phk_stream_t) {
+  if (!Qn || !KVn || !out_bf16 || n_seq <= 0 || n <= 0 || heads <= 0) return PHK_E_ARG;
+  emu::submit([=]() {
+    const __nv_bfloat16* q = (const __nv_bfloat16*)Qn;
+    const __nv_bfloat16* kv = (const __nv_bfloat16*)KVn;
+    __nv_bfloat16* out = (__nv_bfloat16*)out_bf16;
+    const int64_t I = (int64_t)heads * 64;
+    std::vector<float> sc(n);
+    for (int s_ = 0; s_ < n_seq; ++s_)
+      for (int h = 0; h < heads; ++h)
+        for (int i = 0; i < n; ++i) {
+          const __nv_bfloat16* qi = q + ((int64_t)s_ * n + i) * ld_q + h * 64;
+          float m = -INFINITY;
+          for (int j = 0; j < n; ++j) {
+            const __nv_bfloat16* kj = kv + ((int64_t)s_ * n + j) * ld_kv + h * 64;
+            float a = 0.f;
+            for (int d = 0; d < 64; ++d) a += __bfloat162float(qi[d]) * __bfloat162float(kj[d]);
+            if (bias) a += bias[((int64_t)h * n + i) * n + j];
+            sc[j] = a;
+            m = fmaxf(m, a);
+          }
+          float sum = 0.f, o[64];
+          for (int d = 0; d < 64; ++d) o[d] = 0.f;
+          for (int j = 0; j < n; ++j) {
+            const float e = expf(sc[j] - m);
+            sum += e;
+            const float eb = __bfloat162float(__float2bfloat16_rn(e));
+            const __nv_bfloat16* vj = kv + ((int64_t)s_ * n + j) * ld_kv + I + h * 64;
+            for (int d = 0; d < 64; ++d) o[d] += eb * __bfloat162float(vj[d]);
+          }
+          for (int d = 0; d < 64; ++d) out[((int64_t)s_ * n + i) * I + h * 64 + d] = __float2bfloat16_rn(o[d] / sum);
+        }
+  });
+  return 0;
+}
+// phk_gemm_bf16_qkv contract: the q and k,v projections with the attention core's operands as output (bf16): per 64-column
+// head l2-normalised (eps 1e-12) * learned scale (* sim_scale for q); the value half only converted
+extern "C" int phk_gemm_bf16_qkv(const void* xn, const void* xraw, int64_t lda, const void* Wq, const void* Wkv, int64_t ldw,
+                                 void* Qn, void* KVn, int64_t M, int32_t I, int32_t K, const float* q_scale,
+                                 const float* k_scale, float sim_scale, phk_stream_t) {
+  if (!xn || !xraw || !Wq || !Wkv || !Qn || !KVn || !q_scale || !k_scale || I % 128 || lda % 8 || ldw % 8) return PHK_E_ARG;
+  emu::submit([=]() {
+    auto project = [&](const void* A_, const void* W_, int N, int norm_cols, const float* scale, float mul, void* C_) {
+      const __nv_bfloat16* a = (const __nv_bfloat16*)A_;
+      const __nv_bfloat16* w = (const __nv_bfloat16*)W_;
+      __nv_bfloat16* c = (__nv_bfloat16*)C_;
+      std::vector<float> row(N);
+      for (int64_t m = 0; m < M; ++m) {
+        for (int nn = 0; nn < N; ++nn) {
+          float acc = 0.f;
+          for (int k = 0; k < K; ++k) acc += __bfloat162float(a[m * lda + k]) * __bfloat162float(w[(int64_t)nn * ldw + k]);
+          row[nn] = acc;
+        }
+        for (int h0 = 0; h0 < N; h0 += 64) {
+          if (h0 < norm_cols) {
+            float ss = 0.f;
+            for (int d = 0; d < 64; ++d) ss += row[h0 + d] * row[h0 + d];
+            const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+            for (int d = 0; d < 64; ++d) c[m * N + h0 + d] = __float2bfloat16_rn((row[h0 + d] * inv) * (scale[d] * mul));
+          } else {
+            for (int d = 0; d < 64; ++d) c[m * N + h0 + d] = __float2bfloat16_rn(row[h0 + d]);
+          }
+        }
+      }
+    };
+    project(xn, Wq, I, I, q_scale, sim_scale, Qn);
+    project(xraw, Wkv, 2 * I, I, k_scale, 1.0f, KVn);
+  });
+  return 0;
+}
 // phk_layernorm_cfg / phk_head_sample (head_sample.cu, tcgen05) from their include/phk.h contracts, for the drivers'
 // wiring tests: e = s * norm(x_cond) + (1 - s) * norm(x_null) in bf16; logits = e W^T + bias in fp32, then the REAL
 // phk_sample_tokens kernel (the documented equivalence: same Philox counter layout as phk_sample_tokens with u == NULL)

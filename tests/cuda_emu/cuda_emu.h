@@ -49,6 +49,7 @@ static inline float __bfloat162float(__nv_bfloat16 h) {
   return f;
 }
 struct __nv_bfloat162 { __nv_bfloat16 x, y; };
+static inline float2 __bfloat1622float2(__nv_bfloat162 v) { return float2{__bfloat162float(v.x), __bfloat162float(v.y)}; }
 static inline __nv_bfloat162 __floats2bfloat162_rn(float a, float b) {
   return __nv_bfloat162{__float2bfloat16_rn(a), __float2bfloat16_rn(b)};
 }
@@ -195,6 +196,27 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 
 // same definitions as csrc/phk_common.cuh
+static inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+static inline uint32_t __float_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+constexpr int kNoiseRounds = 7;
+template <int ROUNDS>
+static inline void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out) {
+  for (int r = 0; r < ROUNDS; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+static inline float fast_lg2(float x) { return log2f(x); }
+static inline float fast_ex2(float x) { return exp2f(x); }
+static inline float gumbel_from_bits(uint32_t r) {
+  const float u = __uint_as_float(0x3f800000u | (r >> 9)) - 0.99999994f;
+  const float e = -fast_lg2(u);
+  return fmaf(-0.69314718f, fast_lg2(e), 0.36651292f);
+}
 
 // One-time per-DEVICE kernel configuration (cudaFuncSetAttribute is a per-device setting; a process may drive several
 // devices): `mask` is a call-site static, bit d = "done on device d".

@@ -34,13 +34,27 @@ def val(r, m):
     return f"{v:.1f}" if "%" in dict(M)[m] else f"{v:.0f}"
 
 
+STALL = [h for h in hdr if "issue_stalled" in h and h.endswith(".ratio") and "not_issued" not in h]
+
+
+def stalls(r):
+    """top warp-stall reasons (cycles a warp waits in that state per issued instruction), WarpStateStats section"""
+    vals = []
+    for h in STALL:
+        try:
+            vals.append((float(r[col[h]].replace(",", "")), h.split("issue_stalled_")[1].split("_per_")[0]))
+        except (ValueError, IndexError):
+            pass
+    return " ".join(f"{n}={v:.1f}" for v, n in sorted(vals, reverse=True)[:5])
+
+
 seen, out = {}, []
 for r in rows[2:]:
     key = (r[col["Kernel Name"]].split("(")[0].replace("void ", "").replace("phk::", "").replace("<unnamed>::", ""), r[col["Grid Size"]])
     seen[key] = seen.get(key, 0) + 1
     if seen[key] > 1:
         continue
-    out.append([key[0], key[1]] + [val(r, m) for m, _ in M])
+    out.append([key[0], key[1]] + [val(r, m) for m, _ in M] + [stalls(r)])
 w = csv.writer(open(sys.argv[2], "w", newline="") if len(sys.argv) > 2 else sys.stdout)
-w.writerow(["kernel", "grid"] + [n for _, n in M])
+w.writerow(["kernel", "grid"] + [n for _, n in M] + ["top_stalls_cycles_per_issue"])
 w.writerows(out)
