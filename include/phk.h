@@ -18,6 +18,12 @@
  *     PHK_PREC_F32  fp32 FFMA GEMMs (parity mode, token ids identical to the fp32 reference);
  *     PHK_PREC_BF16 bf16 operands on tcgen05 tensor cores with fp32 TMEM accumulation (the
  *                   dtype flow of the reference under torch.autocast(bfloat16)).
+ *     PHK_PREC_BF16X3 fp32-grade products ON the tensor cores: every nn.Linear operand is split into two bf16 terms
+ *                   (x = hi + lo, |x - hi - lo| <= 2^-17 |x|) and C = A_hi W_hi + A_hi W_lo + A_lo W_hi is ONE tcgen05
+ *                   GEMM over the concatenated K' = 3K ([hi | hi | lo] x [hi | lo | hi], fp32 TMEM accumulation);
+ *                   everything else (LayerNorm, attention core, GEGLU, PEG, fp32 activations) is the parity mode's.
+ *                   Token ids equal the fp32 reference's at the bars of tests/test_gpu_parity_at_size.py without
+ *                   the FFMA GEMMs' cost.  Inference only (the training step treats it as PHK_PREC_F32).
  *   - token ids are int64 (reference dtype), masks are uint8 (0/1).
  */
 #ifndef PHK_H_
@@ -31,7 +37,7 @@ extern "C" {
 
 typedef struct CUstream_st* phk_stream_t; /* == cudaStream_t */
 
-enum { PHK_PREC_F32 = 0, PHK_PREC_BF16 = 1 };
+enum { PHK_PREC_F32 = 0, PHK_PREC_BF16 = 1, PHK_PREC_BF16X3 = 2 };
 enum {
   PHK_E_ARG = -1,      /* null pointer / non-positive size            */
   PHK_E_SHAPE = -2,    /* shape contract violated (reference asserts) */
@@ -198,6 +204,12 @@ int phk_gemm_bf16_x2(const void* A1, int64_t lda1, const void* W1, int64_t ldw1,
 int phk_gemm_bf16_qkv(const void* xn, const void* xraw, int64_t lda, const void* Wq, const void* Wkv, int64_t ldw,
                       void* Qn, void* KVn, int64_t M, int32_t I, int32_t K, const float* q_scale, const float* k_scale,
                       float sim_scale, phk_stream_t s);
+
+/* PHK_PREC_BF16X3 operand split: x fp32 [rows, ld] (K valid columns) -> bf16 [rows, 3 * Kp], Kp = K rounded up to 8:
+ * [hi | hi | lo] (weights == 0: the activation side) or [hi | lo | hi] (weights != 0), hi = bf16(x), lo = bf16(x - hi),
+ * zero in the padding columns.  With both sides split this way a plain bf16 GEMM over K' = 3 Kp computes
+ * A_hi W_hi + A_hi W_lo + A_lo W_hi. */
+int phk_split3(const float* x, int64_t ld, void* out, int64_t rows, int32_t K, int32_t weights, phk_stream_t s);
 
 /* debug aid: per-CTA clock64 phase stamps of phk_gemm_bf16 (16 x int64 per CTA); NULL disables */
 int phk_debug_gemm_trace(long long* device_buffer);
@@ -391,7 +403,7 @@ int phk_cvivit_decode(const phk_cvivit_dec_t* m, const int64_t* ids, const float
 /* context_norm + to_kv of every cross-attention layer (attention.py:137-144).  Depends only on
  * the text embedding, so Phenaki.sample computes it once per call instead of once per forward.
  * context (b,L,dim_context) fp32; out_kv [depth, b*L, 2*heads*dim_head] fp32;
- * scratch b*L*dim_context floats. */
+ * scratch 3*b*L*dim_context floats (the normalised text rows; behind them, PHK_PREC_BF16X3 only, their split copy). */
 int phk_maskgit_context_kv(const phk_maskgit_t* m, const float* context, int32_t b, int32_t L,
                            float* out_kv, float* scratch, int32_t prec, phk_stream_t s);
 

@@ -52,6 +52,10 @@ struct SeqView {  // how sequences map onto rows of the [R, dim] residual stream
   int64_t outer, inner, tok;  // strides in ROWS
 };
 
+// Contraction type of one driver call + the PHK_PREC_BF16X3 split scratch (bf16 [rows, 3 * Kp] of the largest activation)
+struct Lin { int prec; void* a3; int64_t a3_bytes; };
+static inline int64_t x3_bytes(int64_t rows, int64_t Kmax) { return rows * 3 * ((Kmax + 7) / 8 * 8) * 2 + 256; }
+
 struct TfCall {
   const phk_transformer_t* T;
   float* x;      // residual stream [R, dim] (in/out)
@@ -68,6 +72,7 @@ struct TfCall {
   const uint8_t* ctx_mask;     // [ctx_b, L]
   int ctx_mask_off_from;       // sequences >= this see no text (CFG null half), -1: none
   int prec;
+  Lin lin;                     // contraction type + split scratch of the nn.Linear products (prec is its .prec)
   void* out_cfg; float cfg_scale;  // bf16 [R/2, dim]: norm_out of the null half + scale * (cond - null) (fused head)
   // decoder tail: norm_out gathered into two dense operands (activation type of the mode) -- rows of the first
   // frame (t == 0) and of the remaining frames, each in (b,t,h,w) order (cvivit.py:506)
@@ -88,12 +93,28 @@ static int64_t tf_scratch_bytes(const phk_transformer_t* T, int64_t R) {
   return 256 * 12 + R * 4 * (T->dim + I + 2 * I + I + 2 * inner + inner) + R * I * 6 + 64 * 64 * 2 * (R / 64 + 64);
 }
 
-// y = act @ W^T (+bias)(+residual) in the selected contraction type.  `act` is fp32 (parity mode) or bf16.
-static int linear(int prec, const void* act, int64_t lda, const float* w32, const void* w16, int64_t ldw, float* C,
+static int64_t tf_kmax(const phk_transformer_t* T) {  // largest K of a transformer's nn.Linear products
+  int64_t k = T->dim > T->heads * T->dim_head ? T->dim : T->heads * T->dim_head;
+  for (int l = 0; l < T->depth; ++l) k = k > T->layers[l].ff.inner ? k : T->layers[l].ff.inner;
+  return k;
+}
+static inline bool known_prec(int prec) { return prec == PHK_PREC_F32 || prec == PHK_PREC_BF16 || prec == PHK_PREC_BF16X3; }
+
+// y = act @ W^T (+bias)(+residual) in the selected contraction type.  `act` is fp32 (parity / split-bf16 modes) or bf16.
+//   PHK_PREC_BF16X3: `act` fp32 is split into [hi | hi | lo] bf16 and multiplied with the [hi | lo | hi] weight pack
+//   (w16, ld 3 * Kp) by ONE tcgen05 GEMM over K' = 3 Kp: fp32-grade products on the tensor cores.
+static int linear(const Lin& ln, const void* act, int64_t lda, const float* w32, const void* w16, int64_t ldw, float* C,
                   int64_t ldc, int64_t M, int N, int K, const float* bias, const float* residual, phk_stream_t s) {
-  if (prec == PHK_PREC_BF16) {
+  if (ln.prec == PHK_PREC_BF16) {
     PHK_REQUIRE(w16, PHK_E_ARG, "bf16 mode needs the packed bf16 weight copies (*_h) in the weight table");
     return phk_gemm_bf16(act, lda, w16, ldw, C, ldc, M, N, K, bias, residual, 0, 0, 0, 0, s);
+  }
+  if (ln.prec == PHK_PREC_BF16X3) {
+    PHK_REQUIRE(w16, PHK_E_ARG, "split-bf16 mode needs the [hi | lo | hi] weight packs (*_h) in the weight table");
+    const int Kp = (K + 7) / 8 * 8;
+    PHK_REQUIRE(ln.a3 && ln.a3_bytes >= M * 3 * (int64_t)Kp * 2, PHK_E_WORKSPACE, "split-bf16 mode: operand scratch too small");
+    PHK_TRY(phk_split3((const float*)act, lda, ln.a3, M, K, 0, s));
+    return phk_gemm_bf16(ln.a3, 3 * (int64_t)Kp, w16, 3 * (int64_t)Kp, C, ldc, M, N, 3 * Kp, bias, residual, 0, 0, 0, 0, s);
   }
   return phk_gemm_f32((const float*)act, lda, w32, ldw, C, ldc, M, N, K, bias, residual, 0, 0, 0, s);
 }
@@ -107,7 +128,8 @@ static int linear(int prec, const void* act, int64_t lda, const float* w32, cons
 static int transformer_forward(const TfCall& c, Arena scratch, float* out, void* out_h, cudaStream_t st) {
   const phk_transformer_t* T = c.T;
   const bool h16 = c.prec == PHK_PREC_BF16;
-  PHK_REQUIRE(c.prec == PHK_PREC_F32 || h16, PHK_E_ARG, "transformer: unknown precision mode");
+  PHK_REQUIRE(c.prec == PHK_PREC_F32 || c.prec == PHK_PREC_BF16X3 || h16, PHK_E_ARG, "transformer: unknown precision mode");
+  PHK_REQUIRE(c.lin.prec == c.prec, PHK_E_ARG, "transformer: contraction descriptor not initialised");
   const int D = T->dim, H = T->heads, DH = T->dim_head, I = H * DH;
   const int64_t R = c.R;
   int inner_max = 0;
@@ -167,8 +189,8 @@ static int transformer_forward(const TfCall& c, Arena scratch, float* out, void*
         if (h16 && Rl > 128 && A.wq_h && A.wkv_h) {  // both projections in one launch (their tiles pipeline)
           PHK_TRY(phk_gemm_bf16_x2(xn, D, A.wq_h, D, q, I, Rl, I, D, nullptr, xraw, D, A.wkv_h, D, kv, 2 * I, Rl, 2 * I, D, nullptr, s));
         } else {
-          PHK_TRY(linear(c.prec, xn, D, A.wq, A.wq_h, D, q, I, Rl, I, D, nullptr, nullptr, s));
-          PHK_TRY(linear(c.prec, h16 ? xraw : (const void*)x, D, A.wkv, A.wkv_h, D, kv, 2 * I, Rl, 2 * I, D, nullptr, nullptr, s));
+          PHK_TRY(linear(c.lin, xn, D, A.wq, A.wq_h, D, q, I, Rl, I, D, nullptr, nullptr, s));
+          PHK_TRY(linear(c.lin, h16 ? xraw : (const void*)x, D, A.wkv, A.wkv_h, D, kv, 2 * I, Rl, 2 * I, D, nullptr, nullptr, s));
         }
         if (tc_ok) {  // tcgen05 path from fp32 projections (PHK_FUSE_QKV=0): operands prepared by attention_prep_kernel
           const int64_t ab = phk_attention_tc_scratch_bytes(n_outer, c.seq.n_tok, H);
@@ -180,7 +202,7 @@ static int transformer_forward(const TfCall& c, Arena scratch, float* out, void*
           PHK_TRY(phk_attention(q, kv, A.null_kv, A.q_scale, A.k_scale, c.attn_bias, c.self_mask, T->alibi_slopes, o, &g, s));
         }
       }
-      PHK_TRY(linear(c.prec, o, I, A.wo, A.wo_h, I, x, D, Rl, D, I, nullptr, x, s));
+      PHK_TRY(linear(c.lin, o, I, A.wo, A.wo_h, I, x, D, Rl, D, I, nullptr, x, s));
     }
     if (dup)  // the null half continues from the same rows
       PHK_CUDA(cudaMemcpyAsync(x + Rl * D, x, Rl * D * 4, cudaMemcpyDeviceToDevice, st));
@@ -188,7 +210,7 @@ static int transformer_forward(const TfCall& c, Arena scratch, float* out, void*
       const phk_attn_t& A = L.cross_attn;
       PHK_REQUIRE(c.seq.n_inner == 1, PHK_E_UNSUPPORTED, "cross attention needs (b, n) sequences");
       PHK_TRY(phk_layernorm(x, A.norm_g, A.norm_b, xn, nullptr, R, D, h16, 0, 0, 0, s));
-      PHK_TRY(linear(c.prec, xn, D, A.wq, A.wq_h, D, q, I, R, I, D, nullptr, nullptr, s));
+      PHK_TRY(linear(c.lin, xn, D, A.wq, A.wq_h, D, q, I, R, I, D, nullptr, nullptr, s));
       phk_attn_geom_t g;
       std::memset(&g, 0, sizeof(g));
       g.n_outer = c.seq.n_outer; g.n_inner = 1; g.n_q = c.seq.n_tok; g.n_k = c.ctx_L;
@@ -200,7 +222,7 @@ static int transformer_forward(const TfCall& c, Arena scratch, float* out, void*
       g.out_bf16 = h16; g.scale = 8.f;
       const float* kvl = c.ctx_kv + (int64_t)l * c.ctx_b * c.ctx_L * 2 * I;
       PHK_TRY(phk_attention(q, kvl, A.null_kv, A.q_scale, A.k_scale, nullptr, c.ctx_mask, nullptr, o, &g, s));
-      PHK_TRY(linear(c.prec, o, I, A.wo, A.wo_h, I, x, D, R, D, I, nullptr, x, s));
+      PHK_TRY(linear(c.lin, o, I, A.wo, A.wo_h, I, x, D, R, D, I, nullptr, x, s));
     }
     {  // x = ff(x) + x  (attention.py:45-53, 330)
       const phk_ff_t& Fw = L.ff;
@@ -212,9 +234,9 @@ static int transformer_forward(const TfCall& c, Arena scratch, float* out, void*
         PHK_TRY(phk_gemm_bf16(xn, D, Fw.w1_h, D, gbuf, Fw.inner_pad, R, 2 * Fw.inner_pad, D, nullptr, nullptr, 0, 0, 0, 2, s));
         PHK_TRY(phk_gemm_bf16(gbuf, Fw.inner_pad, Fw.w2_h, Fw.inner_pad, x, D, R, D, Fw.inner_pad, nullptr, x, 0, 0, 0, 0, s));
       } else {
-        PHK_TRY(phk_gemm_f32((const float*)xn, D, Fw.w1, D, hbuf, 2 * Fw.inner, R, 2 * Fw.inner, D, nullptr, nullptr, 0, 0, 0, s));
+        PHK_TRY(linear(c.lin, xn, D, Fw.w1, Fw.w1_h, D, hbuf, 2 * Fw.inner, R, 2 * Fw.inner, D, nullptr, nullptr, s));
         PHK_TRY(phk_geglu(hbuf, (float*)gbuf, R, Fw.inner, s));
-        PHK_TRY(phk_gemm_f32((const float*)gbuf, Fw.inner, Fw.w2, Fw.inner, x, D, R, D, Fw.inner, nullptr, x, 0, 0, 0, s));
+        PHK_TRY(linear(c.lin, gbuf, Fw.inner, Fw.w2, Fw.w2_h, Fw.inner, x, D, R, D, Fw.inner, nullptr, x, s));
       }
     }
   }
@@ -298,7 +320,13 @@ extern "C" int64_t phk_cvivit_workspace_bytes(const phk_cvivit_t* m, int32_t B, 
   bytes += (int64_t)m->heads * hw * hw * 4 + phk_cpb_scratch_floats(&m->spatial_bias, hh, ww, 1) * 4;
   const int64_t a = tf_scratch_bytes(&m->spatial, R), b = tf_scratch_bytes(&m->temporal, R);
   bytes += a > b ? a : b;
-  if (m->codebook) bytes += phk_vq_cosine_scratch_bytes(R, m->codebook_size, prec) + 256;
+  if (m->codebook) bytes += phk_vq_cosine_scratch_bytes(R, m->codebook_size, prec == PHK_PREC_BF16 ? prec : PHK_PREC_F32) + 256;
+  if (prec == PHK_PREC_BF16X3) {
+    int64_t k = K2;
+    k = k > tf_kmax(&m->spatial) ? k : tf_kmax(&m->spatial);
+    k = k > tf_kmax(&m->temporal) ? k : tf_kmax(&m->temporal);
+    bytes += x3_bytes(R, k);
+  }
   return bytes;
 }
 
@@ -311,7 +339,7 @@ static int cvivit_encode_impl(const phk_cvivit_t* m, const float* video, int32_t
   PHK_REQUIRE(video && ids && workspace, PHK_E_ARG, "cvivit_encode: null pointer");
   PHK_TRY(check_transformer(&m->spatial));
   PHK_TRY(check_transformer(&m->temporal));
-  PHK_REQUIRE(prec == PHK_PREC_F32 || prec == PHK_PREC_BF16, PHK_E_ARG, "cvivit_encode: unknown precision mode");
+  PHK_REQUIRE(known_prec(prec), PHK_E_ARG, "cvivit_encode: unknown precision mode");
   const int h16 = prec == PHK_PREC_BF16;
   cudaStream_t st = to_stream(s);
   const int D = m->dim, hw = hh * ww;
@@ -324,6 +352,15 @@ static int cvivit_encode_impl(const phk_cvivit_t* m, const float* video, int32_t
   float* bias_buf = (float*)ar.take((int64_t)m->heads * hw * hw * 4);
   float* cpb_scratch = (float*)ar.take(phk_cpb_scratch_floats(&m->spatial_bias, hh, ww, 1) * 4);
   PHK_REQUIRE(A && P && x && x_alt && bias_buf && cpb_scratch, PHK_E_WORKSPACE, "cvivit_encode: workspace too small");
+  Lin lin{prec, nullptr, 0};
+  if (prec == PHK_PREC_BF16X3) {
+    int64_t k = K2;
+    k = k > tf_kmax(&m->spatial) ? k : tf_kmax(&m->spatial);
+    k = k > tf_kmax(&m->temporal) ? k : tf_kmax(&m->temporal);
+    lin.a3_bytes = x3_bytes(R, k);
+    lin.a3 = ar.take(lin.a3_bytes);
+    PHK_REQUIRE(lin.a3, PHK_E_WORKSPACE, "cvivit_encode: workspace too small (split operands)");
+  }
 
   // ---- to_patch_emb_first_frame / to_patch_emb (cvivit.py:542-549), rows land in (b,t,h,w) order
   const int C = m->channels, H = m->image_h, W = m->image_w;
@@ -343,13 +380,13 @@ static int cvivit_encode_impl(const phk_cvivit_t* m, const float* video, int32_t
                           (int64_t)Tp * hw, hw, s));
   } else {
   PHK_TRY(phk_patchify_ln(video, B, C, F, H, W, 0, 1, 1, m->patch_h, m->patch_w, m->pf_ln1_g, m->pf_ln1_b, A, h16, s));
-  PHK_TRY(linear(prec, A, K1, m->pf_w, m->pf_w_h, K1, P, D, (int64_t)B * hw, D, (int)K1, m->pf_b, nullptr, s));
+  PHK_TRY(linear(lin, A, K1, m->pf_w, m->pf_w_h, K1, P, D, (int64_t)B * hw, D, (int)K1, m->pf_b, nullptr, s));
   PHK_TRY(phk_layernorm(P, m->pf_ln2_g, m->pf_ln2_b, x, nullptr, (int64_t)B * hw, D, 0, hw, (int64_t)Tp * hw, 0, s));
   if (Tp > 1) {
     const int64_t rows = (int64_t)B * (Tp - 1) * hw;
     PHK_TRY(phk_patchify_ln(video, B, C, F, H, W, 1, Tp - 1, m->patch_t, m->patch_h, m->patch_w, m->pr_ln1_g,
                             m->pr_ln1_b, A, h16, s));
-    PHK_TRY(linear(prec, A, K2, m->pr_w, m->pr_w_h, K2, P, D, rows, D, (int)K2, m->pr_b, nullptr, s));
+    PHK_TRY(linear(lin, A, K2, m->pr_w, m->pr_w_h, K2, P, D, rows, D, (int)K2, m->pr_b, nullptr, s));
     PHK_TRY(phk_layernorm(P, m->pr_ln2_g, m->pr_ln2_b, x, nullptr, rows, D, 0, (int64_t)(Tp - 1) * hw,
                           (int64_t)Tp * hw, hw, s));
   }
@@ -367,7 +404,7 @@ static int cvivit_encode_impl(const phk_cvivit_t* m, const float* video, int32_t
   c.T = &m->spatial; c.x = x; c.x_alt = x_alt; c.R = R;
   c.seq = SeqView{B * Tp, 1, hw, hw, 0, 1};
   c.pegB = B; c.pegT = Tp; c.pegH = hh; c.pegW = ww; c.peg_layout = 0;
-  c.attn_bias = spatial_bias; c.ctx_mask_off_from = -1; c.prec = prec;
+  c.attn_bias = spatial_bias; c.ctx_mask_off_from = -1; c.prec = prec; c.lin = lin;
   PHK_TRY(transformer_forward(c, tf, P, nullptr, st));  // P <- norm_out(spatial)
   if (tap_spatial) PHK_CUDA(cudaMemcpyAsync(tap_spatial, P, R * D * 4, cudaMemcpyDeviceToDevice, st));
 
@@ -384,13 +421,14 @@ static int cvivit_encode_impl(const phk_cvivit_t* m, const float* video, int32_t
   if (m->codebook) {
     // lookup_free_quantization=False (cvivit.py:321, 568-570): norm_out, then the nearest unit codebook row by cosine
     PHK_REQUIRE(m->codebook_size > 0, PHK_E_ARG, "cvivit_encode: codebook without a size");
-    const int64_t vb = phk_vq_cosine_scratch_bytes(R, m->codebook_size, prec);
+    const int vprec = prec == PHK_PREC_BF16 ? prec : PHK_PREC_F32;  // (split-bf16 mode: the fp32 similarity path)
+    const int64_t vb = phk_vq_cosine_scratch_bytes(R, m->codebook_size, vprec);
     void* vsc = tf.take(vb);
     PHK_REQUIRE(vsc, PHK_E_WORKSPACE, "cvivit_encode: workspace too small (codebook lookup)");
     if (tap_temporal || !h16) PHK_TRY(phk_layernorm(xf, m->temporal.out_g, m->temporal.out_b, norm_buf, nullptr, R, D, 0, 0, 0, 0, s));
     if (tap_temporal) PHK_CUDA(cudaMemcpyAsync(tap_temporal, norm_buf, R * D * 4, cudaMemcpyDeviceToDevice, st));
     if (h16) PHK_TRY(phk_layernorm(xf, m->temporal.out_g, m->temporal.out_b, norm_buf, nullptr, R, D, 1, 0, 0, 0, s));
-    return phk_vq_cosine_ids(norm_buf, m->codebook, m->codebook_h, ids, R, D, m->codebook_size, vsc, vb, prec, s);
+    return phk_vq_cosine_ids(norm_buf, m->codebook, m->codebook_h, ids, R, D, m->codebook_size, vsc, vb, vprec, s);
   }
   PHK_TRY(phk_layernorm_lfq(xf, m->temporal.out_g, m->temporal.out_b, m->vq_w, m->vq_b, ids,
                             (tap_temporal || D % 128 != 0 || D > 1024 || m->codebook_bits > 16) ? norm_buf : nullptr,
@@ -628,7 +666,7 @@ extern "C" int64_t phk_cvivit_decode_workspace_bytes(const phk_cvivit_dec_t* m, 
   bytes += (int64_t)m->heads * hw * hw * 4 + phk_cpb_scratch_floats(&m->spatial_bias, hh, ww, 1) * 4;
   const int64_t a = tf_scratch_bytes(&m->spatial, R), b = tf_scratch_bytes(&m->temporal, R);
   bytes += a > b ? a : b;
-  (void)prec;
+  if (prec == PHK_PREC_BF16X3) bytes += x3_bytes(R, tf_kmax(&m->spatial) > tf_kmax(&m->temporal) ? tf_kmax(&m->spatial) : tf_kmax(&m->temporal));
   return bytes;
 }
 
@@ -641,7 +679,7 @@ extern "C" int phk_cvivit_decode(const phk_cvivit_dec_t* m, const int64_t* ids, 
   PHK_REQUIRE((ids || tokens) && video && workspace, PHK_E_ARG, "cvivit_decode: null pointer");
   PHK_TRY(check_transformer(&m->spatial));
   PHK_TRY(check_transformer(&m->temporal));
-  PHK_REQUIRE(prec == PHK_PREC_F32 || prec == PHK_PREC_BF16, PHK_E_ARG, "cvivit_decode: unknown precision mode");
+  PHK_REQUIRE(known_prec(prec), PHK_E_ARG, "cvivit_decode: unknown precision mode");
   const int h16 = prec == PHK_PREC_BF16;
   cudaStream_t st = to_stream(s);
   const int D = m->dim, hw = hh * ww, C = m->channels;
@@ -660,6 +698,12 @@ extern "C" int phk_cvivit_decode(const phk_cvivit_dec_t* m, const int64_t* ids, 
   float* cpb_scratch = (float*)ar.take(phk_cpb_scratch_floats(&m->spatial_bias, hh, ww, 1) * 4);
   PHK_REQUIRE(x && x_alt && P && Afirst && Arest && G && bias_buf && cpb_scratch, PHK_E_WORKSPACE,
               "cvivit_decode: workspace too small");
+  Lin lin{prec, nullptr, 0};
+  if (prec == PHK_PREC_BF16X3) {
+    lin.a3_bytes = x3_bytes(R, tf_kmax(&m->spatial) > tf_kmax(&m->temporal) ? tf_kmax(&m->spatial) : tf_kmax(&m->temporal));
+    lin.a3 = ar.take(lin.a3_bytes);
+    PHK_REQUIRE(lin.a3, PHK_E_WORKSPACE, "cvivit_decode: workspace too small (split operands)");
+  }
 
   // ---- codes = vq.indices_to_codes(ids) (cvivit.py:437-439), rows in (b,t,h,w) order
   if (ids) PHK_TRY(phk_lfq_codes(ids, m->vq_out_w, m->vq_out_b, x, R, D, m->codebook_bits, s));
@@ -674,7 +718,7 @@ extern "C" int phk_cvivit_decode(const phk_cvivit_dec_t* m, const int64_t* ids, 
   c.seq = SeqView{B, hw, Tp, (int64_t)Tp * hw, 1, hw};
   c.pegB = B; c.pegT = Tp; c.pegH = hh; c.pegW = ww;
   c.peg_layout = 1;  // same raw-reshape quirk as the encoder (attention.py:71, cvivit.py:489-491)
-  c.ctx_mask_off_from = -1; c.prec = prec;
+  c.ctx_mask_off_from = -1; c.prec = prec; c.lin = lin;
   PHK_TRY(transformer_forward(c, tf, P, nullptr, st));  // P <- norm_out(temporal)
   if (tap_temporal) PHK_CUDA(cudaMemcpyAsync(tap_temporal, P, R * D * 4, cudaMemcpyDeviceToDevice, st));
 
@@ -690,10 +734,10 @@ extern "C" int phk_cvivit_decode(const phk_cvivit_dec_t* m, const int64_t* ids, 
   PHK_TRY(transformer_forward(c, tf, tap_spatial, nullptr, st));
 
   // ---- to_pixels_first_frame / to_pixels (cvivit.py:506-514): Linear + un-patchify scatter
-  PHK_TRY(linear(prec, Afirst, D, m->px_first_w, m->px_first_w_h, D, G, K1, rows1, (int)K1, D, m->px_first_b, nullptr, s));
+  PHK_TRY(linear(lin, Afirst, D, m->px_first_w, m->px_first_w_h, D, G, K1, rows1, (int)K1, D, m->px_first_b, nullptr, s));
   PHK_TRY(phk_unpatchify(G, K1, video, B, C, F, m->image_h, m->image_w, 0, 1, 1, m->patch_h, m->patch_w, s));
   if (Tp > 1) {
-    PHK_TRY(linear(prec, Arest, D, m->px_w, m->px_w_h, D, G, K2, rows2, (int)K2, D, m->px_b, nullptr, s));
+    PHK_TRY(linear(lin, Arest, D, m->px_w, m->px_w_h, D, G, K2, rows2, (int)K2, D, m->px_b, nullptr, s));
     PHK_TRY(phk_unpatchify(G, K2, video, B, C, F, m->image_h, m->image_w, 1, Tp - 1, m->patch_t, m->patch_h,
                            m->patch_w, s));
   }
@@ -710,7 +754,8 @@ extern "C" int64_t phk_maskgit_workspace_bytes(const phk_maskgit_t* m, int32_t b
   int64_t bytes = 256 * 16 + R * m->dim * 4 * 3;
   bytes += tf_scratch_bytes(&m->transformer, R);
   if (m->has_bias) bytes += (int64_t)m->heads * n * n * 4 + (int64_t)8 * n * 8 * m->heads * 4 + (1 << 20);
-  (void)L; (void)prec;
+  if (prec == PHK_PREC_BF16X3) bytes += x3_bytes(R, tf_kmax(&m->transformer));
+  (void)L;
   return bytes;
 }
 
@@ -721,18 +766,25 @@ extern "C" int phk_maskgit_context_kv(const phk_maskgit_t* m, const float* conte
                                       float* out_kv, float* scratch, int32_t prec, phk_stream_t s) {
   PHK_REQUIRE(m && context && out_kv && scratch, PHK_E_ARG, "maskgit_context_kv: null pointer");
   PHK_REQUIRE(b > 0 && L > 0, PHK_E_ARG, "maskgit_context_kv: bad size");
-  PHK_REQUIRE(prec == PHK_PREC_F32 || prec == PHK_PREC_BF16, PHK_E_ARG, "maskgit_context_kv: unknown precision mode");
+  PHK_REQUIRE(known_prec(prec), PHK_E_ARG, "maskgit_context_kv: unknown precision mode");
   const int h16 = prec == PHK_PREC_BF16;
   const phk_transformer_t* T = &m->transformer;
   PHK_TRY(check_transformer(T));
   const int I = T->heads * T->dim_head;
   const int64_t rows = (int64_t)b * L;
+  // split-bf16 mode: the [hi | hi | lo] copy of the normalised text rows lives behind them in `scratch` (3x floats)
+  Lin lin{prec, nullptr, 0};
+  if (prec == PHK_PREC_BF16X3 && T->depth > 0) {
+    const int64_t dc = T->layers[0].cross_attn.dim_context;
+    lin.a3 = reinterpret_cast<char*>(scratch) + ((rows * dc * 4 + 255) / 256) * 256;
+    lin.a3_bytes = rows * dc * 8 - 256;  // what is left of the 3 * rows * dc floats the caller provides
+  }
   for (int l = 0; l < T->depth; ++l) {
     const phk_layer_t& Ly = T->layers[l];
     PHK_REQUIRE(Ly.has_cross, PHK_E_SHAPE, "maskgit_context_kv: layer has no cross attention");
     const phk_attn_t& A = Ly.cross_attn;
     PHK_TRY(phk_layernorm(context, A.ctx_g, A.ctx_b, scratch, nullptr, rows, A.dim_context, h16, 0, 0, 0, s));
-    PHK_TRY(linear(prec, scratch, A.dim_context, A.wkv, A.wkv_h, A.dim_context, out_kv + (int64_t)l * rows * 2 * I, 2 * I,
+    PHK_TRY(linear(lin, scratch, A.dim_context, A.wkv, A.wkv_h, A.dim_context, out_kv + (int64_t)l * rows * 2 * I, 2 * I,
                    rows, 2 * I, A.dim_context, nullptr, nullptr, s));
   }
   return 0;
@@ -748,7 +800,7 @@ extern "C" int phk_maskgit_forward(const phk_maskgit_t* m, const int64_t* ids, i
   PHK_REQUIRE((int64_t)pt * ph * pw == n, PHK_E_SHAPE, "video patch shape must cover the token sequence");
   PHK_REQUIRE(n <= m->max_seq_len, PHK_E_SHAPE,
               "the video token sequence length is greater than max_seq_len (phenaki_pytorch.py:196)");
-  PHK_REQUIRE(prec == PHK_PREC_F32 || prec == PHK_PREC_BF16, PHK_E_ARG, "maskgit_forward: unknown precision mode");
+  PHK_REQUIRE(known_prec(prec), PHK_E_ARG, "maskgit_forward: unknown precision mode");
   const int h16 = prec == PHK_PREC_BF16;
   PHK_REQUIRE(!ctx_kv || text_mask, PHK_E_ARG, "maskgit_forward: context without text mask");
   const phk_transformer_t* T = &m->transformer;
@@ -762,6 +814,12 @@ extern "C" int phk_maskgit_forward(const phk_maskgit_t* m, const int64_t* ids, i
   float* x_alt = (float*)ar.take(R * D * 4);
   float* emb = (float*)ar.take(R * D * 4);
   PHK_REQUIRE(x && x_alt && emb, PHK_E_WORKSPACE, "maskgit_forward: workspace too small");
+  Lin lin{prec, nullptr, 0};
+  if (prec == PHK_PREC_BF16X3) {
+    lin.a3_bytes = x3_bytes(R, tf_kmax(T));
+    lin.a3 = ar.take(lin.a3_bytes);
+    PHK_REQUIRE(lin.a3, PHK_E_WORKSPACE, "maskgit_forward: workspace too small (split operands)");
+  }
   if (m->has_bias && !pos_bias) {
     float* bias_buf = (float*)ar.take((int64_t)m->heads * n * n * 4);
     float* sc = (float*)ar.take(phk_cpb_scratch_floats(&m->pos_bias, pt, ph, pw) * 4);
@@ -781,11 +839,11 @@ extern "C" int phk_maskgit_forward(const phk_maskgit_t* m, const int64_t* ids, i
   c.ctx_kv = ctx_kv; c.ctx_b = b; c.ctx_L = L; c.ctx_mask = text_mask;
   c.ctx_mask_off_from = cfg_pair ? b : -1;
   c.dup_halves = cfg_pair ? 1 : 0;  // phk_token_embed wrote the same embeddings for both halves
-  c.prec = prec;
+  c.prec = prec; c.lin = lin;
   if (return_embeds || m->is_critic) return transformer_forward(c, ar, out, nullptr, st);
   // to_logits (phenaki_pytorch.py:213): the final LayerNorm feeds the head GEMM directly (bf16 operand in bf16 mode)
   PHK_TRY(transformer_forward(c, ar, h16 ? nullptr : emb, h16 ? (void*)emb : nullptr, st));
-  PHK_TRY(linear(prec, emb, D, m->head_w, m->head_w_h, D, out, m->num_tokens, R, m->num_tokens, D, m->head_b, nullptr, s));
+  PHK_TRY(linear(lin, emb, D, m->head_w, m->head_w_h, D, out, m->num_tokens, R, m->num_tokens, D, m->head_b, nullptr, s));
   return 0;
 }
 
@@ -851,7 +909,7 @@ static int sample_step_impl(const phk_maskgit_t* m, const int64_t* ids_in, int32
   c.attn_bias = m->has_bias ? pos_bias : nullptr;
   c.self_mask = video_mask; c.self_mask_mod = b;
   c.ctx_kv = ctx_kv; c.ctx_b = b; c.ctx_L = L; c.ctx_mask = text_mask; c.ctx_mask_off_from = b;
-  c.prec = PHK_PREC_BF16; c.out_cfg = emb_h; c.cfg_scale = cond_scale;
+  c.prec = PHK_PREC_BF16; c.lin = Lin{PHK_PREC_BF16, nullptr, 0}; c.out_cfg = emb_h; c.cfg_scale = cond_scale;
   c.dup_halves = 1;  // phk_token_embed wrote the same embeddings for both halves
   float* xf = nullptr;
   c.x_final = &xf;  // the residual stream before norm_out: rows [0, tokens) conditional, [tokens, 2 tokens) null

@@ -970,6 +970,55 @@ extern "C" int phk_geglu(const float* h, float* out, int64_t rows, int32_t inner
   return 0;
 }
 
+// PHK_PREC_BF16X3 operand split (see include/phk.h): one thread per 4 columns, 8-byte bf16x4 stores into three segments
+__global__ void __launch_bounds__(256) split3_kernel(const float* __restrict__ x, int64_t ld, __nv_bfloat16* __restrict__ out,
+                                                     int64_t rows, int K, int Kp, int weights) {
+  pdl_prologue();
+  const int q = Kp / 4;  // float4 groups per row (Kp % 8 == 0)
+  const int64_t total = rows * q;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / q;
+    const int c = (int)(i - r * q) * 4;
+    float v[4];
+    const float* xr = x + r * ld + c;
+    if (c + 3 < K && (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+      const float4 t = *reinterpret_cast<const float4*>(xr);
+      v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = (c + j < K) ? xr[j] : 0.f;
+    }
+    float hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      hi[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
+      lo[j] = v[j] - hi[j];  // exact in fp32
+    }
+    const uint2 H = make_uint2(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]));
+    const uint2 Lo = make_uint2(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]));
+    __nv_bfloat16* o = out + r * 3 * (int64_t)Kp + c;
+    *reinterpret_cast<uint2*>(o) = H;
+    *reinterpret_cast<uint2*>(o + Kp) = weights ? Lo : H;
+    *reinterpret_cast<uint2*>(o + 2 * (int64_t)Kp) = weights ? H : Lo;
+  }
+}
+
+extern "C" int phk_split3(const float* x, int64_t ld, void* out, int64_t rows, int32_t K, int32_t weights, phk_stream_t s) {
+  Prof prof_(FAM_GEMM_BF16, s, 0.0);
+  PHK_REQUIRE(x && out, PHK_E_ARG, "phk_split3: null pointer");
+  PHK_REQUIRE(rows >= 0 && K > 0 && ld >= K, PHK_E_ARG, "phk_split3: bad size");
+  PHK_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, PHK_E_ARG, "phk_split3: output must be 16-byte aligned");
+  if (rows == 0) return 0;
+  const int Kp = (K + 7) / 8 * 8;
+  const int64_t total = rows * (Kp / 4);
+  const int64_t want = (total + 255) / 256;
+  const unsigned blocks = (unsigned)(want < 148 * 16 ? want : 148 * 16);
+  PHK_CUDA(launch_pdl(split3_kernel, dim3(blocks), dim3(256), (size_t)0, to_stream(s), x, ld, (__nv_bfloat16*)out, rows, (int)K, Kp,
+                      (int)weights));
+  PHK_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int phk_token_embed(const int64_t* ids, const float* tok, const float* pos, float* out, int32_t b, int32_t n,
                                int32_t dim, int32_t vocab_rows, float alpha, int32_t replicas, phk_stream_t s) {
   Prof prof_(FAM_EMBED, s);

@@ -190,6 +190,7 @@ class CViViT(nn.Module):
         if self._tables is None or sig != self._sig:
             keep = Keep()
             h16 = self.precision == L.PREC_BF16
+            mode = self.precision  # which tensor-core weight copies the table carries (none in parity mode)
             t = L.CvivitT()
             t.dim, t.heads, t.dim_head, t.channels = self.dim, self.heads, self.dim_head, self.channels
             t.image_h, t.image_w = self.image_size
@@ -202,10 +203,10 @@ class CViViT(nn.Module):
             t.pr_ln1_g, t.pr_ln1_b, t.pr_w, t.pr_b = keep.t(r[1].weight), keep.t(r[1].bias), keep.t(r[2].weight), keep.t(r[2].bias)
             t.pr_ln2_g, t.pr_ln2_b = keep.t(r[3].weight), keep.t(r[3].bias)
             t.spatial_bias = cpb_table(self.spatial_rel_pos_bias, keep)
-            t.spatial = transformer_table(self.enc_spatial_transformer, keep, h16)
-            t.temporal = transformer_table(self.enc_temporal_transformer, keep, h16)
-            if h16:
-                t.pf_w_h, t.pr_w_h = keep.h(f[2].weight), keep.h(r[2].weight)
+            t.spatial = transformer_table(self.enc_spatial_transformer, keep, mode)
+            t.temporal = transformer_table(self.enc_temporal_transformer, keep, mode)
+            if mode:
+                t.pf_w_h, t.pr_w_h = keep.w16(f[2].weight, mode), keep.w16(r[2].weight, mode)
             if self.lookup_free_quantization:
                 t.vq_w, t.vq_b = keep.t(self.vq.project_in.weight), keep.t(self.vq.project_in.bias)
             else:  # cosine-sim codebook (unit rows)
@@ -220,7 +221,7 @@ class CViViT(nn.Module):
         sig = (weights_signature(self), self.precision)
         if self._dec_tables is None or sig != self._dec_sig:
             keep = Keep()
-            h16 = self.precision == L.PREC_BF16
+            mode = self.precision
             t = L.CvivitDecT()
             t.dim, t.heads, t.dim_head, t.channels = self.dim, self.heads, self.dim_head, self.channels
             t.image_h, t.image_w = self.image_size
@@ -231,13 +232,13 @@ class CViViT(nn.Module):
                 t.vq_out_w, t.vq_out_b = keep.t(self.vq.project_out.weight), keep.t(self.vq.project_out.bias)
             # (cosine-sim codebook: decode_from_codebook_indices gathers the codes and decodes float tokens)
             t.spatial_bias = cpb_table(self.spatial_rel_pos_bias, keep)
-            t.temporal = transformer_table(self.dec_temporal_transformer, keep, h16)
-            t.spatial = transformer_table(self.dec_spatial_transformer, keep, h16)
+            t.temporal = transformer_table(self.dec_temporal_transformer, keep, mode)
+            t.spatial = transformer_table(self.dec_spatial_transformer, keep, mode)
             f, r = self.to_pixels_first_frame[0], self.to_pixels[0]
             t.px_first_w, t.px_first_b = keep.t(f.weight), keep.t(f.bias)
             t.px_w, t.px_b = keep.t(r.weight), keep.t(r.bias)
-            if h16:
-                t.px_first_w_h, t.px_w_h = keep.h(f.weight), keep.h(r.weight)
+            if mode:
+                t.px_first_w_h, t.px_w_h = keep.w16(f.weight, mode), keep.w16(r.weight, mode)
             self._dec_tables, self._dec_sig = (t, keep), sig
         return self._dec_tables[0]
 

@@ -146,6 +146,32 @@ class Keep:
         self.refs.append(t)
         return t.data_ptr()
 
+    def h3(self, tensor):
+        """[hi | lo | hi] split-bf16 pack of a weight (PHK_PREC_BF16X3)."""
+        if not tensor.is_cuda:
+            raise L.PhkError("module parameters must be on a CUDA device (no CPU path): call .cuda() first")
+        t = split3_weight(tensor)
+        self.refs.append(t)
+        return t.data_ptr()
+
+    def w16(self, tensor, mode):
+        """Tensor-core copy of a weight for precision mode `mode` (None in parity mode)."""
+        return self.h(tensor) if mode == L.PREC_BF16 else self.h3(tensor) if mode == L.PREC_BF16X3 else None
+
+
+def split3_weight(w):
+    """PHK_PREC_BF16X3 weight pack: [N, K] fp32 -> bf16 [N, 3 * Kp] = [hi | lo | hi] with hi = bf16(w), lo = bf16(w - hi),
+    Kp = K rounded up to 8 (zero padding); the activation side is split [hi | hi | lo] by phk_split3, so ONE bf16 GEMM over
+    K' = 3 Kp computes a_hi w_hi + a_hi w_lo + a_lo w_hi (include/phk.h)."""
+    w = w.detach().float()
+    n, k = w.shape
+    kp = (k + 7) // 8 * 8
+    hi = w.to(torch.bfloat16)
+    lo = (w - hi.float()).to(torch.bfloat16)
+    out = torch.zeros((n, 3 * kp), dtype=torch.bfloat16, device=w.device)
+    out[:, :k], out[:, kp:kp + k], out[:, 2 * kp:2 * kp + k] = hi, lo, hi
+    return out
+
 
 def pack_geglu_w1(w1, inner, inner_pad):
     """[2*inner, dim] -> [2*inner_pad, dim] bf16 with rows grouped as [64 value rows | 64 gate rows] per
@@ -167,10 +193,12 @@ def pack_w2(w2, inner, inner_pad):
     return out
 
 
-def attn_table(a: Attention, keep: Keep, bf16=False):
+def attn_table(a: Attention, keep: Keep, mode=0):
+    """mode: L.PREC_* -- which tensor-core weight copies (`*_h`) the table carries (bool accepted: True = PREC_BF16)."""
     t = L.AttnT()
-    if bf16:
-        t.wq_h, t.wkv_h, t.wo_h = keep.h(a.to_q.weight), keep.h(a.to_kv.weight), keep.h(a.to_out.weight)
+    mode = int(mode)
+    if mode:
+        t.wq_h, t.wkv_h, t.wo_h = keep.w16(a.to_q.weight, mode), keep.w16(a.to_kv.weight, mode), keep.w16(a.to_out.weight, mode)
     t.norm_g, t.norm_b = keep.t(a.norm.gamma), keep.t(a.norm.beta)
     if isinstance(a.context_norm, LayerNorm):
         t.ctx_g, t.ctx_b = keep.t(a.context_norm.gamma), keep.t(a.context_norm.beta)
@@ -181,7 +209,9 @@ def attn_table(a: Attention, keep: Keep, bf16=False):
     return t
 
 
-def transformer_table(tf: Transformer, keep: Keep, bf16=False):
+def transformer_table(tf: Transformer, keep: Keep, mode=0):
+    mode = int(mode)
+    bf16 = mode == L.PREC_BF16
     layers = (L.LayerT * tf.depth)()
     for i, (peg, self_attn, cross, ff) in enumerate(tf.layers):
         ly = layers[i]
@@ -190,9 +220,9 @@ def transformer_table(tf: Transformer, keep: Keep, bf16=False):
             d = peg.dsconv.weight.shape[0]
             w = peg.dsconv.weight.detach().reshape(d, 27).t().contiguous()  # tap-major [27, dim]
             ly.peg.w, ly.peg.b, ly.peg.causal = keep.t(w), keep.t(peg.dsconv.bias), int(peg.causal)
-        ly.self_attn = attn_table(self_attn, keep, bf16)
+        ly.self_attn = attn_table(self_attn, keep, mode)
         if cross is not None:
-            ly.cross_attn = attn_table(cross, keep, bf16)
+            ly.cross_attn = attn_table(cross, keep, mode)
         ly.ff.ln_g, ly.ff.ln_b = keep.t(ff[0].weight), keep.t(ff[0].bias)
         ly.ff.w1, ly.ff.w2 = keep.t(ff[1].weight), keep.t(ff[4].weight)
         ly.ff.inner = ff[4].weight.shape[1]
@@ -202,6 +232,8 @@ def transformer_table(tf: Transformer, keep: Keep, bf16=False):
             w2h = pack_w2(ff[4].weight, ly.ff.inner, ly.ff.inner_pad)
             keep.refs += [w1h, w2h]
             ly.ff.w1_h, ly.ff.w2_h = w1h.data_ptr(), w2h.data_ptr()
+        elif mode == L.PREC_BF16X3:  # plain row order (GEGLU stays a separate fp32 kernel), split operands
+            ly.ff.w1_h, ly.ff.w2_h = keep.h3(ff[1].weight), keep.h3(ff[4].weight)
     keep.obj(layers)
     t = L.TransformerT()
     t.dim, t.heads, t.dim_head, t.depth, t.causal = tf.dim, tf.heads, tf.dim_head, tf.depth, int(tf.causal)

@@ -101,11 +101,11 @@ class _TokenTransformer(nn.Module):
             if not self.is_critic:
                 t.pos_bias = cpb_table(self.continuous_pos_bias, keep)
                 t.head_w, t.head_b = keep.t(self.to_logits.weight), keep.t(self.to_logits.bias)
-                if h16:
-                    t.head_w_h = keep.h(self.to_logits.weight)
+                if self.precision:
+                    t.head_w_h = keep.w16(self.to_logits.weight, self.precision)
             else:
                 t.head_w, t.head_b = keep.t(self.to_logits[0].weight), keep.t(self.to_logits[0].bias)
-            t.transformer = transformer_table(tf, keep, h16)
+            t.transformer = transformer_table(tf, keep, self.precision)
             self._tables, self._sig = (t, keep), sig
             self._bias_cache = {}
         return self._tables[0]
@@ -137,7 +137,7 @@ class _TokenTransformer(nn.Module):
         table = self._table()
         inner2 = 2 * tf.heads * tf.dim_head
         out = torch.empty((tf.depth, b * l, inner2), dtype=torch.float32, device=context.device)
-        scratch = torch.empty((b * l, dc), dtype=torch.float32, device=context.device)
+        scratch = torch.empty((b * l, 3 * dc), dtype=torch.float32, device=context.device)  # (+ the split-bf16 operands)
         L.check(lib.phk_maskgit_context_kv(C.byref(table), L.ptr(context), b, l, L.ptr(out), L.ptr(scratch),
                                            self.precision, L.stream_ptr()), "phk_maskgit_context_kv")
         return out
@@ -269,13 +269,14 @@ class _TokenTransformer(nn.Module):
             if keep_logits and not bce:
                 logits = torch.empty((b, n, table.num_tokens), dtype=torch.float32, device=dev)
             loss = torch.zeros((), dtype=torch.float32, device=dev)
-            nbytes = lib.phk_maskgit_train_workspace_bytes(C.byref(table), b, n, ctx_len, int(bce), self.precision)
+            prec = L.PREC_BF16 if self.precision == L.PREC_BF16 else L.PREC_F32  # (split-bf16 is an inference mode)
+            nbytes = lib.phk_maskgit_train_workspace_bytes(C.byref(table), b, n, ctx_len, int(bce), prec)
             ws = self._ws.get(nbytes, dev)
             pt, ph, pw = (int(v) for v in patch_shape)
             L.check(lib.phk_maskgit_train_step(C.byref(table), C.byref(gtable), L.ptr(ids_in), L.ptr(targets),
                                                L.ptr(token_mask), L.ptr(labels), b, n, pt, ph, pw, L.ptr(context),
                                                ctx_len, L.ptr(text_mask), L.ptr(video_mask), float(loss_scale),
-                                               L.ptr(loss), L.ptr(logits), L.ptr(ws), ws.numel(), self.precision,
+                                               L.ptr(loss), L.ptr(logits), L.ptr(ws), ws.numel(), prec,
                                                L.stream_ptr()),
                     "phk_maskgit_train_step")
         return loss, gk, logits

@@ -95,6 +95,13 @@ def route_product_to_emulator(lib, patch=_Setter):
         return t.data_ptr()
 
     patch.setattr(M.Keep, "h", keep_h)
+
+    def keep_h3(self, tensor):
+        t = M.split3_weight(tensor)
+        self.refs.append(t)
+        return t.data_ptr()
+
+    patch.setattr(M.Keep, "h3", keep_h3)
     def poisoned_workspace(self, nbytes, device):
         # fresh host pages are zero and would hide a kernel that reads scratch it never wrote: hand out 0xFF bytes
         # (fp32 NaN, int64 -1) on every call instead
