@@ -394,6 +394,97 @@ def bench_maskgit(dev, prec, world, barrier, sampler, samples_timed=6):
     return out
 
 
+def bench_train(dev, prec, world, barrier, sampler, steps_timed=5):
+    """BASELINE configs[3]: Phenaki.forward + backward (C-ViViT tokenises the raw videos, MaskGit masked-token
+    cross entropy, hand-written backward kernels), 4 videos of (3,17,256,256) per GPU, data parallel: the flat fp32
+    gradient bucket is averaged over the ranks by ONE NCCL all-reduce per step (what the reference gets from DDP)."""
+    import torch
+    import torch.distributed as dist
+    import phenaki_pytorch_b200 as P
+    from phenaki_pytorch_b200 import sharding as S
+    torch.manual_seed(2)
+    cv = P.CViViT(**CFG2).to(dev)
+    mg = P.MaskGit(**CFG3).to(dev)
+    cv.precision = mg.precision = prec
+    ph = P.Phenaki(cvivit=cv, maskgit=mg, steps=CFG3_RUN["steps"], text_embed_dim=768).to(dev).train()
+    ph.cvivit.precision = prec
+    b = 4
+    videos = torch.randn((b, 3, 17, 256, 256), device=dev)
+    ctx = torch.randn((b, CFG3_RUN["ctx_len"], 768), device=dev)
+
+    def step():
+        for p_ in mg.parameters():
+            p_.grad = None
+        loss = ph(videos, text_embeds=ctx)
+        loss.backward()   # hands out the gradients the C call computed; averages the bucket over the ranks (NCCL)
+        return loss
+
+    for _ in range(2):
+        loss = step()
+    ms_total, window, loss = _timed(step, steps_timed, barrier)
+    ms = S.max_over_ranks(ms_total, dev) / steps_timed
+    nparams = sum(p_.numel() for p_ in mg.parameters())
+    out = dict(metric="phenaki_train_tokens_per_s", value=world * b * 576 / ms * 1e3, unit="tokens/s", ms_per_step=ms,
+               videos_per_s=world * b / ms * 1e3, steps_timed=steps_timed, loss=float(loss), n_gpus=world,
+               config=dict(workload="BASELINE.json configs[3]: Phenaki forward+backward (C-ViViT encode of the raw videos, "
+                                    f"MaskGit(dim=512,depth=6,V=65536) masked CE), {b} x (3,17,256,256) per GPU, bf16 products",
+                           global_batch=b * world, parallelism=f"dp{world}: one flat fp32 gradient bucket, one NCCL all-reduce per step"),
+               approx_tflops=3 * MASKGIT_FWD_GFLOP * b / 4 / ms,
+               maskgit_parameters=nparams, peak_mem_gb=torch.cuda.max_memory_allocated(dev) / 2 ** 30,
+               clocks=sampler.report(window) if sampler is not None else None)
+    if world > 1:  # the collective alone: bus bandwidth of the bucket all-reduce
+        flat = torch.zeros(nparams, dtype=torch.float32, device=dev)
+        for _ in range(2):
+            dist.all_reduce(flat)
+        ar_ms, _, _ = _timed(lambda: dist.all_reduce(flat), 5, barrier)
+        ar_ms = S.max_over_ranks(ar_ms, dev) / 5
+        out["all_reduce"] = dict(bytes=nparams * 4, ms=ar_ms, algbw_gbs=nparams * 4 / ar_ms / 1e6,
+                                 busbw_gbs=nparams * 4 / ar_ms / 1e6 * 2 * (world - 1) / world,
+                                 share_of_step=ar_ms / ms)
+    return out
+
+
+def bench_make_video(dev, prec, world, barrier, sampler, chains_timed=2, b=2):
+    """BASELINE configs[4]: Phenaki.sample with a TokenCritic and cond_scale 5, sliding-window scene chain of
+    3 scenes x (17, 14, 14) frames primed with the last 5 frames of the previous scene (make_video,
+    phenaki_pytorch.py:692-714), `b` prompts per GPU (batch-sharded over the GPUs, no collective)."""
+    import torch
+    import phenaki_pytorch_b200 as P
+    from phenaki_pytorch_b200 import sharding as S
+    torch.manual_seed(3)
+    cv = P.CViViT(**CFG2).to(dev)
+    mg = P.MaskGit(**CFG3).to(dev)
+    cr = P.TokenCritic(dim=512, num_tokens=65536, max_seq_len=1024, has_cross_attn=True, depth=6, dim_context=768).to(dev)
+    cv.precision = mg.precision = cr.precision = prec
+    ph = P.Phenaki(cvivit=cv, maskgit=mg, critic=cr, steps=CFG3_RUN["steps"], text_embed_dim=768)
+    ph.cvivit.precision = prec
+    frames, prime = (17, 14, 14), 5
+    embeds = [torch.randn((b, CFG3_RUN["ctx_len"], 768), device=dev) for _ in frames]
+
+    def chain():
+        scenes, pf = [], None
+        for nf, e in zip(frames, embeds):
+            video = ph.sample(text_embeds=e, prime_frames=pf, num_frames=nf, cond_scale=5.0)
+            scenes.append(video)
+            pf = video[:, :, -prime:].contiguous()
+        return torch.cat(scenes, dim=2)
+
+    video = chain()
+    assert tuple(video.shape) == (b, 3, sum(frames), 256, 256) and bool(torch.isfinite(video).all())
+    ms_total, window, _ = _timed(chain, chains_timed, barrier)
+    ms = S.max_over_ranks(ms_total, dev) / chains_timed
+    new_tokens = sum(cv.num_tokens_per_frames(nf, include_first_frame=(i == 0)) for i, nf in enumerate(frames))
+    return dict(metric="make_video_tokens_per_s", value=world * b * new_tokens * CFG3_RUN["steps"] / ms * 1e3, unit="tokens/s",
+                ms_per_chain=ms, videos_per_s=world * b / ms * 1e3, frames_per_s=world * b * sum(frames) / ms * 1e3,
+                chains_timed=chains_timed, n_gpus=world,
+                config=dict(workload=f"BASELINE.json configs[4]: 3-scene chain x {frames} frames, prime {prime}, TokenCritic "
+                                     f"(cross-attn, depth 6), cond_scale 5, 18 steps per scene, {b} prompts per GPU; each "
+                                     "scene = tokenise prime frames + demasking loop (MaskGit + critic CFG pairs) + C-ViViT decode",
+                            prompts_per_gpu=b, global_prompts=b * world, new_tokens_per_video=new_tokens,
+                            parallelism=f"dp{world}: prompts batch-sharded, no data-path collective"),
+                clocks=sampler.report(window) if sampler is not None else None)
+
+
 def reference_gpu_leg(dev, maskgit=True):
     """the reference's own PyTorch path on this B200 (oracle port on CUDA, eager fp32 and autocast
     bf16) -- the same-box bar the build must beat."""
@@ -415,6 +506,8 @@ def main():
     ap.add_argument("--no-maskgit", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-refgpu", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the configs[3] training-step block")
+    ap.add_argument("--no-makevideo", action="store_true", help="skip the configs[4] make_video block")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -616,6 +709,32 @@ def main():
                                                                    "ms_per_decode_step")}}
         except Exception as ex:  # the headline line must still print
             out["maskgit"] = {"error": repr(ex)}
+    # BASELINE configs[3] / configs[4] ("next" rows of SURVEY 8f): every rank takes part (the training step all-reduces).
+    # The headline above is complete at this point: a watchdog thread prints it if one of these blocks ever hangs
+    # (a rank-asymmetric failure inside a collective), so the extras can never cost the line.
+    printed = threading.Event()
+
+    def emit():
+        if rank == 0 and not printed.is_set():
+            printed.set()
+            print(json.dumps(out), flush=True)
+
+    def watchdog(deadline_s=420.0):
+        if not printed.wait(deadline_s):
+            out.setdefault("extras_watchdog", f"a block after the headline did not finish within {deadline_s:.0f} s")
+            emit()
+            os._exit(0)
+
+    threading.Thread(target=watchdog, daemon=True).start()
+    if prec == L.PREC_BF16:
+        for key, fn, skip in (("train_step", bench_train, args.no_train), ("make_video", bench_make_video, args.no_makevideo)):
+            if skip:
+                continue
+            try:
+                torch.cuda.empty_cache()
+                out[key] = fn(dev, prec, world, barrier, sampler if rank == 0 else None)
+            except Exception as ex:
+                out[key] = {"error": repr(ex)}
     if rank == 0 and world == 1 and not args.no_refgpu:
         try:
             out["reference_gpu"] = reference_gpu_leg(dev, maskgit=not args.no_maskgit)
@@ -627,7 +746,8 @@ def main():
             out["reference_gpu"] = {"error": repr(ex)}
     if rank == 0:
         sampler.stop()
-        print(json.dumps(out))
+    emit()
+    printed.set()
     if world > 1:
         dist.destroy_process_group()
 

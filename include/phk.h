@@ -205,6 +205,14 @@ int phk_gemm_bf16_qkv(const void* xn, const void* xraw, int64_t lda, const void*
                       void* Qn, void* KVn, int64_t M, int32_t I, int32_t K, const float* q_scale, const float* k_scale,
                       float sim_scale, phk_stream_t s);
 
+/* x = A W^T (+bias) + x IN PLACE (C is the fp32 residual stream, nn.Linear + residual of attention.py:322-330) and, from
+ * the same epilogue, the LayerNorm the NEXT sub-block applies to x: ln_out[M, ln_ld] = bf16(LayerNorm(x) * ln_g + ln_b)
+ * (ln_b may be NULL), raw_out (optional) = bf16(x).  N = row width in {128, 256, 512, 1024}: the N / 128 CTAs of a
+ * 128-row tile form a cluster and sum their row statistics through distributed shared memory. */
+int phk_gemm_bf16_ln(const void* A, int64_t lda, const void* W, int64_t ldw, float* C, int64_t ldc, int64_t M, int32_t N,
+                     int32_t K, const float* bias, const float* ln_g, const float* ln_b, float ln_eps, void* ln_out,
+                     void* raw_out, int64_t ln_ld, phk_stream_t s);
+
 /* PHK_PREC_BF16X3 operand split: x fp32 [rows, ld] (K valid columns) -> bf16 [rows, 3 * Kp], Kp = K rounded up to 8:
  * [hi | hi | lo] (weights == 0: the activation side) or [hi | lo | hi] (weights != 0), hi = bf16(x), lo = bf16(x - hi),
  * zero in the padding columns.  With both sides split this way a plain bf16 GEMM over K' = 3 Kp computes
@@ -463,6 +471,13 @@ int phk_sample_tail(const float* x_cond, const float* x_null, const float* gamma
                     int32_t dim, float temperature, uint64_t seed, uint64_t offset, const uint64_t* rng_state,
                     const uint8_t* mask, int64_t* ids, int64_t* pred_out, float* score_out, void* scratch,
                     int64_t scratch_bytes, phk_stream_t s);
+/* The same when the residual stream carries a prime prefix: the row of sampled token t of sequence i is
+ * i * src_stride + src_off + t (src_stride = prime_len + n, src_off = prime_len; phenaki_pytorch.py:493, 503-504). */
+int phk_sample_tail_rows(const float* x_cond, const float* x_null, const float* gamma, const float* beta, float cond_scale,
+                         const void* head_w, int64_t ldw, const float* head_b, int32_t b, int32_t n, int32_t k, int32_t V,
+                         int32_t dim, float temperature, uint64_t seed, uint64_t offset, const uint64_t* rng_state,
+                         const uint8_t* mask, int64_t* ids, int64_t* pred_out, float* score_out, int32_t src_stride,
+                         int32_t src_off, void* scratch, int64_t scratch_bytes, phk_stream_t s);
 
 /* One demasking iteration's network half for the sampling loop (phenaki_pytorch.py:495-509, 547-550): MaskGit forward
  * of the CFG pair (as phk_maskgit_forward with cfg_pair=1) + phk_head_sample.  bf16 weights required, cond_scale != 1,
@@ -477,6 +492,15 @@ int phk_maskgit_sample_step(const phk_maskgit_t* m, const int64_t* ids_in, int32
                             uint64_t seed, uint64_t offset, const uint8_t* mask, int64_t* ids, int64_t* pred_out,
                             float* score_out, int32_t masked_per_seq, void* workspace, int64_t workspace_bytes,
                             phk_stream_t s);
+/* With a prime prefix (Phenaki.sample(prime_frames=...), the scene chains of make_video): ids_in (b, n) = prime ids
+ * followed by the tokens being sampled, n = prime_len + sampled tokens; mask / ids / pred_out / score_out
+ * (b, n - prime_len) cover the sampled tokens; masked_per_seq > 0 is required (the head runs on the masked rows only). */
+int phk_maskgit_sample_step_primed(const phk_maskgit_t* m, const int64_t* ids_in, int32_t b, int32_t n, int32_t pt,
+                                   int32_t ph, int32_t pw, const float* ctx_kv, int32_t L, const uint8_t* text_mask,
+                                   const float* pos_bias, float cond_scale, float temperature, uint64_t seed,
+                                   uint64_t offset, const uint8_t* mask, int64_t* ids, int64_t* pred_out, float* score_out,
+                                   int32_t masked_per_seq, int32_t prime_len, void* workspace, int64_t workspace_bytes,
+                                   phk_stream_t s);
 
 /* rng_state[1] += stride on the stream (device-resident noise key, see phk_head_sample_rng) */
 int phk_rng_advance(uint64_t* rng_state, uint64_t stride, phk_stream_t s);

@@ -108,6 +108,7 @@ PROTOTYPES = {
     "phk_attention_tc": [vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, vp, i64, vp],
     "phk_attention_tc_bf16": [vp, i64, vp, i64, vp, vp, i32, i32, i32, vp],
     "phk_attention_small_bf16": [vp, vp, vp, vp, C.POINTER(AttnGeomT), vp],
+    "phk_gemm_bf16_ln": [vp, i64, vp, i64, vp, i64, i64, i32, i32, vp, vp, vp, f32, vp, vp, i64, vp],
     "phk_split3": [vp, i64, vp, i64, i32, i32, vp],
     "phk_gemm_bf16_qkv": [vp, vp, i64, vp, vp, i64, vp, vp, i64, i32, i32, vp, vp, f32, vp],
     "phk_peg3d": [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
@@ -140,6 +141,10 @@ PROTOTYPES = {
     "phk_maskgit_sample_step": [C.POINTER(MaskgitT), vp, i32, i32, i32, i32, i32, vp, i32, vp, vp, vp, f32, f32, u64,
                                 u64, vp, vp, vp, vp, i32, vp, i64, vp],
     "phk_sample_tail_scratch_bytes": [i32, i32, i32],
+    "phk_sample_tail_rows": [vp, vp, vp, vp, f32, vp, i64, vp, i32, i32, i32, i32, i32, f32, u64, u64, vp, vp, vp, vp, vp, i32,
+                             i32, vp, i64, vp],
+    "phk_maskgit_sample_step_primed": [C.POINTER(MaskgitT), vp, i32, i32, i32, i32, i32, vp, i32, vp, vp, f32, f32, u64, u64,
+                                       vp, vp, vp, vp, i32, i32, vp, i64, vp],
     "phk_sample_tail": [vp, vp, vp, vp, f32, vp, i64, vp, i32, i32, i32, i32, i32, f32, u64, u64, vp, vp, vp, vp, vp, vp,
                         i64, vp],
     "phk_head_sample_rng": [vp, i64, i64, vp, i64, vp, i32, i32, i32, f32, u64, u64, vp, vp, vp, vp, vp, vp, i64, vp],

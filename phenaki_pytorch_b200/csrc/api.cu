@@ -148,6 +148,12 @@ static int transformer_forward(const TfCall& c, Arena scratch, float* out, void*
   float* x = c.x;
   float* x_alt = c.x_alt;
 
+  // bf16 mode: the LayerNorm that follows a residual GEMM (out-projection -> cross-attention / feed-forward norm,
+  // feed-forward -> the next layer's attention norm when no PEG sits in between) is computed by that GEMM's epilogue
+  // (phk_gemm_bf16_ln: cluster-wide row statistics) instead of a separate pass over the residual stream
+  static const bool fuse_ln_env = [] { const char* e = std::getenv("PHK_FUSE_LN"); return !(e && e[0] == '0'); }();
+  const bool fuse_ln = fuse_ln_env && h16 && (D == 128 || D == 256 || D == 512 || D == 1024);
+  bool ln_ready = false;  // xn (+ xraw) already hold this layer's self-attention LayerNorm (written by the previous FF2)
   for (int l = 0; l < T->depth; ++l) {
     const phk_layer_t& L = T->layers[l];
     // first layer of a CFG pair with identical halves: PEG + self-attention on the first half only
@@ -155,6 +161,7 @@ static int transformer_forward(const TfCall& c, Arena scratch, float* out, void*
     const int64_t Rl = dup ? R / 2 : R;
     const int n_outer = dup ? c.seq.n_outer / 2 : c.seq.n_outer;
     const int pegB = dup ? c.pegB / 2 : c.pegB;
+    bool norm_done = false;  // xn already holds the LayerNorm the next sub-block needs (written by a GEMM epilogue)
     if (L.has_peg) {  // x = peg(x) + x
       PHK_REQUIRE((int64_t)pegB * c.pegT * c.pegH * c.pegW == Rl, PHK_E_SHAPE, "PEG: video shape does not cover the tokens");
       PHK_TRY(phk_peg3d(x, L.peg.w, L.peg.b, x_alt, pegB, c.pegT, c.pegH, c.pegW, D, L.peg.causal, c.peg_layout, s));
@@ -162,7 +169,8 @@ static int transformer_forward(const TfCall& c, Arena scratch, float* out, void*
     }
     {  // x = self_attn(x) + x ; q from LN(x), k/v from RAW x (attention.py:140-144)
       const phk_attn_t& A = L.self_attn;
-      PHK_TRY(phk_layernorm(x, A.norm_g, A.norm_b, xn, xraw, Rl, D, h16, 0, 0, 0, s));
+      if (!ln_ready) PHK_TRY(phk_layernorm(x, A.norm_g, A.norm_b, xn, xraw, Rl, D, h16, 0, 0, 0, s));
+      ln_ready = false;
       phk_attn_geom_t g;
       std::memset(&g, 0, sizeof(g));
       g.n_outer = n_outer; g.n_inner = c.seq.n_inner; g.n_q = c.seq.n_tok; g.n_k = c.seq.n_tok;
@@ -202,14 +210,25 @@ static int transformer_forward(const TfCall& c, Arena scratch, float* out, void*
           PHK_TRY(phk_attention(q, kv, A.null_kv, A.q_scale, A.k_scale, c.attn_bias, c.self_mask, T->alibi_slopes, o, &g, s));
         }
       }
-      PHK_TRY(linear(c.lin, o, I, A.wo, A.wo_h, I, x, D, Rl, D, I, nullptr, x, s));
+      if (fuse_ln && A.wo_h) {  // x += o Wo^T and the next sub-block's LayerNorm of the new x in one kernel
+        const bool to_cross = L.has_cross && c.ctx_kv;
+        const float* ng = to_cross ? L.cross_attn.norm_g : L.ff.ln_g;
+        const float* nb = to_cross ? L.cross_attn.norm_b : L.ff.ln_b;
+        PHK_TRY(phk_gemm_bf16_ln(o, I, A.wo_h, I, x, D, Rl, D, I, nullptr, ng, nb, 1e-5f, xn, nullptr, D, s));
+        norm_done = true;
+      } else {
+        PHK_TRY(linear(c.lin, o, I, A.wo, A.wo_h, I, x, D, Rl, D, I, nullptr, x, s));
+      }
     }
-    if (dup)  // the null half continues from the same rows
+    if (dup) {  // the null half continues from the same rows
       PHK_CUDA(cudaMemcpyAsync(x + Rl * D, x, Rl * D * 4, cudaMemcpyDeviceToDevice, st));
+      if (norm_done) PHK_CUDA(cudaMemcpyAsync((char*)xn + Rl * D * 2, xn, Rl * D * 2, cudaMemcpyDeviceToDevice, st));
+    }
     if (L.has_cross && c.ctx_kv) {  // x = cross_attn(x, context) + x   (attention.py:327-328)
       const phk_attn_t& A = L.cross_attn;
       PHK_REQUIRE(c.seq.n_inner == 1, PHK_E_UNSUPPORTED, "cross attention needs (b, n) sequences");
-      PHK_TRY(phk_layernorm(x, A.norm_g, A.norm_b, xn, nullptr, R, D, h16, 0, 0, 0, s));
+      if (!norm_done) PHK_TRY(phk_layernorm(x, A.norm_g, A.norm_b, xn, nullptr, R, D, h16, 0, 0, 0, s));
+      norm_done = false;
       PHK_TRY(linear(c.lin, xn, D, A.wq, A.wq_h, D, q, I, R, I, D, nullptr, nullptr, s));
       phk_attn_geom_t g;
       std::memset(&g, 0, sizeof(g));
@@ -222,17 +241,31 @@ static int transformer_forward(const TfCall& c, Arena scratch, float* out, void*
       g.out_bf16 = h16; g.scale = 8.f;
       const float* kvl = c.ctx_kv + (int64_t)l * c.ctx_b * c.ctx_L * 2 * I;
       PHK_TRY(phk_attention(q, kvl, A.null_kv, A.q_scale, A.k_scale, nullptr, c.ctx_mask, nullptr, o, &g, s));
-      PHK_TRY(linear(c.lin, o, I, A.wo, A.wo_h, I, x, D, R, D, I, nullptr, x, s));
+      if (fuse_ln && A.wo_h) {
+        PHK_TRY(phk_gemm_bf16_ln(o, I, A.wo_h, I, x, D, R, D, I, nullptr, L.ff.ln_g, L.ff.ln_b, 1e-5f, xn, nullptr, D, s));
+        norm_done = true;
+      } else {
+        PHK_TRY(linear(c.lin, o, I, A.wo, A.wo_h, I, x, D, R, D, I, nullptr, x, s));
+      }
     }
     {  // x = ff(x) + x  (attention.py:45-53, 330)
       const phk_ff_t& Fw = L.ff;
-      PHK_TRY(phk_layernorm(x, Fw.ln_g, Fw.ln_b, xn, nullptr, R, D, h16, 0, 0, 0, s));
+      if (!norm_done) PHK_TRY(phk_layernorm(x, Fw.ln_g, Fw.ln_b, xn, nullptr, R, D, h16, 0, 0, 0, s));
+      norm_done = false;
       if (h16) {
         PHK_REQUIRE(Fw.w1_h && Fw.w2_h && Fw.inner_pad % 64 == 0 && Fw.inner_pad >= Fw.inner, PHK_E_ARG,
                     "bf16 mode needs the packed feed-forward weights");
         // first linear + GEGLU in one kernel (value/gate rows interleaved per 64), bf16 [R, inner_pad] out
         PHK_TRY(phk_gemm_bf16(xn, D, Fw.w1_h, D, gbuf, Fw.inner_pad, R, 2 * Fw.inner_pad, D, nullptr, nullptr, 0, 0, 0, 2, s));
-        PHK_TRY(phk_gemm_bf16(gbuf, Fw.inner_pad, Fw.w2_h, Fw.inner_pad, x, D, R, D, Fw.inner_pad, nullptr, x, 0, 0, 0, 0, s));
+        const bool next_plain = l + 1 < T->depth && !T->layers[l + 1].has_peg;
+        if (fuse_ln && next_plain) {  // ... + the next layer's attention LayerNorm and its raw bf16 rows
+          const phk_attn_t& NA = T->layers[l + 1].self_attn;
+          PHK_TRY(phk_gemm_bf16_ln(gbuf, Fw.inner_pad, Fw.w2_h, Fw.inner_pad, x, D, R, D, Fw.inner_pad, nullptr, NA.norm_g,
+                                   NA.norm_b, 1e-5f, xn, xraw, D, s));
+          ln_ready = true;
+        } else {
+          PHK_TRY(phk_gemm_bf16(gbuf, Fw.inner_pad, Fw.w2_h, Fw.inner_pad, x, D, R, D, Fw.inner_pad, nullptr, x, 0, 0, 0, 0, s));
+        }
       } else {
         PHK_TRY(linear(c.lin, xn, D, Fw.w1, Fw.w1_h, D, hbuf, 2 * Fw.inner, R, 2 * Fw.inner, D, nullptr, nullptr, s));
         PHK_TRY(phk_geglu(hbuf, (float*)gbuf, R, Fw.inner, s));
@@ -866,10 +899,16 @@ static int sample_step_impl(const phk_maskgit_t* m, const int64_t* ids_in, int32
                             const uint8_t* text_mask, const uint8_t* video_mask, const float* pos_bias,
                             float cond_scale, float temperature, uint64_t seed, uint64_t offset, const uint64_t* rng_state,
                             const uint8_t* mask, int64_t* ids, int64_t* pred_out, float* score_out,
-                            int32_t masked_per_seq, void* workspace, int64_t workspace_bytes,
+                            int32_t masked_per_seq, int32_t prime_len, void* workspace, int64_t workspace_bytes,
                             phk_stream_t s) {
+  // n = prime_len + sampled tokens per sequence (phenaki_pytorch.py:493: the prime ids are prepended at every step);
+  // mask / ids / pred_out / score_out cover the sampled tokens only
   PHK_REQUIRE(m && ids_in && workspace, PHK_E_ARG, "maskgit_sample_step: null pointer");
-  PHK_REQUIRE(masked_per_seq >= 0 && masked_per_seq <= n, PHK_E_ARG, "maskgit_sample_step: masked_per_seq out of range");
+  PHK_REQUIRE(prime_len >= 0 && prime_len < n, PHK_E_ARG, "maskgit_sample_step: prime_len out of range");
+  const int32_t n_new = n - prime_len;
+  PHK_REQUIRE(masked_per_seq >= 0 && masked_per_seq <= n_new, PHK_E_ARG, "maskgit_sample_step: masked_per_seq out of range");
+  PHK_REQUIRE(prime_len == 0 || (mask && ids && masked_per_seq > 0), PHK_E_ARG,
+              "maskgit_sample_step: a primed step needs the mask, the ids and the masked-token count");
   PHK_REQUIRE(b > 0 && n > 0 && (int64_t)pt * ph * pw == n, PHK_E_SHAPE, "video patch shape must cover the token sequence");
   PHK_REQUIRE(n <= m->max_seq_len, PHK_E_SHAPE,
               "the video token sequence length is greater than max_seq_len (phenaki_pytorch.py:196)");
@@ -888,7 +927,7 @@ static int sample_step_impl(const phk_maskgit_t* m, const int64_t* ids_in, int32
   float* x_alt = (float*)ar.take(R * D * 4);
   // masked rows only (phk_sample_tail) when the caller vouches for the per-sequence count and it saves work
   static const bool compact_ok = [] { const char* e = std::getenv("PHK_HEAD_COMPACT"); return !(e && e[0] == '0'); }();
-  const bool compact = compact_ok && mask && ids && masked_per_seq > 0 && masked_per_seq < n;
+  const bool compact = (compact_ok || prime_len > 0) && mask && ids && masked_per_seq > 0 && masked_per_seq < n;
   const int64_t hb = compact ? phk_sample_tail_scratch_bytes(b, masked_per_seq, D) : phk_head_sample_scratch_bytes((int32_t)tokens);
   void* emb_h = compact ? nullptr : ar.take(tokens * D * 2);
   void* hsc = ar.take(hb);
@@ -915,9 +954,9 @@ static int sample_step_impl(const phk_maskgit_t* m, const int64_t* ids_in, int32
   c.x_final = &xf;  // the residual stream before norm_out: rows [0, tokens) conditional, [tokens, 2 tokens) null
   PHK_TRY(transformer_forward(c, ar, nullptr, nullptr, st));
   if (compact)
-    return phk_sample_tail(xf, xf + tokens * D, T->out_g, T->out_b, cond_scale, m->head_w_h, D, m->head_b, b, n,
-                           masked_per_seq, m->num_tokens, D, temperature, seed, offset, rng_state, mask, ids, pred_out,
-                           score_out, hsc, hb, s);
+    return phk_sample_tail_rows(xf, xf + tokens * D, T->out_g, T->out_b, cond_scale, m->head_w_h, D, m->head_b, b, n_new,
+                                masked_per_seq, m->num_tokens, D, temperature, seed, offset, rng_state, mask, ids, pred_out,
+                                score_out, n, prime_len, hsc, hb, s);
   return phk_head_sample_rng(emb_h, D, tokens, m->head_w_h, D, m->head_b, (int32_t)tokens, m->num_tokens, D, temperature,
                              seed, offset, rng_state, mask, ids, pred_out, score_out, hsc, hb, s);
 }
@@ -930,7 +969,20 @@ extern "C" int phk_maskgit_sample_step(const phk_maskgit_t* m, const int64_t* id
                                        int32_t masked_per_seq, void* workspace, int64_t workspace_bytes,
                                        phk_stream_t s) {
   return sample_step_impl(m, ids_in, b, n, pt, ph, pw, ctx_kv, L, text_mask, video_mask, pos_bias, cond_scale, temperature,
-                          seed, offset, nullptr, mask, ids, pred_out, score_out, masked_per_seq, workspace, workspace_bytes, s);
+                          seed, offset, nullptr, mask, ids, pred_out, score_out, masked_per_seq, 0, workspace, workspace_bytes, s);
+}
+
+// The same with a prime prefix (Phenaki.sample(prime_frames=...), make_video's scene chains): ids_in (b, n) = prime ids
+// followed by the tokens being sampled; mask / ids / pred_out / score_out (b, n - prime_len) cover the sampled tokens.
+extern "C" int phk_maskgit_sample_step_primed(const phk_maskgit_t* m, const int64_t* ids_in, int32_t b, int32_t n, int32_t pt,
+                                              int32_t ph, int32_t pw, const float* ctx_kv, int32_t L,
+                                              const uint8_t* text_mask, const float* pos_bias, float cond_scale,
+                                              float temperature, uint64_t seed, uint64_t offset, const uint8_t* mask,
+                                              int64_t* ids, int64_t* pred_out, float* score_out, int32_t masked_per_seq,
+                                              int32_t prime_len, void* workspace, int64_t workspace_bytes, phk_stream_t s) {
+  return sample_step_impl(m, ids_in, b, n, pt, ph, pw, ctx_kv, L, text_mask, nullptr, pos_bias, cond_scale, temperature, seed,
+                          offset, nullptr, mask, ids, pred_out, score_out, masked_per_seq, prime_len, workspace,
+                          workspace_bytes, s);
 }
 
 // ---- one whole demasking iteration, optionally replayed as a CUDA graph ---------------------------------------------
@@ -944,7 +996,7 @@ static int demask_iteration_impl(const phk_maskgit_t* m, int64_t* ids, uint8_t* 
                                  phk_stream_t s) {
   if (k_remask > 0) PHK_TRY(phk_topk_mask(scores, b, n, k_remask, mask, ids, (int64_t)m->num_tokens, s));
   PHK_TRY(sample_step_impl(m, ids, b, n, pt, ph, pw, ctx_kv, L, text_mask, nullptr, pos_bias, cond_scale, temperature, 0, 0,
-                           rng_state, mask, ids, pred, scores, k_remask > 0 ? k_remask : n, workspace, workspace_bytes, s));
+                           rng_state, mask, ids, pred, scores, k_remask > 0 ? k_remask : n, 0, workspace, workspace_bytes, s));
   // counters of one V-wide draw, rounded up to a multiple of 4 (phenaki.py: _noise_stride)
   const uint64_t stride = ((uint64_t)b * (uint64_t)n * (uint64_t)((m->num_tokens + 3) / 4) + 1 + 3) / 4 * 4;
   return phk_rng_advance(rng_state, stride, s);

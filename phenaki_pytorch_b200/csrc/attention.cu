@@ -9,6 +9,7 @@
 // Sequences are addressed with (outer, inner, token) strides so neither the spatial
 // '(b t)(h w)' nor the temporal '(b h w) t' view is ever materialised (cvivit.py:458,468).
 #include "phk_common.cuh"
+#include <cstdlib>
 
 namespace phk {
 
@@ -724,6 +725,136 @@ __global__ void __launch_bounds__(256) attention_warp64_kernel(const void* __res
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Temporal attention on pre-normalised bf16 operands with warp-level tensor-core MMAs (mma.sync m16n8k16): one warp per
+// (sequence, head), n <= 16 tokens.  The shuffle kernel above spends ~2.8 k instructions per warp on 45 dot products
+// reduced across lanes; here S = Q K^T is 8 MMAs, P V another 8, and the softmax runs on the accumulator fragments
+// (rows live in lane quads).  Q / K / V rows (128 B each) are staged in shared memory with 16-byte loads (row stride
+// 144 B: conflict-free ldmatrix), rows >= n are zero.  [not compiled for the CPU executor: PHK_CUDA_EMU]
+// ------------------------------------------------------------------------------------------
+#ifndef PHK_CUDA_EMU
+constexpr int MMA_WARPS = 4, MMA_LD = 72;  // 4 x 3 x 16 x 144 B = 27 KB static shared memory  // bf16 elements per staged row (64 + 8 pad)
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* p) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* p) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(MMA_WARPS * 32) attention_small_mma_kernel(const __nv_bfloat16* __restrict__ q,
+                                                                            const __nv_bfloat16* __restrict__ kv,
+                                                                            const float* __restrict__ alibi_slopes,
+                                                                            __nv_bfloat16* __restrict__ out, phk_attn_geom_t g) {
+  pdl_prologue();
+  __shared__ __align__(16) __nv_bfloat16 sm[MMA_WARPS][3][16][MMA_LD];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t pair = (int64_t)blockIdx.x * MMA_WARPS + w;
+  const int64_t npairs = (int64_t)g.n_outer * g.n_inner * g.heads;
+  if (pair >= npairs) return;  // whole warp exits together (no block-wide barrier below)
+  const int h = (int)(pair % g.heads);
+  const int seq = (int)(pair / g.heads);
+  const int so = seq / g.n_inner, si = seq - so * g.n_inner;
+  const int n = g.n_q, I = g.heads * 64;
+  const __nv_bfloat16* qb = q + (int64_t)so * g.q_outer + (int64_t)si * g.q_inner + (int64_t)h * 64;
+  const __nv_bfloat16* kb = kv + (int64_t)so * g.k_outer + (int64_t)si * g.k_inner + (int64_t)h * 64;
+  __nv_bfloat16 (*sQ)[MMA_LD] = sm[w][0];
+  __nv_bfloat16 (*sK)[MMA_LD] = sm[w][1];
+  __nv_bfloat16 (*sV)[MMA_LD] = sm[w][2];
+  // stage: 3 operands x 16 rows x 8 chunks of 16 B = 384 chunks, 12 per lane; rows >= n are zero
+#pragma unroll
+  for (int it = 0; it < 12; ++it) {
+    const int idx = it * 32 + lane;
+    const int op = idx >> 7, row = (idx >> 3) & 15, ch = idx & 7;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (row < n) {
+      const __nv_bfloat16* src = op == 0 ? qb + (int64_t)row * g.q_tok : kb + (int64_t)row * g.k_tok + (op == 2 ? I : 0);
+      v = *reinterpret_cast<const uint4*>(src + ch * 8);
+    }
+    *reinterpret_cast<uint4*>(&sm[w][op][row][ch * 8]) = v;
+  }
+  __syncwarp();
+  const int gq = lane >> 2, t = lane & 3;
+  // S[16 x 16] = Q K^T: two key tiles of 8, four k-steps of 16 dims
+  float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    uint32_t a[4], b[4];
+    ldmatrix_x4(a, &sQ[(lane & 7) + 8 * ((lane >> 3) & 1)][ks * 16 + 8 * (lane >> 4)]);
+    ldmatrix_x4(b, &sK[(lane & 7) + 8 * (lane >> 4)][ks * 16 + 8 * ((lane >> 3) & 1)]);
+    mma_bf16_16816(s0, a, b[0], b[1]);  // keys 0..7
+    mma_bf16_16816(s1, a, b[2], b[3]);  // keys 8..15
+  }
+  // softmax over the 16 keys of rows gq (c0, c1) and gq + 8 (c2, c3); key of element e of tile tl: tl * 8 + 2 t + e
+  const float slope = (g.causal && alibi_slopes) ? alibi_slopes[h] : 0.f;
+  float p[2][4];  // [key tile][c0..c3]
+#pragma unroll
+  for (int tl = 0; tl < 2; ++tl)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int row = gq + 8 * (e >> 1), key = tl * 8 + 2 * t + (e & 1);
+      float v = tl == 0 ? s0[e] : s1[e];
+      if (g.causal) v += -fabsf((float)(key - row)) * slope;  // ALiBi (attention.py:214-227)
+      const bool ok = key < n && (!g.causal || key <= row);
+      p[tl][e] = ok ? v : -FLT_MAX;
+    }
+  float inv[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {  // r = 0: row gq, r = 1: row gq + 8
+    float m = fmaxf(fmaxf(p[0][2 * r], p[0][2 * r + 1]), fmaxf(p[1][2 * r], p[1][2 * r + 1]));
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+    float sum = 0.f;
+#pragma unroll
+    for (int tl = 0; tl < 2; ++tl)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const float v = p[tl][2 * r + e];
+        const float ex = v == -FLT_MAX ? 0.f : __expf(v - m);
+        p[tl][2 * r + e] = ex;
+        sum += ex;
+      }
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    inv[r] = sum > 0.f ? __fdividef(1.f, sum) : 0.f;  // (rows >= n: all keys masked, never stored)
+  }
+  // P as the A operand of P V (16 x 16, k = keys): the accumulator layout of S IS the A-fragment layout
+  uint32_t pa[4];
+  pa[0] = pack_bf16x2(p[0][0], p[0][1]);  // row gq,     keys 2t, 2t+1
+  pa[1] = pack_bf16x2(p[0][2], p[0][3]);  // row gq + 8, keys 2t, 2t+1
+  pa[2] = pack_bf16x2(p[1][0], p[1][1]);  // row gq,     keys 8 + 2t, ..
+  pa[3] = pack_bf16x2(p[1][2], p[1][3]);  // row gq + 8, keys 8 + 2t, ..
+  const int64_t ob = (int64_t)so * g.o_outer + (int64_t)si * g.o_inner + (int64_t)h * 64;
+#pragma unroll
+  for (int dp = 0; dp < 4; ++dp) {  // two 8-dim tiles per ldmatrix.x4.trans
+    uint32_t b[4];
+    ldmatrix_x4_trans(b, &sV[(lane & 7) + 8 * ((lane >> 3) & 1)][(2 * dp + (lane >> 4)) * 8]);
+    float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
+    mma_bf16_16816(o0, pa, b[0], b[1]);  // dims (2 dp) * 8 ..
+    mma_bf16_16816(o1, pa, b[2], b[3]);  // dims (2 dp + 1) * 8 ..
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int row = gq + 8 * r;
+      if (row < n) {
+        __nv_bfloat16* orow = out + ob + (int64_t)row * g.o_tok;
+        *reinterpret_cast<uint32_t*>(orow + (2 * dp) * 8 + 2 * t) = pack_bf16x2(o0[2 * r] * inv[r], o0[2 * r + 1] * inv[r]);
+        *reinterpret_cast<uint32_t*>(orow + (2 * dp + 1) * 8 + 2 * t) = pack_bf16x2(o1[2 * r] * inv[r], o1[2 * r + 1] * inv[r]);
+      }
+    }
+  }
+}
+#endif  // PHK_CUDA_EMU
+
 template <int NMAX, bool PRE = false>
 static int launch_attention_warp64(const void* q, const void* kv, const float* q_scale, const float* k_scale,
                                    const float* alibi_slopes, void* out, const phk_attn_geom_t& g, cudaStream_t st) {
@@ -877,6 +1008,19 @@ extern "C" int phk_attention_small_bf16(const void* Qn, const void* KVn, const f
               PHK_E_ARG, "phk_attention_small_bf16: operands must be 8-byte aligned with even strides");
   cudaStream_t st = to_stream(s);
   const int n = g->n_q;
+#ifndef PHK_CUDA_EMU
+  // warp-level tensor-core kernel: needs 16-byte aligned rows (token strides multiples of 8 elements)
+  static const bool use_mma = [] { const char* e = std::getenv("PHK_SMALL_ATTN_MMA"); return !(e && e[0] == '0'); }();
+  if (use_mma && g->out_bf16 && g->q_tok % 8 == 0 && g->q_outer % 8 == 0 && g->q_inner % 8 == 0 && g->k_tok % 8 == 0 &&
+      g->k_outer % 8 == 0 && g->k_inner % 8 == 0 && (g->heads * 64) % 8 == 0 &&
+      ((reinterpret_cast<uintptr_t>(Qn) | reinterpret_cast<uintptr_t>(KVn)) & 15) == 0) {
+    const int64_t npairs = (int64_t)g->n_outer * g->n_inner * g->heads;
+    PHK_CUDA(launch_pdl(attention_small_mma_kernel, dim3((unsigned)((npairs + MMA_WARPS - 1) / MMA_WARPS)), dim3(MMA_WARPS * 32),
+                        (size_t)0, st, (const __nv_bfloat16*)Qn, (const __nv_bfloat16*)KVn, alibi_slopes, (__nv_bfloat16*)out, *g));
+    PHK_LAUNCH_CHECK();
+    return 0;
+  }
+#endif
   if (n <= 3) return launch_attention_warp64<3, true>(Qn, KVn, nullptr, nullptr, alibi_slopes, out, *g, st);
   if (n <= 5) return launch_attention_warp64<5, true>(Qn, KVn, nullptr, nullptr, alibi_slopes, out, *g, st);
   if (n <= 9) return launch_attention_warp64<9, true>(Qn, KVn, nullptr, nullptr, alibi_slopes, out, *g, st);

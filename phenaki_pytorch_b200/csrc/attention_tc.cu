@@ -263,21 +263,34 @@ __global__ void __launch_bounds__(ATHREADS, 2) attention_tc_kernel(const __grid_
         __syncwarp();
         if (lane == 0) mbar_arrive(b_bempty);  // tile consumed (values are in registers)
       }
+      // scores in the log2 domain (one FFMA + ex2.approx.ftz per element; __expf costs a range test, two multiplies and
+      // a select on top of the MUFU -- the softmax warps are the kernel's bottleneck, ncu source page in profiles/)
+      constexpr float LOG2E = 1.4426950408889634f;
       float mx = -INFINITY;
+      if (k0 + AKC <= p.n_k) {  // whole chunk inside the sequence (warp-uniform): no per-element bounds tests
 #pragma unroll
-      for (int c = 0; c < AKC; ++c) {
-        float s = __uint_as_float(sv[c >> 5][c & 31]) + bv[c];
-        if (k0 + c >= p.n_k) s = -INFINITY;  // zero-filled padding keys
-        bv[c] = s;
-        mx = fmaxf(mx, s);
+        for (int c = 0; c < AKC; ++c) {
+          const float s = __uint_as_float(sv[c >> 5][c & 31]) + bv[c];
+          bv[c] = s;
+          mx = fmaxf(mx, s);
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < AKC; ++c) {
+          float s = __uint_as_float(sv[c >> 5][c & 31]) + bv[c];
+          if (k0 + c >= p.n_k) s = -INFINITY;  // zero-filled padding keys
+          bv[c] = s;
+          mx = fmaxf(mx, s);
+        }
       }
       const float m_new = fmaxf(m_run, mx);
-      const float alpha = __expf(m_run - m_new);  // 0 on the first chunk (m_run = -inf)
+      const float alpha = fast_ex2((m_run - m_new) * LOG2E);  // 0 on the first chunk (m_run = -inf)
+      const float m2 = m_new * LOG2E;
       float lsum = 0.f;
       uint32_t pk[AKC / 2];
 #pragma unroll
       for (int c = 0; c < AKC; c += 2) {
-        const float p0 = __expf(bv[c] - m_new), p1 = __expf(bv[c + 1] - m_new);
+        const float p0 = fast_ex2(fmaf(bv[c], LOG2E, -m2)), p1 = fast_ex2(fmaf(bv[c + 1], LOG2E, -m2));
         lsum += p0 + p1;
         pk[c >> 1] = pack_bf16x2(p0, p1);
       }

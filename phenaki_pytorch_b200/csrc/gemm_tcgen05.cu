@@ -43,6 +43,10 @@ constexpr int CPAD = 132;                          // fp32 staging row stride (f
 constexpr int CSTAGE_BYTES = GM * CPAD * 4;        // 67.6 KB
 constexpr int RING_BYTES = GSTAGES * 2 * STAGE_BYTES;
 constexpr int SMEM_TOTAL = RING_BYTES + CSTAGE_BYTES + 256 /*barriers*/ + 1024 /*manual 1024-B alignment*/;
+// epilogue 4: per-part row sums [4][128] float2 + the cluster exchange [2 buffers][8 ranks][128 rows] float2
+constexpr int LN_MAX_CLUSTER = 8;
+constexpr int LN_ROWSTAT_BYTES = EPI_PARTS * GM * 8, LN_XSTAT_BYTES = 2 * LN_MAX_CLUSTER * GM * 8;
+constexpr int SMEM_TOTAL_LN = SMEM_TOTAL + LN_ROWSTAT_BYTES + LN_XSTAT_BYTES;
 
 struct EpiParams {
   void* C; int64_t ldc; int64_t M; int N; int K;
@@ -58,6 +62,11 @@ struct EpiParams {
   // per 64-column head (F.normalize, eps 1e-12), multiplied by nscale[col % 64] (q_scale / k_scale) and by nmul (the
   // fixed similarity scale 8 folded into q); columns >= norm_cols (the value half of to_kv) are only converted
   const float* nscale; int norm_cols; float nmul;
+  // epilogue 4 (residual + the NEXT LayerNorm, attention.py:311-332): C = A W^T + C in place (fp32, bulk-stored) and, from
+  // the same registers, LayerNorm(C) * ln_g + ln_b -> bf16 ln_out [M, ln_ld] (+ optionally the un-normalised row as bf16
+  // in raw_out: the k,v projection input of attention.py:140-144).  One CTA holds 128 of the N columns of a row, so the
+  // row statistics are summed over the cluster of n_tiles CTAs that share the m-tile (distributed shared memory).
+  const float* ln_g; const float* ln_b; void* ln_out; void* raw_out; int64_t ln_ld; float ln_eps;
   alignas(64) CUtensorMap tmC;
 };
 
@@ -491,6 +500,136 @@ __device__ __forceinline__ void epi_chunk(const EpiParams& p, float* cstage, uin
   epi_bar_sync();  // staging buffer free for the next chunk
 }
 
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank) {  // shared::cta -> shared::cluster
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {  // acquire at cluster scope
+  long long t0 = 0;
+  for (uint32_t spin = 0;; ++spin) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+    if ((spin & 1023u) == 1023u) {
+      if (t0 == 0) t0 = clock64();
+      else if (clock64() - t0 > 4000000000LL) __trap();
+    }
+  }
+}
+__device__ __forceinline__ uint32_t cluster_size() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_f2(uint32_t cluster_addr, float a, float b) {  // distributed shared memory store
+  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(cluster_addr), "f"(a), "f"(b) : "memory");
+}
+
+// Epilogue 4, after the accumulator-ready wait: x = acc + x (bulk-stored like epi_tma_finish) and LayerNorm(x) of the
+// same registers -> bf16.  Row statistics: every thread sums its 32 columns, the four column parts meet in `rowstat`,
+// the n_tiles CTAs of the cluster (same m-tile, adjacent 128-column slices) exchange their 128-column partials through
+// distributed shared memory: thread (row r, part 0) of CTA c stores its partial into xstat[buf][c][r] of EVERY CTA of the
+// cluster and arrives on that CTA's `bar_stat` (128 * cluster_size arrivals per tile, release / acquire at cluster scope).
+// Two exchange buffers: a CTA can be at most one tile ahead of a peer (it needs the peer's arrival to get further).
+template <typename Release>
+__device__ __forceinline__ void epi_tma_finish_ln(const EpiParams& p, uint8_t* stage, uint32_t stage_s, uint32_t bar_res,
+                                                  uint32_t& res_phase, uint32_t tmem_chunk, int m0, int n0, int ew, int lg,
+                                                  int part, int lane, float2* rowstat, const float2* xstat, uint32_t xstat_s,
+                                                  uint32_t bar_stat,
+                                                  uint32_t& stat_phase, uint32_t& stat_buf, uint32_t my_rank, uint32_t csize,
+                                                  Release&& release) {
+  const uint32_t trow = tmem_chunk + ((uint32_t)(lg * 32) << 16);
+  uint32_t v[32];
+  tmem_ld32(trow + part * 32, v);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncwarp();
+  release();
+  const int r = lg * 32 + lane;
+  float4* box_row = reinterpret_cast<float4*>(stage + part * (GM * 128) + r * 128);
+  if (p.residual) { mbar_wait(bar_res, res_phase); res_phase ^= 1; }
+  const int col0 = n0 + part * 32;
+  float4 o[8];
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    o[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                       __uint_as_float(v[4 * j + 3]));
+    const int pos = j ^ (r & 7);
+    if (p.residual) { const float4 rr = box_row[pos]; o[j].x += rr.x; o[j].y += rr.y; o[j].z += rr.z; o[j].w += rr.w; }
+    if (p.bias) {
+      const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
+      o[j].x += bv.x; o[j].y += bv.y; o[j].z += bv.z; o[j].w += bv.w;
+    }
+    box_row[pos] = o[j];
+    s1 += (o[j].x + o[j].y) + (o[j].z + o[j].w);
+    s2 += (o[j].x * o[j].x + o[j].y * o[j].y) + (o[j].z * o[j].z + o[j].w * o[j].w);
+  }
+  rowstat[part * GM + r] = make_float2(s1, s2);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the TMA unit
+  epi_bar_sync();  // whole chunk staged, the four parts of every row are in rowstat
+  if (ew == 0 && lane == 0) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (n0 + 32 * c < p.N) tma_store_2d(&p.tmC, stage_s + c * (GM * 128), n0 + 32 * c, m0);
+    tma_store_commit();
+  }
+  if (part == 0) {  // 128 threads, one per row: this CTA's 128-column partial to every CTA of the cluster
+    float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+    for (int q = 0; q < EPI_PARTS; ++q) { const float2 e = rowstat[q * GM + r]; t1 += e.x; t2 += e.y; }
+    const uint32_t slot = xstat_s + ((stat_buf * LN_MAX_CLUSTER + my_rank) * GM + r) * 8;
+    for (uint32_t dst = 0; dst < csize; ++dst) {
+      st_cluster_f2(map_to_cta(slot, dst), t1, t2);
+      mbar_arrive_remote(map_to_cta(bar_stat, dst));
+    }
+  }
+  mbar_wait_cluster(bar_stat, stat_phase);
+  stat_phase ^= 1;
+  float t1 = 0.f, t2 = 0.f;
+  for (uint32_t c = 0; c < csize; ++c) { const float2 e = xstat[(stat_buf * LN_MAX_CLUSTER + c) * GM + r]; t1 += e.x; t2 += e.y; }
+  stat_buf ^= 1;
+  const float inv_n = 1.0f / (float)p.N;
+  const float mean = t1 * inv_n;
+  const float rstd = rsqrtf(fmaxf(t2 * inv_n - mean * mean, 0.f) + p.ln_eps);
+  if ((uint32_t)(m0 + r) < (uint32_t)p.M) {
+    __nv_bfloat16* lrow = reinterpret_cast<__nv_bfloat16*>(p.ln_out) + (int64_t)(m0 + r) * p.ln_ld + col0;
+    __nv_bfloat16* rrow = p.raw_out ? reinterpret_cast<__nv_bfloat16*>(p.raw_out) + (int64_t)(m0 + r) * p.ln_ld + col0 : nullptr;
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.ln_g + col0) + j), g1 = __ldg(reinterpret_cast<const float4*>(p.ln_g + col0) + j + 1);
+      float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+      if (p.ln_b) { b0 = __ldg(reinterpret_cast<const float4*>(p.ln_b + col0) + j); b1 = __ldg(reinterpret_cast<const float4*>(p.ln_b + col0) + j + 1); }
+      const float4 a = o[j], c = o[j + 1];
+      *reinterpret_cast<uint4*>(lrow + 4 * j) = make_uint4(
+          pack_bf16x2(fmaf((a.x - mean) * rstd, g0.x, b0.x), fmaf((a.y - mean) * rstd, g0.y, b0.y)),
+          pack_bf16x2(fmaf((a.z - mean) * rstd, g0.z, b0.z), fmaf((a.w - mean) * rstd, g0.w, b0.w)),
+          pack_bf16x2(fmaf((c.x - mean) * rstd, g1.x, b1.x), fmaf((c.y - mean) * rstd, g1.y, b1.y)),
+          pack_bf16x2(fmaf((c.z - mean) * rstd, g1.z, b1.z), fmaf((c.w - mean) * rstd, g1.w, b1.w)));
+      if (rrow)
+        *reinterpret_cast<uint4*>(rrow + 4 * j) = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w),
+                                                             pack_bf16x2(c.x, c.y), pack_bf16x2(c.z, c.w));
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // One-CTA kernel: 128 x 128 tiles, tcgen05.mma.cta_group::1 (small problems: fewer than 256 rows)
 // ---------------------------------------------------------------------------------------------------
@@ -517,9 +656,14 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_bf16_kernel(const __grid_con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles1 = p.m_tiles * p.n_tiles;
   const int num_tiles = tiles1 + (DUAL ? p2.m_tiles * p2.n_tiles : 0);
+  // epilogue 4: clusters of n_tiles CTAs own one m-tile at a time (CTA rank = n-tile), round-robin over the m-tiles
+  const uint32_t crank = EPI == 4 ? cluster_rank() : 0u, csize = EPI == 4 ? cluster_size() : 1u;
+  const int cluster_id = (int)blockIdx.x / (int)csize, n_clusters = (int)gridDim.x / (int)csize;
   // tile schedule: round-robin over all tiles (problem 1 first), m-fastest; returns true for a tile of problem 2
-  const int my_tiles = (int)blockIdx.x < num_tiles ? (num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int my_tiles = EPI == 4 ? (cluster_id < p.m_tiles ? (p.m_tiles - 1 - cluster_id) / n_clusters + 1 : 0)
+                                : ((int)blockIdx.x < num_tiles ? (num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0);
   auto tile_of = [&](int i, int& m0, int& n0) -> bool {
+    if (EPI == 4) { m0 = (cluster_id + i * n_clusters) * GM; n0 = (int)crank * GN; return false; }
     int tile = (int)blockIdx.x + i * (int)gridDim.x;
     const bool second = DUAL && tile >= tiles1;
     if (second) tile -= tiles1;
@@ -548,6 +692,7 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_bf16_kernel(const __grid_con
       mbar_init(bar_tempty + 8 * a, EPI_WARPS);  // one arrival per epilogue warp
     }
     mbar_init(tmem_slot + 8, 1);  // residual tile landed (TMA epilogue)
+    if (EPI == 4) mbar_init(tmem_slot + 16, GM * csize);  // row statistics of the whole cluster landed (epilogue 4)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {  // TMEM: two 128-column fp32 accumulators
@@ -557,6 +702,7 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_bf16_kernel(const __grid_con
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (EPI == 4) { __syncwarp(); cluster_sync_all(); }  // every CTA of the cluster runs and has its barriers initialised
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -624,21 +770,28 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_bf16_kernel(const __grid_con
     const int ew = warp - 2;        // 0..15: rows ew, ew+16, ... in the coalesced write-out
     const int lg = warp & 3;        // TMEM lane group this warp may access (rows lg*32 .. +31 of the tile)
     const int part = ew >> 2;       // which quarter of the accumulator columns this warp drains
-    const uint32_t bar_res = tmem_slot + 8;
-    uint32_t res_phase = 0;
+    const uint32_t bar_res = tmem_slot + 8, bar_stat = tmem_slot + 16;
+    uint32_t res_phase = 0, stat_phase = 0, stat_buf = 0;
+    float2* rowstat = reinterpret_cast<float2*>(base_ptr + RING_BYTES + CSTAGE_BYTES + 256);
+    const float2* xstat = rowstat + EPI_PARTS * GM;
+    const uint32_t xstat_s = base + RING_BYTES + CSTAGE_BYTES + 256 + LN_ROWSTAT_BYTES;
     for (int it = 0; it < my_tiles; ++it) {
       const int acc = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
       int m0, n0;
       const EpiParams& pp = tile_of(it, m0, n0) ? p2 : p;
-      const bool tma = EPI == 0 && pp.tma_epi;
+      const bool tma = (EPI == 0 && pp.tma_epi) || EPI == 4;
       bool res_vec = false;
       if (tma) epi_tma_begin(pp, base + RING_BYTES, bar_res, m0, n0, ew, lane);
       else res_vec = epi_residual_prefetch<EPI>(pp, cstage, m0, n0, ew, lane);
       mbar_wait(bar_tfull + 8 * acc, use & 1);
       if (it == 0 && threadIdx.x == 64) PHK_STAMP(6);      // accumulator ready
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (tma)
+      if (EPI == 4)
+        epi_tma_finish_ln(pp, reinterpret_cast<uint8_t*>(cstage), base + RING_BYTES, bar_res, res_phase,
+                          tmem_base + acc * GN, m0, n0, ew, lg, part, lane, rowstat, xstat, xstat_s, bar_stat, stat_phase,
+                          stat_buf, crank, csize, [&]() { if (lane == 0) mbar_arrive(bar_tempty + 8 * acc); });
+      else if (tma)
         epi_tma_finish(pp, reinterpret_cast<uint8_t*>(cstage), base + RING_BYTES, bar_res, res_phase,
                        tmem_base + acc * GN, m0, n0, ew, lg, part, lane,
                        [&]() { if (lane == 0) mbar_arrive(bar_tempty + 8 * acc); });
@@ -651,10 +804,11 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_bf16_kernel(const __grid_con
                        [&]() { if (lane == 0) mbar_arrive(bar_tempty + 8 * acc); });
       if (it == 0 && threadIdx.x == 64) PHK_STAMP(8);      // tile written out
     }
-    if (EPI == 0 && ew == 0 && lane == 0) tma_store_wait_all();  // bulk stores complete before the CTA exits
+    if ((EPI == 0 || EPI == 4) && ew == 0 && lane == 0) tma_store_wait_all();  // bulk stores complete before the CTA exits
   }
   __syncthreads();
   if (threadIdx.x == 0) PHK_STAMP(9);  // CTA done
+  if (EPI == 4) { __syncwarp(); cluster_sync_all(); }  // no CTA exits while a peer may still write its exchange buffer
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * GN) : "memory");
@@ -672,40 +826,6 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_bf16_kernel(const __grid_con
 //     "accumulator ready" arrivals to the barriers at the same offset in both CTAs;
 //   * the peer's epilogue warps release an accumulator with a remote arrive on the leader's barrier.
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t cluster_rank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank) {  // shared::cta -> shared::cluster
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {  // acquire at cluster scope
-  long long t0 = 0;
-  for (uint32_t spin = 0;; ++spin) {
-    uint32_t done;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) return;
-    if ((spin & 1023u) == 1023u) {
-      if (t0 == 0) t0 = clock64();
-      else if (clock64() - t0 > 4000000000LL) __trap();
-    }
-  }
-}
 __device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint32_t leader_bar, uint32_t dst, int c0,
                                                  int c1) {
   asm volatile(
@@ -1191,6 +1311,54 @@ extern "C" int phk_gemm_bf16_x2(const void* A1, int64_t lda1, const void* W1, in
               "phk_gemm_bf16_x2: too many tiles");
   // (measured: the bulk-store epilogue does not pay for the two-problem launch -- 16.2 vs 15.5 us -- so it stays off)
   return launch_gemm_dual<0>(ta, tb, p, ta2, tb2, p2, to_stream(s));
+}
+
+// x = A W^T + x in place (fp32 residual stream) AND the LayerNorm the next sub-block applies to it (attention.py:311-332:
+// x = attn(x) + x is followed by ff's / the cross-attention's LayerNorm, x = ff(x) + x by the next layer's), written as
+// the bf16 operand of the next GEMM from the epilogue's registers: ln_out[M, ln_ld] = LayerNorm(x) * ln_g (+ ln_b), and
+// optionally raw_out = bf16(x) (the k,v projection reads the un-normalised rows, attention.py:140-144).  N = the model
+// width: N / 128 in {1, 2, 4, 8} CTAs form a cluster per 128-row tile and share the row statistics.
+extern "C" int phk_gemm_bf16_ln(const void* A, int64_t lda, const void* W, int64_t ldw, float* C, int64_t ldc, int64_t M,
+                                int32_t N, int32_t K, const float* bias, const float* ln_g, const float* ln_b, float ln_eps,
+                                void* ln_out, void* raw_out, int64_t ln_ld, phk_stream_t s) {
+  Prof prof_(FAM_GEMM_BF16, s, 2.0 * (double)M * N * K);
+  PHK_REQUIRE(A && W && C && ln_g && ln_out, PHK_E_ARG, "phk_gemm_bf16_ln: null pointer");
+  PHK_REQUIRE(M > 0 && N > 0 && K > 0 && lda >= K && ldw >= K && ldc >= N && ln_ld >= N, PHK_E_ARG, "phk_gemm_bf16_ln: bad size");
+  const int nt = N / GN;
+  PHK_REQUIRE(N % GN == 0 && (nt == 1 || nt == 2 || nt == 4 || nt == 8), PHK_E_UNSUPPORTED,
+              "phk_gemm_bf16_ln: the row width must be 128, 256, 512 or 1024");
+  PHK_REQUIRE(lda % 8 == 0 && ldw % 8 == 0 && ldc % 4 == 0 && ln_ld % 8 == 0 &&
+                  ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(C) |
+                    reinterpret_cast<uintptr_t>(ln_g) | reinterpret_cast<uintptr_t>(ln_b) | reinterpret_cast<uintptr_t>(bias) |
+                    reinterpret_cast<uintptr_t>(ln_out) | reinterpret_cast<uintptr_t>(raw_out)) & 15) == 0,
+              PHK_E_ARG, "phk_gemm_bf16_ln: operands must be 16-byte aligned with leading dimensions multiple of 8 (TMA)");
+  PHK_REQUIRE(M < (1LL << 31) - GM, PHK_E_UNSUPPORTED, "phk_gemm_bf16_ln: M too large");
+  CUtensorMap ta, tb;
+  PHK_TRY(get_tensor_map(A, M, K, lda, GM, &ta));
+  PHK_TRY(get_tensor_map(W, N, K, ldw, GN, &tb));
+  EpiParams p{C, ldc, M, N, K, bias, C, 0, 0, 0, (int)((M + GM - 1) / GM), nt, nullptr};
+  PHK_TRY(get_c_map(C, M, N, ldc, &p.tmC));
+  p.tma_epi = 1;
+  p.ln_g = ln_g; p.ln_b = ln_b; p.ln_out = ln_out; p.raw_out = raw_out; p.ln_ld = ln_ld; p.ln_eps = ln_eps;
+  static unsigned long long configured_mask = 0;
+  const bool configured = device_configured(&configured_mask);
+  if (!configured) {
+    PHK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL_LN));
+    mark_configured(&configured_mask);
+  }
+  const int max_clusters = kNumSMs / nt;
+  const int clusters = p.m_tiles < max_clusters ? p.m_tiles : max_clusters;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(clusters * nt); cfg.blockDim = dim3(GTHREADS); cfg.dynamicSmemBytes = SMEM_TOTAL_LN; cfg.stream = to_stream(s);
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = nt; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 2;
+  PHK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<4, false>, ta, tb, p, ta, tb, p));
+  PHK_LAUNCH_CHECK();
+  return 0;
 }
 
 // The q and k,v projections of a self-attention block (attention.py:140-157) in one launch, written as the bf16 operands

@@ -53,12 +53,16 @@ template <int VEC>
 __global__ void __launch_bounds__(256) ln_cfg_gather_kernel(const float* __restrict__ xc, const float* __restrict__ xn,
                                                             const float* __restrict__ g, const float* __restrict__ b,
                                                             float scale, const int* __restrict__ index,
-                                                            __nv_bfloat16* __restrict__ out, int64_t rows, int dim) {
+                                                            __nv_bfloat16* __restrict__ out, int64_t rows, int dim,
+                                                            int seq_n, int src_stride, int src_off) {
   pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
-  const int src = index[row];
+  // index = sequence * seq_n + position among the sampled tokens; the residual stream may carry a prime prefix:
+  // its row is sequence * src_stride + src_off + position (phenaki_pytorch.py:493, 503-504)
+  const int idx = index[row];
+  const int src = idx < 0 ? -1 : (idx / seq_n) * src_stride + src_off + idx % seq_n;
   float4 o[VEC];
 #pragma unroll
   for (int j = 0; j < VEC; ++j) o[j] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -153,12 +157,13 @@ extern "C" int64_t phk_sample_tail_scratch_bytes(int32_t b, int32_t k, int32_t d
   return carve(nullptr, (int64_t)b * k, dim, nullptr);
 }
 
-extern "C" int phk_sample_tail(const float* x_cond, const float* x_null, const float* gamma, const float* beta,
-                               float cond_scale, const void* head_w, int64_t ldw, const float* head_b, int32_t b,
-                               int32_t n, int32_t k, int32_t V, int32_t dim, float temperature, uint64_t seed,
-                               uint64_t offset, const uint64_t* rng_state, const uint8_t* mask, int64_t* ids,
-                               int64_t* pred_out, float* score_out, void* scratch, int64_t scratch_bytes,
-                               phk_stream_t s) {
+extern "C" int phk_sample_tail_rows(const float* x_cond, const float* x_null, const float* gamma, const float* beta,
+                                    float cond_scale, const void* head_w, int64_t ldw, const float* head_b, int32_t b,
+                                    int32_t n, int32_t k, int32_t V, int32_t dim, float temperature, uint64_t seed,
+                                    uint64_t offset, const uint64_t* rng_state, const uint8_t* mask, int64_t* ids,
+                                    int64_t* pred_out, float* score_out, int32_t src_stride, int32_t src_off,
+                                    void* scratch, int64_t scratch_bytes, phk_stream_t s) {
+  PHK_REQUIRE(src_stride >= n && src_off >= 0 && src_off + n <= src_stride, PHK_E_ARG, "phk_sample_tail: bad source row map");
   PHK_REQUIRE(x_cond && x_null && gamma && beta && head_w && mask && ids && scratch, PHK_E_ARG, "phk_sample_tail: null pointer");
   PHK_REQUIRE(b > 0 && n > 0 && k > 0 && k <= n && V > 0, PHK_E_ARG, "phk_sample_tail: bad size");
   PHK_REQUIRE(dim % 128 == 0 && dim <= 1024, PHK_E_UNSUPPORTED, "phk_sample_tail: dim must be a multiple of 128, <= 1024");
@@ -173,14 +178,14 @@ extern "C" int phk_sample_tail(const float* x_cond, const float* x_null, const f
   PHK_LAUNCH_CHECK();
   const dim3 grid((unsigned)((rows + 7) / 8)), block(256);
   switch (dim / 128) {
-    case 1: PHK_CUDA(launch_pdl(ln_cfg_gather_kernel<1>, grid, block, (size_t)0, st, x_cond, x_null, gamma, beta, cond_scale, t.index, t.emb, rows, dim)); break;
-    case 2: PHK_CUDA(launch_pdl(ln_cfg_gather_kernel<2>, grid, block, (size_t)0, st, x_cond, x_null, gamma, beta, cond_scale, t.index, t.emb, rows, dim)); break;
-    case 3: PHK_CUDA(launch_pdl(ln_cfg_gather_kernel<3>, grid, block, (size_t)0, st, x_cond, x_null, gamma, beta, cond_scale, t.index, t.emb, rows, dim)); break;
-    case 4: PHK_CUDA(launch_pdl(ln_cfg_gather_kernel<4>, grid, block, (size_t)0, st, x_cond, x_null, gamma, beta, cond_scale, t.index, t.emb, rows, dim)); break;
-    case 5: PHK_CUDA(launch_pdl(ln_cfg_gather_kernel<5>, grid, block, (size_t)0, st, x_cond, x_null, gamma, beta, cond_scale, t.index, t.emb, rows, dim)); break;
-    case 6: PHK_CUDA(launch_pdl(ln_cfg_gather_kernel<6>, grid, block, (size_t)0, st, x_cond, x_null, gamma, beta, cond_scale, t.index, t.emb, rows, dim)); break;
-    case 7: PHK_CUDA(launch_pdl(ln_cfg_gather_kernel<7>, grid, block, (size_t)0, st, x_cond, x_null, gamma, beta, cond_scale, t.index, t.emb, rows, dim)); break;
-    default: PHK_CUDA(launch_pdl(ln_cfg_gather_kernel<8>, grid, block, (size_t)0, st, x_cond, x_null, gamma, beta, cond_scale, t.index, t.emb, rows, dim)); break;
+    case 1: PHK_CUDA(launch_pdl(ln_cfg_gather_kernel<1>, grid, block, (size_t)0, st, x_cond, x_null, gamma, beta, cond_scale, t.index, t.emb, rows, dim, (int)n, (int)src_stride, (int)src_off)); break;
+    case 2: PHK_CUDA(launch_pdl(ln_cfg_gather_kernel<2>, grid, block, (size_t)0, st, x_cond, x_null, gamma, beta, cond_scale, t.index, t.emb, rows, dim, (int)n, (int)src_stride, (int)src_off)); break;
+    case 3: PHK_CUDA(launch_pdl(ln_cfg_gather_kernel<3>, grid, block, (size_t)0, st, x_cond, x_null, gamma, beta, cond_scale, t.index, t.emb, rows, dim, (int)n, (int)src_stride, (int)src_off)); break;
+    case 4: PHK_CUDA(launch_pdl(ln_cfg_gather_kernel<4>, grid, block, (size_t)0, st, x_cond, x_null, gamma, beta, cond_scale, t.index, t.emb, rows, dim, (int)n, (int)src_stride, (int)src_off)); break;
+    case 5: PHK_CUDA(launch_pdl(ln_cfg_gather_kernel<5>, grid, block, (size_t)0, st, x_cond, x_null, gamma, beta, cond_scale, t.index, t.emb, rows, dim, (int)n, (int)src_stride, (int)src_off)); break;
+    case 6: PHK_CUDA(launch_pdl(ln_cfg_gather_kernel<6>, grid, block, (size_t)0, st, x_cond, x_null, gamma, beta, cond_scale, t.index, t.emb, rows, dim, (int)n, (int)src_stride, (int)src_off)); break;
+    case 7: PHK_CUDA(launch_pdl(ln_cfg_gather_kernel<7>, grid, block, (size_t)0, st, x_cond, x_null, gamma, beta, cond_scale, t.index, t.emb, rows, dim, (int)n, (int)src_stride, (int)src_off)); break;
+    default: PHK_CUDA(launch_pdl(ln_cfg_gather_kernel<8>, grid, block, (size_t)0, st, x_cond, x_null, gamma, beta, cond_scale, t.index, t.emb, rows, dim, (int)n, (int)src_stride, (int)src_off)); break;
   }
   PHK_LAUNCH_CHECK();
   PHK_CUDA(cudaMemsetAsync(t.ones, 1, rows, st));
@@ -194,6 +199,16 @@ extern "C" int phk_sample_tail(const float* x_cond, const float* x_null, const f
                       (const float*)t.score_c, ids, pred_out, score_out, rows));
   PHK_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int phk_sample_tail(const float* x_cond, const float* x_null, const float* gamma, const float* beta,
+                               float cond_scale, const void* head_w, int64_t ldw, const float* head_b, int32_t b,
+                               int32_t n, int32_t k, int32_t V, int32_t dim, float temperature, uint64_t seed,
+                               uint64_t offset, const uint64_t* rng_state, const uint8_t* mask, int64_t* ids,
+                               int64_t* pred_out, float* score_out, void* scratch, int64_t scratch_bytes,
+                               phk_stream_t s) {
+  return phk_sample_tail_rows(x_cond, x_null, gamma, beta, cond_scale, head_w, ldw, head_b, b, n, k, V, dim, temperature, seed,
+                              offset, rng_state, mask, ids, pred_out, score_out, n, 0, scratch, scratch_bytes, s);
 }
 
 extern "C" int phk_rng_advance(uint64_t* rng_state, uint64_t stride, phk_stream_t s) {

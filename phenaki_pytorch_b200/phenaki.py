@@ -173,7 +173,7 @@ class _TokenTransformer(nn.Module):
         return out
 
     def _sample_step(self, ids_in, patch_shape, *, ctx_kv, ctx_len, text_mask, cond_scale, temperature, seed,
-                     offset, mask, ids, pred, scores, masked_per_seq=0):
+                     offset, mask, ids, pred, scores, masked_per_seq=0, prime_len=0):
         """Fused demasking iteration (bf16 mode): CFG-pair forward + logits head + gumbel argmax + confidence in
         libphk (phk_maskgit_sample_step); the (2b, n, V) logits are never materialised.  ``masked_per_seq``: how many
         tokens of EVERY sequence are masked, when known (the demasking schedule knows it): the final LayerNorm, the
@@ -189,6 +189,14 @@ class _TokenTransformer(nn.Module):
             if text_mask is not None:
                 text_mask = L.require_cuda(text_mask.to(torch.uint8), "text mask")
             pt, ph, pw = (int(v) for v in patch_shape)
+            if prime_len:  # ids_in = prime ids + the tokens being sampled; mask / ids / pred / scores cover the latter
+                L.check(lib.phk_maskgit_sample_step_primed(C.byref(table), L.ptr(ids_in), b, n, pt, ph, pw, L.ptr(ctx_kv),
+                                                           ctx_len, L.ptr(text_mask), L.ptr(bias), float(cond_scale),
+                                                           float(temperature), seed, offset, L.ptr(mask), L.ptr(ids),
+                                                           L.ptr(pred), L.ptr(scores), int(masked_per_seq), int(prime_len),
+                                                           L.ptr(ws), ws.numel(), L.stream_ptr()),
+                        "phk_maskgit_sample_step_primed")
+                return
             L.check(lib.phk_maskgit_sample_step(C.byref(table), L.ptr(ids_in), b, n, pt, ph, pw, L.ptr(ctx_kv), ctx_len,
                                                 L.ptr(text_mask), None, L.ptr(bias), float(cond_scale),
                                                 float(temperature), seed, offset, L.ptr(mask), L.ptr(ids), L.ptr(pred),
@@ -612,7 +620,7 @@ class Phenaki(nn.Module):
                 use_cfg = cond_scale != 1
                 temperature = starting_temperature * (til_x0 / steps)
                 offset = _rng_take(dev, seed, _noise_stride(b * n, vocab))
-                fused = (self.fused_head and mg.precision == L.PREC_BF16 and noise_fn is None and use_cfg and plen == 0
+                fused = (self.fused_head and mg.precision == L.PREC_BF16 and noise_fn is None and use_cfg
                          and trace is None and self._fused_step_supported())
                 if fused:
                     # one launch sequence per iteration, logits never leave the SM (statistical-noise mode)
@@ -621,7 +629,7 @@ class Phenaki(nn.Module):
                     mg._sample_step(inp, patch_shape, ctx_kv=ctx_kv, ctx_len=ctx_len, text_mask=text_mask,
                                     cond_scale=cond_scale, temperature=temperature, seed=seed & (2 ** 64 - 1),
                                     offset=offset, mask=mask, ids=ids, pred=pred, scores=scores,
-                                    masked_per_seq=n if step == 0 else ks[step - 1])
+                                    masked_per_seq=n if step == 0 else ks[step - 1], prime_len=plen)
                 else:
                     logits = mg._run(inp, patch_shape, ctx_kv=ctx_kv, ctx_len=ctx_len, text_mask=text_mask,
                                      cfg_pair=use_cfg)

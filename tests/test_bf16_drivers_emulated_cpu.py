@@ -17,7 +17,8 @@ _NAMES = ["test_cvivit_bf16_mode_against_fp32_reference_golden", "test_maskgit_b
           "test_layernorm_cfg_combination",
           "test_fused_sample_step_agrees_with_unfused_path", "test_bf16_sampling_with_fused_head_is_deterministic",
           "test_fused_sample_step_on_masked_rows_equals_the_all_rows_step",
-          "test_cosine_vq_ids_in_bf16_mode_against_fp32_reference_golden"]
+          "test_cosine_vq_ids_in_bf16_mode_against_fp32_reference_golden",
+          "test_primed_fused_sample_step_equals_the_unprimed_step_on_the_same_rows"]
 for _n in _NAMES:
     globals()[_n] = getattr(G, _n) if hasattr(G, _n) else getattr(Z, _n)
 

@@ -107,3 +107,27 @@ def test_small_attention_on_prenormalised_operands(n_outer, n_inner, n, heads, c
     torch.cuda.synchronize()
     err = (out.cpu().float()[idx] - ref).abs().max().item()
     assert err <= 0.02, f"max |err| {err}"
+
+
+@pytest.mark.parametrize("M,N,K,raw", [(4608, 512, 512, False), (4608, 512, 1408, True), (300, 256, 192, True), (129, 128, 64, False),
+                                       (2304, 1024, 512, True), (40000, 512, 512, False)])
+def test_residual_gemm_with_layernorm_epilogue(M, N, K, raw):
+    """phk_gemm_bf16_ln: x += A W^T in place (fp32) and bf16 LayerNorm(x) (+ raw bf16 x) from the same epilogue; row
+    statistics summed over the cluster of N / 128 CTAs.  40000 rows: more m-tiles than clusters (persistent loop, both
+    exchange buffers in use)."""
+    a = TC.seeded_randn((M, K), 430).bfloat16()
+    w = (TC.seeded_randn((N, K), 431) / K ** 0.5).bfloat16()
+    x = TC.seeded_randn((M, N), 432) * 2 + 0.5
+    g, b = TC.seeded_randn((N,), 433) * 0.2 + 1.0, TC.seeded_randn((N,), 434) * 0.1
+    ref_x = x + a.float() @ w.float().t()
+    ref_ln = F.layer_norm(ref_x, (N,), g, b)
+    ad, wd, xd, gd, bd = a.to(DEV), w.to(DEV), x.clone().to(DEV), g.to(DEV), b.to(DEV)
+    ln = torch.full((M, N), 9.0, dtype=torch.bfloat16, device=DEV)
+    rw = torch.full((M, N), 9.0, dtype=torch.bfloat16, device=DEV) if raw else None
+    L.check(L.lib().phk_gemm_bf16_ln(L.ptr(ad), K, L.ptr(wd), K, L.ptr(xd), N, M, N, K, None, L.ptr(gd), L.ptr(bd), 1e-5,
+                                     L.ptr(ln), L.ptr(rw), N, L.stream_ptr()), "phk_gemm_bf16_ln")
+    torch.cuda.synchronize()
+    torch.testing.assert_close(xd.cpu(), ref_x, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(ln.cpu().float(), ref_ln, rtol=1e-2, atol=2e-2)
+    if raw:
+        torch.testing.assert_close(rw.cpu().float(), ref_x, rtol=1e-2, atol=2e-2)

@@ -116,3 +116,41 @@ def test_cfg3_masked_rows_step_equals_all_rows_step_at_full_size(k):
     torch.testing.assert_close(sc_a[m & same], sc_b[m & same], rtol=1e-3, atol=1e-4)
     assert bool((sc_b[~m] == -1e4).all()) and torch.equal(ids_b[~m], ids0.cpu()[~m])
     assert bool(((ids_b[m] >= 0) & (ids_b[m] < 65536)).all())
+
+
+def test_primed_fused_sample_step_equals_the_unprimed_step_on_the_same_rows():
+    """phk_maskgit_sample_step_primed (scene chains of make_video, phenaki_pytorch.py:493, 503-504): with a prime prefix of
+    `plen` ids the head runs on the masked rows of the sampled tokens only.  The step sees the same network input whether
+    the prefix is declared as prime or the whole sequence is treated as sampled with the prefix unmasked, so at temperature
+    0 both calls must produce the same ids / confidences on the sampled tokens."""
+    torch.manual_seed(9)
+    cfg = dict(dim=128, num_tokens=1000, max_seq_len=256, heads=2, dim_head=64, depth=2, dim_context=96)
+    mg = P.MaskGit(**cfg).to(DEV).eval()
+    mg.precision = L.PREC_BF16
+    b, shape, n_total, plen = 2, (4, 4, 6), 96, 24
+    n = n_total - plen
+    g = torch.Generator().manual_seed(4)
+    full = torch.randint(0, cfg["num_tokens"], (b, n_total), generator=g)
+    k = 40
+    mask_new = torch.zeros((b, n), dtype=torch.uint8)
+    for i in range(b):
+        mask_new[i, torch.randperm(n, generator=g)[:k]] = 1
+    full[:, plen:][mask_new.bool()] = cfg["num_tokens"]  # masked positions carry the mask id
+    ctx = C.synthetic_text_embeds(b, 5, 96, (5, 3), 6).to(DEV)
+    tmask = torch.any(ctx != 0, dim=-1)
+    kv = mg.context_kv(ctx)
+    full_d, mask_new_d = full.to(DEV), mask_new.to(DEV)
+    # (a) primed: mask / ids / pred / scores cover the n sampled tokens
+    ids_a, pred_a, sc_a = full_d[:, plen:].clone(), torch.empty((b, n), dtype=torch.int64, device=DEV), torch.empty((b, n), device=DEV)
+    mg._sample_step(full_d, shape, ctx_kv=kv, ctx_len=5, text_mask=tmask, cond_scale=3.0, temperature=0.0, seed=5, offset=0,
+                    mask=mask_new_d, ids=ids_a, pred=pred_a, scores=sc_a, masked_per_seq=k, prime_len=plen)
+    # (b) unprimed: the whole sequence, prefix unmasked
+    mask_full = torch.cat((torch.zeros((b, plen), dtype=torch.uint8), mask_new), dim=1).to(DEV)
+    ids_b, pred_b, sc_b = full_d.clone(), torch.empty_like(full_d), torch.empty((b, n_total), device=DEV)
+    mg._sample_step(full_d, shape, ctx_kv=kv, ctx_len=5, text_mask=tmask, cond_scale=3.0, temperature=0.0, seed=5, offset=0,
+                    mask=mask_full, ids=ids_b, pred=pred_b, scores=sc_b, masked_per_seq=k)
+    if DEV == "cuda":
+        torch.cuda.synchronize()
+    assert torch.equal(ids_a.cpu(), ids_b[:, plen:].cpu())
+    torch.testing.assert_close(sc_a.cpu(), sc_b[:, plen:].cpu(), rtol=1e-5, atol=1e-6)
+    assert torch.equal(ids_b[:, :plen].cpu(), full[:, :plen])
