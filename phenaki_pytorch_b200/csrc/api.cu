@@ -148,10 +148,13 @@ static int transformer_forward(const TfCall& c, Arena scratch, float* out, void*
   float* x = c.x;
   float* x_alt = c.x_alt;
 
-  // bf16 mode: the LayerNorm that follows a residual GEMM (out-projection -> cross-attention / feed-forward norm,
-  // feed-forward -> the next layer's attention norm when no PEG sits in between) is computed by that GEMM's epilogue
-  // (phk_gemm_bf16_ln: cluster-wide row statistics) instead of a separate pass over the residual stream
-  static const bool fuse_ln_env = [] { const char* e = std::getenv("PHK_FUSE_LN"); return !(e && e[0] == '0'); }();
+  // bf16 mode, opt-in (PHK_FUSE_LN=1): the LayerNorm that follows a residual GEMM (out-projection -> cross-attention /
+  // feed-forward norm, feed-forward -> the next layer's attention norm when no PEG sits in between) computed by that
+  // GEMM's epilogue (phk_gemm_bf16_ln: row statistics summed over a cluster of N / 128 CTAs through distributed shared
+  // memory).  Correct (tests/test_gpu_fused_qkv.py) but NOT faster on the B200 at dim 512: a cluster of 4 full-SM CTAs
+  // needs 4 free SMs of one GPC, only ~32 such clusters are resident at once and the 36 row tiles of 4608 tokens take two
+  // waves -- 30.3 us against 12.2 us (GEMM) + 4.7 us (LayerNorm kernel), profiles/r02/encode_bf16_launches_c4_fuse_ln.txt.
+  static const bool fuse_ln_env = [] { const char* e = std::getenv("PHK_FUSE_LN"); return e && e[0] == '1'; }();
   const bool fuse_ln = fuse_ln_env && h16 && (D == 128 || D == 256 || D == 512 || D == 1024);
   bool ln_ready = false;  // xn (+ xraw) already hold this layer's self-attention LayerNorm (written by the previous FF2)
   for (int l = 0; l < T->depth; ++l) {

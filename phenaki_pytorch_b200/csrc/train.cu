@@ -15,6 +15,7 @@
 // STATUS: written after the round's GPU budget was spent -- compiled for sm_100a and executed on the CPU by tests/cuda_emu
 // (this very source, g++-compiled) against the reference's gradients; not yet run on a GPU.
 #include "phk_common.cuh"
+#include <cstdlib>
 // the kernels of this file are ordinary stream-ordered launches (they do not use programmatic dependent launch)
 #define PHK_KERNEL_LAUNCH(kernel, grid, block, smem, st, ...) PHK_CUDA(launch_plain(kernel, grid, block, smem, st, __VA_ARGS__))
 #include <cstring>
@@ -435,10 +436,12 @@ __device__ __forceinline__ void l2norm_scale_bwd(const float* __restrict__ raw, 
 constexpr int kDPL = 4;  // dim_head <= 128
 
 // one warp per (sequence, head, query): dqh = 8 * sum_j dS[i,j] kh[j,:]; 8 warps per CTA share one dq_scale reduction
+// `pre` (optional): dS.kh already computed as a batched register-tiled product [b*H, n, dh] (long sequences: the warp-per-
+// row loop below re-reads the whole key block per query)
 __global__ void __launch_bounds__(256) attn_bwd_dq_kernel(const float* __restrict__ q, const float* __restrict__ kh,
                                                           const float* __restrict__ dS, const float* __restrict__ q_scale,
                                                           float* __restrict__ dq, float* __restrict__ dq_scale,
-                                                          AttnBwdGeom g) {
+                                                          const float* __restrict__ pre, AttnBwdGeom g) {
   __shared__ float red[8][32 * kDPL];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int nkt = g.nnull + g.m;
@@ -453,10 +456,15 @@ __global__ void __launch_bounds__(256) attn_bwd_dq_kernel(const float* __restric
     const float* dSr = dS + (((int64_t)bi * g.H + h) * g.n + i) * nkt;
     const float* kb = kh + ((int64_t)bi * g.H + h) * nkt * g.dh;
     float acc[kDPL] = {0.f, 0.f, 0.f, 0.f};
-    for (int j = 0; j < nkt; ++j) {
-      const float s = dSr[j];
+    if (pre) {
 #pragma unroll
-      for (int c = 0; c < kDPL; ++c) { const int d = lane + 32 * c; if (d < g.dh) acc[c] = fmaf(s, kb[(int64_t)j * g.dh + d], acc[c]); }
+      for (int c = 0; c < kDPL; ++c) { const int d = lane + 32 * c; if (d < g.dh) acc[c] = pre[w * g.dh + d]; }
+    } else {
+      for (int j = 0; j < nkt; ++j) {
+        const float s = dSr[j];
+#pragma unroll
+        for (int c = 0; c < kDPL; ++c) { const int d = lane + 32 * c; if (d < g.dh) acc[c] = fmaf(s, kb[(int64_t)j * g.dh + d], acc[c]); }
+      }
     }
 #pragma unroll
     for (int c = 0; c < kDPL; ++c) acc[c] *= 8.0f;
@@ -483,6 +491,7 @@ __global__ void __launch_bounds__(256) attn_bwd_dkv_kernel(const float* __restri
                                                            const float* __restrict__ P, const float* __restrict__ dS,
                                                            const float* __restrict__ k_scale, float* __restrict__ dkv,
                                                            float* __restrict__ dnull_kv, float* __restrict__ dk_scale,
+                                                           const float* __restrict__ preK, const float* __restrict__ preV,
                                                            AttnBwdGeom g) {
   __shared__ float red[8][32 * kDPL];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -500,12 +509,20 @@ __global__ void __launch_bounds__(256) attn_bwd_dkv_kernel(const float* __restri
     const float* qb = qh + ((int64_t)bi * g.H + h) * g.n * g.dh;
     const float* dob = dO + (int64_t)bi * g.n * I + (int64_t)h * g.dh;
     float ak[kDPL] = {0.f, 0.f, 0.f, 0.f}, av[kDPL] = {0.f, 0.f, 0.f, 0.f};
-    for (int i = 0; i < g.n; ++i) {
-      const float s = dSb[(int64_t)i * nkt], p = Pb[(int64_t)i * nkt];
+    if (preK) {  // dS^T.qh and P^T.dO from the batched products [b*H, nkt, dh]
 #pragma unroll
       for (int c = 0; c < kDPL; ++c) {
         const int d = lane + 32 * c;
-        if (d < g.dh) { ak[c] = fmaf(s, qb[(int64_t)i * g.dh + d], ak[c]); av[c] = fmaf(p, dob[(int64_t)i * I + d], av[c]); }
+        if (d < g.dh) { ak[c] = preK[w * g.dh + d]; av[c] = preV[w * g.dh + d]; }
+      }
+    } else {
+      for (int i = 0; i < g.n; ++i) {
+        const float s = dSb[(int64_t)i * nkt], p = Pb[(int64_t)i * nkt];
+#pragma unroll
+        for (int c = 0; c < kDPL; ++c) {
+          const int d = lane + 32 * c;
+          if (d < g.dh) { ak[c] = fmaf(s, qb[(int64_t)i * g.dh + d], ak[c]); av[c] = fmaf(p, dob[(int64_t)i * I + d], av[c]); }
+        }
       }
     }
 #pragma unroll
@@ -552,7 +569,8 @@ __global__ void attn_bwd_dbias_kernel(const float* __restrict__ dS, float* __res
 struct AttnBwdBufs { float *qh, *kh, *vv, *P, *dS; };
 
 int64_t attn_bwd_scratch_floats(int b, int H, int n, int nkt, int dh) {
-  return (int64_t)b * H * ((int64_t)n * dh + 2 * (int64_t)nkt * dh + 2 * (int64_t)n * nkt) + 64;
+  // qh, kh, vv, P, dS + the batched-product outputs dS.kh [n, dh], dS^T.qh and P^T.dO [nkt, dh]
+  return (int64_t)b * H * (2 * (int64_t)n * dh + 4 * (int64_t)nkt * dh + 2 * (int64_t)n * nkt) + 64;
 }
 
 // q [b*n, I], kv [b*m, 2I], dO [b*n, I] -> dq [b*n, I], dkv [b*m, 2I]; parameter gradients accumulate
@@ -583,10 +601,26 @@ int attention_backward(const float* q, const float* kv, const phk_attn_t& A, con
   PHK_TRY(sgemm_batched(dO, I, 1, B.vv, 1, g.dh, B.dS, nkt, g.n, nkt, g.dh, 0, bd, st));
   PHK_KERNEL_LAUNCH(attn_bwd_softmax_kernel, dim3((unsigned)((bh * g.n + 7) / 8)), dim3(256), (size_t)(0), st, bias, key_mask, B.P, B.dS, g);
   PHK_LAUNCH_CHECK();
-  PHK_KERNEL_LAUNCH(attn_bwd_dq_kernel, dim3((unsigned)((bh * g.n + 7) / 8)), dim3(256), (size_t)(0), st, q, B.kh, B.dS, A.q_scale, dq, (float*)G.q_scale, g);
+  // dq / dk / dv contractions: batched register-tiled products for long sequences (the warp-per-row loops of the two
+  // kernels walk a column of dS / P with a stride of nkt floats: 1.5 ms per layer at n = 576), loops for short ones
+  float* preQ = nullptr; float* preK = nullptr; float* preV = nullptr;
+  static const int force_gemm = [] { const char* e = std::getenv("PHK_ATTN_BWD_GEMM"); return e ? (e[0] == '0' ? 0 : 1) : -1; }();
+  if (force_gemm == 1 || (force_gemm < 0 && (int64_t)g.n * nkt >= 64 * 64)) {
+    preQ = B.dS + bh * g.n * nkt;
+    preK = preQ + bh * g.n * g.dh;
+    preV = preK + bh * nkt * g.dh;
+    const GemmBatch bq{(int)bh, 1, (int64_t)g.n * nkt, 0, (int64_t)nkt * g.dh, 0, (int64_t)g.n * g.dh, 0};
+    PHK_TRY(sgemm_batched(B.dS, nkt, 1, B.kh, g.dh, 1, preQ, g.dh, g.n, g.dh, nkt, 0, bq, st));             // dS . kh
+    const GemmBatch bk{(int)bh, 1, (int64_t)g.n * nkt, 0, (int64_t)g.n * g.dh, 0, (int64_t)nkt * g.dh, 0};
+    PHK_TRY(sgemm_batched(B.dS, 1, nkt, B.qh, g.dh, 1, preK, g.dh, nkt, g.dh, g.n, 0, bk, st));             // dS^T . qh
+    const GemmBatch bv{(int)bh, g.H, (int64_t)g.H * g.n * nkt, (int64_t)g.n * nkt, (int64_t)g.n * I, (int64_t)g.dh,
+                       (int64_t)g.H * nkt * g.dh, (int64_t)nkt * g.dh};
+    PHK_TRY(sgemm_batched(B.P, 1, nkt, dO, I, 1, preV, g.dh, nkt, g.dh, g.n, 0, bv, st));                    // P^T . dO
+  }
+  PHK_KERNEL_LAUNCH(attn_bwd_dq_kernel, dim3((unsigned)((bh * g.n + 7) / 8)), dim3(256), (size_t)(0), st, q, B.kh, B.dS, A.q_scale, dq, (float*)G.q_scale, (const float*)preQ, g);
   PHK_LAUNCH_CHECK();
   PHK_KERNEL_LAUNCH(attn_bwd_dkv_kernel, dim3((unsigned)((bh * nkt + 7) / 8)), dim3(256), (size_t)(0), st, kv, A.null_kv, B.qh, dO, B.P, B.dS, A.k_scale, dkv,
-                                                                     (float*)G.null_kv, (float*)G.k_scale, g);
+                                                                     (float*)G.null_kv, (float*)G.k_scale, (const float*)preK, (const float*)preV, g);
   PHK_LAUNCH_CHECK();
   if (dbias) {
     const int64_t total = (int64_t)g.H * g.n * g.m;
@@ -603,11 +637,47 @@ int attention_backward(const float* q, const float* kv, const phk_attn_t& A, con
 // One CTA per position (neighbour rows resolved once), threads over channels.  The weights arrive tap-major [27, D]
 // (the forward's layout); the gradient is accumulated in the parameter's own layout dsconv.weight[D, 1, 3, 3, 3].
 // ------------------------------------------------------------------------------------------------------------------
+// dw[d, tap] += sum_o dy[o, d] * x[o + off(tap), d]: one CTA per (tap, chunk of positions), the sum over the chunk stays in
+// registers (threads over channels, coalesced rows) and leaves as ONE atomic per (channel, tap, chunk) -- the per-position
+// atomics this replaces (27 * D per position onto 27 * D addresses) took 0.5 ms per layer at 2304 positions.
+constexpr int PEG_DW_CHUNKS = 16, PEG_DW_MAXJ = 8;  // D <= 128 * 8
+__global__ void __launch_bounds__(128) peg_bwd_dw_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                         float* __restrict__ dw, int64_t P, int T, int H, int W, int D,
+                                                         int pad_t0) {
+  const int tap = blockIdx.x;
+  const int kt = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
+  const int HW = H * W;
+  const int64_t per = (P + gridDim.y - 1) / gridDim.y;
+  const int64_t p0 = (int64_t)blockIdx.y * per, p1 = p0 + per < P ? p0 + per : P;
+  float acc[PEG_DW_MAXJ];
+#pragma unroll
+  for (int j = 0; j < PEG_DW_MAXJ; ++j) acc[j] = 0.f;
+  for (int64_t p = p0; p < p1; ++p) {
+    int rem = (int)(p % ((int64_t)T * HW));
+    const int64_t bi = p / ((int64_t)T * HW);
+    const int t = rem / HW; rem -= t * HW;
+    const int h = rem / W;
+    const int wq = rem - h * W;
+    const int ts = t + (kt - pad_t0), hs = h + (kh - 1), ws = wq + (kw - 1);
+    if (ts < 0 || ts >= T || hs < 0 || hs >= H || ws < 0 || ws >= W) continue;  // uniform over the CTA
+    const int64_t src = ((bi * T + ts) * H + hs) * W + ws;
+#pragma unroll
+    for (int j = 0; j < PEG_DW_MAXJ; ++j) {
+      const int d = threadIdx.x + 128 * j;
+      if (d < D) acc[j] = fmaf(dy[p * D + d], x[src * D + d], acc[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < PEG_DW_MAXJ; ++j) {
+    const int d = threadIdx.x + 128 * j;
+    if (d < D && p1 > p0) atomicAdd(dw + (int64_t)d * 27 + tap, acc[j]);  // dsconv.weight[d, 0, kt, kh, kw]
+  }
+}
+
 __global__ void __launch_bounds__(128) peg_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                       const float* __restrict__ dy, float* __restrict__ dx,
-                                                      float* __restrict__ dw, int T, int H, int W, int D, int pad_t0) {
+                                                      int T, int H, int W, int D, int pad_t0) {
   __shared__ int s_out[27];  // output position that reads THIS position through tap, or -1
-  __shared__ int s_src[27];  // source position THIS output reads through tap, or -1
   const int p = blockIdx.x;
   const int HW = H * W;
   if (threadIdx.x < 27) {
@@ -619,8 +689,6 @@ __global__ void __launch_bounds__(128) peg_bwd_kernel(const float* __restrict__ 
     const int kt = threadIdx.x / 9, kh = (threadIdx.x / 3) % 3, kw = threadIdx.x % 3;
     const int to = t - (kt - pad_t0), ho = h - (kh - 1), wo = wq - (kw - 1);
     s_out[threadIdx.x] = (to >= 0 && to < T && ho >= 0 && ho < H && wo >= 0 && wo < W) ? ((bi * T + to) * H + ho) * W + wo : -1;
-    const int ts = t + (kt - pad_t0), hs = h + (kh - 1), ws = wq + (kw - 1);
-    s_src[threadIdx.x] = (ts >= 0 && ts < T && hs >= 0 && hs < H && ws >= 0 && ws < W) ? ((bi * T + ts) * H + hs) * W + ws : -1;
   }
   __syncthreads();
   for (int d = threadIdx.x; d < D; d += blockDim.x) {
@@ -630,8 +698,6 @@ __global__ void __launch_bounds__(128) peg_bwd_kernel(const float* __restrict__ 
     for (int tap = 0; tap < 27; ++tap) {
       const int o = s_out[tap];
       if (o >= 0) acc = fmaf(w[(int64_t)tap * D + d], dy[(int64_t)o * D + d], acc);
-      const int sidx = s_src[tap];
-      if (sidx >= 0) atomicAdd(dw + (int64_t)d * 27 + tap, dyp * x[(int64_t)sidx * D + d]);  // dsconv.weight[d, 0, kt, kh, kw]
     }
     dx[(int64_t)p * D + d] = acc;
   }
@@ -1136,7 +1202,10 @@ extern "C" int phk_maskgit_train_step(const phk_maskgit_t* m, const phk_maskgit_
     }
     // PEG: x1 = x0 + conv(x0) + b
     PHK_TRY(colsum(dx, R, D, D, (float*)Gy.peg.b, st));
-    PHK_KERNEL_LAUNCH(peg_bwd_kernel, dim3((unsigned)R), dim3(128), (size_t)(0), st, S.x0, Ly.peg.w, dx, dx_alt, (float*)Gy.peg.w, pt, ph, pw, D, Ly.peg.causal ? 2 : 1);
+    PHK_REQUIRE(D <= 128 * PEG_DW_MAXJ, PHK_E_UNSUPPORTED, "maskgit_train_step: dim > 1024");
+    PHK_KERNEL_LAUNCH(peg_bwd_dw_kernel, dim3(27, PEG_DW_CHUNKS), dim3(128), (size_t)(0), st, S.x0, dx, (float*)Gy.peg.w, R, pt, ph, pw, D, Ly.peg.causal ? 2 : 1);
+    PHK_LAUNCH_CHECK();
+    PHK_KERNEL_LAUNCH(peg_bwd_kernel, dim3((unsigned)R), dim3(128), (size_t)(0), st, S.x0, Ly.peg.w, dx, dx_alt, pt, ph, pw, D, Ly.peg.causal ? 2 : 1);
     PHK_LAUNCH_CHECK();
     float* t = dx; dx = dx_alt; dx_alt = t;
   }

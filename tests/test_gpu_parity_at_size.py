@@ -52,6 +52,22 @@ def test_cfg2_token_ids_of_all_8_videos_against_both_reference_dtypes():
         assert x3["bit_agreement"] >= 0.99995 and x3["max_margin"] <= 5e-4, x3
 
 
+def test_cfg2_cosine_vq_tokenizer_at_full_codebook_size():
+    """SURVEY 8f-3 at size: configs[1] encoder + cosine-sim VectorQuantize with K = 65536 codes (309 GFLOP nearest-code
+    search, fused tcgen05 head in bf16 mode), all 8 videos against the oracle on CUDA."""
+    import parity_report as R
+    rep = _REPORT["cfg2_cosine_vq_K65536"] = R.cfg2_cosine_vq_report(batch=8)
+    _save()
+    print(json.dumps(rep, indent=1))
+    f32 = rep["ours_fp32"]
+    # ids of the fp32 mode equal the reference's except where two codes tie to fp32 summation order
+    assert f32["id_agreement_vs_reference_fp32"] >= 0.999 and f32["worst_similarity_loss_of_a_differing_id"] <= 1e-5, f32
+    b16 = rep["ours_bf16"]
+    ref16 = rep["reference_autocast_bf16_vs_reference_fp32"]["id_agreement"]
+    assert b16["worst_similarity_loss_of_a_differing_id"] <= 0.03, b16       # never a clearly worse code
+    assert b16["id_agreement_vs_reference_fp32"] >= min(0.85, ref16 - 0.05), (b16, ref16)
+
+
 def test_cfg3_logits_against_both_reference_dtypes():
     import parity_report as R
     rep = _REPORT["cfg3_logits"] = R.cfg3_logits_report(batch=4)

@@ -86,6 +86,52 @@ def cfg2_report(batch=8):
     return rep
 
 
+def cfg2_cosine_vq_report(batch=8):
+    """SURVEY 8f-3 at size: the cosine-sim VectorQuantize tokenizer (lookup_free_quantization=False, cvivit.py:321,
+    564-570) with the configs[1] encoder and K = 65536 codes: ids of all videos against the oracle on CUDA (fp32 and
+    autocast-bf16), plus the time of the whole encode call and of the nearest-code search alone."""
+    _exact_fp32()
+    torch.manual_seed(6)
+    model = P.CViViT(**dict(CFG2, lookup_free_quantization=False)).eval()
+    sd = {k: v.detach().clone().to(DEV) for k, v in model.state_dict().items()}
+    video = torch.randn((batch, 3, 17, 256, 256), generator=torch.Generator().manual_seed(7)).to(DEV)
+    model = model.to(DEV)
+    with torch.no_grad():
+        ref32, sims = O.cvivit_codebook_ids(video, sd, (256, 256), (32, 32), return_margin=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            ref16 = O.cvivit_codebook_ids(video, sd, (256, 256), (32, 32))
+    sims = sims.reshape(-1, sims.shape[-1]).float()
+    top2 = sims.topk(2, dim=-1).values
+    rep = dict(videos=batch, tokens=int(ref32.numel()), codebook_size=int(sims.shape[-1]),
+               reference_top1_top2_similarity_gap=dict(median=float((top2[:, 0] - top2[:, 1]).median()),
+                                                       min=float((top2[:, 0] - top2[:, 1]).min())),
+               reference_autocast_bf16_vs_reference_fp32=dict(id_agreement=id_agreement(ref16, ref32)))
+    for name, prec in modes().items():
+        model.precision = prec
+        ids = model(video, return_only_codebook_ids=True)
+        flat, want = ids.reshape(-1), ref32.reshape(-1)
+        differ = torch.nonzero(flat != want).flatten()
+        worst = 0.0
+        if differ.numel():  # how much worse (in cosine units) is the chosen code than the reference's, at worst
+            rows = sims[differ]
+            worst = float((rows.gather(1, want[differ, None]) - rows.gather(1, flat[differ, None])).max())
+        for _ in range(3):
+            model(video, return_only_codebook_ids=True)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            model(video, return_only_codebook_ids=True)
+        e1.record()
+        torch.cuda.synchronize()
+        rep[f"ours_{name}"] = dict(id_agreement_vs_reference_fp32=id_agreement(ids, ref32),
+                                   id_agreement_vs_reference_autocast_bf16=id_agreement(ids, ref16),
+                                   worst_similarity_loss_of_a_differing_id=worst,
+                                   encode_ms=e0.elapsed_time(e1) / 10,
+                                   frames_per_s=batch * 17 / (e0.elapsed_time(e1) / 10) * 1e3)
+    return rep
+
+
 def _err(a, ref):
     e = (a.float() - ref.float()).abs()
     return dict(max_abs=float(e.max()), mean_abs=float(e.mean()), ref_rms=float(ref.float().pow(2).mean().sqrt()),
@@ -187,6 +233,8 @@ def cfg3_loop_report(batch=1, steps=18):
 def main():
     rep = dict(device=torch.cuda.get_device_name(0), torch=torch.__version__)
     rep["cfg2_encode_ids"] = cfg2_report()
+    torch.cuda.empty_cache()
+    rep["cfg2_cosine_vq_K65536"] = cfg2_cosine_vq_report()
     torch.cuda.empty_cache()
     rep["cfg3_logits"] = cfg3_logits_report()
     torch.cuda.empty_cache()
