@@ -555,6 +555,10 @@ int phk_maskgit_train_step(const phk_maskgit_t* m, const phk_maskgit_t* grads, c
                            int32_t pt, int32_t ph, int32_t pw, const float* context, int32_t L,
                            const uint8_t* text_mask, const uint8_t* video_mask, float loss_scale, float* loss_out,
                            float* logits_out, void* workspace, int64_t workspace_bytes, int32_t prec, phk_stream_t s);
+/* Data-parallel overlap: `events` (cudaEvent_t handles, count >= depth + 2) are recorded by the NEXT phk_maskgit_train_step
+ * call of the calling thread, on its stream, as gradient groups become final: events[0] head + norm_out, events[1 + k]
+ * transformer layer depth-1-k, events[depth + 1] embeddings + position-bias MLP (= all).  One-shot; NULL clears. */
+int phk_train_set_progress_events(void** events, int32_t count);
 
 #ifdef __cplusplus
 }

@@ -26,10 +26,11 @@ namespace {
 constexpr int AQ = 128;   // queries per CTA (UMMA M)
 constexpr int AKC = 64;   // keys per chunk (UMMA N for S, K extent for PV)
 constexpr int ADH = 64;   // dim_head
-constexpr int ATHREADS = 192;
+constexpr int ATHREADS = 64 + 256;  // TMA producer, MMA issuer, eight softmax warps
 constexpr int SQ_BYTES = AQ * ADH * 2, SK_BYTES = AKC * ADH * 2, SV_BYTES = ADH * AKC * 2, SP_BYTES = AQ * AKC * 2;
 constexpr int SB_BYTES = 2 * AQ * 128;  // bias tile: two [128 rows x 32 fp32] SWIZZLE_128B boxes
-constexpr int ATT_SMEM = SQ_BYTES + SK_BYTES + SV_BYTES + SP_BYTES + SB_BYTES + 128 + 1024;
+constexpr int SMX_BYTES = 4 * AQ * 4;  // row-maximum exchange [2 buffers][2 halves][128 rows]
+constexpr int ATT_SMEM = SQ_BYTES + SK_BYTES + SV_BYTES + SP_BYTES + SB_BYTES + 128 + SMX_BYTES + 1024;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -142,6 +143,7 @@ __global__ void __launch_bounds__(ATHREADS, 2) attention_tc_kernel(const __grid_
   const uint32_t sBias = sP + SP_BYTES;
   const uint8_t* sBias_ptr = sP_ptr + SP_BYTES;
   const uint32_t bars = sBias + SB_BYTES;
+  float* s_mx = reinterpret_cast<float*>(base_ptr + SQ_BYTES + SK_BYTES + SV_BYTES + SP_BYTES + SB_BYTES + 128);
   const uint32_t b_qfull = bars, b_kfull = bars + 8, b_kempty = bars + 16, b_vfull = bars + 24, b_vempty = bars + 32,
                  b_sfull = bars + 40, b_sempty = bars + 48, b_pfull = bars + 56, b_pvdone = bars + 64,
                  b_bfull = bars + 72, b_bempty = bars + 80, tmem_slot = bars + 88;
@@ -154,8 +156,8 @@ __global__ void __launch_bounds__(ATHREADS, 2) attention_tc_kernel(const __grid_
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmK) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmV) : "memory");
     mbar_init(b_qfull, 1); mbar_init(b_kfull, 1); mbar_init(b_kempty, 1); mbar_init(b_vfull, 1);
-    mbar_init(b_vempty, 1); mbar_init(b_sfull, 1); mbar_init(b_sempty, 4); mbar_init(b_pfull, 4);
-    mbar_init(b_pvdone, 1); mbar_init(b_bfull, 1); mbar_init(b_bempty, 4);
+    mbar_init(b_vempty, 1); mbar_init(b_sfull, 1); mbar_init(b_sempty, 8); mbar_init(b_pfull, 8);
+    mbar_init(b_pvdone, 1); mbar_init(b_bfull, 1); mbar_init(b_bempty, 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -195,7 +197,10 @@ __global__ void __launch_bounds__(ATHREADS, 2) attention_tc_kernel(const __grid_
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(AKC >> 3) << 17) | ((uint32_t)(AQ >> 4) << 24);
       const uint32_t idesc_pv = idesc | (1u << 16);  // B (= V) MN-major: N = 64 dims contiguous, K = keys along rows
       mbar_wait(b_qfull, 0);
-      for (int j = 0; j < nch; ++j) {
+      // software pipeline: S(j+1) = Q K(j+1)^T is issued BEFORE waiting for the probabilities of chunk j, so the score
+      // product and its commit / barrier round trip hide behind the softmax of chunk j (S is free as soon as the
+      // softmax warps have pulled S(j) into registers, long before they finish with it)
+      auto issue_qk = [&](int j) {
         mbar_wait(b_kfull, j & 1);
         mbar_wait(b_sempty, (j & 1) ^ 1);  // softmax has read S of the previous chunk
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -204,6 +209,10 @@ __global__ void __launch_bounds__(ATHREADS, 2) attention_tc_kernel(const __grid_
         for (int k = 0; k < ADH / 16; ++k) umma_f16(tS, dq + 2 * k, dk + 2 * k, idesc, k != 0);
         umma_commit(b_kempty);
         umma_commit(b_sfull);
+      };
+      issue_qk(0);
+      for (int j = 0; j < nch; ++j) {
+        if (j + 1 < nch) issue_qk(j + 1);
         mbar_wait(b_pfull, j & 1);          // P written (and O rescaled) by the softmax warps
         mbar_wait(b_vfull, j & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -216,80 +225,87 @@ __global__ void __launch_bounds__(ATHREADS, 2) attention_tc_kernel(const __grid_
       }
     }
   } else {
-    const int lg = warp & 3;
+    // softmax: EIGHT warps, thread = (query row, half of the chunk's 64 keys).  A warp may only touch the TMEM lanes of
+    // its lane group (warp % 4), so the two warps of a lane group split the columns.  One row per thread (four warps)
+    // made the per-chunk math a 64-element serial chain per thread -- the kernel's critical path (ncu: tensor pipe 18 %
+    // active at n = 576); halves cut that chain and the register footprint in two.  Only the running MAXIMUM has to be
+    // agreed on per chunk (exchanged through shared memory); each half keeps its own partial sum until the end.
+    const int sw = warp - 2;            // 0..7
+    const int lg = warp & 3;            // TMEM lane group
+    const int hf = sw >> 2;             // which 32 of the 64 keys of a chunk / which 32 of the 64 output dims
     const int r = lg * 32 + lane;       // query row inside the tile == TMEM lane
     const int qi = q0 + r;
     const bool valid = qi < p.n_q;
     const uint32_t lane_off = (uint32_t)(lg * 32) << 16;
     const float* brow = (p.bias && valid) ? p.bias + ((int64_t)h * p.n_q + qi) * p.n_k : nullptr;
     const bool bias_vec = (p.n_k % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
+    constexpr int HC = AKC / 2;         // 32 columns per thread
+    constexpr float LOG2E = 1.4426950408889634f;
     float m_run = -INFINITY, l_run = 0.f;
     for (int j = 0; j < nch; ++j) {
-      const int k0 = j * AKC;
-      float bv[AKC];
+      const int k0 = j * AKC + hf * HC;
+      float bv[HC];
       if (!p.bias_tma) {
         // direct path (no bias, or a bias whose row pitch TMA cannot address): issued before waiting for S
-        if (brow && bias_vec && k0 + AKC <= p.n_k) {
+        if (brow && bias_vec && k0 + HC <= p.n_k) {
 #pragma unroll
-          for (int c = 0; c < AKC / 4; ++c) {
+          for (int c = 0; c < HC / 4; ++c) {
             const float4 t = __ldg(reinterpret_cast<const float4*>(brow + k0) + c);
             bv[4 * c] = t.x; bv[4 * c + 1] = t.y; bv[4 * c + 2] = t.z; bv[4 * c + 3] = t.w;
           }
         } else {
 #pragma unroll
-          for (int c = 0; c < AKC; ++c) bv[c] = (brow && k0 + c < p.n_k) ? __ldg(brow + k0 + c) : 0.f;
+          for (int c = 0; c < HC; ++c) bv[c] = (brow && k0 + c < p.n_k) ? __ldg(brow + k0 + c) : 0.f;
         }
       }
       mbar_wait(b_sfull, j & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      uint32_t sv[2][32];
-      tmem_ld32(tS + lane_off, sv[0]);
-      tmem_ld32(tS + lane_off + 32, sv[1]);
+      uint32_t sv[HC];
+      tmem_ld32(tS + lane_off + hf * HC, sv);
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(b_sempty);  // S may be overwritten by the next QK^T
+      if (lane == 0) mbar_arrive(b_sempty);  // S may be overwritten by the next QK^T (8 arrivals)
       if (p.bias_tma) {
-        // this row of the TMA-staged tile: 16-byte chunk c of row r sits at chunk (c ^ (r & 7)) (SWIZZLE_128B)
+        // this row of the TMA-staged tile (box `hf` = this half's 32 columns): 16-byte chunk c of row r sits at chunk
+        // (c ^ (r & 7)) (SWIZZLE_128B)
         mbar_wait(b_bfull, j & 1);
+        const uint8_t* rowp = sBias_ptr + hf * (AQ * 128) + r * 128;
 #pragma unroll
-        for (int sb = 0; sb < 2; ++sb) {
-          const uint8_t* rowp = sBias_ptr + sb * (AQ * 128) + r * 128;
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const float4 t = *reinterpret_cast<const float4*>(rowp + ((c ^ (r & 7)) << 4));
-            bv[sb * 32 + 4 * c] = t.x; bv[sb * 32 + 4 * c + 1] = t.y; bv[sb * 32 + 4 * c + 2] = t.z; bv[sb * 32 + 4 * c + 3] = t.w;
-          }
+        for (int c = 0; c < 8; ++c) {
+          const float4 t = *reinterpret_cast<const float4*>(rowp + ((c ^ (r & 7)) << 4));
+          bv[4 * c] = t.x; bv[4 * c + 1] = t.y; bv[4 * c + 2] = t.z; bv[4 * c + 3] = t.w;
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(b_bempty);  // tile consumed (values are in registers)
       }
-      // scores in the log2 domain (one FFMA + ex2.approx.ftz per element; __expf costs a range test, two multiplies and
-      // a select on top of the MUFU -- the softmax warps are the kernel's bottleneck, ncu source page in profiles/)
-      constexpr float LOG2E = 1.4426950408889634f;
       float mx = -INFINITY;
-      if (k0 + AKC <= p.n_k) {  // whole chunk inside the sequence (warp-uniform): no per-element bounds tests
+      if (k0 + HC <= p.n_k) {  // this half inside the sequence (warp-uniform): no per-element bounds tests
 #pragma unroll
-        for (int c = 0; c < AKC; ++c) {
-          const float s = __uint_as_float(sv[c >> 5][c & 31]) + bv[c];
-          bv[c] = s;
-          mx = fmaxf(mx, s);
+        for (int c = 0; c < HC; ++c) {
+          const float sc = __uint_as_float(sv[c]) + bv[c];
+          bv[c] = sc;
+          mx = fmaxf(mx, sc);
         }
       } else {
 #pragma unroll
-        for (int c = 0; c < AKC; ++c) {
-          float s = __uint_as_float(sv[c >> 5][c & 31]) + bv[c];
-          if (k0 + c >= p.n_k) s = -INFINITY;  // zero-filled padding keys
-          bv[c] = s;
-          mx = fmaxf(mx, s);
+        for (int c = 0; c < HC; ++c) {
+          float sc = __uint_as_float(sv[c]) + bv[c];
+          if (k0 + c >= p.n_k) sc = -INFINITY;  // zero-filled padding keys
+          bv[c] = sc;
+          mx = fmaxf(mx, sc);
         }
       }
+      // the row maximum of the chunk over both halves (double-buffered exchange: a thread may be one chunk ahead)
+      s_mx[((j & 1) * 2 + hf) * AQ + r] = mx;
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      mx = fmaxf(mx, s_mx[((j & 1) * 2 + (hf ^ 1)) * AQ + r]);
       const float m_new = fmaxf(m_run, mx);
-      const float alpha = fast_ex2((m_run - m_new) * LOG2E);  // 0 on the first chunk (m_run = -inf)
-      const float m2 = m_new * LOG2E;
+      const float alpha = fast_ex2((m_run - m_new) * LOG2E);  // 0 on the first chunk (m_run = -inf); m_new is finite:
+      const float m2 = m_new * LOG2E;                          // the first half of every chunk holds valid keys
       float lsum = 0.f;
-      uint32_t pk[AKC / 2];
+      uint32_t pk[HC / 2];
 #pragma unroll
-      for (int c = 0; c < AKC; c += 2) {
+      for (int c = 0; c < HC; c += 2) {
         const float p0 = fast_ex2(fmaf(bv[c], LOG2E, -m2)), p1 = fast_ex2(fmaf(bv[c + 1], LOG2E, -m2));
         lsum += p0 + p1;
         pk[c >> 1] = pack_bf16x2(p0, p1);
@@ -299,35 +315,35 @@ __global__ void __launch_bounds__(ATHREADS, 2) attention_tc_kernel(const __grid_
       if (j > 0) {
         mbar_wait(b_pvdone, (j - 1) & 1);  // previous P.V finished: P buffer free, O stable
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (__any_sync(0xffffffffu, alpha != 1.0f)) {  // rescale the running output in TMEM
+        if (__any_sync(0xffffffffu, alpha != 1.0f)) {  // rescale this thread's half of the running output in TMEM
+          uint32_t ov[32];
+          tmem_ld32(tO + lane_off + hf * 32, ov);
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            uint32_t ov[32];
-            tmem_ld32(tO + lane_off + half * 32, ov);
-#pragma unroll
-            for (int c = 0; c < 32; ++c) ov[c] = __float_as_uint(__uint_as_float(ov[c]) * alpha);
-            tmem_st32(tO + lane_off + half * 32, ov);
-          }
+          for (int c = 0; c < 32; ++c) ov[c] = __float_as_uint(__uint_as_float(ov[c]) * alpha);
+          tmem_st32(tO + lane_off + hf * 32, ov);
         }
       }
-      // P row -> SWIZZLE_128B K-major tile: 16-byte chunk c of row r lives at chunk (c ^ (r & 7))
+      // this half of the P row -> SWIZZLE_128B K-major tile: 16-byte chunk c of row r lives at chunk (c ^ (r & 7))
       uint8_t* prow = sP_ptr + r * 128;
 #pragma unroll
-      for (int c = 0; c < 8; ++c)
-        *reinterpret_cast<uint4*>(prow + ((c ^ (r & 7)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+      for (int c = 0; c < 4; ++c)
+        *reinterpret_cast<uint4*>(prow + (((hf * 4 + c) ^ (r & 7)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(b_pfull);
+      if (lane == 0) mbar_arrive(b_pfull);  // (8 arrivals)
     }
+    // total row sum = the two halves' partial sums (same running maximum on both sides); exchanged through the buffer the
+    // LAST chunk did not use (a partner may still be reading that chunk's maxima)
+    s_mx[((nch & 1) * 2 + hf) * AQ + r] = l_run;
+    asm volatile("bar.sync 2, 256;" ::: "memory");
+    const float inv = 1.f / (l_run + s_mx[((nch & 1) * 2 + (hf ^ 1)) * AQ + r]);
     mbar_wait(b_pvdone, (nch - 1) & 1);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const float inv = 1.f / l_run;
     __nv_bfloat16* orow = p.out + (int64_t)seq * p.o_seq + (int64_t)qi * p.o_tok + h * ADH;
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
+    {
       uint32_t ov[32];
-      tmem_ld32(tO + lane_off + half * 32, ov);
+      tmem_ld32(tO + lane_off + hf * 32, ov);
       if (valid) {
 #pragma unroll
         for (int c = 0; c < 32; c += 8) {
@@ -335,7 +351,7 @@ __global__ void __launch_bounds__(ATHREADS, 2) attention_tc_kernel(const __grid_
 #pragma unroll
           for (int e = 0; e < 4; ++e)
             w[e] = pack_bf16x2(__uint_as_float(ov[c + 2 * e]) * inv, __uint_as_float(ov[c + 2 * e + 1]) * inv);
-          *reinterpret_cast<uint4*>(orow + half * 32 + c) = make_uint4(w[0], w[1], w[2], w[3]);
+          *reinterpret_cast<uint4*>(orow + hf * 32 + c) = make_uint4(w[0], w[1], w[2], w[3]);
         }
       }
     }

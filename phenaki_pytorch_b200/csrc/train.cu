@@ -953,6 +953,22 @@ int64_t tc_scratch_elems(const phk_maskgit_t* m, int64_t R, int64_t CR, bool bce
 
 using namespace phk;
 
+// Data-parallel overlap: the caller may hand in CUDA events that the NEXT phk_maskgit_train_step call of this
+// thread records on its stream as groups of gradients become final -- events[0]: the head + norm_out, events[1 + k]:
+// transformer layer depth-1-k (backward order), events[depth + 1]: embeddings + position-bias MLP = everything.  A side
+// stream can then all-reduce each finished slice of the flat gradient bucket while the layers below still run.
+static thread_local void** g_progress_events = nullptr;
+static thread_local int g_progress_count = 0;
+extern "C" int phk_train_set_progress_events(void** events, int32_t count) {
+  g_progress_events = events;
+  g_progress_count = events ? count : 0;
+  return 0;
+}
+static inline int progress_mark(void** ev, int n, int idx, cudaStream_t st) {
+  if (ev && idx < n && ev[idx]) PHK_CUDA(cudaEventRecord(reinterpret_cast<cudaEvent_t>(ev[idx]), st));
+  return 0;
+}
+
 extern "C" int64_t phk_maskgit_train_workspace_bytes(const phk_maskgit_t* m, int32_t b, int32_t n, int32_t L,
                                                      int32_t bce_head, int32_t prec) {
   if (!m || b <= 0 || n <= 0 || L < 0 || !m->transformer.layers) return -1;
@@ -1010,6 +1026,9 @@ extern "C" int phk_maskgit_train_step(const phk_maskgit_t* m, const phk_maskgit_
               "maskgit_train_step: transformer table / gradient table mismatch");
   PHK_REQUIRE(m->dim % 4 == 0, PHK_E_UNSUPPORTED, "maskgit_train_step: dim must be a multiple of 4");
   cudaStream_t st = to_stream(s);
+  void** prog = g_progress_events;  // one-shot: consumed by this call
+  const int nprog = g_progress_count;
+  g_progress_events = nullptr; g_progress_count = 0;
   const int D = m->dim, H = T->heads, DH = T->dim_head, I = H * DH, V = m->num_tokens;
   const int64_t R = (int64_t)b * n, CR = (int64_t)b * L;
   Arena ar{(char*)workspace, workspace_bytes, 0};
@@ -1156,6 +1175,7 @@ extern "C" int phk_maskgit_train_step(const phk_maskgit_t* m, const phk_maskgit_
   float* dx = dxa;      // d loss / d (current residual stream)
   float* dx_alt = dxb;
   PHK_TRY(ln_backward(xf, T->out_g, dtmp, dx, 0, (float*)GT->out_g, nullptr, stats, R, D, st));
+  PHK_TRY(progress_mark(prog, nprog, 0, st));  // head + norm_out gradients final
   for (int l = T->depth - 1; l >= 0; --l) {
     const phk_layer_t& Ly = T->layers[l];
     const phk_layer_t& Gy = GT->layers[l];
@@ -1208,6 +1228,9 @@ extern "C" int phk_maskgit_train_step(const phk_maskgit_t* m, const phk_maskgit_
     PHK_KERNEL_LAUNCH(peg_bwd_kernel, dim3((unsigned)R), dim3(128), (size_t)(0), st, S.x0, Ly.peg.w, dx, dx_alt, pt, ph, pw, D, Ly.peg.causal ? 2 : 1);
     PHK_LAUNCH_CHECK();
     float* t = dx; dx = dx_alt; dx_alt = t;
+    // this layer's parameter gradients are final -- except, with a context, the cross-attention's context_norm / to_kv
+    // share nothing with other layers either; the position-bias gradient (dbias, all layers) is finished below
+    PHK_TRY(progress_mark(prog, nprog, 1 + (T->depth - 1 - l), st));
   }
   // ---------------------------------------------------------------- embeddings, position-bias MLP
   PHK_KERNEL_LAUNCH(embed_bwd_kernel, dim3((unsigned)R), dim3(128), (size_t)(0), st, ids_in, dx, (float*)grads->token_emb, (float*)grads->pos_emb, n, D,
@@ -1218,5 +1241,6 @@ extern "C" int phk_maskgit_train_step(const phk_maskgit_t* m, const phk_maskgit_
     PHK_REQUIRE(csc, PHK_E_WORKSPACE, "maskgit_train_step: workspace too small (position-bias backward)");
     PHK_TRY(cpb_backward(m->pos_bias, grads->pos_bias, dbias, pt, ph, pw, csc, st));
   }
+  PHK_TRY(progress_mark(prog, nprog, T->depth + 1, st));
   return 0;
 }

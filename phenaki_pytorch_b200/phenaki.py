@@ -208,7 +208,19 @@ class _TokenTransformer(nn.Module):
         """Zero-filled gradient buffers (one flat fp32 bucket in ``owner.parameters()`` order) and the
         phk_maskgit_t-shaped table that addresses them; same member-by-member layout as ``_table``.
         ``head``: an nn.Linear(dim, 1) that replaces the network's own head (SelfCritic.to_pred)."""
+        # one bucket + table per (owner, head, cross) is kept and re-zeroed while no backward() is pending on it (building the
+        # 150-entry table and a 380 MB allocation per step cost more host time than the step's launches)
+        cache = self.__dict__.setdefault("_grad_cache", {})
+        key = (id(owner), id(head), bool(with_cross), weights_signature(owner if owner is not None else self)[:1],
+               next(self.parameters()).device)
+        hit = cache.get(key)
+        if hit is not None and not hit[1].busy and hit[2] == [id(p) for p in (owner if owner is not None else self).parameters()]:
+            hit[1].flat.zero_()
+            hit[1].reduced = None
+            hit[1].busy = True
+            return hit[0], hit[1]
         gk = GradKeep((owner if owner is not None else self).parameters())
+        gk.busy, gk.reduced = True, None
         t = L.MaskgitT()
         tf = self.transformer
         t.dim, t.heads, t.dim_head = tf.dim, tf.heads, tf.dim_head
@@ -225,10 +237,13 @@ class _TokenTransformer(nn.Module):
         else:
             t.head_w, t.head_b = gk.g(self.to_logits[0].weight), gk.g(self.to_logits[0].bias)
         t.transformer = transformer_grad_table(tf, gk, with_cross)
+        if hit is None or not hit[1].busy:
+            cache[key] = (t, gk, [id(p) for p in (owner if owner is not None else self).parameters()])
         return t, gk
 
     def train_step(self, ids_in, patch_shape, *, targets=None, token_mask=None, labels=None, context=None,
-                   text_mask=None, video_mask=None, loss_scale=1.0, keep_logits=False, head=None, owner=None):
+                   text_mask=None, video_mask=None, loss_scale=1.0, keep_logits=False, head=None, owner=None,
+                   overlap_all_reduce=False):
         """One forward + loss + backward in libphk (phk_maskgit_train_step; ``self.precision`` selects fp32 FFMA or
         tcgen05 bf16 products, everything else is fp32 in both modes): returns (loss 0-d tensor,
         GradKeep with d(loss_scale * loss)/d(parameter), logits or None).  ``labels`` given: Linear(dim, 1) head + BCE
@@ -281,13 +296,70 @@ class _TokenTransformer(nn.Module):
             nbytes = lib.phk_maskgit_train_workspace_bytes(C.byref(table), b, n, ctx_len, int(bce), prec)
             ws = self._ws.get(nbytes, dev)
             pt, ph, pw = (int(v) for v in patch_shape)
+            plan = self._overlap_plan(gk, owner if owner is not None else self, dev) if overlap_all_reduce else None
+            if plan is not None:  # the C call records these events as gradient groups become final
+                L.check(lib.phk_train_set_progress_events(plan["handles"], len(plan["events"])), "phk_train_set_progress_events")
             L.check(lib.phk_maskgit_train_step(C.byref(table), C.byref(gtable), L.ptr(ids_in), L.ptr(targets),
                                                L.ptr(token_mask), L.ptr(labels), b, n, pt, ph, pw, L.ptr(context),
                                                ctx_len, L.ptr(text_mask), L.ptr(video_mask), float(loss_scale),
                                                L.ptr(loss), L.ptr(logits), L.ptr(ws), ws.numel(), prec,
                                                L.stream_ptr()),
                     "phk_maskgit_train_step")
+            if plan is not None:
+                self._launch_overlapped_all_reduce(gk, plan)
         return loss, gk, logits
+
+    def _overlap_plan(self, gk, owner, dev):
+        """Data parallel, NCCL: slices of the flat gradient bucket in the order the backward finishes them (head +
+        norm_out, layers depth-1 .. 0, embeddings + position-bias MLP) and one CUDA event per slice for
+        phk_train_set_progress_events.  None when there is nothing to overlap (single process, non-NCCL backend)."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 and gk.flat.is_cuda
+                and dist.get_backend() == "nccl"):
+            return None
+        depth = self.transformer.depth
+        base, esz = gk.flat.data_ptr(), gk.flat.element_size()
+        groups = [[None, None] for _ in range(depth + 2)]  # [lo, hi) in elements, by completion index
+        for name, p in owner.named_parameters():
+            lo = (gk.views[p].data_ptr() - base) // esz
+            hi = lo + (p.numel() + 63) // 64 * 64
+            idx = depth + 1  # embeddings, position-bias MLP: final at the very end
+            if "transformer.layers." in name:
+                idx = 1 + (depth - 1 - int(name.split("transformer.layers.")[1].split(".")[0]))
+            elif "norm_out" in name or "to_logits" in name or "to_pred" in name:
+                idx = 0
+            g = groups[idx]
+            g[0] = lo if g[0] is None else min(g[0], lo)
+            g[1] = hi if g[1] is None else max(g[1], hi)
+        spans = sorted((g[0], g[1]) for g in groups if g[0] is not None)
+        if any(a[1] > b[0] for a, b in zip(spans, spans[1:])):  # groups interleave in the bucket: no slicing
+            return None
+        cache = self.__dict__.setdefault("_overlap_cache", {})
+        key = (dev, depth)
+        if key not in cache:
+            events = [torch.cuda.Event() for _ in range(depth + 2)]
+            for e in events:
+                e.record()  # creates the CUDA event behind the (lazily initialised) torch object
+            handles = (C.c_void_p * len(events))(*[e.cuda_event for e in events])
+            cache[key] = dict(events=events, handles=handles, stream=torch.cuda.Stream(device=dev))
+        return dict(cache[key], groups=groups)
+
+    def _launch_overlapped_all_reduce(self, gk, plan):
+        """One all-reduce (mean) per finished slice on a side stream, each waiting only for its own event: the
+        collective of the head / upper layers runs while the layers below are still in their backward kernels."""
+        import torch.distributed as dist
+        side, world = plan["stream"], dist.get_world_size()
+        gk.flat.record_stream(side)
+        for ev, (lo, hi) in zip(plan["events"], plan["groups"]):
+            if lo is None:
+                continue
+            side.wait_event(ev)
+            with torch.cuda.stream(side):
+                part = gk.flat[lo:hi]
+                dist.all_reduce(part, op=dist.ReduceOp.SUM)
+                part.div_(world)
+        gk.reduced = torch.cuda.Event()
+        gk.reduced.record(side)
 
     def _check_ids(self, x):
         """nn.Embedding raises on an id outside the table (phenaki_pytorch.py:194); the kernels only clamp.  One device
@@ -466,9 +538,15 @@ class _TrainStepFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gout):
         if ctx.sync:  # data parallel: average the one flat gradient bucket over the ranks (DDP's all-reduce)
-            sharding.all_reduce_mean_(ctx.keep.flat)
+            reduced = getattr(ctx.keep, "reduced", None)
+            if reduced is not None:  # already launched slice by slice on the side stream, overlapped with the backward
+                torch.cuda.current_stream().wait_event(reduced)
+            else:
+                sharding.all_reduce_mean_(ctx.keep.flat)
             ctx.sync = False
-        return (None, None, None, *[None if g is None else g * gout for g in ctx.grads])
+        out = (None, None, None, *[None if g is None else g * gout for g in ctx.grads])  # copies: the bucket is free again
+        ctx.keep.busy = False
+        return out
 
 
 def get_mask_subset_with_prob(mask, prob, u=None):
@@ -802,7 +880,8 @@ class Phenaki(nn.Module):
             video_mask = self.cvivit.calculate_video_token_mask(videos, video_frame_mask=video_frame_mask)
         patch_shape = tuple(int(v) for v in video_codebook_ids.shape[1:])
         ids = video_codebook_ids.reshape(video_codebook_ids.shape[0], -1).to(dev)
-        mg._check_ids(ids)
+        if videos is None:  # caller-supplied ids: nn.Embedding would raise on an id outside the table (one device sync)
+            mg._check_ids(ids)
         batch, seq = ids.shape
         draw = draw_fn if draw_fn is not None else (lambda shape, tag: None)
         rand_step = draw((batch,), "rand_step")
@@ -824,7 +903,7 @@ class Phenaki(nn.Module):
                                  video_mask=video_mask)
         else:
             ce, gk, logits = mg.train_step(masked_input, patch_shape, targets=ids, token_mask=mask_token_mask,
-                                           keep_logits=need_critic, **kw)
+                                           keep_logits=need_critic, overlap_all_reduce=self.sync_gradients, **kw)
             loss = _TrainStepFn.apply(ce, gk, self.sync_gradients, *mg.parameters())
         if not need_critic:
             return loss
@@ -846,7 +925,8 @@ class Phenaki(nn.Module):
         weight = 1.0 if only_train_critic else self.critic_loss_weight
         ckw = kw if self.critic.has_cross_attn else dict(video_mask=video_mask)
         # (a SelfCritic differentiates MaskGit a second time: autograd adds the two contributions to p.grad)
-        bce, cgk, _ = self.critic.train_step(critic_input, patch_shape, labels=labels, **ckw)
+        bce, cgk, _ = self.critic.train_step(critic_input, patch_shape, labels=labels,
+                                             overlap_all_reduce=self.sync_gradients, **ckw)
         critic_loss = _TrainStepFn.apply(bce, cgk, self.sync_gradients, *self.critic.parameters())
         return critic_loss * weight if loss is None else loss + critic_loss * weight
 

@@ -47,7 +47,7 @@ def _fake_train_step(module, heads):
     restatement of the kernels."""
 
     def run(ids_in, patch_shape, *, targets=None, token_mask=None, labels=None, context=None, text_mask=None,
-            video_mask=None, loss_scale=1.0, keep_logits=False):
+            video_mask=None, loss_scale=1.0, keep_logits=False, overlap_all_reduce=False):
         sd = {k: v.detach() for k, v in module.state_dict().items()}
         with torch.no_grad():
             loss, grads, logits = TM.train_step(sd, ids_in, targets, token_mask, labels, patch_shape=patch_shape,
