@@ -855,6 +855,170 @@ __global__ void __launch_bounds__(MMA_WARPS * 32) attention_small_mma_kernel(con
 }
 #endif  // PHK_CUDA_EMU
 
+
+// ------------------------------------------------------------------------------------------
+// Cross-attention over a short text context (null-kv + L <= 32 keys, dim_head 64, bf16 output: the bf16 mode of
+// MaskGit / TokenCritic, attention.py:137-181) on warp-level tensor-core MMAs.  CTA = 128 queries of one (sequence,
+// head): the keys are l2-normalised, scaled and converted once per CTA into shared memory (like attention_fewkeys_kernel),
+// every warp owns 16 queries: it loads their fp32 rows straight into A-fragment order (float2 per lane), normalises them
+// with quad shuffles, S = Q K^T is 16 mma.sync.m16n8k16, the softmax runs on the accumulator fragments, P V another 16.
+// attention_fewkeys_kernel (one thread per query, broadcast reads) needs ~5x the issue slots; it remains the path for
+// fp32 output, other head sizes and the CPU executor.  [not compiled for the CPU executor: PHK_CUDA_EMU]
+// ------------------------------------------------------------------------------------------
+#ifndef PHK_CUDA_EMU
+constexpr int XK = 32;  // key slots (null-kv + text), XK / 8 score tiles per warp
+
+__global__ void __launch_bounds__(256) attention_cross_mma_kernel(const float* __restrict__ q, const float* __restrict__ kv,
+                                                                  const float* __restrict__ null_kv,
+                                                                  const float* __restrict__ q_scale,
+                                                                  const float* __restrict__ k_scale,
+                                                                  const uint8_t* __restrict__ key_mask,
+                                                                  __nv_bfloat16* __restrict__ out, phk_attn_geom_t g) {
+  pdl_prologue();
+  __shared__ __align__(16) __nv_bfloat16 sK[XK][MMA_LD];
+  __shared__ __align__(16) __nv_bfloat16 sV[XK][MMA_LD];
+  __shared__ float s_dead[XK];  // 0: live key, 1: masked / padding
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int h = blockIdx.y, seq = blockIdx.z;
+  const int so = seq / g.n_inner, si = seq - so * g.n_inner;
+  const int I = g.heads * 64, nnull = g.num_null_kv, nk_all = g.n_k + nnull;
+  const int kv_so = g.kv_outer_mod > 0 ? so % g.kv_outer_mod : so;
+  const int mask_row = g.mask_outer_mod > 0 ? so % g.mask_outer_mod : so;
+  const bool mask_dropped = g.mask_off_from >= 0 && so >= g.mask_off_from;
+  // null half of a CFG pair: every text key is masked and contributes exp(-FLT_MAX - m) = 0 exactly -> only the null keys
+  const int nk = (mask_dropped && key_mask) ? nnull : nk_all;
+  const float* kbase = kv + (int64_t)kv_so * g.k_outer + (int64_t)si * g.k_inner + (int64_t)h * 64;
+  for (int j = w; j < XK; j += 8) {  // warp per key slot: l2-normalise * k_scale -> bf16; value -> bf16; zero padding
+    float2 kx = make_float2(0.f, 0.f), vx = make_float2(0.f, 0.f);
+    bool dead = true;
+    if (j < nk) {
+      const float* kp;
+      const float* vp;
+      if (j < nnull) { kp = null_kv + ((int64_t)h * 2 * nnull + 2 * j) * 64; vp = kp + 64; }   // 'h (n r) d' (:148)
+      else { kp = kbase + (int64_t)(j - nnull) * g.k_tok; vp = kp + I; }
+      kx = reinterpret_cast<const float2*>(kp)[lane];
+      vx = reinterpret_cast<const float2*>(vp)[lane];
+      const float inv = 1.0f / fmaxf(sqrtf(warp_sum(kx.x * kx.x + kx.y * kx.y)), 1e-12f);
+      const float2 ks = reinterpret_cast<const float2*>(k_scale)[lane];
+      kx.x = (kx.x * inv) * ks.x; kx.y = (kx.y * inv) * ks.y;
+      const int kj = j - nnull;
+      dead = key_mask && kj >= 0 && (mask_dropped || !key_mask[(int64_t)mask_row * g.n_k + kj]);
+    }
+    reinterpret_cast<uint32_t*>(&sK[j][0])[lane] = pack_bf16x2(kx.x, kx.y);
+    reinterpret_cast<uint32_t*>(&sV[j][0])[lane] = pack_bf16x2(vx.x, vx.y);
+    if (lane == 0) s_dead[j] = dead ? 1.f : 0.f;
+  }
+  __syncthreads();
+  const int gq = lane >> 2, t = lane & 3;
+  const int r0 = blockIdx.x * 128 + w * 16;  // this warp's 16 queries
+  if (r0 >= g.n_q) return;
+  const float* qbase = q + (int64_t)so * g.q_outer + (int64_t)si * g.q_inner + (int64_t)h * 64;
+  // A fragments of the normalised queries: lane (gq, t) holds rows gq / gq + 8, columns ks*16 + {2t, 2t+1, 2t+8, 2t+9}
+  float2 qa[4][4];
+  float ss0 = 0.f, ss1 = 0.f;
+  const bool v0 = r0 + gq < g.n_q, v1 = r0 + gq + 8 < g.n_q;
+  const float* q0p = qbase + (int64_t)(r0 + gq) * g.q_tok;
+  const float* q1p = qbase + (int64_t)(r0 + gq + 8) * g.q_tok;
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    const int c = ks * 16 + 2 * t;
+    qa[ks][0] = v0 ? *reinterpret_cast<const float2*>(q0p + c) : make_float2(0.f, 0.f);
+    qa[ks][1] = v1 ? *reinterpret_cast<const float2*>(q1p + c) : make_float2(0.f, 0.f);
+    qa[ks][2] = v0 ? *reinterpret_cast<const float2*>(q0p + c + 8) : make_float2(0.f, 0.f);
+    qa[ks][3] = v1 ? *reinterpret_cast<const float2*>(q1p + c + 8) : make_float2(0.f, 0.f);
+    ss0 += qa[ks][0].x * qa[ks][0].x + qa[ks][0].y * qa[ks][0].y + qa[ks][2].x * qa[ks][2].x + qa[ks][2].y * qa[ks][2].y;
+    ss1 += qa[ks][1].x * qa[ks][1].x + qa[ks][1].y * qa[ks][1].y + qa[ks][3].x * qa[ks][3].x + qa[ks][3].y * qa[ks][3].y;
+  }
+  ss0 += __shfl_xor_sync(0xffffffffu, ss0, 1); ss0 += __shfl_xor_sync(0xffffffffu, ss0, 2);
+  ss1 += __shfl_xor_sync(0xffffffffu, ss1, 1); ss1 += __shfl_xor_sync(0xffffffffu, ss1, 2);
+  const float i0 = g.scale / fmaxf(sqrtf(ss0), 1e-12f), i1 = g.scale / fmaxf(sqrtf(ss1), 1e-12f);
+  uint32_t a[4][4];
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    const int c = ks * 16 + 2 * t;
+    const float2 s_lo = *reinterpret_cast<const float2*>(q_scale + c), s_hi = *reinterpret_cast<const float2*>(q_scale + c + 8);
+    a[ks][0] = pack_bf16x2(qa[ks][0].x * i0 * s_lo.x, qa[ks][0].y * i0 * s_lo.y);
+    a[ks][1] = pack_bf16x2(qa[ks][1].x * i1 * s_lo.x, qa[ks][1].y * i1 * s_lo.y);
+    a[ks][2] = pack_bf16x2(qa[ks][2].x * i0 * s_hi.x, qa[ks][2].y * i0 * s_hi.y);
+    a[ks][3] = pack_bf16x2(qa[ks][3].x * i1 * s_hi.x, qa[ks][3].y * i1 * s_hi.y);
+  }
+  // S[16 x 32] = Q K^T: four key tiles of 8, four k-steps of 16 dims
+  float sc[4][4];
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) sc[nt][e] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+    for (int np = 0; np < 2; ++np) {
+      uint32_t b[4];
+      ldmatrix_x4(b, &sK[(lane & 7) + 8 * (lane >> 4) + 16 * np][ks * 16 + 8 * ((lane >> 3) & 1)]);
+      mma_bf16_16816(sc[2 * np], a[ks], b[0], b[1]);
+      mma_bf16_16816(sc[2 * np + 1], a[ks], b[2], b[3]);
+    }
+  // softmax over the key slots; masked / padding keys: the reference fills -finfo.max (:168) -> weight exactly 0 next to
+  // the always-live null keys (the dispatcher only takes this kernel when num_null_kv > 0)
+  float inv[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    float m = -FLT_MAX;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int key = nt * 8 + 2 * t + e;
+        if (s_dead[key] != 0.f) sc[nt][2 * r + e] = -FLT_MAX;
+        m = fmaxf(m, sc[nt][2 * r + e]);
+      }
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+    float sum = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const float v = sc[nt][2 * r + e];
+        const float ex = v == -FLT_MAX ? 0.f : __expf(v - m);
+        sc[nt][2 * r + e] = ex;
+        sum += ex;
+      }
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    inv[r] = sum > 0.f ? __fdividef(1.f, sum) : 0.f;
+  }
+  uint32_t pa[2][4];  // P as the A operand of P V, two k-steps of 16 keys
+#pragma unroll
+  for (int kk = 0; kk < 2; ++kk) {
+    pa[kk][0] = pack_bf16x2(sc[2 * kk][0], sc[2 * kk][1]);
+    pa[kk][1] = pack_bf16x2(sc[2 * kk][2], sc[2 * kk][3]);
+    pa[kk][2] = pack_bf16x2(sc[2 * kk + 1][0], sc[2 * kk + 1][1]);
+    pa[kk][3] = pack_bf16x2(sc[2 * kk + 1][2], sc[2 * kk + 1][3]);
+  }
+  const int64_t ob = (int64_t)so * g.o_outer + (int64_t)si * g.o_inner + (int64_t)h * 64;
+#pragma unroll
+  for (int dp = 0; dp < 4; ++dp) {
+    float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+      uint32_t b[4];
+      ldmatrix_x4_trans(b, &sV[(lane & 7) + 8 * ((lane >> 3) & 1) + 16 * kk][(2 * dp + (lane >> 4)) * 8]);
+      mma_bf16_16816(o0, pa[kk], b[0], b[1]);
+      mma_bf16_16816(o1, pa[kk], b[2], b[3]);
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int row = r0 + gq + 8 * r;
+      if (row < g.n_q) {
+        __nv_bfloat16* orow = out + ob + (int64_t)row * g.o_tok;
+        *reinterpret_cast<uint32_t*>(orow + (2 * dp) * 8 + 2 * t) = pack_bf16x2(o0[2 * r] * inv[r], o0[2 * r + 1] * inv[r]);
+        *reinterpret_cast<uint32_t*>(orow + (2 * dp + 1) * 8 + 2 * t) = pack_bf16x2(o1[2 * r] * inv[r], o1[2 * r + 1] * inv[r]);
+      }
+    }
+  }
+}
+#endif  // PHK_CUDA_EMU
+
 template <int NMAX, bool PRE = false>
 static int launch_attention_warp64(const void* q, const void* kv, const float* q_scale, const float* k_scale,
                                    const float* alibi_slopes, void* out, const phk_attn_geom_t& g, cudaStream_t st) {
@@ -975,6 +1139,23 @@ extern "C" int phk_attention(const float* q, const float* kv, const float* null_
     if (g->dim_head == 64) return launch_attention_small<64>(q, kv, q_scale, k_scale, alibi_slopes, out, *g, st);
     return launch_attention_small<32>(q, kv, q_scale, k_scale, alibi_slopes, out, *g, st);
   }
+#ifndef PHK_CUDA_EMU
+  {  // bf16-mode cross-attention over <= 32 key slots on warp-level MMAs
+    static const bool cross_mma = [] { const char* e = std::getenv("PHK_CROSS_ATTN_MMA"); return !(e && e[0] == '0'); }();
+    if (cross_mma && !g->causal && !bias && g->out_bf16 && g->dim_head == 64 && g->num_null_kv > 0 &&
+        g->n_k + g->num_null_kv <= XK && g->q_tok % 2 == 0 && g->q_outer % 2 == 0 && g->q_inner % 2 == 0 && g->k_tok % 2 == 0 &&
+        g->k_outer % 2 == 0 && g->k_inner % 2 == 0 && g->o_tok % 2 == 0 && g->o_outer % 2 == 0 && g->o_inner % 2 == 0 &&
+        ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(kv) | reinterpret_cast<uintptr_t>(null_kv) |
+          reinterpret_cast<uintptr_t>(q_scale) | reinterpret_cast<uintptr_t>(k_scale)) & 7) == 0 &&
+        (reinterpret_cast<uintptr_t>(out) & 3) == 0) {
+      dim3 grid((unsigned)((g->n_q + 127) / 128), (unsigned)g->heads, (unsigned)(g->n_outer * g->n_inner));
+      PHK_CUDA(launch_pdl(attention_cross_mma_kernel, grid, dim3(256), (size_t)0, st, q, kv, null_kv, q_scale, k_scale, key_mask,
+                          (__nv_bfloat16*)out, *g));
+      PHK_LAUNCH_CHECK();
+      return 0;
+    }
+  }
+#endif
   if (!g->causal && !bias && g->n_k + g->num_null_kv <= FEW_KEYS && (g->dim_head == 64 || g->dim_head == 32) &&
       g->q_tok % 4 == 0 && g->q_outer % 4 == 0 && g->q_inner % 4 == 0 && g->o_tok % 8 == 0 && g->o_outer % 8 == 0 &&
       g->o_inner % 8 == 0 && (reinterpret_cast<uintptr_t>(q) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {

@@ -113,7 +113,7 @@ class CViViT(nn.Module):
         # built here: the tokenizer constructs with the reference's defaults, encodes and decodes, and loads the
         # reference's checkpoints (load_state_dict drops their `discr.*` entries); forward() raises for the loss paths.
         self.use_vgg_and_gan = use_vgg_and_gan
-        self.precision = L.PREC_F32
+        self.precision = L.default_precision()
         self._tables = None
         self._sig = None
         self._dec_tables = None

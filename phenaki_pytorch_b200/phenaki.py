@@ -62,7 +62,7 @@ class _TokenTransformer(nn.Module):
     is_critic = False
 
     def _init_runtime(self):
-        self.precision = L.PREC_F32
+        self.precision = L.default_precision()
         self._tables, self._sig = None, None
         self._ws = Workspace()
         self._bias_cache = {}

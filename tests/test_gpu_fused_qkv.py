@@ -131,3 +131,43 @@ def test_residual_gemm_with_layernorm_epilogue(M, N, K, raw):
     torch.testing.assert_close(ln.cpu().float(), ref_ln, rtol=1e-2, atol=2e-2)
     if raw:
         torch.testing.assert_close(rw.cpu().float(), ref_x, rtol=1e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize("b,n,L,heads,cfg", [(4, 576, 16, 8, True), (2, 130, 29, 4, False), (3, 64, 7, 2, True)])
+def test_cross_attention_bf16_output_on_warp_mma(b, n, L, heads, cfg):
+    """phk_attention's bf16-output cross-attention path (attention_cross_mma_kernel: null-kv + text keys <= 32 slots) against
+    the fp32 oracle core: text masks, the CFG null half (sequences >= mask_off_from see only the null keys), ragged tails."""
+    from oracle import phenaki_oracle as O
+    I, nnull = heads * 64, 2
+    seqs = 2 * b if cfg else b
+    q = TC.seeded_randn((seqs, n, I), 440)
+    ctx_kv = TC.seeded_randn((b, L, 2 * I), 441)
+    null_kv = TC.seeded_randn((heads, 2 * nnull, 64), 442)
+    qs, ks = TC.seeded_randn((64,), 443).abs() * 0.3 + 0.7, TC.seeded_randn((64,), 444).abs() * 0.3 + 0.7
+    tmask = torch.ones((b, L), dtype=torch.bool)
+    for i in range(b):
+        tmask[i, max(1, L - 3 * i):] = False
+    split = lambda t_: t_.reshape(t_.shape[0], t_.shape[1], heads, 64).permute(0, 2, 1, 3)
+    kvs = ctx_kv.repeat(2, 1, 1) if cfg else ctx_kv
+    k, v = kvs.chunk(2, dim=-1)
+    nk = null_kv[:, 0::2].unsqueeze(0).expand(seqs, -1, -1, -1)
+    nv = null_kv[:, 1::2].unsqueeze(0).expand(seqs, -1, -1, -1)
+    mask = torch.cat((tmask, torch.zeros_like(tmask)), dim=0) if cfg else tmask
+    ref = O.attention_core(split(q), torch.cat((nk, split(k)), dim=-2), torch.cat((nv, split(v)), dim=-2), qs, ks, heads=heads,
+                           num_null_kv=nnull, mask=mask)
+    ref = ref.permute(0, 2, 1, 3).reshape(seqs, n, I)
+    g = L.AttnGeomT()
+    g.n_outer, g.n_inner, g.n_q, g.n_k, g.heads, g.dim_head, g.num_null_kv = seqs, 1, n, L, heads, 64, nnull
+    g.q_outer, g.q_tok = n * I, I
+    g.k_outer, g.k_tok = L * 2 * I, 2 * I
+    g.o_outer, g.o_tok = n * I, I
+    g.kv_outer_mod, g.mask_outer_mod, g.mask_off_from = b, b, (b if cfg else -1)
+    g.out_bf16, g.scale = 1, 8.0
+    d = lambda t_: t_.contiguous().to(DEV)
+    qd, kvd, nd, qsd, ksd, md = d(q), d(ctx_kv), d(null_kv), d(qs), d(ks), d(tmask.to(torch.uint8))
+    out = torch.empty((seqs, n, I), dtype=torch.bfloat16, device=DEV)
+    L.check(L.lib().phk_attention(L.ptr(qd), L.ptr(kvd), L.ptr(nd), L.ptr(qsd), L.ptr(ksd), None, L.ptr(md), None, L.ptr(out),
+                                  C.byref(g), L.stream_ptr()), "phk_attention")
+    torch.cuda.synchronize()
+    err = (out.cpu().float() - ref).abs().max().item()
+    assert err <= 0.03, f"max |err| {err}"
