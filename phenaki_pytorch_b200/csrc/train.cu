@@ -38,7 +38,10 @@ constexpr int GB = 64, GK = 16;
 
 // blockIdx.z = z selects one product of a batch: operand X starts at X + (z / div) * x_outer + (z % div) * x_inner
 // (two levels, e.g. (sequence, head) over a token-major [b, n, heads * dim_head] tensor); {1, 1, 0...} = one product
-struct GemmBatch { int count, div; int64_t a_outer, a_inner, b_outer, b_inner, c_outer, c_inner; };
+struct GemmBatch {
+  int count, div; int64_t a_outer, a_inner, b_outer, b_inner, c_outer, c_inner;
+  int k_total;  // > 0: split-K -- batch z multiplies the K range [z * K, min((z + 1) * K, k_total)) (atomic accumulation)
+};
 
 __global__ void __launch_bounds__(256) sgemm_strided_kernel(const float* __restrict__ A, int64_t sam, int64_t sak,
                                                             const float* __restrict__ B, int64_t sbk, int64_t sbn,
@@ -51,6 +54,11 @@ __global__ void __launch_bounds__(256) sgemm_strided_kernel(const float* __restr
     A += zo * gb.a_outer + zi * gb.a_inner;
     B += zo * gb.b_outer + zi * gb.b_inner;
     C += zo * gb.c_outer + zi * gb.c_inner;
+  }
+  if (gb.k_total > 0) {  // split-K slice of this batch entry
+    const int left = gb.k_total - (int)blockIdx.z * K;
+    K = left < K ? left : K;
+    if (K <= 0) return;
   }
   const int m0 = blockIdx.y * GB, n0 = blockIdx.x * GB;
   const int t = threadIdx.x;
@@ -96,7 +104,8 @@ __global__ void __launch_bounds__(256) sgemm_strided_kernel(const float* __restr
       const int n = n0 + tx * 4 + j;
       if (n >= N) continue;
       float* c = C + (int64_t)m * ldc + n;
-      *c = accumulate ? *c + acc[i][j] : acc[i][j];
+      if (accumulate == 2) atomicAdd(c, acc[i][j]);  // split-K partial sums
+      else *c = accumulate ? *c + acc[i][j] : acc[i][j];
     }
   }
 }
@@ -114,7 +123,7 @@ int sgemm_batched(const float* A, int64_t sam, int64_t sak, const float* B, int6
 }
 int sgemm(const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbk, int64_t sbn, float* C, int64_t ldc,
           int64_t M, int64_t N, int64_t K, int accumulate, cudaStream_t st) {
-  return sgemm_batched(A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, accumulate, GemmBatch{1, 1, 0, 0, 0, 0, 0, 0}, st);
+  return sgemm_batched(A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, accumulate, GemmBatch{1, 1, 0, 0, 0, 0, 0, 0, 0}, st);
 }
 // dX[M,K] (+)= dY[M,N] . W[N,K]        (nn.Linear dgrad)
 int dgrad(const float* dY, const float* W, float* dX, int64_t M, int64_t N, int64_t K, int accumulate, cudaStream_t st) {
@@ -122,6 +131,15 @@ int dgrad(const float* dY, const float* W, float* dX, int64_t M, int64_t N, int6
 }
 // dW[N,K] += dY[M,N]^T . X[M,K]        (nn.Linear wgrad)
 int wgrad(const float* dY, const float* X, float* dW, int64_t M, int64_t N, int64_t K, cudaStream_t st) {
+  // small weight, long reduction (the position-bias MLP over thousands of coordinate deltas: [64 x 64] += over 3825 rows
+  // was ONE CTA for 0.3 ms): split the reduction over the batch dimension, partial sums meet in dW through atomics
+  static const int force_split = [] { const char* e = std::getenv("PHK_WGRAD_SPLITK"); return e ? (e[0] == '0' ? 0 : 1) : -1; }();
+  if (force_split != 0 && N * K <= 4 * GB * GB && (M >= 1024 || (force_split == 1 && M > 8))) {
+    const int64_t chunk = force_split == 1 && M < 1024 ? 8 : 256;
+    const int parts = (int)((M + chunk - 1) / chunk);
+    const GemmBatch gb{parts, 1, chunk * N, 0, chunk * K, 0, 0, 0, (int)M};
+    return sgemm_batched(dY, 1, N, X, K, 1, dW, K, N, K, chunk, 2, gb, st);
+  }
   return sgemm(dY, 1, N, X, K, 1, dW, K, N, K, M, 1, st);
 }
 inline unsigned ew_grid_fwd(int64_t total) {
