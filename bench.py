@@ -390,6 +390,10 @@ def bench_maskgit(dev, prec, world, barrier, sampler, samples_timed=6):
                                   "iteration); executed = head on the still-masked rows only, first layer's PEG + "
                                   "self-attention once per CFG pair"),
                gpu_launches=int(launches), kernels_per_iteration=launches / (samples_timed * steps),
+               launches_per_iteration=1 if getattr(ph, "iteration_call", False) else launches / (samples_timed * steps),
+               launch_scheme=("one cudaGraphLaunch per demasking iteration (phk_maskgit_demask_iteration: re-mask, CFG-pair "
+                              "forward, logits head on the masked rows, noise-counter advance = kernels_per_iteration kernels "
+                              "inside the graph)" if getattr(ph, "iteration_call", False) else "one PDL-chained launch sequence per iteration"),
                clocks=sampler.report(window) if sampler is not None else None)
     return out
 

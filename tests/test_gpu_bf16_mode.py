@@ -178,3 +178,17 @@ def test_bf16_sampling_with_fused_head_is_deterministic():
     assert torch.equal(outs[0], outs[1]) and not torch.equal(outs[0], outs[2])
     assert (outs[0] >= 0).all() and (outs[0] < 256).all()
 
+
+
+@pytest.mark.parametrize("dim", [192, 768])
+def test_bf16_sampling_falls_back_to_the_unfused_step_for_widths_the_fused_head_does_not_take(dim):
+    """The fused demasking step keeps a token tile's whole embedding row in shared memory (dim <= 512, dim % 128 == 0);
+    other widths must take phk_maskgit_forward + phk_sample_tokens instead of raising."""
+    torch.manual_seed(3)
+    cv = P.CViViT(**C.SAMPLE_CVIVIT)
+    mg = P.MaskGit(dim=dim, num_tokens=256, max_seq_len=64, heads=2, dim_head=64, depth=1, dim_context=48)
+    mg.precision = L.PREC_BF16
+    ph = P.Phenaki(cvivit=cv.to(DEV), maskgit=mg.to(DEV), steps=4, text_embed_dim=48)
+    ctx = C.synthetic_text_embeds(2, 6, 48, (6, 3), 3).to(DEV)
+    ids = ph.sample(num_frames=7, text_embeds=ctx, return_token_ids=True).cpu()
+    assert tuple(ids.shape) == (2, 18) and bool(((ids >= 0) & (ids < 256)).all())
