@@ -192,3 +192,26 @@ def test_bf16_sampling_falls_back_to_the_unfused_step_for_widths_the_fused_head_
     ctx = C.synthetic_text_embeds(2, 6, 48, (6, 3), 3).to(DEV)
     ids = ph.sample(num_frames=7, text_embeds=ctx, return_token_ids=True).cpu()
     assert tuple(ids.shape) == (2, 18) and bool(((ids >= 0) & (ids < 256)).all())
+
+
+def test_one_graph_launch_per_iteration_equals_the_per_step_loop():
+    """BASELINE north_star "one kernel launch per decode iteration": phk_maskgit_demask_iteration (default; eager on the
+    first sample with a shape, captured on the second, ONE cudaGraphLaunch per iteration from the third on) against the
+    per-step loop (PHK_STEP_GRAPH=0 path): same noise counters, so the ids of four consecutive samples are identical."""
+    torch.manual_seed(2)
+    cv = P.CViViT(**C.SAMPLE_CVIVIT)
+    mg = P.MaskGit(dim=128, num_tokens=256, max_seq_len=64, heads=2, dim_head=64, depth=2, dim_context=48)
+    mg.precision = L.PREC_BF16
+    ph = P.Phenaki(cvivit=cv.to(DEV), maskgit=mg.to(DEV), steps=6, text_embed_dim=48)
+    ctx = C.synthetic_text_embeds(2, 6, 48, (6, 3), 3).to(DEV)
+    runs = {}
+    for graph in (True, False):
+        ph.iteration_call = graph
+        torch.manual_seed(21)
+        l0 = L.lib().phk_launch_count()
+        runs[graph] = [ph.sample(num_frames=7, text_embeds=ctx, return_token_ids=True).cpu() for _ in range(4)]
+        runs[graph, "launches"] = L.lib().phk_launch_count() - l0
+    for a, b in zip(runs[True], runs[False]):
+        assert torch.equal(a, b)
+    assert not torch.equal(runs[True][0], runs[True][1])  # fresh noise per sample
+    assert bool(((runs[True][3] >= 0) & (runs[True][3] < 256)).all())
