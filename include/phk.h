@@ -213,6 +213,17 @@ int phk_gemm_bf16_ln(const void* A, int64_t lda, const void* W, int64_t ldw, flo
                      int32_t K, const float* bias, const float* ln_g, const float* ln_b, float ln_eps, void* ln_out,
                      void* raw_out, int64_t ln_ld, phk_stream_t s);
 
+/* The same product with the row statistics exchanged through global memory instead of a cluster (the N / 128 CTAs of a
+ * 128-row tile are ordinary CTAs of a grid of at most one CTA per SM, all resident; no GPC-local cluster placement).
+ *   stat_ws : PHK_LN_STAT_BYTES bytes of device scratch, 16-byte aligned, any content;
+ *   counters: PHK_LN_COUNTERS zero-initialised 32-bit device words, consumed by the call (left non-zero) -- give every
+ *             call of a stream-ordered sequence its own words and clear them together once per sequence. */
+#define PHK_LN_STAT_BYTES (2 * 148 * 128 * 8)
+#define PHK_LN_COUNTERS 160
+int phk_gemm_bf16_ln_ws(const void* A, int64_t lda, const void* W, int64_t ldw, float* C, int64_t ldc, int64_t M,
+                        int32_t N, int32_t K, const float* bias, const float* ln_g, const float* ln_b, float ln_eps,
+                        void* ln_out, void* raw_out, int64_t ln_ld, void* stat_ws, uint32_t* counters, phk_stream_t s);
+
 /* PHK_PREC_BF16X3 operand split: x fp32 [rows, ld] (K valid columns) -> bf16 [rows, 3 * Kp], Kp = K rounded up to 8:
  * [hi | hi | lo] (weights == 0: the activation side) or [hi | lo | hi] (weights != 0), hi = bf16(x), lo = bf16(x - hi),
  * zero in the padding columns.  With both sides split this way a plain bf16 GEMM over K' = 3 Kp computes

@@ -9,6 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libphk.so")
 
 PREC_F32, PREC_BF16, PREC_BF16X3 = 0, 1, 2
+LN_STAT_BYTES, LN_COUNTERS = 2 * 148 * 128 * 8, 160   # phk_gemm_bf16_ln_ws scratch (include/phk.h)
 
 
 def default_precision():
@@ -122,6 +123,7 @@ PROTOTYPES = {
     "phk_attention_tc_bf16": [vp, i64, vp, i64, vp, vp, i32, i32, i32, vp],
     "phk_attention_small_bf16": [vp, vp, vp, vp, C.POINTER(AttnGeomT), vp],
     "phk_gemm_bf16_ln": [vp, i64, vp, i64, vp, i64, i64, i32, i32, vp, vp, vp, f32, vp, vp, i64, vp],
+    "phk_gemm_bf16_ln_ws": [vp, i64, vp, i64, vp, i64, i64, i32, i32, vp, vp, vp, f32, vp, vp, i64, vp, vp, vp],
     "phk_train_set_progress_events": [vp, i32],
     "phk_split3": [vp, i64, vp, i64, i32, i32, vp],
     "phk_gemm_bf16_qkv": [vp, vp, i64, vp, vp, i64, vp, vp, i64, i32, i32, vp, vp, f32, vp],

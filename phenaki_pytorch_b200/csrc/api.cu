@@ -84,13 +84,18 @@ struct TfCall {
   int dup_halves;
 };
 
+constexpr int kFuseLnDefault = 0;     // PHK_FUSE_LN default: 0 separate LayerNorm kernels, 1 cluster epilogue, 2 global exchange
+constexpr int kLnFusedLaunches = 64;  // LayerNorm-in-epilogue GEMMs per transformer call that get their own arrival counters
+
 static int64_t tf_scratch_bytes(const phk_transformer_t* T, int64_t R) {
   const int64_t I = (int64_t)T->heads * T->dim_head;
   int64_t inner = 0;
   for (int l = 0; l < T->depth; ++l) inner = inner > T->layers[l].ff.inner ? inner : T->layers[l].ff.inner;
   // xn, q, kv, o, h(2*inner), g(inner)  -- all fp32 in parity mode
   // + head-major bf16 q/k/v^T operands of the tensor-core attention (bf16 mode): 3 * R * I * 2 bytes + padding
-  return 256 * 12 + R * 4 * (T->dim + I + 2 * I + I + 2 * inner + inner) + R * I * 6 + 64 * 64 * 2 * (R / 64 + 64);
+  // + the statistics exchange and arrival counters of the LayerNorm-in-epilogue GEMMs (phk_gemm_bf16_ln_ws)
+  return 256 * 14 + R * 4 * (T->dim + I + 2 * I + I + 2 * inner + inner) + R * I * 6 + 64 * 64 * 2 * (R / 64 + 64) +
+         PHK_LN_STAT_BYTES + kLnFusedLaunches * PHK_LN_COUNTERS * 4;
 }
 
 static int64_t tf_kmax(const phk_transformer_t* T) {  // largest K of a transformer's nn.Linear products
@@ -154,8 +159,27 @@ static int transformer_forward(const TfCall& c, Arena scratch, float* out, void*
   // memory).  Correct (tests/test_gpu_fused_qkv.py) but NOT faster on the B200 at dim 512: a cluster of 4 full-SM CTAs
   // needs 4 free SMs of one GPC, only ~32 such clusters are resident at once and the 36 row tiles of 4608 tokens take two
   // waves -- 30.3 us against 12.2 us (GEMM) + 4.7 us (LayerNorm kernel), profiles/r02/encode_bf16_launches_c4_fuse_ln.txt.
-  static const bool fuse_ln_env = [] { const char* e = std::getenv("PHK_FUSE_LN"); return e && e[0] == '1'; }();
-  const bool fuse_ln = fuse_ln_env && h16 && (D == 128 || D == 256 || D == 512 || D == 1024);
+  // PHK_FUSE_LN=2: the same fusion without clusters -- the CTAs of a row tile exchange the statistics through global
+  // memory (phk_gemm_bf16_ln_ws; one set of arrival counters per fused launch, cleared together by one memset here).
+  static const int fuse_ln_env = [] { const char* e = std::getenv("PHK_FUSE_LN"); return e && e[0] >= '0' && e[0] <= '2' ? e[0] - '0' : kFuseLnDefault; }();
+  const bool fuse_ln = fuse_ln_env != 0 && h16 && (D == 128 || D == 256 || D == 512 || D == 1024);
+  void* ln_stat = nullptr;
+  uint32_t* ln_counters = nullptr;
+  int ln_launch = 0;
+  if (fuse_ln && fuse_ln_env == 2) {
+    ln_stat = scratch.take(PHK_LN_STAT_BYTES);
+    ln_counters = (uint32_t*)scratch.take((int64_t)kLnFusedLaunches * PHK_LN_COUNTERS * 4);
+    PHK_REQUIRE(ln_stat && ln_counters, PHK_E_WORKSPACE, "transformer: workspace too small (LayerNorm statistics exchange)");
+    PHK_CUDA(cudaMemsetAsync(ln_counters, 0, (size_t)kLnFusedLaunches * PHK_LN_COUNTERS * 4, st));
+  }
+  // residual GEMM + the following LayerNorm in one launch (cluster or global-exchange variant)
+  auto gemm_ln = [&](const void* a, int64_t lda, const void* w, int64_t ldw, float* xio, int64_t rows, int K, const float* g,
+                     const float* b, void* ln_o, void* raw_o) -> int {
+    if (ln_stat && ln_launch < kLnFusedLaunches)
+      return phk_gemm_bf16_ln_ws(a, lda, w, ldw, xio, D, rows, D, K, nullptr, g, b, 1e-5f, ln_o, raw_o, D, ln_stat,
+                                 ln_counters + (int64_t)(ln_launch++) * PHK_LN_COUNTERS, s);
+    return phk_gemm_bf16_ln(a, lda, w, ldw, xio, D, rows, D, K, nullptr, g, b, 1e-5f, ln_o, raw_o, D, s);
+  };
   bool ln_ready = false;  // xn (+ xraw) already hold this layer's self-attention LayerNorm (written by the previous FF2)
   for (int l = 0; l < T->depth; ++l) {
     const phk_layer_t& L = T->layers[l];
@@ -217,7 +241,7 @@ static int transformer_forward(const TfCall& c, Arena scratch, float* out, void*
         const bool to_cross = L.has_cross && c.ctx_kv;
         const float* ng = to_cross ? L.cross_attn.norm_g : L.ff.ln_g;
         const float* nb = to_cross ? L.cross_attn.norm_b : L.ff.ln_b;
-        PHK_TRY(phk_gemm_bf16_ln(o, I, A.wo_h, I, x, D, Rl, D, I, nullptr, ng, nb, 1e-5f, xn, nullptr, D, s));
+        PHK_TRY(gemm_ln(o, I, A.wo_h, I, x, Rl, I, ng, nb, xn, nullptr));
         norm_done = true;
       } else {
         PHK_TRY(linear(c.lin, o, I, A.wo, A.wo_h, I, x, D, Rl, D, I, nullptr, x, s));
@@ -245,7 +269,7 @@ static int transformer_forward(const TfCall& c, Arena scratch, float* out, void*
       const float* kvl = c.ctx_kv + (int64_t)l * c.ctx_b * c.ctx_L * 2 * I;
       PHK_TRY(phk_attention(q, kvl, A.null_kv, A.q_scale, A.k_scale, nullptr, c.ctx_mask, nullptr, o, &g, s));
       if (fuse_ln && A.wo_h) {
-        PHK_TRY(phk_gemm_bf16_ln(o, I, A.wo_h, I, x, D, R, D, I, nullptr, L.ff.ln_g, L.ff.ln_b, 1e-5f, xn, nullptr, D, s));
+        PHK_TRY(gemm_ln(o, I, A.wo_h, I, x, R, I, L.ff.ln_g, L.ff.ln_b, xn, nullptr));
         norm_done = true;
       } else {
         PHK_TRY(linear(c.lin, o, I, A.wo, A.wo_h, I, x, D, R, D, I, nullptr, x, s));
@@ -263,8 +287,7 @@ static int transformer_forward(const TfCall& c, Arena scratch, float* out, void*
         const bool next_plain = l + 1 < T->depth && !T->layers[l + 1].has_peg;
         if (fuse_ln && next_plain) {  // ... + the next layer's attention LayerNorm and its raw bf16 rows
           const phk_attn_t& NA = T->layers[l + 1].self_attn;
-          PHK_TRY(phk_gemm_bf16_ln(gbuf, Fw.inner_pad, Fw.w2_h, Fw.inner_pad, x, D, R, D, Fw.inner_pad, nullptr, NA.norm_g,
-                                   NA.norm_b, 1e-5f, xn, xraw, D, s));
+          PHK_TRY(gemm_ln(gbuf, Fw.inner_pad, Fw.w2_h, Fw.inner_pad, x, R, Fw.inner_pad, NA.norm_g, NA.norm_b, xn, xraw));
           ln_ready = true;
         } else {
           PHK_TRY(phk_gemm_bf16(gbuf, Fw.inner_pad, Fw.w2_h, Fw.inner_pad, x, D, R, D, Fw.inner_pad, nullptr, x, 0, 0, 0, 0, s));

@@ -24,7 +24,7 @@
 //              bf16 [M, N/2]: accumulator read out of TMEM and released at once, fitted sigmoid-form GELU, swizzled
 //              bf16 staging tile, coalesced 16-byte stores.
 #include "phk_common.cuh"
-#include <cuda.h>
+#include "phk_sm100.cuh"
 #include <cstdlib>
 #include <mutex>
 #include <unordered_map>
@@ -67,89 +67,15 @@ struct EpiParams {
   // in raw_out: the k,v projection input of attention.py:140-144).  One CTA holds 128 of the N columns of a row, so the
   // row statistics are summed over the cluster of n_tiles CTAs that share the m-tile (distributed shared memory).
   const float* ln_g; const float* ln_b; void* ln_out; void* raw_out; int64_t ln_ld; float ln_eps;
+  // epilogue 5: the same result without a cluster -- the n_tiles CTAs of a group (consecutive block indices, all resident:
+  // the grid is at most one CTA per SM) exchange their 128-column row statistics through global memory: xstat_g
+  // [2][gridDim][128] float2 slots (double-buffered by tile parity) and one arrival counter per group (ln_counter[group],
+  // zero when the kernel starts; release / acquire at gpu scope).
+  float2* xstat_g; unsigned int* ln_counter;
   alignas(64) CUtensorMap tmC;
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-// Bounded wait: a protocol bug must surface as a trap (launch failure), never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  long long t0 = 0;
-  for (uint32_t spin = 0;; ++spin) {
-    uint32_t done;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) return;
-    if ((spin & 1023u) == 1023u) {
-      if (t0 == 0) t0 = clock64();
-      else if (clock64() - t0 > 4000000000LL) __trap();
-    }
-  }
-}
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-// K-major, SWIZZLE_128B smem operand descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO=1 | SBO=1024B>>4 |
-// version=1 (bit 46) | layout SWIZZLE_128B=2 (bits 61..63)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-__device__ __forceinline__ void umma_f16(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_c), "l"(da), "l"(db), "r"(idesc), "r"(acc)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory"); }
 
 // gelu_erf(g) * v for the bf16 GEGLU epilogue (attention.py:40-43).  Phi(g) = 0.5 (1 + erf(g / sqrt2)) is evaluated
@@ -549,13 +475,13 @@ __device__ __forceinline__ void st_cluster_f2(uint32_t cluster_addr, float a, fl
 // distributed shared memory: thread (row r, part 0) of CTA c stores its partial into xstat[buf][c][r] of EVERY CTA of the
 // cluster and arrives on that CTA's `bar_stat` (128 * cluster_size arrivals per tile, release / acquire at cluster scope).
 // Two exchange buffers: a CTA can be at most one tile ahead of a peer (it needs the peer's arrival to get further).
-template <typename Release>
+template <bool GLOBAL, typename Release>
 __device__ __forceinline__ void epi_tma_finish_ln(const EpiParams& p, uint8_t* stage, uint32_t stage_s, uint32_t bar_res,
                                                   uint32_t& res_phase, uint32_t tmem_chunk, int m0, int n0, int ew, int lg,
                                                   int part, int lane, float2* rowstat, const float2* xstat, uint32_t xstat_s,
                                                   uint32_t bar_stat,
                                                   uint32_t& stat_phase, uint32_t& stat_buf, uint32_t my_rank, uint32_t csize,
-                                                  Release&& release) {
+                                                  int iter, int group, Release&& release) {
   const uint32_t trow = tmem_chunk + ((uint32_t)(lg * 32) << 16);
   uint32_t v[32];
   tmem_ld32(trow + part * 32, v);
@@ -591,9 +517,40 @@ __device__ __forceinline__ void epi_tma_finish_ln(const EpiParams& p, uint8_t* s
       if (n0 + 32 * c < p.N) tma_store_2d(&p.tmC, stage_s + c * (GM * 128), n0 + 32 * c, m0);
     tma_store_commit();
   }
-  if (part == 0) {  // 128 threads, one per row: this CTA's 128-column partial to every CTA of the cluster
-    float t1 = 0.f, t2 = 0.f;
+  float t1 = 0.f, t2 = 0.f;
+  if (GLOBAL) {
+    // global-memory exchange: slot [buf][block][row]; one arrival per CTA and tile on the group's counter
+    float2* mine = p.xstat_g + ((size_t)stat_buf * gridDim.x + blockIdx.x) * GM;
+    if (part == 0) {
+      float a1 = 0.f, a2 = 0.f;
 #pragma unroll
+      for (int q = 0; q < EPI_PARTS; ++q) { const float2 e = rowstat[q * GM + r]; a1 += e.x; a2 += e.y; }
+      __stcg(mine + r, make_float2(a1, a2));
+      __threadfence();
+    }
+    epi_bar_sync();  // the 128 partials of this CTA are written and fenced
+    if (ew == 0 && lane == 0) {
+      unsigned int* ctr = p.ln_counter + group;
+      const unsigned int target = (unsigned int)(iter + 1) * csize;
+      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+      long long t0 = 0;
+      for (uint32_t spin = 0;; ++spin) {
+        unsigned int seen;
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
+        if (seen >= target) break;
+        if ((spin & 255u) == 255u) {
+          if (t0 == 0) t0 = clock64();
+          else if (clock64() - t0 > 4000000000LL) __trap();  // a peer CTA never arrived
+        }
+      }
+    }
+    epi_bar_sync();  // every peer's partials are visible
+    const float2* grp = p.xstat_g + ((size_t)stat_buf * gridDim.x + (size_t)group * csize) * GM;
+    for (uint32_t c = 0; c < csize; ++c) { const float2 e = __ldcg(grp + (size_t)c * GM + r); t1 += e.x; t2 += e.y; }
+    stat_buf ^= 1;
+  } else {
+  if (part == 0) {  // 128 threads, one per row: this CTA's 128-column partial to every CTA of the cluster
+  #pragma unroll
     for (int q = 0; q < EPI_PARTS; ++q) { const float2 e = rowstat[q * GM + r]; t1 += e.x; t2 += e.y; }
     const uint32_t slot = xstat_s + ((stat_buf * LN_MAX_CLUSTER + my_rank) * GM + r) * 8;
     for (uint32_t dst = 0; dst < csize; ++dst) {
@@ -603,9 +560,9 @@ __device__ __forceinline__ void epi_tma_finish_ln(const EpiParams& p, uint8_t* s
   }
   mbar_wait_cluster(bar_stat, stat_phase);
   stat_phase ^= 1;
-  float t1 = 0.f, t2 = 0.f;
   for (uint32_t c = 0; c < csize; ++c) { const float2 e = xstat[(stat_buf * LN_MAX_CLUSTER + c) * GM + r]; t1 += e.x; t2 += e.y; }
   stat_buf ^= 1;
+  }
   const float inv_n = 1.0f / (float)p.N;
   const float mean = t1 * inv_n;
   const float rstd = rsqrtf(fmaxf(t2 * inv_n - mean * mean, 0.f) + p.ln_eps);
@@ -657,13 +614,15 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_bf16_kernel(const __grid_con
   const int tiles1 = p.m_tiles * p.n_tiles;
   const int num_tiles = tiles1 + (DUAL ? p2.m_tiles * p2.n_tiles : 0);
   // epilogue 4: clusters of n_tiles CTAs own one m-tile at a time (CTA rank = n-tile), round-robin over the m-tiles
-  const uint32_t crank = EPI == 4 ? cluster_rank() : 0u, csize = EPI == 4 ? cluster_size() : 1u;
+  constexpr bool LN_EPI = EPI == 4 || EPI == 5;
+  const uint32_t csize = EPI == 4 ? cluster_size() : EPI == 5 ? (uint32_t)p.n_tiles : 1u;
+  const uint32_t crank = EPI == 4 ? cluster_rank() : EPI == 5 ? blockIdx.x % csize : 0u;
   const int cluster_id = (int)blockIdx.x / (int)csize, n_clusters = (int)gridDim.x / (int)csize;
   // tile schedule: round-robin over all tiles (problem 1 first), m-fastest; returns true for a tile of problem 2
-  const int my_tiles = EPI == 4 ? (cluster_id < p.m_tiles ? (p.m_tiles - 1 - cluster_id) / n_clusters + 1 : 0)
+  const int my_tiles = LN_EPI ? (cluster_id < p.m_tiles ? (p.m_tiles - 1 - cluster_id) / n_clusters + 1 : 0)
                                 : ((int)blockIdx.x < num_tiles ? (num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0);
   auto tile_of = [&](int i, int& m0, int& n0) -> bool {
-    if (EPI == 4) { m0 = (cluster_id + i * n_clusters) * GM; n0 = (int)crank * GN; return false; }
+    if (LN_EPI) { m0 = (cluster_id + i * n_clusters) * GM; n0 = (int)crank * GN; return false; }
     int tile = (int)blockIdx.x + i * (int)gridDim.x;
     const bool second = DUAL && tile >= tiles1;
     if (second) tile -= tiles1;
@@ -780,17 +739,17 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_bf16_kernel(const __grid_con
       const uint32_t use = (uint32_t)(it >> 1);
       int m0, n0;
       const EpiParams& pp = tile_of(it, m0, n0) ? p2 : p;
-      const bool tma = (EPI == 0 && pp.tma_epi) || EPI == 4;
+      const bool tma = (EPI == 0 && pp.tma_epi) || LN_EPI;
       bool res_vec = false;
       if (tma) epi_tma_begin(pp, base + RING_BYTES, bar_res, m0, n0, ew, lane);
       else res_vec = epi_residual_prefetch<EPI>(pp, cstage, m0, n0, ew, lane);
       mbar_wait(bar_tfull + 8 * acc, use & 1);
       if (it == 0 && threadIdx.x == 64) PHK_STAMP(6);      // accumulator ready
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (EPI == 4)
-        epi_tma_finish_ln(pp, reinterpret_cast<uint8_t*>(cstage), base + RING_BYTES, bar_res, res_phase,
+      if (LN_EPI)
+        epi_tma_finish_ln<EPI == 5>(pp, reinterpret_cast<uint8_t*>(cstage), base + RING_BYTES, bar_res, res_phase,
                           tmem_base + acc * GN, m0, n0, ew, lg, part, lane, rowstat, xstat, xstat_s, bar_stat, stat_phase,
-                          stat_buf, crank, csize, [&]() { if (lane == 0) mbar_arrive(bar_tempty + 8 * acc); });
+                          stat_buf, crank, csize, it, cluster_id, [&]() { if (lane == 0) mbar_arrive(bar_tempty + 8 * acc); });
       else if (tma)
         epi_tma_finish(pp, reinterpret_cast<uint8_t*>(cstage), base + RING_BYTES, bar_res, res_phase,
                        tmem_base + acc * GN, m0, n0, ew, lg, part, lane,
@@ -804,7 +763,7 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_bf16_kernel(const __grid_con
                        [&]() { if (lane == 0) mbar_arrive(bar_tempty + 8 * acc); });
       if (it == 0 && threadIdx.x == 64) PHK_STAMP(8);      // tile written out
     }
-    if ((EPI == 0 || EPI == 4) && ew == 0 && lane == 0) tma_store_wait_all();  // bulk stores complete before the CTA exits
+    if ((EPI == 0 || LN_EPI) && ew == 0 && lane == 0) tma_store_wait_all();  // bulk stores complete before the CTA exits
   }
   __syncthreads();
   if (threadIdx.x == 0) PHK_STAMP(9);  // CTA done
@@ -1048,22 +1007,6 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_bf16_pair_kernel(const __gri
 // host side: tensor maps (driver entry point resolved at run time: libphk.so has no link-time libcuda dependency,
 // so it also loads on a CPU-only box for the ABI tests)
 // ---------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  });
-  return fn;
-}
 
 struct MapKey {
   const void* ptr; int64_t rows, cols, ld; int box_rows;
@@ -1318,9 +1261,9 @@ extern "C" int phk_gemm_bf16_x2(const void* A1, int64_t lda1, const void* W1, in
 // the bf16 operand of the next GEMM from the epilogue's registers: ln_out[M, ln_ld] = LayerNorm(x) * ln_g (+ ln_b), and
 // optionally raw_out = bf16(x) (the k,v projection reads the un-normalised rows, attention.py:140-144).  N = the model
 // width: N / 128 in {1, 2, 4, 8} CTAs form a cluster per 128-row tile and share the row statistics.
-extern "C" int phk_gemm_bf16_ln(const void* A, int64_t lda, const void* W, int64_t ldw, float* C, int64_t ldc, int64_t M,
-                                int32_t N, int32_t K, const float* bias, const float* ln_g, const float* ln_b, float ln_eps,
-                                void* ln_out, void* raw_out, int64_t ln_ld, phk_stream_t s) {
+static int gemm_bf16_ln_impl(const void* A, int64_t lda, const void* W, int64_t ldw, float* C, int64_t ldc, int64_t M,
+                             int32_t N, int32_t K, const float* bias, const float* ln_g, const float* ln_b, float ln_eps,
+                             void* ln_out, void* raw_out, int64_t ln_ld, void* stat_ws, uint32_t* counters, phk_stream_t s) {
   Prof prof_(FAM_GEMM_BF16, s, 2.0 * (double)M * N * K);
   PHK_REQUIRE(A && W && C && ln_g && ln_out, PHK_E_ARG, "phk_gemm_bf16_ln: null pointer");
   PHK_REQUIRE(M > 0 && N > 0 && K > 0 && lda >= K && ldw >= K && ldc >= N && ln_ld >= N, PHK_E_ARG, "phk_gemm_bf16_ln: bad size");
@@ -1344,10 +1287,19 @@ extern "C" int phk_gemm_bf16_ln(const void* A, int64_t lda, const void* W, int64
   const bool configured = device_configured(&configured_mask);
   if (!configured) {
     PHK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL_LN));
+    PHK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL_LN));
     mark_configured(&configured_mask);
   }
   const int max_clusters = kNumSMs / nt;
   const int clusters = p.m_tiles < max_clusters ? p.m_tiles : max_clusters;
+  if (stat_ws) {  // groups of nt CTAs without a cluster: statistics through global memory (epilogue 5)
+    p.xstat_g = reinterpret_cast<float2*>(stat_ws);
+    p.ln_counter = counters;
+    PHK_CUDA(launch_pdl(gemm_bf16_kernel<5, false>, dim3(clusters * nt), dim3(GTHREADS), (size_t)(SMEM_TOTAL_LN), to_stream(s),
+                        ta, tb, p, ta, tb, p));
+    PHK_LAUNCH_CHECK();
+    return 0;
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(clusters * nt); cfg.blockDim = dim3(GTHREADS); cfg.dynamicSmemBytes = SMEM_TOTAL_LN; cfg.stream = to_stream(s);
   cudaLaunchAttribute attr[2];
@@ -1359,6 +1311,27 @@ extern "C" int phk_gemm_bf16_ln(const void* A, int64_t lda, const void* W, int64
   PHK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<4, false>, ta, tb, p, ta, tb, p));
   PHK_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int phk_gemm_bf16_ln(const void* A, int64_t lda, const void* W, int64_t ldw, float* C, int64_t ldc, int64_t M,
+                                int32_t N, int32_t K, const float* bias, const float* ln_g, const float* ln_b, float ln_eps,
+                                void* ln_out, void* raw_out, int64_t ln_ld, phk_stream_t s) {
+  return gemm_bf16_ln_impl(A, lda, W, ldw, C, ldc, M, N, K, bias, ln_g, ln_b, ln_eps, ln_out, raw_out, ln_ld, nullptr, nullptr, s);
+}
+
+// The same product with the row statistics exchanged through global memory instead of a cluster's distributed shared
+// memory: the N / 128 CTAs of a 128-row tile are ordinary CTAs of a grid of at most one CTA per SM (all resident), so
+// the GPC-local cluster placement that limits phk_gemm_bf16_ln to ~32 resident row tiles at N = 512 does not apply.
+//   stat_ws : PHK_LN_STAT_BYTES bytes of scratch (any content);
+//   counters: PHK_LN_COUNTERS zero-initialised 32-bit words, consumed by the call (left non-zero): give every call of a
+//             stream-ordered sequence its own words and clear them together once per sequence.
+extern "C" int phk_gemm_bf16_ln_ws(const void* A, int64_t lda, const void* W, int64_t ldw, float* C, int64_t ldc, int64_t M,
+                                   int32_t N, int32_t K, const float* bias, const float* ln_g, const float* ln_b,
+                                   float ln_eps, void* ln_out, void* raw_out, int64_t ln_ld, void* stat_ws,
+                                   uint32_t* counters, phk_stream_t s) {
+  PHK_REQUIRE(stat_ws && counters && (reinterpret_cast<uintptr_t>(stat_ws) & 15) == 0, PHK_E_ARG,
+              "phk_gemm_bf16_ln_ws: statistics scratch / counters missing or misaligned");
+  return gemm_bf16_ln_impl(A, lda, W, ldw, C, ldc, M, N, K, bias, ln_g, ln_b, ln_eps, ln_out, raw_out, ln_ld, stat_ws, counters, s);
 }
 
 // The q and k,v projections of a self-attention block (attention.py:140-157) in one launch, written as the bf16 operands

@@ -293,6 +293,14 @@ extern "C" int phk_gemm_bf16_ln(const void* A, int64_t lda, const void* W, int64
   });
   return 0;
 }
+// phk_gemm_bf16_ln_ws: the same contract (the statistics scratch and the arrival counters are only touched by the GPU kernel)
+extern "C" int phk_gemm_bf16_ln_ws(const void* A, int64_t lda, const void* W, int64_t ldw, float* C, int64_t ldc, int64_t M,
+                                   int32_t N, int32_t K, const float* bias, const float* ln_g, const float* ln_b,
+                                   float ln_eps, void* ln_out, void* raw_out, int64_t ln_ld, void* stat_ws,
+                                   uint32_t* counters, phk_stream_t s) {
+  if (!stat_ws || !counters) return PHK_E_ARG;
+  return phk_gemm_bf16_ln(A, lda, W, ldw, C, ldc, M, N, K, bias, ln_g, ln_b, ln_eps, ln_out, raw_out, ln_ld, s);
+}
 // phk_gemm_bf16_qkv contract: the q and k,v projections with the attention core's operands as output (bf16): per 64-column
 // head l2-normalised (eps 1e-12) * learned scale (* sim_scale for q); the value half only converted
 extern "C" int phk_gemm_bf16_qkv(const void* xn, const void* xraw, int64_t lda, const void* Wq, const void* Wkv, int64_t ldw,
