@@ -236,6 +236,13 @@ int phk_debug_gemm_trace(long long* device_buffer);
  * (cta_group::2) with 256x128 tiles, 3 CTA pairs with 256x256 tiles (2 and 3 apply when M > 128); < 0 restores the
  * PHK_GEMM_MODE environment default. */
 int phk_debug_gemm_mode(int32_t mode);
+/* tests / A-B measurements: declare (1) or withdraw (0), for the calling thread, that the W operands of the following
+ * phk_gemm_bf16* calls are not written by earlier kernels of the stream -- the kernel then requests their first tiles before
+ * its programmatic-dependent-launch wait.  The forward drivers (phk_cvivit_*, phk_maskgit_*) set this themselves. */
+int phk_debug_static_weights(int32_t on);
+/* tests / A-B measurements: phk_attention_tc* variant -- 0 probabilities through a shared-memory tile (two CTAs per SM),
+ * 1 probabilities in tensor memory as the TMEM A operand of P.V (three CTAs per SM); < 0 restores the default. */
+int phk_debug_attention_tc_variant(int32_t variant);
 
 /* GEGLU (attention.py:40-43): out[r, j] = gelu_erf(h[r, inner + j]) * h[r, j] */
 int phk_geglu(const float* h, float* out, int64_t rows, int32_t inner, phk_stream_t s);

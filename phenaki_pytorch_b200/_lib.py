@@ -116,6 +116,8 @@ PROTOTYPES = {
     "phk_gemm_bf16_x2": [vp, i64, vp, i64, vp, i64, i64, i32, i32, vp, vp, i64, vp, i64, vp, i64, i64, i32, i32, vp, vp],
     "phk_debug_gemm_trace": [vp],
     "phk_debug_gemm_mode": [i32],
+    "phk_debug_static_weights": [i32],
+    "phk_debug_attention_tc_variant": [i32],
     "phk_geglu": [vp, vp, i64, i32, vp],
     "phk_attention": [vp, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(AttnGeomT), vp],
     "phk_attention_tc_scratch_bytes": [i32, i32, i32],

@@ -133,6 +133,7 @@ static int linear(const Lin& ln, const void* act, int64_t lda, const float* w32,
 static int transformer_forward(const TfCall& c, Arena scratch, float* out, void* out_h, cudaStream_t st) {
   const phk_transformer_t* T = c.T;
   const bool h16 = c.prec == PHK_PREC_BF16;
+  StaticWeightsScope static_weights;  // the weight table is not rewritten inside a forward call
   PHK_REQUIRE(c.prec == PHK_PREC_F32 || c.prec == PHK_PREC_BF16X3 || h16, PHK_E_ARG, "transformer: unknown precision mode");
   PHK_REQUIRE(c.lin.prec == c.prec, PHK_E_ARG, "transformer: contraction descriptor not initialised");
   const int D = T->dim, H = T->heads, DH = T->dim_head, I = H * DH;

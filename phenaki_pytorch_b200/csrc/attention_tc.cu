@@ -17,6 +17,7 @@
 //   S and P never touch HBM; 48 KB smem + 128 TMEM columns per CTA -> several CTAs per SM overlap MMA and softmax.
 #include "phk_common.cuh"
 #include "phk_sm100.cuh"
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -31,6 +32,8 @@ constexpr int SQ_BYTES = AQ * ADH * 2, SK_BYTES = AKC * ADH * 2, SV_BYTES = ADH 
 constexpr int SB_BYTES = 2 * AQ * 128;  // bias tile: two [128 rows x 32 fp32] SWIZZLE_128B boxes
 constexpr int SMX_BYTES = 4 * AQ * 4;  // row-maximum exchange [2 buffers][2 halves][128 rows]
 constexpr int ATT_SMEM = SQ_BYTES + SK_BYTES + SV_BYTES + SP_BYTES + SB_BYTES + 128 + SMX_BYTES + 1024;
+// PT variant (probabilities in tensor memory): no P tile in shared memory -> 69 KB, three CTAs per SM
+constexpr int ATT_SMEM_PT = SQ_BYTES + SK_BYTES + SV_BYTES + SB_BYTES + 128 + SMX_BYTES + 1024;
 
 
 struct AttTcParams {
@@ -41,21 +44,28 @@ struct AttTcParams {
   int bias_tma;  // 1: the bias tile arrives through TMA (tmB) into shared memory, 0: direct loads
 };
 
-__global__ void __launch_bounds__(ATHREADS, 2) attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
-                                                                   const __grid_constant__ CUtensorMap tmK,
-                                                                   const __grid_constant__ CUtensorMap tmV,
-                                                                   const __grid_constant__ CUtensorMap tmB,
-                                                                   AttTcParams p) {
+// PT = true: the probabilities never leave tensor memory -- the softmax warps tcgen05.st their bf16 P row into 32 extra
+// TMEM columns and P.V reads its A operand from there (tcgen05.mma with a TMEM A operand).  Without the 16 KB P tile a
+// CTA needs 69 KB of shared memory and (at <= 64 registers) THREE fit on an SM: the 320 CTAs of the MaskGit shape
+// (5 query tiles x 8 heads x 8 sequences) are resident at once instead of 296 + a 24-CTA tail wave that cost a whole
+// second CTA lifetime (ncu r2c7: 38 us, warps active 28 %).
+template <bool PT>
+__global__ void __launch_bounds__(ATHREADS, PT ? 3 : 2) attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                                            const __grid_constant__ CUtensorMap tmK,
+                                                                            const __grid_constant__ CUtensorMap tmV,
+                                                                            const __grid_constant__ CUtensorMap tmB,
+                                                                            AttTcParams p) {
   pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  constexpr int SPB = PT ? 0 : SP_BYTES;  // no P tile in the TMEM variant
   const uint32_t sQ = base, sK = sQ + SQ_BYTES, sV = sK + SK_BYTES, sP = sV + SV_BYTES;
   uint8_t* sP_ptr = base_ptr + SQ_BYTES + SK_BYTES + SV_BYTES;
-  const uint32_t sBias = sP + SP_BYTES;
-  const uint8_t* sBias_ptr = sP_ptr + SP_BYTES;
+  const uint32_t sBias = sP + SPB;
+  const uint8_t* sBias_ptr = sP_ptr + SPB;
   const uint32_t bars = sBias + SB_BYTES;
-  float* s_mx = reinterpret_cast<float*>(base_ptr + SQ_BYTES + SK_BYTES + SV_BYTES + SP_BYTES + SB_BYTES + 128);
+  float* s_mx = reinterpret_cast<float*>(base_ptr + SQ_BYTES + SK_BYTES + SV_BYTES + SPB + SB_BYTES + 128);
   const uint32_t b_qfull = bars, b_kfull = bars + 8, b_kempty = bars + 16, b_vfull = bars + 24, b_vempty = bars + 32,
                  b_sfull = bars + 40, b_sempty = bars + 48, b_pfull = bars + 56, b_pvdone = bars + 64,
                  b_bfull = bars + 72, b_bempty = bars + 80, tmem_slot = bars + 88;
@@ -74,6 +84,8 @@ __global__ void __launch_bounds__(ATHREADS, 2) attention_tc_kernel(const __grid_
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(128) : "memory");
+    if (PT)  // second allocation: 32 columns for the bf16 probabilities (128 + 32 per CTA, three CTAs = 480 of 512)
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot + 4), "n"(32) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -82,6 +94,8 @@ __global__ void __launch_bounds__(ATHREADS, 2) attention_tc_kernel(const __grid_
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   const uint32_t tS = tmem_base, tO = tmem_base + AKC;
+  uint32_t tP = 0;
+  if (PT) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tP) : "r"(tmem_slot + 4));
   pdl_wait();  // prologue above overlapped the previous kernel
 
   if (warp == 0) {
@@ -130,8 +144,10 @@ __global__ void __launch_bounds__(ATHREADS, 2) attention_tc_kernel(const __grid_
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint64_t dp = umma_desc(sP), dv = umma_desc_mn(sV);
 #pragma unroll
-        for (int k = 0; k < AKC / 16; ++k)  // 16 keys = two 8-row atoms of V = 2048 B (128 descriptor units) per step
-          umma_f16(tO, dp + 2 * k, dv + 128 * k, idesc_pv, (j | k) != 0);
+        for (int k = 0; k < AKC / 16; ++k) {  // 16 keys = two 8-row atoms of V = 2048 B (128 descriptor units) per step
+          if (PT) umma_f16_ts(tO, tP + 8 * k, dv + 128 * k, idesc_pv, (j | k) != 0);  // 16 bf16 keys = 8 TMEM columns
+          else umma_f16(tO, dp + 2 * k, dv + 128 * k, idesc_pv, (j | k) != 0);
+        }
         umma_commit(b_vempty);
         umma_commit(b_pvdone);
       }
@@ -156,55 +172,50 @@ __global__ void __launch_bounds__(ATHREADS, 2) attention_tc_kernel(const __grid_
     float m_run = -INFINITY, l_run = 0.f;
     for (int j = 0; j < nch; ++j) {
       const int k0 = j * AKC + hf * HC;
-      float bv[HC];
-      if (!p.bias_tma) {
-        // direct path (no bias, or a bias whose row pitch TMA cannot address): issued before waiting for S
-        if (brow && bias_vec && k0 + HC <= p.n_k) {
+      float sc[HC];  // scores of this thread's 32 keys (logit + bias), then reused by the exponentials
+      mbar_wait(b_sfull, j & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      {
+        uint32_t sv[HC];
+        tmem_ld32(tS + lane_off + hf * HC, sv);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(b_sempty);  // S may be overwritten by the next QK^T (8 arrivals)
+        if (p.bias_tma) {
+          // this row of the TMA-staged tile (box `hf` = this half's 32 columns): 16-byte chunk c of row r sits at chunk
+          // (c ^ (r & 7)) (SWIZZLE_128B); added straight into the score registers
+          mbar_wait(b_bfull, j & 1);
+          const uint8_t* rowp = sBias_ptr + hf * (AQ * 128) + r * 128;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 t = *reinterpret_cast<const float4*>(rowp + ((c ^ (r & 7)) << 4));
+            sc[4 * c] = __uint_as_float(sv[4 * c]) + t.x; sc[4 * c + 1] = __uint_as_float(sv[4 * c + 1]) + t.y;
+            sc[4 * c + 2] = __uint_as_float(sv[4 * c + 2]) + t.z; sc[4 * c + 3] = __uint_as_float(sv[4 * c + 3]) + t.w;
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(b_bempty);  // tile consumed (values are in registers)
+        } else if (brow && bias_vec && k0 + HC <= p.n_k) {
+          // direct path (a bias whose row pitch TMA cannot address)
 #pragma unroll
           for (int c = 0; c < HC / 4; ++c) {
             const float4 t = __ldg(reinterpret_cast<const float4*>(brow + k0) + c);
-            bv[4 * c] = t.x; bv[4 * c + 1] = t.y; bv[4 * c + 2] = t.z; bv[4 * c + 3] = t.w;
+            sc[4 * c] = __uint_as_float(sv[4 * c]) + t.x; sc[4 * c + 1] = __uint_as_float(sv[4 * c + 1]) + t.y;
+            sc[4 * c + 2] = __uint_as_float(sv[4 * c + 2]) + t.z; sc[4 * c + 3] = __uint_as_float(sv[4 * c + 3]) + t.w;
           }
         } else {
 #pragma unroll
-          for (int c = 0; c < HC; ++c) bv[c] = (brow && k0 + c < p.n_k) ? __ldg(brow + k0 + c) : 0.f;
+          for (int c = 0; c < HC; ++c) sc[c] = __uint_as_float(sv[c]) + ((brow && k0 + c < p.n_k) ? __ldg(brow + k0 + c) : 0.f);
         }
-      }
-      mbar_wait(b_sfull, j & 1);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      uint32_t sv[HC];
-      tmem_ld32(tS + lane_off + hf * HC, sv);
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(b_sempty);  // S may be overwritten by the next QK^T (8 arrivals)
-      if (p.bias_tma) {
-        // this row of the TMA-staged tile (box `hf` = this half's 32 columns): 16-byte chunk c of row r sits at chunk
-        // (c ^ (r & 7)) (SWIZZLE_128B)
-        mbar_wait(b_bfull, j & 1);
-        const uint8_t* rowp = sBias_ptr + hf * (AQ * 128) + r * 128;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float4 t = *reinterpret_cast<const float4*>(rowp + ((c ^ (r & 7)) << 4));
-          bv[4 * c] = t.x; bv[4 * c + 1] = t.y; bv[4 * c + 2] = t.z; bv[4 * c + 3] = t.w;
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(b_bempty);  // tile consumed (values are in registers)
       }
       float mx = -INFINITY;
       if (k0 + HC <= p.n_k) {  // this half inside the sequence (warp-uniform): no per-element bounds tests
 #pragma unroll
-        for (int c = 0; c < HC; ++c) {
-          const float sc = __uint_as_float(sv[c]) + bv[c];
-          bv[c] = sc;
-          mx = fmaxf(mx, sc);
-        }
+        for (int c = 0; c < HC; ++c) mx = fmaxf(mx, sc[c]);
       } else {
 #pragma unroll
         for (int c = 0; c < HC; ++c) {
-          float sc = __uint_as_float(sv[c]) + bv[c];
-          if (k0 + c >= p.n_k) sc = -INFINITY;  // zero-filled padding keys
-          bv[c] = sc;
-          mx = fmaxf(mx, sc);
+          if (k0 + c >= p.n_k) sc[c] = -INFINITY;  // zero-filled padding keys
+          mx = fmaxf(mx, sc[c]);
         }
       }
       // the row maximum of the chunk over both halves (double-buffered exchange: a thread may be one chunk ahead)
@@ -218,7 +229,7 @@ __global__ void __launch_bounds__(ATHREADS, 2) attention_tc_kernel(const __grid_
       uint32_t pk[HC / 2];
 #pragma unroll
       for (int c = 0; c < HC; c += 2) {
-        const float p0 = fast_ex2(fmaf(bv[c], LOG2E, -m2)), p1 = fast_ex2(fmaf(bv[c + 1], LOG2E, -m2));
+        const float p0 = fast_ex2(fmaf(sc[c], LOG2E, -m2)), p1 = fast_ex2(fmaf(sc[c + 1], LOG2E, -m2));
         lsum += p0 + p1;
         pk[c >> 1] = pack_bf16x2(p0, p1);
       }
@@ -228,19 +239,28 @@ __global__ void __launch_bounds__(ATHREADS, 2) attention_tc_kernel(const __grid_
         mbar_wait(b_pvdone, (j - 1) & 1);  // previous P.V finished: P buffer free, O stable
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (__any_sync(0xffffffffu, alpha != 1.0f)) {  // rescale this thread's half of the running output in TMEM
-          uint32_t ov[32];
-          tmem_ld32(tO + lane_off + hf * 32, ov);
 #pragma unroll
-          for (int c = 0; c < 32; ++c) ov[c] = __float_as_uint(__uint_as_float(ov[c]) * alpha);
-          tmem_st32(tO + lane_off + hf * 32, ov);
+          for (int part = 0; part < 2; ++part) {  // 16 columns at a time: the packed probabilities stay live meanwhile
+            uint32_t ov[16];
+            tmem_ld16(tO + lane_off + hf * 32 + part * 16, ov);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 16; ++c) ov[c] = __float_as_uint(__uint_as_float(ov[c]) * alpha);
+            tmem_st16(tO + lane_off + hf * 32 + part * 16, ov);
+          }
         }
       }
-      // this half of the P row -> SWIZZLE_128B K-major tile: 16-byte chunk c of row r lives at chunk (c ^ (r & 7))
-      uint8_t* prow = sP_ptr + r * 128;
+      if (PT) {
+        // this half of the P row -> TMEM columns [hf*16, hf*16+16) of the probability block (two bf16 keys per column)
+        tmem_st16(tP + lane_off + hf * (HC / 2), pk);
+      } else {
+        // this half of the P row -> SWIZZLE_128B K-major tile: 16-byte chunk c of row r lives at chunk (c ^ (r & 7))
+        uint8_t* prow = sP_ptr + r * 128;
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
-        *reinterpret_cast<uint4*>(prow + (((hf * 4 + c) ^ (r & 7)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA
+        for (int c = 0; c < 4; ++c)
+          *reinterpret_cast<uint4*>(prow + (((hf * 4 + c) ^ (r & 7)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA
+      }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(b_pfull);  // (8 arrivals)
@@ -273,6 +293,7 @@ __global__ void __launch_bounds__(ATHREADS, 2) attention_tc_kernel(const __grid_
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(128) : "memory");
+    if (PT) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tP), "n"(32) : "memory");
   }
 }
 
@@ -341,6 +362,9 @@ int make_map_4d(const void* ptr, int64_t n, int64_t heads, int64_t n_seq, int64_
   return 0;
 }
 
+constexpr int kProbabilitiesInTmem = 1;  // default variant (PHK_ATTN_P_TMEM overrides)
+int g_attn_variant = -1;                // phk_debug_attention_tc_variant
+
 }  // namespace
 }  // namespace phk
 
@@ -370,7 +394,8 @@ extern "C" int phk_attention_tc_bf16(const void* Qn, int64_t ld_q, const void* K
   static unsigned long long configured_mask = 0;
   const bool configured = device_configured(&configured_mask);
   if (!configured) {
-    PHK_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    PHK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    PHK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_PT));
     mark_configured(&configured_mask);
   }
   const int bias_tma = bias && (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(bias) & 15) == 0);
@@ -378,8 +403,21 @@ extern "C" int phk_attention_tc_bf16(const void* Qn, int64_t ld_q, const void* K
   if (bias_tma) PHK_TRY(make_map_bias(bias, (int64_t)heads * n, n, &tb));
   AttTcParams p{bias, (__nv_bfloat16*)out_bf16, n, n, heads, (int64_t)n * heads * 64, (int64_t)heads * 64, bias_tma};
   dim3 grid((unsigned)((n + AQ - 1) / AQ), (unsigned)heads, (unsigned)n_seq);
-  PHK_CUDA(launch_pdl(attention_tc_kernel, dim3(grid), dim3(ATHREADS), (size_t)(ATT_SMEM), st, tq, tk, tv, tb, p));
+  static const int env_variant = [] { const char* e = std::getenv("PHK_ATTN_P_TMEM"); return e ? (e[0] != '0') : kProbabilitiesInTmem; }();
+  const int variant = g_attn_variant >= 0 ? g_attn_variant : env_variant;
+  if (variant)
+    PHK_CUDA(launch_pdl(attention_tc_kernel<true>, dim3(grid), dim3(ATHREADS), (size_t)(ATT_SMEM_PT), st, tq, tk, tv, tb, p));
+  else
+    PHK_CUDA(launch_pdl(attention_tc_kernel<false>, dim3(grid), dim3(ATHREADS), (size_t)(ATT_SMEM), st, tq, tk, tv, tb, p));
   PHK_LAUNCH_CHECK();
+  return 0;
+}
+
+// tests / A-B measurements: 0 probabilities through a shared-memory tile (two CTAs per SM), 1 probabilities in tensor
+// memory (three CTAs per SM); < 0 restores the PHK_ATTN_P_TMEM environment default
+extern "C" int phk_debug_attention_tc_variant(int32_t variant) {
+  PHK_REQUIRE(variant <= 1, PHK_E_ARG, "phk_debug_attention_tc_variant: 0, 1 or < 0");
+  g_attn_variant = variant;
   return 0;
 }
 

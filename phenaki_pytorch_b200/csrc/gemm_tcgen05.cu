@@ -72,6 +72,9 @@ struct EpiParams {
   // [2][gridDim][128] float2 slots (double-buffered by tile parity) and one arrival counter per group (ln_counter[group],
   // zero when the kernel starts; release / acquire at gpu scope).
   float2* xstat_g; unsigned int* ln_counter;
+  // the W operand is not written by the kernels that precede this one in the stream (inference weights): its first tiles
+  // are requested BEFORE griddepcontrol.wait, while the previous kernel drains
+  int w_static;
   alignas(64) CUtensorMap tmC;
 };
 
@@ -549,19 +552,20 @@ __device__ __forceinline__ void epi_tma_finish_ln(const EpiParams& p, uint8_t* s
     for (uint32_t c = 0; c < csize; ++c) { const float2 e = __ldcg(grp + (size_t)c * GM + r); t1 += e.x; t2 += e.y; }
     stat_buf ^= 1;
   } else {
-  if (part == 0) {  // 128 threads, one per row: this CTA's 128-column partial to every CTA of the cluster
-  #pragma unroll
-    for (int q = 0; q < EPI_PARTS; ++q) { const float2 e = rowstat[q * GM + r]; t1 += e.x; t2 += e.y; }
-    const uint32_t slot = xstat_s + ((stat_buf * LN_MAX_CLUSTER + my_rank) * GM + r) * 8;
-    for (uint32_t dst = 0; dst < csize; ++dst) {
-      st_cluster_f2(map_to_cta(slot, dst), t1, t2);
-      mbar_arrive_remote(map_to_cta(bar_stat, dst));
+    if (part == 0) {  // 128 threads, one per row: this CTA's 128-column partial to every CTA of the cluster
+      float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+      for (int q = 0; q < EPI_PARTS; ++q) { const float2 e = rowstat[q * GM + r]; a1 += e.x; a2 += e.y; }
+      const uint32_t slot = xstat_s + ((stat_buf * LN_MAX_CLUSTER + my_rank) * GM + r) * 8;
+      for (uint32_t dst = 0; dst < csize; ++dst) {
+        st_cluster_f2(map_to_cta(slot, dst), a1, a2);
+        mbar_arrive_remote(map_to_cta(bar_stat, dst));
+      }
     }
-  }
-  mbar_wait_cluster(bar_stat, stat_phase);
-  stat_phase ^= 1;
-  for (uint32_t c = 0; c < csize; ++c) { const float2 e = xstat[(stat_buf * LN_MAX_CLUSTER + c) * GM + r]; t1 += e.x; t2 += e.y; }
-  stat_buf ^= 1;
+    mbar_wait_cluster(bar_stat, stat_phase);
+    stat_phase ^= 1;
+    for (uint32_t c = 0; c < csize; ++c) { const float2 e = xstat[(stat_buf * LN_MAX_CLUSTER + c) * GM + r]; t1 += e.x; t2 += e.y; }
+    stat_buf ^= 1;
   }
   const float inv_n = 1.0f / (float)p.N;
   const float mean = t1 * inv_n;
@@ -665,7 +669,18 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_bf16_kernel(const __grid_con
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-  pdl_wait();  // everything above (barriers, tensor-map prefetch, TMEM allocation) overlapped the previous kernel
+  int pre_kb = 0;  // k-blocks of the first tile whose W half is already in flight (producer thread only)
+  if (threadIdx.x == 0 && my_tiles > 0 && p.w_static) {
+    int m0, n0;
+    const bool second = tile_of(0, m0, n0);
+    const int num_kb = kblocks(second);
+    pre_kb = num_kb < GSTAGES ? num_kb : GSTAGES;
+    for (int kb = 0; kb < pre_kb; ++kb) {
+      mbar_expect_tx(bars + 8 * kb, 2 * STAGE_BYTES);  // both halves; the A half is requested after the wait
+      tma_load_2d(second ? &tmB2 : &tmB, bars + 8 * kb, sB + kb * STAGE_BYTES, kb * GK, n0);
+    }
+  }
+  pdl_wait();  // everything above (barriers, tensor-map prefetch, TMEM allocation, W prefetch) overlapped the previous kernel
   if (threadIdx.x == 0) PHK_STAMP(0);  // setup done
 
   if (warp == 0) {
@@ -682,9 +697,13 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_bf16_kernel(const __grid_con
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(bars + 8 * (GSTAGES + stage), phase ^ 1);  // slot free (passes immediately on the first lap)
           const uint32_t full = bars + 8 * stage;
-          mbar_expect_tx(full, 2 * STAGE_BYTES);
-          tma_load_2d(ma, full, sA + stage * STAGE_BYTES, kb * GK, m0);
-          tma_load_2d(mb, full, sB + stage * STAGE_BYTES, kb * GK, n0);
+          if (it == 0 && kb < pre_kb) {  // W half requested before the wait (stage == kb on the first lap)
+            tma_load_2d(ma, full, sA + stage * STAGE_BYTES, kb * GK, m0);
+          } else {
+            mbar_expect_tx(full, 2 * STAGE_BYTES);
+            tma_load_2d(ma, full, sA + stage * STAGE_BYTES, kb * GK, m0);
+            tma_load_2d(mb, full, sB + stage * STAGE_BYTES, kb * GK, n0);
+          }
           if (it == 0 && kb == 0) PHK_STAMP(1);            // first TMA issued
           if (it == 0 && kb == num_kb - 1) PHK_STAMP(2);   // last TMA of the first tile issued
           if (++stage == GSTAGES) { stage = 0; phase ^= 1; }
@@ -763,7 +782,7 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_bf16_kernel(const __grid_con
                        [&]() { if (lane == 0) mbar_arrive(bar_tempty + 8 * acc); });
       if (it == 0 && threadIdx.x == 64) PHK_STAMP(8);      // tile written out
     }
-    if ((EPI == 0 || LN_EPI) && ew == 0 && lane == 0) tma_store_wait_all();  // bulk stores complete before the CTA exits
+    if ((EPI == 0 || LN_EPI) && ew == 0 && lane == 0) tma_store_wait_read();  // staging read out before the CTA exits (the writes complete with the grid)
   }
   __syncthreads();
   if (threadIdx.x == 0) PHK_STAMP(9);  // CTA done
@@ -991,7 +1010,7 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_bf16_pair_kernel(const __gri
       }
       if (it == 0 && threadIdx.x == 64) PHK_STAMP(8);
     }
-    if (EPI == 0 && ew == 0 && lane == 0) tma_store_wait_all();  // bulk stores complete before the CTA exits
+    if (EPI == 0 && ew == 0 && lane == 0) tma_store_wait_read();  // staging read out before the CTA exits (the writes complete with the grid)
   }
   __syncthreads();
   if (threadIdx.x == 0) PHK_STAMP(9);
@@ -1089,8 +1108,14 @@ static int maybe_tma_epilogue(EpiParams& p, int epilogue) {
 
 static long long* g_gemm_trace = nullptr;
 
+// set by the inference drivers (api.cu) around their GEMM calls: the W operands are weights nothing in the stream rewrites
+static thread_local int t_static_weights = 0;
+void gemm_static_weights(bool on) { t_static_weights = on ? 1 : 0; }
+
 template <int EPI>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const EpiParams& p, cudaStream_t st) {
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const EpiParams& p_in, cudaStream_t st) {
+  EpiParams p = p_in;
+  p.w_static = t_static_weights;
   static unsigned long long configured_mask = 0;
   const bool configured = device_configured(&configured_mask);
   if (!configured) {
@@ -1105,8 +1130,10 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const EpiPa
 }
 
 template <int EPI>
-static int launch_gemm_dual(const CUtensorMap& ta, const CUtensorMap& tb, const EpiParams& p, const CUtensorMap& ta2,
+static int launch_gemm_dual(const CUtensorMap& ta, const CUtensorMap& tb, const EpiParams& p_in, const CUtensorMap& ta2,
                             const CUtensorMap& tb2, const EpiParams& p2, cudaStream_t st) {
+  EpiParams p = p_in;
+  p.w_static = t_static_weights;  // (read from the first problem's parameters for both)
   static unsigned long long configured_mask = 0;
   const bool configured = device_configured(&configured_mask);
   if (!configured) {
@@ -1283,6 +1310,7 @@ static int gemm_bf16_ln_impl(const void* A, int64_t lda, const void* W, int64_t 
   PHK_TRY(get_c_map(C, M, N, ldc, &p.tmC));
   p.tma_epi = 1;
   p.ln_g = ln_g; p.ln_b = ln_b; p.ln_out = ln_out; p.raw_out = raw_out; p.ln_ld = ln_ld; p.ln_eps = ln_eps;
+  p.w_static = t_static_weights;
   static unsigned long long configured_mask = 0;
   const bool configured = device_configured(&configured_mask);
   if (!configured) {
@@ -1371,6 +1399,11 @@ extern "C" int phk_gemm_bf16_qkv(const void* xn, const void* xraw, int64_t lda, 
 extern "C" int phk_debug_gemm_mode(int32_t mode) {
   PHK_REQUIRE(mode <= 3, PHK_E_ARG, "phk_debug_gemm_mode: mode must be <= 3");
   g_gemm_mode_override = mode;
+  return 0;
+}
+
+extern "C" int phk_debug_static_weights(int32_t on) {
+  gemm_static_weights(on != 0);
   return 0;
 }
 

@@ -156,4 +156,12 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// inference drivers bracket their GEMM calls with this: the W operands are weights that no kernel of the stream rewrites,
+// so the tcgen05 GEMM may request their first tiles before its programmatic-dependent-launch wait (gemm_tcgen05.cu)
+void gemm_static_weights(bool on);
+struct StaticWeightsScope {
+  StaticWeightsScope() { gemm_static_weights(true); }
+  ~StaticWeightsScope() { gemm_static_weights(false); }
+};
+
 }  // namespace phk

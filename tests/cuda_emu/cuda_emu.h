@@ -247,4 +247,5 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   t = warp_sum(t);
   return t;
 }
+struct StaticWeightsScope {};  // the GPU GEMM's weight prefetch hint (phk_common.cuh): nothing to do on the CPU executor
 }  // namespace phk

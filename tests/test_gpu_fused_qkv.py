@@ -62,8 +62,21 @@ def _core_reference(qn, kvn, n_seq, n, heads, bias=None, causal_slopes=None):
     return out.permute(0, 2, 1, 3).reshape(n_seq * n, I)
 
 
-@pytest.mark.parametrize("n_seq,n,heads,with_bias", [(72, 64, 8, True), (2, 576, 8, True), (1, 200, 4, False), (3, 130, 2, True)])
-def test_attention_tc_on_prenormalised_token_major_operands(n_seq, n, heads, with_bias):
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("n_seq,n,heads,with_bias", [(72, 64, 8, True), (2, 576, 8, True), (1, 200, 4, False), (3, 130, 2, True),
+                                                     (8, 576, 8, True), (2, 1024, 8, True), (5, 199, 3, True)])
+def test_attention_tc_on_prenormalised_token_major_operands(n_seq, n, heads, with_bias, variant):
+    """variant 0: probabilities through a shared-memory tile (two CTAs per SM); 1: probabilities in tensor memory, read by
+    P.V as a TMEM A operand (three CTAs per SM).  (8, 576, 8): the MaskGit shape, 320 CTAs; n = 199: bias rows TMA cannot
+    address (direct loads) and a ragged last chunk."""
+    L.check(L.lib().phk_debug_attention_tc_variant(variant))
+    try:
+        _attention_tc_case(n_seq, n, heads, with_bias)
+    finally:
+        L.lib().phk_debug_attention_tc_variant(-1)
+
+
+def _attention_tc_case(n_seq, n, heads, with_bias):
     I = heads * 64
     rows = n_seq * n
     qn = (F.normalize(TC.seeded_randn((rows, heads, 64), 410), dim=-1) * 8.0).reshape(rows, I).bfloat16()
@@ -194,20 +207,20 @@ def test_transformer_with_layernorm_in_gemm_epilogue_matches_separate_kernels(fu
     assert flipped <= 0.002 * a.numel() * 16, f"{flipped} of {a.numel() * 16} token-id bits differ"
 
 
-@pytest.mark.parametrize("b,n,L,heads,cfg", [(4, 576, 16, 8, True), (2, 130, 29, 4, False), (3, 64, 7, 2, True)])
-def test_cross_attention_bf16_output_on_warp_mma(b, n, L, heads, cfg):
+@pytest.mark.parametrize("b,n,ctx_len,heads,cfg", [(4, 576, 16, 8, True), (2, 130, 29, 4, False), (3, 64, 7, 2, True)])
+def test_cross_attention_bf16_output_on_warp_mma(b, n, ctx_len, heads, cfg):
     """phk_attention's bf16-output cross-attention path (attention_cross_mma_kernel: null-kv + text keys <= 32 slots) against
     the fp32 oracle core: text masks, the CFG null half (sequences >= mask_off_from see only the null keys), ragged tails."""
     from oracle import phenaki_oracle as O
     I, nnull = heads * 64, 2
     seqs = 2 * b if cfg else b
     q = TC.seeded_randn((seqs, n, I), 440)
-    ctx_kv = TC.seeded_randn((b, L, 2 * I), 441)
+    ctx_kv = TC.seeded_randn((b, ctx_len, 2 * I), 441)
     null_kv = TC.seeded_randn((heads, 2 * nnull, 64), 442)
     qs, ks = TC.seeded_randn((64,), 443).abs() * 0.3 + 0.7, TC.seeded_randn((64,), 444).abs() * 0.3 + 0.7
-    tmask = torch.ones((b, L), dtype=torch.bool)
+    tmask = torch.ones((b, ctx_len), dtype=torch.bool)
     for i in range(b):
-        tmask[i, max(1, L - 3 * i):] = False
+        tmask[i, max(1, ctx_len - 3 * i):] = False
     split = lambda t_: t_.reshape(t_.shape[0], t_.shape[1], heads, 64).permute(0, 2, 1, 3)
     kvs = ctx_kv.repeat(2, 1, 1) if cfg else ctx_kv
     k, v = kvs.chunk(2, dim=-1)
@@ -218,9 +231,9 @@ def test_cross_attention_bf16_output_on_warp_mma(b, n, L, heads, cfg):
                            num_null_kv=nnull, mask=mask)
     ref = ref.permute(0, 2, 1, 3).reshape(seqs, n, I)
     g = L.AttnGeomT()
-    g.n_outer, g.n_inner, g.n_q, g.n_k, g.heads, g.dim_head, g.num_null_kv = seqs, 1, n, L, heads, 64, nnull
+    g.n_outer, g.n_inner, g.n_q, g.n_k, g.heads, g.dim_head, g.num_null_kv = seqs, 1, n, ctx_len, heads, 64, nnull
     g.q_outer, g.q_tok = n * I, I
-    g.k_outer, g.k_tok = L * 2 * I, 2 * I
+    g.k_outer, g.k_tok = ctx_len * 2 * I, 2 * I
     g.o_outer, g.o_tok = n * I, I
     g.kv_outer_mod, g.mask_outer_mod, g.mask_off_from = b, b, (b if cfg else -1)
     g.out_bf16, g.scale = 1, 8.0
