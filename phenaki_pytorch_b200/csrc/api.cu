@@ -133,7 +133,10 @@ static int linear(const Lin& ln, const void* act, int64_t lda, const float* w32,
 static int transformer_forward(const TfCall& c, Arena scratch, float* out, void* out_h, cudaStream_t st) {
   const phk_transformer_t* T = c.T;
   const bool h16 = c.prec == PHK_PREC_BF16;
-  StaticWeightsScope static_weights;  // the weight table is not rewritten inside a forward call
+  // (StaticWeightsScope -- requesting the first weight tiles BEFORE the programmatic-dependent-launch wait -- measured
+  //  slower on the B200: 8.8 vs 7.6 us for the 4608x512x512 product, 14.3 vs 11.8 us at K = 1408,
+  //  profiles/r02/op_bench_c8.txt; griddepcontrol.wait appears to drain the thread's outstanding bulk copies first, so the
+  //  activation tiles are requested a full TMA latency later.  The hint stays available through phk_debug_static_weights.)
   PHK_REQUIRE(c.prec == PHK_PREC_F32 || c.prec == PHK_PREC_BF16X3 || h16, PHK_E_ARG, "transformer: unknown precision mode");
   PHK_REQUIRE(c.lin.prec == c.prec, PHK_E_ARG, "transformer: contraction descriptor not initialised");
   const int D = T->dim, H = T->heads, DH = T->dim_head, I = H * DH;

@@ -362,7 +362,7 @@ int make_map_4d(const void* ptr, int64_t n, int64_t heads, int64_t n_seq, int64_
   return 0;
 }
 
-constexpr int kProbabilitiesInTmem = 1;  // default variant (PHK_ATTN_P_TMEM overrides)
+constexpr int kTmemVariantFromTokens = 256;  // sequences at least this long take the TMEM-probabilities variant by default
 int g_attn_variant = -1;                // phk_debug_attention_tc_variant
 
 }  // namespace
@@ -403,8 +403,11 @@ extern "C" int phk_attention_tc_bf16(const void* Qn, int64_t ld_q, const void* K
   if (bias_tma) PHK_TRY(make_map_bias(bias, (int64_t)heads * n, n, &tb));
   AttTcParams p{bias, (__nv_bfloat16*)out_bf16, n, n, heads, (int64_t)n * heads * 64, (int64_t)heads * 64, bias_tma};
   dim3 grid((unsigned)((n + AQ - 1) / AQ), (unsigned)heads, (unsigned)n_seq);
-  static const int env_variant = [] { const char* e = std::getenv("PHK_ATTN_P_TMEM"); return e ? (e[0] != '0') : kProbabilitiesInTmem; }();
-  const int variant = g_attn_variant >= 0 ? g_attn_variant : env_variant;
+  // default: probabilities in tensor memory (three CTAs per SM) for long sequences -- 24.2 vs 30.5 us at 8 x 576 tokens, where
+  // 320 CTAs no longer need a second wave; single-chunk sequences (n = 64: 8.9 vs 10.2 us) keep the shared-memory tile
+  // (profiles/r02/op_bench_c8.txt).  PHK_ATTN_P_TMEM=0/1 or phk_debug_attention_tc_variant force one.
+  static const int env_variant = [] { const char* e = std::getenv("PHK_ATTN_P_TMEM"); return e ? (e[0] != '0' ? 1 : 0) : -1; }();
+  const int variant = g_attn_variant >= 0 ? g_attn_variant : env_variant >= 0 ? env_variant : (n >= kTmemVariantFromTokens);
   if (variant)
     PHK_CUDA(launch_pdl(attention_tc_kernel<true>, dim3(grid), dim3(ATHREADS), (size_t)(ATT_SMEM_PT), st, tq, tk, tv, tb, p));
   else
