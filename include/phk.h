@@ -538,6 +538,28 @@ int phk_maskgit_demask_iteration(const phk_maskgit_t* m, int64_t* ids, uint8_t* 
                                  uint64_t* rng_state, int32_t k_remask, void* workspace, int64_t workspace_bytes,
                                  phk_stream_t s);
 
+/* The iteration of a sample WITH a critic and / or a prime prefix (phenaki_pytorch.py:478-550; make_video's scene chains),
+ * one call, replayed as a CUDA graph like phk_maskgit_demask_iteration:
+ *   [k_remask > 0: phk_topk_mask on `scores`] -> ids copied behind the prime ids in token_in -> MaskGit forward of the CFG
+ *   pair + tail on the masked rows: ids / pred / scores updated in place -> rng_state[1] += stride
+ *   -> unless `last`: ids -> token_in, critic forward of the CFG pair, scores = head(cond, null, cond_scale) +
+ *      noise_K * (u - 0.5) * noise_mult (:534-545).
+ * token_in [b, prime_len + n] int64: prime ids in the first prime_len columns (written once by the caller); with
+ * prime_len == 0 pass token_in == ids.  pt*ph*pw == prime_len + n.  critic: a TokenCritic table (is_critic), ctx via
+ * critic_ctx_kv (or NULL: no cross attention); critic == NULL: SelfCritic -- the MaskGit's own embeddings under head_w /
+ * head_b (fp32 [dim], [1]).  critic_noise: [b, n] uniform draws the caller refreshes before every call (device buffer at a
+ * stable address), or NULL.  Same buffer-stability rule as phk_maskgit_demask_iteration; bf16 weights, cond_scale != 1. */
+int64_t phk_maskgit_demask_iteration_critic_workspace_bytes(const phk_maskgit_t* m, const phk_maskgit_t* critic, int32_t b,
+                                                            int32_t n_total, int32_t L);
+int phk_maskgit_demask_iteration_critic(const phk_maskgit_t* m, const phk_maskgit_t* critic, const float* head_w,
+                                        const float* head_b, int64_t* token_in, int64_t* ids, uint8_t* mask, float* scores,
+                                        int64_t* pred, int32_t b, int32_t n, int32_t prime_len, int32_t pt, int32_t ph,
+                                        int32_t pw, const float* ctx_kv, const float* critic_ctx_kv, int32_t L,
+                                        const uint8_t* text_mask, const float* pos_bias, float cond_scale, float temperature,
+                                        uint64_t* rng_state, int32_t k_remask, const float* critic_noise, float noise_K,
+                                        float noise_mult, int32_t last, void* workspace, int64_t workspace_bytes,
+                                        phk_stream_t s);
+
 /* tests / A-B runs: 1 = phk_maskgit_demask_iteration replays a CUDA graph, 0 = eager, < 0 = the PHK_STEP_GRAPH default */
 int phk_debug_step_graph(int32_t on);
 

@@ -1043,6 +1043,58 @@ static int step_graphs_enabled() {
 // tests / A-B runs: 1 replays phk_maskgit_demask_iteration as a CUDA graph, 0 keeps it eager, < 0 back to PHK_STEP_GRAPH
 extern "C" int phk_debug_step_graph(int32_t on) { g_step_graph.store(on < 0 ? -1 : (on ? 1 : 0)); return 0; }
 
+// Launch-sequence cache shared by the iteration entries: `key` identifies the call (table contents, every pointer and
+// scalar), `run(stream)` issues the launches.  First sighting of a key: eager; second: captured; later: one cudaGraphLaunch.
+template <typename Run>
+static int replay_or_capture(uint64_t key, phk_stream_t s, Run&& run) {
+  struct Entry { cudaGraphExec_t exec; int launches; };
+  static std::unordered_map<uint64_t, Entry> cache;
+  static std::mutex mu;
+  static cudaStream_t cap = nullptr;
+  static bool broken = false;
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = cache.find(key);
+  if (it != cache.end() && it->second.exec) {
+    PHK_CUDA(cudaGraphLaunch(it->second.exec, to_stream(s)));
+    count_launch(it->second.launches);
+    return 0;
+  }
+  if (broken || it == cache.end()) {  // first sighting (or graphs unusable): eager
+    if (!broken) {
+      if (cache.size() > 1024) {
+        for (auto& kv : cache) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+        cache.clear();
+      }
+      cache.emplace(key, Entry{nullptr, 0});
+    }
+    return run(s);
+  }
+  if (!cap) PHK_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+  const int64_t l0 = g_launches.load();
+  cudaGraph_t graph = nullptr;
+  cudaError_t e = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
+  int rc = 0;
+  if (e == cudaSuccess) {
+    rc = run(reinterpret_cast<phk_stream_t>(cap));
+    e = cudaStreamEndCapture(cap, &graph);
+  }
+  const int launches = (int)(g_launches.load() - l0);
+  g_launches.store(l0);  // the captured launches did not execute
+  cudaGraphExec_t exec = nullptr;
+  if (e == cudaSuccess && rc == 0 && graph) e = cudaGraphInstantiate(&exec, graph, 0);
+  if (graph) cudaGraphDestroy(graph);
+  if (e != cudaSuccess || rc != 0 || !exec) {
+    cudaGetLastError();
+    broken = true;
+    return run(s);
+  }
+  it->second.exec = exec;
+  it->second.launches = launches;
+  PHK_CUDA(cudaGraphLaunch(exec, to_stream(s)));
+  count_launch(launches);
+  return 0;
+}
+
 extern "C" int phk_maskgit_demask_iteration(const phk_maskgit_t* m, int64_t* ids, uint8_t* mask, float* scores,
                                             int64_t* pred, int32_t b, int32_t n, int32_t pt, int32_t ph, int32_t pw,
                                             const float* ctx_kv, int32_t L, const uint8_t* text_mask, const float* pos_bias,
@@ -1050,14 +1102,11 @@ extern "C" int phk_maskgit_demask_iteration(const phk_maskgit_t* m, int64_t* ids
                                             void* workspace, int64_t workspace_bytes, phk_stream_t s) {
   PHK_REQUIRE(m && ids && mask && scores && pred && rng_state && workspace, PHK_E_ARG, "maskgit_demask_iteration: null pointer");
   PHK_REQUIRE(k_remask >= 0 && k_remask <= n, PHK_E_ARG, "maskgit_demask_iteration: k_remask out of range");
-  if (!step_graphs_enabled() || !pos_bias || g_prof_on.load(std::memory_order_relaxed))
+  auto run = [&](phk_stream_t st) {
     return demask_iteration_impl(m, ids, mask, scores, pred, b, n, pt, ph, pw, ctx_kv, L, text_mask, pos_bias, cond_scale,
-                                 temperature, rng_state, k_remask, workspace, workspace_bytes, s);
-  struct Entry { cudaGraphExec_t exec; int launches; };
-  static std::unordered_map<uint64_t, Entry> cache;
-  static std::mutex mu;
-  static cudaStream_t cap = nullptr;
-  static bool broken = false;
+                                 temperature, rng_state, k_remask, workspace, workspace_bytes, st);
+  };
+  if (!step_graphs_enabled() || !pos_bias || g_prof_on.load(std::memory_order_relaxed)) return run(s);
   int dev = 0;
   PHK_CUDA(cudaGetDevice(&dev));
   // key: table contents + every pointer and scalar of the call (a 64-bit FNV of them; the values behind the pointers
@@ -1070,48 +1119,101 @@ extern "C" int phk_maskgit_demask_iteration(const phk_maskgit_t* m, int64_t* ids
   key = fnv(ints, sizeof(ints), key);
   const float fl[] = {cond_scale, temperature};
   key = fnv(fl, sizeof(fl), key);
-  std::lock_guard<std::mutex> lk(mu);
-  auto it = cache.find(key);
-  if (it != cache.end() && it->second.exec) {
-    PHK_CUDA(cudaGraphLaunch(it->second.exec, to_stream(s)));
-    count_launch(it->second.launches);
+  return replay_or_capture(key, s, run);
+}
+
+// ---- the iteration of a sample with a critic and / or a prime prefix (phenaki_pytorch.py:478-550; make_video's scenes) ----
+// token_in [b, prime_len + n]: the MaskGit / critic input -- the prime ids in the first prime_len columns (written once by
+// the caller), the sampled tokens copied in by the call (prime_len == 0: token_in may be `ids` itself).
+//   [k_remask > 0: re-mask the k_remask lowest-confidence... (phk_topk_mask on `scores`)]
+//   -> ids -> token_in -> MaskGit CFG pair + tail on the masked rows -> ids / pred / scores (logit confidence) in place
+//   -> rng_state[1] += stride
+//   -> unless `last`: ids -> token_in -> critic forward of the CFG pair (critic: a TokenCritic table; NULL: the MaskGit's own
+//      embeddings, SelfCritic) -> scores = critic head with guidance + noise_K * (u - 0.5) * noise_mult  (:534-545)
+extern "C" int64_t phk_maskgit_demask_iteration_critic_workspace_bytes(const phk_maskgit_t* m, const phk_maskgit_t* critic,
+                                                                       int32_t b, int32_t n_total, int32_t L) {
+  if (!m || b <= 0 || n_total <= 0) return -1;
+  const int64_t a = phk_maskgit_sample_workspace_bytes(m, b, n_total, L);
+  const int64_t c = phk_maskgit_workspace_bytes(critic ? critic : m, b, n_total, L, 1, PHK_PREC_BF16);
+  return (a > c ? a : c) + 2 * (int64_t)b * n_total * m->dim * 4 + 512;
+}
+
+static int demask_iteration_critic_impl(const phk_maskgit_t* m, const phk_maskgit_t* critic, const float* head_w,
+                                        const float* head_b, int64_t* token_in, int64_t* ids, uint8_t* mask, float* scores,
+                                        int64_t* pred, int32_t b, int32_t n, int32_t prime_len, int32_t pt, int32_t ph,
+                                        int32_t pw, const float* ctx_kv, const float* critic_ctx_kv, int32_t L,
+                                        const uint8_t* text_mask, const float* pos_bias, float cond_scale, float temperature,
+                                        uint64_t* rng_state, int32_t k_remask, const float* critic_noise, float noise_K,
+                                        float noise_mult, int32_t last, void* workspace, int64_t workspace_bytes,
+                                        phk_stream_t s) {
+  cudaStream_t st = to_stream(s);
+  const int32_t nt = prime_len + n;
+  const int64_t need = phk_maskgit_demask_iteration_critic_workspace_bytes(m, critic, b, nt, L);
+  PHK_REQUIRE(workspace_bytes >= need, PHK_E_WORKSPACE, "maskgit_demask_iteration_critic: workspace too small");
+  const int64_t emb_bytes = 2 * (int64_t)b * nt * m->dim * 4;
+  float* emb = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + ((workspace_bytes - emb_bytes) & ~(int64_t)255));
+  const int64_t body_bytes = reinterpret_cast<char*>(emb) - reinterpret_cast<char*>(workspace);
+  auto ids_to_input = [&]() -> int {
+    if (token_in == ids) return 0;
+    PHK_CUDA(cudaMemcpy2DAsync(token_in + prime_len, (size_t)nt * 8, ids, (size_t)n * 8, (size_t)n * 8, (size_t)b,
+                               cudaMemcpyDeviceToDevice, st));
     return 0;
+  };
+  if (k_remask > 0) PHK_TRY(phk_topk_mask(scores, b, n, k_remask, mask, ids, (int64_t)m->num_tokens, s));
+  PHK_TRY(ids_to_input());
+  PHK_TRY(sample_step_impl(m, token_in, b, nt, pt, ph, pw, ctx_kv, L, text_mask, nullptr, pos_bias, cond_scale, temperature, 0, 0,
+                           rng_state, mask, ids, pred, scores, k_remask > 0 ? k_remask : n, prime_len, workspace, body_bytes, s));
+  const uint64_t stride = ((uint64_t)b * (uint64_t)n * (uint64_t)((m->num_tokens + 3) / 4) + 1 + 3) / 4 * 4;
+  PHK_TRY(phk_rng_advance(rng_state, stride, s));
+  if (last) return 0;
+  PHK_TRY(ids_to_input());
+  const phk_maskgit_t* net = critic ? critic : m;
+  PHK_TRY(phk_maskgit_forward(net, token_in, b, nt, pt, ph, pw, critic ? critic_ctx_kv : ctx_kv, L,
+                              (critic ? critic_ctx_kv : ctx_kv) ? text_mask : nullptr, nullptr, 1, 1,
+                              net->has_bias ? pos_bias : nullptr, emb, workspace, body_bytes, PHK_PREC_BF16, s));
+  const int64_t half = (int64_t)b * nt * m->dim;
+  return phk_critic_scores(emb, emb + half, head_w, head_b, critic_noise, cond_scale, noise_K, noise_mult, scores,
+                           (int64_t)b * n, m->dim, prime_len ? n : 0, prime_len ? nt : 0, prime_len ? prime_len : 0, s);
+}
+
+extern "C" int phk_maskgit_demask_iteration_critic(const phk_maskgit_t* m, const phk_maskgit_t* critic, const float* head_w,
+                                                   const float* head_b, int64_t* token_in, int64_t* ids, uint8_t* mask,
+                                                   float* scores, int64_t* pred, int32_t b, int32_t n, int32_t prime_len,
+                                                   int32_t pt, int32_t ph, int32_t pw, const float* ctx_kv,
+                                                   const float* critic_ctx_kv, int32_t L, const uint8_t* text_mask,
+                                                   const float* pos_bias, float cond_scale, float temperature,
+                                                   uint64_t* rng_state, int32_t k_remask, const float* critic_noise,
+                                                   float noise_K, float noise_mult, int32_t last, void* workspace,
+                                                   int64_t workspace_bytes, phk_stream_t s) {
+  PHK_REQUIRE(m && token_in && ids && mask && scores && pred && rng_state && workspace, PHK_E_ARG,
+              "maskgit_demask_iteration_critic: null pointer");
+  PHK_REQUIRE(n > 0 && prime_len >= 0 && k_remask >= 0 && k_remask <= n, PHK_E_ARG,
+              "maskgit_demask_iteration_critic: prime_len / k_remask out of range");
+  PHK_REQUIRE(prime_len > 0 || token_in == ids, PHK_E_ARG,
+              "maskgit_demask_iteration_critic: without a prime prefix the input buffer is the id buffer");
+  PHK_REQUIRE(last || (head_w && head_b), PHK_E_ARG, "maskgit_demask_iteration_critic: critic head missing");
+  PHK_REQUIRE(!critic || (critic->is_critic && critic->dim == m->dim), PHK_E_ARG,
+              "maskgit_demask_iteration_critic: the critic table must be a TokenCritic of the MaskGit's width");
+  auto run = [&](phk_stream_t st) {
+    return demask_iteration_critic_impl(m, critic, head_w, head_b, token_in, ids, mask, scores, pred, b, n, prime_len, pt, ph, pw,
+                                        ctx_kv, critic_ctx_kv, L, text_mask, pos_bias, cond_scale, temperature, rng_state,
+                                        k_remask, critic_noise, noise_K, noise_mult, last, workspace, workspace_bytes, st);
+  };
+  if (!step_graphs_enabled() || !pos_bias || g_prof_on.load(std::memory_order_relaxed)) return run(s);
+  int dev = 0;
+  PHK_CUDA(cudaGetDevice(&dev));
+  uint64_t key = fnv(m, sizeof(*m), 0xcbf29ce484222325ull);
+  key = hash_transformer(m->transformer, key);
+  if (critic) {
+    key = fnv(critic, sizeof(*critic), key);
+    key = hash_transformer(critic->transformer, key);
   }
-  if (broken || it == cache.end()) {  // first sighting (or graphs unusable): eager
-    if (!broken) {
-      if (cache.size() > 512) {
-        for (auto& kv : cache) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
-        cache.clear();
-      }
-      cache.emplace(key, Entry{nullptr, 0});
-    }
-    return demask_iteration_impl(m, ids, mask, scores, pred, b, n, pt, ph, pw, ctx_kv, L, text_mask, pos_bias, cond_scale,
-                                 temperature, rng_state, k_remask, workspace, workspace_bytes, s);
-  }
-  if (!cap) PHK_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
-  const int64_t l0 = g_launches.load();
-  cudaGraph_t graph = nullptr;
-  cudaError_t e = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
-  int rc = 0;
-  if (e == cudaSuccess) {
-    rc = demask_iteration_impl(m, ids, mask, scores, pred, b, n, pt, ph, pw, ctx_kv, L, text_mask, pos_bias, cond_scale,
-                               temperature, rng_state, k_remask, workspace, workspace_bytes, reinterpret_cast<phk_stream_t>(cap));
-    e = cudaStreamEndCapture(cap, &graph);
-  }
-  const int launches = (int)(g_launches.load() - l0);
-  g_launches.store(l0);  // the captured launches did not execute
-  cudaGraphExec_t exec = nullptr;
-  if (e == cudaSuccess && rc == 0 && graph) e = cudaGraphInstantiate(&exec, graph, 0);
-  if (graph) cudaGraphDestroy(graph);
-  if (e != cudaSuccess || rc != 0 || !exec) {
-    cudaGetLastError();
-    broken = true;
-    return demask_iteration_impl(m, ids, mask, scores, pred, b, n, pt, ph, pw, ctx_kv, L, text_mask, pos_bias, cond_scale,
-                                 temperature, rng_state, k_remask, workspace, workspace_bytes, s);
-  }
-  it->second.exec = exec;
-  it->second.launches = launches;
-  PHK_CUDA(cudaGraphLaunch(exec, to_stream(s)));
-  count_launch(launches);
-  return 0;
+  const void* ptrs[] = {head_w, head_b, token_in, ids, mask, scores, pred, ctx_kv, critic_ctx_kv, text_mask, pos_bias, rng_state,
+                        critic_noise, workspace};
+  key = fnv(ptrs, sizeof(ptrs), key);
+  const int64_t ints[] = {b, n, prime_len, pt, ph, pw, L, k_remask, last, dev, workspace_bytes, 0x63726974 /* "crit" */};
+  key = fnv(ints, sizeof(ints), key);
+  const float fl[] = {cond_scale, temperature, noise_K, noise_mult};
+  key = fnv(fl, sizeof(fl), key);
+  return replay_or_capture(key, s, run);
 }

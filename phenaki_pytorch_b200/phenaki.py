@@ -682,11 +682,21 @@ class Phenaki(nn.Module):
             seed = _noise_seed(dev)
             vocab = mg.to_logits.weight.shape[0]
             have_scores = False
-            if (self.iteration_call and self.fused_head and mg.precision == L.PREC_BF16 and noise_fn is None
-                    and cond_scale != 1 and plen == 0 and trace is None and self.critic is None
-                    and self._fused_step_supported()):
+            iterations = (self.iteration_call and self.fused_head and mg.precision == L.PREC_BF16 and noise_fn is None
+                          and cond_scale != 1 and trace is None and self._fused_step_supported())
+            if iterations and plen == 0 and self.critic is None:
                 return self._sample_by_iterations(b, n, patch_shape, ctx_kv, ctx_len, text_mask, cond_scale,
                                                   starting_temperature, ks, seed, vocab, dev)
+            critic_ok = self.critic is None or isinstance(self.critic, SelfCritic) or (
+                isinstance(self.critic, TokenCritic) and self.critic.precision == L.PREC_BF16)
+            if iterations and critic_ok and self.critic_noise_anneal_schedule in ("fixed", "decay", "increase"):
+                return self._sample_by_critic_iterations(b, n, plen, prime_token_ids, patch_shape, ctx_kv, critic_kv, ctx_len,
+                                                         text_mask, cond_scale, starting_temperature, noise_K, ks, seed,
+                                                         vocab, dev)
+            # the whole sample's V-wide noise counters are reserved up front (iteration s uses first + s * stride), as the
+            # iteration entries do: the critic's torch.rand draws then follow them in the generator stream on every path
+            stride = _noise_stride(b * n, vocab)
+            first_offset = _rng_take(dev, seed, stride * steps)
             for step in range(steps):
                 last = step == steps - 1
                 til_x0 = steps - (step + 1)
@@ -697,7 +707,7 @@ class Phenaki(nn.Module):
                     inp[:, plen:].copy_(ids)
                 use_cfg = cond_scale != 1
                 temperature = starting_temperature * (til_x0 / steps)
-                offset = _rng_take(dev, seed, _noise_stride(b * n, vocab))
+                offset = first_offset + step * stride
                 fused = (self.fused_head and mg.precision == L.PREC_BF16 and noise_fn is None and use_cfg
                          and trace is None and self._fused_step_supported())
                 if fused:
@@ -793,6 +803,73 @@ class Phenaki(nn.Module):
                     b, n, pt, ph, pw, L.ptr(bufs["ctx_kv"]), ctx_len, L.ptr(bufs["text_mask"]), L.ptr(bias),
                     float(cond_scale), float(temperature), L.ptr(bufs["rng"]), 0 if step == 0 else ks[step - 1],
                     L.ptr(ws), ws.numel(), L.stream_ptr()), "phk_maskgit_demask_iteration")
+        return bufs["ids"].clone()
+
+    def _sample_by_critic_iterations(self, b, n, plen, prime_token_ids, patch_shape, ctx_kv, critic_kv, ctx_len, text_mask,
+                                     cond_scale, starting_temperature, noise_K, ks, seed, vocab, dev):
+        """The demasking loop with a critic and / or a prime prefix as ``steps`` calls of
+        phk_maskgit_demask_iteration_critic: re-mask, MaskGit CFG pair + tail, critic CFG pair + scores are ONE launch
+        sequence per iteration that the library replays as a CUDA graph (every per-call value lives in the persistent
+        buffers below; temperature, k and the critic-noise multiplier of iteration s are the same in every sample)."""
+        lib, mg, steps, critic = L.lib(), self.maskgit, self.steps, self.critic
+        token_critic = isinstance(critic, TokenCritic)
+        key = ("critic", b, n, plen, ctx_len, dev, None if critic is None else id(critic),
+               None if critic_kv is None else tuple(critic_kv.shape))
+        bufs = self._iter_bufs.get(key)
+        if bufs is None:
+            z = lambda shape, dt: torch.empty(shape, dtype=dt, device=dev)
+            bufs = self._iter_bufs[key] = dict(
+                ids=z((b, n), torch.int64), mask=z((b, n), torch.uint8), scores=z((b, n), torch.float32),
+                pred=z((b, n), torch.int64), rng=z((2,), torch.int64), noise=z((b, n), torch.float32),
+                inp=z((b, plen + n), torch.int64) if plen else None,
+                ctx_kv=None if ctx_kv is None else torch.empty_like(ctx_kv),
+                critic_kv=None if critic_kv is None else torch.empty_like(critic_kv),
+                text_mask=None if text_mask is None else z(tuple(text_mask.shape), torch.uint8))
+        bufs["ids"].fill_(self.mask_id)
+        bufs["mask"].fill_(1)
+        bufs["scores"].zero_()
+        if plen:
+            bufs["inp"][:, :plen].copy_(prime_token_ids)
+        if ctx_kv is not None:
+            bufs["ctx_kv"].copy_(ctx_kv)
+            bufs["text_mask"].copy_(text_mask.to(torch.uint8))
+        if critic_kv is not None:
+            bufs["critic_kv"].copy_(critic_kv)
+        stride = _noise_stride(b * n, vocab)
+        as_i64 = lambda v: v - (1 << 64) if v >= (1 << 63) else v
+        first = _rng_take(dev, seed, stride * steps)
+        bufs["rng"].copy_(torch.tensor([as_i64(seed & (2 ** 64 - 1)), as_i64(first)], dtype=torch.int64))
+        with torch.cuda.device(dev):
+            table = mg._table()
+            ctable, head_w, head_b, keep = None, None, None, None
+            if token_critic:
+                ctable = critic._table()
+                head_w, head_b = ctable.head_w, ctable.head_b
+            elif critic is not None:  # SelfCritic: Linear(dim, 1) on the MaskGit's embeddings
+                keep = (L.require_cuda(critic.to_pred[0].weight.detach(), "to_pred.weight", torch.float32),
+                        L.require_cuda(critic.to_pred[0].bias.detach(), "to_pred.bias", torch.float32))
+                head_w, head_b = L.ptr(keep[0]), L.ptr(keep[1])
+            cref = C.byref(ctable) if ctable is not None else None
+            nbytes = lib.phk_maskgit_demask_iteration_critic_workspace_bytes(C.byref(table), cref, b, plen + n, ctx_len)
+            ws = mg._ws.get(nbytes, dev)
+            bias = mg._pos_bias(table, patch_shape, dev)
+            pt, ph, pw = (int(v) for v in patch_shape)
+            inp = bufs["inp"] if plen else bufs["ids"]
+            for step in range(steps):
+                last = step == steps - 1
+                til_x0 = steps - (step + 1)
+                temperature = starting_temperature * (til_x0 / steps)
+                mult = {"fixed": 1.0, "decay": til_x0 / steps, "increase": (step + 1) / steps}[self.critic_noise_anneal_schedule]
+                with_critic = critic is not None and not last
+                if with_critic:
+                    bufs["noise"].uniform_()  # torch.rand((b, n)) of the per-step loop, drawn into the stable buffer
+                L.check(lib.phk_maskgit_demask_iteration_critic(
+                    C.byref(table), cref, head_w, head_b, L.ptr(inp), L.ptr(bufs["ids"]), L.ptr(bufs["mask"]),
+                    L.ptr(bufs["scores"]), L.ptr(bufs["pred"]), b, n, plen, pt, ph, pw, L.ptr(bufs["ctx_kv"]),
+                    L.ptr(bufs["critic_kv"]) if token_critic else None, ctx_len, L.ptr(bufs["text_mask"]), L.ptr(bias),
+                    float(cond_scale), float(temperature), L.ptr(bufs["rng"]), 0 if step == 0 else ks[step - 1],
+                    L.ptr(bufs["noise"]) if with_critic else None, float(noise_K), float(mult), int(not with_critic),
+                    L.ptr(ws), ws.numel(), L.stream_ptr()), "phk_maskgit_demask_iteration_critic")
         return bufs["ids"].clone()
 
     @torch.no_grad()

@@ -152,6 +152,13 @@ static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, int,
   ::emu::submit([=]() { memmove(d, s, n); });
   return 0;
 }
+static inline cudaError_t cudaMemcpy2DAsync(void* d, size_t dpitch, const void* s, size_t spitch, size_t width, size_t height,
+                                            int, cudaStream_t) {
+  ::emu::submit([=]() {
+    for (size_t r = 0; r < height; ++r) memmove((char*)d + r * dpitch, (const char*)s + r * spitch, width);
+  });
+  return 0;
+}
 static inline cudaError_t cudaGetLastError() { return 0; }
 
 namespace phk {

@@ -72,3 +72,48 @@ def test_demasking_iterations_as_replayed_graphs_equal_the_default_loop(_emu_lib
         assert replays == (10 if graph else 0)  # 5 iterations each: captured + launched in call 2, replayed in call 3
         for i in range(3):
             assert torch.equal(got[i], base[i]), f"graph={graph}, call {i}"
+
+
+@pytest.mark.parametrize("critic_kind,primed", [("token", True), ("self", False), (None, True), ("token", False)])
+def test_critic_and_primed_iterations_as_replayed_graphs_equal_the_per_step_loop(_emu_lib, critic_kind, primed):
+    """phk_maskgit_demask_iteration_critic (re-mask + MaskGit CFG pair + tail + critic CFG pair + scores per call; prime ids
+    ahead of the sampled tokens) against the per-step Python loop: three consecutive samples (eager, captured, replayed),
+    fresh V-wide noise and fresh critic noise per call -- a value wrongly baked into a graph shows up as a difference."""
+    from phenaki_pytorch_b200 import _lib as L
+    from tests import cases as C
+    import phenaki_pytorch_b200 as P
+
+    def run(iteration_call, graph):
+        torch.manual_seed(31)
+        cv = P.CViViT(**C.SAMPLE_CVIVIT)
+        mg = P.MaskGit(dim=128, num_tokens=256, max_seq_len=64, heads=2, dim_head=64, depth=2, dim_context=48)
+        critic = None
+        if critic_kind == "token":
+            critic = P.TokenCritic(dim=128, num_tokens=256, max_seq_len=64, has_cross_attn=True, heads=2, dim_head=64, depth=1,
+                                   dim_context=48)
+            critic.precision = L.PREC_BF16
+        elif critic_kind == "self":
+            critic = P.SelfCritic(mg)
+        mg.precision = L.PREC_BF16
+        ph = P.Phenaki(cvivit=cv, maskgit=mg, critic=critic, steps=5, text_embed_dim=48, critic_noise_anneal_schedule="decay")
+        ph.iteration_call = iteration_call
+        _emu_lib.phk_debug_step_graph(graph)
+        ctx = C.synthetic_text_embeds(2, 6, 48, (6, 3), 3)
+        prime = torch.randint(0, 256, (2, 16), generator=torch.Generator().manual_seed(5)) if primed else None
+        n = 32 if primed else 48
+        torch.manual_seed(12)
+        outs = [ph.sample_token_ids(num_tokens=n, patch_shape=(3, 4, 4), batch_size=2, text_embeds=ctx, prime_token_ids=prime,
+                                    cond_scale=3.0).clone() for _ in range(3)]
+        _emu_lib.phk_debug_step_graph(-1)
+        return outs
+
+    base = run(False, 0)
+    assert not torch.equal(base[0], base[1])
+    _emu_lib.phk_emu_graph_launches.restype = ctypes.c_long
+    for graph in (0, 1):
+        before = _emu_lib.phk_emu_graph_launches()
+        got = run(True, graph)
+        replays = _emu_lib.phk_emu_graph_launches() - before
+        assert replays == (10 if graph else 0)
+        for i in range(3):
+            assert torch.equal(got[i], base[i]), f"graph={graph}, call {i}"

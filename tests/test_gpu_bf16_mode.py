@@ -215,3 +215,36 @@ def test_one_graph_launch_per_iteration_equals_the_per_step_loop():
         assert torch.equal(a, b)
     assert not torch.equal(runs[True][0], runs[True][1])  # fresh noise per sample
     assert bool(((runs[True][3] >= 0) & (runs[True][3] < 256)).all())
+
+
+@pytest.mark.parametrize("critic_kind,primed", [("token", True), ("self", False), (None, True)])
+def test_critic_and_primed_iterations_equal_the_per_step_loop(critic_kind, primed):
+    """phk_maskgit_demask_iteration_critic (re-mask + MaskGit CFG pair + tail + critic CFG pair + scores in ONE launch
+    sequence per iteration, replayed as a graph from the third sample on; make_video's primed scenes) against the per-step
+    loop: same V-wide noise counters and the same torch generator draws for the critic noise -> identical ids, four
+    consecutive samples."""
+    torch.manual_seed(31)
+    cv = P.CViViT(**C.SAMPLE_CVIVIT)
+    mg = P.MaskGit(dim=128, num_tokens=256, max_seq_len=64, heads=2, dim_head=64, depth=2, dim_context=48)
+    critic = None
+    if critic_kind == "token":
+        critic = P.TokenCritic(dim=128, num_tokens=256, max_seq_len=64, has_cross_attn=True, heads=2, dim_head=64, depth=1,
+                               dim_context=48).to(DEV)
+        critic.precision = L.PREC_BF16
+    mg = mg.to(DEV)
+    if critic_kind == "self":
+        critic = P.SelfCritic(mg).to(DEV)
+    mg.precision = L.PREC_BF16
+    ph = P.Phenaki(cvivit=cv.to(DEV), maskgit=mg, critic=critic, steps=5, text_embed_dim=48)
+    ctx = C.synthetic_text_embeds(2, 6, 48, (6, 3), 3).to(DEV)
+    prime = torch.randint(0, 256, (2, 16), generator=torch.Generator().manual_seed(5)).to(DEV) if primed else None
+    n = 32 if primed else 48
+    runs = {}
+    for graph in (True, False):
+        ph.iteration_call = graph
+        torch.manual_seed(12)
+        runs[graph] = [ph.sample_token_ids(num_tokens=n, patch_shape=(3, 4, 4), batch_size=2, text_embeds=ctx,
+                                           prime_token_ids=prime, cond_scale=3.0).cpu() for _ in range(4)]
+    for a, b in zip(runs[True], runs[False]):
+        assert torch.equal(a, b)
+    assert not torch.equal(runs[True][0], runs[True][1])
