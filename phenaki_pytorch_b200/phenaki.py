@@ -790,7 +790,10 @@ class Phenaki(nn.Module):
         stride = _noise_stride(b * n, vocab)
         as_i64 = lambda v: v - (1 << 64) if v >= (1 << 63) else v  # uint64 bit pattern in an int64 tensor
         first = _rng_take(dev, seed, stride * steps)  # the library advances the device-side counter by `stride` per iteration
-        bufs["rng"].copy_(torch.tensor([as_i64(seed & (2 ** 64 - 1)), as_i64(first)], dtype=torch.int64))
+        # two scalar fills, not a host tensor: a pageable H2D copy synchronises the stream first, which stalled the host at the
+        # start of every sample until the previous scene's decode had drained (make_video was host-bound through it)
+        bufs["rng"][0].fill_(as_i64(seed & (2 ** 64 - 1)))
+        bufs["rng"][1].fill_(as_i64(first))
         with torch.cuda.device(dev):
             table = mg._table()
             ws = mg._ws.get(lib.phk_maskgit_sample_workspace_bytes(C.byref(table), b, n, ctx_len), dev)
@@ -838,7 +841,10 @@ class Phenaki(nn.Module):
         stride = _noise_stride(b * n, vocab)
         as_i64 = lambda v: v - (1 << 64) if v >= (1 << 63) else v
         first = _rng_take(dev, seed, stride * steps)
-        bufs["rng"].copy_(torch.tensor([as_i64(seed & (2 ** 64 - 1)), as_i64(first)], dtype=torch.int64))
+        # two scalar fills, not a host tensor: a pageable H2D copy synchronises the stream first, which stalled the host at the
+        # start of every sample until the previous scene's decode had drained (make_video was host-bound through it)
+        bufs["rng"][0].fill_(as_i64(seed & (2 ** 64 - 1)))
+        bufs["rng"][1].fill_(as_i64(first))
         with torch.cuda.device(dev):
             table = mg._table()
             ctable, head_w, head_b, keep = None, None, None, None
