@@ -82,7 +82,7 @@ class ClockSampler:
                 i += 1
             except Exception:
                 pass
-            time.sleep(0.001)
+            time.sleep(0.003)  # (a 1 ms poll took a measurable share of a core from the launching thread)
 
     def start(self):
         if self.nvml is not None:
@@ -130,7 +130,7 @@ class ClockSampler:
             mx = None
         return dict(sm_mhz=statistics.median(s for s, _, _ in samples), sm_max_mhz=mx,
                     power_w_max=max(p for _, _, p in samples), samples=len(samples), reasons=reasons,
-                    source="nvml, 2 ms period")
+                    source="nvml, ~4 ms period")
 
     def stop(self):
         if self.nvml is not None:
@@ -331,7 +331,7 @@ def bench_maskgit(dev, prec, world, barrier, sampler, samples_timed=6):
     cv = P.CViViT(**CFG2).to(dev)
     mg = P.MaskGit(**CFG3).to(dev)
     cv.precision = mg.precision = prec
-    ph = P.Phenaki(cvivit=cv, maskgit=mg, steps=CFG3_RUN["steps"], text_embed_dim=768)
+    ph = P.Phenaki(cvivit=cv, maskgit=mg, steps=CFG3_RUN["steps"], text_embed_dim=768).eval()
     ph.cvivit.precision = prec
     if os.environ.get("PHK_FUSED_HEAD") is not None:   # A/B: fused logits-head kernel vs head GEMM + sampling kernel
         ph.fused_head = os.environ["PHK_FUSED_HEAD"] != "0"
@@ -461,7 +461,7 @@ def bench_make_video(dev, prec, world, barrier, sampler, chains_timed=3, b=2):
     mg = P.MaskGit(**CFG3).to(dev)
     cr = P.TokenCritic(dim=512, num_tokens=65536, max_seq_len=1024, has_cross_attn=True, depth=6, dim_context=768).to(dev)
     cv.precision = mg.precision = cr.precision = prec
-    ph = P.Phenaki(cvivit=cv, maskgit=mg, critic=cr, steps=CFG3_RUN["steps"], text_embed_dim=768)
+    ph = P.Phenaki(cvivit=cv, maskgit=mg, critic=cr, steps=CFG3_RUN["steps"], text_embed_dim=768).eval()
     ph.cvivit.precision = prec
     frames, prime = (17, 14, 14), 5
     embeds = [torch.randn((b, CFG3_RUN["ctx_len"], 768), device=dev) for _ in frames]

@@ -884,8 +884,12 @@ class Phenaki(nn.Module):
                noise_fn=None):
         """phenaki_pytorch.py:418-560.  Extra keywords: ``text_embeds`` (precomputed T5 output),
         ``return_token_ids`` (skip the final C-ViViT decode), ``noise_fn`` (inject the uniform draws)."""
+        # eval_decorator (phenaki_pytorch.py:31-38).  The mode flags only matter to dropout, which the kernels do not have
+        # (construction rejects attn_dropout / ff_dropout > 0 for training); the walk over ~600 submodules cost ~2 ms of
+        # host time per call, twice per sample, so it is skipped when the model is already in eval mode.
         was_training = self.training
-        self.eval()
+        if was_training:
+            self.eval()
         try:
             prime_ids, prime_num_frames = None, 0
             if prime_frames is not None:
@@ -919,7 +923,8 @@ class Phenaki(nn.Module):
                 video = video[:, :, prime_num_frames:]
             return video
         finally:
-            self.train(was_training)
+            if was_training:
+                self.train(True)
 
     def sample_images(self, *, texts=None, batch_size=1, cond_scale=3.0, starting_temperature=0.9, noise_K=1.0):
         video = self.sample(texts=texts, num_frames=1, cond_scale=cond_scale,

@@ -53,6 +53,8 @@ over = grads(True, True)
 used_overlap = getattr(mg, "_overlap_cache", None) is not None
 worst_a = worst_b = 0.0
 for k in mean_g:
+    if mean_g[k].numel() == 0:
+        continue
     scale = max(mean_g[k].abs().max().item(), 1e-12)
     worst_a = max(worst_a, (plain[k] - mean_g[k]).abs().max().item() / scale if scale > 1e-7 else 0.0)
     worst_b = max(worst_b, (over[k] - mean_g[k]).abs().max().item() / scale if scale > 1e-7 else 0.0)
