@@ -309,17 +309,14 @@ class _TokenTransformer(nn.Module):
                 self._launch_overlapped_all_reduce(gk, plan)
         return loss, gk, logits
 
-    def _overlap_plan(self, gk, owner, dev):
-        """Data parallel, NCCL: slices of the flat gradient bucket in the order the backward finishes them (head +
-        norm_out, layers depth-1 .. 0, embeddings + position-bias MLP) and one CUDA event per slice for
-        phk_train_set_progress_events.  None when there is nothing to overlap (single process, non-NCCL backend)."""
-        import torch.distributed as dist
-        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 and gk.flat.is_cuda
-                and dist.get_backend() == "nccl"):
-            return None
+    def _gradient_groups(self, gk, owner):
+        """Spans [lo, hi) (elements of the flat gradient bucket) by completion index of the backward: 0 = head + norm_out,
+        1 .. depth = transformer layers depth-1 .. 0, depth + 1 = embeddings + position-bias MLP.  A group's parameters need
+        not be adjacent in the bucket (token_emb / pos_emb open it, the position-bias MLP sits behind the layers): adjacent
+        spans are merged, every element of the bucket belongs to exactly one span."""
         depth = self.transformer.depth
         base, esz = gk.flat.data_ptr(), gk.flat.element_size()
-        groups = [[None, None] for _ in range(depth + 2)]  # [lo, hi) in elements, by completion index
+        groups = [[] for _ in range(depth + 2)]  # spans [lo, hi) in elements, by completion index
         for name, p in owner.named_parameters():
             lo = (gk.views[p].data_ptr() - base) // esz
             hi = lo + (p.numel() + 63) // 64 * 64
@@ -328,12 +325,33 @@ class _TokenTransformer(nn.Module):
                 idx = 1 + (depth - 1 - int(name.split("transformer.layers.")[1].split(".")[0]))
             elif "norm_out" in name or "to_logits" in name or "to_pred" in name:
                 idx = 0
-            g = groups[idx]
-            g[0] = lo if g[0] is None else min(g[0], lo)
-            g[1] = hi if g[1] is None else max(g[1], hi)
-        spans = sorted((g[0], g[1]) for g in groups if g[0] is not None)
-        if any(a[1] > b[0] for a, b in zip(spans, spans[1:])):  # groups interleave in the bucket: no slicing
+            if p.numel():
+                groups[idx].append((lo, hi))
+        for i, spans in enumerate(groups):  # a group's parameters need not be adjacent in the bucket: merge what is
+            merged = []
+            for lo, hi in sorted(spans):
+                if merged and lo <= merged[-1][1]:
+                    merged[-1][1] = max(merged[-1][1], hi)
+                else:
+                    merged.append([lo, hi])
+            groups[i] = merged
+        flat = sorted(sp for spans in groups for sp in spans)
+        if any(a[1] > b[0] for a, b in zip(flat, flat[1:])):  # (padded spans of different groups overlap: no slicing)
             return None
+        return groups
+
+    def _overlap_plan(self, gk, owner, dev):
+        """Data parallel, NCCL: slices of the flat gradient bucket in the order the backward finishes them (head +
+        norm_out, layers depth-1 .. 0, embeddings + position-bias MLP) and one CUDA event per slice for
+        phk_train_set_progress_events.  None when there is nothing to overlap (single process, non-NCCL backend)."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 and gk.flat.is_cuda
+                and dist.get_backend() == "nccl") or os.environ.get("PHK_OVERLAP_ALL_REDUCE") == "0":
+            return None  # (PHK_OVERLAP_ALL_REDUCE=0: one all-reduce of the whole bucket after the step, for A/B runs)
+        groups = self._gradient_groups(gk, owner)
+        if groups is None:
+            return None
+        depth = self.transformer.depth
         cache = self.__dict__.setdefault("_overlap_cache", {})
         key = (dev, depth)
         if key not in cache:
@@ -350,14 +368,15 @@ class _TokenTransformer(nn.Module):
         import torch.distributed as dist
         side, world = plan["stream"], dist.get_world_size()
         gk.flat.record_stream(side)
-        for ev, (lo, hi) in zip(plan["events"], plan["groups"]):
-            if lo is None:
+        for ev, spans in zip(plan["events"], plan["groups"]):
+            if not spans:
                 continue
             side.wait_event(ev)
             with torch.cuda.stream(side):
-                part = gk.flat[lo:hi]
-                dist.all_reduce(part, op=dist.ReduceOp.SUM)
-                part.div_(world)
+                for lo, hi in spans:
+                    part = gk.flat[lo:hi]
+                    dist.all_reduce(part, op=dist.ReduceOp.SUM)
+                    part.div_(world)
         gk.reduced = torch.cuda.Event()
         gk.reduced.record(side)
 

@@ -59,3 +59,30 @@ def test_default_precision_follows_the_environment(monkeypatch):
     assert P.MaskGit(**C.SAMPLE_MASKGIT).precision == L.PREC_BF16
     monkeypatch.delenv("PHK_PREC")
     assert P.MaskGit(**C.SAMPLE_MASKGIT).precision == L.default_precision()
+
+
+def test_gradient_groups_cover_the_bucket_once_in_completion_order():
+    """The slices the overlapped all-reduce launches as the backward finishes them: every element of the flat gradient
+    bucket in exactly one span, head first, layers top-down, embeddings + position-bias MLP last -- for the MaskGit of
+    BASELINE configs[3] and for a SelfCritic owner (MaskGit parameters followed by to_pred).  (A zero-element parameter --
+    the self-attention's null_kv (heads, 0, dim_head) -- has no address in the bucket and must not drag a group's span to offset "minus base".)"""
+    import phenaki_pytorch_b200 as P
+    from phenaki_pytorch_b200.modules import GradKeep
+    mg = P.MaskGit(dim=64, num_tokens=128, max_seq_len=64, heads=2, dim_head=32, depth=3, dim_context=48)
+    assert any(p.numel() == 0 for p in mg.parameters())
+    for owner in (mg, P.SelfCritic(mg)):
+        gk = GradKeep(owner.parameters())
+        groups = mg._gradient_groups(gk, owner)
+        assert groups is not None and len(groups) == mg.transformer.depth + 2
+        covered = torch.zeros(gk.flat.numel(), dtype=torch.int32)
+        for spans in groups:
+            for lo, hi in spans:
+                covered[lo:hi] += 1
+        assert int(covered.min()) == 1 and int(covered.max()) == 1
+        names = dict(owner.named_parameters())
+        where = lambda n: (gk.views[names[n]].data_ptr() - gk.flat.data_ptr()) // 4
+        inside = lambda n, g: any(lo <= where(n) < hi for lo, hi in groups[g])
+        prefix = "maskgit." if owner is not mg else ""
+        assert inside(prefix + "to_logits.weight", 0) and inside(prefix + "transformer.norm_out.gamma", 0)
+        assert inside(prefix + "transformer.layers.2.0.dsconv.weight", 1) and inside(prefix + "transformer.layers.0.1.q_scale", 3)
+        assert inside(prefix + "token_emb.weight", 4) and inside(prefix + "continuous_pos_bias.net.0.0.weight", 4)
