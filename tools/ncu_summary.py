@@ -48,13 +48,25 @@ def stalls(r):
     return " ".join(f"{n}={v:.1f}" for v, n in sorted(vals, reverse=True)[:5])
 
 
-seen, out = {}, []
+def dram_mb(r):
+    t = 0.0
+    for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+        if m in col and r[col[m]] not in ("", "no data", "n/a"):
+            t += float(r[col[m]].replace(",", "")) * SC.get(units[col[m]], 1) / 1e6
+    return t
+
+
+seen, out, traffic = {}, [], {}
 for r in rows[2:]:
     key = (r[col["Kernel Name"]].split("(")[0].replace("void ", "").replace("phk::", "").replace("<unnamed>::", ""), r[col["Grid Size"]])
     seen[key] = seen.get(key, 0) + 1
+    traffic[key] = traffic.get(key, 0.0) + dram_mb(r)
     if seen[key] > 1:
         continue
     out.append([key[0], key[1]] + [val(r, m) for m, _ in M] + [stalls(r)])
+for row in out:  # how many launches of this (kernel, grid) the capture holds and their mean DRAM traffic (read + write)
+    k = (row[0], row[1])
+    row += [seen[k], f"{traffic[k] / seen[k]:.3f} MB"]
 w = csv.writer(open(sys.argv[2], "w", newline="") if len(sys.argv) > 2 else sys.stdout)
-w.writerow(["kernel", "grid"] + [n for _, n in M] + ["top_stalls_cycles_per_issue"])
+w.writerow(["kernel", "grid"] + [n for _, n in M] + ["top_stalls_cycles_per_issue", "launches_captured", "dram_rd_wr_mean"])
 w.writerows(out)
