@@ -361,6 +361,23 @@ int phk_sample_tokens(const float* cond, const float* null_logits, int64_t ld, c
 int phk_topk_mask(const float* scores, int32_t b, int32_t n, int32_t k, uint8_t* mask,
                   int64_t* ids, int64_t mask_id, phk_stream_t s);
 
+/* Cross-attention on packed operands (bf16 mode; attention.py:137-181 with null keys + at most 32 key slots, dim_head 64).
+ * phk_cross_kv_pack: once per transformer call, for every layer l: pack[(l * ctx_b + b) * heads + h] = { K^ [32][64] bf16
+ *   (null keys first, then the text keys; l2-normalised * k_scale; zero padding), V [32][64] bf16 }, dead[(l * ctx_b + b)][32]
+ *   = 1 for a masked text key or a padding slot.  kv[l]: fp32 [ctx_b * L, 2 * heads * 64] (phk_maskgit_context_kv), null_kv[l]:
+ *   [heads, 2 * nnull, 64], k_scale[l]: [64], key_mask [ctx_b, L] or NULL.  pack: depth * ctx_b * heads * 8192 bytes.
+ * phk_gemm_bf16_qnorm: Qn[M, I] = normalize_per_head(xn Wq^T) * q_scale * sim_scale as bf16 (the q projection's epilogue).
+ * phk_attention_cross_packed: one layer; sequence s uses the text s % ctx_b, sequences >= null_from (-1: none) attend to the
+ *   null keys only (the null half of a CFG pair). */
+int phk_cross_kv_pack(const float* const* kv, const float* const* null_kv, const float* const* k_scale, int32_t depth,
+                      const uint8_t* key_mask, int32_t ctx_b, int32_t L, int32_t heads, int32_t nnull, void* pack, float* dead,
+                      phk_stream_t s);
+int phk_gemm_bf16_qnorm(const void* xn, int64_t lda, const void* Wq, int64_t ldw, void* Qn, int64_t M, int32_t I, int32_t K,
+                        const float* q_scale, float sim_scale, phk_stream_t s);
+int phk_attention_cross_packed(const void* Qn, int64_t ld_q, const void* pack, const float* dead, void* out, int64_t ld_o,
+                               int32_t n_seq, int32_t n_q, int32_t heads, int32_t ctx_b, int32_t nnull, int32_t null_from,
+                               phk_stream_t s);
+
 /* critic score (phenaki_pytorch.py:246-249, 263, 544-545):
  *   sc = x @ w + b per row; out = null + (cond - null)*scale + noise_K*(u-0.5)*noise_mult  */
 int phk_critic_scores(const float* x_cond, const float* x_null, const float* w, const float* b,

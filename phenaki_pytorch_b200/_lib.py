@@ -128,6 +128,9 @@ PROTOTYPES = {
     "phk_gemm_bf16_ln_ws": [vp, i64, vp, i64, vp, i64, i64, i32, i32, vp, vp, vp, f32, vp, vp, i64, vp, vp, vp],
     "phk_train_set_progress_events": [vp, i32],
     "phk_split3": [vp, i64, vp, i64, i32, i32, vp],
+    "phk_cross_kv_pack": [vp, vp, vp, i32, vp, i32, i32, i32, i32, vp, vp, vp],
+    "phk_gemm_bf16_qnorm": [vp, i64, vp, i64, vp, i64, i32, i32, vp, f32, vp],
+    "phk_attention_cross_packed": [vp, i64, vp, vp, vp, i64, i32, i32, i32, i32, i32, i32, vp],
     "phk_gemm_bf16_qkv": [vp, vp, i64, vp, vp, i64, vp, vp, i64, i32, i32, vp, vp, f32, vp],
     "phk_peg3d": [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
     "phk_cpb_scratch_floats": [C.POINTER(CpbT), i32, i32, i32],

@@ -184,6 +184,42 @@ static int transformer_forward(const TfCall& c, Arena scratch, float* out, void*
                                  ln_counters + (int64_t)(ln_launch++) * PHK_LN_COUNTERS, s);
     return phk_gemm_bf16_ln(a, lda, w, ldw, xio, D, rows, D, K, nullptr, g, b, 1e-5f, ln_o, raw_o, D, s);
   };
+  // bf16 mode: cross-attention on packed operands -- the text keys / values of all layers are l2-normalised, scaled and
+  // converted ONCE per call (phk_cross_kv_pack) instead of once per attention CTA, and the q projection's epilogue writes the
+  // normalised bf16 queries (phk_gemm_bf16_qnorm): the attention kernel is 32 MMAs behind an 8 KB copy.
+  void* cross_pack = nullptr;
+  float* cross_dead = nullptr;
+  int cross_nnull = 0;
+#ifndef PHK_CUDA_EMU
+  {
+    static const bool pack_env = [] { const char* e = std::getenv("PHK_CROSS_PACK"); return !(e && e[0] == '0'); }();
+    bool ok = pack_env && h16 && c.ctx_kv && DH == 64 && I % 128 == 0 && T->depth <= 16 && c.seq.n_inner == 1 && c.seq.tok == 1 &&
+              c.seq.outer == c.seq.n_tok && c.ctx_b > 0;
+    for (int l = 0; ok && l < T->depth; ++l) {
+      const phk_layer_t& Ly = T->layers[l];
+      ok = Ly.has_cross && Ly.cross_attn.wq_h && Ly.cross_attn.num_null_kv > 0 && Ly.cross_attn.null_kv &&
+           Ly.cross_attn.num_null_kv == T->layers[0].cross_attn.num_null_kv &&
+           Ly.cross_attn.num_null_kv + c.ctx_L <= 32;
+    }
+    if (ok) {
+      Arena tmp = scratch;
+      void* pk = tmp.take((int64_t)T->depth * c.ctx_b * H * 8192);
+      float* dd = (float*)tmp.take((int64_t)T->depth * c.ctx_b * 32 * 4);
+      if (pk && dd) {  // (a workspace sized by an older build: the unpacked kernel takes over)
+        scratch = tmp;
+        const float* kvp[16]; const float* nkp[16]; const float* ksp[16];
+        for (int l = 0; l < T->depth; ++l) {
+          kvp[l] = c.ctx_kv + (int64_t)l * c.ctx_b * c.ctx_L * 2 * I;
+          nkp[l] = T->layers[l].cross_attn.null_kv;
+          ksp[l] = T->layers[l].cross_attn.k_scale;
+        }
+        cross_nnull = T->layers[0].cross_attn.num_null_kv;
+        PHK_TRY(phk_cross_kv_pack(kvp, nkp, ksp, T->depth, c.ctx_mask, c.ctx_b, c.ctx_L, H, cross_nnull, pk, dd, s));
+        cross_pack = pk; cross_dead = dd;
+      }
+    }
+  }
+#endif
   bool ln_ready = false;  // xn (+ xraw) already hold this layer's self-attention LayerNorm (written by the previous FF2)
   for (int l = 0; l < T->depth; ++l) {
     const phk_layer_t& L = T->layers[l];
@@ -260,6 +296,15 @@ static int transformer_forward(const TfCall& c, Arena scratch, float* out, void*
       PHK_REQUIRE(c.seq.n_inner == 1, PHK_E_UNSUPPORTED, "cross attention needs (b, n) sequences");
       if (!norm_done) PHK_TRY(phk_layernorm(x, A.norm_g, A.norm_b, xn, nullptr, R, D, h16, 0, 0, 0, s));
       norm_done = false;
+#ifndef PHK_CUDA_EMU
+      if (cross_pack) {
+        PHK_TRY(phk_gemm_bf16_qnorm(xn, D, A.wq_h, D, q, R, I, D, A.q_scale, 8.f, s));  // bf16 [R, I] in the fp32-sized q buffer
+        PHK_TRY(phk_attention_cross_packed(q, I, (char*)cross_pack + (int64_t)l * c.ctx_b * H * 8192,
+                                           cross_dead + (int64_t)l * c.ctx_b * 32, o, I, c.seq.n_outer, c.seq.n_tok, H, c.ctx_b,
+                                           cross_nnull, c.ctx_mask ? c.ctx_mask_off_from : -1, s));
+      } else
+#endif
+      {
       PHK_TRY(linear(c.lin, xn, D, A.wq, A.wq_h, D, q, I, R, I, D, nullptr, nullptr, s));
       phk_attn_geom_t g;
       std::memset(&g, 0, sizeof(g));
@@ -272,6 +317,7 @@ static int transformer_forward(const TfCall& c, Arena scratch, float* out, void*
       g.out_bf16 = h16; g.scale = 8.f;
       const float* kvl = c.ctx_kv + (int64_t)l * c.ctx_b * c.ctx_L * 2 * I;
       PHK_TRY(phk_attention(q, kvl, A.null_kv, A.q_scale, A.k_scale, nullptr, c.ctx_mask, nullptr, o, &g, s));
+      }
       if (fuse_ln && A.wo_h) {
         PHK_TRY(gemm_ln(o, I, A.wo_h, I, x, R, I, L.ff.ln_g, L.ff.ln_b, xn, nullptr));
         norm_done = true;
@@ -818,6 +864,8 @@ extern "C" int64_t phk_maskgit_workspace_bytes(const phk_maskgit_t* m, int32_t b
   bytes += tf_scratch_bytes(&m->transformer, R);
   if (m->has_bias) bytes += (int64_t)m->heads * n * n * 4 + (int64_t)8 * n * 8 * m->heads * 4 + (1 << 20);
   if (prec == PHK_PREC_BF16X3) bytes += x3_bytes(R, tf_kmax(&m->transformer));
+  // packed cross-attention operands of every layer (phk_cross_kv_pack): 8 KB per (layer, text, head) + the dead-key flags
+  bytes += (int64_t)m->transformer.depth * b * m->transformer.heads * 8192 + (int64_t)m->transformer.depth * b * 128 + 512;
   (void)L;
   return bytes;
 }

@@ -1019,6 +1019,167 @@ __global__ void __launch_bounds__(256) attention_cross_mma_kernel(const float* _
 }
 #endif  // PHK_CUDA_EMU
 
+// ------------------------------------------------------------------------------------------
+// The same cross-attention on PACKED operands.  The keys / values of a sample do not change over its demasking iterations
+// nor between the query tiles of an iteration, yet attention_cross_mma_kernel re-normalised them in every CTA (one extra
+// dependent global-load latency + 32 warp reductions per CTA).  cross_kv_pack_kernel does it once per transformer call for
+// all layers: pack[(l * ctx_b + b) * heads + h] = { K^ [32 slots][64] bf16 (l2-normalised * k_scale; null keys first, zero
+// padding), V [32][64] bf16 }, dead[(l * ctx_b + b)][32] (1: masked text key or padding).  The queries arrive as the bf16
+// operand phk_gemm_bf16_qnorm writes (normalised, scaled), so the attention CTA only copies 8 KB, loads its A fragments
+// and runs the 32 MMAs.  [not compiled for the CPU executor]
+// ------------------------------------------------------------------------------------------
+#ifndef PHK_CUDA_EMU
+struct CrossPackLayer { const float* kv; const float* null_kv; const float* k_scale; };
+struct CrossPackArgs { CrossPackLayer layer[16]; };
+
+__global__ void __launch_bounds__(256) cross_kv_pack_kernel(CrossPackArgs a, const uint8_t* __restrict__ key_mask,
+                                                            __nv_bfloat16* __restrict__ pack, float* __restrict__ dead,
+                                                            int depth, int ctx_b, int L, int heads, int nnull) {
+  pdl_prologue();
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int64_t total = (int64_t)depth * ctx_b * heads * XK;
+  if (warp >= total) return;
+  const int j = (int)(warp % XK);
+  const int h = (int)((warp / XK) % heads);
+  const int b = (int)((warp / ((int64_t)XK * heads)) % ctx_b);
+  const int l = (int)(warp / ((int64_t)XK * heads * ctx_b));
+  const CrossPackLayer& ly = a.layer[l];
+  const int I = heads * 64;
+  float2 kx = make_float2(0.f, 0.f), vx = make_float2(0.f, 0.f);
+  bool is_dead = true;
+  if (j < nnull + L) {
+    const float* kp;
+    const float* vp;
+    if (j < nnull) { kp = ly.null_kv + ((int64_t)h * 2 * nnull + 2 * j) * 64; vp = kp + 64; }   // 'h (n r) d' (:148)
+    else { kp = ly.kv + ((int64_t)b * L + (j - nnull)) * 2 * I + (int64_t)h * 64; vp = kp + I; }
+    kx = reinterpret_cast<const float2*>(kp)[lane];
+    vx = reinterpret_cast<const float2*>(vp)[lane];
+    const float inv = 1.0f / fmaxf(sqrtf(warp_sum(kx.x * kx.x + kx.y * kx.y)), 1e-12f);
+    const float2 ks = reinterpret_cast<const float2*>(ly.k_scale)[lane];
+    kx.x = (kx.x * inv) * ks.x; kx.y = (kx.y * inv) * ks.y;
+    is_dead = key_mask && j >= nnull && !key_mask[(int64_t)b * L + (j - nnull)];
+  }
+  __nv_bfloat16* base = pack + (((int64_t)l * ctx_b + b) * heads + h) * (2 * XK * 64);
+  reinterpret_cast<uint32_t*>(base + j * 64)[lane] = pack_bf16x2(kx.x, kx.y);
+  reinterpret_cast<uint32_t*>(base + XK * 64 + j * 64)[lane] = pack_bf16x2(vx.x, vx.y);
+  if (h == 0 && lane == 0) dead[((int64_t)l * ctx_b + b) * XK + j] = is_dead ? 1.f : 0.f;
+}
+
+// grid (ceil(n_q / 128), heads, sequences); sequence `seq` reads the pack of text seq % ctx_b; sequences >= null_from (the
+// null half of a CFG pair) see only the null keys.  Qn / out: token-major bf16 rows, sequence stride n_q rows.
+__global__ void __launch_bounds__(256) attention_cross_packed_kernel(const __nv_bfloat16* __restrict__ Qn, int64_t ld_q,
+                                                                     const __nv_bfloat16* __restrict__ pack,
+                                                                     const float* __restrict__ dead,
+                                                                     __nv_bfloat16* __restrict__ out, int64_t ld_o, int n_q,
+                                                                     int heads, int ctx_b, int nnull, int null_from) {
+  pdl_prologue();
+  __shared__ __align__(16) __nv_bfloat16 sK[XK][MMA_LD];
+  __shared__ __align__(16) __nv_bfloat16 sV[XK][MMA_LD];
+  __shared__ float s_dead[XK];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int h = blockIdx.y, seq = blockIdx.z;
+  const int b = seq % ctx_b;
+  const bool null_half = null_from >= 0 && seq >= null_from;
+  const __nv_bfloat16* pk = pack + ((int64_t)b * heads + h) * (2 * XK * 64);
+  for (int i = threadIdx.x; i < 2 * XK * 8; i += 256) {  // 2 x 32 rows x 8 sixteen-byte pieces
+    const int which = i / (XK * 8), r = (i / 8) % XK, c = i % 8;
+    const uint4 v = reinterpret_cast<const uint4*>(pk + which * (XK * 64) + r * 64)[c];
+    *reinterpret_cast<uint4*>(which ? &sV[r][c * 8] : &sK[r][c * 8]) = v;
+  }
+  if (threadIdx.x < XK) s_dead[threadIdx.x] = (null_half && threadIdx.x >= nnull) ? 1.f : dead[(int64_t)b * XK + threadIdx.x];
+  const int gq = lane >> 2, t = lane & 3;
+  const int r0 = blockIdx.x * 128 + w * 16;  // this warp's 16 queries
+  // A fragments straight from the bf16 rows: lane (gq, t) holds rows gq / gq + 8, columns ks*16 + {2t, 2t+1} and + 8
+  uint32_t a[4][4];
+  const bool v0 = r0 + gq < n_q, v1 = r0 + gq + 8 < n_q;
+  const __nv_bfloat16* q0p = Qn + ((int64_t)seq * n_q + r0 + gq) * ld_q + h * 64;
+  const __nv_bfloat16* q1p = q0p + 8 * ld_q;
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    const int c = ks * 16 + 2 * t;
+    a[ks][0] = v0 ? *reinterpret_cast<const uint32_t*>(q0p + c) : 0u;
+    a[ks][1] = v1 ? *reinterpret_cast<const uint32_t*>(q1p + c) : 0u;
+    a[ks][2] = v0 ? *reinterpret_cast<const uint32_t*>(q0p + c + 8) : 0u;
+    a[ks][3] = v1 ? *reinterpret_cast<const uint32_t*>(q1p + c + 8) : 0u;
+  }
+  __syncthreads();
+  if (r0 >= n_q) return;
+  float sc[4][4];
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) sc[nt][e] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+    for (int np = 0; np < 2; ++np) {
+      uint32_t bfr[4];
+      ldmatrix_x4(bfr, &sK[(lane & 7) + 8 * (lane >> 4) + 16 * np][ks * 16 + 8 * ((lane >> 3) & 1)]);
+      mma_bf16_16816(sc[2 * np], a[ks], bfr[0], bfr[1]);
+      mma_bf16_16816(sc[2 * np + 1], a[ks], bfr[2], bfr[3]);
+    }
+  float inv[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    float m = -FLT_MAX;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int key = nt * 8 + 2 * t + e;
+        if (s_dead[key] != 0.f) sc[nt][2 * r + e] = -FLT_MAX;
+        m = fmaxf(m, sc[nt][2 * r + e]);
+      }
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+    float sum = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const float v = sc[nt][2 * r + e];
+        const float ex = v == -FLT_MAX ? 0.f : __expf(v - m);
+        sc[nt][2 * r + e] = ex;
+        sum += ex;
+      }
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    inv[r] = sum > 0.f ? __fdividef(1.f, sum) : 0.f;
+  }
+  uint32_t pa[2][4];
+#pragma unroll
+  for (int kk = 0; kk < 2; ++kk) {
+    pa[kk][0] = pack_bf16x2(sc[2 * kk][0], sc[2 * kk][1]);
+    pa[kk][1] = pack_bf16x2(sc[2 * kk][2], sc[2 * kk][3]);
+    pa[kk][2] = pack_bf16x2(sc[2 * kk + 1][0], sc[2 * kk + 1][1]);
+    pa[kk][3] = pack_bf16x2(sc[2 * kk + 1][2], sc[2 * kk + 1][3]);
+  }
+  __nv_bfloat16* obase = out + ((int64_t)seq * n_q) * ld_o + h * 64;
+#pragma unroll
+  for (int dp = 0; dp < 4; ++dp) {
+    float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+      uint32_t bfr[4];
+      ldmatrix_x4_trans(bfr, &sV[(lane & 7) + 8 * ((lane >> 3) & 1) + 16 * kk][(2 * dp + (lane >> 4)) * 8]);
+      mma_bf16_16816(o0, pa[kk], bfr[0], bfr[1]);
+      mma_bf16_16816(o1, pa[kk], bfr[2], bfr[3]);
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int row = r0 + gq + 8 * r;
+      if (row < n_q) {
+        __nv_bfloat16* orow = obase + (int64_t)row * ld_o;
+        *reinterpret_cast<uint32_t*>(orow + (2 * dp) * 8 + 2 * t) = pack_bf16x2(o0[2 * r] * inv[r], o0[2 * r + 1] * inv[r]);
+        *reinterpret_cast<uint32_t*>(orow + (2 * dp + 1) * 8 + 2 * t) = pack_bf16x2(o1[2 * r] * inv[r], o1[2 * r + 1] * inv[r]);
+      }
+    }
+  }
+}
+#endif  // PHK_CUDA_EMU
+
+
 template <int NMAX, bool PRE = false>
 static int launch_attention_warp64(const void* q, const void* kv, const float* q_scale, const float* k_scale,
                                    const float* alibi_slopes, void* out, const phk_attn_geom_t& g, cudaStream_t st) {
@@ -1208,3 +1369,48 @@ extern "C" int phk_attention_small_bf16(const void* Qn, const void* KVn, const f
   if (n <= 12) return launch_attention_warp64<12, true>(Qn, KVn, nullptr, nullptr, alibi_slopes, out, *g, st);
   return launch_attention_warp64<16, true>(Qn, KVn, nullptr, nullptr, alibi_slopes, out, *g, st);
 }
+
+#ifndef PHK_CUDA_EMU
+// Packed cross-attention operands of every layer of a transformer call (see cross_kv_pack_kernel).  kv[l]: fp32 [ctx_b * L,
+// 2 * heads * 64] (phk_maskgit_context_kv), null_kv[l]: [heads, 2 * nnull, 64], k_scale[l]: [64]; key_mask [ctx_b, L] or
+// NULL.  pack: depth * ctx_b * heads * 8192 bytes, dead: depth * ctx_b * 32 floats.  nnull + L <= 32, depth <= 16.
+extern "C" int phk_cross_kv_pack(const float* const* kv, const float* const* null_kv, const float* const* k_scale, int32_t depth,
+                                 const uint8_t* key_mask, int32_t ctx_b, int32_t L, int32_t heads, int32_t nnull, void* pack,
+                                 float* dead, phk_stream_t s) {
+  PHK_REQUIRE(kv && null_kv && k_scale && pack && dead, PHK_E_ARG, "phk_cross_kv_pack: null pointer");
+  PHK_REQUIRE(depth > 0 && depth <= 16 && ctx_b > 0 && L >= 0 && heads > 0 && nnull > 0 && nnull + L <= XK, PHK_E_UNSUPPORTED,
+              "phk_cross_kv_pack: at most 16 layers and 32 key slots (null keys + text)");
+  CrossPackArgs a;
+  for (int l = 0; l < depth; ++l) {
+    PHK_REQUIRE(kv[l] && null_kv[l] && k_scale[l], PHK_E_ARG, "phk_cross_kv_pack: null layer pointer");
+    a.layer[l] = CrossPackLayer{kv[l], null_kv[l], k_scale[l]};
+  }
+  const int64_t warps = (int64_t)depth * ctx_b * heads * XK;
+  PHK_CUDA(launch_pdl(cross_kv_pack_kernel, dim3((unsigned)((warps + 7) / 8)), dim3(256), (size_t)0, to_stream(s), a, key_mask,
+                      (__nv_bfloat16*)pack, dead, (int)depth, (int)ctx_b, (int)L, (int)heads, (int)nnull));
+  PHK_LAUNCH_CHECK();
+  return 0;
+}
+
+// Cross-attention of one layer on the packed operands: Qn bf16 [n_seq * n_q, ld_q] (phk_gemm_bf16_qnorm), pack / dead of THIS
+// layer (pack + l * ctx_b * heads * 8192 bytes, dead + l * ctx_b * 32), out bf16 [n_seq * n_q, ld_o].  Sequence s uses the text
+// s % ctx_b; sequences >= null_from (or none: -1) attend to the null keys only (the CFG null half).
+extern "C" int phk_attention_cross_packed(const void* Qn, int64_t ld_q, const void* pack, const float* dead, void* out,
+                                          int64_t ld_o, int32_t n_seq, int32_t n_q, int32_t heads, int32_t ctx_b, int32_t nnull,
+                                          int32_t null_from, phk_stream_t s) {
+  Prof prof_(FAM_ATTENTION, s, 4.0 * (double)n_seq * heads * n_q * XK * 64);
+  PHK_REQUIRE(Qn && pack && dead && out, PHK_E_ARG, "phk_attention_cross_packed: null pointer");
+  PHK_REQUIRE(n_seq > 0 && n_seq <= 65535 && n_q > 0 && heads > 0 && heads <= 65535 && ctx_b > 0 && nnull > 0 && nnull <= XK,
+              PHK_E_ARG, "phk_attention_cross_packed: bad geometry");
+  PHK_REQUIRE(ld_q >= heads * 64 && ld_o >= heads * 64 && ld_q % 2 == 0 && ld_o % 2 == 0 &&
+                  ((reinterpret_cast<uintptr_t>(Qn) | reinterpret_cast<uintptr_t>(out)) & 3) == 0 &&
+                  (reinterpret_cast<uintptr_t>(pack) & 15) == 0,
+              PHK_E_ARG, "phk_attention_cross_packed: misaligned operands");
+  dim3 grid((unsigned)((n_q + 127) / 128), (unsigned)heads, (unsigned)n_seq);
+  PHK_CUDA(launch_pdl(attention_cross_packed_kernel, grid, dim3(256), (size_t)0, to_stream(s), (const __nv_bfloat16*)Qn, ld_q,
+                      (const __nv_bfloat16*)pack, dead, (__nv_bfloat16*)out, ld_o, (int)n_q, (int)heads, (int)ctx_b, (int)nnull,
+                      (int)null_from));
+  PHK_LAUNCH_CHECK();
+  return 0;
+}
+#endif

@@ -1394,6 +1394,27 @@ extern "C" int phk_gemm_bf16_qkv(const void* xn, const void* xraw, int64_t lda, 
   return launch_gemm_dual<3>(ta, tb, p, ta2, tb2, p2, to_stream(s));
 }
 
+// The q projection of a cross-attention block (attention.py:139, 153-157) written as the bf16 operand of the attention
+// core: Qn[M, I] = normalize_per_head(xn Wq^T) * q_scale * sim_scale (epilogue 3 on one problem).  dim_head 64, I % 128 == 0.
+extern "C" int phk_gemm_bf16_qnorm(const void* xn, int64_t lda, const void* Wq, int64_t ldw, void* Qn, int64_t M, int32_t I,
+                                   int32_t K, const float* q_scale, float sim_scale, phk_stream_t s) {
+  Prof prof_(FAM_GEMM_BF16, s, 2.0 * (double)M * I * K);
+  PHK_REQUIRE(xn && Wq && Qn && q_scale, PHK_E_ARG, "phk_gemm_bf16_qnorm: null pointer");
+  PHK_REQUIRE(M > 0 && I > 0 && I % 128 == 0 && K > 0 && lda >= K && ldw >= K, PHK_E_ARG,
+              "phk_gemm_bf16_qnorm: heads * 64 must be a multiple of 128");
+  PHK_REQUIRE(lda % 8 == 0 && ldw % 8 == 0 &&
+                  ((reinterpret_cast<uintptr_t>(xn) | reinterpret_cast<uintptr_t>(Wq) | reinterpret_cast<uintptr_t>(q_scale)) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(Qn) & 7) == 0,
+              PHK_E_ARG, "phk_gemm_bf16_qnorm: operands must be 16-byte aligned with leading dimensions multiple of 8 (TMA)");
+  PHK_REQUIRE(M < (1LL << 31) - 2 * GM, PHK_E_UNSUPPORTED, "phk_gemm_bf16_qnorm: M too large");
+  CUtensorMap ta, tb;
+  PHK_TRY(get_tensor_map(xn, M, K, lda, GM, &ta));
+  PHK_TRY(get_tensor_map(Wq, I, K, ldw, GN, &tb));
+  EpiParams p{Qn, I, M, I, K, nullptr, nullptr, 0, 0, 0, (int)((M + GM - 1) / GM), I / GN, nullptr};
+  p.tma_epi = 0; p.nscale = q_scale; p.norm_cols = I; p.nmul = sim_scale;
+  return launch_gemm<3>(ta, tb, p, to_stream(s));
+}
+
 // debug / tests: force the kernel choice (0 automatic, 1 one-CTA, 2 CTA pairs 256x128, 3 CTA pairs 256x256; < 0 returns
 // to the PHK_GEMM_MODE environment default)
 extern "C" int phk_debug_gemm_mode(int32_t mode) {

@@ -245,3 +245,49 @@ def test_cross_attention_bf16_output_on_warp_mma(b, n, ctx_len, heads, cfg):
     torch.cuda.synchronize()
     err = (out.cpu().float() - ref).abs().max().item()
     assert err <= 0.03, f"max |err| {err}"
+
+
+@pytest.mark.parametrize("b,n,ctx_len,heads,cfg", [(4, 576, 16, 8, True), (2, 130, 29, 4, False), (3, 64, 7, 2, True)])
+def test_cross_attention_on_packed_operands(b, n, ctx_len, heads, cfg):
+    """phk_cross_kv_pack (keys l2-normalised * k_scale, values, dead flags; two layers packed in one launch) +
+    phk_attention_cross_packed on pre-normalised bf16 queries, against the fp32 oracle core: text masks, the CFG null half,
+    ragged query tails."""
+    from oracle import phenaki_oracle as O
+    I, nnull, depth = heads * 64, 2, 2
+    seqs = 2 * b if cfg else b
+    q = TC.seeded_randn((seqs, n, I), 450)
+    qs, ks = TC.seeded_randn((64,), 453).abs() * 0.3 + 0.7, TC.seeded_randn((64,), 454).abs() * 0.3 + 0.7
+    tmask = torch.ones((b, ctx_len), dtype=torch.bool)
+    for i in range(b):
+        tmask[i, max(1, ctx_len - 3 * i):] = False
+    split = lambda t_: t_.reshape(t_.shape[0], t_.shape[1], heads, 64).permute(0, 2, 1, 3)
+    layers = [(TC.seeded_randn((b, ctx_len, 2 * I), 460 + l), TC.seeded_randn((heads, 2 * nnull, 64), 470 + l)) for l in range(depth)]
+    d = lambda t_: t_.contiguous().to(DEV)
+    kv_d = [d(kv) for kv, _ in layers]
+    nk_d = [d(nkv) for _, nkv in layers]
+    ks_d = d(ks)
+    PtrArr = C.c_void_p * depth
+    pack = torch.empty((depth, b, heads, 2 * 32 * 64), dtype=torch.bfloat16, device=DEV)
+    dead = torch.empty((depth, b, 32), dtype=torch.float32, device=DEV)
+    md = d(tmask.to(torch.uint8))
+    L.check(L.lib().phk_cross_kv_pack(PtrArr(*[t.data_ptr() for t in kv_d]), PtrArr(*[t.data_ptr() for t in nk_d]),
+                                      PtrArr(*[ks_d.data_ptr()] * depth), depth, L.ptr(md), b, ctx_len, heads, nnull,
+                                      L.ptr(pack), L.ptr(dead), L.stream_ptr()), "phk_cross_kv_pack")
+    # what phk_gemm_bf16_qnorm's epilogue writes: per-head l2-normalised queries * q_scale * 8, bf16
+    qn = (F.normalize(q.reshape(seqs, n, heads, 64), dim=-1) * qs * 8.0).reshape(seqs * n, I).bfloat16()
+    qd = d(qn)
+    mask = torch.cat((tmask, torch.zeros_like(tmask)), dim=0) if cfg else tmask
+    for l, (ctx_kv, null_kv) in enumerate(layers):
+        kvs = ctx_kv.repeat(2, 1, 1) if cfg else ctx_kv
+        k, v = kvs.chunk(2, dim=-1)
+        nk = null_kv[:, 0::2].unsqueeze(0).expand(seqs, -1, -1, -1)
+        nv = null_kv[:, 1::2].unsqueeze(0).expand(seqs, -1, -1, -1)
+        ref = O.attention_core(split(q), torch.cat((nk, split(k)), dim=-2), torch.cat((nv, split(v)), dim=-2), qs, ks, heads=heads,
+                               num_null_kv=nnull, mask=mask)
+        ref = ref.permute(0, 2, 1, 3).reshape(seqs * n, I)
+        out = torch.full((seqs * n, I), 7.0, dtype=torch.bfloat16, device=DEV)
+        L.check(L.lib().phk_attention_cross_packed(L.ptr(qd), I, L.ptr(pack[l]), L.ptr(dead[l]), L.ptr(out), I, seqs, n, heads, b,
+                                                   nnull, b if cfg else -1, L.stream_ptr()), "phk_attention_cross_packed")
+        torch.cuda.synchronize()
+        err = (out.cpu().float() - ref).abs().max().item()
+        assert err <= 0.04, f"layer {l}: max |err| {err}"
