@@ -30,6 +30,13 @@ ENCODE_GFLOP = 264.8        # whole encode call
 ENCODE_GEMM_GFLOP = 259.28  # its nn.Linear products: patch embed 27.38 + 2 x (projections 38.66 + feed-forward 77.29)
 MASKGIT_FWD_GFLOP = 277.1   # one MaskGit forward at b=4, N=576, L=16 (head 154.6, FF 58.0, self 45.3, cross 15.6, ...)
 MASKGIT_HEAD_GFLOP = 154.6  # to_logits over all b*N rows, one forward
+# algorithmic operand + output bytes of the encode's 33 GEMM launches, MB (M = 4608 tokens, dim 512, bf16 operands):
+#   8 x out-proj  (A 4.7 + W 0.5 + fp32 residual in 9.4 + out 9.4)      = 24.0 each
+#   8 x FF2       (A 13.0 + W 1.4 + residual in 9.4 + out 9.4)         = 33.2
+#   8 x FF1+GEGLU (A 4.7 + W 2.9 + bf16 out 12.6)                      = 20.2
+#   8 x q / k,v   (A 2 x 4.7 + W 1.6 + bf16 out 14.2)                  = 25.2
+#   1 x patch embeddings (A 50.3 + 3.1, W 6.3 + 3.1, fp32 out 9.4)     = 72.2
+ENCODE_GEMM_ALGORITHMIC_MB_PER_LAUNCH = (8 * 24.0 + 8 * 33.2 + 8 * 20.2 + 8 * 25.2 + 72.2) / 33
 
 
 def peaks():
@@ -676,6 +683,8 @@ def main():
             tj = json.load(open(tpath)).get(dom)
             if tj:
                 roof["traffic"], roof["traffic_source"] = tj["dram_bytes_per_launch"], tj["source"]
+                if dom == "gemm_bf16":  # what the same launches move algorithmically: traffic above it = wasted re-reads
+                    roof["algorithmic_bytes_per_launch"] = ENCODE_GEMM_ALGORITHMIC_MB_PER_LAUNCH * 1e6
                 break
     roof["family_share_of_step"] = shares
     roof["family_launches_per_step"] = {k: v[1] // PROF_STEPS for k, v in fam.items()}
