@@ -6,6 +6,7 @@
 #include <float.h>
 #include <utility>
 #include "../../include/phk.h"
+#include <cstdlib>
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
 #error "libphk is written for sm_100a (B200) only"
@@ -71,9 +72,11 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
                                      Args&&... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  // PHK_PDL=0 (A/B measurements): plain stream order -- the kernels' griddepcontrol instructions are then no-ops
+  static const bool pdl = [] { const char* e = std::getenv("PHK_PDL"); return !(e && e[0] == '0'); }();
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
   cfg.attrs = attr; cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
