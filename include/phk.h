@@ -284,6 +284,10 @@ int phk_attention_tc_bf16(const void* Qn, int64_t ld_q, const void* KVn, int64_t
  * head); geometry strides in elements as for phk_attention. */
 int phk_attention_small_bf16(const void* Qn, const void* KVn, const float* alibi_slopes, void* out,
                              const phk_attn_geom_t* g, phk_stream_t s);
+/* The same core for 16 < n <= 64 tokens per sequence (the spatial transformer's frames) on warp-level MMAs: one CTA per
+ * (sequence, head), all resident at once; arguments as phk_attention_tc_bf16. */
+int phk_attention_mid_bf16(const void* Qn, int64_t ld_q, const void* KVn, int64_t ld_kv, const float* bias, void* out_bf16,
+                           int32_t n_seq, int32_t n, int32_t heads, phk_stream_t s);
 int64_t phk_attention_tc_scratch_bytes(int32_t n_seq, int32_t n, int32_t heads);
 int phk_attention_tc(const float* q, const float* kv, const float* q_scale, const float* k_scale,
                      const float* bias, void* out_bf16, int32_t n_seq, int32_t n, int32_t heads, float scale,

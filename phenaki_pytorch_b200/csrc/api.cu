@@ -250,14 +250,25 @@ static int transformer_forward(const TfCall& c, Arena scratch, float* out, void*
       const bool tc_ok = plain && !T->causal && c.seq.n_inner == 1 && c.seq.tok == 1 && c.seq.outer == c.seq.n_tok &&
                          c.seq.n_tok >= 64;
       const bool small_ok = plain && !c.attn_bias && c.seq.n_tok <= 16;
+      // 16 < n <= 64 (the spatial transformer's 8 x 8 frames): warp-level MMAs, all (sequence, head) CTAs resident at once
+      bool mid_ok = false;
+#ifndef PHK_CUDA_EMU
+      static const bool mid_env = [] { const char* e = std::getenv("PHK_MID_ATTN_MMA"); return !(e && e[0] == '0'); }();
+      mid_ok = mid_env && plain && !T->causal && c.seq.n_inner == 1 && c.seq.tok == 1 && c.seq.outer == c.seq.n_tok &&
+               c.seq.n_tok > 16 && c.seq.n_tok <= 64;
+#endif
       static const bool fuse_qkv = [] { const char* e = std::getenv("PHK_FUSE_QKV"); return !(e && e[0] == '0'); }();
-      if ((tc_ok || small_ok) && fuse_qkv && I % 128 == 0 && A.wq_h && A.wkv_h) {
+      if ((tc_ok || small_ok || mid_ok) && fuse_qkv && I % 128 == 0 && A.wq_h && A.wkv_h) {
         // q / k,v projections in ONE launch whose epilogue writes the attention core's bf16 operands directly
         // (l2-normalised q, k times their learned scales, the similarity scale 8 folded into q, v converted): no fp32
         // q / kv round trip and no separate normalisation pass (attention.py:146-157)
         void* qn = q;    // [Rl, I] bf16 in the fp32-sized q buffer
         void* kvn = kv;  // [Rl, 2I] bf16
         PHK_TRY(phk_gemm_bf16_qkv(xn, xraw, D, A.wq_h, A.wkv_h, D, qn, kvn, Rl, I, D, A.q_scale, A.k_scale, 8.f, s));
+#ifndef PHK_CUDA_EMU
+        if (mid_ok) PHK_TRY(phk_attention_mid_bf16(qn, I, kvn, 2 * I, c.attn_bias, o, n_outer, c.seq.n_tok, H, s));
+        else
+#endif
         if (tc_ok) PHK_TRY(phk_attention_tc_bf16(qn, I, kvn, 2 * I, c.attn_bias, o, n_outer, c.seq.n_tok, H, s));
         else PHK_TRY(phk_attention_small_bf16(qn, kvn, T->alibi_slopes, o, &g, s));
       } else {

@@ -857,6 +857,135 @@ __global__ void __launch_bounds__(MMA_WARPS * 32) attention_small_mma_kernel(con
 
 
 // ------------------------------------------------------------------------------------------
+// Self-attention of short sequences (16 < n <= 64: the spatial transformer's 8 x 8 token frames) on the pre-normalised
+// token-major bf16 operands, warp-level MMAs: one CTA of four warps per (sequence, head), every warp owns 16 query rows.
+// The tcgen05 kernel (attention_tc_kernel) spends its life in prologue / barrier round trips at this size -- one 64-key
+// chunk, half of its 128-row tile empty, 576 CTAs on 296 resident slots = two rounds (8.9 us at 72 x 64 x 8 heads);
+// here 576 CTAs of 128 threads and 27 KB are resident at once and a CTA is a 24 KB copy + 64 MMAs per warp.
+// Position bias fp32 [heads, n, n] or NULL; no masks, not causal (those take phk_attention).  [not on the CPU executor]
+// ------------------------------------------------------------------------------------------
+#ifndef PHK_CUDA_EMU
+constexpr int MID_N = 64;
+
+__global__ void __launch_bounds__(128) attention_mid_mma_kernel(const __nv_bfloat16* __restrict__ Qn, int64_t ld_q,
+                                                                const __nv_bfloat16* __restrict__ KVn, int64_t ld_kv,
+                                                                const float* __restrict__ bias,
+                                                                __nv_bfloat16* __restrict__ out, int64_t ld_o, int n,
+                                                                int heads) {
+  pdl_prologue();
+  __shared__ __align__(16) __nv_bfloat16 sm[3][MID_N][MMA_LD];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int h = blockIdx.x, seq = blockIdx.y;
+  const int I = heads * 64;
+  const __nv_bfloat16* qb = Qn + (int64_t)seq * n * ld_q + (int64_t)h * 64;
+  const __nv_bfloat16* kb = KVn + (int64_t)seq * n * ld_kv + (int64_t)h * 64;
+  // stage: 3 operands x 64 rows x 8 chunks of 16 B = 1536 chunks, 12 per thread; rows >= n are zero
+#pragma unroll
+  for (int it = 0; it < 12; ++it) {
+    const int idx = it * 128 + threadIdx.x;
+    const int op = idx >> 9, row = (idx >> 3) & 63, ch = idx & 7;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (row < n) {
+      const __nv_bfloat16* src = op == 0 ? qb + (int64_t)row * ld_q : kb + (int64_t)row * ld_kv + (op == 2 ? I : 0);
+      v = *reinterpret_cast<const uint4*>(src + ch * 8);
+    }
+    *reinterpret_cast<uint4*>(&sm[op][row][ch * 8]) = v;
+  }
+  __syncthreads();
+  const int r0 = w * 16;
+  if (r0 >= n) return;
+  __nv_bfloat16 (*sQ)[MMA_LD] = sm[0];
+  __nv_bfloat16 (*sK)[MMA_LD] = sm[1];
+  __nv_bfloat16 (*sV)[MMA_LD] = sm[2];
+  const int gq = lane >> 2, t = lane & 3;
+  uint32_t a[4][4];
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) ldmatrix_x4(a[ks], &sQ[r0 + (lane & 7) + 8 * ((lane >> 3) & 1)][ks * 16 + 8 * (lane >> 4)]);
+  // S[16 x 64] = Q K^T: eight key tiles of 8, four k-steps of 16 dims
+  float sc[8][4];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) sc[nt][e] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+      uint32_t b[4];
+      ldmatrix_x4(b, &sK[(lane & 7) + 8 * (lane >> 4) + 16 * np][ks * 16 + 8 * ((lane >> 3) & 1)]);
+      mma_bf16_16816(sc[2 * np], a[ks], b[0], b[1]);
+      mma_bf16_16816(sc[2 * np + 1], a[ks], b[2], b[3]);
+    }
+  // + position bias, padding keys masked; element e of tile nt: row r0 + gq + 8 (e >> 1), key nt * 8 + 2 t + (e & 1)
+  const bool bias_vec = bias && (n % 2 == 0) && ((reinterpret_cast<uintptr_t>(bias) & 7) == 0);
+  float inv[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int row = r0 + gq + 8 * r;
+    const float* brow = (bias && row < n) ? bias + ((int64_t)h * n + row) * n : nullptr;
+    float m = -FLT_MAX;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int key = nt * 8 + 2 * t;
+      float b0 = 0.f, b1 = 0.f;
+      if (brow) {
+        if (bias_vec && key + 1 < n) { const float2 bb = __ldg(reinterpret_cast<const float2*>(brow + key)); b0 = bb.x; b1 = bb.y; }
+        else { if (key < n) b0 = __ldg(brow + key); if (key + 1 < n) b1 = __ldg(brow + key + 1); }
+      }
+      const float v0 = key < n ? sc[nt][2 * r] + b0 : -FLT_MAX, v1 = key + 1 < n ? sc[nt][2 * r + 1] + b1 : -FLT_MAX;
+      sc[nt][2 * r] = v0; sc[nt][2 * r + 1] = v1;
+      m = fmaxf(m, fmaxf(v0, v1));
+    }
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+    float sum = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const float v = sc[nt][2 * r + e];
+        const float ex = v == -FLT_MAX ? 0.f : __expf(v - m);
+        sc[nt][2 * r + e] = ex;
+        sum += ex;
+      }
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    inv[r] = sum > 0.f ? __fdividef(1.f, sum) : 0.f;
+  }
+  uint32_t pa[4][4];  // P as the A operand of P V: four k-steps of 16 keys (the accumulator layout of S IS the A layout)
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    pa[kk][0] = pack_bf16x2(sc[2 * kk][0], sc[2 * kk][1]);
+    pa[kk][1] = pack_bf16x2(sc[2 * kk][2], sc[2 * kk][3]);
+    pa[kk][2] = pack_bf16x2(sc[2 * kk + 1][0], sc[2 * kk + 1][1]);
+    pa[kk][3] = pack_bf16x2(sc[2 * kk + 1][2], sc[2 * kk + 1][3]);
+  }
+  __nv_bfloat16* obase = out + (int64_t)seq * n * ld_o + (int64_t)h * 64;
+#pragma unroll
+  for (int dp = 0; dp < 4; ++dp) {
+    float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      uint32_t b[4];
+      ldmatrix_x4_trans(b, &sV[(lane & 7) + 8 * ((lane >> 3) & 1) + 16 * kk][(2 * dp + (lane >> 4)) * 8]);
+      mma_bf16_16816(o0, pa[kk], b[0], b[1]);
+      mma_bf16_16816(o1, pa[kk], b[2], b[3]);
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int row = r0 + gq + 8 * r;
+      if (row < n) {
+        __nv_bfloat16* orow = obase + (int64_t)row * ld_o;
+        *reinterpret_cast<uint32_t*>(orow + (2 * dp) * 8 + 2 * t) = pack_bf16x2(o0[2 * r] * inv[r], o0[2 * r + 1] * inv[r]);
+        *reinterpret_cast<uint32_t*>(orow + (2 * dp + 1) * 8 + 2 * t) = pack_bf16x2(o1[2 * r] * inv[r], o1[2 * r + 1] * inv[r]);
+      }
+    }
+  }
+}
+#endif  // PHK_CUDA_EMU
+
+
+// ------------------------------------------------------------------------------------------
 // Cross-attention over a short text context (null-kv + L <= 32 keys, dim_head 64, bf16 output: the bf16 mode of
 // MaskGit / TokenCritic, attention.py:137-181) on warp-level tensor-core MMAs.  CTA = 128 queries of one (sequence,
 // head): the keys are l2-normalised, scaled and converted once per CTA into shared memory (like attention_fewkeys_kernel),
@@ -1410,6 +1539,29 @@ extern "C" int phk_attention_cross_packed(const void* Qn, int64_t ld_q, const vo
   PHK_CUDA(launch_pdl(attention_cross_packed_kernel, grid, dim3(256), (size_t)0, to_stream(s), (const __nv_bfloat16*)Qn, ld_q,
                       (const __nv_bfloat16*)pack, dead, (__nv_bfloat16*)out, ld_o, (int)n_q, (int)heads, (int)ctx_b, (int)nnull,
                       (int)null_from));
+  PHK_LAUNCH_CHECK();
+  return 0;
+}
+#endif
+
+#ifndef PHK_CUDA_EMU
+// Self-attention core for 16 < n <= 64 tokens per sequence on the bf16 operands phk_gemm_bf16_qkv writes (same arguments as
+// phk_attention_tc_bf16): Qn [n_seq*n, ld_q], KVn [n_seq*n, ld_kv] (keys | values), bias fp32 [heads, n, n] or NULL ->
+// out bf16 [n_seq*n, heads*64].
+extern "C" int phk_attention_mid_bf16(const void* Qn, int64_t ld_q, const void* KVn, int64_t ld_kv, const float* bias,
+                                      void* out_bf16, int32_t n_seq, int32_t n, int32_t heads, phk_stream_t s) {
+  Prof prof_(FAM_ATTENTION, s, 4.0 * (double)n_seq * heads * n * n * 64);
+  PHK_REQUIRE(Qn && KVn && out_bf16, PHK_E_ARG, "phk_attention_mid_bf16: null pointer");
+  PHK_REQUIRE(n_seq > 0 && n_seq <= 65535 && n > 0 && n <= MID_N && heads > 0, PHK_E_ARG,
+              "phk_attention_mid_bf16: at most 64 tokens per sequence, 65535 sequences");
+  const int64_t I = (int64_t)heads * 64;
+  PHK_REQUIRE(ld_q >= I && ld_kv >= 2 * I && ld_q % 8 == 0 && ld_kv % 8 == 0 &&
+                  ((reinterpret_cast<uintptr_t>(Qn) | reinterpret_cast<uintptr_t>(KVn)) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(out_bf16) & 3) == 0,
+              PHK_E_ARG, "phk_attention_mid_bf16: operands must be 16-byte aligned with leading dimensions multiple of 8");
+  PHK_CUDA(launch_pdl(attention_mid_mma_kernel, dim3((unsigned)heads, (unsigned)n_seq), dim3(128), (size_t)0, to_stream(s),
+                      (const __nv_bfloat16*)Qn, ld_q, (const __nv_bfloat16*)KVn, ld_kv, bias, (__nv_bfloat16*)out_bf16, I, (int)n,
+                      (int)heads));
   PHK_LAUNCH_CHECK();
   return 0;
 }

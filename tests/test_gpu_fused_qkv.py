@@ -76,7 +76,15 @@ def test_attention_tc_on_prenormalised_token_major_operands(n_seq, n, heads, wit
         L.lib().phk_debug_attention_tc_variant(-1)
 
 
-def _attention_tc_case(n_seq, n, heads, with_bias):
+@pytest.mark.parametrize("n_seq,n,heads,with_bias", [(72, 64, 8, True), (5, 49, 3, True), (3, 17, 2, False), (2, 64, 4, False),
+                                                     (4, 36, 8, True)])
+def test_attention_mid_mma_on_prenormalised_token_major_operands(n_seq, n, heads, with_bias):
+    """phk_attention_mid_bf16 (16 < n <= 64, one CTA of four warps per (sequence, head), mma.sync): the spatial transformer's
+    72 x 64 shape, odd lengths (scalar bias loads, warps without rows), no bias."""
+    _attention_tc_case(n_seq, n, heads, with_bias, entry="phk_attention_mid_bf16")
+
+
+def _attention_tc_case(n_seq, n, heads, with_bias, entry="phk_attention_tc_bf16"):
     I = heads * 64
     rows = n_seq * n
     qn = (F.normalize(TC.seeded_randn((rows, heads, 64), 410), dim=-1) * 8.0).reshape(rows, I).bfloat16()
@@ -87,8 +95,7 @@ def _attention_tc_case(n_seq, n, heads, with_bias):
     qd, kvd = qn.to(DEV), kvn.to(DEV)
     bd = bias.to(DEV) if with_bias else None
     out = torch.empty((rows, I), dtype=torch.bfloat16, device=DEV)
-    L.check(L.lib().phk_attention_tc_bf16(L.ptr(qd), I, L.ptr(kvd), 2 * I, L.ptr(bd), L.ptr(out), n_seq, n, heads,
-                                          L.stream_ptr()), "phk_attention_tc_bf16")
+    L.check(getattr(L.lib(), entry)(L.ptr(qd), I, L.ptr(kvd), 2 * I, L.ptr(bd), L.ptr(out), n_seq, n, heads, L.stream_ptr()), entry)
     torch.cuda.synchronize()
     err = (out.cpu().float() - ref).abs().max().item()
     assert err <= 0.02, f"max |err| {err}"

@@ -121,6 +121,9 @@ for (ns, n) in [(72, 64), (8, 576)]:
         timeit(f"attention tc core ({ns} seq x {n}) {label}", lambda: L.check(lib.phk_attention_tc_bf16(L.ptr(qn_h), I, L.ptr(kvn_h), 2 * I, L.ptr(bias), L.ptr(o_h), ns, n, 8, sp())),
                4.0 * ns * 8 * n * n * 64, "TFLOP/s")
 L.check(lib.phk_debug_attention_tc_variant(-1))
+bias64 = torch.randn(8, 64, 64, device=dev)
+timeit("attention mid mma (72 seq x 64), one CTA per (sequence, head)", lambda: L.check(lib.phk_attention_mid_bf16(L.ptr(qn_h), I, L.ptr(kvn_h), 2 * I, L.ptr(bias64), L.ptr(o_h), 72, 64, 8, sp())),
+       4.0 * 72 * 8 * 64 * 64 * 64, "TFLOP/s")
 
 # spatial attention (72 seq x 64) and MaskGit self-attention (8 seq x 576) on tensor cores
 for (ns, n) in [(72, 64), (8, 576)]:
