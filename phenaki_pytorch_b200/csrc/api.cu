@@ -253,9 +253,12 @@ static int transformer_forward(const TfCall& c, Arena scratch, float* out, void*
       // 16 < n <= 64 (the spatial transformer's 8 x 8 frames): warp-level MMAs, all (sequence, head) CTAs resident at once
       bool mid_ok = false;
 #ifndef PHK_CUDA_EMU
-      static const bool mid_env = [] { const char* e = std::getenv("PHK_MID_ATTN_MMA"); return !(e && e[0] == '0'); }();
-      mid_ok = mid_env && plain && !T->causal && c.seq.n_inner == 1 && c.seq.tok == 1 && c.seq.outer == c.seq.n_tok &&
-               c.seq.n_tok > 16 && c.seq.n_tok <= 64;
+      // (at exactly 64 tokens the tcgen05 kernel is faster -- 8.9 vs 11.6 us at 72 sequences x 8 heads,
+      //  profiles/r02/op_bench_c17.txt -- so the MMA kernel takes 17..63 tokens, which used to fall back to the fp32 kernel;
+      //  PHK_MID_ATTN_MMA=1 forces it for 64 as well, =0 disables it)
+      static const int mid_env = [] { const char* e = std::getenv("PHK_MID_ATTN_MMA"); return e ? (e[0] == '0' ? 0 : 2) : 1; }();
+      mid_ok = mid_env != 0 && plain && !T->causal && c.seq.n_inner == 1 && c.seq.tok == 1 && c.seq.outer == c.seq.n_tok &&
+               c.seq.n_tok > 16 && c.seq.n_tok <= (mid_env == 2 ? 64 : 63);
 #endif
       static const bool fuse_qkv = [] { const char* e = std::getenv("PHK_FUSE_QKV"); return !(e && e[0] == '0'); }();
       if ((tc_ok || small_ok || mid_ok) && fuse_qkv && I % 128 == 0 && A.wq_h && A.wkv_h) {
