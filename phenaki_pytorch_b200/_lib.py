@@ -19,10 +19,10 @@ def default_precision():
     bf16   bf16 products on tcgen05 -- the reference's autocast(bfloat16) dtype flow, 3x faster again (benchmarked mode)
     `model.precision = _lib.PREC_*` switches a module at any time."""
     name = os.environ.get("PHK_PREC", DEFAULT_PRECISION_NAME).lower()
-    return {"f32": PREC_F32, "fp32": PREC_F32, "bf16": PREC_BF16, "bf16x3": PREC_BF16X3}.get(name, PREC_F32)
+    return {"f32": PREC_F32, "fp32": PREC_F32, "bf16": PREC_BF16, "bf16x3": PREC_BF16X3}.get(name, PREC_BF16X3)
 
 
-DEFAULT_PRECISION_NAME = "f32"
+DEFAULT_PRECISION_NAME = "bf16x3"  # exact token ids on the tensor cores (round 2; the whole CPU and GPU suites pass under it)
 
 c_f = C.c_void_p  # device pointers travel as void*
 
