@@ -72,9 +72,6 @@ typedef struct {
   const float* wq; const float* wkv; const float* wo; /* [I,dim] [2I,dim_context] [dim,I]      */
   const void* wq_h; const void* wkv_h; const void* wo_h;
   int32_t num_null_kv; int32_t dim_context;
-  /* bf16 mode, LayerNorm fold (phk_gemm_bf16_qnorm_fold): wq_f = bf16(norm.gamma[k] * wq[n,k]) [I, dim],
-   * fold_c[n] = sum_k wq_f[n,k], fold_d[n] = sum_k norm.beta[k] * wq[n,k] (or NULL); all NULL = no fold */
-  const void* wq_f; const float* fold_c; const float* fold_d;
 } phk_attn_t;
 
 /* attention.py:45-53 FeedForward: LN(affine) -> Linear(dim,2*inner) -> GEGLU -> Linear(inner,dim) */
@@ -83,9 +80,6 @@ typedef struct {
   const float* w1; const float* w2;               /* [2*inner, dim], [dim, inner]               */
   const void* w1_h; const void* w2_h;             /* bf16: w1 rows interleaved val/gate per 64, */
   int32_t inner; int32_t inner_pad;               /* w2 K padded to inner_pad (multiple of 64)  */
-  /* bf16 mode, LayerNorm fold (phk_gemm_bf16_geglu_fold): w1_f = bf16(ln_g[k] * w1[n,k]) in the packed row order of w1_h,
-   * fold_c / fold_d [2 * inner_pad] in the same order (see phk_attn_t) */
-  const void* w1_f; const float* fold_c; const float* fold_d;
 } phk_ff_t;
 
 /* attention.py:57-85 PEG: depthwise Conv3d(dim,dim,3,groups=dim); w tap-major [27, dim]
@@ -387,22 +381,6 @@ int phk_gemm_bf16_qnorm(const void* xn, int64_t lda, const void* Wq, int64_t ldw
 int phk_attention_cross_packed(const void* Qn, int64_t ld_q, const void* pack, const float* dead, void* out, int64_t ld_o,
                                int32_t n_seq, int32_t n_q, int32_t heads, int32_t ctx_b, int32_t nnull, int32_t null_from,
                                phk_stream_t s);
-
-/* LayerNorm without a kernel (bf16 mode; attention.py:311-332: every residual product is followed by a LayerNorm whose output
- * feeds exactly one product).  phk_gemm_bf16_res_stats: x += A W^T in place + raw_out = bf16(x) + per-row PARTIAL statistics
- * stats[row * (N / 128) + j] = (sum, sum of squares) of columns [128 j, 128 j + 128).  The consuming products take the raw bf16
- * rows and weights pre-multiplied by the LayerNorm gain, and apply the normalisation in their epilogue:
- *   LayerNorm(x) W^T = rstd * (x Wf^T - mean * c) + d,  Wf[n,k] = bf16(g[k] W[n,k]),  c[n] = sum_k Wf[n,k],  d[n] = sum_k b[k] W[n,k]
- * phk_gemm_bf16_geglu_fold = FeedForward's first linear + GEGLU (as phk_gemm_bf16 epilogue 2), phk_gemm_bf16_qnorm_fold = the
- * cross-attention q projection (as phk_gemm_bf16_qnorm).  stats: `slots` float2 per row over K elements; d may be NULL. */
-int phk_gemm_bf16_res_stats(const void* A, int64_t lda, const void* W, int64_t ldw, float* C, int64_t ldc, int64_t M, int32_t N,
-                            int32_t K, const float* bias, void* raw_out, int64_t ld_raw, float* stats, phk_stream_t s);
-int phk_gemm_bf16_geglu_fold(const void* xraw, int64_t lda, const void* W1f, int64_t ldw, void* G, int64_t ldg, int64_t M,
-                             int32_t N2, int32_t K, const float* stats, int32_t slots, const float* c, const float* d, float eps,
-                             phk_stream_t s);
-int phk_gemm_bf16_qnorm_fold(const void* xraw, int64_t lda, const void* Wqf, int64_t ldw, void* Qn, int64_t M, int32_t I,
-                             int32_t K, const float* q_scale, float sim_scale, const float* stats, int32_t slots, const float* c,
-                             const float* d, float eps, phk_stream_t s);
 
 /* critic score (phenaki_pytorch.py:246-249, 263, 544-545):
  *   sc = x @ w + b per row; out = null + (cond - null)*scale + noise_K*(u-0.5)*noise_mult  */

@@ -31,14 +31,12 @@ class AttnT(C.Structure):
     _fields_ = [("norm_g", c_f), ("norm_b", c_f), ("ctx_g", c_f), ("ctx_b", c_f), ("null_kv", c_f),
                 ("q_scale", c_f), ("k_scale", c_f), ("wq", c_f), ("wkv", c_f), ("wo", c_f),
                 ("wq_h", c_f), ("wkv_h", c_f), ("wo_h", c_f),
-                ("num_null_kv", C.c_int32), ("dim_context", C.c_int32),
-                ("wq_f", c_f), ("fold_c", c_f), ("fold_d", c_f)]
+                ("num_null_kv", C.c_int32), ("dim_context", C.c_int32)]
 
 
 class FFT(C.Structure):
     _fields_ = [("ln_g", c_f), ("ln_b", c_f), ("w1", c_f), ("w2", c_f), ("w1_h", c_f), ("w2_h", c_f),
-                ("inner", C.c_int32), ("inner_pad", C.c_int32),
-                ("w1_f", c_f), ("fold_c", c_f), ("fold_d", c_f)]
+                ("inner", C.c_int32), ("inner_pad", C.c_int32)]
 
 
 class PegT(C.Structure):
@@ -133,9 +131,6 @@ PROTOTYPES = {
     "phk_split3": [vp, i64, vp, i64, i32, i32, vp],
     "phk_cross_kv_pack": [vp, vp, vp, i32, vp, i32, i32, i32, i32, vp, vp, vp],
     "phk_gemm_bf16_qnorm": [vp, i64, vp, i64, vp, i64, i32, i32, vp, f32, vp],
-    "phk_gemm_bf16_qnorm_fold": [vp, i64, vp, i64, vp, i64, i32, i32, vp, f32, vp, i32, vp, vp, f32, vp],
-    "phk_gemm_bf16_geglu_fold": [vp, i64, vp, i64, vp, i64, i64, i32, i32, vp, i32, vp, vp, f32, vp],
-    "phk_gemm_bf16_res_stats": [vp, i64, vp, i64, vp, i64, i64, i32, i32, vp, vp, i64, vp, vp],
     "phk_attention_cross_packed": [vp, i64, vp, vp, vp, i64, i32, i32, i32, i32, i32, i32, vp],
     "phk_gemm_bf16_qkv": [vp, vp, i64, vp, vp, i64, vp, vp, i64, i32, i32, vp, vp, f32, vp],
     "phk_peg3d": [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],

@@ -85,7 +85,6 @@ struct TfCall {
 };
 
 constexpr int kFuseLnDefault = 0;     // PHK_FUSE_LN default: 0 separate LayerNorm kernels, 1 cluster epilogue, 2 global exchange
-constexpr int kLnFoldDefault = 0;     // PHK_LN_FOLD default (LayerNorm folded into the consuming products)
 constexpr int kLnFusedLaunches = 64;  // LayerNorm-in-epilogue GEMMs per transformer call that get their own arrival counters
 
 static int64_t tf_scratch_bytes(const phk_transformer_t* T, int64_t R) {
@@ -95,9 +94,8 @@ static int64_t tf_scratch_bytes(const phk_transformer_t* T, int64_t R) {
   // xn, q, kv, o, h(2*inner), g(inner)  -- all fp32 in parity mode
   // + head-major bf16 q/k/v^T operands of the tensor-core attention (bf16 mode): 3 * R * I * 2 bytes + padding
   // + the statistics exchange and arrival counters of the LayerNorm-in-epilogue GEMMs (phk_gemm_bf16_ln_ws)
-  // + the partial row statistics of the LayerNorm fold: dim / 128 float2 per row
-  return 256 * 15 + R * 4 * (T->dim + I + 2 * I + I + 2 * inner + inner) + R * I * 6 + 64 * 64 * 2 * (R / 64 + 64) +
-         PHK_LN_STAT_BYTES + kLnFusedLaunches * PHK_LN_COUNTERS * 4 + R * ((T->dim + 127) / 128) * 8;
+  return 256 * 14 + R * 4 * (T->dim + I + 2 * I + I + 2 * inner + inner) + R * I * 6 + 64 * 64 * 2 * (R / 64 + 64) +
+         PHK_LN_STAT_BYTES + kLnFusedLaunches * PHK_LN_COUNTERS * 4;
 }
 
 static int64_t tf_kmax(const phk_transformer_t* T) {  // largest K of a transformer's nn.Linear products
@@ -222,28 +220,6 @@ static int transformer_forward(const TfCall& c, Arena scratch, float* out, void*
     }
   }
 #endif
-  // bf16 mode, LayerNorm fold (PHK_LN_FOLD): the LayerNorm in front of the feed-forward and of the cross-attention is not a
-  // kernel -- the residual product before it (self / cross out-projection) also writes the bf16 copy of the new rows and
-  // their partial row statistics (phk_gemm_bf16_res_stats), the product after it takes those raw rows with gain-scaled
-  // weights and normalises in its epilogue (phk_gemm_bf16_geglu_fold, phk_gemm_bf16_qnorm_fold).
-  float* fold_stats = nullptr;
-  const int fold_slots = D / 128;
-#ifndef PHK_CUDA_EMU
-  {
-    static const int fold_env = [] { const char* e = std::getenv("PHK_LN_FOLD"); return e ? (e[0] != '0') : kLnFoldDefault; }();
-    bool ok = fold_env && h16 && !fuse_ln && D % 128 == 0 && D <= 8192;
-    for (int l = 0; ok && l < T->depth; ++l) {
-      const phk_layer_t& Ly = T->layers[l];
-      ok = Ly.ff.w1_f && Ly.ff.fold_c && Ly.self_attn.wo_h &&
-           (!(Ly.has_cross && c.ctx_kv) || (cross_pack && Ly.cross_attn.wq_f && Ly.cross_attn.fold_c && Ly.cross_attn.wo_h));
-    }
-    if (ok) {
-      Arena tmp = scratch;
-      float* st_buf = (float*)tmp.take(R * fold_slots * 8);
-      if (st_buf) { scratch = tmp; fold_stats = st_buf; }
-    }
-  }
-#endif
   bool ln_ready = false;  // xn (+ xraw) already hold this layer's self-attention LayerNorm (written by the previous FF2)
   for (int l = 0; l < T->depth; ++l) {
     const phk_layer_t& L = T->layers[l];
@@ -321,23 +297,13 @@ static int transformer_forward(const TfCall& c, Arena scratch, float* out, void*
         const float* nb = to_cross ? L.cross_attn.norm_b : L.ff.ln_b;
         PHK_TRY(gemm_ln(o, I, A.wo_h, I, x, Rl, I, ng, nb, xn, nullptr));
         norm_done = true;
-#ifndef PHK_CUDA_EMU
-      } else if (fold_stats) {  // x += o Wo^T, bf16 copy of the new rows (xraw is free again) and their partial statistics
-        PHK_TRY(phk_gemm_bf16_res_stats(o, I, A.wo_h, I, x, D, Rl, D, I, nullptr, xraw, D, fold_stats, s));
-        norm_done = true;
-#endif
       } else {
         PHK_TRY(linear(c.lin, o, I, A.wo, A.wo_h, I, x, D, Rl, D, I, nullptr, x, s));
       }
     }
     if (dup) {  // the null half continues from the same rows
       PHK_CUDA(cudaMemcpyAsync(x + Rl * D, x, Rl * D * 4, cudaMemcpyDeviceToDevice, st));
-      if (norm_done && fold_stats) {
-        PHK_CUDA(cudaMemcpyAsync((char*)xraw + Rl * D * 2, xraw, Rl * D * 2, cudaMemcpyDeviceToDevice, st));
-        PHK_CUDA(cudaMemcpyAsync(fold_stats + Rl * fold_slots * 2, fold_stats, Rl * fold_slots * 8, cudaMemcpyDeviceToDevice, st));
-      } else if (norm_done) {
-        PHK_CUDA(cudaMemcpyAsync((char*)xn + Rl * D * 2, xn, Rl * D * 2, cudaMemcpyDeviceToDevice, st));
-      }
+      if (norm_done) PHK_CUDA(cudaMemcpyAsync((char*)xn + Rl * D * 2, xn, Rl * D * 2, cudaMemcpyDeviceToDevice, st));
     }
     if (L.has_cross && c.ctx_kv) {  // x = cross_attn(x, context) + x   (attention.py:327-328)
       const phk_attn_t& A = L.cross_attn;
@@ -346,10 +312,6 @@ static int transformer_forward(const TfCall& c, Arena scratch, float* out, void*
       norm_done = false;
 #ifndef PHK_CUDA_EMU
       if (cross_pack) {
-        if (fold_stats)  // (norm_done was set by the out-projection above: the LayerNorm kernel did not run)
-          PHK_TRY(phk_gemm_bf16_qnorm_fold(xraw, D, A.wq_f, D, q, R, I, D, A.q_scale, 8.f, fold_stats, fold_slots, A.fold_c,
-                                           A.fold_d, 1e-5f, s));
-        else
         PHK_TRY(phk_gemm_bf16_qnorm(xn, D, A.wq_h, D, q, R, I, D, A.q_scale, 8.f, s));  // bf16 [R, I] in the fp32-sized q buffer
         PHK_TRY(phk_attention_cross_packed(q, I, (char*)cross_pack + (int64_t)l * c.ctx_b * H * 8192,
                                            cross_dead + (int64_t)l * c.ctx_b * 32, o, I, c.seq.n_outer, c.seq.n_tok, H, c.ctx_b,
@@ -373,11 +335,6 @@ static int transformer_forward(const TfCall& c, Arena scratch, float* out, void*
       if (fuse_ln && A.wo_h) {
         PHK_TRY(gemm_ln(o, I, A.wo_h, I, x, R, I, L.ff.ln_g, L.ff.ln_b, xn, nullptr));
         norm_done = true;
-#ifndef PHK_CUDA_EMU
-      } else if (fold_stats) {
-        PHK_TRY(phk_gemm_bf16_res_stats(o, I, A.wo_h, I, x, D, R, D, I, nullptr, xraw, D, fold_stats, s));
-        norm_done = true;
-#endif
       } else {
         PHK_TRY(linear(c.lin, o, I, A.wo, A.wo_h, I, x, D, R, D, I, nullptr, x, s));
       }
@@ -390,12 +347,6 @@ static int transformer_forward(const TfCall& c, Arena scratch, float* out, void*
         PHK_REQUIRE(Fw.w1_h && Fw.w2_h && Fw.inner_pad % 64 == 0 && Fw.inner_pad >= Fw.inner, PHK_E_ARG,
                     "bf16 mode needs the packed feed-forward weights");
         // first linear + GEGLU in one kernel (value/gate rows interleaved per 64), bf16 [R, inner_pad] out
-#ifndef PHK_CUDA_EMU
-        if (fold_stats)  // raw rows + gain-scaled weights, LayerNorm applied in the epilogue
-          PHK_TRY(phk_gemm_bf16_geglu_fold(xraw, D, Fw.w1_f, D, gbuf, Fw.inner_pad, R, 2 * Fw.inner_pad, D, fold_stats, fold_slots,
-                                           Fw.fold_c, Fw.fold_d, 1e-5f, s));
-        else
-#endif
         PHK_TRY(phk_gemm_bf16(xn, D, Fw.w1_h, D, gbuf, Fw.inner_pad, R, 2 * Fw.inner_pad, D, nullptr, nullptr, 0, 0, 0, 2, s));
         const bool next_plain = l + 1 < T->depth && !T->layers[l + 1].has_peg;
         if (fuse_ln && next_plain) {  // ... + the next layer's attention LayerNorm and its raw bf16 rows

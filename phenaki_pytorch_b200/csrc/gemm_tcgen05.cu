@@ -72,32 +72,12 @@ struct EpiParams {
   // [2][gridDim][128] float2 slots (double-buffered by tile parity) and one arrival counter per group (ln_counter[group],
   // zero when the kernel starts; release / acquire at gpu scope).
   float2* xstat_g; unsigned int* ln_counter;
-  // epilogue 6: x += A W^T (fp32, bulk-stored) + the bf16 copy of the new rows (raw_out) + the PARTIAL row statistics of this
-  // CTA's 128 columns, stats_out[row * n_tiles + n_tile] = (sum, sum of squares): no exchange, no LayerNorm here -- the GEMM
-  // that consumes the rows applies it ("LayerNorm fold", below).
-  float2* stats_out;
-  // LayerNorm fold of the CONSUMING product (epilogues 2 and 3): the A operand is the raw bf16 row x, the weights are
-  // W'[n,k] = g[k] W[n,k], and with mean / rstd of the row (from fold_stats: fold_slots partials per row over fold_dim
-  // elements) the epilogue turns acc = sum_k x_k W'[n,k] into LayerNorm(x) W^T = rstd * (acc - mean * c[n]) + d[n],
-  // c[n] = sum_k W'[n,k], d[n] = sum_k b[k] W[n,k]; applied to columns < fold_cols (the rest, e.g. the k,v projection of
-  // the un-normalised rows, is left as it is).
-  const float2* fold_stats; int fold_slots; int fold_dim; int fold_cols; float fold_eps;
-  const float* fold_c; const float* fold_d;
   // the W operand is not written by the kernels that precede this one in the stream (inference weights): its first tiles
   // are requested BEFORE griddepcontrol.wait, while the previous kernel drains
   int w_static;
   alignas(64) CUtensorMap tmC;
 };
 
-
-__device__ __forceinline__ float2 fold_mean_rstd(const EpiParams& p, uint32_t m) {
-  float s1 = 0.f, s2 = 0.f;
-  const float2* st = p.fold_stats + (int64_t)m * p.fold_slots;
-  for (int i = 0; i < p.fold_slots; ++i) { const float2 e = __ldcg(st + i); s1 += e.x; s2 += e.y; }
-  const float inv_n = 1.0f / (float)p.fold_dim;
-  const float mean = s1 * inv_n;
-  return make_float2(mean, rsqrtf(fmaxf(s2 * inv_n - mean * mean, 0.f) + p.fold_eps));
-}
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory"); }
 
@@ -180,30 +160,6 @@ __device__ __forceinline__ void epi_geglu_tile(const EpiParams& p, void* stage, 
   const bool coalesced = (p.ldc % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
   const int r = lg * 32 + lane;  // this thread's row of the tile
   uint4* srow = reinterpret_cast<uint4*>(stage) + r * U;
-  if (p.fold_stats) {  // LayerNorm fold: acc -> rstd * (acc - mean * c[n]) + d[n] before the GEGLU (c, d in the packed row order)
-    const uint32_t mrow = (uint32_t)m0 + r;
-    const float2 mr = fold_mean_rstd(p, mrow < (uint32_t)p.M ? mrow : 0u);
-    const float mrs = -mr.x * mr.y;
-#pragma unroll
-    for (int h = 0; h < NCH; ++h) {
-      const int cv = n0 + h * 128 + part * W;
-      if (cv < p.N) {
-#pragma unroll
-        for (int j = 0; j < W; j += 4) {
-          const float4 c1 = __ldg(reinterpret_cast<const float4*>(p.fold_c + cv + j)), c2 = __ldg(reinterpret_cast<const float4*>(p.fold_c + cv + 64 + j));
-          float4 d1 = make_float4(0.f, 0.f, 0.f, 0.f), d2 = d1;
-          if (p.fold_d) { d1 = __ldg(reinterpret_cast<const float4*>(p.fold_d + cv + j)); d2 = __ldg(reinterpret_cast<const float4*>(p.fold_d + cv + 64 + j)); }
-          const float cc1[4] = {c1.x, c1.y, c1.z, c1.w}, cc2[4] = {c2.x, c2.y, c2.z, c2.w};
-          const float dd1[4] = {d1.x, d1.y, d1.z, d1.w}, dd2[4] = {d2.x, d2.y, d2.z, d2.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            val[h][j + e] = __float_as_uint(fmaf(mr.y, __uint_as_float(val[h][j + e]), fmaf(mrs, cc1[e], dd1[e])));
-            gate[h][j + e] = __float_as_uint(fmaf(mr.y, __uint_as_float(gate[h][j + e]), fmaf(mrs, cc2[e], dd2[e])));
-          }
-        }
-      }
-    }
-  }
 #pragma unroll
   for (int h = 0; h < NCH; ++h) {
     uint32_t pk[W / 2];
@@ -421,12 +377,6 @@ __device__ __forceinline__ void epi_chunk(const EpiParams& p, float* cstage, uin
     // the squared norm of a (row, head) is a 4-step xor-shuffle over the half warp
     const int col = ncol0 + lane * 4;
     const bool norm = ncol0 < p.norm_cols;   // chunks are 128-aligned and norm_cols % 128 == 0 (checked on the host)
-    const bool fold = p.fold_stats && ncol0 < p.fold_cols;  // (fold_cols % 128 == 0 too)
-    float4 fc = make_float4(0.f, 0.f, 0.f, 0.f), fd = fc;
-    if (fold && col + 3 < nlim) {
-      fc = __ldg(reinterpret_cast<const float4*>(p.fold_c + col));
-      if (p.fold_d) fd = __ldg(reinterpret_cast<const float4*>(p.fold_d + col));
-    }
     float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
     if (norm) {
       const float4 t = __ldg(reinterpret_cast<const float4*>(p.nscale + ((lane * 4) & 63)));
@@ -437,12 +387,6 @@ __device__ __forceinline__ void epi_chunk(const EpiParams& p, float* cstage, uin
       const int r = rr * EPI_WARPS + ew;
       const uint32_t m = (uint32_t)m0 + r;
       float4 o = *reinterpret_cast<const float4*>(cstage + r * CPAD + lane * 4);
-      if (fold) {  // LayerNorm of the A row applied after the product
-        const float2 mr = fold_mean_rstd(p, m < (uint32_t)p.M ? m : 0u);
-        const float mrs = -mr.x * mr.y;
-        o.x = fmaf(mr.y, o.x, fmaf(mrs, fc.x, fd.x)); o.y = fmaf(mr.y, o.y, fmaf(mrs, fc.y, fd.y));
-        o.z = fmaf(mr.y, o.z, fmaf(mrs, fc.z, fd.z)); o.w = fmaf(mr.y, o.w, fmaf(mrs, fc.w, fd.w));
-      }
       if (norm) {
         float ss = o.x * o.x + o.y * o.y + o.z * o.z + o.w * o.w;
 #pragma unroll
@@ -534,7 +478,7 @@ __device__ __forceinline__ void st_cluster_f2(uint32_t cluster_addr, float a, fl
 // distributed shared memory: thread (row r, part 0) of CTA c stores its partial into xstat[buf][c][r] of EVERY CTA of the
 // cluster and arrives on that CTA's `bar_stat` (128 * cluster_size arrivals per tile, release / acquire at cluster scope).
 // Two exchange buffers: a CTA can be at most one tile ahead of a peer (it needs the peer's arrival to get further).
-template <int MODE, typename Release>  // 0: cluster exchange (epilogue 4), 1: global exchange (5), 2: partial statistics only (6)
+template <bool GLOBAL, typename Release>
 __device__ __forceinline__ void epi_tma_finish_ln(const EpiParams& p, uint8_t* stage, uint32_t stage_s, uint32_t bar_res,
                                                   uint32_t& res_phase, uint32_t tmem_chunk, int m0, int n0, int ew, int lg,
                                                   int part, int lane, float2* rowstat, const float2* xstat, uint32_t xstat_s,
@@ -576,27 +520,8 @@ __device__ __forceinline__ void epi_tma_finish_ln(const EpiParams& p, uint8_t* s
       if (n0 + 32 * c < p.N) tma_store_2d(&p.tmC, stage_s + c * (GM * 128), n0 + 32 * c, m0);
     tma_store_commit();
   }
-  if (MODE == 2) {
-    // epilogue 6: this CTA's partial (sum, sum of squares) per row + the bf16 copy of the new rows; the consumer normalises
-    if (part == 0 && (uint32_t)(m0 + r) < (uint32_t)p.M) {
-      float a1 = 0.f, a2 = 0.f;
-#pragma unroll
-      for (int q = 0; q < EPI_PARTS; ++q) { const float2 e = rowstat[q * GM + r]; a1 += e.x; a2 += e.y; }
-      p.stats_out[(int64_t)(m0 + r) * p.n_tiles + n0 / GN] = make_float2(a1, a2);
-    }
-    if ((uint32_t)(m0 + r) < (uint32_t)p.M) {
-      __nv_bfloat16* rrow = reinterpret_cast<__nv_bfloat16*>(p.raw_out) + (int64_t)(m0 + r) * p.ln_ld + col0;
-#pragma unroll
-      for (int j = 0; j < 8; j += 2) {
-        const float4 a = o[j], c = o[j + 1];
-        *reinterpret_cast<uint4*>(rrow + 4 * j) = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w),
-                                                             pack_bf16x2(c.x, c.y), pack_bf16x2(c.z, c.w));
-      }
-    }
-    return;
-  }
   float t1 = 0.f, t2 = 0.f;
-  if (MODE == 1) {
+  if (GLOBAL) {
     // global-memory exchange: slot [buf][block][row]; one arrival per CTA and tile on the group's counter
     float2* mine = p.xstat_g + ((size_t)stat_buf * gridDim.x + blockIdx.x) * GM;
     if (part == 0) {
@@ -833,15 +758,15 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_bf16_kernel(const __grid_con
       const uint32_t use = (uint32_t)(it >> 1);
       int m0, n0;
       const EpiParams& pp = tile_of(it, m0, n0) ? p2 : p;
-      const bool tma = (EPI == 0 && pp.tma_epi) || LN_EPI || EPI == 6;
+      const bool tma = (EPI == 0 && pp.tma_epi) || LN_EPI;
       bool res_vec = false;
       if (tma) epi_tma_begin(pp, base + RING_BYTES, bar_res, m0, n0, ew, lane);
       else res_vec = epi_residual_prefetch<EPI>(pp, cstage, m0, n0, ew, lane);
       mbar_wait(bar_tfull + 8 * acc, use & 1);
       if (it == 0 && threadIdx.x == 64) PHK_STAMP(6);      // accumulator ready
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (LN_EPI || EPI == 6)
-        epi_tma_finish_ln<EPI == 6 ? 2 : EPI == 5 ? 1 : 0>(pp, reinterpret_cast<uint8_t*>(cstage), base + RING_BYTES, bar_res, res_phase,
+      if (LN_EPI)
+        epi_tma_finish_ln<EPI == 5>(pp, reinterpret_cast<uint8_t*>(cstage), base + RING_BYTES, bar_res, res_phase,
                           tmem_base + acc * GN, m0, n0, ew, lg, part, lane, rowstat, xstat, xstat_s, bar_stat, stat_phase,
                           stat_buf, crank, csize, it, cluster_id, [&]() { if (lane == 0) mbar_arrive(bar_tempty + 8 * acc); });
       else if (tma)
@@ -857,7 +782,7 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_bf16_kernel(const __grid_con
                        [&]() { if (lane == 0) mbar_arrive(bar_tempty + 8 * acc); });
       if (it == 0 && threadIdx.x == 64) PHK_STAMP(8);      // tile written out
     }
-    if ((EPI == 0 || LN_EPI || EPI == 6) && ew == 0 && lane == 0) tma_store_wait_read();  // staging read out before the CTA exits (the writes complete with the grid)
+    if ((EPI == 0 || LN_EPI) && ew == 0 && lane == 0) tma_store_wait_read();  // staging read out before the CTA exits (the writes complete with the grid)
   }
   __syncthreads();
   if (threadIdx.x == 0) PHK_STAMP(9);  // CTA done
@@ -1271,24 +1196,9 @@ static int gemm_mode() {
 
 using namespace phk;
 
-// LayerNorm fold of a consuming product (EpiParams::fold_*): statistics of the A rows + the per-column correction vectors
-struct FoldArgs { const float2* stats; int slots; int dim; int cols; float eps; const float* c; const float* d; };
-static void set_fold(EpiParams& p, const FoldArgs* f) {
-  if (!f) return;
-  p.fold_stats = f->stats; p.fold_slots = f->slots; p.fold_dim = f->dim; p.fold_cols = f->cols; p.fold_eps = f->eps;
-  p.fold_c = f->c; p.fold_d = f->d;
-}
-static int check_fold(const FoldArgs& f, int32_t N) {
-  PHK_REQUIRE(f.stats && f.c && f.slots > 0 && f.slots <= 64 && f.dim > 0 && f.cols > 0 && f.cols % 128 == 0 && N % 4 == 0 &&
-                  ((reinterpret_cast<uintptr_t>(f.stats) & 7) == 0) &&
-                  ((reinterpret_cast<uintptr_t>(f.c) | reinterpret_cast<uintptr_t>(f.d)) & 15) == 0,
-              PHK_E_ARG, "LayerNorm fold: statistics / correction vectors missing or misaligned");
-  return 0;
-}
-
-static int gemm_bf16_impl(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int64_t M,
-                          int32_t N, int32_t K, const float* bias, const float* residual, int64_t seg_len,
-                          int64_t seg_stride, int64_t seg_off, int32_t epilogue, const FoldArgs* fold, phk_stream_t s) {
+extern "C" int phk_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int64_t M,
+                             int32_t N, int32_t K, const float* bias, const float* residual, int64_t seg_len,
+                             int64_t seg_stride, int64_t seg_off, int32_t epilogue, phk_stream_t s) {
   Prof prof_(FAM_GEMM_BF16, s, 2.0 * (double)M * N * K);
   PHK_REQUIRE(A && W && C, PHK_E_ARG, "phk_gemm_bf16: null pointer");
   PHK_REQUIRE(M >= 0 && N > 0 && K > 0 && lda >= K && ldw >= K, PHK_E_ARG, "phk_gemm_bf16: bad size");
@@ -1320,75 +1230,15 @@ static int gemm_bf16_impl(const void* A, int64_t lda, const void* W, int64_t ldw
     EpiParams p{C, ldc, M, N, K, bias, residual, seg_len, seg_stride, seg_off, m_pairs, (N + bn - 1) / bn, g_gemm_trace};
     PHK_REQUIRE((int64_t)p.m_tiles * p.n_tiles < (1LL << 31), PHK_E_UNSUPPORTED, "phk_gemm_bf16: too many tiles");
     PHK_TRY(maybe_tma_epilogue(p, epilogue));
-    set_fold(p, fold);
     return wide ? launch_gemm_pair_epi<256>(epilogue, ta, tb, p, st) : launch_gemm_pair_epi<128>(epilogue, ta, tb, p, st);
   }
   PHK_TRY(get_tensor_map(W, N, K, ldw, GN, &tb));
   EpiParams p{C, ldc, M, N, K, bias, residual, seg_len, seg_stride, seg_off, (int)((M + GM - 1) / GM), (N + GN - 1) / GN, g_gemm_trace};
   PHK_REQUIRE((int64_t)p.m_tiles * p.n_tiles < (1LL << 31), PHK_E_UNSUPPORTED, "phk_gemm_bf16: too many tiles");
   PHK_TRY(maybe_tma_epilogue(p, epilogue));
-  set_fold(p, fold);
   if (epilogue == 2) return launch_gemm<2>(ta, tb, p, st);
   if (epilogue == 1) return launch_gemm<1>(ta, tb, p, st);
   return launch_gemm<0>(ta, tb, p, st);
-}
-
-extern "C" int phk_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int64_t M,
-                             int32_t N, int32_t K, const float* bias, const float* residual, int64_t seg_len,
-                             int64_t seg_stride, int64_t seg_off, int32_t epilogue, phk_stream_t s) {
-  return gemm_bf16_impl(A, lda, W, ldw, C, ldc, M, N, K, bias, residual, seg_len, seg_stride, seg_off, epilogue, nullptr, s);
-}
-
-// FeedForward's first linear + GEGLU (epilogue 2) with the LayerNorm in front of it FOLDED into the product
-// (attention.py:45-53): A = the raw bf16 rows x [M, K], W1f = bf16(g[k] * W1[n, k]) in the packed value / gate row order,
-// stats = partial (sum, sum of squares) of the rows (`slots` float2 per row over `fold_dim` = K elements: written by
-// phk_gemm_bf16_res_stats), c[n] = sum_k W1f[n, k] (over the bf16 values), d[n] = sum_k b[k] W1[n, k] or NULL.
-extern "C" int phk_gemm_bf16_geglu_fold(const void* xraw, int64_t lda, const void* W1f, int64_t ldw, void* G, int64_t ldg,
-                                        int64_t M, int32_t N2, int32_t K, const float* stats, int32_t slots, const float* c,
-                                        const float* d, float eps, phk_stream_t s) {
-  FoldArgs f{reinterpret_cast<const float2*>(stats), slots, K, N2, eps, c, d};
-  PHK_TRY(check_fold(f, N2));
-  PHK_REQUIRE(N2 % 128 == 0, PHK_E_ARG, "phk_gemm_bf16_geglu_fold: N must be a multiple of 128");
-  return gemm_bf16_impl(xraw, lda, W1f, ldw, G, ldg, M, N2, K, nullptr, nullptr, 0, 0, 0, 2, &f, s);
-}
-
-// x += A W^T in place (fp32 residual stream, bulk-stored), raw_out = bf16(x) and the partial row statistics of the new x:
-// stats[row * (N / 128) + j] = (sum, sum of squares) over columns [128 j, 128 j + 128) -- what the LayerNorm-folded products
-// (phk_gemm_bf16_geglu_fold, phk_gemm_bf16_qnorm_fold) need of the LayerNorm that follows this residual GEMM
-// (attention.py:311-332).  N % 128 == 0; no exchange between CTAs, any M.
-extern "C" int phk_gemm_bf16_res_stats(const void* A, int64_t lda, const void* W, int64_t ldw, float* C, int64_t ldc,
-                                       int64_t M, int32_t N, int32_t K, const float* bias, void* raw_out, int64_t ld_raw,
-                                       float* stats, phk_stream_t s) {
-  Prof prof_(FAM_GEMM_BF16, s, 2.0 * (double)M * N * K);
-  PHK_REQUIRE(A && W && C && raw_out && stats, PHK_E_ARG, "phk_gemm_bf16_res_stats: null pointer");
-  PHK_REQUIRE(M > 0 && N > 0 && N % GN == 0 && K > 0 && lda >= K && ldw >= K && ldc >= N && ld_raw >= N, PHK_E_ARG,
-              "phk_gemm_bf16_res_stats: bad size (N must be a multiple of 128)");
-  PHK_REQUIRE(lda % 8 == 0 && ldw % 8 == 0 && ldc % 4 == 0 && ld_raw % 8 == 0 &&
-                  ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(C) |
-                    reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(raw_out)) & 15) == 0 &&
-                  (reinterpret_cast<uintptr_t>(stats) & 7) == 0,
-              PHK_E_ARG, "phk_gemm_bf16_res_stats: operands must be 16-byte aligned with leading dimensions multiple of 8 (TMA)");
-  PHK_REQUIRE(M < (1LL << 31) - GM, PHK_E_UNSUPPORTED, "phk_gemm_bf16_res_stats: M too large");
-  CUtensorMap ta, tb;
-  PHK_TRY(get_tensor_map(A, M, K, lda, GM, &ta));
-  PHK_TRY(get_tensor_map(W, N, K, ldw, GN, &tb));
-  EpiParams p{C, ldc, M, N, K, bias, C, 0, 0, 0, (int)((M + GM - 1) / GM), N / GN, nullptr};
-  PHK_TRY(get_c_map(C, M, N, ldc, &p.tmC));
-  p.tma_epi = 1;
-  p.raw_out = raw_out; p.ln_ld = ld_raw; p.stats_out = reinterpret_cast<float2*>(stats);
-  static unsigned long long configured_mask = 0;
-  const bool configured = device_configured(&configured_mask);
-  if (!configured) {
-    PHK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL_LN));
-    mark_configured(&configured_mask);
-  }
-  const int64_t tiles = (int64_t)p.m_tiles * p.n_tiles;
-  PHK_REQUIRE(tiles < (1LL << 31), PHK_E_UNSUPPORTED, "phk_gemm_bf16_res_stats: too many tiles");
-  const int grid = tiles < kNumSMs ? (int)tiles : kNumSMs;
-  p.w_static = 0;
-  PHK_CUDA(launch_pdl(gemm_bf16_kernel<6, false>, dim3(grid), dim3(GTHREADS), (size_t)(SMEM_TOTAL_LN), to_stream(s), ta, tb, p, ta, tb, p));
-  PHK_LAUNCH_CHECK();
-  return 0;
 }
 
 // Two independent products C1 = A1 W1^T (+bias1) [M1,N1] and C2 = A2 W2^T (+bias2) [M2,N2] (fp32 outputs) in one
@@ -1546,8 +1396,8 @@ extern "C" int phk_gemm_bf16_qkv(const void* xn, const void* xraw, int64_t lda, 
 
 // The q projection of a cross-attention block (attention.py:139, 153-157) written as the bf16 operand of the attention
 // core: Qn[M, I] = normalize_per_head(xn Wq^T) * q_scale * sim_scale (epilogue 3 on one problem).  dim_head 64, I % 128 == 0.
-static int gemm_bf16_qnorm_impl(const void* xn, int64_t lda, const void* Wq, int64_t ldw, void* Qn, int64_t M, int32_t I,
-                                int32_t K, const float* q_scale, float sim_scale, const FoldArgs* fold, phk_stream_t s) {
+extern "C" int phk_gemm_bf16_qnorm(const void* xn, int64_t lda, const void* Wq, int64_t ldw, void* Qn, int64_t M, int32_t I,
+                                   int32_t K, const float* q_scale, float sim_scale, phk_stream_t s) {
   Prof prof_(FAM_GEMM_BF16, s, 2.0 * (double)M * I * K);
   PHK_REQUIRE(xn && Wq && Qn && q_scale, PHK_E_ARG, "phk_gemm_bf16_qnorm: null pointer");
   PHK_REQUIRE(M > 0 && I > 0 && I % 128 == 0 && K > 0 && lda >= K && ldw >= K, PHK_E_ARG,
@@ -1562,23 +1412,7 @@ static int gemm_bf16_qnorm_impl(const void* xn, int64_t lda, const void* Wq, int
   PHK_TRY(get_tensor_map(Wq, I, K, ldw, GN, &tb));
   EpiParams p{Qn, I, M, I, K, nullptr, nullptr, 0, 0, 0, (int)((M + GM - 1) / GM), I / GN, nullptr};
   p.tma_epi = 0; p.nscale = q_scale; p.norm_cols = I; p.nmul = sim_scale;
-  set_fold(p, fold);
   return launch_gemm<3>(ta, tb, p, to_stream(s));
-}
-
-extern "C" int phk_gemm_bf16_qnorm(const void* xn, int64_t lda, const void* Wq, int64_t ldw, void* Qn, int64_t M, int32_t I,
-                                   int32_t K, const float* q_scale, float sim_scale, phk_stream_t s) {
-  return gemm_bf16_qnorm_impl(xn, lda, Wq, ldw, Qn, M, I, K, q_scale, sim_scale, nullptr, s);
-}
-
-// The same with the LayerNorm in front of the projection folded into it (see phk_gemm_bf16_geglu_fold): A = raw bf16 rows,
-// Wqf = bf16(g[k] * Wq[n, k]), c[n] = sum_k Wqf[n, k], d[n] = sum_k b[k] Wq[n, k] or NULL.
-extern "C" int phk_gemm_bf16_qnorm_fold(const void* xraw, int64_t lda, const void* Wqf, int64_t ldw, void* Qn, int64_t M,
-                                        int32_t I, int32_t K, const float* q_scale, float sim_scale, const float* stats,
-                                        int32_t slots, const float* c, const float* d, float eps, phk_stream_t s) {
-  FoldArgs f{reinterpret_cast<const float2*>(stats), slots, K, I, eps, c, d};
-  PHK_TRY(check_fold(f, I));
-  return gemm_bf16_qnorm_impl(xraw, lda, Wqf, ldw, Qn, M, I, K, q_scale, sim_scale, &f, s);
 }
 
 // debug / tests: force the kernel choice (0 automatic, 1 one-CTA, 2 CTA pairs 256x128, 3 CTA pairs 256x256; < 0 returns

@@ -173,13 +173,13 @@ def split3_weight(w):
     return out
 
 
-def pack_geglu_w1(w1, inner, inner_pad, dtype=torch.bfloat16):
+def pack_geglu_w1(w1, inner, inner_pad):
     """[2*inner, dim] -> [2*inner_pad, dim] bf16 with rows grouped as [64 value rows | 64 gate rows] per
     128-row tile, so the GEMM epilogue can apply gelu(gate) * value inside one accumulator tile
     (attention.py:40-43: value = first half, gate = second half).  Padding rows are zero."""
     dim = w1.shape[1]
-    w = w1.detach().to(dtype)
-    val = torch.zeros((inner_pad, dim), dtype=dtype, device=w.device)
+    w = w1.detach().to(torch.bfloat16)
+    val = torch.zeros((inner_pad, dim), dtype=torch.bfloat16, device=w.device)
     gate = torch.zeros_like(val)
     val[:inner], gate[:inner] = w[:inner], w[inner:]
     g = inner_pad // 64
@@ -206,21 +206,7 @@ def attn_table(a: Attention, keep: Keep, mode=0):
     t.q_scale, t.k_scale = keep.t(a.q_scale), keep.t(a.k_scale)
     t.wq, t.wkv, t.wo = keep.t(a.to_q.weight), keep.t(a.to_kv.weight), keep.t(a.to_out.weight)
     t.num_null_kv, t.dim_context = a.num_null_kv, a.dim_context
-    if mode == L.PREC_BF16:  # LayerNorm fold of the q projection (phk_gemm_bf16_qnorm_fold)
-        wf, c, d = fold_layernorm(a.to_q.weight, a.norm.gamma, a.norm.beta)
-        keep.refs += [wf, c, d]
-        t.wq_f, t.fold_c, t.fold_d = wf.data_ptr(), c.data_ptr(), d.data_ptr()
     return t
-
-
-def fold_layernorm(w, gamma, beta):
-    """LayerNorm(x) W^T = rstd * (x Wf^T - mean * c) + d with Wf = bf16(gamma[k] * W[n,k]), c[n] = sum_k Wf[n,k] (over the
-    ROUNDED weights, so the mean cancels exactly against the product the tensor cores compute) and d[n] = sum_k beta[k] W[n,k]."""
-    w32 = w.detach().float()
-    wf = (w32 * gamma.detach().float()[None, :]).to(torch.bfloat16).contiguous()
-    c = wf.float().sum(dim=1).contiguous()
-    d = (w32 @ beta.detach().float()).contiguous()
-    return wf, c, d
 
 
 def transformer_table(tf: Transformer, keep: Keep, mode=0):
@@ -246,14 +232,6 @@ def transformer_table(tf: Transformer, keep: Keep, mode=0):
             w2h = pack_w2(ff[4].weight, ly.ff.inner, ly.ff.inner_pad)
             keep.refs += [w1h, w2h]
             ly.ff.w1_h, ly.ff.w2_h = w1h.data_ptr(), w2h.data_ptr()
-            # LayerNorm fold of the first linear (phk_gemm_bf16_geglu_fold): gain folded into the weights BEFORE the packing,
-            # correction vectors packed like the weight rows ([64 value | 64 gate] per 128)
-            w32 = ff[1].weight.detach().float()
-            w1f = pack_geglu_w1(w32 * ff[0].weight.detach().float()[None, :], ly.ff.inner, ly.ff.inner_pad)
-            fc = w1f.float().sum(dim=1).contiguous()
-            fd = pack_geglu_w1((w32 @ ff[0].bias.detach().float())[:, None], ly.ff.inner, ly.ff.inner_pad, dtype=torch.float32)[:, 0].contiguous()
-            keep.refs += [w1f, fc, fd]
-            ly.ff.w1_f, ly.ff.fold_c, ly.ff.fold_d = w1f.data_ptr(), fc.data_ptr(), fd.data_ptr()
         elif mode == L.PREC_BF16X3:  # plain row order (GEGLU stays a separate fp32 kernel), split operands
             ly.ff.w1_h, ly.ff.w2_h = keep.h3(ff[1].weight), keep.h3(ff[4].weight)
     keep.obj(layers)

@@ -298,115 +298,3 @@ def test_cross_attention_on_packed_operands(b, n, ctx_len, heads, cfg):
         torch.cuda.synchronize()
         err = (out.cpu().float() - ref).abs().max().item()
         assert err <= 0.04, f"layer {l}: max |err| {err}"
-
-
-def _partial_stats(x, slots):
-    """what phk_gemm_bf16_res_stats writes: per row, `slots` (sum, sum of squares) over consecutive 128-column groups"""
-    g = x.reshape(x.shape[0], slots, -1)
-    return torch.stack((g.sum(-1), (g * g).sum(-1)), dim=-1).contiguous()
-
-
-@pytest.mark.parametrize("M,N,K", [(4608, 512, 512), (4608, 512, 1408), (300, 256, 192), (40000, 512, 512)])
-def test_residual_gemm_with_raw_rows_and_partial_statistics(M, N, K):
-    """phk_gemm_bf16_res_stats: x += A W^T in place, bf16 copy of the new rows, (sum, sum of squares) per row and 128-column
-    group -- the producer side of the LayerNorm fold.  40000 rows: several tiles per CTA."""
-    a = TC.seeded_randn((M, K), 480).bfloat16()
-    w = (TC.seeded_randn((N, K), 481) / K ** 0.5).bfloat16()
-    x = TC.seeded_randn((M, N), 482) * 2 + 0.5
-    ref_x = x + a.float() @ w.float().t()
-    ad, wd, xd = a.to(DEV), w.to(DEV), x.clone().to(DEV)
-    raw = torch.full((M, N), 9.0, dtype=torch.bfloat16, device=DEV)
-    stats = torch.full((M, N // 128, 2), float("nan"), dtype=torch.float32, device=DEV)
-    L.check(L.lib().phk_gemm_bf16_res_stats(L.ptr(ad), K, L.ptr(wd), K, L.ptr(xd), N, M, N, K, None, L.ptr(raw), N, L.ptr(stats),
-                                            L.stream_ptr()), "phk_gemm_bf16_res_stats")
-    torch.cuda.synchronize()
-    torch.testing.assert_close(xd.cpu(), ref_x, rtol=1e-4, atol=1e-4)
-    torch.testing.assert_close(raw.cpu().float(), ref_x, rtol=1e-2, atol=2e-2)
-    torch.testing.assert_close(stats.cpu(), _partial_stats(ref_x, N // 128), rtol=1e-4, atol=2e-3)
-
-
-@pytest.mark.parametrize("M,D,inner", [(4608, 512, 1365), (300, 256, 100), (129, 128, 64)])
-def test_geglu_product_with_folded_layernorm(M, D, inner):
-    """phk_gemm_bf16_geglu_fold on raw bf16 rows + gain-scaled weights + partial statistics == LayerNorm -> Linear -> GEGLU
-    (attention.py:40-53) within one bf16 rounding of the hidden activations; mean 0.7 / std 2 rows, affine LayerNorm."""
-    from phenaki_pytorch_b200 import modules as Mo
-    x = TC.seeded_randn((M, D), 490) * 2 + 0.7
-    g, b = TC.seeded_randn((D,), 491) * 0.2 + 1.0, TC.seeded_randn((D,), 492) * 0.1
-    w1 = TC.seeded_randn((2 * inner, D), 493) / D ** 0.5
-    h = F.layer_norm(x, (D,), g, b) @ w1.t()
-    ref = F.gelu(h[:, inner:]) * h[:, :inner]
-    inner_pad = (inner + 63) // 64 * 64
-    w1f = Mo.pack_geglu_w1(w1 * g[None, :], inner, inner_pad)
-    c = w1f.float().sum(dim=1)
-    dvec = Mo.pack_geglu_w1((w1 @ b)[:, None], inner, inner_pad, dtype=torch.float32)[:, 0].contiguous()
-    xr = x.bfloat16()
-    stats = _partial_stats(x, D // 128)
-    out = torch.full((M, inner_pad), 9.0, dtype=torch.bfloat16, device=DEV)
-    dv = lambda t_: t_.contiguous().to(DEV)
-    xrd, wd, cd, dd, sd = dv(xr), dv(w1f), dv(c), dv(dvec), dv(stats)
-    L.check(L.lib().phk_gemm_bf16_geglu_fold(L.ptr(xrd), D, L.ptr(wd), D, L.ptr(out), inner_pad, M, 2 * inner_pad, D, L.ptr(sd),
-                                             D // 128, L.ptr(cd), L.ptr(dd), 1e-5, L.stream_ptr()), "phk_gemm_bf16_geglu_fold")
-    torch.cuda.synchronize()
-    got = out.cpu().float()
-    torch.testing.assert_close(got[:, :inner], ref, rtol=3e-2, atol=3e-2)
-    assert float(got[:, inner:].abs().max()) == 0.0 if inner_pad > inner else True
-
-
-@pytest.mark.parametrize("M,D,heads", [(4608, 512, 8), (300, 256, 2)])
-def test_q_projection_with_folded_layernorm(M, D, heads):
-    """phk_gemm_bf16_qnorm_fold == LayerNorm -> to_q -> per-head l2norm * q_scale * 8 (attention.py:139, 153-157)."""
-    from phenaki_pytorch_b200 import modules as Mo
-    I = heads * 64
-    x = TC.seeded_randn((M, D), 495) * 1.5 - 0.4
-    g, b = TC.seeded_randn((D,), 496) * 0.2 + 1.0, TC.seeded_randn((D,), 497) * 0.1
-    wq = TC.seeded_randn((I, D), 498) / D ** 0.5
-    qs = TC.seeded_randn((64,), 499).abs() * 0.3 + 0.7
-    q = F.layer_norm(x, (D,), g, b) @ wq.t()
-    ref = (F.normalize(q.reshape(M, heads, 64), dim=-1) * qs * 8.0).reshape(M, I)
-    wf, c, dvec = Mo.fold_layernorm(wq, g, b)
-    dv = lambda t_: t_.contiguous().to(DEV)
-    xrd, wd, cd, dd, sd, qsd = dv(x.bfloat16()), dv(wf), dv(c), dv(dvec), dv(_partial_stats(x, D // 128)), dv(qs)
-    out = torch.full((M, I), 9.0, dtype=torch.bfloat16, device=DEV)
-    L.check(L.lib().phk_gemm_bf16_qnorm_fold(L.ptr(xrd), D, L.ptr(wd), D, L.ptr(out), M, I, D, L.ptr(qsd), 8.0, L.ptr(sd), D // 128,
-                                             L.ptr(cd), L.ptr(dd), 1e-5, L.stream_ptr()), "phk_gemm_bf16_qnorm_fold")
-    torch.cuda.synchronize()
-    torch.testing.assert_close(out.cpu().float(), ref, rtol=2e-2, atol=6e-2)
-
-
-def test_transformer_with_folded_layernorms_matches_separate_kernels():
-    """PHK_LN_FOLD (read once per process): the bf16 MaskGit logits of one CFG-pair forward and the bf16 C-ViViT ids with the
-    feed-forward / cross-attention LayerNorms folded into the products, against the separate-kernel path (child processes)."""
-    import json
-    import os
-    import subprocess
-    import sys
-    code = (
-        "import json, torch\\n"
-        "import phenaki_pytorch_b200 as P\\n"
-        "from phenaki_pytorch_b200 import _lib as L\\n"
-        "torch.manual_seed(0)\\n"
-        "cv = P.CViViT(dim=512, codebook_size=65536, image_size=256, patch_size=32, temporal_patch_size=2, spatial_depth=4,\\n"
-        "              temporal_depth=4, dim_head=64, heads=8, use_vgg_and_gan=False).cuda().eval()\\n"
-        "mg = P.MaskGit(dim=512, num_tokens=65536, max_seq_len=1024, dim_context=768, depth=6).cuda().eval()\\n"
-        "cv.precision = mg.precision = L.PREC_BF16\\n"
-        "v = torch.randn((2, 3, 17, 256, 256), generator=torch.Generator().manual_seed(77)).cuda()\\n"
-        "ids = cv(v, return_only_codebook_ids=True)\\n"
-        "g = torch.Generator().manual_seed(5)\\n"
-        "tok = torch.randint(0, 65536, (2, 576), generator=g).cuda()\\n"
-        "ctx = torch.randn((2, 16, 768), generator=g).cuda()\\n"
-        "lg = mg.forward_with_cond_scale(tok, cond_scale=3.0, context=ctx, video_patch_shape=(9, 8, 8))\\n"
-        "print(json.dumps(dict(ids=ids.flatten().tolist(), logits=lg.float().flatten()[::997].tolist(), amax=lg.argmax(-1).flatten().tolist())))\\n")
-    outs = {}
-    for mode in ("0", "1"):
-        env = dict(os.environ, PHK_LN_FOLD=mode)
-        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600,
-                           cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-        assert r.returncode == 0, r.stderr[-2000:]
-        outs[mode] = json.loads(r.stdout.strip().splitlines()[-1])
-    a, b = torch.tensor(outs["0"]["ids"]), torch.tensor(outs["1"]["ids"])
-    flipped = sum(bin(int(x)).count("1") for x in (a ^ b).tolist())
-    assert flipped <= 0.002 * a.numel() * 16, f"{flipped} of {a.numel() * 16} token-id bits differ"
-    la, lb = torch.tensor(outs["0"]["logits"]), torch.tensor(outs["1"]["logits"])
-    assert float((la - lb).abs().max()) <= 0.03, float((la - lb).abs().max())
-    agree = (torch.tensor(outs["0"]["amax"]) == torch.tensor(outs["1"]["amax"])).float().mean().item()
-    assert agree >= 0.95, agree

@@ -92,30 +92,6 @@ for (K, name) in [(512, "out-proj"), (1408, "FF2")]:
         slot[0] += 1
     timeit(f"gemm {name} (+res) + LayerNorm, global exchange {R}x{D}x{K}", ln_ws, 2.0 * R * D * K, "TFLOP/s")
 L.check(lib.phk_debug_static_weights(0))
-# LayerNorm fold: producer (residual GEMM + raw rows + partial statistics) and consumers (GEGLU / q projection on raw rows)
-stats4 = torch.zeros(R, D // 128, 2, device=dev)
-raw_o = torch.empty(R, D, dtype=bf, device=dev)
-for (K, name) in [(512, "out-proj"), (1408, "FF2")]:
-    a = torch.randn(R, K, device=dev).to(bf)
-    w = (torch.randn(D, K, device=dev) / K ** 0.5).to(bf)
-    c = torch.zeros(R, D, device=dev)
-    timeit(f"gemm {name} (+res) + raw rows + partial statistics {R}x{D}x{K}", lambda: L.check(lib.phk_gemm_bf16_res_stats(L.ptr(a), K, L.ptr(w), K, L.ptr(c), D, R, D, K, None, L.ptr(raw_o), D, L.ptr(stats4), sp())),
-           2.0 * R * D * K, "TFLOP/s")
-xr = torch.randn(R, D, device=dev).to(bf)
-stats4.copy_(torch.stack((xr.float().reshape(R, 4, 128).sum(-1), (xr.float() ** 2).reshape(R, 4, 128).sum(-1)), dim=-1))
-w1f = torch.randn(2816, D, device=dev).to(bf)
-fc, fd = w1f.float().sum(1).contiguous(), torch.zeros(2816, device=dev)
-gout = torch.empty(R, 1408, dtype=bf, device=dev)
-timeit("gemm FF1 + GEGLU with folded LayerNorm 4608x2816x512", lambda: L.check(lib.phk_gemm_bf16_geglu_fold(L.ptr(xr), D, L.ptr(w1f), D, L.ptr(gout), 1408, R, 2816, D, L.ptr(stats4), 4, L.ptr(fc), L.ptr(fd), 1e-5, sp())),
-       2.0 * R * 2816 * D, "TFLOP/s")
-wqf = torch.randn(I, D, device=dev).to(bf)
-qc, qd = wqf.float().sum(1).contiguous(), torch.zeros(I, device=dev)
-qo = torch.empty(R, I, dtype=bf, device=dev)
-ones64 = torch.ones(64, device=dev)
-timeit("gemm cross q-proj with folded LayerNorm 4608x512x512", lambda: L.check(lib.phk_gemm_bf16_qnorm_fold(L.ptr(xr), D, L.ptr(wqf), D, L.ptr(qo), R, I, D, L.ptr(ones64), 8.0, L.ptr(stats4), 4, L.ptr(qc), L.ptr(qd), 1e-5, sp())),
-       2.0 * R * I * D, "TFLOP/s")
-timeit("gemm cross q-proj (normalising epilogue, LayerNorm separate) 4608x512x512", lambda: L.check(lib.phk_gemm_bf16_qnorm(L.ptr(xr), D, L.ptr(wqf), D, L.ptr(qo), R, I, D, L.ptr(ones64), 8.0, sp())),
-       2.0 * R * I * D, "TFLOP/s")
 
 a1 = torch.randn(R, D, device=dev).to(bf); a2 = torch.randn(R, D, device=dev).to(bf)
 w1 = torch.randn(I, D, device=dev).to(bf); w2 = torch.randn(2 * I, D, device=dev).to(bf)
