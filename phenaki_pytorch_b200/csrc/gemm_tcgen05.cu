@@ -89,10 +89,13 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" 
 // fitted quintic would turn over, while the sigmoid is already saturated.
 __device__ __forceinline__ float geglu_fast(float g, float v) {
   const float g2 = fminf(g * g, 64.0f);
-#ifdef PHK_GEGLU_TANH
-  // A/B variant: sigmoid(z) = 0.5 + 0.5 tanh(z / 2) on ONE MUFU op (tanh.approx, relative error 2^-11) instead of ex2 + rcp:
-  // the same fitted quintic with its coefficients times -ln2 / 2.  Phi is then good to 2.4e-4 absolute (not relative: the
-  // negative tail loses its accuracy), still below the bf16 rounding of the hidden activations.
+#ifndef PHK_GEGLU_EX2_RCP
+  // sigmoid(z) = 0.5 + 0.5 tanh(z / 2) on ONE MUFU op (tanh.approx.f32, relative error 2^-11) instead of ex2 + rcp: the same
+  // fitted quintic with its coefficients times -ln2 / 2.  The epilogue's math phase was MUFU-paced (2 ops x 32 outputs x 16
+  // warps per tile = 2048 of its ~4200 cycles): FF1 + GEGLU 15.6 -> 14.7 us, encode 0.675 -> 0.666 ms
+  // (profiles/r02/ab_geglu_tanh_c20.txt).  Phi is good to 2.4e-4 absolute -- below the bf16 rounding of the hidden
+  // activations; the at-size parity figures did not move (cfg3 logits mean |err| 0.001215 in both builds, 83 vs 87 flipped
+  // LFQ bits).  -DPHK_GEGLU_EX2_RCP restores the two-op form (2.5e-5, and relative accuracy in the negative tail).
   float u = fmaf(g2, -0.00035151678851506f, 0.037005646021930225f);
   u = fmaf(u, g2, 0.7975078842858219f);
   float t;
