@@ -460,6 +460,14 @@ __device__ __forceinline__ void cluster_sync_all() {
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// "Accumulator drained" signal of the pair kernel's epilogue warps to the leader's MMA warp.  Nothing the generic proxy wrote has
+// to become visible with it -- the TMEM reads are complete (tcgen05.wait::ld) and fenced (tcgen05.fence::before_thread_sync) --
+// so the arrive carries the default CTA scope (the form CUTLASS uses for this barrier).  With .release.cluster the compiler
+// emitted an ERRBAR in front of it that waited for the thread's outstanding global stores of the PREVIOUS tile: 10 % of the
+// FF1 + GEGLU kernel's stall samples sat on that one instruction (ncu source page, call 21).
+__device__ __forceinline__ void mbar_arrive_remote_acc(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {  // acquire at cluster scope
   long long t0 = 0;
   for (uint32_t spin = 0;; ++spin) {
@@ -1008,11 +1016,11 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_bf16_pair_kernel(const __gri
           const bool last = h == BN / 128 - 1;
           epi_tma_finish(pp, reinterpret_cast<uint8_t*>(cstage), stage_s, bar_res, res_phase,
                          tmem_base + acc * BN + h * 128, m0, n0 + h * 128, ew, lg, part, lane,
-                         [&]() { if (last && lane == 0) mbar_arrive_remote(tempty_leader + 8 * acc); });
+                         [&]() { if (last && lane == 0) mbar_arrive_remote_acc(tempty_leader + 8 * acc); });
         }
       } else if (EPI == 2) {
         epi_geglu_tile<BN / 128>(pp, cstage, tmem_base + acc * BN, m0, n0, ew, lg, part, lane,
-                                 [&]() { if (lane == 0) mbar_arrive_remote(tempty_leader + 8 * acc); },
+                                 [&]() { if (lane == 0) mbar_arrive_remote_acc(tempty_leader + 8 * acc); },
                                  [&](int slot) { if (it == 0 && threadIdx.x == 64) PHK_STAMP(slot); });
       } else {
 #pragma unroll
@@ -1020,7 +1028,7 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_bf16_pair_kernel(const __gri
           if (h > 0) res_vec = epi_residual_prefetch<EPI>(pp, cstage, m0, n0 + h * 128, ew, lane);
           const bool last = h == BN / 128 - 1;
           epi_chunk<EPI>(pp, cstage, tmem_base + acc * BN + h * 128, m0, n0 + h * 128, res_vec, ew, lg, part, lane,
-                         [&]() { if (last && lane == 0) mbar_arrive_remote(tempty_leader + 8 * acc); });
+                         [&]() { if (last && lane == 0) mbar_arrive_remote_acc(tempty_leader + 8 * acc); });
         }
       }
       if (it == 0 && threadIdx.x == 64) PHK_STAMP(8);
