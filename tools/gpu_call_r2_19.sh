@@ -1,5 +1,7 @@
 #!/bin/bash
 # Round 2, GPU call 19: LayerNorm fold, stage 1 (feed-forward and cross-attention LayerNorms inside the products).
+# Kept for provenance: it ran at commit a205ec7; the code it exercises (PHK_LN_FOLD, phk_gemm_bf16_res_stats, ..._fold) was
+# reverted by fa35a21 after these measurements (profiles/r02/*_c19_*).
 set -u
 O=gpurun_out/r2c19
 mkdir -p $O
