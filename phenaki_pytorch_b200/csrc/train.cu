@@ -110,13 +110,106 @@ __global__ void __launch_bounds__(256) sgemm_strided_kernel(const float* __restr
   }
 }
 
+#ifndef PHK_CUDA_EMU
+// The same batched product on warp-level tensor-core MMAs (bf16 training mode: the attention-backward contractions dP, dq,
+// dk, dv -- everything but the score recomputation, whose softmax needs fp32-grade logits).  fp32 operands with arbitrary
+// strides are converted to bf16 on their way into shared memory (A as [m][k], B as [n][k], 80-byte rows: 16-byte aligned,
+// conflict-free ldmatrix), fp32 accumulation, the SIMT kernel's accumulate modes.  64 x 64 tile per CTA, 8 warps of 16 x 32.
+constexpr int HK = 32, HLD = HK + 8;
+__device__ __forceinline__ void t_ldmatrix_x4(uint32_t (&r)[4], const void* p) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void t_mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(256, 3) hgemm_strided_kernel(const float* __restrict__ A, int64_t sam, int64_t sak,
+                                                            const float* __restrict__ B, int64_t sbk, int64_t sbn,
+                                                            float* __restrict__ C, int64_t ldc, int M, int N, int K,
+                                                            int accumulate, GemmBatch gb) {
+  __shared__ __align__(16) __nv_bfloat16 As[GB][HLD];
+  __shared__ __align__(16) __nv_bfloat16 Bs[GB][HLD];
+  {
+    const int z = blockIdx.z, zo = z / gb.div, zi = z - zo * gb.div;
+    A += zo * gb.a_outer + zi * gb.a_inner;
+    B += zo * gb.b_outer + zi * gb.b_inner;
+    C += zo * gb.c_outer + zi * gb.c_inner;
+  }
+  if (gb.k_total > 0) {
+    const int left = gb.k_total - (int)blockIdx.z * K;
+    K = left < K ? left : K;
+    if (K <= 0) return;
+  }
+  const int m0 = blockIdx.y * GB, n0 = blockIdx.x * GB;
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const int wm = (w & 3) * 16, wn = (w >> 2) * 32;  // this warp's 16 x 32 corner of the tile
+  const bool a_kfast = sak == 1, b_kfast = sbk == 1;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += HK) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {  // 64 x 32 elements per operand, 8 per thread; consecutive threads along the contiguous index
+      int mm, kk;
+      if (a_kfast) { kk = t & 31; mm = (t >> 5) + 8 * i; } else { mm = t & 63; kk = (t >> 6) + 4 * i; }
+      const int m = m0 + mm, k = k0 + kk;
+      As[mm][kk] = __float2bfloat16_rn((m < M && k < K) ? A[(int64_t)m * sam + (int64_t)k * sak] : 0.f);
+      int nn, k2;
+      if (b_kfast) { k2 = t & 31; nn = (t >> 5) + 8 * i; } else { nn = t & 63; k2 = (t >> 6) + 4 * i; }
+      const int n = n0 + nn, kb = k0 + k2;
+      Bs[nn][k2] = __float2bfloat16_rn((n < N && kb < K) ? B[(int64_t)kb * sbk + (int64_t)n * sbn] : 0.f);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int ks = 0; ks < HK / 16; ++ks) {
+      uint32_t a[4];
+      t_ldmatrix_x4(a, &As[wm + (lane & 7) + 8 * ((lane >> 3) & 1)][ks * 16 + 8 * (lane >> 4)]);
+#pragma unroll
+      for (int np = 0; np < 2; ++np) {
+        uint32_t b[4];
+        t_ldmatrix_x4(b, &Bs[wn + (lane & 7) + 8 * (lane >> 4) + 16 * np][ks * 16 + 8 * ((lane >> 3) & 1)]);
+        t_mma_bf16_16816(acc[2 * np], a, b[0], b[1]);
+        t_mma_bf16_16816(acc[2 * np + 1], a, b[2], b[3]);
+      }
+    }
+    __syncthreads();
+  }
+  const int gq = lane >> 2, tq = lane & 3;
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int m = m0 + wm + gq + 8 * (e >> 1), n = n0 + wn + nt * 8 + 2 * tq + (e & 1);
+      if (m >= M || n >= N) continue;
+      float* c = C + (int64_t)m * ldc + n;
+      if (accumulate == 2) atomicAdd(c, acc[nt][e]);
+      else *c = accumulate ? *c + acc[nt][e] : acc[nt][e];
+    }
+}
+#endif
+
 int sgemm_batched(const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbk, int64_t sbn, float* C, int64_t ldc,
-                  int64_t M, int64_t N, int64_t K, int accumulate, const GemmBatch& gb, cudaStream_t st) {
+                  int64_t M, int64_t N, int64_t K, int accumulate, const GemmBatch& gb, cudaStream_t st, bool bf16_products = false) {
   PHK_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0, PHK_E_ARG, "train: bad GEMM arguments");
   PHK_REQUIRE(M < (1LL << 31) && N < (1LL << 31) && K < (1LL << 31), PHK_E_UNSUPPORTED, "train: GEMM too large");
   PHK_REQUIRE(gb.count >= 1 && gb.count <= 65535 && gb.div >= 1, PHK_E_UNSUPPORTED, "train: GEMM batch too large");
   dim3 grid((unsigned)((N + GB - 1) / GB), (unsigned)((M + GB - 1) / GB), (unsigned)gb.count);
   PHK_REQUIRE(grid.y <= 65535, PHK_E_UNSUPPORTED, "train: GEMM M too large");
+#ifndef PHK_CUDA_EMU
+  static const bool mma_env = [] { const char* e = std::getenv("PHK_ATTN_BWD_MMA"); return !(e && e[0] == '0'); }();
+  if (bf16_products && mma_env) {
+    PHK_KERNEL_LAUNCH(hgemm_strided_kernel, dim3(grid), dim3(256), (size_t)(0), st, A, sam, sak, B, sbk, sbn, C, ldc, (int)M, (int)N, (int)K, accumulate, gb);
+    PHK_LAUNCH_CHECK();
+    return 0;
+  }
+#endif
+  (void)bf16_products;
   PHK_KERNEL_LAUNCH(sgemm_strided_kernel, dim3(grid), dim3(256), (size_t)(0), st, A, sam, sak, B, sbk, sbn, C, ldc, (int)M, (int)N, (int)K, accumulate, gb);
   PHK_LAUNCH_CHECK();
   return 0;
@@ -594,7 +687,7 @@ int64_t attn_bwd_scratch_floats(int b, int H, int n, int nkt, int dh) {
 // q [b*n, I], kv [b*m, 2I], dO [b*n, I] -> dq [b*n, I], dkv [b*m, 2I]; parameter gradients accumulate
 int attention_backward(const float* q, const float* kv, const phk_attn_t& A, const phk_attn_t& G, const float* bias,
                        const uint8_t* key_mask, const float* dO, float* dq, float* dkv, float* dbias,
-                       const AttnBwdGeom& g, float* scratch, cudaStream_t st) {
+                       const AttnBwdGeom& g, float* scratch, cudaStream_t st, bool bf16_products = false) {
   PHK_REQUIRE(g.dh <= 32 * kDPL, PHK_E_UNSUPPORTED, "train: dim_head > 128");
   PHK_REQUIRE(g.nnull == 0 || (A.null_kv && G.null_kv), PHK_E_ARG, "train: null_kv (gradient) missing");
   const int nkt = g.nnull + g.m;
@@ -616,7 +709,7 @@ int attention_backward(const float* q, const float* kv, const phk_attn_t& A, con
   PHK_TRY(sgemm_batched(B.qh, g.dh, 1, B.kh, 1, g.dh, B.P, nkt, g.n, nkt, g.dh, 0, bs, st));
   const GemmBatch bd{(int)bh, g.H, (int64_t)g.n * I, (int64_t)g.dh, (int64_t)g.H * nkt * g.dh, (int64_t)nkt * g.dh,
                      (int64_t)g.H * g.n * nkt, (int64_t)g.n * nkt};
-  PHK_TRY(sgemm_batched(dO, I, 1, B.vv, 1, g.dh, B.dS, nkt, g.n, nkt, g.dh, 0, bd, st));
+  PHK_TRY(sgemm_batched(dO, I, 1, B.vv, 1, g.dh, B.dS, nkt, g.n, nkt, g.dh, 0, bd, st, bf16_products));
   PHK_KERNEL_LAUNCH(attn_bwd_softmax_kernel, dim3((unsigned)((bh * g.n + 7) / 8)), dim3(256), (size_t)(0), st, bias, key_mask, B.P, B.dS, g);
   PHK_LAUNCH_CHECK();
   // dq / dk / dv contractions: batched register-tiled products for long sequences (the warp-per-row loops of the two
@@ -628,12 +721,12 @@ int attention_backward(const float* q, const float* kv, const phk_attn_t& A, con
     preK = preQ + bh * g.n * g.dh;
     preV = preK + bh * nkt * g.dh;
     const GemmBatch bq{(int)bh, 1, (int64_t)g.n * nkt, 0, (int64_t)nkt * g.dh, 0, (int64_t)g.n * g.dh, 0};
-    PHK_TRY(sgemm_batched(B.dS, nkt, 1, B.kh, g.dh, 1, preQ, g.dh, g.n, g.dh, nkt, 0, bq, st));             // dS . kh
+    PHK_TRY(sgemm_batched(B.dS, nkt, 1, B.kh, g.dh, 1, preQ, g.dh, g.n, g.dh, nkt, 0, bq, st, bf16_products));  // dS . kh
     const GemmBatch bk{(int)bh, 1, (int64_t)g.n * nkt, 0, (int64_t)g.n * g.dh, 0, (int64_t)nkt * g.dh, 0};
-    PHK_TRY(sgemm_batched(B.dS, 1, nkt, B.qh, g.dh, 1, preK, g.dh, nkt, g.dh, g.n, 0, bk, st));             // dS^T . qh
+    PHK_TRY(sgemm_batched(B.dS, 1, nkt, B.qh, g.dh, 1, preK, g.dh, nkt, g.dh, g.n, 0, bk, st, bf16_products));  // dS^T . qh
     const GemmBatch bv{(int)bh, g.H, (int64_t)g.H * g.n * nkt, (int64_t)g.n * nkt, (int64_t)g.n * I, (int64_t)g.dh,
                        (int64_t)g.H * nkt * g.dh, (int64_t)nkt * g.dh};
-    PHK_TRY(sgemm_batched(B.P, 1, nkt, dO, I, 1, preV, g.dh, nkt, g.dh, g.n, 0, bv, st));                    // P^T . dO
+    PHK_TRY(sgemm_batched(B.P, 1, nkt, dO, I, 1, preV, g.dh, nkt, g.dh, g.n, 0, bv, st, bf16_products));     // P^T . dO
   }
   PHK_KERNEL_LAUNCH(attn_bwd_dq_kernel, dim3((unsigned)((bh * g.n + 7) / 8)), dim3(256), (size_t)(0), st, q, B.kh, B.dS, A.q_scale, dq, (float*)G.q_scale, (const float*)preQ, g);
   PHK_LAUNCH_CHECK();
@@ -1216,7 +1309,7 @@ extern "C" int phk_maskgit_train_step(const phk_maskgit_t* m, const phk_maskgit_
       PHK_TRY(dgrad_p(prec, tc, dx, Cx.wo, dob, R, D, I, 0, s));
       PHK_TRY(wgrad_p(prec, tc, dx, S.o2, (float*)Gx.wo, R, D, I, s));
       const AttnBwdGeom g2{b, H, n, L, Cx.num_null_kv, DH};
-      PHK_TRY(attention_backward(S.q2, S.ckv, Cx, Gx, nullptr, text_mask, dob, dq, dckv, nullptr, g2, asc, st));
+      PHK_TRY(attention_backward(S.q2, S.ckv, Cx, Gx, nullptr, text_mask, dob, dq, dckv, nullptr, g2, asc, st, prec == PHK_PREC_BF16));
       PHK_TRY(wgrad_p(prec, tc, dq, S.xn2, (float*)Gx.wq, R, I, D, s));
       PHK_TRY(dgrad_p(prec, tc, dq, Cx.wq, dtmp, R, I, D, 0, s));
       PHK_TRY(ln_backward(S.x2, Cx.norm_g, dtmp, dx, 1, (float*)Gx.norm_g, nullptr, stats, R, D, st));
@@ -1231,7 +1324,7 @@ extern "C" int phk_maskgit_train_step(const phk_maskgit_t* m, const phk_maskgit_
       PHK_TRY(dgrad_p(prec, tc, dx, A.wo, dob, R, D, I, 0, s));
       PHK_TRY(wgrad_p(prec, tc, dx, S.o1, (float*)GA.wo, R, D, I, s));
       const AttnBwdGeom g1{b, H, n, n, 0, DH};
-      PHK_TRY(attention_backward(S.q1, S.kv1, A, GA, bias, video_mask, dob, dq, dkv, dbias, g1, asc, st));
+      PHK_TRY(attention_backward(S.q1, S.kv1, A, GA, bias, video_mask, dob, dq, dkv, dbias, g1, asc, st, prec == PHK_PREC_BF16));
       PHK_TRY(wgrad_p(prec, tc, dq, S.xn1, (float*)GA.wq, R, I, D, s));
       PHK_TRY(wgrad_p(prec, tc, dkv, S.x1, (float*)GA.wkv, R, 2 * I, D, s));
       PHK_TRY(dgrad_p(prec, tc, dq, A.wq, dtmp, R, I, D, 0, s));
