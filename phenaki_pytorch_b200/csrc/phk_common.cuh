@@ -154,22 +154,6 @@ __device__ __forceinline__ float gumbel_from_bits(uint32_t r) {
   return fmaf(-0.69314718f, fast_lg2(e), 0.36651292f);
 }
 
-// acc += x * w on four lanes as two packed FFMA2 (fma.rn.f32x2: per component the same IEEE fused multiply-add as fmaf, half
-// the issue slots).  Used where fp32 FMAs are the kernel's instruction bulk (the PEG stencil).
-__device__ __forceinline__ void ffma4(float4& acc, const float4& x, const float4& w) {
-  unsigned long long a0, a1, x0, x1, w0, w1;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(a0) : "f"(acc.x), "f"(acc.y));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(a1) : "f"(acc.z), "f"(acc.w));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(x0) : "f"(x.x), "f"(x.y));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(x1) : "f"(x.z), "f"(x.w));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(w0) : "f"(w.x), "f"(w.y));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(w1) : "f"(w.z), "f"(w.w));
-  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a0) : "l"(x0), "l"(w0));
-  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a1) : "l"(x1), "l"(w1));
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(acc.x), "=f"(acc.y) : "l"(a0));
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(acc.z), "=f"(acc.w) : "l"(a1));
-}
-
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

@@ -539,7 +539,12 @@ __global__ void __launch_bounds__(256) peg_tiled_kernel(const float* __restrict_
       for (int kw = 0; kw < 3; ++kw) {
         const float4 wv = s_w[((kt * 3 + kh) * 3 + kw) * (PEG_CH / 4) + c4];
 #pragma unroll
-        for (int i = 0; i < WW; ++i) ffma4(acc[i], xr[i + kw], wv);  // two packed FFMA2: the stencil is FMA-issue bound
+        for (int i = 0; i < WW; ++i) {
+          acc[i].x = fmaf(xr[i + kw].x, wv.x, acc[i].x);
+          acc[i].y = fmaf(xr[i + kw].y, wv.y, acc[i].y);
+          acc[i].z = fmaf(xr[i + kw].z, wv.z, acc[i].z);
+          acc[i].w = fmaf(xr[i + kw].w, wv.w, acc[i].w);
+        }
       }
     }
   }

@@ -255,7 +255,4 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return t;
 }
 struct StaticWeightsScope {};  // the GPU GEMM's weight prefetch hint (phk_common.cuh): nothing to do on the CPU executor
-__device__ __forceinline__ void ffma4(float4& acc, const float4& x, const float4& w) {  // (phk_common.cuh: two FFMA2 on the GPU)
-  acc.x = fmaf(x.x, w.x, acc.x); acc.y = fmaf(x.y, w.y, acc.y); acc.z = fmaf(x.z, w.z, acc.z); acc.w = fmaf(x.w, w.w, acc.w);
-}
 }  // namespace phk
