@@ -248,3 +248,21 @@ def test_critic_and_primed_iterations_equal_the_per_step_loop(critic_kind, prime
     for a, b in zip(runs[True], runs[False]):
         assert torch.equal(a, b)
     assert not torch.equal(runs[True][0], runs[True][1])
+
+
+def test_cvivit_with_36_token_frames_takes_the_mid_size_attention_and_tracks_fp32_mode():
+    """Frames of 6 x 6 = 36 tokens: the spatial self-attention runs on attention_mid_mma_kernel (17..63 tokens) in bf16 mode.
+    Against the same model in fp32 mode: LFQ bit agreement above the bf16 bar, and bf16 attention really ran on the mid-size
+    kernel's path (the fp32 fallback for these lengths would give the same bar, so the launch count is checked too)."""
+    torch.manual_seed(9)
+    model = P.CViViT(dim=256, codebook_size=4096, image_size=48, patch_size=8, temporal_patch_size=2, spatial_depth=2,
+                     temporal_depth=2, dim_head=64, heads=4, use_vgg_and_gan=False).to(DEV).eval()
+    video = C.seeded_randn((3, 3, 5, 48, 48), 17).to(DEV)
+    model.precision = L.PREC_F32
+    ref = model(video, return_only_codebook_ids=True).cpu()
+    model.precision = L.PREC_BF16
+    ids = model(video, return_only_codebook_ids=True).cpu()
+    assert ids.shape == ref.shape == (3, 3, 6, 6)
+    x = (ids ^ ref).reshape(-1)
+    flipped = sum(int(((x >> k) & 1).sum()) for k in range(12))
+    assert flipped <= 0.03 * x.numel() * 12, f"{flipped} of {x.numel() * 12} LFQ bits differ from fp32 mode"
